@@ -1,0 +1,567 @@
+// oracle/o_bsdf.h -- TEST INFRASTRUCTURE ONLY (CPU oracle; never linked into the product).
+//
+// Restates the two hair BSDF plugins of the reference, quirks included:
+//   KajiyaKay           src/bsdfs/kajiyakay.cpp:60-273
+//   MarschnerDiffuse    src/bsdfs/marschner_diffuse.cpp:39-109,113-160,193-247,279-374,377-847
+//   (the plugin that is actually built as `marschner`, src/bsdfs/SConscript:30-31)
+//   RoughTransmittance  src/bsdfs/rtrans.h:81-149,183-408; splines src/libcore/spline.cpp:23-60,236-304,~380-447
+//   GaussLegendre<140>  src/bsdfs/gausssexylingerie.hpp;  InterpolatedDistribution1D.hpp
+#pragma once
+#include "o_math.h"
+#include <cstdio>
+#include <memory>
+
+namespace orc {
+
+// BSDF::EBSDFType bits used on this path (include/mitsuba/render/bsdf.h:230-270)
+enum { ENull = 0x1, EDiffuseReflection = 0x2, EGlossyReflection = 0x8, EDeltaReflection = 0x20 };
+
+struct BSDFSample {
+    V3 wo; V3 weight; float pdf = 0; int sampledType = 0; int sampledComponent = -1; float eta = 1;
+};
+
+// ---------------------------------------------------------------------------------------------
+// KajiyaKay
+// ---------------------------------------------------------------------------------------------
+struct KajiyaKay {
+    V3 diffuse, specular; float exponent; float specularSamplingWeight;
+
+    // kajiyakay.cpp:60-107 (+ ensureEnergyConservation src/librender/bsdf.cpp:115-146)
+    void configure(V3 diff, V3 spec, float expo) {
+        float actualMax = maxc(spec + diff);
+        if (actualMax > 1.0f) {
+            float scale = 0.99f * (1.0f / actualMax);
+            spec = spec * scale; diff = diff * scale;
+        }
+        diffuse = diff; specular = spec; exponent = expo;
+        float dAvg = luminance(diff), sAvg = luminance(spec);
+        specularSamplingWeight = sAvg / (dAvg + sAvg);
+    }
+    static V3 reflect(const V3 &wi) { return V3(-wi.x, -wi.y, wi.z); }
+
+    // kajiyakay.cpp:122-180
+    V3 eval(const V3 &wi, const V3 &wo) const {
+        if (wi.z <= 0 || wo.z <= 0) return V3(0.0f);
+        V3 result(0.0f);
+        float tl = std::abs(wi.x), te = std::abs(wo.x);
+        float sin_tl = std::sqrt(1 - tl * tl), sin_te = std::sqrt(1 - te * te);
+        float alpha = tl * te + sin_tl * sin_te;
+        if (alpha > 0.0f && wi.x * wo.x < 0) {
+            V3 res = 0.15f * specular * ((exponent + 2) * kInvFourPi * std::pow(alpha, exponent));
+            result += res;
+        }
+        result += diffuse * kInvPi;
+        return result * wo.z;
+    }
+    // kajiyakay.cpp:182-214
+    float pdf(const V3 &wi, const V3 &wo) const {
+        if (wi.z <= 0 || wo.z <= 0) return 0.0f;
+        float diffuseProb = kInvPi * wo.z; // warp::squareToCosineHemispherePdf
+        float specProb = 0.0f;
+        float alpha = dot(wo, reflect(wi));
+        if (alpha > 0) specProb = std::pow(alpha, exponent) * (exponent + 1.0f) / (2.0f * kPi);
+        return specularSamplingWeight * specProb + (1 - specularSamplingWeight) * diffuseProb;
+    }
+    // kajiyakay.cpp:216-273
+    BSDFSample sample(const V3 &wi, float sx, float sy) const {
+        BSDFSample r; r.weight = V3(0.0f);
+        bool choseSpecular = true;
+        if (sx <= specularSamplingWeight) {
+            sx /= specularSamplingWeight;
+        } else {
+            sx = (sx - specularSamplingWeight) / (1 - specularSamplingWeight);
+            choseSpecular = false;
+        }
+        if (choseSpecular) {
+            V3 R = reflect(wi);
+            float sinAlpha = std::sqrt(1 - std::pow(sy, 2 / (exponent + 1)));
+            float cosAlpha = std::pow(sy, 1 / (exponent + 1));
+            float phi = (2.0f * kPi) * sx;
+            V3 localDir(sinAlpha * std::cos(phi), sinAlpha * std::sin(phi), cosAlpha);
+            r.wo = Frame(R).toWorld(localDir);
+            r.sampledComponent = 1; r.sampledType = EGlossyReflection; // labels swapped in the reference
+            if (r.wo.z <= 0) return r;
+        } else {
+            r.wo = squareToCosineHemisphere(sx, sy);
+            r.sampledComponent = 0; r.sampledType = EDiffuseReflection;
+        }
+        r.eta = 1.0f;
+        r.pdf = pdf(wi, r.wo);
+        if (r.pdf == 0) return r;
+        r.weight = eval(wi, r.wo) / r.pdf;
+        return r;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Cubic-spline helpers (src/libcore/spline.cpp)
+// ---------------------------------------------------------------------------------------------
+// spline.cpp:23-60
+static inline float evalCubicInterp1D(float x, const float *values, size_t size, float mn, float mx) {
+    if (!(x >= mn && x <= mx)) return 0.0f;
+    float t = ((x - mn) * (size - 1)) / (mx - mn);
+    size_t k = std::max((size_t) 0, std::min((size_t) t, size - 2));
+    float f0 = values[k], f1 = values[k + 1], d0, d1;
+    if (k > 0) d0 = 0.5f * (values[k + 1] - values[k - 1]); else d0 = values[k + 1] - values[k];
+    if (k + 2 < size) d1 = 0.5f * (values[k + 2] - values[k]); else d1 = values[k + 1] - values[k];
+    t = t - (float) k;
+    float t2 = t * t, t3 = t2 * t;
+    return (2 * t3 - 3 * t2 + 1) * f0 + (-2 * t3 + 3 * t2) * f1 + (t3 - 2 * t2 + t) * d0 + (t3 - t2) * d1;
+}
+// per-dimension knot weights shared by the 2-D/3-D variants (spline.cpp:242-287)
+static inline bool splineWeights(float p, size_t size, size_t &knot, float *weights) {
+    if (!(p >= 0.0f && p <= 1.0f)) return false;
+    float t = ((p - 0.0f) * (size - 1)) / (1.0f - 0.0f);
+    knot = std::min((size_t) t, size - 2);
+    t = t - (float) knot;
+    float t2 = t * t, t3 = t2 * t;
+    weights[0] = 0.0f; weights[1] = 2 * t3 - 3 * t2 + 1; weights[2] = -2 * t3 + 3 * t2; weights[3] = 0.0f;
+    float d0 = t3 - 2 * t2 + t, d1 = t3 - t2;
+    if (knot > 0) { weights[2] += 0.5f * d0; weights[0] -= 0.5f * d0; }
+    else { weights[2] += d0; weights[1] -= d0; }
+    if (knot + 2 < size) { weights[3] += 0.5f * d1; weights[1] -= 0.5f * d1; }
+    else { weights[2] += d1; weights[1] -= d1; }
+    return true;
+}
+// spline.cpp:236-304 (min=0,max=1)
+static inline float evalCubicInterp2D(float px, float py, const float *values, size_t sx, size_t sy) {
+    float w[2][4]; size_t knot[2];
+    if (!splineWeights(px, sx, knot[0], w[0])) return 0.0f;
+    if (!splineWeights(py, sy, knot[1], w[1])) return 0.0f;
+    float result = 0.0f;
+    for (int y = -1; y <= 2; ++y) {
+        float wy = w[1][y + 1];
+        for (int x = -1; x <= 2; ++x) {
+            float wxy = w[0][x + 1] * wy;
+            if (wxy == 0) continue;
+            size_t pos = (knot[1] + y) * sx + knot[0] + x;
+            result += values[pos] * wxy;
+        }
+    }
+    return result;
+}
+// spline.cpp (evalCubicInterp3D, ~:380-447)
+static inline float evalCubicInterp3D(float px, float py, float pz, const float *values, size_t sx, size_t sy, size_t sz) {
+    float w[3][4]; size_t knot[3];
+    if (!splineWeights(px, sx, knot[0], w[0])) return 0.0f;
+    if (!splineWeights(py, sy, knot[1], w[1])) return 0.0f;
+    if (!splineWeights(pz, sz, knot[2], w[2])) return 0.0f;
+    float result = 0.0f;
+    for (int z = -1; z <= 2; ++z) {
+        float wz = w[2][z + 1];
+        for (int y = -1; y <= 2; ++y) {
+            float wyz = w[1][y + 1] * wz;
+            for (int x = -1; x <= 2; ++x) {
+                float wxyz = w[0][x + 1] * wyz;
+                if (wxyz == 0) continue;
+                size_t pos = ((knot[2] + z) * sy + (knot[1] + y)) * sx + knot[0] + x;
+                result += values[pos] * wxyz;
+            }
+        }
+    }
+    return result;
+}
+
+// ---------------------------------------------------------------------------------------------
+// RoughTransmittance (src/bsdfs/rtrans.h)
+// ---------------------------------------------------------------------------------------------
+struct RoughTransmittance {
+    size_t etaSamples = 0, alphaSamples = 0, thetaSamples = 0;
+    bool etaFixed = false, alphaFixed = false;
+    float etaMin = 0, etaMax = 0, alphaMin = 0, alphaMax = 0;
+    std::vector<float> trans, diffTrans;
+
+    // rtrans.h:81-149
+    void load(const std::string &path) {
+        FILE *f = std::fopen(path.c_str(), "rb");
+        if (!f) throw std::runtime_error("oracle: cannot open " + path);
+        char hdr[17];
+        if (std::fread(hdr, 1, 17, f) != 17 || std::memcmp(hdr, "MTS_TRANSMITTANCE", 17) != 0) { std::fclose(f); throw std::runtime_error("oracle: bad transmittance file"); }
+        uint64_t sz[3];
+        if (std::fread(sz, 8, 3, f) != 3) { std::fclose(f); throw std::runtime_error("oracle: bad transmittance file"); }
+        etaSamples = sz[0]; alphaSamples = sz[1]; thetaSamples = sz[2];
+        size_t transSize = 2 * etaSamples * alphaSamples * thetaSamples, diffSize = 2 * etaSamples * alphaSamples;
+        float rng[4];
+        if (std::fread(rng, 4, 4, f) != 4) { std::fclose(f); throw std::runtime_error("oracle: bad transmittance file"); }
+        etaMin = rng[0]; etaMax = rng[1]; alphaMin = rng[2]; alphaMax = rng[3];
+        std::vector<float> temp(transSize + diffSize);
+        if (std::fread(temp.data(), 4, temp.size(), f) != temp.size()) { std::fclose(f); throw std::runtime_error("oracle: truncated transmittance file"); }
+        std::fclose(f);
+        trans.resize(transSize); diffTrans.resize(diffSize);
+        const float *ptr = temp.data(); size_t fdr = 0, de = 0;
+        for (size_t i = 0; i < 2 * etaSamples; ++i)
+            for (size_t j = 0; j < alphaSamples; ++j) {
+                for (size_t k = 0; k < thetaSamples; ++k) trans[de++] = *ptr++;
+                diffTrans[fdr++] = *ptr++;
+            }
+        etaFixed = alphaFixed = false;
+    }
+    float warpAlpha(float alpha) const { return std::pow((alpha - alphaMin) / (alphaMax - alphaMin), 0.25f); }
+    // rtrans.h:292-343
+    void setEta(float eta) {
+        if (etaFixed) return;
+        const float *tr = trans.data(), *dt = diffTrans.data();
+        if (eta < 1) { tr += etaSamples * alphaSamples * thetaSamples; dt += etaSamples * alphaSamples; eta = 1.0f / eta; }
+        if (eta < etaMin) eta = etaMin;
+        float warpedEta = std::pow((eta - etaMin) / (etaMax - etaMin), 0.25f);
+        std::vector<float> nt(alphaSamples * thetaSamples), nd(alphaSamples);
+        float dAlpha = 1.0f / (alphaSamples - 1), dTheta = 1.0f / (thetaSamples - 1);
+        for (size_t i = 0; i < alphaSamples; ++i) {
+            for (size_t j = 0; j < thetaSamples; ++j)
+                nt[i * thetaSamples + j] = evalCubicInterp3D(j * dTheta, i * dAlpha, warpedEta, tr, thetaSamples, alphaSamples, etaSamples);
+            nd[i] = evalCubicInterp2D(i * dAlpha, warpedEta, dt, alphaSamples, etaSamples);
+        }
+        trans.swap(nt); diffTrans.swap(nd); etaFixed = true;
+    }
+    // rtrans.h:351-384
+    void setAlpha(float alpha) {
+        if (!etaFixed) throw std::runtime_error("setAlpha(): needs a preceding call to setEta()!");
+        if (alphaFixed) return;
+        float wa = warpAlpha(alpha);
+        std::vector<float> nt(thetaSamples), nd(1);
+        float dTheta = 1.0f / (thetaSamples - 1);
+        for (size_t i = 0; i < thetaSamples; ++i)
+            nt[i] = evalCubicInterp2D(i * dTheta, wa, trans.data(), thetaSamples, alphaSamples);
+        nd[0] = evalCubicInterp1D(wa, diffTrans.data(), alphaSamples, 0.0f, 1.0f);
+        trans.swap(nt); diffTrans.swap(nd); alphaFixed = true;
+    }
+    // rtrans.h:183-234 (only the branches reachable on this path)
+    float eval(float cosTheta, float alpha = 0) const {
+        float warpedCosTheta = std::pow(std::abs(cosTheta), 0.25f), result;
+        if (alphaFixed && etaFixed) {
+            if (!(cosTheta >= 0)) return 0.f;
+            result = evalCubicInterp1D(warpedCosTheta, trans.data(), thetaSamples, 0.0f, 1.0f);
+        } else if (etaFixed) {
+            if (!(cosTheta >= 0)) return 0.f;
+            result = evalCubicInterp2D(warpedCosTheta, warpAlpha(alpha), trans.data(), thetaSamples, alphaSamples);
+        } else throw std::runtime_error("oracle: 3-D rough transmittance lookup not on this path");
+        return std::min(1.0f, std::max(0.0f, result));
+    }
+    // rtrans.h:249-290
+    float evalDiffuse(float alpha = 0) const {
+        float result;
+        if (alphaFixed && etaFixed) result = diffTrans[0];
+        else if (etaFixed) result = evalCubicInterp1D(warpAlpha(alpha), diffTrans.data(), alphaSamples, 0.0f, 1.0f);
+        else throw std::runtime_error("oracle: 2-D diffuse transmittance lookup not on this path");
+        return std::min(1.0f, std::max(0.0f, result));
+    }
+    void checkRanges(float eta, float alpha) const { // rtrans.h:386-405
+        if (alpha < alphaMin || alpha > alphaMax) throw std::runtime_error("roughness outside the supported range");
+        if (eta < 1) eta = 1 / eta;
+        if (eta < etaMin || eta > etaMax) throw std::runtime_error("IOR outside the supported range");
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Gauss-Legendre nodes (gausssexylingerie.hpp:14-68) -- roots/weights in double, rounded to float
+// ---------------------------------------------------------------------------------------------
+template <int N> struct GaussLegendre {
+    float points[N], weights[N];
+    static double legendre(double x, int n) {
+        if (n == 0) return 1.0;
+        if (n == 1) return x;
+        double P0 = 1.0, P1 = x;
+        for (int i = 2; i <= n; ++i) { double Pi = ((2.0 * i - 1.0) * x * P1 - (i - 1.0) * P0) / i; P0 = P1; P1 = Pi; }
+        return P1;
+    }
+    static double legendreDeriv(double x, int n) { return n / (x * x - 1.0) * (x * legendre(x, n) - legendre(x, n - 1)); }
+    static double kthRoot(int k) {
+        double x = std::cos(kPi * (4.0 * k - 1.0) / (4.0 * N + 2.0)) * (1.0 - 1.0 / (8.0 * N * N) + 1.0 / (8.0 * N * N * N));
+        for (int i = 0; i < 100; ++i) {
+            double f = legendre(x, N);
+            x -= f / legendreDeriv(x, N);
+            if (std::abs(f) < 1e-6) break;
+        }
+        return x;
+    }
+    GaussLegendre() {
+        for (int i = 0; i < N; ++i) {
+            points[i] = float(kthRoot(i + 1));
+            weights[i] = float(2.0 / ((1.0 - points[i] * points[i]) * legendreDeriv(points[i], N) * legendreDeriv(points[i], N)));
+        }
+    }
+};
+
+// InterpolatedDistribution1D.hpp:37-110
+struct InterpolatedDistribution1D {
+    int size = 0, num = 0;
+    std::vector<float> pdfs, cdfs, sums;
+    float &cdf(int x, int d) { return cdfs[x + d * (size + 1)]; }
+    float cdf(int x, int d) const { return cdfs[x + d * (size + 1)]; }
+    float &pdfv(int x, int d) { return pdfs[x + d * size]; }
+    float pdfv(int x, int d) const { return pdfs[x + d * size]; }
+    void init(std::vector<float> weights, int size_, int num_) {
+        size = size_; num = num_; pdfs = std::move(weights);
+        cdfs.assign((size + 1) * num, 0.0f); sums.assign(num, 0.0f);
+        for (int dist = 0; dist < num; ++dist) {
+            cdf(0, dist) = 0.0f;
+            for (int x = 0; x < size; ++x) cdf(x + 1, dist) = pdfv(x, dist) + cdf(x, dist);
+            sums[dist] = cdf(size, dist);
+            if (sums[dist] < 1e-4f) {
+                float ratio = 1.0f / size;
+                for (int x = 0; x < size; ++x) { pdfv(x, dist) = ratio; cdf(x, dist) = x * ratio; }
+            } else {
+                float scale = 1.0f / sums[dist];
+                for (int x = 0; x < size; ++x) { pdfv(x, dist) *= scale; cdf(x, dist) *= scale; }
+            }
+            cdf(size, dist) = 1.0f;
+        }
+    }
+    void warp(float distribution, float &u, int &x) const {
+        int d0 = clampi(int(distribution), 0, num - 1);
+        int d1 = std::min(d0 + 1, num - 1);
+        float v = clampf(distribution - d0, 0.0f, 1.0f);
+        int lower = 0, upper = size;
+        float lowerU = 0.0f, upperU = 1.0f;
+        while (upper - lower != 1) {
+            int midpoint = (upper + lower) / 2;
+            float midpointU = cdf(midpoint, d0) * (1.0f - v) + cdf(midpoint, d1) * v;
+            if (midpointU < u) { lower = midpoint; lowerU = midpointU; }
+            else { upper = midpoint; upperU = midpointU; }
+        }
+        x = lower;
+        u = clampf((u - lowerU) / (upperU - lowerU), 0.0f, 1.0f);
+    }
+    float sum(float distribution) const {
+        int d0 = clampi(int(distribution), 0, num - 1);
+        int d1 = std::min(d0 + 1, num - 1);
+        float v = clampf(distribution - d0, 0.0f, 1.0f);
+        return sums[d0] * (1.0f - v) + sums[d1] * v;
+    }
+};
+
+// marschner_diffuse.cpp:39-109
+struct Azimuthal {
+    static const int Res = 64;
+    std::vector<V3> table;
+    InterpolatedDistribution1D sampler;
+    void init(std::vector<V3> t) {
+        table = std::move(t);
+        const int Size = Res;
+        std::vector<float> weights(Size * Size);
+        for (int i = 0; i < Size * Size; ++i) weights[i] = maxc(table[i]);
+        for (int y = 0; y < Size; ++y) {
+            for (int x = 0; x < Size - 1; ++x) weights[x + y * Size] = std::max(weights[x + y * Size], weights[x + 1 + y * Size]);
+            for (int x = Size - 1; x > 0; --x) weights[x + y * Size] = std::max(weights[x + y * Size], weights[x - 1 + y * Size]);
+        }
+        for (int x = 0; x < Size; ++x) {
+            for (int y = 0; y < Size - 1; ++y) weights[x + y * Size] = std::max(weights[x + y * Size], weights[x + (y + 1) * Size]);
+            for (int y = Size - 1; y > 0; --y) weights[x + y * Size] = std::max(weights[x + y * Size], weights[x + (y - 1) * Size]);
+        }
+        sampler.init(std::move(weights), Size, Size);
+    }
+    void sample(float cosThetaD, float xi, float &phi) const {
+        float v = (Res - 1) * cosThetaD;
+        int x;
+        sampler.warp(v, xi, x);
+        phi = 2.0f * kPi * (x + xi) * (1.0f / Res);
+    }
+    V3 eval(float phi, float cosThetaD) const {
+        float u = (Res - 1) * phi * (1.0f / (2.0f * kPi));
+        float v = (Res - 1) * cosThetaD;
+        int x0 = clampi(int(u), 0, Res - 2), y0 = clampi(int(v), 0, Res - 2);
+        int x1 = x0 + 1, y1 = y0 + 1;
+        u = clampf(u - x0, 0.0f, 1.0f);
+        v = clampf(v - y0, 0.0f, 1.0f);
+        return (table[x0 + y0 * Res] * (1.0f - u) + table[x1 + y0 * Res] * u) * (1.0f - v) +
+               (table[x0 + y1 * Res] * (1.0f - u) + table[x1 + y1 * Res] * u) * v;
+    }
+    float weight(float cosThetaD) const {
+        float v = (Res - 1) * cosThetaD;
+        return sampler.sum(v) * (2.0f * kPi / Res);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// MarschnerDiffuse (the `marschner` plugin as built)
+// ---------------------------------------------------------------------------------------------
+struct Marschner {
+    float eta = 1.5046f / 1.000277f;
+    V3 sigmaA = V3(0.5f), diffuse = V3(0.5f), specularReflectance = V3(0.5f);
+    bool nonlinear = false;
+    float alpha = 0.1f;
+    int distribution = 0; // 0 beckmann, 1 ggx, 2 phong
+    float betaR = 0.1f, betaTT = 0.05f, betaTRT = 0.2f, scaleAngleRad = -0.1f;
+    float vR, vTT, vTRT, invEta2, specularSamplingWeight;
+    Azimuthal nR, nTT, nTRT;
+    RoughTransmittance extRT, intRT;
+
+    static float I0(float x) { // :279-290
+        float result = 1.0f, xSq = x * x, xi = xSq, denom = 4.0f;
+        for (int i = 1; i <= 10; ++i) { result += xi / denom; xi *= xSq; denom *= 4.0f * float((i + 1) * (i + 1)); }
+        return result;
+    }
+    static float logI0(float x) { // :292-299
+        if (x > 12.0f) return x + 0.5f * (std::log(1.0f / (kPi * 2.0f * x)) + 1.0f / (8.0f * x));
+        else return std::log(I0(x));
+    }
+    static float g(float beta, float theta) { return std::exp(-theta * theta / (2.0f * beta * beta)) / (std::sqrt(2.0f * kPi) * beta); } // :301-303
+    static float D(float beta, float phi) { // :305-315
+        float result = 0.0f, delta, shift = 0.0f;
+        do {
+            delta = g(beta, phi + shift) + g(beta, phi - shift - 2 * kPi);
+            result += delta;
+            shift += 2 * kPi;
+        } while (delta > 1e-4f);
+        return result;
+    }
+    static float Phi(float gammaI, float gammaT, int p) { return 2.0f * p * gammaT - 2.0f * gammaI + p * kPi; } // :317-319
+    static float M(float v, float sinThetaI, float sinThetaO, float cosThetaI, float cosThetaO) { // :364-374
+        float a = cosThetaI * cosThetaO / v, b = sinThetaI * sinThetaO / v;
+        if (v < 0.1f) return std::exp(-b + logI0(a) - 1.0f / v + 0.6931f + std::log(1.0f / (2.0f * v)));
+        else return std::exp(-b) * I0(a) / (2.0f * v * std::sinh(1.0f / v));
+    }
+    static float trigInverse(float x) { return std::min(std::sqrt(std::max(1.0f - x * x, 0.0f)), 1.0f); } // :484-486
+
+    // :751-847
+    void precomputeAzimuthalDistributions() {
+        const int Resolution = Azimuthal::Res;
+        std::vector<V3> valuesR(Resolution * Resolution), valuesTT(Resolution * Resolution), valuesTRT(Resolution * Resolution);
+        const int NumPoints = 140;
+        GaussLegendre<NumPoints> integrator;
+        const float *points = integrator.points, *weights = integrator.weights;
+        float gammaIs[NumPoints];
+        for (int i = 0; i < NumPoints; ++i) gammaIs[i] = std::asin(points[i]);
+        const int NumGaussianSamples = 2048;
+        std::vector<float> Ds(NumGaussianSamples); // identical for p=0,1,2: all use _betaR (:778)
+        for (int i = 0; i < NumGaussianSamples; ++i) Ds[i] = D(betaR, i / (NumGaussianSamples - 1.0f) * 2 * kPi);
+        auto approxD = [&](float phi) {
+            float u = (float) std::abs(phi * (1.0 / (2 * kPi) * (NumGaussianSamples - 1))); // double arithmetic as in :783
+            int x0 = int(u), x1 = x0 + 1;
+            u -= x0;
+            return Ds[x0 % NumGaussianSamples] * (1.0f - u) + Ds[x1 % NumGaussianSamples] * u;
+        };
+        for (int y = 0; y < Resolution; ++y) {
+            float cosHalfAngle = y / (Resolution - 1.0f);
+            float iorPrime = std::sqrt(eta * eta - (1.0f - cosHalfAngle * cosHalfAngle)) / cosHalfAngle;
+            float cosThetaT = std::sqrt(1.0f - (1.0f - cosHalfAngle * cosHalfAngle) * (1.0f / eta) * (1.0f / eta));
+            V3 sigmaAPrime = sigmaA / cosThetaT;
+            float fresnelTerms[NumPoints], gammaTs[NumPoints]; V3 absorptions[NumPoints];
+            for (int i = 0; i < NumPoints; ++i) {
+                gammaTs[i] = std::asin(clampf(points[i] / iorPrime, -1.0f, 1.0f));
+                fresnelTerms[i] = fresnelDielectricExt(1.0f / eta, cosHalfAngle * std::cos(gammaIs[i])); // swapped arguments, verbatim (:809)
+                V3 e = -sigmaAPrime * 2.0f * std::cos(gammaTs[i]);
+                absorptions[i] = V3(std::exp(e.x), std::exp(e.y), std::exp(e.z));
+            }
+            for (int phiI = 0; phiI < Resolution; ++phiI) {
+                float phi = kPi * 2 * phiI / (Resolution - 1.0f);
+                float integralR = 0.0f; V3 integralTT(0.0f), integralTRT(0.0f);
+                for (int i = 0; i < NumPoints; ++i) {
+                    float fR = fresnelTerms[i]; V3 T = absorptions[i];
+                    float AR = fR;
+                    V3 ATT = (1.0f - fR) * (1.0f - fR) * T;
+                    V3 ATRT = ATT * fR * T;
+                    integralR += weights[i] * approxD(phi - Phi(gammaIs[i], gammaTs[i], 0)) * AR;
+                    integralTT += weights[i] * approxD(phi - Phi(gammaIs[i], gammaTs[i], 1)) * ATT;
+                    integralTRT += weights[i] * approxD(phi - Phi(gammaIs[i], gammaTs[i], 2)) * ATRT;
+                }
+                valuesR[phiI + y * Resolution] = V3(0.5f * integralR);
+                valuesTT[phiI + y * Resolution] = 0.5f * integralTT;
+                valuesTRT[phiI + y * Resolution] = 0.5f * integralTRT;
+            }
+        }
+        nR.init(std::move(valuesR)); nTT.init(std::move(valuesTT)); nTRT.init(std::move(valuesTRT));
+    }
+
+    // ctor :113-160 + configure :193-247.  `dataDir` must contain microfacet/<distr>.dat
+    void configure(float intIOR, float extIOR, V3 diff, V3 specRefl, float alpha_, int distr, bool nonlin, const std::string &dataDir) {
+        eta = intIOR / extIOR;
+        sigmaA = V3(0.5f);
+        nonlinear = nonlin; distribution = distr;
+        alpha = std::max(alpha_, 1e-4f); // microfacet.h:131
+        precomputeAzimuthalDistributions();
+        vR = betaR * betaR; vTT = betaTT * betaTT; vTRT = betaTRT * betaTRT;
+        float mx = maxc(specRefl); // ensureEnergyConservation(specularReflectance, 1.0) bsdf.cpp:88-113
+        if (mx > 1.0f) specRefl = specRefl * (0.99f * (1.0f / mx));
+        specularReflectance = specRefl; diffuse = diff;
+        float dAvg = luminance(diff), sAvg = luminance(specRefl);
+        specularSamplingWeight = sAvg / (dAvg + sAvg);
+        invEta2 = 1.0f / (eta * eta);
+        static const char *names[3] = {"beckmann", "ggx", "phong"};
+        extRT.load(dataDir + "/microfacet/" + names[distr] + ".dat");
+        extRT.checkRanges(eta, alpha);
+        intRT = extRT;          // clone() before setEta (:230)
+        extRT.setEta(eta);
+        intRT.setEta(1 / eta);
+        extRT.setAlpha(alpha);
+    }
+
+    // :377-482
+    V3 eval(const V3 &wi, const V3 &wo) const {
+        float sinThetaI = wi.y, sinThetaO = wo.y;
+        float cosThetaO = trigInverse(sinThetaO);
+        float thetaI = std::asin(clampf(sinThetaI, -1.0f, 1.0f));
+        float thetaO = std::asin(clampf(sinThetaO, -1.0f, 1.0f));
+        float thetaD = (thetaO - thetaI) * 0.5f;
+        float cosThetaD = std::cos(thetaD);
+        float phi = std::atan2(wo.x, wo.z);
+        if (phi < 0.0f) phi += kPi * 2.0f;
+        float thetaIR = thetaI - 2.0f * scaleAngleRad;
+        float thetaITT = thetaI + scaleAngleRad;
+        float thetaITRT = thetaI + 4.0f * scaleAngleRad;
+        float MR = M(vR, std::sin(thetaIR), sinThetaO, std::cos(thetaIR), cosThetaO);
+        float MTT = M(vTT, std::sin(thetaITT), sinThetaO, std::cos(thetaITT), cosThetaO);
+        float MTRT = M(vTRT, std::sin(thetaITRT), sinThetaO, std::cos(thetaITRT), cosThetaO);
+        V3 result = 0.15f * MR * nR.eval(phi, cosThetaD) + MTT * nTT.eval(phi, cosThetaD) + MTRT * nTRT.eval(phi, cosThetaD);
+        // diffuse term (typeMask=EAll, component=-1 on this path)
+        V3 diff = diffuse;
+        float T12 = extRT.eval(wi.z, alpha);
+        float T21 = extRT.eval(wo.z, alpha);
+        float Fdr = 1 - intRT.evalDiffuse(alpha);
+        if (nonlinear) diff = V3(diff.x / (1.0f - diff.x * Fdr), diff.y / (1.0f - diff.y * Fdr), diff.z / (1.0f - diff.z * Fdr));
+        else diff = diff / (1 - Fdr);
+        result += diff * (kInvPi * wo.z * T12 * T21 * invEta2);
+        return result;
+    }
+    // :488-520 -- constant 1 whenever the diffuse component is requested (always here)
+    float pdf(const V3 &, const V3 &) const { return 1.0f; }
+    // :582-592
+    float sampleM(float v, float sinThetaI, float cosThetaI, float xi1, float xi2) const {
+        float cosTheta = 1.0f + v * std::log(xi1 + (1.0f - xi1) * std::exp(-2.0f / v));
+        float sinTheta = trigInverse(cosTheta);
+        float cosPhi = std::cos(2 * kPi * xi2);
+        return -cosTheta * sinThetaI + sinTheta * cosPhi * cosThetaI;
+    }
+    // :594-744
+    BSDFSample sample(const V3 &wi, float sx, float sy) const {
+        BSDFSample r;
+        float sinThetaI = wi.y;
+        float cosThetaI = trigInverse(sinThetaI);
+        float thetaI = std::asin(clampf(sinThetaI, -1.0f, 1.0f));
+        float thetaIR = thetaI - 2.0f * scaleAngleRad;
+        float thetaITT = thetaI + scaleAngleRad;
+        float thetaITRT = thetaI + 4.0f * scaleAngleRad;
+        float weightR = nR.weight(cosThetaI), weightTT = nTT.weight(cosThetaI), weightTRT = nTRT.weight(cosThetaI);
+        const Azimuthal *lobe; float v, theta;
+        float target = sx * (weightR + weightTT + weightTRT);
+        if (target < weightR) { r.sampledComponent = 5; v = vR; theta = thetaIR; lobe = &nR; }
+        else if (target < weightR + weightTT) { r.sampledComponent = 6; v = vTT; theta = thetaITT; lobe = &nTT; }
+        else { r.sampledComponent = 7; v = vTRT; theta = thetaITRT; lobe = &nTRT; }
+        float sinThetaO = sampleM(v, std::sin(theta), std::cos(theta), sx, sy);
+        float cosThetaO = trigInverse(sinThetaO);
+        float thetaO = std::asin(clampf(sinThetaO, -1.0f, 1.0f));
+        float thetaD = (thetaO - thetaI) * 0.5f;
+        float cosThetaD = std::cos(thetaD);
+        float phi;
+        lobe->sample(cosThetaD, sy, phi);
+        float sinPhi = std::sin(phi), cosPhi = std::cos(phi);
+        float probSpecular = 1 - extRT.eval(wi.z, alpha);
+        probSpecular = (probSpecular * specularSamplingWeight) /
+                       (probSpecular * specularSamplingWeight + (1 - probSpecular) * (1 - specularSamplingWeight));
+        bool choseSpecular = sy < probSpecular;
+        if (choseSpecular) {
+            r.wo = V3(sinPhi * cosThetaO, sinThetaO, cosPhi * cosThetaO);
+            r.sampledType = EDeltaReflection;
+        } else {
+            r.sampledComponent = 1;
+            r.sampledType = EDiffuseReflection;
+            r.wo = squareToCosineHemisphere(sx, sy);
+        }
+        r.eta = 1.0f;
+        r.pdf = 1.0f;
+        r.weight = eval(wi, r.wo) / r.pdf;
+        return r;
+    }
+};
+
+} // namespace orc

@@ -1,0 +1,469 @@
+// oracle/o_hair.h -- TEST INFRASTRUCTURE ONLY (CPU oracle; never linked into the product).
+//
+// Restates the HairShape geometry path of the reference: file loader + vertex merge
+// (src/shapes/hair.cpp:609-785), segment/miter helpers (:551-596), segment bounds (:246-286,
+// :368-397), the FP64 mitred-cylinder test (:485-542), the two-level closest/any query
+// (src/librender/skdtree.cpp:112-142,207-226; hair.cpp:200-237) and the intersection frame
+// (hair.cpp:825-862; include/mitsuba/render/skdtree.h:426-427).
+// The reference's SAH kd-trees are replaced by (a) a brute-force loop in segment order and
+// (b) a plain binned-SAH BVH used only to make oracle renders finish; both apply the
+// reference's interval logic per primitive test, so results agree except for equal-t ties.
+#pragma once
+#include "o_math.h"
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+
+namespace orc {
+
+struct AABB {
+    V3 mn, mx;
+    AABB() : mn(kInf), mx(-kInf) {}
+    void expand(const V3 &p) {
+        mn = V3(std::min(mn.x, p.x), std::min(mn.y, p.y), std::min(mn.z, p.z));
+        mx = V3(std::max(mx.x, p.x), std::max(mx.y, p.y), std::max(mx.z, p.z));
+    }
+    void expand(const AABB &b) { expand(b.mn); expand(b.mx); }
+    V3 center() const { return (mx + mn) * 0.5f; } // aabb.h getCenter
+    // include/mitsuba/core/aabb.h:308-338
+    bool rayIntersect(const V3 &o, const V3 &d, const V3 &dRcp, float &nearT, float &farT) const {
+        nearT = -kInf; farT = kInf;
+        for (int i = 0; i < 3; i++) {
+            const float origin = o[i], minVal = mn[i], maxVal = mx[i];
+            if (d[i] == 0) {
+                if (origin < minVal || origin > maxVal) return false;
+            } else {
+                float t1 = (minVal - origin) * dRcp[i];
+                float t2 = (maxVal - origin) * dRcp[i];
+                if (t1 > t2) std::swap(t1, t2);
+                nearT = std::max(t1, nearT);
+                farT = std::min(t2, farT);
+                if (!(nearT <= farT)) return false;
+            }
+        }
+        return true;
+    }
+};
+
+struct Ray {
+    V3 o, d, dRcp;
+    float mint, maxt;
+    Ray() {}
+    Ray(V3 o_, V3 d_, float mint_ = kEpsilon, float maxt_ = kInf) : o(o_), d(d_), mint(mint_), maxt(maxt_) {
+        dRcp = V3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); // include/mitsuba/core/ray.h:72-93
+    }
+};
+
+struct HairShape {
+    std::vector<V3> verts;
+    std::vector<uint8_t> startsFiber; // size verts.size()+1, sentinel = 1 (hair.cpp:782)
+    std::vector<uint32_t> segIndex;   // iv of each segment (hair.cpp:117-124)
+    float radius = 0;
+    int bsdf = 0;
+    AABB aabb;                        // union of segment bounds (gkdtree.h:997-1002)
+
+    // --- hair.cpp:551-596 ---
+    V3 firstVertex(uint32_t iv) const { return verts[iv]; }
+    V3 secondVertex(uint32_t iv) const { return verts[iv + 1]; }
+    bool prevSegmentExists(uint32_t iv) const { return !startsFiber[iv]; }
+    bool nextSegmentExists(uint32_t iv) const { return !startsFiber[iv + 2]; }
+    V3 tangent(uint32_t iv) const { return normalize(verts[iv + 1] - verts[iv]); }
+    D3 tangentD(uint32_t iv) const { return normalize(D3(verts[iv + 1]) - D3(verts[iv])); }
+    V3 prevTangent(uint32_t iv) const { return normalize(verts[iv] - verts[iv - 1]); }
+    D3 prevTangentD(uint32_t iv) const { return normalize(D3(verts[iv]) - D3(verts[iv - 1])); }
+    V3 nextTangent(uint32_t iv) const { return normalize(verts[iv + 2] - verts[iv + 1]); }
+    D3 nextTangentD(uint32_t iv) const { return normalize(D3(verts[iv + 2]) - D3(verts[iv + 1])); }
+    V3 firstMiterNormal(uint32_t iv) const {
+        return prevSegmentExists(iv) ? normalize(prevTangent(iv) + tangent(iv)) : tangent(iv);
+    }
+    V3 secondMiterNormal(uint32_t iv) const {
+        return nextSegmentExists(iv) ? normalize(tangent(iv) + nextTangent(iv)) : tangent(iv);
+    }
+    D3 firstMiterNormalD(uint32_t iv) const {
+        return prevSegmentExists(iv) ? normalize(prevTangentD(iv) + tangentD(iv)) : tangentD(iv);
+    }
+    D3 secondMiterNormalD(uint32_t iv) const {
+        return nextSegmentExists(iv) ? normalize(tangentD(iv) + nextTangentD(iv)) : tangentD(iv);
+    }
+
+    // hair.cpp:246-286 (intersectCylPlane)
+    static bool intersectCylPlane(V3 planePt, V3 planeNrml, V3 cylPt, V3 cylD, float radius,
+                                  V3 &center, V3 *axes, float *lengths) {
+        if (std::abs(dot(planeNrml, cylD)) < kEpsilon) return false;
+        V3 B, A = cylD - dot(cylD, planeNrml) * planeNrml;
+        float len = length(A);
+        bool same = planeNrml.x == cylD.x && planeNrml.y == cylD.y && planeNrml.z == cylD.z;
+        if (len > kEpsilon && !same) {
+            A = A / len;
+            B = cross(planeNrml, A);
+        } else {
+            coordinateSystem(planeNrml, A, B);
+        }
+        V3 delta = planePt - cylPt, deltaProj = delta - cylD * dot(delta, cylD);
+        float aDotD = dot(A, cylD), bDotD = dot(B, cylD);
+        float c0 = 1 - aDotD * aDotD, c1 = 1 - bDotD * bDotD;
+        float c2 = 2 * dot(A, deltaProj), c3 = 2 * dot(B, deltaProj);
+        float c4 = dot(delta, deltaProj) - radius * radius;
+        float lambda = (c2 * c2 / (4 * c0) + c3 * c3 / (4 * c1) - c4) / (c0 * c1);
+        float alpha0 = -c2 / (2 * c0), beta0 = -c3 / (2 * c1);
+        lengths[0] = std::sqrt(c1 * lambda);
+        lengths[1] = std::sqrt(c0 * lambda);
+        center = planePt + alpha0 * A + beta0 * B;
+        axes[0] = A; axes[1] = B;
+        return true;
+    }
+
+    // hair.cpp:368-397 (tight bound of the two miter-cut end ellipses, radius*(1-Epsilon))
+    AABB segmentAABB(uint32_t iv) const {
+        V3 center, axes[2]; float lengths[2];
+        AABB result;
+        for (int end = 0; end < 2; ++end) {
+            V3 pt = end == 0 ? firstVertex(iv) : secondVertex(iv);
+            V3 nrm = end == 0 ? firstMiterNormal(iv) : secondMiterNormal(iv);
+            bool ok = intersectCylPlane(pt, nrm, pt, tangent(iv), radius * (1 - kEpsilon), center, axes, lengths);
+            (void) ok;
+            axes[0] *= lengths[0]; axes[1] *= lengths[1];
+            for (int i = 0; i < 3; ++i) {
+                float range = std::sqrt(axes[0][i] * axes[0][i] + axes[1][i] * axes[1][i]);
+                result.mn[i] = std::min(result.mn[i], center[i] - range);
+                result.mx[i] = std::max(result.mx[i], center[i] + range);
+            }
+        }
+        return result;
+    }
+
+    void finalize() {
+        // hair.cpp:117-124
+        segIndex.clear();
+        for (size_t i = 0; i + 1 < verts.size(); i++)
+            if (!startsFiber[i + 1]) segIndex.push_back((uint32_t) i);
+        aabb = AABB();
+        for (uint32_t iv : segIndex) aabb.expand(segmentAABB(iv));
+    }
+
+    // hair.cpp:485-542.  Returns true on hit; t is the fp32-rounded root, p the fp32 hit point.
+    bool intersect(const Ray &ray, uint32_t iv, float mint, float maxt, float &t, V3 &p) const {
+        D3 axis = tangentD(iv);
+        D3 rayO(ray.o), rayD(ray.d), v1(verts[iv]);
+        D3 relOrigin = rayO - v1;
+        D3 projOrigin = relOrigin - dot(axis, relOrigin) * axis;
+        D3 projDirection = rayD - dot(axis, rayD) * axis;
+        const double A = dot(projDirection, projDirection);
+        const double B = 2 * dot(projOrigin, projDirection);
+        const double C = dot(projOrigin, projOrigin) - radius * radius; // m_radius*m_radius is a float product
+        double nearT, farT;
+        if (!solveQuadraticDouble(A, B, C, nearT, farT)) return false;
+        if (!(nearT <= maxt && farT >= mint)) return false;
+        D3 pointNear = rayO + rayD * nearT, pointFar = rayO + rayD * farT;
+        D3 n1 = firstMiterNormalD(iv), n2 = secondMiterNormalD(iv), v2(verts[iv + 1]);
+        if (dot(pointNear - v1, n1) >= 0 && dot(pointNear - v2, n2) <= 0 && nearT >= mint) {
+            D3 q = rayO + rayD * nearT;
+            p = V3((float) q.x, (float) q.y, (float) q.z);
+            t = (float) nearT;
+        } else if (dot(pointFar - v1, n1) >= 0 && dot(pointFar - v2, n2) <= 0) {
+            if (farT > maxt) return false;
+            D3 q = rayO + rayD * farT;
+            p = V3((float) q.x, (float) q.y, (float) q.z);
+            t = (float) farT;
+        } else {
+            return false;
+        }
+        return true;
+    }
+};
+
+// hair.cpp:609-785.  `reduction` needs the reference's SFMT `Random`; only 0 is supported.
+static inline void loadHairFile(const std::string &path, float radius, float angleThresholdDeg,
+                                const M44 &toWorld, HairShape &out) {
+    float angleThreshold = angleThresholdDeg * (kPi / 180.0f);
+    float dpThresh = std::cos(angleThreshold);
+    radius *= length(xfmVector(toWorld, V3(0, 0, 1)));
+    std::ifstream bs(path, std::ios::binary);
+    if (!bs) throw std::runtime_error("oracle: cannot open hair file " + path);
+    char temp[11] = {0};
+    bs.read(temp, 11);
+    bool binaryFormat = bs.gcount() == 11 && std::memcmp(temp, "BINARY_HAIR", 11) == 0;
+
+    std::vector<V3> &vertices = out.verts;
+    std::vector<uint8_t> &vsf = out.startsFiber;
+    vertices.clear(); vsf.clear();
+    V3 tangent(0.0f), p, lastP(0.0f);
+    bool newFiber = true;
+
+    auto consume = [&](V3 pt) {
+        p = xfmPoint(toWorld, pt);
+        if (newFiber) {
+            vertices.push_back(p); vsf.push_back(1);
+            lastP = p; tangent = V3(0.0f);
+        } else if (!(p.x == lastP.x && p.y == lastP.y && p.z == lastP.z)) {
+            if (isZero(tangent)) {
+                vertices.push_back(p); vsf.push_back(0);
+                tangent = normalize(p - lastP);
+                lastP = p;
+            } else {
+                V3 nextTangent = normalize(p - lastP);
+                if (dot(nextTangent, tangent) > dpThresh) {
+                    tangent = normalize(p - vertices[vertices.size() - 2]);
+                    vertices[vertices.size() - 1] = p;
+                } else {
+                    vertices.push_back(p); vsf.push_back(0);
+                    tangent = nextTangent;
+                }
+                lastP = p;
+            }
+        }
+        newFiber = false;
+    };
+
+    if (binaryFormat) {
+        uint32_t vertexCount = 0;
+        bs.read((char *) &vertexCount, 4);
+        size_t verticesRead = 0;
+        auto readSingle = [&]() { float f = 0; bs.read((char *) &f, 4); if (!bs) throw std::runtime_error("oracle: truncated hair file"); return f; };
+        while (verticesRead != vertexCount) {
+            float value = readSingle();
+            V3 q;
+            if (std::isinf(value)) {
+                q.x = readSingle(); q.y = readSingle(); q.z = readSingle();
+                newFiber = true;
+            } else {
+                q.x = value; q.y = readSingle(); q.z = readSingle();
+            }
+            verticesRead++;
+            consume(q);
+        }
+    } else {
+        std::ifstream is(path);
+        std::string line;
+        while (is.good()) {
+            std::getline(is, line);
+            if (line.length() > 0 && line[0] == '#') { newFiber = true; continue; }
+            std::istringstream iss(line);
+            V3 q;
+            iss >> q.x >> q.y >> q.z;
+            if (!iss.fail()) consume(q);
+            else newFiber = true;
+        }
+    }
+    vsf.push_back(1);
+    out.radius = radius;
+    out.finalize();
+}
+
+struct Hit {
+    float t = kInf;
+    int shape = -1;
+    uint32_t iv = 0;
+    V3 p;      // fp32 hit point stored by HairKDTree::intersect
+};
+
+// Result of fillIntersectionRecord (hair.cpp:825-862 + skdtree.h:426-427)
+struct Intersection {
+    bool valid = false;
+    float t = kInf;
+    int shape = -1;
+    uint32_t iv = 0;
+    V3 p;
+    Frame geoFrame, shFrame;
+    V3 wi;
+};
+
+struct BVHNode { AABB box; uint32_t left, right; uint32_t first, count; }; // leaf if count>0
+
+struct Geometry {
+    std::vector<HairShape> shapes;
+    AABB aabb; // scene kd-tree bounds (union of shape bounds; skdtree.h:213-221)
+    // oracle-only acceleration structure
+    struct PrimRef { uint32_t shape, iv; };
+    std::vector<PrimRef> prims;
+    std::vector<BVHNode> nodes;
+
+    void finalize() {
+        aabb = AABB();
+        for (auto &s : shapes) aabb.expand(s.aabb);
+        buildBVH();
+    }
+
+    // skdtree.cpp:112-142 (closest) / :207-226 (shadow): scene-level interval set-up.
+    // Returns false if the ray misses the scene bounds or the interval is empty.
+    bool sceneInterval(const Ray &ray, bool shadow, float &mint, float &maxt) const {
+        if (!aabb.rayIntersect(ray.o, ray.d, ray.dRcp, mint, maxt)) return false;
+        float rayMinT = ray.mint;
+        if (rayMinT == kEpsilon) {
+            float m = std::max(std::max(std::abs(ray.o.x), std::abs(ray.o.y)), std::abs(ray.o.z));
+            if (!shadow) m = std::max(m, kEpsilon);
+            rayMinT *= m;
+        }
+        if (rayMinT > mint) mint = rayMinT;
+        if (ray.maxt < maxt) maxt = ray.maxt;
+        return maxt > mint;
+    }
+    // hair.cpp:200-217: per-shape interval clip
+    bool shapeInterval(const HairShape &s, const Ray &ray, float _mint, float _maxt, float &mint, float &maxt) const {
+        if (!s.aabb.rayIntersect(ray.o, ray.d, ray.dRcp, mint, maxt)) return false;
+        if (_mint > mint) mint = _mint;
+        if (_maxt < maxt) maxt = _maxt;
+        return maxt > mint;
+    }
+
+    // Brute force in (shape, segment) order -- the reference semantics with a trivial visiting order.
+    bool intersectBrute(const Ray &ray, bool shadow, Hit &hit) const {
+        float mint, maxt;
+        hit = Hit();
+        if (!sceneInterval(ray, shadow, mint, maxt)) return false;
+        bool found = false;
+        for (size_t si = 0; si < shapes.size(); ++si) {
+            const HairShape &s = shapes[si];
+            float smin, smax;
+            if (!shapeInterval(s, ray, mint, maxt, smin, smax)) continue;
+            for (uint32_t iv : s.segIndex) {
+                float t; V3 p;
+                if (s.intersect(ray, iv, smin, smax, t, p)) {
+                    if (shadow) { hit.t = t; hit.shape = (int) si; hit.iv = iv; return true; }
+                    smax = t; maxt = t; // sahkdtree3.h:287-291 (maxt = t at both levels)
+                    hit.t = t; hit.shape = (int) si; hit.iv = iv; hit.p = p;
+                    found = true;
+                }
+            }
+        }
+        return found;
+    }
+
+    void buildBVH() {
+        prims.clear(); nodes.clear();
+        std::vector<AABB> boxes;
+        for (size_t si = 0; si < shapes.size(); ++si)
+            for (uint32_t iv : shapes[si].segIndex) {
+                prims.push_back({(uint32_t) si, iv});
+                boxes.push_back(shapes[si].segmentAABB(iv));
+            }
+        if (prims.empty()) return;
+        std::vector<uint32_t> order(prims.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t) i;
+        nodes.reserve(prims.size() * 2);
+        nodes.push_back(BVHNode());
+        buildRec(0, order, boxes, 0, (uint32_t) order.size());
+        std::vector<PrimRef> sorted(prims.size());
+        for (size_t i = 0; i < order.size(); ++i) sorted[i] = prims[order[i]];
+        prims.swap(sorted);
+    }
+
+    void buildRec(uint32_t ni, std::vector<uint32_t> &order, const std::vector<AABB> &boxes, uint32_t lo, uint32_t hi) {
+        AABB box, cbox;
+        for (uint32_t i = lo; i < hi; ++i) { box.expand(boxes[order[i]]); cbox.expand(boxes[order[i]].center()); }
+        nodes[ni].box = box;
+        uint32_t n = hi - lo;
+        if (n <= 4) { nodes[ni].first = lo; nodes[ni].count = n; nodes[ni].left = nodes[ni].right = 0; return; }
+        V3 ext = cbox.mx - cbox.mn;
+        int axis = ext.x > ext.y ? (ext.x > ext.z ? 0 : 2) : (ext.y > ext.z ? 1 : 2);
+        uint32_t mid = (lo + hi) / 2;
+        if (ext[axis] > 0) {
+            const int NB = 16;
+            AABB bb[NB]; uint32_t bc[NB] = {0};
+            float k = NB * (1 - 1e-6f) / ext[axis];
+            auto binOf = [&](uint32_t id) { return clampi((int) ((boxes[id].center()[axis] - cbox.mn[axis]) * k), 0, NB - 1); };
+            for (uint32_t i = lo; i < hi; ++i) { int b = binOf(order[i]); bb[b].expand(boxes[order[i]]); bc[b]++; }
+            auto area = [](const AABB &b) { V3 e = b.mx - b.mn; return 2 * (e.x * e.y + e.y * e.z + e.z * e.x); };
+            float best = kInf; int bestSplit = -1;
+            float rightArea[NB]; uint32_t rightCount[NB];
+            AABB acc; uint32_t cnt = 0;
+            for (int b = NB - 1; b > 0; --b) { acc.expand(bb[b]); cnt += bc[b]; rightArea[b] = cnt ? area(acc) : 0; rightCount[b] = cnt; }
+            acc = AABB(); cnt = 0;
+            for (int b = 0; b < NB - 1; ++b) {
+                acc.expand(bb[b]); cnt += bc[b];
+                if (cnt == 0 || rightCount[b + 1] == 0) continue;
+                float cost = area(acc) * cnt + rightArea[b + 1] * rightCount[b + 1];
+                if (cost < best) { best = cost; bestSplit = b; }
+            }
+            if (bestSplit >= 0) {
+                auto it = std::partition(order.begin() + lo, order.begin() + hi, [&](uint32_t id) { return binOf(id) <= bestSplit; });
+                mid = (uint32_t) (it - order.begin());
+            }
+            if (mid == lo || mid == hi) {
+                mid = (lo + hi) / 2;
+                std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi,
+                                 [&](uint32_t a, uint32_t b) { return boxes[a].center()[axis] < boxes[b].center()[axis]; });
+            }
+        }
+        uint32_t l = (uint32_t) nodes.size(); nodes.push_back(BVHNode());
+        uint32_t r = (uint32_t) nodes.size(); nodes.push_back(BVHNode());
+        nodes[ni].left = l; nodes[ni].right = r; nodes[ni].count = 0; nodes[ni].first = 0;
+        buildRec(l, order, boxes, lo, mid);
+        buildRec(r, order, boxes, mid, hi);
+    }
+
+    // BVH query with the reference's per-primitive interval logic.
+    bool intersectBVH(const Ray &ray, bool shadow, Hit &hit) const {
+        float mint, maxt;
+        hit = Hit();
+        if (nodes.empty() || !sceneInterval(ray, shadow, mint, maxt)) return false;
+        // per-shape clipped intervals (hair.cpp:205-209), computed once per ray
+        float smin[16], smaxv[16]; bool sok[16];
+        size_t ns = std::min<size_t>(shapes.size(), 16);
+        std::vector<float> vmin, vmax; std::vector<char> vok;
+        float *pmin = smin, *pmax = smaxv; bool *pok = sok;
+        if (shapes.size() > 16) throw std::runtime_error("oracle: >16 shapes unsupported in BVH path");
+        for (size_t si = 0; si < ns; ++si) pok[si] = shapeInterval(shapes[si], ray, mint, maxt, pmin[si], pmax[si]);
+        bool found = false;
+        uint32_t stack[128]; int sp = 0;
+        stack[sp++] = 0;
+        while (sp) {
+            const BVHNode &nd = nodes[stack[--sp]];
+            float n0, f0;
+            if (!nd.box.rayIntersect(ray.o, ray.d, ray.dRcp, n0, f0)) continue;
+            if (n0 > maxt || f0 < mint) continue;
+            if (nd.count) {
+                for (uint32_t i = nd.first; i < nd.first + nd.count; ++i) {
+                    const PrimRef &pr = prims[i];
+                    if (!pok[pr.shape]) continue;
+                    float hi = std::min(pmax[pr.shape], maxt);
+                    if (!(hi > pmin[pr.shape])) continue; // hair.cpp:209 `maxt > mint`
+                    float t; V3 p;
+                    if (shapes[pr.shape].intersect(ray, pr.iv, pmin[pr.shape], hi, t, p)) {
+                        if (shadow) { hit.t = t; hit.shape = (int) pr.shape; hit.iv = pr.iv; return true; }
+                        maxt = t; hit.t = t; hit.shape = (int) pr.shape; hit.iv = pr.iv; hit.p = p; found = true;
+                    }
+                }
+            } else {
+                float nl, fl, nr, fr;
+                bool hl = nodes[nd.left].box.rayIntersect(ray.o, ray.d, ray.dRcp, nl, fl) && nl <= maxt && fl >= mint;
+                bool hr = nodes[nd.right].box.rayIntersect(ray.o, ray.d, ray.dRcp, nr, fr) && nr <= maxt && fr >= mint;
+                if (hl && hr) {
+                    if (nl < nr) { stack[sp++] = nd.right; stack[sp++] = nd.left; }
+                    else { stack[sp++] = nd.left; stack[sp++] = nd.right; }
+                } else if (hl) stack[sp++] = nd.left;
+                else if (hr) stack[sp++] = nd.right;
+            }
+        }
+        return found;
+    }
+
+    // hair.cpp:825-862 followed by skdtree.h:426-427
+    void fillIntersection(const Ray &ray, const Hit &hit, Intersection &its) const {
+        const HairShape &s = shapes[hit.shape];
+        its.valid = true; its.t = hit.t; its.shape = hit.shape; its.iv = hit.iv;
+        its.p = hit.p;
+        const V3 axis = s.tangent(hit.iv);
+        its.geoFrame.s = axis;
+        const V3 relHitPoint = its.p - s.firstVertex(hit.iv);
+        its.geoFrame.n = normalize(relHitPoint - dot(axis, relHitPoint) * axis);
+        its.geoFrame.t = cross(its.geoFrame.n, its.geoFrame.s);
+        const V3 local = its.geoFrame.toLocal(relHitPoint);
+        its.p += its.geoFrame.n * (s.radius - std::sqrt(local.y * local.y + local.z * local.z));
+        its.shFrame = its.geoFrame;
+        V3 dpdu = its.geoFrame.s;
+        computeShadingFrame(its.shFrame.n, dpdu, its.shFrame);
+        its.wi = its.shFrame.toLocal(-ray.d);
+    }
+
+    bool rayIntersect(const Ray &ray, Intersection &its) const {
+        Hit h;
+        its = Intersection();
+        if (!intersectBVH(ray, false, h)) return false;
+        fillIntersection(ray, h, its);
+        return true;
+    }
+    bool rayOccluded(const Ray &ray) const { Hit h; return intersectBVH(ray, true, h); }
+};
+
+} // namespace orc

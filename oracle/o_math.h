@@ -1,0 +1,305 @@
+// oracle/o_math.h -- TEST INFRASTRUCTURE ONLY (CPU oracle; never linked into the product).
+//
+// Small numeric helpers restated from the reference (Mitsuba 0.5 fork, SINGLE_PRECISION,
+// SPECTRUM_SAMPLES=3).  Each function cites the reference file:line it follows
+// (paths relative to /root/reference).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <algorithm>
+#include <limits>
+#include <vector>
+#include <string>
+#include <stdexcept>
+
+namespace orc {
+
+// include/mitsuba/core/constants.h:28-31,63-69 (single-precision build)
+static const float kEpsilon = 1e-4f;
+static const float kShadowEpsilon = 1e-3f;
+static const float kPi = 3.14159265358979323846f;
+static const float kInvPi = 0.31830988618379067154f;
+static const float kInvTwoPi = 0.15915494309189533577f;
+static const float kInvFourPi = 0.07957747154594766788f;
+static const float kInf = std::numeric_limits<float>::infinity();
+
+struct V3 {
+    float x, y, z;
+    V3() : x(0), y(0), z(0) {}
+    V3(float a) : x(a), y(a), z(a) {}
+    V3(float a, float b, float c) : x(a), y(b), z(c) {}
+    float operator[](int i) const { return (&x)[i]; }
+    float &operator[](int i) { return (&x)[i]; }
+};
+static inline V3 operator+(V3 a, V3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline V3 operator-(V3 a, V3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline V3 operator-(V3 a) { return V3(-a.x, -a.y, -a.z); }
+static inline V3 operator*(V3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
+static inline V3 operator*(float s, V3 a) { return V3(a.x * s, a.y * s, a.z * s); }
+static inline V3 operator*(V3 a, V3 b) { return V3(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline V3 operator/(V3 a, float s) { float r = 1.0f / s; return V3(a.x * r, a.y * r, a.z * r); } // vector.h: multiplies by reciprocal
+static inline V3 &operator+=(V3 &a, V3 b) { a = a + b; return a; }
+static inline V3 &operator*=(V3 &a, V3 b) { a = a * b; return a; }
+static inline V3 &operator*=(V3 &a, float s) { a = a * s; return a; }
+static inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline V3 cross(V3 a, V3 b) {
+    return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+static inline float length(V3 a) { return std::sqrt(dot(a, a)); }
+static inline V3 normalize(V3 a) { return a / length(a); }
+static inline bool isZero(V3 a) { return a.x == 0 && a.y == 0 && a.z == 0; }
+static inline float maxc(V3 a) { return std::max(a.x, std::max(a.y, a.z)); }
+// include/mitsuba/core/spectrum.h:724-727 (RGB luminance)
+static inline float luminance(V3 c) { return c.x * 0.212671f + c.y * 0.715160f + c.z * 0.072169f; }
+
+struct D3 {
+    double x, y, z;
+    D3() : x(0), y(0), z(0) {}
+    D3(double a, double b, double c) : x(a), y(b), z(c) {}
+    explicit D3(V3 v) : x(v.x), y(v.y), z(v.z) {}
+};
+static inline D3 operator+(D3 a, D3 b) { return D3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline D3 operator-(D3 a, D3 b) { return D3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline D3 operator*(D3 a, double s) { return D3(a.x * s, a.y * s, a.z * s); }
+static inline D3 operator*(double s, D3 a) { return D3(a.x * s, a.y * s, a.z * s); }
+static inline double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline D3 normalize(D3 a) { double r = 1.0 / std::sqrt(dot(a, a)); return a * r; }
+
+static inline float clampf(float v, float lo, float hi) { return std::min(hi, std::max(lo, v)); }
+static inline int clampi(int v, int lo, int hi) { return std::min(hi, std::max(lo, v)); }
+static inline float safe_sqrt(float v) { return std::sqrt(std::max(0.0f, v)); }  // math.h:260
+static inline float safe_acos(float v) { return std::acos(std::min(1.0f, std::max(-1.0f, v))); } // math.h:250
+static inline int floorToInt(float v) { return (int) std::floor(v); } // math.h:100
+static inline int modulo(int a, int b) { int r = a % b; return (r < 0) ? r + b : r; } // math.h:67
+
+// src/libcore/util.cpp:592-601
+static inline void coordinateSystem(const V3 &a, V3 &b, V3 &c) {
+    if (std::abs(a.x) > std::abs(a.y)) {
+        float invLen = 1.0f / std::sqrt(a.x * a.x + a.z * a.z);
+        c = V3(a.z * invLen, 0.0f, -a.x * invLen);
+    } else {
+        float invLen = 1.0f / std::sqrt(a.y * a.y + a.z * a.z);
+        c = V3(0.0f, a.z * invLen, -a.y * invLen);
+    }
+    b = cross(c, a);
+}
+
+// include/mitsuba/core/frame.h:55-85
+struct Frame {
+    V3 s, t, n;
+    Frame() {}
+    explicit Frame(const V3 &n_) : n(n_) { coordinateSystem(n, s, t); }
+    V3 toLocal(const V3 &v) const { return V3(dot(v, s), dot(v, t), dot(v, n)); }
+    V3 toWorld(const V3 &v) const { return s * v.x + t * v.y + n * v.z; }
+};
+
+// src/libcore/util.cpp:603-608
+static inline void computeShadingFrame(const V3 &n, const V3 &dpdu, Frame &frame) {
+    frame.n = n;
+    frame.s = normalize(dpdu - frame.n * dot(frame.n, dpdu));
+    frame.t = cross(frame.n, frame.s);
+}
+
+// src/libcore/util.cpp:487-525
+static inline bool solveQuadraticDouble(double a, double b, double c, double &x0, double &x1) {
+    if (a == 0) {
+        if (b != 0) { x0 = x1 = -c / b; return true; }
+        return false;
+    }
+    double discrim = b * b - 4.0f * a * c;
+    if (discrim < 0) return false;
+    double temp, sqrtDiscrim = std::sqrt(discrim);
+    if (b < 0) temp = -0.5f * (b - sqrtDiscrim);
+    else       temp = -0.5f * (b + sqrtDiscrim);
+    x0 = temp / a;
+    x1 = c / temp;
+    if (x0 > x1) std::swap(x0, x1);
+    return true;
+}
+
+// src/libcore/util.cpp:448-482 (single-precision variant, used by BSphere::rayIntersect)
+static inline bool solveQuadratic(float a, float b, float c, float &x0, float &x1) {
+    if (a == 0) {
+        if (b != 0) { x0 = x1 = -c / b; return true; }
+        return false;
+    }
+    float discrim = b * b - 4.0f * a * c;
+    if (discrim < 0) return false;
+    float temp, sqrtDiscrim = std::sqrt(discrim);
+    if (b < 0) temp = -0.5f * (b - sqrtDiscrim);
+    else       temp = -0.5f * (b + sqrtDiscrim);
+    x0 = temp / a;
+    x1 = c / temp;
+    if (x0 > x1) std::swap(x0, x1);
+    return true;
+}
+
+// src/libcore/util.cpp:651-681 (+ the 2-argument wrapper include/mitsuba/core/util.h:479)
+static inline float fresnelDielectricExt(float cosThetaI_, float eta) {
+    if (eta == 1) return 0.0f;
+    float scale = (cosThetaI_ > 0) ? 1 / eta : eta,
+          cosThetaTSqr = 1 - (1 - cosThetaI_ * cosThetaI_) * (scale * scale);
+    if (cosThetaTSqr <= 0.0f) return 1.0f;
+    float cosThetaI = std::abs(cosThetaI_);
+    float cosThetaT = std::sqrt(cosThetaTSqr);
+    float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
+    float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    return 0.5f * (Rs * Rs + Rp * Rp);
+}
+
+// src/libcore/warp.cpp:81-102
+static inline void squareToUniformDiskConcentric(float sx, float sy, float &ox, float &oy) {
+    float r1 = 2.0f * sx - 1.0f;
+    float r2 = 2.0f * sy - 1.0f;
+    float phi, r;
+    if (r1 == 0 && r2 == 0) {
+        r = phi = 0;
+    } else if (r1 * r1 > r2 * r2) {
+        r = r1;
+        phi = (kPi / 4.0f) * (r2 / r1);
+    } else {
+        r = r2;
+        phi = (kPi / 2.0f) - (r1 / r2) * (kPi / 4.0f);
+    }
+    float cosPhi = std::cos(phi), sinPhi = std::sin(phi);
+    ox = r * cosPhi; oy = r * sinPhi;
+}
+
+// src/libcore/warp.cpp:43-52
+static inline V3 squareToCosineHemisphere(float sx, float sy) {
+    float px, py;
+    squareToUniformDiskConcentric(sx, sy, px, py);
+    float z = safe_sqrt(1.0f - px * px - py * py);
+    if (z == 0) z = 1e-10f;
+    return V3(px, py, z);
+}
+
+// src/libcore/warp.cpp:54-63
+static inline V3 squareToUniformCone(float cosCutoff, float sx, float sy) {
+    float cosTheta = (1 - sx) + sx * cosCutoff;
+    float sinTheta = safe_sqrt(1.0f - cosTheta * cosTheta);
+    float phi = 2.0f * kPi * sy;
+    return V3(std::cos(phi) * sinTheta, std::sin(phi) * sinTheta, cosTheta);
+}
+
+// src/libcore/warp.cpp:143-162
+static inline float intervalToTent(float sample) {
+    float sign;
+    if (sample < 0.5f) { sign = 1; sample *= 2; }
+    else { sign = -1; sample = 2 * (sample - 0.5f); }
+    return sign * (1 - std::sqrt(sample));
+}
+
+// ---------------------------------------------------------------------------
+// Counter-based RNG shared (by specification, not by code) with the CUDA path:
+// Philox4x32-10 (Salmon et al. 2011), key = 64-bit seed, counter =
+// (pixel index, sample index, path vertex, block).  Replaces the reference's
+// sampler plugins (include/mitsuba/render/sampler.h:105-117) as north_star asks.
+// Dimension layout: vertex 0 block 0 -> {jitter.x, jitter.y};
+// vertex k>=1 block 0 -> {nee.x, nee.y, bsdf.x, bsdf.y}; vertex k block 1 -> {rr}.
+// ---------------------------------------------------------------------------
+struct Philox4 { uint32_t v[4]; };
+static inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t) M0 * c0, p1 = (uint64_t) M1 * c2;
+        uint32_t n0 = (uint32_t) (p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t) p1;
+        uint32_t n2 = (uint32_t) (p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t) p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    Philox4 o; o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3; return o;
+}
+static inline float u32_to_unit(uint32_t x) { return (float) (x >> 8) * (1.0f / 16777216.0f); } // [0,1)
+
+// IEEE binary16 round-to-nearest-even quantisation (OpenEXR `half`, used for envmap texels:
+// src/emitters/envmap.cpp:102-103)
+static inline uint16_t float_to_half(float f) {
+    uint32_t x; std::memcpy(&x, &f, 4);
+    uint32_t sign = (x >> 16) & 0x8000u;
+    int32_t exp = (int32_t) ((x >> 23) & 0xff) - 127 + 15;
+    uint32_t man = x & 0x7fffffu;
+    if (((x >> 23) & 0xff) == 0xff) return (uint16_t) (sign | 0x7c00u | (man ? 0x200u : 0)); // inf/nan
+    if (exp >= 31) return (uint16_t) (sign | 0x7c00u); // overflow -> inf
+    if (exp <= 0) {
+        if (exp < -10) return (uint16_t) sign; // underflow to zero
+        man |= 0x800000u;
+        int shift = 14 - exp; // 14..24
+        uint32_t h = man >> shift;
+        uint32_t rem = man & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (h & 1))) h++;
+        return (uint16_t) (sign | h);
+    }
+    uint32_t h = ((uint32_t) exp << 10) | (man >> 13);
+    uint32_t rem = man & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) h++; // may carry into exponent (correct)
+    return (uint16_t) (sign | h);
+}
+static inline float half_to_float(uint16_t h) {
+    uint32_t sign = (uint32_t) (h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1f, man = h & 0x3ffu, x;
+    if (exp == 0) {
+        if (man == 0) x = sign;
+        else {
+            int e = -1;
+            do { e++; man <<= 1; } while (!(man & 0x400u));
+            x = sign | ((uint32_t) (127 - 15 - e) << 23) | ((man & 0x3ffu) << 13);
+        }
+    } else if (exp == 31) x = sign | 0x7f800000u | (man << 13);
+    else x = sign | ((exp - 15 + 127) << 23) | (man << 13);
+    float f; std::memcpy(&f, &x, 4); return f;
+}
+
+// 4x4 row-major matrix helpers (include/mitsuba/core/transform.h: point transform divides by w)
+struct M44 {
+    float m[4][4];
+    static M44 identity() { M44 r; std::memset(r.m, 0, sizeof(r.m)); for (int i = 0; i < 4; ++i) r.m[i][i] = 1; return r; }
+    static M44 fromRowMajor(const float *p) { M44 r; std::memcpy(r.m, p, 64); return r; }
+};
+static inline M44 mul(const M44 &a, const M44 &b) {
+    M44 r;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+        float s = 0;
+        for (int k = 0; k < 4; ++k) s += a.m[i][k] * b.m[k][j];
+        r.m[i][j] = s;
+    }
+    return r;
+}
+static inline V3 xfmPoint(const M44 &t, const V3 &p) { // transform.h: Point operator()
+    float x = t.m[0][0] * p.x + t.m[0][1] * p.y + t.m[0][2] * p.z + t.m[0][3];
+    float y = t.m[1][0] * p.x + t.m[1][1] * p.y + t.m[1][2] * p.z + t.m[1][3];
+    float z = t.m[2][0] * p.x + t.m[2][1] * p.y + t.m[2][2] * p.z + t.m[2][3];
+    float w = t.m[3][0] * p.x + t.m[3][1] * p.y + t.m[3][2] * p.z + t.m[3][3];
+    if (w == 1.0f) return V3(x, y, z);
+    return V3(x, y, z) / w;
+}
+static inline V3 xfmVector(const M44 &t, const V3 &v) {
+    return V3(t.m[0][0] * v.x + t.m[0][1] * v.y + t.m[0][2] * v.z,
+              t.m[1][0] * v.x + t.m[1][1] * v.y + t.m[1][2] * v.z,
+              t.m[2][0] * v.x + t.m[2][1] * v.y + t.m[2][2] * v.z);
+}
+// General 4x4 inverse (Gauss-Jordan with partial pivoting, computed in double then rounded;
+// the reference uses src/libcore/matrix.cpp Matrix4x4::invert in fp32 -- results agree to fp32 rounding)
+static inline bool invert(const M44 &a, M44 &out) {
+    double t[4][8];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { t[i][j] = a.m[i][j]; t[i][j + 4] = (i == j); }
+    for (int c = 0; c < 4; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 4; ++r) if (std::abs(t[r][c]) > std::abs(t[piv][c])) piv = r;
+        if (t[piv][c] == 0) return false;
+        if (piv != c) for (int j = 0; j < 8; ++j) std::swap(t[piv][j], t[c][j]);
+        double inv = 1.0 / t[c][c];
+        for (int j = 0; j < 8; ++j) t[c][j] *= inv;
+        for (int r = 0; r < 4; ++r) if (r != c) {
+            double f = t[r][c];
+            if (f != 0) for (int j = 0; j < 8; ++j) t[r][j] -= f * t[c][j];
+        }
+    }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out.m[i][j] = (float) t[i][j + 4];
+    return true;
+}
+
+} // namespace orc

@@ -1,0 +1,367 @@
+// oracle/oracle_api.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// C entry points of the CPU oracle (a restatement of the reference's hair path-tracing hot path,
+// see o_*.h for the file:line citations).  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library; the product never does.
+//
+// Parity status: UNPINNED by reference tests -- the reference has no test, golden vector or fixture
+// for hair, Marschner or Kajiya-Kay and cannot be built here.  The pieces of
+// the reference that do compile standalone (GaussLegendre, InterpolatedDistribution1D, the Hosek-Wilkie
+// sky model) are compiled from /root/reference into oracle/_ref and used to pin the corresponding
+// restatements (tests/test_oracle_pinning.py).
+#include "o_math.h"
+#include "o_hair.h"
+#include "o_bsdf.h"
+#include "o_env.h"
+#include "o_render.h"
+#include <dlfcn.h>
+
+using namespace orc;
+
+static thread_local std::string g_err;
+#define ORC_TRY try {
+#define ORC_CATCH } catch (const std::exception &e) { g_err = e.what(); return -1; } catch (...) { g_err = "unknown error"; return -1; }
+
+extern "C" {
+
+const char *orc_last_error() { return g_err.c_str(); }
+
+void *orc_scene_create() { return new Scene(); }
+void orc_scene_destroy(void *s) { delete (Scene *) s; }
+
+int orc_add_bsdf_kajiyakay(void *sp, const float *diffuse, const float *specular, float exponent) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    BSDFAny b; b.kind = 0;
+    b.kk.configure(V3(diffuse[0], diffuse[1], diffuse[2]), V3(specular[0], specular[1], specular[2]), exponent);
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+    ORC_CATCH
+}
+
+int orc_add_bsdf_marschner(void *sp, float intIOR, float extIOR, const float *diffuse, const float *specRefl,
+                           float alpha, int distribution, int nonlinear, const char *dataDir) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    BSDFAny b; b.kind = 1;
+    b.ma = std::make_shared<Marschner>();
+    b.ma->configure(intIOR, extIOR, V3(diffuse[0], diffuse[1], diffuse[2]), V3(specRefl[0], specRefl[1], specRefl[2]),
+                    alpha, distribution, nonlinear != 0, dataDir);
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+    ORC_CATCH
+}
+
+int orc_add_hair(void *sp, const float *xyz, const uint8_t *startsFiber, uint32_t n, float radius, int bsdf) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    HairShape h;
+    h.verts.resize(n);
+    for (uint32_t i = 0; i < n; ++i) h.verts[i] = V3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    h.startsFiber.assign(startsFiber, startsFiber + n);
+    h.startsFiber.push_back(1);
+    h.radius = radius; h.bsdf = bsdf;
+    h.finalize();
+    s->geo.shapes.push_back(std::move(h));
+    return (int) s->geo.shapes.size() - 1;
+    ORC_CATCH
+}
+
+// Two-phase hair file load: returns a handle, then sizes / copies.
+void *orc_hair_file_load(const char *path, float radius, float angleThresholdDeg, const float *toWorld16) {
+    try {
+        HairShape *h = new HairShape();
+        loadHairFile(path, radius, angleThresholdDeg, M44::fromRowMajor(toWorld16), *h);
+        return h;
+    } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
+}
+uint32_t orc_hair_file_vertex_count(void *h) { return (uint32_t) ((HairShape *) h)->verts.size(); }
+uint32_t orc_hair_file_segment_count(void *h) { return (uint32_t) ((HairShape *) h)->segIndex.size(); }
+float orc_hair_file_radius(void *h) { return ((HairShape *) h)->radius; }
+void orc_hair_file_copy(void *hp, float *xyz, uint8_t *startsFiber) {
+    HairShape *h = (HairShape *) hp;
+    for (size_t i = 0; i < h->verts.size(); ++i) { xyz[3 * i] = h->verts[i].x; xyz[3 * i + 1] = h->verts[i].y; xyz[3 * i + 2] = h->verts[i].z; startsFiber[i] = h->startsFiber[i]; }
+}
+void orc_hair_file_free(void *h) { delete (HairShape *) h; }
+
+int orc_set_envmap(void *sp, const float *rgb, int w, int h, const float *toWorld16, float scale) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    s->env.init(rgb, w, h, M44::fromRowMajor(toWorld16), scale);
+    s->hasEnv = true;
+    return 0;
+    ORC_CATCH
+}
+int orc_set_camera(void *sp, const float *toWorld16, float fovX, float nearClip, float farClip, int w, int h) {
+    Scene *s = (Scene *) sp;
+    s->cam.toWorld = M44::fromRowMajor(toWorld16); s->cam.xfov = fovX; s->cam.nearClip = nearClip; s->cam.farClip = farClip;
+    s->cam.filmW = w; s->cam.filmH = h;
+    return 0;
+}
+int orc_set_film(void *sp, int filterType, float param, int hasAlpha) {
+    Scene *s = (Scene *) sp;
+    s->filter.type = filterType;
+    if (filterType == 0 && param > 0) s->filter.radius = param;
+    if (filterType == 2 && param > 0) s->filter.stddev = param;
+    s->filmHasAlpha = hasAlpha != 0;
+    return 0;
+}
+int orc_set_integrator(void *sp, int maxDepth, int rrDepth, int strictNormals, int hideEmitters) {
+    Scene *s = (Scene *) sp;
+    s->maxDepth = maxDepth; s->rrDepth = rrDepth; s->strictNormals = strictNormals != 0; s->hideEmitters = hideEmitters != 0;
+    return 0;
+}
+int orc_finalize(void *sp) {
+    ORC_TRY
+    ((Scene *) sp)->finalize();
+    return 0;
+    ORC_CATCH
+}
+
+int orc_scene_bounds(void *sp, float *aabb6, float *bsphere4) {
+    Scene *s = (Scene *) sp;
+    aabb6[0] = s->geo.aabb.mn.x; aabb6[1] = s->geo.aabb.mn.y; aabb6[2] = s->geo.aabb.mn.z;
+    aabb6[3] = s->geo.aabb.mx.x; aabb6[4] = s->geo.aabb.mx.y; aabb6[5] = s->geo.aabb.mx.z;
+    bsphere4[0] = s->env.sceneBSphere.center.x; bsphere4[1] = s->env.sceneBSphere.center.y; bsphere4[2] = s->env.sceneBSphere.center.z; bsphere4[3] = s->env.sceneBSphere.radius;
+    return 0;
+}
+
+int orc_segment_bounds(void *sp, int shape, float *out6n) {
+    Scene *s = (Scene *) sp;
+    const HairShape &h = s->geo.shapes[shape];
+    for (size_t i = 0; i < h.segIndex.size(); ++i) {
+        AABB b = h.segmentAABB(h.segIndex[i]);
+        float *o = out6n + 6 * i;
+        o[0] = b.mn.x; o[1] = b.mn.y; o[2] = b.mn.z; o[3] = b.mx.x; o[4] = b.mx.y; o[5] = b.mx.z;
+    }
+    return 0;
+}
+
+int orc_bsdf_eval_batch(void *sp, int bsdf, uint64_t n, const float *wi, const float *wo, float *outEval, float *outPdf) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    const BSDFAny &b = s->bsdfs.at(bsdf);
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), c(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+        V3 e = b.eval(a, c);
+        outEval[3 * i] = e.x; outEval[3 * i + 1] = e.y; outEval[3 * i + 2] = e.z;
+        outPdf[i] = b.pdf(a, c);
+    }
+    return 0;
+    ORC_CATCH
+}
+int orc_bsdf_sample_batch(void *sp, int bsdf, uint64_t n, const float *wi, const float *sample, float *outWo, float *outWeight,
+                          float *outPdf, int32_t *outType) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    const BSDFAny &b = s->bsdfs.at(bsdf);
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+        BSDFSample r = b.sample(a, sample[2 * i], sample[2 * i + 1]);
+        outWo[3 * i] = r.wo.x; outWo[3 * i + 1] = r.wo.y; outWo[3 * i + 2] = r.wo.z;
+        outWeight[3 * i] = r.weight.x; outWeight[3 * i + 1] = r.weight.y; outWeight[3 * i + 2] = r.weight.z;
+        outPdf[i] = r.pdf; outType[i] = r.sampledType | (r.sampledComponent << 8);
+    }
+    return 0;
+    ORC_CATCH
+}
+
+// Marschner precomputed tables: out = 3 lobes x 64 x 64 x RGB; cdfs = 3 x 64 x 65; sums = 3 x 64; rt = 100 T samples + Fdr const
+int orc_marschner_tables(void *sp, int bsdf, float *outTables, float *outPdfs, float *outCdfs, float *outSums, float *outRT, float *outConsts) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    const BSDFAny &b = s->bsdfs.at(bsdf);
+    if (b.kind != 1) throw std::runtime_error("not a marschner bsdf");
+    const Azimuthal *lobes[3] = {&b.ma->nR, &b.ma->nTT, &b.ma->nTRT};
+    for (int l = 0; l < 3; ++l) {
+        for (int i = 0; i < 64 * 64; ++i) { outTables[(l * 4096 + i) * 3] = lobes[l]->table[i].x; outTables[(l * 4096 + i) * 3 + 1] = lobes[l]->table[i].y; outTables[(l * 4096 + i) * 3 + 2] = lobes[l]->table[i].z; }
+        std::memcpy(outPdfs + l * 4096, lobes[l]->sampler.pdfs.data(), 4096 * 4);
+        std::memcpy(outCdfs + l * 64 * 65, lobes[l]->sampler.cdfs.data(), 64 * 65 * 4);
+        std::memcpy(outSums + l * 64, lobes[l]->sampler.sums.data(), 64 * 4);
+    }
+    std::memcpy(outRT, b.ma->extRT.trans.data(), b.ma->extRT.thetaSamples * 4);
+    outConsts[0] = 1 - b.ma->intRT.evalDiffuse(b.ma->alpha); // Fdr
+    outConsts[1] = b.ma->specularSamplingWeight;
+    outConsts[2] = b.ma->eta;
+    outConsts[3] = (float) b.ma->extRT.thetaSamples;
+    return 0;
+    ORC_CATCH
+}
+
+// mode: 0 = BVH closest, 1 = BVH any-hit, 2 = brute closest, 3 = brute any-hit
+int orc_intersect_batch(void *sp, uint64_t n, const float *o, const float *d, const float *mint, const float *maxt, int mode,
+                        int32_t *outShape, uint32_t *outPrim, float *outT) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray r(V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), mint[i], maxt[i]);
+        Hit h; bool hit;
+        if (mode < 2) hit = s->geo.intersectBVH(r, mode == 1, h);
+        else hit = s->geo.intersectBrute(r, mode == 3, h);
+        outShape[i] = hit ? h.shape : -1; outPrim[i] = hit ? h.iv : 0xffffffffu; outT[i] = hit ? h.t : kInf;
+    }
+    return 0;
+    ORC_CATCH
+}
+// All segments hit by the ray inside [mint,maxt] with their t (tie analysis for the bit-exact prim-id test)
+int orc_intersect_candidates(void *sp, const float *o, const float *d, float mint, float maxt, int maxOut, int32_t *outShape, uint32_t *outPrim, float *outT) {
+    Scene *s = (Scene *) sp;
+    Ray r(V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), mint, maxt);
+    int cnt = 0;
+    float smin, smax;
+    if (!s->geo.sceneInterval(r, false, smin, smax)) return 0;
+    for (size_t si = 0; si < s->geo.shapes.size(); ++si) {
+        const HairShape &h = s->geo.shapes[si];
+        float a, b;
+        if (!s->geo.shapeInterval(h, r, smin, smax, a, b)) continue;
+        for (uint32_t iv : h.segIndex) {
+            float t; V3 p;
+            if (h.intersect(r, iv, a, b, t, p) && cnt < maxOut) { outShape[cnt] = (int) si; outPrim[cnt] = iv; outT[cnt] = t; cnt++; }
+        }
+    }
+    return cnt;
+}
+// closest hit + intersection record: outRec = p(3) n(3) s(3) t(3) wi(3) per ray
+int orc_intersect_full_batch(void *sp, uint64_t n, const float *o, const float *d, const float *mint, const float *maxt,
+                             int32_t *outShape, uint32_t *outPrim, float *outT, float *outRec) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray r(V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), mint[i], maxt[i]);
+        Intersection its;
+        bool hit = s->geo.rayIntersect(r, its);
+        outShape[i] = hit ? its.shape : -1; outPrim[i] = hit ? its.iv : 0xffffffffu; outT[i] = hit ? its.t : kInf;
+        float *rec = outRec + 15 * i;
+        V3 vs[5] = {its.p, its.shFrame.n, its.shFrame.s, its.shFrame.t, its.wi};
+        for (int k = 0; k < 5; ++k) { rec[3 * k] = hit ? vs[k].x : 0; rec[3 * k + 1] = hit ? vs[k].y : 0; rec[3 * k + 2] = hit ? vs[k].z : 0; }
+    }
+    return 0;
+    ORC_CATCH
+}
+
+int orc_camera_rays(void *sp, uint64_t n, const float *pxy, float *outO, float *outD, float *outMinMax) {
+    Scene *s = (Scene *) sp;
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray r; V3 rx, ry;
+        s->cam.sampleRayDifferential(pxy[2 * i], pxy[2 * i + 1], r, rx, ry);
+        outO[3 * i] = r.o.x; outO[3 * i + 1] = r.o.y; outO[3 * i + 2] = r.o.z;
+        outD[3 * i] = r.d.x; outD[3 * i + 1] = r.d.y; outD[3 * i + 2] = r.d.z;
+        outMinMax[2 * i] = r.mint; outMinMax[2 * i + 1] = r.maxt;
+    }
+    return 0;
+}
+
+// Environment map hooks: eval (no differentials), sampleDirect from `ref`, pdfDirect
+int orc_env_eval_batch(void *sp, uint64_t n, const float *d, float *outRGB, float *outPdf) {
+    Scene *s = (Scene *) sp;
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 dir(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        V3 v = s->env.evalEnvironment(dir);
+        outRGB[3 * i] = v.x; outRGB[3 * i + 1] = v.y; outRGB[3 * i + 2] = v.z;
+        outPdf[i] = s->env.pdfDirect(dir);
+    }
+    return 0;
+}
+int orc_env_sample_batch(void *sp, uint64_t n, const float *ref, const float *sample, float *outD, float *outValue, float *outPdfDist) {
+    Scene *s = (Scene *) sp;
+    for (uint64_t i = 0; i < n; ++i) {
+        EnvMap::DirectSample r = s->env.sampleDirect(V3(ref[3 * i], ref[3 * i + 1], ref[3 * i + 2]), sample[2 * i], sample[2 * i + 1]);
+        outD[3 * i] = r.d.x; outD[3 * i + 1] = r.d.y; outD[3 * i + 2] = r.d.z;
+        outValue[3 * i] = r.value.x; outValue[3 * i + 1] = r.value.y; outValue[3 * i + 2] = r.value.z;
+        outPdfDist[2 * i] = r.pdf; outPdfDist[2 * i + 1] = r.dist;
+    }
+    return 0;
+}
+int orc_env_tables(void *sp, float *outCdfRows, float *outCdfCols, float *outRowWeights, float *outNormalization, uint16_t *outTexels) {
+    Scene *s = (Scene *) sp;
+    std::memcpy(outCdfRows, s->env.cdfRows.data(), s->env.cdfRows.size() * 4);
+    std::memcpy(outCdfCols, s->env.cdfCols.data(), s->env.cdfCols.size() * 4);
+    std::memcpy(outRowWeights, s->env.rowWeights.data(), s->env.rowWeights.size() * 4);
+    *outNormalization = s->env.normalization;
+    if (outTexels) std::memcpy(outTexels, s->env.texels.data(), s->env.texels.size() * 2);
+    return 0;
+}
+
+int orc_filter_table(void *sp, float *out32) { Scene *s = (Scene *) sp; std::memcpy(out32, s->filter.values, 32 * 4); return 0; }
+
+// Render sample range [sBegin,sEnd) of spp into outFilm (5 x w x h, accumulated sums; not normalised)
+int orc_render(void *sp, uint32_t spp, uint64_t seed, uint32_t sBegin, uint32_t sEnd, int nThreads, float *outFilm, uint64_t *outStats) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    s->seed = seed;
+    s->stats.rays = 0; s->stats.shadowRays = 0; s->stats.paths = 0; s->stats.pathLength = 0; s->stats.dropped = 0;
+    Film film; film.init(s->cam.filmW, s->cam.filmH);
+    s->render(film, spp, sBegin, sEnd, nThreads);
+    std::memcpy(outFilm, film.data.data(), film.data.size() * 4);
+    if (outStats) { outStats[0] = s->stats.rays; outStats[1] = s->stats.shadowRays; outStats[2] = s->stats.paths; outStats[3] = s->stats.pathLength; outStats[4] = s->stats.dropped; outStats[5] = (uint64_t) s->env.unsupportedFiltered; }
+    return 0;
+    ORC_CATCH
+}
+
+// Per-sample radiance for path-by-path comparison: pixels (x,y), sample index -> Li, sample position, depth
+int orc_render_samples(void *sp, uint64_t n, const uint32_t *xy, const uint32_t *samp, uint32_t spp, uint64_t seed, float *outLi, float *outPos) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    s->seed = seed;
+    Film film; film.init(s->cam.filmW, s->cam.filmH);
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 L; float pos[2];
+        s->renderSample(film, xy[2 * i], xy[2 * i + 1], samp[i], spp, &L, pos);
+        outLi[3 * i] = L.x; outLi[3 * i + 1] = L.y; outLi[3 * i + 2] = L.z;
+        outPos[2 * i] = pos[0]; outPos[2 * i + 1] = pos[1];
+    }
+    return 0;
+    ORC_CATCH
+}
+
+// Film splat of explicit samples (F1 parity hook): pos(2), value(3), alpha per sample -> film
+int orc_splat_batch(void *sp, uint64_t n, const float *pos, const float *rgb, const float *alpha, float *outFilm) {
+    Scene *s = (Scene *) sp;
+    Film film; film.init(s->cam.filmW, s->cam.filmH);
+    for (uint64_t i = 0; i < n; ++i) film.put(s->filter, pos[2 * i], pos[2 * i + 1], V3(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]), alpha[i]);
+    std::memcpy(outFilm, film.data.data(), film.data.size() * 4);
+    return 0;
+}
+
+// sunsky bake through the compiled reference pieces (oracle/_ref/libref_pieces.so)
+int orc_bake_sunsky(const char *refLib, float turbidity, float albedo, const float *sunDir, float skyScale, float sunScale,
+                    float sunRadiusScale, int resolution, float *outRGB) {
+    ORC_TRY
+    void *h = dlopen(refLib, RTLD_NOW | RTLD_LOCAL);
+    if (!h) throw std::runtime_error(std::string("oracle/_ref not built: ") + dlerror());
+    RefPieces ref;
+    ref.sky_alloc = (void *(*)(double, double, double)) dlsym(h, "ref_sky_alloc");
+    ref.sky_radiance = (double (*)(void *, double, double, int)) dlsym(h, "ref_sky_radiance");
+    ref.sky_free = (void (*)(void *)) dlsym(h, "ref_sky_free");
+    auto cie = (int (*)(const float **, const float **, const float **, const float **)) dlsym(h, "ref_cie_tables");
+    if (!ref.sky_alloc || !ref.sky_radiance || !ref.sky_free || !cie) throw std::runtime_error("oracle/_ref library lacks expected symbols");
+    ref.cie_n = cie(&ref.cie_wl, &ref.cie_x, &ref.cie_y, &ref.cie_z);
+    SunSkyParams P; P.turbidity = turbidity; P.albedo = albedo; P.sunDirection = V3(sunDir[0], sunDir[1], sunDir[2]);
+    P.skyScale = skyScale; P.sunScale = sunScale; P.sunRadiusScale = sunRadiusScale; P.resolution = resolution;
+    std::vector<float> rgb; int W, H;
+    bakeSunSky(P, ref, rgb, W, H);
+    std::memcpy(outRGB, rgb.data(), rgb.size() * 4);
+    return 0;
+    ORC_CATCH
+}
+
+// Small exported helpers used by the pinning tests
+void orc_gauss_legendre_140(float *points, float *weights) {
+    GaussLegendre<140> g; std::memcpy(points, g.points, 140 * 4); std::memcpy(weights, g.weights, 140 * 4);
+}
+void orc_interp_dist(const float *weights, int size, int num, float *outPdfs, float *outCdfs, float *outSums) {
+    InterpolatedDistribution1D d; d.init(std::vector<float>(weights, weights + size * num), size, num);
+    std::memcpy(outPdfs, d.pdfs.data(), d.pdfs.size() * 4); std::memcpy(outCdfs, d.cdfs.data(), d.cdfs.size() * 4); std::memcpy(outSums, d.sums.data(), d.sums.size() * 4);
+}
+void orc_interp_dist_warp(const float *weights, int size, int num, int n, const float *distribution, const float *u, float *outU, int *outX) {
+    InterpolatedDistribution1D d; d.init(std::vector<float>(weights, weights + size * num), size, num);
+    for (int i = 0; i < n; ++i) { float uu = u[i]; int x; d.warp(distribution[i], uu, x); outU[i] = uu; outX[i] = x; }
+}
+void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4) {
+    Philox4 p = philox4x32_10(c0, c1, c2, c3, k0, k1); std::memcpy(out4, p.v, 16);
+}
+void orc_half_roundtrip(const float *in, int n, uint16_t *outHalf, float *outFloat) {
+    for (int i = 0; i < n; ++i) { outHalf[i] = float_to_half(in[i]); outFloat[i] = half_to_float(outHalf[i]); }
+}
+
+} // extern "C"
