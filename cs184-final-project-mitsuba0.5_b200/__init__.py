@@ -1,0 +1,310 @@
+"""cudapath -- B200-native hair path-tracing hot path behind Mitsuba 0.5's scene format (host-side Python mirror).
+
+The product is the C-ABI shared library `libcudapath.so` (include/cudapath.h); this module is a thin ctypes mirror of it that
+keeps the reference's plugin vocabulary (`kajiyakay`, `marschner`, `hair`, `perspective`, `path`, `sunsky`).  There is no CPU
+fallback: if the CUDA library is missing the import of `lib()` fails loudly.
+"""
+import ctypes
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, 'libcudapath.so')
+DEFAULT_DATA_DIR = os.environ.get('CUDAPATH_DATA_DIR', os.path.join(_REPO, 'refdata'))
+
+_lib = None
+
+
+class CudapathError(RuntimeError):
+    """Mirrors the reference's Log(EError, ...) -> std::runtime_error (src/libcore/logger.cpp:100,147)."""
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in ('paths', 'rays', 'shadow_rays', 'kernel_launches', 'bounces', 'nodes_visited', 'prims_tested',
+                                               'unsupported_filtered_lookups', 'dropped_samples', 'segments', 'bvh_nodes')] + \
+               [('build_ms', ctypes.c_double), ('render_ms', ctypes.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def lib():
+    """Loads libcudapath.so (built by `__graft_entry__.build()` / csrc/Makefile).  Never falls back to anything else."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CudapathError('CUDA extension %s is missing -- run `python -c "import __graft_entry__ as g; g.build()"`' % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.cudapath_last_error.restype = ctypes.c_char_p
+        L.cudapath_hair_file_radius.restype = ctypes.c_float
+        L.cudapath_hair_file_vertex_count.restype = ctypes.c_uint32
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _check(rc):
+    if rc < 0:
+        raise CudapathError(lib().cudapath_last_error().decode())
+    return rc
+
+
+_IDENTITY = np.eye(4, dtype=np.float32)
+_DISTRIBUTIONS = {'beckmann': 0, 'ggx': 1, 'phong': 2, 'as': 2}
+_FILTERS = {'tent': 0, 'box': 1, 'gaussian': 2}
+_IOR = {'air': 1.000277, 'bk7': 1.5046, 'vacuum': 1.0, 'water': 1.3330}    # subset of src/bsdfs/ior.h
+
+
+def load_hair_file(filename, radius=0.025, angleThreshold=1.0, reduction=0.0, toWorld=None):
+    """HairShape(props) file loader (src/shapes/hair.cpp:609-785) -> (xyz (n,3) f32, starts_fiber (n,) u8, world radius)."""
+    L = lib()
+    h = ctypes.c_void_p()
+    tw = _f32(_IDENTITY if toWorld is None else toWorld).reshape(16)
+    _check(L.cudapath_hair_file_load(filename.encode(), ctypes.c_float(radius), ctypes.c_float(angleThreshold), ctypes.c_float(reduction), _p(tw), ctypes.byref(h)))
+    n = L.cudapath_hair_file_vertex_count(h)
+    xyz = np.zeros((n, 3), np.float32); starts = np.zeros(n, np.uint8)
+    L.cudapath_hair_file_copy(h, _p(xyz), _p(starts))
+    r = L.cudapath_hair_file_radius(h)
+    L.cudapath_hair_file_free(h)
+    return xyz, starts, float(r)
+
+
+def bake_sunsky(turbidity=3.0, albedo=(0.2, 0.2, 0.2), sunDirection=(0, 1, 0), skyScale=1.0, sunScale=1.0, sunRadiusScale=1.0, resolution=512,
+                data_dir=None):
+    """SunSkyEmitter bake (src/emitters/sunsky.cpp:100-216) -> (resolution/2, resolution, 3) fp32 lat-long map."""
+    out = np.zeros((resolution // 2, resolution, 3), np.float32)
+    _check(lib().cudapath_bake_sunsky((data_dir or DEFAULT_DATA_DIR).encode(), ctypes.c_float(turbidity), _p(_f32(albedo)), _p(_f32(sunDirection)),
+                                      ctypes.c_float(skyScale), ctypes.c_float(sunScale), ctypes.c_float(sunRadiusScale), int(resolution), _p(out)))
+    return out
+
+
+def develop(film):
+    """Film::develop normalisation (src/libcore/fmtconv.cpp:955-1056): (h,w,5) accumulated film -> (h,w,3) RGB."""
+    film = _f32(film)
+    h, w = film.shape[:2]
+    out = np.zeros((h, w, 3), np.float32)
+    _check(lib().cudapath_develop(_p(film), w, h, _p(out)))
+    return out
+
+
+class Context:
+    """One GPU context = the flattened scene + the wavefront path integrator (replaces Scene + `path` integrator for this path)."""
+
+    def __init__(self, device=0, data_dir=None):
+        self._h = ctypes.c_void_p()
+        self._L = lib()
+        _check(self._L.cudapath_create(int(device), ctypes.byref(self._h)))
+        _check(self._L.cudapath_set_data_dir(self._h, (data_dir or DEFAULT_DATA_DIR).encode()))
+        self.width = self.height = 0
+        self.spp = 0
+
+    def close(self):
+        if self._h:
+            self._L.cudapath_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- plugins -------------------------------------------------------------------------------------------------
+    def add_bsdf(self, type, **props):
+        """`<bsdf type=...>`: kajiyakay (src/bsdfs/kajiyakay.cpp:60-73) or marschner (src/bsdfs/marschner_diffuse.cpp:113-160)."""
+        if type == 'kajiyakay':
+            d = _f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3)); s = _f32(np.broadcast_to(props.get('specularReflectance', 0.2), 3))
+            return _check(self._L.cudapath_add_bsdf_kajiyakay(self._h, _p(d), _p(s), ctypes.c_float(props.get('exponent', 30.0))))
+        if type == 'marschner':
+            ior = lambda v: float(_IOR[v.lower()]) if isinstance(v, str) else float(v)
+            d = _f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3)); s = _f32(np.broadcast_to(props.get('specularReflectance', 0.5), 3))
+            distr = props.get('distribution', 'beckmann').lower()
+            if distr not in _DISTRIBUTIONS:
+                raise CudapathError('Specified an invalid distribution "%s", must be "beckmann", "ggx", or "phong"/"as"!' % distr)
+            return _check(self._L.cudapath_add_bsdf_marschner(self._h, ctypes.c_float(ior(props.get('intIOR', 'bk7'))), ctypes.c_float(ior(props.get('extIOR', 'air'))),
+                                                              _p(d), _p(s), ctypes.c_float(props.get('alpha', 0.1)), _DISTRIBUTIONS[distr],
+                                                              1 if props.get('nonlinear', False) else 0))
+        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner)' % type)
+
+    def add_hair(self, xyz, starts_fiber, radius, bsdf_id):
+        xyz = _f32(xyz).reshape(-1, 3); st = np.ascontiguousarray(starts_fiber, dtype=np.uint8)
+        if len(st) != len(xyz):
+            raise CudapathError('starts_fiber must have one entry per vertex')
+        return _check(self._L.cudapath_add_hair(self._h, _p(xyz), _p(st), ctypes.c_uint32(len(st)), ctypes.c_float(radius), int(bsdf_id)))
+
+    def add_hair_file(self, filename, bsdf_id, radius=0.025, angleThreshold=1.0, reduction=0.0, toWorld=None):
+        tw = _f32(_IDENTITY if toWorld is None else toWorld).reshape(16)
+        return _check(self._L.cudapath_add_hair_file(self._h, filename.encode(), ctypes.c_float(radius), ctypes.c_float(angleThreshold), ctypes.c_float(reduction), _p(tw), int(bsdf_id)))
+
+    def set_envmap(self, rgb, toWorld=None, scale=1.0):
+        rgb = _f32(rgb); h, w = rgb.shape[:2]
+        tw = _f32(_IDENTITY if toWorld is None else toWorld).reshape(16)
+        _check(self._L.cudapath_set_envmap(self._h, _p(rgb), w, h, _p(tw), ctypes.c_float(scale)))
+
+    def set_sunsky(self, turbidity=3.0, albedo=(0.2, 0.2, 0.2), sunDirection=(0, 1, 0), skyScale=1.0, sunScale=1.0, sunRadiusScale=1.0, resolution=512):
+        _check(self._L.cudapath_set_sunsky(self._h, ctypes.c_float(turbidity), _p(_f32(albedo)), _p(_f32(sunDirection)), ctypes.c_float(skyScale),
+                                           ctypes.c_float(sunScale), ctypes.c_float(sunRadiusScale), int(resolution)))
+
+    def set_camera(self, toWorld, fov=35.0, nearClip=1e-2, farClip=1e4, width=768, height=576):
+        tw = _f32(toWorld).reshape(16)
+        _check(self._L.cudapath_set_camera_perspective(self._h, _p(tw), ctypes.c_float(fov), ctypes.c_float(nearClip), ctypes.c_float(farClip), int(width), int(height)))
+        self.width, self.height = int(width), int(height)
+
+    def set_film(self, rfilter='tent', param=0.0, has_alpha=False):
+        _check(self._L.cudapath_set_film(self._h, _FILTERS[rfilter], ctypes.c_float(param), 1 if has_alpha else 0))
+
+    def set_integrator(self, maxDepth=-1, rrDepth=5, strictNormals=False, hideEmitters=False):
+        _check(self._L.cudapath_set_integrator(self._h, int(maxDepth), int(rrDepth), 1 if strictNormals else 0, 1 if hideEmitters else 0))
+
+    def set_options(self, wave_size=0, collect_stats=False):
+        _check(self._L.cudapath_set_options(self._h, ctypes.c_uint32(wave_size), 1 if collect_stats else 0))
+
+    def load_xml(self, filename, defines=None):
+        """SceneHandler for the hair scenes; `defines` = dict for $name substitution (mitsuba -D).  Returns sampleCount."""
+        spp = ctypes.c_uint32(0)
+        d = ';'.join('%s=%s' % kv for kv in (defines or {}).items())
+        _check(self._L.cudapath_load_scene_xml(self._h, filename.encode(), d.encode(), ctypes.byref(spp)))
+        self.spp = spp.value
+        return spp.value
+
+    def build(self):
+        _check(self._L.cudapath_build(self._h))
+        st = self.stats()
+        return st
+
+    # ---- render ----------------------------------------------------------------------------------------------------
+    def film_shape(self):
+        w = ctypes.c_int(0); h = ctypes.c_int(0)
+        _check(self._L.cudapath_film_size(self._h, ctypes.byref(w), ctypes.byref(h)))
+        self.width, self.height = w.value, h.value
+        return (self.height, self.width, 5)
+
+    def render(self, spp, seed=0, sample_begin=0, sample_end=None):
+        """Accumulated film (h,w,5) for sample indices [sample_begin, sample_end) of spp; host buffer in/out (the e2e path)."""
+        out = np.zeros(self.film_shape(), np.float32)
+        _check(self._L.cudapath_render(self._h, ctypes.c_uint32(spp), ctypes.c_uint64(seed), ctypes.c_uint32(sample_begin),
+                                       ctypes.c_uint32(spp if sample_end is None else sample_end), _p(out)))
+        return out
+
+    def render_into(self, film_dev_ptr, spp, seed=0, sample_begin=0, sample_end=None, stream=0):
+        """Accumulates into a caller-owned DEVICE film (e.g. a torch tensor's data_ptr()); used for the NCCL film reduce."""
+        _check(self._L.cudapath_render_dev(self._h, ctypes.c_uint32(spp), ctypes.c_uint64(seed), ctypes.c_uint32(sample_begin),
+                                           ctypes.c_uint32(spp if sample_end is None else sample_end), ctypes.c_void_p(film_dev_ptr), ctypes.c_void_p(stream)))
+
+    def stats(self):
+        s = Stats()
+        _check(self._L.cudapath_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+    def scene_bounds(self):
+        a = np.zeros(6, np.float32); b = np.zeros(4, np.float32)
+        _check(self._L.cudapath_scene_bounds(self._h, _p(a), _p(b)))
+        return a, b
+
+    # ---- parity hooks (host buffers) --------------------------------------------------------------------------------
+    def bsdf_eval(self, bsdf_id, wi, wo):
+        wi = _f32(wi).reshape(-1, 3); wo = _f32(wo).reshape(-1, 3); n = len(wi)
+        ev = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32)
+        _check(self._L.cudapath_bsdf_eval_batch(self._h, int(bsdf_id), ctypes.c_uint64(n), _p(wi), _p(wo), _p(ev), _p(pdf)))
+        return ev, pdf
+
+    def bsdf_sample(self, bsdf_id, wi, sample):
+        wi = _f32(wi).reshape(-1, 3); sample = _f32(sample).reshape(-1, 2); n = len(wi)
+        wo = np.zeros((n, 3), np.float32); wt = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32); ty = np.zeros(n, np.int32)
+        _check(self._L.cudapath_bsdf_sample_batch(self._h, int(bsdf_id), ctypes.c_uint64(n), _p(wi), _p(sample), _p(wo), _p(wt), _p(pdf), _p(ty)))
+        return wo, wt, pdf, ty
+
+    def intersect(self, o, d, mint, maxt, any_hit=False, record=False):
+        o = _f32(o).reshape(-1, 3); d = _f32(d).reshape(-1, 3); n = len(o)
+        mint = _f32(np.broadcast_to(mint, n)); maxt = _f32(np.broadcast_to(maxt, n))
+        sh = np.zeros(n, np.int32); pr = np.zeros(n, np.uint32); t = np.zeros(n, np.float32)
+        rec = np.zeros((n, 15), np.float32) if record else None
+        _check(self._L.cudapath_intersect_batch(self._h, ctypes.c_uint64(n), _p(o), _p(d), _p(mint), _p(maxt), 1 if any_hit else 0, _p(sh), _p(pr), _p(t),
+                                                _p(rec) if record else None))
+        return (sh, pr, t, rec) if record else (sh, pr, t)
+
+    def env_eval(self, d):
+        d = _f32(d).reshape(-1, 3); n = len(d)
+        rgb = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32)
+        _check(self._L.cudapath_env_eval_batch(self._h, ctypes.c_uint64(n), _p(d), _p(rgb), _p(pdf)))
+        return rgb, pdf
+
+    def env_sample(self, ref, sample):
+        ref = _f32(ref).reshape(-1, 3); sample = _f32(sample).reshape(-1, 2); n = len(ref)
+        d = np.zeros((n, 3), np.float32); v = np.zeros((n, 3), np.float32); pd = np.zeros((n, 2), np.float32)
+        _check(self._L.cudapath_env_sample_batch(self._h, ctypes.c_uint64(n), _p(ref), _p(sample), _p(d), _p(v), _p(pd)))
+        return d, v, pd[:, 0].copy(), pd[:, 1].copy()
+
+    def camera_rays(self, pixel_sample):
+        ps = _f32(pixel_sample).reshape(-1, 2); n = len(ps)
+        o = np.zeros((n, 3), np.float32); d = np.zeros((n, 3), np.float32); mm = np.zeros((n, 2), np.float32)
+        _check(self._L.cudapath_camera_rays_batch(self._h, ctypes.c_uint64(n), _p(ps), _p(o), _p(d), _p(mm)))
+        return o, d, mm[:, 0].copy(), mm[:, 1].copy()
+
+    def splat(self, pos, rgb, alpha):
+        pos = _f32(pos).reshape(-1, 2); rgb = _f32(rgb).reshape(-1, 3); alpha = _f32(alpha).reshape(-1); n = len(pos)
+        out = np.zeros(self.film_shape(), np.float32)
+        _check(self._L.cudapath_splat_batch(self._h, ctypes.c_uint64(n), _p(pos), _p(rgb), _p(alpha), _p(out)))
+        return out
+
+    def marschner_tables(self, bsdf_id):
+        tab = np.zeros((3, 64, 64, 3), np.float32); pdf = np.zeros((3, 64, 64), np.float32); cdf = np.zeros((3, 64, 65), np.float32)
+        sums = np.zeros((3, 64), np.float32); rt = np.zeros(1024, np.float32); consts = np.zeros(4, np.float32)
+        _check(self._L.cudapath_marschner_tables(self._h, int(bsdf_id), _p(tab), _p(pdf), _p(cdf), _p(sums), _p(rt), _p(consts)))
+        return dict(tables=tab, pdfs=pdf, cdfs=cdf, sums=sums, rt=rt[:int(consts[3])].copy(), Fdr=float(consts[0]), specW=float(consts[1]), eta=float(consts[2]))
+
+    def env_tables(self, w, h):
+        rows = np.zeros(h + 1, np.float32); cols = np.zeros((h, w + 1), np.float32); rw = np.zeros(h, np.float32); nrm = ctypes.c_float(0)
+        _check(self._L.cudapath_env_tables(self._h, _p(rows), _p(cols), _p(rw), ctypes.byref(nrm)))
+        return rows, cols, rw, nrm.value
+
+    def filter_table(self):
+        t = np.zeros(32, np.float32)
+        _check(self._L.cudapath_filter_table(self._h, _p(t)))
+        return t
+
+    # ---- device-resident stage benchmarks (pointers are raw device addresses, e.g. torch tensors' data_ptr()) ------
+    def bsdf_eval_dev(self, bsdf_id, n, wi, wo, out_eval, out_pdf, stream=0):
+        _check(self._L.cudapath_bsdf_eval_batch_dev(self._h, int(bsdf_id), ctypes.c_uint64(n), ctypes.c_void_p(wi), ctypes.c_void_p(wo),
+                                                    ctypes.c_void_p(out_eval), ctypes.c_void_p(out_pdf), ctypes.c_void_p(stream)))
+
+    def bsdf_sample_dev(self, bsdf_id, n, wi, sample, out_wo, out_weight, out_pdf, out_type, stream=0):
+        _check(self._L.cudapath_bsdf_sample_batch_dev(self._h, int(bsdf_id), ctypes.c_uint64(n), ctypes.c_void_p(wi), ctypes.c_void_p(sample), ctypes.c_void_p(out_wo),
+                                                      ctypes.c_void_p(out_weight), ctypes.c_void_p(out_pdf), ctypes.c_void_p(out_type), ctypes.c_void_p(stream)))
+
+    def intersect_dev(self, n, o, d, mint, maxt, out_shape, out_prim, out_t, any_hit=False, out_stats=0, stream=0):
+        _check(self._L.cudapath_intersect_batch_dev(self._h, ctypes.c_uint64(n), ctypes.c_void_p(o), ctypes.c_void_p(d), ctypes.c_void_p(mint), ctypes.c_void_p(maxt),
+                                                    1 if any_hit else 0, ctypes.c_void_p(out_shape), ctypes.c_void_p(out_prim), ctypes.c_void_p(out_t),
+                                                    ctypes.c_void_p(out_stats) if out_stats else None, ctypes.c_void_p(stream)))
+
+
+def scene_from_description(name, device=0, scale=1.0, overrides=None, data_dir=None):
+    """Builds a Context for one of scenes.SCENES directly from flattened arrays (the path a librender plugin would take)."""
+    from . import scenes
+    sc = dict(scenes.SCENES[name]); sc.update(overrides or {})
+    ctx = Context(device, data_dir)
+    for sh in sc['shapes']:
+        b = dict(sh['bsdf']); btype = b.pop('type'); b.pop('id', None)
+        bid = ctx.add_bsdf(btype, **b)
+        xyz, starts = scenes.generate(sh, scale)
+        ctx.add_hair(xyz, starts, sh['radius'], bid)
+    ctx.set_sunsky(**scenes.sunsky_params(name))
+    ctx.set_camera(np.array(sc['camera'], np.float32).reshape(4, 4), sc['fov'], width=sc['width'], height=sc['height'])
+    ctx.set_film('tent')
+    ctx.set_integrator(maxDepth=sc['maxDepth'], rrDepth=5, strictNormals=True)
+    ctx.spp = sc['spp']
+    return ctx

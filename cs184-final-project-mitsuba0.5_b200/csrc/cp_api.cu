@@ -1,0 +1,585 @@
+// cp_api.cu -- implementation of the C ABI declared in include/cudapath.h
+#include "../../include/cudapath.h"
+#include "cp_host.h"
+#include "cp_wavefront.h"
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include <memory>
+
+using namespace cp;
+
+static thread_local std::string g_lastError;
+static int fail(const std::string &msg) { g_lastError = msg; return -1; }
+#define CKA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+namespace {
+struct EnvHost { std::vector<float> rgb; int w = 0, h = 0; float toWorld[16]; float scale = 1; bool present = false; };
+struct CamHost { float toWorld[16]; float fov = 35, nearClip = 1e-2f, farClip = 1e4f; int w = 0, h = 0; bool present = false; };
+struct BsdfHost { BsdfDev dev; MarschnerTables tables; float *rt = nullptr; };
+
+// 4x4 helpers (row-major, double)
+void mat_mul(const double *a, const double *b, double *r) {
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j]; r[i * 4 + j] = s; }
+}
+bool mat_inv(const double *a, double *out) {
+    double t[4][8];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { t[i][j] = a[i * 4 + j]; t[i][j + 4] = i == j; }
+    for (int c = 0; c < 4; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 4; ++r) if (std::fabs(t[r][c]) > std::fabs(t[piv][c])) piv = r;
+        if (t[piv][c] == 0) return false;
+        if (piv != c) for (int j = 0; j < 8; ++j) std::swap(t[piv][j], t[c][j]);
+        const double inv = 1.0 / t[c][c];
+        for (int j = 0; j < 8; ++j) t[c][j] *= inv;
+        for (int r = 0; r < 4; ++r) if (r != c && t[r][c] != 0) { const double f = t[r][c]; for (int j = 0; j < 8; ++j) t[r][j] -= f * t[c][j]; }
+    }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out[i * 4 + j] = t[i][j + 4];
+    return true;
+}
+V3 h_xfm_point(const float *m, V3 p) {
+    float x = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], y = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
+    float z = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11], w = m[12] * p.x + m[13] * p.y + m[14] * p.z + m[15];
+    if (w == 1.0f) return V3(x, y, z);
+    return V3(x, y, z) / w;
+}
+}
+
+struct cudapath_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string dataDir;
+    std::vector<BsdfHost> bsdfs;
+    std::vector<float4> vtx;
+    std::vector<ShapeDev> shapes;
+    EnvHost env; EnvTables envTables;
+    CamHost cam;
+    int filterType = 0; float filterParam = 0; int hasAlpha = 0;
+    IntegratorDev integ{-1, 5, 0, 0};
+    // device
+    float4 *d_vtx = nullptr; ShapeDev *d_shapes = nullptr; BsdfDev *d_bsdfs = nullptr;
+    BVHDev bvh;
+    SceneDev scene;
+    bool built = false;
+    Wavefront wf;
+    uint32_t waveSize = 1u << 22; int collectStats = 0;
+    cudapath_stats stats{};
+    float sceneAABB[6] = {0, 0, 0, 0, 0, 0};
+
+    void freeBuilt() {
+        cudaFree(d_vtx); cudaFree(d_shapes); cudaFree(d_bsdfs); cudaFree((void *) bvh.nodes); cudaFree((void *) bvh.prims);
+        cudaFree(envTables.texels); cudaFree(envTables.cdfCols); cudaFree(envTables.cdfRows); cudaFree(envTables.rowWeights);
+        d_vtx = nullptr; d_shapes = nullptr; d_bsdfs = nullptr; bvh = BVHDev(); envTables = EnvTables(); built = false;
+    }
+    ~cudapath_ctx() {
+        cudaSetDevice(device);
+        freeBuilt();
+        for (auto &b : bsdfs) { cudaFree(b.tables.tab); cudaFree(b.tables.cdf); cudaFree(b.tables.sums); cudaFree(b.tables.pdf); cudaFree(b.rt); }
+        wf.release();
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct cudapath_hair_file { HairFileData data; };
+
+static int require_built(cudapath_ctx *ctx) {
+    if (!ctx) return fail("null context");
+    if (!ctx->built) return fail("cudapath_build() has not been called");
+    CKA(cudaSetDevice(ctx->device));
+    return 0;
+}
+
+extern "C" {
+
+const char *cudapath_last_error(void) { return g_lastError.c_str(); }
+// used by the host-side translation units (scene loader) to report through the same channel
+int cudapath_set_error_message(const char *msg) { g_lastError = msg ? msg : ""; return -1; }
+
+int cudapath_create(int cuda_device, cudapath_ctx **out) {
+    if (!out) return fail("null output pointer");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(std::string("no CUDA device available: ") + cudaGetErrorString(e));
+    if (cuda_device < 0 || cuda_device >= count) return fail("CUDA device index out of range");
+    CKA(cudaSetDevice(cuda_device));
+    std::unique_ptr<cudapath_ctx> ctx(new cudapath_ctx());
+    ctx->device = cuda_device;
+    CKA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    *out = ctx.release();
+    return 0;
+}
+void cudapath_destroy(cudapath_ctx *ctx) { delete ctx; }
+
+int cudapath_set_data_dir(cudapath_ctx *ctx, const char *path) { if (!ctx || !path) return fail("null argument"); ctx->dataDir = path; return 0; }
+
+int cudapath_add_bsdf_kajiyakay(cudapath_ctx *ctx, const float d[3], const float s[3], float exponent) {
+    if (!ctx || !d || !s) return fail("null argument");
+    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    V3 diff(d[0], d[1], d[2]), spec(s[0], s[1], s[2]);
+    // BSDF::ensureEnergyConservation (src/librender/bsdf.cpp:115-146)
+    const float actualMax = maxc(spec + diff);
+    if (actualMax > 1.0f) { const float scale = 0.99f * (1.0f / actualMax); spec = spec * scale; diff = diff * scale; }
+    b.dev.kind = 0; b.dev.diffuse = diff; b.dev.specular = spec; b.dev.exponent = exponent;
+    const float dAvg = luminance(diff), sAvg = luminance(spec);
+    b.dev.specW = sAvg / (dAvg + sAvg);                    // kajiyakay.cpp:96-98
+    ctx->bsdfs.push_back(b); ctx->built = false;
+    return (int) ctx->bsdfs.size() - 1;
+}
+
+int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior, const float d[3], const float s[3], float alpha, int distribution, int nonlinear) {
+    if (!ctx || !d || !s) return fail("null argument");
+    if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
+    if (ctx->dataDir.empty()) return fail("marschner needs data/microfacet/*.dat: call cudapath_set_data_dir() first");
+    CKA(cudaSetDevice(ctx->device));
+    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    b.dev.kind = 1;
+    b.dev.eta = int_ior / ext_ior;
+    b.dev.invEta2 = 1.0f / (b.dev.eta * b.dev.eta);
+    b.dev.alpha = std::max(alpha, 1e-4f);                  // microfacet.h:131
+    b.dev.nonlinear = nonlinear ? 1 : 0;
+    const float betaR = 0.1f, betaTT = betaR * 0.5f, betaTRT = betaR * 2.0f;   // marschner_diffuse.cpp:152-155 (hard-coded)
+    b.dev.vR = betaR * betaR; b.dev.vTT = betaTT * betaTT; b.dev.vTRT = betaTRT * betaTRT;
+    b.dev.scaleAngle = -0.1f;
+    V3 spec(s[0], s[1], s[2]);
+    { const float mx = maxc(spec); if (mx > 1.0f) spec = spec * (0.99f * (1.0f / mx)); }   // bsdf.cpp:88-113
+    b.dev.diffuse = V3(d[0], d[1], d[2]); b.dev.specular = spec;
+    const float dAvg = luminance(b.dev.diffuse), sAvg = luminance(spec);
+    b.dev.specW = sAvg / (dAvg + sAvg);                    // marschner_diffuse.cpp:214-216
+    std::vector<float> T; float Fdr; std::string err;
+    if (!rough_transmittance_slice(ctx->dataDir, distribution, b.dev.eta, b.dev.alpha, T, Fdr, err)) return fail(err);
+    b.dev.Fdr = Fdr; b.dev.rtSize = (int) T.size();
+    CKA(cudaMalloc(&b.rt, T.size() * 4));
+    CKA(cudaMemcpyAsync(b.rt, T.data(), T.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    float pts[140], wts[140];
+    gauss_legendre_140(pts, wts);
+    const float sigmaA[3] = {0.5f, 0.5f, 0.5f};           // marschner_diffuse.cpp:125 (hard-coded)
+    if (!build_marschner_tables(b.dev.eta, betaR, sigmaA, pts, wts, ctx->stream, b.tables, err)) return fail(err);
+    b.dev.tab = b.tables.tab; b.dev.cdf = b.tables.cdf; b.dev.sums = b.tables.sums; b.dev.rt = b.rt;
+    ctx->bsdfs.push_back(b); ctx->built = false;
+    return (int) ctx->bsdfs.size() - 1;
+}
+
+int cudapath_add_hair(cudapath_ctx *ctx, const float *xyz, const uint8_t *starts, uint32_t n, float radius, int bsdf_id) {
+    if (!ctx || !xyz || !starts) return fail("null argument");
+    if (bsdf_id < 0 || bsdf_id >= (int) ctx->bsdfs.size()) return fail("hair shape references an unknown bsdf id");
+    if (n < 2) return fail("hair shape needs at least two vertices");
+    if (!starts[0]) return fail("the first hair vertex must start a fiber");
+    if (ctx->shapes.size() >= (1u << 23)) return fail("too many shapes");
+    ShapeDev sd; std::memset(&sd, 0, sizeof(sd));
+    sd.radius = radius; sd.bsdf = bsdf_id; sd.vertexOffset = (uint32_t) ctx->vtx.size(); sd.vertexCount = n;
+    const uint32_t shapeBits = (uint32_t) ctx->shapes.size() << 8;
+    ctx->vtx.reserve(ctx->vtx.size() + n + 1);
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t bits = shapeBits | (starts[i] ? 1u : 0u);
+        float w; std::memcpy(&w, &bits, 4);
+        ctx->vtx.push_back(make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], w));
+    }
+    { uint32_t bits = shapeBits | 1u; float w; std::memcpy(&w, &bits, 4); ctx->vtx.push_back(make_float4(0, 0, 0, w)); }   // sentinel (hair.cpp:782)
+    ctx->shapes.push_back(sd); ctx->built = false;
+    return (int) ctx->shapes.size() - 1;
+}
+
+int cudapath_hair_file_load(const char *filename, float radius, float angle_threshold_deg, float reduction, const float to_world[16], cudapath_hair_file **out) {
+    if (!filename || !to_world || !out) return fail("null argument");
+    std::unique_ptr<cudapath_hair_file> h(new cudapath_hair_file());
+    std::string err;
+    if (!load_hair_file(filename, radius, angle_threshold_deg, reduction, to_world, h->data, err)) return fail(err);
+    *out = h.release();
+    return 0;
+}
+uint32_t cudapath_hair_file_vertex_count(const cudapath_hair_file *h) { return h ? (uint32_t) h->data.startsFiber.size() : 0; }
+float cudapath_hair_file_radius(const cudapath_hair_file *h) { return h ? h->data.radius : 0.0f; }
+void cudapath_hair_file_copy(const cudapath_hair_file *h, float *xyz, uint8_t *starts) {
+    if (!h) return;
+    if (xyz) std::memcpy(xyz, h->data.xyz.data(), h->data.xyz.size() * 4);
+    if (starts) std::memcpy(starts, h->data.startsFiber.data(), h->data.startsFiber.size());
+}
+void cudapath_hair_file_free(cudapath_hair_file *h) { delete h; }
+
+int cudapath_add_hair_file(cudapath_ctx *ctx, const char *filename, float radius, float angle_threshold_deg, float reduction, const float to_world[16], int bsdf_id) {
+    cudapath_hair_file *h = nullptr;
+    if (cudapath_hair_file_load(filename, radius, angle_threshold_deg, reduction, to_world, &h) != 0) return -1;
+    int r = cudapath_add_hair(ctx, h->data.xyz.data(), h->data.startsFiber.data(), (uint32_t) h->data.startsFiber.size(), h->data.radius, bsdf_id);
+    cudapath_hair_file_free(h);
+    return r;
+}
+
+int cudapath_set_envmap(cudapath_ctx *ctx, const float *rgb, int w, int h, const float to_world[16], float scale) {
+    if (!ctx || !rgb || !to_world) return fail("null argument");
+    if (w <= 0 || h <= 0 || std::max(w, h) > 0xFFFF) return fail("Environment maps images must be smaller than 65536 pixels in width and height");
+    ctx->env.rgb.assign(rgb, rgb + (size_t) 3 * w * h);
+    ctx->env.w = w; ctx->env.h = h; ctx->env.scale = scale; std::memcpy(ctx->env.toWorld, to_world, 64);
+    ctx->env.present = true; ctx->built = false;
+    return 0;
+}
+
+int cudapath_bake_sunsky(const char *data_dir, float turbidity, const float albedo[3], const float sun_direction[3], float sky_scale,
+                         float sun_scale, float sun_radius_scale, int resolution, float *out_rgb) {
+    if (!data_dir || !albedo || !sun_direction || !out_rgb) return fail("null argument");
+    SunSkyParams p; p.turbidity = turbidity; p.skyScale = sky_scale; p.sunScale = sun_scale; p.sunRadiusScale = sun_radius_scale; p.resolution = resolution;
+    for (int i = 0; i < 3; ++i) { p.albedo[i] = albedo[i]; p.sunDirection[i] = sun_direction[i]; }
+    std::vector<float> rgb; int w, h; std::string err;
+    if (!bake_sunsky(data_dir, p, rgb, w, h, err)) return fail(err);
+    std::memcpy(out_rgb, rgb.data(), rgb.size() * 4);
+    return 0;
+}
+int cudapath_set_sunsky(cudapath_ctx *ctx, float turbidity, const float albedo[3], const float sun_direction[3], float sky_scale,
+                        float sun_scale, float sun_radius_scale, int resolution) {
+    if (!ctx) return fail("null context");
+    if (ctx->dataDir.empty()) return fail("sunsky needs the sky-model data: call cudapath_set_data_dir() first");
+    if (resolution <= 1) return fail("invalid sunsky resolution");
+    std::vector<float> rgb((size_t) 3 * resolution * (resolution / 2));
+    if (cudapath_bake_sunsky(ctx->dataDir.c_str(), turbidity, albedo, sun_direction, sky_scale, sun_scale, sun_radius_scale, resolution, rgb.data()) != 0) return -1;
+    const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    return cudapath_set_envmap(ctx, rgb.data(), resolution, resolution / 2, ident, 1.0f);
+}
+
+int cudapath_set_camera_perspective(cudapath_ctx *ctx, const float to_world[16], float fov, float nearClip, float farClip, int w, int h) {
+    if (!ctx || !to_world) return fail("null argument");
+    if (nearClip <= 0) return fail("The 'nearClip' parameter must be greater than zero!");
+    if (nearClip >= farClip) return fail("The 'nearClip' parameter must be smaller than 'farClip'.");
+    if (fov <= 0 || fov >= 180) return fail("The horizontal field of view must be in the interval (0, 180)!");
+    if (w <= 0 || h <= 0) return fail("invalid film size");
+    std::memcpy(ctx->cam.toWorld, to_world, 64);
+    ctx->cam.fov = fov; ctx->cam.nearClip = nearClip; ctx->cam.farClip = farClip; ctx->cam.w = w; ctx->cam.h = h; ctx->cam.present = true;
+    ctx->built = false;
+    return 0;
+}
+int cudapath_set_film(cudapath_ctx *ctx, int filter, float param, int has_alpha) {
+    if (!ctx) return fail("null context");
+    if (filter < 0 || filter > 2) return fail("unsupported reconstruction filter");
+    ctx->filterType = filter; ctx->filterParam = param; ctx->hasAlpha = has_alpha ? 1 : 0; ctx->built = false;
+    return 0;
+}
+int cudapath_set_integrator(cudapath_ctx *ctx, int max_depth, int rr_depth, int strict_normals, int hide_emitters) {
+    if (!ctx) return fail("null context");
+    if (max_depth <= 0 && max_depth != -1) return fail("'maxDepth' must be set to -1 (infinite) or a value greater than zero!");  // integrator.cpp:208-210
+    if (rr_depth <= 0) return fail("'rrDepth' must be set to a value greater than zero!");
+    ctx->integ.maxDepth = max_depth; ctx->integ.rrDepth = rr_depth; ctx->integ.strictNormals = strict_normals ? 1 : 0; ctx->integ.hideEmitters = hide_emitters ? 1 : 0;
+    if (ctx->built) ctx->scene.integ = ctx->integ;
+    return 0;
+}
+int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stats) {
+    if (!ctx) return fail("null context");
+    if (wave_size) ctx->waveSize = std::max(wave_size, 1024u);
+    ctx->collectStats = collect_stats;
+    return 0;
+}
+
+int cudapath_build(cudapath_ctx *ctx) {
+    if (!ctx) return fail("null context");
+    if (ctx->shapes.empty()) return fail("the scene contains no shapes");
+    if (!ctx->cam.present) return fail("no sensor set");
+    CKA(cudaSetDevice(ctx->device));
+    ctx->freeBuilt();
+    std::string err;
+    cudaEvent_t e0, e1; CKA(cudaEventCreate(&e0)); CKA(cudaEventCreate(&e1));
+    CKA(cudaEventRecord(e0, ctx->stream));
+    // geometry
+    CKA(cudaMalloc(&ctx->d_vtx, sizeof(float4) * (ctx->vtx.size() + 4)));
+    CKA(cudaMemsetAsync(ctx->d_vtx, 0, sizeof(float4) * (ctx->vtx.size() + 4), ctx->stream));
+    CKA(cudaMemcpyAsync(ctx->d_vtx, ctx->vtx.data(), sizeof(float4) * ctx->vtx.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CKA(cudaMalloc(&ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size()));
+    CKA(cudaMemcpyAsync(ctx->d_shapes, ctx->shapes.data(), sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    BuildInfo info;
+    if (!build_bvh(ctx->d_vtx, (uint32_t) ctx->vtx.size(), ctx->d_shapes, (int) ctx->shapes.size(), ctx->stream, ctx->bvh, info, err)) return fail(err);
+    CKA(cudaMemcpyAsync(ctx->shapes.data(), ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    // bsdfs
+    std::vector<BsdfDev> devs; for (auto &b : ctx->bsdfs) devs.push_back(b.dev);
+    CKA(cudaMalloc(&ctx->d_bsdfs, sizeof(BsdfDev) * std::max<size_t>(devs.size(), 1)));
+    CKA(cudaMemcpyAsync(ctx->d_bsdfs, devs.data(), sizeof(BsdfDev) * devs.size(), cudaMemcpyHostToDevice, ctx->stream));
+
+    SceneDev &S = ctx->scene;
+    std::memset(&S, 0, sizeof(S));
+    S.vtx = ctx->d_vtx; S.vtxCount = (uint32_t) ctx->vtx.size(); S.shapes = ctx->d_shapes; S.shapeCount = (int) ctx->shapes.size();
+    S.bsdfs = ctx->d_bsdfs; S.bsdfCount = (int) devs.size(); S.bvh = ctx->bvh; S.integ = ctx->integ;
+    for (int k = 0; k < 3; ++k) { S.sceneMin[k] = INFINITY; S.sceneMax[k] = -INFINITY; }
+    for (auto &sh : ctx->shapes) for (int k = 0; k < 3; ++k) { S.sceneMin[k] = std::min(S.sceneMin[k], sh.bmin[k]); S.sceneMax[k] = std::max(S.sceneMax[k], sh.bmax[k]); }
+    for (int k = 0; k < 3; ++k) { ctx->sceneAABB[k] = S.sceneMin[k]; ctx->sceneAABB[3 + k] = S.sceneMax[k]; }
+
+    // camera (perspective.cpp:126-160; Transform::perspective transform.cpp:99-121)
+    {
+        CameraDev &C = S.cam;
+        const CamHost &H = ctx->cam;
+        const double aspect = (double) ((float) H.w / (float) H.h);
+        const float recip = 1.0f / (H.farClip - H.nearClip);
+        const float cot = 1.0f / std::tan((H.fov / 2.0f) * (kPi / 180.0f));
+        const double P[16] = {cot, 0, 0, 0, 0, cot, 0, 0, 0, 0, H.farClip * recip, -H.nearClip * H.farClip * recip, 0, 0, 1, 0};
+        const double T[16] = {1, 0, 0, -1, 0, 1, 0, -1.0 / aspect, 0, 0, 1, 0, 0, 0, 0, 1};
+        const double Sc[16] = {-0.5, 0, 0, 0, 0, -0.5 * aspect, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        double TP[16], STP[16], inv[16];
+        mat_mul(T, P, TP); mat_mul(Sc, TP, STP);
+        if (!mat_inv(STP, inv)) return fail("singular camera projection");
+        for (int i = 0; i < 16; ++i) { C.s2c[i] = (float) inv[i]; C.toWorld[i] = H.toWorld[i]; }
+        C.invResX = 1.0f / H.w; C.invResY = 1.0f / H.h; C.nearClip = H.nearClip; C.farClip = H.farClip; C.filmW = H.w; C.filmH = H.h;
+        const V3 p0 = h_xfm_point(C.s2c, V3(0.0f)), px = h_xfm_point(C.s2c, V3(C.invResX, 0, 0)), py = h_xfm_point(C.s2c, V3(0, C.invResY, 0));
+        const V3 dx = px - p0, dy = py - p0;
+        C.dx[0] = dx.x; C.dx[1] = dx.y; C.dx[2] = dx.z; C.dy[0] = dy.x; C.dy[1] = dy.y; C.dy[2] = dy.z;
+    }
+    // film filter (rfilter.cpp:37-55; tent.cpp:42-44, box.cpp, gaussian.cpp)
+    {
+        FilmDev &F = S.film;
+        float radius = 1.0f, stddev = ctx->filterParam > 0 ? ctx->filterParam : 0.5f;
+        if (ctx->filterType == 0 && ctx->filterParam > 0) radius = ctx->filterParam;
+        if (ctx->filterType == 1) radius = 0.5f;
+        if (ctx->filterType == 2) radius = 4 * stddev;
+        auto ev = [&](float x) -> float {
+            if (ctx->filterType == 0) return std::max(0.0f, 1.0f - std::fabs(x / radius));
+            if (ctx->filterType == 1) return std::fabs(x) <= radius ? 1.0f : 0.0f;
+            const float a = -1.0f / (2.0f * stddev * stddev);
+            return std::max(0.0f, std::exp(a * x * x) - std::exp(a * radius * radius));
+        };
+        float sum = 0.0f;
+        for (int i = 0; i < 31; ++i) { F.filterValues[i] = ev((radius * i) / 31); sum += F.filterValues[i]; }
+        F.filterValues[31] = 0.0f;
+        sum *= 2 * radius / 31;
+        const float norm = 1.0f / sum;
+        for (int i = 0; i < 31; ++i) F.filterValues[i] *= norm;
+        F.filterRadius = radius; F.filterScale = 31 / radius; F.hasAlpha = ctx->hasAlpha;
+        if (radius > 7.5f) return fail("reconstruction filter radius too large");
+    }
+    // environment map
+    S.env.present = 0;
+    if (ctx->env.present) {
+        float *d_rgb = nullptr;
+        const size_t bytes = ctx->env.rgb.size() * 4;
+        CKA(cudaMalloc(&d_rgb, bytes));
+        CKA(cudaMemcpyAsync(d_rgb, ctx->env.rgb.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+        const bool ok = build_env_tables(d_rgb, ctx->env.w, ctx->env.h, ctx->stream, ctx->envTables, err);
+        cudaFree(d_rgb);
+        if (!ok) return fail(err);
+        EnvDev &E = S.env;
+        E.w = ctx->env.w; E.h = ctx->env.h; E.texels = ctx->envTables.texels; E.cdfCols = ctx->envTables.cdfCols; E.cdfRows = ctx->envTables.cdfRows;
+        E.rowWeights = ctx->envTables.rowWeights; E.normalization = ctx->envTables.normalization; E.scale = ctx->env.scale;
+        E.pixelSizeX = 2 * kPi / E.w; E.pixelSizeY = kPi / E.h;
+        double tw[16], ti[16];
+        for (int i = 0; i < 16; ++i) tw[i] = ctx->env.toWorld[i];
+        if (!mat_inv(tw, ti)) return fail("singular environment map transform");
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { E.toWorld[r * 3 + c] = (float) tw[r * 4 + c]; E.toLocal[r * 3 + c] = (float) ti[r * 4 + c]; }
+        // scene bounds for the emitter: kd-tree AABB + sensor position (scene.cpp:387-413), bounding sphere x1.5 (envmap.cpp:331-341)
+        float mn[3], mx[3];
+        const V3 camPos = h_xfm_point(ctx->cam.toWorld, V3(0.0f));
+        const float cp3[3] = {camPos.x, camPos.y, camPos.z};
+        for (int k = 0; k < 3; ++k) { mn[k] = std::min(S.sceneMin[k], cp3[k]); mx[k] = std::max(S.sceneMax[k], cp3[k]); }
+        float c[3]; for (int k = 0; k < 3; ++k) c[k] = (mx[k] + mn[k]) * 0.5f;
+        const V3 diff(c[0] - mx[0], c[1] - mx[1], c[2] - mx[2]);
+        E.bsCenter[0] = c[0]; E.bsCenter[1] = c[1]; E.bsCenter[2] = c[2];
+        E.bsRadius = std::max(kEpsilon, length(diff) * 1.5f);
+        E.present = 1;
+    }
+    CKA(cudaEventRecord(e1, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; CKA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->stats.build_ms = ms; ctx->stats.segments = info.segments; ctx->stats.bvh_nodes = info.nodes;
+    ctx->built = true;
+    return 0;
+}
+
+int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *film_dev, void *stream) {
+    if (require_built(ctx)) return -1;
+    if (!film_dev) return fail("null film buffer");
+    if (spp == 0 || sample_end > spp || sample_begin > sample_end) return fail("invalid sample range");
+    cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
+    cudaEvent_t e0, e1; CKA(cudaEventCreate(&e0)); CKA(cudaEventCreate(&e1));
+    CKA(cudaEventRecord(e0, st));
+    RenderStats rs; std::string err;
+    const bool ok = ctx->wf.render(ctx->scene, spp, seed, sample_begin, sample_end, film_dev, ctx->waveSize, ctx->collectStats != 0, st, rs, err);
+    if (!ok) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(err); }
+    CKA(cudaEventRecord(e1, st));
+    CKA(cudaEventSynchronize(e1));
+    float ms = 0; CKA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudapath_stats &s = ctx->stats;
+    s.paths = rs.paths; s.rays = rs.rays; s.shadow_rays = rs.shadowRays; s.kernel_launches = rs.launches; s.bounces = rs.bounces;
+    s.nodes_visited = rs.nodesVisited; s.prims_tested = rs.primsTested; s.unsupported_filtered_lookups = rs.unsupportedLookups; s.dropped_samples = rs.droppedSamples;
+    s.render_ms = ms;
+    return 0;
+}
+
+int cudapath_render(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *out_film) {
+    if (require_built(ctx)) return -1;
+    if (!out_film) return fail("null film buffer");
+    const size_t bytes = sizeof(float) * 5 * (size_t) ctx->cam.w * ctx->cam.h;
+    float *d_film = nullptr;
+    CKA(cudaMalloc(&d_film, bytes));
+    CKA(cudaMemsetAsync(d_film, 0, bytes, ctx->stream));
+    int r = cudapath_render_dev(ctx, spp, seed, sample_begin, sample_end, d_film, ctx->stream);
+    if (r == 0) {
+        cudaError_t e = cudaMemcpyAsync(out_film, d_film, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(d_film); return fail(std::string("film copy: ") + cudaGetErrorString(e)); }
+    }
+    cudaFree(d_film);
+    return r;
+}
+
+int cudapath_develop(const float *film, int w, int h, float *out_rgb) {
+    if (!film || !out_rgb) return fail("null argument");
+    for (size_t i = 0; i < (size_t) w * h; ++i) {
+        const float wt = film[5 * i + 4];
+        const float inv = wt != 0 ? 1.0f / wt : 0.0f;      // fmtconv.cpp: invWeight = weight != 0 ? 1/weight : 0
+        for (int k = 0; k < 3; ++k) out_rgb[3 * i + k] = film[5 * i + k] * inv;
+    }
+    return 0;
+}
+
+int cudapath_get_stats(cudapath_ctx *ctx, cudapath_stats *out) { if (!ctx || !out) return fail("null argument"); *out = ctx->stats; return 0; }
+int cudapath_film_size(cudapath_ctx *ctx, int *w, int *h) {
+    if (!ctx || !w || !h) return fail("null argument");
+    if (!ctx->cam.present) return fail("no sensor set");
+    *w = ctx->cam.w; *h = ctx->cam.h;
+    return 0;
+}
+int cudapath_scene_bounds(cudapath_ctx *ctx, float aabb[6], float bs[4]) {
+    if (require_built(ctx)) return -1;
+    std::memcpy(aabb, ctx->sceneAABB, 24);
+    for (int k = 0; k < 3; ++k) bs[k] = ctx->scene.env.bsCenter[k];
+    bs[3] = ctx->scene.env.bsRadius;
+    return 0;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------ host-buffer hooks
+namespace {
+struct DevBuf {
+    void *p = nullptr; size_t bytes = 0;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t b) { bytes = b; return cudaMalloc(&p, b ? b : 1); }
+    cudaError_t upload(const void *src, size_t b, cudaStream_t s) { cudaError_t e = alloc(b); if (e != cudaSuccess) return e; return cudaMemcpyAsync(p, src, b, cudaMemcpyHostToDevice, s); }
+    cudaError_t download(void *dst, cudaStream_t s) const { return cudaMemcpyAsync(dst, p, bytes, cudaMemcpyDeviceToHost, s); }
+    template <typename T> T *as() { return (T *) p; }
+};
+}
+
+extern "C" {
+
+int cudapath_bsdf_eval_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf) {
+    if (require_built(ctx)) return -1;
+    DevBuf a, b, e, p; std::string err;
+    CKA(a.upload(wi, n * 12, ctx->stream)); CKA(b.upload(wo, n * 12, ctx->stream)); CKA(e.alloc(n * 12)); CKA(p.alloc(n * 4));
+    if (!bsdf_eval_batch(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
+    CKA(e.download(out_eval, ctx->stream)); CKA(p.download(out_pdf, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cudapath_bsdf_sample_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type) {
+    if (require_built(ctx)) return -1;
+    DevBuf a, s, wo, wt, p, t; std::string err;
+    CKA(a.upload(wi, n * 12, ctx->stream)); CKA(s.upload(sample, n * 8, ctx->stream));
+    CKA(wo.alloc(n * 12)); CKA(wt.alloc(n * 12)); CKA(p.alloc(n * 4)); CKA(t.alloc(n * 4));
+    if (!bsdf_sample_batch(ctx->scene, bsdf_id, n, a.as<float>(), s.as<float>(), wo.as<float>(), wt.as<float>(), p.as<float>(), t.as<int32_t>(), ctx->stream, err)) return fail(err);
+    CKA(wo.download(out_wo, ctx->stream)); CKA(wt.download(out_weight, ctx->stream)); CKA(p.download(out_pdf, ctx->stream)); CKA(t.download(out_type, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cudapath_intersect_batch(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,
+                             int any_hit, int32_t *out_shape, uint32_t *out_prim, float *out_t, float *out_record) {
+    if (require_built(ctx)) return -1;
+    DevBuf o, d, mn, mx, sh, pr, t, rec; std::string err;
+    CKA(o.upload(origin, n * 12, ctx->stream)); CKA(d.upload(direction, n * 12, ctx->stream)); CKA(mn.upload(mint, n * 4, ctx->stream)); CKA(mx.upload(maxt, n * 4, ctx->stream));
+    CKA(sh.alloc(n * 4)); CKA(pr.alloc(n * 4)); CKA(t.alloc(n * 4));
+    if (out_record) CKA(rec.alloc(n * 60));
+    if (!intersect_batch(ctx->scene, n, o.as<float>(), d.as<float>(), mn.as<float>(), mx.as<float>(), any_hit, false, sh.as<int32_t>(), pr.as<uint32_t>(), t.as<float>(),
+                         out_record ? rec.as<float>() : nullptr, nullptr, ctx->stream, err)) return fail(err);
+    CKA(sh.download(out_shape, ctx->stream)); CKA(pr.download(out_prim, ctx->stream)); CKA(t.download(out_t, ctx->stream));
+    if (out_record) CKA(rec.download(out_record, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cudapath_env_eval_batch(cudapath_ctx *ctx, uint64_t n, const float *direction, float *out_rgb, float *out_pdf) {
+    if (require_built(ctx)) return -1;
+    DevBuf d, c, p; std::string err;
+    CKA(d.upload(direction, n * 12, ctx->stream)); CKA(c.alloc(n * 12)); CKA(p.alloc(n * 4));
+    if (!env_eval_batch(ctx->scene, n, d.as<float>(), c.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
+    CKA(c.download(out_rgb, ctx->stream)); CKA(p.download(out_pdf, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cudapath_env_sample_batch(cudapath_ctx *ctx, uint64_t n, const float *ref_point, const float *sample, float *out_direction, float *out_value, float *out_pdf_dist) {
+    if (require_built(ctx)) return -1;
+    DevBuf r, s, d, v, p; std::string err;
+    CKA(r.upload(ref_point, n * 12, ctx->stream)); CKA(s.upload(sample, n * 8, ctx->stream)); CKA(d.alloc(n * 12)); CKA(v.alloc(n * 12)); CKA(p.alloc(n * 8));
+    if (!env_sample_batch(ctx->scene, n, r.as<float>(), s.as<float>(), d.as<float>(), v.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
+    CKA(d.download(out_direction, ctx->stream)); CKA(v.download(out_value, ctx->stream)); CKA(p.download(out_pdf_dist, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cudapath_camera_rays_batch(cudapath_ctx *ctx, uint64_t n, const float *pixel_sample, float *out_origin, float *out_direction, float *out_mint_maxt) {
+    if (require_built(ctx)) return -1;
+    DevBuf p, o, d, m; std::string err;
+    CKA(p.upload(pixel_sample, n * 8, ctx->stream)); CKA(o.alloc(n * 12)); CKA(d.alloc(n * 12)); CKA(m.alloc(n * 8));
+    if (!camera_rays_batch(ctx->scene, n, p.as<float>(), o.as<float>(), d.as<float>(), m.as<float>(), ctx->stream, err)) return fail(err);
+    CKA(o.download(out_origin, ctx->stream)); CKA(d.download(out_direction, ctx->stream)); CKA(m.download(out_mint_maxt, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cudapath_splat_batch(cudapath_ctx *ctx, uint64_t n, const float *position, const float *rgb, const float *alpha, float *out_film) {
+    if (require_built(ctx)) return -1;
+    DevBuf p, c, a, f; std::string err;
+    const size_t fb = sizeof(float) * 5 * (size_t) ctx->cam.w * ctx->cam.h;
+    CKA(p.upload(position, n * 8, ctx->stream)); CKA(c.upload(rgb, n * 12, ctx->stream)); CKA(a.upload(alpha, n * 4, ctx->stream));
+    CKA(f.alloc(fb)); CKA(cudaMemsetAsync(f.p, 0, fb, ctx->stream));
+    if (!splat_batch(ctx->scene, p.as<float>(), c.as<float>(), a.as<float>(), n, f.as<float>(), ctx->stream, err)) return fail(err);
+    CKA(f.download(out_film, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cudapath_marschner_tables(cudapath_ctx *ctx, int bsdf_id, float *out_tables, float *out_pdfs, float *out_cdfs, float *out_sums, float *out_rt, float *out_consts) {
+    if (!ctx) return fail("null context");
+    if (bsdf_id < 0 || bsdf_id >= (int) ctx->bsdfs.size() || ctx->bsdfs[bsdf_id].dev.kind != 1) return fail("not a marschner bsdf");
+    CKA(cudaSetDevice(ctx->device));
+    const BsdfHost &b = ctx->bsdfs[bsdf_id];
+    std::vector<float4> t(3 * 4096);
+    CKA(cudaMemcpyAsync(t.data(), b.tables.tab, sizeof(float4) * t.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CKA(cudaMemcpyAsync(out_pdfs, b.tables.pdf, 4 * 3 * 4096, cudaMemcpyDeviceToHost, ctx->stream));
+    CKA(cudaMemcpyAsync(out_cdfs, b.tables.cdf, 4 * 3 * 64 * 65, cudaMemcpyDeviceToHost, ctx->stream));
+    CKA(cudaMemcpyAsync(out_sums, b.tables.sums, 4 * 3 * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CKA(cudaMemcpyAsync(out_rt, b.rt, 4 * (size_t) b.dev.rtSize, cudaMemcpyDeviceToHost, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < t.size(); ++i) { out_tables[3 * i] = t[i].x; out_tables[3 * i + 1] = t[i].y; out_tables[3 * i + 2] = t[i].z; }
+    out_consts[0] = b.dev.Fdr; out_consts[1] = b.dev.specW; out_consts[2] = b.dev.eta; out_consts[3] = (float) b.dev.rtSize;
+    return 0;
+}
+int cudapath_env_tables(cudapath_ctx *ctx, float *out_cdf_rows, float *out_cdf_cols, float *out_row_weights, float *out_normalization) {
+    if (require_built(ctx)) return -1;
+    if (!ctx->scene.env.present) return fail("no environment map set");
+    const EnvDev &E = ctx->scene.env;
+    CKA(cudaMemcpyAsync(out_cdf_rows, E.cdfRows, 4 * (size_t) (E.h + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CKA(cudaMemcpyAsync(out_cdf_cols, E.cdfCols, 4 * (size_t) (E.w + 1) * E.h, cudaMemcpyDeviceToHost, ctx->stream));
+    CKA(cudaMemcpyAsync(out_row_weights, E.rowWeights, 4 * (size_t) E.h, cudaMemcpyDeviceToHost, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    *out_normalization = E.normalization;
+    return 0;
+}
+int cudapath_filter_table(cudapath_ctx *ctx, float out32[32]) {
+    if (require_built(ctx)) return -1;
+    std::memcpy(out32, ctx->scene.film.filterValues, 128);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ device-resident variants
+int cudapath_bsdf_eval_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf, void *stream) {
+    if (require_built(ctx)) return -1;
+    std::string err;
+    if (!bsdf_eval_batch(ctx->scene, bsdf_id, n, wi, wo, out_eval, out_pdf, stream ? (cudaStream_t) stream : ctx->stream, err)) return fail(err);
+    return 0;
+}
+int cudapath_bsdf_sample_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type, void *stream) {
+    if (require_built(ctx)) return -1;
+    std::string err;
+    if (!bsdf_sample_batch(ctx->scene, bsdf_id, n, wi, sample, out_wo, out_weight, out_pdf, out_type, stream ? (cudaStream_t) stream : ctx->stream, err)) return fail(err);
+    return 0;
+}
+int cudapath_intersect_batch_dev(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,
+                                 int any_hit, int32_t *out_shape, uint32_t *out_prim, float *out_t, unsigned long long *out_stats, void *stream) {
+    if (require_built(ctx)) return -1;
+    std::string err;
+    if (!intersect_batch(ctx->scene, n, origin, direction, mint, maxt, any_hit, out_stats != nullptr, out_shape, out_prim, out_t, nullptr, out_stats,
+                         stream ? (cudaStream_t) stream : ctx->stream, err)) return fail(err);
+    return 0;
+}
+
+} // extern "C"

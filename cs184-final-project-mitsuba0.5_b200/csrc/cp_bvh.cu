@@ -1,0 +1,339 @@
+// cp_bvh.cu -- device-side BVH construction over hair segments (sm_100a).
+//
+// Replaces HairKDTree / ShapeKDTree construction (src/shapes/hair.cpp:108-159,
+// include/mitsuba/render/gkdtree.h:958-2400, src/librender/skdtree.cpp:68-110) for this path.  The SAH
+// kd-trees are NOT reproduced; the only build products the ray query's results depend on are kept
+// bit-compatible with the reference: the segment list (hair.cpp:117-124), the per-shape bounds
+// (union of getAABB(index), hair.cpp:368-397, gkdtree.h:997-1002) and the scene bounds.
+//
+// Pipeline (all on the device): segment compaction -> bounds + centroid box -> 63-bit Morton keys ->
+// radix sort (cub::DeviceRadixSort, build-time only) -> Karras 2012 binary radix tree -> bottom-up refit
+// -> collapse into 128-byte 4-wide nodes with leaves of up to CP_LEAF_MAX consecutive sorted segments.
+#include "cp_scene.cuh"
+#include "cp_host.h"
+#include <cub/cub.cuh>
+#include <vector>
+
+namespace cp {
+
+#define CP_LEAF_MAX 4
+
+__device__ __forceinline__ void atomicMinFloat(float *addr, float v) {
+    if (v >= 0) atomicMin((int *) addr, __float_as_int(v)); else atomicMax((unsigned int *) addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomicMaxFloat(float *addr, float v) {
+    if (v >= 0) atomicMax((int *) addr, __float_as_int(v)); else atomicMin((unsigned int *) addr, __float_as_uint(v));
+}
+
+struct IsSegmentStart {
+    const float4 *vtx; uint32_t n;
+    __device__ bool operator()(uint32_t i) const { return i + 1 < n && !(__float_as_uint(vtx[i + 1].w) & 1u); }
+};
+
+// per segment: reference-tight bounds -> per-shape union (atomics), conservative BVH box, centroid box
+__global__ void k_segment_bounds(const float4 *__restrict__ vtx, const uint32_t *__restrict__ segs, uint32_t nSeg,
+                                 ShapeDev *shapes, float *leafBox /*6*nSeg*/, float *centroidBox /*6*/) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nSeg) return;
+    const uint32_t gv = segs[i];
+    const float4 v1 = vtx[gv], v2 = vtx[gv + 1], v0 = vtx[gv > 0 ? gv - 1 : 0], v3 = vtx[gv + 2];
+    ShapeDev &sd = shapes[vtx_shape(v1)];
+    float bmin[3], bmax[3];
+    segment_bounds(v0, v1, v2, v3, sd.radius, bmin, bmax);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { atomicMinFloat(&sd.bmin[k], bmin[k]); atomicMaxFloat(&sd.bmax[k], bmax[k]); }
+    // The reference's bound uses radius*(1-Epsilon); widen it so that every point the FP64 test can accept
+    // lies strictly inside the leaf box (radius*Epsilon for the shrink + rounding slack).
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float pad = sd.radius * 4e-4f + 4e-7f * fmaxf(fabsf(bmin[k]), fabsf(bmax[k]));
+        bmin[k] -= pad; bmax[k] += pad;
+        leafBox[6 * (size_t) i + k] = bmin[k]; leafBox[6 * (size_t) i + 3 + k] = bmax[k];
+        float c = 0.5f * (bmin[k] + bmax[k]);
+        atomicMinFloat(&centroidBox[k], c); atomicMaxFloat(&centroidBox[3 + k], c);
+    }
+}
+
+__device__ __forceinline__ uint64_t expandBits21(uint64_t v) {
+    v &= 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+__global__ void k_morton(const float *__restrict__ leafBox, uint32_t nSeg, const float *__restrict__ centroidBox, uint64_t *keys, uint32_t *ids) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nSeg) return;
+    uint64_t code = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float c = 0.5f * (leafBox[6 * (size_t) i + k] + leafBox[6 * (size_t) i + 3 + k]);
+        float ext = centroidBox[3 + k] - centroidBox[k];
+        float f = ext > 0 ? (c - centroidBox[k]) / ext : 0.0f;
+        uint64_t q = (uint64_t) fminf(fmaxf(f * 2097152.0f, 0.0f), 2097151.0f);
+        code |= expandBits21(q) << (2 - k);
+    }
+    keys[i] = code; ids[i] = i;
+}
+
+// Karras 2012, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees"
+__device__ __forceinline__ int delta(const uint64_t *__restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long) (a ^ b));
+}
+// child encoding in the binary tree: >= 0 inner node, < 0 -> ~leaf index (sorted position)
+__global__ void k_radix_tree(const uint64_t *__restrict__ keys, int n, int2 *children, int *parentInner, int *parentLeaf, int2 *ranges) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int left = (lo == gamma) ? ~gamma : gamma;
+    int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    children[i] = make_int2(left, right);
+    ranges[i] = make_int2(lo, hi);
+    if (left >= 0) parentInner[left] = i; else parentLeaf[~left] = i;
+    if (right >= 0) parentInner[right] = i; else parentLeaf[~right] = i;
+    if (i == 0) parentInner[0] = -1;
+}
+
+__global__ void k_gather_leaf_boxes(const float *__restrict__ leafBox, const uint32_t *__restrict__ ids, const uint32_t *__restrict__ segs,
+                                    uint32_t n, float *sortedBox, uint32_t *sortedPrims) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t src = ids[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sortedBox[6 * (size_t) i + k] = leafBox[6 * (size_t) src + k];
+    sortedPrims[i] = segs[src];
+}
+
+__global__ void k_refit(const int2 *__restrict__ children, const int *__restrict__ parentInner, const int *__restrict__ parentLeaf,
+                        const float *__restrict__ sortedBox, int n, float *innerBox, int *flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int node = parentLeaf[i];
+    while (node >= 0) {
+        if (atomicAdd(&flags[node], 1) == 0) return;      // first arrival waits for the sibling
+        __threadfence();
+        int2 ch = children[node];
+        float b[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            float a = ch.x >= 0 ? __ldcg(&innerBox[6 * (size_t) ch.x + k]) : sortedBox[6 * (size_t) (~ch.x) + k];
+            float c = ch.y >= 0 ? __ldcg(&innerBox[6 * (size_t) ch.y + k]) : sortedBox[6 * (size_t) (~ch.y) + k];
+            b[k] = k < 3 ? fminf(a, c) : fmaxf(a, c);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) __stcg(&innerBox[6 * (size_t) node + k], b[k]);
+        __threadfence();
+        node = parentInner[node];
+    }
+}
+
+struct CollapseItem { int bin; int wide; };
+
+__device__ __forceinline__ float boxArea(const float *b) {
+    float ex = b[3] - b[0], ey = b[4] - b[1], ez = b[5] - b[2];
+    return ex * ey + ey * ez + ez * ex;
+}
+
+// One thread per wide node to emit.  A binary subtree with <= CP_LEAF_MAX segments becomes a leaf reference.
+__global__ void k_collapse(const CollapseItem *__restrict__ in, int nIn, CollapseItem *out, int *outCount, int *wideCount,
+                           const int2 *__restrict__ children, const int2 *__restrict__ ranges,
+                           const float *__restrict__ innerBox, const float *__restrict__ sortedBox, BVH4Node *nodes, int maxWide, int *err) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nIn) return;
+    const CollapseItem it = in[idx];
+    int cand[4]; int nc = 0;
+    int2 ch = children[it.bin];
+    cand[nc++] = ch.x; cand[nc++] = ch.y;
+    auto expandable = [&](int c) { return c >= 0 && (ranges[c].y - ranges[c].x + 1) > CP_LEAF_MAX; };
+    while (nc < 4) {
+        int best = -1; float bestArea = -1.0f;
+        for (int k = 0; k < nc; ++k) if (expandable(cand[k])) {
+            float a = boxArea(innerBox + 6 * (size_t) cand[k]);
+            if (a > bestArea) { bestArea = a; best = k; }
+        }
+        if (best < 0) break;
+        int2 c2 = children[cand[best]];
+        cand[best] = c2.x; cand[nc++] = c2.y;
+    }
+    float lo[3][4], hi[3][4]; int ref[4];
+    for (int k = 0; k < 4; ++k) {
+        if (k >= nc) {
+            for (int a = 0; a < 3; ++a) { lo[a][k] = CP_INF; hi[a][k] = -CP_INF; }
+            ref[k] = (int) 0x80000000; // empty slot (skipped by the traversal)
+            continue;
+        }
+        int c = cand[k];
+        const float *b = c >= 0 ? innerBox + 6 * (size_t) c : sortedBox + 6 * (size_t) (~c);
+        for (int a = 0; a < 3; ++a) { lo[a][k] = b[a]; hi[a][k] = b[3 + a]; }
+        if (c < 0) ref[k] = ~(int) ((((uint32_t) ~c) << 3) | 0u);
+        else if (!expandable(c)) {
+            int2 r = ranges[c];
+            ref[k] = ~(int) ((((uint32_t) r.x) << 3) | (uint32_t) (r.y - r.x));
+        } else {
+            int w = atomicAdd(wideCount, 1);
+            if (w >= maxWide) { *err = 1; ref[k] = (int) 0x80000000; continue; }
+            ref[k] = w;
+            int o = atomicAdd(outCount, 1);
+            out[o].bin = c; out[o].wide = w;
+        }
+    }
+    BVH4Node nd;
+    for (int a = 0; a < 3; ++a) {
+        nd.lo[a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
+        nd.hi[a] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
+    }
+    nd.child = make_int4(ref[0], ref[1], ref[2], ref[3]);
+    nd.pad = make_int4(0, 0, 0, 0);
+    nodes[it.wide] = nd;
+}
+
+__global__ void k_single_leaf_root(const float *__restrict__ sortedBox, int n, BVH4Node *nodes) {
+    // n <= CP_LEAF_MAX segments: one inner node with one leaf child covering all of them
+    float b[6] = {CP_INF, CP_INF, CP_INF, -CP_INF, -CP_INF, -CP_INF};
+    for (int i = 0; i < n; ++i) for (int k = 0; k < 6; ++k) b[k] = k < 3 ? fminf(b[k], sortedBox[6 * i + k]) : fmaxf(b[k], sortedBox[6 * i + k]);
+    BVH4Node nd;
+    for (int a = 0; a < 3; ++a) { nd.lo[a] = make_float4(b[a], CP_INF, CP_INF, CP_INF); nd.hi[a] = make_float4(b[3 + a], -CP_INF, -CP_INF, -CP_INF); }
+    int leaf = ~(int) ((0u << 3) | (uint32_t) (n - 1));
+    nd.child = make_int4(leaf, (int) 0x80000000, (int) 0x80000000, (int) 0x80000000);
+    nd.pad = make_int4(0, 0, 0, 0);
+    nodes[0] = nd;
+}
+
+__global__ void k_init_shape_bounds(ShapeDev *shapes, int n, float *centroidBox) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) for (int k = 0; k < 3; ++k) { shapes[i].bmin[k] = CP_INF; shapes[i].bmax[k] = -CP_INF; }
+    if (i == 0) for (int k = 0; k < 3; ++k) { centroidBox[k] = CP_INF; centroidBox[3 + k] = -CP_INF; }
+}
+
+namespace {
+struct Scratch {
+    std::vector<void *> ptrs;
+    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T> cudaError_t alloc(T **p, size_t bytes) {
+        cudaError_t e = cudaMalloc((void **) p, bytes ? bytes : 1);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+    void release(void *p) { for (auto &q : ptrs) if (q == p) q = nullptr; }
+};
+}
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
+
+// Builds the BVH for the vertex array already resident on the device.  On success the caller owns
+// out.nodes / out.prims (cudaFree).  `shapes` is updated in place with the per-shape bounds.
+bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, cudaStream_t stream,
+               BVHDev &out, BuildInfo &info, std::string &err) {
+    out = BVHDev(); info = BuildInfo();
+    Scratch S;
+    uint32_t *d_segs = nullptr, *d_ids = nullptr, *d_idsSorted = nullptr, *d_prims = nullptr;
+    uint64_t *d_keys = nullptr, *d_keysSorted = nullptr;
+    float *d_leafBox = nullptr, *d_sortedBox = nullptr, *d_innerBox = nullptr, *d_cbox = nullptr;
+    int *d_num = nullptr, *d_parentInner = nullptr, *d_parentLeaf = nullptr, *d_flags = nullptr, *d_counters = nullptr;
+    int2 *d_children = nullptr, *d_ranges = nullptr;
+    CollapseItem *d_q0 = nullptr, *d_q1 = nullptr;
+    BVH4Node *d_wide = nullptr, *d_final = nullptr;
+    void *d_temp = nullptr; size_t need = 0;
+    uint32_t nSeg = 0; int wideCount = 0;
+    const int B = 256;
+    cub::CountingInputIterator<uint32_t> counting(0);
+
+    CK(S.alloc(&d_segs, sizeof(uint32_t) * (size_t) (vtxCount + 1)));
+    CK(S.alloc(&d_num, sizeof(int) * 4));
+    CK(S.alloc(&d_cbox, sizeof(float) * 6));
+    k_init_shape_bounds<<<(shapeCount + B - 1) / B + 1, B, 0, stream>>>(d_shapes, shapeCount, d_cbox);
+    {
+        IsSegmentStart pred{d_vtx, vtxCount};
+        CK(cub::DeviceSelect::If(nullptr, need, counting, d_segs, d_num, (int) vtxCount, pred, stream));
+        CK(S.alloc(&d_temp, need));
+        CK(cub::DeviceSelect::If(d_temp, need, counting, d_segs, d_num, (int) vtxCount, pred, stream));
+        int h = 0;
+        CK(cudaMemcpyAsync(&h, d_num, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        nSeg = (uint32_t) h;
+    }
+    info.segments = nSeg;
+    if (nSeg == 0) { err = "scene contains no hair segments"; return false; }
+    if (nSeg >= (1u << 28)) { err = "too many segments for the leaf encoding"; return false; }
+
+    CK(S.alloc(&d_leafBox, sizeof(float) * 6 * (size_t) nSeg));
+    k_segment_bounds<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_vtx, d_segs, nSeg, d_shapes, d_leafBox, d_cbox);
+    CK(S.alloc(&d_keys, sizeof(uint64_t) * (size_t) nSeg)); CK(S.alloc(&d_keysSorted, sizeof(uint64_t) * (size_t) nSeg));
+    CK(S.alloc(&d_ids, sizeof(uint32_t) * (size_t) nSeg)); CK(S.alloc(&d_idsSorted, sizeof(uint32_t) * (size_t) nSeg));
+    k_morton<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_leafBox, nSeg, d_cbox, d_keys, d_ids);
+    {
+        void *d_temp2 = nullptr;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, need, d_keys, d_keysSorted, d_ids, d_idsSorted, (int) nSeg, 0, 63, stream));
+        CK(S.alloc(&d_temp2, need));
+        CK(cub::DeviceRadixSort::SortPairs(d_temp2, need, d_keys, d_keysSorted, d_ids, d_idsSorted, (int) nSeg, 0, 63, stream));
+    }
+    CK(S.alloc(&d_sortedBox, sizeof(float) * 6 * (size_t) nSeg));
+    CK(S.alloc(&d_prims, sizeof(uint32_t) * (size_t) nSeg));
+    k_gather_leaf_boxes<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_leafBox, d_idsSorted, d_segs, nSeg, d_sortedBox, d_prims);
+
+    if (nSeg <= CP_LEAF_MAX) {
+        CK(S.alloc(&d_final, sizeof(BVH4Node)));
+        k_single_leaf_root<<<1, 1, 0, stream>>>(d_sortedBox, (int) nSeg, d_final);
+        wideCount = 1;
+    } else {
+        const int nInner = (int) nSeg - 1;
+        CK(S.alloc(&d_children, sizeof(int2) * (size_t) nInner)); CK(S.alloc(&d_ranges, sizeof(int2) * (size_t) nInner));
+        CK(S.alloc(&d_parentInner, sizeof(int) * (size_t) nInner)); CK(S.alloc(&d_parentLeaf, sizeof(int) * (size_t) nSeg));
+        CK(S.alloc(&d_flags, sizeof(int) * (size_t) nInner)); CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * (size_t) nInner, stream));
+        CK(S.alloc(&d_innerBox, sizeof(float) * 6 * (size_t) nInner));
+        k_radix_tree<<<(nInner + B - 1) / B, B, 0, stream>>>(d_keysSorted, (int) nSeg, d_children, d_parentInner, d_parentLeaf, d_ranges);
+        k_refit<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_children, d_parentInner, d_parentLeaf, d_sortedBox, (int) nSeg, d_innerBox, d_flags);
+        // Collapse level by level.  A wide node is created only for a binary inner node (the one it absorbs),
+        // and distinct wide nodes absorb distinct binary nodes, so nInner bounds the wide-node count.
+        CK(S.alloc(&d_wide, sizeof(BVH4Node) * (size_t) nInner));
+        CK(S.alloc(&d_q0, sizeof(CollapseItem) * (size_t) nInner)); CK(S.alloc(&d_q1, sizeof(CollapseItem) * (size_t) nInner));
+        CK(S.alloc(&d_counters, sizeof(int) * 4));
+        CollapseItem root{0, 0};
+        int init[4] = {0, 1, 0, 0}; // [0]=next-level count, [1]=wide count, [2]=error
+        CK(cudaMemcpyAsync(d_q0, &root, sizeof(root), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_counters, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+        int nIn = 1; int levels = 0;
+        while (nIn > 0) {
+            k_collapse<<<(nIn + 127) / 128, 128, 0, stream>>>(d_q0, nIn, d_q1, d_counters, d_counters + 1, d_children, d_ranges,
+                                                             d_innerBox, d_sortedBox, d_wide, nInner, d_counters + 2);
+            int h[3];
+            CK(cudaMemcpyAsync(h, d_counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            if (h[2]) { err = "BVH collapse overflow"; return false; }
+            nIn = h[0]; wideCount = h[1];
+            CK(cudaMemsetAsync(d_counters, 0, sizeof(int), stream));
+            std::swap(d_q0, d_q1);
+            if (++levels > 4096) { err = "BVH collapse did not terminate"; return false; }
+        }
+        info.levels = levels;
+        CK(S.alloc(&d_final, sizeof(BVH4Node) * (size_t) wideCount));
+        CK(cudaMemcpyAsync(d_final, d_wide, sizeof(BVH4Node) * (size_t) wideCount, cudaMemcpyDeviceToDevice, stream));
+    }
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaGetLastError());
+    out.nodes = d_final; out.prims = d_prims; out.nodeCount = (uint32_t) wideCount; out.primCount = nSeg;
+    info.nodes = (uint32_t) wideCount;
+    S.release(d_final); S.release(d_prims);
+    return true;
+}
+
+} // namespace cp

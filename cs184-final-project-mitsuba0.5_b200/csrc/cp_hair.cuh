@@ -1,0 +1,154 @@
+// cp_hair.cuh -- HairShape segment geometry on the device (sm_100a).
+//
+// Replaces (reference file:line):
+//   miter helpers                     src/shapes/hair.cpp:551-596
+//   HairKDTree::intersect (FP64)      src/shapes/hair.cpp:485-542  (+ solveQuadraticDouble src/libcore/util.cpp:487-525)
+//   HairShape::fillIntersectionRecord src/shapes/hair.cpp:825-862 (+ include/mitsuba/render/skdtree.h:426-427)
+//   segment bounds getAABB(index)     src/shapes/hair.cpp:246-286, 368-397
+//
+// HBM layout: all shapes share one vertex array `float4 vtx[]` = (x, y, z, bits) with
+//   bits & 1      = vertexStartsFiber[i]           (hair.cpp:649-650, sentinel included)
+//   bits >> 8     = shape index
+// so one segment test reads vtx[gv-1 .. gv+2] = 64 contiguous bytes.  A primitive is identified by
+// `gv`, the global index of the segment's first vertex; the reference's primitive id is the
+// shape-local vertex index iv = gv - shape.vertexOffset (hair.cpp:151-155).
+#pragma once
+#include "cp_common.cuh"
+
+namespace cp {
+
+struct ShapeDev {
+    float bmin[3], bmax[3];   // union of segment bounds = HairKDTree::m_aabb (gkdtree.h:997-1002)
+    float radius;
+    uint32_t vertexOffset, vertexCount;
+    int bsdf;
+};
+
+CP_D uint32_t vtx_bits(const float4 &v) { return __float_as_uint(v.w); }
+CP_D bool vtx_starts(const float4 &v) { return vtx_bits(v) & 1u; }
+CP_D uint32_t vtx_shape(const float4 &v) { return vtx_bits(v) >> 8; }
+CP_D V3 vtx_pos(const float4 &v) { return V3(v.x, v.y, v.z); }
+
+// aabb.h:308-338 -- slab test returning the signed near/far distances
+CP_D bool aabb_ray(const float *bmin, const float *bmax, const V3 &o, const V3 &d, const V3 &dRcp, float &nearT, float &farT) {
+    nearT = -CP_INF; farT = CP_INF;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float origin = comp(o, i), dir = comp(d, i), minVal = bmin[i], maxVal = bmax[i];
+        if (dir == 0) {
+            if (origin < minVal || origin > maxVal) return false;
+        } else {
+            float t1 = (minVal - origin) * comp(dRcp, i), t2 = (maxVal - origin) * comp(dRcp, i);
+            if (t1 > t2) { float t = t1; t1 = t2; t2 = t; }
+            nearT = fmaxf(t1, nearT);
+            farT = fminf(t2, farT);
+            if (!(nearT <= farT)) return false;
+        }
+    }
+    return true;
+}
+
+// hair.cpp:485-542.  v0..v3 = vtx[gv-1..gv+2] (v0/v3 are only read when the neighbour segment exists).
+// mint/maxt are the shape-clipped global interval with maxt already shrunk to the current best hit.
+CP_D bool segment_intersect(const float4 &v0, const float4 &v1, const float4 &v2, const float4 &v3, float radius,
+                            const V3 &ro, const V3 &rd, float mint, float maxt, float &tOut, V3 &pOut) {
+    const D3 p1(vtx_pos(v1)), p2(vtx_pos(v2));
+    const D3 axis = normalize(p2 - p1);
+    const D3 rayO(ro), rayD(rd);
+    const D3 relOrigin = rayO - p1;
+    const D3 projOrigin = relOrigin - axis * dot(axis, relOrigin);
+    const D3 projDirection = rayD - axis * dot(axis, rayD);
+    const double A = dot(projDirection, projDirection);
+    const double B = 2 * dot(projOrigin, projDirection);
+    const double C = dot(projOrigin, projOrigin) - (double) (radius * radius);
+    double nearT, farT;
+    // solveQuadraticDouble
+    if (A == 0) {
+        if (B != 0) nearT = farT = -C / B; else return false;
+    } else {
+        double discrim = B * B - 4.0 * A * C;
+        if (discrim < 0) return false;
+        double sqrtDiscrim = sqrt(discrim), temp;
+        if (B < 0) temp = -0.5 * (B - sqrtDiscrim); else temp = -0.5 * (B + sqrtDiscrim);
+        nearT = temp / A; farT = C / temp;
+        if (nearT > farT) { double t = nearT; nearT = farT; farT = t; }
+    }
+    if (!(nearT <= (double) maxt && farT >= (double) mint)) return false;   // NaN-aware
+    // miter planes (hair.cpp:584-596): previous segment exists iff !startsFiber[iv], next iff !startsFiber[iv+2]
+    D3 n1 = axis, n2 = axis;
+    if (!vtx_starts(v1)) n1 = normalize(normalize(p1 - D3(vtx_pos(v0))) + axis);
+    if (!vtx_starts(v3)) n2 = normalize(axis + normalize(D3(vtx_pos(v3)) - p2));
+    const D3 pointNear = rayO + rayD * nearT, pointFar = rayO + rayD * farT;
+    if (dot(pointNear - p1, n1) >= 0 && dot(pointNear - p2, n2) <= 0 && nearT >= (double) mint) {
+        tOut = (float) nearT;
+        pOut = V3((float) pointNear.x, (float) pointNear.y, (float) pointNear.z);   // Point(rayO + rayD * nearT), hair.cpp:524
+    } else if (dot(pointFar - p1, n1) >= 0 && dot(pointFar - p2, n2) <= 0) {
+        if (farT > (double) maxt) return false;
+        tOut = (float) farT;                                                // rays starting inside a fiber exit through its far wall
+        pOut = V3((float) pointFar.x, (float) pointFar.y, (float) pointFar.z);
+    } else return false;
+    return true;
+}
+
+struct HitRecord { V3 p; Frame sh; V3 geoN; V3 wi; };
+
+// hair.cpp:825-862 then computeShadingFrame (util.cpp:603-608) and wi = toLocal(-ray.d)
+CP_D void fill_intersection(const float4 &v1, const float4 &v2, float radius, const V3 &pHit, const V3 &rd, HitRecord &rec) {
+    const V3 axis = normalize(vtx_pos(v2) - vtx_pos(v1));
+    const V3 rel = pHit - vtx_pos(v1);
+    V3 n = normalize(rel - dot(axis, rel) * axis);
+    V3 gt = cross(n, axis);
+    // its.geoFrame.toLocal(rel) = (dot(rel,s), dot(rel,t), dot(rel,n))
+    float ly = dot(rel, gt), lz = dot(rel, n);
+    rec.p = pHit + n * (radius - sqrtf(ly * ly + lz * lz));
+    rec.geoN = n;
+    rec.sh.n = n;
+    rec.sh.s = normalize(axis - n * dot(n, axis));
+    rec.sh.t = cross(n, rec.sh.s);
+    rec.wi = rec.sh.toLocal(-rd);
+}
+
+// ----- segment bounds (build only): tight box of the two miter-cut end ellipses, radius*(1-Epsilon)
+CP_D bool cyl_plane_ellipse(V3 planePt, V3 planeNrml, V3 cylPt, V3 cylD, float radius, V3 &center, V3 &ax0, V3 &ax1) {
+    if (fabsf(dot(planeNrml, cylD)) < kEpsilon) return false;
+    V3 B, A = cylD - dot(cylD, planeNrml) * planeNrml;
+    float len = length(A);
+    bool same = planeNrml.x == cylD.x && planeNrml.y == cylD.y && planeNrml.z == cylD.z;
+    if (len > kEpsilon && !same) { A = A / len; B = cross(planeNrml, A); }
+    else coordinateSystem(planeNrml, A, B);
+    V3 delta = planePt - cylPt, deltaProj = delta - cylD * dot(delta, cylD);
+    float aDotD = dot(A, cylD), bDotD = dot(B, cylD);
+    float c0 = 1 - aDotD * aDotD, c1 = 1 - bDotD * bDotD;
+    float c2 = 2 * dot(A, deltaProj), c3 = 2 * dot(B, deltaProj);
+    float c4 = dot(delta, deltaProj) - radius * radius;
+    float lambda = (c2 * c2 / (4 * c0) + c3 * c3 / (4 * c1) - c4) / (c0 * c1);
+    float alpha0 = -c2 / (2 * c0), beta0 = -c3 / (2 * c1);
+    center = planePt + alpha0 * A + beta0 * B;
+    ax0 = A * sqrtf(c1 * lambda);
+    ax1 = B * sqrtf(c0 * lambda);
+    return true;
+}
+CP_D void segment_bounds(const float4 &v0, const float4 &v1, const float4 &v2, const float4 &v3, float radius, float *bmin, float *bmax) {
+    const V3 p1 = vtx_pos(v1), p2 = vtx_pos(v2);
+    const V3 tangent = normalize(p2 - p1);
+    V3 n1 = tangent, n2 = tangent;
+    if (!vtx_starts(v1)) n1 = normalize(normalize(p1 - vtx_pos(v0)) + tangent);
+    if (!vtx_starts(v3)) n2 = normalize(tangent + normalize(vtx_pos(v3) - p2));
+    bmin[0] = bmin[1] = bmin[2] = CP_INF; bmax[0] = bmax[1] = bmax[2] = -CP_INF;
+    const float r = radius * (1 - kEpsilon);
+#pragma unroll
+    for (int end = 0; end < 2; ++end) {
+        V3 c, a0, a1;
+        const V3 pt = end ? p2 : p1, nn = end ? n2 : n1;
+        if (!cyl_plane_ellipse(pt, nn, pt, tangent, r, c, a0, a1)) {
+            // degenerate miter (never for loader output): fall back to a conservative sphere bound
+            c = pt; a0 = V3(radius * 2, 0, 0); a1 = V3(0, radius * 2, radius * 2);
+        }
+        float rx = sqrtf(a0.x * a0.x + a1.x * a1.x), ry = sqrtf(a0.y * a0.y + a1.y * a1.y), rz = sqrtf(a0.z * a0.z + a1.z * a1.z);
+        bmin[0] = fminf(bmin[0], c.x - rx); bmax[0] = fmaxf(bmax[0], c.x + rx);
+        bmin[1] = fminf(bmin[1], c.y - ry); bmax[1] = fmaxf(bmax[1], c.y + ry);
+        bmin[2] = fminf(bmin[2], c.z - rz); bmax[2] = fmaxf(bmax[2], c.z + rz);
+    }
+}
+
+} // namespace cp

@@ -1,0 +1,39 @@
+// cp_host.h -- host-side declarations shared by the translation units of libcudapath.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "cp_scene.cuh"
+
+namespace cp {
+
+struct BuildInfo { uint32_t segments = 0, nodes = 0; int levels = 0; };
+
+// cp_bvh.cu
+bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, cudaStream_t stream,
+               BVHDev &out, BuildInfo &info, std::string &err);
+
+// cp_tables.cu -- device-side precomputation of the Marschner azimuthal tables and the envmap CDFs
+struct MarschnerTables { float4 *tab = nullptr; float *cdf = nullptr; float *sums = nullptr; float *pdf = nullptr; };
+bool build_marschner_tables(float eta, float betaR, const float sigmaA[3], const float *glPoints140, const float *glWeights140,
+                            cudaStream_t stream, MarschnerTables &out, std::string &err);
+struct EnvTables { float4 *texels = nullptr; float *cdfCols = nullptr; float *cdfRows = nullptr; float *rowWeights = nullptr; float normalization = 0; };
+bool build_env_tables(const float *d_rgb, int w, int h, cudaStream_t stream, EnvTables &out, std::string &err);
+
+// cp_host_data.cpp -- host-side set-up that stays on the CPU (file parsing, tiny tables)
+void gauss_legendre_140(float *points, float *weights);
+// Loads <dataDir>/microfacet/<beckmann|ggx|phong>.dat and reduces it to the 1-D slice used by the Marschner
+// diffuse term: out T(|cos|^(1/4)) samples for (eta, alpha) and the internal diffuse reflectance Fdr.
+bool rough_transmittance_slice(const std::string &dataDir, int distribution, float eta, float alpha,
+                               std::vector<float> &outT, float &outFdr, std::string &err);
+
+struct HairFileData { std::vector<float> xyz; std::vector<uint8_t> startsFiber; float radius = 0; };
+bool load_hair_file(const std::string &path, float radius, float angleThresholdDeg, float reduction, const float toWorld[16],
+                    HairFileData &out, std::string &err);
+
+// cp_host_sunsky.cpp
+struct SunSkyParams { float turbidity = 3, albedo[3] = {0.2f, 0.2f, 0.2f}, sunDirection[3] = {0, 1, 0}, skyScale = 1, sunScale = 1, sunRadiusScale = 1, stretch = 1; int resolution = 512; };
+bool bake_sunsky(const std::string &dataDir, const SunSkyParams &p, std::vector<float> &rgb, int &w, int &h, std::string &err);
+
+} // namespace cp

@@ -1,0 +1,73 @@
+// cp_scene.cuh -- device-resident scene description shared by all kernels (sm_100a).
+#pragma once
+#include "cp_common.cuh"
+#include "cp_hair.cuh"
+#include "cp_bsdf.cuh"
+
+namespace cp {
+
+// 4-wide BVH node, 128 B = one L2 line, read as 8 x LDG.128.
+//   lo[0..2] = child min x/y/z (4 lanes each), hi[0..2] = child max x/y/z
+//   child[i] >= 0  : index of an inner node
+//   child[i] <  0  : leaf, ~child = (firstPrim << 3) | (primCount - 1), primCount in [1,8]
+//   unused slots have an inverted box (+inf, -inf) and are never entered.
+struct __align__(128) BVH4Node {
+    float4 lo[3];
+    float4 hi[3];
+    int4 child;
+    int4 pad;
+};
+static_assert(sizeof(BVH4Node) == 128, "BVH4Node must be one 128-byte line");
+
+struct BVHDev {
+    const BVH4Node *nodes;
+    const uint32_t *prims;      // sorted primitive list: global first-vertex index gv of each segment
+    uint32_t nodeCount, primCount;
+};
+
+struct EnvDev {
+    int w, h;
+    const float4 *texels;       // half-quantised RGB stored as exact fp32 (envmap.cpp:102-103)
+    const float *cdfCols;       // (w+1) x h
+    const float *cdfRows;       // h+1
+    const float *rowWeights;    // h
+    float normalization, scale;
+    float pixelSizeX, pixelSizeY;
+    float toWorld[9], toLocal[9]; // 3x3 linear parts (directions only)
+    float bsCenter[3], bsRadius;  // scene bounding sphere x1.5 (envmap.cpp:331-341)
+    int present;
+};
+
+struct CameraDev {
+    float s2c[16];              // sampleToCamera (row-major 4x4)
+    float toWorld[16];
+    float dx[3], dy[3];         // near-plane position differentials (perspective.cpp:156-159)
+    float nearClip, farClip;
+    float invResX, invResY;
+    int filmW, filmH;
+};
+
+struct FilmDev {
+    float filterValues[32];     // discretised reconstruction filter (rfilter.cpp:37-55)
+    float filterRadius, filterScale;
+    int hasAlpha;
+};
+
+struct IntegratorDev { int maxDepth, rrDepth, strictNormals, hideEmitters; };
+
+struct SceneDev {
+    const float4 *vtx;          // see cp_hair.cuh
+    uint32_t vtxCount;
+    const ShapeDev *shapes;
+    int shapeCount;
+    const BsdfDev *bsdfs;
+    int bsdfCount;
+    BVHDev bvh;
+    float sceneMin[3], sceneMax[3];   // ShapeKDTree::m_aabb
+    EnvDev env;
+    CameraDev cam;
+    FilmDev film;
+    IntegratorDev integ;
+};
+
+} // namespace cp

@@ -1,0 +1,149 @@
+/* cudapath.h -- C ABI of the B200-native hair path-tracing hot path.
+ *
+ * This is the boundary a librender-based `cudapath` integrator plugin binds: the plugin
+ * flattens the loaded Mitsuba scene into plain arrays and calls these entry points; nothing C++ crosses it.
+ * All pointers are caller-owned HOST memory unless the name ends in `_dev`.  Every function returns 0 (or a
+ * non-negative id) on success and a negative value on failure; cudapath_last_error() then returns a message
+ * (the reference reports errors by throwing from Log(EError), src/libcore/logger.cpp:100,147).
+ * One context owns one CUDA device; a context is thread-compatible (use it from one thread at a time).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference tree).
+ */
+#ifndef CUDAPATH_H
+#define CUDAPATH_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cudapath_ctx cudapath_ctx;
+
+/* ---- context ---------------------------------------------------------------------------------------------- */
+/* Replaces Scheduler/LocalWorker set-up for this path (src/mitsuba/mitsuba.cpp:280-329): one context per GPU. */
+int cudapath_create(int cuda_device, cudapath_ctx **out);
+void cudapath_destroy(cudapath_ctx *ctx);
+const char *cudapath_last_error(void);
+/* Directory holding a Mitsuba `data/` tree (microfacet/{beckmann,ggx,phong}.dat, and for the sunsky helper
+ * sunsky/hosek_rgb.f64 + cie1931.f32).  Replaces FileResolver look-ups (src/bsdfs/rtrans.h:95-97). */
+int cudapath_set_data_dir(cudapath_ctx *ctx, const char *path);
+
+/* ---- BSDF plugins ------------------------------------------------------------------------------------------ */
+/* `kajiyakay` plugin: KajiyaKay(props)+configure(), src/bsdfs/kajiyakay.cpp:60-107. Returns the bsdf id. */
+int cudapath_add_bsdf_kajiyakay(cudapath_ctx *ctx, const float diffuse_reflectance[3], const float specular_reflectance[3], float exponent);
+/* `marschner` plugin as built (class MarschnerDiffuse): ctor+configure(), src/bsdfs/marschner_diffuse.cpp:113-160,193-247;
+ * builds the azimuthal tables (:751-847) on the device.  distribution: 0 beckmann, 1 ggx, 2 phong
+ * (src/bsdfs/microfacet.h:99-135).  Returns the bsdf id. */
+int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior, const float diffuse_reflectance[3],
+                                const float specular_reflectance[3], float alpha, int distribution, int nonlinear);
+
+/* ---- shapes ------------------------------------------------------------------------------------------------ */
+/* `hair` shape from already-loaded fibers: HairShape::getVertices()/getStartFiber() (src/shapes/hair.h:51-57) and the
+ * world-space radius of HairKDTree (src/shapes/hair.cpp:108-124).  starts_fiber has n_vertices entries (the sentinel
+ * of hair.cpp:782 is added internally).  Returns the shape id. */
+int cudapath_add_hair(cudapath_ctx *ctx, const float *xyz, const uint8_t *starts_fiber, uint32_t n_vertices, float radius, int bsdf_id);
+/* `hair` shape from a .mitshair file (binary "BINARY_HAIR" or ASCII): HairShape::HairShape(props), src/shapes/hair.cpp:609-785.
+ * Applies to_world (row-major 4x4), the radius scaling and the angle-threshold vertex merge.  Returns the shape id. */
+int cudapath_add_hair_file(cudapath_ctx *ctx, const char *filename, float radius, float angle_threshold_deg, float reduction,
+                           const float to_world[16], int bsdf_id);
+/* Loader only (no context): returns a handle to query/copy, for hosts that want the flattened arrays. */
+typedef struct cudapath_hair_file cudapath_hair_file;
+int cudapath_hair_file_load(const char *filename, float radius, float angle_threshold_deg, float reduction, const float to_world[16], cudapath_hair_file **out);
+uint32_t cudapath_hair_file_vertex_count(const cudapath_hair_file *h);
+float cudapath_hair_file_radius(const cudapath_hair_file *h);
+void cudapath_hair_file_copy(const cudapath_hair_file *h, float *xyz, uint8_t *starts_fiber);
+void cudapath_hair_file_free(cudapath_hair_file *h);
+
+/* ---- emitter ----------------------------------------------------------------------------------------------- */
+/* `envmap` emitter from a lat-long RGB fp32 bitmap (what SunSkyEmitter hands to its nested envmap, src/emitters/sunsky.cpp:218-229):
+ * EnvironmentMap ctor + configure(), src/emitters/envmap.cpp:100-190,260-329 (half quantisation, CDFs built on the device). */
+int cudapath_set_envmap(cudapath_ctx *ctx, const float *rgb, int width, int height, const float to_world[16], float scale);
+/* `sunsky` emitter: SunSkyEmitter ctor, src/emitters/sunsky.cpp:100-236 (bakes the map on the host, then cudapath_set_envmap). */
+int cudapath_set_sunsky(cudapath_ctx *ctx, float turbidity, const float albedo[3], const float sun_direction[3], float sky_scale,
+                        float sun_scale, float sun_radius_scale, int resolution);
+/* Bake only: writes resolution x resolution/2 x 3 floats. */
+int cudapath_bake_sunsky(const char *data_dir, float turbidity, const float albedo[3], const float sun_direction[3], float sky_scale,
+                         float sun_scale, float sun_radius_scale, int resolution, float *out_rgb);
+
+/* ---- sensor / film / integrator ---------------------------------------------------------------------------- */
+/* `perspective` sensor: ProjectiveCamera/PerspectiveCamera props + configure(), src/librender/sensor.cpp:156-160,225-300,
+ * src/sensors/perspective.cpp:126-160.  fov is along x. */
+int cudapath_set_camera_perspective(cudapath_ctx *ctx, const float to_world[16], float fov_x_deg, float near_clip, float far_clip,
+                                    int film_width, int film_height);
+/* film + reconstruction filter: ReconstructionFilter::configure(), src/libcore/rfilter.cpp:37-55.
+ * filter: 0 tent (radius 1), 1 box, 2 gaussian (param = stddev, default 0.5). has_alpha: film pixelFormat carries alpha. */
+int cudapath_set_film(cudapath_ctx *ctx, int filter, float param, int has_alpha);
+/* `path` integrator params: MonteCarloIntegrator(props), src/librender/integrator.cpp:190-225. */
+int cudapath_set_integrator(cudapath_ctx *ctx, int max_depth, int rr_depth, int strict_normals, int hide_emitters);
+
+/* ---- build + render ---------------------------------------------------------------------------------------- */
+/* Scene::initialize(), src/librender/scene.cpp:322-413: uploads the geometry, builds the BVH on the device (replacing
+ * ShapeKDTree::build / HairKDTree), computes shape/scene bounds and the environment bounding sphere. */
+int cudapath_build(cudapath_ctx *ctx);
+/* SamplingIntegrator::render -> renderBlock -> Li -> ImageBlock::put for sample indices [sample_begin, sample_end) of `spp`
+ * (src/librender/integrator.cpp:95-188, src/integrators/path/path.cpp:119-294).  Writes the ACCUMULATED film
+ * (width*height*5 floats: sum w*R, w*G, w*B, w*alpha, w) to host memory.  Films of disjoint sample ranges add up. */
+int cudapath_render(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *out_film);
+/* Same, accumulating into a caller-provided DEVICE buffer on a caller-provided CUDA stream (cudaStream_t as void*, may be 0);
+ * the buffer must be zeroed by the caller before the first range.  Used with torch/NCCL for the multi-GPU film reduce. */
+int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *film_dev, void *stream);
+/* Film::develop normalisation, src/libcore/fmtconv.cpp:955-1056: rgb = sum / weight (0 where weight == 0). */
+int cudapath_develop(const float *film, int width, int height, float *out_rgb);
+/* Tunables: wave size in paths (0 = default), collect traversal statistics (slower). */
+int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stats);
+
+typedef struct cudapath_stats {
+    uint64_t paths, rays, shadow_rays;          /* same definitions as the reference's "Normal rays traced"/"Shadow rays traced" (src/librender/skdtree.cpp:46-47) */
+    uint64_t kernel_launches, bounces;
+    uint64_t nodes_visited, prims_tested;       /* only with collect_stats */
+    uint64_t unsupported_filtered_lookups, dropped_samples;
+    uint64_t segments, bvh_nodes;
+    double build_ms, render_ms;                 /* device time of the last build / render (CUDA events) */
+} cudapath_stats;
+int cudapath_get_stats(cudapath_ctx *ctx, cudapath_stats *out);
+int cudapath_scene_bounds(cudapath_ctx *ctx, float aabb_min_max[6], float bsphere_center_radius[4]);
+/* Film::getSize() (include/mitsuba/render/film.h:49-92) */
+int cudapath_film_size(cudapath_ctx *ctx, int *width, int *height);
+
+/* ---- parity hooks (host buffers; same device functions as the render path) ---------------------------------- */
+/* BSDF::eval + BSDF::pdf (include/mitsuba/render/bsdf.h:369-441), wi/wo local, measure = ESolidAngle, typeMask = EAll */
+int cudapath_bsdf_eval_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf);
+/* BSDF::sample: out_type = sampledType | sampledComponent << 8 */
+int cudapath_bsdf_sample_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo,
+                               float *out_weight, float *out_pdf, int32_t *out_type);
+/* Scene::rayIntersect (any_hit = 0) / shadow-ray query (any_hit = 1).  out_prim = shape-local first-vertex index iv
+ * (the reference's primitive id, src/shapes/hair.cpp:151-155); out_record (optional) = p, n, s, t, wi (15 floats per ray)
+ * as filled by HairShape::fillIntersectionRecord (src/shapes/hair.cpp:825-862). */
+int cudapath_intersect_batch(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,
+                             int any_hit, int32_t *out_shape, uint32_t *out_prim, float *out_t, float *out_record);
+int cudapath_env_eval_batch(cudapath_ctx *ctx, uint64_t n, const float *direction, float *out_rgb, float *out_pdf);
+int cudapath_env_sample_batch(cudapath_ctx *ctx, uint64_t n, const float *ref_point, const float *sample, float *out_direction,
+                              float *out_value, float *out_pdf_dist);
+int cudapath_camera_rays_batch(cudapath_ctx *ctx, uint64_t n, const float *pixel_sample, float *out_origin, float *out_direction, float *out_mint_maxt);
+int cudapath_splat_batch(cudapath_ctx *ctx, uint64_t n, const float *position, const float *rgb, const float *alpha, float *out_film);
+/* Precomputed tables, for table-level parity: 3x64x64x3 azimuthal values, 3x64x64 pdfs, 3x64x65 cdfs, 3x64 sums,
+ * rt_size rough-transmittance samples, consts = {Fdr, specularSamplingWeight, eta, rt_size}. */
+int cudapath_marschner_tables(cudapath_ctx *ctx, int bsdf_id, float *out_tables, float *out_pdfs, float *out_cdfs, float *out_sums,
+                              float *out_rt, float *out_consts);
+int cudapath_env_tables(cudapath_ctx *ctx, float *out_cdf_rows, float *out_cdf_cols, float *out_row_weights, float *out_normalization);
+int cudapath_filter_table(cudapath_ctx *ctx, float out32[32]);
+
+/* ---- device-resident variants for stage benchmarks (all pointers are DEVICE memory; asynchronous on `stream`) ---- */
+int cudapath_bsdf_eval_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf, void *stream);
+int cudapath_bsdf_sample_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo,
+                                   float *out_weight, float *out_pdf, int32_t *out_type, void *stream);
+/* out_stats (optional, device, 2 x uint64): nodes visited, primitives tested (enables the counting variant of the kernel) */
+int cudapath_intersect_batch_dev(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,
+                                 int any_hit, int32_t *out_shape, uint32_t *out_prim, float *out_t, unsigned long long *out_stats, void *stream);
+
+/* ---- scene files -------------------------------------------------------------------------------------------- */
+/* SceneHandler (src/librender/scenehandler.cpp:70-250) for the subset of tags the hair scenes use: integrator `path`,
+ * sensor `perspective` (+ film, rfilter, sampler sampleCount), bsdf `kajiyakay` / `marschner`, shape `hair`, emitter
+ * `sunsky` / `envmap`-from-memory.  `defines` is a ';'-separated list of name=value pairs replacing $name in the file
+ * (mitsuba -D, src/mitsuba/mitsuba.cpp:168).  Hair files that are missing are reported as an error.  On success the
+ * scene is loaded into ctx (cudapath_build still has to be called) and *out_spp receives the sampler's sampleCount. */
+int cudapath_load_scene_xml(cudapath_ctx *ctx, const char *filename, const char *defines, uint32_t *out_spp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUDAPATH_H */

@@ -1,0 +1,310 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): BSDF eval/pdf within 1e-4 relative; hit primitive index bit-exact except grazing ties
+within 1e-6 in t; images within relMSE < 1e-3 (checked here at reduced size; same counter-based RNG on both sides).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HAIR_RGB = (0.143016, 0.0156076, 1.80928e-005)
+
+
+def sphere_dirs(rng, n):
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    return v.astype(np.float32)
+
+
+def rel_err(a, b, floor):
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+@pytest.fixture(scope='module')
+def bsdf_pair(cp, oracle):
+    """Same three materials on both sides: C1's kajiyakay, C2's marschner (beckmann 0.1), C3's marschner (ggx 0.2)."""
+    ctx = cp.Context(0)
+    osc = oracle.Scene()
+    mats = [('kajiyakay', dict(diffuseReflectance=HAIR_RGB, exponent=10.0)),
+            ('marschner', dict(intIOR=1.55, extIOR=1.0, specularReflectance=(0.592384, 0.32628, 0.0528657))),
+            ('marschner', dict(intIOR=1.55, extIOR=1.0, alpha=0.2, distribution='ggx', diffuseReflectance=HAIR_RGB)),
+            ('kajiyakay', dict(diffuseReflectance=(0.7, 0.6, 0.5), specularReflectance=(0.6, 0.6, 0.6), exponent=30.0)),   # energy-conservation rescale
+            ('marschner', dict(intIOR='bk7', extIOR='air', nonlinear=True, diffuseReflectance=(0.3, 0.2, 0.1)))]
+    for t, p in mats:
+        ctx.add_bsdf(t, **p)
+        q = dict(p)
+        if q.get('intIOR') == 'bk7':
+            q['intIOR'] = 1.5046; q['extIOR'] = 1.000277
+        osc.add_bsdf(t, **q)
+    # a minimal scene so that cudapath_build() succeeds
+    xyz = np.array([[0, 0, 0], [0, 1, 0], [0.1, 2, 0]], np.float32); st = np.array([1, 0, 0], np.uint8)
+    ctx.add_hair(xyz, st, 0.05, 0)
+    ctx.set_camera(np.eye(4, dtype=np.float32), 35.0, width=16, height=16)
+    ctx.build()
+    yield ctx, osc, len(mats)
+    ctx.close()
+
+
+def test_marschner_tables_match_oracle(bsdf_pair):
+    ctx, osc, _ = bsdf_pair
+    for b in (1, 2, 4):
+        g, o = ctx.marschner_tables(b), osc.marschner_tables(b)
+        assert g['eta'] == o['eta'] and abs(g['specW'] - o['specW']) < 1e-7 and abs(g['Fdr'] - o['Fdr']) <= 1e-6 * abs(o['Fdr'])
+        scale = np.abs(o['tables']).max()
+        finite = np.isfinite(o['tables'])
+        assert np.array_equal(finite, np.isfinite(g['tables']))
+        assert np.abs(g['tables'][finite] - o['tables'][finite]).max() <= 2e-5 * scale
+        assert np.abs(g['sums'] - o['sums']).max() <= 2e-5 * np.abs(o['sums']).max()
+        assert np.abs(g['cdfs'] - o['cdfs']).max() <= 2e-5
+        assert np.abs(g['pdfs'] - o['pdfs']).max() <= 2e-5
+        assert np.abs(g['rt'] - o['rt']).max() <= 1e-6, 'rough transmittance slice'
+
+
+@pytest.mark.parametrize('n', [0, 1, 100003])
+def test_bsdf_eval_pdf(bsdf_pair, n):
+    ctx, osc, nm = bsdf_pair
+    rng = np.random.default_rng(1234 + n)
+    wi, wo = sphere_dirs(rng, n), sphere_dirs(rng, n)
+    if n > 10:  # edge cases: grazing, axis-aligned, exactly horizontal
+        wi[0] = (0, 0, 1); wo[0] = (0, 0, 1); wi[1] = (1, 0, 0); wo[1] = (-1, 0, 0); wi[2] = (0, 1, 0); wo[2] = (0, -1, 0)
+        wi[3] = (0.6, 0, 0.8); wo[3] = (-0.6, 0, 0.8); wi[4] = (0, 0, -1); wo[5] = (0, 0, -1)
+    for b in range(nm):
+        ge, gp = ctx.bsdf_eval(b, wi, wo)
+        oe, op = osc.bsdf_eval(b, wi, wo)
+        if n == 0:
+            assert ge.shape == (0, 3)
+            continue
+        assert np.isfinite(ge).all() == np.isfinite(oe).all()
+        scale = max(float(np.abs(oe).max()), 1e-12)
+        err = rel_err(ge, oe, 1e-6 * scale)
+        assert err.max() <= 1e-4, 'bsdf %d eval rel err %g' % (b, err.max())
+        assert rel_err(gp, op, 1e-9).max() <= 1e-4, 'bsdf %d pdf' % b
+
+
+def test_bsdf_sample(bsdf_pair):
+    ctx, osc, nm = bsdf_pair
+    n = 100003
+    rng = np.random.default_rng(99)
+    wi = sphere_dirs(rng, n)
+    smp = rng.random((n, 2)).astype(np.float32)
+    for b in range(nm):
+        gwo, gwt, gpdf, gty = ctx.bsdf_sample(b, wi, smp)
+        owo, owt, opdf, oty = osc.bsdf_sample(b, wi, smp)
+        same = gty == oty                      # discrete decisions (lobe / spec-vs-diffuse) can flip on 1-ulp ties
+        assert same.mean() > 0.9995, 'bsdf %d: %d discrete mismatches' % (b, (~same).sum())
+        valid = same & (np.abs(owt).sum(axis=1) > 0)
+        assert np.abs(gwo[valid] - owo[valid]).max() <= 2e-4, 'bsdf %d sampled direction' % b
+        scale = float(np.abs(owt[valid]).max())
+        err = rel_err(gwt[valid], owt[valid], 1e-6 * scale)
+        # the weight is eval(wo_sampled)/pdf: allow the direction's rounding to propagate through the sharp lobes
+        assert np.quantile(err, 0.999) <= 1e-3 and err.max() <= 5e-2, 'bsdf %d weight rel err q99.9=%g max=%g' % (b, np.quantile(err, 0.999), err.max())
+        assert rel_err(gpdf[valid], opdf[valid], 1e-9).max() <= 1e-4
+        zero_both = (np.abs(owt).sum(axis=1) == 0) & same
+        assert (np.abs(gwt[zero_both]).sum(axis=1) == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------ geometry
+@pytest.fixture(scope='module')
+def geo_pair(cp, oracle):
+    """hair-curl at reduced strand count: 4 shapes / 4 BSDFs (exercises the per-shape interval clip), tiny radius."""
+    ov = dict(width=96, height=96, spp=4, maxDepth=6)
+    ctx = cp.scene_from_description('hair-curl', scale=0.02, overrides=ov)
+    ctx.build()
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params('hair-curl'))
+    osc = oracle.scene_from_description('hair-curl', scale=0.02, overrides=ov, envmap=env)
+    yield ctx, osc
+    ctx.close()
+
+
+def chord_rays(rng, n, center, radius):
+    """kdbench-style rays (src/utils/kdbench.cpp:223-229): chords between two uniform points of the bounding sphere."""
+    p1 = center + radius * sphere_dirs(rng, n); p2 = center + radius * sphere_dirs(rng, n)
+    d = p2 - p1; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return p1.astype(np.float32), d.astype(np.float32)
+
+
+def check_hits(ctx, osc, o, d, mint, maxt):
+    gs, gp, gt = ctx.intersect(o, d, mint, maxt)
+    os_, op, ot = osc.intersect(o, d, mint, maxt, mode=0)
+    mism = np.nonzero((gs != os_) | (gp != op))[0]
+    bad = 0
+    for i in mism:       # a mismatch is tolerated only when both answers are within 1e-6 in t (grazing / joint ties)
+        if gs[i] >= 0 and os_[i] >= 0 and abs(float(gt[i]) - float(ot[i])) <= 1e-6 * max(1.0, abs(float(ot[i]))):
+            continue
+        bad += 1
+    hit = (gs >= 0) & (os_ >= 0) & (gs == os_) & (gp == op)
+    assert bad == 0, '%d of %d rays disagree beyond ties' % (bad, len(o))
+    assert np.array_equal(gt[hit], ot[hit]), 'hit distances must be bit-identical for identical primitives'
+    return hit.sum(), len(mism)
+
+
+def test_scene_bounds_match(geo_pair):
+    ctx, osc = geo_pair
+    ga, gb = ctx.scene_bounds(); oa, ob = osc.scene_bounds()
+    assert np.allclose(ga, oa, rtol=1e-6, atol=1e-7) and np.allclose(gb, ob, rtol=1e-6, atol=1e-7)
+
+
+def test_closest_hit_prim_ids(geo_pair):
+    ctx, osc = geo_pair
+    rng = np.random.default_rng(5)
+    aabb, bs = osc.scene_bounds()
+    o, d = chord_rays(rng, 200000, bs[:3], bs[3] / 1.5 * 0.8)
+    nh, nm = check_hits(ctx, osc, o, d, 0.0, np.inf)
+    assert nh > 2000
+    # rays aimed at fibers from close by, with mint = Epsilon (adaptive epsilon path) and finite maxt
+    sh, pr, t = osc.intersect(o, d, 0.0, np.inf)
+    m = sh >= 0
+    hitp = o[m] + d[m] * t[m][:, None]
+    d2 = sphere_dirs(rng, m.sum())
+    o2 = (hitp - d2 * 0.05).astype(np.float32)
+    check_hits(ctx, osc, o2, d2, 1e-4, 10.0)
+    # secondary-like rays starting ON fiber surfaces (inside-cylinder exits, self-intersection epsilon)
+    check_hits(ctx, osc, hitp.astype(np.float32), d2, 1e-4, np.inf)
+
+
+def test_brute_force_agrees_with_oracle_bvh(geo_pair):
+    _, osc = geo_pair
+    rng = np.random.default_rng(6)
+    aabb, bs = osc.scene_bounds()
+    o, d = chord_rays(rng, 300, bs[:3], bs[3] / 1.5 * 0.5)
+    a = osc.intersect(o, d, 0.0, np.inf, mode=0); b = osc.intersect(o, d, 0.0, np.inf, mode=2)
+    same = (a[0] == b[0]) & (a[1] == b[1])
+    assert (same | (np.abs(a[2] - b[2]) <= 1e-6)).all()
+
+
+def test_any_hit_and_records(geo_pair):
+    ctx, osc = geo_pair
+    rng = np.random.default_rng(7)
+    aabb, bs = osc.scene_bounds()
+    o, d = chord_rays(rng, 100000, bs[:3], bs[3] / 1.5 * 0.8)
+    gs, _, _ = ctx.intersect(o, d, 1e-4, 5.0, any_hit=True)
+    os_, _, _ = osc.intersect(o, d, 1e-4, 5.0, mode=1)
+    assert np.array_equal(gs >= 0, os_ >= 0)
+    gs, gp, gt, grec = ctx.intersect(o, d, 0.0, np.inf, record=True)
+    os_, op, ot, orec = osc.intersect_full(o, d, 0.0, np.inf)
+    m = (gs >= 0) & (gs == os_) & (gp == op)
+    assert m.sum() > 1000
+    assert np.abs(grec[m] - orec[m]).max() <= 2e-5       # p, frame and wi (normalisations differ by an ulp or two)
+
+
+def test_degenerate_rays(geo_pair):
+    ctx, osc = geo_pair
+    o = np.array([[0, 100, 0], [0, 5, 30], [0, 5, 30], [1e30, 0, 0]], np.float32)
+    d = np.array([[0, 1, 0], [0, 0, -1], [0, 0, 1], [1, 0, 0]], np.float32)           # pointing away, axis-parallel (zero components), far away
+    gs, gp, gt = ctx.intersect(o, d, 0.0, np.inf)
+    os_, op, ot = osc.intersect(o, d, 0.0, np.inf)
+    assert np.array_equal(gs, os_) and np.array_equal(gp, op)
+    e = ctx.intersect(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), 0.0, 1.0)
+    assert len(e[0]) == 0
+
+
+# ------------------------------------------------------------------------------------------------ emitter / camera / film
+def test_env_tables_eval_sample(geo_pair):
+    ctx, osc = geo_pair
+    gr, gc, gw, gn = ctx.env_tables(512, 256); or_, oc, ow, on = osc.env_tables()
+    assert np.abs(gr - or_).max() <= 2e-6 and np.abs(gc - oc).max() <= 2e-6 and np.abs(gw - ow).max() <= 1e-6
+    assert abs(gn - on) <= 2e-6 * abs(on)
+    rng = np.random.default_rng(8)
+    d = sphere_dirs(rng, 100000)
+    grgb, gpdf = ctx.env_eval(d); orgb, opdf = osc.env_eval(d)
+    assert rel_err(grgb, orgb, 1e-4 * np.abs(orgb).max()).max() <= 1e-3
+    assert rel_err(gpdf, opdf, 1e-6).max() <= 1e-3
+    ref = (rng.normal(size=(100000, 3)) * 2 + np.array([0, 6, 0])).astype(np.float32)
+    smp = rng.random((100000, 2)).astype(np.float32)
+    gd, gv, gp, gdist = ctx.env_sample(ref, smp); od, ov, op, odist = osc.env_sample(ref, smp)
+    ok = np.abs(gd - od).max(axis=1) < 1e-3          # a 1-ulp CDF difference can move a sample to the neighbouring texel
+    assert ok.mean() > 0.999
+    assert rel_err(gp[ok], op[ok], 1e-6).max() <= 2e-3 and rel_err(gdist[ok], odist[ok], 1e-6).max() <= 1e-4
+    assert rel_err(gv[ok], ov[ok], 1e-3).max() <= 2e-3
+
+
+def test_camera_rays(geo_pair):
+    ctx, osc = geo_pair
+    rng = np.random.default_rng(9)
+    pxy = (rng.random((50000, 2)) * 96).astype(np.float32)
+    pxy[0] = (0, 0); pxy[1] = (96, 96); pxy[2] = (48, 48)
+    go, gd, gmin, gmax = ctx.camera_rays(pxy); oo, od, omin, omax = osc.camera_rays(pxy)
+    assert np.array_equal(go, oo)
+    assert np.abs(gd - od).max() <= 3e-7 and rel_err(gmin, omin, 1e-9).max() <= 1e-6 and rel_err(gmax, omax, 1e-9).max() <= 1e-6
+
+
+def test_film_splat(geo_pair):
+    ctx, osc = geo_pair
+    assert np.array_equal(ctx.filter_table(), osc.filter_table())
+    rng = np.random.default_rng(10)
+    n = 20000
+    pos = (rng.random((n, 2)) * 96).astype(np.float32)
+    pos[0] = (0.0, 0.0); pos[1] = (95.999, 95.999); pos[2] = (0.5, 0.5); pos[3] = (10.0, 20.0)
+    rgb = rng.random((n, 3)).astype(np.float32) * 3
+    rgb[4] = (np.nan, 1, 1); rgb[5] = (-1, 0, 0); rgb[6] = (np.inf, 0, 0)       # invalid samples are dropped whole (imageblock.h:148-151)
+    alpha = np.ones(n, np.float32)
+    g = ctx.splat(pos, rgb, alpha); o = osc.splat(pos, rgb, alpha)
+    assert np.isfinite(g).all()
+    assert np.abs(g - o).max() <= 1e-4 * np.abs(o).max()       # fp32 atomics: order-dependent rounding only
+    assert abs(g[..., 4].sum() - o[..., 4].sum()) <= 1e-4 * o[..., 4].sum()
+
+
+# ------------------------------------------------------------------------------------------------ whole path
+def rel_mse(a, b):
+    return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))
+
+
+@pytest.mark.parametrize('name,scale', [('straight-hair', 0.02), ('hair-curl', 0.02), ('curly-hair', 0.01), ('furball', 0.02)])
+def test_render_matches_oracle(cp, oracle, name, scale):
+    ov = dict(width=72, height=56, spp=8, maxDepth=8)            # not multiples of 8: exercises the padded tiles
+    ctx = cp.scene_from_description(name, scale=scale, overrides=ov)
+    ctx.build()
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params(name))
+    osc = oracle.scene_from_description(name, scale=scale, overrides=ov, envmap=env)
+    g = ctx.render(8, seed=42)
+    o = osc.render(8, seed=42)
+    st = ctx.stats()
+    assert st['paths'] == 72 * 56 * 8 == osc.last_stats['paths']
+    assert st['unsupported_filtered_lookups'] == osc.last_stats['unsupported'] == 0
+    # identical RNG streams: weight channel must agree to rounding, ray counts nearly exactly
+    assert np.abs(g[..., 4] - o[..., 4]).max() <= 1e-4 * o[..., 4].max()
+    assert abs(st['rays'] - osc.last_stats['rays']) <= 2e-3 * osc.last_stats['rays']
+    assert abs(st['shadow_rays'] - osc.last_stats['shadow_rays']) <= 2e-3 * osc.last_stats['shadow_rays']
+    a, b = cp.develop(g), cp.develop(o)
+    assert np.isfinite(a).all()
+    assert rel_mse(a, b) < 1e-3, 'relMSE %g' % rel_mse(a, b)
+    # per-pixel agreement for the overwhelming majority of pixels (paths are replayed sample by sample)
+    close = np.abs(a - b).max(axis=2) <= 1e-3 * (np.abs(b).max(axis=2) + 1e-3)
+    assert close.mean() > 0.97, 'only %.3f of the pixels agree to 1e-3' % close.mean()
+    # sample-range additivity (what the multi-GPU film reduce relies on)
+    g2 = ctx.render(8, seed=42, sample_begin=0, sample_end=3) + ctx.render(8, seed=42, sample_begin=3, sample_end=8)
+    assert np.abs(g2 - g).max() <= 1e-4 * np.abs(g).max()
+    ctx.close()
+
+
+def test_xml_scene_roundtrip(cp, oracle, tmp_path):
+    """The XML + .mitshair path (SceneHandler + HairShape loader) yields the same film as the flattened-array path."""
+    ov = dict(width=48, height=48, spp=4, maxDepth=5)
+    path = cp.scenes.write_scene('straight-hair', str(tmp_path), scale=0.01, overrides=ov)
+    ctx = cp.Context(0)
+    assert ctx.load_xml(path) == 4
+    ctx.build()
+    a = ctx.render(4, seed=3)
+    ctx2 = cp.scene_from_description('straight-hair', scale=0.01, overrides=ov)
+    ctx2.build()
+    b = ctx2.render(4, seed=3)
+    assert a.shape == (48, 48, 5)
+    assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max()
+    ctx.close(); ctx2.close()
+
+
+def test_error_paths(cp):
+    ctx = cp.Context(0)
+    with pytest.raises(cp.CudapathError):
+        ctx.build()                                        # empty scene
+    with pytest.raises(cp.CudapathError):
+        ctx.add_bsdf('roughplastic')
+    b = ctx.add_bsdf('kajiyakay')
+    with pytest.raises(cp.CudapathError):
+        ctx.add_hair(np.zeros((3, 3), np.float32), np.array([1, 0, 0], np.uint8), 0.1, b + 5)
+    with pytest.raises(cp.CudapathError):
+        ctx.set_integrator(maxDepth=0)
+    with pytest.raises(cp.CudapathError):
+        ctx.render(4)                                      # not built
+    ctx.close()
