@@ -304,7 +304,7 @@ int cudapath_build(cudapath_ctx *ctx) {
         const CamHost &H = ctx->cam;
         const double aspect = (double) ((float) H.w / (float) H.h);
         const float recip = 1.0f / (H.farClip - H.nearClip);
-        const float cot = 1.0f / std::tan((H.fov / 2.0f) * (kPi / 180.0f));
+        const float cot = 1.0f / (float) std::tan((double) ((H.fov / 2.0f) * (kPi / 180.0f)));
         const double P[16] = {cot, 0, 0, 0, 0, cot, 0, 0, 0, 0, H.farClip * recip, -H.nearClip * H.farClip * recip, 0, 0, 1, 0};
         const double T[16] = {1, 0, 0, -1, 0, 1, 0, -1.0 / aspect, 0, 0, 1, 0, 0, 0, 0, 1};
         const double Sc[16] = {-0.5, 0, 0, 0, 0, -0.5 * aspect, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
@@ -328,7 +328,7 @@ int cudapath_build(cudapath_ctx *ctx) {
             if (ctx->filterType == 0) return std::max(0.0f, 1.0f - std::fabs(x / radius));
             if (ctx->filterType == 1) return std::fabs(x) <= radius ? 1.0f : 0.0f;
             const float a = -1.0f / (2.0f * stddev * stddev);
-            return std::max(0.0f, std::exp(a * x * x) - std::exp(a * radius * radius));
+            return std::max(0.0f, cr_exp(a * x * x) - cr_exp(a * radius * radius));
         };
         float sum = 0.0f;
         for (int i = 0; i < 31; ++i) { F.filterValues[i] = ev((radius * i) / 31); sum += F.filterValues[i]; }

@@ -1,0 +1,101 @@
+// cp_batch_shade.cu -- per-stage batch kernels: parity hooks and the config-5 stage micro-benchmarks (sm_100a).
+//
+// These run exactly the device functions the wavefront uses (cp_bsdf.cuh, cp_traverse.cuh, cp_env.cuh,
+// cp_camera.cuh) on flat device-resident batches, mirroring the reference interfaces
+//   BSDF::eval / pdf / sample                 include/mitsuba/render/bsdf.h:369-441
+//   Scene::rayIntersect (closest / shadow)    include/mitsuba/render/scene.h:187-189, src/librender/skdtree.cpp:112-142,207-226
+//   Emitter::evalEnvironment / sampleDirect / pdfDirect   src/emitters/envmap.cpp:380-410,516-556
+//   Sensor::sampleRayDifferential             src/sensors/perspective.cpp:271-298
+// Input streams are read as coalesced fp32 arrays; one thread per tuple / ray.
+#include "cp_host.h"
+#include "cp_env.cuh"
+#include "cp_camera.cuh"
+#include "cp_wavefront.h"
+
+namespace cp {
+
+__global__ void __launch_bounds__(256) k_bsdf_eval(const BsdfDev *__restrict__ bsdfs, int bsdf, uint64_t n, const float *__restrict__ wi,
+                                                   const float *__restrict__ wo, float *eval, float *pdf) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const BsdfDev &b = bsdfs[bsdf];
+    const V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), c(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+    const V3 e = bsdf_eval(b, a, c);
+    eval[3 * i] = e.x; eval[3 * i + 1] = e.y; eval[3 * i + 2] = e.z;
+    pdf[i] = bsdf_pdf(b, a, c);
+}
+__global__ void __launch_bounds__(256) k_bsdf_sample(const BsdfDev *__restrict__ bsdfs, int bsdf, uint64_t n, const float *__restrict__ wi,
+                                                     const float *__restrict__ sample, float *wo, float *weight, float *pdf, int32_t *type) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const BsdfDev &b = bsdfs[bsdf];
+    const BsdfSampleOut r = bsdf_sample(b, V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), sample[2 * i], sample[2 * i + 1]);
+    wo[3 * i] = r.wo.x; wo[3 * i + 1] = r.wo.y; wo[3 * i + 2] = r.wo.z;
+    weight[3 * i] = r.weight.x; weight[3 * i + 1] = r.weight.y; weight[3 * i + 2] = r.weight.z;
+    pdf[i] = r.pdf; type[i] = r.type | (r.component << 8);
+}
+
+__global__ void k_env_eval(SceneDev S, uint64_t n, const float *__restrict__ dir, float *rgb, float *pdf) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V3 d(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+    const V3 v = env_eval(S.env, d);
+    rgb[3 * i] = v.x; rgb[3 * i + 1] = v.y; rgb[3 * i + 2] = v.z;
+    pdf[i] = env_pdf_direct(S.env, d);
+}
+__global__ void k_env_sample(SceneDev S, uint64_t n, const float *__restrict__ ref, const float *__restrict__ sample, float *dir, float *value, float *pdfDist) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const EnvSample r = env_sample_direct(S.env, V3(ref[3 * i], ref[3 * i + 1], ref[3 * i + 2]), sample[2 * i], sample[2 * i + 1]);
+    dir[3 * i] = r.d.x; dir[3 * i + 1] = r.d.y; dir[3 * i + 2] = r.d.z;
+    value[3 * i] = r.value.x; value[3 * i + 1] = r.value.y; value[3 * i + 2] = r.value.z;
+    pdfDist[2 * i] = r.pdf; pdfDist[2 * i + 1] = r.dist;
+}
+__global__ void k_camera_rays(SceneDev S, uint64_t n, const float *__restrict__ pxy, float *o, float *d, float *minmax) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CameraRay r = camera_ray(S.cam, pxy[2 * i], pxy[2 * i + 1], 1.0f);
+    o[3 * i] = r.o.x; o[3 * i + 1] = r.o.y; o[3 * i + 2] = r.o.z;
+    d[3 * i] = r.d.x; d[3 * i + 1] = r.d.y; d[3 * i + 2] = r.d.z;
+    minmax[2 * i] = r.mint; minmax[2 * i + 1] = r.maxt;
+}
+
+#define CKB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
+static inline unsigned grid_for(uint64_t n, int block) { return (unsigned) ((n + block - 1) / block); }
+
+bool bsdf_eval_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err) {
+    if (bsdf < 0 || bsdf >= S.bsdfCount) { err = "bsdf id out of range"; return false; }
+    if (n == 0) return true;
+    k_bsdf_eval<<<grid_for(n, 256), 256, 0, s>>>(S.bsdfs, bsdf, n, d_wi, d_wo, d_eval, d_pdf);
+    CKB(cudaGetLastError());
+    return true;
+}
+bool bsdf_sample_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_sample, float *d_wo, float *d_weight, float *d_pdf, int32_t *d_type, cudaStream_t s, std::string &err) {
+    if (bsdf < 0 || bsdf >= S.bsdfCount) { err = "bsdf id out of range"; return false; }
+    if (n == 0) return true;
+    k_bsdf_sample<<<grid_for(n, 256), 256, 0, s>>>(S.bsdfs, bsdf, n, d_wi, d_sample, d_wo, d_weight, d_pdf, d_type);
+    CKB(cudaGetLastError());
+    return true;
+}
+bool env_eval_batch(const SceneDev &S, uint64_t n, const float *d_dir, float *d_rgb, float *d_pdf, cudaStream_t s, std::string &err) {
+    if (!S.env.present) { err = "no environment map set"; return false; }
+    if (n == 0) return true;
+    k_env_eval<<<grid_for(n, 256), 256, 0, s>>>(S, n, d_dir, d_rgb, d_pdf);
+    CKB(cudaGetLastError());
+    return true;
+}
+bool env_sample_batch(const SceneDev &S, uint64_t n, const float *d_ref, const float *d_sample, float *d_dir, float *d_value, float *d_pdfDist, cudaStream_t s, std::string &err) {
+    if (!S.env.present) { err = "no environment map set"; return false; }
+    if (n == 0) return true;
+    k_env_sample<<<grid_for(n, 256), 256, 0, s>>>(S, n, d_ref, d_sample, d_dir, d_value, d_pdfDist);
+    CKB(cudaGetLastError());
+    return true;
+}
+bool camera_rays_batch(const SceneDev &S, uint64_t n, const float *d_pxy, float *d_o, float *d_d, float *d_minmax, cudaStream_t s, std::string &err) {
+    if (n == 0) return true;
+    k_camera_rays<<<grid_for(n, 256), 256, 0, s>>>(S, n, d_pxy, d_o, d_d, d_minmax);
+    CKB(cudaGetLastError());
+    return true;
+}
+
+} // namespace cp

@@ -8,9 +8,10 @@
 //   RoughTransmittance::eval (1-D)      src/bsdfs/rtrans.h:183-194 + src/libcore/spline.cpp:23-60
 //
 // Numerics: everything is fp32 like the reference.  The longitudinal term M() exponentiates a sum of
-// O(1/v) = O(400) terms, so a 1-ulp difference in sin/cos(theta_i + shift) becomes ~3e-5 relative in
-// the result.  To stay inside the 1e-4 parity tolerance against a CPU libm, the three shifted
-// sin/cos pairs and asin are evaluated in fp64 and rounded once (correctly rounded fp32).
+// O(1/v) = O(400) terms, so a 1-ulp difference in any input (a libm call, a fused multiply-add) becomes
+// ~3e-5 relative in the result, and sampleM() feeds such values back into M().  To stay inside the 1e-4
+// parity tolerance every elementary function is correctly rounded (cr_* in cp_common.cuh) and the translation
+// units that contain BSDF code are compiled with -fmad=false (the reference's x86 build has no FMA either).
 #pragma once
 #include "cp_common.cuh"
 
@@ -33,9 +34,6 @@ struct BsdfDev {
 
 struct BsdfSampleOut { V3 wo, weight; float pdf; int type; int component; };
 
-CP_D float sin_cr(float x) { return (float) sin((double) x); }
-CP_D float cos_cr(float x) { return (float) cos((double) x); }
-CP_D float asin_cr(float x) { return (float) asin((double) x); }
 
 // ------------------------------------------------------------------------------------------ KajiyaKay
 CP_D V3 kk_reflect(const V3 &wi) { return V3(-wi.x, -wi.y, wi.z); }
@@ -47,7 +45,7 @@ CP_D V3 kk_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float sin_tl = sqrtf(1 - tl * tl), sin_te = sqrtf(1 - te * te);
     float alpha = tl * te + sin_tl * sin_te;
     if (alpha > 0.0f && wi.x * wo.x < 0)  // no back-scatter lobe (kajiyakay.cpp:157)
-        result += 0.15f * b.specular * ((b.exponent + 2) * kInvFourPi * powf(alpha, b.exponent));
+        result += 0.15f * b.specular * ((b.exponent + 2) * kInvFourPi * cr_pow(alpha, b.exponent));
     result += b.diffuse * kInvPi;
     return result * wo.z;
 }
@@ -56,7 +54,7 @@ CP_D float kk_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float diffuseProb = kInvPi * wo.z;
     float specProb = 0.0f;
     float alpha = dot(wo, kk_reflect(wi));
-    if (alpha > 0) specProb = powf(alpha, b.exponent) * (b.exponent + 1.0f) / (2.0f * kPi);
+    if (alpha > 0) specProb = cr_pow(alpha, b.exponent) * (b.exponent + 1.0f) / (2.0f * kPi);
     return b.specW * specProb + (1 - b.specW) * diffuseProb;
 }
 CP_D BsdfSampleOut kk_sample(const BsdfDev &b, const V3 &wi, float sx, float sy) {
@@ -66,10 +64,10 @@ CP_D BsdfSampleOut kk_sample(const BsdfDev &b, const V3 &wi, float sx, float sy)
     else { sx = (sx - b.specW) / (1 - b.specW); choseSpecular = false; }
     if (choseSpecular) {
         V3 R = kk_reflect(wi);
-        float sinAlpha = sqrtf(1 - powf(sy, 2 / (b.exponent + 1)));
-        float cosAlpha = powf(sy, 1 / (b.exponent + 1));
+        float sinAlpha = sqrtf(1 - cr_pow(sy, 2 / (b.exponent + 1)));
+        float cosAlpha = cr_pow(sy, 1 / (b.exponent + 1));
         float phi = (2.0f * kPi) * sx, sp, cp_;
-        sincosf(phi, &sp, &cp_);
+        cr_sincos(phi, &sp, &cp_);
         V3 localDir(sinAlpha * cp_, sinAlpha * sp, cosAlpha);
         r.wo = Frame(R).toWorld(localDir);
         r.component = 1; r.type = EGlossyReflection;   // component labels swapped in the reference (:255-263)
@@ -85,7 +83,8 @@ CP_D BsdfSampleOut kk_sample(const BsdfDev &b, const V3 &wi, float sx, float sy)
 }
 
 // ------------------------------------------------------------------------------------------ Marschner
-CP_D float ma_trigInverse(float x) { return fminf(sqrtf(fmaxf(1.0f - x * x, 0.0f)), 1.0f); } // :484-486
+// :484-486.  1 - x*x is evaluated un-fused (the reference's x86 build has no FMA) because it feeds the ill-conditioned M()
+CP_D float ma_trigInverse(float x) { return fminf(sqrtf(fmaxf(__fsub_rn(1.0f, __fmul_rn(x, x)), 0.0f)), 1.0f); }
 
 CP_D float ma_I0(float x) { // :279-290
     float result = 1.0f, xSq = x * x, xi = xSq, denom = 4.0f;
@@ -94,13 +93,13 @@ CP_D float ma_I0(float x) { // :279-290
     return result;
 }
 CP_D float ma_logI0(float x) { // :292-299
-    if (x > 12.0f) return x + 0.5f * (logf(1.0f / (kPi * 2.0f * x)) + 1.0f / (8.0f * x));
-    return logf(ma_I0(x));
+    if (x > 12.0f) return x + 0.5f * (cr_log(1.0f / (kPi * 2.0f * x)) + 1.0f / (8.0f * x));
+    return cr_log(ma_I0(x));
 }
 CP_D float ma_M(float v, float sinThetaI, float sinThetaO, float cosThetaI, float cosThetaO) { // :364-374
     float a = cosThetaI * cosThetaO / v, b = sinThetaI * sinThetaO / v;
-    if (v < 0.1f) return expf(-b + ma_logI0(a) - 1.0f / v + 0.6931f + logf(1.0f / (2.0f * v)));
-    return expf(-b) * ma_I0(a) / (2.0f * v * sinhf(1.0f / v));
+    if (v < 0.1f) return cr_exp(-b + ma_logI0(a) - 1.0f / v + 0.6931f + cr_log(1.0f / (2.0f * v)));
+    return cr_exp(-b) * ma_I0(a) / (2.0f * v * cr_sinh(1.0f / v));
 }
 
 // Azimuthal::eval :79-92 -- bilinear lookup in one 64x64 RGB table
@@ -142,7 +141,7 @@ CP_D float ma_sample_phi(const float *__restrict__ cdf, float cosThetaD, float x
 }
 // RoughTransmittance::eval, alpha and eta fixed (rtrans.h:183-194,233) -> Catmull-Rom over rtSize samples
 CP_D float ma_T(const BsdfDev &b, float cosTheta) {
-    float warped = powf(fabsf(cosTheta), 0.25f);
+    float warped = cr_pow(fabsf(cosTheta), 0.25f);
     if (!(cosTheta >= 0)) return 0.0f;
     float x = warped;
     if (!(x >= 0.0f && x <= 1.0f)) return 0.0f;       // spline.cpp:25-26 (min(1,max(0,0)) = 0)
@@ -161,18 +160,18 @@ CP_D float ma_T(const BsdfDev &b, float cosTheta) {
 CP_D V3 ma_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float sinThetaI = wi.y, sinThetaO = wo.y;            // the `t` axis, not the tangent (quirk 2)
     float cosThetaO = ma_trigInverse(sinThetaO);
-    float thetaI = asin_cr(clampf(sinThetaI, -1.0f, 1.0f));
-    float thetaO = asin_cr(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
+    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
     float thetaD = (thetaO - thetaI) * 0.5f;
-    float cosThetaD = cosf(thetaD);
-    float phi = atan2f(wo.x, wo.z);                       // depends on wo only (quirk 2)
+    float cosThetaD = cr_cos(thetaD);
+    float phi = cr_atan2(wo.x, wo.z);                     // depends on wo only (quirk 2)
     if (phi < 0.0f) phi += kPi * 2.0f;
     float thetaIR = thetaI - 2.0f * b.scaleAngle;
     float thetaITT = thetaI + b.scaleAngle;
     float thetaITRT = thetaI + 4.0f * b.scaleAngle;
-    float MR = ma_M(b.vR, sin_cr(thetaIR), sinThetaO, cos_cr(thetaIR), cosThetaO);
-    float MTT = ma_M(b.vTT, sin_cr(thetaITT), sinThetaO, cos_cr(thetaITT), cosThetaO);
-    float MTRT = ma_M(b.vTRT, sin_cr(thetaITRT), sinThetaO, cos_cr(thetaITRT), cosThetaO);
+    float MR = ma_M(b.vR, cr_sin(thetaIR), sinThetaO, cr_cos(thetaIR), cosThetaO);
+    float MTT = ma_M(b.vTT, cr_sin(thetaITT), sinThetaO, cr_cos(thetaITT), cosThetaO);
+    float MTRT = ma_M(b.vTRT, cr_sin(thetaITRT), sinThetaO, cr_cos(thetaITRT), cosThetaO);
     V3 result = 0.15f * MR * ma_azimuthal(b.tab, phi, cosThetaD)
               + MTT * ma_azimuthal(b.tab + 4096, phi, cosThetaD)
               + MTRT * ma_azimuthal(b.tab + 8192, phi, cosThetaD);
@@ -184,30 +183,30 @@ CP_D V3 ma_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     return result;
 }
 CP_D float ma_sampleM(float v, float sinThetaI, float cosThetaI, float xi1, float xi2) { // :582-592
-    float cosTheta = 1.0f + v * logf(xi1 + (1.0f - xi1) * expf(-2.0f / v));
+    float cosTheta = 1.0f + v * cr_log(xi1 + (1.0f - xi1) * cr_exp(-2.0f / v));
     float sinTheta = ma_trigInverse(cosTheta);
-    float cosPhi = cosf(2 * kPi * xi2);
+    float cosPhi = cr_cos(2 * kPi * xi2);
     return -cosTheta * sinThetaI + sinTheta * cosPhi * cosThetaI;
 }
 CP_D BsdfSampleOut ma_sample(const BsdfDev &b, const V3 &wi, float sx, float sy) {
     BsdfSampleOut r;
     float sinThetaI = wi.y;
     float cosThetaI = ma_trigInverse(sinThetaI);
-    float thetaI = asin_cr(clampf(sinThetaI, -1.0f, 1.0f));
+    float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
     float weightR = ma_weight(b.sums, cosThetaI), weightTT = ma_weight(b.sums + 64, cosThetaI), weightTRT = ma_weight(b.sums + 128, cosThetaI);
     float v, theta; int lobe;
     float target = sx * (weightR + weightTT + weightTRT);
     if (target < weightR) { r.component = 5; v = b.vR; theta = thetaI - 2.0f * b.scaleAngle; lobe = 0; }
     else if (target < weightR + weightTT) { r.component = 6; v = b.vTT; theta = thetaI + b.scaleAngle; lobe = 1; }
     else { r.component = 7; v = b.vTRT; theta = thetaI + 4.0f * b.scaleAngle; lobe = 2; }
-    float sinThetaO = ma_sampleM(v, sin_cr(theta), cos_cr(theta), sx, sy);   // one 2-D sample reused (quirk 4)
+    float sinThetaO = ma_sampleM(v, cr_sin(theta), cr_cos(theta), sx, sy);   // one 2-D sample reused (quirk 4)
     float cosThetaO = ma_trigInverse(sinThetaO);
-    float thetaO = asin_cr(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
     float thetaD = (thetaO - thetaI) * 0.5f;
-    float cosThetaD = cosf(thetaD);
+    float cosThetaD = cr_cos(thetaD);
     float phi = ma_sample_phi(b.cdf + lobe * 64 * 65, cosThetaD, sy);
     float sinPhi, cosPhi;
-    sincosf(phi, &sinPhi, &cosPhi);
+    cr_sincos(phi, &sinPhi, &cosPhi);
     float probSpecular = 1 - ma_T(b, wi.z);
     probSpecular = (probSpecular * b.specW) / (probSpecular * b.specW + (1 - probSpecular) * (1 - b.specW));
     if (sy < probSpecular) {

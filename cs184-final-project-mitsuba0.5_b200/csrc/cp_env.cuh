@@ -35,7 +35,7 @@ CP_D V3 env_bilinear(const EnvDev &E, float uvx, float uvy) {
 // evalEnvironment for rays without differentials (every bounce ray: Ray(...) clears them, ray.h:196-208)
 CP_D V3 env_eval(const EnvDev &E, const V3 &d) {
     V3 v = mul3(E.toLocal, d);
-    float uvx = atan2f(v.x, -v.z) * kInvTwoPi, uvy = safe_acos(v.y) * kInvPi;
+    float uvx = cr_atan2(v.x, -v.z) * kInvTwoPi, uvy = safe_acos(v.y) * kInvPi;
     return env_bilinear(E, uvx, uvy) * E.scale;
 }
 // evalEnvironment for camera rays (EWA filter type, maxAnisotropy 10).  Footprints below one texel resolve
@@ -43,16 +43,16 @@ CP_D V3 env_eval(const EnvDev &E, const V3 &d) {
 // pyramid, which is not built -- they are counted in `unsupported` and answered at level 0.
 CP_D V3 env_eval_filtered(const EnvDev &E, const V3 &d, const V3 &rxDir, const V3 &ryDir, unsigned long long *unsupported) {
     V3 v = mul3(E.toLocal, d);
-    float uvx = atan2f(v.x, -v.z) * kInvTwoPi, uvy = safe_acos(v.y) * kInvPi;
+    float uvx = cr_atan2(v.x, -v.z) * kInvTwoPi, uvy = safe_acos(v.y) * kInvPi;
     V3 dvdx = mul3(E.toLocal, rxDir) - v, dvdy = mul3(E.toLocal, ryDir) - v;
     float t1 = kInvTwoPi / (v.x * v.x + v.z * v.z), t2 = -kInvPi / fmaxf(safe_sqrt(1.0f - v.y * v.y), kEpsilon);
     float du0 = t1 * (dvdx.z * v.x - dvdx.x * v.z) * E.w, dv0 = t2 * dvdx.y * E.h;
     float du1 = t1 * (dvdy.z * v.x - dvdy.x * v.z) * E.w, dv1 = t2 * dvdy.y * E.h;
     float A = dv0 * dv0 + dv1 * dv1, B = -2.0f * (du0 * dv0 + du1 * dv1), C = du0 * du0 + du1 * du1, F = A * C - B * B * 0.25f;
-    float root = hypotf(A - C, B), Aprime = 0.5f * (A + C - root), Cprime = 0.5f * (A + C + root);
+    float root = cr_hypot(A - C, B), Aprime = 0.5f * (A + C - root), Cprime = 0.5f * (A + C + root);
     float majorRadius = Aprime != 0 ? sqrtf(F / Aprime) : 0, minorRadius = Cprime != 0 ? sqrtf(F / Cprime) : 0;
     bool level0;
-    if (!(minorRadius > 0) || !(majorRadius > 0) || F < 0) level0 = floorf(log2f(fmaxf(majorRadius, kEpsilon))) < 0;
+    if (!(minorRadius > 0) || !(majorRadius > 0) || F < 0) level0 = floorf(cr_log2(fmaxf(majorRadius, kEpsilon))) < 0;
     else level0 = majorRadius < 1;
     if (!level0 && unsupported) atomicAdd(unsupported, 1ull);
     return env_bilinear(E, uvx, uvy) * E.scale;
@@ -88,8 +88,8 @@ CP_D EnvSample env_sample_direct(const EnvDev &E, const V3 &ref, float sx, float
     float pdf = (luminance(value1) * __ldg(E.rowWeights + clampi(yPos, 0, E.h - 1)) +
                  luminance(value2) * __ldg(E.rowWeights + clampi(yPos + 1, 0, E.h - 1))) * E.normalization;
     float sinPhi, cosPhi, sinTheta, cosTheta;
-    sincosf(E.pixelSizeX * (posx + 0.5f), &sinPhi, &cosPhi);
-    sincosf(E.pixelSizeY * (posy + 0.5f), &sinTheta, &cosTheta);
+    cr_sincos(E.pixelSizeX * (posx + 0.5f), &sinPhi, &cosPhi);
+    cr_sincos(E.pixelSizeY * (posy + 0.5f), &sinTheta, &cosTheta);
     V3 d(sinPhi * sinTheta, cosTheta, -cosPhi * sinTheta);
     pdf /= fmaxf(fabsf(sinTheta), kEpsilon);
     V3 dw = mul3(E.toWorld, d);
@@ -104,7 +104,7 @@ CP_D EnvSample env_sample_direct(const EnvDev &E, const V3 &ref, float sx, float
 
 CP_D float env_pdf_direct(const EnvDev &E, const V3 &dWorld) {
     V3 d = mul3(E.toLocal, dWorld);
-    float uvx = atan2f(d.x, -d.z) * kInvTwoPi, uvy = safe_acos(d.y) * kInvPi;
+    float uvx = cr_atan2(d.x, -d.z) * kInvTwoPi, uvy = safe_acos(d.y) * kInvPi;
     if (!isfinite(uvx) || !isfinite(uvy)) return 0.0f;
     float u = uvx * E.w - 0.5f, v = uvy * E.h - 0.5f;
     int xPos = (int) floorf(u), yPos = (int) floorf(v);

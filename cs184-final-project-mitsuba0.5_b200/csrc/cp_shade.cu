@@ -1,0 +1,205 @@
+// cp_shade.cu -- shading stages of the wavefront path tracer (sm_100a), compiled with -fmad=false.
+//
+// Replaces (reference file:line):
+//   SamplingIntegrator::renderBlock      src/librender/integrator.cpp:140-188   (jitter, sensor ray, put)
+//   PerspectiveCameraImpl::sampleRayDifferential  src/sensors/perspective.cpp:271-298
+//   MIPathTracer::Li                     src/integrators/path/path.cpp:119-300  (NEE + MIS + BSDF sampling + RR)
+//   Scene::sampleEmitterDirect           src/librender/scene.cpp:828-853        (shadow ray [Epsilon, dist(1-ShadowEpsilon)])
+//   ImageBlock::put                      include/mitsuba/render/imageblock.h:144-186 (discretised filter splat)
+// No fused multiply-adds here: the reference's x86 build has none, and the Marschner lobes amplify last-bit differences.
+#include "cp_host.h"
+#include "cp_env.cuh"
+#include "cp_camera.cuh"
+#include "cp_wavefront.h"
+
+namespace cp {
+
+__global__ void __launch_bounds__(256) k_raygen(SceneDev S, WaveParams wp, PathQueue q, float4 *liAcc, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x, y, samp;
+    const bool valid = path_to_pixel(wp, wp.waveBase + i, x, y, samp);
+    liAcc[i] = make_float4(0, 0, 0, 1.0f);
+    if (!valid) {
+        q.ro[i] = make_float4(0, 0, 0, 1.0f); q.rd[i] = make_float4(0, 0, 1, 0.0f);
+        q.thr[i] = make_float4(0, 0, 0, 0); q.id[i] = make_uint2(i, F_INVALID | F_FIRST | 1u);
+        return;
+    }
+    const Philox4 u = philox4x32_10(y * wp.filmW + x, samp, 0u, 0u, wp.seedLo, wp.seedHi);
+    const float px = (float) x + u32_to_unit(u.v[0]), py = (float) y + u32_to_unit(u.v[1]);
+    const CameraRay r = camera_ray(S.cam, px, py, wp.diffScale);
+    q.ro[i] = make_float4(r.o.x, r.o.y, r.o.z, r.mint);
+    q.rd[i] = make_float4(r.d.x, r.d.y, r.d.z, r.maxt);
+    q.thr[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    q.id[i] = make_uint2(i, F_FIRST | 1u);                 // depth starts at 1 (integrator.h:218-224)
+}
+
+__device__ __forceinline__ float mi_weight(float pdfA, float pdfB) { pdfA *= pdfA; pdfB *= pdfB; return pdfA / (pdfA + pdfB); } // path.cpp:296-300
+
+__global__ void __launch_bounds__(128) k_shade(SceneDev S, WaveParams wp, PathQueue in, uint32_t n, const float4 *__restrict__ hitPT,
+                                               const uint32_t *__restrict__ hitPrim, PathQueue out, ShadowQueue sq, float4 *liAcc,
+                                               uint32_t *counters, unsigned long long *unsupportedLookups) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool survive = false, wantShadow = false;
+    float4 nro, nrd, nthr; uint2 nid;
+    float4 so, sd, sc;
+    if (i < n) {
+        const float4 ro4 = in.ro[i], rd4 = in.rd[i], thr4 = in.thr[i];
+        const uint2 id = in.id[i];
+        const uint32_t pathId = id.x, flags = id.y;
+        do {
+            if (flags & F_INVALID) break;
+            const V3 rayO(ro4.x, ro4.y, ro4.z), rayD(rd4.x, rd4.y, rd4.z);
+            V3 thr(thr4.x, thr4.y, thr4.z);
+            const uint32_t gv = hitPrim[i];
+            const bool first = flags & F_FIRST;
+            int depth = (int) (flags & 0xffffu);
+            uint32_t x, y, samp;
+            path_to_pixel(wp, wp.waveBase + pathId, x, y, samp);
+            const uint32_t pix = y * wp.filmW + x;
+
+            if (gv == 0xffffffffu) {
+                // ---- the ray escaped
+                float4 acc = liAcc[pathId];
+                if (first) {
+                    acc.w = S.film.hasAlpha ? 0.0f : 1.0f;                      // records.inl:117-135
+                    if (S.env.present && !S.integ.hideEmitters) {               // path.cpp:136-143
+                        const Philox4 u = philox4x32_10(pix, samp, 0u, 0u, wp.seedLo, wp.seedHi);
+                        const CameraRay cr = camera_ray(S.cam, (float) x + u32_to_unit(u.v[0]), (float) y + u32_to_unit(u.v[1]), wp.diffScale);
+                        V3 L = thr * env_eval_filtered(S.env, rayD, cr.rx, cr.ry, unsupportedLookups);
+                        acc.x += L.x; acc.y += L.y; acc.z += L.z;
+                    }
+                } else if (S.env.present) {                                     // path.cpp:233-264
+                    const V3 value = env_eval(S.env, rayD);
+                    if (env_fill_direct(S.env, rayO, rayD)) {
+                        const float lumPdf = (flags & F_DELTA) ? 0.0f : env_pdf_direct(S.env, rayD);
+                        V3 L = thr * value * mi_weight(thr4.w, lumPdf);
+                        acc.x += L.x; acc.y += L.y; acc.z += L.z;
+                    }
+                }
+                liAcc[pathId] = acc;
+                break;
+            }
+            if (!first) {
+                // ---- tail of the previous iteration: Russian roulette (path.cpp:276-286); eta == 1 for both hair BSDFs
+                if (depth >= S.integ.rrDepth) {
+                    const float qv = fminf(maxc(thr), 0.95f);
+                    const Philox4 ur = philox4x32_10(pix, samp, (uint32_t) depth, 1u, wp.seedLo, wp.seedHi);
+                    if (u32_to_unit(ur.v[0]) >= qv) break;
+                    thr = thr / qv;
+                }
+                depth++;
+                if (!(depth <= S.integ.maxDepth || S.integ.maxDepth < 0)) break;  // loop condition path.cpp:135
+            }
+            // ---- intersection record
+            const float4 hp = hitPT[i];
+            const float4 v1 = __ldg(S.vtx + gv), v2 = __ldg(S.vtx + gv + 1);
+            const ShapeDev &shape = S.shapes[vtx_shape(v1)];
+            HitRecord rec;
+            fill_intersection(v1, v2, shape.radius, V3(hp.x, hp.y, hp.z), rayD, rec);
+            if ((depth >= S.integ.maxDepth && S.integ.maxDepth > 0) ||
+                (S.integ.strictNormals && dot(rayD, rec.geoN) * rec.wi.z >= 0)) break;   // path.cpp:156-165
+            const BsdfDev &bsdf = S.bsdfs[shape.bsdf];
+            const Philox4 u = philox4x32_10(pix, samp, (uint32_t) depth, 0u, wp.seedLo, wp.seedHi);
+            // ---- emitter sampling (path.cpp:174-200)
+            if (S.env.present) {
+                const EnvSample es = env_sample_direct(S.env, rec.p, u32_to_unit(u.v[0]), u32_to_unit(u.v[1]));
+                if (es.pdf != 0) {
+                    // The shadow ray is always traced when pdf != 0 (scene.cpp:838-845); its contribution may be zero.
+                    V3 contrib(0.0f);
+                    if (!isZero(es.value)) {
+                        const V3 wo = rec.sh.toLocal(es.d);
+                        const V3 bsdfVal = bsdf_eval(bsdf, rec.wi, wo);
+                        if (!isZero(bsdfVal) && (!S.integ.strictNormals || dot(rec.geoN, es.d) * wo.z > 0)) {
+                            const float bsdfPdf = bsdf_pdf(bsdf, rec.wi, wo);
+                            contrib = thr * es.value * bsdfVal * mi_weight(es.pdf, bsdfPdf);
+                        }
+                    }
+                    wantShadow = true;
+                    so = make_float4(rec.p.x, rec.p.y, rec.p.z, kEpsilon);
+                    sd = make_float4(es.d.x, es.d.y, es.d.z, es.dist * (1 - kShadowEpsilon));
+                    sc = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(pathId));
+                }
+            }
+            // ---- BSDF sampling (path.cpp:207-226)
+            const BsdfSampleOut bs = bsdf_sample(bsdf, rec.wi, u32_to_unit(u.v[2]), u32_to_unit(u.v[3]));
+            if (isZero(bs.weight)) break;
+            const V3 wo = rec.sh.toWorld(bs.wo);
+            if (S.integ.strictNormals && dot(rec.geoN, wo) * bs.wo.z <= 0) break;
+            thr = thr * bs.weight;
+            nro = make_float4(rec.p.x, rec.p.y, rec.p.z, kEpsilon);
+            nrd = make_float4(wo.x, wo.y, wo.z, CP_INF);
+            nthr = make_float4(thr.x, thr.y, thr.z, bs.pdf);
+            nid = make_uint2(pathId, (uint32_t) depth | ((bs.type & EDeltaReflection) ? F_DELTA : 0u));
+            survive = true;
+        } while (false);
+    }
+    const uint32_t oi = warp_append(counters + 0, survive);
+    if (survive) { out.ro[oi] = nro; out.rd[oi] = nrd; out.thr[oi] = nthr; out.id[oi] = nid; }
+    const uint32_t si = warp_append(counters + 1, wantShadow);
+    if (wantShadow) { sq.o[si] = so; sq.d[si] = sd; sq.c[si] = sc; }
+}
+
+// imageblock.h:144-186 with offset 0 / border 0 (the film itself, ldrfilm.cpp:226-228): 5 channels R,G,B,alpha,weight
+__device__ __forceinline__ void film_put(const FilmDev &F, float *film, int W, int H, float posx, float posy, const V3 &spec, float alpha,
+                                         unsigned long long *dropped) {
+    const float value[5] = {spec.x, spec.y, spec.z, alpha, 1.0f};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) if (!isfinite(value[k]) || value[k] < 0) { if (dropped) atomicAdd(dropped, 1ull); return; }
+    const float px = posx - 0.5f, py = posy - 0.5f, r = F.filterRadius;
+    const int minx = max((int) ceilf(px - r), 0), miny = max((int) ceilf(py - r), 0);
+    const int maxx = min((int) floorf(px + r), W - 1), maxy = min((int) floorf(py + r), H - 1);
+    for (int yy = miny; yy <= maxy; ++yy) {
+        const float wy = F.filterValues[min((int) fabsf((yy - py) * F.filterScale), 31)];
+        for (int xx = minx; xx <= maxx; ++xx) {
+            const float wgt = F.filterValues[min((int) fabsf((xx - px) * F.filterScale), 31)] * wy;
+            if (wgt == 0.0f) continue;                      // adding +0 is a no-op in the reference as well
+            float *dest = film + ((size_t) yy * W + xx) * 5;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) atomicAdd(dest + k, wgt * value[k]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_splat(SceneDev S, WaveParams wp, const float4 *__restrict__ liAcc, uint32_t n, float *film,
+                                               unsigned long long *dropped) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x, y, samp;
+    if (!path_to_pixel(wp, wp.waveBase + i, x, y, samp)) return;
+    const Philox4 u = philox4x32_10(y * wp.filmW + x, samp, 0u, 0u, wp.seedLo, wp.seedHi);
+    const float4 acc = liAcc[i];
+    film_put(S.film, film, (int) wp.filmW, (int) wp.filmH, (float) x + u32_to_unit(u.v[0]), (float) y + u32_to_unit(u.v[1]),
+             V3(acc.x, acc.y, acc.z), acc.w, dropped);
+}
+
+// Parity hook for F1: splat explicit samples
+__global__ void k_splat_batch(SceneDev S, const float *__restrict__ pos, const float *__restrict__ rgb, const float *__restrict__ alpha,
+                              uint64_t n, float *film, int W, int H) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    film_put(S.film, film, W, H, pos[2 * i], pos[2 * i + 1], V3(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]), alpha[i], nullptr);
+}
+
+
+void launch_raygen(const SceneDev &S, const WaveParams &wp, PathQueue q, float4 *liAcc, uint32_t n, cudaStream_t stream) {
+    k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(S, wp, q, liAcc, n);
+}
+void launch_shade(const SceneDev &S, const WaveParams &wp, PathQueue in, uint32_t n, const float4 *hitPT, const uint32_t *hitPrim, PathQueue out,
+                  ShadowQueue sq, float4 *liAcc, uint32_t *counters, unsigned long long *unsupportedLookups, cudaStream_t stream) {
+    k_shade<<<(n + 127) / 128, 128, 0, stream>>>(S, wp, in, n, hitPT, hitPrim, out, sq, liAcc, counters, unsupportedLookups);
+}
+void launch_splat(const SceneDev &S, const WaveParams &wp, const float4 *liAcc, uint32_t n, float *film, unsigned long long *dropped, cudaStream_t stream) {
+    k_splat<<<(n + 255) / 256, 256, 0, stream>>>(S, wp, liAcc, n, film, dropped);
+}
+
+#define CKW(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
+bool splat_batch(const SceneDev &S, const float *d_pos, const float *d_rgb, const float *d_alpha, uint64_t n, float *d_film, cudaStream_t stream, std::string &err) {
+    if (n == 0) return true;
+    k_splat_batch<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(S, d_pos, d_rgb, d_alpha, n, d_film, S.cam.filmW, S.cam.filmH);
+    CKW(cudaStreamSynchronize(stream));
+    CKW(cudaGetLastError());
+    return true;
+}
+
+} // namespace cp

@@ -45,6 +45,39 @@ struct Wavefront {
     ~Wavefront() { release(); }
 };
 
+// shared by the stage kernels ----------------------------------------------------------------------------------------
+// flags word: bits 0..15 depth, bit 16 first (camera) segment, bit 17 last BSDF sample was EDelta, bit 18 invalid (padding pixel)
+enum : uint32_t { F_FIRST = 1u << 16, F_DELTA = 1u << 17, F_INVALID = 1u << 18 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (!pred) return 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t) __popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+// wave-local path index -> (pixel x, pixel y, sample index).  Pixels are enumerated in 8x8 tiles so that a warp
+// covers an 8x4 block of the image (coherent camera rays, film atomics spread over 4 rows).
+__device__ __forceinline__ bool path_to_pixel(const WaveParams &wp, uint64_t g, uint32_t &x, uint32_t &y, uint32_t &samp) {
+    const uint64_t s = g / wp.pixPadded;
+    const uint32_t rank = (uint32_t) (g - s * wp.pixPadded);
+    const uint32_t tile = rank >> 6, within = rank & 63u;
+    x = (tile % wp.tilesX) * 8u + (within & 7u);
+    y = (tile / wp.tilesX) * 8u + (within >> 3);
+    samp = wp.sampleBegin + (uint32_t) s;
+    return x < wp.filmW && y < wp.filmH;
+}
+#endif
+
+// cp_shade.cu (built with -fmad=false)
+void launch_raygen(const SceneDev &S, const WaveParams &wp, PathQueue q, float4 *liAcc, uint32_t n, cudaStream_t stream);
+void launch_shade(const SceneDev &S, const WaveParams &wp, PathQueue in, uint32_t n, const float4 *hitPT, const uint32_t *hitPrim, PathQueue out,
+                  ShadowQueue sq, float4 *liAcc, uint32_t *counters, unsigned long long *unsupportedLookups, cudaStream_t stream);
+void launch_splat(const SceneDev &S, const WaveParams &wp, const float4 *liAcc, uint32_t n, float *film, unsigned long long *dropped, cudaStream_t stream);
 bool splat_batch(const SceneDev &S, const float *d_pos, const float *d_rgb, const float *d_alpha, uint64_t n, float *d_film, cudaStream_t stream, std::string &err);
 
 // cp_batch.cu -- parity hooks / stage micro-benchmarks on device-resident batches

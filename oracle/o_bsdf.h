@@ -47,7 +47,7 @@ struct KajiyaKay {
         float sin_tl = std::sqrt(1 - tl * tl), sin_te = std::sqrt(1 - te * te);
         float alpha = tl * te + sin_tl * sin_te;
         if (alpha > 0.0f && wi.x * wo.x < 0) {
-            V3 res = 0.15f * specular * ((exponent + 2) * kInvFourPi * std::pow(alpha, exponent));
+            V3 res = 0.15f * specular * ((exponent + 2) * kInvFourPi * cr::pow(alpha, exponent));
             result += res;
         }
         result += diffuse * kInvPi;
@@ -59,7 +59,7 @@ struct KajiyaKay {
         float diffuseProb = kInvPi * wo.z; // warp::squareToCosineHemispherePdf
         float specProb = 0.0f;
         float alpha = dot(wo, reflect(wi));
-        if (alpha > 0) specProb = std::pow(alpha, exponent) * (exponent + 1.0f) / (2.0f * kPi);
+        if (alpha > 0) specProb = cr::pow(alpha, exponent) * (exponent + 1.0f) / (2.0f * kPi);
         return specularSamplingWeight * specProb + (1 - specularSamplingWeight) * diffuseProb;
     }
     // kajiyakay.cpp:216-273
@@ -74,10 +74,10 @@ struct KajiyaKay {
         }
         if (choseSpecular) {
             V3 R = reflect(wi);
-            float sinAlpha = std::sqrt(1 - std::pow(sy, 2 / (exponent + 1)));
-            float cosAlpha = std::pow(sy, 1 / (exponent + 1));
+            float sinAlpha = std::sqrt(1 - cr::pow(sy, 2 / (exponent + 1)));
+            float cosAlpha = cr::pow(sy, 1 / (exponent + 1));
             float phi = (2.0f * kPi) * sx;
-            V3 localDir(sinAlpha * std::cos(phi), sinAlpha * std::sin(phi), cosAlpha);
+            V3 localDir(sinAlpha * cr::cos(phi), sinAlpha * cr::sin(phi), cosAlpha);
             r.wo = Frame(R).toWorld(localDir);
             r.sampledComponent = 1; r.sampledType = EGlossyReflection; // labels swapped in the reference
             if (r.wo.z <= 0) return r;
@@ -196,14 +196,14 @@ struct RoughTransmittance {
             }
         etaFixed = alphaFixed = false;
     }
-    float warpAlpha(float alpha) const { return std::pow((alpha - alphaMin) / (alphaMax - alphaMin), 0.25f); }
+    float warpAlpha(float alpha) const { return cr::pow((alpha - alphaMin) / (alphaMax - alphaMin), 0.25f); }
     // rtrans.h:292-343
     void setEta(float eta) {
         if (etaFixed) return;
         const float *tr = trans.data(), *dt = diffTrans.data();
         if (eta < 1) { tr += etaSamples * alphaSamples * thetaSamples; dt += etaSamples * alphaSamples; eta = 1.0f / eta; }
         if (eta < etaMin) eta = etaMin;
-        float warpedEta = std::pow((eta - etaMin) / (etaMax - etaMin), 0.25f);
+        float warpedEta = cr::pow((eta - etaMin) / (etaMax - etaMin), 0.25f);
         std::vector<float> nt(alphaSamples * thetaSamples), nd(alphaSamples);
         float dAlpha = 1.0f / (alphaSamples - 1), dTheta = 1.0f / (thetaSamples - 1);
         for (size_t i = 0; i < alphaSamples; ++i) {
@@ -227,7 +227,7 @@ struct RoughTransmittance {
     }
     // rtrans.h:183-234 (only the branches reachable on this path)
     float eval(float cosTheta, float alpha = 0) const {
-        float warpedCosTheta = std::pow(std::abs(cosTheta), 0.25f), result;
+        float warpedCosTheta = cr::pow(std::abs(cosTheta), 0.25f), result;
         if (alphaFixed && etaFixed) {
             if (!(cosTheta >= 0)) return 0.f;
             result = evalCubicInterp1D(warpedCosTheta, trans.data(), thetaSamples, 0.0f, 1.0f);
@@ -392,10 +392,10 @@ struct Marschner {
         return result;
     }
     static float logI0(float x) { // :292-299
-        if (x > 12.0f) return x + 0.5f * (std::log(1.0f / (kPi * 2.0f * x)) + 1.0f / (8.0f * x));
-        else return std::log(I0(x));
+        if (x > 12.0f) return x + 0.5f * (cr::log(1.0f / (kPi * 2.0f * x)) + 1.0f / (8.0f * x));
+        else return cr::log(I0(x));
     }
-    static float g(float beta, float theta) { return std::exp(-theta * theta / (2.0f * beta * beta)) / (std::sqrt(2.0f * kPi) * beta); } // :301-303
+    static float g(float beta, float theta) { return cr::exp(-theta * theta / (2.0f * beta * beta)) / (std::sqrt(2.0f * kPi) * beta); } // :301-303
     static float D(float beta, float phi) { // :305-315
         float result = 0.0f, delta, shift = 0.0f;
         do {
@@ -408,8 +408,8 @@ struct Marschner {
     static float Phi(float gammaI, float gammaT, int p) { return 2.0f * p * gammaT - 2.0f * gammaI + p * kPi; } // :317-319
     static float M(float v, float sinThetaI, float sinThetaO, float cosThetaI, float cosThetaO) { // :364-374
         float a = cosThetaI * cosThetaO / v, b = sinThetaI * sinThetaO / v;
-        if (v < 0.1f) return std::exp(-b + logI0(a) - 1.0f / v + 0.6931f + std::log(1.0f / (2.0f * v)));
-        else return std::exp(-b) * I0(a) / (2.0f * v * std::sinh(1.0f / v));
+        if (v < 0.1f) return cr::exp(-b + logI0(a) - 1.0f / v + 0.6931f + cr::log(1.0f / (2.0f * v)));
+        else return cr::exp(-b) * I0(a) / (2.0f * v * cr::sinh(1.0f / v));
     }
     static float trigInverse(float x) { return std::min(std::sqrt(std::max(1.0f - x * x, 0.0f)), 1.0f); } // :484-486
 
@@ -421,7 +421,7 @@ struct Marschner {
         GaussLegendre<NumPoints> integrator;
         const float *points = integrator.points, *weights = integrator.weights;
         float gammaIs[NumPoints];
-        for (int i = 0; i < NumPoints; ++i) gammaIs[i] = std::asin(points[i]);
+        for (int i = 0; i < NumPoints; ++i) gammaIs[i] = cr::asin(points[i]);
         const int NumGaussianSamples = 2048;
         std::vector<float> Ds(NumGaussianSamples); // identical for p=0,1,2: all use _betaR (:778)
         for (int i = 0; i < NumGaussianSamples; ++i) Ds[i] = D(betaR, i / (NumGaussianSamples - 1.0f) * 2 * kPi);
@@ -438,10 +438,10 @@ struct Marschner {
             V3 sigmaAPrime = sigmaA / cosThetaT;
             float fresnelTerms[NumPoints], gammaTs[NumPoints]; V3 absorptions[NumPoints];
             for (int i = 0; i < NumPoints; ++i) {
-                gammaTs[i] = std::asin(clampf(points[i] / iorPrime, -1.0f, 1.0f));
-                fresnelTerms[i] = fresnelDielectricExt(1.0f / eta, cosHalfAngle * std::cos(gammaIs[i])); // swapped arguments, verbatim (:809)
-                V3 e = -sigmaAPrime * 2.0f * std::cos(gammaTs[i]);
-                absorptions[i] = V3(std::exp(e.x), std::exp(e.y), std::exp(e.z));
+                gammaTs[i] = cr::asin(clampf(points[i] / iorPrime, -1.0f, 1.0f));
+                fresnelTerms[i] = fresnelDielectricExt(1.0f / eta, cosHalfAngle * cr::cos(gammaIs[i])); // swapped arguments, verbatim (:809)
+                V3 e = -sigmaAPrime * 2.0f * cr::cos(gammaTs[i]);
+                absorptions[i] = V3(cr::exp(e.x), cr::exp(e.y), cr::exp(e.z));
             }
             for (int phiI = 0; phiI < Resolution; ++phiI) {
                 float phi = kPi * 2 * phiI / (Resolution - 1.0f);
@@ -490,18 +490,18 @@ struct Marschner {
     V3 eval(const V3 &wi, const V3 &wo) const {
         float sinThetaI = wi.y, sinThetaO = wo.y;
         float cosThetaO = trigInverse(sinThetaO);
-        float thetaI = std::asin(clampf(sinThetaI, -1.0f, 1.0f));
-        float thetaO = std::asin(clampf(sinThetaO, -1.0f, 1.0f));
+        float thetaI = cr::asin(clampf(sinThetaI, -1.0f, 1.0f));
+        float thetaO = cr::asin(clampf(sinThetaO, -1.0f, 1.0f));
         float thetaD = (thetaO - thetaI) * 0.5f;
-        float cosThetaD = std::cos(thetaD);
-        float phi = std::atan2(wo.x, wo.z);
+        float cosThetaD = cr::cos(thetaD);
+        float phi = cr::atan2(wo.x, wo.z);
         if (phi < 0.0f) phi += kPi * 2.0f;
         float thetaIR = thetaI - 2.0f * scaleAngleRad;
         float thetaITT = thetaI + scaleAngleRad;
         float thetaITRT = thetaI + 4.0f * scaleAngleRad;
-        float MR = M(vR, std::sin(thetaIR), sinThetaO, std::cos(thetaIR), cosThetaO);
-        float MTT = M(vTT, std::sin(thetaITT), sinThetaO, std::cos(thetaITT), cosThetaO);
-        float MTRT = M(vTRT, std::sin(thetaITRT), sinThetaO, std::cos(thetaITRT), cosThetaO);
+        float MR = M(vR, cr::sin(thetaIR), sinThetaO, cr::cos(thetaIR), cosThetaO);
+        float MTT = M(vTT, cr::sin(thetaITT), sinThetaO, cr::cos(thetaITT), cosThetaO);
+        float MTRT = M(vTRT, cr::sin(thetaITRT), sinThetaO, cr::cos(thetaITRT), cosThetaO);
         V3 result = 0.15f * MR * nR.eval(phi, cosThetaD) + MTT * nTT.eval(phi, cosThetaD) + MTRT * nTRT.eval(phi, cosThetaD);
         // diffuse term (typeMask=EAll, component=-1 on this path)
         V3 diff = diffuse;
@@ -517,9 +517,9 @@ struct Marschner {
     float pdf(const V3 &, const V3 &) const { return 1.0f; }
     // :582-592
     float sampleM(float v, float sinThetaI, float cosThetaI, float xi1, float xi2) const {
-        float cosTheta = 1.0f + v * std::log(xi1 + (1.0f - xi1) * std::exp(-2.0f / v));
+        float cosTheta = 1.0f + v * cr::log(xi1 + (1.0f - xi1) * cr::exp(-2.0f / v));
         float sinTheta = trigInverse(cosTheta);
-        float cosPhi = std::cos(2 * kPi * xi2);
+        float cosPhi = cr::cos(2 * kPi * xi2);
         return -cosTheta * sinThetaI + sinTheta * cosPhi * cosThetaI;
     }
     // :594-744
@@ -527,7 +527,7 @@ struct Marschner {
         BSDFSample r;
         float sinThetaI = wi.y;
         float cosThetaI = trigInverse(sinThetaI);
-        float thetaI = std::asin(clampf(sinThetaI, -1.0f, 1.0f));
+        float thetaI = cr::asin(clampf(sinThetaI, -1.0f, 1.0f));
         float thetaIR = thetaI - 2.0f * scaleAngleRad;
         float thetaITT = thetaI + scaleAngleRad;
         float thetaITRT = thetaI + 4.0f * scaleAngleRad;
@@ -537,14 +537,14 @@ struct Marschner {
         if (target < weightR) { r.sampledComponent = 5; v = vR; theta = thetaIR; lobe = &nR; }
         else if (target < weightR + weightTT) { r.sampledComponent = 6; v = vTT; theta = thetaITT; lobe = &nTT; }
         else { r.sampledComponent = 7; v = vTRT; theta = thetaITRT; lobe = &nTRT; }
-        float sinThetaO = sampleM(v, std::sin(theta), std::cos(theta), sx, sy);
+        float sinThetaO = sampleM(v, cr::sin(theta), cr::cos(theta), sx, sy);
         float cosThetaO = trigInverse(sinThetaO);
-        float thetaO = std::asin(clampf(sinThetaO, -1.0f, 1.0f));
+        float thetaO = cr::asin(clampf(sinThetaO, -1.0f, 1.0f));
         float thetaD = (thetaO - thetaI) * 0.5f;
-        float cosThetaD = std::cos(thetaD);
+        float cosThetaD = cr::cos(thetaD);
         float phi;
         lobe->sample(cosThetaD, sy, phi);
-        float sinPhi = std::sin(phi), cosPhi = std::cos(phi);
+        float sinPhi = cr::sin(phi), cosPhi = cr::cos(phi);
         float probSpecular = 1 - extRT.eval(wi.z, alpha);
         probSpecular = (probSpecular * specularSamplingWeight) /
                        (probSpecular * specularSamplingWeight + (1 - probSpecular) * (1 - specularSamplingWeight));

@@ -68,7 +68,7 @@ struct EnvMap {
             float norm = 1.0f / colSum;
             for (int x = 1; x < w; ++x) cdfCols[colPos - x - 1] *= norm;
             cdfCols[colPos - 1] = 1.0f;
-            float weight = std::sin((y + 0.5f) * kPi / h);
+            float weight = cr::sin((y + 0.5f) * kPi / h);
             rowWeights[y] = weight;
             rowSum += colSum * weight;
             cdfRows[rowPos++] = rowSum;
@@ -90,7 +90,7 @@ struct EnvMap {
     // envmap.cpp:380-410.  hasDiff: camera rays carry differentials (rx/ry directions)
     V3 evalEnvironment(const V3 &d, bool hasDiff = false, const V3 &rxDir = V3(), const V3 &ryDir = V3()) const {
         V3 v = xfmVector(toLocal, d);
-        float uvx = std::atan2(v.x, -v.z) * kInvTwoPi, uvy = safe_acos(v.y) * kInvPi;
+        float uvx = cr::atan2(v.x, -v.z) * kInvTwoPi, uvy = safe_acos(v.y) * kInvPi;
         V3 value;
         if (!hasDiff) {
             value = evalBilinear(uvx, uvy);
@@ -110,10 +110,10 @@ struct EnvMap {
     V3 evalFiltered(float uvx, float uvy, float d0x, float d0y, float d1x, float d1y) const {
         float du0 = d0x * w, dv0 = d0y * h, du1 = d1x * w, dv1 = d1y * h;
         float A = dv0 * dv0 + dv1 * dv1, B = -2.0f * (du0 * dv0 + du1 * dv1), C = du0 * du0 + du1 * du1, F = A * C - B * B * 0.25f;
-        float root = std::hypot(A - C, B), Aprime = 0.5f * (A + C - root), Cprime = 0.5f * (A + C + root);
+        float root = cr::hypot(A - C, B), Aprime = 0.5f * (A + C - root), Cprime = 0.5f * (A + C + root);
         float majorRadius = Aprime != 0 ? std::sqrt(F / Aprime) : 0, minorRadius = Cprime != 0 ? std::sqrt(F / Cprime) : 0;
         if (!(minorRadius > 0) || !(majorRadius > 0) || F < 0) {
-            float level = std::log2(std::max(majorRadius, kEpsilon));
+            float level = cr::log2(std::max(majorRadius, kEpsilon));
             if (floorToInt(level) < 0) return evalBilinear(uvx, uvy);
             unsupportedFiltered++;
             return evalBilinear(uvx, uvy);
@@ -142,13 +142,13 @@ struct EnvMap {
         value = (value1 + value2) * scale;
         pdf = (luminance(value1) * rowWeights[clampi(yPos, 0, h - 1)] + luminance(value2) * rowWeights[clampi(yPos + 1, 0, h - 1)]) * normalization;
         float phi = pixelSizeX * (posx + 0.5f), theta = pixelSizeY * (posy + 0.5f);
-        float sinPhi = std::sin(phi), cosPhi = std::cos(phi), sinTheta = std::sin(theta), cosTheta = std::cos(theta);
+        float sinPhi = cr::sin(phi), cosPhi = cr::cos(phi), sinTheta = cr::sin(theta), cosTheta = cr::cos(theta);
         d = V3(sinPhi * sinTheta, cosTheta, -cosPhi * sinTheta);
         pdf /= std::max(std::abs(sinTheta), kEpsilon);
     }
     // envmap.cpp:603-635
     float internalPdfDirection(const V3 &d) const {
-        float uvx = std::atan2(d.x, -d.z) * kInvTwoPi, uvy = safe_acos(d.y) * kInvPi;
+        float uvx = cr::atan2(d.x, -d.z) * kInvTwoPi, uvy = safe_acos(d.y) * kInvPi;
         if (!std::isfinite(uvx) || !std::isfinite(uvy)) return 0.0f;
         float u = uvx * w - 0.5f, v = uvy * h - 0.5f;
         int xPos = floorToInt(u), yPos = floorToInt(v);
@@ -253,17 +253,17 @@ static inline V3 computeSunRadiance(float theta, float turbidity, const RefPiece
                    k_waCurve(k_waWavelengths, k_waAmplitudes, 13), solCurve(solWavelengths, solAmplitudes, 38);
     float data[91], wavelengths[91];
     float beta = 0.04608365822050f * turbidity - 0.04586025928522f;
-    float m = 1.0f / (std::cos(theta) + 0.15f * std::pow(93.885f - theta / kPi * 180.0f, -1.253f));
+    float m = 1.0f / (cr::cos(theta) + 0.15f * cr::pow(93.885f - theta / kPi * 180.0f, -1.253f));
     float lambda = 350;
     for (int i = 0; i < 91; i++, lambda += 5) {
-        float tauR = std::exp(-m * 0.008735f * std::pow(lambda / 1000.0f, (float) -4.08));
+        float tauR = cr::exp(-m * 0.008735f * cr::pow(lambda / 1000.0f, (float) -4.08));
         const float alpha = 1.3f;
-        float tauA = std::exp(-m * beta * std::pow(lambda / 1000.0f, -alpha));
+        float tauA = cr::exp(-m * beta * cr::pow(lambda / 1000.0f, -alpha));
         const float lOzone = .35f;
-        float tauO = std::exp(-m * k_oCurve.eval(lambda) * lOzone);
-        float tauG = std::exp(-1.41f * k_gCurve.eval(lambda) * m / std::pow(1 + 118.93f * k_gCurve.eval(lambda) * m, 0.45f));
+        float tauO = cr::exp(-m * k_oCurve.eval(lambda) * lOzone);
+        float tauG = cr::exp(-1.41f * k_gCurve.eval(lambda) * m / cr::pow(1 + 118.93f * k_gCurve.eval(lambda) * m, 0.45f));
         const float w = 2.0;
-        float tauWA = std::exp(-0.2385f * k_waCurve.eval(lambda) * w * m / std::pow(1 + 20.07f * k_waCurve.eval(lambda) * w * m, 0.45f));
+        float tauWA = cr::exp(-0.2385f * k_waCurve.eval(lambda) * w * m / cr::pow(1 + 20.07f * k_waCurve.eval(lambda) * w * m, 0.45f));
         data[i] = solCurve.eval(lambda) * tauR * tauA * tauO * tauG * tauWA;
         wavelengths[i] = lambda;
     }
@@ -290,7 +290,7 @@ static inline void bakeSunSky(const SunSkyParams &P, const RefPieces &ref, std::
     rgb.assign((size_t) 3 * W * H, 0.0f);
     // sunmodel.h:98-105,206-208 (fromSphere of the normalised direction)
     V3 sd = normalize(P.sunDirection);
-    float sunAzimuth = std::atan2(sd.x, -sd.z), sunElevation = safe_acos(sd.y);
+    float sunAzimuth = cr::atan2(sd.x, -sd.z), sunElevation = safe_acos(sd.y);
     if (sunAzimuth < 0) sunAzimuth += 2 * kPi;
     // sky.cpp:219-256
     float sunElev = 0.5f * kPi - sunElevation;
@@ -303,15 +303,15 @@ static inline void bakeSunSky(const SunSkyParams &P, const RefPieces &ref, std::
         for (int x = 0; x < W; ++x) {
             float phi0 = (x + .5f) * factorX;
             // sunsky.cpp:140-145: ray direction toSphere(theta,phi); sky.cpp:392 fromSphere() of it
-            float st = std::sin(theta0), ct = std::cos(theta0), sp = std::sin(phi0), cp = std::cos(phi0);
+            float st = cr::sin(theta0), ct = cr::cos(theta0), sp = cr::sin(phi0), cp = cr::cos(phi0);
             V3 d(sp * st, ct, -cp * st);
-            float azimuth = std::atan2(d.x, -d.z), elevation = safe_acos(d.y);
+            float azimuth = cr::atan2(d.x, -d.z), elevation = safe_acos(d.y);
             if (azimuth < 0) azimuth += 2 * kPi;
             // sky.cpp:413-447 getSkyRadiance
             float theta = elevation / P.stretch;
             V3 result(0.0f);
-            if (!(std::cos(theta) <= 0)) {
-                float cosGamma = std::cos(theta) * std::cos(sunElevation) + std::sin(theta) * std::sin(sunElevation) * std::cos(azimuth - sunAzimuth);
+            if (!(cr::cos(theta) <= 0)) {
+                float cosGamma = cr::cos(theta) * cr::cos(sunElevation) + cr::sin(theta) * cr::sin(sunElevation) * cr::cos(azimuth - sunAzimuth);
                 float gamma = safe_acos(cosGamma);
                 for (int i = 0; i < 3; i++)
                     result[i] = std::max((float) (ref.sky_radiance(state[i], theta, gamma, i) / 106.856980), 0.0f);
@@ -325,16 +325,16 @@ static inline void bakeSunSky(const SunSkyParams &P, const RefPieces &ref, std::
     // sun disc: sunsky.cpp:163-216
     V3 sunRadiance = computeSunRadiance(sunElevation, P.turbidity, ref) * P.sunScale;
     float sElev = sunElevation * P.stretch;
-    float sst = std::sin(sElev), sct = std::cos(sElev), ssp = std::sin(sunAzimuth), scp = std::cos(sunAzimuth);
+    float sst = cr::sin(sElev), sct = cr::cos(sElev), ssp = cr::sin(sunAzimuth), scp = cr::cos(sunAzimuth);
     Frame sunFrame(V3(ssp * sst, sct, -scp * sst));
     float theta = (0.5358f * 0.5f) * (kPi / 180.0f); // SUN_APP_RADIUS = 0.5358
     if (P.sunRadiusScale == 0) throw std::runtime_error("oracle: sunRadiusScale=0 (directional sun) is not on this path");
     size_t pixelCount = (size_t) P.resolution * P.resolution / 2;
-    float cosTheta = std::cos(theta * P.sunRadiusScale);
+    float cosTheta = cr::cos(theta * P.sunRadiusScale);
     float coveredPortion = 0.5f * (1 - cosTheta);
     size_t nSamples = (size_t) std::max(100.0f, (pixelCount * coveredPortion * 1000));
     float fx = W / (2 * kPi), fy = H / kPi;
-    V3 value = sunRadiance * (2 * kPi * (1 - std::cos(theta))) * (float) (W * H) / (2 * kPi * kPi * nSamples);
+    V3 value = sunRadiance * (2 * kPi * (1 - cr::cos(theta))) * (float) (W * H) / (2 * kPi * kPi * nSamples);
     for (size_t i = 0; i < nSamples; ++i) {
         // qmc.h:43-60,82-87,115-120 sample02: (van der Corput, Sobol' dim 2)
         uint32_t n = (uint32_t) i, rv = __builtin_bswap32(n);
@@ -347,7 +347,7 @@ static inline void bakeSunSky(const SunSkyParams &P, const RefPieces &ref, std::
         float s1 = (float) scramble / (float) (1ULL << 32);
         V3 dir = sunFrame.toWorld(squareToUniformCone(cosTheta, s0, s1));
         float sinTheta = safe_sqrt(1 - dir.y * dir.y);
-        float az = std::atan2(dir.x, -dir.z), el = safe_acos(dir.y);
+        float az = cr::atan2(dir.x, -dir.z), el = safe_acos(dir.y);
         if (az < 0) az += 2 * kPi;
         int px = std::min(std::max(0, (int) (az * fx)), W - 1), py = std::min(std::max(0, (int) (el * fy)), H - 1);
         V3 add = value / std::max(1e-3f, sinTheta);

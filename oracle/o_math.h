@@ -66,10 +66,29 @@ static inline D3 operator*(double s, D3 a) { return D3(a.x * s, a.y * s, a.z * s
 static inline double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 static inline D3 normalize(D3 a) { double r = 1.0 / std::sqrt(dot(a, a)); return a * r; }
 
+// Elementary functions.  The reference calls the platform's fp32 libm (sinf, expf, ...), whose last bit differs between
+// libm builds; several formulas on this path amplify that bit by O(1/v) = O(400).  The oracle therefore pins every
+// elementary function to its correctly rounded fp32 value (fp64 evaluation rounded once) -- any faithful libm agrees with
+// that to 1 ulp -- and the CUDA path does the same, so oracle and device can be compared almost bit for bit.
+namespace cr {
+static inline float sin(float x) { return (float) std::sin((double) x); }
+static inline float cos(float x) { return (float) std::cos((double) x); }
+static inline float tan(float x) { return (float) std::tan((double) x); }
+static inline float asin(float x) { return (float) std::asin((double) x); }
+static inline float acos(float x) { return (float) std::acos((double) x); }
+static inline float atan2(float y, float x) { return (float) std::atan2((double) y, (double) x); }
+static inline float exp(float x) { return (float) std::exp((double) x); }
+static inline float log(float x) { return (float) std::log((double) x); }
+static inline float log2(float x) { return (float) std::log2((double) x); }
+static inline float pow(float x, float y) { return (float) std::pow((double) x, (double) y); }
+static inline float sinh(float x) { return (float) std::sinh((double) x); }
+static inline float hypot(float x, float y) { return (float) std::sqrt((double) x * x + (double) y * y); }
+}
+
 static inline float clampf(float v, float lo, float hi) { return std::min(hi, std::max(lo, v)); }
 static inline int clampi(int v, int lo, int hi) { return std::min(hi, std::max(lo, v)); }
 static inline float safe_sqrt(float v) { return std::sqrt(std::max(0.0f, v)); }  // math.h:260
-static inline float safe_acos(float v) { return std::acos(std::min(1.0f, std::max(-1.0f, v))); } // math.h:250
+static inline float safe_acos(float v) { return cr::acos(std::min(1.0f, std::max(-1.0f, v))); } // math.h:250
 static inline int floorToInt(float v) { return (int) std::floor(v); } // math.h:100
 static inline int modulo(int a, int b) { int r = a % b; return (r < 0) ? r + b : r; } // math.h:67
 
@@ -162,7 +181,7 @@ static inline void squareToUniformDiskConcentric(float sx, float sy, float &ox, 
         r = r2;
         phi = (kPi / 2.0f) - (r1 / r2) * (kPi / 4.0f);
     }
-    float cosPhi = std::cos(phi), sinPhi = std::sin(phi);
+    float cosPhi = cr::cos(phi), sinPhi = cr::sin(phi);
     ox = r * cosPhi; oy = r * sinPhi;
 }
 
@@ -180,7 +199,7 @@ static inline V3 squareToUniformCone(float cosCutoff, float sx, float sy) {
     float cosTheta = (1 - sx) + sx * cosCutoff;
     float sinTheta = safe_sqrt(1.0f - cosTheta * cosTheta);
     float phi = 2.0f * kPi * sy;
-    return V3(std::cos(phi) * sinTheta, std::sin(phi) * sinTheta, cosTheta);
+    return V3(cr::cos(phi) * sinTheta, cr::sin(phi) * sinTheta, cosTheta);
 }
 
 // src/libcore/warp.cpp:143-162

@@ -31,7 +31,7 @@ struct Camera {
         aspect = (float) filmW / (float) filmH;
         invResX = 1.0f / filmW; invResY = 1.0f / filmH;
         float recip = 1.0f / (farClip - nearClip);
-        float cot = 1.0f / std::tan((xfov / 2.0f) * (kPi / 180.0f));
+        float cot = 1.0f / cr::tan((xfov / 2.0f) * (kPi / 180.0f));
         M44 persp; std::memset(persp.m, 0, sizeof(persp.m));
         persp.m[0][0] = cot; persp.m[1][1] = cot; persp.m[2][2] = farClip * recip; persp.m[2][3] = -nearClip * farClip * recip; persp.m[3][2] = 1;
         M44 tr = M44::identity(); tr.m[0][3] = -1.0f; tr.m[1][3] = -1.0f / aspect;
@@ -64,7 +64,7 @@ struct ReconFilter {
         if (type == 0) return std::max(0.0f, 1.0f - std::abs(x / radius));
         if (type == 1) return std::abs(x) <= radius ? 1.0f : 0.0f; // src/rfilters/box.cpp
         float alpha = -1.0f / (2.0f * stddev * stddev); // src/rfilters/gaussian.cpp
-        return std::max(0.0f, std::exp(alpha * x * x) - std::exp(alpha * radius * radius));
+        return std::max(0.0f, cr::exp(alpha * x * x) - cr::exp(alpha * radius * radius));
     }
     void configure() {
         if (type == 1) radius = 0.5f;
