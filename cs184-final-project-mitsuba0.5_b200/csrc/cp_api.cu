@@ -62,7 +62,7 @@ struct cudapath_ctx {
     SceneDev scene;
     bool built = false;
     Wavefront wf;
-    uint32_t waveSize = 1u << 22; int collectStats = 0;
+    uint32_t waveSize = 1u << 22; int collectStats = 0, profileStages = 0;
     cudapath_stats stats{};
     float sceneAABB[6] = {0, 0, 0, 0, 0, 0};
 
@@ -259,10 +259,10 @@ int cudapath_set_integrator(cudapath_ctx *ctx, int max_depth, int rr_depth, int 
     if (ctx->built) ctx->scene.integ = ctx->integ;
     return 0;
 }
-int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stats) {
+int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stats, int profile_stages) {
     if (!ctx) return fail("null context");
     if (wave_size) ctx->waveSize = std::max(wave_size, 1024u);
-    ctx->collectStats = collect_stats;
+    ctx->collectStats = collect_stats; ctx->profileStages = profile_stages;
     return 0;
 }
 
@@ -385,7 +385,7 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
     cudaEvent_t e0, e1; CKA(cudaEventCreate(&e0)); CKA(cudaEventCreate(&e1));
     CKA(cudaEventRecord(e0, st));
     RenderStats rs; std::string err;
-    const bool ok = ctx->wf.render(ctx->scene, spp, seed, sample_begin, sample_end, film_dev, ctx->waveSize, ctx->collectStats != 0, st, rs, err);
+    const bool ok = ctx->wf.render(ctx->scene, spp, seed, sample_begin, sample_end, film_dev, ctx->waveSize, ctx->collectStats != 0, ctx->profileStages != 0, st, rs, err);
     if (!ok) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(err); }
     CKA(cudaEventRecord(e1, st));
     CKA(cudaEventSynchronize(e1));
@@ -393,7 +393,9 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudapath_stats &s = ctx->stats;
     s.paths = rs.paths; s.rays = rs.rays; s.shadow_rays = rs.shadowRays; s.kernel_launches = rs.launches; s.bounces = rs.bounces;
-    s.nodes_visited = rs.nodesVisited; s.prims_tested = rs.primsTested; s.unsupported_filtered_lookups = rs.unsupportedLookups; s.dropped_samples = rs.droppedSamples;
+    s.nodes_visited = rs.nodesVisited; s.prims_tested = rs.primsTested; s.shadow_nodes_visited = rs.shadowNodesVisited; s.shadow_prims_tested = rs.shadowPrimsTested;
+    s.intersect_ms = rs.stageMs[0]; s.shade_ms = rs.stageMs[1]; s.shadow_ms = rs.stageMs[2]; s.raygen_ms = rs.stageMs[3]; s.splat_ms = rs.stageMs[4];
+    s.intersect_launches = rs.stageLaunches[0]; s.shade_launches = rs.stageLaunches[1]; s.shadow_launches = rs.stageLaunches[2]; s.unsupported_filtered_lookups = rs.unsupportedLookups; s.dropped_samples = rs.droppedSamples;
     s.render_ms = ms;
     return 0;
 }

@@ -27,13 +27,9 @@ __global__ void __launch_bounds__(128) k_intersect_batch(SceneDev S, uint64_t n,
         const float4 v1 = __ldg(S.vtx + h.gv);
         const uint32_t sh = vtx_shape(v1);
         shape[i] = (int32_t) sh; prim[i] = h.gv - S.shapes[sh].vertexOffset; tOut[i] = h.t;
-        if (rec) {
-            HitRecord r;
-            fill_intersection(v1, __ldg(S.vtx + h.gv + 1), S.shapes[sh].radius, h.p, rd, r);
+        if (rec) {   // raw hit for the (un-fused) record kernel in cp_batch_shade.cu: stored hit point + global primitive
             float *p = rec + 15 * i;
-            p[0] = r.p.x; p[1] = r.p.y; p[2] = r.p.z; p[3] = r.sh.n.x; p[4] = r.sh.n.y; p[5] = r.sh.n.z;
-            p[6] = r.sh.s.x; p[7] = r.sh.s.y; p[8] = r.sh.s.z; p[9] = r.sh.t.x; p[10] = r.sh.t.y; p[11] = r.sh.t.z;
-            p[12] = r.wi.x; p[13] = r.wi.y; p[14] = r.wi.z;
+            p[0] = h.p.x; p[1] = h.p.y; p[2] = h.p.z; p[3] = __uint_as_float(h.gv);
         }
     } else {
         shape[i] = -1; prim[i] = 0xffffffffu; tOut[i] = CP_INF;
@@ -59,6 +55,7 @@ bool intersect_batch(const SceneDev &S, uint64_t n, const float *d_o, const floa
         if (stats) k_intersect_batch<false, true><<<g, 128, 0, s>>>(S, n, d_o, d_d, d_mint, d_maxt, d_shape, d_prim, d_t, d_rec, d_stats, d_err);
         else k_intersect_batch<false, false><<<g, 128, 0, s>>>(S, n, d_o, d_d, d_mint, d_maxt, d_shape, d_prim, d_t, d_rec, d_stats, d_err);
     }
+    if (d_rec && !anyHit) fill_records_batch(S, n, d_d, d_shape, d_rec, s);
     int herr = 0;
     CKB(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
     CKB(cudaStreamSynchronize(s));

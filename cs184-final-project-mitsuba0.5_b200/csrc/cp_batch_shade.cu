@@ -60,6 +60,22 @@ __global__ void k_camera_rays(SceneDev S, uint64_t n, const float *__restrict__ 
     minmax[2 * i] = r.mint; minmax[2 * i + 1] = r.maxt;
 }
 
+// HairShape::fillIntersectionRecord + computeShadingFrame for the hits of k_intersect_batch (in place: rec[0..3] = p, gv)
+__global__ void k_fill_records(SceneDev S, uint64_t n, const float *__restrict__ d, const int32_t *__restrict__ shape, float *rec) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || shape[i] < 0) return;
+    float *p = rec + 15 * i;
+    const uint32_t gv = __float_as_uint(p[3]);
+    HitRecord r;
+    fill_intersection(__ldg(S.vtx + gv), __ldg(S.vtx + gv + 1), S.shapes[shape[i]].radius, V3(p[0], p[1], p[2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), r);
+    p[0] = r.p.x; p[1] = r.p.y; p[2] = r.p.z; p[3] = r.sh.n.x; p[4] = r.sh.n.y; p[5] = r.sh.n.z;
+    p[6] = r.sh.s.x; p[7] = r.sh.s.y; p[8] = r.sh.s.z; p[9] = r.sh.t.x; p[10] = r.sh.t.y; p[11] = r.sh.t.z;
+    p[12] = r.wi.x; p[13] = r.wi.y; p[14] = r.wi.z;
+}
+void fill_records_batch(const SceneDev &S, uint64_t n, const float *d_d, const int32_t *d_shape, float *d_rec, cudaStream_t s) {
+    if (n) k_fill_records<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(S, n, d_d, d_shape, d_rec);
+}
+
 #define CKB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 static inline unsigned grid_for(uint64_t n, int block) { return (unsigned) ((n + block - 1) / block); }
 

@@ -16,6 +16,7 @@
 #include "cp_host.h"
 #include "cp_traverse.cuh"
 #include "cp_wavefront.h"
+#include <vector>
 
 namespace cp {
 
@@ -85,9 +86,14 @@ void Wavefront::release() {
 
 // Accumulates sample indices [sampleBegin, sampleEnd) of `spp` for every pixel into `d_film` (5 x W x H fp32).
 bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t sampleBegin, uint32_t sampleEnd, float *d_film,
-                       uint32_t waveSize, bool collectStats, cudaStream_t stream, RenderStats &rs, std::string &err) {
+                       uint32_t waveSize, bool collectStats, bool profileStages, cudaStream_t stream, RenderStats &rs, std::string &err) {
     if (sampleEnd <= sampleBegin) return true;
     if (!reserve(waveSize, err)) return false;
+    // optional per-launch stage timing: one event pair per launch, resolved after the last wave
+    struct Span { cudaEvent_t a, b; int stage; };
+    std::vector<Span> spans;
+    auto begin = [&](int stage) { if (!profileStages) return; Span sp; cudaEventCreate(&sp.a); cudaEventCreate(&sp.b); sp.stage = stage; cudaEventRecord(sp.a, stream); spans.push_back(sp); };
+    auto end = [&]() { if (profileStages) cudaEventRecord(spans.back().b, stream); };
     WaveParams wp;
     wp.filmW = (uint32_t) S.cam.filmW; wp.filmH = (uint32_t) S.cam.filmH;
     wp.tilesX = (wp.filmW + 7) / 8;
@@ -102,26 +108,32 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
     for (uint64_t base = 0; base < total; base += waveSize) {
         const uint32_t n = (uint32_t) std::min<uint64_t>(waveSize, total - base);
         wp.waveBase = base;
-        launch_raygen(S, wp, q[0], liAcc, n, stream);
+        begin(3); launch_raygen(S, wp, q[0], liAcc, n, stream); end();
         rs.launches++;
         uint32_t nActive = n; int cur = 0;
         while (nActive > 0) {
             CKW(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 4, stream));
+            begin(0);
             if (collectStats) k_intersect<true><<<(nActive + 127) / 128, 128, 0, stream>>>(S, q[cur], nActive, hitPT, hitPrim, stats, errFlag);
             else k_intersect<false><<<(nActive + 127) / 128, 128, 0, stream>>>(S, q[cur], nActive, hitPT, hitPrim, stats, errFlag);
+            end();
+            begin(1);
             launch_shade(S, wp, q[cur], nActive, hitPT, hitPrim, q[cur ^ 1], sq, liAcc, counters, stats + 4, stream);
+            end();
             CKW(cudaMemcpyAsync(hCounters, counters, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, stream));
             CKW(cudaStreamSynchronize(stream));
             rs.launches += 2; rs.rays += nActive; rs.bounces++;
             const uint32_t nNext = hCounters[0], nShadow = hCounters[1];
             if (nShadow) {
+                begin(2);
                 if (collectStats) k_shadow<true><<<(nShadow + 127) / 128, 128, 0, stream>>>(S, sq, nShadow, liAcc, stats, errFlag);
                 else k_shadow<false><<<(nShadow + 127) / 128, 128, 0, stream>>>(S, sq, nShadow, liAcc, stats, errFlag);
+                end();
                 rs.launches++; rs.shadowRays += nShadow;
             }
             cur ^= 1; nActive = nNext;
         }
-        launch_splat(S, wp, liAcc, n, d_film, stats + 5, stream);
+        begin(4); launch_splat(S, wp, liAcc, n, d_film, stats + 5, stream); end();
         rs.launches++;
         rs.paths += n;
     }
@@ -131,7 +143,12 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
     CKW(cudaStreamSynchronize(stream));
     CKW(cudaGetLastError());
     if (herr) { err = "BVH traversal stack overflow"; return false; }
-    rs.nodesVisited += hs[0] + hs[2]; rs.primsTested += hs[1] + hs[3]; rs.unsupportedLookups += hs[4]; rs.droppedSamples += hs[5];
+    for (auto &sp : spans) {
+        float ms = 0; cudaEventElapsedTime(&ms, sp.a, sp.b);
+        rs.stageMs[sp.stage] += ms; rs.stageLaunches[sp.stage]++;
+        cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    }
+    rs.nodesVisited += hs[0]; rs.primsTested += hs[1]; rs.shadowNodesVisited += hs[2]; rs.shadowPrimsTested += hs[3]; rs.unsupportedLookups += hs[4]; rs.droppedSamples += hs[5];
     // the invalid padding "paths" (image sizes that are not multiples of 8) are not camera paths
     const uint64_t realPix = (uint64_t) wp.filmW * wp.filmH, padPix = wp.pixPadded - realPix;
     rs.paths -= padPix * (uint64_t) (sampleEnd - sampleBegin);

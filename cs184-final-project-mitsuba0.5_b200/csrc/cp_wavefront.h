@@ -26,7 +26,9 @@ struct WaveParams {
 };
 struct RenderStats {
     uint64_t paths = 0, rays = 0, shadowRays = 0, launches = 0, bounces = 0;
-    uint64_t nodesVisited = 0, primsTested = 0, unsupportedLookups = 0, droppedSamples = 0;
+    uint64_t nodesVisited = 0, primsTested = 0, shadowNodesVisited = 0, shadowPrimsTested = 0, unsupportedLookups = 0, droppedSamples = 0;
+    double stageMs[5] = {0, 0, 0, 0, 0};       // intersect, shade, shadow, raygen, splat
+    uint64_t stageLaunches[5] = {0, 0, 0, 0, 0};
 };
 
 struct Wavefront {
@@ -41,7 +43,7 @@ struct Wavefront {
     bool reserve(uint32_t waveSize, std::string &err);
     void release();
     bool render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t sampleBegin, uint32_t sampleEnd, float *d_film,
-                uint32_t waveSize, bool collectStats, cudaStream_t stream, RenderStats &rs, std::string &err);
+                uint32_t waveSize, bool collectStats, bool profileStages, cudaStream_t stream, RenderStats &rs, std::string &err);
     ~Wavefront() { release(); }
 };
 
@@ -85,6 +87,7 @@ bool bsdf_eval_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi,
 bool bsdf_sample_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_sample, float *d_wo, float *d_weight, float *d_pdf, int32_t *d_type, cudaStream_t s, std::string &err);
 bool intersect_batch(const SceneDev &S, uint64_t n, const float *d_o, const float *d_d, const float *d_mint, const float *d_maxt, int anyHit, bool stats,
                      int32_t *d_shape, uint32_t *d_prim, float *d_t, float *d_rec /*15 floats per ray or null*/, unsigned long long *d_stats, cudaStream_t s, std::string &err);
+void fill_records_batch(const SceneDev &S, uint64_t n, const float *d_d, const int32_t *d_shape, float *d_rec, cudaStream_t s);
 bool env_eval_batch(const SceneDev &S, uint64_t n, const float *d_dir, float *d_rgb, float *d_pdf, cudaStream_t s, std::string &err);
 bool env_sample_batch(const SceneDev &S, uint64_t n, const float *d_ref, const float *d_sample, float *d_dir, float *d_value, float *d_pdfDist, cudaStream_t s, std::string &err);
 bool camera_rays_batch(const SceneDev &S, uint64_t n, const float *d_pxy, float *d_o, float *d_d, float *d_minmax, cudaStream_t s, std::string &err);

@@ -88,16 +88,22 @@ int cudapath_render(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sam
 int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *film_dev, void *stream);
 /* Film::develop normalisation, src/libcore/fmtconv.cpp:955-1056: rgb = sum / weight (0 where weight == 0). */
 int cudapath_develop(const float *film, int width, int height, float *out_rgb);
-/* Tunables: wave size in paths (0 = default), collect traversal statistics (slower). */
-int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stats);
+/* Tunables: wave size in paths (0 = default), collect traversal statistics (slower, counting kernels),
+ * profile_stages (CUDA events around every stage launch). */
+int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stats, int profile_stages);
 
 typedef struct cudapath_stats {
     uint64_t paths, rays, shadow_rays;          /* same definitions as the reference's "Normal rays traced"/"Shadow rays traced" (src/librender/skdtree.cpp:46-47) */
     uint64_t kernel_launches, bounces;
-    uint64_t nodes_visited, prims_tested;       /* only with collect_stats */
+    uint64_t nodes_visited, prims_tested;       /* closest-hit rays; only with collect_stats */
+    uint64_t shadow_nodes_visited, shadow_prims_tested;
     uint64_t unsupported_filtered_lookups, dropped_samples;
     uint64_t segments, bvh_nodes;
     double build_ms, render_ms;                 /* device time of the last build / render (CUDA events) */
+    /* per-stage device time of the last render, summed over launches (CUDA events on the launching stream; only with
+     * profile_stages) and the number of launches of each stage */
+    double intersect_ms, shade_ms, shadow_ms, raygen_ms, splat_ms;
+    uint64_t intersect_launches, shade_launches, shadow_launches;
 } cudapath_stats;
 int cudapath_get_stats(cudapath_ctx *ctx, cudapath_stats *out);
 int cudapath_scene_bounds(cudapath_ctx *ctx, float aabb_min_max[6], float bsphere_center_radius[4]);

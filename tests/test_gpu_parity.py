@@ -170,7 +170,8 @@ def test_brute_force_agrees_with_oracle_bvh(geo_pair):
     o, d = chord_rays(rng, 300, bs[:3], bs[3] / 1.5 * 0.5)
     a = osc.intersect(o, d, 0.0, np.inf, mode=0); b = osc.intersect(o, d, 0.0, np.inf, mode=2)
     same = (a[0] == b[0]) & (a[1] == b[1])
-    assert (same | (np.abs(a[2] - b[2]) <= 1e-6)).all()
+    with np.errstate(invalid='ignore'):
+        assert (same | (np.abs(a[2] - b[2]) <= 1e-6)).all()
 
 
 def test_any_hit_and_records(geo_pair):
@@ -203,7 +204,9 @@ def test_degenerate_rays(geo_pair):
 def test_env_tables_eval_sample(geo_pair):
     ctx, osc = geo_pair
     gr, gc, gw, gn = ctx.env_tables(512, 256); or_, oc, ow, on = osc.env_tables()
-    assert np.abs(gr - or_).max() <= 2e-6 and np.abs(gc - oc).max() <= 2e-6 and np.abs(gw - ow).max() <= 1e-6
+    # rows below the horizon are black: 1/colSum = inf turns their conditional CDF into NaN in the reference as well
+    assert np.array_equal(np.isnan(gc), np.isnan(oc))
+    assert np.abs(gr - or_).max() <= 2e-6 and np.nanmax(np.abs(gc - oc)) <= 2e-6 and np.abs(gw - ow).max() <= 1e-6
     assert abs(gn - on) <= 2e-6 * abs(on)
     rng = np.random.default_rng(8)
     d = sphere_dirs(rng, 100000)
