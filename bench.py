@@ -182,6 +182,7 @@ def main():
     ap.add_argument('--spp', type=int, default=0, help='override samples per pixel (default: the config value)')
     ap.add_argument('--cpu-spp', type=int, default=1, help='sample indices per pixel in the bounded CPU sample')
     ap.add_argument('--wave', type=int, default=0)
+    ap.add_argument('--max-split', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
@@ -203,6 +204,8 @@ def main():
     W, H, spp = sc['width'], sc['height'], sc['spp']
     total_spp = spp * world                         # weak scaling: every rank renders `spp` sample indices of a world*spp image
     ctx = make_context(cudapath, sc, shapes, env, local)
+    if args.max_split:
+        ctx.set_build_options(args.max_split)
     if args.wave:
         ctx.set_options(wave_size=args.wave)
     ctx.build()
@@ -298,7 +301,7 @@ def main():
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (fp64 cylinder test)', 'data': 'synthetic',
                 'config': workload_config(args, sc), 'mrays_per_s': mrays, 'rays_per_path': (rays + shadow) / args.steps / paths_per_step,
                 'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roof, 'cpu_baseline': cpu,
-                'build': {'segments': build['segments'], 'bvh_nodes': build['bvh_nodes'], 'build_ms': build['build_ms']}}
+                'build': {'segments': build['segments'], 'bvh_references': build['bvh_references'], 'bvh_nodes': build['bvh_nodes'], 'build_ms': build['build_ms']}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

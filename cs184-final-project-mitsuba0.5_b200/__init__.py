@@ -23,7 +23,7 @@ class CudapathError(RuntimeError):
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ('paths', 'rays', 'shadow_rays', 'kernel_launches', 'bounces', 'nodes_visited', 'prims_tested',
                                                'shadow_nodes_visited', 'shadow_prims_tested',
-                                               'unsupported_filtered_lookups', 'dropped_samples', 'segments', 'bvh_nodes')] + \
+                                               'unsupported_filtered_lookups', 'dropped_samples', 'segments', 'bvh_nodes', 'bvh_references')] + \
                [(n, ctypes.c_double) for n in ('build_ms', 'render_ms', 'intersect_ms', 'shade_ms', 'shadow_ms', 'raygen_ms', 'splat_ms')] + \
                [(n, ctypes.c_uint64) for n in ('intersect_launches', 'shade_launches', 'shadow_launches')]
 
@@ -174,6 +174,9 @@ class Context:
 
     def set_options(self, wave_size=0, collect_stats=False, profile_stages=False):
         _check(self._L.cudapath_set_options(self._h, ctypes.c_uint32(wave_size), 1 if collect_stats else 0, 1 if profile_stages else 0))
+
+    def set_build_options(self, max_split=8):
+        _check(self._L.cudapath_set_build_options(self._h, int(max_split)))
 
     def load_xml(self, filename, defines=None):
         """SceneHandler for the hair scenes; `defines` = dict for $name substitution (mitsuba -D).  Returns sampleCount."""

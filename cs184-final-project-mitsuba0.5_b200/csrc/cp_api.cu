@@ -63,6 +63,7 @@ struct cudapath_ctx {
     bool built = false;
     Wavefront wf;
     uint32_t waveSize = 1u << 22; int collectStats = 0, profileStages = 0;
+    int maxSplit = 8;
     cudapath_stats stats{};
     float sceneAABB[6] = {0, 0, 0, 0, 0, 0};
 
@@ -282,7 +283,7 @@ int cudapath_build(cudapath_ctx *ctx) {
     CKA(cudaMalloc(&ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size()));
     CKA(cudaMemcpyAsync(ctx->d_shapes, ctx->shapes.data(), sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyHostToDevice, ctx->stream));
     BuildInfo info;
-    if (!build_bvh(ctx->d_vtx, (uint32_t) ctx->vtx.size(), ctx->d_shapes, (int) ctx->shapes.size(), ctx->stream, ctx->bvh, info, err)) return fail(err);
+    if (!build_bvh(ctx->d_vtx, (uint32_t) ctx->vtx.size(), ctx->d_shapes, (int) ctx->shapes.size(), ctx->maxSplit, ctx->stream, ctx->bvh, info, err)) return fail(err);
     CKA(cudaMemcpyAsync(ctx->shapes.data(), ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     // bsdfs
@@ -372,7 +373,7 @@ int cudapath_build(cudapath_ctx *ctx) {
     CKA(cudaStreamSynchronize(ctx->stream));
     float ms = 0; CKA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    ctx->stats.build_ms = ms; ctx->stats.segments = info.segments; ctx->stats.bvh_nodes = info.nodes;
+    ctx->stats.build_ms = ms; ctx->stats.segments = info.segments; ctx->stats.bvh_nodes = info.nodes; ctx->stats.bvh_references = info.references;
     ctx->built = true;
     return 0;
 }
@@ -427,6 +428,12 @@ int cudapath_develop(const float *film, int w, int h, float *out_rgb) {
     return 0;
 }
 
+int cudapath_set_build_options(cudapath_ctx *ctx, int max_split) {
+    if (!ctx) return fail("null context");
+    if (max_split < 1 || max_split > 64) return fail("max_split must be in [1, 64]");
+    ctx->maxSplit = max_split; ctx->built = false;
+    return 0;
+}
 int cudapath_get_stats(cudapath_ctx *ctx, cudapath_stats *out) { if (!ctx || !out) return fail("null argument"); *out = ctx->stats; return 0; }
 int cudapath_film_size(cudapath_ctx *ctx, int *w, int *h) {
     if (!ctx || !w || !h) return fail("null argument");

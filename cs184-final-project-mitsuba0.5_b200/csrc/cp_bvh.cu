@@ -30,27 +30,63 @@ struct IsSegmentStart {
     __device__ bool operator()(uint32_t i) const { return i + 1 < n && !(__float_as_uint(vtx[i + 1].w) & 1u); }
 };
 
-// per segment: reference-tight bounds -> per-shape union (atomics), conservative BVH box, centroid box
-__global__ void k_segment_bounds(const float4 *__restrict__ vtx, const uint32_t *__restrict__ segs, uint32_t nSeg,
-                                 ShapeDev *shapes, float *leafBox /*6*nSeg*/, float *centroidBox /*6*/) {
+// Number of BVH references a segment is split into.  Hair segments are long and thin, so the box of a diagonal segment
+// is almost empty; cutting the segment into pieces along its axis (each piece keeps the parent's primitive id) shrinks the
+// summed box volume by ~1/k^2.  This only affects which boxes lead to a primitive test, never the test itself.
+__device__ __forceinline__ int split_count(const float4 &v1, const float4 &v2, float radius, int maxSplit) {
+    const V3 a = vtx_pos(v2) - vtx_pos(v1);
+    const float ext = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fabsf(a.z));
+    int k = (int) (ext / (8.0f * radius));
+    return max(1, min(k, maxSplit));
+}
+__global__ void k_split_counts(const float4 *__restrict__ vtx, const uint32_t *__restrict__ segs, uint32_t nSeg, const ShapeDev *__restrict__ shapes,
+                               int maxSplit, uint32_t *counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nSeg) return;
+    const uint32_t gv = segs[i];
+    const float4 v1 = vtx[gv], v2 = vtx[gv + 1];
+    counts[i] = (uint32_t) split_count(v1, v2, shapes[vtx_shape(v1)].radius, maxSplit);
+}
+
+// per segment: reference-tight bounds -> per-shape union (atomics); per reference: conservative BVH box; centroid box
+__global__ void k_segment_bounds(const float4 *__restrict__ vtx, const uint32_t *__restrict__ segs, uint32_t nSeg, const uint32_t *__restrict__ refOffset,
+                                 int maxSplit, ShapeDev *shapes, float *leafBox /*6*nRef*/, uint32_t *refPrim, float *centroidBox /*6*/) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nSeg) return;
     const uint32_t gv = segs[i];
     const float4 v1 = vtx[gv], v2 = vtx[gv + 1], v0 = vtx[gv > 0 ? gv - 1 : 0], v3 = vtx[gv + 2];
     ShapeDev &sd = shapes[vtx_shape(v1)];
-    float bmin[3], bmax[3];
-    segment_bounds(v0, v1, v2, v3, sd.radius, bmin, bmax);
+    const float radius = sd.radius;
+    float minA[3], maxA[3], minB[3], maxB[3];
+    segment_end_boxes(v0, v1, v2, v3, radius, minA, maxA, minB, maxB);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { atomicMinFloat(&sd.bmin[k], bmin[k]); atomicMaxFloat(&sd.bmax[k], bmax[k]); }
-    // The reference's bound uses radius*(1-Epsilon); widen it so that every point the FP64 test can accept
-    // lies strictly inside the leaf box (radius*Epsilon for the shrink + rounding slack).
+    for (int k = 0; k < 3; ++k) { atomicMinFloat(&sd.bmin[k], fminf(minA[k], minB[k])); atomicMaxFloat(&sd.bmax[k], fmaxf(maxA[k], maxB[k])); }
+    const int nPieces = split_count(v1, v2, radius, maxSplit);
+    const uint32_t base = refOffset[i];
+    const V3 p1 = vtx_pos(v1), a = vtx_pos(v2) - p1;
+    const float invLen = 1.0f / length(a);
+    // half-extent of a perpendicular cross-section disc along each coordinate axis
+    const float ex = radius * sqrtf(fmaxf(0.0f, 1.0f - (a.x * invLen) * (a.x * invLen)));
+    const float ey = radius * sqrtf(fmaxf(0.0f, 1.0f - (a.y * invLen) * (a.y * invLen)));
+    const float ez = radius * sqrtf(fmaxf(0.0f, 1.0f - (a.z * invLen) * (a.z * invLen)));
+    for (int j = 0; j < nPieces; ++j) {
+        const float t0 = (float) j / nPieces, t1 = (float) (j + 1) / nPieces;
+        const V3 q0 = p1 + a * t0, q1 = p1 + a * t1;
+        float bmin[3] = {fminf(q0.x, q1.x) - ex, fminf(q0.y, q1.y) - ey, fminf(q0.z, q1.z) - ez};
+        float bmax[3] = {fmaxf(q0.x, q1.x) + ex, fmaxf(q0.y, q1.y) + ey, fmaxf(q0.z, q1.z) + ez};
+        if (j == 0) for (int k = 0; k < 3; ++k) { bmin[k] = fminf(bmin[k], minA[k]); bmax[k] = fmaxf(bmax[k], maxA[k]); }             // miter-cut end ellipses
+        if (j == nPieces - 1) for (int k = 0; k < 3; ++k) { bmin[k] = fminf(bmin[k], minB[k]); bmax[k] = fmaxf(bmax[k], maxB[k]); }
+        // The reference's bound uses radius*(1-Epsilon); widen so that every point the FP64 test can accept lies strictly
+        // inside the box (radius*Epsilon for the shrink + rounding slack of the fp32 box arithmetic).
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float pad = sd.radius * 4e-4f + 4e-7f * fmaxf(fabsf(bmin[k]), fabsf(bmax[k]));
-        bmin[k] -= pad; bmax[k] += pad;
-        leafBox[6 * (size_t) i + k] = bmin[k]; leafBox[6 * (size_t) i + 3 + k] = bmax[k];
-        float c = 0.5f * (bmin[k] + bmax[k]);
-        atomicMinFloat(&centroidBox[k], c); atomicMaxFloat(&centroidBox[3 + k], c);
+        for (int k = 0; k < 3; ++k) {
+            const float pad = radius * 4e-4f + 4e-7f * fmaxf(fabsf(bmin[k]), fabsf(bmax[k]));
+            bmin[k] -= pad; bmax[k] += pad;
+            leafBox[6 * (size_t) (base + j) + k] = bmin[k]; leafBox[6 * (size_t) (base + j) + 3 + k] = bmax[k];
+            const float c = 0.5f * (bmin[k] + bmax[k]);
+            atomicMinFloat(&centroidBox[k], c); atomicMaxFloat(&centroidBox[3 + k], c);
+        }
+        refPrim[base + j] = gv;
     }
 }
 
@@ -114,14 +150,14 @@ __global__ void k_radix_tree(const uint64_t *__restrict__ keys, int n, int2 *chi
     if (i == 0) parentInner[0] = -1;
 }
 
-__global__ void k_gather_leaf_boxes(const float *__restrict__ leafBox, const uint32_t *__restrict__ ids, const uint32_t *__restrict__ segs,
+__global__ void k_gather_leaf_boxes(const float *__restrict__ leafBox, const uint32_t *__restrict__ ids, const uint32_t *__restrict__ refPrim,
                                     uint32_t n, float *sortedBox, uint32_t *sortedPrims) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t src = ids[i];
 #pragma unroll
     for (int k = 0; k < 6; ++k) sortedBox[6 * (size_t) i + k] = leafBox[6 * (size_t) src + k];
-    sortedPrims[i] = segs[src];
+    sortedPrims[i] = refPrim[src];
 }
 
 __global__ void k_refit(const int2 *__restrict__ children, const int *__restrict__ parentInner, const int *__restrict__ parentLeaf,
@@ -241,7 +277,7 @@ struct Scratch {
 
 // Builds the BVH for the vertex array already resident on the device.  On success the caller owns
 // out.nodes / out.prims (cudaFree).  `shapes` is updated in place with the per-shape bounds.
-bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, cudaStream_t stream,
+bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, int maxSplit, cudaStream_t stream,
                BVHDev &out, BuildInfo &info, std::string &err) {
     out = BVHDev(); info = BuildInfo();
     Scratch S;
@@ -275,8 +311,26 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
     if (nSeg == 0) { err = "scene contains no hair segments"; return false; }
     if (nSeg >= (1u << 28)) { err = "too many segments for the leaf encoding"; return false; }
 
-    CK(S.alloc(&d_leafBox, sizeof(float) * 6 * (size_t) nSeg));
-    k_segment_bounds<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_vtx, d_segs, nSeg, d_shapes, d_leafBox, d_cbox);
+    // references: every segment contributes split_count() boxes
+    uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_refPrim = nullptr;
+    uint32_t nRef = 0;
+    {
+        CK(S.alloc(&d_counts, sizeof(uint32_t) * (size_t) (nSeg + 1))); CK(S.alloc(&d_offsets, sizeof(uint32_t) * (size_t) (nSeg + 1)));
+        CK(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t) (nSeg + 1), stream));
+        k_split_counts<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_vtx, d_segs, nSeg, d_shapes, maxSplit, d_counts);
+        void *d_temp3 = nullptr;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, need, d_counts, d_offsets, (int) nSeg + 1, stream));
+        CK(S.alloc(&d_temp3, need));
+        CK(cub::DeviceScan::ExclusiveSum(d_temp3, need, d_counts, d_offsets, (int) nSeg + 1, stream));
+        CK(cudaMemcpyAsync(&nRef, d_offsets + nSeg, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+    info.references = nRef;
+    if (nRef >= (1u << 28)) { err = "too many BVH references for the leaf encoding"; return false; }
+    CK(S.alloc(&d_leafBox, sizeof(float) * 6 * (size_t) nRef));
+    CK(S.alloc(&d_refPrim, sizeof(uint32_t) * (size_t) nRef));
+    k_segment_bounds<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_vtx, d_segs, nSeg, d_offsets, maxSplit, d_shapes, d_leafBox, d_refPrim, d_cbox);
+    nSeg = nRef;   // from here on the builder works on references
     CK(S.alloc(&d_keys, sizeof(uint64_t) * (size_t) nSeg)); CK(S.alloc(&d_keysSorted, sizeof(uint64_t) * (size_t) nSeg));
     CK(S.alloc(&d_ids, sizeof(uint32_t) * (size_t) nSeg)); CK(S.alloc(&d_idsSorted, sizeof(uint32_t) * (size_t) nSeg));
     k_morton<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_leafBox, nSeg, d_cbox, d_keys, d_ids);
@@ -288,7 +342,7 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
     }
     CK(S.alloc(&d_sortedBox, sizeof(float) * 6 * (size_t) nSeg));
     CK(S.alloc(&d_prims, sizeof(uint32_t) * (size_t) nSeg));
-    k_gather_leaf_boxes<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_leafBox, d_idsSorted, d_segs, nSeg, d_sortedBox, d_prims);
+    k_gather_leaf_boxes<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_leafBox, d_idsSorted, d_refPrim, nSeg, d_sortedBox, d_prims);
 
     if (nSeg <= CP_LEAF_MAX) {
         CK(S.alloc(&d_final, sizeof(BVH4Node)));

@@ -128,27 +128,33 @@ CP_D bool cyl_plane_ellipse(V3 planePt, V3 planeNrml, V3 cylPt, V3 cylD, float r
     ax1 = B * sqrtf(c0 * lambda);
     return true;
 }
-CP_D void segment_bounds(const float4 &v0, const float4 &v1, const float4 &v2, const float4 &v3, float radius, float *bmin, float *bmax) {
+// Boxes of the two miter-cut end ellipses (radius*(1-Epsilon)); their union is the reference's getAABB(index).
+CP_D void segment_end_boxes(const float4 &v0, const float4 &v1, const float4 &v2, const float4 &v3, float radius,
+                            float *minA, float *maxA, float *minB, float *maxB) {
     const V3 p1 = vtx_pos(v1), p2 = vtx_pos(v2);
     const V3 tangent = normalize(p2 - p1);
     V3 n1 = tangent, n2 = tangent;
     if (!vtx_starts(v1)) n1 = normalize(normalize(p1 - vtx_pos(v0)) + tangent);
     if (!vtx_starts(v3)) n2 = normalize(tangent + normalize(vtx_pos(v3) - p2));
-    bmin[0] = bmin[1] = bmin[2] = CP_INF; bmax[0] = bmax[1] = bmax[2] = -CP_INF;
     const float r = radius * (1 - kEpsilon);
 #pragma unroll
     for (int end = 0; end < 2; ++end) {
         V3 c, a0, a1;
         const V3 pt = end ? p2 : p1, nn = end ? n2 : n1;
         if (!cyl_plane_ellipse(pt, nn, pt, tangent, r, c, a0, a1)) {
-            // degenerate miter (never for loader output): fall back to a conservative sphere bound
+            // degenerate miter (never for loader output): fall back to a conservative bound
             c = pt; a0 = V3(radius * 2, 0, 0); a1 = V3(0, radius * 2, radius * 2);
         }
-        float rx = sqrtf(a0.x * a0.x + a1.x * a1.x), ry = sqrtf(a0.y * a0.y + a1.y * a1.y), rz = sqrtf(a0.z * a0.z + a1.z * a1.z);
-        bmin[0] = fminf(bmin[0], c.x - rx); bmax[0] = fmaxf(bmax[0], c.x + rx);
-        bmin[1] = fminf(bmin[1], c.y - ry); bmax[1] = fmaxf(bmax[1], c.y + ry);
-        bmin[2] = fminf(bmin[2], c.z - rz); bmax[2] = fmaxf(bmax[2], c.z + rz);
+        const float rx = sqrtf(a0.x * a0.x + a1.x * a1.x), ry = sqrtf(a0.y * a0.y + a1.y * a1.y), rz = sqrtf(a0.z * a0.z + a1.z * a1.z);
+        float *mn = end ? minB : minA, *mx = end ? maxB : maxA;
+        mn[0] = c.x - rx; mx[0] = c.x + rx; mn[1] = c.y - ry; mx[1] = c.y + ry; mn[2] = c.z - rz; mx[2] = c.z + rz;
     }
+}
+CP_D void segment_bounds(const float4 &v0, const float4 &v1, const float4 &v2, const float4 &v3, float radius, float *bmin, float *bmax) {
+    float minA[3], maxA[3], minB[3], maxB[3];
+    segment_end_boxes(v0, v1, v2, v3, radius, minA, maxA, minB, maxB);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { bmin[k] = fminf(minA[k], minB[k]); bmax[k] = fmaxf(maxA[k], maxB[k]); }
 }
 
 } // namespace cp

@@ -8,10 +8,10 @@
 
 namespace cp {
 
-struct BuildInfo { uint32_t segments = 0, nodes = 0; int levels = 0; };
+struct BuildInfo { uint32_t segments = 0, references = 0, nodes = 0; int levels = 0; };
 
 // cp_bvh.cu
-bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, cudaStream_t stream,
+bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, int maxSplit, cudaStream_t stream,
                BVHDev &out, BuildInfo &info, std::string &err);
 
 // cp_tables.cu -- device-side precomputation of the Marschner azimuthal tables and the envmap CDFs

@@ -21,6 +21,7 @@ struct RayHit { float t; uint32_t gv; V3 p; };
 template <bool ANY, bool STATS>
 CP_D bool traverse(const SceneDev &S, const V3 &o, const V3 &d, float rayMint, float rayMaxt, RayHit &hit,
                    uint32_t &nodesVisited, uint32_t &primsTested, int &overflow) {
+    uint32_t fullTests = 0; (void) fullTests;
     hit.t = CP_INF; hit.gv = 0xffffffffu;
     const V3 dRcp(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     float mint, maxt;
@@ -97,6 +98,21 @@ CP_D bool traverse(const SceneDev &S, const V3 &o, const V3 &d, float rayMint, f
             for (uint32_t i = 0; i < count; ++i) {
                 const uint32_t gv = __ldg(prims + first + i);
                 const float4 v1 = __ldg(vtx + gv), v2 = __ldg(vtx + gv + 1);
+                if (STATS) primsTested++;
+                // fp32 early-out: the ray misses the infinite cylinder if its distance to the axis line exceeds the
+                // radius by more than a margin that bounds the fp32 rounding of this estimate (never rejects a hit the
+                // FP64 test would accept; skipped for nearly parallel ray/axis pairs where the estimate is ill-conditioned)
+                {
+                    const V3 a = vtx_pos(v2) - vtx_pos(v1), w = vtx_pos(v1) - o, n = cross(d, a);
+                    const float nn = dot(n, n), aa = dot(a, a), wn = dot(w, n);
+                    const float sin2 = nn / (aa * dot(d, d));
+                    if (sin2 > 4e-4f) {
+                        const float wmax = fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fabsf(w.z));
+                        const float R = (multiShape ? S.shapes[vtx_shape(v1)].radius : radius) * 1.02f + wmax * (1e-6f + 1e-6f * rsqrtf(sin2));
+                        if (wn * wn > R * R * nn) continue;
+                    }
+                }
+                if (STATS) fullTests++;
                 const float4 v0 = __ldg(vtx + (gv > 0 ? gv - 1 : 0)), v3 = __ldg(vtx + gv + 2);
                 float tmin = mint, tmax = maxt;
                 if (multiShape) {
@@ -112,7 +128,6 @@ CP_D bool traverse(const SceneDev &S, const V3 &o, const V3 &d, float rayMint, f
                     if (sFar < tmax) tmax = sFar;
                     if (!(tmax > tmin)) continue;
                 }
-                if (STATS) primsTested++;
                 float t; V3 p;
                 if (segment_intersect(v0, v1, v2, v3, radius, o, d, tmin, tmax, t, p)) {
                     hit.t = t; hit.gv = gv; hit.p = p;

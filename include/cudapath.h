@@ -92,13 +92,16 @@ int cudapath_develop(const float *film, int width, int height, float *out_rgb);
  * profile_stages (CUDA events around every stage launch). */
 int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stats, int profile_stages);
 
+/* BVH build tunable: a long thin segment is referenced by up to max_split boxes cut along its axis (default 8; 1 = off). */
+int cudapath_set_build_options(cudapath_ctx *ctx, int max_split);
+
 typedef struct cudapath_stats {
     uint64_t paths, rays, shadow_rays;          /* same definitions as the reference's "Normal rays traced"/"Shadow rays traced" (src/librender/skdtree.cpp:46-47) */
     uint64_t kernel_launches, bounces;
     uint64_t nodes_visited, prims_tested;       /* closest-hit rays; only with collect_stats */
     uint64_t shadow_nodes_visited, shadow_prims_tested;
     uint64_t unsupported_filtered_lookups, dropped_samples;
-    uint64_t segments, bvh_nodes;
+    uint64_t segments, bvh_nodes, bvh_references;
     double build_ms, render_ms;                 /* device time of the last build / render (CUDA events) */
     /* per-stage device time of the last render, summed over launches (CUDA events on the launching stream; only with
      * profile_stages) and the number of launches of each stage */
