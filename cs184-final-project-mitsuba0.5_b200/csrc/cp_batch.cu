@@ -14,29 +14,35 @@
 
 namespace cp {
 
-template <bool ANY, bool STATS>
-__global__ void __launch_bounds__(128) k_intersect_batch(SceneDev S, uint64_t n, const float *__restrict__ o, const float *__restrict__ d,
-                                                         const float *__restrict__ mint, const float *__restrict__ maxt,
-                                                         int32_t *shape, uint32_t *prim, float *tOut, float *rec, unsigned long long *stats, int *errFlag) {
-    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const V3 ro(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rd(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
-    RayHit h; uint32_t nv = 0, np = 0; int ovf = 0;
-    const bool hit = traverse<ANY, STATS>(S, ro, rd, mint[i], maxt[i], h, nv, np, ovf);
-    if (hit) {
-        const float4 v1 = __ldg(S.vtx + h.gv);
-        const uint32_t sh = vtx_shape(v1);
-        shape[i] = (int32_t) sh; prim[i] = h.gv - S.shapes[sh].vertexOffset; tOut[i] = h.t;
-        if (rec) {   // raw hit for the (un-fused) record kernel in cp_batch_shade.cu: stored hit point + global primitive
-            float *p = rec + 15 * i;
-            p[0] = h.p.x; p[1] = h.p.y; p[2] = h.p.z; p[3] = __uint_as_float(h.gv);
-        }
-    } else {
-        shape[i] = -1; prim[i] = 0xffffffffu; tOut[i] = CP_INF;
-        if (rec) for (int k = 0; k < 15; ++k) rec[15 * i + k] = 0.0f;
+// ray source / sink over flat fp32 arrays
+struct BatchIO {
+    const float *o, *d, *mint, *maxt; int32_t *shape; uint32_t *prim; float *tOut; float *rec;
+    const float4 *vtx; const ShapeDev *shapes;
+    CP_D bool load(uint32_t i, V3 &ro, V3 &rd, float &mn, float &mx) const {
+        ro = V3(o[3 * (size_t) i], o[3 * (size_t) i + 1], o[3 * (size_t) i + 2]); rd = V3(d[3 * (size_t) i], d[3 * (size_t) i + 1], d[3 * (size_t) i + 2]);
+        mn = mint[i]; mx = maxt[i];
+        return true;
     }
+    CP_D void store(uint32_t i, bool hit, const RayHit &h) const {
+        if (hit) {
+            const uint32_t sh = vtx_shape(__ldg(vtx + h.gv));
+            shape[i] = (int32_t) sh; prim[i] = h.gv - shapes[sh].vertexOffset; tOut[i] = h.t;
+            if (rec) {   // raw hit for the (un-fused) record kernel in cp_batch_shade.cu: stored hit point + global primitive
+                float *p = rec + 15 * (size_t) i;
+                p[0] = h.p.x; p[1] = h.p.y; p[2] = h.p.z; p[3] = __uint_as_float(h.gv);
+            }
+        } else {
+            shape[i] = -1; prim[i] = 0xffffffffu; tOut[i] = CP_INF;
+            if (rec) for (int k = 0; k < 15; ++k) rec[15 * (size_t) i + k] = 0.0f;
+        }
+    }
+};
+template <bool ANY, bool STATS>
+__global__ void __launch_bounds__(128) k_intersect_batch(SceneDev S, BatchIO io, uint32_t n, uint32_t *rayCounter, unsigned long long *stats, int *errFlag) {
+    TraceCounters tc = {0, 0, 0}; int ovf = 0;
+    trace_persistent<ANY, STATS>(S, io, n, rayCounter, tc, ovf);
     if (ovf) *errFlag = 1;
-    if (STATS) { atomicAdd(stats + 0, (unsigned long long) nv); atomicAdd(stats + 1, (unsigned long long) np); }
+    if (STATS) { atomicAdd(stats + 0, tc.nodes); atomicAdd(stats + 1, tc.prims); }
 }
 
 #define CKB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
@@ -45,21 +51,26 @@ static inline unsigned grid_for(uint64_t n, int block) { return (unsigned) ((n +
 bool intersect_batch(const SceneDev &S, uint64_t n, const float *d_o, const float *d_d, const float *d_mint, const float *d_maxt, int anyHit, bool stats,
                      int32_t *d_shape, uint32_t *d_prim, float *d_t, float *d_rec, unsigned long long *d_stats, cudaStream_t s, std::string &err) {
     if (n == 0) return true;
-    int *d_err = nullptr;
-    CKB(cudaMalloc(&d_err, sizeof(int))); CKB(cudaMemsetAsync(d_err, 0, sizeof(int), s));
-    const unsigned g = grid_for(n, 128);
+    if (n > 0xfffffff0ull) { err = "ray batch too large (split it into chunks below 2^32 rays)"; return false; }
+    static int numSMs = 0;
+    if (!numSMs) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev); }
+    int *d_ctl = nullptr;   // [0] overflow flag, [1] persistent ray counter
+    CKB(cudaMalloc(&d_ctl, 2 * sizeof(int))); CKB(cudaMemsetAsync(d_ctl, 0, 2 * sizeof(int), s));
+    const unsigned need = (unsigned) ((n + 127) / 128), g = need < (unsigned) numSMs * 8u ? need : (unsigned) numSMs * 8u;
+    BatchIO io{d_o, d_d, d_mint, d_maxt, d_shape, d_prim, d_t, anyHit ? nullptr : d_rec, S.vtx, S.shapes};
+    uint32_t *ctr = (uint32_t *) (d_ctl + 1);
     if (anyHit) {
-        if (stats) k_intersect_batch<true, true><<<g, 128, 0, s>>>(S, n, d_o, d_d, d_mint, d_maxt, d_shape, d_prim, d_t, d_rec, d_stats, d_err);
-        else k_intersect_batch<true, false><<<g, 128, 0, s>>>(S, n, d_o, d_d, d_mint, d_maxt, d_shape, d_prim, d_t, d_rec, d_stats, d_err);
+        if (stats) k_intersect_batch<true, true><<<g, 128, 0, s>>>(S, io, (uint32_t) n, ctr, d_stats, d_ctl);
+        else k_intersect_batch<true, false><<<g, 128, 0, s>>>(S, io, (uint32_t) n, ctr, d_stats, d_ctl);
     } else {
-        if (stats) k_intersect_batch<false, true><<<g, 128, 0, s>>>(S, n, d_o, d_d, d_mint, d_maxt, d_shape, d_prim, d_t, d_rec, d_stats, d_err);
-        else k_intersect_batch<false, false><<<g, 128, 0, s>>>(S, n, d_o, d_d, d_mint, d_maxt, d_shape, d_prim, d_t, d_rec, d_stats, d_err);
+        if (stats) k_intersect_batch<false, true><<<g, 128, 0, s>>>(S, io, (uint32_t) n, ctr, d_stats, d_ctl);
+        else k_intersect_batch<false, false><<<g, 128, 0, s>>>(S, io, (uint32_t) n, ctr, d_stats, d_ctl);
     }
     if (d_rec && !anyHit) fill_records_batch(S, n, d_d, d_shape, d_rec, s);
     int herr = 0;
-    CKB(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CKB(cudaMemcpyAsync(&herr, d_ctl, sizeof(int), cudaMemcpyDeviceToHost, s));
     CKB(cudaStreamSynchronize(s));
-    cudaFree(d_err);
+    cudaFree(d_ctl);
     CKB(cudaGetLastError());
     if (herr) { err = "BVH traversal stack overflow"; return false; }
     return true;

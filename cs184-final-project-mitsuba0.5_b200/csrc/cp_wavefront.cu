@@ -20,38 +20,59 @@
 
 namespace cp {
 
-template <bool STATS>
-__global__ void __launch_bounds__(128) k_intersect(SceneDev S, PathQueue q, uint32_t n, float4 *hitPT, uint32_t *hitPrim,
-                                                   unsigned long long *stats, int *errFlag) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 ro = q.ro[i], rd = q.rd[i];
-    const uint2 id = q.id[i];
-    RayHit h; h.t = CP_INF; h.gv = 0xffffffffu; h.p = V3(0.0f);
-    uint32_t nv = 0, np = 0; int ovf = 0;
-    if (!(id.y & F_INVALID))
-        traverse<false, STATS>(S, V3(ro.x, ro.y, ro.z), V3(rd.x, rd.y, rd.z), ro.w, rd.w, h, nv, np, ovf);
-    hitPT[i] = make_float4(h.p.x, h.p.y, h.p.z, h.t);
-    hitPrim[i] = h.gv;
-    if (ovf) *errFlag = 1;
-    if (STATS) { atomicAdd(stats + 0, (unsigned long long) nv); atomicAdd(stats + 1, (unsigned long long) np); }
-}
-
-template <bool STATS>
-__global__ void __launch_bounds__(128) k_shadow(SceneDev S, ShadowQueue sq, uint32_t n, float4 *liAcc, unsigned long long *stats, int *errFlag) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 o = sq.o[i], d = sq.d[i], c = sq.c[i];
-    RayHit h; uint32_t nv = 0, np = 0; int ovf = 0;
-    const bool occluded = traverse<true, STATS>(S, V3(o.x, o.y, o.z), V3(d.x, d.y, d.z), o.w, d.w, h, nv, np, ovf);
-    if (!occluded && (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f)) {
-        const uint32_t pathId = __float_as_uint(c.w);      // one shadow ray per path and bounce: no atomics needed
+// ray source / sink of the closest-hit stage: the active path queue -> dense hit records
+struct PathIO {
+    PathQueue q; float4 *hitPT; uint32_t *hitPrim;
+    CP_D bool load(uint32_t i, V3 &o, V3 &d, float &mint, float &maxt) const {
+        const float4 ro = q.ro[i], rd = q.rd[i];
+        o = V3(ro.x, ro.y, ro.z); d = V3(rd.x, rd.y, rd.z); mint = ro.w; maxt = rd.w;
+        return !(q.id[i].y & F_INVALID);
+    }
+    CP_D void store(uint32_t i, bool, const RayHit &h) const { hitPT[i] = make_float4(h.p.x, h.p.y, h.p.z, h.t); hitPrim[i] = h.gv; }
+};
+// shadow stage: unoccluded rays add their emitter sample to the owning path (one shadow ray per path and bounce: no atomics)
+struct ShadowIO {
+    ShadowQueue sq; float4 *liAcc;
+    CP_D bool load(uint32_t i, V3 &o, V3 &d, float &mint, float &maxt) const {
+        const float4 ro = sq.o[i], rd = sq.d[i];
+        o = V3(ro.x, ro.y, ro.z); d = V3(rd.x, rd.y, rd.z); mint = ro.w; maxt = rd.w;
+        return true;
+    }
+    CP_D void store(uint32_t i, bool occluded, const RayHit &) const {
+        if (occluded) return;
+        const float4 c = sq.c[i];
+        if (c.x == 0.0f && c.y == 0.0f && c.z == 0.0f) return;
+        const uint32_t pathId = __float_as_uint(c.w);
         float4 acc = liAcc[pathId];
         acc.x += c.x; acc.y += c.y; acc.z += c.z;
         liAcc[pathId] = acc;
     }
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_intersect(SceneDev S, PathIO io, uint32_t n, uint32_t *rayCounter, unsigned long long *stats, int *errFlag) {
+    TraceCounters tc = {0, 0, 0}; int ovf = 0;
+    trace_persistent<false, STATS>(S, io, n, rayCounter, tc, ovf);
     if (ovf) *errFlag = 1;
-    if (STATS) { atomicAdd(stats + 2, (unsigned long long) nv); atomicAdd(stats + 3, (unsigned long long) np); }
+    if (STATS) { atomicAdd(stats + 0, tc.nodes); atomicAdd(stats + 1, tc.prims); atomicAdd(stats + 6, tc.fullTests); }
+}
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_shadow(SceneDev S, ShadowIO io, uint32_t n, uint32_t *rayCounter, unsigned long long *stats, int *errFlag) {
+    TraceCounters tc = {0, 0, 0}; int ovf = 0;
+    trace_persistent<true, STATS>(S, io, n, rayCounter, tc, ovf);
+    if (ovf) *errFlag = 1;
+    if (STATS) { atomicAdd(stats + 2, tc.nodes); atomicAdd(stats + 3, tc.prims); atomicAdd(stats + 7, tc.fullTests); }
+}
+
+// persistent launch: enough CTAs to fill the machine, never more than the work needs
+static unsigned persistent_grid(const void *kernel, uint32_t n) {
+    static int numSMs = 0;
+    if (!numSMs) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev); }
+    int perSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, 128, 0);
+    if (perSM < 1) perSM = 1;
+    const unsigned full = (unsigned) (numSMs * perSM), need = (n + 127u) / 128u;
+    return need < full ? need : full;
 }
 
 // ------------------------------------------------------------------------------------------ host driver
@@ -114,8 +135,11 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
         while (nActive > 0) {
             CKW(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 4, stream));
             begin(0);
-            if (collectStats) k_intersect<true><<<(nActive + 127) / 128, 128, 0, stream>>>(S, q[cur], nActive, hitPT, hitPrim, stats, errFlag);
-            else k_intersect<false><<<(nActive + 127) / 128, 128, 0, stream>>>(S, q[cur], nActive, hitPT, hitPrim, stats, errFlag);
+            {
+                PathIO io{q[cur], hitPT, hitPrim};
+                if (collectStats) k_intersect<true><<<persistent_grid((const void *) k_intersect<true>, nActive), 128, 0, stream>>>(S, io, nActive, counters + 2, stats, errFlag);
+                else k_intersect<false><<<persistent_grid((const void *) k_intersect<false>, nActive), 128, 0, stream>>>(S, io, nActive, counters + 2, stats, errFlag);
+            }
             end();
             begin(1);
             launch_shade(S, wp, q[cur], nActive, hitPT, hitPrim, q[cur ^ 1], sq, liAcc, counters, stats + 4, stream);
@@ -126,8 +150,9 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
             const uint32_t nNext = hCounters[0], nShadow = hCounters[1];
             if (nShadow) {
                 begin(2);
-                if (collectStats) k_shadow<true><<<(nShadow + 127) / 128, 128, 0, stream>>>(S, sq, nShadow, liAcc, stats, errFlag);
-                else k_shadow<false><<<(nShadow + 127) / 128, 128, 0, stream>>>(S, sq, nShadow, liAcc, stats, errFlag);
+                ShadowIO io{sq, liAcc};
+                if (collectStats) k_shadow<true><<<persistent_grid((const void *) k_shadow<true>, nShadow), 128, 0, stream>>>(S, io, nShadow, counters + 3, stats, errFlag);
+                else k_shadow<false><<<persistent_grid((const void *) k_shadow<false>, nShadow), 128, 0, stream>>>(S, io, nShadow, counters + 3, stats, errFlag);
                 end();
                 rs.launches++; rs.shadowRays += nShadow;
             }
