@@ -10,7 +10,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, 'libcudapath.so')
+LIB_PATH = os.environ.get('CUDAPATH_LIB', os.path.join(_HERE, 'libcudapath.so'))   # CUDAPATH_LIB: alternative builds for tuning experiments
 DEFAULT_DATA_DIR = os.environ.get('CUDAPATH_DATA_DIR', os.path.join(_REPO, 'refdata'))
 
 _lib = None

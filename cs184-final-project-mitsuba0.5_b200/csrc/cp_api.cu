@@ -62,7 +62,7 @@ struct cudapath_ctx {
     SceneDev scene;
     bool built = false;
     Wavefront wf;
-    uint32_t waveSize = 1u << 22; int collectStats = 0, profileStages = 0;
+    uint32_t waveSize = 1u << 24; int collectStats = 0, profileStages = 0;
     int maxSplit = 8;
     cudapath_stats stats{};
     float sceneAABB[6] = {0, 0, 0, 0, 0, 0};

@@ -15,4 +15,5 @@ if _NAME not in sys.modules:
 _mod = sys.modules[_NAME]
 import importlib as _il
 scenes = _il.import_module(_NAME + '.scenes')
+dist = _il.import_module(_NAME + '.dist')
 globals().update({k: v for k, v in vars(_mod).items() if not k.startswith('__')})

@@ -1,0 +1,59 @@
+#!/usr/bin/env python3
+"""Generates the golden vectors under tests/golden/ from the CPU oracle (run from the repo root: python tests/golden/make_golden.py).
+
+The reference holds no golden vector for the hair path and cannot be run here, so these fixtures are
+outputs of the oracle restatement on fixed seeded inputs; they pin the oracle against accidental drift and give the GPU tests a
+second, file-based target.  Needs refdata/ (data/microfacet/*.dat) and, for the render fixture, oracle/_ref.
+"""
+import os
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, 'tests'))
+import orc
+import cudapath
+
+HAIR_RGB = (0.143016, 0.0156076, 1.80928e-005)
+
+
+def sphere_dirs(rng, n):
+    v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    return v.astype(np.float32)
+
+
+def main():
+    rng = np.random.default_rng(0x5eed)
+    n = 4096
+    s = orc.Scene()
+    s.add_bsdf('kajiyakay', diffuseReflectance=HAIR_RGB, exponent=10.0)
+    s.add_bsdf('marschner', intIOR=1.55, extIOR=1.0, specularReflectance=(0.592384, 0.32628, 0.0528657))
+    s.add_bsdf('marschner', intIOR=1.55, extIOR=1.0, alpha=0.2, distribution='ggx', diffuseReflectance=HAIR_RGB)
+    out = dict(wi=sphere_dirs(rng, n), wo=sphere_dirs(rng, n), sample=rng.random((n, 2)).astype(np.float32))
+    for b in range(3):
+        out['eval_%d' % b], out['pdf_%d' % b] = s.bsdf_eval(b, out['wi'], out['wo'])
+        wo, wt, pdf, ty = s.bsdf_sample(b, out['wi'], out['sample'])
+        out['swo_%d' % b], out['swt_%d' % b], out['spdf_%d' % b], out['sty_%d' % b] = wo, wt, pdf, ty
+    np.savez_compressed(os.path.join(HERE, 'bsdf_golden.npz'), **out)
+
+    # intersection: furball at 0.2 % of the strands, kdbench-style chords + surface rays
+    ov = dict(width=32, height=24, spp=4, maxDepth=6)
+    env = cudapath.bake_sunsky(**cudapath.scenes.sunsky_params('furball'))
+    g = orc.scene_from_description('furball', scale=0.002, overrides=ov, envmap=env)
+    aabb, bs = g.scene_bounds()
+    m = 20000
+    p1 = bs[:3] + bs[3] / 1.5 * 0.9 * sphere_dirs(rng, m); p2 = bs[:3] + bs[3] / 1.5 * 0.9 * sphere_dirs(rng, m)
+    d = p2 - p1; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = p1.astype(np.float32); d = d.astype(np.float32)
+    sh, pr, t = g.intersect(o, d, 0.0, np.inf, mode=2)          # brute force = the reference semantics with a trivial visiting order
+    np.savez_compressed(os.path.join(HERE, 'intersect_golden.npz'), o=o, d=d, shape=sh, prim=pr, t=t)
+
+    c = orc.scene_from_description('curly-hair', scale=0.004, overrides=ov, envmap=cudapath.bake_sunsky(**cudapath.scenes.sunsky_params('curly-hair')))
+    film = c.render(4, seed=5, threads=2)
+    np.savez_compressed(os.path.join(HERE, 'render_golden.npz'), film=film)
+    print('golden vectors written:', [f for f in os.listdir(HERE) if f.endswith('.npz')])
+
+
+if __name__ == '__main__':
+    main()

@@ -311,3 +311,34 @@ def test_error_paths(cp):
     with pytest.raises(cp.CudapathError):
         ctx.render(4)                                      # not built
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ committed golden vectors
+import os
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def test_bsdf_against_golden_file(bsdf_pair):
+    ctx, _, _ = bsdf_pair
+    g = np.load(os.path.join(GOLDEN, 'bsdf_golden.npz'))
+    for b in range(3):
+        ev, pdf = ctx.bsdf_eval(b, g['wi'], g['wo'])
+        scale = float(np.abs(g['eval_%d' % b]).max())
+        assert rel_err(ev, g['eval_%d' % b], 1e-6 * scale).max() <= 1e-4 and rel_err(pdf, g['pdf_%d' % b], 1e-9).max() <= 1e-4
+        wo, wt, p, ty = ctx.bsdf_sample(b, g['wi'], g['sample'])
+        same = ty == g['sty_%d' % b]
+        assert same.mean() > 0.9995 and np.abs(wo[same] - g['swo_%d' % b][same]).max() <= 2e-4
+
+
+def test_intersection_against_golden_file(cp):
+    g = np.load(os.path.join(GOLDEN, 'intersect_golden.npz'))
+    ov = dict(width=32, height=24, spp=4, maxDepth=6)
+    ctx = cp.scene_from_description('furball', scale=0.002, overrides=ov)
+    ctx.build()
+    sh, pr, t = ctx.intersect(g['o'], g['d'], 0.0, np.inf)
+    mism = (sh != g['shape']) | (pr != g['prim'])
+    ties = mism & (sh >= 0) & (g['shape'] >= 0) & (np.abs(t - g['t']) <= 1e-6 * np.maximum(1, np.abs(g['t'])))
+    assert (mism & ~ties).sum() == 0 and (g['shape'] >= 0).sum() > 500
+    ok = ~mism & (sh >= 0)
+    assert np.array_equal(t[ok], g['t'][ok])
+    ctx.close()

@@ -1,0 +1,388 @@
+"""CPU tests (run with -m "not gpu"): the oracle against the compiled reference pieces and closed forms, the product's
+host-side code (file loaders, sunsky bake, develop) against the oracle, and the committed golden vectors."""
+import ctypes
+import os
+import struct
+import numpy as np
+import pytest
+
+HAIR_RGB = (0.143016, 0.0156076, 1.80928e-005)
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def sphere_dirs(rng, n):
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    return v.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ pinning against oracle/_ref
+needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(GOLDEN), '..', 'oracle', '_ref', 'libref_pieces.so')),
+                               reason='oracle/_ref not built (needs /root/reference)')
+
+
+@needs_ref
+def test_gauss_legendre_bitwise_vs_reference(oracle):
+    L, R = oracle.lib(), oracle.ref_lib()
+    a = [np.zeros(140, np.float32) for _ in range(4)]
+    L.orc_gauss_legendre_140(oracle.p(a[0]), oracle.p(a[1])); R.ref_gauss_legendre_140(oracle.p(a[2]), oracle.p(a[3]))
+    assert np.array_equal(a[0], a[2]) and np.array_equal(a[1], a[3])
+    assert abs(a[1].sum() - 2.0) < 1e-5 and a[0][0] > 0.9998 and np.all(np.diff(a[0]) < 0)     # weights sum to 2, nodes descend from +1
+
+
+@needs_ref
+def test_interpolated_distribution_bitwise_vs_reference(oracle):
+    L, R = oracle.lib(), oracle.ref_lib()
+    rng = np.random.default_rng(3)
+    size, num, n = 64, 64, 20000
+    w = rng.random(size * num).astype(np.float32) ** 4
+    w[5 * size:6 * size] = 0                                   # near-degenerate row -> uniform fallback (hpp:49-56)
+    dist = (rng.random(n) * 70 - 3).astype(np.float32); u = rng.random(n).astype(np.float32)
+    u[:3] = (0.0, 1.0, 0.5)
+    ou, ox = np.zeros(n, np.float32), np.zeros(n, np.int32)
+    ru, rx, rp, rs = np.zeros(n, np.float32), np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    L.orc_interp_dist_warp(oracle.p(w), size, num, n, oracle.p(dist), oracle.p(u), oracle.p(ou), oracle.p(ox))
+    R.ref_interp_dist(oracle.p(w), size, num, n, oracle.p(dist), oracle.p(u), oracle.p(ru), oracle.p(rx), oracle.p(rp), oracle.p(rs))
+    assert np.array_equal(ox, rx) and np.array_equal(ou, ru)
+
+
+@needs_ref
+def test_sunsky_bake_product_vs_oracle(cp, oracle):
+    """Product bake (own Hosek-Wilkie evaluation reading refdata) vs oracle bake (the reference's skymodel.cpp compiled as is)."""
+    for name in ('straight-hair', 'hair-curl'):
+        sp = cp.scenes.sunsky_params(name)
+        a = cp.bake_sunsky(**sp)
+        b = oracle.bake_sunsky(sp['turbidity'], 0.2, sp['sunDirection'], sp['skyScale'], sp['sunScale'], sp['sunRadiusScale'], 512)
+        assert a.shape == (256, 512, 3) and (b[128:] == 0).all()             # below the horizon: black
+        sky = b < 20                                                         # texels without sun-disc samples
+        assert np.abs(a[sky] - b[sky]).max() <= 2e-5 * b[sky].max()
+        # sun texels: a QMC sample on a texel border may land in the neighbouring texel -> compare the total energy instead
+        assert abs(a.sum() - b.sum()) <= 1e-5 * b.sum()
+        assert (np.abs(a - b) / np.maximum(b, 1e-3) > 1e-3).sum() < 200
+
+
+def test_sunsky_sun_disc_energy(oracle):
+    """Closed form: the sun-disc splat adds radiance * solidAngle * W*H / (2 pi^2) / sin(theta) in total (sunsky.cpp:195-214)."""
+    if not oracle.have_ref():
+        pytest.skip('oracle/_ref not built')
+    d = (0.3, 0.8, 0.2)
+    with_sun = oracle.bake_sunsky(3.0, 0.2, d, 1.0, 1.0, 10.0, 512)
+    sky_only = oracle.bake_sunsky(3.0, 0.2, d, 1.0, 0.0, 10.0, 512)
+    disc = (with_sun - sky_only)
+    assert disc.min() >= 0 and disc.sum() > 0
+    ys, xs = np.nonzero(disc[..., 1] > 0)
+    # the splat lies around the sun direction
+    dn = np.array(d) / np.linalg.norm(d)
+    az = np.arctan2(dn[0], -dn[2]) % (2 * np.pi); el = np.arccos(dn[1])
+    assert abs(xs.mean() - az * 512 / (2 * np.pi)) < 8 and abs(ys.mean() - el * 256 / np.pi) < 8
+
+
+# ------------------------------------------------------------------------------------------------ closed forms / invariants of the oracle
+def test_philox_known_answer(oracle):
+    """Random123 known-answer vectors for Philox4x32-10 (Salmon et al. 2011, kat_vectors)."""
+    out = np.zeros(4, np.uint32)
+    oracle.lib().orc_philox(0, 0, 0, 0, 0, 0, oracle.p(out))
+    assert [hex(x) for x in out] == ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    oracle.lib().orc_philox(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, oracle.p(out))
+    assert [hex(x) for x in out] == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
+    oracle.lib().orc_philox(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0, oracle.p(out))
+    assert [hex(x) for x in out] == ['0xd16cfe09', '0x94fdcceb', '0x5001e420', '0x24126ea1']
+
+
+def test_half_quantisation_matches_numpy(oracle):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.normal(size=5000) * 100, rng.random(5000) * 1e-6, [0, 65504, 65520, 1e9, 6e-8, 5.96e-8, 2.98e-8, 1.0009766]]).astype(np.float32)
+    h = np.zeros(len(x), np.uint16); f = np.zeros(len(x), np.float32)
+    oracle.lib().orc_half_roundtrip(oracle.p(x), len(x), oracle.p(h), oracle.p(f))
+    with np.errstate(over='ignore'):
+        ref = x.astype(np.float16)
+    assert np.array_equal(h, ref.view(np.uint16)) and np.array_equal(f, ref.astype(np.float32))
+
+
+def make_bsdf_scene(oracle):
+    s = oracle.Scene()
+    s.add_bsdf('kajiyakay', diffuseReflectance=HAIR_RGB, exponent=10.0)
+    s.add_bsdf('marschner', intIOR=1.55, extIOR=1.0, specularReflectance=(0.592384, 0.32628, 0.0528657))
+    s.add_bsdf('marschner', intIOR=1.55, extIOR=1.0, alpha=0.2, distribution='ggx', diffuseReflectance=HAIR_RGB)
+    return s
+
+
+def test_kajiyakay_closed_forms(oracle):
+    s = make_bsdf_scene(oracle)
+    wi = np.array([[0.6, 0.0, 0.8]] * 3, np.float32)
+    wo = np.array([[-0.6, 0.0, 0.8], [0.6, 0.0, 0.8], [0.0, 0.0, -1.0]], np.float32)
+    ev, pdf = s.bsdf_eval(0, wi, wo)
+    spec = 0.2                                   # default specularReflectance (kajiyakay.cpp:64-65)
+    e = 10.0
+    # forward scatter: tl=te=0.6, alpha=1 -> 0.15*spec*(e+2)/(4 pi) + diffuse/pi, times cos(theta_o)
+    expect = (0.15 * spec * (e + 2) / (4 * np.pi) + np.array(HAIR_RGB) / np.pi) * 0.8
+    assert np.allclose(ev[0], expect, rtol=1e-5)
+    assert np.allclose(ev[1], np.array(HAIR_RGB) / np.pi * 0.8, rtol=1e-5)     # wi.x*wo.x > 0: no specular lobe (kajiyakay.cpp:157)
+    assert (ev[2] == 0).all() and pdf[2] == 0                                  # below the horizon
+    # pdf integrates to ~1 over the hemisphere (Phong lobe about the mirror direction + cosine lobe)
+    rng = np.random.default_rng(1)
+    d = sphere_dirs(rng, 400000); d[:, 2] = np.abs(d[:, 2])
+    _, p = s.bsdf_eval(0, np.repeat(wi[:1], len(d), 0), d)
+    assert abs(p.mean() * 2 * np.pi - 1.0) < 0.02
+
+
+def test_marschner_quirks(oracle):
+    s = make_bsdf_scene(oracle)
+    rng = np.random.default_rng(2)
+    n = 2000
+    wi, wo = sphere_dirs(rng, n), sphere_dirs(rng, n)
+    ev, pdf = s.bsdf_eval(2, wi, wo)
+    assert (pdf == 1).all()                                                    # quirk 1
+    assert np.isfinite(ev).all() and (ev >= 0).all()
+    # quirk 2: the specular term depends on wi only through wi.y; the diffuse term vanishes for wo.z < 0 (T(c<0) = 0)
+    wo_b = wo.copy(); wo_b[:, 2] = -np.abs(wo_b[:, 2]) - 1e-3; wo_b /= np.linalg.norm(wo_b, axis=1, keepdims=True)
+    wi2 = wi.copy()
+    ang = rng.random(n) * 2 * np.pi
+    r = np.sqrt(np.maximum(1 - wi[:, 1] ** 2, 0))
+    wi2[:, 0] = r * np.cos(ang); wi2[:, 2] = r * np.sin(ang)
+    e1, _ = s.bsdf_eval(2, wi, wo_b); e2, _ = s.bsdf_eval(2, wi2.astype(np.float32), wo_b)
+    assert np.allclose(e1, e2, rtol=2e-4, atol=1e-7 * e1.max())
+    # sample(): weight == eval(wi, wo_sampled) (pdf 1), spec branch flagged EDeltaReflection with components 5/6/7
+    smp = rng.random((n, 2)).astype(np.float32)
+    swo, swt, spdf, sty = s.bsdf_sample(2, wi, smp)
+    ev2, _ = s.bsdf_eval(2, wi, swo)
+    assert np.array_equal(ev2, swt) and (spdf == 1).all()
+    types, comps = sty & 0xff, sty >> 8
+    assert set(np.unique(types)) <= {0x20, 0x2} and set(np.unique(comps[types == 0x20])) <= {5, 6, 7} and (comps[types == 0x2] == 1).all()
+
+
+def test_marschner_table_symmetries(oracle):
+    s = make_bsdf_scene(oracle)
+    t = s.marschner_tables(1)
+    tab = t['tables']
+    assert np.isfinite(tab[:, 1:]).all()                 # row 0 is cos(theta_d) = 0: iorPrime = inf/0 -> NaN handling as in the reference
+    assert np.allclose(tab[0, 1:, :, 0], tab[0, 1:, :, 1]) and np.allclose(tab[0, 1:, :, 0], tab[0, 1:, :, 2])     # R lobe is grey
+    assert (np.abs(t['cdfs'][:, :, 0]) == 0).all() and (t['cdfs'][:, :, -1] == 1).all()
+    assert (np.diff(t['cdfs'], axis=2) >= -1e-7).all()
+    assert 0 < t['Fdr'] < 1 and len(t['rt']) == 100 and (np.diff(t['rt']) >= -1e-4).all()
+    sw = t['specW']
+    lum = lambda c: 0.212671 * c[0] + 0.715160 * c[1] + 0.072169 * c[2]
+    assert abs(sw - lum((0.592384, 0.32628, 0.0528657)) / (lum((0.592384, 0.32628, 0.0528657)) + 0.5)) < 1e-6
+
+
+def tiny_hair():
+    # three fibers: a straight one along x, a bent one, and a 2-vertex stub
+    xyz = np.array([[-1, 0, 0], [0, 0, 0], [1, 0, 0], [2, 0.5, 0],
+                    [0, 1, -1], [0, 1, 0], [0.3, 1, 1],
+                    [3, 3, 3], [3, 4, 3]], np.float32)
+    st = np.array([1, 0, 0, 0, 1, 0, 0, 1, 0], np.uint8)
+    return xyz, st
+
+
+def test_cylinder_intersection_analytic(oracle):
+    s = oracle.Scene()
+    b = s.add_bsdf('kajiyakay')
+    xyz, st = tiny_hair()
+    s.add_hair(xyz, st, 0.1, b)
+    s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=8, height=8)
+    s.build()
+    o = np.array([[-0.5, 0, 5], [-0.5, 0, 0], [-0.5, 5, 0], [10, 10, 10], [3, 3.5, 8]], np.float32)
+    d = np.array([[0, 0, -1], [0, 0, -1], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32)
+    for mode in (0, 2):
+        sh, pr, t = s.intersect(o, d, 0.0, np.inf, mode=mode)
+        assert list(sh) == [0, 0, 0, -1, 0] and list(pr[[0, 1, 2, 4]]) == [0, 0, 0, 7]
+        assert abs(t[0] - 4.9) < 1e-6 and abs(t[1] - 0.1) < 1e-6 and abs(t[2] - 4.9) < 1e-6   # t[1]: a ray from inside exits through the far wall
+        # Quirk of the reference's interval logic: the stub fiber is the scene's z-extreme, its bounds use radius*(1-Epsilon)
+        # (hair.cpp:375), so the scene-AABB entry distance (4.90001) is PAST the near root (4.9) and `nearT >= mint` fails
+        # (hair.cpp:521-523): the far wall is reported.
+        assert abs(t[4] - 5.1) < 1e-6
+    # any-hit respects [mint, maxt]
+    assert list(s.intersect(o[:1], d[:1], 0.0, 4.0, mode=1)[0]) == [-1]
+    assert list(s.intersect(o[:1], d[:1], 0.0, 4.95, mode=1)[0]) == [0]
+    # the record: p lies on the cylinder, n is radial, s is the fiber tangent, wi = toLocal(-d)
+    sh, pr, t, rec = s.intersect_full(o[:1], d[:1], 0.0, np.inf)
+    p, n, sx, tx, wi = rec[0, 0:3], rec[0, 3:6], rec[0, 6:9], rec[0, 9:12], rec[0, 12:15]
+    assert np.allclose(p, (-0.5, 0, 0.1), atol=1e-6) and np.allclose(n, (0, 0, 1), atol=1e-6) and np.allclose(np.abs(sx), (1, 0, 0), atol=1e-6)
+    assert np.allclose(wi, (0, 0, 1), atol=1e-6) and abs(np.dot(n, sx)) < 1e-6 and np.allclose(np.cross(n, sx), tx, atol=1e-6)
+
+
+def test_miter_joint_has_no_gap_or_overlap(oracle):
+    """At a joint between two segments the miter planes coincide: a ray through the joint hits exactly one of them."""
+    s = oracle.Scene()
+    b = s.add_bsdf('kajiyakay')
+    xyz, st = tiny_hair()
+    s.add_hair(xyz, st, 0.1, b)
+    s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=8, height=8)
+    s.build()
+    xs = np.linspace(0.9, 1.2, 301).astype(np.float32)                 # crosses the joint at x = 1 of the bent fiber
+    o = np.stack([xs, np.full_like(xs, 0.02), np.full_like(xs, 5.0)], 1); d = np.tile(np.array([[0, 0, -1]], np.float32), (len(xs), 1))
+    sh, pr, t = s.intersect(o, d, 0.0, np.inf, mode=2)
+    assert (sh == 0).all() and set(pr) == {1, 2}
+    for i in range(len(xs)):
+        c = s.candidates(o[i], d[i], 0.0, np.inf)
+        assert len(c[1]) == 1, 'ray %d is claimed by %s' % (i, c[1])
+
+
+def test_segment_bounds_contain_the_segment(oracle):
+    s = oracle.Scene()
+    b = s.add_bsdf('kajiyakay')
+    xyz, st = tiny_hair()
+    s.add_hair(xyz, st, 0.1, b)
+    s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=8, height=8)
+    s.build()
+    boxes = s.segment_bounds(0, 6)
+    assert np.allclose(boxes[0], [-1, -0.09999, -0.09999, 0, 0.09999, 0.09999], atol=2e-5)      # axis-aligned, radius*(1-Epsilon)
+    aabb, _ = s.scene_bounds()
+    assert np.allclose(aabb[:3], boxes[:, :3].min(0)) and np.allclose(aabb[3:], boxes[:, 3:].max(0))
+
+
+def test_film_filter_table_and_splat(oracle):
+    s = oracle.Scene()
+    s.add_hair(*tiny_hair(), 0.1, s.add_bsdf('kajiyakay'))
+    s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=8, height=6)
+    s.set_film('tent')
+    s.build()
+    t = s.filter_table()
+    assert t[31] == 0 and abs(t[:31].sum() * 2 / 31 - 1.0) < 1e-6 and np.all(np.diff(t[:31]) < 0)    # discretised tent, unit integral
+    f = s.splat(np.array([[3.5, 2.5]], np.float32), np.array([[1, 2, 3]], np.float32), np.array([1], np.float32))
+    assert f[2, 3, 4] == pytest.approx(t[0] * t[0]) and np.allclose(f[2, 3, :3] / f[2, 3, 4], [1, 2, 3])
+    assert np.count_nonzero(f[..., 4]) == 1                              # centred sample: neighbours get index >= 31 -> weight 0
+    f = s.splat(np.array([[4.0, 3.0]], np.float32), np.array([[1, 1, 1]], np.float32), np.array([1], np.float32))
+    assert np.count_nonzero(f[..., 4]) == 4 and np.allclose(f[2:4, 3:5, 4], t[15] * t[15])
+    bad = s.splat(np.array([[4.0, 3.0]] * 3, np.float32), np.array([[np.nan, 0, 0], [-1, 0, 0], [np.inf, 0, 0]], np.float32), np.ones(3, np.float32))
+    assert (bad == 0).all()                                              # invalid samples are dropped whole (imageblock.h:148-151)
+
+
+def test_camera_rays(oracle):
+    s = oracle.Scene()
+    s.add_hair(*tiny_hair(), 0.1, s.add_bsdf('kajiyakay'))
+    cam = np.eye(4, dtype=np.float32); cam[:3, 3] = (1, 2, 3)
+    s.set_camera(cam, 90.0, nearClip=0.5, farClip=100.0, width=64, height=32)
+    s.build()
+    o, d, mn, mx = s.camera_rays(np.array([[32, 16], [0, 16], [64, 16], [32, 0]], np.float32))
+    assert np.allclose(o, (1, 2, 3)) and np.allclose(d[0], (0, 0, 1), atol=1e-6) and mn[0] == pytest.approx(0.5) and mx[0] == pytest.approx(100.0)
+    assert np.allclose(d[1], np.array([1, 0, 1]) / np.sqrt(2), atol=1e-6) and np.allclose(d[2], np.array([-1, 0, 1]) / np.sqrt(2), atol=1e-6)   # x is mirrored (perspective.cpp:150)
+    assert np.allclose(d[3], np.array([0, 0.5, 1]) / np.linalg.norm([0, 0.5, 1]), atol=1e-6) and mn[1] == pytest.approx(0.5 * np.sqrt(2), rel=1e-6)
+
+
+def test_envmap_sampling_matches_pdf(oracle):
+    """Importance sampling consistency: E[value/pdf] over samples == integral of the map; pdfDirect agrees with sampleDirect's pdf."""
+    rng = np.random.default_rng(5)
+    env = (rng.random((16, 32, 3)) ** 3).astype(np.float32); env[3, 7] = 50
+    s = oracle.Scene()
+    s.add_hair(*tiny_hair(), 0.1, s.add_bsdf('kajiyakay'))
+    s.set_envmap(env)
+    s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=8, height=8)
+    s.build()
+    n = 200000
+    d, v, pdf, dist = s.env_sample(np.zeros((n, 3), np.float32), rng.random((n, 2)).astype(np.float32))
+    ok = pdf > 0
+    assert ok.mean() > 0.99 and np.allclose(np.linalg.norm(d[ok], axis=1), 1, atol=1e-5)
+    # the tent offset can carry a sample of the first/last row across the pole, where the reference's (u,v) <-> direction
+    # mapping is not one-to-one (envmap.cpp:577,594-599): pdfDirect and sampleDirect legitimately disagree there
+    ok &= np.abs(d[:, 1]) < 0.97
+    rgb, pdf2 = s.env_eval(d[ok])
+    assert np.allclose(pdf2, pdf[ok], rtol=2e-3, atol=1e-6)
+    assert np.allclose(rgb, v[ok] * pdf[ok][:, None], rtol=2e-3, atol=1e-4)
+    # Monte-Carlo estimate of the map's integral vs a brute-force quadrature of evalEnvironment
+    est = v[pdf > 0].mean(0) * (pdf > 0).mean()
+    dirs = sphere_dirs(rng, 400000)
+    quad = s.env_eval(dirs)[0].mean(0) * 4 * np.pi
+    assert np.allclose(est, quad, rtol=0.03)
+    rows, cols, rw, nrm = s.env_tables()
+    assert rows[0] == 0 and rows[-1] == 1 and np.all(np.diff(rows) >= 0) and np.allclose(cols[:, -1], 1)
+
+
+# ------------------------------------------------------------------------------------------------ product host code vs oracle (no GPU needed)
+def write_ascii(path, xyz, st):
+    with open(path, 'w') as f:
+        for p, s in zip(xyz, st):
+            if s:
+                f.write('\n')
+            f.write('%.9g %.9g %.9g\n' % tuple(p))
+
+
+def test_hair_loader_binary_and_ascii(cp, oracle, tmp_path):
+    rng = np.random.default_rng(11)
+    xyz, st = cp.scenes.gen_curly(strands=200, segments=20)
+    # make the loader work for its living: duplicates, nearly collinear runs, a degenerate 1-vertex fiber
+    xyz = xyz.copy(); st = st.copy()
+    xyz[5] = xyz[4]                                           # exact duplicate -> dropped (hair.cpp:712-714)
+    xyz[30:34] = xyz[29] + np.outer(np.arange(1, 5), [0.01, 0.0, 0.0]).astype(np.float32)   # collinear run -> merged (hair.cpp:699-704)
+    st[100] = 1
+    b = str(tmp_path / 'h.mitshair'); a = str(tmp_path / 'h.txt')
+    cp.scenes.write_mitshair(b, xyz, st); write_ascii(a, xyz, st)
+    tw = np.array([[2, 0, 0, 1], [0, 0, -2, 0], [0, 2, 0, -3], [0, 0, 0, 1]], np.float32)      # rotation+scale 2 -> radius doubles
+    for path in (b, a):
+        for kw in (dict(), dict(toWorld=tw, angleThreshold=5.0)):
+            pa = cp.load_hair_file(path, radius=0.01, **kw)
+            pb = oracle.load_hair_file(path, radius=0.01, **kw)
+            assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1]) and pa[2] == pb[2]
+            assert len(pa[1]) < len(st) and pa[1][0] == 1
+    assert cp.load_hair_file(b, radius=0.01, toWorld=tw)[2] == pytest.approx(0.02)
+    x1 = cp.load_hair_file(b, radius=0.01)[0]; x2 = cp.load_hair_file(a, radius=0.01)[0]
+    assert np.array_equal(x1, x2)                              # %.9g round-trips fp32
+    with pytest.raises(cp.CudapathError):
+        cp.load_hair_file(str(tmp_path / 'missing.mitshair'))
+    with pytest.raises(cp.CudapathError):
+        cp.load_hair_file(b, reduction=1.5)
+    # truncated binary file
+    raw = open(b, 'rb').read()
+    open(str(tmp_path / 'trunc.mitshair'), 'wb').write(raw[:len(raw) // 2])
+    with pytest.raises(cp.CudapathError):
+        cp.load_hair_file(str(tmp_path / 'trunc.mitshair'))
+    # empty fiber list
+    open(str(tmp_path / 'empty.mitshair'), 'wb').write(b'BINARY_HAIR' + struct.pack('<I', 0))
+    assert len(cp.load_hair_file(str(tmp_path / 'empty.mitshair'))[1]) == 0
+
+
+def test_develop(cp):
+    film = np.zeros((2, 3, 5), np.float32)
+    film[0, 0] = (2, 4, 6, 2, 2); film[1, 2] = (1, 1, 1, 0.5, 0.5)
+    rgb = cp.develop(film)
+    assert np.allclose(rgb[0, 0], (1, 2, 3)) and np.allclose(rgb[1, 2], (2, 2, 2)) and (rgb[0, 1] == 0).all()      # weight 0 -> 0
+
+
+def test_c_abi_exports_every_declared_symbol(cp):
+    """The shared library loads (without a GPU) and exports every function include/cudapath.h declares."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(GOLDEN), '..', 'include', 'cudapath.h')).read()
+    names = sorted(set(re.findall(r'\b(cudapath_[a-z0-9_]+)\s*\(', hdr)))
+    assert len(names) > 35
+    L = cp.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_no_gpu_fails_loudly(cp):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip('a GPU is present')
+    with pytest.raises(cp.CudapathError, match='CUDA'):
+        cp.Context(0)
+
+
+def test_scene_xml_text(cp):
+    txt = cp.scenes.scene_xml('hair-curl')
+    assert txt.count('<shape type="hair">') == 4 and txt.count('<bsdf type="marschner"') == 4 and 'version="0.6.0"' in txt
+    assert cp.scenes.SCENES['straight-hair']['shapes'][0]['bsdf']['type'] == 'kajiyakay'
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors
+def test_oracle_matches_committed_golden_vectors(oracle):
+    g = np.load(os.path.join(GOLDEN, 'bsdf_golden.npz'))
+    s = make_bsdf_scene(oracle)
+    for b in range(3):
+        ev, pdf = s.bsdf_eval(b, g['wi'], g['wo'])
+        assert np.array_equal(ev, g['eval_%d' % b]) and np.array_equal(pdf, g['pdf_%d' % b])
+        wo, wt, p, ty = s.bsdf_sample(b, g['wi'], g['sample'])
+        assert np.array_equal(wo, g['swo_%d' % b]) and np.array_equal(wt, g['swt_%d' % b]) and np.array_equal(ty, g['sty_%d' % b])
+
+
+def test_oracle_render_matches_golden_film(cp, oracle):
+    if not oracle.have_ref():
+        pytest.skip('oracle/_ref not built')
+    g = np.load(os.path.join(GOLDEN, 'render_golden.npz'))
+    ov = dict(width=32, height=24, spp=4, maxDepth=6)
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params('curly-hair'))
+    film = oracle.scene_from_description('curly-hair', scale=0.004, overrides=ov, envmap=env).render(4, seed=5, threads=2)
+    assert np.allclose(film, g['film'], rtol=1e-5, atol=1e-6)
