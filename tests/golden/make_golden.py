@@ -40,10 +40,11 @@ def main():
     # intersection: furball at 0.2 % of the strands, kdbench-style chords + surface rays
     ov = dict(width=32, height=24, spp=4, maxDepth=6)
     env = cudapath.bake_sunsky(**cudapath.scenes.sunsky_params('furball'))
-    g = orc.scene_from_description('furball', scale=0.002, overrides=ov, envmap=env)
+    g = orc.scene_from_description('furball', scale=0.01, overrides=ov, envmap=env)
     aabb, bs = g.scene_bounds()
     m = 20000
-    p1 = bs[:3] + bs[3] / 1.5 * 0.9 * sphere_dirs(rng, m); p2 = bs[:3] + bs[3] / 1.5 * 0.9 * sphere_dirs(rng, m)
+    c = 0.5 * (aabb[:3] + aabb[3:]); r = 0.5 * np.linalg.norm(aabb[3:] - aabb[:3])       # chords of the fiber ball's own bounding sphere
+    p1 = c + r * sphere_dirs(rng, m); p2 = c + r * sphere_dirs(rng, m)
     d = p2 - p1; d /= np.linalg.norm(d, axis=1, keepdims=True)
     o = p1.astype(np.float32); d = d.astype(np.float32)
     sh, pr, t = g.intersect(o, d, 0.0, np.inf, mode=2)          # brute force = the reference semantics with a trivial visiting order

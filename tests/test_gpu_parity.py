@@ -333,7 +333,7 @@ def test_bsdf_against_golden_file(bsdf_pair):
 def test_intersection_against_golden_file(cp):
     g = np.load(os.path.join(GOLDEN, 'intersect_golden.npz'))
     ov = dict(width=32, height=24, spp=4, maxDepth=6)
-    ctx = cp.scene_from_description('furball', scale=0.002, overrides=ov)
+    ctx = cp.scene_from_description('furball', scale=0.01, overrides=ov)
     ctx.build()
     sh, pr, t = ctx.intersect(g['o'], g['d'], 0.0, np.inf)
     mism = (sh != g['shape']) | (pr != g['prim'])
