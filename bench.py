@@ -280,7 +280,7 @@ def main():
         te2e = torch.tensor([float(np.mean(times))], dtype=torch.float64, device='cuda')
         if world > 1:
             dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
-        e2e = {'value': paths_per_step / float(te2e[0]) / 1e6, 'unit': 'Mpaths/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+        e2e = {'times_s': [round(t, 4) for t in times], 'value': paths_per_step / float(te2e[0]) / 1e6, 'unit': 'Mpaths/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                'includes': 'context creation, Marschner table build, geometry+envmap upload, device BVH build, render, film read-back'}
 
     if rank == 0:

@@ -6,6 +6,9 @@
 #include <cmath>
 #include <algorithm>
 #include <memory>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 using namespace cp;
 
@@ -50,7 +53,10 @@ struct cudapath_ctx {
     cudaStream_t stream = nullptr;
     std::string dataDir;
     std::vector<BsdfHost> bsdfs;
-    std::vector<float4> vtx;
+    // per shape: raw caller arrays staged on the device (xyz fp32 triples + starts bytes); packed into `d_vtx` by build()
+    struct Staged { float *xyz = nullptr; uint8_t *starts = nullptr; uint32_t n = 0; };
+    std::vector<Staged> staged;
+    uint32_t vtxTotal = 0;
     std::vector<ShapeDev> shapes;
     EnvHost env; EnvTables envTables;
     CamHost cam;
@@ -75,6 +81,7 @@ struct cudapath_ctx {
     ~cudapath_ctx() {
         cudaSetDevice(device);
         freeBuilt();
+        for (auto &st : staged) { cudaFree(st.xyz); cudaFree(st.starts); }
         for (auto &b : bsdfs) { cudaFree(b.tables.tab); cudaFree(b.tables.cdf); cudaFree(b.tables.sums); cudaFree(b.tables.pdf); cudaFree(b.rt); }
         wf.release();
         if (stream) cudaStreamDestroy(stream);
@@ -106,6 +113,11 @@ int cudapath_create(int cuda_device, cudapath_ctx **out) {
     std::unique_ptr<cudapath_ctx> ctx(new cudapath_ctx());
     ctx->device = cuda_device;
     CKA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {   // scratch and queue memory comes from the stream-ordered pool; keep freed blocks cached so that repeated builds /
+        // renders in one process do not go back to the driver (cudaMalloc of several GB costs ~0.2 s)
+        cudaMemPool_t pool; uint64_t keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, cuda_device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     *out = ctx.release();
     return 0;
 }
@@ -166,16 +178,20 @@ int cudapath_add_hair(cudapath_ctx *ctx, const float *xyz, const uint8_t *starts
     if (n < 2) return fail("hair shape needs at least two vertices");
     if (!starts[0]) return fail("the first hair vertex must start a fiber");
     if (ctx->shapes.size() >= (1u << 23)) return fail("too many shapes");
+    if ((uint64_t) ctx->vtxTotal + n + 1 >= 0xfffffff0ull) return fail("too many hair vertices");
+    CKA(cudaSetDevice(ctx->device));
     ShapeDev sd; std::memset(&sd, 0, sizeof(sd));
-    sd.radius = radius; sd.bsdf = bsdf_id; sd.vertexOffset = (uint32_t) ctx->vtx.size(); sd.vertexCount = n;
-    const uint32_t shapeBits = (uint32_t) ctx->shapes.size() << 8;
-    ctx->vtx.reserve(ctx->vtx.size() + n + 1);
-    for (uint32_t i = 0; i < n; ++i) {
-        uint32_t bits = shapeBits | (starts[i] ? 1u : 0u);
-        float w; std::memcpy(&w, &bits, 4);
-        ctx->vtx.push_back(make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], w));
-    }
-    { uint32_t bits = shapeBits | 1u; float w; std::memcpy(&w, &bits, 4); ctx->vtx.push_back(make_float4(0, 0, 0, w)); }   // sentinel (hair.cpp:782)
+    sd.radius = radius; sd.bsdf = bsdf_id; sd.vertexOffset = ctx->vtxTotal; sd.vertexCount = n;
+    // The caller's arrays go straight to the device (a true DMA when they are page-locked); the float4 vertex stream with
+    // the start-of-fiber / shape bits and the sentinel of hair.cpp:782 is assembled by a kernel in cudapath_build().
+    cudapath_ctx::Staged st; st.n = n;
+    CKA(cudaMallocAsync((void **) &st.xyz, sizeof(float) * 3 * (size_t) n, ctx->stream));
+    CKA(cudaMallocAsync((void **) &st.starts, (size_t) n, ctx->stream));
+    CKA(cudaMemcpyAsync(st.xyz, xyz, sizeof(float) * 3 * (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
+    CKA(cudaMemcpyAsync(st.starts, starts, (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));              // the caller may release its buffers when this returns
+    ctx->staged.push_back(st);
+    ctx->vtxTotal += n + 1;
     ctx->shapes.push_back(sd); ctx->built = false;
     return (int) ctx->shapes.size() - 1;
 }
@@ -277,13 +293,14 @@ int cudapath_build(cudapath_ctx *ctx) {
     cudaEvent_t e0, e1; CKA(cudaEventCreate(&e0)); CKA(cudaEventCreate(&e1));
     CKA(cudaEventRecord(e0, ctx->stream));
     // geometry
-    CKA(cudaMalloc(&ctx->d_vtx, sizeof(float4) * (ctx->vtx.size() + 4)));
-    CKA(cudaMemsetAsync(ctx->d_vtx, 0, sizeof(float4) * (ctx->vtx.size() + 4), ctx->stream));
-    CKA(cudaMemcpyAsync(ctx->d_vtx, ctx->vtx.data(), sizeof(float4) * ctx->vtx.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CKA(cudaMalloc(&ctx->d_vtx, sizeof(float4) * ((size_t) ctx->vtxTotal + 4)));
+    CKA(cudaMemsetAsync(ctx->d_vtx, 0, sizeof(float4) * ((size_t) ctx->vtxTotal + 4), ctx->stream));
+    for (size_t i = 0; i < ctx->staged.size(); ++i)
+        pack_vertices(ctx->staged[i].xyz, ctx->staged[i].starts, ctx->staged[i].n, (uint32_t) i, ctx->d_vtx + ctx->shapes[i].vertexOffset, ctx->stream);
     CKA(cudaMalloc(&ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size()));
     CKA(cudaMemcpyAsync(ctx->d_shapes, ctx->shapes.data(), sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyHostToDevice, ctx->stream));
     BuildInfo info;
-    if (!build_bvh(ctx->d_vtx, (uint32_t) ctx->vtx.size(), ctx->d_shapes, (int) ctx->shapes.size(), ctx->maxSplit, ctx->stream, ctx->bvh, info, err)) return fail(err);
+    if (!build_bvh(ctx->d_vtx, ctx->vtxTotal, ctx->d_shapes, (int) ctx->shapes.size(), ctx->maxSplit, ctx->stream, ctx->bvh, info, err)) return fail(err);
     CKA(cudaMemcpyAsync(ctx->shapes.data(), ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     // bsdfs
@@ -293,7 +310,7 @@ int cudapath_build(cudapath_ctx *ctx) {
 
     SceneDev &S = ctx->scene;
     std::memset(&S, 0, sizeof(S));
-    S.vtx = ctx->d_vtx; S.vtxCount = (uint32_t) ctx->vtx.size(); S.shapes = ctx->d_shapes; S.shapeCount = (int) ctx->shapes.size();
+    S.vtx = ctx->d_vtx; S.vtxCount = ctx->vtxTotal; S.shapes = ctx->d_shapes; S.shapeCount = (int) ctx->shapes.size();
     S.bsdfs = ctx->d_bsdfs; S.bsdfCount = (int) devs.size(); S.bvh = ctx->bvh; S.integ = ctx->integ;
     for (int k = 0; k < 3; ++k) { S.sceneMin[k] = INFINITY; S.sceneMax[k] = -INFINITY; }
     for (auto &sh : ctx->shapes) for (int k = 0; k < 3; ++k) { S.sceneMin[k] = std::min(S.sceneMin[k], sh.bmin[k]); S.sceneMax[k] = std::max(S.sceneMax[k], sh.bmax[k]); }
@@ -405,16 +422,24 @@ int cudapath_render(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sam
     if (require_built(ctx)) return -1;
     if (!out_film) return fail("null film buffer");
     const size_t bytes = sizeof(float) * 5 * (size_t) ctx->cam.w * ctx->cam.h;
+    const bool trace = getenv("CUDAPATH_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     float *d_film = nullptr;
-    CKA(cudaMalloc(&d_film, bytes));
+    CKA(cudaMallocAsync((void **) &d_film, bytes, ctx->stream));
     CKA(cudaMemsetAsync(d_film, 0, bytes, ctx->stream));
+    const double t1 = now();
     int r = cudapath_render_dev(ctx, spp, seed, sample_begin, sample_end, d_film, ctx->stream);
+    const double t2 = now();
     if (r == 0) {
         cudaError_t e = cudaMemcpyAsync(out_film, d_film, bytes, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { cudaFree(d_film); return fail(std::string("film copy: ") + cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { cudaFreeAsync(d_film, ctx->stream); return fail(std::string("film copy: ") + cudaGetErrorString(e)); }
     }
-    cudaFree(d_film);
+    const double t3 = now();
+    cudaFreeAsync(d_film, ctx->stream);
+    if (trace) fprintf(stderr, "[cudapath] render: film alloc %.3f s, render_dev %.3f s (device %.3f s), read-back %.3f s, free %.3f s\n", t1 - t0, t2 - t1,
+                       ctx->stats.render_ms * 1e-3, t3 - t2, now() - t3);
     return r;
 }
 

@@ -25,6 +25,17 @@ __device__ __forceinline__ void atomicMaxFloat(float *addr, float v) {
     if (v >= 0) atomicMax((int *) addr, __float_as_int(v)); else atomicMin((unsigned int *) addr, __float_as_uint(v));
 }
 
+// (x, y, z, bits) vertex stream of one shape + its sentinel (see cp_hair.cuh)
+__global__ void k_pack_vertices(const float *__restrict__ xyz, const uint8_t *__restrict__ starts, uint32_t n, uint32_t shape, float4 *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const uint32_t bits = (shape << 8) | ((i == n || starts[i]) ? 1u : 0u);
+    out[i] = i == n ? make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(bits)) : make_float4(xyz[3 * (size_t) i], xyz[3 * (size_t) i + 1], xyz[3 * (size_t) i + 2], __uint_as_float(bits));
+}
+void pack_vertices(const float *d_xyz, const uint8_t *d_starts, uint32_t n, uint32_t shape, float4 *d_out, cudaStream_t stream) {
+    k_pack_vertices<<<(n + 1 + 255) / 256, 256, 0, stream>>>(d_xyz, d_starts, n, shape, d_out);
+}
+
 struct IsSegmentStart {
     const float4 *vtx; uint32_t n;
     __device__ bool operator()(uint32_t i) const { return i + 1 < n && !(__float_as_uint(vtx[i + 1].w) & 1u); }
@@ -262,11 +273,12 @@ __global__ void k_init_shape_bounds(ShapeDev *shapes, int n, float *centroidBox)
 }
 
 namespace {
-struct Scratch {
-    std::vector<void *> ptrs;
-    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
+struct Scratch {   // stream-ordered scratch allocations (returned to the pool, not to the driver)
+    std::vector<void *> ptrs; cudaStream_t stream;
+    explicit Scratch(cudaStream_t s) : stream(s) {}
+    ~Scratch() { for (void *p : ptrs) if (p) cudaFreeAsync(p, stream); }
     template <typename T> cudaError_t alloc(T **p, size_t bytes) {
-        cudaError_t e = cudaMalloc((void **) p, bytes ? bytes : 1);
+        cudaError_t e = cudaMallocAsync((void **) p, bytes ? bytes : 1, stream);
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
@@ -280,7 +292,7 @@ struct Scratch {
 bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, int maxSplit, cudaStream_t stream,
                BVHDev &out, BuildInfo &info, std::string &err) {
     out = BVHDev(); info = BuildInfo();
-    Scratch S;
+    Scratch S(stream);
     uint32_t *d_segs = nullptr, *d_ids = nullptr, *d_idsSorted = nullptr, *d_prims = nullptr;
     uint64_t *d_keys = nullptr, *d_keysSorted = nullptr;
     float *d_leafBox = nullptr, *d_sortedBox = nullptr, *d_innerBox = nullptr, *d_cbox = nullptr;

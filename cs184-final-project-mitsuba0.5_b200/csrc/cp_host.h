@@ -14,6 +14,8 @@ struct BuildInfo { uint32_t segments = 0, references = 0, nodes = 0; int levels 
 bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, int maxSplit, cudaStream_t stream,
                BVHDev &out, BuildInfo &info, std::string &err);
 
+void pack_vertices(const float *d_xyz, const uint8_t *d_starts, uint32_t n, uint32_t shape, float4 *d_out, cudaStream_t stream);
+
 // cp_tables.cu -- device-side precomputation of the Marschner azimuthal tables and the envmap CDFs
 struct MarschnerTables { float4 *tab = nullptr; float *cdf = nullptr; float *sums = nullptr; float *pdf = nullptr; };
 bool build_marschner_tables(float eta, float betaR, const float sigmaA[3], const float *glPoints140, const float *glWeights140,

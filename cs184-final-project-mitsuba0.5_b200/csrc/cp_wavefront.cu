@@ -17,6 +17,10 @@
 #include "cp_traverse.cuh"
 #include "cp_wavefront.h"
 #include <vector>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 
 namespace cp {
 
@@ -78,28 +82,29 @@ static unsigned persistent_grid(const void *kernel, uint32_t n) {
 // ------------------------------------------------------------------------------------------ host driver
 #define CKW(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
-bool Wavefront::reserve(uint32_t waveSize, std::string &err) {
+bool Wavefront::reserve(uint32_t waveSize, cudaStream_t stream, std::string &err) {
     if (waveSize <= capacity) return true;
     release();
+    allocStream = stream;
     for (int k = 0; k < 2; ++k) {
-        CKW(cudaMalloc(&q[k].ro, sizeof(float4) * (size_t) waveSize)); CKW(cudaMalloc(&q[k].rd, sizeof(float4) * (size_t) waveSize));
-        CKW(cudaMalloc(&q[k].thr, sizeof(float4) * (size_t) waveSize)); CKW(cudaMalloc(&q[k].id, sizeof(uint2) * (size_t) waveSize));
+        CKW(cudaMallocAsync((void **) &q[k].ro, sizeof(float4) * (size_t) waveSize, stream)); CKW(cudaMallocAsync((void **) &q[k].rd, sizeof(float4) * (size_t) waveSize, stream));
+        CKW(cudaMallocAsync((void **) &q[k].thr, sizeof(float4) * (size_t) waveSize, stream)); CKW(cudaMallocAsync((void **) &q[k].id, sizeof(uint2) * (size_t) waveSize, stream));
     }
-    CKW(cudaMalloc(&sq.o, sizeof(float4) * (size_t) waveSize)); CKW(cudaMalloc(&sq.d, sizeof(float4) * (size_t) waveSize));
-    CKW(cudaMalloc(&sq.c, sizeof(float4) * (size_t) waveSize));
-    CKW(cudaMalloc(&hitPT, sizeof(float4) * (size_t) waveSize)); CKW(cudaMalloc(&hitPrim, sizeof(uint32_t) * (size_t) waveSize));
-    CKW(cudaMalloc(&liAcc, sizeof(float4) * (size_t) waveSize));
-    CKW(cudaMalloc(&counters, sizeof(uint32_t) * 4));
-    CKW(cudaMalloc(&stats, sizeof(unsigned long long) * 8));
-    CKW(cudaMalloc(&errFlag, sizeof(int)));
+    CKW(cudaMallocAsync((void **) &sq.o, sizeof(float4) * (size_t) waveSize, stream)); CKW(cudaMallocAsync((void **) &sq.d, sizeof(float4) * (size_t) waveSize, stream));
+    CKW(cudaMallocAsync((void **) &sq.c, sizeof(float4) * (size_t) waveSize, stream));
+    CKW(cudaMallocAsync((void **) &hitPT, sizeof(float4) * (size_t) waveSize, stream)); CKW(cudaMallocAsync((void **) &hitPrim, sizeof(uint32_t) * (size_t) waveSize, stream));
+    CKW(cudaMallocAsync((void **) &liAcc, sizeof(float4) * (size_t) waveSize, stream));
+    CKW(cudaMallocAsync((void **) &counters, sizeof(uint32_t) * 4, stream));
+    CKW(cudaMallocAsync((void **) &stats, sizeof(unsigned long long) * 8, stream));
+    CKW(cudaMallocAsync((void **) &errFlag, sizeof(int), stream));
     CKW(cudaMallocHost(&hCounters, sizeof(uint32_t) * 4));
     capacity = waveSize;
     return true;
 }
 void Wavefront::release() {
-    for (int k = 0; k < 2; ++k) { cudaFree(q[k].ro); cudaFree(q[k].rd); cudaFree(q[k].thr); cudaFree(q[k].id); q[k] = PathQueue(); }
-    cudaFree(sq.o); cudaFree(sq.d); cudaFree(sq.c); sq = ShadowQueue();
-    cudaFree(hitPT); cudaFree(hitPrim); cudaFree(liAcc); cudaFree(counters); cudaFree(stats); cudaFree(errFlag);
+    void *ptrs[] = {q[0].ro, q[0].rd, q[0].thr, q[0].id, q[1].ro, q[1].rd, q[1].thr, q[1].id, sq.o, sq.d, sq.c, hitPT, hitPrim, liAcc, counters, stats, errFlag};
+    for (void *p : ptrs) if (p) cudaFreeAsync(p, allocStream);
+    q[0] = PathQueue(); q[1] = PathQueue(); sq = ShadowQueue();
     if (hCounters) cudaFreeHost(hCounters);
     hitPT = nullptr; hitPrim = nullptr; liAcc = nullptr; counters = nullptr; stats = nullptr; errFlag = nullptr; hCounters = nullptr;
     capacity = 0;
@@ -109,7 +114,15 @@ void Wavefront::release() {
 bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t sampleBegin, uint32_t sampleEnd, float *d_film,
                        uint32_t waveSize, bool collectStats, bool profileStages, cudaStream_t stream, RenderStats &rs, std::string &err) {
     if (sampleEnd <= sampleBegin) return true;
-    if (!reserve(waveSize, err)) return false;
+    {   // never allocate more queue slots than there are paths
+        const uint64_t tiles = (uint64_t) ((S.cam.filmW + 7) / 8) * ((S.cam.filmH + 7) / 8) * 64ull * (sampleEnd - sampleBegin);
+        if (tiles < waveSize) waveSize = (uint32_t) std::max<uint64_t>(tiles, 1024);
+    }
+    const bool trace = getenv("CUDAPATH_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tr0 = now();
+    if (!reserve(waveSize, stream, err)) return false;
+    if (trace) { cudaStreamSynchronize(stream); fprintf(stderr, "[cudapath] queue reserve (%u paths): %.3f s\n", waveSize, now() - tr0); }
     // optional per-launch stage timing: one event pair per launch, resolved after the last wave
     struct Span { cudaEvent_t a, b; int stage; };
     std::vector<Span> spans;

@@ -40,7 +40,8 @@ struct Wavefront {
     unsigned long long *stats = nullptr;
     int *errFlag = nullptr;
     uint32_t capacity = 0;
-    bool reserve(uint32_t waveSize, std::string &err);
+    cudaStream_t allocStream = nullptr;
+    bool reserve(uint32_t waveSize, cudaStream_t stream, std::string &err);
     void release();
     bool render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t sampleBegin, uint32_t sampleEnd, float *d_film,
                 uint32_t waveSize, bool collectStats, bool profileStages, cudaStream_t stream, RenderStats &rs, std::string &err);
