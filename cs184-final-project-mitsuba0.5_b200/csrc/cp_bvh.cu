@@ -25,12 +25,26 @@ __device__ __forceinline__ void atomicMaxFloat(float *addr, float v) {
     if (v >= 0) atomicMax((int *) addr, __float_as_int(v)); else atomicMin((unsigned int *) addr, __float_as_uint(v));
 }
 
-// (x, y, z, bits) vertex stream of one shape + its sentinel (see cp_hair.cuh)
+// (x, y, z, bits) vertex stream of one shape + its sentinel (see cp_hair.cuh).  bits: 1 = starts a fiber, 2 = the miter joint
+// at this vertex bends by at most 120 degrees (or the vertex is a fiber end), i.e. the miter plane overshoots the
+// perpendicular end cut by at most r*tan(60 deg) < 2r -- lets the fp32 pre-test bound the segment's axial extent.
 __global__ void k_pack_vertices(const float *__restrict__ xyz, const uint8_t *__restrict__ starts, uint32_t n, uint32_t shape, float4 *out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
-    const uint32_t bits = (shape << 8) | ((i == n || starts[i]) ? 1u : 0u);
-    out[i] = i == n ? make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(bits)) : make_float4(xyz[3 * (size_t) i], xyz[3 * (size_t) i + 1], xyz[3 * (size_t) i + 2], __uint_as_float(bits));
+    const bool st = (i == n) || starts[i];
+    uint32_t bits = (shape << 8) | (st ? 1u : 0u);
+    if (i < n) {
+        const V3 p(xyz[3 * (size_t) i], xyz[3 * (size_t) i + 1], xyz[3 * (size_t) i + 2]);
+        const bool hasPrev = !st && i > 0, hasNext = (i + 1 < n) && !starts[i + 1];
+        bool mild = true;
+        if (hasPrev && hasNext) {
+            const V3 a = normalize(p - V3(xyz[3 * (size_t) (i - 1)], xyz[3 * (size_t) (i - 1) + 1], xyz[3 * (size_t) (i - 1) + 2]));
+            const V3 b = normalize(V3(xyz[3 * (size_t) (i + 1)], xyz[3 * (size_t) (i + 1) + 1], xyz[3 * (size_t) (i + 1) + 2]) - p);
+            mild = dot(a, b) >= -0.45f;      // cos(120 deg) = -0.5, with slack for fp32 rounding
+        }
+        if (mild) bits |= 2u;
+        out[i] = make_float4(p.x, p.y, p.z, __uint_as_float(bits));
+    } else out[i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(bits | 2u));
 }
 void pack_vertices(const float *d_xyz, const uint8_t *d_starts, uint32_t n, uint32_t shape, float4 *d_out, cudaStream_t stream) {
     k_pack_vertices<<<(n + 1 + 255) / 256, 256, 0, stream>>>(d_xyz, d_starts, n, shape, d_out);

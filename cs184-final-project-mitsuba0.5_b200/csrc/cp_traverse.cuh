@@ -22,7 +22,7 @@ namespace cp {
 
 struct RayHit { float t; uint32_t gv; V3 p; };
 
-#define CP_STACK_SIZE 64
+#define CP_STACK_SIZE 56
 #define CP_EMPTY_CHILD ((int) 0x80000000)
 #ifndef CP_REFILL_THRESHOLD
 #define CP_REFILL_THRESHOLD 8      // refill a warp once this many lanes are idle
@@ -41,8 +41,7 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanesBelow = (1u << lane) - 1u;
 
-    int stackN[CP_STACK_SIZE];
-    float stackT[CP_STACK_SIZE];
+    uint2 stack[CP_STACK_SIZE];          // (node reference, entry distance bits): one 8-byte local store per push
     // per-lane ray state
     bool idle = true, exhausted = false;
     uint32_t rayIdx = 0;
@@ -96,7 +95,7 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
 // pop the next node whose entry distance is still inside the (shrinking) interval; an empty stack finishes the ray
 #define CP_POP() { \
             bool got_ = false; \
-            while (sp > 0) { --sp; if (ANY || stackT[sp] <= maxt) { cur = stackN[sp]; got_ = true; break; } } \
+            while (sp > 0) { --sp; const uint2 e_ = stack[sp]; if (ANY || __uint_as_float(e_.y) <= maxt) { cur = (int) e_.x; got_ = true; break; } } \
             if (!got_) { io.store(rayIdx, found, hit); idle = true; cur = CP_EMPTY_CHILD; } }
 
         // ------------------------------------------------------------------ phase 1: descend inner nodes until this lane holds a leaf
@@ -106,60 +105,74 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
             const float4 lox = __ldg(np + 0), loy = __ldg(np + 1), loz = __ldg(np + 2);
             const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
             const int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 6));
-            float tn[4]; int ci[4]; int nh = 0;
-#define CP_SLAB(LX, LY, LZ, HX, HY, HZ, C) { \
+            // entry distances of the four children (+inf = not entered); everything stays in registers
+#define CP_SLAB(T, LX, LY, LZ, HX, HY, HZ, C) { \
                 float x0 = (LX - o.x) * dRcp.x, x1 = (HX - o.x) * dRcp.x; \
                 float y0 = (LY - o.y) * dRcp.y, y1 = (HY - o.y) * dRcp.y; \
                 float z0 = (LZ - o.z) * dRcp.z, z1 = (HZ - o.z) * dRcp.z; \
                 float tnear = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), mint)); \
                 float tfar = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), maxt)); \
-                if (C != CP_EMPTY_CHILD && tnear <= tfar * 1.0000004f) { tn[nh] = tnear; ci[nh] = C; nh++; } }
-            CP_SLAB(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, ch.x)
-            CP_SLAB(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, ch.y)
-            CP_SLAB(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, ch.z)
-            CP_SLAB(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, ch.w)
+                T = (C != CP_EMPTY_CHILD && tnear <= tfar * 1.0000004f) ? tnear : CP_INF; }
+            float t0, t1, t2, t3; int c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+            CP_SLAB(t0, lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, ch.x)
+            CP_SLAB(t1, lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, ch.y)
+            CP_SLAB(t2, lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, ch.z)
+            CP_SLAB(t3, lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, ch.w)
 #undef CP_SLAB
-            if (nh == 0) { CP_POP() continue; }
-            if (nh > 1) {   // nearest child first, the others are pushed far-to-near
-#define CP_CSWAP(a, b) if (tn[a] > tn[b]) { float tt = tn[a]; tn[a] = tn[b]; tn[b] = tt; int cc = ci[a]; ci[a] = ci[b]; ci[b] = cc; }
-                if (nh == 2) { CP_CSWAP(0, 1) }
-                else if (nh == 3) { CP_CSWAP(0, 1) CP_CSWAP(1, 2) CP_CSWAP(0, 1) }
-                else { CP_CSWAP(0, 1) CP_CSWAP(2, 3) CP_CSWAP(0, 2) CP_CSWAP(1, 3) CP_CSWAP(1, 2) }
+            // 5-comparator sorting network, ascending entry distance (misses sink to the end)
+#define CP_CSWAP(TA, CA, TB, CB) if (TA > TB) { float tt = TA; TA = TB; TB = tt; int cc = CA; CA = CB; CB = cc; }
+            CP_CSWAP(t0, c0, t1, c1) CP_CSWAP(t2, c2, t3, c3) CP_CSWAP(t0, c0, t2, c2) CP_CSWAP(t1, c1, t3, c3) CP_CSWAP(t1, c1, t2, c2)
 #undef CP_CSWAP
-                for (int i = nh - 1; i >= 1; --i) {
-                    if (sp < CP_STACK_SIZE) { stackN[sp] = ci[i]; stackT[sp] = tn[i]; sp++; } else overflow = 1;
-                }
-            }
-            cur = ci[0];
+            if (t0 == CP_INF) { CP_POP() continue; }
+            // nearest child first, the others are pushed far-to-near
+            if (t3 != CP_INF) { if (sp < CP_STACK_SIZE) stack[sp++] = make_uint2((uint32_t) c3, __float_as_uint(t3)); else overflow = 1; }
+            if (t2 != CP_INF) { if (sp < CP_STACK_SIZE) stack[sp++] = make_uint2((uint32_t) c2, __float_as_uint(t2)); else overflow = 1; }
+            if (t1 != CP_INF) { if (sp < CP_STACK_SIZE) stack[sp++] = make_uint2((uint32_t) c1, __float_as_uint(t1)); else overflow = 1; }
+            cur = c0;
         }
 
         // ------------------------------------------------------------------ phase 2: fp32 pre-test of the leaf's segments (all lanes holding a leaf)
-        uint32_t cand[4]; int nCand = 0;
+        uint32_t candMask = 0, leafFirst = 0;
         const bool inLeaf = !idle && cur < 0;
         if (inLeaf) {
             const uint32_t ref = ~(uint32_t) cur;
-            const uint32_t first = ref >> 3, count = (ref & 7u) + 1u;
+            const uint32_t count = (ref & 7u) + 1u;
+            leafFirst = ref >> 3;
             for (uint32_t i = 0; i < count; ++i) {
-                const uint32_t gv = __ldg(prims + first + i);
+                const uint32_t gv = __ldg(prims + leafFirst + i);
                 const float4 v1 = __ldg(vtx + gv), v2 = __ldg(vtx + gv + 1);
                 if (STATS) tc.prims++;
-                // The ray misses the infinite cylinder if its distance to the axis line exceeds the radius by more than
-                // a margin that bounds the fp32 rounding of this estimate: never rejects a hit the FP64 test would
-                // accept; skipped for nearly parallel ray/axis pairs where the estimate is ill-conditioned.
+                // Conservative fp32 rejection (never rejects a hit the FP64 test would accept).  With n = d x a the ray and the
+                // axis line are closest at ray parameter tc and axis parameter sc; every point of the infinite cylinder the
+                // ray can touch lies within R/sin(theta) of tc and within R/(sin(theta)|a|) of sc.  R carries a margin that
+                // bounds the fp32 rounding of these estimates; nearly parallel ray/axis pairs skip the test.
                 const V3 a = vtx_pos(v2) - vtx_pos(v1), w = vtx_pos(v1) - o, nrm = cross(d, a);
-                const float nn = dot(nrm, nrm), aa = dot(a, a), wn = dot(w, nrm);
-                const float sin2 = nn / (aa * dot(d, d));
+                const float nn = dot(nrm, nrm), aa = dot(a, a), dd = dot(d, d), wn = dot(w, nrm);
+                const float sin2 = nn / (aa * dd);
                 if (sin2 > 4e-4f) {
                     const float wmax = fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fabsf(w.z));
-                    const float R = (multiShape ? S.shapes[vtx_shape(v1)].radius : radius) * 1.02f + wmax * (1e-6f + 1e-6f * rsqrtf(sin2));
-                    if (wn * wn > R * R * nn) continue;
+                    const float rsin = rsqrtf(sin2);
+                    const float rad = multiShape ? S.shapes[vtx_shape(v1)].radius : radius;
+                    const float R = rad * 1.02f + wmax * (2e-6f + 2e-6f * rsin);
+                    if (wn * wn > R * R * nn) continue;                                   // farther than R from the axis line
+                    const float inn = 1.0f / nn;
+                    const float tcl = dot(cross(w, a), nrm) * inn;                        // ray parameter of closest approach
+                    const float slack = 1.01f * R * rsin * rsqrtf(dd) + 1e-5f * fabsf(tcl);
+                    if (tcl + slack < mint || tcl - slack > maxt) continue;               // outside the ray interval / behind the best hit
+                    if (vtx_bits(v1) & vtx_bits(v2) & 2u) {                                // both joints bend mildly: miter overshoot <= 2 r
+                        const float scl = dot(cross(w, d), nrm) * inn;                    // axis parameter in [0,1] of closest approach
+                        const float sslack = 1.01f * (R * rsin + 2.0f * rad) * rsqrtf(aa) + 1e-5f * (1.0f + fabsf(scl));
+                        if (scl + sslack < 0.0f || scl - sslack > 1.0f) continue;         // beyond the segment's ends
+                    }
                 }
-                if (nCand < 4) cand[nCand++] = gv; else overflow = 1;   // leaves hold at most 4 references
+                candMask |= 1u << i;
             }
         }
         // ------------------------------------------------------------------ phase 3: FP64 mitred-cylinder test of the survivors
-        for (int c = 0; c < nCand; ++c) {
-            const uint32_t gv = cand[c];
+        while (candMask) {
+            const int ci = __ffs(candMask) - 1;
+            candMask &= candMask - 1;
+            const uint32_t gv = __ldg(prims + leafFirst + ci);
             const float4 v1 = __ldg(vtx + gv), v2 = __ldg(vtx + gv + 1);
             const float4 v0 = __ldg(vtx + (gv > 0 ? gv - 1 : 0)), v3 = __ldg(vtx + gv + 2);
             float tmin = mint, tmax = maxt;
