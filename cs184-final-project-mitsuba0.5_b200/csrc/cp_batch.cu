@@ -38,7 +38,7 @@ struct BatchIO {
     }
 };
 template <bool ANY, bool STATS>
-__global__ void __launch_bounds__(128) k_intersect_batch(SceneDev S, BatchIO io, uint32_t n, uint32_t *rayCounter, unsigned long long *stats, int *errFlag) {
+__global__ void __launch_bounds__(128, CP_MIN_BLOCKS) k_intersect_batch(SceneDev S, BatchIO io, uint32_t n, uint32_t *rayCounter, unsigned long long *stats, int *errFlag) {
     TraceCounters tc = {0, 0, 0}; int ovf = 0;
     trace_persistent<ANY, STATS>(S, io, n, rayCounter, tc, ovf);
     if (ovf) *errFlag = 1;

@@ -54,14 +54,14 @@ struct ShadowIO {
 };
 
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_intersect(SceneDev S, PathIO io, uint32_t n, uint32_t *rayCounter, unsigned long long *stats, int *errFlag) {
+__global__ void __launch_bounds__(128, CP_MIN_BLOCKS) k_intersect(SceneDev S, PathIO io, uint32_t n, uint32_t *rayCounter, unsigned long long *stats, int *errFlag) {
     TraceCounters tc = {0, 0, 0}; int ovf = 0;
     trace_persistent<false, STATS>(S, io, n, rayCounter, tc, ovf);
     if (ovf) *errFlag = 1;
     if (STATS) { atomicAdd(stats + 0, tc.nodes); atomicAdd(stats + 1, tc.prims); atomicAdd(stats + 6, tc.fullTests); }
 }
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_shadow(SceneDev S, ShadowIO io, uint32_t n, uint32_t *rayCounter, unsigned long long *stats, int *errFlag) {
+__global__ void __launch_bounds__(128, CP_MIN_BLOCKS) k_shadow(SceneDev S, ShadowIO io, uint32_t n, uint32_t *rayCounter, unsigned long long *stats, int *errFlag) {
     TraceCounters tc = {0, 0, 0}; int ovf = 0;
     trace_persistent<true, STATS>(S, io, n, rayCounter, tc, ovf);
     if (ovf) *errFlag = 1;
