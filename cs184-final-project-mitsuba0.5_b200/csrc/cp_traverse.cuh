@@ -28,6 +28,10 @@ struct RayHit { float t; uint32_t gv; V3 p; };
 #define CP_REFILL_THRESHOLD 8      // refill a warp once this many lanes are idle
 #endif
 
+#ifndef CP_MIN_BLOCKS
+#define CP_MIN_BLOCKS 6        // resident CTAs per SM the traversal kernels are compiled for (80 registers; measured best of 4/5/6/8)
+#endif
+
 struct TraceCounters { unsigned long long nodes, prims, fullTests; };
 
 // IO concept:  bool load(uint32_t i, V3 &o, V3 &d, float &mint, float &maxt)   (false: slot carries no ray)
