@@ -74,7 +74,7 @@ struct cudapath_ctx {
     float sceneAABB[6] = {0, 0, 0, 0, 0, 0};
 
     void freeBuilt() {
-        cudaFree(d_vtx); cudaFree(d_shapes); cudaFree(d_bsdfs); cudaFree((void *) bvh.nodes); cudaFree((void *) bvh.prims);
+        cudaFree(d_vtx); cudaFree(d_shapes); cudaFree(d_bsdfs); cudaFree((void *) bvh.nodes); cudaFree((void *) bvh.prims); cudaFree((void *) bvh.leafSeg);
         cudaFree(envTables.texels); cudaFree(envTables.cdfCols); cudaFree(envTables.cdfRows); cudaFree(envTables.rowWeights);
         d_vtx = nullptr; d_shapes = nullptr; d_bsdfs = nullptr; bvh = BVHDev(); envTables = EnvTables(); built = false;
     }

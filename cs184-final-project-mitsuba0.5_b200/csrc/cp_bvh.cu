@@ -185,6 +185,17 @@ __global__ void k_gather_leaf_boxes(const float *__restrict__ leafBox, const uin
     sortedPrims[i] = refPrim[src];
 }
 
+// leaf records: flags = vertex bits of the first vertex (bit 0 starts fiber, bit 1 mild joint, bits 8.. shape) | bit 2 = mild joint at the second vertex
+__global__ void k_leaf_records(const float4 *__restrict__ vtx, const uint32_t *__restrict__ sortedPrims, uint32_t n, float4 *leafSeg) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t gv = sortedPrims[i];
+    const float4 v1 = vtx[gv], v2 = vtx[gv + 1];
+    const uint32_t flags = __float_as_uint(v1.w) | ((__float_as_uint(v2.w) & 2u) ? 4u : 0u);
+    leafSeg[2 * (size_t) i] = make_float4(v1.x, v1.y, v1.z, __uint_as_float(flags));
+    leafSeg[2 * (size_t) i + 1] = make_float4(v2.x, v2.y, v2.z, __uint_as_float(gv));
+}
+
 __global__ void k_refit(const int2 *__restrict__ children, const int *__restrict__ parentInner, const int *__restrict__ parentLeaf,
                         const float *__restrict__ sortedBox, int n, float *innerBox, int *flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -369,6 +380,9 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
     CK(S.alloc(&d_sortedBox, sizeof(float) * 6 * (size_t) nSeg));
     CK(S.alloc(&d_prims, sizeof(uint32_t) * (size_t) nSeg));
     k_gather_leaf_boxes<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_leafBox, d_idsSorted, d_refPrim, nSeg, d_sortedBox, d_prims);
+    float4 *d_leafSeg = nullptr;
+    CK(S.alloc(&d_leafSeg, sizeof(float4) * 2 * (size_t) nSeg));
+    k_leaf_records<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_vtx, d_prims, nSeg, d_leafSeg);
 
     if (nSeg <= CP_LEAF_MAX) {
         CK(S.alloc(&d_final, sizeof(BVH4Node)));
@@ -410,9 +424,9 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
     }
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());
-    out.nodes = d_final; out.prims = d_prims; out.nodeCount = (uint32_t) wideCount; out.primCount = nSeg;
+    out.nodes = d_final; out.prims = d_prims; out.leafSeg = d_leafSeg; out.nodeCount = (uint32_t) wideCount; out.primCount = nSeg;
     info.nodes = (uint32_t) wideCount;
-    S.release(d_final); S.release(d_prims);
+    S.release(d_final); S.release(d_prims); S.release(d_leafSeg);
     return true;
 }
 

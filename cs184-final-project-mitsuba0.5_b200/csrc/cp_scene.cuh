@@ -21,7 +21,9 @@ static_assert(sizeof(BVH4Node) == 128, "BVH4Node must be one 128-byte line");
 
 struct BVHDev {
     const BVH4Node *nodes;
-    const uint32_t *prims;      // sorted primitive list: global first-vertex index gv of each segment
+    const uint32_t *prims;      // sorted reference list: global first-vertex index gv of each reference's segment
+    const float4 *leafSeg;      // per reference, in leaf order: (p1.xyz, flags) (p2.xyz, gv bits) -- what the fp32 pre-test reads,
+                                // so a leaf visit is one dependent load (32 contiguous bytes per reference) instead of index -> vertex
     uint32_t nodeCount, primCount;
 };
 

@@ -32,6 +32,10 @@ struct RayHit { float t; uint32_t gv; V3 p; };
 #define CP_MIN_BLOCKS 6        // resident CTAs per SM the traversal kernels are compiled for (80 registers; measured best of 4/5/6/8)
 #endif
 
+#ifndef CP_DESCENT_MIN_LANES
+#define CP_DESCENT_MIN_LANES 8
+#endif
+
 struct TraceCounters { unsigned long long nodes, prims, fullTests; };
 
 // IO concept:  bool load(uint32_t i, V3 &o, V3 &d, float &mint, float &maxt)   (false: slot carries no ray)
@@ -39,7 +43,7 @@ struct TraceCounters { unsigned long long nodes, prims, fullTests; };
 template <bool ANY, bool STATS, class IO>
 CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__restrict__ rayCounter, TraceCounters &tc, int &overflow) {
     const BVH4Node *__restrict__ nodes = S.bvh.nodes;
-    const uint32_t *__restrict__ prims = S.bvh.prims;
+    const float4 *__restrict__ leafSeg = S.bvh.leafSeg;
     const float4 *__restrict__ vtx = S.vtx;
     const bool multiShape = S.shapeCount > 1;
     const unsigned lane = threadIdx.x & 31u;
@@ -133,6 +137,9 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
             if (t2 != CP_INF) { if (sp < CP_STACK_SIZE) stack[sp++] = make_uint2((uint32_t) c2, __float_as_uint(t2)); else overflow = 1; }
             if (t1 != CP_INF) { if (sp < CP_STACK_SIZE) stack[sp++] = make_uint2((uint32_t) c1, __float_as_uint(t1)); else overflow = 1; }
             cur = c0;
+            // Leave the descent once most of the warp is already waiting with a leaf: the stragglers resume next round,
+            // together with the lanes that will have finished their leaves (keeps both phases reasonably full).
+            if (__popc(__activemask()) <= CP_DESCENT_MIN_LANES) break;
         }
 
         // ------------------------------------------------------------------ phase 2: fp32 pre-test of the leaf's segments (all lanes holding a leaf)
@@ -143,8 +150,7 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
             const uint32_t count = (ref & 7u) + 1u;
             leafFirst = ref >> 3;
             for (uint32_t i = 0; i < count; ++i) {
-                const uint32_t gv = __ldg(prims + leafFirst + i);
-                const float4 v1 = __ldg(vtx + gv), v2 = __ldg(vtx + gv + 1);
+                const float4 v1 = __ldg(leafSeg + 2 * (size_t) (leafFirst + i)), v2 = __ldg(leafSeg + 2 * (size_t) (leafFirst + i) + 1);
                 if (STATS) tc.prims++;
                 // Conservative fp32 rejection (never rejects a hit the FP64 test would accept).  With n = d x a the ray and the
                 // axis line are closest at ray parameter tc and axis parameter sc; every point of the infinite cylinder the
@@ -163,7 +169,7 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
                     const float tcl = dot(cross(w, a), nrm) * inn;                        // ray parameter of closest approach
                     const float slack = 1.01f * R * rsin * rsqrtf(dd) + 1e-5f * fabsf(tcl);
                     if (tcl + slack < mint || tcl - slack > maxt) continue;               // outside the ray interval / behind the best hit
-                    if (vtx_bits(v1) & vtx_bits(v2) & 2u) {                                // both joints bend mildly: miter overshoot <= 2 r
+                    if ((vtx_bits(v1) & 6u) == 6u) {                                       // both joints bend mildly: miter overshoot <= 2 r
                         const float scl = dot(cross(w, d), nrm) * inn;                    // axis parameter in [0,1] of closest approach
                         const float sslack = 1.01f * (R * rsin + 2.0f * rad) * rsqrtf(aa) + 1e-5f * (1.0f + fabsf(scl));
                         if (scl + sslack < 0.0f || scl - sslack > 1.0f) continue;         // beyond the segment's ends
@@ -176,7 +182,7 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
         while (candMask) {
             const int ci = __ffs(candMask) - 1;
             candMask &= candMask - 1;
-            const uint32_t gv = __ldg(prims + leafFirst + ci);
+            const uint32_t gv = __float_as_uint(__ldg(leafSeg + 2 * (size_t) (leafFirst + ci) + 1).w);
             const float4 v1 = __ldg(vtx + gv), v2 = __ldg(vtx + gv + 1);
             const float4 v0 = __ldg(vtx + (gv > 0 ? gv - 1 : 0)), v3 = __ldg(vtx + gv + 2);
             float tmin = mint, tmax = maxt;
