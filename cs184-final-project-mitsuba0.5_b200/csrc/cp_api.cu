@@ -70,6 +70,7 @@ struct cudapath_ctx {
     Wavefront wf;
     uint32_t waveSize = 1u << 24; int collectStats = 0, profileStages = 0;
     int maxSplit = 8;
+    int sortRays = getenv("CUDAPATH_NO_SORT") ? 0 : 1;
     cudapath_stats stats{};
     float sceneAABB[6] = {0, 0, 0, 0, 0, 0};
 
@@ -403,6 +404,7 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
     cudaEvent_t e0, e1; CKA(cudaEventCreate(&e0)); CKA(cudaEventCreate(&e1));
     CKA(cudaEventRecord(e0, st));
     RenderStats rs; std::string err;
+    ctx->wf.sortRays = ctx->sortRays != 0;
     const bool ok = ctx->wf.render(ctx->scene, spp, seed, sample_begin, sample_end, film_dev, ctx->waveSize, ctx->collectStats != 0, ctx->profileStages != 0, st, rs, err);
     if (!ok) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(err); }
     CKA(cudaEventRecord(e1, st));

@@ -17,6 +17,7 @@
 #include "cp_traverse.cuh"
 #include "cp_wavefront.h"
 #include <vector>
+#include <cub/cub.cuh>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -25,26 +26,32 @@
 namespace cp {
 
 // ray source / sink of the closest-hit stage: the active path queue -> dense hit records
+// `perm` (optional) is the coherence order of the rays: slot k of the persistent counter traces queue entry perm[k]; results are
+// written back at the queue index, so the shading stage keeps reading and writing dense, unpermuted streams.
 struct PathIO {
-    PathQueue q; float4 *hitPT; uint32_t *hitPrim;
-    CP_D bool load(uint32_t i, V3 &o, V3 &d, float &mint, float &maxt) const {
+    PathQueue q; float4 *hitPT; uint32_t *hitPrim; const uint32_t *perm;
+    CP_D uint32_t slot(uint32_t i) const { return perm ? __ldg(perm + i) : i; }
+    CP_D bool load(uint32_t k, V3 &o, V3 &d, float &mint, float &maxt) const {
+        const uint32_t i = slot(k);
         const float4 ro = q.ro[i], rd = q.rd[i];
         o = V3(ro.x, ro.y, ro.z); d = V3(rd.x, rd.y, rd.z); mint = ro.w; maxt = rd.w;
         return !(q.id[i].y & F_INVALID);
     }
-    CP_D void store(uint32_t i, bool, const RayHit &h) const { hitPT[i] = make_float4(h.p.x, h.p.y, h.p.z, h.t); hitPrim[i] = h.gv; }
+    CP_D void store(uint32_t k, bool, const RayHit &h) const { const uint32_t i = slot(k); hitPT[i] = make_float4(h.p.x, h.p.y, h.p.z, h.t); hitPrim[i] = h.gv; }
 };
 // shadow stage: unoccluded rays add their emitter sample to the owning path (one shadow ray per path and bounce: no atomics)
 struct ShadowIO {
-    ShadowQueue sq; float4 *liAcc;
-    CP_D bool load(uint32_t i, V3 &o, V3 &d, float &mint, float &maxt) const {
+    ShadowQueue sq; float4 *liAcc; const uint32_t *perm;
+    CP_D uint32_t slot(uint32_t i) const { return perm ? __ldg(perm + i) : i; }
+    CP_D bool load(uint32_t k, V3 &o, V3 &d, float &mint, float &maxt) const {
+        const uint32_t i = slot(k);
         const float4 ro = sq.o[i], rd = sq.d[i];
         o = V3(ro.x, ro.y, ro.z); d = V3(rd.x, rd.y, rd.z); mint = ro.w; maxt = rd.w;
         return true;
     }
-    CP_D void store(uint32_t i, bool occluded, const RayHit &) const {
+    CP_D void store(uint32_t k, bool occluded, const RayHit &) const {
         if (occluded) return;
-        const float4 c = sq.c[i];
+        const float4 c = sq.c[slot(k)];
         if (c.x == 0.0f && c.y == 0.0f && c.z == 0.0f) return;
         const uint32_t pathId = __float_as_uint(c.w);
         float4 acc = liAcc[pathId];
@@ -66,6 +73,24 @@ __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) k_shadow(SceneDev S, Shado
     trace_persistent<true, STATS>(S, io, n, rayCounter, tc, ovf);
     if (ovf) *errFlag = 1;
     if (STATS) { atomicAdd(stats + 2, tc.nodes); atomicAdd(stats + 3, tc.prims); atomicAdd(stats + 7, tc.fullTests); }
+}
+
+// Coherence keys: 27-bit Morton code of the ray origin inside the scene bounds, then the direction octant.  Rays that start
+// close together (and head the same way) end up in the same warp, walk the same part of the tree and hit in L1/L2.
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+    v &= 0x3ffu; v = (v | (v << 16)) & 0x030000ffu; v = (v | (v << 8)) & 0x0300f00fu; v = (v | (v << 4)) & 0x030c30c3u; v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void k_ray_keys(const float4 *__restrict__ ro, const float4 *__restrict__ rd, uint32_t n, float3 smin, float3 sinv, uint32_t *keys, uint32_t *vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = ro[i], d = rd[i];
+    const uint32_t x = (uint32_t) fminf(fmaxf((o.x - smin.x) * sinv.x, 0.0f), 511.0f);
+    const uint32_t y = (uint32_t) fminf(fmaxf((o.y - smin.y) * sinv.y, 0.0f), 511.0f);
+    const uint32_t z = (uint32_t) fminf(fmaxf((o.z - smin.z) * sinv.z, 0.0f), 511.0f);
+    const uint32_t oct = (d.x < 0 ? 1u : 0u) | (d.y < 0 ? 2u : 0u) | (d.z < 0 ? 4u : 0u);
+    keys[i] = (((spread10(x) << 2) | (spread10(y) << 1) | spread10(z)) << 3) | oct;
+    vals[i] = i;
 }
 
 // persistent launch: enough CTAs to fill the machine, never more than the work needs
@@ -97,14 +122,34 @@ bool Wavefront::reserve(uint32_t waveSize, cudaStream_t stream, std::string &err
     CKW(cudaMallocAsync((void **) &counters, sizeof(uint32_t) * 4, stream));
     CKW(cudaMallocAsync((void **) &stats, sizeof(unsigned long long) * 8, stream));
     CKW(cudaMallocAsync((void **) &errFlag, sizeof(int), stream));
+    for (int k = 0; k < 2; ++k) {
+        CKW(cudaMallocAsync((void **) &sortKeys[k], sizeof(uint32_t) * (size_t) waveSize, stream));
+        CKW(cudaMallocAsync((void **) &sortVals[k], sizeof(uint32_t) * (size_t) waveSize, stream));
+    }
+    sortTempBytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sortTempBytes, sortKeys[0], sortKeys[1], sortVals[0], sortVals[1], (int) waveSize, 0, 30, stream);
+    CKW(cudaMallocAsync(&sortTemp, sortTempBytes, stream));
     CKW(cudaMallocHost(&hCounters, sizeof(uint32_t) * 4));
     capacity = waveSize;
     return true;
 }
+// sorts ray indices by coherence key; returns the permutation (device pointer) or nullptr when sorting is off / not worthwhile
+const uint32_t *Wavefront::coherence_order(const SceneDev &S, const float4 *ro, const float4 *rd, uint32_t n, cudaStream_t stream) {
+    if (!sortRays || n < 65536u) return nullptr;
+    const float3 smin = make_float3(S.sceneMin[0], S.sceneMin[1], S.sceneMin[2]);
+    const float3 sinv = make_float3(512.0f / fmaxf(S.sceneMax[0] - S.sceneMin[0], 1e-20f), 512.0f / fmaxf(S.sceneMax[1] - S.sceneMin[1], 1e-20f),
+                                    512.0f / fmaxf(S.sceneMax[2] - S.sceneMin[2], 1e-20f));
+    k_ray_keys<<<(n + 255) / 256, 256, 0, stream>>>(ro, rd, n, smin, sinv, sortKeys[0], sortVals[0]);
+    size_t need = sortTempBytes;
+    cub::DeviceRadixSort::SortPairs(sortTemp, need, sortKeys[0], sortKeys[1], sortVals[0], sortVals[1], (int) n, 0, 30, stream);
+    return sortVals[1];
+}
+
 void Wavefront::release() {
-    void *ptrs[] = {q[0].ro, q[0].rd, q[0].thr, q[0].id, q[1].ro, q[1].rd, q[1].thr, q[1].id, sq.o, sq.d, sq.c, hitPT, hitPrim, liAcc, counters, stats, errFlag};
+    void *ptrs[] = {sortKeys[0], sortKeys[1], sortVals[0], sortVals[1], sortTemp, q[0].ro, q[0].rd, q[0].thr, q[0].id, q[1].ro, q[1].rd, q[1].thr, q[1].id, sq.o, sq.d, sq.c, hitPT, hitPrim, liAcc, counters, stats, errFlag};
     for (void *p : ptrs) if (p) cudaFreeAsync(p, allocStream);
     q[0] = PathQueue(); q[1] = PathQueue(); sq = ShadowQueue();
+    sortKeys[0] = sortKeys[1] = sortVals[0] = sortVals[1] = nullptr; sortTemp = nullptr;
     if (hCounters) cudaFreeHost(hCounters);
     hitPT = nullptr; hitPrim = nullptr; liAcc = nullptr; counters = nullptr; stats = nullptr; errFlag = nullptr; hCounters = nullptr;
     capacity = 0;
@@ -144,12 +189,14 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
         wp.waveBase = base;
         begin(3); launch_raygen(S, wp, q[0], liAcc, n, stream); end();
         rs.launches++;
-        uint32_t nActive = n; int cur = 0;
+        uint32_t nActive = n; int cur = 0, bounce = 0;
         while (nActive > 0) {
             CKW(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 4, stream));
             begin(0);
             {
-                PathIO io{q[cur], hitPT, hitPrim};
+                // camera rays leave raygen in pixel order (already coherent); later bounces are re-ordered
+                const uint32_t *perm = bounce > 0 ? coherence_order(S, q[cur].ro, q[cur].rd, nActive, stream) : nullptr;
+                PathIO io{q[cur], hitPT, hitPrim, perm};
                 if (collectStats) k_intersect<true><<<persistent_grid((const void *) k_intersect<true>, nActive), 128, 0, stream>>>(S, io, nActive, counters + 2, stats, errFlag);
                 else k_intersect<false><<<persistent_grid((const void *) k_intersect<false>, nActive), 128, 0, stream>>>(S, io, nActive, counters + 2, stats, errFlag);
             }
@@ -163,13 +210,13 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
             const uint32_t nNext = hCounters[0], nShadow = hCounters[1];
             if (nShadow) {
                 begin(2);
-                ShadowIO io{sq, liAcc};
+                ShadowIO io{sq, liAcc, coherence_order(S, sq.o, sq.d, nShadow, stream)};
                 if (collectStats) k_shadow<true><<<persistent_grid((const void *) k_shadow<true>, nShadow), 128, 0, stream>>>(S, io, nShadow, counters + 3, stats, errFlag);
                 else k_shadow<false><<<persistent_grid((const void *) k_shadow<false>, nShadow), 128, 0, stream>>>(S, io, nShadow, counters + 3, stats, errFlag);
                 end();
                 rs.launches++; rs.shadowRays += nShadow;
             }
-            cur ^= 1; nActive = nNext;
+            cur ^= 1; nActive = nNext; bounce++;
         }
         begin(4); launch_splat(S, wp, liAcc, n, d_film, stats + 5, stream); end();
         rs.launches++;

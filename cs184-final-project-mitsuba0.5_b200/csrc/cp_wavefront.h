@@ -39,6 +39,10 @@ struct Wavefront {
     uint32_t *counters = nullptr, *hCounters = nullptr;
     unsigned long long *stats = nullptr;
     int *errFlag = nullptr;
+    uint32_t *sortKeys[2] = {nullptr, nullptr}, *sortVals[2] = {nullptr, nullptr};
+    void *sortTemp = nullptr; size_t sortTempBytes = 0;
+    bool sortRays = true;
+    const uint32_t *coherence_order(const SceneDev &S, const float4 *ro, const float4 *rd, uint32_t n, cudaStream_t stream);
     uint32_t capacity = 0;
     cudaStream_t allocStream = nullptr;
     bool reserve(uint32_t waveSize, cudaStream_t stream, std::string &err);
