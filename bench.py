@@ -57,11 +57,13 @@ class ClockSampler(threading.Thread):
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
-                self.samples.append([x.strip() for x in line.split(',')])
+                self.samples.append((time.time(), [x.strip() for x in line.split(',')]))
         except Exception:
             pass
 
-    def finish(self):
+    def finish(self, t_begin=None, t_end=None):
+        """Median SM clock / throttle reasons of the samples taken inside [t_begin, t_end] (the timed region); when the region is
+        shorter than the sampling period, of the samples taken under load since the sampler started (warm-up included)."""
         self.stop_flag = True
         if self.proc:
             try:
@@ -69,7 +71,8 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
         sm, mx, reasons = [], [], set()
-        for s in self.samples:
+        inside = [s for (t, s) in self.samples if t_begin is not None and t_begin <= t <= t_end + 0.25]
+        for s in (inside if len(inside) >= 2 else [s for (_, s) in self.samples]):
             try:
                 sm.append(float(s[1])); mx.append(float(s[2]))
                 for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[4:8]):
@@ -221,6 +224,7 @@ def main():
         if world > 1:
             dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
 
+    sampler = ClockSampler(local); sampler.start()
     for w in range(args.warmup):
         step(100 + w)
     # one profiled pass (stage timing by CUDA events around every launch) and one counting pass (nodes / primitives) -- both untimed
@@ -230,10 +234,10 @@ def main():
     step(7); torch.cuda.synchronize(); cnt = ctx.stats()
     ctx.set_options(wave_size=args.wave)
 
-    sampler = ClockSampler(local); sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    t_begin = time.time()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     launches = 0; rays = 0; shadow = 0
     e0.record(stream)
@@ -245,7 +249,7 @@ def main():
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.finish()
+    clocks = sampler.finish(t_begin, time.time())
     t = torch.tensor([ms, float(rays), float(shadow), float(launches)], dtype=torch.float64, device='cuda')
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
