@@ -23,7 +23,7 @@ class CudapathError(RuntimeError):
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ('paths', 'rays', 'shadow_rays', 'kernel_launches', 'bounces', 'nodes_visited', 'prims_tested',
                                                'shadow_nodes_visited', 'shadow_prims_tested',
-                                               'unsupported_filtered_lookups', 'dropped_samples', 'segments', 'bvh_nodes', 'bvh_references')] + \
+                                               'unsupported_filtered_lookups', 'dropped_samples', 'segments', 'bvh_nodes', 'bvh_references', 'triangles')] + \
                [(n, ctypes.c_double) for n in ('build_ms', 'render_ms', 'intersect_ms', 'shade_ms', 'shadow_ms', 'raygen_ms', 'splat_ms')] + \
                [(n, ctypes.c_uint64) for n in ('intersect_launches', 'shade_launches', 'shadow_launches')]
 
@@ -140,7 +140,19 @@ class Context:
             return _check(self._L.cudapath_add_bsdf_marschner(self._h, ctypes.c_float(ior(props.get('intIOR', 'bk7'))), ctypes.c_float(ior(props.get('extIOR', 'air'))),
                                                               _p(d), _p(s), ctypes.c_float(props.get('alpha', 0.1)), _DISTRIBUTIONS[distr],
                                                               1 if props.get('nonlinear', False) else 0))
-        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner)' % type)
+        if type in ('diffuse', 'twosided'):
+            # `diffuse` with a constant reflectance (src/bsdfs/diffuse.cpp:70-103); type 'twosided' = <bsdf type="twosided"><bsdf type="diffuse"/></bsdf>
+            r = _f32(np.broadcast_to(props.get('reflectance', 0.5), 3))
+            return _check(self._L.cudapath_add_bsdf_diffuse(self._h, _p(r), 1 if (type == 'twosided' or props.get('twoSided', False)) else 0))
+        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner, diffuse, twosided)' % type)
+
+    def add_mesh(self, xyz, indices, bsdf_id, normals=None):
+        """Triangle mesh (TriMesh positions / optional vertex normals / index triples); joins the fibers in the device BVH."""
+        xyz = _f32(xyz).reshape(-1, 3); idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
+        nrm = None if normals is None else _f32(normals).reshape(-1, 3)
+        if nrm is not None and len(nrm) != len(xyz):
+            raise CudapathError('normals must have one entry per vertex')
+        return _check(self._L.cudapath_add_mesh(self._h, _p(xyz), None if nrm is None else _p(nrm), ctypes.c_uint32(len(xyz)), _p(idx), ctypes.c_uint32(len(idx)), int(bsdf_id)))
 
     def add_hair(self, xyz, starts_fiber, radius, bsdf_id):
         xyz = _f32(xyz).reshape(-1, 3); st = np.ascontiguousarray(starts_fiber, dtype=np.uint8)
@@ -302,11 +314,7 @@ def scene_from_description(name, device=0, scale=1.0, overrides=None, data_dir=N
     from . import scenes
     sc = dict(scenes.SCENES[name]); sc.update(overrides or {})
     ctx = Context(device, data_dir)
-    for sh in sc['shapes']:
-        b = dict(sh['bsdf']); btype = b.pop('type'); b.pop('id', None)
-        bid = ctx.add_bsdf(btype, **b)
-        xyz, starts = scenes.generate(sh, scale)
-        ctx.add_hair(xyz, starts, sh['radius'], bid)
+    scenes.add_shapes(ctx, sc, scale)
     ctx.set_sunsky(**scenes.sunsky_params(name))
     ctx.set_camera(np.array(sc['camera'], np.float32).reshape(4, 4), sc['fov'], width=sc['width'], height=sc['height'])
     ctx.set_film('tent')

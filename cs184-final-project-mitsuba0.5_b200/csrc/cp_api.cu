@@ -54,9 +54,11 @@ struct cudapath_ctx {
     std::string dataDir;
     std::vector<BsdfHost> bsdfs;
     // per shape: raw caller arrays staged on the device (xyz fp32 triples + starts bytes); packed into `d_vtx` by build()
-    struct Staged { float *xyz = nullptr; uint8_t *starts = nullptr; uint32_t n = 0; };
+    // (meshes: xyz / optional normals fp32 triples + shape-local uint32 index triples)
+    struct Staged { float *xyz = nullptr; uint8_t *starts = nullptr; uint32_t n = 0; float *nrm = nullptr; uint32_t *idx = nullptr; uint32_t nTris = 0; };
     std::vector<Staged> staged;
-    uint32_t vtxTotal = 0;
+    uint32_t vtxTotal = 0, meshVtxTotal = 0, triTotal = 0;
+    float4 *d_meshPos = nullptr, *d_meshNrm = nullptr, *d_triAccel = nullptr; uint32_t *d_meshIdx = nullptr;
     std::vector<ShapeDev> shapes;
     EnvHost env; EnvTables envTables;
     CamHost cam;
@@ -76,13 +78,15 @@ struct cudapath_ctx {
 
     void freeBuilt() {
         cudaFree(d_vtx); cudaFree(d_shapes); cudaFree(d_bsdfs); cudaFree((void *) bvh.nodes); cudaFree((void *) bvh.prims); cudaFree((void *) bvh.leafSeg);
+        cudaFree(d_meshPos); cudaFree(d_meshNrm); cudaFree(d_triAccel); cudaFree(d_meshIdx);
+        d_meshPos = d_meshNrm = d_triAccel = nullptr; d_meshIdx = nullptr;
         cudaFree(envTables.texels); cudaFree(envTables.cdfCols); cudaFree(envTables.cdfRows); cudaFree(envTables.rowWeights);
         d_vtx = nullptr; d_shapes = nullptr; d_bsdfs = nullptr; bvh = BVHDev(); envTables = EnvTables(); built = false;
     }
     ~cudapath_ctx() {
         cudaSetDevice(device);
         freeBuilt();
-        for (auto &st : staged) { cudaFree(st.xyz); cudaFree(st.starts); }
+        for (auto &st : staged) { cudaFree(st.xyz); cudaFree(st.starts); cudaFree(st.nrm); cudaFree(st.idx); }
         for (auto &b : bsdfs) { cudaFree(b.tables.tab); cudaFree(b.tables.cdf); cudaFree(b.tables.sums); cudaFree(b.tables.pdf); cudaFree(b.rt); }
         wf.release();
         if (stream) cudaStreamDestroy(stream);
@@ -171,6 +175,43 @@ int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior,
     b.dev.tab = b.tables.tab; b.dev.cdf = b.tables.cdf; b.dev.sums = b.tables.sums; b.dev.rt = b.rt;
     ctx->bsdfs.push_back(b); ctx->built = false;
     return (int) ctx->bsdfs.size() - 1;
+}
+
+int cudapath_add_bsdf_diffuse(cudapath_ctx *ctx, const float reflectance[3], int two_sided) {
+    if (!ctx || !reflectance) return fail("null argument");
+    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    V3 r(reflectance[0], reflectance[1], reflectance[2]);
+    { const float mx = maxc(r); if (mx > 1.0f) r = r * (0.99f * (1.0f / mx)); }           // ensureEnergyConservation, bsdf.cpp:88-113
+    b.dev.kind = 2; b.dev.twoSided = two_sided ? 1 : 0; b.dev.diffuse = r; b.dev.specular = V3(0.0f);
+    ctx->bsdfs.push_back(b); ctx->built = false;
+    return (int) ctx->bsdfs.size() - 1;
+}
+
+int cudapath_add_mesh(cudapath_ctx *ctx, const float *xyz, const float *normals, uint32_t n_vertices, const uint32_t *indices, uint32_t n_triangles, int bsdf_id) {
+    if (!ctx || !xyz || !indices) return fail("null argument");
+    if (bsdf_id < 0 || bsdf_id >= (int) ctx->bsdfs.size()) return fail("mesh references an unknown bsdf id");
+    if (n_vertices == 0 || n_triangles == 0) return fail("mesh needs at least one vertex and one triangle");
+    if (ctx->shapes.size() >= (1u << 23)) return fail("too many shapes");
+    if ((uint64_t) ctx->triTotal + n_triangles >= (1ull << 28) || (uint64_t) ctx->meshVtxTotal + n_vertices >= 0xfffffff0ull) return fail("too many triangles");
+    for (size_t i = 0; i < 3 * (size_t) n_triangles; ++i) if (indices[i] >= n_vertices) return fail("mesh index out of range");
+    CKA(cudaSetDevice(ctx->device));
+    ShapeDev sd; std::memset(&sd, 0, sizeof(sd));
+    sd.kind = 1; sd.bsdf = bsdf_id; sd.vertexOffset = ctx->meshVtxTotal; sd.vertexCount = n_vertices; sd.triOffset = ctx->triTotal; sd.triCount = n_triangles;
+    sd.hasNormals = normals ? 1 : 0;
+    cudapath_ctx::Staged st; st.n = n_vertices; st.nTris = n_triangles;
+    CKA(cudaMallocAsync((void **) &st.xyz, sizeof(float) * 3 * (size_t) n_vertices, ctx->stream));
+    CKA(cudaMemcpyAsync(st.xyz, xyz, sizeof(float) * 3 * (size_t) n_vertices, cudaMemcpyHostToDevice, ctx->stream));
+    if (normals) {
+        CKA(cudaMallocAsync((void **) &st.nrm, sizeof(float) * 3 * (size_t) n_vertices, ctx->stream));
+        CKA(cudaMemcpyAsync(st.nrm, normals, sizeof(float) * 3 * (size_t) n_vertices, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CKA(cudaMallocAsync((void **) &st.idx, sizeof(uint32_t) * 3 * (size_t) n_triangles, ctx->stream));
+    CKA(cudaMemcpyAsync(st.idx, indices, sizeof(uint32_t) * 3 * (size_t) n_triangles, cudaMemcpyHostToDevice, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    ctx->staged.push_back(st);
+    ctx->meshVtxTotal += n_vertices; ctx->triTotal += n_triangles;
+    ctx->shapes.push_back(sd); ctx->built = false;
+    return (int) ctx->shapes.size() - 1;
 }
 
 int cudapath_add_hair(cudapath_ctx *ctx, const float *xyz, const uint8_t *starts, uint32_t n, float radius, int bsdf_id) {
@@ -296,12 +337,30 @@ int cudapath_build(cudapath_ctx *ctx) {
     // geometry
     CKA(cudaMalloc(&ctx->d_vtx, sizeof(float4) * ((size_t) ctx->vtxTotal + 4)));
     CKA(cudaMemsetAsync(ctx->d_vtx, 0, sizeof(float4) * ((size_t) ctx->vtxTotal + 4), ctx->stream));
-    for (size_t i = 0; i < ctx->staged.size(); ++i)
-        pack_vertices(ctx->staged[i].xyz, ctx->staged[i].starts, ctx->staged[i].n, (uint32_t) i, ctx->d_vtx + ctx->shapes[i].vertexOffset, ctx->stream);
+    MeshDev mesh; std::memset(&mesh, 0, sizeof(mesh));
+    if (ctx->triTotal) {
+        CKA(cudaMalloc(&ctx->d_meshPos, sizeof(float4) * (size_t) ctx->meshVtxTotal)); CKA(cudaMalloc(&ctx->d_meshNrm, sizeof(float4) * (size_t) ctx->meshVtxTotal));
+        CKA(cudaMalloc(&ctx->d_meshIdx, sizeof(uint32_t) * 3 * (size_t) ctx->triTotal)); CKA(cudaMalloc(&ctx->d_triAccel, sizeof(float4) * 3 * (size_t) ctx->triTotal));
+        mesh.triAccel = ctx->d_triAccel; mesh.pos = ctx->d_meshPos; mesh.nrm = ctx->d_meshNrm; mesh.idx = ctx->d_meshIdx;
+        mesh.triCount = ctx->triTotal; mesh.vertCount = ctx->meshVtxTotal;
+    }
+    int hairShapes = 0;
+    for (size_t i = 0; i < ctx->staged.size(); ++i) {
+        const cudapath_ctx::Staged &st = ctx->staged[i];
+        const ShapeDev &sd = ctx->shapes[i];
+        if (sd.kind == 1) {
+            pack_mesh(st.xyz, st.nrm, st.n, ctx->d_meshPos + sd.vertexOffset, ctx->d_meshNrm + sd.vertexOffset, ctx->stream);
+            build_tri_accel(st.idx, st.nTris, sd.vertexOffset, (uint32_t) i, ctx->d_meshPos, ctx->d_meshIdx + 3 * (size_t) sd.triOffset,
+                            ctx->d_triAccel + 3 * (size_t) sd.triOffset, ctx->stream);
+        } else {
+            pack_vertices(st.xyz, st.starts, st.n, (uint32_t) i, ctx->d_vtx + sd.vertexOffset, ctx->stream);
+            hairShapes++;
+        }
+    }
     CKA(cudaMalloc(&ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size()));
     CKA(cudaMemcpyAsync(ctx->d_shapes, ctx->shapes.data(), sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyHostToDevice, ctx->stream));
     BuildInfo info;
-    if (!build_bvh(ctx->d_vtx, ctx->vtxTotal, ctx->d_shapes, (int) ctx->shapes.size(), ctx->maxSplit, ctx->stream, ctx->bvh, info, err)) return fail(err);
+    if (!build_bvh(ctx->d_vtx, ctx->vtxTotal, ctx->d_shapes, (int) ctx->shapes.size(), mesh, ctx->maxSplit, ctx->stream, ctx->bvh, info, err)) return fail(err);
     CKA(cudaMemcpyAsync(ctx->shapes.data(), ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     // bsdfs
@@ -313,6 +372,7 @@ int cudapath_build(cudapath_ctx *ctx) {
     std::memset(&S, 0, sizeof(S));
     S.vtx = ctx->d_vtx; S.vtxCount = ctx->vtxTotal; S.shapes = ctx->d_shapes; S.shapeCount = (int) ctx->shapes.size();
     S.bsdfs = ctx->d_bsdfs; S.bsdfCount = (int) devs.size(); S.bvh = ctx->bvh; S.integ = ctx->integ;
+    S.mesh = mesh; S.clipPerShape = (hairShapes > 1 || ctx->triTotal > 0) ? 1 : 0;
     for (int k = 0; k < 3; ++k) { S.sceneMin[k] = INFINITY; S.sceneMax[k] = -INFINITY; }
     for (auto &sh : ctx->shapes) for (int k = 0; k < 3; ++k) { S.sceneMin[k] = std::min(S.sceneMin[k], sh.bmin[k]); S.sceneMax[k] = std::max(S.sceneMax[k], sh.bmax[k]); }
     for (int k = 0; k < 3; ++k) { ctx->sceneAABB[k] = S.sceneMin[k]; ctx->sceneAABB[3 + k] = S.sceneMax[k]; }
@@ -391,7 +451,7 @@ int cudapath_build(cudapath_ctx *ctx) {
     CKA(cudaStreamSynchronize(ctx->stream));
     float ms = 0; CKA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    ctx->stats.build_ms = ms; ctx->stats.segments = info.segments; ctx->stats.bvh_nodes = info.nodes; ctx->stats.bvh_references = info.references;
+    ctx->stats.build_ms = ms; ctx->stats.segments = info.segments; ctx->stats.triangles = info.triangles; ctx->stats.bvh_nodes = info.nodes; ctx->stats.bvh_references = info.references;
     ctx->built = true;
     return 0;
 }

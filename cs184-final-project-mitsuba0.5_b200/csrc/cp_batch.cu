@@ -17,7 +17,7 @@ namespace cp {
 // ray source / sink over flat fp32 arrays
 struct BatchIO {
     const float *o, *d, *mint, *maxt; int32_t *shape; uint32_t *prim; float *tOut; float *rec;
-    const float4 *vtx; const ShapeDev *shapes;
+    const float4 *vtx; const ShapeDev *shapes; const float4 *triAccel;
     CP_D bool load(uint32_t i, V3 &ro, V3 &rd, float &mn, float &mx) const {
         ro = V3(o[3 * (size_t) i], o[3 * (size_t) i + 1], o[3 * (size_t) i + 2]); rd = V3(d[3 * (size_t) i], d[3 * (size_t) i + 1], d[3 * (size_t) i + 2]);
         mn = mint[i]; mx = maxt[i];
@@ -25,8 +25,14 @@ struct BatchIO {
     }
     CP_D void store(uint32_t i, bool hit, const RayHit &h) const {
         if (hit) {
-            const uint32_t sh = vtx_shape(__ldg(vtx + h.gv));
-            shape[i] = (int32_t) sh; prim[i] = h.gv - shapes[sh].vertexOffset; tOut[i] = h.t;
+            if (h.gv & CP_TRI_FLAG) {   // triangle: shape / primitive index come from the TriAccel record (skdtree.h:296-299)
+                const float4 C = __ldg(triAccel + 3 * (size_t) (h.gv & ~CP_TRI_FLAG) + 2);
+                shape[i] = (int32_t) __float_as_uint(C.z); prim[i] = __float_as_uint(C.w);
+            } else {
+                const uint32_t sh = vtx_shape(__ldg(vtx + h.gv));
+                shape[i] = (int32_t) sh; prim[i] = h.gv - shapes[sh].vertexOffset;
+            }
+            tOut[i] = h.t;
             if (rec) {   // raw hit for the (un-fused) record kernel in cp_batch_shade.cu: stored hit point + global primitive
                 float *p = rec + 15 * (size_t) i;
                 p[0] = h.p.x; p[1] = h.p.y; p[2] = h.p.z; p[3] = __uint_as_float(h.gv);
@@ -37,10 +43,10 @@ struct BatchIO {
         }
     }
 };
-template <bool ANY, bool STATS>
+template <bool ANY, bool STATS, bool MESH>
 __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) k_intersect_batch(SceneDev S, BatchIO io, uint32_t n, uint32_t *rayCounter, unsigned long long *stats, int *errFlag) {
     TraceCounters tc = {0, 0, 0}; int ovf = 0;
-    trace_persistent<ANY, STATS>(S, io, n, rayCounter, tc, ovf);
+    trace_persistent<ANY, STATS, MESH>(S, io, n, rayCounter, tc, ovf);
     if (ovf) *errFlag = 1;
     if (STATS) { atomicAdd(stats + 0, tc.nodes); atomicAdd(stats + 1, tc.prims); }
 }
@@ -57,14 +63,15 @@ bool intersect_batch(const SceneDev &S, uint64_t n, const float *d_o, const floa
     int *d_ctl = nullptr;   // [0] overflow flag, [1] persistent ray counter
     CKB(cudaMalloc(&d_ctl, 2 * sizeof(int))); CKB(cudaMemsetAsync(d_ctl, 0, 2 * sizeof(int), s));
     const unsigned need = (unsigned) ((n + 127) / 128), g = need < (unsigned) numSMs * 8u ? need : (unsigned) numSMs * 8u;
-    BatchIO io{d_o, d_d, d_mint, d_maxt, d_shape, d_prim, d_t, anyHit ? nullptr : d_rec, S.vtx, S.shapes};
+    BatchIO io{d_o, d_d, d_mint, d_maxt, d_shape, d_prim, d_t, anyHit ? nullptr : d_rec, S.vtx, S.shapes, S.mesh.triAccel};
     uint32_t *ctr = (uint32_t *) (d_ctl + 1);
-    if (anyHit) {
-        if (stats) k_intersect_batch<true, true><<<g, 128, 0, s>>>(S, io, (uint32_t) n, ctr, d_stats, d_ctl);
-        else k_intersect_batch<true, false><<<g, 128, 0, s>>>(S, io, (uint32_t) n, ctr, d_stats, d_ctl);
-    } else {
-        if (stats) k_intersect_batch<false, true><<<g, 128, 0, s>>>(S, io, (uint32_t) n, ctr, d_stats, d_ctl);
-        else k_intersect_batch<false, false><<<g, 128, 0, s>>>(S, io, (uint32_t) n, ctr, d_stats, d_ctl);
+#define CP_LAUNCH_BATCH(AN, ST, ME) k_intersect_batch<AN, ST, ME><<<g, 128, 0, s>>>(S, io, (uint32_t) n, ctr, d_stats, d_ctl)
+    const int variant = (anyHit ? 4 : 0) | (stats ? 2 : 0) | (S.mesh.triCount > 0 ? 1 : 0);
+    switch (variant) {
+        case 0: CP_LAUNCH_BATCH(false, false, false); break; case 1: CP_LAUNCH_BATCH(false, false, true); break;
+        case 2: CP_LAUNCH_BATCH(false, true, false); break;  case 3: CP_LAUNCH_BATCH(false, true, true); break;
+        case 4: CP_LAUNCH_BATCH(true, false, false); break;  case 5: CP_LAUNCH_BATCH(true, false, true); break;
+        case 6: CP_LAUNCH_BATCH(true, true, false); break;   default: CP_LAUNCH_BATCH(true, true, true); break;
     }
     if (d_rec && !anyHit) fill_records_batch(S, n, d_d, d_shape, d_rec, s);
     int herr = 0;

@@ -67,7 +67,8 @@ __global__ void k_fill_records(SceneDev S, uint64_t n, const float *__restrict__
     float *p = rec + 15 * i;
     const uint32_t gv = __float_as_uint(p[3]);
     HitRecord r;
-    fill_intersection(__ldg(S.vtx + gv), __ldg(S.vtx + gv + 1), S.shapes[shape[i]].radius, V3(p[0], p[1], p[2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), r);
+    if (gv & CP_TRI_FLAG) fill_intersection_mesh(S.mesh, S.shapes, gv & ~CP_TRI_FLAG, p[0], p[1], V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), r);
+    else fill_intersection(__ldg(S.vtx + gv), __ldg(S.vtx + gv + 1), S.shapes[shape[i]].radius, V3(p[0], p[1], p[2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), r);
     p[0] = r.p.x; p[1] = r.p.y; p[2] = r.p.z; p[3] = r.sh.n.x; p[4] = r.sh.n.y; p[5] = r.sh.n.z;
     p[6] = r.sh.s.x; p[7] = r.sh.s.y; p[8] = r.sh.s.z; p[9] = r.sh.t.x; p[10] = r.sh.t.y; p[11] = r.sh.t.z;
     p[12] = r.wi.x; p[13] = r.wi.y; p[14] = r.wi.z;

@@ -18,7 +18,8 @@
 namespace cp {
 
 struct BsdfDev {
-    int kind;            // 0 = kajiyakay, 1 = marschner
+    int kind;            // 0 = kajiyakay, 1 = marschner, 2 = diffuse (constant reflectance in `diffuse`; meshes)
+    int twoSided;        // kind 2 only: wrapped in `twosided` with the same nested BRDF on both sides
     // kajiyakay (kajiyakay.cpp:60-107) / marschner diffuse colour
     V3 diffuse, specular;
     float exponent;
@@ -221,11 +222,36 @@ CP_D BsdfSampleOut ma_sample(const BsdfDev &b, const V3 &wi, float sx, float sy)
     return r;
 }
 
+// ------------------------------------------------------------------------------------------ SmoothDiffuse (+ TwoSided)
+// src/bsdfs/diffuse.cpp:109-156 with a constant reflectance; src/bsdfs/twosided.cpp:101-181 when b.twoSided
+CP_D V3 df_eval(const BsdfDev &b, V3 wi, V3 wo) {
+    if (b.twoSided && wi.z <= 0) { wi.z *= -1; wo.z *= -1; }
+    if (wi.z <= 0 || wo.z <= 0) return V3(0.0f);
+    return b.diffuse * (kInvPi * wo.z);
+}
+CP_D float df_pdf(const BsdfDev &b, V3 wi, V3 wo) {
+    if (b.twoSided && wi.z <= 0) { wi.z *= -1; wo.z *= -1; }
+    if (wi.z <= 0 || wo.z <= 0) return 0.0f;
+    return kInvPi * wo.z;
+}
+CP_D BsdfSampleOut df_sample(const BsdfDev &b, V3 wi, float sx, float sy) {
+    BsdfSampleOut r; r.wo = V3(0.0f); r.weight = V3(0.0f); r.pdf = 0.0f; r.type = 0; r.component = -1;
+    bool flipped = false;
+    if (b.twoSided && wi.z < 0) { wi.z *= -1; flipped = true; }
+    if (wi.z <= 0) return r;
+    r.wo = squareToCosineHemisphere(sx, sy);
+    r.component = 0; r.type = EDiffuseReflection;
+    r.pdf = kInvPi * r.wo.z;
+    r.weight = b.diffuse;
+    if (flipped && !isZero(r.weight) && r.pdf != 0) { r.wo.z *= -1; r.component += 1; }
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------ dispatch
-CP_D V3 bsdf_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) { return b.kind == 0 ? kk_eval(b, wi, wo) : ma_eval(b, wi, wo); }
-CP_D float bsdf_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) { return b.kind == 0 ? kk_pdf(b, wi, wo) : 1.0f; }
+CP_D V3 bsdf_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) { return b.kind == 0 ? kk_eval(b, wi, wo) : b.kind == 1 ? ma_eval(b, wi, wo) : df_eval(b, wi, wo); }
+CP_D float bsdf_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) { return b.kind == 0 ? kk_pdf(b, wi, wo) : b.kind == 1 ? 1.0f : df_pdf(b, wi, wo); }
 CP_D BsdfSampleOut bsdf_sample(const BsdfDev &b, const V3 &wi, float sx, float sy) {
-    return b.kind == 0 ? kk_sample(b, wi, sx, sy) : ma_sample(b, wi, sx, sy);
+    return b.kind == 0 ? kk_sample(b, wi, sx, sy) : b.kind == 1 ? ma_sample(b, wi, sx, sy) : df_sample(b, wi, sx, sy);
 }
 
 } // namespace cp

@@ -1,4 +1,4 @@
-// cp_bvh.cu -- device-side BVH construction over hair segments (sm_100a).
+// cp_bvh.cu -- device-side BVH construction over hair segments and triangles (sm_100a).
 //
 // Replaces HairKDTree / ShapeKDTree construction (src/shapes/hair.cpp:108-159,
 // include/mitsuba/render/gkdtree.h:958-2400, src/librender/skdtree.cpp:68-110) for this path.  The SAH
@@ -115,6 +115,28 @@ __global__ void k_segment_bounds(const float4 *__restrict__ vtx, const uint32_t 
     }
 }
 
+// per triangle: exact vertex box -> per-shape union (Triangle::getAABB, triangle.h:40-45); one padded BVH reference
+__global__ void k_tri_bounds(MeshDev mesh, uint32_t refBase, ShapeDev *shapes, float *leafBox, uint32_t *refPrim, float *centroidBox) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= mesh.triCount) return;
+    const float4 p0 = mesh.pos[mesh.idx[3 * (size_t) j]], p1 = mesh.pos[mesh.idx[3 * (size_t) j + 1]], p2 = mesh.pos[mesh.idx[3 * (size_t) j + 2]];
+    float bmin[3] = {fminf(fminf(p0.x, p1.x), p2.x), fminf(fminf(p0.y, p1.y), p2.y), fminf(fminf(p0.z, p1.z), p2.z)};
+    float bmax[3] = {fmaxf(fmaxf(p0.x, p1.x), p2.x), fmaxf(fmaxf(p0.y, p1.y), p2.y), fmaxf(fmaxf(p0.z, p1.z), p2.z)};
+    ShapeDev &sd = shapes[__float_as_uint(mesh.triAccel[3 * (size_t) j + 2].z)];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { atomicMinFloat(&sd.bmin[k], bmin[k]); atomicMaxFloat(&sd.bmax[k], bmax[k]); }
+    // A box only decides which tests run: pad it so that hits on the rim of a (possibly flat) box survive the fp32 slab test.
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float pad = 1e-5f * (bmax[k] - bmin[k]) + 2e-6f * fmaxf(fabsf(bmin[k]), fabsf(bmax[k])) + 1e-30f;
+        bmin[k] -= pad; bmax[k] += pad;
+        leafBox[6 * (size_t) (refBase + j) + k] = bmin[k]; leafBox[6 * (size_t) (refBase + j) + 3 + k] = bmax[k];
+        const float c = 0.5f * (bmin[k] + bmax[k]);
+        atomicMinFloat(&centroidBox[k], c); atomicMaxFloat(&centroidBox[3 + k], c);
+    }
+    refPrim[refBase + j] = CP_TRI_FLAG | j;
+}
+
 __device__ __forceinline__ uint64_t expandBits21(uint64_t v) {
     v &= 0x1fffffull;
     v = (v | v << 32) & 0x1f00000000ffffull;
@@ -190,6 +212,11 @@ __global__ void k_leaf_records(const float4 *__restrict__ vtx, const uint32_t *_
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t gv = sortedPrims[i];
+    if (gv & CP_TRI_FLAG) {   // triangle reference: bit 3 of the flags, id slot = CP_TRI_FLAG | triangle index (tested from MeshDev::triAccel)
+        leafSeg[2 * (size_t) i] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(8u));
+        leafSeg[2 * (size_t) i + 1] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(gv));
+        return;
+    }
     const float4 v1 = vtx[gv], v2 = vtx[gv + 1];
     const uint32_t flags = __float_as_uint(v1.w) | ((__float_as_uint(v2.w) & 2u) ? 4u : 0u);
     leafSeg[2 * (size_t) i] = make_float4(v1.x, v1.y, v1.z, __uint_as_float(flags));
@@ -314,7 +341,7 @@ struct Scratch {   // stream-ordered scratch allocations (returned to the pool, 
 
 // Builds the BVH for the vertex array already resident on the device.  On success the caller owns
 // out.nodes / out.prims (cudaFree).  `shapes` is updated in place with the per-shape bounds.
-bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, int maxSplit, cudaStream_t stream,
+bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, const MeshDev &mesh, int maxSplit, cudaStream_t stream,
                BVHDev &out, BuildInfo &info, std::string &err) {
     out = BVHDev(); info = BuildInfo();
     Scratch S(stream);
@@ -344,8 +371,8 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
         CK(cudaStreamSynchronize(stream));
         nSeg = (uint32_t) h;
     }
-    info.segments = nSeg;
-    if (nSeg == 0) { err = "scene contains no hair segments"; return false; }
+    info.segments = nSeg; info.triangles = mesh.triCount;
+    if (nSeg == 0 && mesh.triCount == 0) { err = "scene contains no hair segments and no triangles"; return false; }
     if (nSeg >= (1u << 28)) { err = "too many segments for the leaf encoding"; return false; }
 
     // references: every segment contributes split_count() boxes
@@ -354,7 +381,7 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
     {
         CK(S.alloc(&d_counts, sizeof(uint32_t) * (size_t) (nSeg + 1))); CK(S.alloc(&d_offsets, sizeof(uint32_t) * (size_t) (nSeg + 1)));
         CK(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t) (nSeg + 1), stream));
-        k_split_counts<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_vtx, d_segs, nSeg, d_shapes, maxSplit, d_counts);
+        if (nSeg) k_split_counts<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_vtx, d_segs, nSeg, d_shapes, maxSplit, d_counts);
         void *d_temp3 = nullptr;
         CK(cub::DeviceScan::ExclusiveSum(nullptr, need, d_counts, d_offsets, (int) nSeg + 1, stream));
         CK(S.alloc(&d_temp3, need));
@@ -362,11 +389,14 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
         CK(cudaMemcpyAsync(&nRef, d_offsets + nSeg, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
     }
+    const uint32_t nHairRef = nRef;
+    nRef += mesh.triCount;     // one reference per triangle, after the hair references
     info.references = nRef;
-    if (nRef >= (1u << 28)) { err = "too many BVH references for the leaf encoding"; return false; }
+    if ((uint64_t) nHairRef + mesh.triCount >= (1u << 28)) { err = "too many BVH references for the leaf encoding"; return false; }
     CK(S.alloc(&d_leafBox, sizeof(float) * 6 * (size_t) nRef));
     CK(S.alloc(&d_refPrim, sizeof(uint32_t) * (size_t) nRef));
-    k_segment_bounds<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_vtx, d_segs, nSeg, d_offsets, maxSplit, d_shapes, d_leafBox, d_refPrim, d_cbox);
+    if (nSeg) k_segment_bounds<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_vtx, d_segs, nSeg, d_offsets, maxSplit, d_shapes, d_leafBox, d_refPrim, d_cbox);
+    if (mesh.triCount) k_tri_bounds<<<(mesh.triCount + B - 1) / B, B, 0, stream>>>(mesh, nHairRef, d_shapes, d_leafBox, d_refPrim, d_cbox);
     nSeg = nRef;   // from here on the builder works on references
     CK(S.alloc(&d_keys, sizeof(uint64_t) * (size_t) nSeg)); CK(S.alloc(&d_keysSorted, sizeof(uint64_t) * (size_t) nSeg));
     CK(S.alloc(&d_ids, sizeof(uint32_t) * (size_t) nSeg)); CK(S.alloc(&d_idsSorted, sizeof(uint32_t) * (size_t) nSeg));

@@ -18,10 +18,13 @@
 namespace cp {
 
 struct ShapeDev {
-    float bmin[3], bmax[3];   // union of segment bounds = HairKDTree::m_aabb (gkdtree.h:997-1002)
+    float bmin[3], bmax[3];   // union of segment bounds = HairKDTree::m_aabb (gkdtree.h:997-1002); meshes: union of the triangle boxes
     float radius;
-    uint32_t vertexOffset, vertexCount;
+    uint32_t vertexOffset, vertexCount;   // hair: range in SceneDev::vtx; mesh: range in MeshDev::pos / nrm
     int bsdf;
+    int kind;                 // 0 = hair, 1 = triangle mesh (cp_tri.cuh)
+    uint32_t triOffset, triCount;
+    int hasNormals;
 };
 
 CP_D uint32_t vtx_bits(const float4 &v) { return __float_as_uint(v.w); }

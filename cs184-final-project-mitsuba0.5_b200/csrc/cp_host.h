@@ -8,11 +8,16 @@
 
 namespace cp {
 
-struct BuildInfo { uint32_t segments = 0, references = 0, nodes = 0; int levels = 0; };
+struct BuildInfo { uint32_t segments = 0, triangles = 0, references = 0, nodes = 0; int levels = 0; };
 
 // cp_bvh.cu
-bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, int maxSplit, cudaStream_t stream,
+bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, const MeshDev &mesh, int maxSplit, cudaStream_t stream,
                BVHDev &out, BuildInfo &info, std::string &err);
+
+// cp_mesh.cu
+void pack_mesh(const float *d_xyz, const float *d_nrm, uint32_t nVerts, float4 *d_pos, float4 *d_outNrm, cudaStream_t stream);
+void build_tri_accel(const uint32_t *d_localIdx, uint32_t nTris, uint32_t vertexOffset, uint32_t shapeIndex, const float4 *d_pos,
+                     uint32_t *d_outIdx, float4 *d_outAccel, cudaStream_t stream);
 
 void pack_vertices(const float *d_xyz, const uint8_t *d_starts, uint32_t n, uint32_t shape, float4 *d_out, cudaStream_t stream);
 

@@ -2,6 +2,7 @@
 #pragma once
 #include "cp_common.cuh"
 #include "cp_hair.cuh"
+#include "cp_tri.cuh"
 #include "cp_bsdf.cuh"
 
 namespace cp {
@@ -23,7 +24,8 @@ struct BVHDev {
     const BVH4Node *nodes;
     const uint32_t *prims;      // sorted reference list: global first-vertex index gv of each reference's segment
     const float4 *leafSeg;      // per reference, in leaf order: (p1.xyz, flags) (p2.xyz, gv bits) -- what the fp32 pre-test reads,
-                                // so a leaf visit is one dependent load (32 contiguous bytes per reference) instead of index -> vertex
+                                // so a leaf visit is one dependent load (32 contiguous bytes per reference) instead of index -> vertex.
+                                // Triangle references carry flags bit 3 and CP_TRI_FLAG | triangle index in the id slot.
     uint32_t nodeCount, primCount;
 };
 
@@ -65,6 +67,9 @@ struct SceneDev {
     const BsdfDev *bsdfs;
     int bsdfCount;
     BVHDev bvh;
+    MeshDev mesh;               // triangle meshes (cp_tri.cuh); triCount == 0 for pure hair scenes
+    int clipPerShape;           // hair primitives see the ray interval clipped to their own shape's bounds (hair.cpp:205-209):
+                                // needed as soon as the scene bounds differ from a hair shape's bounds (several shapes, or meshes)
     float sceneMin[3], sceneMax[3];   // ShapeKDTree::m_aabb
     EnvDev env;
     CameraDev cam;

@@ -93,10 +93,15 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev S, WaveParams wp, PathQu
             }
             // ---- intersection record
             const float4 hp = hitPT[i];
-            const float4 v1 = __ldg(S.vtx + gv), v2 = __ldg(S.vtx + gv + 1);
-            const ShapeDev &shape = S.shapes[vtx_shape(v1)];
             HitRecord rec;
-            fill_intersection(v1, v2, shape.radius, V3(hp.x, hp.y, hp.z), rayD, rec);
+            uint32_t shapeIdx;
+            if (gv & CP_TRI_FLAG) shapeIdx = fill_intersection_mesh(S.mesh, S.shapes, gv & ~CP_TRI_FLAG, hp.x, hp.y, rayD, rec);
+            else {
+                const float4 v1 = __ldg(S.vtx + gv), v2 = __ldg(S.vtx + gv + 1);
+                shapeIdx = vtx_shape(v1);
+                fill_intersection(v1, v2, S.shapes[shapeIdx].radius, V3(hp.x, hp.y, hp.z), rayD, rec);
+            }
+            const ShapeDev &shape = S.shapes[shapeIdx];
             if ((depth >= S.integ.maxDepth && S.integ.maxDepth > 0) ||
                 (S.integ.strictNormals && dot(rayD, rec.geoN) * rec.wi.z >= 0)) break;   // path.cpp:156-165
             const BsdfDev &bsdf = S.bsdfs[shape.bsdf];

@@ -40,12 +40,14 @@ struct TraceCounters { unsigned long long nodes, prims, fullTests; };
 
 // IO concept:  bool load(uint32_t i, V3 &o, V3 &d, float &mint, float &maxt)   (false: slot carries no ray)
 //              void store(uint32_t i, bool hit, const RayHit &h)
-template <bool ANY, bool STATS, class IO>
+// MESH: the scene also holds triangles (cp_tri.cuh).  They live in the same BVH; a triangle reference skips the fp32 pre-test
+// and is tested against the scene-level interval, as in the reference's top-level tree (skdtree.h:293-304).
+template <bool ANY, bool STATS, bool MESH, class IO>
 CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__restrict__ rayCounter, TraceCounters &tc, int &overflow) {
     const BVH4Node *__restrict__ nodes = S.bvh.nodes;
     const float4 *__restrict__ leafSeg = S.bvh.leafSeg;
     const float4 *__restrict__ vtx = S.vtx;
-    const bool multiShape = S.shapeCount > 1;
+    const bool multiShape = S.clipPerShape != 0;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanesBelow = (1u << lane) - 1u;
 
@@ -152,6 +154,7 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
             for (uint32_t i = 0; i < count; ++i) {
                 const float4 v1 = __ldg(leafSeg + 2 * (size_t) (leafFirst + i)), v2 = __ldg(leafSeg + 2 * (size_t) (leafFirst + i) + 1);
                 if (STATS) tc.prims++;
+                if (MESH && (vtx_bits(v1) & 8u)) { candMask |= 1u << i; continue; }     // triangle reference
                 // Conservative fp32 rejection (never rejects a hit the FP64 test would accept).  With n = d x a the ray and the
                 // axis line are closest at ray parameter tc and axis parameter sc; every point of the infinite cylinder the
                 // ray can touch lies within R/sin(theta) of tc and within R/(sin(theta)|a|) of sc.  R carries a margin that
@@ -183,6 +186,18 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
             const int ci = __ffs(candMask) - 1;
             candMask &= candMask - 1;
             const uint32_t gv = __float_as_uint(__ldg(leafSeg + 2 * (size_t) (leafFirst + ci) + 1).w);
+            if (MESH && (gv & CP_TRI_FLAG)) {
+                const float4 *ta = S.mesh.triAccel + 3 * (size_t) (gv & ~CP_TRI_FLAG);
+                const float4 A = __ldg(ta), B = __ldg(ta + 1), C = __ldg(ta + 2);
+                if (STATS) tc.fullTests++;
+                float t, u, v;
+                if (tri_intersect(A, B, C, o, d, mint, maxt, u, v, t)) {
+                    hit.t = t; hit.gv = gv; hit.p = V3(u, v, 0.0f); found = true;       // barycentrics ride in the point slot
+                    if (ANY) break;
+                    maxt = t;
+                }
+                continue;
+            }
             const float4 v1 = __ldg(vtx + gv), v2 = __ldg(vtx + gv + 1);
             const float4 v0 = __ldg(vtx + (gv > 0 ? gv - 1 : 0)), v3 = __ldg(vtx + gv + 2);
             float tmin = mint, tmax = maxt;

@@ -60,17 +60,17 @@ struct ShadowIO {
     }
 };
 
-template <bool STATS>
+template <bool STATS, bool MESH>
 __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) k_intersect(SceneDev S, PathIO io, uint32_t n, uint32_t *rayCounter, unsigned long long *stats, int *errFlag) {
     TraceCounters tc = {0, 0, 0}; int ovf = 0;
-    trace_persistent<false, STATS>(S, io, n, rayCounter, tc, ovf);
+    trace_persistent<false, STATS, MESH>(S, io, n, rayCounter, tc, ovf);
     if (ovf) *errFlag = 1;
     if (STATS) { atomicAdd(stats + 0, tc.nodes); atomicAdd(stats + 1, tc.prims); atomicAdd(stats + 6, tc.fullTests); }
 }
-template <bool STATS>
+template <bool STATS, bool MESH>
 __global__ void __launch_bounds__(128, CP_MIN_BLOCKS) k_shadow(SceneDev S, ShadowIO io, uint32_t n, uint32_t *rayCounter, unsigned long long *stats, int *errFlag) {
     TraceCounters tc = {0, 0, 0}; int ovf = 0;
-    trace_persistent<true, STATS>(S, io, n, rayCounter, tc, ovf);
+    trace_persistent<true, STATS, MESH>(S, io, n, rayCounter, tc, ovf);
     if (ovf) *errFlag = 1;
     if (STATS) { atomicAdd(stats + 2, tc.nodes); atomicAdd(stats + 3, tc.prims); atomicAdd(stats + 7, tc.fullTests); }
 }
@@ -163,6 +163,7 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
         const uint64_t tiles = (uint64_t) ((S.cam.filmW + 7) / 8) * ((S.cam.filmH + 7) / 8) * 64ull * (sampleEnd - sampleBegin);
         if (tiles < waveSize) waveSize = (uint32_t) std::max<uint64_t>(tiles, 1024);
     }
+    const bool hasMesh = S.mesh.triCount > 0;
     const bool trace = getenv("CUDAPATH_TRACE") != nullptr;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tr0 = now();
@@ -197,8 +198,9 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
                 // camera rays leave raygen in pixel order (already coherent); later bounces are re-ordered
                 const uint32_t *perm = bounce > 0 ? coherence_order(S, q[cur].ro, q[cur].rd, nActive, stream) : nullptr;
                 PathIO io{q[cur], hitPT, hitPrim, perm};
-                if (collectStats) k_intersect<true><<<persistent_grid((const void *) k_intersect<true>, nActive), 128, 0, stream>>>(S, io, nActive, counters + 2, stats, errFlag);
-                else k_intersect<false><<<persistent_grid((const void *) k_intersect<false>, nActive), 128, 0, stream>>>(S, io, nActive, counters + 2, stats, errFlag);
+#define CP_LAUNCH_TRACE(K, ST, ME, N, CTR) K<ST, ME><<<persistent_grid((const void *) K<ST, ME>, N), 128, 0, stream>>>(S, io, N, CTR, stats, errFlag)
+                if (hasMesh) { if (collectStats) CP_LAUNCH_TRACE(k_intersect, true, true, nActive, counters + 2); else CP_LAUNCH_TRACE(k_intersect, false, true, nActive, counters + 2); }
+                else { if (collectStats) CP_LAUNCH_TRACE(k_intersect, true, false, nActive, counters + 2); else CP_LAUNCH_TRACE(k_intersect, false, false, nActive, counters + 2); }
             }
             end();
             begin(1);
@@ -211,8 +213,8 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
             if (nShadow) {
                 begin(2);
                 ShadowIO io{sq, liAcc, coherence_order(S, sq.o, sq.d, nShadow, stream)};
-                if (collectStats) k_shadow<true><<<persistent_grid((const void *) k_shadow<true>, nShadow), 128, 0, stream>>>(S, io, nShadow, counters + 3, stats, errFlag);
-                else k_shadow<false><<<persistent_grid((const void *) k_shadow<false>, nShadow), 128, 0, stream>>>(S, io, nShadow, counters + 3, stats, errFlag);
+                if (hasMesh) { if (collectStats) CP_LAUNCH_TRACE(k_shadow, true, true, nShadow, counters + 3); else CP_LAUNCH_TRACE(k_shadow, false, true, nShadow, counters + 3); }
+                else { if (collectStats) CP_LAUNCH_TRACE(k_shadow, true, false, nShadow, counters + 3); else CP_LAUNCH_TRACE(k_shadow, false, false, nShadow, counters + 3); }
                 end();
                 rs.launches++; rs.shadowRays += nShadow;
             }

@@ -45,7 +45,73 @@ SCENES = {
     # C4: models/furball/scene.xml geometry/camera + the Marschner block, maxDepth 32, 2048x2048, 256 spp
     'furball': dict(camera=_CAM_FURBALL, fov=35.0, sun=_SUN_B, width=2048, height=2048, spp=256, maxDepth=32,
                     shapes=[dict(generator='furball', radius=0.00216667, bsdf=dict(_MARSCHNER_C3, id='hair'))]),
+    # T1: the straight-hair fibers on a head -- an ellipsoid mesh with smooth vertex normals under the scalp points and a
+    # ground quad with face normals (both `diffuse`, the quad inside `twosided`), i.e. fibers and triangles in one BVH
+    'hair-on-head': dict(camera=_CAM_STRAIGHT, fov=35.0, sun=_SUN_A, width=512, height=512, spp=16, maxDepth=8,
+                         shapes=[dict(generator='straight', radius=0.00566563, bsdf=dict(_KKAY, id='hair')),
+                                 dict(mesh='ellipsoid', center=(0.15, 13.0, 0.5), radii=(3.55, 4.15, 3.95), res=48,
+                                      bsdf=dict(type='diffuse', id='skin', reflectance=(0.55, 0.38, 0.30))),
+                                 dict(mesh='quad', center=(0.15, -1.0, 0.0), half=(14.0, 14.0),
+                                      bsdf=dict(type='twosided', id='ground', reflectance=(0.4, 0.4, 0.4)))]),
 }
+
+
+# ------------------------------------------------------------------------------------------------ mesh generators
+def gen_ellipsoid(center, radii, res=48):
+    """UV-sphere scaled to an ellipsoid: (xyz (n,3) f32, idx (m,3) u32, unit vertex normals (n,3) f32)."""
+    lat = np.linspace(0.0, np.pi, res + 1)[1:-1]
+    lon = np.linspace(0.0, 2 * np.pi, 2 * res, endpoint=False)
+    d = [np.array([[0.0, 1.0, 0.0]])]
+    for th in lat:
+        d.append(np.stack([np.sin(th) * np.cos(lon), np.full_like(lon, np.cos(th)), np.sin(th) * np.sin(lon)], axis=1))
+    d.append(np.array([[0.0, -1.0, 0.0]]))
+    d = np.concatenate(d)
+    radii = np.asarray(radii, np.float64); center = np.asarray(center, np.float64)
+    xyz = center + d * radii
+    nrm = d / radii
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    L = 2 * res
+    idx = []
+    ring = lambda r: 1 + r * L
+    for j in range(L):
+        idx.append((0, ring(0) + (j + 1) % L, ring(0) + j))
+    for r in range(len(lat) - 1):
+        for j in range(L):
+            a, b = ring(r) + j, ring(r) + (j + 1) % L
+            c, e = ring(r + 1) + j, ring(r + 1) + (j + 1) % L
+            idx.append((a, b, e)); idx.append((a, e, c))
+    last = len(d) - 1
+    for j in range(L):
+        idx.append((last, ring(len(lat) - 1) + j, ring(len(lat) - 1) + (j + 1) % L))
+    return xyz.astype(np.float32), np.asarray(idx, np.uint32), nrm.astype(np.float32)
+
+
+def gen_quad(center, half):
+    """Horizontal quad (two triangles, counter-clockwise seen from +y), no vertex normals (face normals)."""
+    cx, cy, cz = center; hx, hz = half
+    xyz = np.array([[cx - hx, cy, cz - hz], [cx - hx, cy, cz + hz], [cx + hx, cy, cz + hz], [cx + hx, cy, cz - hz]], np.float32)
+    return xyz, np.array([[0, 1, 2], [0, 2, 3]], np.uint32), None
+
+
+def generate_mesh(shape_desc):
+    if shape_desc['mesh'] == 'ellipsoid':
+        return gen_ellipsoid(shape_desc['center'], shape_desc['radii'], shape_desc.get('res', 48))
+    if shape_desc['mesh'] == 'quad':
+        return gen_quad(shape_desc['center'], shape_desc['half'])
+    raise ValueError('unknown mesh generator %r' % shape_desc['mesh'])
+
+
+def add_shapes(target, sc, scale=1.0):
+    """Adds the BSDFs and shapes of a scene description to `target` (a cudapath.Context or its oracle twin: same method names)."""
+    for sh in sc['shapes']:
+        b = dict(sh['bsdf']); btype = b.pop('type'); b.pop('id', None)
+        bid = target.add_bsdf(btype, **b)
+        if 'mesh' in sh:
+            xyz, idx, nrm = generate_mesh(sh)
+            target.add_mesh(xyz, idx, bid, normals=nrm)
+        else:
+            xyz, starts = generate(sh, scale)
+            target.add_hair(xyz, starts, sh['radius'], bid)
 
 
 # ------------------------------------------------------------------------------------------------ fiber generators

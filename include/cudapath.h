@@ -36,7 +36,17 @@ int cudapath_add_bsdf_kajiyakay(cudapath_ctx *ctx, const float diffuse_reflectan
 int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior, const float diffuse_reflectance[3],
                                 const float specular_reflectance[3], float alpha, int distribution, int nonlinear);
 
+/* `diffuse` plugin with a constant reflectance: SmoothDiffuse ctor+configure(), src/bsdfs/diffuse.cpp:70-103; two_sided != 0
+ * wraps it in the `twosided` adapter (src/bsdfs/twosided.cpp:50-181) with the same BRDF on both sides.  For triangle meshes
+ * that accompany the fibers (a scalp or head under the hair).  Returns the bsdf id. */
+int cudapath_add_bsdf_diffuse(cudapath_ctx *ctx, const float reflectance[3], int two_sided);
+
 /* ---- shapes ------------------------------------------------------------------------------------------------ */
+/* Triangle mesh as ShapeKDTree sees it: TriMesh::getVertexPositions() / getVertexNormals() (NULL = face normals) /
+ * getTriangles() after configure() (include/mitsuba/render/trimesh.h:60-140).  Triangles join the hair segments in the device
+ * BVH and are tested with Wald's projection test (TriAccel, include/mitsuba/render/triaccel.h:61-158).  Returns the shape id. */
+int cudapath_add_mesh(cudapath_ctx *ctx, const float *xyz, const float *normals, uint32_t n_vertices, const uint32_t *indices,
+                      uint32_t n_triangles, int bsdf_id);
 /* `hair` shape from already-loaded fibers: HairShape::getVertices()/getStartFiber() (src/shapes/hair.h:51-57) and the
  * world-space radius of HairKDTree (src/shapes/hair.cpp:108-124).  starts_fiber has n_vertices entries (the sentinel
  * of hair.cpp:782 is added internally).  Returns the shape id. */
@@ -101,7 +111,7 @@ typedef struct cudapath_stats {
     uint64_t nodes_visited, prims_tested;       /* closest-hit rays; only with collect_stats */
     uint64_t shadow_nodes_visited, shadow_prims_tested;
     uint64_t unsupported_filtered_lookups, dropped_samples;
-    uint64_t segments, bvh_nodes, bvh_references;
+    uint64_t segments, bvh_nodes, bvh_references, triangles;
     double build_ms, render_ms;                 /* device time of the last build / render (CUDA events) */
     /* per-stage device time of the last render, summed over launches (CUDA events on the launching stream; only with
      * profile_stages) and the number of launches of each stage */
@@ -120,8 +130,9 @@ int cudapath_bsdf_eval_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const f
 int cudapath_bsdf_sample_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo,
                                float *out_weight, float *out_pdf, int32_t *out_type);
 /* Scene::rayIntersect (any_hit = 0) / shadow-ray query (any_hit = 1).  out_prim = shape-local first-vertex index iv
- * (the reference's primitive id, src/shapes/hair.cpp:151-155); out_record (optional) = p, n, s, t, wi (15 floats per ray)
- * as filled by HairShape::fillIntersectionRecord (src/shapes/hair.cpp:825-862). */
+ * (the reference's primitive id, src/shapes/hair.cpp:151-155) or, for a mesh, the triangle index within the mesh
+ * (TriAccel::primIndex); out_record (optional) = p, n, s, t, wi (15 floats per ray) as filled by
+ * HairShape::fillIntersectionRecord (src/shapes/hair.cpp:825-862) / the mesh branch of include/mitsuba/render/skdtree.h:346-427. */
 int cudapath_intersect_batch(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,
                              int any_hit, int32_t *out_shape, uint32_t *out_prim, float *out_t, float *out_record);
 int cudapath_env_eval_batch(cudapath_ctx *ctx, uint64_t n, const float *direction, float *out_rgb, float *out_pdf);

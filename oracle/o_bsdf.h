@@ -564,4 +564,39 @@ struct Marschner {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// SmoothDiffuse (`diffuse` plugin, constant reflectance) -- src/bsdfs/diffuse.cpp:92-156, optionally wrapped in
+// `twosided` (src/bsdfs/twosided.cpp:101-181) with the same nested BRDF on both sides.  Used for triangle meshes.
+// ---------------------------------------------------------------------------------------------
+struct SmoothDiffuse {
+    V3 reflectance; bool twoSided = false;
+    void configure(V3 r, bool two) {
+        const float mx = maxc(r);                       // ensureEnergyConservation(tex, "reflectance", 1.0f), bsdf.cpp:88-113
+        if (mx > 1.0f) r = r * (0.99f * (1.0f / mx));
+        reflectance = r; twoSided = two;
+    }
+    V3 eval(V3 wi, V3 wo) const {
+        if (twoSided && wi.z <= 0) { wi.z *= -1; wo.z *= -1; }     // twosided.cpp:101-115 (wi.z > 0 ? front : flipped)
+        if (wi.z <= 0 || wo.z <= 0) return V3(0.0f);
+        return reflectance * (kInvPi * wo.z);
+    }
+    float pdf(V3 wi, V3 wo) const {
+        if (twoSided && wi.z <= 0) { wi.z *= -1; wo.z *= -1; }
+        if (wi.z <= 0 || wo.z <= 0) return 0.0f;
+        return kInvPi * wo.z;                                       // warp::squareToCosineHemispherePdf
+    }
+    BSDFSample sample(V3 wi, float sx, float sy) const {
+        BSDFSample r; r.weight = V3(0.0f); r.pdf = 0;
+        bool flipped = false;
+        if (twoSided && wi.z < 0) { wi.z *= -1; flipped = true; }   // twosided.cpp:162-181
+        if (wi.z <= 0) return r;
+        r.wo = squareToCosineHemisphere(sx, sy);
+        r.eta = 1.0f; r.sampledComponent = 0; r.sampledType = EDiffuseReflection;
+        r.pdf = kInvPi * r.wo.z;
+        r.weight = reflectance;
+        if (flipped && !isZero(r.weight) && r.pdf != 0) { r.wo.z *= -1; r.sampledComponent += 1; }
+        return r;
+    }
+};
+
 } // namespace orc

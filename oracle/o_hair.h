@@ -5,6 +5,9 @@
 // :368-397), the FP64 mitred-cylinder test (:485-542), the two-level closest/any query
 // (src/librender/skdtree.cpp:112-142,207-226; hair.cpp:200-237) and the intersection frame
 // (hair.cpp:825-862; include/mitsuba/render/skdtree.h:426-427).
+// Triangle meshes in the same scene (T1): TriAccel::load/rayIntersect (include/mitsuba/render/triaccel.h:61-158),
+// the triangle branch of ShapeKDTree::intersect (skdtree.h:293-304,330-338) and of fillIntersectionRecord
+// (skdtree.h:346-427), Triangle::getAABB (include/mitsuba/core/triangle.h:40-45).
 // The reference's SAH kd-trees are replaced by (a) a brute-force loop in segment order and
 // (b) a plain binned-SAH BVH used only to make oracle renders finish; both apply the
 // reference's interval logic per primitive test, so results agree except for equal-t ties.
@@ -54,7 +57,58 @@ struct Ray {
     }
 };
 
+// include/mitsuba/render/triaccel.h:29-158 (Wald's projection test, 48 bytes per triangle)
+struct TriAccel {
+    uint32_t k = 3;
+    float n_u = 0, n_v = 0, n_d = 0, a_u = 0, a_v = 0, b_nu = 0, b_nv = 0, c_nu = 0, c_nv = 0;
+    uint32_t shapeIndex = 0, primIndex = 0;
+
+    int load(const V3 &A, const V3 &B, const V3 &C) { // :61-97
+        static const int waldModulo[4] = {1, 2, 0, 1};
+        V3 b = C - A, c = B - A, N = cross(c, b);
+        k = 0;
+        for (int j = 0; j < 3; j++) if (std::abs(N[j]) > std::abs(N[k])) k = (uint32_t) j;
+        uint32_t u = (uint32_t) waldModulo[k], v = (uint32_t) waldModulo[k + 1];
+        const float n_k = N[k], denom = b[u] * c[v] - b[v] * c[u];
+        if (denom == 0) { k = 3; return 1; }
+        n_u = N[u] / n_k; n_v = N[v] / n_k; n_d = dot(A, N) / n_k;
+        b_nu = b[u] / denom; b_nv = -b[v] / denom;
+        a_u = A[u]; a_v = A[v];
+        c_nu = c[v] / denom; c_nv = -c[u] / denom;
+        return 0;
+    }
+    bool rayIntersect(const V3 &ro, const V3 &rd, float mint, float maxt, float &u, float &v, float &t) const { // :99-158
+        float o_u, o_v, o_k, d_u, d_v, d_k;
+        switch (k) {
+            case 0: o_u = ro.y; o_v = ro.z; o_k = ro.x; d_u = rd.y; d_v = rd.z; d_k = rd.x; break;
+            case 1: o_u = ro.z; o_v = ro.x; o_k = ro.y; d_u = rd.z; d_v = rd.x; d_k = rd.y; break;
+            case 2: o_u = ro.x; o_v = ro.y; o_k = ro.z; d_u = rd.x; d_v = rd.y; d_k = rd.z; break;
+            default: return false;
+        }
+        t = (n_d - o_u * n_u - o_v * n_v - o_k) / (d_u * n_u + d_v * n_v + d_k);
+        if (t < mint || t > maxt) return false;
+        const float hu = o_u + t * d_u - a_u;
+        const float hv = o_v + t * d_v - a_v;
+        u = hv * b_nu + hu * b_nv;
+        v = hu * c_nu + hv * c_nv;
+        return u >= 0 && v >= 0 && u + v <= 1.0f;
+    }
+};
+
+// A triangle mesh as ShapeKDTree sees it (TriMesh::getVertexPositions/Normals/Triangles after configure()).
+struct TriMesh {
+    std::vector<V3> pos, nrm;       // nrm empty = face normals (skdtree.h:389-391)
+    std::vector<uint32_t> idx;      // 3 per triangle
+    std::vector<TriAccel> accel;    // skdtree.cpp:78-110
+    size_t triCount() const { return idx.size() / 3; }
+    AABB triAABB(uint32_t j) const { // triangle.h:40-45
+        AABB r; r.expand(pos[idx[3 * j]]); r.expand(pos[idx[3 * j + 1]]); r.expand(pos[idx[3 * j + 2]]); return r;
+    }
+};
+
 struct HairShape {
+    bool isMesh = false;              // a TriMesh entry of the shape list (then only `mesh`, `bsdf`, `aabb` are used)
+    TriMesh mesh;
     std::vector<V3> verts;
     std::vector<uint8_t> startsFiber; // size verts.size()+1, sentinel = 1 (hair.cpp:782)
     std::vector<uint32_t> segIndex;   // iv of each segment (hair.cpp:117-124)
@@ -130,6 +184,18 @@ struct HairShape {
             }
         }
         return result;
+    }
+
+    // skdtree.cpp:78-110: TriAccel per triangle; bounds = union of the triangle boxes (what the kd-tree build sees)
+    void finalizeMesh(uint32_t shapeIndex) {
+        isMesh = true;
+        mesh.accel.resize(mesh.triCount());
+        aabb = AABB();
+        for (uint32_t j = 0; j < mesh.triCount(); ++j) {
+            mesh.accel[j].load(mesh.pos[mesh.idx[3 * j]], mesh.pos[mesh.idx[3 * j + 1]], mesh.pos[mesh.idx[3 * j + 2]]);
+            mesh.accel[j].shapeIndex = shapeIndex; mesh.accel[j].primIndex = j;
+            aabb.expand(mesh.triAABB(j));
+        }
     }
 
     void finalize() {
@@ -255,6 +321,7 @@ struct Hit {
     int shape = -1;
     uint32_t iv = 0;
     V3 p;      // fp32 hit point stored by HairKDTree::intersect
+    float u = 0, v = 0; // barycentrics stored by ShapeKDTree::intersect for triangles (skdtree.h:296-300); iv = triangle index
 };
 
 // Result of fillIntersectionRecord (hair.cpp:825-862 + skdtree.h:426-427)
@@ -314,6 +381,16 @@ struct Geometry {
         bool found = false;
         for (size_t si = 0; si < shapes.size(); ++si) {
             const HairShape &s = shapes[si];
+            if (s.isMesh) { // triangles live in the top-level tree: they see [mint, maxt] directly (skdtree.h:293-304)
+                for (uint32_t j = 0; j < s.mesh.triCount(); ++j) {
+                    float t, u, v;
+                    if (s.mesh.accel[j].rayIntersect(ray.o, ray.d, mint, maxt, u, v, t)) {
+                        if (shadow) { hit.t = t; hit.shape = (int) si; hit.iv = j; return true; }
+                        maxt = t; hit.t = t; hit.shape = (int) si; hit.iv = j; hit.u = u; hit.v = v; found = true;
+                    }
+                }
+                continue;
+            }
             float smin, smax;
             if (!shapeInterval(s, ray, mint, maxt, smin, smax)) continue;
             for (uint32_t iv : s.segIndex) {
@@ -332,11 +409,22 @@ struct Geometry {
     void buildBVH() {
         prims.clear(); nodes.clear();
         std::vector<AABB> boxes;
-        for (size_t si = 0; si < shapes.size(); ++si)
+        for (size_t si = 0; si < shapes.size(); ++si) {
+            if (shapes[si].isMesh) {
+                for (uint32_t j = 0; j < shapes[si].mesh.triCount(); ++j) {
+                    prims.push_back({(uint32_t) si, j});
+                    AABB b = shapes[si].mesh.triAABB(j);   // padded: a box only decides which tests run, and flat boxes must not lose edge hits to rounding
+                    V3 pad = (b.mx - b.mn) * 1e-5f + V3(1e-6f) + V3(std::abs(b.mx.x) + std::abs(b.mn.x), std::abs(b.mx.y) + std::abs(b.mn.y), std::abs(b.mx.z) + std::abs(b.mn.z)) * 1e-6f;
+                    b.mn = b.mn - pad; b.mx = b.mx + pad;
+                    boxes.push_back(b);
+                }
+                continue;
+            }
             for (uint32_t iv : shapes[si].segIndex) {
                 prims.push_back({(uint32_t) si, iv});
                 boxes.push_back(shapes[si].segmentAABB(iv));
             }
+        }
         if (prims.empty()) return;
         std::vector<uint32_t> order(prims.size());
         for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t) i;
@@ -403,7 +491,7 @@ struct Geometry {
         std::vector<float> vmin, vmax; std::vector<char> vok;
         float *pmin = smin, *pmax = smaxv; bool *pok = sok;
         if (shapes.size() > 16) throw std::runtime_error("oracle: >16 shapes unsupported in BVH path");
-        for (size_t si = 0; si < ns; ++si) pok[si] = shapeInterval(shapes[si], ray, mint, maxt, pmin[si], pmax[si]);
+        for (size_t si = 0; si < ns; ++si) pok[si] = shapes[si].isMesh ? true : shapeInterval(shapes[si], ray, mint, maxt, pmin[si], pmax[si]);
         bool found = false;
         uint32_t stack[128]; int sp = 0;
         stack[sp++] = 0;
@@ -415,6 +503,14 @@ struct Geometry {
             if (nd.count) {
                 for (uint32_t i = nd.first; i < nd.first + nd.count; ++i) {
                     const PrimRef &pr = prims[i];
+                    if (shapes[pr.shape].isMesh) {
+                        float t, u, v;
+                        if (shapes[pr.shape].mesh.accel[pr.iv].rayIntersect(ray.o, ray.d, mint, maxt, u, v, t)) {
+                            if (shadow) { hit.t = t; hit.shape = (int) pr.shape; hit.iv = pr.iv; return true; }
+                            maxt = t; hit.t = t; hit.shape = (int) pr.shape; hit.iv = pr.iv; hit.u = u; hit.v = v; found = true;
+                        }
+                        continue;
+                    }
                     if (!pok[pr.shape]) continue;
                     float hi = std::min(pmax[pr.shape], maxt);
                     if (!(hi > pmin[pr.shape])) continue; // hair.cpp:209 `maxt > mint`
@@ -442,6 +538,26 @@ struct Geometry {
     void fillIntersection(const Ray &ray, const Hit &hit, Intersection &its) const {
         const HairShape &s = shapes[hit.shape];
         its.valid = true; its.t = hit.t; its.shape = hit.shape; its.iv = hit.iv;
+        if (s.isMesh) { // skdtree.h:346-427 with BarycentricPos = true (skdtree.cpp:136)
+            const TriMesh &m = s.mesh;
+            const V3 b(1 - hit.u - hit.v, hit.u, hit.v);
+            const uint32_t idx0 = m.idx[3 * hit.iv], idx1 = m.idx[3 * hit.iv + 1], idx2 = m.idx[3 * hit.iv + 2];
+            const V3 &p0 = m.pos[idx0], &p1 = m.pos[idx1], &p2 = m.pos[idx2];
+            its.p = p0 * b.x + p1 * b.y + p2 * b.z;
+            V3 side1(p1 - p0), side2(p2 - p0);
+            V3 faceNormal = cross(side1, side2);
+            float length = std::sqrt(dot(faceNormal, faceNormal));
+            if (!(faceNormal.x == 0 && faceNormal.y == 0 && faceNormal.z == 0)) faceNormal = faceNormal / length;
+            V3 dpdu = side1;
+            if (!m.nrm.empty()) {
+                its.shFrame.n = normalize(m.nrm[idx0] * b.x + m.nrm[idx1] * b.y + m.nrm[idx2] * b.z);
+                if (dot(faceNormal, its.shFrame.n) < 0) faceNormal = -faceNormal;
+            } else its.shFrame.n = faceNormal;
+            its.geoFrame = Frame(faceNormal);
+            computeShadingFrame(its.shFrame.n, dpdu, its.shFrame);
+            its.wi = its.shFrame.toLocal(-ray.d);
+            return;
+        }
         its.p = hit.p;
         const V3 axis = s.tangent(hit.iv);
         its.geoFrame.s = axis;

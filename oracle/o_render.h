@@ -107,12 +107,13 @@ struct Film {
 };
 
 struct BSDFAny {
-    int kind = 0; // 0 KajiyaKay, 1 Marschner
+    int kind = 0; // 0 KajiyaKay, 1 Marschner, 2 SmoothDiffuse (meshes)
     KajiyaKay kk;
     std::shared_ptr<Marschner> ma;
-    V3 eval(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.eval(wi, wo) : ma->eval(wi, wo); }
-    float pdf(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.pdf(wi, wo) : ma->pdf(wi, wo); }
-    BSDFSample sample(const V3 &wi, float sx, float sy) const { return kind == 0 ? kk.sample(wi, sx, sy) : ma->sample(wi, sx, sy); }
+    SmoothDiffuse df;
+    V3 eval(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.eval(wi, wo) : kind == 1 ? ma->eval(wi, wo) : df.eval(wi, wo); }
+    float pdf(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.pdf(wi, wo) : kind == 1 ? ma->pdf(wi, wo) : df.pdf(wi, wo); }
+    BSDFSample sample(const V3 &wi, float sx, float sy) const { return kind == 0 ? kk.sample(wi, sx, sy) : kind == 1 ? ma->sample(wi, sx, sy) : df.sample(wi, sx, sy); }
 };
 
 struct RenderStats { std::atomic<uint64_t> rays{0}, shadowRays{0}, paths{0}, pathLength{0}, dropped{0}; };
@@ -199,7 +200,7 @@ struct Scene {
             cameraRay = false;
             stats.rays++;
             if (geo.rayIntersect(ray, its)) {
-                /* hair is never an emitter */
+                /* neither hair nor the meshes of this path are emitters */
             } else {
                 if (hasEnv) {
                     if (hideEmitters && !scattered) break;

@@ -52,6 +52,34 @@ int orc_add_bsdf_marschner(void *sp, float intIOR, float extIOR, const float *di
     ORC_CATCH
 }
 
+// `diffuse` plugin with a constant reflectance (src/bsdfs/diffuse.cpp), optionally inside `twosided`
+int orc_add_bsdf_diffuse(void *sp, const float *reflectance, int twoSided) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    BSDFAny b; b.kind = 2;
+    b.df.configure(V3(reflectance[0], reflectance[1], reflectance[2]), twoSided != 0);
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+    ORC_CATCH
+}
+
+// Triangle mesh as TriMesh exposes it after configure(): positions, optional vertex normals (null = face normals), indices
+int orc_add_mesh(void *sp, const float *xyz, const float *normals, uint32_t nVerts, const uint32_t *indices, uint32_t nTris, int bsdf) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    HairShape h;
+    h.mesh.pos.resize(nVerts);
+    for (uint32_t i = 0; i < nVerts; ++i) h.mesh.pos[i] = V3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    if (normals) { h.mesh.nrm.resize(nVerts); for (uint32_t i = 0; i < nVerts; ++i) h.mesh.nrm[i] = V3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]); }
+    h.mesh.idx.assign(indices, indices + 3 * (size_t) nTris);
+    for (uint32_t i : h.mesh.idx) if (i >= nVerts) throw std::runtime_error("mesh index out of range");
+    h.bsdf = bsdf;
+    h.finalizeMesh((uint32_t) s->geo.shapes.size());
+    s->geo.shapes.push_back(std::move(h));
+    return (int) s->geo.shapes.size() - 1;
+    ORC_CATCH
+}
+
 int orc_add_hair(void *sp, const float *xyz, const uint8_t *startsFiber, uint32_t n, float radius, int bsdf) {
     ORC_TRY
     Scene *s = (Scene *) sp;
@@ -213,6 +241,13 @@ int orc_intersect_candidates(void *sp, const float *o, const float *d, float min
     for (size_t si = 0; si < s->geo.shapes.size(); ++si) {
         const HairShape &h = s->geo.shapes[si];
         float a, b;
+        if (h.isMesh) {
+            for (uint32_t j = 0; j < h.mesh.triCount(); ++j) {
+                float t, u, v;
+                if (h.mesh.accel[j].rayIntersect(r.o, r.d, smin, smax, u, v, t) && cnt < maxOut) { outShape[cnt] = (int) si; outPrim[cnt] = j; outT[cnt] = t; cnt++; }
+            }
+            continue;
+        }
         if (!s->geo.shapeInterval(h, r, smin, smax, a, b)) continue;
         for (uint32_t iv : h.segIndex) {
             float t; V3 p;

@@ -98,6 +98,9 @@ class Scene:
         if type == 'kajiyakay':
             d = f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3)); s = f32(np.broadcast_to(props.get('specularReflectance', 0.2), 3))
             return check(self.L.orc_add_bsdf_kajiyakay(self.h, p(d), p(s), ctypes.c_float(props.get('exponent', 30.0))))
+        if type in ('diffuse', 'twosided'):
+            r = f32(np.broadcast_to(props.get('reflectance', 0.5), 3))
+            return check(self.L.orc_add_bsdf_diffuse(self.h, p(r), 1 if (type == 'twosided' or props.get('twoSided', False)) else 0))
         d = f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3)); s = f32(np.broadcast_to(props.get('specularReflectance', 0.5), 3))
         return check(self.L.orc_add_bsdf_marschner(self.h, ctypes.c_float(props.get('intIOR', 1.5046)), ctypes.c_float(props.get('extIOR', 1.000277)), p(d), p(s),
                                                    ctypes.c_float(props.get('alpha', 0.1)), DISTR[props.get('distribution', 'beckmann')],
@@ -106,6 +109,11 @@ class Scene:
     def add_hair(self, xyz, starts, radius, bsdf):
         xyz = f32(xyz).reshape(-1, 3); st = np.ascontiguousarray(starts, dtype=np.uint8)
         return check(self.L.orc_add_hair(self.h, p(xyz), p(st), ctypes.c_uint32(len(st)), ctypes.c_float(radius), int(bsdf)))
+
+    def add_mesh(self, xyz, indices, bsdf, normals=None):
+        xyz = f32(xyz).reshape(-1, 3); idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
+        nrm = None if normals is None else f32(normals).reshape(-1, 3)
+        return check(self.L.orc_add_mesh(self.h, p(xyz), None if nrm is None else p(nrm), ctypes.c_uint32(len(xyz)), p(idx), ctypes.c_uint32(len(idx)), int(bsdf)))
 
     def set_envmap(self, rgb, toWorld=None, scale=1.0):
         rgb = f32(rgb); h, w = rgb.shape[:2]
@@ -230,11 +238,7 @@ def scene_from_description(name, scale=1.0, overrides=None, envmap=None):
     scenes = cudapath.scenes
     sc = dict(scenes.SCENES[name]); sc.update(overrides or {})
     s = Scene()
-    for sh in sc['shapes']:
-        b = dict(sh['bsdf']); btype = b.pop('type'); b.pop('id', None)
-        bid = s.add_bsdf(btype, **b)
-        xyz, starts = scenes.generate(sh, scale)
-        s.add_hair(xyz, starts, sh['radius'], bid)
+    scenes.add_shapes(s, sc, scale)
     if envmap is None:
         sp = scenes.sunsky_params(name)
         envmap = bake_sunsky(sp['turbidity'], sp['albedo'][0], sp['sunDirection'], sp['skyScale'], sp['sunScale'], sp['sunRadiusScale'], sp['resolution'])

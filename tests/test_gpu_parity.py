@@ -200,6 +200,87 @@ def test_degenerate_rays(geo_pair):
     assert len(e[0]) == 0
 
 
+# ------------------------------------------------------------------------------------------------ triangle meshes (T1)
+@pytest.fixture(scope='module')
+def mesh_pair(cp, oracle):
+    """hair-on-head: Kajiya-Kay fibers + an ellipsoid with vertex normals + a two-triangle ground quad with face normals."""
+    ov = dict(width=80, height=64, spp=8, maxDepth=8)
+    ctx = cp.scene_from_description('hair-on-head', scale=0.02, overrides=ov)
+    ctx.build()
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params('hair-on-head'))
+    osc = oracle.scene_from_description('hair-on-head', scale=0.02, overrides=ov, envmap=env)
+    yield ctx, osc
+    ctx.close()
+
+
+def test_mesh_scene_bounds_and_counts(mesh_pair):
+    ctx, osc = mesh_pair
+    ga, gb = ctx.scene_bounds(); oa, ob = osc.scene_bounds()
+    assert np.allclose(ga, oa, rtol=1e-6, atol=1e-7) and np.allclose(gb, ob, rtol=1e-6, atol=1e-7)
+    st = ctx.stats()
+    assert st['triangles'] == 2 * 96 * 47 + 2 and st['segments'] == 1000 * 25
+
+
+def test_mesh_closest_and_any_hit(mesh_pair):
+    """Triangle hits are bit-exact (primitive, t, barycentric point); the hair segments next to them keep their parity."""
+    ctx, osc = mesh_pair
+    rng = np.random.default_rng(15)
+    aabb, bs = osc.scene_bounds()
+    c = np.array([0.15, 11.0, 0.5], np.float32)
+    o, d = chord_rays(rng, 200000, c, 9.0)
+    gs, gp, gt, grec = ctx.intersect(o, d, 0.0, np.inf, record=True)
+    os_, op, ot, orec = osc.intersect_full(o, d, 0.0, np.inf)
+    check_hits(ctx, osc, o, d, 0.0, np.inf)
+    tri = (os_ >= 1) & (gs == os_) & (gp == op)
+    assert (os_ == 1).sum() > 5000 and (os_ == 2).sum() > 500 and (os_ == 0).sum() > 5000
+    assert np.array_equal(gt[tri], ot[tri])
+    assert np.abs(grec[tri] - orec[tri]).max() <= 1e-5 * np.abs(orec[tri]).max()
+    hair = (os_ == 0) & (gs == 0) & (gp == op)
+    assert np.abs(grec[hair] - orec[hair]).max() <= 2e-5 * max(1.0, np.abs(orec[hair]).max())
+    # secondary-like rays leaving the surfaces (mint = Epsilon: adaptive epsilon), closest and any hit
+    m = os_ >= 0
+    hitp = orec[m, :3]; d2 = sphere_dirs(rng, m.sum())
+    check_hits(ctx, osc, hitp, d2, 1e-4, np.inf)
+    ga = ctx.intersect(hitp, d2, 1e-4, 6.0, any_hit=True)[0]; oa = osc.intersect(hitp, d2, 1e-4, 6.0, mode=1)[0]
+    assert np.array_equal(ga >= 0, oa >= 0)
+
+
+def test_mesh_only_scene(cp, oracle):
+    """A scene without any hair: the BVH builder and the traversal must not need fibers."""
+    xyz, idx, nrm = cp.scenes.gen_ellipsoid((0, 0, 0), (1, 1, 1), 12)
+    ctx = cp.Context(0); osc = oracle.Scene()
+    for s in (ctx, osc):
+        b = s.add_bsdf('diffuse', reflectance=0.5)
+        s.add_mesh(xyz, idx, b, normals=nrm)
+        s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=16, height=16)
+        s.build()
+    rng = np.random.default_rng(16)
+    o, d = chord_rays(rng, 50000, np.zeros(3, np.float32), 2.0)
+    gs, gp, gt = ctx.intersect(o, d, 0.0, np.inf); os_, op, ot = osc.intersect(o, d, 0.0, np.inf, mode=2)
+    assert np.array_equal(gs, os_) and np.array_equal(gt, ot)
+    same_t_other_prim = (gp != op) & (gs >= 0)
+    assert same_t_other_prim.mean() < 1e-3                               # shared-edge ties only
+    ctx.close()
+
+
+def test_diffuse_bsdf_bit_exact(cp, oracle):
+    ctx = cp.Context(0); osc = oracle.Scene()
+    for s in (ctx, osc):
+        s.add_bsdf('diffuse', reflectance=(0.5, 0.4, 0.3)); s.add_bsdf('twosided', reflectance=(1.5, 0.4, 0.3))
+        s.add_mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), [[0, 1, 2]], 0)
+        s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=16, height=16)
+        s.build()
+    rng = np.random.default_rng(17)
+    wi, wo = sphere_dirs(rng, 100000), sphere_dirs(rng, 100000); smp = rng.random((100000, 2)).astype(np.float32)
+    for b in (0, 1):
+        ge, gp = ctx.bsdf_eval(b, wi, wo); oe, op = osc.bsdf_eval(b, wi, wo)
+        assert np.array_equal(ge, oe) and np.array_equal(gp, op)
+        g = ctx.bsdf_sample(b, wi, smp); o = osc.bsdf_sample(b, wi, smp)
+        for a, c in zip(g, o):
+            assert np.array_equal(a, c)
+    ctx.close()
+
+
 # ------------------------------------------------------------------------------------------------ emitter / camera / film
 def test_env_tables_eval_sample(geo_pair):
     ctx, osc = geo_pair
@@ -253,7 +334,7 @@ def rel_mse(a, b):
     return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))
 
 
-@pytest.mark.parametrize('name,scale', [('straight-hair', 0.02), ('hair-curl', 0.02), ('curly-hair', 0.01), ('furball', 0.02)])
+@pytest.mark.parametrize('name,scale', [('straight-hair', 0.02), ('hair-curl', 0.02), ('curly-hair', 0.01), ('furball', 0.02), ('hair-on-head', 0.02)])
 def test_render_matches_oracle(cp, oracle, name, scale):
     ov = dict(width=72, height=56, spp=8, maxDepth=8)            # not multiples of 8: exercises the padded tiles
     ctx = cp.scene_from_description(name, scale=scale, overrides=ov)

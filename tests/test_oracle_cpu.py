@@ -231,6 +231,81 @@ def test_segment_bounds_contain_the_segment(oracle):
     assert np.allclose(aabb[:3], boxes[:, :3].min(0)) and np.allclose(aabb[3:], boxes[:, 3:].max(0))
 
 
+# ------------------------------------------------------------------------------------------------ triangle meshes (T1)
+def _unit_tri_scene(oracle, tris, pos, normals=None, two_sided=False):
+    s = oracle.Scene()
+    b = s.add_bsdf('twosided' if two_sided else 'diffuse', reflectance=(0.5, 0.4, 0.3))
+    s.add_mesh(pos, tris, b, normals=normals)
+    s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=8, height=8)
+    s.build()
+    return s
+
+
+def test_triangle_intersection_analytic(oracle):
+    """TriAccel (triaccel.h:61-158): plane distance, barycentric acceptance u>=0, v>=0, u+v<=1, inclusive [mint, maxt]."""
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [5, 5, -5], [5, 5, -5], [5, 5, -5], [-5, -5, 9], [-5, -5, 9], [-5, -5, 9]], np.float32)
+    s = _unit_tri_scene(oracle, [[0, 1, 2], [3, 4, 5], [6, 7, 8]], pos)   # the other two are degenerate (k = 3, never hit); they only widen the scene box
+    o = np.array([[0.25, 0.25, 2], [0.25, 0.25, -3], [0.9, 0.9, 2], [-0.1, 0.5, 2], [0.5, 0.5, 2], [0.0, 0.0, 2], [5, 5, 7]], np.float32)
+    d = np.array([[0, 0, -1], [0, 0, 1], [0, 0, -1], [0, 0, -1], [0, 0, -1], [0, 0, -1], [0, 0, -1]], np.float32)
+    sh, pr, t = s.intersect(o, d, 0.0, np.inf, mode=2)
+    assert list(sh) == [0, 0, -1, -1, 0, 0, -1]                       # inside (both sides), u+v>1, u<0, on the hypotenuse, on a vertex, degenerate
+    assert np.allclose(t[[0, 1, 4, 5]], [2, 3, 2, 2]) and (pr[[0, 1, 4, 5]] == 0).all()
+    # the interval is inclusive at both ends (t < mint || t > maxt rejects)
+    assert s.intersect(o[:1], d[:1], 2.0, 2.5, mode=2)[0][0] == 0 and s.intersect(o[:1], d[:1], 1.5, 2.0, mode=2)[0][0] == 0
+    assert s.intersect(o[:1], d[:1], 2.0001, 10.0, mode=2)[0][0] == -1 and s.intersect(o[:1], d[:1], 0.0, 1.9999, mode=2)[0][0] == -1
+    # record: barycentric hit point, face normal (no vertex normals), dpdu = p1 - p0 -> s = x axis
+    _, _, _, rec = s.intersect_full(o[:2], d[:2], 0.0, np.inf)
+    assert np.allclose(rec[0, :3], [0.25, 0.25, 0], atol=1e-7) and np.allclose(rec[0, 3:6], [0, 0, 1]) and np.allclose(rec[0, 6:9], [1, 0, 0])
+    assert np.allclose(rec[0, 12:15], [0, 0, 1]) and np.allclose(rec[1, 12:15], [0, 0, -1])      # wi.z < 0 from behind: one-sided diffuse is black there
+
+
+def test_mesh_normals_and_bvh_vs_brute(oracle, cp):
+    """Interpolated vertex normals; geometric normal flipped to the shading side (skdtree.h:381-391); BVH == brute force; hair + mesh."""
+    xyz, idx, nrm = cp.scenes.gen_ellipsoid((0, 0, 0), (1.0, 1.5, 0.8), 10)
+    s = oracle.Scene()
+    b = s.add_bsdf('diffuse', reflectance=0.5)
+    k = s.add_bsdf('kajiyakay')
+    s.add_mesh(xyz, idx, b, normals=-nrm)                               # inward normals: geoFrame.n must follow them
+    fib = np.array([[-2, 0, 1.5], [0, 0.2, 1.5], [2, 0, 1.5], [-2, 1, -1.5], [2, 1.2, -1.5]], np.float32)
+    s.add_hair(fib, np.array([1, 0, 0, 1, 0], np.uint8), 0.05, k)
+    s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=8, height=8)
+    s.build()
+    aabb, _ = s.scene_bounds()
+    assert np.allclose(aabb[:3], [-2.0, -1.5, -1.55], atol=2e-2) and np.allclose(aabb[3:], [2.0, 1.5, 1.55], atol=2e-2)   # union of both kinds of shapes
+    rng = np.random.default_rng(3)
+    o = rng.normal(size=(4000, 3)); o = (4 * o / np.linalg.norm(o, axis=1, keepdims=True)).astype(np.float32)
+    d = -o / 4 + 0.35 * rng.normal(size=(4000, 3)); d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    a = s.intersect(o, d, 0.0, np.inf, mode=0); bf = s.intersect(o, d, 0.0, np.inf, mode=2)
+    assert np.array_equal(a[0], bf[0]) and np.array_equal(a[1], bf[1]) and np.array_equal(a[2], bf[2])
+    assert (a[0] == 0).sum() > 500 and (a[0] == 1).sum() > 20
+    assert np.array_equal(s.intersect(o, d, 1e-4, 3.5, mode=1)[0] >= 0, s.intersect(o, d, 1e-4, 3.5, mode=3)[0] >= 0)
+    sh, pr, t, rec = s.intersect_full(o, d, 0.0, np.inf)
+    m = sh == 0
+    P, N, WI = rec[m, :3], rec[m, 3:6], rec[m, 12:15]
+    q = P / np.array([1.0, 1.5, 0.8])
+    assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 0.06           # on the faceted ellipsoid
+    assert ((N * P).sum(1) < 0).all()                                    # shading normals point inward as given
+    assert (WI[:, 2] < 0).mean() > 0.97                                  # rays from outside arrive on the back side (silhouette facets aside)
+
+
+def test_diffuse_and_twosided_closed_forms(oracle):
+    s = oracle.Scene()
+    d = s.add_bsdf('diffuse', reflectance=(0.5, 0.4, 0.3)); t2 = s.add_bsdf('twosided', reflectance=(2.0, 1.0, 0.5))   # > 1: rescaled by 0.99/max
+    up = np.array([[0.3, 0.1, 0.9]], np.float32); up /= np.linalg.norm(up); down = up * np.array([1, 1, -1], np.float32)
+    wo = np.array([[-0.2, 0.4, 0.6]], np.float32); wo /= np.linalg.norm(wo)
+    ev, pdf = s.bsdf_eval(d, up, wo)
+    assert np.allclose(ev[0], np.array([0.5, 0.4, 0.3]) * wo[0, 2] / np.pi, rtol=1e-6) and np.isclose(pdf[0], wo[0, 2] / np.pi, rtol=1e-6)
+    assert not s.bsdf_eval(d, down, wo)[0].any() and not s.bsdf_eval(d, up, wo * np.array([1, 1, -1], np.float32))[0].any()
+    ev2, pdf2 = s.bsdf_eval(t2, down, wo * np.array([1, 1, -1], np.float32))
+    assert np.allclose(ev2[0], np.array([0.99, 0.495, 0.2475]) * wo[0, 2] / np.pi, rtol=1e-6) and np.isclose(pdf2[0], wo[0, 2] / np.pi, rtol=1e-6)
+    assert not s.bsdf_eval(t2, down, wo)[0].any()                        # opposite hemispheres
+    smp = np.array([[0.3, 0.7]], np.float32)
+    w1, wt1, p1, ty1 = s.bsdf_sample(d, up, smp); w2, wt2, p2, ty2 = s.bsdf_sample(t2, down, smp)
+    assert w1[0, 2] > 0 and np.allclose(wt1[0], [0.5, 0.4, 0.3]) and np.isclose(p1[0], w1[0, 2] / np.pi, rtol=1e-6) and ty1[0] == 0x2
+    assert np.allclose(w2[0], w1[0] * np.array([1, 1, -1])) and ty2[0] == (0x2 | (1 << 8))      # flipped: component index + 1
+    assert not s.bsdf_sample(d, down, smp)[1].any()
+
+
 def test_film_filter_table_and_splat(oracle):
     s = oracle.Scene()
     s.add_hair(*tiny_hair(), 0.1, s.add_bsdf('kajiyakay'))
