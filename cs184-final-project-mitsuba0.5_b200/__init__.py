@@ -41,6 +41,8 @@ def lib():
         L.cudapath_last_error.restype = ctypes.c_char_p
         L.cudapath_hair_file_radius.restype = ctypes.c_float
         L.cudapath_hair_file_vertex_count.restype = ctypes.c_uint32
+        L.cudapath_mesh_file_vertex_count.restype = ctypes.c_uint32
+        L.cudapath_mesh_file_triangle_count.restype = ctypes.c_uint32
         _lib = L
     return _lib
 
@@ -77,6 +79,21 @@ def load_hair_file(filename, radius=0.025, angleThreshold=1.0, reduction=0.0, to
     r = L.cudapath_hair_file_radius(h)
     L.cudapath_hair_file_free(h)
     return xyz, starts, float(r)
+
+
+def load_obj_file(filename, toWorld=None, faceNormals=False, flipNormals=False):
+    """WavefrontOBJ(props) + TriMesh::computeNormals (src/shapes/obj.cpp:186-349, src/librender/trimesh.cpp:608-672) ->
+    (xyz (n,3) f32, indices (m,3) u32, normals (n,3) f32 or None)."""
+    L = lib()
+    h = ctypes.c_void_p()
+    tw = _f32(_IDENTITY if toWorld is None else toWorld).reshape(16)
+    _check(L.cudapath_mesh_file_load(filename.encode(), _p(tw), 1 if faceNormals else 0, 1 if flipNormals else 0, ctypes.byref(h)))
+    nv, nt = L.cudapath_mesh_file_vertex_count(h), L.cudapath_mesh_file_triangle_count(h)
+    xyz = np.zeros((nv, 3), np.float32); idx = np.zeros((nt, 3), np.uint32)
+    nrm = np.zeros((nv, 3), np.float32) if L.cudapath_mesh_file_has_normals(h) else None
+    L.cudapath_mesh_file_copy(h, _p(xyz), None if nrm is None else _p(nrm), _p(idx))
+    L.cudapath_mesh_file_free(h)
+    return xyz, idx, nrm
 
 
 def bake_sunsky(turbidity=3.0, albedo=(0.2, 0.2, 0.2), sunDirection=(0, 1, 0), skyScale=1.0, sunScale=1.0, sunRadiusScale=1.0, resolution=512,
@@ -159,6 +176,10 @@ class Context:
         if len(st) != len(xyz):
             raise CudapathError('starts_fiber must have one entry per vertex')
         return _check(self._L.cudapath_add_hair(self._h, _p(xyz), _p(st), ctypes.c_uint32(len(st)), ctypes.c_float(radius), int(bsdf_id)))
+
+    def add_mesh_file(self, filename, bsdf_id, toWorld=None, faceNormals=False, flipNormals=False):
+        tw = _f32(_IDENTITY if toWorld is None else toWorld).reshape(16)
+        return _check(self._L.cudapath_add_mesh_file(self._h, filename.encode(), _p(tw), 1 if faceNormals else 0, 1 if flipNormals else 0, int(bsdf_id)))
 
     def add_hair_file(self, filename, bsdf_id, radius=0.025, angleThreshold=1.0, reduction=0.0, toWorld=None):
         tw = _f32(_IDENTITY if toWorld is None else toWorld).reshape(16)

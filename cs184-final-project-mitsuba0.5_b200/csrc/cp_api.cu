@@ -94,6 +94,7 @@ struct cudapath_ctx {
 };
 
 struct cudapath_hair_file { HairFileData data; };
+struct cudapath_mesh_file { MeshFileData data; };
 
 static int require_built(cudapath_ctx *ctx) {
     if (!ctx) return fail("null context");
@@ -212,6 +213,34 @@ int cudapath_add_mesh(cudapath_ctx *ctx, const float *xyz, const float *normals,
     ctx->meshVtxTotal += n_vertices; ctx->triTotal += n_triangles;
     ctx->shapes.push_back(sd); ctx->built = false;
     return (int) ctx->shapes.size() - 1;
+}
+
+int cudapath_mesh_file_load(const char *filename, const float to_world[16], int face_normals, int flip_normals, cudapath_mesh_file **out) {
+    if (!filename || !to_world || !out) return fail("null argument");
+    std::unique_ptr<cudapath_mesh_file> m(new cudapath_mesh_file());
+    std::string err;
+    if (!load_obj_file(filename, to_world, face_normals != 0, flip_normals != 0, true, m->data, err)) return fail(err);
+    *out = m.release();
+    return 0;
+}
+uint32_t cudapath_mesh_file_vertex_count(const cudapath_mesh_file *m) { return m ? (uint32_t) (m->data.xyz.size() / 3) : 0; }
+uint32_t cudapath_mesh_file_triangle_count(const cudapath_mesh_file *m) { return m ? (uint32_t) (m->data.indices.size() / 3) : 0; }
+int cudapath_mesh_file_has_normals(const cudapath_mesh_file *m) { return m && !m->data.normals.empty() ? 1 : 0; }
+void cudapath_mesh_file_copy(const cudapath_mesh_file *m, float *xyz, float *normals, uint32_t *indices) {
+    if (!m) return;
+    if (xyz) std::memcpy(xyz, m->data.xyz.data(), m->data.xyz.size() * 4);
+    if (normals && !m->data.normals.empty()) std::memcpy(normals, m->data.normals.data(), m->data.normals.size() * 4);
+    if (indices) std::memcpy(indices, m->data.indices.data(), m->data.indices.size() * 4);
+}
+void cudapath_mesh_file_free(cudapath_mesh_file *m) { delete m; }
+
+int cudapath_add_mesh_file(cudapath_ctx *ctx, const char *filename, const float to_world[16], int face_normals, int flip_normals, int bsdf_id) {
+    cudapath_mesh_file *m = nullptr;
+    if (cudapath_mesh_file_load(filename, to_world, face_normals, flip_normals, &m) != 0) return -1;
+    int r = cudapath_add_mesh(ctx, m->data.xyz.data(), m->data.normals.empty() ? nullptr : m->data.normals.data(), (uint32_t) (m->data.xyz.size() / 3),
+                              m->data.indices.data(), (uint32_t) (m->data.indices.size() / 3), bsdf_id);
+    cudapath_mesh_file_free(m);
+    return r;
 }
 
 int cudapath_add_hair(cudapath_ctx *ctx, const float *xyz, const uint8_t *starts, uint32_t n, float radius, int bsdf_id) {

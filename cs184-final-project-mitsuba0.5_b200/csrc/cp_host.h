@@ -39,6 +39,9 @@ struct HairFileData { std::vector<float> xyz; std::vector<uint8_t> startsFiber; 
 bool load_hair_file(const std::string &path, float radius, float angleThresholdDeg, float reduction, const float toWorld[16],
                     HairFileData &out, std::string &err);
 
+struct MeshFileData { std::vector<float> xyz, normals /* empty = face normals */; std::vector<uint32_t> indices; };
+bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNormals, bool flipNormals, bool flipTexCoords, MeshFileData &out, std::string &err);
+
 // cp_host_sunsky.cpp
 struct SunSkyParams { float turbidity = 3, albedo[3] = {0.2f, 0.2f, 0.2f}, sunDirection[3] = {0, 1, 0}, skyScale = 1, sunScale = 1, sunRadiusScale = 1, stretch = 1; int resolution = 512; };
 bool bake_sunsky(const std::string &dataDir, const SunSkyParams &p, std::vector<float> &rgb, int &w, int &h, std::string &err);

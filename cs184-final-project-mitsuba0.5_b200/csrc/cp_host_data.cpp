@@ -12,6 +12,8 @@
 #include <fstream>
 #include <sstream>
 #include <algorithm>
+#include <map>
+#include <array>
 
 namespace cp {
 
@@ -230,6 +232,143 @@ bool load_hair_file(const std::string &path, float radius, float angleThresholdD
             newFiber = false;
         }
     }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------ Wavefront OBJ meshes
+// WavefrontOBJ(props) with collapse = true semantics: every face of the file lands in ONE mesh (src/shapes/obj.cpp:186-349):
+// `v` / `vn` / `vt` / `f` lines (n-gons as a fan :316-323, negative indices :640-645), vertices transformed by toWorld and merged
+// when position, normal and uv agree (createMesh :608-700, key order :584-606), then TriMesh::computeNormals
+// (src/librender/trimesh.cpp:608-672): faceNormals drops the normals (flipNormals then swaps the winding), given normals are kept
+// (negated by flipNormals), missing normals are generated angle-weighted (Thuermer & Wuethrich).  Materials (mtllib / usemtl)
+// and groups are ignored: the mesh takes the bsdf of the <shape> element.
+namespace {
+inline Vec crossv(Vec a, Vec b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline float lenv(Vec a) { return std::sqrt(dotv(a, a)); }
+inline Vec divv(Vec a, float f) { const float r = 1.0f / f; return {a.x * r, a.y * r, a.z * r}; }   // vector.h: multiply by the reciprocal
+// util.h:309-314
+inline float unit_angle(Vec u, Vec v) {
+    const float kPiF = 3.14159265358979323846f;
+    if (dotv(u, v) < 0) return kPiF - 2 * std::asin(0.5f * lenv({v.x + u.x, v.y + u.y, v.z + u.z}));
+    return 2 * std::asin(0.5f * lenv(sub(v, u)));
+}
+}
+
+bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNormals, bool flipNormals, bool flipTexCoords, MeshFileData &out, std::string &err) {
+    out = MeshFileData();
+    std::ifstream is(path);
+    if (!is) { err = "Wavefront OBJ file '" + path + "' not found!"; return false; }
+    // normals transform with the inverse transpose of the linear part (transform.h:203-211)
+    double inv[9];
+    {
+        const double a = toWorld[0], b = toWorld[1], c = toWorld[2], d = toWorld[4], e = toWorld[5], f = toWorld[6], g = toWorld[8], h = toWorld[9], i = toWorld[10];
+        const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+        if (det == 0) { err = "obj: singular toWorld transform"; return false; }
+        const double r = 1.0 / det;
+        inv[0] = (e * i - f * h) * r; inv[1] = (c * h - b * i) * r; inv[2] = (b * f - c * e) * r;
+        inv[3] = (f * g - d * i) * r; inv[4] = (a * i - c * g) * r; inv[5] = (c * d - a * f) * r;
+        inv[6] = (d * h - e * g) * r; inv[7] = (b * g - a * h) * r; inv[8] = (a * e - b * d) * r;
+    }
+    auto xfmN = [&](Vec v) -> Vec {
+        const float m[9] = {(float) inv[0], (float) inv[1], (float) inv[2], (float) inv[3], (float) inv[4], (float) inv[5], (float) inv[6], (float) inv[7], (float) inv[8]};
+        return {m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z, m[2] * v.x + m[5] * v.y + m[8] * v.z};
+    };
+    std::vector<Vec> vertices, normals; std::vector<std::array<float, 2>> texcoords;
+    struct Corner { int p = 0, n = 0, uv = 0; };
+    std::vector<std::array<Corner, 3>> faces;
+    auto parseCorner = [&](const std::string &str, Corner &c) -> bool {          // obj.cpp:371-390
+        std::vector<std::string> tok; size_t b = 0;
+        while (b <= str.size()) { size_t e = str.find('/', b); if (e == std::string::npos) e = str.size(); if (e > b) tok.push_back(str.substr(b, e - b)); b = e + 1; }
+        c = Corner();
+        if (tok.size() == 1) c.p = atoi(tok[0].c_str());
+        else if (tok.size() == 2) { c.p = atoi(tok[0].c_str()); if (str.find("//") == std::string::npos) c.uv = atoi(tok[1].c_str()); else c.n = atoi(tok[1].c_str()); }
+        else if (tok.size() == 3) { c.p = atoi(tok[0].c_str()); c.uv = atoi(tok[1].c_str()); c.n = atoi(tok[2].c_str()); }
+        else return false;
+        return true;
+    };
+    std::string line, buf;
+    while (std::getline(is, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        std::istringstream iss(line);
+        if (!(iss >> buf)) continue;
+        if (buf == "v") { Vec p{0, 0, 0}; iss >> p.x >> p.y >> p.z; vertices.push_back(p); }
+        else if (buf == "vn") { Vec n{0, 0, 0}; iss >> n.x >> n.y >> n.z; normals.push_back(n); }
+        else if (buf == "vt") { float u = 0, v = 0; iss >> u >> v; if (flipTexCoords) v = 1 - v; texcoords.push_back({u, v}); }
+        else if (buf == "f") {
+            std::string tmp; std::array<Corner, 3> t;
+            for (int k = 0; k < 3; ++k) { if (!(iss >> tmp) || !parseCorner(tmp, t[k])) { err = "Invalid OBJ face format!"; return false; } }
+            faces.push_back(t);
+            while (iss >> tmp) { t[1] = t[2]; if (!parseCorner(tmp, t[2])) { err = "Invalid OBJ face format!"; return false; } faces.push_back(t); }
+        }
+    }
+    if (faces.empty()) { err = "obj: the file contains no faces"; return false; }
+    struct Key { float v[8]; bool operator<(const Key &o) const { for (int i = 0; i < 8; ++i) { if (v[i] < o.v[i]) return true; if (v[i] > o.v[i]) return false; } return false; } };
+    std::map<Key, uint32_t> vertexMap;
+    bool hasNormals = false;
+    std::vector<Vec> P, N;
+    for (auto &f : faces) {
+        for (int j = 0; j < 3; ++j) {
+            int vid = f[j].p, nid = f[j].n, uid = f[j].uv;
+            if (vid < 0) vid += (int) vertices.size() + 1;
+            if (nid < 0) nid += (int) normals.size() + 1;
+            if (uid < 0) uid += (int) texcoords.size() + 1;
+            if (vid > (int) vertices.size() || vid <= 0) { err = "Out of bounds: tried to access vertex " + std::to_string(vid) + " (max: " + std::to_string(vertices.size()) + ")"; return false; }
+            const Vec p = xfmP(toWorld, vertices[vid - 1]);
+            Vec n{0, 0, 0};
+            if (nid != 0) {
+                if (nid > (int) normals.size() || nid < 0) { err = "Out of bounds: tried to access normal " + std::to_string(nid); return false; }
+                n = xfmN(normals[nid - 1]);
+                if (!(n.x == 0 && n.y == 0 && n.z == 0)) n = divv(n, lenv(n));
+                hasNormals = true;
+            }
+            float uv[2] = {0, 0};
+            if (uid != 0) {
+                if (uid > (int) texcoords.size() || uid < 0) { err = "Out of bounds: tried to access uv " + std::to_string(uid); return false; }
+                uv[0] = texcoords[uid - 1][0]; uv[1] = texcoords[uid - 1][1];
+            }
+            const Key key{{p.x, p.y, p.z, n.x, n.y, n.z, uv[0], uv[1]}};
+            auto it = vertexMap.find(key);
+            uint32_t id;
+            if (it != vertexMap.end()) id = it->second;
+            else { id = (uint32_t) P.size(); vertexMap[key] = id; P.push_back(p); N.push_back(n); }
+            out.indices.push_back(id);
+        }
+    }
+    const size_t nTri = out.indices.size() / 3;
+    // TriMesh::computeNormals (trimesh.cpp:608-672)
+    if (faceNormals) {
+        hasNormals = false;
+        if (flipNormals) for (size_t i = 0; i < nTri; ++i) std::swap(out.indices[3 * i], out.indices[3 * i + 1]);
+    } else if (hasNormals) {
+        if (flipNormals) for (Vec &n : N) n = {n.x * -1, n.y * -1, n.z * -1};
+    } else {
+        std::fill(N.begin(), N.end(), Vec{0, 0, 0});
+        for (size_t i = 0; i < nTri; ++i) {
+            Vec n{0, 0, 0};
+            for (int k = 0; k < 3; ++k) {
+                const Vec v0 = P[out.indices[3 * i + k]], v1 = P[out.indices[3 * i + (k + 1) % 3]], v2 = P[out.indices[3 * i + (k + 2) % 3]];
+                const Vec sideA = sub(v1, v0), sideB = sub(v2, v0);
+                if (k == 0) {
+                    n = crossv(sideA, sideB);
+                    const float length = lenv(n);
+                    if (length == 0) break;
+                    n = divv(n, length);
+                }
+                const float angle = unit_angle(divv(sideA, lenv(sideA)), divv(sideB, lenv(sideB)));
+                Vec &dst = N[out.indices[3 * i + k]];
+                dst = {dst.x + n.x * angle, dst.y + n.y * angle, dst.z + n.z * angle};
+            }
+        }
+        for (Vec &n : N) {
+            float length = lenv(n);
+            if (flipNormals) length *= -1;
+            if (length != 0) n = divv(n, length); else n = {1, 0, 0};
+        }
+        hasNormals = true;
+    }
+    out.xyz.reserve(3 * P.size());
+    for (const Vec &p : P) { out.xyz.push_back(p.x); out.xyz.push_back(p.y); out.xyz.push_back(p.z); }
+    if (hasNormals) { out.normals.reserve(3 * N.size()); for (const Vec &n : N) { out.normals.push_back(n.x); out.normals.push_back(n.y); out.normals.push_back(n.z); } }
     return true;
 }
 

@@ -7,7 +7,7 @@
 //   Transform::lookAt / rotate / translate / scale                            src/libcore/transform.cpp
 //   PerspectiveCamera fov handling                                            src/librender/sensor.cpp:225-300
 // Plugins understood: integrator `path`; sensor `perspective` (film `ldrfilm`/`hdrfilm`, rfilter `tent`/`box`/`gaussian`,
-// any sampler: only sampleCount is used); bsdf `kajiyakay`, `marschner`; shape `hair`; emitter `sunsky`.
+// any sampler: only sampleCount is used); bsdf `kajiyakay`, `marschner`, `diffuse`, `twosided`; shape `hair`, `obj`; emitter `sunsky`.
 // Anything else raises an error naming the plugin (the reference would dlopen plugins/<type>.so, src/libcore/plugin.cpp:222-245).
 #include "../../include/cudapath.h"
 #include <cmath>
@@ -203,23 +203,48 @@ struct Loader {
             if (child(n, "float", "alphaU") || child(n, "float", "alphaV")) throw std::runtime_error("The 'marschner' plugin does not support anisotropic microfacet distributions!");
             id = cudapath_add_bsdf_marschner(ctx, (float) ior("intIOR", 1.5046), (float) ior("extIOR", 1.000277), d, s, (float) getFloat(n, "alpha", 0.1),
                                              di, getBool(n, "nonlinear", false) ? 1 : 0);
-        } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner)");
+        } else if (type == "diffuse" || type == "twosided") {
+            // `diffuse` with a constant reflectance (diffuse.cpp:70-76: "reflectance" or "diffuseReflectance"); `twosided` around one nested `diffuse`
+            const Node *d = &n;
+            if (type == "twosided") {
+                d = nullptr;
+                for (auto &c : n.children) if (c->tag == "bsdf") {
+                    if (d) throw std::runtime_error("twosided: two different nested BRDFs are not supported");
+                    if (c->get("type") != "diffuse") throw std::runtime_error("twosided: only a nested `diffuse` is supported on this path");
+                    d = c.get();
+                }
+                if (!d) throw std::runtime_error("twosided: A nested one-sided material is required.");
+            }
+            if (child(*d, "texture", "reflectance") || child(*d, "texture", "diffuseReflectance")) throw std::runtime_error("diffuse: textured reflectance is not supported");
+            float r[3]; getColor(*d, "reflectance", 0.5f, r);
+            if (child(*d, "rgb", "diffuseReflectance") || child(*d, "spectrum", "diffuseReflectance")) getColor(*d, "diffuseReflectance", 0.5f, r);
+            id = cudapath_add_bsdf_diffuse(ctx, r, type == "twosided" ? 1 : 0);
+        } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner, diffuse, twosided)");
         check(id);
         if (n.has("id")) bsdfIds[n.get("id")] = id;
         return id;
     }
     void loadShape(const Node &n) {
-        if (n.get("type") != "hair") throw std::runtime_error("shape plugin \"" + n.get("type") + "\" is outside the hair hot path (supported: hair)");
+        const bool isObj = n.get("type") == "obj";
+        if (n.get("type") != "hair" && !isObj) throw std::runtime_error("shape plugin \"" + n.get("type") + "\" is outside the hair hot path (supported: hair, obj)");
         int bsdf = -1;
         for (auto &c : n.children) {
             if (c->tag == "bsdf") bsdf = loadBsdf(*c);
             else if (c->tag == "ref") { auto it = bsdfIds.find(c->get("id")); if (it == bsdfIds.end()) throw std::runtime_error("unknown reference id \"" + c->get("id") + "\""); bsdf = it->second; }
         }
-        if (bsdf < 0) throw std::runtime_error("hair shape without a supported bsdf (the reference would fall back to `diffuse`)");
+        if (bsdf < 0) {          // Shape::configure falls back to a default `diffuse` (src/librender/shape.cpp)
+            const float half[3] = {0.5f, 0.5f, 0.5f};
+            check(bsdf = cudapath_add_bsdf_diffuse(ctx, half, 0));
+        }
         std::string file = getString(n, "filename", "");
-        if (file.empty()) throw std::runtime_error("hair shape: missing 'filename'");
+        if (file.empty()) throw std::runtime_error(n.get("type") + " shape: missing 'filename'");
         if (file[0] != '/') file = baseDir + "/" + file;
         float tw[16]; toFloat(getTransform(n, "toWorld"), tw);
+        if (isObj) {
+            if (child(n, "float", "maxSmoothAngle")) throw std::runtime_error("obj: 'maxSmoothAngle' is not supported");
+            check(cudapath_add_mesh_file(ctx, file.c_str(), tw, getBool(n, "faceNormals", false) ? 1 : 0, getBool(n, "flipNormals", false) ? 1 : 0, bsdf));
+            return;
+        }
         check(cudapath_add_hair_file(ctx, file.c_str(), (float) getFloat(n, "radius", 0.025), (float) getFloat(n, "angleThreshold", 1.0),
                                      (float) getFloat(n, "reduction", 0.0), tw, bsdf));
     }

@@ -248,6 +248,19 @@ def write_mitshair(path, xyz, starts):
         f.write(flat[keep].astype('<f4').tobytes())
 
 
+def write_obj(path, xyz, idx, normals=None):
+    """Wavefront OBJ with `v` / `vn` / `f a//a` records (%.9g round-trips fp32 exactly)."""
+    with open(path, 'w') as f:
+        for p in xyz:
+            f.write('v %.9g %.9g %.9g\n' % tuple(float(c) for c in p))
+        if normals is not None:
+            for n in normals:
+                f.write('vn %.9g %.9g %.9g\n' % tuple(float(c) for c in n))
+        for t in idx:
+            a, b, c = (int(i) + 1 for i in t)
+            f.write(('f %d//%d %d//%d %d//%d\n' % (a, a, b, b, c, c)) if normals is not None else ('f %d %d %d\n' % (a, b, c)))
+
+
 def _fmt(v):
     return ', '.join(repr(float(x)) for x in v)
 
@@ -265,6 +278,10 @@ def scene_xml(name, overrides=None):
              '\t\t\t<string name="pixelFormat" value="rgb"/>', '\t\t\t<rfilter type="tent"/>', '\t\t</film>', '\t</sensor>']
     for i, sh in enumerate(sc['shapes']):
         b = sh['bsdf']
+        if b['type'] == 'twosided':
+            lines += ['\t<bsdf type="twosided" id="%s">' % b['id'], '\t\t<bsdf type="diffuse">',
+                      '\t\t\t<rgb name="reflectance" value="%s"/>' % _fmt(b['reflectance']), '\t\t</bsdf>', '\t</bsdf>']
+            continue
         lines.append('\t<bsdf type="%s" id="%s">' % (b['type'], b['id']))
         for k, v in b.items():
             if k in ('type', 'id'):
@@ -277,6 +294,12 @@ def scene_xml(name, overrides=None):
                 lines.append('\t\t<float name="%s" value="%r"/>' % (k, float(v)))
         lines.append('\t</bsdf>')
     for i, sh in enumerate(sc['shapes']):
+        if 'mesh' in sh:
+            lines += ['\t<shape type="obj">', '\t\t<string name="filename" value="models/%s.obj"/>' % sh['bsdf']['id']]
+            if sh['mesh'] == 'quad':
+                lines.append('\t\t<boolean name="faceNormals" value="true"/>')
+            lines += ['\t\t<ref id="%s"/>' % sh['bsdf']['id'], '\t</shape>']
+            continue
         lines += ['\t<shape type="hair">', '\t\t<float name="radius" value="%r"/>' % sh['radius'],
                   '\t\t<string name="filename" value="models/%s.mitshair"/>' % sh['bsdf']['id'], '\t\t<ref id="%s"/>' % sh['bsdf']['id'], '\t</shape>']
     lines += ['\t<emitter type="sunsky">', '\t\t<float name="turbidity" value="%r"/>' % _SUNSKY['turbidity'],
@@ -291,6 +314,10 @@ def write_scene(name, directory, scale=1.0, overrides=None):
     os.makedirs(os.path.join(directory, 'models'), exist_ok=True)
     sc = SCENES[name]
     for sh in sc['shapes']:
+        if 'mesh' in sh:
+            xyz, idx, nrm = generate_mesh(sh)
+            write_obj(os.path.join(directory, 'models', sh['bsdf']['id'] + '.obj'), xyz, idx, nrm)
+            continue
         xyz, starts = generate(sh, scale)
         write_mitshair(os.path.join(directory, 'models', sh['bsdf']['id'] + '.mitshair'), xyz, starts)
     path = os.path.join(directory, 'scene.xml')

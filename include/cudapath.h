@@ -47,6 +47,18 @@ int cudapath_add_bsdf_diffuse(cudapath_ctx *ctx, const float reflectance[3], int
  * BVH and are tested with Wald's projection test (TriAccel, include/mitsuba/render/triaccel.h:61-158).  Returns the shape id. */
 int cudapath_add_mesh(cudapath_ctx *ctx, const float *xyz, const float *normals, uint32_t n_vertices, const uint32_t *indices,
                       uint32_t n_triangles, int bsdf_id);
+/* `obj` shape: WavefrontOBJ(props) with all faces collapsed into one mesh (src/shapes/obj.cpp:186-349, createMesh :608-700) followed
+ * by TriMesh::computeNormals (src/librender/trimesh.cpp:608-672).  Materials of the file are ignored.  Returns the shape id. */
+int cudapath_add_mesh_file(cudapath_ctx *ctx, const char *filename, const float to_world[16], int face_normals, int flip_normals, int bsdf_id);
+/* Loader only (no context, no GPU): the flattened arrays a host would pass to cudapath_add_mesh. */
+typedef struct cudapath_mesh_file cudapath_mesh_file;
+int cudapath_mesh_file_load(const char *filename, const float to_world[16], int face_normals, int flip_normals, cudapath_mesh_file **out);
+uint32_t cudapath_mesh_file_vertex_count(const cudapath_mesh_file *m);
+uint32_t cudapath_mesh_file_triangle_count(const cudapath_mesh_file *m);
+int cudapath_mesh_file_has_normals(const cudapath_mesh_file *m);
+void cudapath_mesh_file_copy(const cudapath_mesh_file *m, float *xyz, float *normals, uint32_t *indices);
+void cudapath_mesh_file_free(cudapath_mesh_file *m);
+
 /* `hair` shape from already-loaded fibers: HairShape::getVertices()/getStartFiber() (src/shapes/hair.h:51-57) and the
  * world-space radius of HairKDTree (src/shapes/hair.cpp:108-124).  starts_fiber has n_vertices entries (the sentinel
  * of hair.cpp:782 is added internally).  Returns the shape id. */
@@ -157,7 +169,7 @@ int cudapath_intersect_batch_dev(cudapath_ctx *ctx, uint64_t n, const float *ori
 
 /* ---- scene files -------------------------------------------------------------------------------------------- */
 /* SceneHandler (src/librender/scenehandler.cpp:70-250) for the subset of tags the hair scenes use: integrator `path`,
- * sensor `perspective` (+ film, rfilter, sampler sampleCount), bsdf `kajiyakay` / `marschner`, shape `hair`, emitter
+ * sensor `perspective` (+ film, rfilter, sampler sampleCount), bsdf `kajiyakay` / `marschner` / `diffuse` / `twosided`, shape `hair` / `obj`, emitter
  * `sunsky` / `envmap`-from-memory.  `defines` is a ';'-separated list of name=value pairs replacing $name in the file
  * (mitsuba -D, src/mitsuba/mitsuba.cpp:168).  Hair files that are missing are reported as an error.  On success the
  * scene is loaded into ctx (cudapath_build still has to be called) and *out_spp receives the sampler's sampleCount. */

@@ -362,15 +362,16 @@ def test_render_matches_oracle(cp, oracle, name, scale):
     ctx.close()
 
 
-def test_xml_scene_roundtrip(cp, oracle, tmp_path):
-    """The XML + .mitshair path (SceneHandler + HairShape loader) yields the same film as the flattened-array path."""
+@pytest.mark.parametrize('name', ['straight-hair', 'hair-on-head'])
+def test_xml_scene_roundtrip(cp, oracle, tmp_path, name):
+    """The XML + .mitshair / .obj path (SceneHandler + HairShape / WavefrontOBJ loaders) yields the same film as the flattened-array path."""
     ov = dict(width=48, height=48, spp=4, maxDepth=5)
-    path = cp.scenes.write_scene('straight-hair', str(tmp_path), scale=0.01, overrides=ov)
+    path = cp.scenes.write_scene(name, str(tmp_path), scale=0.01, overrides=ov)
     ctx = cp.Context(0)
     assert ctx.load_xml(path) == 4
     ctx.build()
     a = ctx.render(4, seed=3)
-    ctx2 = cp.scene_from_description('straight-hair', scale=0.01, overrides=ov)
+    ctx2 = cp.scene_from_description(name, scale=0.01, overrides=ov)
     ctx2.build()
     b = ctx2.render(4, seed=3)
     assert a.shape == (48, 48, 5)

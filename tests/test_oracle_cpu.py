@@ -306,6 +306,38 @@ def test_diffuse_and_twosided_closed_forms(oracle):
     assert not s.bsdf_sample(d, down, smp)[1].any()
 
 
+def test_obj_loader(cp, tmp_path):
+    """WavefrontOBJ + computeNormals: vertex merge, n-gon fans, negative indices, toWorld on points and normals, generated
+    angle-weighted normals, faceNormals / flipNormals (obj.cpp:244-349, 608-700; trimesh.cpp:608-672)."""
+    # a unit cube as 6 quads, no normals: 8 merged vertices, 12 triangles, smooth normals along the diagonals
+    v = [(x, y, z) for x in (0, 1) for y in (0, 1) for z in (0, 1)]
+    quads = [(1, 2, 4, 3), (5, 7, 8, 6), (1, 5, 6, 2), (3, 4, 8, 7), (1, 3, 7, 5), (2, 6, 8, 4)]
+    path = tmp_path / 'cube.obj'
+    path.write_text('# cube\n' + ''.join('v %d %d %d\n' % p for p in v) + 'g faces\n' + ''.join('f %d %d %d %d\n' % q for q in quads))
+    xyz, idx, nrm = cp.load_obj_file(str(path))
+    assert xyz.shape == (8, 3) and idx.shape == (12, 3) and nrm.shape == (8, 3)
+    p = xyz[idx]; fn = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    assert ((fn * (p.mean(1) - 0.5)).sum(1) > 0).all()                      # outward winding preserved by the fans
+    assert np.allclose(nrm, (xyz - 0.5) / np.linalg.norm(xyz - 0.5, axis=1, keepdims=True), atol=1e-6)
+    _, idx_f, nrm_f = cp.load_obj_file(str(path), faceNormals=True, flipNormals=True)
+    assert nrm_f is None and np.array_equal(idx_f[:, [1, 0, 2]], idx)        # flipped winding, no normals
+    _, _, nrm_fl = cp.load_obj_file(str(path), flipNormals=True)
+    assert np.allclose(nrm_fl, -nrm, atol=1e-6)
+    # explicit normals, v//vn corners, negative indices, a scaling + translating toWorld (normals use the inverse transpose)
+    path2 = tmp_path / 'tri.obj'
+    path2.write_text('v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 2\nvn 1 0 1\nvt 0.25 0.75\nf -3//1 -2//1 -1//2\nf 1/1/1 2/1/1 3/1/2\n')
+    tw = np.array([[2, 0, 0, 5], [0, 1, 0, 0], [0, 0, 4, 0], [0, 0, 0, 1]], np.float32)
+    xyz, idx, nrm = cp.load_obj_file(str(path2), toWorld=tw)
+    assert xyz.shape == (6, 3) and idx.shape == (2, 3)                       # same position+normal but different uv: not merged
+    assert np.array_equal(xyz[:3], np.array([[5, 0, 0], [7, 0, 0], [5, 1, 0]], np.float32))
+    assert np.allclose(nrm[0], [0, 0, 1]) and np.allclose(nrm[2], np.array([0.5, 0, 0.25]) / np.hypot(0.5, 0.25), atol=1e-6)
+    with pytest.raises(cp.CudapathError):
+        cp.load_obj_file(str(tmp_path / 'missing.obj'))
+    bad = tmp_path / 'bad.obj'; bad.write_text('v 0 0 0\nf 1 2 3\n')
+    with pytest.raises(cp.CudapathError, match='Out of bounds'):
+        cp.load_obj_file(str(bad))
+
+
 def test_film_filter_table_and_splat(oracle):
     s = oracle.Scene()
     s.add_hair(*tiny_hair(), 0.1, s.add_bsdf('kajiyakay'))
