@@ -299,6 +299,7 @@ def main():
                 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_kind,
                 'bytes_per_launch': alg_bytes / n_launch, 'avg_launch_ms': prof['intersect_ms'] / n_launch, 'launches_per_step': n_launch,
                 'nodes_per_ray': cnt['nodes_visited'] / max(1, cnt['rays']), 'prims_per_ray': cnt['prims_tested'] / max(1, cnt['rays']),
+                'exact_tests_per_ray': cnt['full_tests'] / max(1, cnt['rays']),
                 'stage_share_of_step': {k: prof[k + '_ms'] / max(prof['render_ms'], 1e-9) for k in ('intersect', 'shade', 'shadow', 'raygen', 'splat')}}
         cpu = None
         if not args.no_cpu and world == 1:

@@ -236,6 +236,7 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
         cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
     }
     rs.nodesVisited += hs[0]; rs.primsTested += hs[1]; rs.shadowNodesVisited += hs[2]; rs.shadowPrimsTested += hs[3]; rs.unsupportedLookups += hs[4]; rs.droppedSamples += hs[5];
+    rs.fullTests += hs[6]; rs.shadowFullTests += hs[7];
     // the invalid padding "paths" (image sizes that are not multiples of 8) are not camera paths
     const uint64_t realPix = (uint64_t) wp.filmW * wp.filmH, padPix = wp.pixPadded - realPix;
     rs.paths -= padPix * (uint64_t) (sampleEnd - sampleBegin);
