@@ -295,8 +295,16 @@ def main():
         n_launch = max(1, prof['intersect_launches'])
         alg_bytes = 40.0 * cnt['rays'] + 128.0 * cnt['nodes_visited'] + 52.0 * cnt['prims_tested']
         achieved = alg_bytes / (prof['intersect_ms'] * 1e-3) / 1e9 if prof['intersect_ms'] > 0 else 0.0
+        # DRAM bytes of ONE captured k_intersect launch (ncu --set full, profiles/k_intersect_traffic.json written by tools/summarize_profile.py);
+        # bench.py itself never runs under a profiler
+        traffic = traffic_note = None
+        tp = os.path.join(REPO, 'profiles', 'k_intersect_traffic.json')
+        if os.path.exists(tp) and args.scene == 'hair-curl':
+            with open(tp) as f:
+                tj = json.load(f)
+            traffic = tj['dram_bytes']; traffic_note = '%s; that launch ran %.3f ms under ncu' % (tj['launch'], tj['duration_ms'])
         roof = {'kernel': 'k_intersect (closest-hit BVH4 traversal + FP64 cylinder test)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_kind,
+                'frac': achieved / peak, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': peak_kind,
                 'bytes_per_launch': alg_bytes / n_launch, 'avg_launch_ms': prof['intersect_ms'] / n_launch, 'launches_per_step': n_launch,
                 'nodes_per_ray': cnt['nodes_visited'] / max(1, cnt['rays']), 'prims_per_ray': cnt['prims_tested'] / max(1, cnt['rays']),
                 'exact_tests_per_ray': cnt['full_tests'] / max(1, cnt['rays']),
