@@ -157,11 +157,15 @@ class Context:
             return _check(self._L.cudapath_add_bsdf_marschner(self._h, ctypes.c_float(ior(props.get('intIOR', 'bk7'))), ctypes.c_float(ior(props.get('extIOR', 'air'))),
                                                               _p(d), _p(s), ctypes.c_float(props.get('alpha', 0.1)), _DISTRIBUTIONS[distr],
                                                               1 if props.get('nonlinear', False) else 0))
+        if type == 'marschner_fixed':
+            # the fork's unbuilt src/bsdfs/marschner.cpp ("fixed" mode: TRT-only eval, real pdf); defaults amber / air
+            ior = lambda v: float({'amber': 1.55, **_IOR}[v.lower()]) if isinstance(v, str) else float(v)
+            return _check(self._L.cudapath_add_bsdf_marschner_fixed(self._h, ctypes.c_float(ior(props.get('intIOR', 'amber'))), ctypes.c_float(ior(props.get('extIOR', 'air')))))
         if type in ('diffuse', 'twosided'):
             # `diffuse` with a constant reflectance (src/bsdfs/diffuse.cpp:70-103); type 'twosided' = <bsdf type="twosided"><bsdf type="diffuse"/></bsdf>
             r = _f32(np.broadcast_to(props.get('reflectance', 0.5), 3))
             return _check(self._L.cudapath_add_bsdf_diffuse(self._h, _p(r), 1 if (type == 'twosided' or props.get('twoSided', False)) else 0))
-        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner, diffuse, twosided)' % type)
+        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, diffuse, twosided)' % type)
 
     def add_mesh(self, xyz, indices, bsdf_id, normals=None):
         """Triangle mesh (TriMesh positions / optional vertex normals / index triples); joins the fibers in the device BVH."""
@@ -260,10 +264,11 @@ class Context:
         _check(self._L.cudapath_bsdf_eval_batch(self._h, int(bsdf_id), ctypes.c_uint64(n), _p(wi), _p(wo), _p(ev), _p(pdf)))
         return ev, pdf
 
-    def bsdf_sample(self, bsdf_id, wi, sample):
+    def bsdf_sample(self, bsdf_id, wi, sample, extra=None):
         wi = _f32(wi).reshape(-1, 3); sample = _f32(sample).reshape(-1, 2); n = len(wi)
+        ex = None if extra is None else _f32(extra).reshape(-1, 4)
         wo = np.zeros((n, 3), np.float32); wt = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32); ty = np.zeros(n, np.int32)
-        _check(self._L.cudapath_bsdf_sample_batch(self._h, int(bsdf_id), ctypes.c_uint64(n), _p(wi), _p(sample), _p(wo), _p(wt), _p(pdf), _p(ty)))
+        _check(self._L.cudapath_bsdf_sample_batch_ex(self._h, int(bsdf_id), ctypes.c_uint64(n), _p(wi), _p(sample), None if ex is None else _p(ex), _p(wo), _p(wt), _p(pdf), _p(ty)))
         return wo, wt, pdf, ty
 
     def intersect(self, o, d, mint, maxt, any_hit=False, record=False):

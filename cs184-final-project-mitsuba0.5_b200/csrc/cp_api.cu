@@ -173,7 +173,28 @@ int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior,
     gauss_legendre_140(pts, wts);
     const float sigmaA[3] = {0.5f, 0.5f, 0.5f};           // marschner_diffuse.cpp:125 (hard-coded)
     if (!build_marschner_tables(b.dev.eta, betaR, sigmaA, pts, wts, ctx->stream, b.tables, err)) return fail(err);
-    b.dev.tab = b.tables.tab; b.dev.cdf = b.tables.cdf; b.dev.sums = b.tables.sums; b.dev.rt = b.rt;
+    b.dev.tab = b.tables.tab; b.dev.cdf = b.tables.cdf; b.dev.sums = b.tables.sums; b.dev.pdfs = b.tables.pdf; b.dev.rt = b.rt;
+    ctx->bsdfs.push_back(b); ctx->built = false;
+    return (int) ctx->bsdfs.size() - 1;
+}
+
+int cudapath_add_bsdf_marschner_fixed(cudapath_ctx *ctx, float int_ior, float ext_ior) {
+    if (!ctx) return fail("null context");
+    if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
+    CKA(cudaSetDevice(ctx->device));
+    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    b.dev.kind = 3;
+    b.dev.eta = int_ior / ext_ior;
+    const float betaR = 0.1f, betaTT = betaR * 0.5f, betaTRT = betaR * 2.0f;     // marschner.cpp:130-137 (hard-coded)
+    b.dev.vR = betaR * betaR; b.dev.vTT = betaTT * betaTT; b.dev.vTRT = betaTRT * betaTRT;
+    b.dev.scaleAngle = -0.1f;
+    b.dev.diffuse = V3(0.0f); b.dev.specular = V3(1.0f);
+    float pts[140], wts[140];
+    gauss_legendre_140(pts, wts);
+    const float sigmaA[3] = {0.22f, 0.22f, 0.22f};                               // marschner.cpp:122
+    std::string err;
+    if (!build_marschner_tables(b.dev.eta, betaR, sigmaA, pts, wts, ctx->stream, b.tables, err)) return fail(err);
+    b.dev.tab = b.tables.tab; b.dev.cdf = b.tables.cdf; b.dev.sums = b.tables.sums; b.dev.pdfs = b.tables.pdf;
     ctx->bsdfs.push_back(b); ctx->built = false;
     return (int) ctx->bsdfs.size() - 1;
 }
@@ -603,11 +624,15 @@ int cudapath_bsdf_eval_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const f
     return 0;
 }
 int cudapath_bsdf_sample_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type) {
+    return cudapath_bsdf_sample_batch_ex(ctx, bsdf_id, n, wi, sample, nullptr, out_wo, out_weight, out_pdf, out_type);
+}
+int cudapath_bsdf_sample_batch_ex(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, const float *extra, float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type) {
     if (require_built(ctx)) return -1;
-    DevBuf a, s, wo, wt, p, t; std::string err;
+    DevBuf a, s, x, wo, wt, p, t; std::string err;
     CKA(a.upload(wi, n * 12, ctx->stream)); CKA(s.upload(sample, n * 8, ctx->stream));
+    if (extra) CKA(x.upload(extra, n * 16, ctx->stream));
     CKA(wo.alloc(n * 12)); CKA(wt.alloc(n * 12)); CKA(p.alloc(n * 4)); CKA(t.alloc(n * 4));
-    if (!bsdf_sample_batch(ctx->scene, bsdf_id, n, a.as<float>(), s.as<float>(), wo.as<float>(), wt.as<float>(), p.as<float>(), t.as<int32_t>(), ctx->stream, err)) return fail(err);
+    if (!bsdf_sample_batch(ctx->scene, bsdf_id, n, a.as<float>(), s.as<float>(), extra ? x.as<float>() : nullptr, wo.as<float>(), wt.as<float>(), p.as<float>(), t.as<int32_t>(), ctx->stream, err)) return fail(err);
     CKA(wo.download(out_wo, ctx->stream)); CKA(wt.download(out_weight, ctx->stream)); CKA(p.download(out_pdf, ctx->stream)); CKA(t.download(out_type, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -666,7 +691,7 @@ int cudapath_splat_batch(cudapath_ctx *ctx, uint64_t n, const float *position, c
 }
 int cudapath_marschner_tables(cudapath_ctx *ctx, int bsdf_id, float *out_tables, float *out_pdfs, float *out_cdfs, float *out_sums, float *out_rt, float *out_consts) {
     if (!ctx) return fail("null context");
-    if (bsdf_id < 0 || bsdf_id >= (int) ctx->bsdfs.size() || ctx->bsdfs[bsdf_id].dev.kind != 1) return fail("not a marschner bsdf");
+    if (bsdf_id < 0 || bsdf_id >= (int) ctx->bsdfs.size() || (ctx->bsdfs[bsdf_id].dev.kind != 1 && ctx->bsdfs[bsdf_id].dev.kind != 3)) return fail("not a marschner bsdf");
     CKA(cudaSetDevice(ctx->device));
     const BsdfHost &b = ctx->bsdfs[bsdf_id];
     std::vector<float4> t(3 * 4096);
@@ -674,7 +699,7 @@ int cudapath_marschner_tables(cudapath_ctx *ctx, int bsdf_id, float *out_tables,
     CKA(cudaMemcpyAsync(out_pdfs, b.tables.pdf, 4 * 3 * 4096, cudaMemcpyDeviceToHost, ctx->stream));
     CKA(cudaMemcpyAsync(out_cdfs, b.tables.cdf, 4 * 3 * 64 * 65, cudaMemcpyDeviceToHost, ctx->stream));
     CKA(cudaMemcpyAsync(out_sums, b.tables.sums, 4 * 3 * 64, cudaMemcpyDeviceToHost, ctx->stream));
-    CKA(cudaMemcpyAsync(out_rt, b.rt, 4 * (size_t) b.dev.rtSize, cudaMemcpyDeviceToHost, ctx->stream));
+    if (b.dev.rtSize) CKA(cudaMemcpyAsync(out_rt, b.rt, 4 * (size_t) b.dev.rtSize, cudaMemcpyDeviceToHost, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i < t.size(); ++i) { out_tables[3 * i] = t[i].x; out_tables[3 * i + 1] = t[i].y; out_tables[3 * i + 2] = t[i].z; }
     out_consts[0] = b.dev.Fdr; out_consts[1] = b.dev.specW; out_consts[2] = b.dev.eta; out_consts[3] = (float) b.dev.rtSize;
@@ -707,7 +732,7 @@ int cudapath_bsdf_eval_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, con
 int cudapath_bsdf_sample_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type, void *stream) {
     if (require_built(ctx)) return -1;
     std::string err;
-    if (!bsdf_sample_batch(ctx->scene, bsdf_id, n, wi, sample, out_wo, out_weight, out_pdf, out_type, stream ? (cudaStream_t) stream : ctx->stream, err)) return fail(err);
+    if (!bsdf_sample_batch(ctx->scene, bsdf_id, n, wi, sample, nullptr, out_wo, out_weight, out_pdf, out_type, stream ? (cudaStream_t) stream : ctx->stream, err)) return fail(err);
     return 0;
 }
 int cudapath_intersect_batch_dev(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,

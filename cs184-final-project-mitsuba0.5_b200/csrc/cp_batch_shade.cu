@@ -25,11 +25,13 @@ __global__ void __launch_bounds__(256) k_bsdf_eval(const BsdfDev *__restrict__ b
     pdf[i] = bsdf_pdf(b, a, c);
 }
 __global__ void __launch_bounds__(256) k_bsdf_sample(const BsdfDev *__restrict__ bsdfs, int bsdf, uint64_t n, const float *__restrict__ wi,
-                                                     const float *__restrict__ sample, float *wo, float *weight, float *pdf, int32_t *type) {
+                                                     const float *__restrict__ sample, const float *__restrict__ extra, float *wo, float *weight, float *pdf, int32_t *type) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const BsdfDev &b = bsdfs[bsdf];
-    const BsdfSampleOut r = bsdf_sample(b, V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), sample[2 * i], sample[2 * i + 1]);
+    float4 ex = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (extra) ex = make_float4(extra[4 * i], extra[4 * i + 1], extra[4 * i + 2], extra[4 * i + 3]);
+    const BsdfSampleOut r = bsdf_sample(b, V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), sample[2 * i], sample[2 * i + 1], ex);
     wo[3 * i] = r.wo.x; wo[3 * i + 1] = r.wo.y; wo[3 * i + 2] = r.wo.z;
     weight[3 * i] = r.weight.x; weight[3 * i + 1] = r.weight.y; weight[3 * i + 2] = r.weight.z;
     pdf[i] = r.pdf; type[i] = r.type | (r.component << 8);
@@ -87,10 +89,10 @@ bool bsdf_eval_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi,
     CKB(cudaGetLastError());
     return true;
 }
-bool bsdf_sample_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_sample, float *d_wo, float *d_weight, float *d_pdf, int32_t *d_type, cudaStream_t s, std::string &err) {
+bool bsdf_sample_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_sample, const float *d_extra, float *d_wo, float *d_weight, float *d_pdf, int32_t *d_type, cudaStream_t s, std::string &err) {
     if (bsdf < 0 || bsdf >= S.bsdfCount) { err = "bsdf id out of range"; return false; }
     if (n == 0) return true;
-    k_bsdf_sample<<<grid_for(n, 256), 256, 0, s>>>(S.bsdfs, bsdf, n, d_wi, d_sample, d_wo, d_weight, d_pdf, d_type);
+    k_bsdf_sample<<<grid_for(n, 256), 256, 0, s>>>(S.bsdfs, bsdf, n, d_wi, d_sample, d_extra, d_wo, d_weight, d_pdf, d_type);
     CKB(cudaGetLastError());
     return true;
 }

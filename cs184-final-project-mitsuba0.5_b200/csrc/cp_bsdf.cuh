@@ -18,7 +18,8 @@
 namespace cp {
 
 struct BsdfDev {
-    int kind;            // 0 = kajiyakay, 1 = marschner, 2 = diffuse (constant reflectance in `diffuse`; meshes)
+    int kind;            // 0 = kajiyakay, 1 = marschner (as built), 2 = diffuse (constant reflectance in `diffuse`; meshes),
+                         // 3 = the unbuilt `Marschner` of src/bsdfs/marschner.cpp ("fixed" mode: TRT-only eval, real pdf)
     int twoSided;        // kind 2 only: wrapped in `twosided` with the same nested BRDF on both sides
     // kajiyakay (kajiyakay.cpp:60-107) / marschner diffuse colour
     V3 diffuse, specular;
@@ -30,6 +31,7 @@ struct BsdfDev {
     const float4 *tab;   // 3 lobes x 64x64 x (r,g,b,-)
     const float *cdf;    // 3 x 64 rows x 65
     const float *sums;   // 3 x 64
+    const float *pdfs;   // 3 x 64 rows x 64 (normalised row pdfs; only the fixed mode reads them)
     const float *rt;     // external rough transmittance, 1-D slice (rtSize samples over |cos|^(1/4))
 };
 
@@ -222,6 +224,77 @@ CP_D BsdfSampleOut ma_sample(const BsdfDev &b, const V3 &wi, float sx, float sy)
     return r;
 }
 
+// ------------------------------------------------------------------------------------------ Marschner, "fixed" mode
+// src/bsdfs/marschner.cpp (left out of the fork's build): eval :309-341 keeps the TRT lobe only, pdf :347-407, sample :421-535
+// Azimuthal::pdf :91-96 + InterpolatedDistribution1D::pdf (hpp:94-101)
+CP_D float mf_azimuthal_pdf(const float *__restrict__ pdfs, float phi, float cosThetaD) {
+    float u = 63 * phi * (1.0f / (2.0f * kPi));
+    float dist = 63 * cosThetaD;
+    int d0 = clampi(int(dist), 0, 63), d1 = min(d0 + 1, 63);
+    float v = clampf(dist - d0, 0.0f, 1.0f);
+    const int x = int(u);
+    return (__ldg(pdfs + x + d0 * 64) * (1.0f - v) + __ldg(pdfs + x + d1 * 64) * v) * float(64 * (1.0f / (2.0f * kPi)));
+}
+CP_D V3 mf_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
+    float sinThetaI = wi.y, sinThetaO = wo.y;
+    float cosThetaO = ma_trigInverse(sinThetaO);
+    float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
+    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaD = (thetaO - thetaI) * 0.5f;
+    float cosThetaD = cr_cos(thetaD);
+    float phi = cr_atan2(wo.x, wo.z);
+    if (phi < 0.0f) phi += kPi * 2.0f;
+    float thetaITRT = thetaI + 4.0f * b.scaleAngle;
+    float MTRT = ma_M(b.vTRT, cr_sin(thetaITRT), sinThetaO, cr_cos(thetaITRT), cosThetaO);
+    const V3 zero(0.0f);      // MR = MTT = 0 in the reference (:333-334): their lobes contribute 0 * table value
+    return zero * ma_azimuthal(b.tab, phi, cosThetaD) + zero * ma_azimuthal(b.tab + 4096, phi, cosThetaD) + MTRT * ma_azimuthal(b.tab + 8192, phi, cosThetaD);
+}
+CP_D float mf_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) {
+    float sinThetaI = wi.y, sinThetaO = wo.y;
+    float cosThetaI = ma_trigInverse(sinThetaI), cosThetaO = ma_trigInverse(sinThetaO);
+    float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
+    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaD = (thetaO - thetaI) * 0.5f;
+    float cosThetaD = cr_cos(thetaD);
+    float phi = cr_atan2(wo.x, wo.z);
+    if (phi < 0.0f) phi += 2.0f * kPi;
+    float thetaIR = thetaI - 2.0f * b.scaleAngle, thetaITT = thetaI + b.scaleAngle, thetaITRT = thetaI + 4.0f * b.scaleAngle;
+    float weightR = ma_weight(b.sums, cosThetaI), weightTT = ma_weight(b.sums + 64, cosThetaI), weightTRT = ma_weight(b.sums + 128, cosThetaI);
+    float weightSum = weightR + weightTT + weightTRT;
+    float pdfR = weightR * ma_M(b.vR, cr_sin(thetaIR), sinThetaO, cr_cos(thetaIR), cosThetaO);
+    float pdfTT = weightTT * ma_M(b.vTT, cr_sin(thetaITT), sinThetaO, cr_cos(thetaITT), cosThetaO);
+    float pdfTRT = weightTRT * ma_M(b.vTRT, cr_sin(thetaITRT), sinThetaO, cr_cos(thetaITRT), cosThetaO);
+    return (1.0f / weightSum) * (pdfR * mf_azimuthal_pdf(b.pdfs, phi, cosThetaD) + pdfTT * mf_azimuthal_pdf(b.pdfs + 4096, phi, cosThetaD)
+                                 + pdfTRT * mf_azimuthal_pdf(b.pdfs + 8192, phi, cosThetaD));
+}
+// xiN / xiM: the two extra sampler->next2D() draws of :473-474 (the `sample` argument of the BSDF interface is ignored)
+CP_D BsdfSampleOut mf_sample(const BsdfDev &b, const V3 &wi, float xiNx, float xiNy, float xiMx, float xiMy) {
+    BsdfSampleOut r; r.weight = V3(0.0f);
+    float sinThetaI = wi.y;
+    float cosThetaI = ma_trigInverse(sinThetaI);
+    float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
+    float weightR = ma_weight(b.sums, cosThetaI), weightTT = ma_weight(b.sums + 64, cosThetaI), weightTRT = ma_weight(b.sums + 128, cosThetaI);
+    float v, theta; int lobe;
+    float target = xiNx * (weightR + weightTT + weightTRT);
+    if (target < weightR) { r.component = 0; v = b.vR; theta = thetaI - 2.0f * b.scaleAngle; lobe = 0; }
+    else if (target < weightR + weightTT) { r.component = 1; v = b.vTT; theta = thetaI + b.scaleAngle; lobe = 1; }
+    else { r.component = 2; v = b.vTRT; theta = thetaI + 4.0f * b.scaleAngle; lobe = 2; }
+    float sinThetaO = ma_sampleM(v, cr_sin(theta), cr_cos(theta), xiMx, xiMy);
+    float cosThetaO = ma_trigInverse(sinThetaO);
+    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaD = (thetaO - thetaI) * 0.5f;
+    float cosThetaD = cr_cos(thetaD);
+    float phi = ma_sample_phi(b.cdf + lobe * 64 * 65, cosThetaD, xiNy);
+    float sinPhi, cosPhi;
+    cr_sincos(phi, &sinPhi, &cosPhi);
+    r.wo = V3(sinPhi * cosThetaO, sinThetaO, cosPhi * cosThetaO);
+    r.pdf = mf_pdf(b, wi, r.wo);
+    r.type = EDeltaReflection;
+    if (r.pdf <= 0 || r.pdf > 1) return r;
+    r.weight = mf_eval(b, wi, r.wo) / r.pdf;
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------ SmoothDiffuse (+ TwoSided)
 // src/bsdfs/diffuse.cpp:109-156 with a constant reflectance; src/bsdfs/twosided.cpp:101-181 when b.twoSided
 CP_D V3 df_eval(const BsdfDev &b, V3 wi, V3 wo) {
@@ -248,10 +321,17 @@ CP_D BsdfSampleOut df_sample(const BsdfDev &b, V3 wi, float sx, float sy) {
 }
 
 // ------------------------------------------------------------------------------------------ dispatch
-CP_D V3 bsdf_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) { return b.kind == 0 ? kk_eval(b, wi, wo) : b.kind == 1 ? ma_eval(b, wi, wo) : df_eval(b, wi, wo); }
-CP_D float bsdf_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) { return b.kind == 0 ? kk_pdf(b, wi, wo) : b.kind == 1 ? 1.0f : df_pdf(b, wi, wo); }
-CP_D BsdfSampleOut bsdf_sample(const BsdfDev &b, const V3 &wi, float sx, float sy) {
-    return b.kind == 0 ? kk_sample(b, wi, sx, sy) : b.kind == 1 ? ma_sample(b, wi, sx, sy) : df_sample(b, wi, sx, sy);
+CP_D V3 bsdf_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
+    return b.kind == 0 ? kk_eval(b, wi, wo) : b.kind == 1 ? ma_eval(b, wi, wo) : b.kind == 2 ? df_eval(b, wi, wo) : mf_eval(b, wi, wo);
+}
+CP_D float bsdf_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) {
+    return b.kind == 0 ? kk_pdf(b, wi, wo) : b.kind == 1 ? 1.0f : b.kind == 2 ? df_pdf(b, wi, wo) : mf_pdf(b, wi, wo);
+}
+// true for BSDFs whose sample() pulls more numbers from the sampler than the two it is handed (fixed Marschner: 4)
+CP_D bool bsdf_draws_extra(const BsdfDev &b) { return b.kind == 3; }
+CP_D BsdfSampleOut bsdf_sample(const BsdfDev &b, const V3 &wi, float sx, float sy, const float4 &extra) {
+    return b.kind == 0 ? kk_sample(b, wi, sx, sy) : b.kind == 1 ? ma_sample(b, wi, sx, sy) : b.kind == 2 ? df_sample(b, wi, sx, sy)
+                                                                                         : mf_sample(b, wi, extra.x, extra.y, extra.z, extra.w);
 }
 
 } // namespace cp

@@ -203,6 +203,16 @@ struct Loader {
             if (child(n, "float", "alphaU") || child(n, "float", "alphaV")) throw std::runtime_error("The 'marschner' plugin does not support anisotropic microfacet distributions!");
             id = cudapath_add_bsdf_marschner(ctx, (float) ior("intIOR", 1.5046), (float) ior("extIOR", 1.000277), d, s, (float) getFloat(n, "alpha", 0.1),
                                              di, getBool(n, "nonlinear", false) ? 1 : 0);
+        } else if (type == "marschner_fixed") {      // the class of src/bsdfs/marschner.cpp, which the fork's build leaves out
+            auto ior = [&](const char *name, double def) {
+                if (child(n, "float", name)) return getFloat(n, name, def);
+                auto c = child(n, "string", name);
+                if (!c) return def;
+                std::string v = lower(c->get("value"));
+                if (v == "amber") return 1.55; if (v == "air") return 1.000277; if (v == "bk7") return 1.5046; if (v == "vacuum") return 1.0; if (v == "water") return 1.3330;
+                throw std::runtime_error("Unable to find an IOR value for \"" + v + "\"");
+            };
+            id = cudapath_add_bsdf_marschner_fixed(ctx, (float) ior("intIOR", 1.55), (float) ior("extIOR", 1.000277));
         } else if (type == "diffuse" || type == "twosided") {
             // `diffuse` with a constant reflectance (diffuse.cpp:70-76: "reflectance" or "diffuseReflectance"); `twosided` around one nested `diffuse`
             const Node *d = &n;
@@ -219,7 +229,7 @@ struct Loader {
             float r[3]; getColor(*d, "reflectance", 0.5f, r);
             if (child(*d, "rgb", "diffuseReflectance") || child(*d, "spectrum", "diffuseReflectance")) getColor(*d, "diffuseReflectance", 0.5f, r);
             id = cudapath_add_bsdf_diffuse(ctx, r, type == "twosided" ? 1 : 0);
-        } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner, diffuse, twosided)");
+        } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, diffuse, twosided)");
         check(id);
         if (n.has("id")) bsdfIds[n.get("id")] = id;
         return id;

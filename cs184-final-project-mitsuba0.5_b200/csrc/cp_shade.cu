@@ -127,7 +127,12 @@ __global__ void __launch_bounds__(128) k_shade(SceneDev S, WaveParams wp, PathQu
                 }
             }
             // ---- BSDF sampling (path.cpp:207-226)
-            const BsdfSampleOut bs = bsdf_sample(bsdf, rec.wi, u32_to_unit(u.v[2]), u32_to_unit(u.v[3]));
+            float4 extra = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (bsdf_draws_extra(bsdf)) {          // counter stream 2 of this vertex (0: emitter + BSDF sample, 1: roulette)
+                const Philox4 ue = philox4x32_10(pix, samp, (uint32_t) depth, 2u, wp.seedLo, wp.seedHi);
+                extra = make_float4(u32_to_unit(ue.v[0]), u32_to_unit(ue.v[1]), u32_to_unit(ue.v[2]), u32_to_unit(ue.v[3]));
+            }
+            const BsdfSampleOut bs = bsdf_sample(bsdf, rec.wi, u32_to_unit(u.v[2]), u32_to_unit(u.v[3]), extra);
             if (isZero(bs.weight)) break;
             const V3 wo = rec.sh.toWorld(bs.wo);
             if (S.integ.strictNormals && dot(rec.geoN, wo) * bs.wo.z <= 0) break;

@@ -90,7 +90,7 @@ bool splat_batch(const SceneDev &S, const float *d_pos, const float *d_rgb, cons
 
 // cp_batch.cu -- parity hooks / stage micro-benchmarks on device-resident batches
 bool bsdf_eval_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err);
-bool bsdf_sample_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_sample, float *d_wo, float *d_weight, float *d_pdf, int32_t *d_type, cudaStream_t s, std::string &err);
+bool bsdf_sample_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_sample, const float *d_extra /* 4 per tuple or null */, float *d_wo, float *d_weight, float *d_pdf, int32_t *d_type, cudaStream_t s, std::string &err);
 bool intersect_batch(const SceneDev &S, uint64_t n, const float *d_o, const float *d_d, const float *d_mint, const float *d_maxt, int anyHit, bool stats,
                      int32_t *d_shape, uint32_t *d_prim, float *d_t, float *d_rec /*15 floats per ray or null*/, unsigned long long *d_stats, cudaStream_t s, std::string &err);
 void fill_records_batch(const SceneDev &S, uint64_t n, const float *d_d, const int32_t *d_shape, float *d_rec, cudaStream_t s);

@@ -36,6 +36,11 @@ int cudapath_add_bsdf_kajiyakay(cudapath_ctx *ctx, const float diffuse_reflectan
 int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior, const float diffuse_reflectance[3],
                                 const float specular_reflectance[3], float alpha, int distribution, int nonlinear);
 
+/* The fork's second Marschner class, src/bsdfs/marschner.cpp (NOT part of its build; SURVEY M7, "fixed" mode): ctor :110-138 with the
+ * hard-coded sigmaA = 0.22 / beta = 0.1 / scale angle -0.1, eval with the TRT lobe only (:309-341), the real pdf (:347-407) and a
+ * sample() that draws two additional 2-D numbers from the sampler (:421-535).  Reference defaults: int_ior 1.55 (amber), ext_ior
+ * 1.000277 (air).  Returns the bsdf id. */
+int cudapath_add_bsdf_marschner_fixed(cudapath_ctx *ctx, float int_ior, float ext_ior);
 /* `diffuse` plugin with a constant reflectance: SmoothDiffuse ctor+configure(), src/bsdfs/diffuse.cpp:70-103; two_sided != 0
  * wraps it in the `twosided` adapter (src/bsdfs/twosided.cpp:50-181) with the same BRDF on both sides.  For triangle meshes
  * that accompany the fibers (a scalp or head under the hair).  Returns the bsdf id. */
@@ -142,6 +147,10 @@ int cudapath_bsdf_eval_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const f
 /* BSDF::sample: out_type = sampledType | sampledComponent << 8 */
 int cudapath_bsdf_sample_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo,
                                float *out_weight, float *out_pdf, int32_t *out_type);
+/* Same with the additional sampler draws of BSDFs that pull more than the 2-D sample they are handed (`extra`: 4 floats per
+ * tuple = xiN.x, xiN.y, xiM.x, xiM.y of the fixed Marschner; may be NULL). */
+int cudapath_bsdf_sample_batch_ex(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, const float *extra,
+                                  float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type);
 /* Scene::rayIntersect (any_hit = 0) / shadow-ray query (any_hit = 1).  out_prim = shape-local first-vertex index iv
  * (the reference's primitive id, src/shapes/hair.cpp:151-155) or, for a mesh, the triangle index within the mesh
  * (TriAccel::primIndex); out_record (optional) = p, n, s, t, wi (15 floats per ray) as filled by

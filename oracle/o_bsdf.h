@@ -322,6 +322,12 @@ struct InterpolatedDistribution1D {
         x = lower;
         u = clampf((u - lowerU) / (upperU - lowerU), 0.0f, 1.0f);
     }
+    float pdf(float distribution, int x) const { // InterpolatedDistribution1D.hpp:94-101
+        int d0 = clampi(int(distribution), 0, num - 1);
+        int d1 = std::min(d0 + 1, num - 1);
+        float v = clampf(distribution - d0, 0.0f, 1.0f);
+        return pdfv(x, d0) * (1.0f - v) + pdfv(x, d1) * v;
+    }
     float sum(float distribution) const {
         int d0 = clampi(int(distribution), 0, num - 1);
         int d1 = std::min(d0 + 1, num - 1);
@@ -369,6 +375,12 @@ struct Azimuthal {
     float weight(float cosThetaD) const {
         float v = (Res - 1) * cosThetaD;
         return sampler.sum(v) * (2.0f * kPi / Res);
+    }
+    // marschner.cpp:91-96 (the unbuilt `Marschner`): pdf of the azimuth in the cell that contains phi
+    float pdf(float phi, float cosThetaD) const {
+        float u = (Res - 1) * phi * (1.0f / (2.0f * kPi));
+        float v = (Res - 1) * cosThetaD;
+        return sampler.pdf(v, int(u)) * float(Res * (1.0f / (2.0f * kPi)));
     }
 };
 
@@ -559,6 +571,82 @@ struct Marschner {
         }
         r.eta = 1.0f;
         r.pdf = 1.0f;
+        r.weight = eval(wi, r.wo) / r.pdf;
+        return r;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Marschner ("fixed" mode): src/bsdfs/marschner.cpp, the file the fork leaves out of the build.  Same azimuthal tables
+// with sigmaA = 0.22 and the amber / air default IORs (:110-138); eval keeps only the TRT lobe (MR = MTT = 0, :333-334), pdf is the
+// lobe-weighted product of M and the azimuthal cell pdf (:347-407), sample draws two EXTRA 2-D numbers from the sampler (xiN, xiM,
+// :473-474), ignores its `sample` argument and rejects pdf <= 0 or pdf > 1 (:530).
+// ---------------------------------------------------------------------------------------------
+struct MarschnerFixed {
+    Marschner base;      // tables, variances, scale angle
+    void configure(float intIOR, float extIOR) {
+        base.eta = intIOR / extIOR;
+        base.sigmaA = V3(0.22f);
+        base.precomputeAzimuthalDistributions();
+        base.vR = base.betaR * base.betaR; base.vTT = base.betaTT * base.betaTT; base.vTRT = base.betaTRT * base.betaTRT;
+    }
+    V3 eval(const V3 &wi, const V3 &wo) const { // :309-341
+        float sinThetaI = wi.y, sinThetaO = wo.y;
+        float cosThetaO = Marschner::trigInverse(sinThetaO);
+        float thetaI = cr::asin(clampf(sinThetaI, -1.0f, 1.0f));
+        float thetaO = cr::asin(clampf(sinThetaO, -1.0f, 1.0f));
+        float thetaD = (thetaO - thetaI) * 0.5f;
+        float cosThetaD = cr::cos(thetaD);
+        float phi = cr::atan2(wo.x, wo.z);
+        if (phi < 0.0f) phi += kPi * 2.0f;
+        float thetaITRT = thetaI + 4.0f * base.scaleAngleRad;
+        float MTRT = Marschner::M(base.vTRT, cr::sin(thetaITRT), sinThetaO, cr::cos(thetaITRT), cosThetaO);
+        // MR and MTT are computed and then zeroed in the reference; 0 * eval() contributes exactly +0 for finite tables
+        V3 zero(0.0f);
+        return zero * base.nR.eval(phi, cosThetaD) + zero * base.nTT.eval(phi, cosThetaD) + MTRT * base.nTRT.eval(phi, cosThetaD);
+    }
+    float pdf(const V3 &wi, const V3 &wo) const { // :347-407
+        float sinThetaI = wi.y, sinThetaO = wo.y;
+        float cosThetaI = Marschner::trigInverse(sinThetaI), cosThetaO = Marschner::trigInverse(sinThetaO);
+        float thetaI = cr::asin(clampf(sinThetaI, -1.0f, 1.0f));
+        float thetaO = cr::asin(clampf(sinThetaO, -1.0f, 1.0f));
+        float thetaD = (thetaO - thetaI) * 0.5f;
+        float cosThetaD = cr::cos(thetaD);
+        float phi = cr::atan2(wo.x, wo.z);
+        if (phi < 0.0f) phi += 2.0f * kPi;
+        float thetaIR = thetaI - 2.0f * base.scaleAngleRad, thetaITT = thetaI + base.scaleAngleRad, thetaITRT = thetaI + 4.0f * base.scaleAngleRad;
+        float weightR = base.nR.weight(cosThetaI), weightTT = base.nTT.weight(cosThetaI), weightTRT = base.nTRT.weight(cosThetaI);
+        float weightSum = weightR + weightTT + weightTRT;
+        float pdfR = weightR * Marschner::M(base.vR, cr::sin(thetaIR), sinThetaO, cr::cos(thetaIR), cosThetaO);
+        float pdfTT = weightTT * Marschner::M(base.vTT, cr::sin(thetaITT), sinThetaO, cr::cos(thetaITT), cosThetaO);
+        float pdfTRT = weightTRT * Marschner::M(base.vTRT, cr::sin(thetaITRT), sinThetaO, cr::cos(thetaITRT), cosThetaO);
+        return (1.0f / weightSum) * (pdfR * base.nR.pdf(phi, cosThetaD) + pdfTT * base.nTT.pdf(phi, cosThetaD) + pdfTRT * base.nTRT.pdf(phi, cosThetaD));
+    }
+    // :421-535; xiN / xiM are the two extra sampler->next2D() draws
+    BSDFSample sample(const V3 &wi, float xiNx, float xiNy, float xiMx, float xiMy) const {
+        BSDFSample r; r.weight = V3(0.0f);
+        float sinThetaI = wi.y;
+        float cosThetaI = Marschner::trigInverse(sinThetaI);
+        float thetaI = cr::asin(clampf(sinThetaI, -1.0f, 1.0f));
+        float thetaIR = thetaI - 2.0f * base.scaleAngleRad, thetaITT = thetaI + base.scaleAngleRad, thetaITRT = thetaI + 4.0f * base.scaleAngleRad;
+        float weightR = base.nR.weight(cosThetaI), weightTT = base.nTT.weight(cosThetaI), weightTRT = base.nTRT.weight(cosThetaI);
+        const Azimuthal *lobe; float v, theta;
+        float target = xiNx * (weightR + weightTT + weightTRT);
+        if (target < weightR) { r.sampledComponent = 0; v = base.vR; theta = thetaIR; lobe = &base.nR; }
+        else if (target < weightR + weightTT) { r.sampledComponent = 1; v = base.vTT; theta = thetaITT; lobe = &base.nTT; }
+        else { r.sampledComponent = 2; v = base.vTRT; theta = thetaITRT; lobe = &base.nTRT; }
+        float sinThetaO = base.sampleM(v, cr::sin(theta), cr::cos(theta), xiMx, xiMy);
+        float cosThetaO = Marschner::trigInverse(sinThetaO);
+        float thetaO = cr::asin(clampf(sinThetaO, -1.0f, 1.0f));
+        float thetaD = (thetaO - thetaI) * 0.5f;
+        float cosThetaD = cr::cos(thetaD);
+        float phi;
+        lobe->sample(cosThetaD, xiNy, phi);
+        float sinPhi = cr::sin(phi), cosPhi = cr::cos(phi);
+        r.wo = V3(sinPhi * cosThetaO, sinThetaO, cosPhi * cosThetaO);
+        r.pdf = pdf(wi, r.wo);
+        r.sampledType = EDeltaReflection; r.eta = 1.0f;
+        if (r.pdf <= 0 || r.pdf > 1) return r;               // also lets NaN through, like the reference's comparison
         r.weight = eval(wi, r.wo) / r.pdf;
         return r;
     }

@@ -107,13 +107,18 @@ struct Film {
 };
 
 struct BSDFAny {
-    int kind = 0; // 0 KajiyaKay, 1 Marschner, 2 SmoothDiffuse (meshes)
+    int kind = 0; // 0 KajiyaKay, 1 Marschner (as built), 2 SmoothDiffuse (meshes), 3 Marschner "fixed" (unbuilt marschner.cpp)
     KajiyaKay kk;
     std::shared_ptr<Marschner> ma;
     SmoothDiffuse df;
-    V3 eval(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.eval(wi, wo) : kind == 1 ? ma->eval(wi, wo) : df.eval(wi, wo); }
-    float pdf(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.pdf(wi, wo) : kind == 1 ? ma->pdf(wi, wo) : df.pdf(wi, wo); }
-    BSDFSample sample(const V3 &wi, float sx, float sy) const { return kind == 0 ? kk.sample(wi, sx, sy) : kind == 1 ? ma->sample(wi, sx, sy) : df.sample(wi, sx, sy); }
+    std::shared_ptr<MarschnerFixed> mf;
+    V3 eval(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.eval(wi, wo) : kind == 1 ? ma->eval(wi, wo) : kind == 2 ? df.eval(wi, wo) : mf->eval(wi, wo); }
+    float pdf(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.pdf(wi, wo) : kind == 1 ? ma->pdf(wi, wo) : kind == 2 ? df.pdf(wi, wo) : mf->pdf(wi, wo); }
+    // `extra` = four more uniform numbers: only the fixed Marschner draws them (two sampler->next2D() calls inside its sample())
+    BSDFSample sample(const V3 &wi, float sx, float sy, const float *extra) const {
+        return kind == 0 ? kk.sample(wi, sx, sy) : kind == 1 ? ma->sample(wi, sx, sy) : kind == 2 ? df.sample(wi, sx, sy) : mf->sample(wi, extra[0], extra[1], extra[2], extra[3]);
+    }
+    bool drawsExtra() const { return kind == 3; }
 };
 
 struct RenderStats { std::atomic<uint64_t> rays{0}, shadowRays{0}, paths{0}, pathLength{0}, dropped{0}; };
@@ -188,7 +193,12 @@ struct Scene {
                 }
             }
             /* BSDF sampling */
-            BSDFSample bs = bsdf.sample(its.wi, u32_to_unit(u.v[2]), u32_to_unit(u.v[3]));
+            float extra[4] = {0, 0, 0, 0};
+            if (bsdf.drawsExtra()) {                       // counter stream 2 of this vertex (stream 0: emitter + BSDF sample, 1: roulette)
+                Philox4 ue = philox4x32_10(pix, samp, (uint32_t) depth, 2, k0, k1);
+                for (int k = 0; k < 4; ++k) extra[k] = u32_to_unit(ue.v[k]);
+            }
+            BSDFSample bs = bsdf.sample(its.wi, u32_to_unit(u.v[2]), u32_to_unit(u.v[3]), extra);
             if (isZero(bs.weight)) break;
             scattered |= bs.sampledType != ENull;
             const V3 wo = its.shFrame.toWorld(bs.wo);

@@ -52,6 +52,18 @@ int orc_add_bsdf_marschner(void *sp, float intIOR, float extIOR, const float *di
     ORC_CATCH
 }
 
+// the unbuilt `Marschner` of src/bsdfs/marschner.cpp ("fixed" mode)
+int orc_add_bsdf_marschner_fixed(void *sp, float intIOR, float extIOR) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    BSDFAny b; b.kind = 3;
+    b.mf = std::make_shared<MarschnerFixed>();
+    b.mf->configure(intIOR, extIOR);
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+    ORC_CATCH
+}
+
 // `diffuse` plugin with a constant reflectance (src/bsdfs/diffuse.cpp), optionally inside `twosided`
 int orc_add_bsdf_diffuse(void *sp, const float *reflectance, int twoSided) {
     ORC_TRY
@@ -178,14 +190,16 @@ int orc_bsdf_eval_batch(void *sp, int bsdf, uint64_t n, const float *wi, const f
     return 0;
     ORC_CATCH
 }
-int orc_bsdf_sample_batch(void *sp, int bsdf, uint64_t n, const float *wi, const float *sample, float *outWo, float *outWeight,
+// `extra` (optional, 4 per tuple): the additional sampler draws of the fixed Marschner
+int orc_bsdf_sample_batch(void *sp, int bsdf, uint64_t n, const float *wi, const float *sample, const float *extra, float *outWo, float *outWeight,
                           float *outPdf, int32_t *outType) {
     ORC_TRY
     Scene *s = (Scene *) sp;
     const BSDFAny &b = s->bsdfs.at(bsdf);
+    const float zero[4] = {0, 0, 0, 0};
     for (uint64_t i = 0; i < n; ++i) {
         V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
-        BSDFSample r = b.sample(a, sample[2 * i], sample[2 * i + 1]);
+        BSDFSample r = b.sample(a, sample[2 * i], sample[2 * i + 1], extra ? extra + 4 * i : zero);
         outWo[3 * i] = r.wo.x; outWo[3 * i + 1] = r.wo.y; outWo[3 * i + 2] = r.wo.z;
         outWeight[3 * i] = r.weight.x; outWeight[3 * i + 1] = r.weight.y; outWeight[3 * i + 2] = r.weight.z;
         outPdf[i] = r.pdf; outType[i] = r.sampledType | (r.sampledComponent << 8);
@@ -199,14 +213,16 @@ int orc_marschner_tables(void *sp, int bsdf, float *outTables, float *outPdfs, f
     ORC_TRY
     Scene *s = (Scene *) sp;
     const BSDFAny &b = s->bsdfs.at(bsdf);
-    if (b.kind != 1) throw std::runtime_error("not a marschner bsdf");
-    const Azimuthal *lobes[3] = {&b.ma->nR, &b.ma->nTT, &b.ma->nTRT};
+    if (b.kind != 1 && b.kind != 3) throw std::runtime_error("not a marschner bsdf");
+    const Marschner *m = b.kind == 1 ? b.ma.get() : &b.mf->base;
+    const Azimuthal *lobes[3] = {&m->nR, &m->nTT, &m->nTRT};
     for (int l = 0; l < 3; ++l) {
         for (int i = 0; i < 64 * 64; ++i) { outTables[(l * 4096 + i) * 3] = lobes[l]->table[i].x; outTables[(l * 4096 + i) * 3 + 1] = lobes[l]->table[i].y; outTables[(l * 4096 + i) * 3 + 2] = lobes[l]->table[i].z; }
         std::memcpy(outPdfs + l * 4096, lobes[l]->sampler.pdfs.data(), 4096 * 4);
         std::memcpy(outCdfs + l * 64 * 65, lobes[l]->sampler.cdfs.data(), 64 * 65 * 4);
         std::memcpy(outSums + l * 64, lobes[l]->sampler.sums.data(), 64 * 4);
     }
+    if (b.kind == 3) { outConsts[0] = 0; outConsts[1] = 0; outConsts[2] = m->eta; outConsts[3] = 0; return 0; }   // no rough-transmittance data
     std::memcpy(outRT, b.ma->extRT.trans.data(), b.ma->extRT.thetaSamples * 4);
     outConsts[0] = 1 - b.ma->intRT.evalDiffuse(b.ma->alpha); // Fdr
     outConsts[1] = b.ma->specularSamplingWeight;

@@ -98,6 +98,8 @@ class Scene:
         if type == 'kajiyakay':
             d = f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3)); s = f32(np.broadcast_to(props.get('specularReflectance', 0.2), 3))
             return check(self.L.orc_add_bsdf_kajiyakay(self.h, p(d), p(s), ctypes.c_float(props.get('exponent', 30.0))))
+        if type == 'marschner_fixed':
+            return check(self.L.orc_add_bsdf_marschner_fixed(self.h, ctypes.c_float(props.get('intIOR', 1.55)), ctypes.c_float(props.get('extIOR', 1.000277))))
         if type in ('diffuse', 'twosided'):
             r = f32(np.broadcast_to(props.get('reflectance', 0.5), 3))
             return check(self.L.orc_add_bsdf_diffuse(self.h, p(r), 1 if (type == 'twosided' or props.get('twoSided', False)) else 0))
@@ -151,10 +153,11 @@ class Scene:
         check(self.L.orc_bsdf_eval_batch(self.h, int(bsdf), ctypes.c_uint64(n), p(wi), p(wo), p(ev), p(pdf)))
         return ev, pdf
 
-    def bsdf_sample(self, bsdf, wi, sample):
+    def bsdf_sample(self, bsdf, wi, sample, extra=None):
         wi = f32(wi).reshape(-1, 3); sample = f32(sample).reshape(-1, 2); n = len(wi)
+        ex = None if extra is None else f32(extra).reshape(-1, 4)
         wo = np.zeros((n, 3), np.float32); wt = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32); ty = np.zeros(n, np.int32)
-        check(self.L.orc_bsdf_sample_batch(self.h, int(bsdf), ctypes.c_uint64(n), p(wi), p(sample), p(wo), p(wt), p(pdf), p(ty)))
+        check(self.L.orc_bsdf_sample_batch(self.h, int(bsdf), ctypes.c_uint64(n), p(wi), p(sample), None if ex is None else p(ex), p(wo), p(wt), p(pdf), p(ty)))
         return wo, wt, pdf, ty
 
     def marschner_tables(self, bsdf):

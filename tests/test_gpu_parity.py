@@ -104,6 +104,34 @@ def test_bsdf_sample(bsdf_pair):
         assert (np.abs(gwt[zero_both]).sum(axis=1) == 0).all()
 
 
+def test_marschner_fixed_mode_bit_exact(cp, oracle):
+    """the unbuilt src/bsdfs/marschner.cpp -- tables, eval, pdf and the 4-number sample against the oracle."""
+    ctx = cp.Context(0); osc = oracle.Scene()
+    for s in (ctx, osc):
+        s.add_bsdf('marschner_fixed', intIOR=1.55, extIOR=1.000277)
+        s.add_hair(np.array([[0, 0, 0], [0, 1, 0], [0.1, 2, 0]], np.float32), np.array([1, 0, 0], np.uint8), 0.05, 0)
+        s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=16, height=16)
+        s.build()
+    g, o = ctx.marschner_tables(0), osc.marschner_tables(0)
+    scale = np.abs(o['tables']).max()
+    assert np.abs(g['tables'] - o['tables']).max() <= 2e-5 * scale and np.abs(g['pdfs'] - o['pdfs']).max() <= 2e-5 and np.abs(g['cdfs'] - o['cdfs']).max() <= 2e-5
+    rng = np.random.default_rng(22)
+    n = 200000
+    wi, wo = sphere_dirs(rng, n), sphere_dirs(rng, n)
+    ge, gp = ctx.bsdf_eval(0, wi, wo); oe, op = osc.bsdf_eval(0, wi, wo)
+    # the tables differ by an ulp or two between the device and host builds (fp32 sums in another order): 1e-4 relative, not bit-exact
+    assert rel_err(ge, oe, 1e-6 * np.abs(oe).max()).max() <= 1e-4 and rel_err(gp, op, 1e-6).max() <= 1e-4
+    smp = rng.random((n, 2)).astype(np.float32); ex = rng.random((n, 4)).astype(np.float32)
+    gw, gwt, gpdf, gty = ctx.bsdf_sample(0, wi, smp, ex); ow, owt, opdf, oty = osc.bsdf_sample(0, wi, smp, ex)
+    same = np.abs(gw - ow).max(axis=1) <= 1e-4          # an ulp in a CDF can move a sample into the neighbouring azimuthal cell
+    assert same.mean() > 0.999 and np.array_equal(gty[same], oty[same])
+    both = same & (opdf > 0) & (opdf <= 1) & (gpdf > 0) & (gpdf <= 1)
+    assert rel_err(gpdf[both], opdf[both], 1e-6).max() <= 2e-3
+    err = rel_err(gwt[both], owt[both], 1e-3 * np.abs(owt[both]).max())
+    assert np.quantile(err, 0.999) <= 2e-3
+    ctx.close()
+
+
 # ------------------------------------------------------------------------------------------------ geometry
 @pytest.fixture(scope='module')
 def geo_pair(cp, oracle):
@@ -359,6 +387,23 @@ def test_render_matches_oracle(cp, oracle, name, scale):
     # sample-range additivity (what the multi-GPU film reduce relies on)
     g2 = ctx.render(8, seed=42, sample_begin=0, sample_end=3) + ctx.render(8, seed=42, sample_begin=3, sample_end=8)
     assert np.abs(g2 - g).max() <= 1e-4 * np.abs(g).max()
+    ctx.close()
+
+
+def test_render_fixed_marschner(cp, oracle):
+    """Whole path with the M7 BSDF (extra sampler draws on counter stream 2, real pdf in the MIS weights)."""
+    sh = dict(cp.scenes.SCENES['curly-hair']['shapes'][0], bsdf=dict(type='marschner_fixed', id='hair', intIOR=1.55, extIOR=1.0))
+    ov = dict(width=64, height=48, spp=8, maxDepth=8, shapes=[sh])
+    ctx = cp.scene_from_description('curly-hair', scale=0.01, overrides=ov); ctx.build()
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params('curly-hair'))
+    osc = oracle.scene_from_description('curly-hair', scale=0.01, overrides=ov, envmap=env)
+    g = ctx.render(8, seed=5); o = osc.render(8, seed=5)
+    st = ctx.stats()
+    assert abs(st['rays'] - osc.last_stats['rays']) <= 5e-3 * osc.last_stats['rays']
+    a, b = cp.develop(g), cp.develop(o)
+    assert np.isfinite(a).all() and rel_mse(a, b) < 1e-3, 'relMSE %g' % rel_mse(a, b)
+    close = np.abs(a - b).max(axis=2) <= 1e-3 * (np.abs(b).max(axis=2) + 1e-3)
+    assert close.mean() > 0.95
     ctx.close()
 
 

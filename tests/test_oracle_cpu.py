@@ -231,6 +231,35 @@ def test_segment_bounds_contain_the_segment(oracle):
     assert np.allclose(aabb[:3], boxes[:, :3].min(0)) and np.allclose(aabb[3:], boxes[:, 3:].max(0))
 
 
+def test_marschner_fixed_mode(oracle):
+    """SURVEY M7, src/bsdfs/marschner.cpp: TRT-only eval, lobe-weighted pdf, sample() = eval/pdf with rejection of pdf > 1."""
+    s = oracle.Scene()
+    f = s.add_bsdf('marschner_fixed', intIOR=1.55, extIOR=1.0)
+    m = s.add_bsdf('marschner', intIOR=1.55, extIOR=1.0)
+    tf, tm = s.marschner_tables(f), s.marschner_tables(m)
+    assert tf['eta'] == tm['eta'] == np.float32(1.55)
+    assert np.array_equal(tf['tables'][0], tm['tables'][0])                 # R does not depend on sigmaA
+    assert (tf['tables'][1] >= tm['tables'][1]).all() and (tf['tables'][2] > tm['tables'][2]).any()   # sigmaA 0.22 < 0.5: less absorption
+    rng = np.random.default_rng(21)
+    n = 4000
+    wi = rng.normal(size=(n, 3)); wi /= np.linalg.norm(wi, axis=1, keepdims=True)
+    wo = rng.normal(size=(n, 3)); wo /= np.linalg.norm(wo, axis=1, keepdims=True)
+    ev, pdf = s.bsdf_eval(f, wi, wo)
+    assert np.isfinite(ev).all() and (ev >= 0).all() and np.isfinite(pdf).all() and (pdf >= 0).all()
+    assert (ev.sum(axis=1) > 0).mean() > 0.3                                 # no hemisphere test in this class; the narrow M() lobes underflow elsewhere
+    smp = rng.random((n, 2)).astype(np.float32); ex = rng.random((n, 4)).astype(np.float32)
+    w1, wt1, p1, ty1 = s.bsdf_sample(f, wi, smp, ex)
+    w2, wt2, p2, ty2 = s.bsdf_sample(f, wi, rng.random((n, 2)).astype(np.float32), ex)
+    assert np.array_equal(w1, w2) and np.array_equal(wt1, wt2)               # the handed-in 2-D sample is ignored, only the extra draws matter
+    assert ((ty1 & 0xff) == 0x20).all() and set(np.unique(ty1 >> 8)) <= {0, 1, 2}
+    assert np.allclose(np.linalg.norm(w1, axis=1), 1.0, atol=1e-5)
+    ev_s, pdf_s = s.bsdf_eval(f, wi, w1)
+    assert np.array_equal(pdf_s, p1)
+    ok = (p1 > 0) & (p1 <= 1)
+    assert ok.mean() > 0.3 and not wt1[~ok].any()                            # pdf > 1 is rejected with a zero weight (:530)
+    assert np.allclose(wt1[ok], ev_s[ok] / p1[ok, None], rtol=1e-5, atol=1e-7)
+
+
 # ------------------------------------------------------------------------------------------------ triangle meshes (T1)
 def _unit_tri_scene(oracle, tris, pos, normals=None, two_sided=False):
     s = oracle.Scene()
