@@ -64,7 +64,7 @@ def _check(rc):
 _IDENTITY = np.eye(4, dtype=np.float32)
 _DISTRIBUTIONS = {'beckmann': 0, 'ggx': 1, 'phong': 2, 'as': 2}
 _FILTERS = {'tent': 0, 'box': 1, 'gaussian': 2}
-_IOR = {'air': 1.000277, 'bk7': 1.5046, 'vacuum': 1.0, 'water': 1.3330}    # subset of src/bsdfs/ior.h
+_IOR = {'air': 1.000277, 'bk7': 1.5046, 'vacuum': 1.0, 'water': 1.3330, 'polypropylene': 1.49, 'amber': 1.55}    # subset of src/bsdfs/ior.h
 
 
 def load_hair_file(filename, radius=0.025, angleThreshold=1.0, reduction=0.0, toWorld=None):
@@ -157,15 +157,24 @@ class Context:
             return _check(self._L.cudapath_add_bsdf_marschner(self._h, ctypes.c_float(ior(props.get('intIOR', 'bk7'))), ctypes.c_float(ior(props.get('extIOR', 'air'))),
                                                               _p(d), _p(s), ctypes.c_float(props.get('alpha', 0.1)), _DISTRIBUTIONS[distr],
                                                               1 if props.get('nonlinear', False) else 0))
+        if type == 'roughplastic':
+            ior = lambda v: float(_IOR[v.lower()]) if isinstance(v, str) else float(v)
+            d = _f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3)); s = _f32(np.broadcast_to(props.get('specularReflectance', 1.0), 3))
+            distr = props.get('distribution', 'beckmann').lower()
+            if distr not in _DISTRIBUTIONS:
+                raise CudapathError('Specified an invalid distribution "%s", must be "beckmann", "ggx", or "phong"/"as"!' % distr)
+            return _check(self._L.cudapath_add_bsdf_roughplastic(self._h, ctypes.c_float(ior(props.get('intIOR', 'polypropylene'))), ctypes.c_float(ior(props.get('extIOR', 'air'))),
+                                                                 _p(d), _p(s), ctypes.c_float(props.get('alpha', 0.1)), _DISTRIBUTIONS[distr],
+                                                                 1 if props.get('sampleVisible', True) else 0, 1 if props.get('nonlinear', False) else 0))
         if type == 'marschner_fixed':
             # the fork's unbuilt src/bsdfs/marschner.cpp ("fixed" mode: TRT-only eval, real pdf); defaults amber / air
-            ior = lambda v: float({'amber': 1.55, **_IOR}[v.lower()]) if isinstance(v, str) else float(v)
+            ior = lambda v: float(_IOR[v.lower()]) if isinstance(v, str) else float(v)
             return _check(self._L.cudapath_add_bsdf_marschner_fixed(self._h, ctypes.c_float(ior(props.get('intIOR', 'amber'))), ctypes.c_float(ior(props.get('extIOR', 'air')))))
         if type in ('diffuse', 'twosided'):
             # `diffuse` with a constant reflectance (src/bsdfs/diffuse.cpp:70-103); type 'twosided' = <bsdf type="twosided"><bsdf type="diffuse"/></bsdf>
             r = _f32(np.broadcast_to(props.get('reflectance', 0.5), 3))
             return _check(self._L.cudapath_add_bsdf_diffuse(self._h, _p(r), 1 if (type == 'twosided' or props.get('twoSided', False)) else 0))
-        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, diffuse, twosided)' % type)
+        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, roughplastic, diffuse, twosided)' % type)
 
     def add_mesh(self, xyz, indices, bsdf_id, normals=None):
         """Triangle mesh (TriMesh positions / optional vertex normals / index triples); joins the fibers in the device BVH."""

@@ -178,6 +178,38 @@ int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior,
     return (int) ctx->bsdfs.size() - 1;
 }
 
+int cudapath_add_bsdf_roughplastic(cudapath_ctx *ctx, float int_ior, float ext_ior, const float d[3], const float s[3], float alpha, int distribution,
+                                   int sample_visible, int nonlinear) {
+    if (!ctx || !d || !s) return fail("null argument");
+    if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
+    if (distribution < 0 || distribution > 2) return fail("Specified an invalid distribution, must be \"beckmann\", \"ggx\", or \"phong\"/\"as\"!");
+    if (ctx->dataDir.empty()) return fail("roughplastic needs data/microfacet/*.dat: call cudapath_set_data_dir() first");
+    CKA(cudaSetDevice(ctx->device));
+    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    b.dev.kind = 4;
+    b.dev.eta = int_ior / ext_ior;
+    b.dev.invEta2 = 1.0f / (b.dev.eta * b.dev.eta);
+    b.dev.alpha = std::max(alpha, 1e-4f);                  // microfacet.h:131
+    b.dev.distr = distribution; b.dev.sampleVisible = sample_visible ? 1 : 0;
+    if (distribution == 2) { b.dev.sampleVisible = 0; b.dev.exponent = std::max(2.0f / (b.dev.alpha * b.dev.alpha) - 2.0f, 0.0f); }   // :140-143, :677-680
+    b.dev.nonlinear = nonlinear ? 1 : 0;
+    V3 spec(s[0], s[1], s[2]), diff(d[0], d[1], d[2]);
+    { const float mx = maxc(spec); if (mx > 1.0f) spec = spec * (0.99f * (1.0f / mx)); }   // roughplastic.cpp:260-263 -> bsdf.cpp:88-113
+    { const float mx = maxc(diff); if (mx > 1.0f) diff = diff * (0.99f * (1.0f / mx)); }
+    b.dev.diffuse = diff; b.dev.specular = spec;
+    const float dAvg = luminance(diff), sAvg = luminance(spec);
+    b.dev.specW = sAvg / (dAvg + sAvg);                    // roughplastic.cpp:276-278
+    std::vector<float> T; float Fdr; std::string err;
+    if (!rough_transmittance_slice(ctx->dataDir, distribution, b.dev.eta, b.dev.alpha, T, Fdr, err)) return fail(err);
+    b.dev.Fdr = Fdr; b.dev.rtSize = (int) T.size();
+    CKA(cudaMalloc(&b.rt, T.size() * 4));
+    CKA(cudaMemcpyAsync(b.rt, T.data(), T.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    b.dev.rt = b.rt;
+    ctx->bsdfs.push_back(b); ctx->built = false;
+    return (int) ctx->bsdfs.size() - 1;
+}
+
 int cudapath_add_bsdf_marschner_fixed(cudapath_ctx *ctx, float int_ior, float ext_ior) {
     if (!ctx) return fail("null context");
     if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");

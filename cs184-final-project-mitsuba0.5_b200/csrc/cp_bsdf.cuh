@@ -19,7 +19,8 @@ namespace cp {
 
 struct BsdfDev {
     int kind;            // 0 = kajiyakay, 1 = marschner (as built), 2 = diffuse (constant reflectance in `diffuse`; meshes),
-                         // 3 = the unbuilt `Marschner` of src/bsdfs/marschner.cpp ("fixed" mode: TRT-only eval, real pdf)
+                         // 3 = the unbuilt `Marschner` of src/bsdfs/marschner.cpp ("fixed" mode: TRT-only eval, real pdf),
+                         // 4 = roughplastic (src/bsdfs/roughplastic.cpp; the default BSDF of the models/*/scene.xml files)
     int twoSided;        // kind 2 only: wrapped in `twosided` with the same nested BRDF on both sides
     // kajiyakay (kajiyakay.cpp:60-107) / marschner diffuse colour
     V3 diffuse, specular;
@@ -28,6 +29,7 @@ struct BsdfDev {
     // marschner (marschner_diffuse.cpp:113-160,193-247)
     float eta, invEta2, alpha, Fdr, vR, vTT, vTRT, scaleAngle;
     int nonlinear, rtSize;
+    int distr, sampleVisible;   // roughplastic: microfacet distribution 0 beckmann / 1 ggx / 2 phong (exponent in `exponent`), visible-normal sampling
     const float4 *tab;   // 3 lobes x 64x64 x (r,g,b,-)
     const float *cdf;    // 3 x 64 rows x 65
     const float *sums;   // 3 x 64
@@ -295,6 +297,194 @@ CP_D BsdfSampleOut mf_sample(const BsdfDev &b, const V3 &wi, float xiNx, float x
     return r;
 }
 
+// ------------------------------------------------------------------------------------------ RoughPlastic
+// MicrofacetDistribution (isotropic): src/bsdfs/microfacet.h:184-232 eval, :238-279 sample/pdf, :284-386 sampleAll, :389-447 visible
+// normals, :470-510 smithG1 / G, :555-673 sampleVisible11;  math::erf / erfinv / hypot2: src/libcore/math.cpp:25-86
+// RoughPlastic eval / pdf / sample: src/bsdfs/roughplastic.cpp:325-375, 377-436, 438-494
+CP_D float mfd_signum(float v) { return v < 0 ? -1.0f : (v > 0 ? 1.0f : 0.0f); }
+CP_D float mfd_erfinv(float x) {
+    float w = -cr_log((1.0f - x) * (1.0f + x));
+    float p;
+    if (w < 5.0f) {
+        w = w - 2.5f;
+        p = 2.81022636e-08f; p = 3.43273939e-07f + p * w; p = -3.5233877e-06f + p * w; p = -4.39150654e-06f + p * w;
+        p = 0.00021858087f + p * w; p = -0.00125372503f + p * w; p = -0.00417768164f + p * w; p = 0.246640727f + p * w; p = 1.50140941f + p * w;
+    } else {
+        w = sqrtf(w) - 3.0f;
+        p = -0.000200214257f; p = 0.000100950558f + p * w; p = 0.00134934322f + p * w; p = -0.00367342844f + p * w;
+        p = 0.00573950773f + p * w; p = -0.0076224613f + p * w; p = 0.00943887047f + p * w; p = 1.00167406f + p * w; p = 2.83297682f + p * w;
+    }
+    return p * x;
+}
+CP_D float mfd_erf(float x) {
+    const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f, p = 0.3275911f;
+    const float sign = mfd_signum(x);
+    x = fabsf(x);
+    const float t = 1.0f / (1.0f + p * x);
+    const float y = 1.0f - (((((a5 * t + a4) * t) + a3) * t + a2) * t + a1) * t * cr_exp(-x * x);
+    return sign * y;
+}
+CP_D float mfd_hypot2(float a, float b) {
+    float r;
+    if (fabsf(a) > fabsf(b)) { r = b / a; r = fabsf(a) * sqrtf(1.0f + r * r); }
+    else if (b != 0.0f) { r = a / b; r = fabsf(b) * sqrtf(1.0f + r * r); }
+    else r = 0.0f;
+    return r;
+}
+CP_D float mfd_eval(const BsdfDev &b, const V3 &m) {
+    if (m.z <= 0) return 0.0f;
+    const float alpha = b.alpha, cosTheta2 = m.z * m.z;
+    const float beckmannExponent = ((m.x * m.x) / (alpha * alpha) + (m.y * m.y) / (alpha * alpha)) / cosTheta2;
+    float result;
+    if (b.distr == 0) result = cr_exp(-beckmannExponent) / (kPi * alpha * alpha * cosTheta2 * cosTheta2);
+    else if (b.distr == 1) { const float root = (1.0f + beckmannExponent) * cosTheta2; result = 1.0f / (kPi * alpha * alpha * root * root); }
+    else result = sqrtf((b.exponent + 2) * (b.exponent + 2)) * kInvTwoPi * cr_pow(m.z, b.exponent);
+    if (result * m.z < 1e-20f) result = 0;
+    return result;
+}
+CP_D float mfd_smithG1(const BsdfDev &b, const V3 &v, const V3 &m) {
+    if (dot(v, m) * v.z <= 0) return 0.0f;
+    const float temp = 1 - v.z * v.z;
+    const float tanTheta = temp <= 0.0f ? 0.0f : fabsf(sqrtf(temp) / v.z);
+    if (tanTheta == 0.0f) return 1.0f;
+    if (b.distr != 1) {
+        const float a = 1.0f / (b.alpha * tanTheta);
+        if (a >= 1.6f) return 1.0f;
+        const float aSqr = a * a;
+        return (3.535f * a + 2.181f * aSqr) / (1.0f + 2.276f * a + 2.577f * aSqr);
+    }
+    return 2.0f / (1.0f + mfd_hypot2(1.0f, b.alpha * tanTheta));
+}
+CP_D float mfd_pdf(const BsdfDev &b, const V3 &wi, const V3 &m) {
+    if (!b.sampleVisible) return mfd_eval(b, m) * m.z;
+    if (wi.z == 0) return 0.0f;
+    return mfd_smithG1(b, wi, m) * fabsf(dot(wi, m)) * mfd_eval(b, m) / fabsf(wi.z);
+}
+CP_D V3 mfd_sampleAll(const BsdfDev &b, float sx, float sy) {
+    float cosThetaM, sinPhiM, cosPhiM;
+    cr_sincos((2.0f * kPi) * sy, &sinPhiM, &cosPhiM);
+    if (b.distr == 0) cosThetaM = 1.0f / sqrtf(1.0f + b.alpha * b.alpha * -cr_log(1.0f - sx));
+    else if (b.distr == 1) cosThetaM = 1.0f / sqrtf(1.0f + b.alpha * b.alpha * sx / (1.0f - sx));
+    else cosThetaM = cr_pow(sx, 1.0f / (b.exponent + 2.0f));
+    const float sinThetaM = sqrtf(fmaxf(0.0f, 1 - cosThetaM * cosThetaM));
+    return V3(sinThetaM * cosPhiM, sinThetaM * sinPhiM, cosThetaM);
+}
+CP_D void mfd_sampleVisible11(const BsdfDev &b, float thetaI, float sx, float sy, float &slopeX, float &slopeY) {
+    const float SQRT_PI_INV = 1 / sqrtf(kPi);
+    if (b.distr == 0) {
+        if (thetaI < 1e-4f) {
+            const float r = sqrtf(-cr_log(1.0f - sx));
+            float sinPhi, cosPhi; cr_sincos(2 * kPi * sy, &sinPhi, &cosPhi);
+            slopeX = r * cosPhi; slopeY = r * sinPhi; return;
+        }
+        const float tanThetaI = (float) tan((double) thetaI), cotThetaI = 1 / tanThetaI;
+        float a = -1, c = mfd_erf(cotThetaI);
+        const float sample_x = fmaxf(sx, 1e-6f);
+        const float fit = 1 + thetaI * (-0.876f + thetaI * (0.4265f - 0.0594f * thetaI));
+        float bb = c - (1 + c) * cr_pow(1 - sample_x, fit);
+        const float normalization = 1 / (1 + c + SQRT_PI_INV * tanThetaI * cr_exp(-cotThetaI * cotThetaI));
+        int it = 0;
+        while (++it < 10) {
+            if (!(bb >= a && bb <= c)) bb = 0.5f * (a + c);
+            const float invErf = mfd_erfinv(bb);
+            const float value = normalization * (1 + bb + SQRT_PI_INV * tanThetaI * cr_exp(-invErf * invErf)) - sample_x;
+            const float derivative = normalization * (1 - invErf * tanThetaI);
+            if (fabsf(value) < 1e-5f) break;
+            if (value > 0) c = bb; else a = bb;
+            bb -= value / derivative;
+        }
+        slopeX = mfd_erfinv(bb);
+        slopeY = mfd_erfinv(2.0f * fmaxf(sy, 1e-6f) - 1.0f);
+    } else {
+        if (thetaI < 1e-4f) {
+            const float r = safe_sqrt(sx / (1 - sx));
+            float sinPhi, cosPhi; cr_sincos(2 * kPi * sy, &sinPhi, &cosPhi);
+            slopeX = r * cosPhi; slopeY = r * sinPhi; return;
+        }
+        const float tanThetaI = (float) tan((double) thetaI);
+        const float a = 1 / tanThetaI;
+        const float G1 = 2.0f / (1.0f + safe_sqrt(1.0f + 1.0f / (a * a)));
+        float A = 2.0f * sx / G1 - 1.0f;
+        if (fabsf(A) == 1) A -= mfd_signum(A) * kEpsilon;
+        const float tmp = 1.0f / (A * A - 1.0f);
+        const float B = tanThetaI;
+        const float D = safe_sqrt(B * B * tmp * tmp - (A * A - B * B) * tmp);
+        const float slope_x_1 = B * tmp - D, slope_x_2 = B * tmp + D;
+        slopeX = (A < 0.0f || slope_x_2 > 1.0f / tanThetaI) ? slope_x_1 : slope_x_2;
+        float S;
+        if (sy > 0.5f) { S = 1.0f; sy = 2.0f * (sy - 0.5f); }
+        else { S = -1.0f; sy = 2.0f * (0.5f - sy); }
+        const float z = (sy * (sy * (sy * (-0.365728915865723f) + 0.790235037209296f) - 0.424965825137544f) + 0.000152998850436920f) /
+                        (sy * (sy * (sy * (sy * 0.169507819808272f - 0.397203533833404f) - 0.232500544458471f) + 1.0f) - 0.539825872510702f);
+        slopeY = S * z * sqrtf(1.0f + slopeX * slopeX);
+    }
+}
+CP_D V3 mfd_sample(const BsdfDev &b, const V3 &_wi, float sx, float sy) {
+    if (!b.sampleVisible) return mfd_sampleAll(b, sx, sy);
+    const V3 wi = normalize(V3(b.alpha * _wi.x, b.alpha * _wi.y, _wi.z));
+    float theta = 0, phi = 0;
+    if (wi.z < 0.99999f) { theta = cr_acos(wi.z); phi = cr_atan2(wi.y, wi.x); }
+    float sinPhi, cosPhi; cr_sincos(phi, &sinPhi, &cosPhi);
+    float slx, sly;
+    mfd_sampleVisible11(b, theta, sx, sy, slx, sly);
+    float rx = cosPhi * slx - sinPhi * sly, ry = sinPhi * slx + cosPhi * sly;
+    rx *= b.alpha; ry *= b.alpha;
+    const float normalization = 1.0f / sqrtf(rx * rx + ry * ry + 1.0f);
+    return V3(-rx * normalization, -ry * normalization, normalization);
+}
+
+CP_D V3 rp_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
+    if (wi.z <= 0 || wo.z <= 0) return V3(0.0f);
+    V3 result(0.0f);
+    const V3 H = normalize(wo + wi);
+    const float D = mfd_eval(b, H);
+    const float F = fresnelDielectricExt(dot(wi, H), b.eta);
+    const float G = mfd_smithG1(b, wi, H) * mfd_smithG1(b, wo, H);
+    const float value = F * D * G / (4.0f * wi.z);
+    result += b.specular * value;
+    V3 diff = b.diffuse;
+    const float T12 = ma_T(b, wi.z), T21 = ma_T(b, wo.z);
+    if (b.nonlinear) diff = V3(diff.x / (1.0f - diff.x * b.Fdr), diff.y / (1.0f - diff.y * b.Fdr), diff.z / (1.0f - diff.z * b.Fdr));
+    else diff = diff / (1 - b.Fdr);
+    result += diff * (kInvPi * wo.z * T12 * T21 * b.invEta2);
+    return result;
+}
+CP_D float rp_probSpecular(const BsdfDev &b, float cosThetaI) {
+    const float probSpecular = 1 - ma_T(b, cosThetaI);
+    return (probSpecular * b.specW) / (probSpecular * b.specW + (1 - probSpecular) * (1 - b.specW));
+}
+CP_D float rp_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) {
+    if (wi.z <= 0 || wo.z <= 0) return 0.0f;
+    const V3 H = normalize(wo + wi);
+    const float probSpecular = rp_probSpecular(b, wi.z), probDiffuse = 1 - probSpecular;
+    const float dwh_dwo = 1.0f / (4.0f * dot(wo, H));
+    const float prob = mfd_pdf(b, wi, H);
+    float result = prob * dwh_dwo * probSpecular;
+    result += probDiffuse * (kInvPi * wo.z);
+    return result;
+}
+CP_D BsdfSampleOut rp_sample(const BsdfDev &b, const V3 &wi, float sx, float sy) {
+    BsdfSampleOut r; r.wo = V3(0.0f); r.weight = V3(0.0f); r.pdf = 0.0f; r.type = 0; r.component = -1;
+    if (wi.z <= 0) return r;
+    bool choseSpecular = true;
+    const float probSpecular = rp_probSpecular(b, wi.z);
+    if (sy < probSpecular) sy /= probSpecular;
+    else { sy = (sy - probSpecular) / (1 - probSpecular); choseSpecular = false; }
+    if (choseSpecular) {
+        const V3 m = mfd_sample(b, wi, sx, sy);
+        r.wo = 2 * dot(wi, m) * m - wi;
+        r.component = 0; r.type = EGlossyReflection;
+        if (r.wo.z <= 0) return r;
+    } else {
+        r.component = 1; r.type = EDiffuseReflection;
+        r.wo = squareToCosineHemisphere(sx, sy);
+    }
+    r.pdf = rp_pdf(b, wi, r.wo);
+    if (r.pdf == 0) return r;
+    r.weight = rp_eval(b, wi, r.wo) / r.pdf;
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------ SmoothDiffuse (+ TwoSided)
 // src/bsdfs/diffuse.cpp:109-156 with a constant reflectance; src/bsdfs/twosided.cpp:101-181 when b.twoSided
 CP_D V3 df_eval(const BsdfDev &b, V3 wi, V3 wo) {
@@ -322,16 +512,16 @@ CP_D BsdfSampleOut df_sample(const BsdfDev &b, V3 wi, float sx, float sy) {
 
 // ------------------------------------------------------------------------------------------ dispatch
 CP_D V3 bsdf_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
-    return b.kind == 0 ? kk_eval(b, wi, wo) : b.kind == 1 ? ma_eval(b, wi, wo) : b.kind == 2 ? df_eval(b, wi, wo) : mf_eval(b, wi, wo);
+    return b.kind == 0 ? kk_eval(b, wi, wo) : b.kind == 1 ? ma_eval(b, wi, wo) : b.kind == 2 ? df_eval(b, wi, wo) : b.kind == 3 ? mf_eval(b, wi, wo) : rp_eval(b, wi, wo);
 }
 CP_D float bsdf_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) {
-    return b.kind == 0 ? kk_pdf(b, wi, wo) : b.kind == 1 ? 1.0f : b.kind == 2 ? df_pdf(b, wi, wo) : mf_pdf(b, wi, wo);
+    return b.kind == 0 ? kk_pdf(b, wi, wo) : b.kind == 1 ? 1.0f : b.kind == 2 ? df_pdf(b, wi, wo) : b.kind == 3 ? mf_pdf(b, wi, wo) : rp_pdf(b, wi, wo);
 }
 // true for BSDFs whose sample() pulls more numbers from the sampler than the two it is handed (fixed Marschner: 4)
 CP_D bool bsdf_draws_extra(const BsdfDev &b) { return b.kind == 3; }
 CP_D BsdfSampleOut bsdf_sample(const BsdfDev &b, const V3 &wi, float sx, float sy, const float4 &extra) {
     return b.kind == 0 ? kk_sample(b, wi, sx, sy) : b.kind == 1 ? ma_sample(b, wi, sx, sy) : b.kind == 2 ? df_sample(b, wi, sx, sy)
-                                                                                         : mf_sample(b, wi, extra.x, extra.y, extra.z, extra.w);
+         : b.kind == 3 ? mf_sample(b, wi, extra.x, extra.y, extra.z, extra.w) : rp_sample(b, wi, sx, sy);
 }
 
 } // namespace cp

@@ -7,7 +7,8 @@
 //   Transform::lookAt / rotate / translate / scale                            src/libcore/transform.cpp
 //   PerspectiveCamera fov handling                                            src/librender/sensor.cpp:225-300
 // Plugins understood: integrator `path`; sensor `perspective` (film `ldrfilm`/`hdrfilm`, rfilter `tent`/`box`/`gaussian`,
-// any sampler: only sampleCount is used); bsdf `kajiyakay`, `marschner`, `diffuse`, `twosided`; shape `hair`, `obj`; emitter `sunsky`.
+// any sampler: only sampleCount is used); bsdf `kajiyakay`, `marschner`, `marschner_fixed`, `roughplastic`, `diffuse`, `twosided`; shape `hair`,
+// `obj`; emitter `sunsky`.
 // Anything else raises an error naming the plugin (the reference would dlopen plugins/<type>.so, src/libcore/plugin.cpp:222-245).
 #include "../../include/cudapath.h"
 #include <cmath>
@@ -203,6 +204,24 @@ struct Loader {
             if (child(n, "float", "alphaU") || child(n, "float", "alphaV")) throw std::runtime_error("The 'marschner' plugin does not support anisotropic microfacet distributions!");
             id = cudapath_add_bsdf_marschner(ctx, (float) ior("intIOR", 1.5046), (float) ior("extIOR", 1.000277), d, s, (float) getFloat(n, "alpha", 0.1),
                                              di, getBool(n, "nonlinear", false) ? 1 : 0);
+        } else if (type == "roughplastic") {
+            auto ior = [&](const char *name, double def) {
+                if (child(n, "float", name)) return getFloat(n, name, def);
+                auto c = child(n, "string", name);
+                if (!c) return def;
+                std::string v = lower(c->get("value"));
+                if (v == "polypropylene") return 1.49; if (v == "amber") return 1.55; if (v == "air") return 1.000277; if (v == "bk7") return 1.5046;
+                if (v == "vacuum") return 1.0; if (v == "water") return 1.3330;
+                throw std::runtime_error("Unable to find an IOR value for \"" + v + "\"");
+            };
+            float d[3], s[3]; getColor(n, "diffuseReflectance", 0.5f, d); getColor(n, "specularReflectance", 1.0f, s);
+            std::string distr = lower(getString(n, "distribution", "beckmann"));
+            int di = distr == "beckmann" ? 0 : distr == "ggx" ? 1 : (distr == "phong" || distr == "as") ? 2 : -1;
+            if (di < 0) throw std::runtime_error("Specified an invalid distribution \"" + distr + "\", must be \"beckmann\", \"ggx\", or \"phong\"/\"as\"!");
+            if (child(n, "float", "alphaU") || child(n, "float", "alphaV")) throw std::runtime_error("The 'roughplastic' plugin currently does not support anisotropic microfacet distributions!");
+            if (child(n, "texture", "alpha") || child(n, "texture", "diffuseReflectance") || child(n, "texture", "specularReflectance")) throw std::runtime_error("roughplastic: textured parameters are not supported");
+            id = cudapath_add_bsdf_roughplastic(ctx, (float) ior("intIOR", 1.49), (float) ior("extIOR", 1.000277), d, s, (float) getFloat(n, "alpha", 0.1), di,
+                                                getBool(n, "sampleVisible", true) ? 1 : 0, getBool(n, "nonlinear", false) ? 1 : 0);
         } else if (type == "marschner_fixed") {      // the class of src/bsdfs/marschner.cpp, which the fork's build leaves out
             auto ior = [&](const char *name, double def) {
                 if (child(n, "float", name)) return getFloat(n, name, def);
@@ -229,7 +248,7 @@ struct Loader {
             float r[3]; getColor(*d, "reflectance", 0.5f, r);
             if (child(*d, "rgb", "diffuseReflectance") || child(*d, "spectrum", "diffuseReflectance")) getColor(*d, "diffuseReflectance", 0.5f, r);
             id = cudapath_add_bsdf_diffuse(ctx, r, type == "twosided" ? 1 : 0);
-        } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, diffuse, twosided)");
+        } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, roughplastic, diffuse, twosided)");
         check(id);
         if (n.has("id")) bsdfIds[n.get("id")] = id;
         return id;

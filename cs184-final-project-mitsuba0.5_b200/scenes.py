@@ -24,6 +24,8 @@ _SUNSKY = dict(turbidity=3.0, skyScale=5.0, sunScale=19.0912, sunRadiusScale=37.
 _HAIR_RGB = (0.143016, 0.0156076, 1.80928e-005)
 # Marschner block of models/straight-hair/scene_marschner.xml:31-39
 _MARSCHNER_C3 = dict(type='marschner', alpha=0.2, distribution='ggx', intIOR=1.55, extIOR=1.0, diffuseReflectance=_HAIR_RGB)
+# roughplastic block of the DEFAULT scene files, models/{straight-hair,curly-hair,furball}/scene.xml:31-38
+_ROUGHPLASTIC = dict(type='roughplastic', alpha=0.2, distribution='ggx', intIOR=1.55, extIOR=1.0, nonlinear=False, diffuseReflectance=_HAIR_RGB)
 _KKAY = dict(type='kajiyakay', diffuseReflectance=_HAIR_RGB, exponent=10.0)   # models/straight-hair/scene_kkay.xml:31-34
 
 SCENES = {
@@ -45,6 +47,9 @@ SCENES = {
     # C4: models/furball/scene.xml geometry/camera + the Marschner block, maxDepth 32, 2048x2048, 256 spp
     'furball': dict(camera=_CAM_FURBALL, fov=35.0, sun=_SUN_B, width=2048, height=2048, spp=256, maxDepth=32,
                     shapes=[dict(generator='furball', radius=0.00216667, bsdf=dict(_MARSCHNER_C3, id='hair'))]),
+    # models/straight-hair/scene.xml as shipped (roughplastic on the fibers), reduced to 512x512 / 16 spp / depth 8
+    'straight-hair-default': dict(camera=_CAM_STRAIGHT, fov=35.0, sun=_SUN_A, width=512, height=512, spp=16, maxDepth=8,
+                                  shapes=[dict(generator='straight', radius=0.00566563, bsdf=dict(_ROUGHPLASTIC, id='hair'))]),
     # T1: the straight-hair fibers on a head -- an ellipsoid mesh with smooth vertex normals under the scalp points and a
     # ground quad with face normals (both `diffuse`, the quad inside `twosided`), i.e. fibers and triangles in one BVH
     'hair-on-head': dict(camera=_CAM_STRAIGHT, fov=35.0, sun=_SUN_A, width=512, height=512, spp=16, maxDepth=8,
@@ -286,7 +291,9 @@ def scene_xml(name, overrides=None):
         for k, v in b.items():
             if k in ('type', 'id'):
                 continue
-            if isinstance(v, str):
+            if isinstance(v, bool):
+                lines.append('\t\t<boolean name="%s" value="%s"/>' % (k, 'true' if v else 'false'))
+            elif isinstance(v, str):
                 lines.append('\t\t<string name="%s" value="%s"/>' % (k, v))
             elif isinstance(v, (tuple, list)):
                 lines.append('\t\t<rgb name="%s" value="%s"/>' % (k, _fmt(v)))

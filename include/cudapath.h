@@ -36,6 +36,12 @@ int cudapath_add_bsdf_kajiyakay(cudapath_ctx *ctx, const float diffuse_reflectan
 int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior, const float diffuse_reflectance[3],
                                 const float specular_reflectance[3], float alpha, int distribution, int nonlinear);
 
+/* `roughplastic` plugin (the BSDF of the default models/{straight-hair,curly-hair,furball}/scene.xml): RoughPlastic ctor+configure(),
+ * src/bsdfs/roughplastic.cpp:186-304, with MicrofacetDistribution(props) of src/bsdfs/microfacet.h:99-146.  distribution: 0 beckmann,
+ * 1 ggx, 2 phong; sample_visible as the `sampleVisible` property (default true; ignored for phong).  Reference defaults: int_ior 1.49
+ * (polypropylene), ext_ior 1.000277 (air), alpha 0.1, specular 1, diffuse 0.5.  Returns the bsdf id. */
+int cudapath_add_bsdf_roughplastic(cudapath_ctx *ctx, float int_ior, float ext_ior, const float diffuse_reflectance[3], const float specular_reflectance[3],
+                                   float alpha, int distribution, int sample_visible, int nonlinear);
 /* The fork's second Marschner class, src/bsdfs/marschner.cpp (NOT part of its build; SURVEY M7, "fixed" mode): ctor :110-138 with the
  * hard-coded sigmaA = 0.22 / beta = 0.1 / scale angle -0.1, eval with the TRT lobe only (:309-341), the real pdf (:347-407) and a
  * sample() that draws two additional 2-D numbers from the sampler (:421-535).  Reference defaults: int_ior 1.55 (amber), ext_ior

@@ -653,6 +653,249 @@ struct MarschnerFixed {
 };
 
 // ---------------------------------------------------------------------------------------------
+// RoughPlastic (`roughplastic`, the BSDF of the default models/*/scene.xml files)
+//   MicrofacetDistribution  src/bsdfs/microfacet.h:184-232 (eval), :238-279 (sample/pdf), :284-386 (sampleAll), :389-447 (visible
+//   normals), :470-510 (smithG1, G), :529-538 (projectRoughness), :555-673 (sampleVisible11), :677-680 (Phong exponent)
+//   math::erf / erfinv / hypot2  src/libcore/math.cpp:25-86;  RoughPlastic  src/bsdfs/roughplastic.cpp:186-235,258-304,325-494
+// Isotropic roughness only (the plugin rejects anisotropic distributions, roughplastic.cpp:212-214).
+// ---------------------------------------------------------------------------------------------
+namespace mf {
+static inline float signum(float v) { return v < 0 ? -1.0f : (v > 0 ? 1.0f : 0.0f); }
+static inline float erfinv(float x) { // math.cpp:25-53
+    float w = -cr::log((1.0f - x) * (1.0f + x));
+    float p;
+    if (w < 5.0f) {
+        w = w - 2.5f;
+        p = 2.81022636e-08f; p = 3.43273939e-07f + p * w; p = -3.5233877e-06f + p * w; p = -4.39150654e-06f + p * w;
+        p = 0.00021858087f + p * w; p = -0.00125372503f + p * w; p = -0.00417768164f + p * w; p = 0.246640727f + p * w; p = 1.50140941f + p * w;
+    } else {
+        w = std::sqrt(w) - 3.0f;
+        p = -0.000200214257f; p = 0.000100950558f + p * w; p = 0.00134934322f + p * w; p = -0.00367342844f + p * w;
+        p = 0.00573950773f + p * w; p = -0.0076224613f + p * w; p = 0.00943887047f + p * w; p = 1.00167406f + p * w; p = 2.83297682f + p * w;
+    }
+    return p * x;
+}
+static inline float erf(float x) { // math.cpp:55-72
+    const float a1 = 0.254829592f, a2 = -0.284496736f, a3 = 1.421413741f, a4 = -1.453152027f, a5 = 1.061405429f, p = 0.3275911f;
+    float sign = signum(x);
+    x = std::abs(x);
+    float t = 1.0f / (1.0f + p * x);
+    float y = 1.0f - (((((a5 * t + a4) * t) + a3) * t + a2) * t + a1) * t * cr::exp(-x * x);
+    return sign * y;
+}
+static inline float hypot2(float a, float b) { // math.cpp:74-86
+    float r;
+    if (std::abs(a) > std::abs(b)) { r = b / a; r = std::abs(a) * std::sqrt(1.0f + r * r); }
+    else if (b != 0.0f) { r = a / b; r = std::abs(b) * std::sqrt(1.0f + r * r); }
+    else r = 0.0f;
+    return r;
+}
+}
+
+struct MicrofacetDistribution {
+    int type = 0;            // 0 beckmann, 1 ggx, 2 phong
+    float alpha = 0.1f, exponent = 0;
+    bool sampleVis = true;
+    void configure(int t, float a, bool visible) {
+        type = t; alpha = std::max(a, 1e-4f); sampleVis = visible;
+        if (type == 2) { sampleVis = false; exponent = std::max(2.0f / (alpha * alpha) - 2.0f, 0.0f); }
+    }
+    float eval(const V3 &m) const { // :184-232
+        if (m.z <= 0) return 0.0f;
+        float cosTheta2 = m.z * m.z;
+        float beckmannExponent = ((m.x * m.x) / (alpha * alpha) + (m.y * m.y) / (alpha * alpha)) / cosTheta2;
+        float result;
+        if (type == 0) result = cr::exp(-beckmannExponent) / (kPi * alpha * alpha * cosTheta2 * cosTheta2);
+        else if (type == 1) { float root = (1.0f + beckmannExponent) * cosTheta2; result = 1.0f / (kPi * alpha * alpha * root * root); }
+        else result = std::sqrt((exponent + 2) * (exponent + 2)) * kInvTwoPi * cr::pow(m.z, exponent);
+        if (result * m.z < 1e-20f) result = 0;
+        return result;
+    }
+    float smithG1(const V3 &v, const V3 &m) const { // :470-505
+        if (dot(v, m) * v.z <= 0) return 0.0f;
+        float temp = 1 - v.z * v.z;                      // Frame::tanTheta (frame.h): sqrt(1 - cos^2) / cos, 0 when temp <= 0
+        float tanTheta = temp <= 0.0f ? 0.0f : std::abs(std::sqrt(temp) / v.z);
+        if (tanTheta == 0.0f) return 1.0f;
+        if (type != 1) {
+            float a = 1.0f / (alpha * tanTheta);
+            if (a >= 1.6f) return 1.0f;
+            float aSqr = a * a;
+            return (3.535f * a + 2.181f * aSqr) / (1.0f + 2.276f * a + 2.577f * aSqr);
+        }
+        float root = alpha * tanTheta;
+        return 2.0f / (1.0f + mf::hypot2(1.0f, root));
+    }
+    float G(const V3 &wi, const V3 &wo, const V3 &m) const { return smithG1(wi, m) * smithG1(wo, m); }
+    float pdfVisible(const V3 &wi, const V3 &m) const { // :442-447
+        if (wi.z == 0) return 0.0f;
+        return smithG1(wi, m) * std::abs(dot(wi, m)) * eval(m) / std::abs(wi.z);
+    }
+    float pdf(const V3 &wi, const V3 &m) const { return sampleVis ? pdfVisible(wi, m) : eval(m) * m.z; }
+    V3 sampleAll(float sx, float sy) const { // :284-380 (isotropic)
+        float cosThetaM, sinPhiM, cosPhiM;
+        if (type == 0) {
+            sinPhiM = cr::sin((2.0f * kPi) * sy); cosPhiM = cr::cos((2.0f * kPi) * sy);
+            float tanThetaMSqr = alpha * alpha * -cr::log(1.0f - sx);
+            cosThetaM = 1.0f / std::sqrt(1.0f + tanThetaMSqr);
+        } else if (type == 1) {
+            sinPhiM = cr::sin((2.0f * kPi) * sy); cosPhiM = cr::cos((2.0f * kPi) * sy);
+            float tanThetaMSqr = alpha * alpha * sx / (1.0f - sx);
+            cosThetaM = 1.0f / std::sqrt(1.0f + tanThetaMSqr);
+        } else {
+            float phiM = (2.0f * kPi) * sy;
+            sinPhiM = cr::sin(phiM); cosPhiM = cr::cos(phiM);
+            cosThetaM = cr::pow(sx, 1.0f / (exponent + 2.0f));
+        }
+        float sinThetaM = std::sqrt(std::max(0.0f, 1 - cosThetaM * cosThetaM));
+        return V3(sinThetaM * cosPhiM, sinThetaM * sinPhiM, cosThetaM);
+    }
+    void sampleVisible11(float thetaI, float sx, float sy, float &slopeX, float &slopeY) const { // :555-673
+        const float SQRT_PI_INV = 1 / std::sqrt(kPi);
+        if (type == 0) {
+            if (thetaI < 1e-4f) {
+                float r = std::sqrt(-cr::log(1.0f - sx));
+                float sinPhi = cr::sin(2 * kPi * sy), cosPhi = cr::cos(2 * kPi * sy);
+                slopeX = r * cosPhi; slopeY = r * sinPhi; return;
+            }
+            float tanThetaI = cr::tan(thetaI), cotThetaI = 1 / tanThetaI;
+            float a = -1, c = mf::erf(cotThetaI);
+            float sample_x = std::max(sx, 1e-6f);
+            float fit = 1 + thetaI * (-0.876f + thetaI * (0.4265f - 0.0594f * thetaI));
+            float b = c - (1 + c) * cr::pow(1 - sample_x, fit);
+            float normalization = 1 / (1 + c + SQRT_PI_INV * tanThetaI * cr::exp(-cotThetaI * cotThetaI));
+            int it = 0;
+            while (++it < 10) {
+                if (!(b >= a && b <= c)) b = 0.5f * (a + c);
+                float invErf = mf::erfinv(b);
+                float value = normalization * (1 + b + SQRT_PI_INV * tanThetaI * cr::exp(-invErf * invErf)) - sample_x;
+                float derivative = normalization * (1 - invErf * tanThetaI);
+                if (std::abs(value) < 1e-5f) break;
+                if (value > 0) c = b; else a = b;
+                b -= value / derivative;
+            }
+            slopeX = mf::erfinv(b);
+            slopeY = mf::erfinv(2.0f * std::max(sy, 1e-6f) - 1.0f);
+        } else {
+            if (thetaI < 1e-4f) {
+                float r = safe_sqrt(sx / (1 - sx));
+                float sinPhi = cr::sin(2 * kPi * sy), cosPhi = cr::cos(2 * kPi * sy);
+                slopeX = r * cosPhi; slopeY = r * sinPhi; return;
+            }
+            float tanThetaI = cr::tan(thetaI);
+            float a = 1 / tanThetaI;
+            float G1 = 2.0f / (1.0f + safe_sqrt(1.0f + 1.0f / (a * a)));
+            float A = 2.0f * sx / G1 - 1.0f;
+            if (std::abs(A) == 1) A -= mf::signum(A) * kEpsilon;
+            float tmp = 1.0f / (A * A - 1.0f);
+            float B = tanThetaI;
+            float D = safe_sqrt(B * B * tmp * tmp - (A * A - B * B) * tmp);
+            float slope_x_1 = B * tmp - D, slope_x_2 = B * tmp + D;
+            slopeX = (A < 0.0f || slope_x_2 > 1.0f / tanThetaI) ? slope_x_1 : slope_x_2;
+            float S;
+            if (sy > 0.5f) { S = 1.0f; sy = 2.0f * (sy - 0.5f); }
+            else { S = -1.0f; sy = 2.0f * (0.5f - sy); }
+            float z = (sy * (sy * (sy * (-0.365728915865723f) + 0.790235037209296f) - 0.424965825137544f) + 0.000152998850436920f) /
+                      (sy * (sy * (sy * (sy * 0.169507819808272f - 0.397203533833404f) - 0.232500544458471f) + 1.0f) - 0.539825872510702f);
+            slopeY = S * z * std::sqrt(1.0f + slopeX * slopeX);
+        }
+    }
+    V3 sampleVisible(const V3 &_wi, float sx, float sy) const { // :389-439
+        V3 wi = normalize(V3(alpha * _wi.x, alpha * _wi.y, _wi.z));
+        float theta = 0, phi = 0;
+        if (wi.z < 0.99999f) { theta = cr::acos(wi.z); phi = cr::atan2(wi.y, wi.x); }
+        float sinPhi = cr::sin(phi), cosPhi = cr::cos(phi);
+        float slx, sly;
+        sampleVisible11(theta, sx, sy, slx, sly);
+        float rx = cosPhi * slx - sinPhi * sly, ry = sinPhi * slx + cosPhi * sly;
+        rx *= alpha; ry *= alpha;
+        float normalization = 1.0f / std::sqrt(rx * rx + ry * ry + 1.0f);
+        return V3(-rx * normalization, -ry * normalization, normalization);
+    }
+    V3 sample(const V3 &wi, float sx, float sy) const { return sampleVis ? sampleVisible(wi, sx, sy) : sampleAll(sx, sy); }
+};
+
+struct RoughPlastic {
+    float eta = 1.5f, invEta2 = 0, alpha = 0.1f, specularSamplingWeight = 0;
+    V3 diffuse = V3(0.5f), specular = V3(1.0f);
+    bool nonlinear = false;
+    MicrofacetDistribution distr;
+    RoughTransmittance extRT, intRT;
+    // ctor :186-235 + configure :258-304
+    void configure(float intIOR, float extIOR, V3 diff, V3 spec, float alpha_, int type, bool sampleVisible, bool nonlin, const std::string &dataDir) {
+        eta = intIOR / extIOR;
+        nonlinear = nonlin;
+        distr.configure(type, alpha_, sampleVisible);
+        alpha = distr.alpha;
+        float mx = maxc(spec); if (mx > 1.0f) spec = spec * (0.99f * (1.0f / mx));   // ensureEnergyConservation(.., 1.0f), bsdf.cpp:88-113
+        mx = maxc(diff); if (mx > 1.0f) diff = diff * (0.99f * (1.0f / mx));
+        specular = spec; diffuse = diff;
+        float dAvg = luminance(diff), sAvg = luminance(spec);
+        specularSamplingWeight = sAvg / (dAvg + sAvg);
+        invEta2 = 1.0f / (eta * eta);
+        static const char *names[3] = {"beckmann", "ggx", "phong"};
+        extRT.load(dataDir + "/microfacet/" + names[type] + ".dat");
+        extRT.checkRanges(eta, alpha);
+        intRT = extRT;
+        extRT.setEta(eta);
+        intRT.setEta(1 / eta);
+        extRT.setAlpha(alpha);
+    }
+    V3 eval(const V3 &wi, const V3 &wo) const { // :325-375
+        if (wi.z <= 0 || wo.z <= 0) return V3(0.0f);
+        V3 result(0.0f);
+        const V3 H = normalize(wo + wi);
+        const float D = distr.eval(H);
+        const float F = fresnelDielectricExt(dot(wi, H), eta);
+        const float G = distr.G(wi, wo, H);
+        float value = F * D * G / (4.0f * wi.z);
+        result += specular * value;
+        V3 diff = diffuse;
+        float T12 = extRT.eval(wi.z, alpha), T21 = extRT.eval(wo.z, alpha);
+        float Fdr = 1 - intRT.evalDiffuse(alpha);
+        if (nonlinear) diff = V3(diff.x / (1.0f - diff.x * Fdr), diff.y / (1.0f - diff.y * Fdr), diff.z / (1.0f - diff.z * Fdr));
+        else diff = diff / (1 - Fdr);
+        result += diff * (kInvPi * wo.z * T12 * T21 * invEta2);
+        return result;
+    }
+    float probSpecularOf(float cosThetaI) const {
+        float probSpecular = 1 - extRT.eval(cosThetaI, alpha);
+        return (probSpecular * specularSamplingWeight) / (probSpecular * specularSamplingWeight + (1 - probSpecular) * (1 - specularSamplingWeight));
+    }
+    float pdf(const V3 &wi, const V3 &wo) const { // :377-436
+        if (wi.z <= 0 || wo.z <= 0) return 0.0f;
+        const V3 H = normalize(wo + wi);
+        float probSpecular = probSpecularOf(wi.z), probDiffuse = 1 - probSpecular;
+        const float dwh_dwo = 1.0f / (4.0f * dot(wo, H));
+        const float prob = distr.pdf(wi, H);
+        float result = prob * dwh_dwo * probSpecular;
+        result += probDiffuse * (kInvPi * wo.z);
+        return result;
+    }
+    BSDFSample sample(const V3 &wi, float sx, float sy) const { // :438-494
+        BSDFSample r; r.weight = V3(0.0f); r.pdf = 0;
+        if (wi.z <= 0) return r;
+        bool choseSpecular = true;
+        float probSpecular = probSpecularOf(wi.z);
+        if (sy < probSpecular) sy /= probSpecular;
+        else { sy = (sy - probSpecular) / (1 - probSpecular); choseSpecular = false; }
+        if (choseSpecular) {
+            V3 m = distr.sample(wi, sx, sy);
+            r.wo = 2 * dot(wi, m) * m - wi;
+            r.sampledComponent = 0; r.sampledType = EGlossyReflection;
+            if (r.wo.z <= 0) return r;
+        } else {
+            r.sampledComponent = 1; r.sampledType = EDiffuseReflection;
+            r.wo = squareToCosineHemisphere(sx, sy);
+        }
+        r.eta = 1.0f;
+        r.pdf = pdf(wi, r.wo);
+        if (r.pdf == 0) return r;
+        r.weight = eval(wi, r.wo) / r.pdf;
+        return r;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // SmoothDiffuse (`diffuse` plugin, constant reflectance) -- src/bsdfs/diffuse.cpp:92-156, optionally wrapped in
 // `twosided` (src/bsdfs/twosided.cpp:101-181) with the same nested BRDF on both sides.  Used for triangle meshes.
 // ---------------------------------------------------------------------------------------------

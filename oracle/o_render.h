@@ -112,11 +112,13 @@ struct BSDFAny {
     std::shared_ptr<Marschner> ma;
     SmoothDiffuse df;
     std::shared_ptr<MarschnerFixed> mf;
-    V3 eval(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.eval(wi, wo) : kind == 1 ? ma->eval(wi, wo) : kind == 2 ? df.eval(wi, wo) : mf->eval(wi, wo); }
-    float pdf(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.pdf(wi, wo) : kind == 1 ? ma->pdf(wi, wo) : kind == 2 ? df.pdf(wi, wo) : mf->pdf(wi, wo); }
+    std::shared_ptr<RoughPlastic> rp;      // kind 4: `roughplastic` (default BSDF of the models/*/scene.xml files)
+    V3 eval(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.eval(wi, wo) : kind == 1 ? ma->eval(wi, wo) : kind == 2 ? df.eval(wi, wo) : kind == 3 ? mf->eval(wi, wo) : rp->eval(wi, wo); }
+    float pdf(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.pdf(wi, wo) : kind == 1 ? ma->pdf(wi, wo) : kind == 2 ? df.pdf(wi, wo) : kind == 3 ? mf->pdf(wi, wo) : rp->pdf(wi, wo); }
     // `extra` = four more uniform numbers: only the fixed Marschner draws them (two sampler->next2D() calls inside its sample())
     BSDFSample sample(const V3 &wi, float sx, float sy, const float *extra) const {
-        return kind == 0 ? kk.sample(wi, sx, sy) : kind == 1 ? ma->sample(wi, sx, sy) : kind == 2 ? df.sample(wi, sx, sy) : mf->sample(wi, extra[0], extra[1], extra[2], extra[3]);
+        return kind == 0 ? kk.sample(wi, sx, sy) : kind == 1 ? ma->sample(wi, sx, sy) : kind == 2 ? df.sample(wi, sx, sy)
+             : kind == 3 ? mf->sample(wi, extra[0], extra[1], extra[2], extra[3]) : rp->sample(wi, sx, sy);
     }
     bool drawsExtra() const { return kind == 3; }
 };

@@ -64,6 +64,20 @@ int orc_add_bsdf_marschner_fixed(void *sp, float intIOR, float extIOR) {
     ORC_CATCH
 }
 
+// `roughplastic` plugin (src/bsdfs/roughplastic.cpp); distribution: 0 beckmann, 1 ggx, 2 phong
+int orc_add_bsdf_roughplastic(void *sp, float intIOR, float extIOR, const float *diffuse, const float *specular, float alpha, int distribution,
+                              int sampleVisible, int nonlinear, const char *dataDir) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    BSDFAny b; b.kind = 4;
+    b.rp = std::make_shared<RoughPlastic>();
+    b.rp->configure(intIOR, extIOR, V3(diffuse[0], diffuse[1], diffuse[2]), V3(specular[0], specular[1], specular[2]), alpha, distribution,
+                    sampleVisible != 0, nonlinear != 0, dataDir);
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+    ORC_CATCH
+}
+
 // `diffuse` plugin with a constant reflectance (src/bsdfs/diffuse.cpp), optionally inside `twosided`
 int orc_add_bsdf_diffuse(void *sp, const float *reflectance, int twoSided) {
     ORC_TRY

@@ -98,6 +98,11 @@ class Scene:
         if type == 'kajiyakay':
             d = f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3)); s = f32(np.broadcast_to(props.get('specularReflectance', 0.2), 3))
             return check(self.L.orc_add_bsdf_kajiyakay(self.h, p(d), p(s), ctypes.c_float(props.get('exponent', 30.0))))
+        if type == 'roughplastic':
+            d = f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3)); s = f32(np.broadcast_to(props.get('specularReflectance', 1.0), 3))
+            return check(self.L.orc_add_bsdf_roughplastic(self.h, ctypes.c_float(props.get('intIOR', 1.49)), ctypes.c_float(props.get('extIOR', 1.000277)), p(d), p(s),
+                                                          ctypes.c_float(props.get('alpha', 0.1)), DISTR[props.get('distribution', 'beckmann')],
+                                                          1 if props.get('sampleVisible', True) else 0, 1 if props.get('nonlinear', False) else 0, DATA_DIR.encode()))
         if type == 'marschner_fixed':
             return check(self.L.orc_add_bsdf_marschner_fixed(self.h, ctypes.c_float(props.get('intIOR', 1.55)), ctypes.c_float(props.get('extIOR', 1.000277))))
         if type in ('diffuse', 'twosided'):

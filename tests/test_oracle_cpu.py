@@ -260,6 +260,35 @@ def test_marschner_fixed_mode(oracle):
     assert np.allclose(wt1[ok], ev_s[ok] / p1[ok, None], rtol=1e-5, atol=1e-7)
 
 
+def _upper(rng, n):
+    v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True); v[:, 2] = np.abs(v[:, 2])
+    return v.astype(np.float32)
+
+
+@pytest.mark.parametrize('distr', ['ggx', 'beckmann', 'phong'])
+def test_roughplastic_consistency(oracle, distr):
+    """roughplastic (src/bsdfs/roughplastic.cpp + microfacet.h): sample() weights integrate to the albedo that eval() integrates to,
+    pdf() integrates to ~1 and matches the density of the sampled directions, one-sided, energy <= 1."""
+    s = oracle.Scene()
+    b = s.add_bsdf('roughplastic', intIOR=1.55, extIOR=1.0, alpha=0.2, distribution=distr, diffuseReflectance=(0.143016, 0.0156076, 1.80928e-005))
+    rng = np.random.default_rng(31)
+    n = 200000
+    for wi0 in ([0.0, 0.0, 1.0], [0.5, 0.2, 0.84], [0.95, 0.0, 0.3]):
+        wi = np.tile(np.array([wi0], np.float32), (n, 1)); wi /= np.linalg.norm(wi, axis=1, keepdims=True)
+        wo, wt, pdf, ty = s.bsdf_sample(b, wi, rng.random((n, 2)).astype(np.float32))
+        ok = pdf > 0
+        assert set(np.unique(ty[ok] & 0xff)) <= {0x2, 0x8} and (wo[ok, 2] > 0).all()
+        u = _upper(rng, n)
+        ev, pu = s.bsdf_eval(b, wi, u)
+        albedo_eval = (ev * 2 * np.pi).mean(axis=0); albedo_sample = wt.sum(axis=0) / n
+        assert np.allclose(albedo_eval, albedo_sample, rtol=0.04, atol=2e-3) and (albedo_eval < 1).all()
+        assert abs((pu * 2 * np.pi).mean() - ok.mean()) < 0.03        # pdf mass = fraction of samples that are not rejected below the horizon
+        ev2, p2 = s.bsdf_eval(b, wi[ok], wo[ok])
+        assert np.array_equal(p2, pdf[ok]) and np.allclose(wt[ok], ev2 / p2[:, None], rtol=1e-5)
+    down = np.array([[0.3, 0.1, -0.9]], np.float32)
+    assert not s.bsdf_eval(b, down, _upper(rng, 1))[0].any() and not s.bsdf_sample(b, down, [[0.3, 0.6]])[1].any()
+
+
 # ------------------------------------------------------------------------------------------------ triangle meshes (T1)
 def _unit_tri_scene(oracle, tris, pos, normals=None, two_sided=False):
     s = oracle.Scene()
