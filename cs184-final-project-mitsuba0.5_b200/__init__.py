@@ -96,6 +96,15 @@ def load_obj_file(filename, toWorld=None, faceNormals=False, flipNormals=False):
     return xyz, idx, nrm
 
 
+def validate_scene_xml(filename, defines=None):
+    """Dry run of the scene loader (no GPU): returns the list of objects the file would create; raises CudapathError naming the
+    first unsupported plugin / parameter."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    d = ';'.join('%s=%s' % kv for kv in (defines or {}).items())
+    _check(lib().cudapath_validate_scene_xml(filename.encode(), d.encode(), buf, ctypes.c_size_t(len(buf))))
+    return buf.value.decode().splitlines()
+
+
 def bake_sunsky(turbidity=3.0, albedo=(0.2, 0.2, 0.2), sunDirection=(0, 1, 0), skyScale=1.0, sunScale=1.0, sunRadiusScale=1.0, resolution=512,
                 data_dir=None):
     """SunSkyEmitter bake (src/emitters/sunsky.cpp:100-216) -> (resolution/2, resolution, 3) fp32 lat-long map."""

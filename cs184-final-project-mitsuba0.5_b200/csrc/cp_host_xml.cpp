@@ -11,6 +11,7 @@
 // `obj`; emitter `sunsky`.
 // Anything else raises an error naming the plugin (the reference would dlopen plugins/<type>.so, src/libcore/plugin.cpp:222-245).
 #include "../../include/cudapath.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -104,6 +105,10 @@ std::string lower(std::string s) { for (char &c : s) c = (char) tolower((unsigne
 
 struct Loader {
     cudapath_ctx *ctx; std::string baseDir; std::map<std::string, std::string> defines;
+    // dry run (cudapath_validate_scene_xml): no context, no GPU -- every plugin and parameter is still parsed and checked, the calls
+    // into the C ABI are replaced by entries of `report`
+    bool dry = false; int fakeIds = 0; std::vector<std::string> report;
+    int note(const std::string &what) { report.push_back(what); return fakeIds++; }
     std::map<std::string, int> bsdfIds;
     uint32_t spp = 4;
     bool haveIntegrator = false, haveSensor = false;
@@ -187,8 +192,10 @@ struct Loader {
         int id;
         if (type == "kajiyakay") {
             float d[3], s[3]; getColor(n, "diffuseReflectance", 0.5f, d); getColor(n, "specularReflectance", 0.2f, s);
-            id = cudapath_add_bsdf_kajiyakay(ctx, d, s, (float) getFloat(n, "exponent", 30.0));
-        } else if (type == "marschner") {
+            id = (dry ? note("bsdf kajiyakay") : cudapath_add_bsdf_kajiyakay(ctx, d, s, (float) getFloat(n, "exponent", 30.0)));
+        } else if (type == "marschner" || type == "marschner_diffuse") {
+            // `marschner_diffuse` (models/*/scene_marschner_diffuse.xml, hair_curl_diffuse.xml) is the same class: the fork builds
+            // marschner_diffuse.cpp AS plugins/marschner.so (src/bsdfs/SConscript:30-31), no plugin of the longer name exists
             auto ior = [&](const char *name, double def) {           // ior.h:95-100: a float, or a named material (only the defaults are known here)
                 if (child(n, "float", name)) return getFloat(n, name, def);
                 auto c = child(n, "string", name);
@@ -202,8 +209,8 @@ struct Loader {
             int di = distr == "beckmann" ? 0 : distr == "ggx" ? 1 : (distr == "phong" || distr == "as") ? 2 : -1;
             if (di < 0) throw std::runtime_error("Specified an invalid distribution \"" + distr + "\", must be \"beckmann\", \"ggx\", or \"phong\"/\"as\"!");
             if (child(n, "float", "alphaU") || child(n, "float", "alphaV")) throw std::runtime_error("The 'marschner' plugin does not support anisotropic microfacet distributions!");
-            id = cudapath_add_bsdf_marschner(ctx, (float) ior("intIOR", 1.5046), (float) ior("extIOR", 1.000277), d, s, (float) getFloat(n, "alpha", 0.1),
-                                             di, getBool(n, "nonlinear", false) ? 1 : 0);
+            id = (dry ? note("bsdf marschner") : cudapath_add_bsdf_marschner(ctx, (float) ior("intIOR", 1.5046), (float) ior("extIOR", 1.000277), d, s, (float) getFloat(n, "alpha", 0.1),
+                                             di, getBool(n, "nonlinear", false) ? 1 : 0));
         } else if (type == "roughplastic") {
             auto ior = [&](const char *name, double def) {
                 if (child(n, "float", name)) return getFloat(n, name, def);
@@ -220,8 +227,8 @@ struct Loader {
             if (di < 0) throw std::runtime_error("Specified an invalid distribution \"" + distr + "\", must be \"beckmann\", \"ggx\", or \"phong\"/\"as\"!");
             if (child(n, "float", "alphaU") || child(n, "float", "alphaV")) throw std::runtime_error("The 'roughplastic' plugin currently does not support anisotropic microfacet distributions!");
             if (child(n, "texture", "alpha") || child(n, "texture", "diffuseReflectance") || child(n, "texture", "specularReflectance")) throw std::runtime_error("roughplastic: textured parameters are not supported");
-            id = cudapath_add_bsdf_roughplastic(ctx, (float) ior("intIOR", 1.49), (float) ior("extIOR", 1.000277), d, s, (float) getFloat(n, "alpha", 0.1), di,
-                                                getBool(n, "sampleVisible", true) ? 1 : 0, getBool(n, "nonlinear", false) ? 1 : 0);
+            id = (dry ? note("bsdf roughplastic") : cudapath_add_bsdf_roughplastic(ctx, (float) ior("intIOR", 1.49), (float) ior("extIOR", 1.000277), d, s, (float) getFloat(n, "alpha", 0.1), di,
+                                                getBool(n, "sampleVisible", true) ? 1 : 0, getBool(n, "nonlinear", false) ? 1 : 0));
         } else if (type == "marschner_fixed") {      // the class of src/bsdfs/marschner.cpp, which the fork's build leaves out
             auto ior = [&](const char *name, double def) {
                 if (child(n, "float", name)) return getFloat(n, name, def);
@@ -231,7 +238,7 @@ struct Loader {
                 if (v == "amber") return 1.55; if (v == "air") return 1.000277; if (v == "bk7") return 1.5046; if (v == "vacuum") return 1.0; if (v == "water") return 1.3330;
                 throw std::runtime_error("Unable to find an IOR value for \"" + v + "\"");
             };
-            id = cudapath_add_bsdf_marschner_fixed(ctx, (float) ior("intIOR", 1.55), (float) ior("extIOR", 1.000277));
+            id = (dry ? note("bsdf marschner_fixed") : cudapath_add_bsdf_marschner_fixed(ctx, (float) ior("intIOR", 1.55), (float) ior("extIOR", 1.000277)));
         } else if (type == "diffuse" || type == "twosided") {
             // `diffuse` with a constant reflectance (diffuse.cpp:70-76: "reflectance" or "diffuseReflectance"); `twosided` around one nested `diffuse`
             const Node *d = &n;
@@ -247,7 +254,7 @@ struct Loader {
             if (child(*d, "texture", "reflectance") || child(*d, "texture", "diffuseReflectance")) throw std::runtime_error("diffuse: textured reflectance is not supported");
             float r[3]; getColor(*d, "reflectance", 0.5f, r);
             if (child(*d, "rgb", "diffuseReflectance") || child(*d, "spectrum", "diffuseReflectance")) getColor(*d, "diffuseReflectance", 0.5f, r);
-            id = cudapath_add_bsdf_diffuse(ctx, r, type == "twosided" ? 1 : 0);
+            id = (dry ? note("bsdf diffuse/twosided") : cudapath_add_bsdf_diffuse(ctx, r, type == "twosided" ? 1 : 0));
         } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, roughplastic, diffuse, twosided)");
         check(id);
         if (n.has("id")) bsdfIds[n.get("id")] = id;
@@ -263,12 +270,19 @@ struct Loader {
         }
         if (bsdf < 0) {          // Shape::configure falls back to a default `diffuse` (src/librender/shape.cpp)
             const float half[3] = {0.5f, 0.5f, 0.5f};
-            check(bsdf = cudapath_add_bsdf_diffuse(ctx, half, 0));
+            check(bsdf = (dry ? note("bsdf diffuse (default)") : cudapath_add_bsdf_diffuse(ctx, half, 0)));
         }
         std::string file = getString(n, "filename", "");
         if (file.empty()) throw std::runtime_error(n.get("type") + " shape: missing 'filename'");
         if (file[0] != '/') file = baseDir + "/" + file;
         float tw[16]; toFloat(getTransform(n, "toWorld"), tw);
+        if (dry) {
+            std::ifstream probe(file, std::ios::binary);
+            note(std::string("shape ") + n.get("type") + " \"" + file + "\"" + (probe ? "" : " (file missing)"));
+            if (isObj && child(n, "float", "maxSmoothAngle")) throw std::runtime_error("obj: 'maxSmoothAngle' is not supported");
+            if (!isObj && getFloat(n, "reduction", 0.0) > 0) throw std::runtime_error("reduction > 0 draws from the reference's Mersenne-Twister stream and is not supported");
+            return;
+        }
         if (isObj) {
             if (child(n, "float", "maxSmoothAngle")) throw std::runtime_error("obj: 'maxSmoothAngle' is not supported");
             check(cudapath_add_mesh_file(ctx, file.c_str(), tw, getBool(n, "faceNormals", false) ? 1 : 0, getBool(n, "flipNormals", false) ? 1 : 0, bsdf));
@@ -312,8 +326,8 @@ struct Loader {
             else if (axis != "x") throw std::runtime_error("The 'fovAxis' parameter must be set to one of 'smaller', 'larger', 'diagonal', 'x', or 'y'!");
         }
         float tw[16]; toFloat(getTransform(n, "toWorld"), tw);
-        check(cudapath_set_camera_perspective(ctx, tw, (float) fov, (float) getFloat(n, "nearClip", 1e-2), (float) getFloat(n, "farClip", 1e4), w, h));
-        check(cudapath_set_film(ctx, filter, fparam, alpha ? 1 : 0));
+        check((dry ? note("sensor perspective") : cudapath_set_camera_perspective(ctx, tw, (float) fov, (float) getFloat(n, "nearClip", 1e-2), (float) getFloat(n, "farClip", 1e4), w, h)));
+        check((dry ? note("film") : cudapath_set_film(ctx, filter, fparam, alpha ? 1 : 0)));
         haveSensor = true;
     }
     void loadEmitter(const Node &n) {
@@ -324,14 +338,14 @@ struct Loader {
         float dir[3] = {(float) (sd->has("x") ? num(sd->get("x")) : 0), (float) (sd->has("y") ? num(sd->get("y")) : 0), (float) (sd->has("z") ? num(sd->get("z")) : 0)};
         float albedo[3]; getColor(n, "albedo", 0.2f, albedo);
         const double scale = getFloat(n, "scale", 1.0);
-        check(cudapath_set_sunsky(ctx, (float) getFloat(n, "turbidity", 3.0), albedo, dir, (float) getFloat(n, "skyScale", scale), (float) getFloat(n, "sunScale", scale),
-                                  (float) getFloat(n, "sunRadiusScale", 1.0), (int) getInt(n, "resolution", 512)));
+        check((dry ? note("emitter sunsky") : cudapath_set_sunsky(ctx, (float) getFloat(n, "turbidity", 3.0), albedo, dir, (float) getFloat(n, "skyScale", scale), (float) getFloat(n, "sunScale", scale),
+                                  (float) getFloat(n, "sunRadiusScale", 1.0), (int) getInt(n, "resolution", 512))));
     }
     void loadIntegrator(const Node &n) {
         const std::string t = n.get("type");
         if (t != "path" && t != "cudapath") throw std::runtime_error("integrator plugin \"" + t + "\" is outside the hair hot path (supported: path, cudapath)");
-        check(cudapath_set_integrator(ctx, (int) getInt(n, "maxDepth", -1), (int) getInt(n, "rrDepth", 5), getBool(n, "strictNormals", false) ? 1 : 0,
-                                      getBool(n, "hideEmitters", false) ? 1 : 0));
+        check((dry ? note("integrator path") : cudapath_set_integrator(ctx, (int) getInt(n, "maxDepth", -1), (int) getInt(n, "rrDepth", 5), getBool(n, "strictNormals", false) ? 1 : 0,
+                                      getBool(n, "hideEmitters", false) ? 1 : 0)));
         haveIntegrator = true;
     }
     void load(Node &root) {
@@ -348,7 +362,7 @@ struct Loader {
             else throw std::runtime_error("unsupported scene element <" + c->tag + ">");
         }
         if (!haveSensor) throw std::runtime_error("the scene has no sensor");
-        if (!haveIntegrator) check(cudapath_set_integrator(ctx, -1, 5, 0, 0));
+        if (!haveIntegrator) check((dry ? note("integrator path (default)") : cudapath_set_integrator(ctx, -1, 5, 0, 0)));
     }
 };
 
@@ -356,16 +370,31 @@ struct Loader {
 
 extern "C" int cudapath_set_error_message(const char *msg);
 
+static int load_or_validate(cudapath_ctx *ctx, bool dry, const char *filename, const char *defines, uint32_t *out_spp, std::string *outReport);
+
 extern "C" int cudapath_load_scene_xml(cudapath_ctx *ctx, const char *filename, const char *defines, uint32_t *out_spp) {
+    if (!ctx) { cudapath_set_error_message("null argument"); return -1; }
+    return load_or_validate(ctx, false, filename, defines, out_spp, nullptr);
+}
+
+extern "C" int cudapath_validate_scene_xml(const char *filename, const char *defines, char *report, size_t report_size) {
+    std::string rep; uint32_t spp = 0;
+    const int rc = load_or_validate(nullptr, true, filename, defines, &spp, &rep);
+    if (rc == 0) rep += "sampleCount " + std::to_string(spp) + "\n";
+    if (report && report_size) { const size_t n = std::min(rep.size(), report_size - 1); std::memcpy(report, rep.data(), n); report[n] = 0; }
+    return rc;
+}
+
+static int load_or_validate(cudapath_ctx *ctx, bool dry, const char *filename, const char *defines, uint32_t *out_spp, std::string *outReport) {
     try {
-        if (!ctx || !filename) throw std::runtime_error("null argument");
+        if (!filename) throw std::runtime_error("null argument");
         std::ifstream f(filename, std::ios::binary);
         if (!f) throw std::runtime_error(std::string("cannot open scene file \"") + filename + "\"");
         std::stringstream ss; ss << f.rdbuf();
         const std::string src = ss.str();
         Parser p(src);
         std::unique_ptr<Node> root = p.document();
-        Loader L; L.ctx = ctx;
+        Loader L; L.ctx = ctx; L.dry = dry;
         std::string fn(filename); size_t slash = fn.find_last_of('/');
         L.baseDir = slash == std::string::npos ? "." : fn.substr(0, slash);
         if (defines) {
@@ -379,6 +408,7 @@ extern "C" int cudapath_load_scene_xml(cudapath_ctx *ctx, const char *filename, 
         }
         L.load(*root);
         if (out_spp) *out_spp = L.spp;
+        if (outReport) for (auto &r : L.report) *outReport += r + "\n";
         return 0;
     } catch (const std::exception &e) {
         cudapath_set_error_message(e.what());

@@ -190,6 +190,10 @@ int cudapath_intersect_batch_dev(cudapath_ctx *ctx, uint64_t n, const float *ori
  * (mitsuba -D, src/mitsuba/mitsuba.cpp:168).  Hair files that are missing are reported as an error.  On success the
  * scene is loaded into ctx (cudapath_build still has to be called) and *out_spp receives the sampler's sampleCount. */
 int cudapath_load_scene_xml(cudapath_ctx *ctx, const char *filename, const char *defines, uint32_t *out_spp);
+/* Dry run of the same loader without a context or a GPU: parses the file, checks every plugin and parameter it uses and writes one
+ * line per object it would create into `report` (geometry files that are missing are noted, not treated as errors).  Returns 0 when
+ * the whole file is inside the supported path; otherwise -1 and cudapath_last_error() names the first unsupported element. */
+int cudapath_validate_scene_xml(const char *filename, const char *defines, char *report, size_t report_size);
 
 #ifdef __cplusplus
 }

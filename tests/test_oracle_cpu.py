@@ -533,6 +533,32 @@ def test_scene_xml_text(cp):
 
 
 # ------------------------------------------------------------------------------------------------ golden vectors
+def test_validate_scene_xml_dry_run(cp, tmp_path):
+    """cudapath_validate_scene_xml: the scene loader without a GPU -- lists what a file would create, names what is unsupported."""
+    for name in ('straight-hair', 'hair-curl', 'straight-hair-default', 'hair-on-head'):
+        d = tmp_path / name
+        path = cp.scenes.write_scene(name, str(d), scale=0.002)
+        rep = cp.validate_scene_xml(path)
+        sc = cp.scenes.SCENES[name]
+        assert sum(r.startswith('bsdf') for r in rep) == len(sc['shapes']) and sum(r.startswith('shape') for r in rep) == len(sc['shapes'])
+        assert not any('missing' in r for r in rep) and rep[-1] == 'sampleCount %d' % sc['spp']
+        assert any(r.startswith('integrator path') for r in rep) and any(r.startswith('emitter sunsky') for r in rep)
+    xml = open(path).read()
+    bad = tmp_path / 'bad.xml'
+    bad.write_text(xml.replace('type="kajiyakay"', 'type="roughdielectric"'))
+    with pytest.raises(cp.CudapathError, match='roughdielectric'):
+        cp.validate_scene_xml(str(bad))
+    bad.write_text(xml.replace('models/hair.mitshair', 'models/nothing.mitshair'))
+    assert any('file missing' in r for r in cp.validate_scene_xml(str(bad)))
+    bad.write_text(xml.replace('<scene version="0.6.0">', '<scene>'))
+    with pytest.raises(cp.CudapathError, match='version'):
+        cp.validate_scene_xml(str(bad))
+    bad.write_text(xml.replace('value="8"', 'value="$depth"', 1))
+    with pytest.raises(cp.CudapathError, match='undefined'):
+        cp.validate_scene_xml(str(bad))
+    assert cp.validate_scene_xml(str(bad), defines={'depth': 8})
+
+
 def test_oracle_matches_committed_golden_vectors(oracle):
     g = np.load(os.path.join(GOLDEN, 'bsdf_golden.npz'))
     s = make_bsdf_scene(oracle)
