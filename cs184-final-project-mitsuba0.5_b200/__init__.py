@@ -123,6 +123,15 @@ def develop(film):
     return out
 
 
+def develop_ldr(film, gamma=-1.0, exposure=0.0):
+    """LDRFilm::develop, `gamma` tonemapper (src/films/ldrfilm.cpp:300-321): (h,w,5) accumulated film -> (h,w,3) uint8."""
+    film = _f32(film)
+    h, w = film.shape[:2]
+    out = np.zeros((h, w, 3), np.uint8)
+    _check(lib().cudapath_develop_ldr(_p(film), w, h, ctypes.c_float(gamma), ctypes.c_float(exposure), _p(out)))
+    return out
+
+
 class Context:
     """One GPU context = the flattened scene + the wavefront path integrator (replaces Scene + `path` integrator for this path)."""
 

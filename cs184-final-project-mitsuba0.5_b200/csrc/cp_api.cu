@@ -609,6 +609,32 @@ int cudapath_develop(const float *film, int w, int h, float *out_rgb) {
     return 0;
 }
 
+// LDRFilm::develop with the default `gamma` tonemapper (src/films/ldrfilm.cpp:300-321): Bitmap::convert(ERGB, EUInt8, gamma, 2^exposure)
+// = per pixel value/weight (fmtconv.cpp:984-995), times the multiplier, gamma curve (applyGamma :1104-1111: sRGB when gamma == -1,
+// else pow(v, 1/gamma)), then round-to-nearest and clamp to [0, 255] (convertScalar :1157-1159).
+int cudapath_develop_ldr(const float *film, int w, int h, float gamma, float exposure, uint8_t *out_rgb8) {
+    if (!film || !out_rgb8) return fail("null argument");
+    if (gamma == 0) return fail("gamma must not be zero");
+    const float multiplier = cr_pow(2.0f, exposure);
+    const float invDestGamma = 1.0f / gamma;
+    for (size_t i = 0; i < (size_t) w * h; ++i) {
+        const float wt = film[5 * i + 4];
+        const float inv = wt != 0 ? 1.0f / wt : wt;
+        for (int k = 0; k < 3; ++k) {
+            float value = film[5 * i + k] * inv;
+            value *= multiplier;
+            if (invDestGamma != 1) {
+                if (invDestGamma == -1) value = (value <= 0.0031308f) ? (12.92f * value) : (1.055f * cr_pow(value, (float) (1.0 / 2.4)) - 0.055f);
+                else value = cr_pow(value, invDestGamma);
+            }
+            const float scaled = value * 255.0f + 0.5f;
+            const float lo = (0.0f < scaled) ? scaled : 0.0f;               // std::max((Float) 0, x): NaN -> 0
+            out_rgb8[3 * i + k] = (uint8_t) ((lo < 255.0f) ? lo : 255.0f);  // std::min(255, .)
+        }
+    }
+    return 0;
+}
+
 int cudapath_set_build_options(cudapath_ctx *ctx, int max_split) {
     if (!ctx) return fail("null context");
     if (max_split < 1 || max_split > 64) return fail("max_split must be in [1, 64]");

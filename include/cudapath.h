@@ -121,6 +121,10 @@ int cudapath_render(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sam
 int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *film_dev, void *stream);
 /* Film::develop normalisation, src/libcore/fmtconv.cpp:955-1056: rgb = sum / weight (0 where weight == 0). */
 int cudapath_develop(const float *film, int width, int height, float *out_rgb);
+/* LDRFilm::develop with the `gamma` tonemapper, src/films/ldrfilm.cpp:300-321 -> Bitmap::convert(ERGB, EUInt8, gamma, 2^exposure)
+ * (src/libcore/fmtconv.cpp:984-995,1104-1111,1137-1160): width*height*3 bytes.  gamma = -1 selects the sRGB curve (the ldrfilm
+ * default); the hair scene files use 2.2.  Banner, Reinhard tonemapping and the PNG/JPEG encoders are not part of this path. */
+int cudapath_develop_ldr(const float *film, int width, int height, float gamma, float exposure, uint8_t *out_rgb8);
 /* Tunables: wave size in paths (0 = default), collect traversal statistics (slower, counting kernels),
  * profile_stages (CUDA events around every stage launch). */
 int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stats, int profile_stages);

@@ -503,6 +503,28 @@ def test_develop(cp):
     assert np.allclose(rgb[0, 0], (1, 2, 3)) and np.allclose(rgb[1, 2], (2, 2, 2)) and (rgb[0, 1] == 0).all()      # weight 0 -> 0
 
 
+def test_develop_ldr(cp):
+    """ldrfilm develop: value/weight, 2^exposure, sRGB or pow(1/gamma), round and clamp to 8 bits (fmtconv.cpp:984-995,1104-1160)."""
+    rng = np.random.default_rng(41)
+    film = np.zeros((6, 7, 5), np.float32)
+    film[..., :3] = rng.random((6, 7, 3)).astype(np.float32) * 3
+    film[..., 4] = rng.random((6, 7)).astype(np.float32) * 2 + 0.5
+    film[0, 0] = (1, 1, 1, 1, 0); film[0, 1] = (50, 0, 1e-4, 1, 1); film[0, 2] = (np.nan, -1, 0.5, 1, 1)      # zero weight, clamp, NaN / negative
+    v = film[..., :3] / np.where(film[..., 4:5] != 0, film[..., 4:5], np.inf)
+    def q(x):
+        with np.errstate(invalid='ignore'):
+            y = x * 255.0 + 0.5
+            return np.where(y > 0, np.minimum(y, 255.0), 0).astype(np.uint8)     # NaN -> 0
+    with np.errstate(invalid='ignore'):
+        srgb = np.where(v <= 0.0031308, 12.92 * v, 1.055 * np.power(v.astype(np.float64), 1 / 2.4) - 0.055)
+        g22 = np.power((v * 2.0).astype(np.float64), 1 / 2.2)
+    a = cp.develop_ldr(film); b = cp.develop_ldr(film, gamma=2.2, exposure=1.0)
+    assert a.dtype == np.uint8 and a.shape == (6, 7, 3)
+    assert np.abs(a.astype(int) - q(srgb).astype(int)).max() <= 1 and np.abs(b.astype(int) - q(g22).astype(int)).max() <= 1   # fp32 vs fp64 pow at a rounding boundary
+    assert tuple(a[0, 0]) == (0, 0, 0) and a[0, 1, 0] == 255 and a[0, 2, 0] == 0 and a[0, 2, 1] == 0
+    assert np.array_equal(cp.develop_ldr(film, gamma=1.0), q(v))
+
+
 def test_c_abi_exports_every_declared_symbol(cp):
     """The shared library loads (without a GPU) and exports every function include/cudapath.h declares."""
     import re
