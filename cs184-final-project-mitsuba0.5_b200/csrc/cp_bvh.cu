@@ -16,7 +16,9 @@
 
 namespace cp {
 
-#define CP_LEAF_MAX 4
+#ifndef CP_LEAF_MAX
+#define CP_LEAF_MAX 4      // references per leaf (<= 8: 3 bits of the leaf encoding); measured best of 2/3/4/6/8
+#endif
 
 __device__ __forceinline__ void atomicMinFloat(float *addr, float v) {
     if (v >= 0) atomicMin((int *) addr, __float_as_int(v)); else atomicMax((unsigned int *) addr, __float_as_uint(v));

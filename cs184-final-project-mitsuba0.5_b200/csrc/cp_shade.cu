@@ -36,7 +36,10 @@ __global__ void __launch_bounds__(256) k_raygen(SceneDev S, WaveParams wp, PathQ
 
 __device__ __forceinline__ float mi_weight(float pdfA, float pdfB) { pdfA *= pdfA; pdfB *= pdfB; return pdfA / (pdfA + pdfB); } // path.cpp:296-300
 
-__global__ void __launch_bounds__(128) k_shade(SceneDev S, WaveParams wp, PathQueue in, uint32_t n, const float4 *__restrict__ hitPT,
+#ifndef CP_SHADE_MIN_BLOCKS
+#define CP_SHADE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, WaveParams wp, PathQueue in, uint32_t n, const float4 *__restrict__ hitPT,
                                                const uint32_t *__restrict__ hitPrim, PathQueue out, ShadowQueue sq, float4 *liAcc,
                                                uint32_t *counters, unsigned long long *unsupportedLookups) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
