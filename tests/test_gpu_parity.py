@@ -437,6 +437,34 @@ def test_render_fixed_marschner(cp, oracle):
     ctx.close()
 
 
+def test_independent_seeds_agree_statistically(cp, oracle):
+    """BASELINE.json north_star, third check: images rendered with INDEPENDENT random streams agree within their own noise --
+    per-pixel z-test of the GPU estimate against the oracle estimate (other seed), variances estimated from batches of samples --
+    and the converged images agree in relMSE.  (The path-replay tests above use identical streams and are much stricter; this
+    one would catch an error that is shared by both sides of a replay, e.g. a wrong use of the stream itself.)"""
+    ov = dict(width=40, height=32, spp=512, maxDepth=6)
+    ctx = cp.scene_from_description('straight-hair', scale=0.02, overrides=ov); ctx.build()
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params('straight-hair'))
+    osc = oracle.scene_from_description('straight-hair', scale=0.02, overrides=ov, envmap=env)
+    K = 8                                                       # batches of 64 samples -> variance of the batch means
+    def batches(render, seed):
+        out = []
+        for k in range(K):
+            f = render(512, seed=seed, sample_begin=64 * k, sample_end=64 * (k + 1))
+            out.append(cp.develop(f).astype(np.float64).mean(axis=2))      # luminance-like scalar per pixel
+        b = np.stack(out)
+        return b.mean(axis=0), b.var(axis=0, ddof=1) / K
+    mg, vg = batches(ctx.render, 11)
+    mo, vo = batches(osc.render, 977)
+    z = (mg - mo) / np.sqrt(vg + vo + 1e-12)
+    assert abs(z.mean()) < 0.25, 'systematic offset: mean z = %.3f' % z.mean()
+    assert (np.abs(z) > 3.5).mean() < 0.02 and np.abs(z).max() < 7, 'z-test: %.3f of the pixels beyond 3.5 sigma, max %.1f' % ((np.abs(z) > 3.5).mean(), np.abs(z).max())
+    assert 0.6 < z.std() < 1.6                                  # the variance estimate itself is plausible (heavy tails from fireflies allowed)
+    rel = float(np.mean((mg - mo) ** 2 / (mo ** 2 + 1e-2)))
+    assert rel < 5e-3, 'relMSE at 512 spp: %g' % rel              # noise-limited at this sample count; 1e-3 is the 4096-spp bar
+    ctx.close()
+
+
 @pytest.mark.parametrize('name', ['straight-hair', 'hair-on-head', 'straight-hair-default'])
 def test_xml_scene_roundtrip(cp, oracle, tmp_path, name):
     """The XML + .mitshair / .obj path (SceneHandler + HairShape / WavefrontOBJ loaders) yields the same film as the flattened-array path."""
