@@ -79,16 +79,30 @@ __global__ void k_split_counts(const float4 *__restrict__ vtx, const uint32_t *_
 __global__ void k_segment_bounds(const float4 *__restrict__ vtx, const uint32_t *__restrict__ segs, uint32_t nSeg, const uint32_t *__restrict__ refOffset,
                                  int maxSplit, ShapeDev *shapes, float *leafBox /*6*nRef*/, uint32_t *refPrim, float *centroidBox /*6*/) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nSeg) return;
+    const bool live = i < nSeg;
+    if (!live) i = nSeg - 1;                              // keep the whole warp alive for the reductions below (results of the clone are discarded)
     const uint32_t gv = segs[i];
     const float4 v1 = vtx[gv], v2 = vtx[gv + 1], v0 = vtx[gv > 0 ? gv - 1 : 0], v3 = vtx[gv + 2];
-    ShapeDev &sd = shapes[vtx_shape(v1)];
+    const uint32_t shapeIdx = vtx_shape(v1);
+    ShapeDev &sd = shapes[shapeIdx];
     const float radius = sd.radius;
     float minA[3], maxA[3], minB[3], maxB[3];
     segment_end_boxes(v0, v1, v2, v3, radius, minA, maxA, minB, maxB);
+    {   // per-shape union: min / max are exact, so reducing inside the warp first (when all lanes touch the same shape, the usual
+        // case) gives the same bounds as one atomic per segment at 1/32 of the traffic to the same six words
+        const bool uniform = __match_any_sync(0xffffffffu, shapeIdx) == 0xffffffffu;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { atomicMinFloat(&sd.bmin[k], fminf(minA[k], minB[k])); atomicMaxFloat(&sd.bmax[k], fmaxf(maxA[k], maxB[k])); }
-    const int nPieces = split_count(v1, v2, radius, maxSplit);
+        for (int k = 0; k < 3; ++k) {
+            float lo = fminf(minA[k], minB[k]), hi = fmaxf(maxA[k], maxB[k]);
+            if (uniform) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off)); }
+                if ((threadIdx.x & 31u) == 0u) { atomicMinFloat(&sd.bmin[k], lo); atomicMaxFloat(&sd.bmax[k], hi); }
+            } else { atomicMinFloat(&sd.bmin[k], lo); atomicMaxFloat(&sd.bmax[k], hi); }
+        }
+    }
+    float cmin[3] = {CP_INF, CP_INF, CP_INF}, cmax[3] = {-CP_INF, -CP_INF, -CP_INF};      // centroid box of this thread's references
+    const int nPieces = live ? split_count(v1, v2, radius, maxSplit) : 0;
     const uint32_t base = refOffset[i];
     const V3 p1 = vtx_pos(v1), a = vtx_pos(v2) - p1;
     const float invLen = 1.0f / length(a);
@@ -111,9 +125,16 @@ __global__ void k_segment_bounds(const float4 *__restrict__ vtx, const uint32_t 
             bmin[k] -= pad; bmax[k] += pad;
             leafBox[6 * (size_t) (base + j) + k] = bmin[k]; leafBox[6 * (size_t) (base + j) + 3 + k] = bmax[k];
             const float c = 0.5f * (bmin[k] + bmax[k]);
-            atomicMinFloat(&centroidBox[k], c); atomicMaxFloat(&centroidBox[3 + k], c);
+            cmin[k] = fminf(cmin[k], c); cmax[k] = fmaxf(cmax[k], c);
         }
         refPrim[base + j] = gv;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float lo = cmin[k], hi = cmax[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off)); }
+        if ((threadIdx.x & 31u) == 0u && lo <= hi) { atomicMinFloat(&centroidBox[k], lo); atomicMaxFloat(&centroidBox[3 + k], hi); }
     }
 }
 
