@@ -243,7 +243,7 @@ def main():
     e0.record(stream)
     for k in range(args.steps):
         step(1000 + k)
-        st = ctx.stats(); launches += st['kernel_launches'] + 1; rays += st['rays']; shadow += st['shadow_rays']
+        st = ctx.stats(); launches += st['kernel_launches'] + 1; rays += st['rays']; shadow += st['shadow_rays_traced']      # rays actually traced (zero-contribution shadow rays are only counted)
     e1.record(stream)
     torch.cuda.synchronize()
     if world > 1:

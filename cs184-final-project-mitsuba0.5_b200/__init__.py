@@ -25,7 +25,7 @@ class Stats(ctypes.Structure):
                                                'shadow_nodes_visited', 'shadow_prims_tested',
                                                'unsupported_filtered_lookups', 'dropped_samples', 'segments', 'bvh_nodes', 'bvh_references', 'triangles')] + \
                [(n, ctypes.c_double) for n in ('build_ms', 'render_ms', 'intersect_ms', 'shade_ms', 'shadow_ms', 'raygen_ms', 'splat_ms')] + \
-               [(n, ctypes.c_uint64) for n in ('intersect_launches', 'shade_launches', 'shadow_launches', 'full_tests', 'shadow_full_tests')]
+               [(n, ctypes.c_uint64) for n in ('intersect_launches', 'shade_launches', 'shadow_launches', 'shadow_rays_traced', 'full_tests', 'shadow_full_tests')]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

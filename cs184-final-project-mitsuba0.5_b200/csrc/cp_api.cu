@@ -569,7 +569,7 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
     s.nodes_visited = rs.nodesVisited; s.prims_tested = rs.primsTested; s.shadow_nodes_visited = rs.shadowNodesVisited; s.shadow_prims_tested = rs.shadowPrimsTested;
     s.intersect_ms = rs.stageMs[0]; s.shade_ms = rs.stageMs[1]; s.shadow_ms = rs.stageMs[2]; s.raygen_ms = rs.stageMs[3]; s.splat_ms = rs.stageMs[4];
     s.intersect_launches = rs.stageLaunches[0]; s.shade_launches = rs.stageLaunches[1]; s.shadow_launches = rs.stageLaunches[2]; s.unsupported_filtered_lookups = rs.unsupportedLookups; s.dropped_samples = rs.droppedSamples;
-    s.full_tests = rs.fullTests; s.shadow_full_tests = rs.shadowFullTests;
+    s.full_tests = rs.fullTests; s.shadow_full_tests = rs.shadowFullTests; s.shadow_rays_traced = rs.shadowRaysTraced;
     s.render_ms = ms;
     return 0;
 }

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
                                                const uint32_t *__restrict__ hitPrim, PathQueue out, ShadowQueue sq, float4 *liAcc,
                                                uint32_t *counters, unsigned long long *unsupportedLookups) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool survive = false, wantShadow = false;
+    bool survive = false, wantShadow = false, countOnlyShadow = false;
     float4 nro, nrd, nthr; uint2 nid;
     float4 so, sd, sc;
     if (i < n) {
@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
                             contrib = thr * es.value * bsdfVal * mi_weight(es.pdf, bsdfPdf);
                         }
                     }
-                    wantShadow = true;
+                    // A shadow ray whose sample cannot contribute (BSDF value zero, wrong side) cannot change the image: it is counted
+                    // like the reference counts it, but not traced.
+                    if (isZero(contrib)) { countOnlyShadow = true; }
+                    wantShadow = !countOnlyShadow;
                     so = make_float4(rec.p.x, rec.p.y, rec.p.z, kEpsilon);
                     sd = make_float4(es.d.x, es.d.y, es.d.z, es.dist * (1 - kShadowEpsilon));
                     sc = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(pathId));
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
     if (survive) { out.ro[oi] = nro; out.rd[oi] = nrd; out.thr[oi] = nthr; out.id[oi] = nid; }
     const uint32_t si = warp_append(counters + 1, wantShadow);
     if (wantShadow) { sq.o[si] = so; sq.d[si] = sd; sq.c[si] = sc; }
+    warp_append(counters + 4, countOnlyShadow);
 }
 
 // imageblock.h:144-186 with offset 0 / border 0 (the film itself, ldrfilm.cpp:226-228): 5 channels R,G,B,alpha,weight

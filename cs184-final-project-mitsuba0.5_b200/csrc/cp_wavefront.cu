@@ -119,7 +119,7 @@ bool Wavefront::reserve(uint32_t waveSize, cudaStream_t stream, std::string &err
     CKW(cudaMallocAsync((void **) &sq.c, sizeof(float4) * (size_t) waveSize, stream));
     CKW(cudaMallocAsync((void **) &hitPT, sizeof(float4) * (size_t) waveSize, stream)); CKW(cudaMallocAsync((void **) &hitPrim, sizeof(uint32_t) * (size_t) waveSize, stream));
     CKW(cudaMallocAsync((void **) &liAcc, sizeof(float4) * (size_t) waveSize, stream));
-    CKW(cudaMallocAsync((void **) &counters, sizeof(uint32_t) * 4, stream));
+    CKW(cudaMallocAsync((void **) &counters, sizeof(uint32_t) * 8, stream));
     CKW(cudaMallocAsync((void **) &stats, sizeof(unsigned long long) * 8, stream));
     CKW(cudaMallocAsync((void **) &errFlag, sizeof(int), stream));
     for (int k = 0; k < 2; ++k) {
@@ -129,7 +129,7 @@ bool Wavefront::reserve(uint32_t waveSize, cudaStream_t stream, std::string &err
     sortTempBytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sortTempBytes, sortKeys[0], sortKeys[1], sortVals[0], sortVals[1], (int) waveSize, 0, 30, stream);
     CKW(cudaMallocAsync(&sortTemp, sortTempBytes, stream));
-    CKW(cudaMallocHost(&hCounters, sizeof(uint32_t) * 4));
+    CKW(cudaMallocHost(&hCounters, sizeof(uint32_t) * 8));
     capacity = waveSize;
     return true;
 }
@@ -192,7 +192,7 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
         rs.launches++;
         uint32_t nActive = n; int cur = 0, bounce = 0;
         while (nActive > 0) {
-            CKW(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 4, stream));
+            CKW(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, stream));
             begin(0);
             {
                 // camera rays leave raygen in pixel order (already coherent); later bounces are re-ordered
@@ -206,17 +206,18 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
             begin(1);
             launch_shade(S, wp, q[cur], nActive, hitPT, hitPrim, q[cur ^ 1], sq, liAcc, counters, stats + 4, stream);
             end();
-            CKW(cudaMemcpyAsync(hCounters, counters, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, stream));
+            CKW(cudaMemcpyAsync(hCounters, counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, stream));
             CKW(cudaStreamSynchronize(stream));
             rs.launches += 2; rs.rays += nActive; rs.bounces++;
             const uint32_t nNext = hCounters[0], nShadow = hCounters[1];
+            rs.shadowRays += hCounters[4];              // shadow rays the reference traces although they cannot contribute (see k_shade): counted, not traced
             if (nShadow) {
                 begin(2);
                 ShadowIO io{sq, liAcc, coherence_order(S, sq.o, sq.d, nShadow, stream)};
                 if (hasMesh) { if (collectStats) CP_LAUNCH_TRACE(k_shadow, true, true, nShadow, counters + 3); else CP_LAUNCH_TRACE(k_shadow, false, true, nShadow, counters + 3); }
                 else { if (collectStats) CP_LAUNCH_TRACE(k_shadow, true, false, nShadow, counters + 3); else CP_LAUNCH_TRACE(k_shadow, false, false, nShadow, counters + 3); }
                 end();
-                rs.launches++; rs.shadowRays += nShadow;
+                rs.launches++; rs.shadowRays += nShadow; rs.shadowRaysTraced += nShadow;
             }
             cur ^= 1; nActive = nNext; bounce++;
         }

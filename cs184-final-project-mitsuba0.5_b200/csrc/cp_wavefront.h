@@ -26,6 +26,7 @@ struct WaveParams {
 };
 struct RenderStats {
     uint64_t paths = 0, rays = 0, shadowRays = 0, launches = 0, bounces = 0;
+    uint64_t shadowRaysTraced = 0;      // shadowRays minus the ones whose emitter sample cannot contribute (contribution exactly zero)
     uint64_t nodesVisited = 0, primsTested = 0, shadowNodesVisited = 0, shadowPrimsTested = 0, unsupportedLookups = 0, droppedSamples = 0;
     uint64_t fullTests = 0, shadowFullTests = 0;     // exact (FP64 cylinder / Wald triangle) tests that survived the fp32 pre-test
     double stageMs[5] = {0, 0, 0, 0, 0};       // intersect, shade, shadow, raygen, splat

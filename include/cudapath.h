@@ -144,6 +144,7 @@ typedef struct cudapath_stats {
      * profile_stages) and the number of launches of each stage */
     double intersect_ms, shade_ms, shadow_ms, raygen_ms, splat_ms;
     uint64_t intersect_launches, shade_launches, shadow_launches;
+    uint64_t shadow_rays_traced;                 /* shadow_rays minus those whose emitter sample has an exactly zero contribution (not traced here) */
     uint64_t full_tests, shadow_full_tests;      /* exact primitive tests (FP64 cylinder / Wald triangle) after the fp32 pre-test; only with collect_stats */
 } cudapath_stats;
 int cudapath_get_stats(cudapath_ctx *ctx, cudapath_stats *out);
