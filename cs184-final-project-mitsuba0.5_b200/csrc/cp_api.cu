@@ -445,6 +445,18 @@ int cudapath_build(cudapath_ctx *ctx) {
     if (!build_bvh(ctx->d_vtx, ctx->vtxTotal, ctx->d_shapes, (int) ctx->shapes.size(), mesh, ctx->maxSplit, ctx->stream, ctx->bvh, info, err)) return fail(err);
     CKA(cudaMemcpyAsync(ctx->shapes.data(), ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
+    // KDTreeBase::buildInternal enlarges the box of a finished kd-tree by MTS_KD_AABB_EPSILON = 1e-3, relative to its extent plus
+    // absolute (include/mitsuba/render/gkdtree.h:50,1213-1220; the second line already sees the lowered minimum).  getAABB() returns
+    // that box: HairKDTree clips rays against it (hair.cpp:205) and hands it to the scene-level tree (hair.cpp:944-946), whose own
+    // box -- the union over its primitives, enlarged once more -- is what ShapeKDTree::rayIntersect clips against (skdtree.cpp:124).
+    // Plain fp32 host arithmetic (no FMA), like the reference.
+    auto enlarge = [](float *mn, float *mx) {
+        const float eps = 1e-3f;
+        for (int k = 0; k < 3; ++k) { const volatile float e = (mx[k] - mn[k]) * eps; mn[k] = mn[k] - (e + eps); }
+        for (int k = 0; k < 3; ++k) { const volatile float e = (mx[k] - mn[k]) * eps; mx[k] = mx[k] + (e + eps); }
+    };
+    for (auto &sh : ctx->shapes) if (sh.kind == 0 && sh.bmin[0] <= sh.bmax[0]) enlarge(sh.bmin, sh.bmax);
+    CKA(cudaMemcpyAsync(ctx->d_shapes, ctx->shapes.data(), sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyHostToDevice, ctx->stream));
     // bsdfs
     std::vector<BsdfDev> devs; for (auto &b : ctx->bsdfs) devs.push_back(b.dev);
     CKA(cudaMalloc(&ctx->d_bsdfs, sizeof(BsdfDev) * std::max<size_t>(devs.size(), 1)));
@@ -457,6 +469,7 @@ int cudapath_build(cudapath_ctx *ctx) {
     S.mesh = mesh; S.clipPerShape = (hairShapes > 1 || ctx->triTotal > 0) ? 1 : 0;
     for (int k = 0; k < 3; ++k) { S.sceneMin[k] = INFINITY; S.sceneMax[k] = -INFINITY; }
     for (auto &sh : ctx->shapes) for (int k = 0; k < 3; ++k) { S.sceneMin[k] = std::min(S.sceneMin[k], sh.bmin[k]); S.sceneMax[k] = std::max(S.sceneMax[k], sh.bmax[k]); }
+    enlarge(S.sceneMin, S.sceneMax);
     for (int k = 0; k < 3; ++k) { ctx->sceneAABB[k] = S.sceneMin[k]; ctx->sceneAABB[3 + k] = S.sceneMax[k]; }
 
     // camera (perspective.cpp:126-160; Transform::perspective transform.cpp:99-121)

@@ -48,6 +48,17 @@ struct AABB {
     }
 };
 
+// KDTreeBase::buildInternal, include/mitsuba/render/gkdtree.h:1213-1220: after the build the tree's bounding box is enlarged by
+// MTS_KD_AABB_EPSILON = 1e-3 (gkdtree.h:50), relative + absolute ("necessary e.g. when the scene is planar"); the second line
+// already sees the lowered minimum.  getAABB() returns this enlarged box -- it is what HairKDTree::rayIntersect clips rays against
+// (hair.cpp:205), what HairShape::getAABB() hands to the scene-level tree (hair.cpp:944-946), and, enlarged once more after the
+// scene-level build, what ShapeKDTree::rayIntersect clips against (skdtree.cpp:124).
+static inline void enlargeKDTreeBounds(AABB &a) {
+    const float eps = 1e-3f;
+    a.mn = a.mn - ((a.mx - a.mn) * eps + V3(eps));
+    a.mx = a.mx + ((a.mx - a.mn) * eps + V3(eps));
+}
+
 struct Ray {
     V3 o, d, dRcp;
     float mint, maxt;
@@ -205,6 +216,7 @@ struct HairShape {
             if (!startsFiber[i + 1]) segIndex.push_back((uint32_t) i);
         aabb = AABB();
         for (uint32_t iv : segIndex) aabb.expand(segmentAABB(iv));
+        if (!segIndex.empty()) enlargeKDTreeBounds(aabb);       // HairKDTree is a KDTreeBase: its getAABB() is the enlarged box
     }
 
     // hair.cpp:485-542.  Returns true on hit; t is the fp32-rounded root, p the fp32 hit point.
@@ -347,7 +359,8 @@ struct Geometry {
 
     void finalize() {
         aabb = AABB();
-        for (auto &s : shapes) aabb.expand(s.aabb);
+        for (auto &s : shapes) aabb.expand(s.aabb);   // hair: the shape's (enlarged) tree box; mesh: union of its triangle boxes (skdtree.h:213-221)
+        if (!shapes.empty()) enlargeKDTreeBounds(aabb);
         buildBVH();
     }
 

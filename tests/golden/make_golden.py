@@ -23,7 +23,47 @@ def sphere_dirs(rng, n):
     return v.astype(np.float32)
 
 
+def second_set():
+    """Fixtures added with the mesh / roughplastic / fixed-Marschner rows (the first set is left untouched so that it keeps pinning
+    the state it was generated from)."""
+    rng = np.random.default_rng(0x5eed2)
+    n = 4096
+    s = orc.Scene()
+    mats = [('roughplastic', dict(intIOR=1.55, extIOR=1.0, alpha=0.2, distribution='ggx', diffuseReflectance=HAIR_RGB)),
+            ('roughplastic', dict(intIOR=1.49, extIOR=1.000277, alpha=0.1, distribution='beckmann', nonlinear=True, diffuseReflectance=(0.6, 0.5, 0.4))),
+            ('roughplastic', dict(intIOR=1.55, extIOR=1.0, alpha=0.3, distribution='phong', diffuseReflectance=(0.2, 0.3, 0.4))),
+            ('marschner_fixed', dict(intIOR=1.55, extIOR=1.000277)),
+            ('diffuse', dict(reflectance=(0.5, 0.4, 0.3))), ('twosided', dict(reflectance=(0.5, 0.4, 0.3)))]
+    for t, p in mats:
+        s.add_bsdf(t, **p)
+    out = dict(wi=sphere_dirs(rng, n), wo=sphere_dirs(rng, n), sample=rng.random((n, 2)).astype(np.float32), extra=rng.random((n, 4)).astype(np.float32))
+    for b in range(len(mats)):
+        out['eval_%d' % b], out['pdf_%d' % b] = s.bsdf_eval(b, out['wi'], out['wo'])
+        wo, wt, pdf, ty = s.bsdf_sample(b, out['wi'], out['sample'], out['extra'])
+        out['swo_%d' % b], out['swt_%d' % b], out['spdf_%d' % b], out['sty_%d' % b] = wo, wt, pdf, ty
+    np.savez_compressed(os.path.join(HERE, 'bsdf2_golden.npz'), **out)
+
+    # fibers + triangle meshes in one scene: chords through the head, brute-force answers and full intersection records
+    ov = dict(width=32, height=24, spp=4, maxDepth=6)
+    env = cudapath.bake_sunsky(**cudapath.scenes.sunsky_params('hair-on-head'))
+    g = orc.scene_from_description('hair-on-head', scale=0.004, overrides=ov, envmap=env)
+    m = 20000
+    c = np.array([0.15, 11.0, 0.5]); r = 9.0
+    p1 = c + r * sphere_dirs(rng, m); p2 = c + r * sphere_dirs(rng, m)
+    d = p2 - p1; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = p1.astype(np.float32); d = d.astype(np.float32)
+    sh, pr, t = g.intersect(o, d, 0.0, np.inf, mode=2)
+    sh2, pr2, t2, rec = g.intersect_full(o, d, 0.0, np.inf)
+    np.savez_compressed(os.path.join(HERE, 'mesh_golden.npz'), o=o, d=d, shape=sh, prim=pr, t=t, rec=rec, rec_shape=sh2, rec_prim=pr2)
+    film = g.render(4, seed=9, threads=2)
+    np.savez_compressed(os.path.join(HERE, 'render_mesh_golden.npz'), film=film)
+
+
 def main():
+    if '--second' in sys.argv:
+        second_set()
+        print('second set written')
+        return
     rng = np.random.default_rng(0x5eed)
     n = 4096
     s = orc.Scene()

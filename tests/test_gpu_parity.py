@@ -547,3 +547,39 @@ def test_intersection_against_golden_file(cp):
     ok = ~mism & (sh >= 0)
     assert np.array_equal(t[ok], g['t'][ok])
     ctx.close()
+
+
+def test_second_golden_set(cp):
+    """GPU against the committed bsdf2 / mesh / render_mesh fixtures (roughplastic, fixed Marschner, diffuse; fibers + triangle meshes)."""
+    from test_oracle_cpu import SECOND_SET_MATS
+    g = np.load(os.path.join(GOLDEN, 'bsdf2_golden.npz'))
+    ov = dict(width=32, height=24, spp=4, maxDepth=6)
+    ctx = cp.scene_from_description('hair-on-head', scale=0.004, overrides=ov)
+    first = 3                                                    # bsdf ids 0..2 belong to the scene's own shapes
+    for t, p in SECOND_SET_MATS:
+        ctx.add_bsdf(t, **p)
+    ctx.build()
+    for k in range(len(SECOND_SET_MATS)):
+        b = first + k
+        ev, pdf = ctx.bsdf_eval(b, g['wi'], g['wo'])
+        ge, gp = g['eval_%d' % k], g['pdf_%d' % k]
+        fin = np.isfinite(ge).all(axis=1) & np.isfinite(gp)
+        assert rel_err(ev[fin], ge[fin], 1e-6 * float(np.abs(ge[fin]).max())).max() <= 1e-4 and rel_err(pdf[fin], gp[fin], 1e-9).max() <= 1e-4
+        wo, wt, p_, ty = ctx.bsdf_sample(b, g['wi'], g['sample'], g['extra'])
+        same = (ty == g['sty_%d' % k]) & (np.abs(wo - g['swo_%d' % k]).max(axis=1) <= 2e-4)
+        assert same.mean() > 0.999
+    m = np.load(os.path.join(GOLDEN, 'mesh_golden.npz'))
+    sh, pr, t, rec = ctx.intersect(m['o'], m['d'], 0.0, np.inf, record=True)
+    mism = (sh != m['shape']) | (pr != m['prim'])
+    with np.errstate(invalid='ignore'):
+        ties = mism & (sh >= 0) & (m['shape'] >= 0) & (np.abs(t - m['t']) <= 1e-6 * np.maximum(1, np.abs(m['t'])))
+    assert (mism & ~ties).sum() == 0
+    ok = ~mism & (sh >= 0)
+    assert np.array_equal(t[ok], m['t'][ok])
+    okr = ok & (m['rec_shape'] == sh) & (m['rec_prim'] == pr)
+    assert np.abs(rec[okr] - m['rec'][okr]).max() <= 2e-5 * max(1.0, float(np.abs(m['rec'][okr]).max()))
+    film = ctx.render(4, seed=9)
+    gf = np.load(os.path.join(GOLDEN, 'render_mesh_golden.npz'))['film']
+    a, b2 = cp.develop(film), cp.develop(gf)
+    assert rel_mse(a, b2) < 1e-3
+    ctx.close()

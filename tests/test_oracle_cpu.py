@@ -187,10 +187,10 @@ def test_cylinder_intersection_analytic(oracle):
         sh, pr, t = s.intersect(o, d, 0.0, np.inf, mode=mode)
         assert list(sh) == [0, 0, 0, -1, 0] and list(pr[[0, 1, 2, 4]]) == [0, 0, 0, 7]
         assert abs(t[0] - 4.9) < 1e-6 and abs(t[1] - 0.1) < 1e-6 and abs(t[2] - 4.9) < 1e-6   # t[1]: a ray from inside exits through the far wall
-        # Quirk of the reference's interval logic: the stub fiber is the scene's z-extreme, its bounds use radius*(1-Epsilon)
-        # (hair.cpp:375), so the scene-AABB entry distance (4.90001) is PAST the near root (4.9) and `nearT >= mint` fails
-        # (hair.cpp:521-523): the far wall is reported.
-        assert abs(t[4] - 5.1) < 1e-6
+        # The stub fiber is the scene's z-extreme and segment bounds use radius*(1-Epsilon) (hair.cpp:375), but both kd-trees enlarge
+        # their box by MTS_KD_AABB_EPSILON = 1e-3 after the build (gkdtree.h:1213-1220), so the entry distance of the shape / scene
+        # box (< 4.9) is in front of the near root and the near wall is reported.
+        assert abs(t[4] - 4.9) < 1e-6
     # any-hit respects [mint, maxt]
     assert list(s.intersect(o[:1], d[:1], 0.0, 4.0, mode=1)[0]) == [-1]
     assert list(s.intersect(o[:1], d[:1], 0.0, 4.95, mode=1)[0]) == [0]
@@ -199,6 +199,29 @@ def test_cylinder_intersection_analytic(oracle):
     p, n, sx, tx, wi = rec[0, 0:3], rec[0, 3:6], rec[0, 6:9], rec[0, 9:12], rec[0, 12:15]
     assert np.allclose(p, (-0.5, 0, 0.1), atol=1e-6) and np.allclose(n, (0, 0, 1), atol=1e-6) and np.allclose(np.abs(sx), (1, 0, 0), atol=1e-6)
     assert np.allclose(wi, (0, 0, 1), atol=1e-6) and abs(np.dot(n, sx)) < 1e-6 and np.allclose(np.cross(n, sx), tx, atol=1e-6)
+
+
+def test_kdtree_bounds_are_enlarged(oracle):
+    """gkdtree.h:1213-1220: getAABB() of a built kd-tree = tight bounds enlarged by 1e-3 (relative to the extent, plus absolute); the
+    hair shape's box is enlarged once, the scene box (union of the shape boxes) once more."""
+    s = oracle.Scene()
+    b = s.add_bsdf('kajiyakay')
+    xyz = np.array([[0, 0, 0], [4, 0, 0], [8, 1, 0]], np.float32)
+    s.add_hair(xyz, np.array([1, 0, 0], np.uint8), 0.5, b)
+    s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=8, height=8)
+    s.build()
+    seg = s.segment_bounds(0, 2)
+    tight = np.concatenate([seg[:, :3].min(axis=0), seg[:, 3:].max(axis=0)]).astype(np.float32)
+    def enlarge(a):
+        a = a.astype(np.float32).copy(); eps = np.float32(1e-3)
+        a[:3] = a[:3] - ((a[3:] - a[:3]) * eps + eps)
+        a[3:] = a[3:] + ((a[3:] - a[:3]) * eps + eps)
+        return a
+    aabb, _ = s.scene_bounds()
+    assert np.array_equal(aabb, enlarge(enlarge(tight)))
+    assert (aabb[:3] < tight[:3] - 1e-3).all() and (aabb[3:] > tight[3:] + 1e-3).all()
+    # a ray grazing just outside the tight box but inside the enlarged one is still clipped to a valid interval (and misses the fiber)
+    assert s.intersect([[4.0, tight[4] + 5e-4, 5.0]], [[0, 0, -1]], 0.0, np.inf, mode=2)[0][0] == -1
 
 
 def test_miter_joint_has_no_gap_or_overlap(oracle):
@@ -228,7 +251,9 @@ def test_segment_bounds_contain_the_segment(oracle):
     boxes = s.segment_bounds(0, 6)
     assert np.allclose(boxes[0], [-1, -0.09999, -0.09999, 0, 0.09999, 0.09999], atol=2e-5)      # axis-aligned, radius*(1-Epsilon)
     aabb, _ = s.scene_bounds()
-    assert np.allclose(aabb[:3], boxes[:, :3].min(0)) and np.allclose(aabb[3:], boxes[:, 3:].max(0))
+    lo, hi = boxes[:, :3].min(0), boxes[:, 3:].max(0)
+    assert (aabb[:3] < lo).all() and (aabb[3:] > hi).all()                 # the tree boxes are the tight union, enlarged (gkdtree.h:1213-1220)
+    assert np.allclose(aabb[:3], lo, atol=3e-3 * (1 + np.abs(hi - lo).max())) and np.allclose(aabb[3:], hi, atol=3e-3 * (1 + np.abs(hi - lo).max()))
 
 
 def test_marschner_fixed_mode(oracle):
@@ -599,3 +624,34 @@ def test_oracle_render_matches_golden_film(cp, oracle):
     env = cp.bake_sunsky(**cp.scenes.sunsky_params('curly-hair'))
     film = oracle.scene_from_description('curly-hair', scale=0.004, overrides=ov, envmap=env).render(4, seed=5, threads=2)
     assert np.allclose(film, g['film'], rtol=1e-5, atol=1e-6)
+
+
+SECOND_SET_MATS = [('roughplastic', dict(intIOR=1.55, extIOR=1.0, alpha=0.2, distribution='ggx', diffuseReflectance=(0.143016, 0.0156076, 1.80928e-005))),
+                   ('roughplastic', dict(intIOR=1.49, extIOR=1.000277, alpha=0.1, distribution='beckmann', nonlinear=True, diffuseReflectance=(0.6, 0.5, 0.4))),
+                   ('roughplastic', dict(intIOR=1.55, extIOR=1.0, alpha=0.3, distribution='phong', diffuseReflectance=(0.2, 0.3, 0.4))),
+                   ('marschner_fixed', dict(intIOR=1.55, extIOR=1.000277)),
+                   ('diffuse', dict(reflectance=(0.5, 0.4, 0.3))), ('twosided', dict(reflectance=(0.5, 0.4, 0.3)))]
+
+
+def test_oracle_matches_second_golden_set(cp, oracle):
+    """bsdf2 / mesh / render_mesh fixtures (tests/golden/make_golden.py --second): roughplastic, fixed Marschner, diffuse, fibers + meshes."""
+    g = np.load(os.path.join(GOLDEN, 'bsdf2_golden.npz'))
+    s = oracle.Scene()
+    for t, p in SECOND_SET_MATS:
+        s.add_bsdf(t, **p)
+    for b in range(len(SECOND_SET_MATS)):
+        ev, pdf = s.bsdf_eval(b, g['wi'], g['wo'])
+        assert np.array_equal(ev, g['eval_%d' % b], equal_nan=True) and np.array_equal(pdf, g['pdf_%d' % b], equal_nan=True)
+        wo, wt, p, ty = s.bsdf_sample(b, g['wi'], g['sample'], g['extra'])
+        assert np.array_equal(wo, g['swo_%d' % b], equal_nan=True) and np.array_equal(wt, g['swt_%d' % b], equal_nan=True) and np.array_equal(ty, g['sty_%d' % b])
+    if not oracle.have_ref():
+        pytest.skip('oracle/_ref not built')
+    m = np.load(os.path.join(GOLDEN, 'mesh_golden.npz'))
+    ov = dict(width=32, height=24, spp=4, maxDepth=6)
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params('hair-on-head'))
+    sc = oracle.scene_from_description('hair-on-head', scale=0.004, overrides=ov, envmap=env)
+    sh, pr, t = sc.intersect(m['o'], m['d'], 0.0, np.inf, mode=2)
+    assert np.array_equal(sh, m['shape']) and np.array_equal(pr, m['prim']) and np.array_equal(t, m['t'])
+    assert (sh == 0).sum() > 50 and (sh == 1).sum() > 1000 and (sh == 2).sum() > 100
+    film = sc.render(4, seed=9, threads=2)
+    assert np.allclose(film, np.load(os.path.join(GOLDEN, 'render_mesh_golden.npz'))['film'], rtol=1e-5, atol=1e-6)
