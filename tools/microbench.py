@@ -49,6 +49,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--log2n', type=int, default=26)
     ap.add_argument('--reps', type=int, default=5)
+    ap.add_argument('--bsdf-only', action='store_true', help='stop after C5a (used for the ncu capture of the BSDF kernels)')
     args = ap.parse_args()
     n = 1 << args.log2n
     peak, peak_kind = peaks()
@@ -75,6 +76,8 @@ def main():
                               'roofline': {'bound': 'hbm', 'achieved': by / t / 1e6, 'peak': peak, 'unit': 'GB/s', 'frac': by / t / 1e6 / peak, 'peak_source': peak_kind,
                                            'bytes_per_tuple': by / n}}), flush=True)
     del wi, wo, smp, ev, pdf, swo, swt, sty
+    if args.bsdf_only:
+        return
     torch.cuda.empty_cache()
 
     # ---------------- C5b
