@@ -269,8 +269,10 @@ def main():
         penv, te = pin(env); pinned.append(te)
         h2d = sum(16 * (len(s[1]) + 1) for s in pshapes) + penv.nbytes      # float4 vertex stream (+ sentinel) + envmap fp32
         d2h = W * H * 5 * 4
+        # W untimed warm-up runs (the first ones grow the stream-ordered memory pool and find the GPU at idle clocks), then K timed runs
         times = []
-        for k in range(3):
+        n_warm = max(args.warmup, 0); n_timed = max(args.steps, 1)
+        for k in range(n_warm + n_timed):
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
@@ -281,13 +283,14 @@ def main():
             c2.build()
             c2.render(total_spp, seed=2000 + k, sample_begin=rank * spp, sample_end=(rank + 1) * spp)
             torch.cuda.synchronize()
-            times.append(time.perf_counter() - t0)
+            if k >= n_warm:
+                times.append(time.perf_counter() - t0)
             c2.close()
-        te2e = torch.tensor([float(np.median(times))], dtype=torch.float64, device='cuda')      # median of 3 (the first run grows the memory pool)
+        te2e = torch.tensor([float(np.mean(times))], dtype=torch.float64, device='cuda')       # mean of the K timed runs
         if world > 1:
             dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
         e2e = {'times_s': [round(t, 4) for t in times], 'value': paths_per_step / float(te2e[0]) / 1e6, 'unit': 'Mpaths/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-               'includes': 'context creation, Marschner table build, geometry+envmap upload, device BVH build, render, film read-back'}
+               'warmup_runs': n_warm, 'includes': 'context creation, Marschner table build, geometry+envmap upload, device BVH build, render, film read-back'}
 
     if rank == 0:
         peak, peak_kind = load_peaks()

@@ -99,6 +99,32 @@ def main():
         with open(os.path.join(PROF, 'k_intersect_traffic.json'), 'w') as f:
             json.dump({'source': '%s_k_intersect_ncu_%s.md' % (rnd, tag), 'launch': 'third k_intersect launch of bench.py --spp 8 (8.4 M secondary rays, hair-curl)',
                        'dram_bytes': dram, 'duration_ms': float(d['gpu__time_duration.sum'].replace(',', '')) * ({'ms': 1, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}[u['gpu__time_duration.sum']])}, f, indent=1)
+    # ---- full captures of the other stages (tools/gpu_evidence_stages.sh): k_shade, k_shadow, the BSDF batch kernels of config 5a
+    EXTRA = ['sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fmalite.avg.pct_of_peak_sustained_active',
+             'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+             'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'smsp__thread_inst_executed.sum',
+             'sm__inst_executed_pipe_fp64.sum', 'sm__sass_thread_inst_executed_op_dfma_pred_on.sum', 'sm__sass_thread_inst_executed_op_ffma_pred_on.sum',
+             'smsp__sass_thread_inst_executed_op_fp32_pred_on.sum', 'smsp__sass_thread_inst_executed_op_fp64_pred_on.sum']
+    for stage, cmd in (('k_shade', 'python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e  (-k regex:k_shade -s 2 -c 1)'),
+                       ('k_shadow', 'python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e  (-k regex:k_shadow -s 2 -c 1)'),
+                       ('k_bsdf', 'python tools/microbench.py --log2n 24 --reps 1 --bsdf-only  (-k regex:k_bsdf_ -s 3 -c 2: Marschner eval+pdf, then sample)')):
+        rep = os.path.join(OUT, 'prof_%s_%s.ncu-rep' % (tag, stage))
+        if not os.path.exists(rep):
+            continue
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        rows = list(csv.reader(l for l in raw.splitlines() if l.startswith('"')))
+        hdr, units = rows[0], rows[1]
+        with open(os.path.join(PROF, '%s_%s_ncu_%s.md' % (rnd, stage, tag)), 'w') as f:
+            f.write('# ncu --set full: `%s` (%s)\n\nCommand: `ncu --set full --clock-control none --import-source on ... %s`\n' % (stage, tag, cmd))
+            for vals in rows[2:]:
+                d = dict(zip(hdr, vals)); u = dict(zip(hdr, units))
+                f.write('\nKernel: `%s`\n\n| metric | value | unit |\n|---|---:|---|\n' % d.get('Kernel Name'))
+                for k in KEYS + EXTRA:
+                    if k in d:
+                        f.write('| %s | %s | %s |\n' % (k, d[k], u[k]))
+    for extra in ('microbench_%s.jsonl' % tag, 'e2e_phases_%s.log' % tag):
+        if os.path.exists(os.path.join(OUT, extra)):
+            shutil.copy(os.path.join(OUT, extra), os.path.join(PROF, '%s_%s' % (rnd, extra)))
     print('profiles/ updated for', tag)
 
 
