@@ -64,7 +64,7 @@ def _check(rc):
 _IDENTITY = np.eye(4, dtype=np.float32)
 _DISTRIBUTIONS = {'beckmann': 0, 'ggx': 1, 'phong': 2, 'as': 2}
 _FILTERS = {'tent': 0, 'box': 1, 'gaussian': 2}
-_IOR = {'air': 1.000277, 'bk7': 1.5046, 'vacuum': 1.0, 'water': 1.3330, 'polypropylene': 1.49, 'amber': 1.55}    # subset of src/bsdfs/ior.h
+_IOR = {'air': 1.000277, 'bk7': 1.5046, 'vacuum': 1.0, 'water': 1.3330, 'polypropylene': 1.49, 'amber': 1.55, 'benzene': 1.501}    # subset of src/bsdfs/ior.h
 
 
 def load_hair_file(filename, radius=0.025, angleThreshold=1.0, reduction=0.0, toWorld=None):
@@ -192,7 +192,19 @@ class Context:
             # `diffuse` with a constant reflectance (src/bsdfs/diffuse.cpp:70-103); type 'twosided' = <bsdf type="twosided"><bsdf type="diffuse"/></bsdf>
             r = _f32(np.broadcast_to(props.get('reflectance', 0.5), 3))
             return _check(self._L.cudapath_add_bsdf_diffuse(self._h, _p(r), 1 if (type == 'twosided' or props.get('twoSided', False)) else 0))
-        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, roughplastic, diffuse, twosided)' % type)
+        if type == 'thindielectric':
+            # src/bsdfs/thindielectric.cpp:73-91; defaults bk7 / air, both colours 1
+            ior = lambda v: float(_IOR[v.lower()]) if isinstance(v, str) else float(v)
+            r = _f32(np.broadcast_to(props.get('specularReflectance', 1.0), 3)); t = _f32(np.broadcast_to(props.get('specularTransmittance', 1.0), 3))
+            return _check(self._L.cudapath_add_bsdf_thindielectric(self._h, ctypes.c_float(ior(props.get('intIOR', 'bk7'))), ctypes.c_float(ior(props.get('extIOR', 'air'))), _p(r), _p(t)))
+        if type == 'marschnerdielectric':
+            # the fork's src/bsdfs/marschnerdielectric.cpp:128-167; defaults benzene / air, diffuse 0.5, specular 0.1 / 0.1, exponent 30
+            ior = lambda v: float(_IOR[v.lower()]) if isinstance(v, str) else float(v)
+            d = _f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3))
+            r = _f32(np.broadcast_to(props.get('specularReflectance', 0.1), 3)); t = _f32(np.broadcast_to(props.get('specularTransmittance', 0.1), 3))
+            return _check(self._L.cudapath_add_bsdf_marschnerdielectric(self._h, ctypes.c_float(ior(props.get('intIOR', 'benzene'))), ctypes.c_float(ior(props.get('extIOR', 'air'))),
+                                                                        _p(d), _p(r), _p(t), ctypes.c_float(props.get('exponent', 30.0))))
+        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, marschnerdielectric, thindielectric, roughplastic, diffuse, twosided)' % type)
 
     def add_mesh(self, xyz, indices, bsdf_id, normals=None):
         """Triangle mesh (TriMesh positions / optional vertex normals / index triples); joins the fibers in the device BVH."""
@@ -285,10 +297,11 @@ class Context:
         return a, b
 
     # ---- parity hooks (host buffers) --------------------------------------------------------------------------------
-    def bsdf_eval(self, bsdf_id, wi, wo):
+    def bsdf_eval(self, bsdf_id, wi, wo, discrete=False):
+        """BSDF::eval + BSDF::pdf; measure ESolidAngle, or EDiscrete with discrete=True (delta components of `thindielectric`)."""
         wi = _f32(wi).reshape(-1, 3); wo = _f32(wo).reshape(-1, 3); n = len(wi)
         ev = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32)
-        _check(self._L.cudapath_bsdf_eval_batch(self._h, int(bsdf_id), ctypes.c_uint64(n), _p(wi), _p(wo), _p(ev), _p(pdf)))
+        _check((self._L.cudapath_bsdf_eval_batch_discrete if discrete else self._L.cudapath_bsdf_eval_batch)(self._h, int(bsdf_id), ctypes.c_uint64(n), _p(wi), _p(wo), _p(ev), _p(pdf)))
         return ev, pdf
 
     def bsdf_sample(self, bsdf_id, wi, sample, extra=None):

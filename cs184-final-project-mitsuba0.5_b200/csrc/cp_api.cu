@@ -231,6 +231,41 @@ int cudapath_add_bsdf_marschner_fixed(cudapath_ctx *ctx, float int_ior, float ex
     return (int) ctx->bsdfs.size() - 1;
 }
 
+static V3 ensure_energy_conservation(const float v[3]) {      // BSDF::ensureEnergyConservation for a constant texture, bsdf.cpp:88-113
+    V3 c(v[0], v[1], v[2]);
+    const float mx = maxc(c);
+    if (mx > 1.0f) c = c * (0.99f * (1.0f / mx));
+    return c;
+}
+
+int cudapath_add_bsdf_thindielectric(cudapath_ctx *ctx, float int_ior, float ext_ior, const float r[3], const float t[3]) {
+    if (!ctx || !r || !t) return fail("null argument");
+    if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
+    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    b.dev.kind = 5;
+    b.dev.eta = int_ior / ext_ior;                         // thindielectric.cpp:84
+    b.dev.specular = ensure_energy_conservation(r);        // :112-115
+    b.dev.diffuse = ensure_energy_conservation(t);         // the transmittance rides in the `diffuse` slot
+    ctx->bsdfs.push_back(b); ctx->built = false;
+    return (int) ctx->bsdfs.size() - 1;
+}
+
+int cudapath_add_bsdf_marschnerdielectric(cudapath_ctx *ctx, float int_ior, float ext_ior, const float d[3], const float r[3], const float t[3], float exponent) {
+    if (!ctx || !d || !r || !t) return fail("null argument");
+    if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
+    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    b.dev.kind = 6;
+    b.dev.eta = int_ior / ext_ior;                         // marschnerdielectric.cpp:156
+    b.dev.diffuse = V3(d[0], d[1], d[2]);
+    b.dev.specular = ensure_energy_conservation(r);        // :191-194
+    b.dev.specT = ensure_energy_conservation(t);
+    b.dev.exponent = exponent;                             // only read by the dead cone term of eval()
+    const float dAvg = luminance(b.dev.diffuse), sAvg = luminance(b.dev.specular), tAvg = luminance(b.dev.specT);
+    b.dev.specW = (sAvg + tAvg) / (dAvg + sAvg + tAvg);    // :211-214
+    ctx->bsdfs.push_back(b); ctx->built = false;
+    return (int) ctx->bsdfs.size() - 1;
+}
+
 int cudapath_add_bsdf_diffuse(cudapath_ctx *ctx, const float reflectance[3], int two_sided) {
     if (!ctx || !reflectance) return fail("null argument");
     BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
@@ -690,6 +725,15 @@ int cudapath_bsdf_eval_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const f
     DevBuf a, b, e, p; std::string err;
     CKA(a.upload(wi, n * 12, ctx->stream)); CKA(b.upload(wo, n * 12, ctx->stream)); CKA(e.alloc(n * 12)); CKA(p.alloc(n * 4));
     if (!bsdf_eval_batch(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
+    CKA(e.download(out_eval, ctx->stream)); CKA(p.download(out_pdf, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cudapath_bsdf_eval_batch_discrete(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf) {
+    if (require_built(ctx)) return -1;
+    DevBuf a, b, e, p; std::string err;
+    CKA(a.upload(wi, n * 12, ctx->stream)); CKA(b.upload(wo, n * 12, ctx->stream)); CKA(e.alloc(n * 12)); CKA(p.alloc(n * 4));
+    if (!bsdf_eval_batch(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err, true)) return fail(err);
     CKA(e.download(out_eval, ctx->stream)); CKA(p.download(out_pdf, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     return 0;

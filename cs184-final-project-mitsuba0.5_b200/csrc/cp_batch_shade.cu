@@ -15,14 +15,14 @@
 namespace cp {
 
 __global__ void __launch_bounds__(256) k_bsdf_eval(const BsdfDev *__restrict__ bsdfs, int bsdf, uint64_t n, const float *__restrict__ wi,
-                                                   const float *__restrict__ wo, float *eval, float *pdf) {
+                                                   const float *__restrict__ wo, float *eval, float *pdf, bool discrete) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const BsdfDev &b = bsdfs[bsdf];
     const V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), c(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
-    const V3 e = bsdf_eval(b, a, c);
+    const V3 e = bsdf_eval(b, a, c, discrete);
     eval[3 * i] = e.x; eval[3 * i + 1] = e.y; eval[3 * i + 2] = e.z;
-    pdf[i] = bsdf_pdf(b, a, c);
+    pdf[i] = bsdf_pdf(b, a, c, discrete);
 }
 __global__ void __launch_bounds__(256) k_bsdf_sample(const BsdfDev *__restrict__ bsdfs, int bsdf, uint64_t n, const float *__restrict__ wi,
                                                      const float *__restrict__ sample, const float *__restrict__ extra, float *wo, float *weight, float *pdf, int32_t *type) {
@@ -82,10 +82,10 @@ void fill_records_batch(const SceneDev &S, uint64_t n, const float *d_d, const i
 #define CKB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 static inline unsigned grid_for(uint64_t n, int block) { return (unsigned) ((n + block - 1) / block); }
 
-bool bsdf_eval_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err) {
+bool bsdf_eval_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err, bool discrete) {
     if (bsdf < 0 || bsdf >= S.bsdfCount) { err = "bsdf id out of range"; return false; }
     if (n == 0) return true;
-    k_bsdf_eval<<<grid_for(n, 256), 256, 0, s>>>(S.bsdfs, bsdf, n, d_wi, d_wo, d_eval, d_pdf);
+    k_bsdf_eval<<<grid_for(n, 256), 256, 0, s>>>(S.bsdfs, bsdf, n, d_wi, d_wo, d_eval, d_pdf, discrete);
     CKB(cudaGetLastError());
     return true;
 }

@@ -21,9 +21,12 @@ struct BsdfDev {
     int kind;            // 0 = kajiyakay, 1 = marschner (as built), 2 = diffuse (constant reflectance in `diffuse`; meshes),
                          // 3 = the unbuilt `Marschner` of src/bsdfs/marschner.cpp ("fixed" mode: TRT-only eval, real pdf),
                          // 4 = roughplastic (src/bsdfs/roughplastic.cpp; the default BSDF of the models/*/scene.xml files)
+                         // 5 = thindielectric (src/bsdfs/thindielectric.cpp; specular reflectance in `specular`, transmittance in `diffuse`)
+                         // 6 = marschnerdielectric (src/bsdfs/marschnerdielectric.cpp; transmittance in `specT`)
     int twoSided;        // kind 2 only: wrapped in `twosided` with the same nested BRDF on both sides
     // kajiyakay (kajiyakay.cpp:60-107) / marschner diffuse colour
     V3 diffuse, specular;
+    V3 specT;            // marschnerdielectric: m_specularTransmittance
     float exponent;
     float specW;         // m_specularSamplingWeight
     // marschner (marschner_diffuse.cpp:113-160,193-247)
@@ -510,16 +513,76 @@ CP_D BsdfSampleOut df_sample(const BsdfDev &b, V3 wi, float sx, float sy) {
     return r;
 }
 
+// ------------------------------------------------------------------------------------------ ThinDielectric / MarschnerDielectric
+// src/bsdfs/thindielectric.cpp:143-245 and the fork's src/bsdfs/marschnerdielectric.cpp:245-499 (see oracle/o_bsdf.h for the
+// walk through the latter: its eval() is identically zero as committed, its pdf() is the cosine density of the diffuse component,
+// its sample() is a thin dielectric with probability m_specularSamplingWeight and a dead diffuse branch otherwise).
+// `discrete` selects the EDiscrete measure (common.h:56-67); the path tracer only ever asks for ESolidAngle.
+CP_D float thin_slab_reflectance(float cosThetaI, float eta) {          // R' = R + TRT + TR^3T + ...
+    float R = fresnelDielectricExt(cosThetaI, eta), T = 1 - R;
+    if (R < 1) R += T * T * R / (1 - R * R);
+    return R;
+}
+CP_D V3 td_eval(const BsdfDev &b, const V3 &wi, const V3 &wo, bool discrete) {
+    const float R = thin_slab_reflectance(fabsf(wi.z), b.eta);
+    if (wi.z * wo.z >= 0) {
+        if (!discrete || fabsf(dot(kk_reflect(wi), wo) - 1) > kDeltaEpsilon) return V3(0.0f);
+        return b.specular * R;
+    }
+    if (!discrete || fabsf(dot(V3(-wi.x, -wi.y, -wi.z), wo) - 1) > kDeltaEpsilon) return V3(0.0f);
+    return b.diffuse * (1 - R);
+}
+CP_D float td_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo, bool discrete) {
+    const float R = thin_slab_reflectance(fabsf(wi.z), b.eta);
+    if (wi.z * wo.z >= 0) {
+        if (!discrete || fabsf(dot(kk_reflect(wi), wo) - 1) > kDeltaEpsilon) return 0.0f;
+        return R;
+    }
+    if (!discrete || fabsf(dot(V3(-wi.x, -wi.y, -wi.z), wo) - 1) > kDeltaEpsilon) return 0.0f;
+    return 1 - R;
+}
+CP_D BsdfSampleOut thin_sample(const V3 &wi, float eta, const V3 &specR, const V3 &specT, float sx) {
+    BsdfSampleOut r;
+    const float R = thin_slab_reflectance(fabsf(wi.z), eta);
+    if (sx <= R) { r.component = 0; r.type = EDeltaReflection; r.wo = kk_reflect(wi); r.pdf = R; r.weight = specR; }
+    else { r.component = 1; r.type = ENull; r.wo = V3(-wi.x, -wi.y, -wi.z); r.pdf = 1 - R; r.weight = specT; }
+    return r;
+}
+CP_D float md_pdf(const V3 &wi, const V3 &wo, bool discrete) {
+    if (discrete || wi.z <= 0 || wo.z <= 0) return 0.0f;
+    return kInvPi * wo.z;
+}
+CP_D BsdfSampleOut md_sample(const BsdfDev &b, const V3 &wi, float sx, float sy) {
+    if (sx <= b.specW) return thin_sample(wi, b.eta, b.specular, b.specT, sx / b.specW);
+    sx = (sx - b.specW) / (1 - b.specW);
+    BsdfSampleOut r; r.weight = V3(0.0f);
+    r.wo = squareToCosineHemisphere(sx, sy);
+    r.component = 2; r.type = EDiffuseReflection;
+    r.pdf = md_pdf(wi, r.wo, false);
+    return r;                                           // eval() / pdf == 0: the path ends here
+}
+
 // ------------------------------------------------------------------------------------------ dispatch
-CP_D V3 bsdf_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
+CP_D V3 bsdf_eval(const BsdfDev &b, const V3 &wi, const V3 &wo, bool discrete = false) {
+    if (b.kind == 5) return td_eval(b, wi, wo, discrete);
+    if (b.kind == 6 || discrete) return V3(0.0f);
     return b.kind == 0 ? kk_eval(b, wi, wo) : b.kind == 1 ? ma_eval(b, wi, wo) : b.kind == 2 ? df_eval(b, wi, wo) : b.kind == 3 ? mf_eval(b, wi, wo) : rp_eval(b, wi, wo);
 }
-CP_D float bsdf_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) {
+CP_D float bsdf_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo, bool discrete = false) {
+    if (b.kind == 5) return td_pdf(b, wi, wo, discrete);
+    if (b.kind == 6) return md_pdf(wi, wo, discrete);
+    if (discrete) return 0.0f;
     return b.kind == 0 ? kk_pdf(b, wi, wo) : b.kind == 1 ? 1.0f : b.kind == 2 ? df_pdf(b, wi, wo) : b.kind == 3 ? mf_pdf(b, wi, wo) : rp_pdf(b, wi, wo);
 }
 // true for BSDFs whose sample() pulls more numbers from the sampler than the two it is handed (fixed Marschner: 4)
 CP_D bool bsdf_draws_extra(const BsdfDev &b) { return b.kind == 3; }
+// BSDF::getType() & ESmooth (bsdf.h:278): everything except the thin dielectric, whose two components are discrete
+CP_D bool bsdf_has_smooth(const BsdfDev &b) { return b.kind != 5; }
+// eval() in the solid-angle measure is identically zero: emitter samples are drawn and counted, but can never contribute
+CP_D bool bsdf_eval_is_zero(const BsdfDev &b) { return b.kind == 6; }
 CP_D BsdfSampleOut bsdf_sample(const BsdfDev &b, const V3 &wi, float sx, float sy, const float4 &extra) {
+    if (b.kind == 5) return thin_sample(wi, b.eta, b.specular, b.diffuse, sx);
+    if (b.kind == 6) return md_sample(b, wi, sx, sy);
     return b.kind == 0 ? kk_sample(b, wi, sx, sy) : b.kind == 1 ? ma_sample(b, wi, sx, sy) : b.kind == 2 ? df_sample(b, wi, sx, sy)
          : b.kind == 3 ? mf_sample(b, wi, extra.x, extra.y, extra.z, extra.w) : rp_sample(b, wi, sx, sy);
 }

@@ -15,6 +15,7 @@ namespace cp {
 
 constexpr float kEpsilon = 1e-4f;
 constexpr float kShadowEpsilon = 1e-3f;
+constexpr float kDeltaEpsilon = 1e-3f;
 constexpr float kPi = 3.14159265358979323846f;
 constexpr float kInvPi = 0.31830988618379067154f;
 constexpr float kInvTwoPi = 0.15915494309189533577f;
@@ -22,7 +23,8 @@ constexpr float kInvFourPi = 0.07957747154594766788f;
 #define CP_INF (__int_as_float(0x7f800000))
 
 // BSDF::EBSDFType bits that occur on this path (include/mitsuba/render/bsdf.h:230-270)
-enum : int { ENull = 0x1, EDiffuseReflection = 0x2, EGlossyReflection = 0x8, EDeltaReflection = 0x20 };
+enum : int { ENull = 0x1, EDiffuseReflection = 0x2, EGlossyReflection = 0x8, EDeltaReflection = 0x20, EDeltaTransmission = 0x40,
+              EDelta = ENull | EDeltaReflection | EDeltaTransmission };   // bsdf.h:230-285
 
 struct V3 {
     float x, y, z;

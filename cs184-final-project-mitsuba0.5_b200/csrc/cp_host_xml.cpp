@@ -7,7 +7,7 @@
 //   Transform::lookAt / rotate / translate / scale                            src/libcore/transform.cpp
 //   PerspectiveCamera fov handling                                            src/librender/sensor.cpp:225-300
 // Plugins understood: integrator `path`; sensor `perspective` (film `ldrfilm`/`hdrfilm`, rfilter `tent`/`box`/`gaussian`,
-// any sampler: only sampleCount is used); bsdf `kajiyakay`, `marschner`, `marschner_fixed`, `roughplastic`, `diffuse`, `twosided`; shape `hair`,
+// any sampler: only sampleCount is used); bsdf `kajiyakay`, `marschner`, `marschner_fixed`, `marschnerdielectric`, `thindielectric`, `roughplastic`, `diffuse`, `twosided`; shape `hair`,
 // `obj`; emitter `sunsky`.
 // Anything else raises an error naming the plugin (the reference would dlopen plugins/<type>.so, src/libcore/plugin.cpp:222-245).
 #include "../../include/cudapath.h"
@@ -255,7 +255,29 @@ struct Loader {
             float r[3]; getColor(*d, "reflectance", 0.5f, r);
             if (child(*d, "rgb", "diffuseReflectance") || child(*d, "spectrum", "diffuseReflectance")) getColor(*d, "diffuseReflectance", 0.5f, r);
             id = (dry ? note("bsdf diffuse/twosided") : cudapath_add_bsdf_diffuse(ctx, r, type == "twosided" ? 1 : 0));
-        } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, roughplastic, diffuse, twosided)");
+        } else if (type == "thindielectric" || type == "marschnerdielectric") {
+            // src/bsdfs/thindielectric.cpp:73-91 / src/bsdfs/marschnerdielectric.cpp:128-167 (defaults bk7 resp. benzene over air)
+            auto ior = [&](const char *name, double def) {
+                if (child(n, "float", name)) return getFloat(n, name, def);
+                auto c = child(n, "string", name);
+                if (!c) return def;
+                std::string v = lower(c->get("value"));
+                if (v == "benzene") return 1.501; if (v == "amber") return 1.55; if (v == "air") return 1.000277; if (v == "bk7") return 1.5046;
+                if (v == "vacuum") return 1.0; if (v == "water") return 1.3330;
+                throw std::runtime_error("Unable to find an IOR value for \"" + v + "\"");
+            };
+            if (child(n, "texture", "specularReflectance") || child(n, "texture", "specularTransmittance") || child(n, "texture", "diffuseReflectance"))
+                throw std::runtime_error(type + ": textured parameters are not supported");
+            float r[3], t[3], d[3];
+            if (type == "thindielectric") {
+                getColor(n, "specularReflectance", 1.0f, r); getColor(n, "specularTransmittance", 1.0f, t);
+                id = (dry ? note("bsdf thindielectric") : cudapath_add_bsdf_thindielectric(ctx, (float) ior("intIOR", 1.5046), (float) ior("extIOR", 1.000277), r, t));
+            } else {
+                getColor(n, "specularReflectance", 0.1f, r); getColor(n, "specularTransmittance", 0.1f, t); getColor(n, "diffuseReflectance", 0.5f, d);
+                id = (dry ? note("bsdf marschnerdielectric") : cudapath_add_bsdf_marschnerdielectric(ctx, (float) ior("intIOR", 1.501), (float) ior("extIOR", 1.000277), d, r, t,
+                                                                                                      (float) getFloat(n, "exponent", 30.0)));
+            }
+        } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, marschnerdielectric, thindielectric, roughplastic, diffuse, twosided)");
         check(id);
         if (n.has("id")) bsdfIds[n.get("id")] = id;
         return id;

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
                         V3 L = thr * env_eval_filtered(S.env, rayD, cr.rx, cr.ry, unsupportedLookups);
                         acc.x += L.x; acc.y += L.y; acc.z += L.z;
                     }
-                } else if (S.env.present) {                                     // path.cpp:233-264
+                } else if (S.env.present && !(S.integ.hideEmitters && !(flags & F_SCATTERED))) {   // path.cpp:233-264 (:237-238 hides the emitter from unscattered paths)
                     const V3 value = env_eval(S.env, rayD);
                     if (env_fill_direct(S.env, rayO, rayD)) {
                         const float lumPdf = (flags & F_DELTA) ? 0.0f : env_pdf_direct(S.env, rayD);
@@ -110,12 +110,12 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
             const BsdfDev &bsdf = S.bsdfs[shape.bsdf];
             const Philox4 u = philox4x32_10(pix, samp, (uint32_t) depth, 0u, wp.seedLo, wp.seedHi);
             // ---- emitter sampling (path.cpp:174-200)
-            if (S.env.present) {
+            if (S.env.present && bsdf_has_smooth(bsdf)) {       // path.cpp:174-175: only BSDFs with a smooth component
                 const EnvSample es = env_sample_direct(S.env, rec.p, u32_to_unit(u.v[0]), u32_to_unit(u.v[1]));
                 if (es.pdf != 0) {
                     // The shadow ray is always traced when pdf != 0 (scene.cpp:838-845); its contribution may be zero.
                     V3 contrib(0.0f);
-                    if (!isZero(es.value)) {
+                    if (!isZero(es.value) && !bsdf_eval_is_zero(bsdf)) {
                         const V3 wo = rec.sh.toLocal(es.d);
                         const V3 bsdfVal = bsdf_eval(bsdf, rec.wi, wo);
                         if (!isZero(bsdfVal) && (!S.integ.strictNormals || dot(rec.geoN, es.d) * wo.z > 0)) {
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
             nro = make_float4(rec.p.x, rec.p.y, rec.p.z, kEpsilon);
             nrd = make_float4(wo.x, wo.y, wo.z, CP_INF);
             nthr = make_float4(thr.x, thr.y, thr.z, bs.pdf);
-            nid = make_uint2(pathId, (uint32_t) depth | ((bs.type & EDeltaReflection) ? F_DELTA : 0u));
+            nid = make_uint2(pathId, (uint32_t) depth | ((bs.type & EDelta) ? F_DELTA : 0u) | ((bs.type != ENull || (flags & F_SCATTERED)) ? F_SCATTERED : 0u));
             survive = true;
         } while (false);
     }

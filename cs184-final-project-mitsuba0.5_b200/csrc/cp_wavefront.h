@@ -56,7 +56,8 @@ struct Wavefront {
 
 // shared by the stage kernels ----------------------------------------------------------------------------------------
 // flags word: bits 0..15 depth, bit 16 first (camera) segment, bit 17 last BSDF sample was EDelta, bit 18 invalid (padding pixel)
-enum : uint32_t { F_FIRST = 1u << 16, F_DELTA = 1u << 17, F_INVALID = 1u << 18 };
+// F_SCATTERED: some vertex of the path sampled a component other than ENull (`scattered` of path.cpp:125,213)
+enum : uint32_t { F_FIRST = 1u << 16, F_DELTA = 1u << 17, F_INVALID = 1u << 18, F_SCATTERED = 1u << 19 };
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) {
@@ -90,7 +91,7 @@ void launch_splat(const SceneDev &S, const WaveParams &wp, const float4 *liAcc, 
 bool splat_batch(const SceneDev &S, const float *d_pos, const float *d_rgb, const float *d_alpha, uint64_t n, float *d_film, cudaStream_t stream, std::string &err);
 
 // cp_batch.cu -- parity hooks / stage micro-benchmarks on device-resident batches
-bool bsdf_eval_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err);
+bool bsdf_eval_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err, bool discrete = false);
 bool bsdf_sample_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_sample, const float *d_extra /* 4 per tuple or null */, float *d_wo, float *d_weight, float *d_pdf, int32_t *d_type, cudaStream_t s, std::string &err);
 bool intersect_batch(const SceneDev &S, uint64_t n, const float *d_o, const float *d_d, const float *d_mint, const float *d_maxt, int anyHit, bool stats,
                      int32_t *d_shape, uint32_t *d_prim, float *d_t, float *d_rec /*15 floats per ray or null*/, unsigned long long *d_stats, cudaStream_t s, std::string &err);

@@ -50,6 +50,16 @@ SCENES = {
     # models/straight-hair/scene.xml as shipped (roughplastic on the fibers), reduced to 512x512 / 16 spp / depth 8
     'straight-hair-default': dict(camera=_CAM_STRAIGHT, fov=35.0, sun=_SUN_A, width=512, height=512, spp=16, maxDepth=8,
                                   shapes=[dict(generator='straight', radius=0.00566563, bsdf=dict(_ROUGHPLASTIC, id='hair'))]),
+    # models/straight-hair/scene_dielectric.xml:31-38 (the fork's `marschnerdielectric`) and scene_thindielectric.xml:31-37
+    # (same block with type `thindielectric`, no diffuse colour), reduced to 512x512 / 16 spp; maxDepth 65 as in the files
+    'straight-hair-dielectric': dict(camera=_CAM_STRAIGHT, fov=35.0, sun=_SUN_A, width=512, height=512, spp=16, maxDepth=65,
+                                     shapes=[dict(generator='straight', radius=0.00566563,
+                                                  bsdf=dict(type='marschnerdielectric', id='hair', intIOR=1.55, extIOR=1.0, exponent=5.0, specularTransmittance=_HAIR_RGB,
+                                                            specularReflectance=_HAIR_RGB, diffuseReflectance=_HAIR_RGB))]),
+    'straight-hair-thindielectric': dict(camera=_CAM_STRAIGHT, fov=35.0, sun=_SUN_A, width=512, height=512, spp=16, maxDepth=65,
+                                         shapes=[dict(generator='straight', radius=0.00566563,
+                                                      bsdf=dict(type='thindielectric', id='hair', intIOR=1.55, extIOR=1.0, specularTransmittance=_HAIR_RGB,
+                                                                specularReflectance=_HAIR_RGB))]),
     # T1: the straight-hair fibers on a head -- an ellipsoid mesh with smooth vertex normals under the scalp points and a
     # ground quad with face normals (both `diffuse`, the quad inside `twosided`), i.e. fibers and triangles in one BVH
     'hair-on-head': dict(camera=_CAM_STRAIGHT, fov=35.0, sun=_SUN_A, width=512, height=512, spp=16, maxDepth=8,

@@ -51,6 +51,16 @@ int cudapath_add_bsdf_marschner_fixed(cudapath_ctx *ctx, float int_ior, float ex
  * wraps it in the `twosided` adapter (src/bsdfs/twosided.cpp:50-181) with the same BRDF on both sides.  For triangle meshes
  * that accompany the fibers (a scalp or head under the hair).  Returns the bsdf id. */
 int cudapath_add_bsdf_diffuse(cudapath_ctx *ctx, const float reflectance[3], int two_sided);
+/* `thindielectric` plugin (models/straight-hair/scene_thindielectric.xml): ThinDielectric ctor+configure(),
+ * src/bsdfs/thindielectric.cpp:73-125.  Reference defaults: int_ior 1.5046 (bk7), ext_ior 1.000277 (air), both colours 1.
+ * Two discrete components (EDeltaReflection, ENull): the path tracer does no emitter sampling at such a vertex.  Returns the bsdf id. */
+int cudapath_add_bsdf_thindielectric(cudapath_ctx *ctx, float int_ior, float ext_ior, const float specular_reflectance[3], const float specular_transmittance[3]);
+/* `marschnerdielectric` plugin, the fork's third hair BSDF (models/straight-hair/scene_dielectric*.xml): ctor+configure(),
+ * src/bsdfs/marschnerdielectric.cpp:128-221.  Reference defaults: int_ior 1.501 (benzene), ext_ior 1.000277 (air), diffuse 0.5,
+ * specular reflectance / transmittance 0.1, exponent 30.  Reproduced as committed (eval() identically zero, see cp_bsdf.cuh).
+ * Returns the bsdf id. */
+int cudapath_add_bsdf_marschnerdielectric(cudapath_ctx *ctx, float int_ior, float ext_ior, const float diffuse_reflectance[3],
+                                          const float specular_reflectance[3], const float specular_transmittance[3], float exponent);
 
 /* ---- shapes ------------------------------------------------------------------------------------------------ */
 /* Triangle mesh as ShapeKDTree sees it: TriMesh::getVertexPositions() / getVertexNormals() (NULL = face normals) /
@@ -155,6 +165,8 @@ int cudapath_film_size(cudapath_ctx *ctx, int *width, int *height);
 /* ---- parity hooks (host buffers; same device functions as the render path) ---------------------------------- */
 /* BSDF::eval + BSDF::pdf (include/mitsuba/render/bsdf.h:369-441), wi/wo local, measure = ESolidAngle, typeMask = EAll */
 int cudapath_bsdf_eval_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf);
+/* The same with measure = EDiscrete (include/mitsuba/render/common.h:56-67): non-zero only for discrete components (`thindielectric`) */
+int cudapath_bsdf_eval_batch_discrete(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf);
 /* BSDF::sample: out_type = sampledType | sampledComponent << 8 */
 int cudapath_bsdf_sample_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo,
                                float *out_weight, float *out_pdf, int32_t *out_type);

@@ -14,7 +14,8 @@
 namespace orc {
 
 // BSDF::EBSDFType bits used on this path (include/mitsuba/render/bsdf.h:230-270)
-enum { ENull = 0x1, EDiffuseReflection = 0x2, EGlossyReflection = 0x8, EDeltaReflection = 0x20 };
+enum { ENull = 0x1, EDiffuseReflection = 0x2, EGlossyReflection = 0x8, EDeltaReflection = 0x20, EDeltaTransmission = 0x40,
+       EDelta = ENull | EDeltaReflection | EDeltaTransmission };
 
 struct BSDFSample {
     V3 wo; V3 weight; float pdf = 0; int sampledType = 0; int sampledComponent = -1; float eta = 1;
@@ -927,6 +928,105 @@ struct SmoothDiffuse {
         r.weight = reflectance;
         if (flipped && !isZero(r.weight) && r.pdf != 0) { r.wo.z *= -1; r.sampledComponent += 1; }
         return r;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// ThinDielectric (`thindielectric`, models/straight-hair/scene_thindielectric.xml) -- src/bsdfs/thindielectric.cpp:73-300.
+// Two discrete components (EDeltaReflection, ENull), both sides; nothing smooth, so the path tracer skips emitter sampling
+// at such a vertex (path.cpp:174-175).  eval/pdf are non-zero only in the discrete measure.
+// ---------------------------------------------------------------------------------------------
+static inline V3 ensureEnergyConservationConst(V3 v, float mx = 1.0f) {        // bsdf.cpp:88-113 for a constant texture
+    const float actualMax = maxc(v);
+    if (actualMax > mx) v = v * (0.99f * (mx / actualMax));
+    return v;
+}
+// R' = R + TRT + TR^3T + ...  (thindielectric.cpp:150-154 and five more copies; marschnerdielectric.cpp:268-272 etc.)
+static inline float thinSlabReflectance(float cosThetaI, float eta) {
+    float R = fresnelDielectricExt(cosThetaI, eta), T = 1 - R;
+    if (R < 1) R += T * T * R / (1 - R * R);
+    return R;
+}
+
+struct ThinDielectric {
+    float eta; V3 specR, specT;
+    void configure(float intIOR, float extIOR, V3 r, V3 t) {
+        eta = intIOR / extIOR;
+        specR = ensureEnergyConservationConst(r); specT = ensureEnergyConservationConst(t);
+    }
+    static V3 reflect(const V3 &wi) { return V3(-wi.x, -wi.y, wi.z); }
+    // thindielectric.cpp:143-168
+    V3 eval(const V3 &wi, const V3 &wo, bool discrete) const {
+        const float R = thinSlabReflectance(std::abs(wi.z), eta);
+        if (wi.z * wo.z >= 0) {
+            if (!discrete || std::abs(dot(reflect(wi), wo) - 1) > kDeltaEpsilon) return V3(0.0f);
+            return specR * R;
+        } else {
+            if (!discrete || std::abs(dot(-wi, wo) - 1) > kDeltaEpsilon) return V3(0.0f);
+            return specT * (1 - R);
+        }
+    }
+    // thindielectric.cpp:170-194
+    float pdf(const V3 &wi, const V3 &wo, bool discrete) const {
+        const float R = thinSlabReflectance(std::abs(wi.z), eta);
+        if (wi.z * wo.z >= 0) {
+            if (!discrete || std::abs(dot(reflect(wi), wo) - 1) > kDeltaEpsilon) return 0.0f;
+            return R;
+        } else {
+            if (!discrete || std::abs(dot(-wi, wo) - 1) > kDeltaEpsilon) return 0.0f;
+            return 1 - R;
+        }
+    }
+    // thindielectric.cpp:196-245 (typeMask = EAll: both components)
+    BSDFSample sample(const V3 &wi, float sx, float /*sy*/) const {
+        BSDFSample r; r.eta = 1.0f;
+        const float R = thinSlabReflectance(std::abs(wi.z), eta);
+        if (sx <= R) { r.sampledComponent = 0; r.sampledType = EDeltaReflection; r.wo = reflect(wi); r.pdf = R; r.weight = specR; }
+        else { r.sampledComponent = 1; r.sampledType = ENull; r.wo = -wi; r.pdf = 1 - R; r.weight = specT; }
+        return r;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// MarschnerDielectric (`marschnerdielectric`, models/straight-hair/scene_dielectric*.xml) -- the fork's third hair BSDF,
+// src/bsdfs/marschnerdielectric.cpp:128-167 (ctor), :189-221 (configure), :245-307 (eval), :309-376 (pdf), :419-499 (sample).
+// A thin dielectric with a Kajiya-Kay cone and a diffuse term bolted on.  As committed:
+//   * eval() is identically zero: it returns 0 unless measure == ESolidAngle, and in that measure `sampleReflection` /
+//     `sampleTransmission` (which require EDiscrete) are false, so both branches return before the cone / diffuse terms (:258-260,:274-300);
+//   * pdf() in the solid-angle measure is the cosine-hemisphere density of the diffuse component (:322-347), 0 otherwise;
+//   * sample(): the specular branch (probability m_specularSamplingWeight = (s+t)/(d+s+t), :211-214) behaves like the thin dielectric;
+//     the diffuse branch draws a cosine direction and returns eval()/pdf() = 0, which ends the path (:486-498).
+// It has a diffuse component, so the path tracer does sample the emitter at every vertex (and traces the shadow ray) although the
+// product with eval() is always zero.
+// ---------------------------------------------------------------------------------------------
+struct MarschnerDielectric {
+    float eta, exponent, specularSamplingWeight; V3 diffuse, specR, specT;
+    void configure(float intIOR, float extIOR, V3 d, V3 r, V3 t, float expo) {
+        eta = intIOR / extIOR; exponent = expo; diffuse = d;
+        specR = ensureEnergyConservationConst(r); specT = ensureEnergyConservationConst(t);
+        const float dAvg = luminance(diffuse), sAvg = luminance(specR), tAvg = luminance(specT);
+        specularSamplingWeight = (sAvg + tAvg) / (dAvg + sAvg + tAvg);
+    }
+    V3 eval(const V3 &, const V3 &, bool) const { return V3(0.0f); }
+    float pdf(const V3 &wi, const V3 &wo, bool discrete) const {
+        if (discrete || wi.z <= 0 || wo.z <= 0) return 0.0f;
+        return kInvPi * wo.z;
+    }
+    BSDFSample sample(const V3 &wi, float sx, float sy) const {
+        BSDFSample r; r.weight = V3(0.0f); r.eta = 1.0f;
+        bool choseSpecular = true;
+        if (sx <= specularSamplingWeight) sx /= specularSamplingWeight;
+        else { sx = (sx - specularSamplingWeight) / (1 - specularSamplingWeight); choseSpecular = false; }
+        if (choseSpecular) {
+            const float R = thinSlabReflectance(std::abs(wi.z), eta);
+            if (sx <= R) { r.sampledComponent = 0; r.sampledType = EDeltaReflection; r.wo = ThinDielectric::reflect(wi); r.pdf = R; r.weight = specR; }
+            else { r.sampledComponent = 1; r.sampledType = ENull; r.wo = -wi; r.pdf = 1 - R; r.weight = specT; }
+            return r;
+        }
+        r.wo = squareToCosineHemisphere(sx, sy);
+        r.sampledComponent = 2; r.sampledType = EDiffuseReflection;
+        r.pdf = pdf(wi, r.wo, false);
+        return r;                                   // eval()/pdf = 0 (or pdf == 0): zero weight
     }
 };
 

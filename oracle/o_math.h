@@ -18,6 +18,7 @@ namespace orc {
 // include/mitsuba/core/constants.h:28-31,63-69 (single-precision build)
 static const float kEpsilon = 1e-4f;
 static const float kShadowEpsilon = 1e-3f;
+static const float kDeltaEpsilon = 1e-3f;   // constants.h:28-31
 static const float kPi = 3.14159265358979323846f;
 static const float kInvPi = 0.31830988618379067154f;
 static const float kInvTwoPi = 0.15915494309189533577f;

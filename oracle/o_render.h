@@ -113,13 +113,30 @@ struct BSDFAny {
     SmoothDiffuse df;
     std::shared_ptr<MarschnerFixed> mf;
     std::shared_ptr<RoughPlastic> rp;      // kind 4: `roughplastic` (default BSDF of the models/*/scene.xml files)
-    V3 eval(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.eval(wi, wo) : kind == 1 ? ma->eval(wi, wo) : kind == 2 ? df.eval(wi, wo) : kind == 3 ? mf->eval(wi, wo) : rp->eval(wi, wo); }
-    float pdf(const V3 &wi, const V3 &wo) const { return kind == 0 ? kk.pdf(wi, wo) : kind == 1 ? ma->pdf(wi, wo) : kind == 2 ? df.pdf(wi, wo) : kind == 3 ? mf->pdf(wi, wo) : rp->pdf(wi, wo); }
+    ThinDielectric td;                     // kind 5: `thindielectric` (models/straight-hair/scene_thindielectric.xml)
+    MarschnerDielectric md;                // kind 6: `marschnerdielectric` (models/straight-hair/scene_dielectric*.xml)
+    // measure: ESolidAngle unless `discrete` (only the two dielectric kinds have discrete components)
+    V3 eval(const V3 &wi, const V3 &wo, bool discrete = false) const {
+        if (kind == 5) return td.eval(wi, wo, discrete);
+        if (kind == 6) return md.eval(wi, wo, discrete);
+        if (discrete) return V3(0.0f);
+        return kind == 0 ? kk.eval(wi, wo) : kind == 1 ? ma->eval(wi, wo) : kind == 2 ? df.eval(wi, wo) : kind == 3 ? mf->eval(wi, wo) : rp->eval(wi, wo);
+    }
+    float pdf(const V3 &wi, const V3 &wo, bool discrete = false) const {
+        if (kind == 5) return td.pdf(wi, wo, discrete);
+        if (kind == 6) return md.pdf(wi, wo, discrete);
+        if (discrete) return 0.0f;
+        return kind == 0 ? kk.pdf(wi, wo) : kind == 1 ? ma->pdf(wi, wo) : kind == 2 ? df.pdf(wi, wo) : kind == 3 ? mf->pdf(wi, wo) : rp->pdf(wi, wo);
+    }
     // `extra` = four more uniform numbers: only the fixed Marschner draws them (two sampler->next2D() calls inside its sample())
     BSDFSample sample(const V3 &wi, float sx, float sy, const float *extra) const {
+        if (kind == 5) return td.sample(wi, sx, sy);
+        if (kind == 6) return md.sample(wi, sx, sy);
         return kind == 0 ? kk.sample(wi, sx, sy) : kind == 1 ? ma->sample(wi, sx, sy) : kind == 2 ? df.sample(wi, sx, sy)
              : kind == 3 ? mf->sample(wi, extra[0], extra[1], extra[2], extra[3]) : rp->sample(wi, sx, sy);
     }
+    // BSDF::getType() & ESmooth: the thin dielectric has only discrete components (path.cpp:174-175 then skips emitter sampling)
+    bool hasSmooth() const { return kind != 5; }
     bool drawsExtra() const { return kind == 3; }
 };
 
@@ -175,8 +192,8 @@ struct Scene {
             if ((depth >= maxDepth && maxDepth > 0) || (strictNormals && dot(ray.d, its.geoFrame.n) * its.wi.z >= 0))
                 break;
             Philox4 u = philox4x32_10(pix, samp, (uint32_t) depth, 0, k0, k1);
-            /* direct illumination sampling (both hair BSDFs have a smooth component) */
-            if (hasEnv) {
+            /* direct illumination sampling, only for BSDFs with a smooth component (path.cpp:174-175) */
+            if (hasEnv && bsdf.hasSmooth()) {
                 EnvMap::DirectSample ds = env.sampleDirect(its.p, u32_to_unit(u.v[0]), u32_to_unit(u.v[1]));
                 V3 value(0.0f);
                 if (ds.pdf != 0) {
@@ -224,7 +241,7 @@ struct Scene {
             throughput *= bs.weight;
             eta *= bs.eta;
             if (hitEmitter) {
-                const float lumPdf = (!(bs.sampledType & EDeltaReflection)) ? env.pdfDirect(ray.d) : 0;
+                const float lumPdf = (!(bs.sampledType & EDelta)) ? env.pdfDirect(ray.d) : 0;
                 Li += throughput * value * miWeight(bs.pdf, lumPdf);
             }
             if (!its.valid) break;

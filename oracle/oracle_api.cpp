@@ -78,6 +78,28 @@ int orc_add_bsdf_roughplastic(void *sp, float intIOR, float extIOR, const float 
     ORC_CATCH
 }
 
+// `thindielectric` plugin (src/bsdfs/thindielectric.cpp)
+int orc_add_bsdf_thindielectric(void *sp, float intIOR, float extIOR, const float *specR, const float *specT) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    BSDFAny b; b.kind = 5;
+    b.td.configure(intIOR, extIOR, V3(specR[0], specR[1], specR[2]), V3(specT[0], specT[1], specT[2]));
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+    ORC_CATCH
+}
+
+// `marschnerdielectric` plugin (src/bsdfs/marschnerdielectric.cpp)
+int orc_add_bsdf_marschnerdielectric(void *sp, float intIOR, float extIOR, const float *diffuse, const float *specR, const float *specT, float exponent) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    BSDFAny b; b.kind = 6;
+    b.md.configure(intIOR, extIOR, V3(diffuse[0], diffuse[1], diffuse[2]), V3(specR[0], specR[1], specR[2]), V3(specT[0], specT[1], specT[2]), exponent);
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+    ORC_CATCH
+}
+
 // `diffuse` plugin with a constant reflectance (src/bsdfs/diffuse.cpp), optionally inside `twosided`
 int orc_add_bsdf_diffuse(void *sp, const float *reflectance, int twoSided) {
     ORC_TRY
@@ -200,6 +222,20 @@ int orc_bsdf_eval_batch(void *sp, int bsdf, uint64_t n, const float *wi, const f
         V3 e = b.eval(a, c);
         outEval[3 * i] = e.x; outEval[3 * i + 1] = e.y; outEval[3 * i + 2] = e.z;
         outPdf[i] = b.pdf(a, c);
+    }
+    return 0;
+    ORC_CATCH
+}
+// the same in the discrete measure (EDiscrete, common.h:56-67): non-zero only for the delta components of `thindielectric`
+int orc_bsdf_eval_batch_discrete(void *sp, int bsdf, uint64_t n, const float *wi, const float *wo, float *outEval, float *outPdf) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    const BSDFAny &b = s->bsdfs.at(bsdf);
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), c(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+        V3 e = b.eval(a, c, true);
+        outEval[3 * i] = e.x; outEval[3 * i + 1] = e.y; outEval[3 * i + 2] = e.z;
+        outPdf[i] = b.pdf(a, c, true);
     }
     return 0;
     ORC_CATCH

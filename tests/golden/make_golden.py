@@ -59,7 +59,41 @@ def second_set():
     np.savez_compressed(os.path.join(HERE, 'render_mesh_golden.npz'), film=film)
 
 
+THIRD_SET_MATS = [('thindielectric', dict(intIOR=1.55, extIOR=1.0, specularReflectance=HAIR_RGB, specularTransmittance=HAIR_RGB)),
+                  ('thindielectric', dict(intIOR=1.5046, extIOR=1.000277, specularReflectance=(0.9, 0.5, 0.1), specularTransmittance=(2.0, 1.0, 0.5))),
+                  ('marschnerdielectric', dict(intIOR=1.55, extIOR=1.0, exponent=5.0, specularTransmittance=HAIR_RGB, specularReflectance=HAIR_RGB, diffuseReflectance=HAIR_RGB)),
+                  ('marschnerdielectric', dict(intIOR=1.501, extIOR=1.000277, diffuseReflectance=(0.3, 0.2, 0.1), specularReflectance=(0.4, 0.3, 0.2),
+                                               specularTransmittance=(1.5, 0.6, 0.7)))]
+
+
+def third_set():
+    """Fixtures added with the `thindielectric` / `marschnerdielectric` rows: BSDF tuples in both measures and
+    the two straight-hair dielectric scenes rendered small (ENull vertices, hits from inside the fibers)."""
+    rng = np.random.default_rng(0x5eed3)
+    n = 4096
+    s = orc.Scene()
+    for t, p in THIRD_SET_MATS:
+        s.add_bsdf(t, **p)
+    out = dict(wi=sphere_dirs(rng, n), sample=rng.random((n, 2)).astype(np.float32))
+    for b in range(len(THIRD_SET_MATS)):
+        wo, wt, pdf, ty = s.bsdf_sample(b, out['wi'], out['sample'])
+        out['swo_%d' % b], out['swt_%d' % b], out['spdf_%d' % b], out['sty_%d' % b] = wo, wt, pdf, ty
+        for discrete in (0, 1):        # evaluated at the sampled directions: exactly on the delta directions for the discrete components
+            out['eval_%d_%d' % (b, discrete)], out['pdf_%d_%d' % (b, discrete)] = s.bsdf_eval(b, out['wi'], wo, discrete=bool(discrete))
+    np.savez_compressed(os.path.join(HERE, 'bsdf3_golden.npz'), **out)
+    films = {}
+    for name in ('straight-hair-thindielectric', 'straight-hair-dielectric'):
+        ov = dict(width=32, height=24, spp=4, maxDepth=24)
+        env = cudapath.bake_sunsky(**cudapath.scenes.sunsky_params(name))
+        films[name.replace('-', '_')] = orc.scene_from_description(name, scale=0.004, overrides=ov, envmap=env).render(4, seed=13, threads=2)
+    np.savez_compressed(os.path.join(HERE, 'render_dielectric_golden.npz'), **films)
+
+
 def main():
+    if '--third' in sys.argv:
+        third_set()
+        print('third set written')
+        return
     if '--second' in sys.argv:
         second_set()
         print('second set written')

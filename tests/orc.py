@@ -105,6 +105,14 @@ class Scene:
                                                           1 if props.get('sampleVisible', True) else 0, 1 if props.get('nonlinear', False) else 0, DATA_DIR.encode()))
         if type == 'marschner_fixed':
             return check(self.L.orc_add_bsdf_marschner_fixed(self.h, ctypes.c_float(props.get('intIOR', 1.55)), ctypes.c_float(props.get('extIOR', 1.000277))))
+        if type == 'thindielectric':
+            r = f32(np.broadcast_to(props.get('specularReflectance', 1.0), 3)); t = f32(np.broadcast_to(props.get('specularTransmittance', 1.0), 3))
+            return check(self.L.orc_add_bsdf_thindielectric(self.h, ctypes.c_float(props.get('intIOR', 1.5046)), ctypes.c_float(props.get('extIOR', 1.000277)), p(r), p(t)))
+        if type == 'marschnerdielectric':
+            d = f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3))
+            r = f32(np.broadcast_to(props.get('specularReflectance', 0.1), 3)); t = f32(np.broadcast_to(props.get('specularTransmittance', 0.1), 3))
+            return check(self.L.orc_add_bsdf_marschnerdielectric(self.h, ctypes.c_float(props.get('intIOR', 1.501)), ctypes.c_float(props.get('extIOR', 1.000277)), p(d), p(r), p(t),
+                                                                 ctypes.c_float(props.get('exponent', 30.0))))
         if type in ('diffuse', 'twosided'):
             r = f32(np.broadcast_to(props.get('reflectance', 0.5), 3))
             return check(self.L.orc_add_bsdf_diffuse(self.h, p(r), 1 if (type == 'twosided' or props.get('twoSided', False)) else 0))
@@ -152,10 +160,10 @@ class Scene:
         self.L.orc_segment_bounds(self.h, int(shape), p(out))
         return out
 
-    def bsdf_eval(self, bsdf, wi, wo):
+    def bsdf_eval(self, bsdf, wi, wo, discrete=False):
         wi = f32(wi).reshape(-1, 3); wo = f32(wo).reshape(-1, 3); n = len(wi)
         ev = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32)
-        check(self.L.orc_bsdf_eval_batch(self.h, int(bsdf), ctypes.c_uint64(n), p(wi), p(wo), p(ev), p(pdf)))
+        check((self.L.orc_bsdf_eval_batch_discrete if discrete else self.L.orc_bsdf_eval_batch)(self.h, int(bsdf), ctypes.c_uint64(n), p(wi), p(wo), p(ev), p(pdf)))
         return ev, pdf
 
     def bsdf_sample(self, bsdf, wi, sample, extra=None):

@@ -420,6 +420,63 @@ def test_render_matches_oracle(cp, oracle, name, scale):
     ctx.close()
 
 
+def test_dielectric_bsdfs_bit_exact(cp, oracle):
+    """`thindielectric` (src/bsdfs/thindielectric.cpp) and the fork's `marschnerdielectric` (as committed): eval/pdf in both measures
+    and sample are bit-identical to the oracle, from both sides of the surface."""
+    ctx = cp.Context(0); osc = oracle.Scene()
+    for s in (ctx, osc):
+        s.add_bsdf('thindielectric', intIOR=1.55, extIOR=1.0, specularReflectance=HAIR_RGB, specularTransmittance=HAIR_RGB)
+        s.add_bsdf('thindielectric', intIOR=1.5046, extIOR=1.000277, specularReflectance=(0.9, 0.5, 0.1), specularTransmittance=(2.0, 1.0, 0.5))
+        s.add_bsdf('marschnerdielectric', intIOR=1.55, extIOR=1.0, exponent=5.0, specularTransmittance=HAIR_RGB, specularReflectance=HAIR_RGB, diffuseReflectance=HAIR_RGB)
+        s.add_bsdf('marschnerdielectric', intIOR=1.501, extIOR=1.000277, diffuseReflectance=(0.3, 0.2, 0.1), specularReflectance=(0.4, 0.3, 0.2), specularTransmittance=(1.5, 0.6, 0.7))
+        s.add_hair(np.array([[0, 0, 0], [0, 1, 0], [0.1, 2, 0]], np.float32), np.array([1, 0, 0], np.uint8), 0.05, 0)
+        s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=16, height=16)
+        s.build()
+    rng = np.random.default_rng(23)
+    n = 200000
+    wi = sphere_dirs(rng, n); smp = rng.random((n, 2)).astype(np.float32)
+    wi[:64, 2] = 0.0; wi[64:128] = [0, 0, 1]; wi[128:192] = [0, 0, -1]                  # grazing and normal incidence
+    for b in range(4):
+        g = ctx.bsdf_sample(b, wi, smp); o = osc.bsdf_sample(b, wi, smp)
+        for a, c in zip(g, o):
+            assert np.array_equal(a, c)
+        types = set(np.unique(g[3] & 0xff).tolist())
+        assert types == ({0x1, 0x20} if b < 2 else {0x1, 0x2, 0x20})
+        # evaluate at the sampled directions (exactly on the delta directions) and at perturbed ones, both measures
+        wo = g[0].copy(); wo[::2] = sphere_dirs(rng, (n + 1) // 2)
+        for discrete in (False, True):
+            ge, gp = ctx.bsdf_eval(b, wi, wo, discrete=discrete); oe, op = osc.bsdf_eval(b, wi, wo, discrete=discrete)
+            assert np.array_equal(ge, oe) and np.array_equal(gp, op)
+            if b < 2:
+                assert gp.any() == discrete                    # a delta BSDF is zero in the solid-angle measure
+    ctx.close()
+
+
+@pytest.mark.parametrize('name', ['straight-hair-thindielectric', 'straight-hair-dielectric'])
+def test_render_dielectric_scenes(cp, oracle, name):
+    """models/straight-hair/scene_thindielectric.xml / scene_dielectric.xml: ENull vertices (rays continue straight through the fibers,
+    hits from the inside, `scattered` bookkeeping), no emitter sampling for the BSDF without a smooth component."""
+    for hide in (False, True):
+        ov = dict(width=72, height=56, spp=8, maxDepth=24)
+        ctx = cp.scene_from_description(name, scale=0.02, overrides=ov)
+        ctx.set_integrator(maxDepth=24, rrDepth=5, strictNormals=True, hideEmitters=hide)
+        ctx.build()
+        env = cp.bake_sunsky(**cp.scenes.sunsky_params(name))
+        osc = oracle.scene_from_description(name, scale=0.02, overrides=ov, envmap=env)
+        osc.set_integrator(maxDepth=24, rrDepth=5, strictNormals=True, hideEmitters=hide)
+        g = ctx.render(8, seed=9); o = osc.render(8, seed=9)
+        st = ctx.stats()
+        assert st['paths'] == 72 * 56 * 8 == osc.last_stats['paths']
+        assert abs(st['rays'] - osc.last_stats['rays']) <= 2e-3 * osc.last_stats['rays']
+        assert st['shadow_rays'] == osc.last_stats['shadow_rays'] and (st['shadow_rays'] == 0) == (name == 'straight-hair-thindielectric')
+        a, b = cp.develop(g), cp.develop(o)
+        assert np.isfinite(a).all() and b.sum() > 0
+        assert rel_mse(a, b) < 1e-3, 'relMSE %g' % rel_mse(a, b)
+        close = np.abs(a - b).max(axis=2) <= 1e-3 * (np.abs(b).max(axis=2) + 1e-3)
+        assert close.mean() > 0.97, 'only %.3f of the pixels agree to 1e-3' % close.mean()
+        ctx.close()
+
+
 def test_render_fixed_marschner(cp, oracle):
     """Whole path with the M7 BSDF (extra sampler draws on counter stream 2, real pdf in the MIS weights)."""
     sh = dict(cp.scenes.SCENES['curly-hair']['shapes'][0], bsdf=dict(type='marschner_fixed', id='hair', intIOR=1.55, extIOR=1.0))
@@ -465,7 +522,7 @@ def test_independent_seeds_agree_statistically(cp, oracle):
     ctx.close()
 
 
-@pytest.mark.parametrize('name', ['straight-hair', 'hair-on-head', 'straight-hair-default'])
+@pytest.mark.parametrize('name', ['straight-hair', 'hair-on-head', 'straight-hair-default', 'straight-hair-dielectric', 'straight-hair-thindielectric'])
 def test_xml_scene_roundtrip(cp, oracle, tmp_path, name):
     """The XML + .mitshair / .obj path (SceneHandler + HairShape / WavefrontOBJ loaders) yields the same film as the flattened-array path."""
     ov = dict(width=48, height=48, spp=4, maxDepth=5)
@@ -583,3 +640,30 @@ def test_second_golden_set(cp):
     a, b2 = cp.develop(film), cp.develop(gf)
     assert rel_mse(a, b2) < 1e-3
     ctx.close()
+
+
+def test_third_golden_set(cp):
+    """tests/golden/bsdf3_golden.npz + render_dielectric_golden.npz: the dielectric BSDFs and scenes against the committed files."""
+    import os
+    from test_oracle_cpu import THIRD_SET_MATS, GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'bsdf3_golden.npz'))
+    ctx = cp.Context(0)
+    for t, p in THIRD_SET_MATS:
+        ctx.add_bsdf(t, **p)
+    ctx.add_hair(np.array([[0, 0, 0], [0, 1, 0], [0.1, 2, 0]], np.float32), np.array([1, 0, 0], np.uint8), 0.05, 0)
+    ctx.set_camera(np.eye(4, dtype=np.float32), 35.0, width=16, height=16)
+    ctx.build()
+    for b in range(len(THIRD_SET_MATS)):
+        wo, wt, p, ty = ctx.bsdf_sample(b, g['wi'], g['sample'])
+        assert np.array_equal(wo, g['swo_%d' % b]) and np.array_equal(wt, g['swt_%d' % b]) and np.array_equal(p, g['spdf_%d' % b]) and np.array_equal(ty, g['sty_%d' % b])
+        for discrete in (0, 1):
+            ev, pdf = ctx.bsdf_eval(b, g['wi'], wo, discrete=bool(discrete))
+            assert np.array_equal(ev, g['eval_%d_%d' % (b, discrete)]) and np.array_equal(pdf, g['pdf_%d_%d' % (b, discrete)])
+    ctx.close()
+    films = np.load(os.path.join(GOLDEN, 'render_dielectric_golden.npz'))
+    for name in ('straight-hair-thindielectric', 'straight-hair-dielectric'):
+        ov = dict(width=32, height=24, spp=4, maxDepth=24)
+        c2 = cp.scene_from_description(name, scale=0.004, overrides=ov); c2.build()
+        a, b2 = cp.develop(c2.render(4, seed=13)), cp.develop(films[name.replace('-', '_')])
+        assert rel_mse(a, b2) < 1e-3
+        c2.close()

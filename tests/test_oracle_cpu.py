@@ -389,6 +389,82 @@ def test_diffuse_and_twosided_closed_forms(oracle):
     assert not s.bsdf_sample(d, down, smp)[1].any()
 
 
+def _fresnel_unpolarised(c, eta):
+    """Textbook unpolarised Fresnel reflectance from the outside (cos > 0) of a dielectric with relative index eta."""
+    st = np.sqrt(max(0.0, 1 - c * c)) / eta
+    ct = np.sqrt(max(0.0, 1 - st * st))
+    rs = (c - eta * ct) / (c + eta * ct); rp = (eta * c - ct) / (eta * c + ct)
+    return 0.5 * (rs * rs + rp * rp)
+
+
+def test_thindielectric_closed_forms(oracle):
+    """src/bsdfs/thindielectric.cpp:143-245: R' = R + T^2 R / (1 - R^2); reflection with probability R', else straight through
+    (ENull); non-zero eval/pdf only in the discrete measure; works from both sides."""
+    s = oracle.Scene()
+    b = s.add_bsdf('thindielectric', intIOR=1.55, extIOR=1.0, specularReflectance=(0.9, 0.5, 0.1), specularTransmittance=(2.0, 1.0, 0.5))   # T > 1: rescaled
+    rng = np.random.default_rng(5)
+    wi = sphere_dirs(rng, 4096); smp = rng.random((4096, 2)).astype(np.float32)
+    wo, wt, pdf, ty = s.bsdf_sample(b, wi, smp)
+    for k in range(0, 4096, 97):
+        R = _fresnel_unpolarised(abs(float(wi[k, 2])), 1.55); Rp = R + (1 - R) ** 2 * R / (1 - R * R)
+        if smp[k, 0] <= np.float32(Rp) - 1e-6:
+            assert ty[k] == 0x20 and np.allclose(wo[k], wi[k] * [-1, -1, 1]) and np.isclose(pdf[k], Rp, rtol=2e-5) and np.allclose(wt[k], [0.9, 0.5, 0.1])
+        elif smp[k, 0] > np.float32(Rp) + 1e-6:
+            assert ty[k] == (0x1 | (1 << 8)) and np.allclose(wo[k], -wi[k]) and np.isclose(pdf[k], 1 - Rp, rtol=2e-5) and np.allclose(wt[k], [0.99, 0.495, 0.2475])
+    # discrete measure: eval = colour * probability, pdf = probability, exactly at the two delta directions and nowhere else
+    ev, p = s.bsdf_eval(b, wi, wo, discrete=True)
+    refl = (ty & 0xff) == 0x20
+    assert np.allclose(p, pdf, rtol=1e-6) and np.allclose(ev[refl], np.float32([0.9, 0.5, 0.1]) * pdf[refl, None], rtol=1e-6)
+    assert np.allclose(ev[~refl], np.float32([0.99, 0.495, 0.2475]) * pdf[~refl, None], rtol=1e-6)
+    off = sphere_dirs(rng, 4096)
+    nz = s.bsdf_eval(b, wi, off, discrete=True)[0].any(axis=1)     # DeltaEpsilon = 1e-3: a 2.6 degree cap around each delta direction
+    near = (np.abs((wi * [-1, -1, 1] * off).sum(1) - 1) <= 1e-3) | (np.abs((-wi * off).sum(1) - 1) <= 1e-3)
+    assert nz.sum() < 20 and (nz == near).mean() > 0.999
+    ev0, p0 = s.bsdf_eval(b, wi, wo)                               # solid-angle measure: a delta BSDF evaluates to zero
+    assert not ev0.any() and not p0.any()
+    assert (s.bsdf_sample(b, wi, smp)[2] > 0).all()                 # back side (wi.z < 0) samples as well
+
+
+def test_marschnerdielectric_as_committed(oracle):
+    """src/bsdfs/marschnerdielectric.cpp as committed: eval() == 0 in every measure, pdf() = cosine density of the diffuse component,
+    sample() = thin dielectric with probability (s+t)/(d+s+t) and a zero-weight diffuse branch."""
+    s = oracle.Scene()
+    d, r, t = (0.3, 0.2, 0.1), (0.4, 0.3, 0.2), (0.5, 0.6, 0.7)
+    b = s.add_bsdf('marschnerdielectric', intIOR=1.55, extIOR=1.0, exponent=5.0, diffuseReflectance=d, specularReflectance=r, specularTransmittance=t)
+    lum = lambda c: 0.212671 * c[0] + 0.715160 * c[1] + 0.072169 * c[2]
+    w = (lum(r) + lum(t)) / (lum(d) + lum(r) + lum(t))
+    rng = np.random.default_rng(6)
+    wi = sphere_dirs(rng, 4096); wo = sphere_dirs(rng, 4096); smp = rng.random((4096, 2)).astype(np.float32)
+    ev, pdf = s.bsdf_eval(b, wi, wo)
+    assert not ev.any() and not s.bsdf_eval(b, wi, wo, discrete=True)[0].any() and not s.bsdf_eval(b, wi, wo, discrete=True)[1].any()
+    both = (wi[:, 2] > 0) & (wo[:, 2] > 0)
+    assert np.allclose(pdf[both], wo[both, 2] / np.pi, rtol=1e-6) and not pdf[~both].any()
+    swo, wt, p, ty = s.bsdf_sample(b, wi, smp)
+    spec = smp[:, 0] <= np.float32(w)
+    assert ((ty[~spec] & 0xff) == 0x2).all() and not wt[~spec].any() and (swo[~spec, 2] >= 0).all()       # dead diffuse branch
+    assert np.isin(ty[spec] & 0xff, (0x1, 0x20)).all()
+    refl = spec & ((ty & 0xff) == 0x20); thru = spec & ((ty & 0xff) == 0x1)
+    assert np.allclose(wt[refl], np.float32(r)) and np.allclose(wt[thru], np.float32(t)) and np.allclose(swo[thru], -wi[thru]) and np.allclose(p[refl] + 0 * p[refl], p[refl])
+    k = int(np.nonzero(refl)[0][0])
+    R = _fresnel_unpolarised(abs(float(wi[k, 2])), 1.55); Rp = R + (1 - R) ** 2 * R / (1 - R * R)
+    assert np.isclose(p[k], Rp, rtol=2e-5)
+
+
+def test_dielectric_scenes_render_on_the_oracle(cp, oracle):
+    """The thin dielectric has no smooth component: no shadow rays (path.cpp:174-175).  marschnerdielectric has one, so every vertex
+    draws an emitter sample although its eval() is zero; both images are finite, non-black and differ from each other."""
+    films = {}
+    for name in ('straight-hair-thindielectric', 'straight-hair-dielectric'):
+        ov = dict(width=48, height=48, spp=4)
+        env = cp.bake_sunsky(**cp.scenes.sunsky_params(name))
+        sc = oracle.scene_from_description(name, scale=0.004, overrides=ov, envmap=env)
+        films[name] = sc.render(4, seed=3)
+        st = sc.last_stats
+        assert st['paths'] == 48 * 48 * 4 and np.isfinite(films[name]).all() and films[name][..., :3].sum() > 0
+        assert (st['shadow_rays'] == 0) == (name == 'straight-hair-thindielectric')
+    assert not np.allclose(films['straight-hair-thindielectric'], films['straight-hair-dielectric'])
+
+
 def test_obj_loader(cp, tmp_path):
     """WavefrontOBJ + computeNormals: vertex merge, n-gon fans, negative indices, toWorld on points and normals, generated
     angle-weighted normals, faceNormals / flipNormals (obj.cpp:244-349, 608-700; trimesh.cpp:608-672)."""
@@ -582,7 +658,7 @@ def test_scene_xml_text(cp):
 # ------------------------------------------------------------------------------------------------ golden vectors
 def test_validate_scene_xml_dry_run(cp, tmp_path):
     """cudapath_validate_scene_xml: the scene loader without a GPU -- lists what a file would create, names what is unsupported."""
-    for name in ('straight-hair', 'hair-curl', 'straight-hair-default', 'hair-on-head'):
+    for name in ('hair-curl', 'straight-hair-default', 'hair-on-head', 'straight-hair-dielectric', 'straight-hair-thindielectric', 'straight-hair'):
         d = tmp_path / name
         path = cp.scenes.write_scene(name, str(d), scale=0.002)
         rep = cp.validate_scene_xml(path)
@@ -655,3 +731,32 @@ def test_oracle_matches_second_golden_set(cp, oracle):
     assert (sh == 0).sum() > 50 and (sh == 1).sum() > 1000 and (sh == 2).sum() > 100
     film = sc.render(4, seed=9, threads=2)
     assert np.allclose(film, np.load(os.path.join(GOLDEN, 'render_mesh_golden.npz'))['film'], rtol=1e-5, atol=1e-6)
+
+
+THIRD_SET_MATS = [('thindielectric', dict(intIOR=1.55, extIOR=1.0, specularReflectance=HAIR_RGB, specularTransmittance=HAIR_RGB)),
+                  ('thindielectric', dict(intIOR=1.5046, extIOR=1.000277, specularReflectance=(0.9, 0.5, 0.1), specularTransmittance=(2.0, 1.0, 0.5))),
+                  ('marschnerdielectric', dict(intIOR=1.55, extIOR=1.0, exponent=5.0, specularTransmittance=HAIR_RGB, specularReflectance=HAIR_RGB, diffuseReflectance=HAIR_RGB)),
+                  ('marschnerdielectric', dict(intIOR=1.501, extIOR=1.000277, diffuseReflectance=(0.3, 0.2, 0.1), specularReflectance=(0.4, 0.3, 0.2),
+                                               specularTransmittance=(1.5, 0.6, 0.7)))]
+
+
+def test_oracle_matches_third_golden_set(cp, oracle):
+    """bsdf3 / render_dielectric fixtures (tests/golden/make_golden.py --third): thindielectric and marschnerdielectric."""
+    g = np.load(os.path.join(GOLDEN, 'bsdf3_golden.npz'))
+    s = oracle.Scene()
+    for t, p in THIRD_SET_MATS:
+        s.add_bsdf(t, **p)
+    for b in range(len(THIRD_SET_MATS)):
+        wo, wt, p, ty = s.bsdf_sample(b, g['wi'], g['sample'])
+        assert np.array_equal(wo, g['swo_%d' % b]) and np.array_equal(wt, g['swt_%d' % b]) and np.array_equal(p, g['spdf_%d' % b]) and np.array_equal(ty, g['sty_%d' % b])
+        for discrete in (0, 1):
+            ev, pdf = s.bsdf_eval(b, g['wi'], wo, discrete=bool(discrete))
+            assert np.array_equal(ev, g['eval_%d_%d' % (b, discrete)]) and np.array_equal(pdf, g['pdf_%d_%d' % (b, discrete)])
+    if not oracle.have_ref():
+        pytest.skip('oracle/_ref not built')
+    films = np.load(os.path.join(GOLDEN, 'render_dielectric_golden.npz'))
+    for name in ('straight-hair-thindielectric', 'straight-hair-dielectric'):
+        ov = dict(width=32, height=24, spp=4, maxDepth=24)
+        env = cp.bake_sunsky(**cp.scenes.sunsky_params(name))
+        film = oracle.scene_from_description(name, scale=0.004, overrides=ov, envmap=env).render(4, seed=13, threads=2)
+        assert np.allclose(film, films[name.replace('-', '_')], rtol=1e-5, atol=1e-6)
