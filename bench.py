@@ -270,7 +270,7 @@ def main():
         h2d = sum(16 * (len(s[1]) + 1) for s in pshapes) + penv.nbytes      # float4 vertex stream (+ sentinel) + envmap fp32
         d2h = W * H * 5 * 4
         # W untimed warm-up runs (the first ones grow the stream-ordered memory pool and find the GPU at idle clocks), then K timed runs
-        times = []
+        times = []; phases = []
         n_warm = max(args.warmup, 0); n_timed = max(args.steps, 1)
         for k in range(n_warm + n_timed):
             torch.cuda.synchronize()
@@ -280,16 +280,19 @@ def main():
             c2 = make_context(cudapath, sc, pshapes, penv, local)
             if args.wave:
                 c2.set_options(wave_size=args.wave)
+            t1 = time.perf_counter()
             c2.build()
+            t2 = time.perf_counter()
             c2.render(total_spp, seed=2000 + k, sample_begin=rank * spp, sample_end=(rank + 1) * spp)
             torch.cuda.synchronize()
             if k >= n_warm:
                 times.append(time.perf_counter() - t0)
+                phases.append([round(t1 - t0, 4), round(t2 - t1, 4), round(time.perf_counter() - t2, 4), round(c2.stats()['render_ms'] * 1e-3, 4)])
             c2.close()
         te2e = torch.tensor([float(np.mean(times))], dtype=torch.float64, device='cuda')       # mean of the K timed runs
         if world > 1:
             dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
-        e2e = {'times_s': [round(t, 4) for t in times], 'value': paths_per_step / float(te2e[0]) / 1e6, 'unit': 'Mpaths/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+        e2e = {'times_s': [round(t, 4) for t in times], 'phases_s(create+upload, build, render+readback, of which device render)': phases, 'value': paths_per_step / float(te2e[0]) / 1e6, 'unit': 'Mpaths/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                'warmup_runs': n_warm, 'includes': 'context creation, Marschner table build, geometry+envmap upload, device BVH build, render, film read-back'}
 
     if rank == 0:

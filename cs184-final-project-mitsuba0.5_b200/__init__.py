@@ -375,6 +375,11 @@ class Context:
                                                     ctypes.c_void_p(out_stats) if out_stats else None, ctypes.c_void_p(stream)))
 
 
+def trim_memory(device=0):
+    """Returns the device blocks parked in the library's caching allocator to the driver (cudapath_trim_memory)."""
+    _check(lib().cudapath_trim_memory(int(device)))
+
+
 def scene_from_description(name, device=0, scale=1.0, overrides=None, data_dir=None):
     """Builds a Context for one of scenes.SCENES directly from flattened arrays (the path a librender plugin would take)."""
     from . import scenes

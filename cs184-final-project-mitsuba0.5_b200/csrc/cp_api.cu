@@ -76,20 +76,25 @@ struct cudapath_ctx {
     cudapath_stats stats{};
     float sceneAABB[6] = {0, 0, 0, 0, 0, 0};
 
+    // Everything the context owns on the device comes from the caching allocator (cp_mem.cpp): a context that is created, built,
+    // rendered and destroyed repeatedly never goes back to the driver for memory.  Renders may have run on a caller's stream
+    // (cudapath_render_dev), so freeing first waits for the device.
+    void dfree(const void *p) { dev_free(p); }
     void freeBuilt() {
-        cudaFree(d_vtx); cudaFree(d_shapes); cudaFree(d_bsdfs); cudaFree((void *) bvh.nodes); cudaFree((void *) bvh.prims); cudaFree((void *) bvh.leafSeg);
-        cudaFree(d_meshPos); cudaFree(d_meshNrm); cudaFree(d_triAccel); cudaFree(d_meshIdx);
+        cudaDeviceSynchronize();
+        dfree(d_vtx); dfree(d_shapes); dfree(d_bsdfs); dfree(bvh.nodes); dfree(bvh.prims); dfree(bvh.leafSeg);
+        dfree(d_meshPos); dfree(d_meshNrm); dfree(d_triAccel); dfree(d_meshIdx);
         d_meshPos = d_meshNrm = d_triAccel = nullptr; d_meshIdx = nullptr;
-        cudaFree(envTables.texels); cudaFree(envTables.cdfCols); cudaFree(envTables.cdfRows); cudaFree(envTables.rowWeights);
+        dfree(envTables.texels); dfree(envTables.cdfCols); dfree(envTables.cdfRows); dfree(envTables.rowWeights);
         d_vtx = nullptr; d_shapes = nullptr; d_bsdfs = nullptr; bvh = BVHDev(); envTables = EnvTables(); built = false;
     }
     ~cudapath_ctx() {
         cudaSetDevice(device);
-        freeBuilt();
-        for (auto &st : staged) { cudaFree(st.xyz); cudaFree(st.starts); cudaFree(st.nrm); cudaFree(st.idx); }
-        for (auto &b : bsdfs) { cudaFree(b.tables.tab); cudaFree(b.tables.cdf); cudaFree(b.tables.sums); cudaFree(b.tables.pdf); cudaFree(b.rt); }
+        freeBuilt();                  // synchronises the device
+        for (auto &st : staged) { dfree(st.xyz); dfree(st.starts); dfree(st.nrm); dfree(st.idx); }
+        for (auto &b : bsdfs) { dfree(b.tables.tab); dfree(b.tables.cdf); dfree(b.tables.sums); dfree(b.tables.pdf); dfree(b.rt); }
         wf.release();
-        if (stream) cudaStreamDestroy(stream);
+        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
     }
 };
 
@@ -119,15 +124,17 @@ int cudapath_create(int cuda_device, cudapath_ctx **out) {
     std::unique_ptr<cudapath_ctx> ctx(new cudapath_ctx());
     ctx->device = cuda_device;
     CKA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    {   // scratch and queue memory comes from the stream-ordered pool; keep freed blocks cached so that repeated builds /
-        // renders in one process do not go back to the driver (cudaMalloc of several GB costs ~0.2 s)
-        cudaMemPool_t pool; uint64_t keep = ~0ull;
-        if (cudaDeviceGetDefaultMemPool(&pool, cuda_device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
     *out = ctx.release();
     return 0;
 }
 void cudapath_destroy(cudapath_ctx *ctx) { delete ctx; }
+int cudapath_trim_memory(int cuda_device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || cuda_device < 0 || cuda_device >= count) return fail("CUDA device index out of range");
+    CKA(cudaSetDevice(cuda_device));
+    dev_trim();
+    return 0;
+}
 
 int cudapath_set_data_dir(cudapath_ctx *ctx, const char *path) { if (!ctx || !path) return fail("null argument"); ctx->dataDir = path; return 0; }
 
@@ -167,7 +174,7 @@ int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior,
     std::vector<float> T; float Fdr; std::string err;
     if (!rough_transmittance_slice(ctx->dataDir, distribution, b.dev.eta, b.dev.alpha, T, Fdr, err)) return fail(err);
     b.dev.Fdr = Fdr; b.dev.rtSize = (int) T.size();
-    CKA(cudaMalloc(&b.rt, T.size() * 4));
+    CKA(dev_alloc(&b.rt, T.size() * 4));
     CKA(cudaMemcpyAsync(b.rt, T.data(), T.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     float pts[140], wts[140];
     gauss_legendre_140(pts, wts);
@@ -202,7 +209,7 @@ int cudapath_add_bsdf_roughplastic(cudapath_ctx *ctx, float int_ior, float ext_i
     std::vector<float> T; float Fdr; std::string err;
     if (!rough_transmittance_slice(ctx->dataDir, distribution, b.dev.eta, b.dev.alpha, T, Fdr, err)) return fail(err);
     b.dev.Fdr = Fdr; b.dev.rtSize = (int) T.size();
-    CKA(cudaMalloc(&b.rt, T.size() * 4));
+    CKA(dev_alloc(&b.rt, T.size() * 4));
     CKA(cudaMemcpyAsync(b.rt, T.data(), T.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     b.dev.rt = b.rt;
@@ -288,13 +295,13 @@ int cudapath_add_mesh(cudapath_ctx *ctx, const float *xyz, const float *normals,
     sd.kind = 1; sd.bsdf = bsdf_id; sd.vertexOffset = ctx->meshVtxTotal; sd.vertexCount = n_vertices; sd.triOffset = ctx->triTotal; sd.triCount = n_triangles;
     sd.hasNormals = normals ? 1 : 0;
     cudapath_ctx::Staged st; st.n = n_vertices; st.nTris = n_triangles;
-    CKA(cudaMallocAsync((void **) &st.xyz, sizeof(float) * 3 * (size_t) n_vertices, ctx->stream));
+    CKA(dev_alloc(&st.xyz, sizeof(float) * 3 * (size_t) n_vertices));
     CKA(cudaMemcpyAsync(st.xyz, xyz, sizeof(float) * 3 * (size_t) n_vertices, cudaMemcpyHostToDevice, ctx->stream));
     if (normals) {
-        CKA(cudaMallocAsync((void **) &st.nrm, sizeof(float) * 3 * (size_t) n_vertices, ctx->stream));
+        CKA(dev_alloc(&st.nrm, sizeof(float) * 3 * (size_t) n_vertices));
         CKA(cudaMemcpyAsync(st.nrm, normals, sizeof(float) * 3 * (size_t) n_vertices, cudaMemcpyHostToDevice, ctx->stream));
     }
-    CKA(cudaMallocAsync((void **) &st.idx, sizeof(uint32_t) * 3 * (size_t) n_triangles, ctx->stream));
+    CKA(dev_alloc(&st.idx, sizeof(uint32_t) * 3 * (size_t) n_triangles));
     CKA(cudaMemcpyAsync(st.idx, indices, sizeof(uint32_t) * 3 * (size_t) n_triangles, cudaMemcpyHostToDevice, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     ctx->staged.push_back(st);
@@ -344,8 +351,8 @@ int cudapath_add_hair(cudapath_ctx *ctx, const float *xyz, const uint8_t *starts
     // The caller's arrays go straight to the device (a true DMA when they are page-locked); the float4 vertex stream with
     // the start-of-fiber / shape bits and the sentinel of hair.cpp:782 is assembled by a kernel in cudapath_build().
     cudapath_ctx::Staged st; st.n = n;
-    CKA(cudaMallocAsync((void **) &st.xyz, sizeof(float) * 3 * (size_t) n, ctx->stream));
-    CKA(cudaMallocAsync((void **) &st.starts, (size_t) n, ctx->stream));
+    CKA(dev_alloc(&st.xyz, sizeof(float) * 3 * (size_t) n));
+    CKA(dev_alloc(&st.starts, (size_t) n));
     CKA(cudaMemcpyAsync(st.xyz, xyz, sizeof(float) * 3 * (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
     CKA(cudaMemcpyAsync(st.starts, starts, (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));              // the caller may release its buffers when this returns
@@ -447,17 +454,20 @@ int cudapath_build(cudapath_ctx *ctx) {
     if (ctx->shapes.empty()) return fail("the scene contains no shapes");
     if (!ctx->cam.present) return fail("no sensor set");
     CKA(cudaSetDevice(ctx->device));
+    const bool trace = getenv("CUDAPATH_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tb0 = now();
     ctx->freeBuilt();
     std::string err;
     cudaEvent_t e0, e1; CKA(cudaEventCreate(&e0)); CKA(cudaEventCreate(&e1));
     CKA(cudaEventRecord(e0, ctx->stream));
     // geometry
-    CKA(cudaMalloc(&ctx->d_vtx, sizeof(float4) * ((size_t) ctx->vtxTotal + 4)));
+    CKA(dev_alloc(&ctx->d_vtx, sizeof(float4) * ((size_t) ctx->vtxTotal + 4)));
     CKA(cudaMemsetAsync(ctx->d_vtx, 0, sizeof(float4) * ((size_t) ctx->vtxTotal + 4), ctx->stream));
     MeshDev mesh; std::memset(&mesh, 0, sizeof(mesh));
     if (ctx->triTotal) {
-        CKA(cudaMalloc(&ctx->d_meshPos, sizeof(float4) * (size_t) ctx->meshVtxTotal)); CKA(cudaMalloc(&ctx->d_meshNrm, sizeof(float4) * (size_t) ctx->meshVtxTotal));
-        CKA(cudaMalloc(&ctx->d_meshIdx, sizeof(uint32_t) * 3 * (size_t) ctx->triTotal)); CKA(cudaMalloc(&ctx->d_triAccel, sizeof(float4) * 3 * (size_t) ctx->triTotal));
+        CKA(dev_alloc(&ctx->d_meshPos, sizeof(float4) * (size_t) ctx->meshVtxTotal)); CKA(dev_alloc(&ctx->d_meshNrm, sizeof(float4) * (size_t) ctx->meshVtxTotal));
+        CKA(dev_alloc(&ctx->d_meshIdx, sizeof(uint32_t) * 3 * (size_t) ctx->triTotal)); CKA(dev_alloc(&ctx->d_triAccel, sizeof(float4) * 3 * (size_t) ctx->triTotal));
         mesh.triAccel = ctx->d_triAccel; mesh.pos = ctx->d_meshPos; mesh.nrm = ctx->d_meshNrm; mesh.idx = ctx->d_meshIdx;
         mesh.triCount = ctx->triTotal; mesh.vertCount = ctx->meshVtxTotal;
     }
@@ -474,12 +484,14 @@ int cudapath_build(cudapath_ctx *ctx) {
             hairShapes++;
         }
     }
-    CKA(cudaMalloc(&ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size()));
+    CKA(dev_alloc(&ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size()));
     CKA(cudaMemcpyAsync(ctx->d_shapes, ctx->shapes.data(), sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyHostToDevice, ctx->stream));
     BuildInfo info;
+    const double tb1 = now();
     if (!build_bvh(ctx->d_vtx, ctx->vtxTotal, ctx->d_shapes, (int) ctx->shapes.size(), mesh, ctx->maxSplit, ctx->stream, ctx->bvh, info, err)) return fail(err);
     CKA(cudaMemcpyAsync(ctx->shapes.data(), ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
+    const double tb2 = now();
     // KDTreeBase::buildInternal enlarges the box of a finished kd-tree by MTS_KD_AABB_EPSILON = 1e-3, relative to its extent plus
     // absolute (include/mitsuba/render/gkdtree.h:50,1213-1220; the second line already sees the lowered minimum).  getAABB() returns
     // that box: HairKDTree clips rays against it (hair.cpp:205) and hands it to the scene-level tree (hair.cpp:944-946), whose own
@@ -494,7 +506,7 @@ int cudapath_build(cudapath_ctx *ctx) {
     CKA(cudaMemcpyAsync(ctx->d_shapes, ctx->shapes.data(), sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyHostToDevice, ctx->stream));
     // bsdfs
     std::vector<BsdfDev> devs; for (auto &b : ctx->bsdfs) devs.push_back(b.dev);
-    CKA(cudaMalloc(&ctx->d_bsdfs, sizeof(BsdfDev) * std::max<size_t>(devs.size(), 1)));
+    CKA(dev_alloc(&ctx->d_bsdfs, sizeof(BsdfDev) * std::max<size_t>(devs.size(), 1)));
     CKA(cudaMemcpyAsync(ctx->d_bsdfs, devs.data(), sizeof(BsdfDev) * devs.size(), cudaMemcpyHostToDevice, ctx->stream));
 
     SceneDev &S = ctx->scene;
@@ -553,10 +565,10 @@ int cudapath_build(cudapath_ctx *ctx) {
     if (ctx->env.present) {
         float *d_rgb = nullptr;
         const size_t bytes = ctx->env.rgb.size() * 4;
-        CKA(cudaMalloc(&d_rgb, bytes));
+        CKA(dev_alloc(&d_rgb, bytes));
         CKA(cudaMemcpyAsync(d_rgb, ctx->env.rgb.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
         const bool ok = build_env_tables(d_rgb, ctx->env.w, ctx->env.h, ctx->stream, ctx->envTables, err);
-        cudaFree(d_rgb);
+        dev_free(d_rgb);
         if (!ok) return fail(err);
         EnvDev &E = S.env;
         E.w = ctx->env.w; E.h = ctx->env.h; E.texels = ctx->envTables.texels; E.cdfCols = ctx->envTables.cdfCols; E.cdfRows = ctx->envTables.cdfRows;
@@ -581,6 +593,7 @@ int cudapath_build(cudapath_ctx *ctx) {
     CKA(cudaStreamSynchronize(ctx->stream));
     float ms = 0; CKA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (trace) fprintf(stderr, "[cudapath] build: pack %.4f s, bvh %.4f s, tables+rest %.4f s (device %.4f s)\n", tb1 - tb0, tb2 - tb1, now() - tb2, ms * 1e-3);
     ctx->stats.build_ms = ms; ctx->stats.segments = info.segments; ctx->stats.triangles = info.triangles; ctx->stats.bvh_nodes = info.nodes; ctx->stats.bvh_references = info.references;
     ctx->built = true;
     return 0;
@@ -602,7 +615,7 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
         // never more than 40 % of the memory that is free right now (queues already held by this context count as free).
         size_t freeB = 0, totalB = 0;
         CKA(cudaMemGetInfo(&freeB, &totalB));
-        const double avail = 0.4 * ((double) freeB + 212.0 * ctx->wf.capacity);
+        const double avail = 0.4 * ((double) freeB + (double) dev_cached_bytes() + 212.0 * ctx->wf.capacity);   // blocks parked in the caching allocator are available too
         waveSize = 1u << 26;
         while (waveSize > (1u << 20) && 212.0 * waveSize > avail) waveSize >>= 1;
     }
@@ -630,7 +643,7 @@ int cudapath_render(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sam
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
     float *d_film = nullptr;
-    CKA(cudaMallocAsync((void **) &d_film, bytes, ctx->stream));
+    CKA(dev_alloc(&d_film, bytes));
     CKA(cudaMemsetAsync(d_film, 0, bytes, ctx->stream));
     const double t1 = now();
     int r = cudapath_render_dev(ctx, spp, seed, sample_begin, sample_end, d_film, ctx->stream);
@@ -638,10 +651,10 @@ int cudapath_render(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sam
     if (r == 0) {
         cudaError_t e = cudaMemcpyAsync(out_film, d_film, bytes, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { cudaFreeAsync(d_film, ctx->stream); return fail(std::string("film copy: ") + cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { dev_free(d_film); return fail(std::string("film copy: ") + cudaGetErrorString(e)); }
     }
     const double t3 = now();
-    cudaFreeAsync(d_film, ctx->stream);
+    dev_free(d_film);
     if (trace) fprintf(stderr, "[cudapath] render: film alloc %.3f s, render_dev %.3f s (device %.3f s), read-back %.3f s, free %.3f s\n", t1 - t0, t2 - t1,
                        ctx->stats.render_ms * 1e-3, t3 - t2, now() - t3);
     return r;

@@ -12,6 +12,7 @@
 #include "cp_scene.cuh"
 #include "cp_host.h"
 #include <cub/cub.cuh>
+#include <cstdlib>
 #include <vector>
 
 namespace cp {
@@ -348,12 +349,12 @@ __global__ void k_init_shape_bounds(ShapeDev *shapes, int n, float *centroidBox)
 }
 
 namespace {
-struct Scratch {   // stream-ordered scratch allocations (returned to the pool, not to the driver)
+struct Scratch {   // scratch allocations from the caching allocator (cp_mem.cpp): returned to its free list, not to the driver
     std::vector<void *> ptrs; cudaStream_t stream;
     explicit Scratch(cudaStream_t s) : stream(s) {}
-    ~Scratch() { for (void *p : ptrs) if (p) cudaFreeAsync(p, stream); }
+    ~Scratch() { cudaStreamSynchronize(stream); for (void *p : ptrs) if (p) dev_free(p); }
     template <typename T> cudaError_t alloc(T **p, size_t bytes) {
-        cudaError_t e = cudaMallocAsync((void **) p, bytes ? bytes : 1, stream);
+        cudaError_t e = dev_alloc((void **) p, bytes);
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
@@ -449,27 +450,37 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
         CK(S.alloc(&d_innerBox, sizeof(float) * 6 * (size_t) nInner));
         k_radix_tree<<<(nInner + B - 1) / B, B, 0, stream>>>(d_keysSorted, (int) nSeg, d_children, d_parentInner, d_parentLeaf, d_ranges);
         k_refit<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_children, d_parentInner, d_parentLeaf, d_sortedBox, (int) nSeg, d_innerBox, d_flags);
-        // Collapse level by level.  A wide node is created only for a binary inner node (the one it absorbs),
-        // and distinct wide nodes absorb distinct binary nodes, so nInner bounds the wide-node count.
-        CK(S.alloc(&d_wide, sizeof(BVH4Node) * (size_t) nInner));
+        // Collapse level by level.  A wide node is created only for a binary inner node (the one it absorbs), and distinct wide
+        // nodes absorb distinct binary nodes, so nInner bounds the wide-node count.  In practice a third of that is never reached
+        // (hair scenes: 0.17 nodes per reference), so the scratch array starts there (1.4 GB instead of 4 GB for 32 M references)
+        // and the collapse is repeated with the full bound in the unlikely case that it overflows.
         CK(S.alloc(&d_q0, sizeof(CollapseItem) * (size_t) nInner)); CK(S.alloc(&d_q1, sizeof(CollapseItem) * (size_t) nInner));
         CK(S.alloc(&d_counters, sizeof(int) * 4));
-        CollapseItem root{0, 0};
-        int init[4] = {0, 1, 0, 0}; // [0]=next-level count, [1]=wide count, [2]=error
-        CK(cudaMemcpyAsync(d_q0, &root, sizeof(root), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_counters, init, sizeof(init), cudaMemcpyHostToDevice, stream));
-        int nIn = 1; int levels = 0;
-        while (nIn > 0) {
-            k_collapse<<<(nIn + 127) / 128, 128, 0, stream>>>(d_q0, nIn, d_q1, d_counters, d_counters + 1, d_children, d_ranges,
-                                                             d_innerBox, d_sortedBox, d_wide, nInner, d_counters + 2);
-            int h[3];
-            CK(cudaMemcpyAsync(h, d_counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
-            CK(cudaStreamSynchronize(stream));
-            if (h[2]) { err = "BVH collapse overflow"; return false; }
-            nIn = h[0]; wideCount = h[1];
-            CK(cudaMemsetAsync(d_counters, 0, sizeof(int), stream));
-            std::swap(d_q0, d_q1);
-            if (++levels > 4096) { err = "BVH collapse did not terminate"; return false; }
+        int levels = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            int capacity = attempt == 0 ? (int) std::min<long long>(nInner, (long long) nSeg / 3 + 1024) : nInner;
+            if (attempt == 0 && getenv("CUDAPATH_TEST_COLLAPSE_CAP")) capacity = std::max(1, std::min(nInner, atoi(getenv("CUDAPATH_TEST_COLLAPSE_CAP"))));   // tests: force the retry
+            CK(S.alloc(&d_wide, sizeof(BVH4Node) * (size_t) capacity));
+            CollapseItem root{0, 0};
+            int init[4] = {0, 1, 0, 0}; // [0]=next-level count, [1]=wide count, [2]=error
+            CK(cudaMemcpyAsync(d_q0, &root, sizeof(root), cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(d_counters, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+            int nIn = 1; bool overflow = false;
+            levels = 0;
+            while (nIn > 0) {
+                k_collapse<<<(nIn + 127) / 128, 128, 0, stream>>>(d_q0, nIn, d_q1, d_counters, d_counters + 1, d_children, d_ranges,
+                                                                 d_innerBox, d_sortedBox, d_wide, capacity, d_counters + 2);
+                int h[3];
+                CK(cudaMemcpyAsync(h, d_counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+                if (h[2]) { overflow = true; break; }
+                nIn = h[0]; wideCount = h[1];
+                CK(cudaMemsetAsync(d_counters, 0, sizeof(int), stream));
+                std::swap(d_q0, d_q1);
+                if (++levels > 4096) { err = "BVH collapse did not terminate"; return false; }
+            }
+            if (!overflow) break;
+            if (capacity == nInner) { err = "BVH collapse overflow"; return false; }
         }
         info.levels = levels;
         CK(S.alloc(&d_final, sizeof(BVH4Node) * (size_t) wideCount));

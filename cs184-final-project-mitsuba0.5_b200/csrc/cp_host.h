@@ -8,6 +8,14 @@
 
 namespace cp {
 
+// cp_mem.cpp -- caching device allocator (size-keyed free list over cudaMalloc).  dev_free(): the caller guarantees that no device
+// work touching the block is still pending.
+cudaError_t dev_alloc(void **p, size_t bytes);
+template <typename T> inline cudaError_t dev_alloc(T **p, size_t bytes) { return dev_alloc((void **) p, bytes); }
+void dev_free(const void *p);
+size_t dev_cached_bytes();
+void dev_trim();
+
 struct BuildInfo { uint32_t segments = 0, triangles = 0, references = 0, nodes = 0; int levels = 0; };
 
 // cp_bvh.cu

@@ -126,9 +126,9 @@ __global__ void k_azimuthal_sampler(const float4 *__restrict__ tab, float *pdf, 
 bool build_marschner_tables(float eta, float betaR, const float sigmaA[3], const float *glPoints140, const float *glWeights140,
                             cudaStream_t stream, MarschnerTables &out, std::string &err) {
     float *d_pts = nullptr, *d_wts = nullptr, *d_Ds = nullptr;
-    CKT(cudaMalloc(&d_pts, 140 * 4)); CKT(cudaMalloc(&d_wts, 140 * 4)); CKT(cudaMalloc(&d_Ds, 2048 * 4));
-    CKT(cudaMalloc(&out.tab, sizeof(float4) * 3 * 4096)); CKT(cudaMalloc(&out.pdf, 4 * 3 * 4096));
-    CKT(cudaMalloc(&out.cdf, 4 * 3 * 64 * 65)); CKT(cudaMalloc(&out.sums, 4 * 3 * 64));
+    CKT(dev_alloc(&d_pts, 140 * 4)); CKT(dev_alloc(&d_wts, 140 * 4)); CKT(dev_alloc(&d_Ds, 2048 * 4));
+    CKT(dev_alloc(&out.tab, sizeof(float4) * 3 * 4096)); CKT(dev_alloc(&out.pdf, 4 * 3 * 4096));
+    CKT(dev_alloc(&out.cdf, 4 * 3 * 64 * 65)); CKT(dev_alloc(&out.sums, 4 * 3 * 64));
     CKT(cudaMemcpyAsync(d_pts, glPoints140, 140 * 4, cudaMemcpyHostToDevice, stream));
     CKT(cudaMemcpyAsync(d_wts, glWeights140, 140 * 4, cudaMemcpyHostToDevice, stream));
     k_detector_table<<<8, 256, 0, stream>>>(betaR, d_Ds);
@@ -136,7 +136,7 @@ bool build_marschner_tables(float eta, float betaR, const float sigmaA[3], const
     k_azimuthal_sampler<<<3, 64, 0, stream>>>(out.tab, out.pdf, out.cdf, out.sums);
     CKT(cudaStreamSynchronize(stream));
     CKT(cudaGetLastError());
-    cudaFree(d_pts); cudaFree(d_wts); cudaFree(d_Ds);
+    dev_free(d_pts); dev_free(d_wts); dev_free(d_Ds);
     return true;
 }
 
@@ -185,9 +185,9 @@ __global__ void k_env_marginal(const float *__restrict__ colSums, int w, int h, 
 bool build_env_tables(const float *d_rgb, int w, int h, cudaStream_t stream, EnvTables &out, std::string &err) {
     float *d_colSums = nullptr, *d_norm = nullptr;
     const int n = w * h;
-    CKT(cudaMalloc(&out.texels, sizeof(float4) * (size_t) n)); CKT(cudaMalloc(&out.cdfCols, 4 * (size_t) (w + 1) * h));
-    CKT(cudaMalloc(&out.cdfRows, 4 * (size_t) (h + 1))); CKT(cudaMalloc(&out.rowWeights, 4 * (size_t) h));
-    CKT(cudaMalloc(&d_colSums, 4 * (size_t) h)); CKT(cudaMalloc(&d_norm, 8));
+    CKT(dev_alloc(&out.texels, sizeof(float4) * (size_t) n)); CKT(dev_alloc(&out.cdfCols, 4 * (size_t) (w + 1) * h));
+    CKT(dev_alloc(&out.cdfRows, 4 * (size_t) (h + 1))); CKT(dev_alloc(&out.rowWeights, 4 * (size_t) h));
+    CKT(dev_alloc(&d_colSums, 4 * (size_t) h)); CKT(dev_alloc(&d_norm, 8));
     k_env_quantize<<<(n + 255) / 256, 256, 0, stream>>>(d_rgb, n, out.texels);
     k_env_rows<<<(h + 63) / 64, 64, 0, stream>>>(out.texels, w, h, out.cdfCols, d_colSums);
     k_env_marginal<<<1, 32, 0, stream>>>(d_colSums, w, h, out.cdfRows, out.rowWeights, d_norm);
@@ -195,7 +195,7 @@ bool build_env_tables(const float *d_rgb, int w, int h, cudaStream_t stream, Env
     CKT(cudaMemcpyAsync(hn, d_norm, 8, cudaMemcpyDeviceToHost, stream));
     CKT(cudaStreamSynchronize(stream));
     CKT(cudaGetLastError());
-    cudaFree(d_colSums); cudaFree(d_norm);
+    dev_free(d_colSums); dev_free(d_norm);
     if (!(hn[1] > 0) || !isfinite(hn[1])) { err = "The environment map is completely black or contains invalid values"; return false; }
     out.normalization = hn[0];
     return true;

@@ -16,6 +16,7 @@
 #include "cp_host.h"
 #include "cp_traverse.cuh"
 #include "cp_wavefront.h"
+#include <mutex>
 #include <vector>
 #include <cub/cub.cuh>
 #include <chrono>
@@ -107,29 +108,36 @@ static unsigned persistent_grid(const void *kernel, uint32_t n) {
 // ------------------------------------------------------------------------------------------ host driver
 #define CKW(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
+static std::mutex g_pinnedMutex;
+static std::vector<uint32_t *> g_pinnedFree;
+
 bool Wavefront::reserve(uint32_t waveSize, cudaStream_t stream, std::string &err) {
     if (waveSize <= capacity) return true;
     release();
     allocStream = stream;
     for (int k = 0; k < 2; ++k) {
-        CKW(cudaMallocAsync((void **) &q[k].ro, sizeof(float4) * (size_t) waveSize, stream)); CKW(cudaMallocAsync((void **) &q[k].rd, sizeof(float4) * (size_t) waveSize, stream));
-        CKW(cudaMallocAsync((void **) &q[k].thr, sizeof(float4) * (size_t) waveSize, stream)); CKW(cudaMallocAsync((void **) &q[k].id, sizeof(uint2) * (size_t) waveSize, stream));
+        CKW(dev_alloc(&q[k].ro, sizeof(float4) * (size_t) waveSize)); CKW(dev_alloc(&q[k].rd, sizeof(float4) * (size_t) waveSize));
+        CKW(dev_alloc(&q[k].thr, sizeof(float4) * (size_t) waveSize)); CKW(dev_alloc(&q[k].id, sizeof(uint2) * (size_t) waveSize));
     }
-    CKW(cudaMallocAsync((void **) &sq.o, sizeof(float4) * (size_t) waveSize, stream)); CKW(cudaMallocAsync((void **) &sq.d, sizeof(float4) * (size_t) waveSize, stream));
-    CKW(cudaMallocAsync((void **) &sq.c, sizeof(float4) * (size_t) waveSize, stream));
-    CKW(cudaMallocAsync((void **) &hitPT, sizeof(float4) * (size_t) waveSize, stream)); CKW(cudaMallocAsync((void **) &hitPrim, sizeof(uint32_t) * (size_t) waveSize, stream));
-    CKW(cudaMallocAsync((void **) &liAcc, sizeof(float4) * (size_t) waveSize, stream));
-    CKW(cudaMallocAsync((void **) &counters, sizeof(uint32_t) * 8, stream));
-    CKW(cudaMallocAsync((void **) &stats, sizeof(unsigned long long) * 8, stream));
-    CKW(cudaMallocAsync((void **) &errFlag, sizeof(int), stream));
+    CKW(dev_alloc(&sq.o, sizeof(float4) * (size_t) waveSize)); CKW(dev_alloc(&sq.d, sizeof(float4) * (size_t) waveSize));
+    CKW(dev_alloc(&sq.c, sizeof(float4) * (size_t) waveSize));
+    CKW(dev_alloc(&hitPT, sizeof(float4) * (size_t) waveSize)); CKW(dev_alloc(&hitPrim, sizeof(uint32_t) * (size_t) waveSize));
+    CKW(dev_alloc(&liAcc, sizeof(float4) * (size_t) waveSize));
+    CKW(dev_alloc(&counters, sizeof(uint32_t) * 8));
+    CKW(dev_alloc(&stats, sizeof(unsigned long long) * 8));
+    CKW(dev_alloc(&errFlag, sizeof(int)));
     for (int k = 0; k < 2; ++k) {
-        CKW(cudaMallocAsync((void **) &sortKeys[k], sizeof(uint32_t) * (size_t) waveSize, stream));
-        CKW(cudaMallocAsync((void **) &sortVals[k], sizeof(uint32_t) * (size_t) waveSize, stream));
+        CKW(dev_alloc(&sortKeys[k], sizeof(uint32_t) * (size_t) waveSize));
+        CKW(dev_alloc(&sortVals[k], sizeof(uint32_t) * (size_t) waveSize));
     }
     sortTempBytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sortTempBytes, sortKeys[0], sortKeys[1], sortVals[0], sortVals[1], (int) waveSize, 0, 30, stream);
-    CKW(cudaMallocAsync(&sortTemp, sortTempBytes, stream));
-    CKW(cudaMallocHost(&hCounters, sizeof(uint32_t) * 8));
+    CKW(dev_alloc(&sortTemp, sortTempBytes));
+    {   // page-locked read-back slot: recycled through a process-wide free list (cudaMallocHost / cudaFreeHost cost up to a millisecond and synchronise)
+        std::lock_guard<std::mutex> g(g_pinnedMutex);
+        if (!g_pinnedFree.empty()) { hCounters = g_pinnedFree.back(); g_pinnedFree.pop_back(); }
+    }
+    if (!hCounters) CKW(cudaMallocHost(&hCounters, sizeof(uint32_t) * 8));
     capacity = waveSize;
     return true;
 }
@@ -147,10 +155,11 @@ const uint32_t *Wavefront::coherence_order(const SceneDev &S, const float4 *ro, 
 
 void Wavefront::release() {
     void *ptrs[] = {sortKeys[0], sortKeys[1], sortVals[0], sortVals[1], sortTemp, q[0].ro, q[0].rd, q[0].thr, q[0].id, q[1].ro, q[1].rd, q[1].thr, q[1].id, sq.o, sq.d, sq.c, hitPT, hitPrim, liAcc, counters, stats, errFlag};
-    for (void *p : ptrs) if (p) cudaFreeAsync(p, allocStream);
+    if (capacity) cudaDeviceSynchronize();          // the last render may have run on a caller's stream
+    for (void *p : ptrs) if (p) dev_free(p);
     q[0] = PathQueue(); q[1] = PathQueue(); sq = ShadowQueue();
     sortKeys[0] = sortKeys[1] = sortVals[0] = sortVals[1] = nullptr; sortTemp = nullptr;
-    if (hCounters) cudaFreeHost(hCounters);
+    if (hCounters) { std::lock_guard<std::mutex> g(g_pinnedMutex); g_pinnedFree.push_back(hCounters); }
     hitPT = nullptr; hitPrim = nullptr; liAcc = nullptr; counters = nullptr; stats = nullptr; errFlag = nullptr; hCounters = nullptr;
     capacity = 0;
 }

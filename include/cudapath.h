@@ -22,6 +22,9 @@ typedef struct cudapath_ctx cudapath_ctx;
 /* Replaces Scheduler/LocalWorker set-up for this path (src/mitsuba/mitsuba.cpp:280-329): one context per GPU. */
 int cudapath_create(int cuda_device, cudapath_ctx **out);
 void cudapath_destroy(cudapath_ctx *ctx);
+/* Device memory freed by contexts is parked in a per-device free list and reused by the next build / render of similar size (a
+ * repeated job then never waits for the driver).  This returns the parked blocks of `cuda_device` to the driver. */
+int cudapath_trim_memory(int cuda_device);
 const char *cudapath_last_error(void);
 /* Directory holding a Mitsuba `data/` tree (microfacet/{beckmann,ggx,phong}.dat, and for the sunsky helper
  * sunsky/hosek_rgb.f64 + cie1931.f32).  Replaces FileResolver look-ups (src/bsdfs/rtrans.h:95-97). */

@@ -667,3 +667,39 @@ def test_third_golden_set(cp):
         a, b2 = cp.develop(c2.render(4, seed=13)), cp.develop(films[name.replace('-', '_')])
         assert rel_mse(a, b2) < 1e-3
         c2.close()
+
+
+def test_collapse_scratch_overflow_retries(cp, monkeypatch):
+    """The wide-node scratch array of the BVH collapse starts at a third of its worst case; an overflow repeats the collapse with the
+    full bound and yields the same tree (CUDAPATH_TEST_COLLAPSE_CAP forces the first attempt to overflow)."""
+    ov = dict(width=32, height=32, spp=2, maxDepth=4)
+    films = []
+    for cap in (None, '16'):
+        if cap:
+            monkeypatch.setenv('CUDAPATH_TEST_COLLAPSE_CAP', cap)
+        ctx = cp.scene_from_description('curly-hair', scale=0.004, overrides=ov); ctx.build()
+        st = ctx.stats()
+        films.append((ctx.render(2, seed=1), st['bvh_nodes'], st['bvh_references']))
+        ctx.close()
+    assert films[0][1] == films[1][1] > 16 and films[0][2] == films[1][2]
+    assert np.allclose(films[0][0], films[1][0], rtol=1e-5, atol=1e-6)
+
+
+def test_repeated_jobs_reuse_device_memory(cp):
+    """create / build / render / destroy in a loop: after the first job every device block comes from the caching allocator
+    (cp_mem.cpp); cudapath_trim_memory hands the parked blocks back."""
+    import torch
+    ov = dict(width=64, height=64, spp=4, maxDepth=4)
+    used = []
+    for k in range(4):
+        ctx = cp.scene_from_description('straight-hair', scale=0.01, overrides=ov); ctx.build()
+        f = ctx.render(4, seed=2)
+        ctx.close()
+        torch.cuda.synchronize()
+        free, total = torch.cuda.mem_get_info(0)
+        used.append(total - free)
+        assert np.isfinite(f).all()
+    assert used[1] == used[2] == used[3]                         # steady state: no new driver allocations
+    cp.trim_memory(0)
+    free, total = torch.cuda.mem_get_info(0)
+    assert total - free < used[3]
