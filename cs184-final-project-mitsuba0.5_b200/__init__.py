@@ -10,6 +10,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
+CLI_PATH = os.path.join(_HERE, 'cudapath_render')      # native command-line front end (csrc/cp_cli.cpp)
 LIB_PATH = os.environ.get('CUDAPATH_LIB', os.path.join(_HERE, 'libcudapath.so'))   # CUDAPATH_LIB: alternative builds for tuning experiments
 DEFAULT_DATA_DIR = os.environ.get('CUDAPATH_DATA_DIR', os.path.join(_REPO, 'refdata'))
 
@@ -245,6 +246,17 @@ class Context:
     def set_film(self, rfilter='tent', param=0.0, has_alpha=False):
         _check(self._L.cudapath_set_film(self._h, _FILTERS[rfilter], ctypes.c_float(param), 1 if has_alpha else 0))
 
+    def film_output(self):
+        """(hdr, gamma, exposure) the scene's film asks for (ldrfilm.cpp:180-181); set by load_xml, defaults False, -1 (sRGB), 0."""
+        hdr = ctypes.c_int(); g = ctypes.c_float(); e = ctypes.c_float()
+        _check(self._L.cudapath_get_film_output(self._h, ctypes.byref(hdr), ctypes.byref(g), ctypes.byref(e)))
+        return bool(hdr.value), float(g.value), float(e.value)
+
+    def set_envmap_file(self, path, toWorld=None, scale=1.0):
+        """`<emitter type="envmap"><string name="filename" value="...hdr"/>`: src/emitters/envmap.cpp:100-190 with a Radiance RGBE file."""
+        tw = _f32(np.eye(4) if toWorld is None else toWorld).reshape(16)
+        _check(self._L.cudapath_set_envmap_file(self._h, str(path).encode(), _p(tw), ctypes.c_float(scale)))
+
     def set_integrator(self, maxDepth=-1, rrDepth=5, strictNormals=False, hideEmitters=False):
         _check(self._L.cudapath_set_integrator(self._h, int(maxDepth), int(rrDepth), 1 if strictNormals else 0, 1 if hideEmitters else 0))
 
@@ -373,6 +385,15 @@ class Context:
         _check(self._L.cudapath_intersect_batch_dev(self._h, ctypes.c_uint64(n), ctypes.c_void_p(o), ctypes.c_void_p(d), ctypes.c_void_p(mint), ctypes.c_void_p(maxt),
                                                     1 if any_hit else 0, ctypes.c_void_p(out_shape), ctypes.c_void_p(out_prim), ctypes.c_void_p(out_t),
                                                     ctypes.c_void_p(out_stats) if out_stats else None, ctypes.c_void_p(stream)))
+
+
+def load_rgbe(path):
+    """Radiance RGBE (.hdr) image as a (h, w, 3) float32 array (Bitmap::readRGBE, src/libcore/bitmap.cpp:3590-3678)."""
+    w = ctypes.c_int(); h = ctypes.c_int()
+    _check(lib().cudapath_load_rgbe(str(path).encode(), None, ctypes.byref(w), ctypes.byref(h)))
+    out = np.zeros((h.value, w.value, 3), np.float32)
+    _check(lib().cudapath_load_rgbe(str(path).encode(), _p(out), ctypes.byref(w), ctypes.byref(h)))
+    return out
 
 
 def trim_memory(device=0):

@@ -3,6 +3,7 @@
 #include "cp_host.h"
 #include "cp_wavefront.h"
 #include <cstring>
+#include <cctype>
 #include <cmath>
 #include <algorithm>
 #include <memory>
@@ -63,6 +64,7 @@ struct cudapath_ctx {
     EnvHost env; EnvTables envTables;
     CamHost cam;
     int filterType = 0; float filterParam = 0; int hasAlpha = 0;
+    int filmHdr = 0; float filmGamma = -1.0f, filmExposure = 0.0f;   // how the film asks to be developed (ldrfilm.cpp:180-181); not used by the render
     IntegratorDev integ{-1, 5, 0, 0};
     // device
     float4 *d_vtx = nullptr; ShapeDev *d_shapes = nullptr; BsdfDev *d_bsdfs = nullptr;
@@ -396,6 +398,26 @@ int cudapath_set_envmap(cudapath_ctx *ctx, const float *rgb, int w, int h, const
     return 0;
 }
 
+int cudapath_load_rgbe(const char *filename, float *out_rgb, int *out_width, int *out_height) {
+    if (!filename || !out_width || !out_height) return fail("null argument");
+    std::vector<float> rgb; int w = 0, h = 0; std::string err;
+    if (!load_rgbe_file(filename, rgb, w, h, err)) return fail(err);
+    *out_width = w; *out_height = h;
+    if (out_rgb) std::memcpy(out_rgb, rgb.data(), rgb.size() * 4);
+    return 0;
+}
+int cudapath_set_envmap_file(cudapath_ctx *ctx, const char *filename, const float to_world[16], float scale) {
+    if (!ctx || !filename || !to_world) return fail("null argument");
+    std::string name = filename;
+    const size_t dot = name.rfind('.');
+    std::string ext = dot == std::string::npos ? "" : name.substr(dot + 1);
+    for (auto &c : ext) c = (char) std::tolower((unsigned char) c);
+    if (ext != "hdr" && ext != "rgbe") return fail("envmap: only Radiance RGBE files (.hdr, .rgbe) are read here; other formats go through cudapath_set_envmap");
+    std::vector<float> rgb; int w = 0, h = 0; std::string err;
+    if (!load_rgbe_file(name, rgb, w, h, err)) return fail(err);
+    return cudapath_set_envmap(ctx, rgb.data(), w, h, to_world, scale);
+}
+
 int cudapath_bake_sunsky(const char *data_dir, float turbidity, const float albedo[3], const float sun_direction[3], float sky_scale,
                          float sun_scale, float sun_radius_scale, int resolution, float *out_rgb) {
     if (!data_dir || !albedo || !sun_direction || !out_rgb) return fail("null argument");
@@ -707,6 +729,17 @@ int cudapath_film_size(cudapath_ctx *ctx, int *w, int *h) {
     if (!ctx || !w || !h) return fail("null argument");
     if (!ctx->cam.present) return fail("no sensor set");
     *w = ctx->cam.w; *h = ctx->cam.h;
+    return 0;
+}
+int cudapath_set_film_output(cudapath_ctx *ctx, int hdr, float gamma, float exposure) {
+    if (!ctx) return fail("null context");
+    if (gamma == 0) return fail("gamma must not be zero");
+    ctx->filmHdr = hdr ? 1 : 0; ctx->filmGamma = gamma; ctx->filmExposure = exposure;
+    return 0;
+}
+int cudapath_get_film_output(cudapath_ctx *ctx, int *hdr, float *gamma, float *exposure) {
+    if (!ctx || !hdr || !gamma || !exposure) return fail("null argument");
+    *hdr = ctx->filmHdr; *gamma = ctx->filmGamma; *exposure = ctx->filmExposure;
     return 0;
 }
 int cudapath_scene_bounds(cudapath_ctx *ctx, float aabb[6], float bs[4]) {

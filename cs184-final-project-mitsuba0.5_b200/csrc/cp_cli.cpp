@@ -1,0 +1,126 @@
+// cp_cli.cpp -- `cudapath_render`: renders a scene file of the reference's XML format through libcudapath.so.
+//
+// Mirrors the part of the reference's command line that concerns this path (src/mitsuba/mitsuba.cpp:154-260):
+//   cudapath_render [-o out.{png,pfm,ppm}] [-D name=value]... [-p N] [-q] [--gpu i] [--spp n] [--seed s] scene.xml
+//     -o   output file (mitsuba.cpp:190); default: the scene's name with the extension the film asks for (.png for ldrfilm, .pfm for hdrfilm)
+//     -D   parameter substitution of $name in the file (mitsuba.cpp:168)
+//     -p   accepted for compatibility with `mitsuba -p N`; the CPU core count has no meaning here
+//     -q   quiet
+// and prints the "Render time" line of RenderJob::run (src/librender/renderjob.cpp:108) plus Mpaths/s and Mrays/s.
+// Uses nothing but the C ABI of include/cudapath.h (this file is also the smallest example of a host program on that boundary).
+// Image writers: PNG (8 bit, zlib "stored/deflate" through libz), PPM, PFM (linear float, bottom-up as the format wants it).
+#include "../../include/cudapath.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <zlib.h>
+
+static void put_be32(std::vector<unsigned char> &v, uint32_t x) { for (int k = 3; k >= 0; --k) v.push_back((unsigned char) (x >> (8 * k))); }
+static void png_chunk(FILE *f, const char *type, const std::vector<unsigned char> &data) {
+    std::vector<unsigned char> buf; put_be32(buf, (uint32_t) data.size());
+    fwrite(buf.data(), 1, 4, f);
+    std::vector<unsigned char> body(type, type + 4); body.insert(body.end(), data.begin(), data.end());
+    fwrite(body.data(), 1, body.size(), f);
+    buf.clear(); put_be32(buf, (uint32_t) crc32(0L, body.data(), (uInt) body.size()));
+    fwrite(buf.data(), 1, 4, f);
+}
+static bool write_png(const char *path, const uint8_t *rgb, int w, int h) {
+    FILE *f = fopen(path, "wb"); if (!f) return false;
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    fwrite(sig, 1, 8, f);
+    std::vector<unsigned char> ihdr; put_be32(ihdr, (uint32_t) w); put_be32(ihdr, (uint32_t) h);
+    ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);     // 8 bit, RGB
+    png_chunk(f, "IHDR", ihdr);
+    std::vector<unsigned char> raw((size_t) h * (3 * (size_t) w + 1));
+    for (int y = 0; y < h; ++y) { raw[(size_t) y * (3 * w + 1)] = 0; memcpy(&raw[(size_t) y * (3 * w + 1) + 1], rgb + (size_t) y * 3 * w, (size_t) 3 * w); }
+    uLongf clen = compressBound((uLong) raw.size());
+    std::vector<unsigned char> comp(clen);
+    if (compress2(comp.data(), &clen, raw.data(), (uLong) raw.size(), 6) != Z_OK) { fclose(f); return false; }
+    comp.resize(clen);
+    png_chunk(f, "IDAT", comp);
+    png_chunk(f, "IEND", std::vector<unsigned char>());
+    return fclose(f) == 0;
+}
+static bool write_ppm(const char *path, const uint8_t *rgb, int w, int h) {
+    FILE *f = fopen(path, "wb"); if (!f) return false;
+    fprintf(f, "P6\n%d %d\n255\n", w, h);
+    fwrite(rgb, 1, (size_t) 3 * w * h, f);
+    return fclose(f) == 0;
+}
+static bool write_pfm(const char *path, const float *rgb, int w, int h) {
+    FILE *f = fopen(path, "wb"); if (!f) return false;
+    fprintf(f, "PF\n%d %d\n-1.0\n", w, h);                                   // negative scale: little endian
+    for (int y = h - 1; y >= 0; --y) fwrite(rgb + (size_t) y * 3 * w, 4, (size_t) 3 * w, f);
+    return fclose(f) == 0;
+}
+static bool ends_with(const std::string &s, const char *suffix) { const size_t n = strlen(suffix); return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0; }
+
+static int die(const char *what) { fprintf(stderr, "cudapath_render: %s: %s\n", what, cudapath_last_error()); return 1; }
+
+int main(int argc, char **argv) {
+    std::string out, defines, scene, dataDir;
+    int gpu = 0; long spp = 0; unsigned long long seed = 0; bool quiet = false;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto need = [&](const char *opt) -> const char * { if (i + 1 >= argc) { fprintf(stderr, "cudapath_render: %s needs an argument\n", opt); exit(2); } return argv[++i]; };
+        if (a == "-o") out = need("-o");
+        else if (a == "-D") { if (!defines.empty()) defines += ";"; defines += need("-D"); }
+        else if (a.rfind("-D", 0) == 0 && a.size() > 2) { if (!defines.empty()) defines += ";"; defines += a.substr(2); }
+        else if (a == "-p" || a == "-b") need(a.c_str());
+        else if (a == "-q") quiet = true;
+        else if (a == "--gpu") gpu = atoi(need("--gpu"));
+        else if (a == "--spp") spp = atol(need("--spp"));
+        else if (a == "--seed") seed = strtoull(need("--seed"), nullptr, 10);
+        else if (a == "--data-dir") dataDir = need("--data-dir");
+        else if (a == "-h" || a == "--help") { printf("usage: cudapath_render [-o out.{png,pfm,ppm}] [-D name=value]... [-p N] [-q] [--gpu i] [--spp n] [--seed s] [--data-dir dir] scene.xml\n"); return 0; }
+        else if (!a.empty() && a[0] == '-') { fprintf(stderr, "cudapath_render: unknown option %s\n", a.c_str()); return 2; }
+        else scene = a;
+    }
+    if (scene.empty()) { fprintf(stderr, "cudapath_render: no scene file given (-h for help)\n"); return 2; }
+    if (dataDir.empty()) dataDir = getenv("CUDAPATH_DATA_DIR") ? getenv("CUDAPATH_DATA_DIR") : "refdata";
+
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    cudapath_ctx *ctx = nullptr;
+    if (cudapath_create(gpu, &ctx) != 0) return die("cannot create a context");
+    if (cudapath_set_data_dir(ctx, dataDir.c_str()) != 0) return die("data directory");
+    const double t0 = now();
+    uint32_t fileSpp = 0;
+    if (cudapath_load_scene_xml(ctx, scene.c_str(), defines.empty() ? nullptr : defines.c_str(), &fileSpp) != 0) return die("cannot load the scene");
+    const double t1 = now();
+    if (cudapath_build(ctx) != 0) return die("cannot build the scene");
+    const double t2 = now();
+    const uint32_t n = spp > 0 ? (uint32_t) spp : fileSpp;
+    int w = 0, h = 0, hdr = 0; float gamma = -1, exposure = 0;
+    cudapath_film_size(ctx, &w, &h);
+    cudapath_get_film_output(ctx, &hdr, &gamma, &exposure);
+    std::vector<float> film((size_t) w * h * 5);
+    if (cudapath_render(ctx, n, seed, 0, n, film.data()) != 0) return die("render failed");
+    const double t3 = now();
+    cudapath_stats st; cudapath_get_stats(ctx, &st);
+
+    if (out.empty()) { out = scene; const size_t dot = out.rfind('.'); if (dot != std::string::npos) out.resize(dot); out += hdr ? ".pfm" : ".png"; }
+    bool ok;
+    if (ends_with(out, ".pfm")) {
+        std::vector<float> rgb((size_t) w * h * 3);
+        cudapath_develop(film.data(), w, h, rgb.data());
+        ok = write_pfm(out.c_str(), rgb.data(), w, h);
+    } else {
+        std::vector<uint8_t> rgb8((size_t) w * h * 3);
+        if (cudapath_develop_ldr(film.data(), w, h, gamma, exposure, rgb8.data()) != 0) return die("develop");
+        ok = ends_with(out, ".ppm") ? write_ppm(out.c_str(), rgb8.data(), w, h) : write_png(out.c_str(), rgb8.data(), w, h);
+    }
+    if (!ok) { fprintf(stderr, "cudapath_render: cannot write %s\n", out.c_str()); return 1; }
+    if (!quiet) {
+        const double paths = (double) w * h * n, rays = (double) st.rays + (double) st.shadow_rays;
+        printf("Loaded \"%s\" in %.3f s; %llu segments, %llu triangles -> %llu BVH references, %llu nodes (built in %.3f s)\n", scene.c_str(), t1 - t0,
+               (unsigned long long) st.segments, (unsigned long long) st.triangles, (unsigned long long) st.bvh_references, (unsigned long long) st.bvh_nodes, t2 - t1);
+        printf("Render time: %.4f s  (%dx%d, %u spp: %.1f Mpaths/s, %.1f Mrays/s; device %.4f s)\n", t3 - t2, w, h, n, paths / (t3 - t2) / 1e6, rays / (t3 - t2) / 1e6,
+               st.render_ms * 1e-3);
+        printf("Writing image to \"%s\" ..\n", out.c_str());
+    }
+    cudapath_destroy(ctx);
+    return 0;
+}

@@ -373,3 +373,92 @@ bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNo
 }
 
 } // namespace cp
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Radiance RGBE (.hdr) reader: Bitmap::readRGBE, src/libcore/bitmap.cpp:3590-3678 (+ RGBE_ToFloat :3522-3530, RGBE_ReadPixels :3579-3586,
+// Stream::readLine src/libcore/stream.cpp:392-414).  Output: top-down lat-long RGB fp32, what the `envmap` emitter hands to its MIP map.
+namespace cp {
+namespace {
+struct ByteReader {
+    const std::vector<unsigned char> &d; size_t pos = 0;
+    explicit ByteReader(const std::vector<unsigned char> &v) : d(v) {}
+    void read(unsigned char *out, size_t n) { if (pos + n > d.size()) throw std::runtime_error("readRGBE(): unexpected end of file"); std::memcpy(out, d.data() + pos, n); pos += n; }
+    std::string line() {               // drops CR, ends at LF; a last line without LF is returned as it is
+        std::string r;
+        for (;;) {
+            if (pos >= d.size()) { if (!r.empty()) return r; throw std::runtime_error("readRGBE(): unexpected end of file"); }
+            const char c = (char) d[pos++];
+            if (c == 10) return r;
+            if (c != 13) r += c;
+        }
+    }
+};
+inline void rgbe_to_float(const unsigned char q[4], float *out) {
+    if (q[3]) { const float f = std::ldexp(1.0f, (int) q[3] - (128 + 8)); for (int i = 0; i < 3; ++i) out[i] = q[i] * f; }
+    else out[0] = out[1] = out[2] = 0.0f;
+}
+}
+
+bool load_rgbe_file(const std::string &path, std::vector<float> &rgb, int &w, int &h, std::string &err) {
+    try {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw std::runtime_error("Environment map file \"" + path + "\" could not be found!");
+        std::vector<unsigned char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        ByteReader in(bytes);
+        std::string line = in.line();
+        if (line.length() < 2 || line[0] != '#' || line[1] != '?') throw std::runtime_error("readRGBE(): Invalid header!");
+        bool recognised = false;
+        w = h = 0;
+        for (;;) {
+            line = in.line();
+            if (line.rfind("FORMAT=32-bit_rle_rgbe", 0) == 0) recognised = true;
+            if (line.rfind("-Y ", 0) == 0) {
+                if (std::sscanf(line.c_str(), "-Y %i +X %i", &h, &w) < 2) throw std::runtime_error("readRGBE(): parser error!");
+                break;
+            }
+        }
+        if (!recognised) throw std::runtime_error("readRGBE(): invalid format!");
+        if (w <= 0 || h <= 0) throw std::runtime_error("readRGBE(): invalid image size!");
+        rgb.assign((size_t) 3 * w * h, 0.0f);
+        float *data = rgb.data();
+        auto flat = [&](float *dst, size_t n) { unsigned char q[4]; while (n-- > 0) { in.read(q, 4); rgbe_to_float(q, dst); dst += 3; } };
+        if (w < 8 || w > 0x7fff) { flat(data, (size_t) w * h); return true; }        // run-length encoding is not allowed for these widths
+        std::vector<unsigned char> buffer((size_t) 4 * w);
+        for (int y = 0; y < h; ++y) {
+            unsigned char q[4];
+            in.read(q, 4);
+            if (q[0] != 2 || q[1] != 2 || (q[2] & 0x80)) {                           // not run-length encoded: the rest of the file is flat
+                rgbe_to_float(q, data);
+                flat(data + 3, (size_t) w * h - 1);                                    // (as in the reference, also when y > 0)
+                return true;
+            }
+            if ((((int) q[2]) << 8 | q[3]) != w) throw std::runtime_error("readRGBE(): wrong scanline width!");
+            unsigned char *ptr = buffer.data();
+            for (int i = 0; i < 4; ++i) {
+                unsigned char *end = buffer.data() + (size_t) (i + 1) * w;
+                while (ptr < end) {
+                    unsigned char b[2];
+                    in.read(b, 2);
+                    if (b[0] > 128) {
+                        int count = b[0] - 128;
+                        if (count == 0 || count > end - ptr) throw std::runtime_error("readRGBE(): bad scanline data!");
+                        while (count-- > 0) *ptr++ = b[1];
+                    } else {
+                        int count = b[0];
+                        if (count == 0 || count > end - ptr) throw std::runtime_error("readRGBE(): bad scanline data!");
+                        *ptr++ = b[1];
+                        if (--count > 0) in.read(ptr, (size_t) count);
+                        ptr += count;
+                    }
+                }
+            }
+            for (int i = 0; i < w; ++i) {
+                q[0] = buffer[i]; q[1] = buffer[(size_t) w + i]; q[2] = buffer[(size_t) 2 * w + i]; q[3] = buffer[(size_t) 3 * w + i];
+                rgbe_to_float(q, data);
+                data += 3;
+            }
+        }
+        return true;
+    } catch (const std::exception &e) { err = e.what(); return false; }
+}
+} // namespace cp

@@ -8,7 +8,7 @@
 //   PerspectiveCamera fov handling                                            src/librender/sensor.cpp:225-300
 // Plugins understood: integrator `path`; sensor `perspective` (film `ldrfilm`/`hdrfilm`, rfilter `tent`/`box`/`gaussian`,
 // any sampler: only sampleCount is used); bsdf `kajiyakay`, `marschner`, `marschner_fixed`, `marschnerdielectric`, `thindielectric`, `roughplastic`, `diffuse`, `twosided`; shape `hair`,
-// `obj`; emitter `sunsky`.
+// `obj`; emitter `sunsky`, `envmap` (Radiance .hdr file).
 // Anything else raises an error naming the plugin (the reference would dlopen plugins/<type>.so, src/libcore/plugin.cpp:222-245).
 #include "../../include/cudapath.h"
 #include <algorithm>
@@ -322,6 +322,9 @@ struct Loader {
                 w = (int) getInt(*c, "width", 768); h = (int) getInt(*c, "height", 576);
                 std::string pf = lower(getString(*c, "pixelFormat", c->get("type") == "hdrfilm" ? "rgb" : "rgb"));
                 alpha = pf == "rgba" || pf == "luminancealpha" || pf == "spectrumalpha";
+                if (c->get("type") != "ldrfilm" && c->get("type") != "hdrfilm") throw std::runtime_error("film plugin \"" + c->get("type") + "\" is not supported (ldrfilm, hdrfilm)");
+                if (lower(getString(*c, "tonemapMethod", "gamma")) != "gamma") throw std::runtime_error("ldrfilm: only tonemapMethod=gamma is supported");
+                if (!dry) check(cudapath_set_film_output(ctx, c->get("type") == "hdrfilm" ? 1 : 0, (float) getFloat(*c, "gamma", -1.0), (float) getFloat(*c, "exposure", 0.0)));
                 if (child(*c, "integer", "cropWidth") || child(*c, "integer", "cropOffsetX")) throw std::runtime_error("film crop windows are not supported");
                 for (auto &f : c->children) if (f->tag == "rfilter") {
                     const std::string t = f->get("type");
@@ -353,7 +356,20 @@ struct Loader {
         haveSensor = true;
     }
     void loadEmitter(const Node &n) {
-        if (n.get("type") != "sunsky") throw std::runtime_error("emitter plugin \"" + n.get("type") + "\" is outside the hair hot path (supported: sunsky; raw environment maps go through cudapath_set_envmap)");
+        if (n.get("type") == "envmap") {          // src/emitters/envmap.cpp:100-190 with a Radiance RGBE file
+            std::string file = getString(n, "filename", "");
+            if (file.empty()) throw std::runtime_error("envmap: the 'filename' parameter is required");
+            if (file[0] != '/') file = baseDir + "/" + file;
+            if (getFloat(n, "gamma", 0.0) != 0.0) throw std::runtime_error("envmap: the 'gamma' override is not supported");
+            if (child(n, "float", "intensityScale")) throw std::runtime_error("The 'intensityScale' parameter has been deprecated and is now called scale.");
+            float tw[16]; toFloat(getTransform(n, "toWorld"), tw);
+            if (dry) {
+                std::ifstream probe(file, std::ios::binary);
+                note(std::string("emitter envmap \"") + file + "\"" + (probe ? "" : " (file missing)"));
+            } else check(cudapath_set_envmap_file(ctx, file.c_str(), tw, (float) getFloat(n, "scale", 1.0)));
+            return;
+        }
+        if (n.get("type") != "sunsky") throw std::runtime_error("emitter plugin \"" + n.get("type") + "\" is outside the hair hot path (supported: sunsky, envmap with an .hdr file; raw environment maps go through cudapath_set_envmap)");
         if (child(n, "transform", "toWorld")) throw std::runtime_error("sunsky: a toWorld transform is not supported");
         auto sd = child(n, "vector", "sunDirection");
         if (!sd) throw std::runtime_error("sunsky: only the 'sunDirection' form is supported (no date/time/location)");

@@ -11,6 +11,7 @@
  */
 #ifndef CUDAPATH_H
 #define CUDAPATH_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -103,6 +104,12 @@ void cudapath_hair_file_free(cudapath_hair_file *h);
 /* `envmap` emitter from a lat-long RGB fp32 bitmap (what SunSkyEmitter hands to its nested envmap, src/emitters/sunsky.cpp:218-229):
  * EnvironmentMap ctor + configure(), src/emitters/envmap.cpp:100-190,260-329 (half quantisation, CDFs built on the device). */
 int cudapath_set_envmap(cudapath_ctx *ctx, const float *rgb, int width, int height, const float to_world[16], float scale);
+/* `envmap` emitter from a Radiance RGBE file (`<string name="filename" value="textures/envmap.hdr"/>`, models/teapot/scene.xml):
+ * Bitmap::readRGBE, src/libcore/bitmap.cpp:3590-3678 (flat and run-length encoded scanlines), then as cudapath_set_envmap.  The
+ * `gamma` override and the .mip cache file of the plugin are not part of this path. */
+int cudapath_set_envmap_file(cudapath_ctx *ctx, const char *filename, const float to_world[16], float scale);
+/* The reader alone (host only): width/height always, pixels (top-down RGB fp32, 3*w*h floats) when out_rgb is not NULL. */
+int cudapath_load_rgbe(const char *filename, float *out_rgb, int *out_width, int *out_height);
 /* `sunsky` emitter: SunSkyEmitter ctor, src/emitters/sunsky.cpp:100-236 (bakes the map on the host, then cudapath_set_envmap). */
 int cudapath_set_sunsky(cudapath_ctx *ctx, float turbidity, const float albedo[3], const float sun_direction[3], float sky_scale,
                         float sun_scale, float sun_radius_scale, int resolution);
@@ -164,6 +171,11 @@ int cudapath_get_stats(cudapath_ctx *ctx, cudapath_stats *out);
 int cudapath_scene_bounds(cudapath_ctx *ctx, float aabb_min_max[6], float bsphere_center_radius[4]);
 /* Film::getSize() (include/mitsuba/render/film.h:49-92) */
 int cudapath_film_size(cudapath_ctx *ctx, int *width, int *height);
+/* How the scene's film wants to be developed: `hdrfilm` (linear float output) or `ldrfilm` with its `gamma` (-1 = sRGB, the plugin's
+ * default) and `exposure` (src/films/ldrfilm.cpp:180-181).  Set by the scene loader, read by whoever writes the image
+ * (cudapath_develop / cudapath_develop_ldr); the render itself does not depend on it. */
+int cudapath_set_film_output(cudapath_ctx *ctx, int hdr, float gamma, float exposure);
+int cudapath_get_film_output(cudapath_ctx *ctx, int *out_hdr, float *out_gamma, float *out_exposure);
 
 /* ---- parity hooks (host buffers; same device functions as the render path) ---------------------------------- */
 /* BSDF::eval + BSDF::pdf (include/mitsuba/render/bsdf.h:369-441), wi/wo local, measure = ESolidAngle, typeMask = EAll */

@@ -9,6 +9,9 @@
 // src/emitters/sunsky/skymodel.cpp, compiled into oracle/_ref/libref_pieces.so (see oracle/Makefile).
 #pragma once
 #include "o_math.h"
+#include <cstdio>
+#include <string>
+#include <stdexcept>
 #include "o_hair.h"
 
 namespace orc {
@@ -354,6 +357,77 @@ static inline void bakeSunSky(const SunSkyParams &P, const RefPieces &ref, std::
         float *t = &rgb[3 * ((size_t) py * W + px)];
         t[0] += add.x; t[1] += add.y; t[2] += add.z;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Radiance RGBE reader -- Bitmap::readRGBE (src/libcore/bitmap.cpp:3590-3678), RGBE_ToFloat (:3522-3530), flat reads (:3579-3586),
+// line reads as Stream::readLine (src/libcore/stream.cpp:392-414: CR dropped, LF ends the line).  Written against a FILE* the way
+// the reference walks its Stream; returns top-down RGB triples.
+// ---------------------------------------------------------------------------------------------
+struct RGBEImage { int w = 0, h = 0; std::vector<float> rgb; };
+
+static inline RGBEImage readRGBE(const char *path) {
+    FILE *fp = std::fopen(path, "rb");
+    if (!fp) throw std::runtime_error(std::string("Environment map file \"") + path + "\" could not be found!");
+    struct Closer { FILE *f; ~Closer() { std::fclose(f); } } closer{fp};
+    auto readLine = [&]() {
+        std::string r; int c;
+        while ((c = std::fgetc(fp)) != EOF) { if (c == 10) return r; if (c != 13) r.push_back((char) c); }
+        if (r.empty()) throw std::runtime_error("readRGBE(): unexpected end of file");
+        return r;
+    };
+    auto readBytes = [&](uint8_t *dst, size_t n) { if (std::fread(dst, 1, n, fp) != n) throw std::runtime_error("readRGBE(): unexpected end of file"); };
+    auto toFloat = [](const uint8_t *q, float *out) {
+        if (q[3]) { float f = std::ldexp(1.0f, (int) q[3] - (128 + 8)); out[0] = q[0] * f; out[1] = q[1] * f; out[2] = q[2] * f; }
+        else { out[0] = out[1] = out[2] = 0.0f; }
+    };
+    std::string line = readLine();
+    if (line.size() < 2 || line[0] != '#' || line[1] != '?') throw std::runtime_error("readRGBE(): Invalid header!");
+    RGBEImage img; bool ok = false;
+    while (true) {
+        line = readLine();
+        if (line.compare(0, 22, "FORMAT=32-bit_rle_rgbe") == 0) ok = true;
+        if (line.compare(0, 3, "-Y ") == 0) {
+            if (std::sscanf(line.c_str(), "-Y %i +X %i", &img.h, &img.w) < 2) throw std::runtime_error("readRGBE(): parser error!");
+            break;
+        }
+    }
+    if (!ok) throw std::runtime_error("readRGBE(): invalid format!");
+    if (img.w <= 0 || img.h <= 0) throw std::runtime_error("readRGBE(): invalid image size!");
+    const size_t total = (size_t) img.w * img.h;
+    img.rgb.resize(3 * total);
+    size_t done = 0;                                        // pixels written so far
+    auto readFlat = [&](size_t n) { uint8_t q[4]; for (size_t k = 0; k < n; ++k) { readBytes(q, 4); toFloat(q, &img.rgb[3 * done]); ++done; } };
+    if (img.w < 8 || img.w > 0x7fff) { readFlat(total); return img; }
+    std::vector<uint8_t> chan[4];
+    for (auto &c : chan) c.resize((size_t) img.w);
+    for (int y = 0; y < img.h; ++y) {
+        uint8_t q[4];
+        readBytes(q, 4);
+        if (q[0] != 2 || q[1] != 2 || (q[2] & 0x80)) {       // a flat file: this pixel and total-1 more from the current position
+            toFloat(q, &img.rgb[3 * done]); ++done;
+            const size_t room = total - done;
+            readFlat(std::min(room, total - 1));
+            return img;
+        }
+        if ((((int) q[2]) << 8 | q[3]) != img.w) throw std::runtime_error("readRGBE(): wrong scanline width!");
+        for (int c = 0; c < 4; ++c) {
+            size_t x = 0;
+            while (x < (size_t) img.w) {
+                uint8_t b[2];
+                readBytes(b, 2);
+                size_t count = b[0] > 128 ? b[0] - 128 : b[0];
+                if (count == 0 || count > (size_t) img.w - x) throw std::runtime_error("readRGBE(): bad scanline data!");
+                if (b[0] > 128) { for (size_t k = 0; k < count; ++k) chan[c][x++] = b[1]; }
+                else { chan[c][x++] = b[1]; if (count > 1) { readBytes(&chan[c][x], count - 1); x += count - 1; } }
+            }
+        }
+        for (int x = 0; x < img.w; ++x) {
+            const uint8_t px[4] = {chan[0][x], chan[1][x], chan[2][x], chan[3][x]};
+            toFloat(px, &img.rgb[3 * done]); ++done;
+        }
+    }
+    return img;
 }
 
 } // namespace orc

@@ -15,6 +15,7 @@
 #include "o_env.h"
 #include "o_render.h"
 #include <dlfcn.h>
+#include <cstring>
 
 using namespace orc;
 
@@ -140,6 +141,16 @@ int orc_add_hair(void *sp, const float *xyz, const uint8_t *startsFiber, uint32_
     h.finalize();
     s->geo.shapes.push_back(std::move(h));
     return (int) s->geo.shapes.size() - 1;
+    ORC_CATCH
+}
+
+// Radiance RGBE file -> top-down RGB fp32; sizes always, pixels when out is not null
+int orc_load_rgbe(const char *path, float *out, int *w, int *h) {
+    ORC_TRY
+    RGBEImage img = readRGBE(path);
+    *w = img.w; *h = img.h;
+    if (out) std::memcpy(out, img.rgb.data(), img.rgb.size() * sizeof(float));
+    return 0;
     ORC_CATCH
 }
 

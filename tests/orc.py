@@ -75,6 +75,14 @@ def load_hair_file(path, radius=0.025, angleThreshold=1.0, toWorld=None):
     return xyz, st, float(r), int(nseg)
 
 
+def load_rgbe(path):
+    w = ctypes.c_int(); h = ctypes.c_int()
+    check(lib().orc_load_rgbe(str(path).encode(), None, ctypes.byref(w), ctypes.byref(h)))
+    out = np.zeros((h.value, w.value, 3), np.float32)
+    check(lib().orc_load_rgbe(str(path).encode(), p(out), ctypes.byref(w), ctypes.byref(h)))
+    return out
+
+
 def bake_sunsky(turbidity=3.0, albedo=0.2, sunDirection=(0, 1, 0), skyScale=1.0, sunScale=1.0, sunRadiusScale=1.0, resolution=512):
     out = np.zeros((resolution // 2, resolution, 3), np.float32)
     check(lib().orc_bake_sunsky(REF_LIB.encode(), ctypes.c_float(turbidity), ctypes.c_float(albedo), p(f32(sunDirection)), ctypes.c_float(skyScale),

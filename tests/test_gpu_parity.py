@@ -3,6 +3,7 @@
 Bars (BASELINE.json north_star): BSDF eval/pdf within 1e-4 relative; hit primitive index bit-exact except grazing ties
 within 1e-6 in t; images within relMSE < 1e-3 (checked here at reduced size; same counter-based RNG on both sides).
 """
+import os
 import numpy as np
 import pytest
 
@@ -703,3 +704,79 @@ def test_repeated_jobs_reuse_device_memory(cp):
     cp.trim_memory(0)
     free, total = torch.cuda.mem_get_info(0)
     assert total - free < used[3]
+
+
+def test_native_cli_renders_a_scene_file(cp, tmp_path):
+    """cudapath_render (csrc/cp_cli.cpp, the `mitsuba -o out.png -D name=value scene.xml` of this path): same film as the Python mirror,
+    developed with the film's own gamma; PNG, PFM and $-substitution."""
+    import subprocess
+    from PIL import Image
+    ov = dict(width=64, height=48, spp=4, maxDepth=5)
+    path = cp.scenes.write_scene('straight-hair', str(tmp_path), scale=0.01, overrides=ov)
+    xml = open(path).read().replace('<integer name="maxDepth" value="5"/>', '<integer name="maxDepth" value="$depth"/>')
+    xml = xml.replace('<string name="pixelFormat" value="rgb"/>', '<string name="pixelFormat" value="rgb"/>\n\t\t\t<float name="gamma" value="2.2"/>')
+    open(path, 'w').write(xml)
+    png = str(tmp_path / 'out.png'); pfm = str(tmp_path / 'out.pfm')
+    env = dict(os.environ, CUDAPATH_DATA_DIR=cp.DEFAULT_DATA_DIR)
+    r = subprocess.run([cp.CLI_PATH, '-p', '8', '-D', 'depth=5', '--seed', '3', '-o', png, path], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert 'Render time:' in r.stdout and 'Mpaths/s' in r.stdout
+    r2 = subprocess.run([cp.CLI_PATH, '-q', '-Ddepth=5', '--seed', '3', '-o', pfm, path], capture_output=True, text=True, env=env)
+    assert r2.returncode == 0 and r2.stdout == ''
+    ctx = cp.Context(0)
+    assert ctx.load_xml(path, defines={'depth': 5}) == 4
+    assert ctx.film_output() == (False, pytest.approx(2.2), 0.0)
+    ctx.build()
+    film = ctx.render(4, seed=3)
+    ctx.close()
+    img = np.asarray(Image.open(png))
+    assert img.shape == (48, 64, 3) and np.array_equal(img, cp.develop_ldr(film, gamma=2.2))
+    with open(pfm, 'rb') as f:
+        assert f.readline() == b'PF\n' and f.readline() == b'64 48\n' and f.readline() == b'-1.0\n'
+        data = np.frombuffer(f.read(), np.float32).reshape(48, 64, 3)[::-1]
+    assert np.array_equal(data, cp.develop(film))
+    bad = subprocess.run([cp.CLI_PATH, '-o', png, path], capture_output=True, text=True, env=env)       # $depth left undefined
+    assert bad.returncode == 1 and 'depth' in bad.stderr
+
+
+def test_envmap_emitter_from_hdr_file(cp, oracle, tmp_path):
+    """`<emitter type="envmap">` with a Radiance .hdr file, a toWorld rotation and a scale (models/teapot/scene.xml:76-81) on the
+    straight-hair fibers: XML path == flattened-array path, and both match the oracle fed with the decoded image."""
+    from test_oracle_cpu import _write_rgbe
+    ov = dict(width=48, height=40, spp=8, maxDepth=5)
+    path = cp.scenes.write_scene('straight-hair', str(tmp_path), scale=0.01, overrides=ov)
+    rng = np.random.default_rng(31)
+    w, h = 64, 32
+    q = np.zeros((h, w, 4), np.uint8)
+    q[..., :3] = rng.integers(20, 256, size=(h, w, 3)); q[..., 3] = 128
+    q[4:7, 40:44] = (250, 240, 200, 135)                                  # a bright blob: something worth importance sampling
+    os.makedirs(tmp_path / 'textures')
+    _write_rgbe(tmp_path / 'textures' / 'env.hdr', q, rle=True)
+    tw = np.array([[-0.922278, 0, 0.386527, 0], [0, 1, 0, 0], [-0.386527, 0, -0.922278, 1.17369], [0, 0, 0, 1]], np.float32)
+    xml = open(path).read()
+    a, b = xml.index('<emitter type="sunsky">'), xml.index('</emitter>') + len('</emitter>')
+    xml = xml[:a] + ('<emitter type="envmap">\n\t\t<transform name="toWorld">\n\t\t\t<matrix value="%s"/>\n\t\t</transform>\n'
+                     '\t\t<string name="filename" value="textures/env.hdr"/>\n\t\t<float name="scale" value="2.5"/>\n\t</emitter>' % ' '.join(repr(float(v)) for v in tw.ravel())) + xml[b:]
+    open(path, 'w').write(xml)
+    assert any('emitter envmap' in r and 'missing' not in r for r in cp.validate_scene_xml(path))
+    ctx = cp.Context(0)
+    assert ctx.load_xml(path) == 8
+    ctx.build()
+    f1 = ctx.render(8, seed=4)
+    ctx.close()
+    img = cp.load_rgbe(tmp_path / 'textures' / 'env.hdr')
+    films = []
+    for mod, S in ((cp, None), (oracle, None)):
+        sc = dict(cp.scenes.SCENES['straight-hair']); sc.update(ov)
+        t = mod.Context(0) if mod is cp else mod.Scene()
+        cp.scenes.add_shapes(t, sc, 0.01)
+        t.set_envmap(img, toWorld=tw, scale=2.5)
+        t.set_camera(np.array(sc['camera'], np.float32).reshape(4, 4), sc['fov'], width=sc['width'], height=sc['height'])
+        t.set_film('tent'); t.set_integrator(maxDepth=sc['maxDepth'], rrDepth=5, strictNormals=True)
+        t.build()
+        films.append(t.render(8, seed=4))
+    assert np.array_equal(f1, films[0])
+    a, b = cp.develop(f1), cp.develop(films[1])
+    assert b.sum() > 0 and rel_mse(a, b) < 1e-3
+    close = np.abs(a - b).max(axis=2) <= 1e-3 * (np.abs(b).max(axis=2) + 1e-3)
+    assert close.mean() > 0.97

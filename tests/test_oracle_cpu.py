@@ -465,6 +465,69 @@ def test_dielectric_scenes_render_on_the_oracle(cp, oracle):
     assert not np.allclose(films['straight-hair-thindielectric'], films['straight-hair-dielectric'])
 
 
+def _write_rgbe(path, rgbe, rle, crlf=False):
+    """Radiance RGBE file from an (h, w, 4) uint8 array; rle=True writes new-style run-length encoded scanlines."""
+    h, w = rgbe.shape[:2]
+    nl = b'\r\n' if crlf else b'\n'
+    out = bytearray(b'#?RADIANCE' + nl + b'# made by a test' + nl + b'FORMAT=32-bit_rle_rgbe' + nl + nl + ('-Y %d +X %d' % (h, w)).encode() + nl)
+    if not rle:
+        out += rgbe.tobytes()
+    else:
+        for y in range(h):
+            out += bytes([2, 2, w >> 8, w & 255])
+            for c in range(4):
+                row = rgbe[y, :, c]; x = 0
+                while x < w:
+                    run = 1
+                    while x + run < w and run < 127 and row[x + run] == row[x]:
+                        run += 1
+                    if run >= 3:
+                        out += bytes([128 + run, int(row[x])]); x += run
+                    else:
+                        n = 1
+                        while x + n < w and n < 128 and not (x + n + 2 < w and row[x + n] == row[x + n + 1] == row[x + n + 2]):
+                            n += 1
+                        out += bytes([n]) + row[x:x + n].tobytes(); x += n
+    open(path, 'wb').write(bytes(out))
+
+
+def test_rgbe_reader(cp, oracle, tmp_path):
+    """Bitmap::readRGBE (src/libcore/bitmap.cpp:3590-3678): flat and run-length encoded files, CR/LF headers, widths that forbid RLE,
+    zero exponents; product loader == oracle loader == direct decode, error messages for broken files."""
+    rng = np.random.default_rng(12)
+    for k, (w, h, rle, crlf) in enumerate([(16, 5, False, False), (16, 5, True, False), (37, 9, True, True), (5, 4, False, False), (300, 3, True, False)]):
+        q = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+        q[:, :, 3] = rng.integers(100, 150, size=(h, w), dtype=np.uint8)
+        q[0, : w // 2] = q[0, 0]                                   # long runs
+        q[h - 1, w // 3:, 3] = 0                                   # zero exponent = black
+        if not rle and w >= 8:
+            q[0, 0, 0] = 7                                          # a flat file must not start with the RLE marker 2,2
+        path = tmp_path / ('t%d.hdr' % k)
+        _write_rgbe(path, q, rle, crlf)
+        expect = q[..., :3].astype(np.float32) * np.ldexp(np.float32(1), q[..., 3].astype(np.int32) - 136)[..., None]
+        expect[q[..., 3] == 0] = 0
+        a = cp.load_rgbe(path); b = oracle.load_rgbe(path)
+        assert a.shape == (h, w, 3) and np.array_equal(a, expect) and np.array_equal(b, expect)
+    raw = open(path, 'rb').read()
+    bad = tmp_path / 'bad.hdr'
+    for data, msg in [(b'RADIANCE\n' + raw[11:], 'Invalid header'), (raw.replace(b'FORMAT=32-bit_rle_rgbe', b'FORMAT=32-bit_rle_xyze'), 'invalid format'),
+                      (raw[:len(raw) - 40], 'end of file')]:
+        bad.write_bytes(data)
+        with pytest.raises(cp.CudapathError, match=msg):
+            cp.load_rgbe(bad)
+        with pytest.raises(RuntimeError, match=msg):
+            oracle.load_rgbe(bad)
+    with pytest.raises(cp.CudapathError, match='could not be found'):
+        cp.load_rgbe(tmp_path / 'nothing.hdr')
+    ref = '/root/reference/models/teapot/textures/envmap.hdr'       # the one image file the reference ships for this emitter
+    if os.path.exists(ref):
+        import hashlib
+        import json
+        a = cp.load_rgbe(ref)
+        gold = json.load(open(os.path.join(GOLDEN, 'envmap_hdr.json')))
+        assert list(a.shape) == gold['shape'] and hashlib.sha256(a.tobytes()).hexdigest() == gold['sha256'] and np.array_equal(a, oracle.load_rgbe(ref))
+
+
 def test_obj_loader(cp, tmp_path):
     """WavefrontOBJ + computeNormals: vertex merge, n-gon fans, negative indices, toWorld on points and normals, generated
     angle-weighted normals, faceNormals / flipNormals (obj.cpp:244-349, 608-700; trimesh.cpp:608-672)."""
@@ -635,6 +698,23 @@ def test_c_abi_exports_every_declared_symbol(cp):
     L = cp.lib()
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
+
+
+def test_header_is_plain_c_and_cli_fails_loudly_without_gpu(cp, tmp_path):
+    """include/cudapath.h compiles as C99 on its own; the native front end (csrc/cp_cli.cpp) refuses to run without a CUDA device."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(os.path.dirname(GOLDEN), '..', 'include', 'cudapath.h')
+    if shutil.which('gcc'):
+        assert subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c', hdr], capture_output=True).returncode == 0
+    assert os.path.exists(cp.CLI_PATH)
+    r = subprocess.run([cp.CLI_PATH, '-h'], capture_output=True, text=True)
+    assert r.returncode == 0 and 'scene.xml' in r.stdout
+    import torch
+    if not torch.cuda.is_available():
+        path = cp.scenes.write_scene('straight-hair', str(tmp_path), scale=0.002)
+        r = subprocess.run([cp.CLI_PATH, '-o', str(tmp_path / 'o.png'), path], capture_output=True, text=True)
+        assert r.returncode == 1 and 'no CUDA device' in r.stderr and not (tmp_path / 'o.png').exists()
 
 
 def test_no_gpu_fails_loudly(cp):
