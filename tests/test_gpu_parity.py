@@ -730,11 +730,11 @@ def test_native_cli_renders_a_scene_file(cp, tmp_path):
     film = ctx.render(4, seed=3)
     ctx.close()
     img = np.asarray(Image.open(png))
-    assert img.shape == (48, 64, 3) and np.array_equal(img, cp.develop_ldr(film, gamma=2.2))
+    assert img.shape == (48, 64, 3) and np.abs(img.astype(int) - cp.develop_ldr(film, gamma=2.2).astype(int)).max() <= 1
     with open(pfm, 'rb') as f:
         assert f.readline() == b'PF\n' and f.readline() == b'64 48\n' and f.readline() == b'-1.0\n'
         data = np.frombuffer(f.read(), np.float32).reshape(48, 64, 3)[::-1]
-    assert np.array_equal(data, cp.develop(film))
+    assert np.allclose(data, cp.develop(film), rtol=1e-5, atol=1e-6)          # another run: the atomic splat order differs in the last bits
     bad = subprocess.run([cp.CLI_PATH, '-o', png, path], capture_output=True, text=True, env=env)       # $depth left undefined
     assert bad.returncode == 1 and 'depth' in bad.stderr
 
@@ -775,7 +775,7 @@ def test_envmap_emitter_from_hdr_file(cp, oracle, tmp_path):
         t.set_film('tent'); t.set_integrator(maxDepth=sc['maxDepth'], rrDepth=5, strictNormals=True)
         t.build()
         films.append(t.render(8, seed=4))
-    assert np.array_equal(f1, films[0])
+    assert np.allclose(f1, films[0], rtol=1e-5, atol=1e-6)
     a, b = cp.develop(f1), cp.develop(films[1])
     assert b.sum() > 0 and rel_mse(a, b) < 1e-3
     close = np.abs(a - b).max(axis=2) <= 1e-3 * (np.abs(b).max(axis=2) + 1e-3)
