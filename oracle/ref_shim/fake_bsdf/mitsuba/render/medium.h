@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE ONLY: stands in for <mitsuba/render/medium.h> when the reference BSDF plugins are compiled for oracle/_ref (see ../../mitsuba_shim.h)
+#include "mitsuba_shim.h"
