@@ -333,6 +333,37 @@ int orc_intersect_candidates(void *sp, const float *o, const float *d, float min
     }
     return cnt;
 }
+// Raw per-segment operations (pinning against the reference text itself, tests/test_oracle_cpu.py): HairKDTree::intersect for
+// (ray, segment, interval) tuples, and HairShape::fillIntersectionRecord for (segment, stored hit point) pairs: out = p n s t
+int orc_segment_intersect_batch(void *sp, int shape, uint64_t n, const float *o, const float *d, const uint32_t *iv, const float *mint, const float *maxt,
+                                int32_t *outHit, float *outT, float *outP) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    const HairShape &h = s->geo.shapes.at(shape);
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray r(V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), mint[i], maxt[i]);
+        float t = 0; V3 p(0.0f);
+        const bool hit = h.intersect(r, iv[i], mint[i], maxt[i], t, p);
+        outHit[i] = hit ? 1 : 0; outT[i] = hit ? t : 0.0f;
+        outP[3 * i] = hit ? p.x : 0; outP[3 * i + 1] = hit ? p.y : 0; outP[3 * i + 2] = hit ? p.z : 0;
+    }
+    return 0;
+    ORC_CATCH
+}
+int orc_segment_record_batch(void *sp, int shape, uint64_t n, const uint32_t *iv, const float *p, float *out12) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    for (uint64_t i = 0; i < n; ++i) {
+        Hit h; h.shape = shape; h.iv = iv[i]; h.t = 1.0f; h.p = V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+        Ray r(V3(0.0f), V3(0.0f, 0.0f, 1.0f), 0.0f, kInf);
+        Intersection its;
+        s->geo.fillIntersection(r, h, its);
+        const V3 vs[4] = {its.p, its.geoFrame.n, its.geoFrame.s, its.geoFrame.t};
+        for (int k = 0; k < 4; ++k) { out12[12 * i + 3 * k] = vs[k].x; out12[12 * i + 3 * k + 1] = vs[k].y; out12[12 * i + 3 * k + 2] = vs[k].z; }
+    }
+    return 0;
+    ORC_CATCH
+}
 // closest hit + intersection record: outRec = p(3) n(3) s(3) t(3) wi(3) per ray
 int orc_intersect_full_batch(void *sp, uint64_t n, const float *o, const float *d, const float *mint, const float *maxt,
                              int32_t *outShape, uint32_t *outPrim, float *outT, float *outRec) {

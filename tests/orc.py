@@ -195,6 +195,19 @@ class Scene:
         check(self.L.orc_intersect_batch(self.h, ctypes.c_uint64(n), p(o), p(d), p(mint), p(maxt), int(mode), p(sh), p(pr), p(t)))
         return sh, pr, t
 
+    def segment_intersect(self, shape, o, d, iv, mint, maxt):
+        o = f32(o).reshape(-1, 3); d = f32(d).reshape(-1, 3); n = len(o)
+        iv = np.ascontiguousarray(iv, np.uint32); mint = f32(np.broadcast_to(mint, n)); maxt = f32(np.broadcast_to(maxt, n))
+        hit = np.zeros(n, np.int32); t = np.zeros(n, np.float32); pt = np.zeros((n, 3), np.float32)
+        check(self.L.orc_segment_intersect_batch(self.h, int(shape), ctypes.c_uint64(n), p(o), p(d), p(iv), p(mint), p(maxt), p(hit), p(t), p(pt)))
+        return hit, t, pt
+
+    def segment_records(self, shape, iv, pts):
+        iv = np.ascontiguousarray(iv, np.uint32); pts = f32(pts).reshape(-1, 3); n = len(iv)
+        out = np.zeros((n, 12), np.float32)
+        check(self.L.orc_segment_record_batch(self.h, int(shape), ctypes.c_uint64(n), p(iv), p(pts), p(out)))
+        return out
+
     def intersect_full(self, o, d, mint, maxt):
         o = f32(o).reshape(-1, 3); d = f32(d).reshape(-1, 3); n = len(o)
         mint = f32(np.broadcast_to(mint, n)); maxt = f32(np.broadcast_to(maxt, n))

@@ -918,6 +918,56 @@ def test_oracle_mesh_and_next_row_bsdfs_pinned_against_compiled_reference_plugin
         assert np.array_equal(rwt[ok], owt[ok]) and np.allclose(rpdf[ok], opdf[ok], rtol=2e-6, atol=1e-6) and np.abs(rwo[ok] - owo[ok]).max() < 1e-5      # sincosf vs correctly rounded
 
 
+REF_GEOM = os.path.join(os.path.dirname(GOLDEN), '..', 'oracle', '_ref', 'libref_geom.so')
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GEOM), reason='oracle/_ref/libref_geom.so not built (needs /root/reference)')
+def test_oracle_hair_geometry_pinned_against_reference_text(cp, oracle):
+    """HairKDTree::intersect (the FP64 mitred-cylinder test with its miter helpers, hair.cpp:480-596), getAABB(index) (:246-286,368-397),
+    HairShape::fillIntersectionRecord (:825-862) and solveQuadraticDouble (util.cpp:487-525), cut out of the reference by line pattern at
+    build time and executed as written (oracle/ref_shim/ref_geom.cpp), against the oracle: hit / miss decisions, t, stored hit points, segment
+    bounds and intersection frames are bit-identical."""
+    L = ctypes.CDLL(REF_GEOM); L.ref_hair_create.restype = ctypes.c_void_p
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rng = np.random.default_rng(53)
+    for name, scale in (('curly-hair', 0.002), ('straight-hair', 0.004), ('furball', 0.004)):
+        sh = cp.scenes.SCENES[name]['shapes'][0]
+        xyz, starts = cp.scenes.generate(sh, scale)
+        xyz = np.ascontiguousarray(xyz, np.float32); starts = np.ascontiguousarray(starts, np.uint8)
+        radius = float(sh['radius'])
+        h = ctypes.c_void_p(L.ref_hair_create(P(xyz), P(starts), len(starts), ctypes.c_float(radius)))
+        nseg = L.ref_hair_segment_count(h)
+        segs = np.zeros(nseg, np.uint32); L.ref_hair_segments(h, P(segs))
+        s = oracle.Scene()
+        b = s.add_bsdf('kajiyakay')
+        s.add_hair(xyz, starts, radius, b)
+        s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=16, height=16); s.build()
+        # ---- segment bounds
+        rb = np.zeros((nseg, 6), np.float32); L.ref_hair_segment_bounds(h, P(rb))
+        ob = s.segment_bounds(0, nseg)
+        assert np.array_equal(rb, ob.reshape(-1, 6))
+        # ---- cylinder test: rays aimed at (and near) random segments from all around, from far away, from on the surface and from inside
+        n = 200000
+        iv = segs[rng.integers(0, nseg, n)]
+        a = xyz[iv]; bb = xyz[iv + 1]
+        target = a + (bb - a) * rng.random((n, 1)).astype(np.float32) + (rng.normal(size=(n, 3)) * radius * 0.8).astype(np.float32)
+        dist = np.where(rng.random(n) < 0.3, rng.random(n) * 3 * radius, 0.5 + 20 * rng.random(n)).astype(np.float32)
+        d = sphere_dirs(rng, n)
+        o = (target - d * dist[:, None]).astype(np.float32)
+        mint = np.where(rng.random(n) < 0.5, 0.0, 1e-4).astype(np.float32)
+        maxt = np.where(rng.random(n) < 0.2, dist, np.inf).astype(np.float32)
+        rhit = np.zeros(n, np.int32); rt = np.zeros(n, np.float32); rp = np.zeros((n, 3), np.float32)
+        L.ref_hair_intersect(h, n, P(o), P(d), P(iv), P(mint), P(maxt), P(rhit), P(rt), P(rp))
+        ohit, ot, op = s.segment_intersect(0, o, d, iv, mint, maxt)
+        assert 0.2 < rhit.mean() < 0.95
+        assert np.array_equal(rhit, ohit) and np.array_equal(rt, ot) and np.array_equal(rp, op)
+        # ---- intersection records at the stored hit points
+        k = np.nonzero(rhit)[0][:50000]
+        rr = np.zeros((len(k), 12), np.float32); L.ref_hair_records(h, len(k), P(np.ascontiguousarray(iv[k])), P(np.ascontiguousarray(rp[k])), P(rr))
+        orr = s.segment_records(0, iv[k], rp[k])
+        assert np.array_equal(rr, orr)
+
+
 # ------------------------------------------------------------------------------------------------ golden vectors
 def test_validate_scene_xml_dry_run(cp, tmp_path):
     """cudapath_validate_scene_xml: the scene loader without a GPU -- lists what a file would create, names what is unsupported."""
