@@ -364,6 +364,34 @@ int orc_segment_record_batch(void *sp, int shape, uint64_t n, const uint32_t *iv
     return 0;
     ORC_CATCH
 }
+// TriAccel::load + rayIntersect and AABB::rayIntersect on flat tuples (pinning against the reference text)
+int orc_triaccel_batch(uint64_t n, const float *A, const float *B, const float *C, const float *o, const float *d, const float *mint, const float *maxt,
+                       float *outAccel, int32_t *outHit, float *outTUV) {
+    ORC_TRY
+    for (uint64_t i = 0; i < n; ++i) {
+        TriAccel acc;
+        acc.load(V3(A[3 * i], A[3 * i + 1], A[3 * i + 2]), V3(B[3 * i], B[3 * i + 1], B[3 * i + 2]), V3(C[3 * i], C[3 * i + 1], C[3 * i + 2]));
+        const float vals[10] = {(float) acc.k, acc.n_u, acc.n_v, acc.n_d, acc.a_u, acc.a_v, acc.b_nu, acc.b_nv, acc.c_nu, acc.c_nv};
+        for (int k = 0; k < 10; ++k) outAccel[10 * i + k] = acc.k == 3 && k > 0 ? 0.0f : vals[k];
+        float u = 0, v = 0, t = 0;
+        const bool hit = acc.rayIntersect(V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), mint[i], maxt[i], u, v, t);
+        outHit[i] = hit ? 1 : 0; outTUV[3 * i] = hit ? t : 0; outTUV[3 * i + 1] = hit ? u : 0; outTUV[3 * i + 2] = hit ? v : 0;
+    }
+    return 0;
+    ORC_CATCH
+}
+int orc_aabb_ray_batch(uint64_t n, const float *bmin, const float *bmax, const float *o, const float *d, int32_t *outHit, float *outNearFar) {
+    ORC_TRY
+    for (uint64_t i = 0; i < n; ++i) {
+        AABB b; b.mn = V3(bmin[3 * i], bmin[3 * i + 1], bmin[3 * i + 2]); b.mx = V3(bmax[3 * i], bmax[3 * i + 1], bmax[3 * i + 2]);
+        Ray r(V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), 0.0f, kInf);
+        float nearT = 0, farT = 0;
+        const bool hit = b.rayIntersect(r.o, r.d, r.dRcp, nearT, farT);
+        outHit[i] = hit ? 1 : 0; outNearFar[2 * i] = hit ? nearT : 0; outNearFar[2 * i + 1] = hit ? farT : 0;
+    }
+    return 0;
+    ORC_CATCH
+}
 // closest hit + intersection record: outRec = p(3) n(3) s(3) t(3) wi(3) per ray
 int orc_intersect_full_batch(void *sp, uint64_t n, const float *o, const float *d, const float *mint, const float *maxt,
                              int32_t *outShape, uint32_t *outPrim, float *outT, float *outRec) {

@@ -7,6 +7,8 @@
 //   ref_hair_aabb.inc        src/shapes/hair.cpp:368-397   getAABB(index): the segment bounds
 //   ref_hair_record.inc      src/shapes/hair.cpp:825-862   HairShape::fillIntersectionRecord
 //   ref_quadratic.inc        src/libcore/util.cpp:487-525  solveQuadraticDouble
+//   ref_triaccel.inc         include/mitsuba/render/triaccel.h:37-158  struct TriAccel, load, rayIntersect (Wald's projection test)
+//   ref_aabb_ray.inc         include/mitsuba/core/aabb.h:308-338       TAABB::rayIntersect (the slab test that clips rays to the kd-tree boxes)
 // (HairKDTree itself derives from the generic kd-tree templates of gkdtree.h / sahkdtree3.h, which need the scheduler and boost and cannot be
 // compiled here; the kd-tree is not reproduced by the product anyway.)  Output: oracle/_ref/libref_geom.so.
 #include "mitsuba_shim.h"
@@ -33,8 +35,14 @@ inline Vector toFloat(const Vector3d &v) { return Vector((Float) v.x, (Float) v.
 // `Point(rayO + rayD * nearT)` (hair.cpp:524,530): the explicit double -> float conversion of TPoint3
 struct PointFromDouble : public Vector { explicit PointFromDouble(const Vector3d &v) : Vector((Float) v.x, (Float) v.y, (Float) v.z) {} };
 
-struct Ray { Point o; Vector d; Float mint = 0, maxt = 0, time = 0; };
-struct AABB { Point min, max; AABB() : min(std::numeric_limits<Float>::infinity()), max(-std::numeric_limits<Float>::infinity()) {} };
+struct Ray { Point o; Vector d, dRcp; Float mint = 0, maxt = 0, time = 0; };
+#define FINLINE inline
+#define MM_ALIGN16
+struct PointDim { static const int dim = 3; };
+struct AABB { Point min, max; AABB() : min(std::numeric_limits<Float>::infinity()), max(-std::numeric_limits<Float>::infinity()) {}
+    typedef Ray RayType; typedef PointDim PointType;
+#include "ref_aabb_ray.inc"
+};
 inline bool operator!=(const Vector &a, const Vector &b) { return a.x != b.x || a.y != b.y || a.z != b.z; }
 
 struct GeoFrame { Vector s, t, n; Vector toLocal(const Vector &v) const { return Vector(dot(v, s), dot(v, t), dot(v, n)); } };   // frame.h:71-77
@@ -42,6 +50,7 @@ struct HairShape;
 struct GeoIntersection { Point p; GeoFrame geoFrame, shFrame; Point2 uv; Vector dpdu, dpdv; const HairShape *shape = nullptr, *instance = nullptr; bool hasUVPartials = false; Float time = 0; };
 
 #include "ref_quadratic.inc"
+#include "ref_triaccel.inc"
 #include "ref_fresnel.inc"           // coordinateSystem (util.cpp:592-601), used by intersectCylPlane; fresnelDielectricExt comes along unused
 
 class HairKDTree {
@@ -102,6 +111,31 @@ void ref_hair_segment_bounds(void *h, float *out) {
     for (size_t i = 0; i < k->m_segIndex.size(); ++i) {
         const AABB b = k->getAABB((HairKDTree::IndexType) i);
         out[6 * i] = b.min.x; out[6 * i + 1] = b.min.y; out[6 * i + 2] = b.min.z; out[6 * i + 3] = b.max.x; out[6 * i + 4] = b.max.y; out[6 * i + 5] = b.max.z;
+    }
+}
+// TriAccel::load + rayIntersect for n (triangle, ray, interval) tuples; outAccel = k, n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv (k as float)
+void ref_triaccel(int n, const float *A, const float *B, const float *C, const float *o, const float *d, const float *mint, const float *maxt,
+                  float *outAccel, int *outHit, float *outTUV) {
+    for (int i = 0; i < n; ++i) {
+        TriAccel acc;
+        acc.load(Vector(A[3 * i], A[3 * i + 1], A[3 * i + 2]), Vector(B[3 * i], B[3 * i + 1], B[3 * i + 2]), Vector(C[3 * i], C[3 * i + 1], C[3 * i + 2]));
+        const float vals[10] = {(float) acc.k, acc.n_u, acc.n_v, acc.n_d, acc.a_u, acc.a_v, acc.b_nu, acc.b_nv, acc.c_nu, acc.c_nv};
+        for (int k = 0; k < 10; ++k) outAccel[10 * i + k] = acc.k == 3 && k > 0 ? 0.0f : vals[k];
+        Ray r; r.o = Vector(o[3 * i], o[3 * i + 1], o[3 * i + 2]); r.d = Vector(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        Float u = 0, v = 0, t = 0;
+        const bool hit = acc.rayIntersect(r, mint[i], maxt[i], u, v, t);
+        outHit[i] = hit ? 1 : 0; outTUV[3 * i] = hit ? t : 0; outTUV[3 * i + 1] = hit ? u : 0; outTUV[3 * i + 2] = hit ? v : 0;
+    }
+}
+// TAABB::rayIntersect for n (box, ray) pairs
+void ref_aabb_ray(int n, const float *bmin, const float *bmax, const float *o, const float *d, int *outHit, float *outNearFar) {
+    for (int i = 0; i < n; ++i) {
+        AABB b; b.min = Vector(bmin[3 * i], bmin[3 * i + 1], bmin[3 * i + 2]); b.max = Vector(bmax[3 * i], bmax[3 * i + 1], bmax[3 * i + 2]);
+        Ray r; r.o = Vector(o[3 * i], o[3 * i + 1], o[3 * i + 2]); r.d = Vector(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        r.dRcp = Vector(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);                                       // ray.h:72-93 (setDirection)
+        Float nearT = 0, farT = 0;
+        const bool hit = b.rayIntersect(r, nearT, farT);
+        outHit[i] = hit ? 1 : 0; outNearFar[2 * i] = hit ? nearT : 0; outNearFar[2 * i + 1] = hit ? farT : 0;
     }
 }
 // HairShape::fillIntersectionRecord for n (segment, stored hit point) pairs: out = p(3) n(3) s(3) t(3)

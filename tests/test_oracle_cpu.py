@@ -968,6 +968,43 @@ def test_oracle_hair_geometry_pinned_against_reference_text(cp, oracle):
         assert np.array_equal(rr, orr)
 
 
+@pytest.mark.skipif(not os.path.exists(REF_GEOM), reason='oracle/_ref/libref_geom.so not built (needs /root/reference)')
+def test_oracle_triangle_and_box_tests_pinned_against_reference_text(oracle):
+    """TriAccel::load / rayIntersect (include/mitsuba/render/triaccel.h:37-158) and TAABB::rayIntersect (include/mitsuba/core/aabb.h:308-338),
+    cut out of the reference headers and executed as written, against the oracle: bit-identical, degenerate triangles, axis-parallel rays and
+    rays starting inside the box included."""
+    L = ctypes.CDLL(REF_GEOM); O = oracle.lib()
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rng = np.random.default_rng(59)
+    n = 300000
+    A = rng.normal(size=(n, 3)).astype(np.float32); B = (A + rng.normal(size=(n, 3)) * 0.5).astype(np.float32); C = (A + rng.normal(size=(n, 3)) * 0.5).astype(np.float32)
+    C[:100] = B[:100]; C[100:200] = A[100:200] + 2 * (B[100:200] - A[100:200])                       # degenerate: zero area / collinear
+    target = (A + (B - A) * rng.random((n, 1)) * 0.7 + (C - A) * rng.random((n, 1)) * 0.7).astype(np.float32)
+    d = sphere_dirs(rng, n); dist = (0.1 + 10 * rng.random(n)).astype(np.float32)
+    o = (target - d * dist[:, None]).astype(np.float32)
+    mint = np.where(rng.random(n) < 0.5, 0.0, 1e-4).astype(np.float32); maxt = np.where(rng.random(n) < 0.2, dist, np.inf).astype(np.float32)
+    out = []
+    for fn in (L.ref_triaccel, O.orc_triaccel_batch):
+        acc = np.zeros((n, 10), np.float32); hit = np.zeros(n, np.int32); tuv = np.zeros((n, 3), np.float32)
+        args = (P(A), P(B), P(C), P(o), P(d), P(mint), P(maxt), P(acc), P(hit), P(tuv))
+        fn(n, *args) if fn is L.ref_triaccel else fn(ctypes.c_uint64(n), *args)
+        out.append((acc, hit, tuv))
+    assert 0.2 < out[0][1].mean() < 0.9 and (out[0][0][:100, 0] == 3).all()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b, equal_nan=True)
+    bmin = rng.normal(size=(n, 3)).astype(np.float32); bmax = (bmin + rng.random((n, 3)) * 2).astype(np.float32)
+    d2 = sphere_dirs(rng, n); d2[:1000, 0] = 0; d2[1000:2000, 1] = -0.0; d2[2000:3000] = [0, 0, 1]
+    o2 = ((bmin + bmax) * 0.5 + rng.normal(size=(n, 3)) * 0.7).astype(np.float32)
+    res = []
+    for fn in (L.ref_aabb_ray, O.orc_aabb_ray_batch):
+        hit = np.zeros(n, np.int32); nf = np.zeros((n, 2), np.float32)
+        args = (P(bmin), P(bmax), P(o2), P(d2), P(hit), P(nf))
+        fn(n, *args) if fn is L.ref_aabb_ray else fn(ctypes.c_uint64(n), *args)
+        res.append((hit, nf))
+    assert 0.05 < res[0][0].mean() < 0.95
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1], equal_nan=True)
+
+
 # ------------------------------------------------------------------------------------------------ golden vectors
 def test_validate_scene_xml_dry_run(cp, tmp_path):
     """cudapath_validate_scene_xml: the scene loader without a GPU -- lists what a file would create, names what is unsupported."""
