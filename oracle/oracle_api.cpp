@@ -4,11 +4,14 @@
 // see o_*.h for the file:line citations).  Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may load this library; the product never does.
 //
-// Parity status: UNPINNED by reference tests -- the reference has no test, golden vector or fixture
-// for hair, Marschner or Kajiya-Kay and cannot be built here.  The pieces of
-// the reference that do compile standalone (GaussLegendre, InterpolatedDistribution1D, the Hosek-Wilkie
-// sky model) are compiled from /root/reference into oracle/_ref and used to pin the corresponding
-// restatements (tests/test_oracle_pinning.py).
+// Parity status: the reference has no test, golden vector or fixture for hair, Marschner or Kajiya-Kay and
+// cannot be built as a whole here, so the oracle is pinned against the reference's own source run as it is (oracle/Makefile `ref`,
+// outputs in oracle/_ref, tests in tests/test_oracle_cpu.py): all eight BSDF plugin files compiled unmodified against interface
+// scaffolding (libref_bsdf.so), the hair cylinder / miter / bounds / intersection-record code, TriAccel, the AABB slab test and the
+// libcore helpers they call executed from text cut out of the reference at build time (libref_geom.so), GaussLegendre,
+// InterpolatedDistribution1D and the Hosek-Wilkie sky model compiled directly (libref_pieces.so).  NOT pinned that way, restatement
+// only: the kd-tree interval logic, MIPathTracer::Li, the envmap emitter, the sunsky bake around the sky model, the perspective
+// sensor, ImageBlock::put and the file loaders ("Parity status").
 #include "o_math.h"
 #include "o_hair.h"
 #include "o_bsdf.h"
