@@ -204,7 +204,9 @@ bool load_hair_file(const std::string &path, float radius, float angleThresholdD
     if (!in) { err = "Could not open \"" + path + "\"!"; return false; }
     char magic[11] = {0};
     in.read(magic, 11);
-    if (in.gcount() == 11 && std::memcmp(magic, "BINARY_HAIR", 11) == 0) {
+    // the reference probes the 11-byte magic through FileStream::read, which throws on a shorter file whatever its format (fstream.cpp:317)
+    if (in.gcount() != 11) { err = "Read less data than expected (11 bytes required) from \"" + path + "\""; return false; }
+    if (std::memcmp(magic, "BINARY_HAIR", 11) == 0) {
         uint32_t count = 0;
         in.read((char *) &count, 4);
         bool newFiber = true;

@@ -260,7 +260,8 @@ static inline void loadHairFile(const std::string &path, float radius, float ang
     if (!bs) throw std::runtime_error("oracle: cannot open hair file " + path);
     char temp[11] = {0};
     bs.read(temp, 11);
-    bool binaryFormat = bs.gcount() == 11 && std::memcmp(temp, "BINARY_HAIR", 11) == 0;
+    if (bs.gcount() != 11) throw std::runtime_error("Read less data than expected (11 bytes required) from \"" + path + "\"");   // FileStream::read, fstream.cpp:317
+    bool binaryFormat = std::memcmp(temp, "BINARY_HAIR", 11) == 0;
 
     std::vector<V3> &vertices = out.verts;
     std::vector<uint8_t> &vsf = out.startsFiber;

@@ -8,6 +8,7 @@ import pytest
 
 HAIR_RGB = (0.143016, 0.0156076, 1.80928e-005)
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+REF_GEOM = os.path.join(os.path.dirname(GOLDEN), '..', 'oracle', '_ref', 'libref_geom.so')     # reference text executed as written (oracle/ref_shim/ref_geom.cpp, ref_loader.cpp)
 
 
 def sphere_dirs(rng, n):
@@ -660,6 +661,57 @@ def test_hair_loader_binary_and_ascii(cp, oracle, tmp_path):
     assert len(cp.load_hair_file(str(tmp_path / 'empty.mitshair'))[1]) == 0
 
 
+@pytest.mark.skipif(not os.path.exists(REF_GEOM), reason='oracle/_ref/libref_geom.so not built (needs /root/reference)')
+def test_hair_loaders_pinned_against_reference_constructor(cp, oracle, tmp_path):
+    """HairShape::HairShape(const Properties &) (src/shapes/hair.cpp:609-785), cut out of the reference and executed as written
+    (oracle/ref_shim/ref_loader.cpp), against the oracle's loader AND the product's host loader: binary and ASCII files, exact duplicates,
+    nearly collinear runs at several angle thresholds, comment / blank-line fiber breaks, a toWorld with rotation, scale and translation --
+    vertices, fiber flags and the scaled radius are bit-identical."""
+    L = ctypes.CDLL(REF_GEOM); L.ref_hair_load.restype = ctypes.c_void_p; L.ref_hair_load_radius.restype = ctypes.c_float
+    rng = np.random.default_rng(61)
+    xyz, st = cp.scenes.gen_curly(strands=300, segments=24)
+    xyz = xyz.copy(); st = st.copy()
+    for k in rng.integers(1, len(st) - 6, 200):               # gentle bends: merged or kept depending on the threshold
+        if not st[k:k + 5].any():
+            d = xyz[k] - xyz[k - 1]
+            for j in range(4):
+                xyz[k + j] = xyz[k + j - 1] + d * (1 + 0.01 * j) + rng.normal(size=3).astype(np.float32) * np.float32(2e-3) * np.linalg.norm(d)
+    for k in rng.integers(1, len(st) - 1, 60):
+        if not st[k]:
+            xyz[k] = xyz[k - 1]                                   # exact duplicates
+    st[rng.integers(1, len(st), 20)] = 1                         # short fibers, some of one vertex
+    b = str(tmp_path / 'h.mitshair'); a = str(tmp_path / 'h.txt')
+    cp.scenes.write_mitshair(b, xyz, st); write_ascii(a, xyz, st)
+    th = np.deg2rad(30.0); c, s_ = np.cos(th), np.sin(th)
+    tw = np.array([[1.5 * c, -1.5 * s_, 0, 0.25], [1.5 * s_, 1.5 * c, 0, -1.0], [0, 0, 1.5, 3.0], [0, 0, 0, 1]], np.float32)
+    for path in (b, a):
+        for kw in (dict(), dict(angleThreshold=0.2), dict(toWorld=tw, angleThreshold=5.0), dict(toWorld=tw, radius=0.003)):
+            radius = kw.get('radius', 0.01); ang = kw.get('angleThreshold', 1.0); m = kw.get('toWorld', np.eye(4, dtype=np.float32))
+            err = ctypes.create_string_buffer(256)
+            m32 = np.ascontiguousarray(m, np.float32)
+            h = L.ref_hair_load(path.encode(), ctypes.c_float(radius), ctypes.c_float(ang), m32.ctypes.data_as(ctypes.c_void_p), err)
+            assert h, err.value
+            h = ctypes.c_void_p(h)
+            n = L.ref_hair_load_count(h) - 1                      # the reference appends the sentinel flag, not a vertex: count = vertices
+            n = L.ref_hair_load_count(h)
+            rx = np.zeros((n, 3), np.float32); rs = np.zeros(n, np.uint8)
+            L.ref_hair_load_copy(h, rx.ctypes.data_as(ctypes.c_void_p), rs.ctypes.data_as(ctypes.c_void_p))
+            rr = float(L.ref_hair_load_radius(h))
+            args = dict(radius=radius, angleThreshold=ang); args.update({k: v for k, v in kw.items() if k == 'toWorld'})
+            for loader in (cp.load_hair_file, oracle.load_hair_file):
+                px, ps, pr = loader(path, **args)[:3]
+                assert np.array_equal(px, rx) and np.array_equal(ps, rs) and np.float32(pr) == np.float32(rr)
+            assert 0 < n < len(st)
+    # a file shorter than the 11-byte magic: the reference's FileStream throws, so do both loaders
+    tiny = str(tmp_path / 'tiny.txt'); open(tiny, 'w').write('0 0 0\n')
+    err = ctypes.create_string_buffer(256)
+    assert not L.ref_hair_load(tiny.encode(), ctypes.c_float(0.01), ctypes.c_float(1.0), np.eye(4, dtype=np.float32).ctypes.data_as(ctypes.c_void_p), err)
+    with pytest.raises(cp.CudapathError, match='11 bytes'):
+        cp.load_hair_file(tiny)
+    with pytest.raises(RuntimeError, match='11 bytes'):
+        oracle.load_hair_file(tiny)
+
+
 def test_develop(cp):
     film = np.zeros((2, 3, 5), np.float32)
     film[0, 0] = (2, 4, 6, 2, 2); film[1, 2] = (1, 1, 1, 0.5, 0.5)
@@ -918,7 +970,6 @@ def test_oracle_mesh_and_next_row_bsdfs_pinned_against_compiled_reference_plugin
         assert np.array_equal(rwt[ok], owt[ok]) and np.allclose(rpdf[ok], opdf[ok], rtol=2e-6, atol=1e-6) and np.abs(rwo[ok] - owo[ok]).max() < 1e-5      # sincosf vs correctly rounded
 
 
-REF_GEOM = os.path.join(os.path.dirname(GOLDEN), '..', 'oracle', '_ref', 'libref_geom.so')
 
 
 @pytest.mark.skipif(not os.path.exists(REF_GEOM), reason='oracle/_ref/libref_geom.so not built (needs /root/reference)')
