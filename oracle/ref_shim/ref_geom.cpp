@@ -9,6 +9,11 @@
 //   ref_quadratic.inc        src/libcore/util.cpp:487-525  solveQuadraticDouble
 //   ref_triaccel.inc         include/mitsuba/render/triaccel.h:37-158  struct TriAccel, load, rayIntersect (Wald's projection test)
 //   ref_aabb_ray.inc         include/mitsuba/core/aabb.h:308-338       TAABB::rayIntersect (the slab test that clips rays to the kd-tree boxes)
+//   ref_hair_rayintersect.inc  src/shapes/hair.cpp:199-237     HairKDTree::rayIntersect (closest / visibility): the per-shape clip of the interval
+//   ref_skd_rayintersect.inc   src/librender/skdtree.cpp:112-142,207-226  ShapeKDTree::rayIntersect (closest / shadow): scene clip + adaptive epsilon
+//   ref_kd_enlarge.inc         include/mitsuba/render/gkdtree.h:1219-1220  the two lines that enlarge a finished kd-tree's box
+// In these, the Havran traversal itself (rayIntersectHavran) is replaced by a scan over all primitives that updates maxt on every accepted
+// hit exactly like the leaf loop of sahkdtree3.h:262-290 -- same answers up to the visiting order of equal-t hits.
 // (HairKDTree itself derives from the generic kd-tree templates of gkdtree.h / sahkdtree3.h, which need the scheduler and boost and cannot be
 // compiled here; the kd-tree is not reproduced by the product anyway.)  Output: oracle/_ref/libref_geom.so.
 #include "mitsuba_shim.h"
@@ -70,6 +75,21 @@ public:
 #include "ref_hair_aabb.inc"
 #include "ref_hair_intersect.inc"
 #undef Point
+    AABB m_aabb;                                                    // enlarged box of the finished tree (getAABB() of gkdtree.h)
+    const AABB &getAABB() const { return m_aabb; }
+    // stand-in for the kd traversal: all segments in index order, maxt shrinks on every accepted hit (sahkdtree3.h:262-290)
+    template <bool shadowRay> bool rayIntersectHavran(const Ray &ray, Float mint, Float maxt, Float &t, void *temp) const {
+        bool found = false;
+        for (IndexType iv : m_segIndex) {
+            Float primT;
+            if (intersect(ray, iv, mint, maxt, primT, temp)) {
+                if (shadowRay) return true;
+                maxt = t = primT; found = true;
+            }
+        }
+        return found;
+    }
+#include "ref_hair_rayintersect.inc"
 };
 
 #define Intersection GeoIntersection
@@ -78,6 +98,45 @@ struct HairShape {
     void fillIntersectionRecord(const Ray &ray, const void *temp, Intersection &its) const;
 };
 #include "ref_hair_record.inc"
+#undef Intersection
+
+// gkdtree.h:50 and :1219-1220 (KDTreeBase::buildInternal): what getAABB() of a finished tree returns
+#define MTS_KD_AABB_EPSILON 1e-3f
+inline void enlargeKDBox(AABB &aabb) {
+    typedef Vector VectorType;
+    const Float eps = MTS_KD_AABB_EPSILON;
+#include "ref_kd_enlarge.inc"
+}
+
+#define MTS_KD_INTERSECTION_TEMP 64
+struct SceneIntersection { Float t = 0; int shapeIndex = -1; uint32_t iv = 0; };
+static long raysTraced = 0, shadowRaysTraced = 0;
+#define Intersection SceneIntersection
+class ShapeKDTree {
+public:
+    AABB m_aabb; std::vector<HairKDTree *> m_shapes;
+    bool rayIntersect(const Ray &ray, Intersection &its) const;
+    bool rayIntersect(const Ray &ray) const;
+    // stand-in for the kd traversal of the scene-level tree: one primitive per hair shape (skdtree.cpp:60-62), tested through
+    // ShapeKDTree::intersect -> Shape::rayIntersect (skdtree.h:271-278, hair.cpp:816-823)
+    template <bool shadowRay> bool rayIntersectHavran(const Ray &ray, Float mint, Float maxt, Float &t, void *temp) const {
+        bool found = false;
+        for (size_t i = 0; i < m_shapes.size(); ++i) {
+            Float primT;
+            HairKDTree::IntersectionStorage st;
+            if (shadowRay ? m_shapes[i]->rayIntersect(ray, mint, maxt) : m_shapes[i]->rayIntersect(ray, mint, maxt, primT, &st)) {
+                if (shadowRay) return true;
+                maxt = t = primT; found = true;
+                SceneIntersection *rec = (SceneIntersection *) temp; rec->shapeIndex = (int) i; rec->iv = st.iv;
+            }
+        }
+        return found;
+    }
+    template <bool bary> void fillIntersectionRecord(const Ray &, const void *temp, Intersection &its) const {
+        const SceneIntersection *rec = (const SceneIntersection *) temp; its.shapeIndex = rec->shapeIndex; its.iv = rec->iv;
+    }
+};
+#include "ref_skd_rayintersect.inc"
 #undef Intersection
 } // namespace mitsuba
 
@@ -111,6 +170,37 @@ void ref_hair_segment_bounds(void *h, float *out) {
     for (size_t i = 0; i < k->m_segIndex.size(); ++i) {
         const AABB b = k->getAABB((HairKDTree::IndexType) i);
         out[6 * i] = b.min.x; out[6 * i + 1] = b.min.y; out[6 * i + 2] = b.min.z; out[6 * i + 3] = b.max.x; out[6 * i + 4] = b.max.y; out[6 * i + 5] = b.max.z;
+    }
+}
+// Scene of several hair shapes: per-shape boxes = union of getAABB(index), enlarged; scene box = their union, enlarged again
+void *ref_scene_create(int nShapes, void **shapes) {
+    ShapeKDTree *sc = new ShapeKDTree();
+    for (int i = 0; i < nShapes; ++i) {
+        HairKDTree *k = (HairKDTree *) shapes[i];
+        AABB box;
+        for (size_t j = 0; j < k->m_segIndex.size(); ++j) {
+            const AABB b = k->getAABB((HairKDTree::IndexType) j);
+            for (int a = 0; a < 3; ++a) { box.min[a] = std::min(box.min[a], b.min[a]); box.max[a] = std::max(box.max[a], b.max[a]); }
+        }
+        enlargeKDBox(box);
+        k->m_aabb = box;
+        for (int a = 0; a < 3; ++a) { sc->m_aabb.min[a] = std::min(sc->m_aabb.min[a], box.min[a]); sc->m_aabb.max[a] = std::max(sc->m_aabb.max[a], box.max[a]); }
+        sc->m_shapes.push_back(k);
+    }
+    enlargeKDBox(sc->m_aabb);
+    return sc;
+}
+void ref_scene_bounds(void *h, float *out6) { const ShapeKDTree *sc = (const ShapeKDTree *) h; for (int a = 0; a < 3; ++a) { out6[a] = sc->m_aabb.min[a]; out6[3 + a] = sc->m_aabb.max[a]; } }
+// ShapeKDTree::rayIntersect (closest: shape, segment, t) and the shadow-ray overload for n rays
+void ref_scene_intersect(void *h, int n, const float *o, const float *d, const float *mint, const float *maxt, int *outShape, uint32_t *outIv, float *outT, int *outOccluded) {
+    const ShapeKDTree *sc = (const ShapeKDTree *) h;
+    for (int i = 0; i < n; ++i) {
+        Ray r; r.o = Vector(o[3 * i], o[3 * i + 1], o[3 * i + 2]); r.d = Vector(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        r.dRcp = Vector(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z); r.mint = mint[i]; r.maxt = maxt[i];
+        SceneIntersection its;
+        const bool hit = sc->rayIntersect(r, its);
+        outShape[i] = hit ? its.shapeIndex : -1; outIv[i] = hit ? its.iv : 0xffffffffu; outT[i] = hit ? its.t : std::numeric_limits<float>::infinity();
+        outOccluded[i] = sc->rayIntersect(r) ? 1 : 0;
     }
 }
 // TriAccel::load + rayIntersect for n (triangle, ray, interval) tuples; outAccel = k, n_u, n_v, n_d, a_u, a_v, b_nu, b_nv, c_nu, c_nv (k as float)

@@ -1056,6 +1056,53 @@ def test_oracle_triangle_and_box_tests_pinned_against_reference_text(oracle):
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1], equal_nan=True)
 
 
+@pytest.mark.skipif(not os.path.exists(REF_GEOM), reason='oracle/_ref/libref_geom.so not built (needs /root/reference)')
+def test_oracle_scene_query_pinned_against_reference_text(cp, oracle):
+    """The two-level ray query as the reference writes it -- ShapeKDTree::rayIntersect closest / shadow (skdtree.cpp:112-142,207-226: scene box
+    clip, adaptive epsilon only when ray.mint == Epsilon, the shadow overload without the inner clamp), HairKDTree::rayIntersect closest /
+    visibility (hair.cpp:199-237: per-shape clip) and the kd-tree box enlargement (gkdtree.h:1219-1220) -- cut out of the reference and executed
+    as written, with the Havran traversal replaced by a scan over all primitives (same answers up to the order of equal-t hits), against the
+    oracle's brute-force query on a four-shape scene: scene bounds, closest shape / segment / t and occlusion are bit-identical."""
+    L = ctypes.CDLL(REF_GEOM); L.ref_hair_create.restype = ctypes.c_void_p; L.ref_scene_create.restype = ctypes.c_void_p
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rng = np.random.default_rng(67)
+    sc = cp.scenes.SCENES['hair-curl']
+    s = oracle.Scene(); b = s.add_bsdf('kajiyakay')
+    handles = []; keep = []
+    for sh in sc['shapes']:
+        xyz, starts = cp.scenes.generate(sh, 0.0015)
+        xyz = np.ascontiguousarray(xyz, np.float32); starts = np.ascontiguousarray(starts, np.uint8); keep += [xyz, starts]
+        handles.append(L.ref_hair_create(P(xyz), P(starts), len(starts), ctypes.c_float(sh['radius'])))
+        s.add_hair(xyz, starts, sh['radius'], b)
+    s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=16, height=16); s.build()
+    arr = (ctypes.c_void_p * len(handles))(*handles)
+    scene = ctypes.c_void_p(L.ref_scene_create(len(handles), arr))
+    rb = np.zeros(6, np.float32); L.ref_scene_bounds(scene, P(rb))
+    ob, _ = s.scene_bounds()
+    assert np.array_equal(rb, ob)
+    n = 40000
+    allv = np.concatenate(keep[0::2])
+    centre = allv.mean(axis=0); rad = float(np.linalg.norm(allv - centre, axis=1).max())
+    # a third from outside (mint 0), a third from fiber surfaces with mint == Epsilon (adaptive epsilon), a third with a finite maxt
+    tgt = allv[rng.integers(0, len(allv), n)] + (rng.normal(size=(n, 3)) * 0.0006).astype(np.float32)
+    d = sphere_dirs(rng, n)
+    kind = rng.integers(0, 3, n)
+    dist = np.where(kind == 0, 2.5 * rad, rng.random(n) * 0.05 * rad).astype(np.float32)
+    o = (tgt - d * dist[:, None]).astype(np.float32)
+    mint = np.where(kind == 0, 0.0, np.float32(1e-4)).astype(np.float32)
+    maxt = np.where(kind == 2, (dist * (0.5 + rng.random(n))).astype(np.float32), np.inf).astype(np.float32)
+    o[:50] = rb[:3]; o[50:100, 1] = rb[4]                                   # origins on the corner / a face of the scene box
+    rsh = np.zeros(n, np.int32); riv = np.zeros(n, np.uint32); rt = np.zeros(n, np.float32); rocc = np.zeros(n, np.int32)
+    L.ref_scene_intersect(scene, n, P(o), P(d), P(mint), P(maxt), P(rsh), P(riv), P(rt), P(rocc))
+    osh, oiv, ot = s.intersect(o, d, mint, maxt, mode=2)
+    oany = s.intersect(o, d, mint, maxt, mode=3)[0] >= 0
+    assert 0.3 < (rsh >= 0).mean() < 0.99 and len(set(rsh[rsh >= 0].tolist())) == 4
+    assert np.array_equal(rocc != 0, oany)
+    assert np.array_equal(rsh, osh) and np.array_equal(rt, ot)
+    same = riv == oiv
+    assert same.mean() > 0.999 and np.array_equal(rt[~same], ot[~same])      # equal t, other segment of a miter joint: visiting order
+
+
 # ------------------------------------------------------------------------------------------------ golden vectors
 def test_validate_scene_xml_dry_run(cp, tmp_path):
     """cudapath_validate_scene_xml: the scene loader without a GPU -- lists what a file would create, names what is unsupported."""
