@@ -488,6 +488,104 @@ int orc_render_samples(void *sp, uint64_t n, const uint32_t *xy, const uint32_t 
     ORC_CATCH
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// The reference's own MIPathTracer::Li (src/integrators/path/path.cpp compiled unmodified into oracle/_ref/libref_path.so) run on THIS
+// scene: geometry, BSDFs, emitter and random numbers are supplied through the callback table of ref_shim/ref_path_callbacks.h, so the
+// outcome isolates the integrator logic.  Same camera rays and Philox counters as renderSample(); compared with orc_render_samples().
+#include "ref_shim/ref_path_callbacks.h"
+namespace {
+struct LiBridge { Scene *s; uint32_t pix, samp, k0, k1; };
+int br_rayIntersect(void *u, const float o[3], const float d[3], float mint, float maxt, RefPathIts *out) {
+    LiBridge *b = (LiBridge *) u;
+    Ray r(V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), mint, maxt);
+    Intersection its;
+    b->s->geo.rayIntersect(r, its);
+    out->valid = its.valid ? 1 : 0;
+    if (!its.valid) return 0;
+    out->t = its.t;
+    const V3 vs[6] = {its.p, its.geoFrame.n, its.shFrame.s, its.shFrame.t, its.shFrame.n, its.wi};
+    float *dst[6] = {out->p, out->geoN, out->shS, out->shT, out->shN, out->wi};
+    for (int k = 0; k < 6; ++k) { dst[k][0] = vs[k].x; dst[k][1] = vs[k].y; dst[k][2] = vs[k].z; }
+    out->bsdf = b->s->geo.shapes[its.shape].bsdf;
+    return 1;
+}
+void br_sampleEmitterDirect(void *u, const float ref[3], float sx, float sy, float value[3], float d[3], float *pdf) {
+    LiBridge *b = (LiBridge *) u;
+    value[0] = value[1] = value[2] = 0; d[0] = d[1] = d[2] = 0; *pdf = 0;
+    if (!b->s->hasEnv) return;
+    const V3 p(ref[0], ref[1], ref[2]);
+    EnvMap::DirectSample ds = b->s->env.sampleDirect(p, sx, sy);          // emitter->sampleDirect, then the visibility test of scene.cpp:838-849
+    d[0] = ds.d.x; d[1] = ds.d.y; d[2] = ds.d.z; *pdf = ds.pdf;
+    if (ds.pdf != 0) {
+        Ray shadow(p, ds.d, kEpsilon, ds.dist * (1 - kShadowEpsilon));
+        if (!b->s->geo.rayOccluded(shadow)) { value[0] = ds.value.x; value[1] = ds.value.y; value[2] = ds.value.z; }
+    }
+}
+void br_evalEnvironment(void *u, const float d[3], int hasDiff, const float rx[3], const float ry[3], float value[3]) {
+    LiBridge *b = (LiBridge *) u;
+    const V3 v = b->s->env.evalEnvironment(V3(d[0], d[1], d[2]), hasDiff != 0, V3(rx[0], rx[1], rx[2]), V3(ry[0], ry[1], ry[2]));
+    value[0] = v.x; value[1] = v.y; value[2] = v.z;
+}
+int br_hasEnvironment(void *u) { return ((LiBridge *) u)->s->hasEnv ? 1 : 0; }
+int br_fillDirect(void *u, const float o[3], const float d[3]) { return ((LiBridge *) u)->s->env.fillDirectSamplingRecord(V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2])) ? 1 : 0; }
+float br_pdfEmitterDirect(void *u, const float d[3]) { return ((LiBridge *) u)->s->env.pdfDirect(V3(d[0], d[1], d[2])); }
+unsigned br_bsdfType(void *u, int id) {
+    const BSDFAny &m = ((LiBridge *) u)->s->bsdfs[id];
+    return m.kind == 5 ? (ENull | EDeltaReflection) : m.kind == 6 ? (ENull | EDeltaReflection | EDiffuseReflection) : (EDiffuseReflection | EGlossyReflection);
+}
+void br_bsdfEval(void *u, int id, const float wi[3], const float wo[3], float out[3]) {
+    const V3 v = ((LiBridge *) u)->s->bsdfs[id].eval(V3(wi[0], wi[1], wi[2]), V3(wo[0], wo[1], wo[2]));
+    out[0] = v.x; out[1] = v.y; out[2] = v.z;
+}
+float br_bsdfPdf(void *u, int id, const float wi[3], const float wo[3]) { return ((LiBridge *) u)->s->bsdfs[id].pdf(V3(wi[0], wi[1], wi[2]), V3(wo[0], wo[1], wo[2])); }
+void br_bsdfSample(void *u, int id, int depth, const float wi[3], float sx, float sy, float wo[3], float weight[3], float *pdf, unsigned *type, float *eta) {
+    LiBridge *b = (LiBridge *) u;
+    const BSDFAny &m = b->s->bsdfs[id];
+    float extra[4] = {0, 0, 0, 0};
+    if (m.drawsExtra()) { Philox4 ue = philox4x32_10(b->pix, b->samp, (uint32_t) depth, 2, b->k0, b->k1); for (int k = 0; k < 4; ++k) extra[k] = u32_to_unit(ue.v[k]); }
+    const BSDFSample bs = m.sample(V3(wi[0], wi[1], wi[2]), sx, sy, extra);
+    wo[0] = bs.wo.x; wo[1] = bs.wo.y; wo[2] = bs.wo.z; weight[0] = bs.weight.x; weight[1] = bs.weight.y; weight[2] = bs.weight.z;
+    *pdf = bs.pdf; *type = (unsigned) bs.sampledType; *eta = bs.eta;
+}
+void br_next2D(void *u, int depth, int which, float out[2]) {
+    LiBridge *b = (LiBridge *) u;
+    const Philox4 v = philox4x32_10(b->pix, b->samp, (uint32_t) depth, 0, b->k0, b->k1);
+    out[0] = u32_to_unit(v.v[which ? 2 : 0]); out[1] = u32_to_unit(v.v[which ? 3 : 1]);
+}
+float br_next1D(void *u, int depth) { LiBridge *b = (LiBridge *) u; return u32_to_unit(philox4x32_10(b->pix, b->samp, (uint32_t) depth, 1, b->k0, b->k1).v[0]); }
+}
+
+int orc_render_samples_ref_li(void *sp, const char *refPathLib, uint64_t n, const uint32_t *xy, const uint32_t *samp, uint32_t spp, uint64_t seed,
+                              float *outLi, float *outAlpha, int32_t *outDepth) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    s->seed = seed;
+    void *lib = dlopen(refPathLib, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) throw std::runtime_error(std::string("cannot load ") + refPathLib + ": " + dlerror());
+    typedef int (*LiFn)(const RefPathCallbacks *, int, int, int, int, int, const float *, const float *, float, float, const float *, const float *, float *, float *);
+    LiFn li = (LiFn) dlsym(lib, "ref_path_li");
+    if (!li) throw std::runtime_error("ref_path_li not found");
+    const uint32_t k0 = (uint32_t) seed, k1 = (uint32_t) (seed >> 32);
+    for (uint64_t i = 0; i < n; ++i) {
+        LiBridge b{s, xy[2 * i + 1] * (uint32_t) s->cam.filmW + xy[2 * i], samp[i], k0, k1};
+        RefPathCallbacks cb{&b, br_rayIntersect, br_sampleEmitterDirect, br_evalEnvironment, br_hasEnvironment, br_fillDirect, br_pdfEmitterDirect,
+                            br_bsdfType, br_bsdfEval, br_bsdfPdf, br_bsdfSample, br_next2D, br_next1D};
+        // the camera ray exactly as Scene::renderSample() makes it (integrator.cpp:140-188)
+        const Philox4 u = philox4x32_10(b.pix, b.samp, 0, 0, k0, k1);
+        const float px = (float) xy[2 * i] + u32_to_unit(u.v[0]), py = (float) xy[2 * i + 1] + u32_to_unit(u.v[1]);
+        Ray ray; V3 rx, ry;
+        s->cam.sampleRayDifferential(px, py, ray, rx, ry);
+        const float ds = 1.0f / std::sqrt((float) spp);
+        rx = ray.d + (rx - ray.d) * ds; ry = ray.d + (ry - ray.d) * ds;
+        float L[3], alpha = 0;
+        const float o[3] = {ray.o.x, ray.o.y, ray.o.z}, d[3] = {ray.d.x, ray.d.y, ray.d.z}, rxa[3] = {rx.x, rx.y, rx.z}, rya[3] = {ry.x, ry.y, ry.z};
+        outDepth[i] = li(&cb, s->maxDepth, s->rrDepth, s->strictNormals ? 1 : 0, s->hideEmitters ? 1 : 0, s->filmHasAlpha ? 1 : 0, o, d, ray.mint, ray.maxt, rxa, rya, L, &alpha);
+        outLi[3 * i] = L[0]; outLi[3 * i + 1] = L[1]; outLi[3 * i + 2] = L[2]; outAlpha[i] = alpha;
+    }
+    return 0;
+    ORC_CATCH
+}
+
 // Film splat of explicit samples (F1 parity hook): pos(2), value(3), alpha per sample -> film
 int orc_splat_batch(void *sp, uint64_t n, const float *pos, const float *rgb, const float *alpha, float *outFilm) {
     Scene *s = (Scene *) sp;

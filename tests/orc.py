@@ -9,6 +9,7 @@ ORACLE_DIR = os.path.join(REPO, 'oracle')
 ORACLE_LIB = os.path.join(ORACLE_DIR, 'liboracle.so')
 REF_LIB = os.path.join(ORACLE_DIR, '_ref', 'libref_pieces.so')
 DATA_DIR = os.path.join(REPO, 'refdata')
+REF_PATH_LIB = os.path.join(REPO, 'oracle', '_ref', 'libref_path.so')
 
 _lib = None
 
@@ -261,6 +262,13 @@ class Scene:
         li = np.zeros((n, 3), np.float32); pos = np.zeros((n, 2), np.float32)
         check(self.L.orc_render_samples(self.h, ctypes.c_uint64(n), p(xy), p(samp), ctypes.c_uint32(spp), ctypes.c_uint64(seed), p(li), p(pos)))
         return li, pos
+
+    def render_samples_ref_li(self, xy, samp, spp, seed=0):
+        """The reference's own MIPathTracer::Li (path.cpp compiled unmodified, oracle/_ref/libref_path.so) on this scene's components."""
+        xy = np.ascontiguousarray(xy, dtype=np.uint32).reshape(-1, 2); samp = np.ascontiguousarray(samp, dtype=np.uint32); n = len(samp)
+        li = np.zeros((n, 3), np.float32); alpha = np.zeros(n, np.float32); depth = np.zeros(n, np.int32)
+        check(self.L.orc_render_samples_ref_li(self.h, REF_PATH_LIB.encode(), ctypes.c_uint64(n), p(xy), p(samp), ctypes.c_uint32(spp), ctypes.c_uint64(seed), p(li), p(alpha), p(depth)))
+        return li, alpha, depth
 
     def splat(self, pos, rgb, alpha):
         pos = f32(pos).reshape(-1, 2); rgb = f32(rgb).reshape(-1, 3); alpha = f32(alpha).reshape(-1); n = len(pos)

@@ -1103,6 +1103,32 @@ def test_oracle_scene_query_pinned_against_reference_text(cp, oracle):
     assert same.mean() > 0.999 and np.array_equal(rt[~same], ot[~same])      # equal t, other segment of a miter joint: visiting order
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(GOLDEN), '..', 'oracle', '_ref', 'libref_path.so')), reason='oracle/_ref/libref_path.so not built (needs /root/reference)')
+@pytest.mark.parametrize('name,variant', [('straight-hair', {}), ('curly-hair', {}), ('hair-on-head', {}), ('straight-hair-default', {}),
+                                          ('straight-hair-thindielectric', dict(maxDepth=24)), ('straight-hair-dielectric', dict(maxDepth=24, hideEmitters=True)),
+                                          ('curly-hair', dict(fixed=True)), ('straight-hair', dict(maxDepth=-1, strictNormals=False, hideEmitters=True, rrDepth=2)),
+                                          ('furball', dict(maxDepth=2))])
+def test_oracle_li_pinned_against_compiled_reference_integrator(cp, oracle, name, variant):
+    """MIPathTracer::Li: src/integrators/path/path.cpp compiled UNMODIFIED from /root/reference (oracle/_ref/libref_path.so) and run on the
+    oracle's own scene components through a callback table -- same camera rays, same Philox counters -- against the oracle's Li():
+    radiance of every path is bit-identical.  Covers emitter sampling + MIS, the ESmooth test, ENull / delta vertices and the `scattered`
+    flag with hideEmitters, strictNormals, maxDepth (finite, 2, infinite), Russian roulette from rrDepth, the extra sampler draws of the
+    fixed Marschner, fibers and meshes."""
+    ov = dict(width=40, height=32, spp=4, maxDepth=variant.get('maxDepth', 8))
+    if variant.get('fixed'):
+        sh = dict(cp.scenes.SCENES[name]['shapes'][0], bsdf=dict(type='marschner_fixed', id='hair', intIOR=1.55, extIOR=1.0)); ov['shapes'] = [sh]
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params(name))
+    sc = oracle.scene_from_description(name, scale=0.004, overrides=ov, envmap=env)
+    sc.set_integrator(maxDepth=ov['maxDepth'], rrDepth=variant.get('rrDepth', 5), strictNormals=variant.get('strictNormals', True), hideEmitters=variant.get('hideEmitters', False))
+    ys, xs, ss = np.meshgrid(np.arange(32), np.arange(40), np.arange(4), indexing='ij')
+    xy = np.stack([xs.ravel(), ys.ravel()], axis=1).astype(np.uint32); samp = ss.ravel().astype(np.uint32)
+    ours, _ = sc.render_samples(xy, samp, 4, seed=21)
+    ref, alpha, depth = sc.render_samples_ref_li(xy, samp, 4, seed=21)
+    assert np.isfinite(ref).all() and ref.sum() > 0 and depth.max() >= 2
+    assert np.array_equal(ours, ref), '%d of %d paths differ' % ((ours != ref).any(axis=1).sum(), len(ref))
+    assert (alpha == 1).all()                                                     # films without an alpha channel: EOpacity is masked out
+
+
 # ------------------------------------------------------------------------------------------------ golden vectors
 def test_validate_scene_xml_dry_run(cp, tmp_path):
     """cudapath_validate_scene_xml: the scene loader without a GPU -- lists what a file would create, names what is unsupported."""
