@@ -6,12 +6,12 @@
 //
 // Parity status: the reference has no test, golden vector or fixture for hair, Marschner or Kajiya-Kay and
 // cannot be built as a whole here, so the oracle is pinned against the reference's own source run as it is (oracle/Makefile `ref`,
-// outputs in oracle/_ref, tests in tests/test_oracle_cpu.py): all eight BSDF plugin files compiled unmodified against interface
-// scaffolding (libref_bsdf.so), the hair cylinder / miter / bounds / intersection-record code, TriAccel, the AABB slab test and the
-// libcore helpers they call executed from text cut out of the reference at build time (libref_geom.so), GaussLegendre,
-// InterpolatedDistribution1D and the Hosek-Wilkie sky model compiled directly (libref_pieces.so).  NOT pinned that way, restatement
-// only: the kd-tree interval logic, MIPathTracer::Li, the envmap emitter, the sunsky bake around the sky model, the perspective
-// sensor, ImageBlock::put and the file loaders ("Parity status").
+// outputs in oracle/_ref, tests in tests/test_oracle_cpu.py): all eight BSDF plugin files and the path integrator (path.cpp) compiled
+// unmodified against interface scaffolding (libref_bsdf.so, libref_path.so); the hair cylinder / miter / bounds / intersection-record
+// code, the two-level ray query, the hair file loader, TriAccel, the AABB slab test, the envmap emitter and the libcore helpers they
+// call executed from text cut out of the reference at build time (libref_geom.so); GaussLegendre, InterpolatedDistribution1D and the
+// Hosek-Wilkie sky model compiled directly (libref_pieces.so).  NOT pinned that way, restatement only: the sunsky bake around the sky
+// model, the perspective sensor, ImageBlock::put, the OBJ / RGBE readers and the film develop ("Parity status").
 #include "o_math.h"
 #include "o_hair.h"
 #include "o_bsdf.h"

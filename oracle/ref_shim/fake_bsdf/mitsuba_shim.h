@@ -103,7 +103,8 @@ inline Float dot(const Vector &a, const Vector &b) { return a.x * b.x + a.y * b.
 inline Float absDot(const Vector &a, const Vector &b) { return std::abs(dot(a, b)); }
 inline Vector cross(const Vector &a, const Vector &b) { return Vector(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }   // vector.h
 struct Point2 { Float x, y; Point2() : x(0), y(0) {} Point2(Float x, Float y) : x(x), y(y) {} explicit Point2(Float v) : x(v), y(v) {}
-    Float &operator[](int i) { return (&x)[i]; } Float operator[](int i) const { return (&x)[i]; } };
+    Float &operator[](int i) { return (&x)[i]; } Float operator[](int i) const { return (&x)[i]; }
+    Point2 operator+(const Point2 &p) const { return Point2(x + p.x, y + p.y); } };
 struct Vector2 { Float x, y; Vector2() : x(0), y(0) {} Vector2(Float x, Float y) : x(x), y(y) {} explicit Vector2(Float v) : x(v), y(v) {} };
 struct Size2 { size_t x, y; Size2() : x(0), y(0) {} Size2(size_t x, size_t y) : x(x), y(y) {} size_t &operator[](int i) { return (&x)[i]; } size_t operator[](int i) const { return (&x)[i]; } };
 struct Size3 { size_t x, y, z; Size3() : x(0), y(0), z(0) {} Size3(size_t x, size_t y, size_t z) : x(x), y(y), z(z) {} size_t &operator[](int i) { return (&x)[i]; } size_t operator[](int i) const { return (&x)[i]; } };
@@ -126,6 +127,8 @@ struct Spectrum {
     Spectrum() { s[0] = s[1] = s[2] = 0; }
     explicit Spectrum(Float v) { s[0] = s[1] = s[2] = v; }
     explicit Spectrum(const Float v[3]) { s[0] = v[0]; s[1] = v[1]; s[2] = v[2]; }
+    // TSpectrum(const TSpectrum<T2, N> &): component-wise conversion from another sample type, e.g. half (spectrum.h)
+    template <typename S2> explicit Spectrum(const S2 &o, typename S2::IsSpectrumType * = nullptr) { s[0] = (Float) o.s[0]; s[1] = (Float) o.s[1]; s[2] = (Float) o.s[2]; }
     void fromLinearRGB(Float r, Float g, Float b) { s[0] = r; s[1] = g; s[2] = b; }        // spectrum.h, SPECTRUM_SAMPLES == 3
     Spectrum operator-(const Spectrum &o) const { Spectrum r; for (int i = 0; i < 3; ++i) r.s[i] = s[i] - o.s[i]; return r; }
     Spectrum operator/(const Spectrum &o) const { Spectrum r; for (int i = 0; i < 3; ++i) r.s[i] = s[i] / o.s[i]; return r; }

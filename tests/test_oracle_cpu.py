@@ -1129,6 +1129,62 @@ def test_oracle_li_pinned_against_compiled_reference_integrator(cp, oracle, name
     assert (alpha == 1).all()                                                     # films without an alpha channel: EOpacity is masked out
 
 
+@pytest.mark.skipif(not os.path.exists(REF_GEOM), reason='oracle/_ref/libref_geom.so not built (needs /root/reference)')
+@pytest.mark.parametrize('which', ['sunsky', 'hdr-rotated'])
+def test_oracle_envmap_pinned_against_reference_text(cp, oracle, which):
+    """The environment-map emitter -- EnvironmentMap::configure (CDFs, row weights, normalisation), evalEnvironment, sampleDirect with
+    internalSampleDirection / sampleReuse, pdfDirect with internalPdfDirection, fillDirectSamplingRecord (src/emitters/envmap.cpp), MIPMap::evalTexel /
+    evalBilinear (mipmap.h), BSphere::rayIntersect, solveQuadratic and squareToTent -- cut out of the reference and executed as written over
+    IEEE half texels (oracle/ref_shim/ref_env.cpp), against the oracle: column CDFs bit-identical, row tables to one ulp; eval / pdf / sampled direction / value to the last
+    bits (the reference calls libm's sinf / sincosf / atan2f / acosf, the oracle rounds correctly)."""
+    L = ctypes.CDLL(REF_GEOM); L.ref_env_create.restype = ctypes.c_void_p
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rng = np.random.default_rng(71)
+    if which == 'sunsky':
+        img = cp.bake_sunsky(**cp.scenes.sunsky_params('curly-hair')); tw = np.eye(4, dtype=np.float32); scale = 1.0
+    else:
+        yy, xx = np.mgrid[0:48, 0:96]                                       # smooth sky + a bright lobe, black rows below the horizon
+        img = np.stack([2 + np.sin(xx / 9.0) * np.cos(yy / 7.0), 1.5 + np.cos(xx / 11.0), 1 + 0.5 * np.sin(yy / 5.0)], axis=2) * 3.0
+        img = (img + 400.0 * np.exp(-((xx - 62) ** 2 + (yy - 7) ** 2) / 6.0)[..., None] * [1.0, 0.9, 0.6]).astype(np.float32); img[40:] = 0
+        tw = np.array([[0, 0, 2, 0], [0, 2, 0, 0], [-2, 0, 0, 0], [0, 0, 0, 1]], np.float32); scale = 2.5                          # quarter turn, scale 2: exact inverse
+    tl = np.linalg.inv(tw.astype(np.float64)).astype(np.float32)
+    assert np.array_equal((tw.astype(np.float64) @ tl.astype(np.float64)), np.eye(4))
+    s = oracle.scene_from_description('curly-hair', scale=0.002, overrides=dict(width=16, height=16, spp=1, maxDepth=2), envmap=img)
+    s.set_envmap(img, toWorld=tw, scale=scale); s.build()
+    aabb, bs = s.scene_bounds()
+    img = np.ascontiguousarray(img, np.float32); h, w = img.shape[:2]
+    e = ctypes.c_void_p(L.ref_env_create(P(img), w, h, P(np.ascontiguousarray(tw)), P(np.ascontiguousarray(tl)), ctypes.c_float(scale), P(np.ascontiguousarray(bs[:3], np.float32)), ctypes.c_float(bs[3])))
+    rows = np.zeros(h + 1, np.float32); cols = np.zeros((h, w + 1), np.float32); rw = np.zeros(h, np.float32); nrm = ctypes.c_float(0)
+    L.ref_env_tables(e, P(rows), P(cols), P(rw), ctypes.byref(nrm))
+    orows, ocols, orw, onrm = s.env_tables()
+    # column CDFs and the normalisation are bit-identical; the row weights are sin((y + 0.5) pi / h) -- libm's sinf in the reference, correctly
+    # rounded in the oracle: a handful differ by one ulp, which moves the same number of row-CDF entries by an ulp
+    assert np.array_equal(cols, ocols, equal_nan=True) and np.isclose(nrm.value, onrm, rtol=2e-7, atol=0)
+    assert np.abs(rw - orw).max() <= 6e-8 and (rw != orw).mean() < 0.1 and np.abs(rows - orows).max() <= 2e-7 and (rows != orows).mean() < 0.1
+    n = 200000
+    d = sphere_dirs(rng, n); d[:10] = [0, 1, 0]; d[10:20] = [0, -1, 0]; d[20:30] = [0, 0, 1]
+    rgb = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32)
+    L.ref_env_eval(e, n, P(d), P(rgb), P(pdf))
+    orgb, opdf = s.env_eval(d)
+    assert np.array_equal(rgb != 0, orgb != 0) and np.array_equal(pdf != 0, opdf != 0)
+    # one ulp of atan2f / acosf in the texture coordinate, times 512 texels, times the gradient at the rim of the sun disc: a few 1e-5 at worst
+    tol = lambda a, b: np.abs(a - b) <= 2e-4 * np.maximum(np.abs(b), 2e-2 * np.abs(b).max())
+    assert tol(rgb, orgb).all() and tol(pdf, opdf).all()
+    assert (rgb == orgb).mean() > 0.8 and (pdf == opdf).mean() > 0.8
+    ref = (np.asarray(bs[:3]) + rng.normal(size=(n, 3)) * 0.3 * bs[3] / 1.5).astype(np.float32)
+    smp = rng.random((n, 2)).astype(np.float32)
+    sd = np.zeros((n, 3), np.float32); sv = np.zeros((n, 3), np.float32); spd = np.zeros((n, 2), np.float32)
+    L.ref_env_sample(e, n, P(ref), P(smp), P(sd), P(sv), P(spd))
+    od, ov, opdf2, odist = s.env_sample(ref, smp)
+    live = spd[:, 0] != 0
+    assert np.array_equal(live, opdf2 != 0) and live.mean() > 0.9
+    assert np.abs(sd[live] - od[live]).max() < 2e-5 and tol(sv[live], ov[live]).all() and tol(spd[live, 0], opdf2[live]).all()
+    assert np.abs(spd[live, 1] - odist[live]).max() <= 1e-5 * bs[3]
+    o = ref; ok = np.zeros(n, np.int32)
+    L.ref_env_fill(e, n, P(o), P(d), P(ok))
+    assert ok.mean() > 0.99                                                   # reference points inside the scene sphere: the record can be filled
+
+
 # ------------------------------------------------------------------------------------------------ golden vectors
 def test_validate_scene_xml_dry_run(cp, tmp_path):
     """cudapath_validate_scene_xml: the scene loader without a GPU -- lists what a file would create, names what is unsupported."""
