@@ -565,7 +565,7 @@ int cudapath_build(cudapath_ctx *ctx) {
         FilmDev &F = S.film;
         float radius = 1.0f, stddev = ctx->filterParam > 0 ? ctx->filterParam : 0.5f;
         if (ctx->filterType == 0 && ctx->filterParam > 0) radius = ctx->filterParam;
-        if (ctx->filterType == 1) radius = 0.5f;
+        if (ctx->filterType == 1) radius = 0.5f + 1e-5f;   // box.cpp:38: props.getFloat("radius", 0.5f) + 1e-5f
         if (ctx->filterType == 2) radius = 4 * stddev;
         auto ev = [&](float x) -> float {
             if (ctx->filterType == 0) return std::max(0.0f, 1.0f - std::fabs(x / radius));

@@ -328,7 +328,7 @@ struct Loader {
                 if (child(*c, "integer", "cropWidth") || child(*c, "integer", "cropOffsetX")) throw std::runtime_error("film crop windows are not supported");
                 for (auto &f : c->children) if (f->tag == "rfilter") {
                     const std::string t = f->get("type");
-                    if (t == "tent") { filter = 0; fparam = (float) getFloat(*f, "radius", 0.0); }
+                    if (t == "tent") { filter = 0; fparam = 0; }          // TentFilter has a fixed radius of 1 (tent.cpp:34); a `radius` property is ignored there as well
                     else if (t == "box") filter = 1;
                     else if (t == "gaussian") { filter = 2; fparam = (float) getFloat(*f, "stddev", 0.5); }
                     else throw std::runtime_error("rfilter plugin \"" + t + "\" is not supported (tent, box, gaussian)");

@@ -67,7 +67,7 @@ struct ReconFilter {
         return std::max(0.0f, cr::exp(alpha * x * x) - cr::exp(alpha * radius * radius));
     }
     void configure() {
-        if (type == 1) radius = 0.5f;
+        if (type == 1) radius = 0.5f + 1e-5f;          // box.cpp:38: props.getFloat("radius", 0.5f) + 1e-5f
         if (type == 2) radius = 4 * stddev;
         float sum = 0.0f;
         for (size_t i = 0; i < RES; ++i) { float v = evalFilter((radius * i) / RES); values[i] = v; sum += v; }

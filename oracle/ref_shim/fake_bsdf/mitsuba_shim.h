@@ -241,6 +241,9 @@ private:
 class Object { public: virtual ~Object() {} };
 class ConfigurableObject {
 public:
+    ConfigurableObject() {}
+    explicit ConfigurableObject(const Properties &) {}
+    ConfigurableObject(Stream *, InstanceManager *) {}
     virtual ~ConfigurableObject() {}
     virtual void configure() {}
     virtual void addChild(const std::string &, ConfigurableObject *) {}

@@ -1185,6 +1185,41 @@ def test_oracle_envmap_pinned_against_reference_text(cp, oracle, which):
     assert ok.mean() > 0.99                                                   # reference points inside the scene sphere: the record can be filled
 
 
+@pytest.mark.skipif(not os.path.exists(REF_GEOM), reason='oracle/_ref/libref_geom.so not built (needs /root/reference)')
+@pytest.mark.parametrize('rfilter,param', [('tent', 0.0), ('box', 0.0), ('gaussian', 0.0), ('gaussian', 0.8)])
+def test_film_splat_pinned_against_reference(cp, oracle, rfilter, param):
+    """ImageBlock::put (imageblock.h:124-186) cut out of the reference and executed as written, over the reference's own filter files compiled
+    unmodified (src/libcore/rfilter.cpp: 31-tap discretisation; src/rfilters/{tent,box,gaussian}.cpp), against the oracle's film: filter tables
+    and the accumulated film (R, G, B, alpha, weight) are bit-identical, invalid samples are refused by both."""
+    L = ctypes.CDLL(REF_GEOM); L.ref_filter_create.restype = ctypes.c_void_p
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    tab = np.zeros(32, np.float32); info = np.zeros(2, np.float32)
+    f = ctypes.c_void_p(L.ref_filter_create({'tent': 0, 'box': 1, 'gaussian': 2}[rfilter], ctypes.c_float(param), P(tab), P(info)))
+    s = oracle.Scene(); b = s.add_bsdf('kajiyakay')
+    s.add_hair(np.array([[0, 0, 0], [0, 1, 0], [0.1, 2, 0]], np.float32), np.array([1, 0, 0], np.uint8), 0.05, b)
+    W, H = 37, 23
+    s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=W, height=H); s.set_film(rfilter, param); s.build()
+    otab = s.filter_table()
+    if rfilter == 'gaussian':                                      # expf of libm vs correctly rounded
+        assert np.abs(tab - otab).max() <= 2e-7 * otab.max() and (tab == otab).mean() > 0.5
+    else:
+        assert np.array_equal(tab, otab)
+    rng = np.random.default_rng(73)
+    n = 60000
+    pos = (rng.random((n, 2)) * [W + 4, H + 4] - 2).astype(np.float32)          # also outside the film: clipped taps
+    rgb = (rng.random((n, 3)) ** 3 * 10).astype(np.float32); alpha = rng.random(n).astype(np.float32)
+    rgb[:20, 0] = np.nan; rgb[20:40, 1] = -1.0; rgb[40:60, 2] = np.inf; alpha[60:80] = -0.5
+    film = np.zeros((H, W, 5), np.float32); ok = np.zeros(n, np.int32)
+    L.ref_film_put(f, W, H, n, P(pos), P(rgb), P(alpha), P(film), P(ok))
+    ofilm = s.splat(pos, rgb, alpha)
+    assert ok[:80].sum() == 0 and ok[80:].all()
+    if rfilter == 'gaussian':
+        assert np.allclose(film, ofilm, rtol=1e-6, atol=1e-6)
+    else:
+        assert np.array_equal(film, ofilm)
+    assert film[..., 4].sum() > 0
+
+
 # ------------------------------------------------------------------------------------------------ golden vectors
 def test_validate_scene_xml_dry_run(cp, tmp_path):
     """cudapath_validate_scene_xml: the scene loader without a GPU -- lists what a file would create, names what is unsupported."""
