@@ -22,23 +22,47 @@ struct EnvHost { std::vector<float> rgb; int w = 0, h = 0; float toWorld[16]; fl
 struct CamHost { float toWorld[16]; float fov = 35, nearClip = 1e-2f, farClip = 1e4f; int w = 0, h = 0; bool present = false; };
 struct BsdfHost { BsdfDev dev; MarschnerTables tables; float *rt = nullptr; };
 
-// 4x4 helpers (row-major, double)
-void mat_mul(const double *a, const double *b, double *r) {
-    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j]; r[i * 4 + j] = s; }
+// 4x4 helpers (row-major, fp32), arithmetic of the reference:
+//   matrix product            include/mitsuba/core/matrix.h:743-757 (sum over k, starting from 0)
+//   Matrix<4,4,float>::invert include/mitsuba/core/matrix.inl:138-193 (Gauss-Jordan with full pivoting, in place) -- what
+//                             Transform(const Matrix4x4 &) runs on every matrix of a scene file and on Transform::perspective
+void mat_mul(const float *a, const float *b, float *r) {
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { float s = 0; for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j]; r[i * 4 + j] = s; }
 }
-bool mat_inv(const double *a, double *out) {
-    double t[4][8];
-    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { t[i][j] = a[i * 4 + j]; t[i][j + 4] = i == j; }
-    for (int c = 0; c < 4; ++c) {
-        int piv = c;
-        for (int r = c + 1; r < 4; ++r) if (std::fabs(t[r][c]) > std::fabs(t[piv][c])) piv = r;
-        if (t[piv][c] == 0) return false;
-        if (piv != c) for (int j = 0; j < 8; ++j) std::swap(t[piv][j], t[c][j]);
-        const double inv = 1.0 / t[c][c];
-        for (int j = 0; j < 8; ++j) t[c][j] *= inv;
-        for (int r = 0; r < 4; ++r) if (r != c && t[r][c] != 0) { const double f = t[r][c]; for (int j = 0; j < 8; ++j) t[r][j] -= f * t[c][j]; }
+bool mat_inv(const float *a, float *out) {
+    const int N = 4;
+    int indxc[N], indxr[N], ipiv[N] = {0, 0, 0, 0};
+    float (*m)[4] = reinterpret_cast<float (*)[4]>(out);
+    std::memcpy(out, a, 64);
+    for (int i = 0; i < N; i++) {
+        int irow = -1, icol = -1;
+        float big = 0;
+        for (int j = 0; j < N; j++) {
+            if (ipiv[j] != 1) {
+                for (int k = 0; k < N; k++) {
+                    if (ipiv[k] == 0) {
+                        if (std::fabs(m[j][k]) >= big) { big = std::fabs(m[j][k]); irow = j; icol = k; }
+                    } else if (ipiv[k] > 1) return false;
+                }
+            }
+        }
+        ++ipiv[icol];
+        if (irow != icol) for (int k = 0; k < N; ++k) std::swap(m[irow][k], m[icol][k]);
+        indxr[i] = irow; indxc[i] = icol;
+        if (m[icol][icol] == 0) return false;
+        const volatile float pivinv = 1.f / m[icol][icol];
+        m[icol][icol] = 1.f;
+        for (int j = 0; j < N; j++) m[icol][j] *= pivinv;
+        for (int j = 0; j < N; j++) {
+            if (j != icol) {
+                const float save = m[j][icol];
+                m[j][icol] = 0;
+                for (int k = 0; k < N; k++) { const volatile float prod = m[icol][k] * save; m[j][k] -= prod; }    // no fused multiply-add, like the x86 build of the reference
+            }
+        }
     }
-    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out[i * 4 + j] = t[i][j + 4];
+    for (int j = N - 1; j >= 0; j--)
+        if (indxr[j] != indxc[j]) for (int k = 0; k < N; k++) std::swap(m[k][indxr[j]], m[k][indxc[j]]);
     return true;
 }
 V3 h_xfm_point(const float *m, V3 p) {
@@ -545,17 +569,23 @@ int cudapath_build(cudapath_ctx *ctx) {
     {
         CameraDev &C = S.cam;
         const CamHost &H = ctx->cam;
-        const double aspect = (double) ((float) H.w / (float) H.h);
+        // fp32 Transform algebra of the reference: every factory carries its inverse (transform.cpp:33-63, perspective inverts numerically
+        // :99-123), a product carries (A.m * B.m, B.inv * A.inv) (transform.cpp:28-31); sampleToCamera is the inverse member of
+        //   scale(1/relSize) * translate(-relOffset) * scale(-0.5, -0.5 aspect, 1) * translate(-1, -1/aspect, 0) * perspective(...)
+        // evaluated left to right (the first two factors are exact identities without a crop window)
+        const float aspect = H.w / (float) H.h;                                        // sensor.cpp:101-102
         const float recip = 1.0f / (H.farClip - H.nearClip);
-        const float cot = 1.0f / (float) std::tan((double) ((H.fov / 2.0f) * (kPi / 180.0f)));
-        const double P[16] = {cot, 0, 0, 0, 0, cot, 0, 0, 0, 0, H.farClip * recip, -H.nearClip * H.farClip * recip, 0, 0, 1, 0};
-        const double T[16] = {1, 0, 0, -1, 0, 1, 0, -1.0 / aspect, 0, 0, 1, 0, 0, 0, 0, 1};
-        const double Sc[16] = {-0.5, 0, 0, 0, 0, -0.5 * aspect, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-        double TP[16], STP[16], inv[16];
-        mat_mul(T, P, TP); mat_mul(Sc, TP, STP);
-        if (!mat_inv(STP, inv)) return fail("singular camera projection");
-        for (int i = 0; i < 16; ++i) { C.s2c[i] = (float) inv[i]; C.toWorld[i] = H.toWorld[i]; }
-        C.invResX = 1.0f / H.w; C.invResY = 1.0f / H.h; C.nearClip = H.nearClip; C.farClip = H.farClip; C.filmW = H.w; C.filmH = H.h;
+        const float cot = 1.0f / std::tan((H.fov / 2.0f) * (kPi / 180.0f));
+        const float P[16] = {cot, 0, 0, 0, 0, cot, 0, 0, 0, 0, H.farClip * recip, -H.nearClip * H.farClip * recip, 0, 0, 1, 0};
+        float Pinv[16];
+        if (!mat_inv(P, Pinv)) return fail("singular camera projection");
+        const float sx = -0.5f, sy = -0.5f * aspect, tx = -1.0f, ty = -1.0f / aspect;
+        const float ScInv[16] = {1.0f / sx, 0, 0, 0, 0, 1.0f / sy, 0, 0, 0, 0, 1.0f / 1.0f, 0, 0, 0, 0, 1};
+        const float TrInv[16] = {1, 0, 0, -tx, 0, 1, 0, -ty, 0, 0, 1, -0.0f, 0, 0, 0, 1};
+        float TS[16], inv[16];
+        mat_mul(TrInv, ScInv, TS); mat_mul(Pinv, TS, inv);
+        for (int i = 0; i < 16; ++i) { C.s2c[i] = inv[i]; C.toWorld[i] = H.toWorld[i]; }
+        C.invResX = (float) 1 / (float) H.w; C.invResY = (float) 1 / (float) H.h; C.nearClip = H.nearClip; C.farClip = H.farClip; C.filmW = H.w; C.filmH = H.h;
         const V3 p0 = h_xfm_point(C.s2c, V3(0.0f)), px = h_xfm_point(C.s2c, V3(C.invResX, 0, 0)), py = h_xfm_point(C.s2c, V3(0, C.invResY, 0));
         const V3 dx = px - p0, dy = py - p0;
         C.dx[0] = dx.x; C.dx[1] = dx.y; C.dx[2] = dx.z; C.dy[0] = dy.x; C.dy[1] = dy.y; C.dy[2] = dy.z;
@@ -596,10 +626,10 @@ int cudapath_build(cudapath_ctx *ctx) {
         E.w = ctx->env.w; E.h = ctx->env.h; E.texels = ctx->envTables.texels; E.cdfCols = ctx->envTables.cdfCols; E.cdfRows = ctx->envTables.cdfRows;
         E.rowWeights = ctx->envTables.rowWeights; E.normalization = ctx->envTables.normalization; E.scale = ctx->env.scale;
         E.pixelSizeX = 2 * kPi / E.w; E.pixelSizeY = kPi / E.h;
-        double tw[16], ti[16];
+        float tw[16], ti[16];
         for (int i = 0; i < 16; ++i) tw[i] = ctx->env.toWorld[i];
-        if (!mat_inv(tw, ti)) return fail("singular environment map transform");
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { E.toWorld[r * 3 + c] = (float) tw[r * 4 + c]; E.toLocal[r * 3 + c] = (float) ti[r * 4 + c]; }
+        if (!mat_inv(tw, ti)) return fail("singular environment map transform");      // Transform(const Matrix4x4 &), transform.h:50-55
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { E.toWorld[r * 3 + c] = tw[r * 4 + c]; E.toLocal[r * 3 + c] = ti[r * 4 + c]; }
         // scene bounds for the emitter: kd-tree AABB + sensor position (scene.cpp:387-413), bounding sphere x1.5 (envmap.cpp:331-341)
         float mn[3], mx[3];
         const V3 camPos = h_xfm_point(ctx->cam.toWorld, V3(0.0f));

@@ -301,24 +301,41 @@ static inline V3 xfmVector(const M44 &t, const V3 &v) {
               t.m[1][0] * v.x + t.m[1][1] * v.y + t.m[1][2] * v.z,
               t.m[2][0] * v.x + t.m[2][1] * v.y + t.m[2][2] * v.z);
 }
-// General 4x4 inverse (Gauss-Jordan with partial pivoting, computed in double then rounded;
-// the reference uses src/libcore/matrix.cpp Matrix4x4::invert in fp32 -- results agree to fp32 rounding)
+// Matrix<4,4,float>::invert (include/mitsuba/core/matrix.inl:138-193): Gauss-Jordan with full pivoting, in place, in fp32 -- what
+// Transform(const Matrix4x4 &) runs on every matrix read from a scene file and on Transform::perspective (transform.h:50-55)
 static inline bool invert(const M44 &a, M44 &out) {
-    double t[4][8];
-    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { t[i][j] = a.m[i][j]; t[i][j + 4] = (i == j); }
-    for (int c = 0; c < 4; ++c) {
-        int piv = c;
-        for (int r = c + 1; r < 4; ++r) if (std::abs(t[r][c]) > std::abs(t[piv][c])) piv = r;
-        if (t[piv][c] == 0) return false;
-        if (piv != c) for (int j = 0; j < 8; ++j) std::swap(t[piv][j], t[c][j]);
-        double inv = 1.0 / t[c][c];
-        for (int j = 0; j < 8; ++j) t[c][j] *= inv;
-        for (int r = 0; r < 4; ++r) if (r != c) {
-            double f = t[r][c];
-            if (f != 0) for (int j = 0; j < 8; ++j) t[r][j] -= f * t[c][j];
+    const int N = 4;
+    int indxc[N], indxr[N], ipiv[N] = {0, 0, 0, 0};
+    std::memcpy(out.m, a.m, sizeof(out.m));
+    for (int i = 0; i < N; i++) {
+        int irow = -1, icol = -1;
+        float big = 0;
+        for (int j = 0; j < N; j++) {
+            if (ipiv[j] != 1) {
+                for (int k = 0; k < N; k++) {
+                    if (ipiv[k] == 0) {
+                        if (std::abs(out.m[j][k]) >= big) { big = std::abs(out.m[j][k]); irow = j; icol = k; }
+                    } else if (ipiv[k] > 1) return false;
+                }
+            }
+        }
+        ++ipiv[icol];
+        if (irow != icol) for (int k = 0; k < N; ++k) std::swap(out.m[irow][k], out.m[icol][k]);
+        indxr[i] = irow; indxc[i] = icol;
+        if (out.m[icol][icol] == 0) return false;
+        float pivinv = 1.f / out.m[icol][icol];
+        out.m[icol][icol] = 1.f;
+        for (int j = 0; j < N; j++) out.m[icol][j] *= pivinv;
+        for (int j = 0; j < N; j++) {
+            if (j != icol) {
+                float save = out.m[j][icol];
+                out.m[j][icol] = 0;
+                for (int k = 0; k < N; k++) out.m[j][k] -= out.m[icol][k] * save;
+            }
         }
     }
-    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out.m[i][j] = (float) t[i][j + 4];
+    for (int j = N - 1; j >= 0; j--)
+        if (indxr[j] != indxc[j]) for (int k = 0; k < N; k++) std::swap(out.m[k][indxr[j]], out.m[k][indxc[j]]);
     return true;
 }
 

@@ -26,18 +26,24 @@ struct Camera {
     M44 sampleToCamera;
     V3 dx, dy;
 
-    // perspective.cpp:126-160 (no crop window); Transform::perspective src/libcore/transform.cpp:99-121
+    // perspective.cpp:126-160 (no crop window) with the fp32 Transform algebra of the reference: every factory returns the matrix AND its
+    // inverse (transform.cpp:33-63; Transform::perspective inverts numerically, :99-123 + matrix.inl:138-193), a product carries
+    // (A.m * B.m, B.inv * A.inv) (transform.cpp:28-31), and sampleToCamera is the inverse member of
+    //   scale(1/relSize) * translate(-relOffset) * scale(-0.5, -0.5 aspect, 1) * translate(-1, -1/aspect, 0) * perspective(xfov, near, far)
+    // evaluated left to right.  The first two factors are exact identities without a crop window.
     void configure() {
-        aspect = (float) filmW / (float) filmH;
-        invResX = 1.0f / filmW; invResY = 1.0f / filmH;
+        aspect = filmW / (float) filmH;                                    // sensor.cpp:101-102
+        invResX = (float) 1 / (float) filmW; invResY = (float) 1 / (float) filmH;
         float recip = 1.0f / (farClip - nearClip);
-        float cot = 1.0f / cr::tan((xfov / 2.0f) * (kPi / 180.0f));
+        float cot = 1.0f / std::tan((xfov / 2.0f) * (kPi / 180.0f));      // libm tanf like the reference; the fov is a scene constant
         M44 persp; std::memset(persp.m, 0, sizeof(persp.m));
         persp.m[0][0] = cot; persp.m[1][1] = cot; persp.m[2][2] = farClip * recip; persp.m[2][3] = -nearClip * farClip * recip; persp.m[3][2] = 1;
-        M44 tr = M44::identity(); tr.m[0][3] = -1.0f; tr.m[1][3] = -1.0f / aspect;
-        M44 sc = M44::identity(); sc.m[0][0] = -0.5f; sc.m[1][1] = -0.5f * aspect;
-        M44 cameraToSample = mul(sc, mul(tr, persp)); // relSize=1, relOffset=0 factors are identities
-        if (!invert(cameraToSample, sampleToCamera)) throw std::runtime_error("oracle: singular camera transform");
+        M44 perspInv;
+        if (!invert(persp, perspInv)) throw std::runtime_error("oracle: singular camera transform");
+        const float sx = -0.5f, sy = -0.5f * aspect, tx = -1.0f, ty = -1.0f / aspect;
+        M44 scInv = M44::identity(); scInv.m[0][0] = 1.0f / sx; scInv.m[1][1] = 1.0f / sy; scInv.m[2][2] = 1.0f / 1.0f;
+        M44 trInv = M44::identity(); trInv.m[0][3] = -tx; trInv.m[1][3] = -ty; trInv.m[2][3] = -0.0f;
+        sampleToCamera = mul(perspInv, mul(trInv, scInv));
         dx = xfmPoint(sampleToCamera, V3(invResX, 0, 0)) - xfmPoint(sampleToCamera, V3(0.0f));
         dy = xfmPoint(sampleToCamera, V3(0, invResY, 0)) - xfmPoint(sampleToCamera, V3(0.0f));
     }

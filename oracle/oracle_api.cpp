@@ -425,6 +425,18 @@ int orc_camera_rays(void *sp, uint64_t n, const float *pxy, float *outO, float *
     return 0;
 }
 
+int orc_camera_differentials(void *sp, float *out6) {
+    Scene *s = (Scene *) sp;
+    out6[0] = s->cam.dx.x; out6[1] = s->cam.dx.y; out6[2] = s->cam.dx.z; out6[3] = s->cam.dy.x; out6[4] = s->cam.dy.y; out6[5] = s->cam.dy.z;
+    return 0;
+}
+int orc_matrix_invert(const float *m16, float *out16) {
+    M44 a = M44::fromRowMajor(m16), b;
+    const bool ok = invert(a, b);
+    std::memcpy(out16, b.m, 64);
+    return ok ? 1 : 0;
+}
+
 // Environment map hooks: eval (no differentials), sampleDirect from `ref`, pdfDirect
 int orc_env_eval_batch(void *sp, uint64_t n, const float *d, float *outRGB, float *outPdf) {
     Scene *s = (Scene *) sp;

@@ -76,6 +76,13 @@ def load_hair_file(path, radius=0.025, angleThreshold=1.0, toWorld=None):
     return xyz, st, float(r), int(nseg)
 
 
+def matrix_invert(m):
+    """Matrix<4,4,float>::invert as the oracle restates it (o_math.h); None when singular."""
+    m = f32(m).reshape(16); out = np.zeros(16, np.float32)
+    ok = lib().orc_matrix_invert(p(m), p(out))
+    return out.reshape(4, 4) if ok == 1 else None
+
+
 def load_rgbe(path):
     w = ctypes.c_int(); h = ctypes.c_int()
     check(lib().orc_load_rgbe(str(path).encode(), None, ctypes.byref(w), ctypes.byref(h)))
@@ -269,6 +276,11 @@ class Scene:
         li = np.zeros((n, 3), np.float32); alpha = np.zeros(n, np.float32); depth = np.zeros(n, np.int32)
         check(self.L.orc_render_samples_ref_li(self.h, REF_PATH_LIB.encode(), ctypes.c_uint64(n), p(xy), p(samp), ctypes.c_uint32(spp), ctypes.c_uint64(seed), p(li), p(alpha), p(depth)))
         return li, alpha, depth
+
+    def camera_differentials(self):
+        out = np.zeros(6, np.float32)
+        self.L.orc_camera_differentials(self.h, p(out))
+        return out
 
     def splat(self, pos, rgb, alpha):
         pos = f32(pos).reshape(-1, 2); rgb = f32(rgb).reshape(-1, 3); alpha = f32(alpha).reshape(-1); n = len(pos)
