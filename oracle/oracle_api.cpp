@@ -8,10 +8,11 @@
 // cannot be built as a whole here, so the oracle is pinned against the reference's own source run as it is (oracle/Makefile `ref`,
 // outputs in oracle/_ref, tests in tests/test_oracle_cpu.py): all eight BSDF plugin files and the path integrator (path.cpp) compiled
 // unmodified against interface scaffolding (libref_bsdf.so, libref_path.so); the hair cylinder / miter / bounds / intersection-record
-// code, the two-level ray query, the hair file loader, TriAccel, the AABB slab test, the envmap emitter, ImageBlock::put with the reconstruction filters and the libcore helpers they
+// code, the two-level ray query, the hair file loader, TriAccel, the AABB slab test, the envmap emitter, the perspective sensor with the fp32 Transform / Matrix algebra, ImageBlock::put with
+// the reconstruction filters and the libcore helpers they
 // call executed from text cut out of the reference at build time (libref_geom.so); GaussLegendre, InterpolatedDistribution1D and the
 // Hosek-Wilkie sky model compiled directly (libref_pieces.so).  NOT pinned that way, restatement only: the sunsky bake around the sky
-// model, the perspective sensor, the OBJ / RGBE readers and the film develop ("Parity status").
+// model, the OBJ / RGBE readers and the film develop ("Parity status").
 #include "o_math.h"
 #include "o_hair.h"
 #include "o_bsdf.h"
