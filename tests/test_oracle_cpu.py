@@ -492,6 +492,16 @@ def _write_rgbe(path, rgbe, rle, crlf=False):
     open(path, 'wb').write(bytes(out))
 
 
+def _ref_load_rgbe(path):
+    L = ctypes.CDLL(REF_GEOM)
+    w = ctypes.c_int(); h = ctypes.c_int(); err = ctypes.create_string_buffer(256)
+    if L.ref_load_rgbe(str(path).encode(), None, ctypes.byref(w), ctypes.byref(h), err) != 0:
+        raise RuntimeError(err.value.decode())
+    out = np.zeros((h.value, w.value, 3), np.float32)
+    L.ref_load_rgbe(str(path).encode(), out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(w), ctypes.byref(h), err)
+    return out
+
+
 def test_rgbe_reader(cp, oracle, tmp_path):
     """Bitmap::readRGBE (src/libcore/bitmap.cpp:3590-3678): flat and run-length encoded files, CR/LF headers, widths that forbid RLE,
     zero exponents; product loader == oracle loader == direct decode, error messages for broken files."""
@@ -509,6 +519,9 @@ def test_rgbe_reader(cp, oracle, tmp_path):
         expect[q[..., 3] == 0] = 0
         a = cp.load_rgbe(path); b = oracle.load_rgbe(path)
         assert a.shape == (h, w, 3) and np.array_equal(a, expect) and np.array_equal(b, expect)
+        if os.path.exists(REF_GEOM):                              # Bitmap::readRGBE itself, cut out of the reference and executed as written
+            c = _ref_load_rgbe(path)
+            assert c.shape == (h, w, 3) and np.array_equal(c, expect)
     raw = open(path, 'rb').read()
     bad = tmp_path / 'bad.hdr'
     for data, msg in [(b'RADIANCE\n' + raw[11:], 'Invalid header'), (raw.replace(b'FORMAT=32-bit_rle_rgbe', b'FORMAT=32-bit_rle_xyze'), 'invalid format'),
@@ -518,6 +531,9 @@ def test_rgbe_reader(cp, oracle, tmp_path):
             cp.load_rgbe(bad)
         with pytest.raises(RuntimeError, match=msg):
             oracle.load_rgbe(bad)
+        if os.path.exists(REF_GEOM):
+            with pytest.raises(RuntimeError):
+                _ref_load_rgbe(bad)
     with pytest.raises(cp.CudapathError, match='could not be found'):
         cp.load_rgbe(tmp_path / 'nothing.hdr')
     ref = '/root/reference/models/teapot/textures/envmap.hdr'       # the one image file the reference ships for this emitter
@@ -527,6 +543,7 @@ def test_rgbe_reader(cp, oracle, tmp_path):
         a = cp.load_rgbe(ref)
         gold = json.load(open(os.path.join(GOLDEN, 'envmap_hdr.json')))
         assert list(a.shape) == gold['shape'] and hashlib.sha256(a.tobytes()).hexdigest() == gold['sha256'] and np.array_equal(a, oracle.load_rgbe(ref))
+        assert np.array_equal(a, _ref_load_rgbe(ref))
 
 
 def test_obj_loader(cp, tmp_path):
