@@ -298,6 +298,21 @@ class Context:
         _check(self._L.cudapath_render_dev(self._h, ctypes.c_uint32(spp), ctypes.c_uint64(seed), ctypes.c_uint32(sample_begin),
                                            ctypes.c_uint32(spp if sample_end is None else sample_end), ctypes.c_void_p(film_dev_ptr), ctypes.c_void_p(stream)))
 
+    def cancel(self):
+        """Integrator::cancel(): may be called from another thread while render() / render_into() blocks; that call then raises
+        CudapathError('render cancelled')."""
+        _check(self._L.cudapath_cancel(self._h))
+
+    def set_progress_callback(self, fn):
+        """fn(paths_done, paths_total) after every finished wave of a render (None removes it)."""
+        if fn is None:
+            self._progress_cb = None
+            _check(self._L.cudapath_set_progress_callback(self._h, None, None))
+            return
+        CB = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64)
+        self._progress_cb = CB(lambda user, done, total: fn(int(done), int(total)))     # kept alive with the context
+        _check(self._L.cudapath_set_progress_callback(self._h, self._progress_cb, None))
+
     def stats(self):
         s = Stats()
         _check(self._L.cudapath_get_stats(self._h, ctypes.byref(s)))

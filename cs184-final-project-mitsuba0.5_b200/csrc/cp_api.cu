@@ -660,6 +660,7 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
     CKA(cudaEventRecord(e0, st));
     RenderStats rs; std::string err;
     ctx->wf.sortRays = ctx->sortRays != 0;
+    if (ctx->wf.cancelRequested.exchange(0)) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail("render cancelled"); }   // cancel() arrived before the render started
     uint32_t waveSize = ctx->waveSize;
     if (!waveSize) {
         // Deep bounces leave only a few live paths per wave, so few, large waves keep the GPU full for longer (hair-curl at 64 spp:
@@ -672,7 +673,7 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
         while (waveSize > (1u << 20) && 212.0 * waveSize > avail) waveSize >>= 1;
     }
     const bool ok = ctx->wf.render(ctx->scene, spp, seed, sample_begin, sample_end, film_dev, waveSize, ctx->collectStats != 0, ctx->profileStages != 0, st, rs, err);
-    if (!ok) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(err); }
+    if (!ok) { ctx->wf.cancelRequested.store(0); cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(err); }
     CKA(cudaEventRecord(e1, st));
     CKA(cudaEventSynchronize(e1));
     float ms = 0; CKA(cudaEventElapsedTime(&ms, e0, e1));
@@ -684,6 +685,18 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
     s.intersect_launches = rs.stageLaunches[0]; s.shade_launches = rs.stageLaunches[1]; s.shadow_launches = rs.stageLaunches[2]; s.unsupported_filtered_lookups = rs.unsupportedLookups; s.dropped_samples = rs.droppedSamples;
     s.full_tests = rs.fullTests; s.shadow_full_tests = rs.shadowFullTests; s.shadow_rays_traced = rs.shadowRaysTraced;
     s.render_ms = ms;
+    return 0;
+}
+
+int cudapath_cancel(cudapath_ctx *ctx) {
+    if (!ctx) return fail("null context");
+    ctx->wf.cancelRequested.store(1);          // the only entry point that may be called while another thread is inside a render
+    return 0;
+}
+
+int cudapath_set_progress_callback(cudapath_ctx *ctx, void (*callback)(void *user, uint64_t paths_done, uint64_t paths_total), void *user) {
+    if (!ctx) return fail("null context");
+    ctx->wf.progress = callback; ctx->wf.progressUser = user;
     return 0;
 }
 

@@ -229,10 +229,17 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
                 rs.launches++; rs.shadowRays += nShadow; rs.shadowRaysTraced += nShadow;
             }
             cur ^= 1; nActive = nNext; bounce++;
+            if (cancelRequested.load(std::memory_order_relaxed)) {      // the unfinished wave is dropped: the film holds whole waves only
+                cudaStreamSynchronize(stream);
+                for (auto &sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+                err = "render cancelled";
+                return false;
+            }
         }
         begin(4); launch_splat(S, wp, liAcc, n, d_film, stats + 5, stream); end();
         rs.launches++;
         rs.paths += n;
+        if (progress) progress(progressUser, std::min<uint64_t>(base + n, total), total);
     }
     unsigned long long hs[8]; int herr = 0;
     CKW(cudaMemcpyAsync(hs, stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));

@@ -1,6 +1,7 @@
 // cp_wavefront.h -- queues and host driver of the wavefront path tracer
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <string>
 #include "cp_scene.cuh"
@@ -44,6 +45,12 @@ struct Wavefront {
     uint32_t *sortKeys[2] = {nullptr, nullptr}, *sortVals[2] = {nullptr, nullptr};
     void *sortTemp = nullptr; size_t sortTempBytes = 0;
     bool sortRays = true;
+    // Integrator::cancel() (include/mitsuba/render/integrator.h:76-84) may be called from another thread while render() blocks: the flag
+    // is looked at once per bounce (after the host has read the queue counters); a cancelled render returns false with "render cancelled".
+    std::atomic<int> cancelRequested{0};
+    // RenderJob progress (ProgressReporter in SamplingIntegrator::render, src/librender/integrator.cpp:95-138): called on the rendering
+    // thread after every finished wave with the camera paths done so far and the total of this call
+    void (*progress)(void *user, uint64_t done, uint64_t total) = nullptr; void *progressUser = nullptr;
     const uint32_t *coherence_order(const SceneDev &S, const float4 *ro, const float4 *rd, uint32_t n, cudaStream_t stream);
     uint32_t capacity = 0;
     cudaStream_t allocStream = nullptr;

@@ -139,6 +139,15 @@ int cudapath_render(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sam
 /* Same, accumulating into a caller-provided DEVICE buffer on a caller-provided CUDA stream (cudaStream_t as void*, may be 0);
  * the buffer must be zeroed by the caller before the first range.  Used with torch/NCCL for the multi-GPU film reduce. */
 int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *film_dev, void *stream);
+/* Integrator::cancel() (include/mitsuba/render/integrator.h:76-84, SamplingIntegrator::cancel src/librender/integrator.cpp:90-93; reached
+ * from RenderJob::cancel, include/mitsuba/render/renderjob.h:81, on another thread while render() blocks and then returns false).  The ONLY entry point that may be called concurrently with a render of the same
+ * context.  The running (or next) cudapath_render / cudapath_render_dev returns -1 with the message "render cancelled" within one
+ * bounce; the film then holds the finished waves only.  The request is consumed by that render. */
+int cudapath_cancel(cudapath_ctx *ctx);
+/* Progress of a render (ProgressReporter of SamplingIntegrator::render, src/librender/integrator.cpp:95-138): `callback` runs on the
+ * rendering thread after every finished wave with the path slots done and the total of the call (pixels are padded to 8x8 tiles).
+ * NULL removes it. */
+int cudapath_set_progress_callback(cudapath_ctx *ctx, void (*callback)(void *user, uint64_t paths_done, uint64_t paths_total), void *user);
 /* Film::develop normalisation, src/libcore/fmtconv.cpp:955-1056: rgb = sum / weight (0 where weight == 0). */
 int cudapath_develop(const float *film, int width, int height, float *out_rgb);
 /* LDRFilm::develop with the `gamma` tonemapper, src/films/ldrfilm.cpp:300-321 -> Bitmap::convert(ERGB, EUInt8, gamma, 2^exposure)

@@ -706,6 +706,40 @@ def test_repeated_jobs_reuse_device_memory(cp):
     assert total - free < used[3]
 
 
+def test_cancel_and_progress(cp):
+    """Integrator::cancel() (include/mitsuba/render/integrator.h:76-84: asynchronous, render() then returns false) and the render job's
+    progress reports (src/librender/integrator.cpp:95-138) at the C ABI: cudapath_cancel from another thread ends a blocking
+    cudapath_render with "render cancelled" within one bounce, the request is consumed, and the next render is complete."""
+    import threading
+    ov = dict(width=64, height=64, spp=32, maxDepth=8)
+    ctx = cp.scene_from_description('straight-hair', scale=0.01, overrides=ov); ctx.build()
+    ctx.set_options(wave_size=8192)                               # 16 waves of two sample indices each
+    total = 64 * 64 * 32
+    seen = []
+    ctx.set_progress_callback(lambda done, tot: seen.append((done, tot)))
+    ref = ctx.render(32, seed=5)
+    assert len(seen) == 16 and seen[-1] == (total, total)
+    assert all(t == total for _, t in seen) and [d for d, _ in seen] == sorted(set(d for d, _ in seen))
+    seen.clear()
+
+    def cancel_after_three(done, tot):
+        seen.append((done, tot))
+        if len(seen) == 3:                                        # from another thread, as RenderJob::cancel does
+            th = threading.Thread(target=ctx.cancel); th.start(); th.join()
+    ctx.set_progress_callback(cancel_after_three)
+    with pytest.raises(cp.CudapathError, match='render cancelled'):
+        ctx.render(32, seed=5)
+    assert len(seen) == 3                                         # the fourth wave was dropped after its first bounce
+    ctx.set_progress_callback(None)
+    again = ctx.render(32, seed=5)                                # the request was consumed
+    assert np.allclose(again, ref, rtol=1e-5, atol=1e-6)
+    ctx.cancel()                                                  # a request that arrives before the render starts
+    with pytest.raises(cp.CudapathError, match='render cancelled'):
+        ctx.render(32, seed=5)
+    assert np.allclose(ctx.render(32, seed=5), ref, rtol=1e-5, atol=1e-6)
+    ctx.close()
+
+
 def test_native_cli_renders_a_scene_file(cp, tmp_path):
     """cudapath_render (csrc/cp_cli.cpp, the `mitsuba -o out.png -D name=value scene.xml` of this path): same film as the Python mirror,
     developed with the film's own gamma; PNG, PFM and $-substitution."""
