@@ -706,6 +706,47 @@ def test_repeated_jobs_reuse_device_memory(cp):
     assert total - free < used[3]
 
 
+@pytest.mark.parametrize('name,size', [('hair-curl', (1024, 1024, 64)), ('straight-hair', (512, 512, 16))])
+def test_full_size_configs(cp, oracle, name, size):
+    """BASELINE.json configs[1] at its FULL size (hair-curl: 4 M segments in 4 shapes, Marschner, 1024x1024 at 64 spp, maxDepth 65), the
+    workload bench.py times, and configs[0] (straight-hair, Kajiya-Kay, 512x512 at 16 spp, maxDepth 8).  Size-independent properties of the whole render (path / sample bookkeeping, finite non-negative film,
+    additivity of sample ranges -- what the multi-GPU film reduce relies on -- and run-to-run agreement), and the first sample index of
+    EVERY pixel replayed by the CPU oracle on the same 4 M-segment scene with the same Philox counters."""
+    sc = cp.scenes.SCENES[name]; W, H, spp = sc['width'], sc['height'], sc['spp']
+    assert (W, H, spp) == size
+    ctx = cp.scene_from_description(name, scale=1.0); ctx.build()
+    full = ctx.render(spp, seed=7)
+    st = ctx.stats()
+    assert st['segments'] == (4000000 if name == 'hair-curl' else st['segments']) > 100000 and st['paths'] == W * H * spp
+    assert st['dropped_samples'] == 0 and st['unsupported_filtered_lookups'] == 0
+    assert st['rays'] >= st['paths'] and st['shadow_rays'] <= st['rays']
+    assert np.isfinite(full).all() and (full >= 0).all()
+    wsum = full[..., 4]
+    assert abs(float(wsum[8:-8, 8:-8].mean()) / spp - 1.0) < 1e-3    # the tent filter's weights sum to one sample per pixel and sample index
+    parts = ctx.render(spp, seed=7, sample_begin=0, sample_end=spp // 3) + ctx.render(spp, seed=7, sample_begin=spp // 3, sample_end=spp)
+    assert np.abs(parts - full).max() <= 1e-4 * np.abs(full).max()
+    again = ctx.render(spp, seed=7)
+    assert np.allclose(again, full, rtol=1e-5, atol=1e-5)            # the order of the film atomics differs in the last bits
+    other = ctx.render(spp, seed=8)
+    assert rel_mse(cp.develop(other), cp.develop(full)) < 0.25 and not np.array_equal(other, full)   # another seed: same image up to 64-spp noise
+    g1 = ctx.render(spp, seed=7, sample_begin=0, sample_end=1)
+    st1 = ctx.stats()
+    ctx.close()
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params(name))
+    osc = oracle.scene_from_description(name, scale=1.0, envmap=env)
+    o1 = osc.render(spp, seed=7, sample_begin=0, sample_end=1)
+    assert st1['paths'] == W * H == osc.last_stats['paths']
+    assert np.abs(g1[..., 4] - o1[..., 4]).max() <= 1e-4 * o1[..., 4].max()
+    assert abs(st1['rays'] - osc.last_stats['rays']) <= 2e-4 * osc.last_stats['rays']              # measured on hair-curl: 1939911 vs 1939957
+    assert abs(st1['shadow_rays'] - osc.last_stats['shadow_rays']) <= 2e-4 * osc.last_stats['shadow_rays']
+    a, b = cp.develop(g1), cp.develop(o1)
+    close = np.abs(a - b).max(axis=2) <= 1e-3 * (np.abs(b).max(axis=2) + 1e-3)
+    print('full-size first-sample replay: %.5f of the pixels agree to 1e-3, relMSE %.3g, rays %d / %d, shadow rays %d / %d'
+          % (close.mean(), rel_mse(a, b), st1['rays'], osc.last_stats['rays'], st1['shadow_rays'], osc.last_stats['shadow_rays']))
+    assert close.mean() > 0.998, 'only %.4f of the pixels agree to 1e-3' % close.mean()                 # measured on hair-curl: 0.99961
+    assert rel_mse(a, b) < 1e-3                                                                         # north_star's image bar; measured 5e-7
+
+
 def test_cancel_and_progress(cp):
     """Integrator::cancel() (include/mitsuba/render/integrator.h:76-84: asynchronous, render() then returns false) and the render job's
     progress reports (src/librender/integrator.cpp:95-138) at the C ABI: cudapath_cancel from another thread ends a blocking
