@@ -51,41 +51,60 @@ CP_D bool aabb_ray(const float *bmin, const float *bmax, const V3 &o, const V3 &
     return true;
 }
 
+// FP64 arithmetic of the cylinder test, one IEEE operation per source operation: the reference is built for x86-64 without FMA
+// (-march=nocona), and a fused multiply-add in the dot products or the discriminant moves the fp64 result by an ulp -- enough to move
+// the fp32 hit distance by one ulp for about 5 hits per million (found by the full-size furball ray batch, 1 of 200 278 hits).
+// -DCP_FP64_FMA restores the contracted arithmetic (tuning experiments only).
+#if defined(__CUDA_ARCH__) && !defined(CP_FP64_FMA)
+CP_D double xmul(double a, double b) { return __dmul_rn(a, b); }
+CP_D double xadd(double a, double b) { return __dadd_rn(a, b); }
+CP_D double xsub(double a, double b) { return __dsub_rn(a, b); }
+#else
+CP_HD double xmul(double a, double b) { return a * b; }
+CP_HD double xadd(double a, double b) { return a + b; }
+CP_HD double xsub(double a, double b) { return a - b; }
+#endif
+CP_HD D3 xadd(D3 a, D3 b) { return D3(xadd(a.x, b.x), xadd(a.y, b.y), xadd(a.z, b.z)); }
+CP_HD D3 xsub(D3 a, D3 b) { return D3(xsub(a.x, b.x), xsub(a.y, b.y), xsub(a.z, b.z)); }
+CP_HD D3 xscale(D3 a, double s) { return D3(xmul(a.x, s), xmul(a.y, s), xmul(a.z, s)); }
+CP_HD double xdot(D3 a, D3 b) { return xadd(xadd(xmul(a.x, b.x), xmul(a.y, b.y)), xmul(a.z, b.z)); }
+CP_HD D3 xnormalize(D3 a) { return xscale(a, 1.0 / sqrt(xdot(a, a))); }
+
 // hair.cpp:485-542.  v0..v3 = vtx[gv-1..gv+2] (v0/v3 are only read when the neighbour segment exists).
 // mint/maxt are the shape-clipped global interval with maxt already shrunk to the current best hit.
 CP_D bool segment_intersect(const float4 &v0, const float4 &v1, const float4 &v2, const float4 &v3, float radius,
                             const V3 &ro, const V3 &rd, float mint, float maxt, float &tOut, V3 &pOut) {
     const D3 p1(vtx_pos(v1)), p2(vtx_pos(v2));
-    const D3 axis = normalize(p2 - p1);
+    const D3 axis = xnormalize(xsub(p2, p1));
     const D3 rayO(ro), rayD(rd);
-    const D3 relOrigin = rayO - p1;
-    const D3 projOrigin = relOrigin - axis * dot(axis, relOrigin);
-    const D3 projDirection = rayD - axis * dot(axis, rayD);
-    const double A = dot(projDirection, projDirection);
-    const double B = 2 * dot(projOrigin, projDirection);
-    const double C = dot(projOrigin, projOrigin) - (double) (radius * radius);
+    const D3 relOrigin = xsub(rayO, p1);
+    const D3 projOrigin = xsub(relOrigin, xscale(axis, xdot(axis, relOrigin)));
+    const D3 projDirection = xsub(rayD, xscale(axis, xdot(axis, rayD)));
+    const double A = xdot(projDirection, projDirection);
+    const double B = xmul(2.0, xdot(projOrigin, projDirection));
+    const double C = xsub(xdot(projOrigin, projOrigin), (double) (radius * radius));
     double nearT, farT;
     // solveQuadraticDouble
     if (A == 0) {
         if (B != 0) nearT = farT = -C / B; else return false;
     } else {
-        double discrim = B * B - 4.0 * A * C;
+        double discrim = xsub(xmul(B, B), xmul(xmul(4.0, A), C));
         if (discrim < 0) return false;
         double sqrtDiscrim = sqrt(discrim), temp;
-        if (B < 0) temp = -0.5 * (B - sqrtDiscrim); else temp = -0.5 * (B + sqrtDiscrim);
+        if (B < 0) temp = xmul(-0.5, xsub(B, sqrtDiscrim)); else temp = xmul(-0.5, xadd(B, sqrtDiscrim));
         nearT = temp / A; farT = C / temp;
         if (nearT > farT) { double t = nearT; nearT = farT; farT = t; }
     }
     if (!(nearT <= (double) maxt && farT >= (double) mint)) return false;   // NaN-aware
     // miter planes (hair.cpp:584-596): previous segment exists iff !startsFiber[iv], next iff !startsFiber[iv+2]
     D3 n1 = axis, n2 = axis;
-    if (!vtx_starts(v1)) n1 = normalize(normalize(p1 - D3(vtx_pos(v0))) + axis);
-    if (!vtx_starts(v3)) n2 = normalize(axis + normalize(D3(vtx_pos(v3)) - p2));
-    const D3 pointNear = rayO + rayD * nearT, pointFar = rayO + rayD * farT;
-    if (dot(pointNear - p1, n1) >= 0 && dot(pointNear - p2, n2) <= 0 && nearT >= (double) mint) {
+    if (!vtx_starts(v1)) n1 = xnormalize(xadd(xnormalize(xsub(p1, D3(vtx_pos(v0)))), axis));
+    if (!vtx_starts(v3)) n2 = xnormalize(xadd(axis, xnormalize(xsub(D3(vtx_pos(v3)), p2))));
+    const D3 pointNear = xadd(rayO, xscale(rayD, nearT)), pointFar = xadd(rayO, xscale(rayD, farT));
+    if (xdot(xsub(pointNear, p1), n1) >= 0 && xdot(xsub(pointNear, p2), n2) <= 0 && nearT >= (double) mint) {
         tOut = (float) nearT;
         pOut = V3((float) pointNear.x, (float) pointNear.y, (float) pointNear.z);   // Point(rayO + rayD * nearT), hair.cpp:524
-    } else if (dot(pointFar - p1, n1) >= 0 && dot(pointFar - p2, n2) <= 0) {
+    } else if (xdot(xsub(pointFar, p1), n1) >= 0 && xdot(xsub(pointFar, p2), n2) <= 0) {
         if (farT > (double) maxt) return false;
         tOut = (float) farT;                                                // rays starting inside a fiber exit through its far wall
         pOut = V3((float) pointFar.x, (float) pointFar.y, (float) pointFar.z);

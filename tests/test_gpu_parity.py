@@ -706,6 +706,32 @@ def test_repeated_jobs_reuse_device_memory(cp):
     assert total - free < used[3]
 
 
+def test_full_size_furball_ray_batch(cp, oracle):
+    """north_star's second check on the scene of BASELINE.json configs[3] / configs[4] at its full size (furball, 1.6 M segments, dense
+    fiber BVH): hit shape / primitive index bit-exact and hit distance bit-identical on a fixed batch of a million kdbench-style chords,
+    of rays fired at fibers from close by with mint = Epsilon, and of secondary-like rays that start ON fiber surfaces; any-hit agrees."""
+    ctx = cp.scene_from_description('furball', scale=1.0); ctx.build()
+    assert ctx.stats()['segments'] == 1600000
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params('furball'))
+    osc = oracle.scene_from_description('furball', scale=1.0, envmap=env)
+    rng = np.random.default_rng(11)
+    aabb, bs = osc.scene_bounds()
+    o, d = chord_rays(rng, 1000000, bs[:3], bs[3] / 1.5 * 0.8)
+    nh, nm = check_hits(ctx, osc, o, d, 0.0, np.inf)
+    assert nh > 100000
+    sh, pr, t = osc.intersect(o[:400000], d[:400000], 0.0, np.inf)
+    m = sh >= 0
+    hitp = o[:400000][m] + d[:400000][m] * t[m][:, None]
+    d2 = sphere_dirs(rng, m.sum())
+    nh2, nm2 = check_hits(ctx, osc, (hitp - d2 * 0.05).astype(np.float32), d2, 1e-4, 10.0)
+    nh3, nm3 = check_hits(ctx, osc, hitp.astype(np.float32), d2, 1e-4, np.inf)
+    gs, _, _ = ctx.intersect(hitp.astype(np.float32), d2, 1e-4, 5.0, any_hit=True)
+    os_, _, _ = osc.intersect(hitp.astype(np.float32), d2, 1e-4, 5.0, mode=1)
+    assert np.array_equal(gs >= 0, os_ >= 0)
+    print('full-size furball ray batch: %d + %d + %d identical hits, %d + %d + %d ties within 1e-6' % (nh, nh2, nh3, nm, nm2, nm3))
+    ctx.close()
+
+
 @pytest.mark.parametrize('name,size', [('hair-curl', (1024, 1024, 64)), ('straight-hair', (512, 512, 16))])
 def test_full_size_configs(cp, oracle, name, size):
     """BASELINE.json configs[1] at its FULL size (hair-curl: 4 M segments in 4 shapes, Marschner, 1024x1024 at 64 spp, maxDepth 65), the
