@@ -105,6 +105,38 @@ def test_bsdf_sample(bsdf_pair):
         assert (np.abs(gwt[zero_both]).sum(axis=1) == 0).all()
 
 
+def test_bsdf_large_batch(bsdf_pair):
+    """north_star's first check at the scale of BASELINE.json configs[4] (its 2^26-tuple batch, a quarter of it here to keep the oracle
+    within half a minute): eval / pdf within 1e-4 relative and sample decisions / directions / pdfs on 2^24 random tuples, for
+    configs[1]'s Marschner material and configs[0]'s Kajiya-Kay -- rare branches that 1e5 tuples never reach."""
+    ctx, osc, nm = bsdf_pair
+    n = 1 << 24
+    rng = np.random.default_rng(2024)
+    wi = rng.normal(size=(n, 3)).astype(np.float32); wi /= np.linalg.norm(wi, axis=1, keepdims=True)
+    wo = rng.normal(size=(n, 3)).astype(np.float32); wo /= np.linalg.norm(wo, axis=1, keepdims=True)
+    smp = rng.random((n, 2), dtype=np.float32)
+    for b in (1, 0):
+        ge, gp = ctx.bsdf_eval(b, wi, wo)
+        oe, op = osc.bsdf_eval(b, wi, wo)
+        assert np.isfinite(ge).all() and np.isfinite(oe).all()
+        scale = float(np.abs(oe).max())
+        err = rel_err(ge, oe, 1e-6 * scale)
+        assert err.max() <= 1e-4, 'bsdf %d eval rel err %g' % (b, err.max())
+        assert rel_err(gp, op, 1e-9).max() <= 1e-4, 'bsdf %d pdf' % b
+        gwo, gwt, gpdf, gty = ctx.bsdf_sample(b, wi, smp)
+        owo, owt, opdf, oty = osc.bsdf_sample(b, wi, smp)
+        same = gty == oty
+        valid = same & (np.abs(owt).sum(axis=1) > 0)
+        werr = rel_err(gwt[valid], owt[valid], 1e-6 * float(np.abs(owt[valid]).max()))
+        print('bsdf %d, 2^24 tuples: eval rel err max %.3g, %d identical eval values of %d, %d sample decisions differ, direction err max %.3g, weight rel err q99.9 %.3g max %.3g'
+              % (b, err.max(), int((ge == oe).all(axis=1).sum()), n, int((~same).sum()), float(np.abs(gwo[valid] - owo[valid]).max()), np.quantile(werr[::16], 0.999), werr.max()))
+        assert (ge == oe).all(axis=1).mean() > 0.9999                 # measured: all 2^24 bit-identical (both sides use the correctly rounded elementary functions)
+        assert same.mean() > 0.9995
+        assert np.abs(gwo[valid] - owo[valid]).max() <= 2e-4
+        assert np.quantile(werr[::16], 0.999) <= 1e-3 and werr.max() <= 5e-2
+        assert rel_err(gpdf[valid], opdf[valid], 1e-9).max() <= 1e-4
+
+
 def test_marschner_fixed_mode_bit_exact(cp, oracle):
     """the unbuilt src/bsdfs/marschner.cpp -- tables, eval, pdf and the 4-number sample against the oracle."""
     ctx = cp.Context(0); osc = oracle.Scene()
