@@ -805,6 +805,35 @@ def test_full_size_configs(cp, oracle, name, size):
     assert rel_mse(a, b) < 1e-3                                                                         # north_star's image bar; measured 5e-7
 
 
+@pytest.mark.parametrize('name,ov', [('curly-hair', None), ('furball', dict(width=1024, height=1024))])
+def test_full_scene_first_sample_replay(cp, oracle, name, ov):
+    """The scenes of BASELINE.json configs[2] / configs[3] with all of their fibers (curly-hair 3.4 M segments, Marschner ggx with NEE,
+    1024x1024; furball 1.6 M segments, maxDepth 32 -- its 2048x2048 film cut to 1024x1024 to keep the oracle within half a minute):
+    the first sample index of every pixel, replayed by the CPU oracle with the same Philox counters."""
+    sc = dict(cp.scenes.SCENES[name]); sc.update(ov or {})
+    W, H, spp = sc['width'], sc['height'], sc['spp']
+    ctx = cp.scene_from_description(name, scale=1.0, overrides=ov); ctx.build()
+    g1 = ctx.render(spp, seed=3, sample_begin=0, sample_end=1)
+    st1 = ctx.stats()
+    ctx.close()
+    assert st1['segments'] > 1500000 and st1['unsupported_filtered_lookups'] == 0
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params(name))
+    osc = oracle.scene_from_description(name, scale=1.0, overrides=ov, envmap=env)
+    o1 = osc.render(spp, seed=3, sample_begin=0, sample_end=1)
+    assert st1['paths'] == W * H == osc.last_stats['paths']
+    print('%s: samples rejected by ImageBlock::put (non-finite or negative, imageblock.h:148-151): %d / %d' % (name, st1['dropped_samples'], osc.last_stats['dropped']))
+    assert st1['dropped_samples'] == osc.last_stats['dropped'] <= 2
+    assert np.abs(g1[..., 4] - o1[..., 4]).max() <= 1e-4 * o1[..., 4].max()
+    a, b = cp.develop(g1), cp.develop(o1)
+    close = np.abs(a - b).max(axis=2) <= 1e-3 * (np.abs(b).max(axis=2) + 1e-3)
+    print('%s first-sample replay: %.5f of the pixels agree to 1e-3, relMSE %.3g, rays %d / %d, shadow rays %d / %d'
+          % (name, close.mean(), rel_mse(a, b), st1['rays'], osc.last_stats['rays'], st1['shadow_rays'], osc.last_stats['shadow_rays']))
+    assert abs(st1['rays'] - osc.last_stats['rays']) <= 2e-4 * osc.last_stats['rays']
+    assert abs(st1['shadow_rays'] - osc.last_stats['shadow_rays']) <= 2e-4 * osc.last_stats['shadow_rays']
+    assert close.mean() > 0.998, 'only %.4f of the pixels agree to 1e-3' % close.mean()
+    assert rel_mse(a, b) < 1e-3
+
+
 def test_cancel_and_progress(cp):
     """Integrator::cancel() (include/mitsuba/render/integrator.h:76-84: asynchronous, render() then returns false) and the render job's
     progress reports (src/librender/integrator.cpp:95-138) at the C ABI: cudapath_cancel from another thread ends a blocking
