@@ -738,19 +738,20 @@ def test_repeated_jobs_reuse_device_memory(cp):
     assert total - free < used[3]
 
 
-def test_full_size_furball_ray_batch(cp, oracle):
-    """north_star's second check on the scene of BASELINE.json configs[3] / configs[4] at its full size (furball, 1.6 M segments, dense
-    fiber BVH): hit shape / primitive index bit-exact and hit distance bit-identical on a fixed batch of a million kdbench-style chords,
+@pytest.mark.parametrize('name,segments', [('furball', 1600000), ('hair-curl', 4000000), ('curly-hair', 3400000)])
+def test_full_size_ray_batch(cp, oracle, name, segments):
+    """north_star's second check on the scenes of BASELINE.json configs[1..4] at their full sizes (furball, 1.6 M segments, dense fiber
+    BVH; hair-curl, 4 M segments in four shapes with per-shape interval clipping and a 0.4 mm radius; curly-hair, 3.4 M segments): hit shape / primitive index bit-exact and hit distance bit-identical on a fixed batch of a million kdbench-style chords,
     of rays fired at fibers from close by with mint = Epsilon, and of secondary-like rays that start ON fiber surfaces; any-hit agrees."""
-    ctx = cp.scene_from_description('furball', scale=1.0); ctx.build()
-    assert ctx.stats()['segments'] == 1600000
-    env = cp.bake_sunsky(**cp.scenes.sunsky_params('furball'))
-    osc = oracle.scene_from_description('furball', scale=1.0, envmap=env)
+    ctx = cp.scene_from_description(name, scale=1.0); ctx.build()
+    assert ctx.stats()['segments'] == segments
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params(name))
+    osc = oracle.scene_from_description(name, scale=1.0, envmap=env)
     rng = np.random.default_rng(11)
     aabb, bs = osc.scene_bounds()
     o, d = chord_rays(rng, 1000000, bs[:3], bs[3] / 1.5 * 0.8)
     nh, nm = check_hits(ctx, osc, o, d, 0.0, np.inf)
-    assert nh > 100000
+    assert nh > 20000
     sh, pr, t = osc.intersect(o[:400000], d[:400000], 0.0, np.inf)
     m = sh >= 0
     hitp = o[:400000][m] + d[:400000][m] * t[m][:, None]
@@ -760,7 +761,7 @@ def test_full_size_furball_ray_batch(cp, oracle):
     gs, _, _ = ctx.intersect(hitp.astype(np.float32), d2, 1e-4, 5.0, any_hit=True)
     os_, _, _ = osc.intersect(hitp.astype(np.float32), d2, 1e-4, 5.0, mode=1)
     assert np.array_equal(gs >= 0, os_ >= 0)
-    print('full-size furball ray batch: %d + %d + %d identical hits, %d + %d + %d ties within 1e-6' % (nh, nh2, nh3, nm, nm2, nm3))
+    print('full-size %s ray batch: %d + %d + %d identical hits, %d + %d + %d ties within 1e-6' % (name, nh, nh2, nh3, nm, nm2, nm3))
     ctx.close()
 
 
