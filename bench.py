@@ -322,7 +322,7 @@ def main():
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (fp64 cylinder test)', 'data': 'synthetic',
                 'config': workload_config(args, sc), 'mrays_per_s': mrays, 'rays_per_path': (rays + shadow) / args.steps / paths_per_step,
                 'gpu_launches': int(launches), 'clocks': clocks, 'e2e': e2e, 'roofline': roof, 'cpu_baseline': cpu,
-                'build': {'segments': build['segments'], 'bvh_references': build['bvh_references'], 'bvh_nodes': build['bvh_nodes'], 'build_ms': build['build_ms']}}
+                'build': {'segments': build['segments'], 'bvh_references': build['bvh_references'], 'bvh_nodes': build['bvh_nodes'], 'build_ms': build['build_ms'], 'build_ms_note': 'first build of the process (cold device allocator); the steady-state build is the second entry of e2e.phases_s'}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
