@@ -6,17 +6,20 @@
 //     -D   parameter substitution of $name in the file (mitsuba.cpp:168)
 //     -p   accepted for compatibility with `mitsuba -p N`; the CPU core count has no meaning here
 //     -q   quiet
+// Ctrl-C cancels the render (cudapath_cancel) and exits with 130 without writing an image; a progress line goes to a terminal's stderr.
 // and prints the "Render time" line of RenderJob::run (src/librender/renderjob.cpp:108) plus Mpaths/s and Mrays/s.
 // Uses nothing but the C ABI of include/cudapath.h (this file is also the smallest example of a host program on that boundary).
 // Image writers: PNG (8 bit, zlib "stored/deflate" through libz), PPM, PFM (linear float, bottom-up as the format wants it).
 #include "../../include/cudapath.h"
 #include <chrono>
+#include <csignal>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 #include <zlib.h>
+#include <unistd.h>
 
 static void put_be32(std::vector<unsigned char> &v, uint32_t x) { for (int k = 3; k >= 0; --k) v.push_back((unsigned char) (x >> (8 * k))); }
 static void png_chunk(FILE *f, const char *type, const std::vector<unsigned char> &data) {
@@ -58,6 +61,11 @@ static bool write_pfm(const char *path, const float *rgb, int w, int h) {
 }
 static bool ends_with(const std::string &s, const char *suffix) { const size_t n = strlen(suffix); return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0; }
 
+// Ctrl-C / SIGTERM cancel the running job the way RenderJob::cancel does (include/mitsuba/render/renderjob.h:81): cudapath_cancel is the one
+// entry point that may run beside a blocking render (it only sets an atomic flag, so it is safe inside a signal handler)
+static cudapath_ctx *volatile g_ctx = nullptr;
+static void on_signal(int) { if (g_ctx) cudapath_cancel(g_ctx); }
+static void on_progress(void *, uint64_t done, uint64_t total) { fprintf(stderr, "\rRendering: %3.0f %%", 100.0 * (double) done / (double) total); if (done == total) fprintf(stderr, "\n"); }
 static int die(const char *what) { fprintf(stderr, "cudapath_render: %s: %s\n", what, cudapath_last_error()); return 1; }
 
 int main(int argc, char **argv) {
@@ -97,7 +105,14 @@ int main(int argc, char **argv) {
     cudapath_film_size(ctx, &w, &h);
     cudapath_get_film_output(ctx, &hdr, &gamma, &exposure);
     std::vector<float> film((size_t) w * h * 5);
-    if (cudapath_render(ctx, n, seed, 0, n, film.data()) != 0) return die("render failed");
+    g_ctx = ctx; signal(SIGINT, on_signal); signal(SIGTERM, on_signal);
+    if (!quiet && isatty(2)) cudapath_set_progress_callback(ctx, on_progress, nullptr);     // the progress bar of the reference's console (ProgressReporter)
+    const int rc = cudapath_render(ctx, n, seed, 0, n, film.data());
+    g_ctx = nullptr; signal(SIGINT, SIG_DFL); signal(SIGTERM, SIG_DFL);
+    if (rc != 0) {
+        if (std::string(cudapath_last_error()) == "render cancelled") { fprintf(stderr, "\ncudapath_render: render cancelled, no image written\n"); cudapath_destroy(ctx); return 130; }
+        return die("render failed");
+    }
     const double t3 = now();
     cudapath_stats st; cudapath_get_stats(ctx, &st);
 
