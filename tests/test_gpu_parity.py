@@ -103,6 +103,12 @@ def test_bsdf_sample(bsdf_pair):
         assert rel_err(gpdf[valid], opdf[valid], 1e-9).max() <= 1e-4
         zero_both = (np.abs(owt).sum(axis=1) == 0) & same
         assert (np.abs(gwt[zero_both]).sum(axis=1) == 0).all()
+        # a first random number of exactly 0: the reference's Marschner sample() returns an infinite direction and weight (reproduced)
+        smp0 = smp[:512].copy(); smp0[:, 0] = 0.0
+        gwo0, gwt0, _, _ = ctx.bsdf_sample(b, wi[:512], smp0); owo0, owt0, _, _ = osc.bsdf_sample(b, wi[:512], smp0)
+        assert np.array_equal(np.isfinite(gwo0), np.isfinite(owo0)) and np.array_equal(np.isfinite(gwt0), np.isfinite(owt0))
+        fin = np.isfinite(owt0).all(axis=1) & np.isfinite(owo0).all(axis=1)
+        assert np.array_equal(gwo0[fin], owo0[fin]) and np.array_equal(gwt0[fin], owt0[fin])
 
 
 def test_bsdf_large_batch(bsdf_pair):
