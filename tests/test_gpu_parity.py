@@ -105,6 +105,8 @@ def test_bsdf_sample(bsdf_pair):
         assert (np.abs(gwt[zero_both]).sum(axis=1) == 0).all()
         # a first random number of exactly 0: the reference's Marschner sample() returns an infinite direction and weight (reproduced)
         smp0 = smp[:512].copy(); smp0[:, 0] = 0.0
+        edge = np.array([0.0, 2.0 ** -24, 0.5, 1.0 - 2.0 ** -24], np.float32)             # the extreme values a [0,1) generator can return, both dimensions
+        smp0[:16] = np.stack(np.meshgrid(edge, edge), -1).reshape(-1, 2); smp0[16:32, 0] = smp[16:32, 0]; smp0[16:32, 1] = np.tile(edge, 4)
         gwo0, gwt0, _, _ = ctx.bsdf_sample(b, wi[:512], smp0); owo0, owt0, _, _ = osc.bsdf_sample(b, wi[:512], smp0)
         assert np.array_equal(np.isfinite(gwo0), np.isfinite(owo0)) and np.array_equal(np.isfinite(gwt0), np.isfinite(owt0))
         fin = np.isfinite(owt0).all(axis=1) & np.isfinite(owo0).all(axis=1)
@@ -392,8 +394,10 @@ def test_env_tables_eval_sample(geo_pair):
     assert np.array_equal(grgb, orgb) and np.array_equal(gpdf, opdf)
     ref = (rng.normal(size=(n, 3)) * 2 + np.array([0, 6, 0])).astype(np.float32)
     smp = rng.random((n, 2)).astype(np.float32)
+    edge = np.array([0.0, 2.0 ** -24, 0.5, 1.0 - 2.0 ** -24], np.float32)                 # the extreme values a [0,1) generator can return
+    smp[:16] = np.stack(np.meshgrid(edge, edge), -1).reshape(-1, 2)
     gd, gv, gp, gdist = ctx.env_sample(ref, smp); od, ov, op, odist = osc.env_sample(ref, smp)
-    assert np.array_equal(gd, od) and np.array_equal(gv, ov) and np.array_equal(gp, op) and np.array_equal(gdist, odist)
+    assert np.array_equal(gd, od, equal_nan=True) and np.array_equal(gv, ov, equal_nan=True) and np.array_equal(gp, op, equal_nan=True) and np.array_equal(gdist, odist, equal_nan=True)
 
 
 def test_camera_rays(geo_pair):
