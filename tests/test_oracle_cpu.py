@@ -758,6 +758,37 @@ def test_develop_ldr(cp):
     assert np.array_equal(cp.develop_ldr(film, gamma=1.0), q(v))
 
 
+def test_develop_pinned_against_reference_text(cp):
+    """Film develop against the reference executed as written: undoGamma / applyGamma / convertScalar cut out of src/libcore/fmtconv.cpp
+    (:1093-1160) at build time, inside the ESpectrumAlphaWeight -> ERGB pixel loop of :984-995 (oracle/ref_shim/ref_develop.cpp), with what
+    LDRFilm::develop passes (gamma, 2^exposure; src/films/ldrfilm.cpp:300-321).  Linear output bit-identical; 8-bit output identical except
+    where the reference's libm powf and the product's correctly rounded pow land on different sides of a rounding boundary (<= 1 level)."""
+    if not os.path.exists(REF_GEOM):
+        pytest.skip('oracle/_ref/libref_geom.so not built (needs /root/reference)')
+    L = ctypes.CDLL(REF_GEOM)
+    rng = np.random.default_rng(77)
+    h, w = 256, 384
+    film = np.zeros((h, w, 5), np.float32)
+    film[..., 4] = rng.random((h, w)).astype(np.float32) * 60 + 4                         # filter weights of ~64 spp
+    film[..., :3] = (rng.random((h, w, 3)) ** 3).astype(np.float32) * film[..., 4:5] * 1.5    # values in [0, 1.5): dark tones, mid tones, clipped highlights
+    film[..., 3] = film[..., 4]
+    film[0, :8, 4] = 0                                                                    # pixels no sample touched
+    film[1, :8, :3] = 0; film[2, :4, 0] = -1.0; film[2, 4:8, 1] = np.inf; film[3, :4, 2] = np.nan
+    film[4, :16, 0] = np.linspace(0.0031308 - 2e-6, 0.0031308 + 2e-6, 16, dtype=np.float32) * film[4, :16, 4]   # around the sRGB knee
+    n = h * w
+    ref_lin = np.zeros((h, w, 3), np.float32)
+    L.ref_develop_hdr(film.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), ref_lin.ctypes.data_as(ctypes.c_void_p))
+    assert np.array_equal(cp.develop(film), ref_lin, equal_nan=True)
+    for gamma, exposure in ((-1.0, 0.0), (2.2, 0.0), (2.2, 1.0), (1.0, -0.5), (1.8, 0.25)):
+        ref8 = np.zeros((h, w, 3), np.uint8)
+        L.ref_develop_ldr(film.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), ctypes.c_float(gamma), ctypes.c_float(exposure), ref8.ctypes.data_as(ctypes.c_void_p))
+        got = cp.develop_ldr(film, gamma=gamma, exposure=exposure)
+        diff = np.abs(got.astype(int) - ref8.astype(int))
+        assert diff.max() <= 1 and (diff != 0).mean() < 1e-4, (gamma, exposure, int(diff.max()), float((diff != 0).mean()))
+        if gamma == 1.0:
+            assert np.array_equal(got, ref8)
+
+
 def test_c_abi_exports_every_declared_symbol(cp):
     """The shared library loads (without a GPU) and exports every function include/cudapath.h declares."""
     import re
