@@ -578,6 +578,45 @@ def test_obj_loader(cp, tmp_path):
         cp.load_obj_file(str(bad))
 
 
+def test_compute_normals_pinned_against_reference_text(cp, tmp_path):
+    """TriMesh::computeNormals (src/librender/trimesh.cpp:606-676) + unitAngle (include/mitsuba/core/util.h:309-314), cut out of the reference
+    at build time and executed as written (oracle/ref_shim/ref_trimesh.cpp), against the PRODUCT's OBJ loader on a bumpy sphere with a
+    degenerate triangle and an unreferenced vertex: generated vertex normals, flipNormals, faceNormals (winding swap, no normals).  The
+    reference calls libm asinf, the product rounds correctly: normals agree to an ulp or two, most of them to the bit."""
+    if not os.path.exists(REF_GEOM):
+        pytest.skip('oracle/_ref/libref_geom.so not built (needs /root/reference)')
+    L = ctypes.CDLL(REF_GEOM)
+    rng = np.random.default_rng(12)
+    nu, nv = 48, 24
+    th = (np.arange(1, nv) / nv * np.pi)[:, None]; ph = (np.arange(nu) / nu * 2 * np.pi)[None, :]
+    r = 1 + 0.15 * rng.random((nv - 1, nu))
+    pts = np.stack([r * np.sin(th) * np.cos(ph), r * np.cos(th) * np.ones_like(ph), r * np.sin(th) * np.sin(ph)], -1).reshape(-1, 3)
+    pts = np.vstack([pts, [[0, 1.2, 0], [0, -1.2, 0], [9, 9, 9]]]).astype(np.float32)            # poles + a vertex no face uses
+    top, bot = len(pts) - 3, len(pts) - 2
+    faces = []
+    for j in range(nv - 2):
+        for i in range(nu):
+            a = j * nu + i; b = j * nu + (i + 1) % nu; c = a + nu; d = b + nu
+            faces.append((a, b, d, c))                                                            # quads: fan-triangulated by the loader
+    for i in range(nu):
+        faces.append((top, (i + 1) % nu, i)); faces.append((bot, (nv - 2) * nu + i, (nv - 2) * nu + (i + 1) % nu))
+    faces.append((0, 0, 1))                                                                       # degenerate
+    path = tmp_path / 'bumpy.obj'
+    path.write_text(''.join('v %.9g %.9g %.9g\n' % tuple(p) for p in pts) + ''.join('f ' + ' '.join(str(k + 1) for k in f) + '\n' for f in faces))
+    for face, flip in ((False, False), (False, True), (True, True), (True, False)):
+        xyz, idx, nrm = cp.load_obj_file(str(path), faceNormals=face, flipNormals=flip)
+        xyz0, idx0, _ = cp.load_obj_file(str(path), faceNormals=True, flipNormals=False)          # the mesh before computeNormals touches it
+        assert np.array_equal(xyz, xyz0)
+        tri = np.ascontiguousarray(idx0, np.uint32).copy(); ref_n = np.zeros_like(xyz)
+        has = L.ref_compute_normals(xyz.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(xyz)), tri.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(tri)),
+                                    int(face), int(flip), ref_n.ctypes.data_as(ctypes.c_void_p))
+        assert np.array_equal(idx, tri)                                                           # winding after computeNormals
+        assert bool(has) == (nrm is not None)
+        if nrm is not None:
+            assert len(nrm) > 1100 and np.abs(nrm - ref_n).max() <= 4e-7 and (nrm == ref_n).mean() > 0.8
+            assert (np.abs(np.linalg.norm(nrm, axis=1) - 1) < 1e-6).all()
+
+
 def test_film_filter_table_and_splat(oracle):
     s = oracle.Scene()
     s.add_hair(*tiny_hair(), 0.1, s.add_bsdf('kajiyakay'))
