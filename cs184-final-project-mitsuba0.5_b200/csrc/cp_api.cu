@@ -29,42 +29,7 @@ struct BsdfHost { BsdfDev dev; MarschnerTables tables; float *rt = nullptr; };
 void mat_mul(const float *a, const float *b, float *r) {
     for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { float s = 0; for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j]; r[i * 4 + j] = s; }
 }
-bool mat_inv(const float *a, float *out) {
-    const int N = 4;
-    int indxc[N], indxr[N], ipiv[N] = {0, 0, 0, 0};
-    float (*m)[4] = reinterpret_cast<float (*)[4]>(out);
-    std::memcpy(out, a, 64);
-    for (int i = 0; i < N; i++) {
-        int irow = -1, icol = -1;
-        float big = 0;
-        for (int j = 0; j < N; j++) {
-            if (ipiv[j] != 1) {
-                for (int k = 0; k < N; k++) {
-                    if (ipiv[k] == 0) {
-                        if (std::fabs(m[j][k]) >= big) { big = std::fabs(m[j][k]); irow = j; icol = k; }
-                    } else if (ipiv[k] > 1) return false;
-                }
-            }
-        }
-        ++ipiv[icol];
-        if (irow != icol) for (int k = 0; k < N; ++k) std::swap(m[irow][k], m[icol][k]);
-        indxr[i] = irow; indxc[i] = icol;
-        if (m[icol][icol] == 0) return false;
-        const volatile float pivinv = 1.f / m[icol][icol];
-        m[icol][icol] = 1.f;
-        for (int j = 0; j < N; j++) m[icol][j] *= pivinv;
-        for (int j = 0; j < N; j++) {
-            if (j != icol) {
-                const float save = m[j][icol];
-                m[j][icol] = 0;
-                for (int k = 0; k < N; k++) { const volatile float prod = m[icol][k] * save; m[j][k] -= prod; }    // no fused multiply-add, like the x86 build of the reference
-            }
-        }
-    }
-    for (int j = N - 1; j >= 0; j--)
-        if (indxr[j] != indxc[j]) for (int k = 0; k < N; k++) std::swap(m[k][indxr[j]], m[k][indxc[j]]);
-    return true;
-}
+bool mat_inv(const float *a, float *out) { return mat4_invert_f32(a, out); }      // cp_host_data.cpp (shared with the OBJ loader)
 V3 h_xfm_point(const float *m, V3 p) {
     float x = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], y = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
     float z = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11], w = m[12] * p.x + m[13] * p.y + m[14] * p.z + m[15];

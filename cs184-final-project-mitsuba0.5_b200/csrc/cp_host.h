@@ -50,6 +50,7 @@ bool load_hair_file(const std::string &path, float radius, float angleThresholdD
 struct MeshFileData { std::vector<float> xyz, normals /* empty = face normals */; std::vector<uint32_t> indices; };
 // Radiance RGBE (.hdr) image -> top-down RGB fp32 (Bitmap::readRGBE, src/libcore/bitmap.cpp:3590-3678)
 bool load_rgbe_file(const std::string &path, std::vector<float> &rgb, int &w, int &h, std::string &err);
+bool mat4_invert_f32(const float *a, float *out);     // Matrix<4,4,float>::invert of the reference (matrix.inl:138-193), row-major
 bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNormals, bool flipNormals, bool flipTexCoords, MeshFileData &out, std::string &err);
 
 // cp_host_sunsky.cpp

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <sstream>
 #include <algorithm>
 #include <map>
@@ -237,6 +238,45 @@ bool load_hair_file(const std::string &path, float radius, float angleThresholdD
     return true;
 }
 
+// Matrix<4,4,float>::invert (include/mitsuba/core/matrix.inl:138-193): Gauss-Jordan with full pivoting, in place, fp32, one rounding per
+// operation -- what Transform(const Matrix4x4 &) runs on every <matrix> of a scene file.  Row-major 4x4; false when singular.
+bool mat4_invert_f32(const float *a, float *out) {
+    const int N = 4;
+    int indxc[N], indxr[N], ipiv[N] = {0, 0, 0, 0};
+    float (*m)[4] = reinterpret_cast<float (*)[4]>(out);
+    std::memcpy(out, a, 64);
+    for (int i = 0; i < N; i++) {
+        int irow = -1, icol = -1;
+        float big = 0;
+        for (int j = 0; j < N; j++) {
+            if (ipiv[j] != 1) {
+                for (int k = 0; k < N; k++) {
+                    if (ipiv[k] == 0) {
+                        if (std::fabs(m[j][k]) >= big) { big = std::fabs(m[j][k]); irow = j; icol = k; }
+                    } else if (ipiv[k] > 1) return false;
+                }
+            }
+        }
+        ++ipiv[icol];
+        if (irow != icol) for (int k = 0; k < N; ++k) std::swap(m[irow][k], m[icol][k]);
+        indxr[i] = irow; indxc[i] = icol;
+        if (m[icol][icol] == 0) return false;
+        const volatile float pivinv = 1.f / m[icol][icol];
+        m[icol][icol] = 1.f;
+        for (int j = 0; j < N; j++) m[icol][j] *= pivinv;
+        for (int j = 0; j < N; j++) {
+            if (j != icol) {
+                const float save = m[j][icol];
+                m[j][icol] = 0;
+                for (int k = 0; k < N; k++) { const volatile float prod = m[icol][k] * save; m[j][k] -= prod; }    // no fused multiply-add, like the x86 build of the reference
+            }
+        }
+    }
+    for (int j = N - 1; j >= 0; j--)
+        if (indxr[j] != indxc[j]) for (int k = 0; k < N; k++) std::swap(m[k][indxr[j]], m[k][indxc[j]]);
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------ Wavefront OBJ meshes
 // WavefrontOBJ(props) with collapse = true semantics: every face of the file lands in ONE mesh (src/shapes/obj.cpp:186-349):
 // `v` / `vn` / `vt` / `f` lines (n-gons as a fan :316-323, negative indices :640-645), vertices transformed by toWorld and merged
@@ -260,20 +300,11 @@ bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNo
     out = MeshFileData();
     std::ifstream is(path);
     if (!is) { err = "Wavefront OBJ file '" + path + "' not found!"; return false; }
-    // normals transform with the inverse transpose of the linear part (transform.h:203-211)
-    double inv[9];
-    {
-        const double a = toWorld[0], b = toWorld[1], c = toWorld[2], d = toWorld[4], e = toWorld[5], f = toWorld[6], g = toWorld[8], h = toWorld[9], i = toWorld[10];
-        const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
-        if (det == 0) { err = "obj: singular toWorld transform"; return false; }
-        const double r = 1.0 / det;
-        inv[0] = (e * i - f * h) * r; inv[1] = (c * h - b * i) * r; inv[2] = (b * f - c * e) * r;
-        inv[3] = (f * g - d * i) * r; inv[4] = (a * i - c * g) * r; inv[5] = (c * d - a * f) * r;
-        inv[6] = (d * h - e * g) * r; inv[7] = (b * g - a * h) * r; inv[8] = (a * e - b * d) * r;
-    }
+    // normals transform with the transpose of the inverse (transform.h:203-211); the inverse is the one Transform(const Matrix4x4 &) computes
+    float inv[16];
+    if (!mat4_invert_f32(toWorld, inv)) { err = "obj: singular toWorld transform"; return false; }
     auto xfmN = [&](Vec v) -> Vec {
-        const float m[9] = {(float) inv[0], (float) inv[1], (float) inv[2], (float) inv[3], (float) inv[4], (float) inv[5], (float) inv[6], (float) inv[7], (float) inv[8]};
-        return {m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z, m[2] * v.x + m[5] * v.y + m[8] * v.z};
+        return {inv[0] * v.x + inv[4] * v.y + inv[8] * v.z, inv[1] * v.x + inv[5] * v.y + inv[9] * v.z, inv[2] * v.x + inv[6] * v.y + inv[10] * v.z};
     };
     std::vector<Vec> vertices, normals; std::vector<std::array<float, 2>> texcoords;
     struct Corner { int p = 0, n = 0, uv = 0; };
@@ -288,9 +319,17 @@ bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNo
         else return false;
         return true;
     };
+    // fetch_line (obj.cpp:165-187): trailing blanks / CR are cut; a line ending in a backslash is glued to the next one (nothing in between)
+    std::function<bool(std::string &)> fetchLine = [&](std::string &l) -> bool {
+        if (!std::getline(is, l)) return false;
+        size_t n = l.size();
+        while (n > 0 && (l[n - 1] == '\r' || l[n - 1] == '\n' || l[n - 1] == '\t' || l[n - 1] == ' ')) --n;
+        if (n > 0 && l[n - 1] == '\\') { std::string next; fetchLine(next); l = l.substr(0, n - 1) + next; }
+        else l.resize(n);
+        return true;
+    };
     std::string line, buf;
-    while (std::getline(is, line)) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
+    while (is.good() && !is.eof() && fetchLine(line)) {
         std::istringstream iss(line);
         if (!(iss >> buf)) continue;
         if (buf == "v") { Vec p{0, 0, 0}; iss >> p.x >> p.y >> p.z; vertices.push_back(p); }
@@ -298,7 +337,8 @@ bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNo
         else if (buf == "vt") { float u = 0, v = 0; iss >> u >> v; if (flipTexCoords) v = 1 - v; texcoords.push_back({u, v}); }
         else if (buf == "f") {
             std::string tmp; std::array<Corner, 3> t;
-            for (int k = 0; k < 3; ++k) { if (!(iss >> tmp) || !parseCorner(tmp, t[k])) { err = "Invalid OBJ face format!"; return false; } }
+            // obj.cpp:311-314 does not check the extraction: a face with fewer than three corners repeats its last token (a degenerate triangle)
+            for (int k = 0; k < 3; ++k) { iss >> tmp; if (!parseCorner(tmp, t[k])) { err = "Invalid OBJ face format!"; return false; } }
             faces.push_back(t);
             while (iss >> tmp) { t[1] = t[2]; if (!parseCorner(tmp, t[2])) { err = "Invalid OBJ face format!"; return false; } faces.push_back(t); }
         }
@@ -318,14 +358,14 @@ bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNo
             const Vec p = xfmP(toWorld, vertices[vid - 1]);
             Vec n{0, 0, 0};
             if (nid != 0) {
-                if (nid > (int) normals.size() || nid < 0) { err = "Out of bounds: tried to access normal " + std::to_string(nid); return false; }
+                if (nid > (int) normals.size() || nid < 0) { err = "Out of bounds: tried to access normal " + std::to_string(nid) + " (max: " + std::to_string(normals.size()) + ")"; return false; }
                 n = xfmN(normals[nid - 1]);
                 if (!(n.x == 0 && n.y == 0 && n.z == 0)) n = divv(n, lenv(n));
                 hasNormals = true;
             }
             float uv[2] = {0, 0};
             if (uid != 0) {
-                if (uid > (int) texcoords.size() || uid < 0) { err = "Out of bounds: tried to access uv " + std::to_string(uid); return false; }
+                if (uid > (int) texcoords.size() || uid < 0) { err = "Out of bounds: tried to access uv " + std::to_string(uid) + " (max: " + std::to_string(texcoords.size()) + ")"; return false; }
                 uv[0] = texcoords[uid - 1][0]; uv[1] = texcoords[uid - 1][1];
             }
             const Key key{{p.x, p.y, p.z, n.x, n.y, n.z, uv[0], uv[1]}};

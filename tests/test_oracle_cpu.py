@@ -617,6 +617,75 @@ def test_compute_normals_pinned_against_reference_text(cp, tmp_path):
             assert (np.abs(np.linalg.norm(nrm, axis=1) - 1) < 1e-6).all()
 
 
+def _ref_obj_load(L, path, toWorld=None):
+    """WavefrontOBJ text loader of the reference executed as written (oracle/ref_shim/ref_obj.cpp) -> (xyz, idx, normals or None)."""
+    tw = np.ascontiguousarray(np.eye(4) if toWorld is None else toWorld, np.float32)
+    h = ctypes.c_void_p(); nv = ctypes.c_size_t(); nt = ctypes.c_size_t(); hn = ctypes.c_int(); ht = ctypes.c_int(); err = ctypes.create_string_buffer(512)
+    if L.ref_obj_load(str(path).encode(), tw.ctypes.data_as(ctypes.c_void_p), 0, ctypes.byref(h), ctypes.byref(nv), ctypes.byref(nt), ctypes.byref(hn), ctypes.byref(ht),
+                      err, ctypes.c_size_t(512)) != 0:
+        raise RuntimeError(err.value.decode())
+    xyz = np.zeros((nv.value, 3), np.float32); nrm = np.zeros((nv.value, 3), np.float32) if hn.value else None; idx = np.zeros((nt.value, 3), np.uint32)
+    L.ref_obj_copy(h, xyz.ctypes.data_as(ctypes.c_void_p), None if nrm is None else nrm.ctypes.data_as(ctypes.c_void_p), None, idx.ctypes.data_as(ctypes.c_void_p))
+    L.ref_obj_free(h)
+    return xyz, idx, nrm
+
+
+def test_obj_text_loader_pinned_against_reference_text(cp, tmp_path):
+    """The line loop of WavefrontOBJ(props), fetch_line, parse and createMesh (src/shapes/obj.cpp:165-187, 245-328, 371-390, 577-715) with
+    tokenize / trim (util.cpp:83-104), Transform(Matrix4x4) (matrix.inl:138-193) and the point / normal transforms (transform.h:108-125,
+    203-211), cut out of the reference at build time and executed as written, against the PRODUCT's OBJ loader: a file with every corner
+    syntax (v, v/vt, v//vn, v/vt/vn), negative indices, n-gons, duplicated positions, a zero normal, trailing blanks, CR line ends,
+    backslash continuation lines, groups / materials (collapsed), under the identity and under a sheared toWorld.  Vertex order after the
+    merge, indices and transformed normals must be BIT-identical; malformed files must raise the same message on both sides."""
+    if not os.path.exists(REF_GEOM):
+        pytest.skip('oracle/_ref/libref_geom.so not built (needs /root/reference)')
+    L = ctypes.CDLL(REF_GEOM)
+    rng = np.random.default_rng(5)
+    n = 300
+    v = rng.normal(size=(n, 3)).astype(np.float32); v[50:60] = v[40:50]                           # equal positions: merged when normal and uv agree
+    vn = rng.normal(size=(40, 3)).astype(np.float32); vn[7] = 0                                   # a zero normal is kept as it is (obj.cpp:658-659)
+    vt = rng.random((30, 2)).astype(np.float32)
+    lines = ['# torture', 'mtllib foo.mtl', 'o thing']
+    for i, p in enumerate(v):
+        lines.append('v %.9g %.9g %.9g' % tuple(p) + ('  \t ' if i % 7 == 0 else '') + ('\r' if i % 5 == 0 else ''))
+        if i == 100:
+            lines += ['g part_a', 'usemtl red']
+    lines += ['vn %.9g %.9g %.9g' % tuple(q) for q in vn] + ['vt %.9g %.9g' % tuple(q) for q in vt] + ['s off']
+    for k in range(400):
+        ids = rng.integers(1, n + 1, int(rng.integers(3, 7)))
+        toks = []
+        for a in ids:
+            a = int(a) if k % 3 else int(a) - n - 1
+            toks.append(('%d' % a, '%d/%d' % (a, rng.integers(1, 31)), '%d//%d' % (a, rng.integers(1, 41)), '%d/%d/%d' % (a, rng.integers(1, 31), -int(rng.integers(1, 41))),
+                         '%d/%d/%d' % (a, -int(rng.integers(1, 31)), rng.integers(1, 41)))[k % 5])
+        lines += ['f ' + ' '.join(toks[:2]) + ' \\', ' '.join(toks[2:])] if k % 11 == 0 else ['f ' + ' '.join(toks)]
+        if k == 150:
+            lines += ['g part_b', 'usemtl blue']
+    lines += ['   f 1 2 3   ', 'f 4 5', 'f 6', '']                                               # leading blanks; short faces repeat their last corner (obj.cpp:311-314)
+    path = tmp_path / 'torture.obj'
+    path.write_bytes(('\n'.join(lines) + '\n').encode())
+    shear = np.array([[1.5, 0.2, 0, 3], [0.1, 0.8, -0.3, -1], [0, 0.4, 2.0, 0.5], [0, 0, 0, 1]], np.float32)
+    for tw in (None, shear):
+        rx, ri, rn = _ref_obj_load(L, path, tw)
+        assert len(rx) > 1500 and len(ri) > 900 and rn is not None
+        px, pi, _ = cp.load_obj_file(str(path), toWorld=tw, faceNormals=True)                     # the mesh before computeNormals touches it
+        assert np.array_equal(px.view(np.uint32), rx.view(np.uint32)) and np.array_equal(pi, ri)
+        _, pi2, pn = cp.load_obj_file(str(path), toWorld=tw)                                      # given normals are kept
+        assert np.array_equal(pi2, ri) and np.array_equal(pn.view(np.uint32), rn.view(np.uint32))
+    cases = {'empty face': 'v 0 0 0\nv 1 0 0\nv 0 1 0\nf\n', 'four tokens': 'v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1/1/1/1 2 3\n', 'vertex': 'v 0 0 0\nf 1 2 3\n',
+             'normal': 'v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//2 3//1\n', 'uv': 'v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nf 1/1 2/5 3/1\n',
+             'negative': 'v 0 0 0\nv 1 0 0\nv 0 1 0\nf -1 -2 -4\n'}
+    for name, text in cases.items():
+        bad = tmp_path / 'bad.obj'; bad.write_text(text)
+        with pytest.raises(RuntimeError) as ref_err:
+            _ref_obj_load(L, bad)
+        with pytest.raises(cp.CudapathError) as prod_err:
+            cp.load_obj_file(str(bad))
+        assert str(prod_err.value) == str(ref_err.value), name
+    ok = tmp_path / 'ok.obj'; ok.write_text('v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1/ 2// /3')   # stray slashes, no final newline
+    assert np.array_equal(cp.load_obj_file(str(ok), faceNormals=True)[1], _ref_obj_load(L, ok)[1])
+
+
 def test_film_filter_table_and_splat(oracle):
     s = oracle.Scene()
     s.add_hair(*tiny_hair(), 0.1, s.add_bsdf('kajiyakay'))
