@@ -115,6 +115,13 @@ def bake_sunsky(turbidity=3.0, albedo=(0.2, 0.2, 0.2), sunDirection=(0, 1, 0), s
     return out
 
 
+def sun_radiance(turbidity=3.0, sunDirection=(0, 1, 0), data_dir=None):
+    """computeSunRadiance (src/emitters/sunsky/sunmodel.h:260-371) in linear RGB -> (3,) fp32."""
+    out = np.zeros(3, np.float32)
+    _check(lib().cudapath_sun_radiance((data_dir or DEFAULT_DATA_DIR).encode(), ctypes.c_float(turbidity), _p(_f32(sunDirection)), _p(out)))
+    return out
+
+
 def develop(film):
     """Film::develop normalisation (src/libcore/fmtconv.cpp:955-1056): (h,w,5) accumulated film -> (h,w,3) RGB."""
     film = _f32(film)

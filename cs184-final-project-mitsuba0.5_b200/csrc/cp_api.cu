@@ -417,6 +417,14 @@ int cudapath_bake_sunsky(const char *data_dir, float turbidity, const float albe
     std::memcpy(out_rgb, rgb.data(), rgb.size() * 4);
     return 0;
 }
+int cudapath_sun_radiance(const char *data_dir, float turbidity, const float sun_direction[3], float out_rgb[3]) {
+    if (!data_dir || !sun_direction || !out_rgb) return fail("null argument");
+    SunSkyParams p; p.turbidity = turbidity; p.resolution = 2;
+    for (int i = 0; i < 3; ++i) p.sunDirection[i] = sun_direction[i];
+    std::vector<float> rgb; int w, h; std::string err;
+    if (!bake_sunsky(data_dir, p, rgb, w, h, err, out_rgb)) return fail(err);
+    return 0;
+}
 int cudapath_set_sunsky(cudapath_ctx *ctx, float turbidity, const float albedo[3], const float sun_direction[3], float sky_scale,
                         float sun_scale, float sun_radius_scale, int resolution) {
     if (!ctx) return fail("null context");

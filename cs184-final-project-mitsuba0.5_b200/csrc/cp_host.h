@@ -55,6 +55,6 @@ bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNo
 
 // cp_host_sunsky.cpp
 struct SunSkyParams { float turbidity = 3, albedo[3] = {0.2f, 0.2f, 0.2f}, sunDirection[3] = {0, 1, 0}, skyScale = 1, sunScale = 1, sunRadiusScale = 1, stretch = 1; int resolution = 512; };
-bool bake_sunsky(const std::string &dataDir, const SunSkyParams &p, std::vector<float> &rgb, int &w, int &h, std::string &err);
+bool bake_sunsky(const std::string &dataDir, const SunSkyParams &p, std::vector<float> &rgb, int &w, int &h, std::string &err, float *sunRadianceOut = nullptr);
 
 } // namespace cp

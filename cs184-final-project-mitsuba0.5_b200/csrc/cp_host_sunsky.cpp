@@ -144,7 +144,7 @@ inline float safeAcos(float v) { return std::acos(std::min(1.0f, std::max(-1.0f,
 
 } // namespace
 
-bool bake_sunsky(const std::string &dataDir, const SunSkyParams &P, std::vector<float> &rgb, int &W, int &H, std::string &err) {
+bool bake_sunsky(const std::string &dataDir, const SunSkyParams &P, std::vector<float> &rgb, int &W, int &H, std::string &err, float *sunRadianceOut) {
     std::vector<double> hosek(3 * 1200);
     std::vector<float> cie(4 * 471);
     if (!readAll(dataDir + "/sunsky/hosek_rgb.f64", hosek.data(), hosek.size() * 8)) { err = "cannot read " + dataDir + "/sunsky/hosek_rgb.f64"; return false; }
@@ -187,6 +187,7 @@ bool bake_sunsky(const std::string &dataDir, const SunSkyParams &P, std::vector<
     float sunRGB[3];
     if (!sunRadianceRGB(sunEl, P.turbidity, cie, sunRGB)) { err = "sun radiance failed"; return false; }
     for (int c = 0; c < 3; ++c) sunRGB[c] *= P.sunScale;
+    if (sunRadianceOut) for (int c = 0; c < 3; ++c) sunRadianceOut[c] = sunRGB[c];
     const float sEl = sunEl * P.stretch;
     const V3 sunDir(std::sin(sunAz) * std::sin(sEl), std::cos(sEl), -std::cos(sunAz) * std::sin(sEl));
     const Frame sunFrame(sunDir);
@@ -196,8 +197,9 @@ bool bake_sunsky(const std::string &dataDir, const SunSkyParams &P, std::vector<
     const float covered = 0.5f * (1 - cosCut);
     const size_t nSamples = (size_t) std::max(100.0f, (pixelCount * covered * 1000));
     const float gx = W / (2 * PI_F), gy = H / PI_F;
-    const float k = (2 * PI_F * (1 - std::cos(halfAngle))) * (float) (W * H) / (2 * PI_F * PI_F * nSamples);
-    const V3 value(sunRGB[0] * k, sunRGB[1] * k, sunRGB[2] * k);
+    // sunRadiance * solidAngle * texels / (2 pi^2 n), one rounding per Spectrum operation; Spectrum / Float multiplies by the reciprocal (sunsky.cpp:195-198, spectrum.h:415-425)
+    const float solid = 2 * PI_F * (1 - std::cos(halfAngle)), texels = (float) (W * H), recip = 1.0f / (2 * PI_F * PI_F * nSamples);
+    const V3 value(sunRGB[0] * solid * texels * recip, sunRGB[1] * solid * texels * recip, sunRGB[2] * solid * texels * recip);
     for (size_t i = 0; i < nSamples; ++i) {
         // (0,2)-sequence point: van der Corput radical inverse and Sobol' dimension 2
         uint32_t n = (uint32_t) i, v = __builtin_bswap32(n);

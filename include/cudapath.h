@@ -116,6 +116,9 @@ int cudapath_set_sunsky(cudapath_ctx *ctx, float turbidity, const float albedo[3
 /* Bake only: writes resolution x resolution/2 x 3 floats. */
 int cudapath_bake_sunsky(const char *data_dir, float turbidity, const float albedo[3], const float sun_direction[3], float sky_scale,
                          float sun_scale, float sun_radius_scale, int resolution, float *out_rgb);
+/* Radiance of the sun disc in linear RGB for a sun direction and turbidity: computeSunRadiance, src/emitters/sunsky/sunmodel.h:260-371, with the
+ * spectrum -> RGB conversion SunSkyEmitter applies (sunsky.cpp:170-171); the value the bake splats.  Host only. */
+int cudapath_sun_radiance(const char *data_dir, float turbidity, const float sun_direction[3], float out_rgb[3]);
 
 /* ---- sensor / film / integrator ---------------------------------------------------------------------------- */
 /* `perspective` sensor: ProjectiveCamera/PerspectiveCamera props + configure(), src/librender/sensor.cpp:156-160,225-300,

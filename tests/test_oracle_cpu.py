@@ -686,6 +686,27 @@ def test_obj_text_loader_pinned_against_reference_text(cp, tmp_path):
     assert np.array_equal(cp.load_obj_file(str(ok), faceNormals=True)[1], _ref_obj_load(L, ok)[1])
 
 
+def test_sun_disc_splat_pinned_against_reference_text(cp):
+    """The QMC rasterisation of the sun disc in SunSkyEmitter (src/emitters/sunsky.cpp:180-211) with toSphere / fromSphere (sunmodel.h:90-105),
+    squareToUniformCone (warp.cpp:54-63), sample02 (qmc.h:43-60,82-87,115-120) and coordinateSystem (util.cpp:592-601), cut out of the
+    reference at build time and executed as written (oracle/ref_shim/ref_sunsplat.cpp), against the PRODUCT's bake with the sky switched off:
+    sample count, texels hit and accumulated radiance BIT-identical (one sample up to ~10^5 per texel, sun at the zenith, near the horizon
+    and behind the seam).  The sun radiance itself (computeSunRadiance -> RGB) comes from the product and is an input on the reference side."""
+    if not os.path.exists(REF_GEOM):
+        pytest.skip('oracle/_ref/libref_geom.so not built (needs /root/reference)')
+    L = ctypes.CDLL(REF_GEOM)
+    L.ref_sun_splat.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_float]
+    for sun_dir, turbidity, res, radius_scale in (((0.3, 0.8, 0.2), 3.0, 512, 1.0), ((-0.5, 0.1, -0.7), 5.0, 256, 4.0), ((0, 1, 0), 2.0, 64, 1.0),
+                                                  ((0.7, 0.02, 0.1), 8.0, 1024, 10.0), ((-1e-3, 0.5, 1.0), 3.0, 128, 6.0)):
+        prod = cp.bake_sunsky(turbidity=turbidity, sunDirection=sun_dir, skyScale=0.0, sunScale=1.5, sunRadiusScale=radius_scale, resolution=res)
+        radiance = cp.sun_radiance(turbidity, sun_dir) * np.float32(1.5)
+        assert np.isfinite(radiance).all() and (radiance >= 0).all() and radiance[0] > 0          # a sun on the horizon at turbidity 8 is red only
+        ref = np.zeros((res // 2, res, 3), np.float32); d = np.asarray(sun_dir, np.float32)
+        L.ref_sun_splat(ref.ctypes.data, res, radiance.ctypes.data, d.ctypes.data, 1.0, radius_scale)
+        assert (ref.sum(-1) > 0).sum() >= 3
+        assert np.array_equal(ref.view(np.uint32), prod.view(np.uint32)), (sun_dir, res)
+
+
 def test_film_filter_table_and_splat(oracle):
     s = oracle.Scene()
     s.add_hair(*tiny_hair(), 0.1, s.add_bsdf('kajiyakay'))
