@@ -25,8 +25,8 @@ class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ('paths', 'rays', 'shadow_rays', 'kernel_launches', 'bounces', 'nodes_visited', 'prims_tested',
                                                'shadow_nodes_visited', 'shadow_prims_tested',
                                                'unsupported_filtered_lookups', 'dropped_samples', 'segments', 'bvh_nodes', 'bvh_references', 'triangles')] + \
-               [(n, ctypes.c_double) for n in ('build_ms', 'render_ms', 'intersect_ms', 'shade_ms', 'shadow_ms', 'raygen_ms', 'splat_ms')] + \
-               [(n, ctypes.c_uint64) for n in ('intersect_launches', 'shade_launches', 'shadow_launches', 'shadow_rays_traced', 'full_tests', 'shadow_full_tests')]
+               [(n, ctypes.c_double) for n in ('build_ms', 'render_ms', 'trace_ms', 'shade_ms', 'sort_ms', 'raygen_ms', 'splat_ms')] + \
+               [(n, ctypes.c_uint64) for n in ('trace_launches', 'shade_launches', 'sort_launches', 'shadow_rays_traced', 'full_tests', 'shadow_full_tests', 'host_waits')]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -44,6 +44,8 @@ def lib():
         L.cudapath_hair_file_vertex_count.restype = ctypes.c_uint32
         L.cudapath_mesh_file_vertex_count.restype = ctypes.c_uint32
         L.cudapath_mesh_file_triangle_count.restype = ctypes.c_uint32
+        if hasattr(L, 'cudapath_last_reduce_ms'):
+            L.cudapath_last_reduce_ms.restype = ctypes.c_double
         _lib = L
     return _lib
 
@@ -144,9 +146,15 @@ class Context:
     """One GPU context = the flattened scene + the wavefront path integrator (replaces Scene + `path` integrator for this path)."""
 
     def __init__(self, device=0, data_dir=None):
+        """device: a CUDA device index, or a list of indices for ONE context spanning several GPUs of the box (cudapath_create_multi:
+        the scene is replicated, render() splits the sample range and sums the films with one ncclReduce onto the first device)."""
         self._h = ctypes.c_void_p()
         self._L = lib()
-        _check(self._L.cudapath_create(int(device), ctypes.byref(self._h)))
+        if isinstance(device, (list, tuple)):
+            devs = (ctypes.c_int * len(device))(*[int(d) for d in device])
+            _check(self._L.cudapath_create_multi(devs, len(device), ctypes.byref(self._h)))
+        else:
+            _check(self._L.cudapath_create(int(device), ctypes.byref(self._h)))
         _check(self._L.cudapath_set_data_dir(self._h, (data_dir or DEFAULT_DATA_DIR).encode()))
         self.width = self.height = 0
         self.spp = 0
@@ -305,6 +313,19 @@ class Context:
         _check(self._L.cudapath_render_dev(self._h, ctypes.c_uint32(spp), ctypes.c_uint64(seed), ctypes.c_uint32(sample_begin),
                                            ctypes.c_uint32(spp if sample_end is None else sample_end), ctypes.c_void_p(film_dev_ptr), ctypes.c_void_p(stream)))
 
+    def device_count(self):
+        return int(self._L.cudapath_device_count(self._h))
+
+    def last_reduce_ms(self):
+        """Device time of the ncclReduce of the last multi-GPU render (0 for one device)."""
+        return float(self._L.cudapath_last_reduce_ms(self._h))
+
+    def measure_read_bandwidth(self, nbytes, iterations):
+        """GB/s of 16-byte L1-bypassing loads over a resident buffer (L2 bandwidth for a buffer well below the L2 size, HBM for GBs)."""
+        out = ctypes.c_double(0)
+        _check(self._L.cudapath_measure_read_bandwidth(self._h, ctypes.c_size_t(nbytes), int(iterations), ctypes.byref(out)))
+        return out.value
+
     def cancel(self):
         """Integrator::cancel(): may be called from another thread while render() / render_into() blocks; that call then raises
         CudapathError('render cancelled')."""
@@ -416,6 +437,11 @@ def load_rgbe(path):
     out = np.zeros((h.value, w.value, 3), np.float32)
     _check(lib().cudapath_load_rgbe(str(path).encode(), _p(out), ctypes.byref(w), ctypes.byref(h)))
     return out
+
+
+def visible_devices():
+    """CUDA devices visible to this process (0 without a driver)."""
+    return int(lib().cudapath_visible_devices())
 
 
 def trim_memory(device=0):

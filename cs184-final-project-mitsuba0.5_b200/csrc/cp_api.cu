@@ -10,6 +10,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
+#include <dlfcn.h>
+#include <nccl.h>          // types and prototypes only: libnccl.so.2 is bound at run time (cp_multi section), never at link time
 
 using namespace cp;
 
@@ -38,8 +41,21 @@ V3 h_xfm_point(const float *m, V3 p) {
 }
 }
 
+// The caller's current device is restored when an entry point returns (the library only borrows the thread's device binding).
+struct DevGuard {
+    int prev = -1; cudaError_t err;
+    explicit DevGuard(int dev) { cudaGetDevice(&prev); err = cudaSetDevice(dev); }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct cudapath_multi;
 struct cudapath_ctx {
     int device = 0;
+    // cudapath_create_multi: the context the caller holds is the one of devices[0]; `peers` are the contexts of the other devices.
+    // Every scene-building call is repeated on them (so all devices hold the same flattened scene, ids included), cudapath_build
+    // builds them concurrently and cudapath_render splits the sample range over all of them (cp_multi section below).
+    std::vector<cudapath_ctx *> peers;
+    cudapath_multi *multi = nullptr;
     cudaStream_t stream = nullptr;
     std::string dataDir;
     std::vector<BsdfHost> bsdfs;
@@ -80,7 +96,7 @@ struct cudapath_ctx {
         d_vtx = nullptr; d_shapes = nullptr; d_bsdfs = nullptr; bvh = BVHDev(); envTables = EnvTables(); built = false;
     }
     ~cudapath_ctx() {
-        cudaSetDevice(device);
+        DevGuard guard_(device);
         freeBuilt();                  // synchronises the device
         for (auto &st : staged) { dfree(st.xyz); dfree(st.starts); dfree(st.nrm); dfree(st.idx); }
         for (auto &b : bsdfs) { dfree(b.tables.tab); dfree(b.tables.cdf); dfree(b.tables.sums); dfree(b.tables.pdf); dfree(b.rt); }
@@ -95,9 +111,19 @@ struct cudapath_mesh_file { MeshFileData data; };
 static int require_built(cudapath_ctx *ctx) {
     if (!ctx) return fail("null context");
     if (!ctx->built) return fail("cudapath_build() has not been called");
-    CKA(cudaSetDevice(ctx->device));
     return 0;
 }
+// Repeats a successful scene-building call on the peer contexts of a multi-device context; all must answer alike.
+template <class F> static int fan_out(cudapath_ctx *ctx, int rc, F &&call) {
+    if (rc < 0 || !ctx) return rc;
+    for (cudapath_ctx *p : ctx->peers) {
+        const int r = call(p);
+        if (r < 0) return r;
+        if (r != rc) return fail("the device contexts of a multi-GPU context diverged");
+    }
+    return rc;
+}
+#define CP_GUARD(ctx) DevGuard guard_((ctx)->device); if (guard_.err != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(guard_.err))
 
 extern "C" {
 
@@ -111,23 +137,31 @@ int cudapath_create(int cuda_device, cudapath_ctx **out) {
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) return fail(std::string("no CUDA device available: ") + cudaGetErrorString(e));
     if (cuda_device < 0 || cuda_device >= count) return fail("CUDA device index out of range");
-    CKA(cudaSetDevice(cuda_device));
+    DevGuard guard_(cuda_device); CKA(guard_.err);
     std::unique_ptr<cudapath_ctx> ctx(new cudapath_ctx());
     ctx->device = cuda_device;
     CKA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     *out = ctx.release();
     return 0;
 }
-void cudapath_destroy(cudapath_ctx *ctx) { delete ctx; }
+static void multi_free(cudapath_multi *m);
+void cudapath_destroy(cudapath_ctx *ctx) {
+    if (!ctx) return;
+    cudapath_multi *m = ctx->multi; ctx->multi = nullptr;
+    std::vector<cudapath_ctx *> peers; peers.swap(ctx->peers);
+    if (m) multi_free(m);            // device films and communicators first
+    for (cudapath_ctx *p : peers) delete p;
+    delete ctx;
+}
 int cudapath_trim_memory(int cuda_device) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || cuda_device < 0 || cuda_device >= count) return fail("CUDA device index out of range");
-    CKA(cudaSetDevice(cuda_device));
+    DevGuard guard_(cuda_device); CKA(guard_.err);
     dev_trim();
     return 0;
 }
 
-int cudapath_set_data_dir(cudapath_ctx *ctx, const char *path) { if (!ctx || !path) return fail("null argument"); ctx->dataDir = path; return 0; }
+int cudapath_set_data_dir(cudapath_ctx *ctx, const char *path) { if (!ctx || !path) return fail("null argument"); ctx->dataDir = path; return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_data_dir(p, path); }); }
 
 int cudapath_add_bsdf_kajiyakay(cudapath_ctx *ctx, const float d[3], const float s[3], float exponent) {
     if (!ctx || !d || !s) return fail("null argument");
@@ -140,14 +174,14 @@ int cudapath_add_bsdf_kajiyakay(cudapath_ctx *ctx, const float d[3], const float
     const float dAvg = luminance(diff), sAvg = luminance(spec);
     b.dev.specW = sAvg / (dAvg + sAvg);                    // kajiyakay.cpp:96-98
     ctx->bsdfs.push_back(b); ctx->built = false;
-    return (int) ctx->bsdfs.size() - 1;
+    return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_kajiyakay(p, d, s, exponent); });
 }
 
 int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior, const float d[3], const float s[3], float alpha, int distribution, int nonlinear) {
     if (!ctx || !d || !s) return fail("null argument");
     if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
     if (ctx->dataDir.empty()) return fail("marschner needs data/microfacet/*.dat: call cudapath_set_data_dir() first");
-    CKA(cudaSetDevice(ctx->device));
+    CP_GUARD(ctx);
     BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
     b.dev.kind = 1;
     b.dev.eta = int_ior / ext_ior;
@@ -173,7 +207,7 @@ int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior,
     if (!build_marschner_tables(b.dev.eta, betaR, sigmaA, pts, wts, ctx->stream, b.tables, err)) return fail(err);
     b.dev.tab = b.tables.tab; b.dev.cdf = b.tables.cdf; b.dev.sums = b.tables.sums; b.dev.pdfs = b.tables.pdf; b.dev.rt = b.rt;
     ctx->bsdfs.push_back(b); ctx->built = false;
-    return (int) ctx->bsdfs.size() - 1;
+    return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_marschner(p, int_ior, ext_ior, d, s, alpha, distribution, nonlinear); });
 }
 
 int cudapath_add_bsdf_roughplastic(cudapath_ctx *ctx, float int_ior, float ext_ior, const float d[3], const float s[3], float alpha, int distribution,
@@ -182,7 +216,7 @@ int cudapath_add_bsdf_roughplastic(cudapath_ctx *ctx, float int_ior, float ext_i
     if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
     if (distribution < 0 || distribution > 2) return fail("Specified an invalid distribution, must be \"beckmann\", \"ggx\", or \"phong\"/\"as\"!");
     if (ctx->dataDir.empty()) return fail("roughplastic needs data/microfacet/*.dat: call cudapath_set_data_dir() first");
-    CKA(cudaSetDevice(ctx->device));
+    CP_GUARD(ctx);
     BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
     b.dev.kind = 4;
     b.dev.eta = int_ior / ext_ior;
@@ -205,13 +239,13 @@ int cudapath_add_bsdf_roughplastic(cudapath_ctx *ctx, float int_ior, float ext_i
     CKA(cudaStreamSynchronize(ctx->stream));
     b.dev.rt = b.rt;
     ctx->bsdfs.push_back(b); ctx->built = false;
-    return (int) ctx->bsdfs.size() - 1;
+    return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_roughplastic(p, int_ior, ext_ior, d, s, alpha, distribution, sample_visible, nonlinear); });
 }
 
 int cudapath_add_bsdf_marschner_fixed(cudapath_ctx *ctx, float int_ior, float ext_ior) {
     if (!ctx) return fail("null context");
     if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
-    CKA(cudaSetDevice(ctx->device));
+    CP_GUARD(ctx);
     BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
     b.dev.kind = 3;
     b.dev.eta = int_ior / ext_ior;
@@ -226,7 +260,7 @@ int cudapath_add_bsdf_marschner_fixed(cudapath_ctx *ctx, float int_ior, float ex
     if (!build_marschner_tables(b.dev.eta, betaR, sigmaA, pts, wts, ctx->stream, b.tables, err)) return fail(err);
     b.dev.tab = b.tables.tab; b.dev.cdf = b.tables.cdf; b.dev.sums = b.tables.sums; b.dev.pdfs = b.tables.pdf;
     ctx->bsdfs.push_back(b); ctx->built = false;
-    return (int) ctx->bsdfs.size() - 1;
+    return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_marschner_fixed(p, int_ior, ext_ior); });
 }
 
 static V3 ensure_energy_conservation(const float v[3]) {      // BSDF::ensureEnergyConservation for a constant texture, bsdf.cpp:88-113
@@ -245,7 +279,7 @@ int cudapath_add_bsdf_thindielectric(cudapath_ctx *ctx, float int_ior, float ext
     b.dev.specular = ensure_energy_conservation(r);        // :112-115
     b.dev.diffuse = ensure_energy_conservation(t);         // the transmittance rides in the `diffuse` slot
     ctx->bsdfs.push_back(b); ctx->built = false;
-    return (int) ctx->bsdfs.size() - 1;
+    return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_thindielectric(p, int_ior, ext_ior, r, t); });
 }
 
 int cudapath_add_bsdf_marschnerdielectric(cudapath_ctx *ctx, float int_ior, float ext_ior, const float d[3], const float r[3], const float t[3], float exponent) {
@@ -261,7 +295,7 @@ int cudapath_add_bsdf_marschnerdielectric(cudapath_ctx *ctx, float int_ior, floa
     const float dAvg = luminance(b.dev.diffuse), sAvg = luminance(b.dev.specular), tAvg = luminance(b.dev.specT);
     b.dev.specW = (sAvg + tAvg) / (dAvg + sAvg + tAvg);    // :211-214
     ctx->bsdfs.push_back(b); ctx->built = false;
-    return (int) ctx->bsdfs.size() - 1;
+    return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_marschnerdielectric(p, int_ior, ext_ior, d, r, t, exponent); });
 }
 
 int cudapath_add_bsdf_diffuse(cudapath_ctx *ctx, const float reflectance[3], int two_sided) {
@@ -271,7 +305,7 @@ int cudapath_add_bsdf_diffuse(cudapath_ctx *ctx, const float reflectance[3], int
     { const float mx = maxc(r); if (mx > 1.0f) r = r * (0.99f * (1.0f / mx)); }           // ensureEnergyConservation, bsdf.cpp:88-113
     b.dev.kind = 2; b.dev.twoSided = two_sided ? 1 : 0; b.dev.diffuse = r; b.dev.specular = V3(0.0f);
     ctx->bsdfs.push_back(b); ctx->built = false;
-    return (int) ctx->bsdfs.size() - 1;
+    return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_diffuse(p, reflectance, two_sided); });
 }
 
 int cudapath_add_mesh(cudapath_ctx *ctx, const float *xyz, const float *normals, uint32_t n_vertices, const uint32_t *indices, uint32_t n_triangles, int bsdf_id) {
@@ -281,7 +315,7 @@ int cudapath_add_mesh(cudapath_ctx *ctx, const float *xyz, const float *normals,
     if (ctx->shapes.size() >= (1u << 23)) return fail("too many shapes");
     if ((uint64_t) ctx->triTotal + n_triangles >= (1ull << 28) || (uint64_t) ctx->meshVtxTotal + n_vertices >= 0xfffffff0ull) return fail("too many triangles");
     for (size_t i = 0; i < 3 * (size_t) n_triangles; ++i) if (indices[i] >= n_vertices) return fail("mesh index out of range");
-    CKA(cudaSetDevice(ctx->device));
+    CP_GUARD(ctx);
     ShapeDev sd; std::memset(&sd, 0, sizeof(sd));
     sd.kind = 1; sd.bsdf = bsdf_id; sd.vertexOffset = ctx->meshVtxTotal; sd.vertexCount = n_vertices; sd.triOffset = ctx->triTotal; sd.triCount = n_triangles;
     sd.hasNormals = normals ? 1 : 0;
@@ -298,7 +332,7 @@ int cudapath_add_mesh(cudapath_ctx *ctx, const float *xyz, const float *normals,
     ctx->staged.push_back(st);
     ctx->meshVtxTotal += n_vertices; ctx->triTotal += n_triangles;
     ctx->shapes.push_back(sd); ctx->built = false;
-    return (int) ctx->shapes.size() - 1;
+    return fan_out(ctx, (int) ctx->shapes.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_mesh(p, xyz, normals, n_vertices, indices, n_triangles, bsdf_id); });
 }
 
 int cudapath_mesh_file_load(const char *filename, const float to_world[16], int face_normals, int flip_normals, cudapath_mesh_file **out) {
@@ -336,7 +370,7 @@ int cudapath_add_hair(cudapath_ctx *ctx, const float *xyz, const uint8_t *starts
     if (!starts[0]) return fail("the first hair vertex must start a fiber");
     if (ctx->shapes.size() >= (1u << 23)) return fail("too many shapes");
     if ((uint64_t) ctx->vtxTotal + n + 1 >= 0xfffffff0ull) return fail("too many hair vertices");
-    CKA(cudaSetDevice(ctx->device));
+    CP_GUARD(ctx);
     ShapeDev sd; std::memset(&sd, 0, sizeof(sd));
     sd.radius = radius; sd.bsdf = bsdf_id; sd.vertexOffset = ctx->vtxTotal; sd.vertexCount = n;
     // The caller's arrays go straight to the device (a true DMA when they are page-locked); the float4 vertex stream with
@@ -350,7 +384,7 @@ int cudapath_add_hair(cudapath_ctx *ctx, const float *xyz, const uint8_t *starts
     ctx->staged.push_back(st);
     ctx->vtxTotal += n + 1;
     ctx->shapes.push_back(sd); ctx->built = false;
-    return (int) ctx->shapes.size() - 1;
+    return fan_out(ctx, (int) ctx->shapes.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_hair(p, xyz, starts, n, radius, bsdf_id); });
 }
 
 int cudapath_hair_file_load(const char *filename, float radius, float angle_threshold_deg, float reduction, const float to_world[16], cudapath_hair_file **out) {
@@ -384,7 +418,7 @@ int cudapath_set_envmap(cudapath_ctx *ctx, const float *rgb, int w, int h, const
     ctx->env.rgb.assign(rgb, rgb + (size_t) 3 * w * h);
     ctx->env.w = w; ctx->env.h = h; ctx->env.scale = scale; std::memcpy(ctx->env.toWorld, to_world, 64);
     ctx->env.present = true; ctx->built = false;
-    return 0;
+    return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_envmap(p, rgb, w, h, to_world, scale); });
 }
 
 int cudapath_load_rgbe(const char *filename, float *out_rgb, int *out_width, int *out_height) {
@@ -445,13 +479,13 @@ int cudapath_set_camera_perspective(cudapath_ctx *ctx, const float to_world[16],
     std::memcpy(ctx->cam.toWorld, to_world, 64);
     ctx->cam.fov = fov; ctx->cam.nearClip = nearClip; ctx->cam.farClip = farClip; ctx->cam.w = w; ctx->cam.h = h; ctx->cam.present = true;
     ctx->built = false;
-    return 0;
+    return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_camera_perspective(p, to_world, fov, nearClip, farClip, w, h); });
 }
 int cudapath_set_film(cudapath_ctx *ctx, int filter, float param, int has_alpha) {
     if (!ctx) return fail("null context");
     if (filter < 0 || filter > 2) return fail("unsupported reconstruction filter");
     ctx->filterType = filter; ctx->filterParam = param; ctx->hasAlpha = has_alpha ? 1 : 0; ctx->built = false;
-    return 0;
+    return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_film(p, filter, param, has_alpha); });
 }
 int cudapath_set_integrator(cudapath_ctx *ctx, int max_depth, int rr_depth, int strict_normals, int hide_emitters) {
     if (!ctx) return fail("null context");
@@ -459,20 +493,20 @@ int cudapath_set_integrator(cudapath_ctx *ctx, int max_depth, int rr_depth, int 
     if (rr_depth <= 0) return fail("'rrDepth' must be set to a value greater than zero!");
     ctx->integ.maxDepth = max_depth; ctx->integ.rrDepth = rr_depth; ctx->integ.strictNormals = strict_normals ? 1 : 0; ctx->integ.hideEmitters = hide_emitters ? 1 : 0;
     if (ctx->built) ctx->scene.integ = ctx->integ;
-    return 0;
+    return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_integrator(p, max_depth, rr_depth, strict_normals, hide_emitters); });
 }
 int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stats, int profile_stages) {
     if (!ctx) return fail("null context");
     if (wave_size) ctx->waveSize = std::max(wave_size, 1024u);
     ctx->collectStats = collect_stats; ctx->profileStages = profile_stages;
-    return 0;
+    return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_options(p, wave_size, collect_stats, profile_stages); });
 }
 
-int cudapath_build(cudapath_ctx *ctx) {
+static int build_one(cudapath_ctx *ctx) {
     if (!ctx) return fail("null context");
     if (ctx->shapes.empty()) return fail("the scene contains no shapes");
     if (!ctx->cam.present) return fail("no sensor set");
-    CKA(cudaSetDevice(ctx->device));
+    CP_GUARD(ctx);
     const bool trace = getenv("CUDAPATH_TRACE") != nullptr;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tb0 = now();
@@ -626,6 +660,7 @@ int cudapath_build(cudapath_ctx *ctx) {
 
 int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *film_dev, void *stream) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     if (!film_dev) return fail("null film buffer");
     if (spp == 0 || sample_end > spp || sample_begin > sample_end) return fail("invalid sample range");
     cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
@@ -633,29 +668,30 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
     CKA(cudaEventRecord(e0, st));
     RenderStats rs; std::string err;
     ctx->wf.sortRays = ctx->sortRays != 0;
-    if (ctx->wf.cancelRequested.exchange(0)) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail("render cancelled"); }   // cancel() arrived before the render started
+    if (const char *e = getenv("CUDAPATH_RUNAHEAD_MAX")) ctx->wf.runAheadMax = (uint32_t) strtoul(e, nullptr, 0);
+    ctx->wf.cancelRequested.store(0); ctx->wf.inRender.store(1);
+    struct RenderScope { Wavefront &w; cudaEvent_t a, b; ~RenderScope() { w.inRender.store(0); w.cancelRequested.store(0); cudaEventDestroy(a); cudaEventDestroy(b); } } scope_{ctx->wf, e0, e1};
     uint32_t waveSize = ctx->waveSize;
     if (!waveSize) {
         // Deep bounces leave only a few live paths per wave, so few, large waves keep the GPU full for longer (hair-curl at 64 spp:
-        // one 2^26 wave is 17 % faster than four 2^24 waves).  A path costs ~212 B of queue space; use up to 2^26 paths (14 GB) but
+        // one 2^26 wave is 17 % faster than four 2^24 waves).  A path costs ~228 B of queue space; use up to 2^26 paths (15 GB) but
         // never more than 40 % of the memory that is free right now (queues already held by this context count as free).
         size_t freeB = 0, totalB = 0;
         CKA(cudaMemGetInfo(&freeB, &totalB));
-        const double avail = 0.4 * ((double) freeB + (double) dev_cached_bytes() + 212.0 * ctx->wf.capacity);   // blocks parked in the caching allocator are available too
+        const double avail = 0.4 * ((double) freeB + (double) dev_cached_bytes() + 228.0 * ctx->wf.capacity);   // blocks parked in the caching allocator are available too
         waveSize = 1u << 26;
-        while (waveSize > (1u << 20) && 212.0 * waveSize > avail) waveSize >>= 1;
+        while (waveSize > (1u << 20) && 228.0 * waveSize > avail) waveSize >>= 1;
     }
     const bool ok = ctx->wf.render(ctx->scene, spp, seed, sample_begin, sample_end, film_dev, waveSize, ctx->collectStats != 0, ctx->profileStages != 0, st, rs, err);
-    if (!ok) { ctx->wf.cancelRequested.store(0); cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(err); }
+    if (!ok) return fail(err);
     CKA(cudaEventRecord(e1, st));
     CKA(cudaEventSynchronize(e1));
     float ms = 0; CKA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudapath_stats &s = ctx->stats;
     s.paths = rs.paths; s.rays = rs.rays; s.shadow_rays = rs.shadowRays; s.kernel_launches = rs.launches; s.bounces = rs.bounces;
     s.nodes_visited = rs.nodesVisited; s.prims_tested = rs.primsTested; s.shadow_nodes_visited = rs.shadowNodesVisited; s.shadow_prims_tested = rs.shadowPrimsTested;
-    s.intersect_ms = rs.stageMs[0]; s.shade_ms = rs.stageMs[1]; s.shadow_ms = rs.stageMs[2]; s.raygen_ms = rs.stageMs[3]; s.splat_ms = rs.stageMs[4];
-    s.intersect_launches = rs.stageLaunches[0]; s.shade_launches = rs.stageLaunches[1]; s.shadow_launches = rs.stageLaunches[2]; s.unsupported_filtered_lookups = rs.unsupportedLookups; s.dropped_samples = rs.droppedSamples;
+    s.trace_ms = rs.stageMs[0]; s.shade_ms = rs.stageMs[1]; s.sort_ms = rs.stageMs[2]; s.raygen_ms = rs.stageMs[3]; s.splat_ms = rs.stageMs[4];
+    s.trace_launches = rs.stageLaunches[0]; s.shade_launches = rs.stageLaunches[1]; s.sort_launches = rs.stageLaunches[2]; s.host_waits = rs.hostSyncs; s.unsupported_filtered_lookups = rs.unsupportedLookups; s.dropped_samples = rs.droppedSamples;
     s.full_tests = rs.fullTests; s.shadow_full_tests = rs.shadowFullTests; s.shadow_rays_traced = rs.shadowRaysTraced;
     s.render_ms = ms;
     return 0;
@@ -663,7 +699,10 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
 
 int cudapath_cancel(cudapath_ctx *ctx) {
     if (!ctx) return fail("null context");
-    ctx->wf.cancelRequested.store(1);          // the only entry point that may be called while another thread is inside a render
+    // the only entry point that may be called while another thread is inside a render; like Integrator::cancel() it acts on the job
+    // that is running -- a request that finds no render in progress is dropped
+    if (ctx->wf.inRender.load()) ctx->wf.cancelRequested.store(1);
+    for (cudapath_ctx *p : ctx->peers) if (p->wf.inRender.load()) p->wf.cancelRequested.store(1);
     return 0;
 }
 
@@ -673,8 +712,11 @@ int cudapath_set_progress_callback(cudapath_ctx *ctx, void (*callback)(void *use
     return 0;
 }
 
+static int render_multi(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *out_film);
 int cudapath_render(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *out_film) {
+    if (ctx && !ctx->peers.empty()) return render_multi(ctx, spp, seed, sample_begin, sample_end, out_film);
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     if (!out_film) return fail("null film buffer");
     const size_t bytes = sizeof(float) * 5 * (size_t) ctx->cam.w * ctx->cam.h;
     const bool trace = getenv("CUDAPATH_TRACE") != nullptr;
@@ -738,7 +780,7 @@ int cudapath_set_build_options(cudapath_ctx *ctx, int max_split) {
     if (!ctx) return fail("null context");
     if (max_split < 1 || max_split > 64) return fail("max_split must be in [1, 64]");
     ctx->maxSplit = max_split; ctx->built = false;
-    return 0;
+    return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_build_options(p, max_split); });
 }
 int cudapath_get_stats(cudapath_ctx *ctx, cudapath_stats *out) { if (!ctx || !out) return fail("null argument"); *out = ctx->stats; return 0; }
 int cudapath_film_size(cudapath_ctx *ctx, int *w, int *h) {
@@ -760,11 +802,191 @@ int cudapath_get_film_output(cudapath_ctx *ctx, int *hdr, float *gamma, float *e
 }
 int cudapath_scene_bounds(cudapath_ctx *ctx, float aabb[6], float bs[4]) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     std::memcpy(aabb, ctx->sceneAABB, 24);
     for (int k = 0; k < 3; ++k) bs[k] = ctx->scene.env.bsCenter[k];
     bs[3] = ctx->scene.env.bsRadius;
     return 0;
 }
+
+} // extern "C"
+
+
+// ------------------------------------------------------------------------------------------ multi-GPU contexts
+// Replaces the tile scheduler of the reference for this path -- BlockedRenderProcess handing 32x32 tiles to the LocalWorkers that
+// `mitsuba -p N` starts, and the mutex-protected Film::put of every finished tile (src/librender/renderproc.cpp:117-182,
+// src/mitsuba/mitsuba.cpp:280-329).  Here every GPU holds the whole flattened scene and renders a contiguous range of SAMPLE INDICES
+// of every pixel into a private full-size film (perfectly balanced wherever the hair is, no tile border to exchange; the RNG is
+// keyed by pixel / sample / vertex, so the image does not depend on the device count up to fp32 summation order); the films are
+// summed onto devices[0] with ONE ncclReduce over NVLink.  libnccl.so.2 is bound with dlopen when the first multi-GPU context is
+// created: a process that already carries an NCCL (torch) shares it, a single-GPU process never needs it.
+namespace {
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load() {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) { error = std::string("multi-GPU rendering needs NCCL: ") + dlerror(); return false; }
+        auto sym = [&](const char *name) { void *p = dlsym(handle, name); if (!p) error = std::string("libnccl lacks ") + name; return p; };
+        CommInitAll = (decltype(CommInitAll)) sym("ncclCommInitAll"); CommDestroy = (decltype(CommDestroy)) sym("ncclCommDestroy");
+        Reduce = (decltype(Reduce)) sym("ncclReduce"); GroupStart = (decltype(GroupStart)) sym("ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd)) sym("ncclGroupEnd"); GetErrorString = (decltype(GetErrorString)) sym("ncclGetErrorString");
+        return CommInitAll && CommDestroy && Reduce && GroupStart && GroupEnd && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+}
+
+struct cudapath_multi {
+    std::vector<cudapath_ctx *> all;        // devices[0] (the context the caller holds) first
+    std::vector<ncclComm_t> comms;
+    std::vector<float *> films;             // per-device film, kept between renders
+    size_t filmBytes = 0;
+    double reduceMs = 0;
+};
+
+static void multi_free(cudapath_multi *m) {
+    if (!m) return;
+    for (size_t i = 0; i < m->films.size(); ++i) if (m->films[i]) { DevGuard g(m->all[i]->device); cudaDeviceSynchronize(); dev_free(m->films[i]); }
+    for (ncclComm_t c : m->comms) if (c && g_nccl.CommDestroy) g_nccl.CommDestroy(c);
+    delete m;
+}
+
+// contiguous, balanced split of [begin, end) over n parts (the first `rem` parts get one index more)
+static void split_range(uint32_t begin, uint32_t end, int n, int i, uint32_t &b, uint32_t &e) {
+    const uint32_t total = end - begin, base = total / (uint32_t) n, rem = total % (uint32_t) n;
+    b = begin + (uint32_t) i * base + std::min<uint32_t>((uint32_t) i, rem);
+    e = b + base + ((uint32_t) i < rem ? 1u : 0u);
+}
+
+static int render_multi(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *out_film) {
+    cudapath_multi *m = ctx->multi;
+    if (!m) return fail("not a multi-GPU context");
+    if (!out_film) return fail("null film buffer");
+    if (spp == 0 || sample_end > spp || sample_begin > sample_end) return fail("invalid sample range");
+    const int n = (int) m->all.size();
+    for (cudapath_ctx *c : m->all) if (!c->built) return fail("cudapath_build() has not been called");
+    const size_t count = 5 * (size_t) ctx->cam.w * ctx->cam.h, bytes = sizeof(float) * count;
+    if (m->filmBytes != bytes) {
+        for (int i = 0; i < n; ++i) { DevGuard g(m->all[i]->device); cudaDeviceSynchronize(); if (m->films[i]) dev_free(m->films[i]); m->films[i] = nullptr; CKA(dev_alloc(&m->films[i], bytes)); }
+        m->filmBytes = bytes;
+    }
+    // one host thread per device: zero the private film, render this device's share of the sample indices
+    std::vector<int> rc(n, 0); std::vector<std::string> msg(n);
+    auto work = [&](int i) {
+        cudapath_ctx *c = m->all[i];
+        DevGuard g(c->device);
+        uint32_t b, e; split_range(sample_begin, sample_end, n, i, b, e);
+        if (cudaMemsetAsync(m->films[i], 0, bytes, c->stream) != cudaSuccess) { rc[i] = -1; msg[i] = "film clear failed"; return; }
+        c->stats.paths = c->stats.rays = c->stats.shadow_rays = c->stats.shadow_rays_traced = c->stats.kernel_launches = c->stats.bounces = 0; c->stats.render_ms = 0;
+        if (e > b) { rc[i] = cudapath_render_dev(c, spp, seed, b, e, m->films[i], c->stream); if (rc[i] < 0) msg[i] = cudapath_last_error(); }
+    };
+    std::vector<std::thread> threads;
+    for (int i = 1; i < n; ++i) threads.emplace_back(work, i);
+    work(0);
+    for (auto &t : threads) t.join();
+    for (int i = 0; i < n; ++i) if (rc[i] < 0) return fail(msg[i]);
+    // ONE collective: sum of the private films onto devices[0], in place on the root
+    cudaEvent_t e0, e1;
+    {
+        DevGuard g(ctx->device);
+        CKA(cudaEventCreate(&e0)); CKA(cudaEventCreate(&e1));
+        CKA(cudaEventRecord(e0, ctx->stream));
+    }
+    ncclResult_t nr = g_nccl.GroupStart();
+    for (int i = 0; i < n && nr == ncclSuccess; ++i) {
+        DevGuard g(m->all[i]->device);
+        nr = g_nccl.Reduce(m->films[i], m->films[0], count, ncclFloat, ncclSum, 0, m->comms[i], m->all[i]->stream);
+    }
+    if (nr == ncclSuccess) nr = g_nccl.GroupEnd(); else g_nccl.GroupEnd();
+    if (nr != ncclSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(std::string("ncclReduce: ") + g_nccl.GetErrorString(nr)); }
+    for (int i = 1; i < n; ++i) { DevGuard g(m->all[i]->device); CKA(cudaStreamSynchronize(m->all[i]->stream)); }
+    {
+        DevGuard g(ctx->device);
+        CKA(cudaEventRecord(e1, ctx->stream));
+        CKA(cudaMemcpyAsync(out_film, m->films[0], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CKA(cudaStreamSynchronize(ctx->stream));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); m->reduceMs = ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    // statistics of the job: counters add up, the render time is that of the slowest device
+    cudapath_stats &s = ctx->stats;
+    for (int i = 1; i < n; ++i) {
+        const cudapath_stats &p = m->all[i]->stats;
+        s.paths += p.paths; s.rays += p.rays; s.shadow_rays += p.shadow_rays; s.shadow_rays_traced += p.shadow_rays_traced; s.kernel_launches += p.kernel_launches;
+        s.bounces += p.bounces; s.unsupported_filtered_lookups += p.unsupported_filtered_lookups; s.dropped_samples += p.dropped_samples;
+        s.nodes_visited += p.nodes_visited; s.prims_tested += p.prims_tested; s.shadow_nodes_visited += p.shadow_nodes_visited; s.shadow_prims_tested += p.shadow_prims_tested;
+        s.full_tests += p.full_tests; s.shadow_full_tests += p.shadow_full_tests; s.host_waits += p.host_waits;
+        s.render_ms = std::max(s.render_ms, p.render_ms);
+    }
+    return 0;
+}
+
+extern "C" {
+
+int cudapath_create_multi(const int *cuda_devices, int n_devices, cudapath_ctx **out) {
+    if (!cuda_devices || !out) return fail("null argument");
+    if (n_devices < 1) return fail("a multi-GPU context needs at least one device");
+    for (int i = 0; i < n_devices; ++i) for (int j = 0; j < i; ++j) if (cuda_devices[i] == cuda_devices[j]) return fail("a device is listed twice");
+    if (n_devices == 1) return cudapath_create(cuda_devices[0], out);
+    if (!g_nccl.load()) return fail(g_nccl.error);
+    std::unique_ptr<cudapath_multi, void (*)(cudapath_multi *)> m(new cudapath_multi(), multi_free);
+    for (int i = 0; i < n_devices; ++i) {
+        cudapath_ctx *c = nullptr;
+        if (cudapath_create(cuda_devices[i], &c) != 0) { for (cudapath_ctx *p : m->all) delete p; m->all.clear(); return -1; }
+        m->all.push_back(c);
+    }
+    m->films.assign(n_devices, nullptr);
+    m->comms.assign(n_devices, nullptr);
+    const ncclResult_t nr = g_nccl.CommInitAll(m->comms.data(), n_devices, cuda_devices);
+    if (nr != ncclSuccess) { for (cudapath_ctx *p : m->all) delete p; m->all.clear(); return fail(std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(nr)); }
+    cudapath_ctx *root = m->all[0];
+    root->peers.assign(m->all.begin() + 1, m->all.end());
+    root->multi = m.release();
+    *out = root;
+    return 0;
+}
+
+int cudapath_device_count(cudapath_ctx *ctx) { return ctx ? 1 + (int) ctx->peers.size() : 0; }
+
+int cudapath_visible_devices(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+
+int cudapath_build(cudapath_ctx *ctx) {
+    if (!ctx) return fail("null context");
+    if (ctx->peers.empty()) return build_one(ctx);
+    // every device builds its own copy of the BVH and the tables, concurrently
+    const int n = 1 + (int) ctx->peers.size();
+    std::vector<int> rc(n, 0); std::vector<std::string> msg(n);
+    auto work = [&](int i) { cudapath_ctx *c = i == 0 ? ctx : ctx->peers[i - 1]; rc[i] = build_one(c); if (rc[i] < 0) msg[i] = cudapath_last_error(); };
+    std::vector<std::thread> threads;
+    for (int i = 1; i < n; ++i) threads.emplace_back(work, i);
+    work(0);
+    for (auto &t : threads) t.join();
+    for (int i = 0; i < n; ++i) if (rc[i] < 0) return fail(msg[i]);
+    return 0;
+}
+
+int cudapath_measure_read_bandwidth(cudapath_ctx *ctx, size_t bytes, int iterations, double *out_gb_per_s) {
+    if (!ctx || !out_gb_per_s) return fail("null argument");
+    CP_GUARD(ctx);
+    std::string err;
+    if (!read_bandwidth_probe(bytes, iterations, ctx->stream, *out_gb_per_s, err)) return fail(err);
+    return 0;
+}
+
+double cudapath_last_reduce_ms(cudapath_ctx *ctx) { return ctx && ctx->multi ? ctx->multi->reduceMs : 0.0; }
 
 } // extern "C"
 
@@ -784,6 +1006,7 @@ extern "C" {
 
 int cudapath_bsdf_eval_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     DevBuf a, b, e, p; std::string err;
     CKA(a.upload(wi, n * 12, ctx->stream)); CKA(b.upload(wo, n * 12, ctx->stream)); CKA(e.alloc(n * 12)); CKA(p.alloc(n * 4));
     if (!bsdf_eval_batch(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
@@ -793,6 +1016,7 @@ int cudapath_bsdf_eval_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const f
 }
 int cudapath_bsdf_eval_batch_discrete(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     DevBuf a, b, e, p; std::string err;
     CKA(a.upload(wi, n * 12, ctx->stream)); CKA(b.upload(wo, n * 12, ctx->stream)); CKA(e.alloc(n * 12)); CKA(p.alloc(n * 4));
     if (!bsdf_eval_batch(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err, true)) return fail(err);
@@ -805,6 +1029,7 @@ int cudapath_bsdf_sample_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const
 }
 int cudapath_bsdf_sample_batch_ex(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, const float *extra, float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     DevBuf a, s, x, wo, wt, p, t; std::string err;
     CKA(a.upload(wi, n * 12, ctx->stream)); CKA(s.upload(sample, n * 8, ctx->stream));
     if (extra) CKA(x.upload(extra, n * 16, ctx->stream));
@@ -817,6 +1042,7 @@ int cudapath_bsdf_sample_batch_ex(cudapath_ctx *ctx, int bsdf_id, uint64_t n, co
 int cudapath_intersect_batch(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,
                              int any_hit, int32_t *out_shape, uint32_t *out_prim, float *out_t, float *out_record) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     DevBuf o, d, mn, mx, sh, pr, t, rec; std::string err;
     CKA(o.upload(origin, n * 12, ctx->stream)); CKA(d.upload(direction, n * 12, ctx->stream)); CKA(mn.upload(mint, n * 4, ctx->stream)); CKA(mx.upload(maxt, n * 4, ctx->stream));
     CKA(sh.alloc(n * 4)); CKA(pr.alloc(n * 4)); CKA(t.alloc(n * 4));
@@ -830,6 +1056,7 @@ int cudapath_intersect_batch(cudapath_ctx *ctx, uint64_t n, const float *origin,
 }
 int cudapath_env_eval_batch(cudapath_ctx *ctx, uint64_t n, const float *direction, float *out_rgb, float *out_pdf) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     DevBuf d, c, p; std::string err;
     CKA(d.upload(direction, n * 12, ctx->stream)); CKA(c.alloc(n * 12)); CKA(p.alloc(n * 4));
     if (!env_eval_batch(ctx->scene, n, d.as<float>(), c.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
@@ -839,6 +1066,7 @@ int cudapath_env_eval_batch(cudapath_ctx *ctx, uint64_t n, const float *directio
 }
 int cudapath_env_sample_batch(cudapath_ctx *ctx, uint64_t n, const float *ref_point, const float *sample, float *out_direction, float *out_value, float *out_pdf_dist) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     DevBuf r, s, d, v, p; std::string err;
     CKA(r.upload(ref_point, n * 12, ctx->stream)); CKA(s.upload(sample, n * 8, ctx->stream)); CKA(d.alloc(n * 12)); CKA(v.alloc(n * 12)); CKA(p.alloc(n * 8));
     if (!env_sample_batch(ctx->scene, n, r.as<float>(), s.as<float>(), d.as<float>(), v.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
@@ -848,6 +1076,7 @@ int cudapath_env_sample_batch(cudapath_ctx *ctx, uint64_t n, const float *ref_po
 }
 int cudapath_camera_rays_batch(cudapath_ctx *ctx, uint64_t n, const float *pixel_sample, float *out_origin, float *out_direction, float *out_mint_maxt) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     DevBuf p, o, d, m; std::string err;
     CKA(p.upload(pixel_sample, n * 8, ctx->stream)); CKA(o.alloc(n * 12)); CKA(d.alloc(n * 12)); CKA(m.alloc(n * 8));
     if (!camera_rays_batch(ctx->scene, n, p.as<float>(), o.as<float>(), d.as<float>(), m.as<float>(), ctx->stream, err)) return fail(err);
@@ -857,6 +1086,7 @@ int cudapath_camera_rays_batch(cudapath_ctx *ctx, uint64_t n, const float *pixel
 }
 int cudapath_splat_batch(cudapath_ctx *ctx, uint64_t n, const float *position, const float *rgb, const float *alpha, float *out_film) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     DevBuf p, c, a, f; std::string err;
     const size_t fb = sizeof(float) * 5 * (size_t) ctx->cam.w * ctx->cam.h;
     CKA(p.upload(position, n * 8, ctx->stream)); CKA(c.upload(rgb, n * 12, ctx->stream)); CKA(a.upload(alpha, n * 4, ctx->stream));
@@ -869,7 +1099,7 @@ int cudapath_splat_batch(cudapath_ctx *ctx, uint64_t n, const float *position, c
 int cudapath_marschner_tables(cudapath_ctx *ctx, int bsdf_id, float *out_tables, float *out_pdfs, float *out_cdfs, float *out_sums, float *out_rt, float *out_consts) {
     if (!ctx) return fail("null context");
     if (bsdf_id < 0 || bsdf_id >= (int) ctx->bsdfs.size() || (ctx->bsdfs[bsdf_id].dev.kind != 1 && ctx->bsdfs[bsdf_id].dev.kind != 3)) return fail("not a marschner bsdf");
-    CKA(cudaSetDevice(ctx->device));
+    CP_GUARD(ctx);
     const BsdfHost &b = ctx->bsdfs[bsdf_id];
     std::vector<float4> t(3 * 4096);
     CKA(cudaMemcpyAsync(t.data(), b.tables.tab, sizeof(float4) * t.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -884,6 +1114,7 @@ int cudapath_marschner_tables(cudapath_ctx *ctx, int bsdf_id, float *out_tables,
 }
 int cudapath_env_tables(cudapath_ctx *ctx, float *out_cdf_rows, float *out_cdf_cols, float *out_row_weights, float *out_normalization) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     if (!ctx->scene.env.present) return fail("no environment map set");
     const EnvDev &E = ctx->scene.env;
     CKA(cudaMemcpyAsync(out_cdf_rows, E.cdfRows, 4 * (size_t) (E.h + 1), cudaMemcpyDeviceToHost, ctx->stream));
@@ -895,6 +1126,7 @@ int cudapath_env_tables(cudapath_ctx *ctx, float *out_cdf_rows, float *out_cdf_c
 }
 int cudapath_filter_table(cudapath_ctx *ctx, float out32[32]) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     std::memcpy(out32, ctx->scene.film.filterValues, 128);
     return 0;
 }
@@ -902,12 +1134,14 @@ int cudapath_filter_table(cudapath_ctx *ctx, float out32[32]) {
 // ------------------------------------------------------------------------------------------ device-resident variants
 int cudapath_bsdf_eval_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf, void *stream) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     std::string err;
     if (!bsdf_eval_batch(ctx->scene, bsdf_id, n, wi, wo, out_eval, out_pdf, stream ? (cudaStream_t) stream : ctx->stream, err)) return fail(err);
     return 0;
 }
 int cudapath_bsdf_sample_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type, void *stream) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     std::string err;
     if (!bsdf_sample_batch(ctx->scene, bsdf_id, n, wi, sample, nullptr, out_wo, out_weight, out_pdf, out_type, stream ? (cudaStream_t) stream : ctx->stream, err)) return fail(err);
     return 0;
@@ -915,6 +1149,7 @@ int cudapath_bsdf_sample_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, c
 int cudapath_intersect_batch_dev(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,
                                  int any_hit, int32_t *out_shape, uint32_t *out_prim, float *out_t, unsigned long long *out_stats, void *stream) {
     if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
     std::string err;
     if (!intersect_batch(ctx->scene, n, origin, direction, mint, maxt, any_hit, out_stats != nullptr, out_shape, out_prim, out_t, nullptr, out_stats,
                          stream ? (cudaStream_t) stream : ctx->stream, err)) return fail(err);

@@ -1,10 +1,12 @@
 // cp_cli.cpp -- `cudapath_render`: renders a scene file of the reference's XML format through libcudapath.so.
 //
 // Mirrors the part of the reference's command line that concerns this path (src/mitsuba/mitsuba.cpp:154-260):
-//   cudapath_render [-o out.{png,pfm,ppm}] [-D name=value]... [-p N] [-q] [--gpu i] [--spp n] [--seed s] scene.xml
+//   cudapath_render [-o out.{png,pfm,ppm}] [-D name=value]... [-p N] [--gpus N] [-q] [--gpu i] [--spp n] [--seed s] scene.xml
 //     -o   output file (mitsuba.cpp:190); default: the scene's name with the extension the film asks for (.png for ldrfilm, .pfm for hdrfilm)
 //     -D   parameter substitution of $name in the file (mitsuba.cpp:168)
-//     -p   accepted for compatibility with `mitsuba -p N`; the CPU core count has no meaning here
+//     -p   `mitsuba -p N` asks for N local workers (mitsuba.cpp:218-222,280-282); the workers of this path are GPUs: the job is split
+//          over min(N, visible GPUs) devices (cudapath_create_multi: sample-range sharding, one ncclReduce of the film)
+//     --gpus N   the same, but N GPUs must exist; --gpu i selects the first device
 //     -q   quiet
 // Ctrl-C cancels the render (cudapath_cancel) and exits with 130 without writing an image; a progress line goes to a terminal's stderr.
 // and prints the "Render time" line of RenderJob::run (src/librender/renderjob.cpp:108) plus Mpaths/s and Mrays/s.
@@ -70,20 +72,22 @@ static int die(const char *what) { fprintf(stderr, "cudapath_render: %s: %s\n", 
 
 int main(int argc, char **argv) {
     std::string out, defines, scene, dataDir;
-    int gpu = 0; long spp = 0; unsigned long long seed = 0; bool quiet = false;
+    int gpu = 0, workers = 0, gpus = 0; long spp = 0; unsigned long long seed = 0; bool quiet = false;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto need = [&](const char *opt) -> const char * { if (i + 1 >= argc) { fprintf(stderr, "cudapath_render: %s needs an argument\n", opt); exit(2); } return argv[++i]; };
         if (a == "-o") out = need("-o");
         else if (a == "-D") { if (!defines.empty()) defines += ";"; defines += need("-D"); }
         else if (a.rfind("-D", 0) == 0 && a.size() > 2) { if (!defines.empty()) defines += ";"; defines += a.substr(2); }
-        else if (a == "-p" || a == "-b") need(a.c_str());
+        else if (a == "-p") workers = atoi(need("-p"));
+        else if (a == "--gpus") gpus = atoi(need("--gpus"));
+        else if (a == "-b") need(a.c_str());
         else if (a == "-q") quiet = true;
         else if (a == "--gpu") gpu = atoi(need("--gpu"));
         else if (a == "--spp") spp = atol(need("--spp"));
         else if (a == "--seed") seed = strtoull(need("--seed"), nullptr, 10);
         else if (a == "--data-dir") dataDir = need("--data-dir");
-        else if (a == "-h" || a == "--help") { printf("usage: cudapath_render [-o out.{png,pfm,ppm}] [-D name=value]... [-p N] [-q] [--gpu i] [--spp n] [--seed s] [--data-dir dir] scene.xml\n"); return 0; }
+        else if (a == "-h" || a == "--help") { printf("usage: cudapath_render [-o out.{png,pfm,ppm}] [-D name=value]... [-p N] [--gpus N] [-q] [--gpu i] [--spp n] [--seed s] [--data-dir dir] scene.xml\n"); return 0; }
         else if (!a.empty() && a[0] == '-') { fprintf(stderr, "cudapath_render: unknown option %s\n", a.c_str()); return 2; }
         else scene = a;
     }
@@ -92,7 +96,12 @@ int main(int argc, char **argv) {
 
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     cudapath_ctx *ctx = nullptr;
-    if (cudapath_create(gpu, &ctx) != 0) return die("cannot create a context");
+    const int visible = cudapath_visible_devices();
+    int nDev = gpus > 0 ? gpus : (workers > 1 ? (workers < visible - gpu ? workers : visible - gpu) : 1);
+    if (nDev < 1) nDev = 1;
+    std::vector<int> devices;
+    for (int k = 0; k < nDev; ++k) devices.push_back(gpu + k);
+    if (cudapath_create_multi(devices.data(), nDev, &ctx) != 0) return die("cannot create a context");
     if (cudapath_set_data_dir(ctx, dataDir.c_str()) != 0) return die("data directory");
     const double t0 = now();
     uint32_t fileSpp = 0;
@@ -132,8 +141,8 @@ int main(int argc, char **argv) {
         const double paths = (double) w * h * n, rays = (double) st.rays + (double) st.shadow_rays;
         printf("Loaded \"%s\" in %.3f s; %llu segments, %llu triangles -> %llu BVH references, %llu nodes (built in %.3f s)\n", scene.c_str(), t1 - t0,
                (unsigned long long) st.segments, (unsigned long long) st.triangles, (unsigned long long) st.bvh_references, (unsigned long long) st.bvh_nodes, t2 - t1);
-        printf("Render time: %.4f s  (%dx%d, %u spp: %.1f Mpaths/s, %.1f Mrays/s; device %.4f s)\n", t3 - t2, w, h, n, paths / (t3 - t2) / 1e6, rays / (t3 - t2) / 1e6,
-               st.render_ms * 1e-3);
+        printf("Render time: %.4f s  (%dx%d, %u spp on %d GPU%s: %.1f Mpaths/s, %.1f Mrays/s; device %.4f s, film reduce %.3f ms)\n", t3 - t2, w, h, n, nDev, nDev > 1 ? "s" : "",
+               paths / (t3 - t2) / 1e6, rays / (t3 - t2) / 1e6, st.render_ms * 1e-3, cudapath_last_reduce_ms(ctx));
         printf("Writing image to \"%s\" ..\n", out.c_str());
     }
     cudapath_destroy(ctx);

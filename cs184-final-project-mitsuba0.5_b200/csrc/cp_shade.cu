@@ -14,9 +14,10 @@
 
 namespace cp {
 
-__global__ void __launch_bounds__(256) k_raygen(SceneDev S, WaveParams wp, PathQueue q, float4 *liAcc, uint32_t n) {
+__global__ void __launch_bounds__(256) k_raygen(SceneDev S, WaveParams wp, PathQueue q, float4 *liAcc, uint32_t n, uint32_t *initSlot) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (i == 0) { initSlot[0] = n; initSlot[1] = 0u; }      // queue lengths the first trace launch reads (closest-hit rays, shadow rays)
     uint32_t x, y, samp;
     const bool valid = path_to_pixel(wp, wp.waveBase + i, x, y, samp);
     liAcc[i] = make_float4(0, 0, 0, 1.0f);
@@ -39,10 +40,12 @@ __device__ __forceinline__ float mi_weight(float pdfA, float pdfB) { pdfA *= pdf
 #ifndef CP_SHADE_MIN_BLOCKS
 #define CP_SHADE_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, WaveParams wp, PathQueue in, uint32_t n, const float4 *__restrict__ hitPT,
+__global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, WaveParams wp, PathQueue in, const uint32_t *__restrict__ nPtr, const float4 *__restrict__ hitPT,
                                                const uint32_t *__restrict__ hitPrim, PathQueue out, ShadowQueue sq, float4 *liAcc,
                                                uint32_t *counters, unsigned long long *unsupportedLookups) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = *nPtr;                   // queue length left by the previous bounce; the grid covers the host's upper bound
+    if (blockIdx.x * blockDim.x >= n) return;
     bool survive = false, wantShadow = false, countOnlyShadow = false;
     float4 nro, nrd, nthr; uint2 nid;
     float4 so, sd, sc;
@@ -199,12 +202,13 @@ __global__ void k_splat_batch(SceneDev S, const float *__restrict__ pos, const f
 }
 
 
-void launch_raygen(const SceneDev &S, const WaveParams &wp, PathQueue q, float4 *liAcc, uint32_t n, cudaStream_t stream) {
-    k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(S, wp, q, liAcc, n);
+void launch_raygen(const SceneDev &S, const WaveParams &wp, PathQueue q, float4 *liAcc, uint32_t n, uint32_t *initSlot, cudaStream_t stream) {
+    k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(S, wp, q, liAcc, n, initSlot);
 }
-void launch_shade(const SceneDev &S, const WaveParams &wp, PathQueue in, uint32_t n, const float4 *hitPT, const uint32_t *hitPrim, PathQueue out,
+void launch_shade(const SceneDev &S, const WaveParams &wp, PathQueue in, const uint32_t *nPtr, uint32_t nUpper, const float4 *hitPT, const uint32_t *hitPrim, PathQueue out,
                   ShadowQueue sq, float4 *liAcc, uint32_t *counters, unsigned long long *unsupportedLookups, cudaStream_t stream) {
-    k_shade<<<(n + 127) / 128, 128, 0, stream>>>(S, wp, in, n, hitPT, hitPrim, out, sq, liAcc, counters, unsupportedLookups);
+    if (nUpper == 0) return;
+    k_shade<<<(nUpper + 127) / 128, 128, 0, stream>>>(S, wp, in, nPtr, hitPT, hitPrim, out, sq, liAcc, counters, unsupportedLookups);
 }
 void launch_splat(const SceneDev &S, const WaveParams &wp, const float4 *liAcc, uint32_t n, float *film, unsigned long long *dropped, cudaStream_t stream) {
     k_splat<<<(n + 255) / 256, 256, 0, stream>>>(S, wp, liAcc, n, film, dropped);

@@ -15,6 +15,15 @@
 // its lanes busy by pulling new rays from a global counter whenever enough lanes have finished, and the loop is split
 // into phases the whole warp enters together (node descent / fp32 segment pre-test / FP64 cylinder test), so lanes in
 // the same phase execute together instead of serialising against each other.
+//
+// One launch serves closest-hit and occlusion rays at once (MODE 2): the wavefront hands the closest-hit rays of bounce
+// b+1 and the shadow rays of bounce b -- which start at the same hit points -- to the same persistent grid, in one
+// coherence order, so a warp walks one part of the tree for both and the tail of one query kind is filled by the other.
+//
+// On-chip state: the top CP_SMEM_STACK entries of every lane's traversal stack live in shared memory (one 8-byte slot per
+// lane and level, conflict-free), only deeper entries go to local memory; the hit point and the ray slot of a lane, which
+// are written once per hit / ray and read once per ray, live there as well (they would otherwise be spilled: the FP64
+// cylinder test pins the kernel at its register cap).
 #pragma once
 #include "cp_scene.cuh"
 
@@ -36,31 +45,52 @@ struct RayHit { float t; uint32_t gv; V3 p; };
 #define CP_DESCENT_MIN_LANES 8
 #endif
 
+#ifndef CP_SMEM_STACK
+#define CP_SMEM_STACK 12       // stack levels per lane kept in shared memory (12 KB per 128-thread CTA)
+#endif
+#ifndef CP_HOLD_MIN
+#define CP_HOLD_MIN 8          // lanes whose leaf produced FP64 candidates wait until this many lanes hold some (0: test at once)
+#endif
+#define CP_TRACE_THREADS 128
+
 struct TraceCounters { unsigned long long nodes, prims, fullTests; };
 
-// IO concept:  bool load(uint32_t i, V3 &o, V3 &d, float &mint, float &maxt)   (false: slot carries no ray)
-//              void store(uint32_t i, bool hit, const RayHit &h)
+enum : int { TRACE_CLOSEST = 0, TRACE_ANY = 1, TRACE_MIXED = 2 };
+
+// IO concept:  bool load(uint32_t k, V3 &o, V3 &d, float &mint, float &maxt, bool &any, uint32_t &slot)   (false: slot carries no ray;
+//                   `any` is only read in TRACE_MIXED; `slot` is handed back to store())
+//              void store(uint32_t slot, bool any, bool hit, const RayHit &h)
 // MESH: the scene also holds triangles (cp_tri.cuh).  They live in the same BVH; a triangle reference skips the fp32 pre-test
 // and is tested against the scene-level interval, as in the reference's top-level tree (skdtree.h:293-304).
-template <bool ANY, bool STATS, bool MESH, class IO>
-CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__restrict__ rayCounter, TraceCounters &tc, int &overflow) {
+// tc[0] counts closest-hit rays, tc[1] occlusion rays (STATS only).
+template <int MODE, bool STATS, bool MESH, class IO>
+CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *rayCounter, TraceCounters *tc, int &overflow) {
     const BVH4Node *__restrict__ nodes = S.bvh.nodes;
     const float4 *__restrict__ leafSeg = S.bvh.leafSeg;
     const float4 *__restrict__ vtx = S.vtx;
     const bool multiShape = S.clipPerShape != 0;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lanesBelow = (1u << lane) - 1u;
+    const unsigned tid = threadIdx.x;
 
-    uint2 stack[CP_STACK_SIZE];          // (node reference, entry distance bits): one 8-byte local store per push
+#if CP_SMEM_STACK > 0
+    __shared__ uint2 s_stack[CP_SMEM_STACK * CP_TRACE_THREADS];
+#endif
+    __shared__ float s_hitP[3 * CP_TRACE_THREADS];
+    __shared__ uint32_t s_slot[CP_TRACE_THREADS];
+    uint2 stack[CP_STACK_SIZE - CP_SMEM_STACK];          // (node reference, entry distance bits): one 8-byte store per push
     // per-lane ray state
-    bool idle = true, exhausted = false;
-    uint32_t rayIdx = 0;
+    bool idle = true, exhausted = false, any = (MODE == TRACE_ANY);
     V3 o(0.0f), d(0.0f), dRcp(0.0f);
     float mint = 0, maxt = 0, radius = 0;
     int sp = 0, cur = CP_EMPTY_CHILD;
-    RayHit hit; hit.t = CP_INF; hit.gv = 0xffffffffu; hit.p = V3(0.0f);
+    float hitT = CP_INF; uint32_t hitGv = 0xffffffffu;
     bool found = false;
     uint32_t cachedShape = 0xffffffffu; float sNear = 0, sFar = 0; bool sOk = true;
+    uint32_t candMask = 0, leafFirst = 0;               // FP64 candidates of the leaf this lane holds (bit i: reference leafFirst + i)
+
+#define CP_STORE_RAY() { RayHit h_; h_.t = hitT; h_.gv = hitGv; h_.p = V3(s_hitP[tid], s_hitP[CP_TRACE_THREADS + tid], s_hitP[2 * CP_TRACE_THREADS + tid]); \
+                         io.store(s_slot[tid], any, found, h_); }
 
     while (true) {
         // ------------------------------------------------------------------ refill idle lanes from the global ray counter
@@ -76,10 +106,12 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
                     const uint32_t idx = base + __popc(idleMask & lanesBelow);
                     if (idx >= n) exhausted = true;
                     else {
-                        rayIdx = idx;
-                        float rmin, rmax;
-                        found = false; hit.t = CP_INF; hit.gv = 0xffffffffu; hit.p = V3(0.0f);
-                        bool alive = io.load(idx, o, d, rmin, rmax) && S.bvh.nodeCount > 0;
+                        float rmin, rmax; uint32_t slot = idx; bool rayAny = (MODE == TRACE_ANY);
+                        found = false; hitT = CP_INF; hitGv = 0xffffffffu;
+                        s_hitP[tid] = 0.0f; s_hitP[CP_TRACE_THREADS + tid] = 0.0f; s_hitP[2 * CP_TRACE_THREADS + tid] = 0.0f;
+                        bool alive = io.load(idx, o, d, rmin, rmax, rayAny, slot) && S.bvh.nodeCount > 0;
+                        if (MODE == TRACE_MIXED) any = rayAny;
+                        s_slot[tid] = slot;
                         if (alive) {
                             dRcp = V3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
                             // scene-level interval (skdtree.cpp:112-142 / :207-226)
@@ -87,30 +119,36 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
                             float rayMinT = rmin;
                             if (rayMinT == kEpsilon) {
                                 float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
-                                if (!ANY) m = fmaxf(m, kEpsilon);
+                                if (!any) m = fmaxf(m, kEpsilon);
                                 rayMinT *= m;
                             }
                             if (rayMinT > mint) mint = rayMinT;
                             if (rmax < maxt) maxt = rmax;
                             alive = alive && (maxt > mint);
                         }
-                        if (alive) { idle = false; sp = 0; cur = 0; cachedShape = 0xffffffffu; radius = S.shapes[0].radius; sOk = true; }
-                        else io.store(idx, false, hit);
+                        if (alive) { idle = false; sp = 0; cur = 0; cachedShape = 0xffffffffu; radius = S.shapes[0].radius; sOk = true; candMask = 0; }
+                        else CP_STORE_RAY()
                     }
                 }
             }
             if (__ballot_sync(0xffffffffu, !idle) == 0u && __ballot_sync(0xffffffffu, idle && !exhausted) == 0u) break;
         }
 
+#if CP_SMEM_STACK > 0
+#define CP_STACK_AT(I) (*((I) < CP_SMEM_STACK ? &s_stack[(I) * CP_TRACE_THREADS + tid] : &stack[(I) - CP_SMEM_STACK]))
+#else
+#define CP_STACK_AT(I) (stack[(I)])
+#endif
+#define CP_PUSH(C, T) { if (sp < CP_STACK_SIZE) { CP_STACK_AT(sp) = make_uint2((uint32_t) (C), __float_as_uint(T)); ++sp; } else overflow = 1; }
 // pop the next node whose entry distance is still inside the (shrinking) interval; an empty stack finishes the ray
 #define CP_POP() { \
             bool got_ = false; \
-            while (sp > 0) { --sp; const uint2 e_ = stack[sp]; if (ANY || __uint_as_float(e_.y) <= maxt) { cur = (int) e_.x; got_ = true; break; } } \
-            if (!got_) { io.store(rayIdx, found, hit); idle = true; cur = CP_EMPTY_CHILD; } }
+            while (sp > 0) { --sp; const uint2 e_ = CP_STACK_AT(sp); if (any || __uint_as_float(e_.y) <= maxt) { cur = (int) e_.x; got_ = true; break; } } \
+            if (!got_) { CP_STORE_RAY() idle = true; cur = CP_EMPTY_CHILD; } }
 
         // ------------------------------------------------------------------ phase 1: descend inner nodes until this lane holds a leaf
         while (!idle && cur >= 0) {
-            if (STATS) tc.nodes++;
+            if (STATS) tc[any ? 1 : 0].nodes++;
             const float4 *np = reinterpret_cast<const float4 *>(nodes + cur);
             const float4 lox = __ldg(np + 0), loy = __ldg(np + 1), loz = __ldg(np + 2);
             const float4 hix = __ldg(np + 3), hiy = __ldg(np + 4), hiz = __ldg(np + 5);
@@ -135,25 +173,24 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
 #undef CP_CSWAP
             if (t0 == CP_INF) { CP_POP() continue; }
             // nearest child first, the others are pushed far-to-near
-            if (t3 != CP_INF) { if (sp < CP_STACK_SIZE) stack[sp++] = make_uint2((uint32_t) c3, __float_as_uint(t3)); else overflow = 1; }
-            if (t2 != CP_INF) { if (sp < CP_STACK_SIZE) stack[sp++] = make_uint2((uint32_t) c2, __float_as_uint(t2)); else overflow = 1; }
-            if (t1 != CP_INF) { if (sp < CP_STACK_SIZE) stack[sp++] = make_uint2((uint32_t) c1, __float_as_uint(t1)); else overflow = 1; }
+            if (t3 != CP_INF) CP_PUSH(c3, t3)
+            if (t2 != CP_INF) CP_PUSH(c2, t2)
+            if (t1 != CP_INF) CP_PUSH(c1, t1)
             cur = c0;
             // Leave the descent once most of the warp is already waiting with a leaf: the stragglers resume next round,
             // together with the lanes that will have finished their leaves (keeps both phases reasonably full).
             if (__popc(__activemask()) <= CP_DESCENT_MIN_LANES) break;
         }
 
-        // ------------------------------------------------------------------ phase 2: fp32 pre-test of the leaf's segments (all lanes holding a leaf)
-        uint32_t candMask = 0, leafFirst = 0;
+        // ------------------------------------------------------------------ phase 2: fp32 pre-test of the leaf's segments (all lanes that just reached a leaf)
         const bool inLeaf = !idle && cur < 0;
-        if (inLeaf) {
+        if (inLeaf && candMask == 0u) {
             const uint32_t ref = ~(uint32_t) cur;
             const uint32_t count = (ref & 7u) + 1u;
             leafFirst = ref >> 3;
             for (uint32_t i = 0; i < count; ++i) {
                 const float4 v1 = __ldg(leafSeg + 2 * (size_t) (leafFirst + i)), v2 = __ldg(leafSeg + 2 * (size_t) (leafFirst + i) + 1);
-                if (STATS) tc.prims++;
+                if (STATS) tc[any ? 1 : 0].prims++;
                 if (MESH && (vtx_bits(v1) & 8u)) { candMask |= 1u << i; continue; }     // triangle reference
                 // Conservative fp32 rejection (never rejects a hit the FP64 test would accept).  With n = d x a the ray and the
                 // axis line are closest at ray parameter tc and axis parameter sc; every point of the infinite cylinder the
@@ -180,53 +217,71 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *__re
                 }
                 candMask |= 1u << i;
             }
+            if (candMask == 0u) CP_POP()
         }
         // ------------------------------------------------------------------ phase 3: FP64 mitred-cylinder test of the survivors
-        while (candMask) {
-            const int ci = __ffs(candMask) - 1;
-            candMask &= candMask - 1;
-            const uint32_t gv = __float_as_uint(__ldg(leafSeg + 2 * (size_t) (leafFirst + ci) + 1).w);
-            if (MESH && (gv & CP_TRI_FLAG)) {
-                const float4 *ta = S.mesh.triAccel + 3 * (size_t) (gv & ~CP_TRI_FLAG);
-                const float4 A = __ldg(ta), B = __ldg(ta + 1), C = __ldg(ta + 2);
-                if (STATS) tc.fullTests++;
-                float t, u, v;
-                if (tri_intersect(A, B, C, o, d, mint, maxt, u, v, t)) {
-                    hit.t = t; hit.gv = gv; hit.p = V3(u, v, 0.0f); found = true;       // barycentrics ride in the point slot
-                    if (ANY) break;
+        // The exact test is ~10x the instructions of a pre-test and only one leaf in twenty produces a candidate: run it when the
+        // lanes holding candidates are many (they wait, the others keep descending) or when nobody else can make progress.
+        {
+            const unsigned holdMask = __ballot_sync(0xffffffffu, candMask != 0u);
+            if (holdMask == 0u) continue;
+#if CP_HOLD_MIN > 1
+            const unsigned walkMask = __ballot_sync(0xffffffffu, !idle && candMask == 0u);
+            if (__popc(holdMask) < CP_HOLD_MIN && walkMask != 0u) continue;
+#endif
+        }
+        if (candMask) {
+            bool done = false;
+            while (candMask) {
+                const int ci = __ffs(candMask) - 1;
+                candMask &= candMask - 1;
+                const uint32_t gv = __float_as_uint(__ldg(leafSeg + 2 * (size_t) (leafFirst + ci) + 1).w);
+                if (MESH && (gv & CP_TRI_FLAG)) {
+                    const float4 *ta = S.mesh.triAccel + 3 * (size_t) (gv & ~CP_TRI_FLAG);
+                    const float4 A = __ldg(ta), B = __ldg(ta + 1), C = __ldg(ta + 2);
+                    if (STATS) tc[any ? 1 : 0].fullTests++;
+                    float t, u, v;
+                    if (tri_intersect(A, B, C, o, d, mint, maxt, u, v, t)) {
+                        hitT = t; hitGv = gv; found = true;       // barycentrics ride in the point slot
+                        s_hitP[tid] = u; s_hitP[CP_TRACE_THREADS + tid] = v; s_hitP[2 * CP_TRACE_THREADS + tid] = 0.0f;
+                        if (any) { done = true; break; }
+                        maxt = t;
+                    }
+                    continue;
+                }
+                const float4 v1 = __ldg(vtx + gv), v2 = __ldg(vtx + gv + 1);
+                const float4 v0 = __ldg(vtx + (gv > 0 ? gv - 1 : 0)), v3 = __ldg(vtx + gv + 2);
+                float tmin = mint, tmax = maxt;
+                if (multiShape) {   // per-shape clipped interval, cached for the last shape seen (hair.cpp:205-209)
+                    const uint32_t sh = vtx_shape(v1);
+                    if (sh != cachedShape) {
+                        cachedShape = sh;
+                        const ShapeDev &sd = S.shapes[sh];
+                        radius = sd.radius;
+                        sOk = aabb_ray(sd.bmin, sd.bmax, o, d, dRcp, sNear, sFar);
+                    }
+                    if (!sOk) continue;
+                    if (sNear > tmin) tmin = sNear;
+                    if (sFar < tmax) tmax = sFar;
+                    if (!(tmax > tmin)) continue;
+                }
+                if (STATS) tc[any ? 1 : 0].fullTests++;
+                float t; V3 p;
+                if (segment_intersect(v0, v1, v2, v3, radius, o, d, tmin, tmax, t, p)) {
+                    hitT = t; hitGv = gv; found = true;
+                    s_hitP[tid] = p.x; s_hitP[CP_TRACE_THREADS + tid] = p.y; s_hitP[2 * CP_TRACE_THREADS + tid] = p.z;
+                    if (any) { done = true; break; }
                     maxt = t;
                 }
-                continue;
             }
-            const float4 v1 = __ldg(vtx + gv), v2 = __ldg(vtx + gv + 1);
-            const float4 v0 = __ldg(vtx + (gv > 0 ? gv - 1 : 0)), v3 = __ldg(vtx + gv + 2);
-            float tmin = mint, tmax = maxt;
-            if (multiShape) {   // per-shape clipped interval, cached for the last shape seen (hair.cpp:205-209)
-                const uint32_t sh = vtx_shape(v1);
-                if (sh != cachedShape) {
-                    cachedShape = sh;
-                    const ShapeDev &sd = S.shapes[sh];
-                    radius = sd.radius;
-                    sOk = aabb_ray(sd.bmin, sd.bmax, o, d, dRcp, sNear, sFar);
-                }
-                if (!sOk) continue;
-                if (sNear > tmin) tmin = sNear;
-                if (sFar < tmax) tmax = sFar;
-                if (!(tmax > tmin)) continue;
-            }
-            if (STATS) tc.fullTests++;
-            float t; V3 p;
-            if (segment_intersect(v0, v1, v2, v3, radius, o, d, tmin, tmax, t, p)) {
-                hit.t = t; hit.gv = gv; hit.p = p; found = true;
-                if (ANY) break;
-                maxt = t;
-            }
-        }
-        if (inLeaf) {
-            if (ANY && found) { io.store(rayIdx, true, hit); idle = true; cur = CP_EMPTY_CHILD; }
+            candMask = 0u;
+            if (done) { CP_STORE_RAY() idle = true; cur = CP_EMPTY_CHILD; }
             else CP_POP()
         }
 #undef CP_POP
+#undef CP_PUSH
+#undef CP_STACK_AT
+#undef CP_STORE_RAY
     }
 }
 

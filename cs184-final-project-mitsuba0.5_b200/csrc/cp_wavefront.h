@@ -26,32 +26,40 @@ struct WaveParams {
     float diffScale = 1.0f;
 };
 struct RenderStats {
-    uint64_t paths = 0, rays = 0, shadowRays = 0, launches = 0, bounces = 0;
+    uint64_t paths = 0, rays = 0, shadowRays = 0, launches = 0, bounces = 0, hostSyncs = 0;
     uint64_t shadowRaysTraced = 0;      // shadowRays minus the ones whose emitter sample cannot contribute (contribution exactly zero)
     uint64_t nodesVisited = 0, primsTested = 0, shadowNodesVisited = 0, shadowPrimsTested = 0, unsupportedLookups = 0, droppedSamples = 0;
     uint64_t fullTests = 0, shadowFullTests = 0;     // exact (FP64 cylinder / Wald triangle) tests that survived the fp32 pre-test
-    double stageMs[5] = {0, 0, 0, 0, 0};       // intersect, shade, shadow, raygen, splat
-    uint64_t stageLaunches[5] = {0, 0, 0, 0, 0};
+    double stageMs[6] = {0, 0, 0, 0, 0, 0};       // trace (closest + occlusion rays in one launch), shade, coherence sort (keys + radix sort), raygen, splat, film clear
+    uint64_t stageLaunches[6] = {0, 0, 0, 0, 0, 0};
 };
 
+#define CP_CTR_RING 4
 struct Wavefront {
     PathQueue q[2];
     ShadowQueue sq;
     float4 *hitPT = nullptr; uint32_t *hitPrim = nullptr;
     float4 *liAcc = nullptr;
+    // Queue counters: a ring of CP_CTR_RING slots of 8 words (one per bounce) + an init slot written by k_raygen.  Slot of bounce b:
+    // [0] paths that survive shade(b) = closest-hit rays of bounce b+1, [1] shadow rays emitted by shade(b), [2] work counter of the
+    // trace launch of bounce b, [4] shadow rays counted but not traced (zero contribution).  Every kernel reads its input counts from
+    // the previous slot ON THE DEVICE; the host only follows two bounces behind (pinned mirror `hCounters`, one event per slot) to size
+    // the next launches and to notice the end of the wave -- it never waits for the bounce it has just launched.
     uint32_t *counters = nullptr, *hCounters = nullptr;
+    cudaEvent_t slotEvent[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long *stats = nullptr;
     int *errFlag = nullptr;
     uint32_t *sortKeys[2] = {nullptr, nullptr}, *sortVals[2] = {nullptr, nullptr};
     void *sortTemp = nullptr; size_t sortTempBytes = 0;
     bool sortRays = true;
+    uint32_t runAheadMax = 1u << 22;    // bounces with more rays than this are sized from exact counters (one host wait), smaller ones run ahead
     // Integrator::cancel() (include/mitsuba/render/integrator.h:76-84) may be called from another thread while render() blocks: the flag
     // is looked at once per bounce (after the host has read the queue counters); a cancelled render returns false with "render cancelled".
-    std::atomic<int> cancelRequested{0};
+    std::atomic<int> cancelRequested{0}, inRender{0};
     // RenderJob progress (ProgressReporter in SamplingIntegrator::render, src/librender/integrator.cpp:95-138): called on the rendering
     // thread after every finished wave with the camera paths done so far and the total of this call
     void (*progress)(void *user, uint64_t done, uint64_t total) = nullptr; void *progressUser = nullptr;
-    const uint32_t *coherence_order(const SceneDev &S, const float4 *ro, const float4 *rd, uint32_t n, cudaStream_t stream);
+    const uint32_t *coherence_order(const SceneDev &S, const PathQueue &q, const ShadowQueue &sq, const uint32_t *prevSlot, uint32_t ubClosest, uint32_t ubShadow, cudaStream_t stream);
     uint32_t capacity = 0;
     cudaStream_t allocStream = nullptr;
     bool reserve(uint32_t waveSize, cudaStream_t stream, std::string &err);
@@ -91,8 +99,9 @@ __device__ __forceinline__ bool path_to_pixel(const WaveParams &wp, uint64_t g, 
 #endif
 
 // cp_shade.cu (built with -fmad=false)
-void launch_raygen(const SceneDev &S, const WaveParams &wp, PathQueue q, float4 *liAcc, uint32_t n, cudaStream_t stream);
-void launch_shade(const SceneDev &S, const WaveParams &wp, PathQueue in, uint32_t n, const float4 *hitPT, const uint32_t *hitPrim, PathQueue out,
+void launch_raygen(const SceneDev &S, const WaveParams &wp, PathQueue q, float4 *liAcc, uint32_t n, uint32_t *initSlot, cudaStream_t stream);
+// nPtr: device word holding the number of paths in `in` (<= nUpper, which only sizes the grid)
+void launch_shade(const SceneDev &S, const WaveParams &wp, PathQueue in, const uint32_t *nPtr, uint32_t nUpper, const float4 *hitPT, const uint32_t *hitPrim, PathQueue out,
                   ShadowQueue sq, float4 *liAcc, uint32_t *counters, unsigned long long *unsupportedLookups, cudaStream_t stream);
 void launch_splat(const SceneDev &S, const WaveParams &wp, const float4 *liAcc, uint32_t n, float *film, unsigned long long *dropped, cudaStream_t stream);
 bool splat_batch(const SceneDev &S, const float *d_pos, const float *d_rgb, const float *d_alpha, uint64_t n, float *d_film, cudaStream_t stream, std::string &err);
@@ -105,6 +114,7 @@ bool intersect_batch(const SceneDev &S, uint64_t n, const float *d_o, const floa
 void fill_records_batch(const SceneDev &S, uint64_t n, const float *d_d, const int32_t *d_shape, float *d_rec, cudaStream_t s);
 bool env_eval_batch(const SceneDev &S, uint64_t n, const float *d_dir, float *d_rgb, float *d_pdf, cudaStream_t s, std::string &err);
 bool env_sample_batch(const SceneDev &S, uint64_t n, const float *d_ref, const float *d_sample, float *d_dir, float *d_value, float *d_pdfDist, cudaStream_t s, std::string &err);
+bool read_bandwidth_probe(size_t bytes, int iters, cudaStream_t s, double &gbs, std::string &err);
 bool camera_rays_batch(const SceneDev &S, uint64_t n, const float *d_pxy, float *d_o, float *d_d, float *d_minmax, cudaStream_t s, std::string &err);
 
 } // namespace cp

@@ -5,7 +5,8 @@
  * All pointers are caller-owned HOST memory unless the name ends in `_dev`.  Every function returns 0 (or a
  * non-negative id) on success and a negative value on failure; cudapath_last_error() then returns a message
  * (the reference reports errors by throwing from Log(EError), src/libcore/logger.cpp:100,147).
- * One context owns one CUDA device; a context is thread-compatible (use it from one thread at a time).
+ * One context owns one CUDA device (cudapath_create) or several of one box (cudapath_create_multi); a context is
+ * thread-compatible (use it from one thread at a time).  Entry points restore the caller's current CUDA device before returning.
  *
  * Each entry point cites the reference interface it replaces (paths relative to the reference tree).
  */
@@ -22,6 +23,21 @@ typedef struct cudapath_ctx cudapath_ctx;
 /* ---- context ---------------------------------------------------------------------------------------------- */
 /* Replaces Scheduler/LocalWorker set-up for this path (src/mitsuba/mitsuba.cpp:280-329): one context per GPU. */
 int cudapath_create(int cuda_device, cudapath_ctx **out);
+/* `mitsuba -p N` (src/mitsuba/mitsuba.cpp:218-222,280-282: N LocalWorkers) and the tile scheduler that feeds them
+ * (BlockedRenderProcess, src/librender/renderproc.cpp:117-182) for this path: ONE context spanning n_devices GPUs of this box.
+ * The returned context is used exactly like a single-device one: every scene-building call is repeated on all devices,
+ * cudapath_build builds them concurrently (one host thread per device), and cudapath_render splits the sample range
+ * [sample_begin, sample_end) into n_devices contiguous parts, renders each on its own device into a private full-size film and
+ * sums the films onto cuda_devices[0] with a single ncclReduce over NVLink before the read-back.  The image does not depend on
+ * n_devices up to fp32 summation order (the RNG is keyed by pixel, sample index and path vertex).  cudapath_render_dev, the
+ * parity hooks and the statistics of a build refer to cuda_devices[0]; cudapath_get_stats after a render holds the job's totals.
+ * n_devices == 1 is cudapath_create.  libnccl.so.2 is bound at run time, only by this call. */
+int cudapath_create_multi(const int *cuda_devices, int n_devices, cudapath_ctx **out);
+/* Number of devices a context spans (1 for cudapath_create) / CUDA devices visible to the process (0 when there is no driver). */
+int cudapath_device_count(cudapath_ctx *ctx);
+int cudapath_visible_devices(void);
+/* Device time of the film reduce of the last multi-GPU cudapath_render, in ms (0 for a single device). */
+double cudapath_last_reduce_ms(cudapath_ctx *ctx);
 void cudapath_destroy(cudapath_ctx *ctx);
 /* Device memory freed by contexts is parked in a per-device free list and reused by the next build / render of similar size (a
  * repeated job then never waits for the driver).  This returns the parked blocks of `cuda_device` to the driver. */
@@ -173,11 +189,13 @@ typedef struct cudapath_stats {
     uint64_t segments, bvh_nodes, bvh_references, triangles;
     double build_ms, render_ms;                 /* device time of the last build / render (CUDA events) */
     /* per-stage device time of the last render, summed over launches (CUDA events on the launching stream; only with
-     * profile_stages) and the number of launches of each stage */
-    double intersect_ms, shade_ms, shadow_ms, raygen_ms, splat_ms;
-    uint64_t intersect_launches, shade_launches, shadow_launches;
+     * profile_stages) and the number of launches of each stage.  trace = BVH traversal (the closest-hit rays of a bounce and the
+     * shadow rays of the bounce before share one launch), sort = coherence keys + radix sort of those rays */
+    double trace_ms, shade_ms, sort_ms, raygen_ms, splat_ms;
+    uint64_t trace_launches, shade_launches, sort_launches;
     uint64_t shadow_rays_traced;                 /* shadow_rays minus those whose emitter sample has an exactly zero contribution (not traced here) */
     uint64_t full_tests, shadow_full_tests;      /* exact primitive tests (FP64 cylinder / Wald triangle) after the fp32 pre-test; only with collect_stats */
+    uint64_t host_waits;                         /* times the host had to wait for the device inside the last render's bounce loops */
 } cudapath_stats;
 int cudapath_get_stats(cudapath_ctx *ctx, cudapath_stats *out);
 int cudapath_scene_bounds(cudapath_ctx *ctx, float aabb_min_max[6], float bsphere_center_radius[4]);
@@ -223,9 +241,14 @@ int cudapath_filter_table(cudapath_ctx *ctx, float out32[32]);
 int cudapath_bsdf_eval_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf, void *stream);
 int cudapath_bsdf_sample_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo,
                                    float *out_weight, float *out_pdf, int32_t *out_type, void *stream);
-/* out_stats (optional, device, 2 x uint64): nodes visited, primitives tested (enables the counting variant of the kernel) */
+/* out_stats (optional, device, 3 x uint64): nodes visited, primitives pre-tested, exact tests (enables the counting variant of the kernel) */
 int cudapath_intersect_batch_dev(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,
                                  int any_hit, int32_t *out_shape, uint32_t *out_prim, float *out_t, unsigned long long *out_stats, void *stream);
+
+/* Roofline denominators for the stage reports, measured on the context's device: read bandwidth of a resident buffer of `bytes`
+ * streamed `iterations` times with 16-byte loads that bypass L1 (a buffer well below the L2 size gives the L2 bandwidth, a
+ * multi-GB one the HBM read bandwidth).  Best of three timed passes, CUDA events. */
+int cudapath_measure_read_bandwidth(cudapath_ctx *ctx, size_t bytes, int iterations, double *out_gb_per_s);
 
 /* ---- scene files -------------------------------------------------------------------------------------------- */
 /* SceneHandler (src/librender/scenehandler.cpp:70-250) for the subset of tags the hair scenes use: integrator `path`,

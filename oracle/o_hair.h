@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <fstream>
 #include <sstream>
+#include <thread>
 
 namespace orc {
 
@@ -348,6 +349,9 @@ struct Intersection {
     V3 wi;
 };
 
+#ifdef ORC_COUNT
+static unsigned long long g_cnt[4];
+#endif
 struct BVHNode { AABB box; uint32_t left, right; uint32_t first, count; }; // leaf if count>0
 
 struct Geometry {
@@ -420,6 +424,299 @@ struct Geometry {
         return found;
     }
 
+#ifdef ORC_FAST
+    // ------------------------------------------------------------------------------------------------------------------------
+    // CPU-BASELINE ACCELERATOR (timing build liboracle_fast.so only; the checker liboracle.so keeps the plain BVH above).
+    // What `mitsuba -p N` has and a plain BVH over whole segments lacks is (a) spatial subdivision of long thin segments -- its SAH
+    // kd-tree clips cylinders against the split planes (src/shapes/hair.cpp:246-444, include/mitsuba/render/gkdtree.h:958-2400) --
+    // and (b) a cheap rejection in front of the FP64 cylinder test (the kd leaf boxes are tight).  This build gets both the same way
+    // the CUDA path does: every segment is referenced by up to 8 boxes cut along its axis, a binned-SAH binary BVH is built over
+    // the references (in parallel), a conservative fp32 distance test runs before the exact test, and an 8-entry mailbox
+    // (sahkdtree3.h:138-152) skips segments already tested for this ray.  The exact test and the interval logic are the
+    // unchanged oracle functions, so results are identical to the checker build except for equal-t ties
+    // (tests/test_oracle_cpu.py::test_fast_accelerator_matches_checker).
+    struct FastRef { uint32_t shapeFlags, iv; };     // shapeFlags: bits 3.. shape, bit 0 mesh triangle, bits 1 / 2 mild miter joint at the first / second vertex (8 bytes: the vertices are read from the shape)
+    struct FastNode { float lo[3], hi[3]; uint32_t a, b; };                         // inner: a = right child (left = self + 1), b = 0; leaf: a = first reference, b = count
+    std::vector<FastRef> frefs;
+    FastNode *fnodes = nullptr; size_t fnodeCap = 0;                                 // binary build product, collapsed into `wide` and released
+    struct Wide { float lo[3][8], hi[3][8]; uint32_t child[8]; };                    // 8-wide node, SoA boxes: child >= 0x80000000: reference index | 0x80000000; 0xffffffff: empty
+    std::vector<Wide> wide;
+    int fastMaxSplit = 8, fastLeaf = 1;
+    ~Geometry() { free(fnodes); }
+    Geometry() = default;
+    Geometry(const Geometry &) = delete; Geometry &operator=(const Geometry &) = delete;
+
+    static const char *accelDescription() { return "8-wide BVH (binned SAH over all three axes, collapsed from a binary tree with one reference per leaf; SoA boxes tested 8 at a time) over segment references pre-split up to 8x along the fiber axis, fp32 pre-test before the FP64 cylinder test, 8-entry mailbox (parallel build)"; }
+
+    void buildBVH() {
+        frefs.clear(); free(fnodes); fnodes = nullptr; fnodeCap = 0;
+        if (const char *e = getenv("ORC_FAST_MAX_SPLIT")) fastMaxSplit = std::max(1, atoi(e));
+        if (const char *e = getenv("ORC_FAST_LEAF")) fastLeaf = std::max(1, atoi(e));
+        std::vector<AABB> boxes;
+        for (size_t si = 0; si < shapes.size(); ++si) {
+            const HairShape &s = shapes[si];
+            if (s.isMesh) {
+                for (uint32_t j = 0; j < s.mesh.triCount(); ++j) {
+                    AABB b = s.mesh.triAABB(j);
+                    V3 pad = (b.mx - b.mn) * 1e-5f + V3(1e-6f) + V3(std::abs(b.mx.x) + std::abs(b.mn.x), std::abs(b.mx.y) + std::abs(b.mn.y), std::abs(b.mx.z) + std::abs(b.mn.z)) * 1e-6f;
+                    b.mn = b.mn - pad; b.mx = b.mx + pad;
+                    FastRef r{}; r.shapeFlags = ((uint32_t) si << 3) | 1u; r.iv = j;
+                    frefs.push_back(r); boxes.push_back(b);
+                }
+                continue;
+            }
+            auto mild = [&](uint32_t v) {          // the miter joint at vertex v bends by at most ~117 degrees (or v ends a fiber): the cut overshoots the end by < 2 r
+                const bool hasPrev = !s.startsFiber[v] && v > 0, hasNext = v + 1 < s.verts.size() && !s.startsFiber[v + 1];
+                if (!(hasPrev && hasNext)) return true;
+                return dot(normalize(s.verts[v] - s.verts[v - 1]), normalize(s.verts[v + 1] - s.verts[v])) >= -0.45f;
+            };
+            for (uint32_t iv : s.segIndex) {
+                const AABB whole = s.segmentAABB(iv);
+                const V3 p1 = s.verts[iv], a = s.verts[iv + 1] - p1;
+                const float ext = std::max(std::max(std::abs(a.x), std::abs(a.y)), std::abs(a.z));
+                const int k = std::max(1, std::min((int) (ext / (8.0f * s.radius)), fastMaxSplit));
+                const float invLen = 1.0f / length(a);
+                const V3 e(s.radius * std::sqrt(std::max(0.0f, 1.0f - (a.x * invLen) * (a.x * invLen))), s.radius * std::sqrt(std::max(0.0f, 1.0f - (a.y * invLen) * (a.y * invLen))),
+                           s.radius * std::sqrt(std::max(0.0f, 1.0f - (a.z * invLen) * (a.z * invLen))));
+                for (int j = 0; j < k; ++j) {
+                    AABB b;
+                    if (k == 1) b = whole;
+                    else {
+                        // a piece's box: its stretch of the axis widened by the cross-section; the two end pieces also cover the miter-cut end
+                        // ellipses by taking the whole segment's bound on the far side of their cut
+                        const V3 q0 = p1 + a * ((float) j / k), q1 = p1 + a * ((float) (j + 1) / k);
+                        for (int c = 0; c < 3; ++c) {
+                            float lo = std::min(q0[c], q1[c]) - e[c] - s.radius * 1e-3f, hi = std::max(q0[c], q1[c]) + e[c] + s.radius * 1e-3f;
+                            const bool towardsMin = a[c] >= 0;       // piece 0 touches the segment's minimum along c when the axis increases
+                            if ((j == 0 && towardsMin) || (j == k - 1 && !towardsMin)) lo = std::min(lo, whole.mn[c]);
+                            if ((j == k - 1 && towardsMin) || (j == 0 && !towardsMin)) hi = std::max(hi, whole.mx[c]);
+                            b.mn[c] = std::max(lo, whole.mn[c]); b.mx[c] = std::min(hi, whole.mx[c]);
+                        }
+                    }
+                    for (int c = 0; c < 3; ++c) {   // every point the FP64 test can accept lies strictly inside (the reference's bound uses radius (1 - Epsilon))
+                        const float pad = s.radius * 4e-4f + 4e-7f * std::max(std::abs(b.mn[c]), std::abs(b.mx[c]));
+                        b.mn[c] -= pad; b.mx[c] += pad;
+                    }
+                    FastRef r{};
+                    r.shapeFlags = ((uint32_t) si << 3) | (mild(iv) ? 2u : 0u) | (mild(iv + 1) ? 4u : 0u); r.iv = iv;
+                    frefs.push_back(r); boxes.push_back(b);
+                }
+            }
+        }
+        if (frefs.empty()) return;
+        const uint32_t n = (uint32_t) frefs.size();
+        std::vector<uint32_t> order(n);
+        for (uint32_t i = 0; i < n; ++i) order[i] = i;
+        fnodeCap = 2 * (size_t) n;
+        fnodes = (FastNode *) calloc(fnodeCap, sizeof(FastNode));      // lazily committed: a subtree over m references owns 2m - 1 consecutive slots
+        if (!fnodes) throw std::runtime_error("oracle: out of memory for the baseline accelerator");
+        fastBuildRec(0, order, boxes, 0, n, 0);
+        std::vector<FastRef> sorted(n);
+        for (uint32_t i = 0; i < n; ++i) sorted[i] = frefs[order[i]];
+        frefs.swap(sorted);
+        // collapse into 8-wide nodes: the children of a wide node are found by opening, largest box first, the inner nodes below it
+        wide.clear(); wide.reserve(n / 4 + 16);
+        wide.push_back(Wide());
+        if (fnodes[0].b) {       // a single leaf
+            Wide &w = wide[0];
+            for (int k = 0; k < 8; ++k) { for (int c = 0; c < 3; ++c) { w.lo[c][k] = kInf; w.hi[c][k] = -kInf; } w.child[k] = 0xffffffffu; }
+            for (uint32_t k = 0; k < fnodes[0].b && k < 8; ++k) { for (int c = 0; c < 3; ++c) { w.lo[c][k] = fnodes[0].lo[c]; w.hi[c][k] = fnodes[0].hi[c]; } w.child[k] = 0x80000000u | (fnodes[0].a + k); }
+        } else {
+            std::vector<std::pair<uint32_t, uint32_t>> work;       // (wide index, binary node)
+            work.push_back({0u, 0u});
+            while (!work.empty()) {
+                const auto [wi, bi] = work.back(); work.pop_back();
+                uint32_t cand[8]; int nc = 0;
+                cand[nc++] = bi + 1; cand[nc++] = fnodes[bi].a;
+                auto areaOf = [&](uint32_t i) { const FastNode &f = fnodes[i]; const float ex = f.hi[0] - f.lo[0], ey = f.hi[1] - f.lo[1], ez = f.hi[2] - f.lo[2]; return ex * ey + ey * ez + ez * ex; };
+                while (nc < 8) {
+                    int bestK = -1; float bestA = -1;
+                    for (int k = 0; k < nc; ++k) if (!fnodes[cand[k]].b) { const float a = areaOf(cand[k]); if (a > bestA) { bestA = a; bestK = k; } }
+                    if (bestK < 0) break;
+                    const uint32_t open = cand[bestK];
+                    cand[bestK] = open + 1; cand[nc++] = fnodes[open].a;
+                }
+                Wide w;
+                for (int k = 0; k < 8; ++k) {
+                    if (k >= nc) { for (int c = 0; c < 3; ++c) { w.lo[c][k] = kInf; w.hi[c][k] = -kInf; } w.child[k] = 0xffffffffu; continue; }
+                    const FastNode &f = fnodes[cand[k]];
+                    for (int c = 0; c < 3; ++c) { w.lo[c][k] = f.lo[c]; w.hi[c][k] = f.hi[c]; }
+                    if (f.b) w.child[k] = 0x80000000u | f.a;      // binary leaves hold exactly one reference
+                    else { w.child[k] = (uint32_t) wide.size(); wide.push_back(Wide()); work.push_back({w.child[k], cand[k]}); }
+                }
+                wide[wi] = w;
+            }
+        }
+        free(fnodes); fnodes = nullptr; fnodeCap = 0;
+        nodes.clear(); nodes.push_back(BVHNode());     // "built" marker for callers that look at nodes.empty()
+    }
+
+    void fastBuildRec(size_t ni, std::vector<uint32_t> &order, const std::vector<AABB> &boxes, uint32_t lo, uint32_t hi, int depth) {
+        AABB box, cbox;
+        for (uint32_t i = lo; i < hi; ++i) { box.expand(boxes[order[i]]); cbox.expand(boxes[order[i]].center()); }
+        FastNode &nd = fnodes[ni];
+        for (int c = 0; c < 3; ++c) { nd.lo[c] = box.mn[c]; nd.hi[c] = box.mx[c]; }
+        const uint32_t n = hi - lo;
+        if (n <= (uint32_t) fastLeaf) { nd.a = lo; nd.b = n; return; }
+        V3 ext = cbox.mx - cbox.mn;
+        uint32_t mid = (lo + hi) / 2;
+        auto area = [](const AABB &b) { V3 e = b.mx - b.mn; return 2 * (e.x * e.y + e.y * e.z + e.z * e.x); };
+        const int NB = 16;
+        float best = kInf; int bestAxis = -1, bestSplit = -1;
+        for (int axis = 0; axis < 3; ++axis) {
+            if (!(ext[axis] > 0)) continue;
+            AABB bb[NB]; uint32_t bc[NB] = {0};
+            const float k = NB * (1 - 1e-6f) / ext[axis];
+            for (uint32_t i = lo; i < hi; ++i) { const uint32_t id = order[i]; const int b = clampi((int) ((boxes[id].center()[axis] - cbox.mn[axis]) * k), 0, NB - 1); bb[b].expand(boxes[id]); bc[b]++; }
+            float rightArea[NB]; uint32_t rightCount[NB];
+            AABB acc; uint32_t cnt = 0;
+            for (int b = NB - 1; b > 0; --b) { acc.expand(bb[b]); cnt += bc[b]; rightArea[b] = cnt ? area(acc) : 0; rightCount[b] = cnt; }
+            acc = AABB(); cnt = 0;
+            for (int b = 0; b < NB - 1; ++b) {
+                acc.expand(bb[b]); cnt += bc[b];
+                if (cnt == 0 || rightCount[b + 1] == 0) continue;
+                const float cost = area(acc) * cnt + rightArea[b + 1] * rightCount[b + 1];
+                if (cost < best) { best = cost; bestAxis = axis; bestSplit = b; }
+            }
+        }
+        if (bestAxis >= 0) {
+            const float k = NB * (1 - 1e-6f) / ext[bestAxis];
+            auto it = std::partition(order.begin() + lo, order.begin() + hi, [&](uint32_t id) { return clampi((int) ((boxes[id].center()[bestAxis] - cbox.mn[bestAxis]) * k), 0, NB - 1) <= bestSplit; });
+            mid = (uint32_t) (it - order.begin());
+        }
+        if (mid == lo || mid == hi) {
+            const int axis = ext.x > ext.y ? (ext.x > ext.z ? 0 : 2) : (ext.y > ext.z ? 1 : 2);
+            mid = (lo + hi) / 2;
+            std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi, [&](uint32_t a, uint32_t b) { return boxes[a].center()[axis] < boxes[b].center()[axis]; });
+        }
+        const size_t left = ni + 1, right = ni + 1 + (2 * (size_t) (mid - lo) - 1);
+        nd.a = (uint32_t) right; nd.b = 0;
+        if (depth < 4 && n > 200000) {          // the top of the tree forks: up to 16 subtrees are built concurrently
+            std::thread t([&]() { fastBuildRec(left, order, boxes, lo, mid, depth + 1); });
+            fastBuildRec(right, order, boxes, mid, hi, depth + 1);
+            t.join();
+        } else {
+            fastBuildRec(left, order, boxes, lo, mid, depth + 1);
+            fastBuildRec(right, order, boxes, mid, hi, depth + 1);
+        }
+    }
+
+    static inline bool slab(const FastNode &nd, const Ray &ray, float mint, float maxt, float &tnear) {
+        float t0 = mint, t1 = maxt;
+        for (int c = 0; c < 3; ++c) {
+            if (ray.d[c] == 0) { if (ray.o[c] < nd.lo[c] || ray.o[c] > nd.hi[c]) return false; continue; }
+            float a = (nd.lo[c] - ray.o[c]) * ray.dRcp[c], b = (nd.hi[c] - ray.o[c]) * ray.dRcp[c];
+            if (a > b) std::swap(a, b);
+            t0 = std::max(t0, a); t1 = std::min(t1, b);
+        }
+        tnear = t0;
+        return t0 <= t1 * 1.0000004f;
+    }
+
+    bool intersectBVH(const Ray &ray, bool shadow, Hit &hit) const {
+        float mint, maxt;
+        hit = Hit();
+        if (wide.empty() || !sceneInterval(ray, shadow, mint, maxt)) return false;
+        float pmin[16], pmax[16]; bool pok[16];
+        if (shapes.size() > 16) throw std::runtime_error("oracle: >16 shapes unsupported in BVH path");
+        for (size_t si = 0; si < shapes.size(); ++si) pok[si] = shapes[si].isMesh ? true : shapeInterval(shapes[si], ray, mint, maxt, pmin[si], pmax[si]);
+        uint64_t mailbox[8]; for (int i = 0; i < 8; ++i) mailbox[i] = ~0ull;
+        const V3 o = ray.o, d = ray.d;
+        const float dd = dot(d, d);
+        // slab arithmetic without branches: a zero direction component keeps the exact containment test of aabb.h:315-318 by
+        // turning the two plane distances into -inf / +inf (inside) or +inf / -inf (outside)
+        float ro[3], rinv[3]; bool flat[3];
+        for (int c = 0; c < 3; ++c) { ro[c] = o[c]; flat[c] = d[c] == 0; rinv[c] = flat[c] ? 0.0f : ray.dRcp[c]; }
+        bool found = false;
+        struct Entry { uint32_t node; float tnear; };
+        Entry stack[256]; int sp = 0;
+        stack[sp++] = {0u, mint};
+        while (sp) {
+            const Entry e = stack[--sp];
+            if (!shadow && e.tnear > maxt) continue;
+            if (e.node & 0x80000000u) {
+#ifdef ORC_COUNT
+                g_cnt[1]++;
+#endif
+                const FastRef &r = frefs[e.node & 0x7fffffffu];
+                const uint32_t rshape = r.shapeFlags >> 3;
+                if (r.shapeFlags & 1u) {
+                    float t, u, v;
+                    if (shapes[rshape].mesh.accel[r.iv].rayIntersect(ray.o, ray.d, mint, maxt, u, v, t)) {
+                        if (shadow) { hit.t = t; hit.shape = (int) rshape; hit.iv = r.iv; return true; }
+                        maxt = t; hit.t = t; hit.shape = (int) rshape; hit.iv = r.iv; hit.u = u; hit.v = v; found = true;
+                    }
+                    continue;
+                }
+                if (!pok[rshape]) continue;
+                const HairShape &sh = shapes[rshape];
+                const float radius = sh.radius;
+                // conservative fp32 rejection (never rejects a hit the FP64 test would accept; same bound as csrc/cp_traverse.cuh)
+                const V3 p1 = sh.verts[r.iv], a = sh.verts[r.iv + 1] - p1, w = p1 - o, nrm = cross(d, a);
+                const float nn = dot(nrm, nrm), aa = dot(a, a), wn = dot(w, nrm);
+                const float sin2 = nn / (aa * dd);
+                if (sin2 > 4e-4f) {
+                    const float wmax = std::max(std::max(std::abs(w.x), std::abs(w.y)), std::abs(w.z));
+                    const float rsin = 1.0f / std::sqrt(sin2);
+                    const float R = radius * 1.02f + wmax * (2e-6f + 2e-6f * rsin);
+                    if (wn * wn > R * R * nn) continue;
+                    const float inn = 1.0f / nn;
+                    const float tcl = dot(cross(w, a), nrm) * inn;
+                    const float slack = 1.01f * R * rsin / std::sqrt(dd) + 1e-5f * std::abs(tcl);
+                    if (tcl + slack < mint || tcl - slack > maxt) continue;
+                    if ((r.shapeFlags & 6u) == 6u) {
+                        const float scl = dot(cross(w, d), nrm) * inn;
+                        const float sslack = 1.01f * (R * rsin + 2.0f * radius) / std::sqrt(aa) + 1e-5f * (1.0f + std::abs(scl));
+                        if (scl + sslack < 0.0f || scl - sslack > 1.0f) continue;
+                    }
+                }
+                const uint64_t key = ((uint64_t) rshape << 32) | r.iv;
+                uint64_t &slot = mailbox[(r.iv * 2654435761u) >> 29];
+                if (slot == key) continue;
+                slot = key;
+#ifdef ORC_COUNT
+                g_cnt[2]++;
+#endif
+                const float hi = std::min(pmax[rshape], maxt);
+                if (!(hi > pmin[rshape])) continue;
+                float t; V3 p;
+                if (sh.intersect(ray, r.iv, pmin[rshape], hi, t, p)) {
+                    if (shadow) { hit.t = t; hit.shape = (int) rshape; hit.iv = r.iv; return true; }
+                    maxt = t; hit.t = t; hit.shape = (int) rshape; hit.iv = r.iv; hit.p = p; found = true;
+                }
+                continue;
+            }
+#ifdef ORC_COUNT
+            g_cnt[0]++;
+#endif
+            const Wide &nd = wide[e.node];
+            float tn[8], tf[8];
+            for (int k = 0; k < 8; ++k) { tn[k] = mint; tf[k] = maxt; }
+            for (int c = 0; c < 3; ++c) {
+                if (flat[c]) {
+                    for (int k = 0; k < 8; ++k) if (ro[c] < nd.lo[c][k] || ro[c] > nd.hi[c][k]) tf[k] = -kInf;
+                } else {
+                    for (int k = 0; k < 8; ++k) {
+                        const float a = (nd.lo[c][k] - ro[c]) * rinv[c], b = (nd.hi[c][k] - ro[c]) * rinv[c];
+                        tn[k] = std::max(tn[k], std::min(a, b)); tf[k] = std::min(tf[k], std::max(a, b));
+                    }
+                }
+            }
+            // children that are entered, nearest last (so that it is popped first)
+            int first = sp;
+            for (int k = 0; k < 8; ++k) {
+                if (nd.child[k] == 0xffffffffu || !(tn[k] <= tf[k] * 1.0000004f)) continue;
+                int pos = sp++;
+                while (pos > first && stack[pos - 1].tnear < tn[k]) { stack[pos] = stack[pos - 1]; --pos; }
+                stack[pos] = {nd.child[k], tn[k]};
+                if (nd.child[k] & 0x80000000u) __builtin_prefetch(&frefs[nd.child[k] & 0x7fffffffu]);
+                else { const char *pf = (const char *) &wide[nd.child[k]]; __builtin_prefetch(pf); __builtin_prefetch(pf + 64); __builtin_prefetch(pf + 128); __builtin_prefetch(pf + 192); }
+            }
+        }
+        return found;
+    }
+#else
+    static const char *accelDescription() { return "plain binned-SAH BVH over whole segments (checker build)"; }
     void buildBVH() {
         prims.clear(); nodes.clear();
         std::vector<AABB> boxes;
@@ -547,6 +844,8 @@ struct Geometry {
         }
         return found;
     }
+
+#endif // ORC_FAST
 
     // hair.cpp:825-862 followed by skdtree.h:426-427
     void fillIntersection(const Ray &ray, const Hit &hit, Intersection &its) const {

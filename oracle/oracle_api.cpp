@@ -29,6 +29,11 @@ static thread_local std::string g_err;
 
 extern "C" {
 
+// what accelerates the ray queries of this build (reported with the CPU baseline)
+const char *orc_accel_description() { return orc::Geometry::accelDescription(); }
+#ifdef ORC_COUNT
+void orc_counts(unsigned long long *out) { for (int i = 0; i < 4; ++i) { out[i] = orc::g_cnt[i]; orc::g_cnt[i] = 0; } }
+#endif
 const char *orc_last_error() { return g_err.c_str(); }
 
 void *orc_scene_create() { return new Scene(); }

@@ -26,12 +26,18 @@ def lib():
         L = ctypes.CDLL(ORACLE_LIB)
         L.orc_scene_create.restype = ctypes.c_void_p
         L.orc_last_error.restype = ctypes.c_char_p
+        L.orc_accel_description.restype = ctypes.c_char_p
         L.orc_hair_file_load.restype = ctypes.c_void_p
         L.orc_hair_file_vertex_count.restype = ctypes.c_uint32
         L.orc_hair_file_segment_count.restype = ctypes.c_uint32
         L.orc_hair_file_radius.restype = ctypes.c_float
         _lib = L
     return _lib
+
+
+def accel_description():
+    """What accelerates the ray queries of the loaded oracle build (the timing build differs from the checker)."""
+    return lib().orc_accel_description().decode()
 
 
 def have_ref():

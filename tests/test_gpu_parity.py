@@ -851,7 +851,8 @@ def test_full_scene_first_sample_replay(cp, oracle, name, ov):
 def test_cancel_and_progress(cp):
     """Integrator::cancel() (include/mitsuba/render/integrator.h:76-84: asynchronous, render() then returns false) and the render job's
     progress reports (src/librender/integrator.cpp:95-138) at the C ABI: cudapath_cancel from another thread ends a blocking
-    cudapath_render with "render cancelled" within one bounce, the request is consumed, and the next render is complete."""
+    cudapath_render with "render cancelled" within one bounce, the request is consumed, and the next render is complete; a request that
+    finds no render running is dropped, as the reference's cancel() only acts on the running job."""
     import threading
     ov = dict(width=64, height=64, spp=32, maxDepth=8)
     ctx = cp.scene_from_description('straight-hair', scale=0.01, overrides=ov); ctx.build()
@@ -875,9 +876,7 @@ def test_cancel_and_progress(cp):
     ctx.set_progress_callback(None)
     again = ctx.render(32, seed=5)                                # the request was consumed
     assert np.allclose(again, ref, rtol=1e-5, atol=1e-6)
-    ctx.cancel()                                                  # a request that arrives before the render starts
-    with pytest.raises(cp.CudapathError, match='render cancelled'):
-        ctx.render(32, seed=5)
+    ctx.cancel()                                                  # no render is running: the request is dropped, not kept for the next job
     assert np.allclose(ctx.render(32, seed=5), ref, rtol=1e-5, atol=1e-6)
     ctx.close()
 
@@ -956,3 +955,63 @@ def test_envmap_emitter_from_hdr_file(cp, oracle, tmp_path):
     assert b.sum() > 0 and rel_mse(a, b) < 1e-3
     close = np.abs(a - b).max(axis=2) <= 1e-3 * (np.abs(b).max(axis=2) + 1e-3)
     assert close.mean() > 0.97
+
+
+@pytest.mark.parametrize('name', ['hair-curl', 'curly-hair'])
+def test_converged_marschner_images(cp, name):
+    """BASELINE.json north_star, third check at its stated size: CONVERGED images (4096 spp) of the Marschner scenes within
+    relMSE < 1e-3 of the CPU side, plus a per-pixel z-test on the variance estimate.  The CPU side is the oracle's 4096-spp render
+    committed as tests/golden/converged_golden.npz (generator: tests/golden/make_converged.py, seed 977); the GPU renders the same
+    scene with an INDEPENDENT random stream (seed 11), so nothing a replay shares -- the use of the counter stream itself, the
+    estimator's expectation -- can hide.  MIPathTracer::Li semantics: src/integrators/path/path.cpp:119-294."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'converged_golden.npz'))
+    key = name.replace('-', '_')
+    scale, W, H, spp, depth, K, _ = g[key + '_cfg']
+    W, H, spp, depth, K = int(W), int(H), int(spp), int(depth), int(K)
+    assert spp == 4096
+    mo, vo = g[key + '_mean'].astype(np.float64), g[key + '_var'].astype(np.float64)
+    ctx = cp.scene_from_description(name, scale=float(scale), overrides=dict(width=W, height=H, spp=spp, maxDepth=depth)); ctx.build()
+    per = spp // K
+    imgs = [cp.develop(ctx.render(spp, seed=11, sample_begin=per * k, sample_end=per * (k + 1))).astype(np.float64) for k in range(K)]
+    st = ctx.stats()
+    assert st['unsupported_filtered_lookups'] == 0
+    ctx.close()
+    b = np.stack(imgs)
+    mg, vg = b.mean(axis=0), b.var(axis=0, ddof=1) / K
+    rel = float(np.mean((mg - mo) ** 2 / (mo ** 2 + 1e-2)))
+    noise = float(np.mean((vg + vo) / (mo ** 2 + 1e-2)))               # what two independent 4096-spp estimates differ by on their own
+    # the three channels of a pixel are almost perfectly correlated (one path, one throughput): use the per-channel statistic of ONE channel for the test
+    zc = (mg[..., 1] - mo[..., 1]) / np.sqrt(vg[..., 1] + vo[..., 1] + 1e-14)
+    print('%s at 4096 spp: relMSE %.3g (noise floor %.3g), z mean %.3f std %.3f, |z| > 3.5 on %.4f of the pixels, max %.1f'
+          % (name, rel, noise, zc.mean(), zc.std(), (np.abs(zc) > 3.5).mean(), np.abs(zc).max()))
+    assert np.isfinite(mg).all()
+    assert rel < 1e-3, 'relMSE of the converged images: %g' % rel
+    assert abs(zc.mean()) < 0.12, 'systematic offset: mean z = %.3f' % zc.mean()
+    assert (np.abs(zc) > 3.5).mean() < 0.01 and np.abs(zc).max() < 8, 'z-test: %.4f of the pixels beyond 3.5 sigma, max %.1f' % ((np.abs(zc) > 3.5).mean(), np.abs(zc).max())
+    assert 0.7 < zc.std() < 1.5
+
+
+def test_multi_gpu_film_equals_single_gpu(cp):
+    """N GPUs behind ONE context (cudapath_create_multi: the scene replicated, the sample range split, one ncclReduce of the films onto the
+    first device -- what replaces the tile scheduler of src/librender/renderproc.cpp:117-182) produce the film of one GPU rendering all
+    N x spp sample indices, up to fp32 summation order; the ray counters add up to the same totals."""
+    n = cp.visible_devices()
+    if n < 2:
+        pytest.skip('needs at least two GPUs (gpurun --gpus 2)')
+    ov = dict(width=160, height=120, spp=8 * n, maxDepth=20)
+    one = cp.scene_from_description('hair-curl', device=0, scale=0.02, overrides=ov); one.build()
+    ref = one.render(8 * n, seed=5); st1 = one.stats(); one.close()
+    multi = cp.scene_from_description('hair-curl', device=list(range(n)), scale=0.02, overrides=ov)
+    assert multi.device_count() == n
+    multi.build()
+    film = multi.render(8 * n, seed=5); stn = multi.stats()
+    assert multi.last_reduce_ms() > 0
+    assert np.isfinite(film).all()
+    assert np.abs(film - ref).max() <= 1e-5 * np.abs(ref).max(), 'N-GPU film differs from the 1-GPU film: %g' % (np.abs(film - ref).max() / np.abs(ref).max())
+    assert (stn['paths'], stn['rays'], stn['shadow_rays']) == (st1['paths'], st1['rays'], st1['shadow_rays'])
+    # uneven split (spp not a multiple of N) and a sub-range
+    part = multi.render(8 * n, seed=5, sample_begin=1, sample_end=4 * n - 1)
+    one = cp.scene_from_description('hair-curl', device=0, scale=0.02, overrides=ov); one.build()
+    refp = one.render(8 * n, seed=5, sample_begin=1, sample_end=4 * n - 1); one.close()
+    assert np.abs(part - refp).max() <= 1e-5 * np.abs(refp).max()
+    multi.close()

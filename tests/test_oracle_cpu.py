@@ -1551,3 +1551,49 @@ def test_oracle_matches_third_golden_set(cp, oracle):
         env = cp.bake_sunsky(**cp.scenes.sunsky_params(name))
         film = oracle.scene_from_description(name, scale=0.004, overrides=ov, envmap=env).render(4, seed=13, threads=2)
         assert np.allclose(film, films[name.replace('-', '_')], rtol=1e-5, atol=1e-6)
+
+
+def test_fast_accelerator_matches_checker(cp, oracle):
+    """The CPU-baseline build of the oracle (liboracle_fast.so: reference optimisation flags, libm, and the ray-query accelerator of
+    oracle/o_hair.h under ORC_FAST -- 8-wide BVH over pre-split segment references, fp32 pre-test, mailbox) answers ray queries like
+    the checker build: same hit / miss, shape and primitive, and the same fp32 distance for fibers (the exact FP64 test is the shared,
+    unchanged function); triangles agree to an ulp (their fp32 arithmetic is compiled with -funsafe-math-optimizations there).
+    The baseline that bench.py times is therefore the same algorithm as the checker, only faster."""
+    import importlib.util
+    fast_path = os.path.join(os.path.dirname(oracle.ORACLE_LIB), 'liboracle_fast.so')
+    if not os.path.exists(fast_path):
+        pytest.skip('liboracle_fast.so not built')
+    spec = importlib.util.spec_from_file_location('orc_fast', oracle.__file__)
+    fast = importlib.util.module_from_spec(spec); spec.loader.exec_module(fast)
+    fast.ORACLE_LIB = fast_path
+    assert 'pre-split' in fast.accel_description() and 'checker' in oracle.accel_description()
+    env = np.ones((16, 32, 3), np.float32)
+    rng = np.random.default_rng(5)
+    for name, scale in (('hair-curl', 0.02), ('furball', 0.02), ('straight-hair', 0.02), ('hair-on-head', 0.004)):
+        a = oracle.scene_from_description(name, scale=scale, envmap=env)
+        b = fast.scene_from_description(name, scale=scale, envmap=env)
+        aabb, bs = a.scene_bounds()
+        n = 60000
+        c = 0.5 * (aabb[:3] + aabb[3:]); r = 0.5 * np.linalg.norm(aabb[3:] - aabb[:3])
+        p1 = c + r * sphere_dirs(rng, n); p2 = c + r * sphere_dirs(rng, n)
+        d = p2 - p1; d /= np.linalg.norm(d, axis=1, keepdims=True)
+        o = p1.astype(np.float32); d = d.astype(np.float32)
+        sa, pa, ta = a.intersect(o, d, 0.0, np.inf)
+        sb, pb, tb = b.intersect(o, d, 0.0, np.inf)
+        hit = sa >= 0
+        assert hit.sum() > 500 and np.array_equal(sa, sb)
+        # secondary-like rays from the hit points (mint = Epsilon: adaptive epsilon, rays starting on / inside fibers), closest and any-hit
+        hp = (o[hit] + d[hit] * ta[hit][:, None]).astype(np.float32); d2 = sphere_dirs(rng, int(hit.sum()))
+        s2a, p2a, t2a = a.intersect(hp, d2, 1e-4, np.inf); s2b, p2b, t2b = b.intersect(hp, d2, 1e-4, np.inf)
+        oa, _, _ = a.intersect(hp, d2, 1e-4, 5.0, mode=1); ob, _, _ = b.intersect(hp, d2, 1e-4, 5.0, mode=1)
+        assert np.array_equal(oa >= 0, ob >= 0)
+        for (s1, q1, t1, s2, q2, t2) in ((sa, pa, ta, sb, pb, tb), (s2a, p2a, t2a, s2b, p2b, t2b)):
+            same = (s1 == s2) & (q1 == q2)
+            ties = ~same & (np.abs(t1 - t2) <= 1e-6 * np.maximum(np.abs(t1), 1.0))          # equal-t hits resolve by visiting order
+            assert (same | ties).all(), '%s: %d rays answer differently' % (name, int((~(same | ties)).sum()))
+            assert ties.sum() <= 1e-3 * len(s1)
+            h = (s1 >= 0) & same
+            if name == 'hair-on-head':
+                assert np.allclose(t1[h], t2[h], rtol=5e-5, atol=2e-4)       # Wald test: cancellation in (n_d - o.n) at |o| ~ 20
+            else:
+                assert np.array_equal(t1[h], t2[h])

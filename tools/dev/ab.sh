@@ -1,7 +1,8 @@
 #!/bin/bash
 # usage: ab.sh <rounds> <variants...> -- <bench args>   interleaved A/B: every variant is benchmarked <rounds> times, round-robin
 # a variant is "base", a library suffix ("_pf" -> libcudapath_pf.so) or "env:NAME=VALUE" (base library with an environment variable)
-P=/root/repo/cs184-final-project-mitsuba0.5_b200
+P=${GRAFT_REPO_ROOT:-/root/repo}/cs184-final-project-mitsuba0.5_b200
+export CUDAPATH_SCENE_CACHE=/tmp/cudapath_scene_cache
 rounds=$1; shift
 sufs=(); while [ "$1" != "--" ] && [ $# -gt 0 ]; do sufs+=("$1"); shift; done; shift
 python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e "$@" > /dev/null 2>&1   # warm the box up

@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage: sweep_lib.sh <suffixes...> -- <bench args>   (runs bench.py once per alternative library build)
-P=/root/repo/cs184-final-project-mitsuba0.5_b200
+P=${GRAFT_REPO_ROOT:-/root/repo}/cs184-final-project-mitsuba0.5_b200
 sufs=(); while [ "$1" != "--" ] && [ $# -gt 0 ]; do sufs+=("$1"); shift; done; shift
 for s in "${sufs[@]}"; do
   lib=$P/libcudapath$s.so
