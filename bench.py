@@ -193,7 +193,7 @@ def workload_config(args, sc):
     return {'workload': '%s: %s BSDF, path integrator maxDepth=%d rrDepth=5 strictNormals, %dx%d at %d spp %s, sunsky envmap 512x256, tent filter'
                         % (args.scene, sc['shapes'][0]['bsdf']['type'], sc['maxDepth'], sc['width'], sc['height'], sc['spp'], per),
             'geometry': 'procedural fibers (reference .mitshair blobs missing), generator scale %.3g' % args.scale,
-            'parallelism': 'sample-range sharding (%s scaling), one NCCL film reduce' % args.scaling,
+            'parallelism': '%s sharding (%s scaling), one NCCL film reduce' % ('sample-range' if args.scaling == 'weak' or args.shard == 'samples' else '64x64 pixel-block', args.scaling),
             'l2_policy': 'inputs larger than L2 (BVH + vertices + path queues >> 126 MB)'}
 
 
@@ -366,6 +366,8 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0, help='strand-count scale of the procedural generators')
     ap.add_argument('--spp', type=int, default=0, help='override samples per pixel (default: the config value)')
     ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'], help='N > 1: split the fixed job (strong) or render spp per GPU (weak)')
+    ap.add_argument('--shard', default='pixels', choices=['pixels', 'samples'], help='strong scaling: split the image by 64x64 pixel blocks or by sample ranges')
+    ap.add_argument('--shard-test', default='', help='development: i/G renders only pixel shard i of G on this GPU')
     ap.add_argument('--config', type=int, default=2, help='5: the per-stage micro-benchmark of BASELINE.json configs[4]')
     ap.add_argument('--log2n', type=int, default=26, help='--config 5: log2 of the batch size')
     ap.add_argument('--cpu-spp', type=int, default=1, help='sample indices per pixel in the bounded CPU sample')
@@ -394,11 +396,17 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     sc, shapes, env = scene_arrays(args.scene, args.scale)
     W, H, spp = sc['width'], sc['height'], sc['spp']
+    shard = (0, 1)
     if args.scaling == 'weak':
         total_spp = spp * world; s_begin, s_end = rank * spp, (rank + 1) * spp          # every rank renders `spp` sample indices of a world*spp image
-    else:
+    elif args.shard == 'samples':
         total_spp = spp; s_begin, s_end = sample_range(spp, rank, world)               # the fixed image, sample indices split over the ranks
+    else:
+        total_spp = spp; s_begin, s_end = 0, spp; shard = (rank, world)                # the fixed image, 64x64 pixel blocks dealt out to the ranks
+    if args.shard_test:                                                                # development: one GPU renders shard i of G of the image
+        i, g = (int(v) for v in args.shard_test.split('/')); shard = (i, g)
     ctx = make_context(cudapath, sc, shapes, env, local)
+    ctx.set_pixel_shard(*shard)
     if args.max_split:
         ctx.set_build_options(args.max_split)
     if args.wave:
@@ -451,6 +459,8 @@ def main():
         ms = float(tmax[0]); rays = float(tsum[1]); shadow = float(tsum[2]); launches = int(tsum[3])
     ms_per_step = ms / args.steps
     paths_per_step = W * H * total_spp
+    if args.shard_test:
+        paths_per_step = cnt['paths']
     value = paths_per_step / (ms_per_step * 1e-3) / 1e6
     mrays = (rays + shadow) / args.steps / (ms_per_step * 1e-3) / 1e6
 
@@ -473,6 +483,7 @@ def main():
                 dist.barrier()
             t0 = time.perf_counter()
             c2 = make_context(cudapath, sc, pshapes, penv, local)
+            c2.set_pixel_shard(*shard)
             if args.wave:
                 c2.set_options(wave_size=args.wave)
             t1 = time.perf_counter()

@@ -117,6 +117,20 @@ def bake_sunsky(turbidity=3.0, albedo=(0.2, 0.2, 0.2), sunDirection=(0, 1, 0), s
     return out
 
 
+def env_pyramid(rgb):
+    """Host-only: the Lanczos MIP pyramid of a lat-long fp32 bitmap (cudapath_env_pyramid_level), fp32 levels before half quantisation."""
+    rgb = _f32(rgb); h, w = rgb.shape[:2]
+    out = []
+    lw = ctypes.c_int(); lh = ctypes.c_int()
+    n = _check(lib().cudapath_env_pyramid_level(_p(rgb), w, h, 0, ctypes.byref(lw), ctypes.byref(lh), None))
+    for l in range(n):
+        _check(lib().cudapath_env_pyramid_level(_p(rgb), w, h, l, ctypes.byref(lw), ctypes.byref(lh), None))
+        a = np.zeros((lh.value, lw.value, 3), np.float32)
+        _check(lib().cudapath_env_pyramid_level(_p(rgb), w, h, l, ctypes.byref(lw), ctypes.byref(lh), _p(a)))
+        out.append(a)
+    return out
+
+
 def sun_radiance(turbidity=3.0, sunDirection=(0, 1, 0), data_dir=None):
     """computeSunRadiance (src/emitters/sunsky/sunmodel.h:260-371) in linear RGB -> (3,) fp32."""
     out = np.zeros(3, np.float32)
@@ -278,6 +292,19 @@ class Context:
     def set_options(self, wave_size=0, collect_stats=False, profile_stages=False):
         _check(self._L.cudapath_set_options(self._h, ctypes.c_uint32(wave_size), 1 if collect_stats else 0, 1 if profile_stages else 0))
 
+    def set_pixel_shard(self, index=0, count=1):
+        """Render only the 64x64-pixel blocks owned by shard `index` of `count` (the films of all shards add up to the image)."""
+        _check(self._L.cudapath_set_pixel_shard(self._h, ctypes.c_uint32(index), ctypes.c_uint32(count)))
+
+    def set_math_mode(self, mode):
+        """'strict' (every elementary function correctly rounded: bit-identical to the oracle) or 'fast' (default; see cudapath.h)."""
+        if mode not in ('strict', 'fast'):
+            raise CudapathError("math mode must be 'strict' or 'fast'")
+        _check(self._L.cudapath_set_math_mode(self._h, 1 if mode == 'strict' else 0))
+
+    def math_mode(self):
+        return 'strict' if self._L.cudapath_get_math_mode(self._h) == 1 else 'fast'
+
     def set_build_options(self, max_split=8):
         _check(self._L.cudapath_set_build_options(self._h, int(max_split)))
 
@@ -359,6 +386,13 @@ class Context:
         _check((self._L.cudapath_bsdf_eval_batch_discrete if discrete else self._L.cudapath_bsdf_eval_batch)(self._h, int(bsdf_id), ctypes.c_uint64(n), _p(wi), _p(wo), _p(ev), _p(pdf)))
         return ev, pdf
 
+    def bsdf_eval_world(self, bsdf_id, frames, wi_world, wo_world):
+        """BSDF::eval + pdf from world-space directions and per-tuple shading frames (n, 3, 3) = rows s, t, n (Frame::toLocal on the device)."""
+        fr = _f32(frames).reshape(-1, 9); wi = _f32(wi_world).reshape(-1, 3); wo = _f32(wo_world).reshape(-1, 3); n = len(wi)
+        ev = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32)
+        _check(self._L.cudapath_bsdf_eval_batch_world(self._h, int(bsdf_id), ctypes.c_uint64(n), _p(fr), _p(wi), _p(wo), _p(ev), _p(pdf)))
+        return ev, pdf
+
     def bsdf_sample(self, bsdf_id, wi, sample, extra=None):
         wi = _f32(wi).reshape(-1, 3); sample = _f32(sample).reshape(-1, 2); n = len(wi)
         ex = None if extra is None else _f32(extra).reshape(-1, 4)
@@ -380,6 +414,25 @@ class Context:
         rgb = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32)
         _check(self._L.cudapath_env_eval_batch(self._h, ctypes.c_uint64(n), _p(d), _p(rgb), _p(pdf)))
         return rgb, pdf
+
+    def env_eval_filtered(self, d, rx, ry):
+        """evalEnvironment of a ray with differentials: EWA lookup in the Lanczos MIP pyramid (envmap.cpp:391-407, mipmap.h:629-836)."""
+        d = _f32(d).reshape(-1, 3); rx = _f32(rx).reshape(-1, 3); ry = _f32(ry).reshape(-1, 3); n = len(d)
+        rgb = np.zeros((n, 3), np.float32)
+        _check(self._L.cudapath_env_eval_filtered_batch(self._h, ctypes.c_uint64(n), _p(d), _p(rx), _p(ry), _p(rgb)))
+        return rgb
+
+    def env_mip_levels(self):
+        """The MIP pyramid of the environment map as stored on the device: list of (h, w, 3) arrays, level 0 first."""
+        out = []
+        w = ctypes.c_int(); h = ctypes.c_int()
+        n = _check(self._L.cudapath_env_mip_level(self._h, 0, ctypes.byref(w), ctypes.byref(h), None))
+        for l in range(n):
+            _check(self._L.cudapath_env_mip_level(self._h, l, ctypes.byref(w), ctypes.byref(h), None))
+            a = np.zeros((h.value, w.value, 3), np.float32)
+            _check(self._L.cudapath_env_mip_level(self._h, l, ctypes.byref(w), ctypes.byref(h), _p(a)))
+            out.append(a)
+        return out
 
     def env_sample(self, ref, sample):
         ref = _f32(ref).reshape(-1, 3); sample = _f32(sample).reshape(-1, 2); n = len(ref)

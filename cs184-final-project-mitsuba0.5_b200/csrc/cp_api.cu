@@ -79,7 +79,11 @@ struct cudapath_ctx {
     Wavefront wf;
     uint32_t waveSize = 0; int collectStats = 0, profileStages = 0;     // 0 = sized from the free device memory at render time
     int maxSplit = 8;
+    uint32_t shardIndex = 0, shardCount = 1;     // cudapath_set_pixel_shard
+    float leafSplitCost = getenv("CUDAPATH_LEAF_SPLIT_COST") ? (float) atof(getenv("CUDAPATH_LEAF_SPLIT_COST")) : 1.0f;    // see k_collapse (cp_bvh.cu); < 0: leaves of up to CP_LEAF_MAX references, never opened
     int sortRays = getenv("CUDAPATH_NO_SORT") ? 0 : 1;
+    // math mode of the shading stages (cudapath_set_math_mode): 1 = fast (default), 0 = strict; CUDAPATH_MATH=strict|fast sets the default
+    int fastMath = (getenv("CUDAPATH_MATH") && std::string(getenv("CUDAPATH_MATH")) == "strict") ? 0 : 1;
     cudapath_stats stats{};
     float sceneAABB[6] = {0, 0, 0, 0, 0, 0};
 
@@ -92,7 +96,7 @@ struct cudapath_ctx {
         dfree(d_vtx); dfree(d_shapes); dfree(d_bsdfs); dfree(bvh.nodes); dfree(bvh.prims); dfree(bvh.leafSeg);
         dfree(d_meshPos); dfree(d_meshNrm); dfree(d_triAccel); dfree(d_meshIdx);
         d_meshPos = d_meshNrm = d_triAccel = nullptr; d_meshIdx = nullptr;
-        dfree(envTables.texels); dfree(envTables.cdfCols); dfree(envTables.cdfRows); dfree(envTables.rowWeights);
+        dfree(envTables.texels); dfree(envTables.cdfCols); dfree(envTables.cdfRows); dfree(envTables.rowWeights); dfree(envTables.mipTexels); dfree(envTables.mipInfo);
         d_vtx = nullptr; d_shapes = nullptr; d_bsdfs = nullptr; bvh = BVHDev(); envTables = EnvTables(); built = false;
     }
     ~cudapath_ctx() {
@@ -124,6 +128,12 @@ template <class F> static int fan_out(cudapath_ctx *ctx, int rc, F &&call) {
     return rc;
 }
 #define CP_GUARD(ctx) DevGuard guard_((ctx)->device); if (guard_.err != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(guard_.err))
+
+// sin / cos of the three lobe shifts of the scale angle (fp32 shifts as the device forms them, fp64 functions): ma_lobe_angles
+static void set_lobe_constants(BsdfDev &d) {
+    const double off[3] = {-(double) (2.0f * d.scaleAngle), (double) d.scaleAngle, (double) (4.0f * d.scaleAngle)};
+    for (int k = 0; k < 3; ++k) { d.lobeSin[k] = std::sin(off[k]); d.lobeCos[k] = std::cos(off[k]); }
+}
 
 extern "C" {
 
@@ -165,7 +175,7 @@ int cudapath_set_data_dir(cudapath_ctx *ctx, const char *path) { if (!ctx || !pa
 
 int cudapath_add_bsdf_kajiyakay(cudapath_ctx *ctx, const float d[3], const float s[3], float exponent) {
     if (!ctx || !d || !s) return fail("null argument");
-    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    BsdfHost b; std::memset((void *) &b.dev, 0, sizeof(b.dev));
     V3 diff(d[0], d[1], d[2]), spec(s[0], s[1], s[2]);
     // BSDF::ensureEnergyConservation (src/librender/bsdf.cpp:115-146)
     const float actualMax = maxc(spec + diff);
@@ -182,7 +192,7 @@ int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior,
     if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
     if (ctx->dataDir.empty()) return fail("marschner needs data/microfacet/*.dat: call cudapath_set_data_dir() first");
     CP_GUARD(ctx);
-    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    BsdfHost b; std::memset((void *) &b.dev, 0, sizeof(b.dev));
     b.dev.kind = 1;
     b.dev.eta = int_ior / ext_ior;
     b.dev.invEta2 = 1.0f / (b.dev.eta * b.dev.eta);
@@ -191,6 +201,7 @@ int cudapath_add_bsdf_marschner(cudapath_ctx *ctx, float int_ior, float ext_ior,
     const float betaR = 0.1f, betaTT = betaR * 0.5f, betaTRT = betaR * 2.0f;   // marschner_diffuse.cpp:152-155 (hard-coded)
     b.dev.vR = betaR * betaR; b.dev.vTT = betaTT * betaTT; b.dev.vTRT = betaTRT * betaTRT;
     b.dev.scaleAngle = -0.1f;
+    set_lobe_constants(b.dev);
     V3 spec(s[0], s[1], s[2]);
     { const float mx = maxc(spec); if (mx > 1.0f) spec = spec * (0.99f * (1.0f / mx)); }   // bsdf.cpp:88-113
     b.dev.diffuse = V3(d[0], d[1], d[2]); b.dev.specular = spec;
@@ -217,7 +228,7 @@ int cudapath_add_bsdf_roughplastic(cudapath_ctx *ctx, float int_ior, float ext_i
     if (distribution < 0 || distribution > 2) return fail("Specified an invalid distribution, must be \"beckmann\", \"ggx\", or \"phong\"/\"as\"!");
     if (ctx->dataDir.empty()) return fail("roughplastic needs data/microfacet/*.dat: call cudapath_set_data_dir() first");
     CP_GUARD(ctx);
-    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    BsdfHost b; std::memset((void *) &b.dev, 0, sizeof(b.dev));
     b.dev.kind = 4;
     b.dev.eta = int_ior / ext_ior;
     b.dev.invEta2 = 1.0f / (b.dev.eta * b.dev.eta);
@@ -246,12 +257,13 @@ int cudapath_add_bsdf_marschner_fixed(cudapath_ctx *ctx, float int_ior, float ex
     if (!ctx) return fail("null context");
     if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
     CP_GUARD(ctx);
-    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    BsdfHost b; std::memset((void *) &b.dev, 0, sizeof(b.dev));
     b.dev.kind = 3;
     b.dev.eta = int_ior / ext_ior;
     const float betaR = 0.1f, betaTT = betaR * 0.5f, betaTRT = betaR * 2.0f;     // marschner.cpp:130-137 (hard-coded)
     b.dev.vR = betaR * betaR; b.dev.vTT = betaTT * betaTT; b.dev.vTRT = betaTRT * betaTRT;
     b.dev.scaleAngle = -0.1f;
+    set_lobe_constants(b.dev);
     b.dev.diffuse = V3(0.0f); b.dev.specular = V3(1.0f);
     float pts[140], wts[140];
     gauss_legendre_140(pts, wts);
@@ -273,7 +285,7 @@ static V3 ensure_energy_conservation(const float v[3]) {      // BSDF::ensureEne
 int cudapath_add_bsdf_thindielectric(cudapath_ctx *ctx, float int_ior, float ext_ior, const float r[3], const float t[3]) {
     if (!ctx || !r || !t) return fail("null argument");
     if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
-    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    BsdfHost b; std::memset((void *) &b.dev, 0, sizeof(b.dev));
     b.dev.kind = 5;
     b.dev.eta = int_ior / ext_ior;                         // thindielectric.cpp:84
     b.dev.specular = ensure_energy_conservation(r);        // :112-115
@@ -285,7 +297,7 @@ int cudapath_add_bsdf_thindielectric(cudapath_ctx *ctx, float int_ior, float ext
 int cudapath_add_bsdf_marschnerdielectric(cudapath_ctx *ctx, float int_ior, float ext_ior, const float d[3], const float r[3], const float t[3], float exponent) {
     if (!ctx || !d || !r || !t) return fail("null argument");
     if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
-    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    BsdfHost b; std::memset((void *) &b.dev, 0, sizeof(b.dev));
     b.dev.kind = 6;
     b.dev.eta = int_ior / ext_ior;                         // marschnerdielectric.cpp:156
     b.dev.diffuse = V3(d[0], d[1], d[2]);
@@ -300,7 +312,7 @@ int cudapath_add_bsdf_marschnerdielectric(cudapath_ctx *ctx, float int_ior, floa
 
 int cudapath_add_bsdf_diffuse(cudapath_ctx *ctx, const float reflectance[3], int two_sided) {
     if (!ctx || !reflectance) return fail("null argument");
-    BsdfHost b; std::memset(&b.dev, 0, sizeof(b.dev));
+    BsdfHost b; std::memset((void *) &b.dev, 0, sizeof(b.dev));
     V3 r(reflectance[0], reflectance[1], reflectance[2]);
     { const float mx = maxc(r); if (mx > 1.0f) r = r * (0.99f * (1.0f / mx)); }           // ensureEnergyConservation, bsdf.cpp:88-113
     b.dev.kind = 2; b.dev.twoSided = two_sided ? 1 : 0; b.dev.diffuse = r; b.dev.specular = V3(0.0f);
@@ -459,6 +471,16 @@ int cudapath_sun_radiance(const char *data_dir, float turbidity, const float sun
     if (!bake_sunsky(data_dir, p, rgb, w, h, err, out_rgb)) return fail(err);
     return 0;
 }
+int cudapath_env_pyramid_level(const float *rgb, int width, int height, int level, int *out_width, int *out_height, float *out_rgb) {
+    if (!rgb || width <= 0 || height <= 0) return fail("null argument");
+    std::vector<EnvMipLevel> levels; float lut[64];
+    build_env_pyramid(rgb, width, height, levels, lut);
+    if (level < 0 || level >= (int) levels.size()) return fail("MIP level out of range");
+    if (out_width) *out_width = levels[level].w;
+    if (out_height) *out_height = levels[level].h;
+    if (out_rgb) std::memcpy(out_rgb, levels[level].rgb.data(), levels[level].rgb.size() * 4);
+    return (int) levels.size();
+}
 int cudapath_set_sunsky(cudapath_ctx *ctx, float turbidity, const float albedo[3], const float sun_direction[3], float sky_scale,
                         float sun_scale, float sun_radius_scale, int resolution) {
     if (!ctx) return fail("null context");
@@ -541,7 +563,7 @@ static int build_one(cudapath_ctx *ctx) {
     CKA(cudaMemcpyAsync(ctx->d_shapes, ctx->shapes.data(), sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyHostToDevice, ctx->stream));
     BuildInfo info;
     const double tb1 = now();
-    if (!build_bvh(ctx->d_vtx, ctx->vtxTotal, ctx->d_shapes, (int) ctx->shapes.size(), mesh, ctx->maxSplit, ctx->stream, ctx->bvh, info, err)) return fail(err);
+    if (!build_bvh(ctx->d_vtx, ctx->vtxTotal, ctx->d_shapes, (int) ctx->shapes.size(), mesh, ctx->maxSplit, ctx->leafSplitCost, ctx->stream, ctx->bvh, info, err)) return fail(err);
     CKA(cudaMemcpyAsync(ctx->shapes.data(), ctx->d_shapes, sizeof(ShapeDev) * ctx->shapes.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     const double tb2 = now();
@@ -629,9 +651,33 @@ static int build_one(cudapath_ctx *ctx) {
         const bool ok = build_env_tables(d_rgb, ctx->env.w, ctx->env.h, ctx->stream, ctx->envTables, err);
         dev_free(d_rgb);
         if (!ok) return fail(err);
+        {   // Lanczos MIP pyramid + EWA weights for camera rays that leave the scene (MIPMap::eval, envmap.cpp:391-407)
+            std::vector<EnvMipLevel> levels; EnvMipInfo info; std::memset(&info, 0, sizeof(info));
+            build_env_pyramid(ctx->env.rgb.data(), ctx->env.w, ctx->env.h, levels, info.lut);
+            if ((int) levels.size() > CP_ENV_MAX_LEVELS) return fail("environment map has too many MIP levels");
+            info.levels = (int) levels.size();
+            size_t total = 0;
+            for (size_t l = 0; l < levels.size(); ++l) {
+                info.w[l] = levels[l].w; info.h[l] = levels[l].h;
+                info.ratioX[l] = (float) levels[l].w / (float) ctx->env.w; info.ratioY[l] = (float) levels[l].h / (float) ctx->env.h;     // m_sizeRatio, mipmap.h:264-266
+                if (l >= 1) { info.offset[l] = (uint32_t) total; total += (size_t) levels[l].w * levels[l].h; }
+            }
+            std::vector<float> upper; upper.reserve(3 * total);
+            for (size_t l = 1; l < levels.size(); ++l) upper.insert(upper.end(), levels[l].rgb.begin(), levels[l].rgb.end());
+            float *d_upper = nullptr;
+            CKA(dev_alloc(&d_upper, std::max<size_t>(upper.size(), 1) * 4));
+            CKA(dev_alloc(&ctx->envTables.mipTexels, std::max<size_t>(total, 1) * sizeof(float4)));
+            CKA(dev_alloc(&ctx->envTables.mipInfo, sizeof(EnvMipInfo)));
+            if (total) CKA(cudaMemcpyAsync(d_upper, upper.data(), upper.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            quantize_texels(d_upper, (int) total, ctx->envTables.mipTexels, ctx->stream);
+            CKA(cudaMemcpyAsync(ctx->envTables.mipInfo, &info, sizeof(info), cudaMemcpyHostToDevice, ctx->stream));
+            CKA(cudaStreamSynchronize(ctx->stream));
+            dev_free(d_upper);
+        }
         EnvDev &E = S.env;
         E.w = ctx->env.w; E.h = ctx->env.h; E.texels = ctx->envTables.texels; E.cdfCols = ctx->envTables.cdfCols; E.cdfRows = ctx->envTables.cdfRows;
         E.rowWeights = ctx->envTables.rowWeights; E.normalization = ctx->envTables.normalization; E.scale = ctx->env.scale;
+        E.mipTexels = ctx->envTables.mipTexels; E.mip = ctx->envTables.mipInfo;
         E.pixelSizeX = 2 * kPi / E.w; E.pixelSizeY = kPi / E.h;
         float tw[16], ti[16];
         for (int i = 0; i < 16; ++i) tw[i] = ctx->env.toWorld[i];
@@ -667,7 +713,8 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
     cudaEvent_t e0, e1; CKA(cudaEventCreate(&e0)); CKA(cudaEventCreate(&e1));
     CKA(cudaEventRecord(e0, st));
     RenderStats rs; std::string err;
-    ctx->wf.sortRays = ctx->sortRays != 0;
+    ctx->wf.sortRays = ctx->sortRays != 0; ctx->wf.fastMath = ctx->fastMath != 0;
+    ctx->wf.shardIndex = ctx->shardIndex; ctx->wf.shardCount = ctx->shardCount;
     if (const char *e = getenv("CUDAPATH_RUNAHEAD_MAX")) ctx->wf.runAheadMax = (uint32_t) strtoul(e, nullptr, 0);
     ctx->wf.cancelRequested.store(0); ctx->wf.inRender.store(1);
     struct RenderScope { Wavefront &w; cudaEvent_t a, b; ~RenderScope() { w.inRender.store(0); w.cancelRequested.store(0); cudaEventDestroy(a); cudaEventDestroy(b); } } scope_{ctx->wf, e0, e1};
@@ -678,7 +725,7 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
         // never more than 40 % of the memory that is free right now (queues already held by this context count as free).
         size_t freeB = 0, totalB = 0;
         CKA(cudaMemGetInfo(&freeB, &totalB));
-        const double avail = 0.4 * ((double) freeB + (double) dev_cached_bytes() + 228.0 * ctx->wf.capacity);   // blocks parked in the caching allocator are available too
+        const double avail = 0.4 * ((double) freeB + (double) dev_cached_bytes() + 228.0 * (double) ctx->wf.capacity);   // blocks parked in the caching allocator are available too
         waveSize = 1u << 26;
         while (waveSize > (1u << 20) && 228.0 * waveSize > avail) waveSize >>= 1;
     }
@@ -775,6 +822,20 @@ int cudapath_develop_ldr(const float *film, int w, int h, float gamma, float exp
     }
     return 0;
 }
+
+int cudapath_set_pixel_shard(cudapath_ctx *ctx, uint32_t shard_index, uint32_t shard_count) {
+    if (!ctx) return fail("null context");
+    if (shard_count < 1 || shard_count > 64 || shard_index >= shard_count) return fail("invalid pixel shard");
+    ctx->shardIndex = shard_index; ctx->shardCount = shard_count;
+    return 0;
+}
+
+int cudapath_set_math_mode(cudapath_ctx *ctx, int strict) {
+    if (!ctx) return fail("null context");
+    ctx->fastMath = strict ? 0 : 1;
+    return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_math_mode(p, strict); });
+}
+int cudapath_get_math_mode(cudapath_ctx *ctx) { return ctx ? (ctx->fastMath ? 0 : 1) : -1; }
 
 int cudapath_set_build_options(cudapath_ctx *ctx, int max_split) {
     if (!ctx) return fail("null context");
@@ -879,12 +940,18 @@ static int render_multi(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
         for (int i = 0; i < n; ++i) { DevGuard g(m->all[i]->device); cudaDeviceSynchronize(); if (m->films[i]) dev_free(m->films[i]); m->films[i] = nullptr; CKA(dev_alloc(&m->films[i], bytes)); }
         m->filmBytes = bytes;
     }
-    // one host thread per device: zero the private film, render this device's share of the sample indices
+    // Which axis of the pixel-sample space is split: pixel blocks when the image has enough of them to balance the devices (every
+    // device then keeps all sample indices of its pixels, i.e. the ray density of the single-device render), sample ranges otherwise.
+    const uint32_t blocks = (uint32_t) ((ctx->cam.w + 63) / 64) * (uint32_t) ((ctx->cam.h + 63) / 64);
+    const bool byPixels = blocks >= 8u * (uint32_t) n && !getenv("CUDAPATH_SHARD_SAMPLES");
+    // one host thread per device: zero the private film, render this device's share
     std::vector<int> rc(n, 0); std::vector<std::string> msg(n);
     auto work = [&](int i) {
         cudapath_ctx *c = m->all[i];
         DevGuard g(c->device);
-        uint32_t b, e; split_range(sample_begin, sample_end, n, i, b, e);
+        uint32_t b = sample_begin, e = sample_end;
+        if (byPixels) { c->shardIndex = (uint32_t) i; c->shardCount = (uint32_t) n; }
+        else { c->shardIndex = 0; c->shardCount = 1; split_range(sample_begin, sample_end, n, i, b, e); }
         if (cudaMemsetAsync(m->films[i], 0, bytes, c->stream) != cudaSuccess) { rc[i] = -1; msg[i] = "film clear failed"; return; }
         c->stats.paths = c->stats.rays = c->stats.shadow_rays = c->stats.shadow_rays_traced = c->stats.kernel_launches = c->stats.bounces = 0; c->stats.render_ms = 0;
         if (e > b) { rc[i] = cudapath_render_dev(c, spp, seed, b, e, m->films[i], c->stream); if (rc[i] < 0) msg[i] = cudapath_last_error(); }
@@ -1009,7 +1076,7 @@ int cudapath_bsdf_eval_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const f
     CP_GUARD(ctx);
     DevBuf a, b, e, p; std::string err;
     CKA(a.upload(wi, n * 12, ctx->stream)); CKA(b.upload(wo, n * 12, ctx->stream)); CKA(e.alloc(n * 12)); CKA(p.alloc(n * 4));
-    if (!bsdf_eval_batch(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
+    if (!(ctx->fastMath ? bsdf_eval_batch_fast : bsdf_eval_batch)(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err, false)) return fail(err);
     CKA(e.download(out_eval, ctx->stream)); CKA(p.download(out_pdf, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1019,7 +1086,18 @@ int cudapath_bsdf_eval_batch_discrete(cudapath_ctx *ctx, int bsdf_id, uint64_t n
     CP_GUARD(ctx);
     DevBuf a, b, e, p; std::string err;
     CKA(a.upload(wi, n * 12, ctx->stream)); CKA(b.upload(wo, n * 12, ctx->stream)); CKA(e.alloc(n * 12)); CKA(p.alloc(n * 4));
-    if (!bsdf_eval_batch(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err, true)) return fail(err);
+    if (!(ctx->fastMath ? bsdf_eval_batch_fast : bsdf_eval_batch)(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err, true)) return fail(err);
+    CKA(e.download(out_eval, ctx->stream)); CKA(p.download(out_pdf, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cudapath_bsdf_eval_batch_world(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *frames, const float *wi_world, const float *wo_world, float *out_eval, float *out_pdf) {
+    if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
+    if (!frames || !wi_world || !wo_world || !out_eval || !out_pdf) return fail("null argument");
+    DevBuf f, a, b, e, p; std::string err;
+    CKA(f.upload(frames, n * 36, ctx->stream)); CKA(a.upload(wi_world, n * 12, ctx->stream)); CKA(b.upload(wo_world, n * 12, ctx->stream)); CKA(e.alloc(n * 12)); CKA(p.alloc(n * 4));
+    if (!(ctx->fastMath ? bsdf_eval_world_batch_fast : bsdf_eval_world_batch)(ctx->scene, bsdf_id, n, f.as<float>(), a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
     CKA(e.download(out_eval, ctx->stream)); CKA(p.download(out_pdf, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1034,7 +1112,7 @@ int cudapath_bsdf_sample_batch_ex(cudapath_ctx *ctx, int bsdf_id, uint64_t n, co
     CKA(a.upload(wi, n * 12, ctx->stream)); CKA(s.upload(sample, n * 8, ctx->stream));
     if (extra) CKA(x.upload(extra, n * 16, ctx->stream));
     CKA(wo.alloc(n * 12)); CKA(wt.alloc(n * 12)); CKA(p.alloc(n * 4)); CKA(t.alloc(n * 4));
-    if (!bsdf_sample_batch(ctx->scene, bsdf_id, n, a.as<float>(), s.as<float>(), extra ? x.as<float>() : nullptr, wo.as<float>(), wt.as<float>(), p.as<float>(), t.as<int32_t>(), ctx->stream, err)) return fail(err);
+    if (!(ctx->fastMath ? bsdf_sample_batch_fast : bsdf_sample_batch)(ctx->scene, bsdf_id, n, a.as<float>(), s.as<float>(), extra ? x.as<float>() : nullptr, wo.as<float>(), wt.as<float>(), p.as<float>(), t.as<int32_t>(), ctx->stream, err)) return fail(err);
     CKA(wo.download(out_wo, ctx->stream)); CKA(wt.download(out_weight, ctx->stream)); CKA(p.download(out_pdf, ctx->stream)); CKA(t.download(out_type, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1059,17 +1137,45 @@ int cudapath_env_eval_batch(cudapath_ctx *ctx, uint64_t n, const float *directio
     CP_GUARD(ctx);
     DevBuf d, c, p; std::string err;
     CKA(d.upload(direction, n * 12, ctx->stream)); CKA(c.alloc(n * 12)); CKA(p.alloc(n * 4));
-    if (!env_eval_batch(ctx->scene, n, d.as<float>(), c.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
+    if (!(ctx->fastMath ? env_eval_batch_fast : env_eval_batch)(ctx->scene, n, d.as<float>(), c.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
     CKA(c.download(out_rgb, ctx->stream)); CKA(p.download(out_pdf, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+int cudapath_env_eval_filtered_batch(cudapath_ctx *ctx, uint64_t n, const float *direction, const float *rx_direction, const float *ry_direction, float *out_rgb) {
+    if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
+    if (!direction || !rx_direction || !ry_direction || !out_rgb) return fail("null argument");
+    DevBuf d, rx, ry, c; std::string err;
+    CKA(d.upload(direction, n * 12, ctx->stream)); CKA(rx.upload(rx_direction, n * 12, ctx->stream)); CKA(ry.upload(ry_direction, n * 12, ctx->stream)); CKA(c.alloc(n * 12));
+    if (!env_eval_filtered_batch(ctx->scene, n, d.as<float>(), rx.as<float>(), ry.as<float>(), c.as<float>(), ctx->stream, err)) return fail(err);
+    CKA(c.download(out_rgb, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cudapath_env_mip_level(cudapath_ctx *ctx, int level, int *out_width, int *out_height, float *out_rgb) {
+    if (require_built(ctx)) return -1;
+    CP_GUARD(ctx);
+    if (!ctx->scene.env.present) return fail("no environment map set");
+    EnvMipInfo info;
+    CKA(cudaMemcpy(&info, ctx->envTables.mipInfo, sizeof(info), cudaMemcpyDeviceToHost));
+    if (level < 0 || level >= info.levels) return fail("MIP level out of range");
+    if (out_width) *out_width = info.w[level];
+    if (out_height) *out_height = info.h[level];
+    if (out_rgb) {
+        const size_t n = (size_t) info.w[level] * info.h[level];
+        std::vector<float4> t(n);
+        CKA(cudaMemcpy(t.data(), level == 0 ? ctx->envTables.texels : ctx->envTables.mipTexels + info.offset[level], n * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i) { out_rgb[3 * i] = t[i].x; out_rgb[3 * i + 1] = t[i].y; out_rgb[3 * i + 2] = t[i].z; }
+    }
+    return info.levels;
 }
 int cudapath_env_sample_batch(cudapath_ctx *ctx, uint64_t n, const float *ref_point, const float *sample, float *out_direction, float *out_value, float *out_pdf_dist) {
     if (require_built(ctx)) return -1;
     CP_GUARD(ctx);
     DevBuf r, s, d, v, p; std::string err;
     CKA(r.upload(ref_point, n * 12, ctx->stream)); CKA(s.upload(sample, n * 8, ctx->stream)); CKA(d.alloc(n * 12)); CKA(v.alloc(n * 12)); CKA(p.alloc(n * 8));
-    if (!env_sample_batch(ctx->scene, n, r.as<float>(), s.as<float>(), d.as<float>(), v.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
+    if (!(ctx->fastMath ? env_sample_batch_fast : env_sample_batch)(ctx->scene, n, r.as<float>(), s.as<float>(), d.as<float>(), v.as<float>(), p.as<float>(), ctx->stream, err)) return fail(err);
     CKA(d.download(out_direction, ctx->stream)); CKA(v.download(out_value, ctx->stream)); CKA(p.download(out_pdf_dist, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1136,14 +1242,14 @@ int cudapath_bsdf_eval_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, con
     if (require_built(ctx)) return -1;
     CP_GUARD(ctx);
     std::string err;
-    if (!bsdf_eval_batch(ctx->scene, bsdf_id, n, wi, wo, out_eval, out_pdf, stream ? (cudaStream_t) stream : ctx->stream, err)) return fail(err);
+    if (!(ctx->fastMath ? bsdf_eval_batch_fast : bsdf_eval_batch)(ctx->scene, bsdf_id, n, wi, wo, out_eval, out_pdf, stream ? (cudaStream_t) stream : ctx->stream, err, false)) return fail(err);
     return 0;
 }
 int cudapath_bsdf_sample_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type, void *stream) {
     if (require_built(ctx)) return -1;
     CP_GUARD(ctx);
     std::string err;
-    if (!bsdf_sample_batch(ctx->scene, bsdf_id, n, wi, sample, nullptr, out_wo, out_weight, out_pdf, out_type, stream ? (cudaStream_t) stream : ctx->stream, err)) return fail(err);
+    if (!(ctx->fastMath ? bsdf_sample_batch_fast : bsdf_sample_batch)(ctx->scene, bsdf_id, n, wi, sample, nullptr, out_wo, out_weight, out_pdf, out_type, stream ? (cudaStream_t) stream : ctx->stream, err)) return fail(err);
     return 0;
 }
 int cudapath_intersect_batch_dev(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,

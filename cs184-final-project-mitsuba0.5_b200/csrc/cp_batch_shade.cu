@@ -7,10 +7,25 @@
 //   Emitter::evalEnvironment / sampleDirect / pdfDirect   src/emitters/envmap.cpp:380-410,516-556
 //   Sensor::sampleRayDifferential             src/sensors/perspective.cpp:271-298
 // Input streams are read as coalesced fp32 arrays; one thread per tuple / ray.
+//
+// Compiled twice like cp_shade.cu: the strict build emits everything; the -DCP_FAST_MATH build emits the BSDF and emitter batches
+// under *_fast names (the math mode of the context picks one).
 #include "cp_host.h"
 #include "cp_env.cuh"
 #include "cp_camera.cuh"
 #include "cp_wavefront.h"
+#ifdef CP_FAST_MATH
+#define k_bsdf_eval k_bsdf_eval_fast
+#define k_bsdf_sample k_bsdf_sample_fast
+#define k_env_eval k_env_eval_fast
+#define k_env_sample k_env_sample_fast
+#define k_bsdf_eval_world k_bsdf_eval_world_fast
+#define bsdf_eval_world_batch bsdf_eval_world_batch_fast
+#define bsdf_eval_batch bsdf_eval_batch_fast
+#define bsdf_sample_batch bsdf_sample_batch_fast
+#define env_eval_batch env_eval_batch_fast
+#define env_sample_batch env_sample_batch_fast
+#endif
 
 namespace cp {
 
@@ -23,6 +38,20 @@ __global__ void __launch_bounds__(256) k_bsdf_eval(const BsdfDev *__restrict__ b
     const V3 e = bsdf_eval(b, a, c, discrete);
     eval[3 * i] = e.x; eval[3 * i + 1] = e.y; eval[3 * i + 2] = e.z;
     pdf[i] = bsdf_pdf(b, a, c, discrete);
+}
+// the same from WORLD-space directions and a shading frame per tuple (s, t, n): wi = frame.toLocal(wiWorld) as the integrator forms it
+// (its.wi = its.toLocal(-ray.d), include/mitsuba/render/skdtree.h:426-427; bRec.wo = its.toLocal(d), src/integrators/path/path.cpp:186)
+__global__ void __launch_bounds__(256) k_bsdf_eval_world(const BsdfDev *__restrict__ bsdfs, int bsdf, uint64_t n, const float *__restrict__ frames,
+                                                         const float *__restrict__ wi, const float *__restrict__ wo, float *eval, float *pdf) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const BsdfDev &b = bsdfs[bsdf];
+    Frame f;
+    f.s = V3(frames[9 * i], frames[9 * i + 1], frames[9 * i + 2]); f.t = V3(frames[9 * i + 3], frames[9 * i + 4], frames[9 * i + 5]); f.n = V3(frames[9 * i + 6], frames[9 * i + 7], frames[9 * i + 8]);
+    const V3 a = f.toLocal(V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2])), c = f.toLocal(V3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]));
+    const V3 e = bsdf_eval(b, a, c, false);
+    eval[3 * i] = e.x; eval[3 * i + 1] = e.y; eval[3 * i + 2] = e.z;
+    pdf[i] = bsdf_pdf(b, a, c, false);
 }
 __global__ void __launch_bounds__(256) k_bsdf_sample(const BsdfDev *__restrict__ bsdfs, int bsdf, uint64_t n, const float *__restrict__ wi,
                                                      const float *__restrict__ sample, const float *__restrict__ extra, float *wo, float *weight, float *pdf, int32_t *type) {
@@ -45,6 +74,14 @@ __global__ void k_env_eval(SceneDev S, uint64_t n, const float *__restrict__ dir
     rgb[3 * i] = v.x; rgb[3 * i + 1] = v.y; rgb[3 * i + 2] = v.z;
     pdf[i] = env_pdf_direct(S.env, d);
 }
+#ifndef CP_FAST_MATH
+__global__ void k_env_eval_filtered(SceneDev S, uint64_t n, const float *__restrict__ dir, const float *__restrict__ rx, const float *__restrict__ ry, float *rgb) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V3 v = env_eval_filtered(S.env, V3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]), V3(rx[3 * i], rx[3 * i + 1], rx[3 * i + 2]), V3(ry[3 * i], ry[3 * i + 1], ry[3 * i + 2]), nullptr);
+    rgb[3 * i] = v.x; rgb[3 * i + 1] = v.y; rgb[3 * i + 2] = v.z;
+}
+#endif
 __global__ void k_env_sample(SceneDev S, uint64_t n, const float *__restrict__ ref, const float *__restrict__ sample, float *dir, float *value, float *pdfDist) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -53,6 +90,7 @@ __global__ void k_env_sample(SceneDev S, uint64_t n, const float *__restrict__ r
     value[3 * i] = r.value.x; value[3 * i + 1] = r.value.y; value[3 * i + 2] = r.value.z;
     pdfDist[2 * i] = r.pdf; pdfDist[2 * i + 1] = r.dist;
 }
+#ifndef CP_FAST_MATH
 __global__ void k_camera_rays(SceneDev S, uint64_t n, const float *__restrict__ pxy, float *o, float *d, float *minmax) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -78,6 +116,7 @@ __global__ void k_fill_records(SceneDev S, uint64_t n, const float *__restrict__
 void fill_records_batch(const SceneDev &S, uint64_t n, const float *d_d, const int32_t *d_shape, float *d_rec, cudaStream_t s) {
     if (n) k_fill_records<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(S, n, d_d, d_shape, d_rec);
 }
+#endif // !CP_FAST_MATH
 
 #define CKB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 static inline unsigned grid_for(uint64_t n, int block) { return (unsigned) ((n + block - 1) / block); }
@@ -86,6 +125,13 @@ bool bsdf_eval_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi,
     if (bsdf < 0 || bsdf >= S.bsdfCount) { err = "bsdf id out of range"; return false; }
     if (n == 0) return true;
     k_bsdf_eval<<<grid_for(n, 256), 256, 0, s>>>(S.bsdfs, bsdf, n, d_wi, d_wo, d_eval, d_pdf, discrete);
+    CKB(cudaGetLastError());
+    return true;
+}
+bool bsdf_eval_world_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_frames, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err) {
+    if (bsdf < 0 || bsdf >= S.bsdfCount) { err = "bsdf id out of range"; return false; }
+    if (n == 0) return true;
+    k_bsdf_eval_world<<<grid_for(n, 256), 256, 0, s>>>(S.bsdfs, bsdf, n, d_frames, d_wi, d_wo, d_eval, d_pdf);
     CKB(cudaGetLastError());
     return true;
 }
@@ -103,6 +149,15 @@ bool env_eval_batch(const SceneDev &S, uint64_t n, const float *d_dir, float *d_
     CKB(cudaGetLastError());
     return true;
 }
+#ifndef CP_FAST_MATH
+bool env_eval_filtered_batch(const SceneDev &S, uint64_t n, const float *d_dir, const float *d_rx, const float *d_ry, float *d_rgb, cudaStream_t s, std::string &err) {
+    if (!S.env.present) { err = "no environment map set"; return false; }
+    if (n == 0) return true;
+    k_env_eval_filtered<<<grid_for(n, 256), 256, 0, s>>>(S, n, d_dir, d_rx, d_ry, d_rgb);
+    CKB(cudaGetLastError());
+    return true;
+}
+#endif
 bool env_sample_batch(const SceneDev &S, uint64_t n, const float *d_ref, const float *d_sample, float *d_dir, float *d_value, float *d_pdfDist, cudaStream_t s, std::string &err) {
     if (!S.env.present) { err = "no environment map set"; return false; }
     if (n == 0) return true;
@@ -110,11 +165,13 @@ bool env_sample_batch(const SceneDev &S, uint64_t n, const float *d_ref, const f
     CKB(cudaGetLastError());
     return true;
 }
+#ifndef CP_FAST_MATH
 bool camera_rays_batch(const SceneDev &S, uint64_t n, const float *d_pxy, float *d_o, float *d_d, float *d_minmax, cudaStream_t s, std::string &err) {
     if (n == 0) return true;
     k_camera_rays<<<grid_for(n, 256), 256, 0, s>>>(S, n, d_pxy, d_o, d_d, d_minmax);
     CKB(cudaGetLastError());
     return true;
 }
+#endif // !CP_FAST_MATH
 
 } // namespace cp

@@ -12,6 +12,12 @@
 // ~3e-5 relative in the result, and sampleM() feeds such values back into M().  To stay inside the 1e-4
 // parity tolerance every elementary function is correctly rounded (cr_* in cp_common.cuh) and the translation
 // units that contain BSDF code are compiled with -fmad=false (the reference's x86 build has no FMA either).
+//
+// Two builds of this header exist in the library (csrc/Makefile): the strict one (every call correctly rounded: bit-identical to
+// the oracle) and the default, -DCP_FAST_MATH one, in which only the amplified chain keeps its exact bits -- thetaI = asin(wi.y)
+// and the sines / cosines of the three shifted lobe angles that enter M() (ma_lobe_angles below: one fp64 sincos and a few fp64
+// multiply-adds instead of six fp64 libm calls) -- while every nc_* call (table coordinates, the exp / log inside M(), whose
+// argument is O(1), sampled directions) uses the 1-2 ulp fp32 functions.  Measured difference between the modes: ~1e-6 relative.
 #pragma once
 #include "cp_common.cuh"
 
@@ -38,6 +44,7 @@ struct BsdfDev {
     const float *sums;   // 3 x 64
     const float *pdfs;   // 3 x 64 rows x 64 (normalised row pdfs; only the fixed mode reads them)
     const float *rt;     // external rough transmittance, 1-D slice (rtSize samples over |cos|^(1/4))
+    double lobeSin[3], lobeCos[3];   // sin / cos of the lobe shifts -2 s, +s, +4 s of the scale angle s (fp32 values, fp64 functions): ma_lobe_angles
 };
 
 struct BsdfSampleOut { V3 wo, weight; float pdf; int type; int component; };
@@ -53,7 +60,7 @@ CP_D V3 kk_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float sin_tl = sqrtf(1 - tl * tl), sin_te = sqrtf(1 - te * te);
     float alpha = tl * te + sin_tl * sin_te;
     if (alpha > 0.0f && wi.x * wo.x < 0)  // no back-scatter lobe (kajiyakay.cpp:157)
-        result += 0.15f * b.specular * ((b.exponent + 2) * kInvFourPi * cr_pow(alpha, b.exponent));
+        result += 0.15f * b.specular * ((b.exponent + 2) * kInvFourPi * nc_pow(alpha, b.exponent));
     result += b.diffuse * kInvPi;
     return result * wo.z;
 }
@@ -62,7 +69,7 @@ CP_D float kk_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float diffuseProb = kInvPi * wo.z;
     float specProb = 0.0f;
     float alpha = dot(wo, kk_reflect(wi));
-    if (alpha > 0) specProb = cr_pow(alpha, b.exponent) * (b.exponent + 1.0f) / (2.0f * kPi);
+    if (alpha > 0) specProb = nc_pow(alpha, b.exponent) * (b.exponent + 1.0f) / (2.0f * kPi);
     return b.specW * specProb + (1 - b.specW) * diffuseProb;
 }
 CP_D BsdfSampleOut kk_sample(const BsdfDev &b, const V3 &wi, float sx, float sy) {
@@ -72,10 +79,10 @@ CP_D BsdfSampleOut kk_sample(const BsdfDev &b, const V3 &wi, float sx, float sy)
     else { sx = (sx - b.specW) / (1 - b.specW); choseSpecular = false; }
     if (choseSpecular) {
         V3 R = kk_reflect(wi);
-        float sinAlpha = sqrtf(1 - cr_pow(sy, 2 / (b.exponent + 1)));
-        float cosAlpha = cr_pow(sy, 1 / (b.exponent + 1));
+        float sinAlpha = sqrtf(1 - nc_pow(sy, 2 / (b.exponent + 1)));
+        float cosAlpha = nc_pow(sy, 1 / (b.exponent + 1));
         float phi = (2.0f * kPi) * sx, sp, cp_;
-        cr_sincos(phi, &sp, &cp_);
+        nc_sincos(phi, &sp, &cp_);
         V3 localDir(sinAlpha * cp_, sinAlpha * sp, cosAlpha);
         r.wo = Frame(R).toWorld(localDir);
         r.component = 1; r.type = EGlossyReflection;   // component labels swapped in the reference (:255-263)
@@ -101,13 +108,13 @@ CP_D float ma_I0(float x) { // :279-290
     return result;
 }
 CP_D float ma_logI0(float x) { // :292-299
-    if (x > 12.0f) return x + 0.5f * (cr_log(1.0f / (kPi * 2.0f * x)) + 1.0f / (8.0f * x));
-    return cr_log(ma_I0(x));
+    if (x > 12.0f) return x + 0.5f * (nc_log(1.0f / (kPi * 2.0f * x)) + 1.0f / (8.0f * x));
+    return nc_log(ma_I0(x));
 }
 CP_D float ma_M(float v, float sinThetaI, float sinThetaO, float cosThetaI, float cosThetaO) { // :364-374
     float a = cosThetaI * cosThetaO / v, b = sinThetaI * sinThetaO / v;
-    if (v < 0.1f) return cr_exp(-b + ma_logI0(a) - 1.0f / v + 0.6931f + cr_log(1.0f / (2.0f * v)));
-    return cr_exp(-b) * ma_I0(a) / (2.0f * v * cr_sinh(1.0f / v));
+    if (v < 0.1f) return nc_exp(-b + ma_logI0(a) - 1.0f / v + 0.6931f + nc_log(1.0f / (2.0f * v)));
+    return nc_exp(-b) * ma_I0(a) / (2.0f * v * nc_sinh(1.0f / v));
 }
 
 // Azimuthal::eval :79-92 -- bilinear lookup in one 64x64 RGB table
@@ -149,7 +156,7 @@ CP_D float ma_sample_phi(const float *__restrict__ cdf, float cosThetaD, float x
 }
 // RoughTransmittance::eval, alpha and eta fixed (rtrans.h:183-194,233) -> Catmull-Rom over rtSize samples
 CP_D float ma_T(const BsdfDev &b, float cosTheta) {
-    float warped = cr_pow(fabsf(cosTheta), 0.25f);
+    float warped = nc_pow(fabsf(cosTheta), 0.25f);
     if (!(cosTheta >= 0)) return 0.0f;
     float x = warped;
     if (!(x >= 0.0f && x <= 1.0f)) return 0.0f;       // spline.cpp:25-26 (min(1,max(0,0)) = 0)
@@ -165,21 +172,49 @@ CP_D float ma_T(const BsdfDev &b, float cosTheta) {
     return fminf(1.0f, fmaxf(0.0f, result));
 }
 
+// Sines and cosines of the three shifted incident angles that enter M() (marschner_diffuse.cpp:433-452: thetaI - 2 s, thetaI + s,
+// thetaI + 4 s for the scale angle s).  M() multiplies them by 1/v <= 400 inside an exponential, so they keep the reference's exact
+// fp32 operation sequence -- fl(thetaI + shift), then a correctly rounded sin / cos of that fp32 angle -- in both math modes.  The
+// strict mode calls the fp64 functions six times; the fast mode evaluates sin / cos of thetaI once in fp64 and rotates by the shift
+// (whose sin / cos are per-material constants, corrected to first order for the rounding of the fp32 addition; the neglected
+// second-order term is below 1e-14), which gives the same fp32 values except on fp64 double-rounding boundaries.
+struct LobeAngles { float sinR, cosR, sinTT, cosTT, sinTRT, cosTRT; };
+CP_D LobeAngles ma_lobe_angles(const BsdfDev &b, float thetaI) {
+    const float thetaIR = thetaI - 2.0f * b.scaleAngle, thetaITT = thetaI + b.scaleAngle, thetaITRT = thetaI + 4.0f * b.scaleAngle;
+    LobeAngles r;
+#if CP_MATH_IS_FAST
+    double s, c;
+    sincos((double) thetaI, &s, &c);
+    const double offR = -(double) (2.0f * b.scaleAngle), offTT = (double) b.scaleAngle, offTRT = (double) (4.0f * b.scaleAngle);
+    const double eR = ((double) thetaIR - (double) thetaI) - offR, eTT = ((double) thetaITT - (double) thetaI) - offTT, eTRT = ((double) thetaITRT - (double) thetaI) - offTRT;
+    double sd, cd;
+    sd = b.lobeSin[0] + eR * b.lobeCos[0]; cd = b.lobeCos[0] - eR * b.lobeSin[0];
+    r.sinR = (float) (s * cd + c * sd); r.cosR = (float) (c * cd - s * sd);
+    sd = b.lobeSin[1] + eTT * b.lobeCos[1]; cd = b.lobeCos[1] - eTT * b.lobeSin[1];
+    r.sinTT = (float) (s * cd + c * sd); r.cosTT = (float) (c * cd - s * sd);
+    sd = b.lobeSin[2] + eTRT * b.lobeCos[2]; cd = b.lobeCos[2] - eTRT * b.lobeSin[2];
+    r.sinTRT = (float) (s * cd + c * sd); r.cosTRT = (float) (c * cd - s * sd);
+#else
+    r.sinR = cr_sin(thetaIR); r.cosR = cr_cos(thetaIR);
+    r.sinTT = cr_sin(thetaITT); r.cosTT = cr_cos(thetaITT);
+    r.sinTRT = cr_sin(thetaITRT); r.cosTRT = cr_cos(thetaITRT);
+#endif
+    return r;
+}
+
 CP_D V3 ma_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float sinThetaI = wi.y, sinThetaO = wo.y;            // the `t` axis, not the tangent (quirk 2)
     float cosThetaO = ma_trigInverse(sinThetaO);
-    float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
-    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));   // feeds the lobe angles: exact in both modes
+    float thetaO = nc_asin(clampf(sinThetaO, -1.0f, 1.0f));
     float thetaD = (thetaO - thetaI) * 0.5f;
-    float cosThetaD = cr_cos(thetaD);
-    float phi = cr_atan2(wo.x, wo.z);                     // depends on wo only (quirk 2)
+    float cosThetaD = nc_cos(thetaD);
+    float phi = nc_atan2(wo.x, wo.z);                     // depends on wo only (quirk 2)
     if (phi < 0.0f) phi += kPi * 2.0f;
-    float thetaIR = thetaI - 2.0f * b.scaleAngle;
-    float thetaITT = thetaI + b.scaleAngle;
-    float thetaITRT = thetaI + 4.0f * b.scaleAngle;
-    float MR = ma_M(b.vR, cr_sin(thetaIR), sinThetaO, cr_cos(thetaIR), cosThetaO);
-    float MTT = ma_M(b.vTT, cr_sin(thetaITT), sinThetaO, cr_cos(thetaITT), cosThetaO);
-    float MTRT = ma_M(b.vTRT, cr_sin(thetaITRT), sinThetaO, cr_cos(thetaITRT), cosThetaO);
+    const LobeAngles la = ma_lobe_angles(b, thetaI);
+    float MR = ma_M(b.vR, la.sinR, sinThetaO, la.cosR, cosThetaO);
+    float MTT = ma_M(b.vTT, la.sinTT, sinThetaO, la.cosTT, cosThetaO);
+    float MTRT = ma_M(b.vTRT, la.sinTRT, sinThetaO, la.cosTRT, cosThetaO);
     V3 result = 0.15f * MR * ma_azimuthal(b.tab, phi, cosThetaD)
               + MTT * ma_azimuthal(b.tab + 4096, phi, cosThetaD)
               + MTRT * ma_azimuthal(b.tab + 8192, phi, cosThetaD);
@@ -191,30 +226,30 @@ CP_D V3 ma_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     return result;
 }
 CP_D float ma_sampleM(float v, float sinThetaI, float cosThetaI, float xi1, float xi2) { // :582-592
-    float cosTheta = 1.0f + v * cr_log(xi1 + (1.0f - xi1) * cr_exp(-2.0f / v));
+    float cosTheta = 1.0f + v * nc_log(xi1 + (1.0f - xi1) * nc_exp(-2.0f / v));
     float sinTheta = ma_trigInverse(cosTheta);
-    float cosPhi = cr_cos(2 * kPi * xi2);
+    float cosPhi = nc_cos(2 * kPi * xi2);
     return -cosTheta * sinThetaI + sinTheta * cosPhi * cosThetaI;
 }
 CP_D BsdfSampleOut ma_sample(const BsdfDev &b, const V3 &wi, float sx, float sy) {
     BsdfSampleOut r;
     float sinThetaI = wi.y;
     float cosThetaI = ma_trigInverse(sinThetaI);
-    float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
+    float thetaI = nc_asin(clampf(sinThetaI, -1.0f, 1.0f));
     float weightR = ma_weight(b.sums, cosThetaI), weightTT = ma_weight(b.sums + 64, cosThetaI), weightTRT = ma_weight(b.sums + 128, cosThetaI);
     float v, theta; int lobe;
     float target = sx * (weightR + weightTT + weightTRT);
     if (target < weightR) { r.component = 5; v = b.vR; theta = thetaI - 2.0f * b.scaleAngle; lobe = 0; }
     else if (target < weightR + weightTT) { r.component = 6; v = b.vTT; theta = thetaI + b.scaleAngle; lobe = 1; }
     else { r.component = 7; v = b.vTRT; theta = thetaI + 4.0f * b.scaleAngle; lobe = 2; }
-    float sinThetaO = ma_sampleM(v, cr_sin(theta), cr_cos(theta), sx, sy);   // one 2-D sample reused (quirk 4)
+    float sinThetaO = ma_sampleM(v, nc_sin(theta), nc_cos(theta), sx, sy);   // one 2-D sample reused (quirk 4)
     float cosThetaO = ma_trigInverse(sinThetaO);
-    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaO = nc_asin(clampf(sinThetaO, -1.0f, 1.0f));
     float thetaD = (thetaO - thetaI) * 0.5f;
-    float cosThetaD = cr_cos(thetaD);
+    float cosThetaD = nc_cos(thetaD);
     float phi = ma_sample_phi(b.cdf + lobe * 64 * 65, cosThetaD, sy);
     float sinPhi, cosPhi;
-    cr_sincos(phi, &sinPhi, &cosPhi);
+    nc_sincos(phi, &sinPhi, &cosPhi);
     float probSpecular = 1 - ma_T(b, wi.z);
     probSpecular = (probSpecular * b.specW) / (probSpecular * b.specW + (1 - probSpecular) * (1 - b.specW));
     if (sy < probSpecular) {
@@ -244,13 +279,13 @@ CP_D V3 mf_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float sinThetaI = wi.y, sinThetaO = wo.y;
     float cosThetaO = ma_trigInverse(sinThetaO);
     float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
-    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaO = nc_asin(clampf(sinThetaO, -1.0f, 1.0f));
     float thetaD = (thetaO - thetaI) * 0.5f;
-    float cosThetaD = cr_cos(thetaD);
-    float phi = cr_atan2(wo.x, wo.z);
+    float cosThetaD = nc_cos(thetaD);
+    float phi = nc_atan2(wo.x, wo.z);
     if (phi < 0.0f) phi += kPi * 2.0f;
-    float thetaITRT = thetaI + 4.0f * b.scaleAngle;
-    float MTRT = ma_M(b.vTRT, cr_sin(thetaITRT), sinThetaO, cr_cos(thetaITRT), cosThetaO);
+    const LobeAngles la = ma_lobe_angles(b, thetaI);
+    float MTRT = ma_M(b.vTRT, la.sinTRT, sinThetaO, la.cosTRT, cosThetaO);
     const V3 zero(0.0f);      // MR = MTT = 0 in the reference (:333-334): their lobes contribute 0 * table value
     return zero * ma_azimuthal(b.tab, phi, cosThetaD) + zero * ma_azimuthal(b.tab + 4096, phi, cosThetaD) + MTRT * ma_azimuthal(b.tab + 8192, phi, cosThetaD);
 }
@@ -258,17 +293,17 @@ CP_D float mf_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float sinThetaI = wi.y, sinThetaO = wo.y;
     float cosThetaI = ma_trigInverse(sinThetaI), cosThetaO = ma_trigInverse(sinThetaO);
     float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
-    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaO = nc_asin(clampf(sinThetaO, -1.0f, 1.0f));
     float thetaD = (thetaO - thetaI) * 0.5f;
-    float cosThetaD = cr_cos(thetaD);
-    float phi = cr_atan2(wo.x, wo.z);
+    float cosThetaD = nc_cos(thetaD);
+    float phi = nc_atan2(wo.x, wo.z);
     if (phi < 0.0f) phi += 2.0f * kPi;
-    float thetaIR = thetaI - 2.0f * b.scaleAngle, thetaITT = thetaI + b.scaleAngle, thetaITRT = thetaI + 4.0f * b.scaleAngle;
+    const LobeAngles la = ma_lobe_angles(b, thetaI);
     float weightR = ma_weight(b.sums, cosThetaI), weightTT = ma_weight(b.sums + 64, cosThetaI), weightTRT = ma_weight(b.sums + 128, cosThetaI);
     float weightSum = weightR + weightTT + weightTRT;
-    float pdfR = weightR * ma_M(b.vR, cr_sin(thetaIR), sinThetaO, cr_cos(thetaIR), cosThetaO);
-    float pdfTT = weightTT * ma_M(b.vTT, cr_sin(thetaITT), sinThetaO, cr_cos(thetaITT), cosThetaO);
-    float pdfTRT = weightTRT * ma_M(b.vTRT, cr_sin(thetaITRT), sinThetaO, cr_cos(thetaITRT), cosThetaO);
+    float pdfR = weightR * ma_M(b.vR, la.sinR, sinThetaO, la.cosR, cosThetaO);
+    float pdfTT = weightTT * ma_M(b.vTT, la.sinTT, sinThetaO, la.cosTT, cosThetaO);
+    float pdfTRT = weightTRT * ma_M(b.vTRT, la.sinTRT, sinThetaO, la.cosTRT, cosThetaO);
     return (1.0f / weightSum) * (pdfR * mf_azimuthal_pdf(b.pdfs, phi, cosThetaD) + pdfTT * mf_azimuthal_pdf(b.pdfs + 4096, phi, cosThetaD)
                                  + pdfTRT * mf_azimuthal_pdf(b.pdfs + 8192, phi, cosThetaD));
 }
@@ -277,21 +312,21 @@ CP_D BsdfSampleOut mf_sample(const BsdfDev &b, const V3 &wi, float xiNx, float x
     BsdfSampleOut r; r.weight = V3(0.0f);
     float sinThetaI = wi.y;
     float cosThetaI = ma_trigInverse(sinThetaI);
-    float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
+    float thetaI = nc_asin(clampf(sinThetaI, -1.0f, 1.0f));
     float weightR = ma_weight(b.sums, cosThetaI), weightTT = ma_weight(b.sums + 64, cosThetaI), weightTRT = ma_weight(b.sums + 128, cosThetaI);
     float v, theta; int lobe;
     float target = xiNx * (weightR + weightTT + weightTRT);
     if (target < weightR) { r.component = 0; v = b.vR; theta = thetaI - 2.0f * b.scaleAngle; lobe = 0; }
     else if (target < weightR + weightTT) { r.component = 1; v = b.vTT; theta = thetaI + b.scaleAngle; lobe = 1; }
     else { r.component = 2; v = b.vTRT; theta = thetaI + 4.0f * b.scaleAngle; lobe = 2; }
-    float sinThetaO = ma_sampleM(v, cr_sin(theta), cr_cos(theta), xiMx, xiMy);
+    float sinThetaO = ma_sampleM(v, nc_sin(theta), nc_cos(theta), xiMx, xiMy);
     float cosThetaO = ma_trigInverse(sinThetaO);
-    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaO = nc_asin(clampf(sinThetaO, -1.0f, 1.0f));
     float thetaD = (thetaO - thetaI) * 0.5f;
-    float cosThetaD = cr_cos(thetaD);
+    float cosThetaD = nc_cos(thetaD);
     float phi = ma_sample_phi(b.cdf + lobe * 64 * 65, cosThetaD, xiNy);
     float sinPhi, cosPhi;
-    cr_sincos(phi, &sinPhi, &cosPhi);
+    nc_sincos(phi, &sinPhi, &cosPhi);
     r.wo = V3(sinPhi * cosThetaO, sinThetaO, cosPhi * cosThetaO);
     r.pdf = mf_pdf(b, wi, r.wo);
     r.type = EDeltaReflection;
@@ -306,7 +341,7 @@ CP_D BsdfSampleOut mf_sample(const BsdfDev &b, const V3 &wi, float xiNx, float x
 // RoughPlastic eval / pdf / sample: src/bsdfs/roughplastic.cpp:325-375, 377-436, 438-494
 CP_D float mfd_signum(float v) { return v < 0 ? -1.0f : (v > 0 ? 1.0f : 0.0f); }
 CP_D float mfd_erfinv(float x) {
-    float w = -cr_log((1.0f - x) * (1.0f + x));
+    float w = -nc_log((1.0f - x) * (1.0f + x));
     float p;
     if (w < 5.0f) {
         w = w - 2.5f;
@@ -324,7 +359,7 @@ CP_D float mfd_erf(float x) {
     const float sign = mfd_signum(x);
     x = fabsf(x);
     const float t = 1.0f / (1.0f + p * x);
-    const float y = 1.0f - (((((a5 * t + a4) * t) + a3) * t + a2) * t + a1) * t * cr_exp(-x * x);
+    const float y = 1.0f - (((((a5 * t + a4) * t) + a3) * t + a2) * t + a1) * t * nc_exp(-x * x);
     return sign * y;
 }
 CP_D float mfd_hypot2(float a, float b) {
@@ -339,9 +374,9 @@ CP_D float mfd_eval(const BsdfDev &b, const V3 &m) {
     const float alpha = b.alpha, cosTheta2 = m.z * m.z;
     const float beckmannExponent = ((m.x * m.x) / (alpha * alpha) + (m.y * m.y) / (alpha * alpha)) / cosTheta2;
     float result;
-    if (b.distr == 0) result = cr_exp(-beckmannExponent) / (kPi * alpha * alpha * cosTheta2 * cosTheta2);
+    if (b.distr == 0) result = nc_exp(-beckmannExponent) / (kPi * alpha * alpha * cosTheta2 * cosTheta2);
     else if (b.distr == 1) { const float root = (1.0f + beckmannExponent) * cosTheta2; result = 1.0f / (kPi * alpha * alpha * root * root); }
-    else result = sqrtf((b.exponent + 2) * (b.exponent + 2)) * kInvTwoPi * cr_pow(m.z, b.exponent);
+    else result = sqrtf((b.exponent + 2) * (b.exponent + 2)) * kInvTwoPi * nc_pow(m.z, b.exponent);
     if (result * m.z < 1e-20f) result = 0;
     return result;
 }
@@ -365,10 +400,10 @@ CP_D float mfd_pdf(const BsdfDev &b, const V3 &wi, const V3 &m) {
 }
 CP_D V3 mfd_sampleAll(const BsdfDev &b, float sx, float sy) {
     float cosThetaM, sinPhiM, cosPhiM;
-    cr_sincos((2.0f * kPi) * sy, &sinPhiM, &cosPhiM);
-    if (b.distr == 0) cosThetaM = 1.0f / sqrtf(1.0f + b.alpha * b.alpha * -cr_log(1.0f - sx));
+    nc_sincos((2.0f * kPi) * sy, &sinPhiM, &cosPhiM);
+    if (b.distr == 0) cosThetaM = 1.0f / sqrtf(1.0f + b.alpha * b.alpha * -nc_log(1.0f - sx));
     else if (b.distr == 1) cosThetaM = 1.0f / sqrtf(1.0f + b.alpha * b.alpha * sx / (1.0f - sx));
-    else cosThetaM = cr_pow(sx, 1.0f / (b.exponent + 2.0f));
+    else cosThetaM = nc_pow(sx, 1.0f / (b.exponent + 2.0f));
     const float sinThetaM = sqrtf(fmaxf(0.0f, 1 - cosThetaM * cosThetaM));
     return V3(sinThetaM * cosPhiM, sinThetaM * sinPhiM, cosThetaM);
 }
@@ -376,21 +411,21 @@ CP_D void mfd_sampleVisible11(const BsdfDev &b, float thetaI, float sx, float sy
     const float SQRT_PI_INV = 1 / sqrtf(kPi);
     if (b.distr == 0) {
         if (thetaI < 1e-4f) {
-            const float r = sqrtf(-cr_log(1.0f - sx));
-            float sinPhi, cosPhi; cr_sincos(2 * kPi * sy, &sinPhi, &cosPhi);
+            const float r = sqrtf(-nc_log(1.0f - sx));
+            float sinPhi, cosPhi; nc_sincos(2 * kPi * sy, &sinPhi, &cosPhi);
             slopeX = r * cosPhi; slopeY = r * sinPhi; return;
         }
-        const float tanThetaI = (float) tan((double) thetaI), cotThetaI = 1 / tanThetaI;
+        const float tanThetaI = nc_tan(thetaI), cotThetaI = 1 / tanThetaI;
         float a = -1, c = mfd_erf(cotThetaI);
         const float sample_x = fmaxf(sx, 1e-6f);
         const float fit = 1 + thetaI * (-0.876f + thetaI * (0.4265f - 0.0594f * thetaI));
-        float bb = c - (1 + c) * cr_pow(1 - sample_x, fit);
-        const float normalization = 1 / (1 + c + SQRT_PI_INV * tanThetaI * cr_exp(-cotThetaI * cotThetaI));
+        float bb = c - (1 + c) * nc_pow(1 - sample_x, fit);
+        const float normalization = 1 / (1 + c + SQRT_PI_INV * tanThetaI * nc_exp(-cotThetaI * cotThetaI));
         int it = 0;
         while (++it < 10) {
             if (!(bb >= a && bb <= c)) bb = 0.5f * (a + c);
             const float invErf = mfd_erfinv(bb);
-            const float value = normalization * (1 + bb + SQRT_PI_INV * tanThetaI * cr_exp(-invErf * invErf)) - sample_x;
+            const float value = normalization * (1 + bb + SQRT_PI_INV * tanThetaI * nc_exp(-invErf * invErf)) - sample_x;
             const float derivative = normalization * (1 - invErf * tanThetaI);
             if (fabsf(value) < 1e-5f) break;
             if (value > 0) c = bb; else a = bb;
@@ -401,10 +436,10 @@ CP_D void mfd_sampleVisible11(const BsdfDev &b, float thetaI, float sx, float sy
     } else {
         if (thetaI < 1e-4f) {
             const float r = safe_sqrt(sx / (1 - sx));
-            float sinPhi, cosPhi; cr_sincos(2 * kPi * sy, &sinPhi, &cosPhi);
+            float sinPhi, cosPhi; nc_sincos(2 * kPi * sy, &sinPhi, &cosPhi);
             slopeX = r * cosPhi; slopeY = r * sinPhi; return;
         }
-        const float tanThetaI = (float) tan((double) thetaI);
+        const float tanThetaI = nc_tan(thetaI);
         const float a = 1 / tanThetaI;
         const float G1 = 2.0f / (1.0f + safe_sqrt(1.0f + 1.0f / (a * a)));
         float A = 2.0f * sx / G1 - 1.0f;
@@ -426,8 +461,8 @@ CP_D V3 mfd_sample(const BsdfDev &b, const V3 &_wi, float sx, float sy) {
     if (!b.sampleVisible) return mfd_sampleAll(b, sx, sy);
     const V3 wi = normalize(V3(b.alpha * _wi.x, b.alpha * _wi.y, _wi.z));
     float theta = 0, phi = 0;
-    if (wi.z < 0.99999f) { theta = cr_acos(wi.z); phi = cr_atan2(wi.y, wi.x); }
-    float sinPhi, cosPhi; cr_sincos(phi, &sinPhi, &cosPhi);
+    if (wi.z < 0.99999f) { theta = nc_acos(wi.z); phi = nc_atan2(wi.y, wi.x); }
+    float sinPhi, cosPhi; nc_sincos(phi, &sinPhi, &cosPhi);
     float slx, sly;
     mfd_sampleVisible11(b, theta, sx, sy, slx, sly);
     float rx = cosPhi * slx - sinPhi * sly, ry = sinPhi * slx + cosPhi * sly;

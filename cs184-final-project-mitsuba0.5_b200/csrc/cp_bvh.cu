@@ -280,14 +280,30 @@ __device__ __forceinline__ float boxArea(const float *b) {
 // One thread per wide node to emit.  A binary subtree with <= CP_LEAF_MAX segments becomes a leaf reference.
 __global__ void k_collapse(const CollapseItem *__restrict__ in, int nIn, CollapseItem *out, int *outCount, int *wideCount,
                            const int2 *__restrict__ children, const int2 *__restrict__ ranges,
-                           const float *__restrict__ innerBox, const float *__restrict__ sortedBox, BVH4Node *nodes, int maxWide, int *err) {
+                           const float *__restrict__ innerBox, const float *__restrict__ sortedBox, BVH4Node *nodes, int maxWide, int *err, float splitCost) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nIn) return;
     const CollapseItem it = in[idx];
     int cand[4]; int nc = 0;
     int2 ch = children[it.bin];
     cand[nc++] = ch.x; cand[nc++] = ch.y;
-    auto expandable = [&](int c) { return c >= 0 && (ranges[c].y - ranges[c].x + 1) > CP_LEAF_MAX; };
+    // A binary subtree with at most CP_LEAF_MAX references may become ONE leaf (one box, every reference pre-tested on entry) or stay
+    // a subtree (a box per child).  Surface-area heuristic, one level deep: it is opened when
+    //     splitCost * A(node) + A(left) n_left + A(right) n_right  <  A(node) n,
+    // i.e. when the children's boxes are so much smaller than their union that testing them first saves pre-tests (short fibers in
+    // open space); bundles of long, diagonal, pre-split fibers, whose pieces' boxes overlap anyway, stay leaves.  splitCost < 0: never.
+    auto expandable = [&](int c) {
+        if (c < 0) return false;
+        const int n = ranges[c].y - ranges[c].x + 1;
+        if (n > CP_LEAF_MAX) return true;
+        if (splitCost < 0.0f) return false;
+        const int2 k = children[c];
+        const float aN = boxArea(innerBox + 6 * (size_t) c);
+        const float aL = k.x >= 0 ? boxArea(innerBox + 6 * (size_t) k.x) : boxArea(sortedBox + 6 * (size_t) (~k.x));
+        const float aR = k.y >= 0 ? boxArea(innerBox + 6 * (size_t) k.y) : boxArea(sortedBox + 6 * (size_t) (~k.y));
+        const int nL = k.x >= 0 ? ranges[k.x].y - ranges[k.x].x + 1 : 1, nR = k.y >= 0 ? ranges[k.y].y - ranges[k.y].x + 1 : 1;
+        return splitCost * aN + aL * nL + aR * nR < aN * n;
+    };
     while (nc < 4) {
         int best = -1; float bestArea = -1.0f;
         for (int k = 0; k < nc; ++k) if (expandable(cand[k])) {
@@ -365,7 +381,7 @@ struct Scratch {   // scratch allocations from the caching allocator (cp_mem.cpp
 
 // Builds the BVH for the vertex array already resident on the device.  On success the caller owns
 // out.nodes / out.prims (cudaFree).  `shapes` is updated in place with the per-shape bounds.
-bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, const MeshDev &mesh, int maxSplit, cudaStream_t stream,
+bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, const MeshDev &mesh, int maxSplit, float leafSplitCost, cudaStream_t stream,
                BVHDev &out, BuildInfo &info, std::string &err) {
     out = BVHDev(); info = BuildInfo();
     Scratch S(stream);
@@ -469,7 +485,7 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
             levels = 0;
             while (nIn > 0) {
                 k_collapse<<<(nIn + 127) / 128, 128, 0, stream>>>(d_q0, nIn, d_q1, d_counters, d_counters + 1, d_children, d_ranges,
-                                                                 d_innerBox, d_sortedBox, d_wide, capacity, d_counters + 2);
+                                                                 d_innerBox, d_sortedBox, d_wide, capacity, d_counters + 2, leafSplitCost);
                 int h[3];
                 CK(cudaMemcpyAsync(h, d_counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
                 CK(cudaStreamSynchronize(stream));

@@ -63,24 +63,14 @@ CP_HD D3 operator*(D3 a, double s) { return D3(a.x * s, a.y * s, a.z * s); }
 CP_HD double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 CP_HD D3 normalize(D3 a) { double r = 1.0 / sqrt(dot(a, a)); return a * r; }
 
-// Elementary functions: correctly rounded fp32 (fp64 evaluation rounded once).  The reference calls the platform's fp32
-// libm, whose last bit is build-dependent, and M() / sampleM() of the Marschner model amplify that bit by O(1/v) = O(400);
-// pinning every call to the correctly rounded value keeps the device within a few ulp of any faithful CPU evaluation.
-// B200 issues fp64 at half the fp32 rate, so this costs little next to BVH traversal.  -DCP_FAST_MATH switches to the
-// 1-2 ulp fp32 CUDA functions (used only to measure what the choice costs).
-#if defined(__CUDA_ARCH__) && defined(CP_FAST_MATH)
-CP_D float cr_sin(float x) { return sinf(x); }
-CP_D float cr_cos(float x) { return cosf(x); }
-CP_D void cr_sincos(float x, float *s, float *c) { sincosf(x, s, c); }
-CP_D float cr_asin(float x) { return asinf(x); }
-CP_D float cr_acos(float x) { return acosf(x); }
-CP_D float cr_atan2(float y, float x) { return atan2f(y, x); }
-CP_D float cr_exp(float x) { return expf(x); }
-CP_D float cr_log(float x) { return logf(x); }
-CP_D float cr_log2(float x) { return log2f(x); }
-CP_D float cr_pow(float x, float y) { return powf(x, y); }
-CP_D float cr_sinh(float x) { return sinhf(x); }
-#else
+// Elementary functions, two families.
+//   cr_*  correctly rounded fp32 (fp64 evaluation rounded once).  The reference calls the platform's fp32 libm, whose last bit is
+//         build-dependent, and M() / sampleM() of the Marschner model amplify that bit by O(1/v) = O(400); pinning a call to the
+//         correctly rounded value keeps the device within a few ulp of any faithful CPU evaluation.
+//   nc_*  "not critical": calls whose last bits are NOT amplified (table coordinates, sampled directions, the exp / log inside M(),
+//         whose argument is O(1) after the cancellation).  Strict translation units (default) map them to cr_*, so device and oracle
+//         agree bit for bit; translation units compiled with -DCP_FAST_MATH map them to the 1-2 ulp fp32 CUDA functions, which
+//         leaves BSDF values within ~1e-6 of the strict mode (north_star asks for 1e-4) at a fraction of the FP64 work.
 CP_HD float cr_sin(float x) { return (float) sin((double) x); }
 CP_HD float cr_cos(float x) { return (float) cos((double) x); }
 CP_HD void cr_sincos(float x, float *s, float *c) { double ds, dc; sincos((double) x, &ds, &dc); *s = (float) ds; *c = (float) dc; }
@@ -92,13 +82,42 @@ CP_HD float cr_log(float x) { return (float) log((double) x); }
 CP_HD float cr_log2(float x) { return (float) log2((double) x); }
 CP_HD float cr_pow(float x, float y) { return (float) pow((double) x, (double) y); }
 CP_HD float cr_sinh(float x) { return (float) sinh((double) x); }
+CP_HD float cr_tan(float x) { return (float) tan((double) x); }
+#if defined(__CUDA_ARCH__) && defined(CP_FAST_MATH)
+#define CP_MATH_IS_FAST 1
+CP_D float nc_sin(float x) { return sinf(x); }
+CP_D float nc_cos(float x) { return cosf(x); }
+CP_D void nc_sincos(float x, float *s, float *c) { sincosf(x, s, c); }
+CP_D float nc_asin(float x) { return asinf(x); }
+CP_D float nc_acos(float x) { return acosf(x); }
+CP_D float nc_atan2(float y, float x) { return atan2f(y, x); }
+CP_D float nc_exp(float x) { return expf(x); }
+CP_D float nc_log(float x) { return logf(x); }
+CP_D float nc_log2(float x) { return log2f(x); }
+CP_D float nc_pow(float x, float y) { return powf(x, y); }
+CP_D float nc_sinh(float x) { return sinhf(x); }
+CP_D float nc_tan(float x) { return tanf(x); }
+#else
+#define CP_MATH_IS_FAST 0
+CP_HD float nc_sin(float x) { return cr_sin(x); }
+CP_HD float nc_cos(float x) { return cr_cos(x); }
+CP_HD void nc_sincos(float x, float *s, float *c) { cr_sincos(x, s, c); }
+CP_HD float nc_asin(float x) { return cr_asin(x); }
+CP_HD float nc_acos(float x) { return cr_acos(x); }
+CP_HD float nc_atan2(float y, float x) { return cr_atan2(y, x); }
+CP_HD float nc_exp(float x) { return cr_exp(x); }
+CP_HD float nc_log(float x) { return cr_log(x); }
+CP_HD float nc_log2(float x) { return cr_log2(x); }
+CP_HD float nc_pow(float x, float y) { return cr_pow(x, y); }
+CP_HD float nc_sinh(float x) { return cr_sinh(x); }
+CP_HD float nc_tan(float x) { return cr_tan(x); }
 #endif
 CP_HD float cr_hypot(float x, float y) { return (float) sqrt((double) x * x + (double) y * y); }
 
 CP_HD float clampf(float v, float lo, float hi) { return fminf(hi, fmaxf(lo, v)); }
 CP_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 CP_HD float safe_sqrt(float v) { return sqrtf(fmaxf(0.0f, v)); }
-CP_HD float safe_acos(float v) { return cr_acos(fminf(1.0f, fmaxf(-1.0f, v))); }
+CP_HD float safe_acos(float v) { return nc_acos(fminf(1.0f, fmaxf(-1.0f, v))); }
 
 // src/libcore/util.cpp:592-601
 CP_HD void coordinateSystem(const V3 &a, V3 &b, V3 &c) {
@@ -159,7 +178,7 @@ CP_HD void squareToUniformDiskConcentric(float sx, float sy, float &ox, float &o
     else if (r1 * r1 > r2 * r2) { r = r1; phi = (kPi / 4.0f) * (r2 / r1); }
     else { r = r2; phi = (kPi / 2.0f) - (r1 / r2) * (kPi / 4.0f); }
     float sinPhi, cosPhi;
-    cr_sincos(phi, &sinPhi, &cosPhi);
+    nc_sincos(phi, &sinPhi, &cosPhi);
     ox = r * cosPhi; oy = r * sinPhi;
 }
 // src/libcore/warp.cpp:43-52

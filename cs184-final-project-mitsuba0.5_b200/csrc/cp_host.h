@@ -19,7 +19,7 @@ void dev_trim();
 struct BuildInfo { uint32_t segments = 0, triangles = 0, references = 0, nodes = 0; int levels = 0; };
 
 // cp_bvh.cu
-bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, const MeshDev &mesh, int maxSplit, cudaStream_t stream,
+bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int shapeCount, const MeshDev &mesh, int maxSplit, float leafSplitCost, cudaStream_t stream,
                BVHDev &out, BuildInfo &info, std::string &err);
 
 // cp_mesh.cu
@@ -33,7 +33,9 @@ void pack_vertices(const float *d_xyz, const uint8_t *d_starts, uint32_t n, uint
 struct MarschnerTables { float4 *tab = nullptr; float *cdf = nullptr; float *sums = nullptr; float *pdf = nullptr; };
 bool build_marschner_tables(float eta, float betaR, const float sigmaA[3], const float *glPoints140, const float *glWeights140,
                             cudaStream_t stream, MarschnerTables &out, std::string &err);
-struct EnvTables { float4 *texels = nullptr; float *cdfCols = nullptr; float *cdfRows = nullptr; float *rowWeights = nullptr; float normalization = 0; };
+struct EnvTables { float4 *texels = nullptr; float *cdfCols = nullptr; float *cdfRows = nullptr; float *rowWeights = nullptr; float normalization = 0;
+                   float4 *mipTexels = nullptr; EnvMipInfo *mipInfo = nullptr; };
+void quantize_texels(const float *d_rgb, int n, float4 *d_texels, cudaStream_t stream);      // fp32 RGB -> half-quantised float4 (cp_tables.cu)
 bool build_env_tables(const float *d_rgb, int w, int h, cudaStream_t stream, EnvTables &out, std::string &err);
 
 // cp_host_data.cpp -- host-side set-up that stays on the CPU (file parsing, tiny tables)
@@ -52,6 +54,10 @@ struct MeshFileData { std::vector<float> xyz, normals /* empty = face normals */
 bool load_rgbe_file(const std::string &path, std::vector<float> &rgb, int &w, int &h, std::string &err);
 bool mat4_invert_f32(const float *a, float *out);     // Matrix<4,4,float>::invert of the reference (matrix.inl:138-193), row-major
 bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNormals, bool flipNormals, bool flipTexCoords, MeshFileData &out, std::string &err);
+
+// cp_host_mip.cpp -- Lanczos MIP pyramid of the environment map + EWA weight table (mipmap.h:180-302)
+struct EnvMipLevel { int w = 0, h = 0; std::vector<float> rgb; };
+void build_env_pyramid(const float *rgb, int w, int h, std::vector<EnvMipLevel> &levels, float lut[64]);
 
 // cp_host_sunsky.cpp
 struct SunSkyParams { float turbidity = 3, albedo[3] = {0.2f, 0.2f, 0.2f}, sunDirection[3] = {0, 1, 0}, skyScale = 1, sunScale = 1, sunRadiusScale = 1, stretch = 1; int resolution = 512; };

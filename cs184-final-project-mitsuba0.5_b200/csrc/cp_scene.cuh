@@ -29,12 +29,24 @@ struct BVHDev {
     uint32_t nodeCount, primCount;
 };
 
+// MIP levels above level 0 (TMIPMap::m_pyramid, m_sizeRatio, m_weightLut: include/mitsuba/render/mipmap.h:245-302)
+#define CP_ENV_MAX_LEVELS 18
+struct EnvMipInfo {
+    int levels;                                  // including level 0
+    int w[CP_ENV_MAX_LEVELS], h[CP_ENV_MAX_LEVELS];
+    uint32_t offset[CP_ENV_MAX_LEVELS];          // level l >= 1 starts at mipTexels + offset[l]
+    float ratioX[CP_ENV_MAX_LEVELS], ratioY[CP_ENV_MAX_LEVELS];
+    float lut[64];                               // EWA Gaussian weights
+};
+
 struct EnvDev {
     int w, h;
     const float4 *texels;       // half-quantised RGB stored as exact fp32 (envmap.cpp:102-103)
     const float *cdfCols;       // (w+1) x h
     const float *cdfRows;       // h+1
     const float *rowWeights;    // h
+    const float4 *mipTexels;    // levels 1.. of the Lanczos pyramid, half-quantised like level 0 (camera rays that miss: EWA lookups)
+    const EnvMipInfo *mip;
     float normalization, scale;
     float pixelSizeX, pixelSizeY;
     float toWorld[9], toLocal[9]; // 3x3 linear parts (directions only)

@@ -7,12 +7,21 @@
 //   Scene::sampleEmitterDirect           src/librender/scene.cpp:828-853        (shadow ray [Epsilon, dist(1-ShadowEpsilon)])
 //   ImageBlock::put                      include/mitsuba/render/imageblock.h:144-186 (discretised filter splat)
 // No fused multiply-adds here: the reference's x86 build has none, and the Marschner lobes amplify last-bit differences.
+//
+// This file is compiled twice (csrc/Makefile): as is -- the strict build, every elementary function correctly rounded, bit-identical
+// to the oracle -- and with -DCP_FAST_MATH, where the calls that are not amplified use the fp32 CUDA functions (cp_common.cuh) and
+// only the shading kernel is emitted, under the name launch_shade_fast.  A context picks one at run time (cudapath_set_math_mode).
 #include "cp_host.h"
 #include "cp_env.cuh"
 #include "cp_camera.cuh"
 #include "cp_wavefront.h"
+#ifdef CP_FAST_MATH
+#define k_shade k_shade_fast
+#define launch_shade launch_shade_fast
+#endif
 
 namespace cp {
+#ifndef CP_FAST_MATH
 
 __global__ void __launch_bounds__(256) k_raygen(SceneDev S, WaveParams wp, PathQueue q, float4 *liAcc, uint32_t n, uint32_t *initSlot) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -34,6 +43,8 @@ __global__ void __launch_bounds__(256) k_raygen(SceneDev S, WaveParams wp, PathQ
     q.thr[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     q.id[i] = make_uint2(i, F_FIRST | 1u);                 // depth starts at 1 (integrator.h:218-224)
 }
+
+#endif // !CP_FAST_MATH
 
 __device__ __forceinline__ float mi_weight(float pdfA, float pdfB) { pdfA *= pdfA; pdfB *= pdfB; return pdfA / (pdfA + pdfB); } // path.cpp:296-300
 
@@ -160,6 +171,7 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
     warp_append(counters + 4, countOnlyShadow);
 }
 
+#ifndef CP_FAST_MATH
 // imageblock.h:144-186 with offset 0 / border 0 (the film itself, ldrfilm.cpp:226-228): 5 channels R,G,B,alpha,weight
 __device__ __forceinline__ void film_put(const FilmDev &F, float *film, int W, int H, float posx, float posy, const V3 &spec, float alpha,
                                          unsigned long long *dropped) {
@@ -205,11 +217,13 @@ __global__ void k_splat_batch(SceneDev S, const float *__restrict__ pos, const f
 void launch_raygen(const SceneDev &S, const WaveParams &wp, PathQueue q, float4 *liAcc, uint32_t n, uint32_t *initSlot, cudaStream_t stream) {
     k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(S, wp, q, liAcc, n, initSlot);
 }
+#endif // !CP_FAST_MATH
 void launch_shade(const SceneDev &S, const WaveParams &wp, PathQueue in, const uint32_t *nPtr, uint32_t nUpper, const float4 *hitPT, const uint32_t *hitPrim, PathQueue out,
                   ShadowQueue sq, float4 *liAcc, uint32_t *counters, unsigned long long *unsupportedLookups, cudaStream_t stream) {
     if (nUpper == 0) return;
     k_shade<<<(nUpper + 127) / 128, 128, 0, stream>>>(S, wp, in, nPtr, hitPT, hitPrim, out, sq, liAcc, counters, unsupportedLookups);
 }
+#ifndef CP_FAST_MATH
 void launch_splat(const SceneDev &S, const WaveParams &wp, const float4 *liAcc, uint32_t n, float *film, unsigned long long *dropped, cudaStream_t stream) {
     k_splat<<<(n + 255) / 256, 256, 0, stream>>>(S, wp, liAcc, n, film, dropped);
 }
@@ -222,5 +236,6 @@ bool splat_batch(const SceneDev &S, const float *d_pos, const float *d_rgb, cons
     CKW(cudaGetLastError());
     return true;
 }
+#endif // !CP_FAST_MATH
 
 } // namespace cp

@@ -147,6 +147,7 @@ __global__ void k_env_quantize(const float *__restrict__ rgb, int n, float4 *tex
     float r = fmaxf(rgb[3 * i], 0.0f), g = fmaxf(rgb[3 * i + 1], 0.0f), b = fmaxf(rgb[3 * i + 2], 0.0f); // mipmap.h:232-240 clamps negatives
     texels[i] = make_float4(__half2float(__float2half_rn(r)), __half2float(__float2half_rn(g)), __half2float(__float2half_rn(b)), 0.0f);
 }
+void quantize_texels(const float *d_rgb, int n, float4 *d_texels, cudaStream_t stream) { if (n > 0) k_env_quantize<<<(n + 255) / 256, 256, 0, stream>>>(d_rgb, n, d_texels); }
 // one thread per row: conditional CDF over luminance (envmap.cpp:284-299)
 __global__ void k_env_rows(const float4 *__restrict__ texels, int w, int h, float *cdfCols, float *colSums) {
     int y = blockIdx.x * blockDim.x + threadIdx.x;

@@ -186,8 +186,31 @@ void Wavefront::release() {
 bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t sampleBegin, uint32_t sampleEnd, float *d_film,
                        uint32_t waveSize, bool collectStats, bool profileStages, cudaStream_t stream, RenderStats &rs, std::string &err) {
     if (sampleEnd <= sampleBegin) return true;
+    WaveParams wp;
+    wp.filmW = (uint32_t) S.cam.filmW; wp.filmH = (uint32_t) S.cam.filmH;
+    wp.tilesX = (wp.filmW + 7) / 8;
+    uint64_t realPix = (uint64_t) wp.filmW * wp.filmH;           // pixels this context renders
+    if (shardCount <= 1) wp.pixPadded = (uint64_t) wp.tilesX * ((wp.filmH + 7) / 8) * 64;
+    else {
+        const uint32_t blocksX = (wp.filmW + 63) / 64, blocksY = (wp.filmH + 63) / 64;
+        wp.shardIndex = shardIndex; wp.shardCount = shardCount;
+        wp.shardSkew = shardCount % 3u == 0u ? 1u : 3u;         // coprime with the shard count for 2, 4, 8 (and 1 otherwise): diagonal bands
+        if (shardCount < 4) wp.shardSkew = 1;
+        wp.blocksPerRow = (blocksX + shardCount - 1) / shardCount;
+        wp.pixPadded = (uint64_t) wp.blocksPerRow * blocksY * 4096ull;
+        realPix = 0;
+        for (uint32_t by = 0; by < blocksY; ++by) {
+            const uint32_t first = (shardIndex + shardCount - (wp.shardSkew * by) % shardCount) % shardCount;
+            for (uint32_t k = 0; k < wp.blocksPerRow; ++k) {
+                const uint32_t bx = first + k * shardCount;
+                if (bx >= blocksX) continue;
+                realPix += (uint64_t) std::min(64u, wp.filmW - bx * 64u) * std::min(64u, wp.filmH - by * 64u);
+            }
+        }
+        if (wp.pixPadded == 0 || realPix == 0) return true;     // this shard owns no pixel
+    }
     {   // never allocate more queue slots than there are paths
-        const uint64_t tiles = (uint64_t) ((S.cam.filmW + 7) / 8) * ((S.cam.filmH + 7) / 8) * 64ull * (sampleEnd - sampleBegin);
+        const uint64_t tiles = wp.pixPadded * (sampleEnd - sampleBegin);
         if (tiles < waveSize) waveSize = (uint32_t) std::max<uint64_t>(tiles, 1024);
     }
     if (waveSize > 0x3fffffffu) waveSize = 0x3fffffffu;
@@ -207,11 +230,6 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
     void (*traceKernel)(SceneDev, WaveIO, const uint32_t *, uint32_t *, unsigned long long *, int *) =
         hasMesh ? (collectStats ? k_trace<true, true> : k_trace<false, true>) : (collectStats ? k_trace<true, false> : k_trace<false, false>);
     const unsigned fullGrid = persistent_grid((const void *) traceKernel);
-    WaveParams wp;
-    wp.filmW = (uint32_t) S.cam.filmW; wp.filmH = (uint32_t) S.cam.filmH;
-    wp.tilesX = (wp.filmW + 7) / 8;
-    const uint32_t tilesY = (wp.filmH + 7) / 8;
-    wp.pixPadded = (uint64_t) wp.tilesX * tilesY * 64;
     wp.sampleBegin = sampleBegin;
     wp.seedLo = (uint32_t) seed; wp.seedHi = (uint32_t) (seed >> 32);
     wp.diffScale = 1.0f / sqrtf((float) spp);
@@ -261,7 +279,7 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
             }
             end();
             begin(1);
-            if (ubClosest) launch_shade(S, wp, q[cur], prevSlot, ubClosest, hitPT, hitPrim, q[cur ^ 1], sq, liAcc, slot, stats + 4, stream);
+            if (ubClosest) (fastMath ? launch_shade_fast : launch_shade)(S, wp, q[cur], prevSlot, ubClosest, hitPT, hitPrim, q[cur ^ 1], sq, liAcc, slot, stats + 4, stream);
             end();
             CKW(cudaMemcpyAsync(hCounters + 8 * (bounce % CP_CTR_RING), slot, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, stream));
             CKW(cudaEventRecord(slotEvent[bounce % CP_CTR_RING], stream));
@@ -297,7 +315,7 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
     rs.nodesVisited += hs[0]; rs.primsTested += hs[1]; rs.shadowNodesVisited += hs[2]; rs.shadowPrimsTested += hs[3]; rs.unsupportedLookups += hs[4]; rs.droppedSamples += hs[5];
     rs.fullTests += hs[6]; rs.shadowFullTests += hs[7];
     // the invalid padding "paths" (image sizes that are not multiples of 8) are not camera paths
-    const uint64_t realPix = (uint64_t) wp.filmW * wp.filmH, padPix = wp.pixPadded - realPix;
+    const uint64_t padPix = wp.pixPadded - realPix;
     rs.paths -= padPix * (uint64_t) (sampleEnd - sampleBegin);
     rs.rays -= padPix * (uint64_t) (sampleEnd - sampleBegin);
     return true;

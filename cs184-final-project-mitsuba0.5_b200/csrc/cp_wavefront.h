@@ -24,6 +24,10 @@ struct WaveParams {
     uint64_t waveBase = 0, pixPadded = 0;
     uint32_t filmW = 0, filmH = 0, tilesX = 0, sampleBegin = 0, seedLo = 0, seedHi = 0;
     float diffScale = 1.0f;
+    // pixel shard (cudapath_set_pixel_shard): this context renders the 64x64-pixel blocks owned by shard `shardIndex` of `shardCount`.
+    // Block (bx, by) of the grid -- its width padded to a multiple of shardCount -- belongs to shard (bx + shardSkew * by) mod shardCount,
+    // so every row of blocks gives each shard blocksPerRow blocks and the owners form diagonal bands across the image.
+    uint32_t shardIndex = 0, shardCount = 1, shardSkew = 1, blocksPerRow = 0;
 };
 struct RenderStats {
     uint64_t paths = 0, rays = 0, shadowRays = 0, launches = 0, bounces = 0, hostSyncs = 0;
@@ -52,6 +56,8 @@ struct Wavefront {
     uint32_t *sortKeys[2] = {nullptr, nullptr}, *sortVals[2] = {nullptr, nullptr};
     void *sortTemp = nullptr; size_t sortTempBytes = 0;
     bool sortRays = true;
+    uint32_t shardIndex = 0, shardCount = 1;    // pixel shard of this context (WaveParams)
+    bool fastMath = true;               // shade with the -DCP_FAST_MATH build of cp_shade.cu (cudapath_set_math_mode)
     uint32_t runAheadMax = 1u << 22;    // bounces with more rays than this are sized from exact counters (one host wait), smaller ones run ahead
     // Integrator::cancel() (include/mitsuba/render/integrator.h:76-84) may be called from another thread while render() blocks: the flag
     // is looked at once per bounce (after the host has read the queue counters); a cancelled render returns false with "render cancelled".
@@ -91,9 +97,18 @@ __device__ __forceinline__ bool path_to_pixel(const WaveParams &wp, uint64_t g, 
     const uint64_t s = g / wp.pixPadded;
     const uint32_t rank = (uint32_t) (g - s * wp.pixPadded);
     const uint32_t tile = rank >> 6, within = rank & 63u;
-    x = (tile % wp.tilesX) * 8u + (within & 7u);
-    y = (tile / wp.tilesX) * 8u + (within >> 3);
     samp = wp.sampleBegin + (uint32_t) s;
+    if (wp.shardCount == 1u) {
+        x = (tile % wp.tilesX) * 8u + (within & 7u);
+        y = (tile / wp.tilesX) * 8u + (within >> 3);
+    } else {      // owned 64x64 block -> 8x8 tile inside it -> pixel
+        const uint32_t block = tile >> 6, t = tile & 63u;
+        const uint32_t by = block / wp.blocksPerRow, k = block - by * wp.blocksPerRow;
+        const uint32_t first = (wp.shardIndex + wp.shardCount - (wp.shardSkew * by) % wp.shardCount) % wp.shardCount;
+        const uint32_t bx = first + k * wp.shardCount;
+        x = bx * 64u + (t & 7u) * 8u + (within & 7u);
+        y = by * 64u + (t >> 3) * 8u + (within >> 3);
+    }
     return x < wp.filmW && y < wp.filmH;
 }
 #endif
@@ -103,16 +118,25 @@ void launch_raygen(const SceneDev &S, const WaveParams &wp, PathQueue q, float4 
 // nPtr: device word holding the number of paths in `in` (<= nUpper, which only sizes the grid)
 void launch_shade(const SceneDev &S, const WaveParams &wp, PathQueue in, const uint32_t *nPtr, uint32_t nUpper, const float4 *hitPT, const uint32_t *hitPrim, PathQueue out,
                   ShadowQueue sq, float4 *liAcc, uint32_t *counters, unsigned long long *unsupportedLookups, cudaStream_t stream);
+void launch_shade_fast(const SceneDev &S, const WaveParams &wp, PathQueue in, const uint32_t *nPtr, uint32_t nUpper, const float4 *hitPT, const uint32_t *hitPrim, PathQueue out,
+                       ShadowQueue sq, float4 *liAcc, uint32_t *counters, unsigned long long *unsupportedLookups, cudaStream_t stream);      // the -DCP_FAST_MATH build of cp_shade.cu
 void launch_splat(const SceneDev &S, const WaveParams &wp, const float4 *liAcc, uint32_t n, float *film, unsigned long long *dropped, cudaStream_t stream);
 bool splat_batch(const SceneDev &S, const float *d_pos, const float *d_rgb, const float *d_alpha, uint64_t n, float *d_film, cudaStream_t stream, std::string &err);
 
 // cp_batch.cu -- parity hooks / stage micro-benchmarks on device-resident batches
 bool bsdf_eval_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err, bool discrete = false);
 bool bsdf_sample_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_sample, const float *d_extra /* 4 per tuple or null */, float *d_wo, float *d_weight, float *d_pdf, int32_t *d_type, cudaStream_t s, std::string &err);
+bool bsdf_eval_world_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_frames, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err);
+bool bsdf_eval_world_batch_fast(const SceneDev &S, int bsdf, uint64_t n, const float *d_frames, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err);
+bool bsdf_eval_batch_fast(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err, bool discrete = false);
+bool bsdf_sample_batch_fast(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_sample, const float *d_extra, float *d_wo, float *d_weight, float *d_pdf, int32_t *d_type, cudaStream_t s, std::string &err);
+bool env_eval_batch_fast(const SceneDev &S, uint64_t n, const float *d_dir, float *d_rgb, float *d_pdf, cudaStream_t s, std::string &err);
+bool env_sample_batch_fast(const SceneDev &S, uint64_t n, const float *d_ref, const float *d_sample, float *d_dir, float *d_value, float *d_pdfDist, cudaStream_t s, std::string &err);
 bool intersect_batch(const SceneDev &S, uint64_t n, const float *d_o, const float *d_d, const float *d_mint, const float *d_maxt, int anyHit, bool stats,
                      int32_t *d_shape, uint32_t *d_prim, float *d_t, float *d_rec /*15 floats per ray or null*/, unsigned long long *d_stats, cudaStream_t s, std::string &err);
 void fill_records_batch(const SceneDev &S, uint64_t n, const float *d_d, const int32_t *d_shape, float *d_rec, cudaStream_t s);
 bool env_eval_batch(const SceneDev &S, uint64_t n, const float *d_dir, float *d_rgb, float *d_pdf, cudaStream_t s, std::string &err);
+bool env_eval_filtered_batch(const SceneDev &S, uint64_t n, const float *d_dir, const float *d_rx, const float *d_ry, float *d_rgb, cudaStream_t s, std::string &err);
 bool env_sample_batch(const SceneDev &S, uint64_t n, const float *d_ref, const float *d_sample, float *d_dir, float *d_value, float *d_pdfDist, cudaStream_t s, std::string &err);
 bool read_bandwidth_probe(size_t bytes, int iters, cudaStream_t s, double &gbs, std::string &err);
 bool camera_rays_batch(const SceneDev &S, uint64_t n, const float *d_pxy, float *d_o, float *d_d, float *d_minmax, cudaStream_t s, std::string &err);

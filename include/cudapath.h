@@ -126,6 +126,11 @@ int cudapath_set_envmap(cudapath_ctx *ctx, const float *rgb, int width, int heig
 int cudapath_set_envmap_file(cudapath_ctx *ctx, const char *filename, const float to_world[16], float scale);
 /* The reader alone (host only): width/height always, pixels (top-down RGB fp32, 3*w*h floats) when out_rgb is not NULL. */
 int cudapath_load_rgbe(const char *filename, float *out_rgb, int *out_width, int *out_height);
+/* Host only (no context, no GPU): level `level` of the MIP pyramid the envmap emitter builds from a lat-long fp32 bitmap -- TMIPMap's
+ * progressive downsampling with the 2-lobed Lanczos filter, ERepeat along u / EClamp along v, clamped to [0, inf)
+ * (include/mitsuba/render/mipmap.h:180-271, src/libcore/bitmap.cpp:2230-2328, include/mitsuba/core/rfilter.h:107-460,
+ * src/rfilters/lanczos.cpp:42-55) -- as fp32 BEFORE the half quantisation of the stored texels.  Returns the number of levels. */
+int cudapath_env_pyramid_level(const float *rgb, int width, int height, int level, int *out_width, int *out_height, float *out_rgb);
 /* `sunsky` emitter: SunSkyEmitter ctor, src/emitters/sunsky.cpp:100-236 (bakes the map on the host, then cudapath_set_envmap). */
 int cudapath_set_sunsky(cudapath_ctx *ctx, float turbidity, const float albedo[3], const float sun_direction[3], float sky_scale,
                         float sun_scale, float sun_radius_scale, int resolution);
@@ -158,6 +163,14 @@ int cudapath_render(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sam
 /* Same, accumulating into a caller-provided DEVICE buffer on a caller-provided CUDA stream (cudaStream_t as void*, may be 0);
  * the buffer must be zeroed by the caller before the first range.  Used with torch/NCCL for the multi-GPU film reduce. */
 int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *film_dev, void *stream);
+/* Pixel-space sharding (the "image tiles" of BlockedRenderProcess, src/librender/renderproc.cpp:117-182, at 64x64 granularity): after
+ * this call cudapath_render / cudapath_render_dev only trace the paths of the pixel blocks owned by shard `shard_index` of `shard_count`
+ * (blocks are dealt out in diagonal bands, so every shard sees every part of the image); all other pixels stay zero except for the
+ * reconstruction filter's one-pixel border, so the films of the `shard_count` shards ADD UP to the full image exactly like the films of
+ * disjoint sample ranges do.  Keeping all sample indices of a pixel on one device keeps the ray density per region of the scene --
+ * and with it the cache hit rates of the traversal -- at the level of the single-device render, which sample-range sharding does
+ * not.  (1, 1)-style reset: shard_index 0 of shard_count 1. */
+int cudapath_set_pixel_shard(cudapath_ctx *ctx, uint32_t shard_index, uint32_t shard_count);
 /* Integrator::cancel() (include/mitsuba/render/integrator.h:76-84, SamplingIntegrator::cancel src/librender/integrator.cpp:90-93; reached
  * from RenderJob::cancel, include/mitsuba/render/renderjob.h:81, on another thread while render() blocks and then returns false).  The ONLY entry point that may be called concurrently with a render of the same
  * context.  The running (or next) cudapath_render / cudapath_render_dev returns -1 with the message "render cancelled" within one
@@ -176,6 +189,16 @@ int cudapath_develop_ldr(const float *film, int width, int height, float gamma, 
 /* Tunables: wave size in paths (0 = default), collect traversal statistics (slower, counting kernels),
  * profile_stages (CUDA events around every stage launch). */
 int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stats, int profile_stages);
+
+/* Math mode of the shading stages (BSDF eval / pdf / sample, emitter lookups).  strict = 1: every elementary function is correctly
+ * rounded fp32 (evaluated in fp64) -- bit-identical to a faithful CPU evaluation, the mode the path-replay parity tests run in.
+ * strict = 0 (default; the environment variable CUDAPATH_MATH=strict changes the default of new contexts): only the amplified chain
+ * of the Marschner lobes (asin of the incident inclination, sin / cos of the three shifted lobe angles that M() multiplies by 1/v)
+ * keeps its exact bits; every other call uses the 1-2 ulp fp32 CUDA functions.  BSDF values then stay within ~1e-6 relative of the
+ * strict mode (BASELINE.json asks for 1e-4 against the reference's CPU build, whose own libm is only defined to an ulp).
+ * Ray queries, the FP64 cylinder test, camera rays and the film are the same in both modes.  get: 1 strict, 0 fast. */
+int cudapath_set_math_mode(cudapath_ctx *ctx, int strict);
+int cudapath_get_math_mode(cudapath_ctx *ctx);
 
 /* BVH build tunable: a long thin segment is referenced by up to max_split boxes cut along its axis (default 8; 1 = off). */
 int cudapath_set_build_options(cudapath_ctx *ctx, int max_split);
@@ -212,6 +235,11 @@ int cudapath_get_film_output(cudapath_ctx *ctx, int *out_hdr, float *out_gamma, 
 int cudapath_bsdf_eval_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf);
 /* The same with measure = EDiscrete (include/mitsuba/render/common.h:56-67): non-zero only for discrete components (`thindielectric`) */
 int cudapath_bsdf_eval_batch_discrete(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, float *out_eval, float *out_pdf);
+/* BSDF::eval + BSDF::pdf from WORLD-space directions and one shading frame per tuple (frames: s, t, n = 9 floats): the directions go
+ * through Frame::toLocal (include/mitsuba/core/frame.h:55-85) on the device, as Intersection::toLocal does for its.wi / bRec.wo
+ * (include/mitsuba/render/skdtree.h:426-427, src/integrators/path/path.cpp:186).  The "random world frame" batch of config 5. */
+int cudapath_bsdf_eval_batch_world(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *frames, const float *wi_world, const float *wo_world,
+                                   float *out_eval, float *out_pdf);
 /* BSDF::sample: out_type = sampledType | sampledComponent << 8 */
 int cudapath_bsdf_sample_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo,
                                float *out_weight, float *out_pdf, int32_t *out_type);
@@ -226,6 +254,13 @@ int cudapath_bsdf_sample_batch_ex(cudapath_ctx *ctx, int bsdf_id, uint64_t n, co
 int cudapath_intersect_batch(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,
                              int any_hit, int32_t *out_shape, uint32_t *out_prim, float *out_t, float *out_record);
 int cudapath_env_eval_batch(cudapath_ctx *ctx, uint64_t n, const float *direction, float *out_rgb, float *out_pdf);
+/* Emitter::evalEnvironment for rays WITH differentials (camera rays that leave the scene): MIPMap::eval with the EWA filter over the
+ * 2-lobed-Lanczos MIP pyramid, maxAnisotropy 10 (src/emitters/envmap.cpp:150-181,391-407; include/mitsuba/render/mipmap.h:629-836).
+ * rx_direction / ry_direction are the offset ray directions of RayDifferential. */
+int cudapath_env_eval_filtered_batch(cudapath_ctx *ctx, uint64_t n, const float *direction, const float *rx_direction, const float *ry_direction, float *out_rgb);
+/* One level of the environment map's MIP pyramid as stored (half-quantised texels, width*height*3 floats; out_rgb may be NULL to query
+ * the size).  Returns the number of levels. */
+int cudapath_env_mip_level(cudapath_ctx *ctx, int level, int *out_width, int *out_height, float *out_rgb);
 int cudapath_env_sample_batch(cudapath_ctx *ctx, uint64_t n, const float *ref_point, const float *sample, float *out_direction,
                               float *out_value, float *out_pdf_dist);
 int cudapath_camera_rays_batch(cudapath_ctx *ctx, uint64_t n, const float *pixel_sample, float *out_origin, float *out_direction, float *out_mint_maxt);

@@ -2,7 +2,10 @@
 //
 // Environment emitter of the hair scenes:
 //   EnvironmentMap  src/emitters/envmap.cpp:260-329 (CDFs), :358-374, :380-410 (eval), :516-662 (sampling/pdf)
-//   MIPMap level-0 lookups  include/mitsuba/render/mipmap.h:503-596, filtered-lookup decision :629-700
+//   MIPMap  include/mitsuba/render/mipmap.h:180-302 (pyramid: progressive 2-lobed-Lanczos downsampling, EWA weight table),
+//           :503-596 (texel / box / bilinear lookups), :629-725 (eval: ellipse from the uv Jacobian, anisotropy clamp, level choice),
+//           :760-836 (evalEWA); Resampler src: include/mitsuba/core/rfilter.h:122-170,216-262,436-457; src/libcore/bitmap.cpp:2230-2328;
+//           src/rfilters/lanczos.cpp:42-55; math::log2 / hypot2 src/libcore/math.cpp:74-86,103-106
 //   SunSkyEmitter bake  src/emitters/sunsky.cpp:100-236, src/emitters/sky.cpp:219-256,413-447,
 //                       src/emitters/sunsky/sunmodel.h:90-105,206-222,316-371
 // The Hosek-Wilkie sky model itself is NOT restated: the oracle calls the reference's own
@@ -32,7 +35,118 @@ struct EnvMap {
     float pixelSizeX = 0, pixelSizeY = 0;
     M44 toWorld = M44::identity(), toLocal = M44::identity();
     BSphere sceneBSphere;
-    mutable long unsupportedFiltered = 0; // camera-ray lookups whose footprint would need the MIP pyramid/EWA
+    mutable long unsupportedFiltered = 0; // kept for the statistics interface: always 0 since the pyramid exists
+    // MIP pyramid: level 0 = `texels`; levels 1.. half-quantised like level 0 (TMIPMap<Spectrum, SpectrumHalf>)
+    struct Level { int w = 0, h = 0; std::vector<uint16_t> t; };
+    std::vector<Level> levels;            // levels[0] is left empty (w, h only)
+    float weightLut[64];
+
+    // LanczosSincFilter::eval with 2 lobes (lanczos.cpp:42-55)
+    static float lanczos(float x) {
+        const float radius = 2.0f;
+        x = std::abs(x);
+        if (x < kEpsilon) return 1.0f;
+        else if (x > radius) return 0.0f;
+        float x1 = kPi * x, x2 = x1 / radius;
+        return (cr::sin(x1) * cr::sin(x2)) / (x1 * x2);
+    }
+    // Resampler<float>(rfilter, bc, sourceRes, targetRes) for targetRes < sourceRes + resampleAndClamp(min 0, max inf) over one line
+    static void resampleLine(const float *source, size_t sourceStride, int sourceRes, float *target, size_t targetStride, int targetRes, bool repeat) {
+        const float scale = (float) sourceRes / (float) targetRes, invScale = 1 / scale, filterRadius = 2.0f * scale;
+        const int taps = ceilToInt(filterRadius * 2);
+        std::vector<float> weights(taps);
+        for (int i = 0; i < targetRes; i++) {
+            float center = (i + 0.5f) / targetRes * sourceRes;
+            int start = floorToInt(center - filterRadius + 0.5f);
+            float sum = 0;
+            for (int j = 0; j < taps; j++) {
+                float pos = start + j + 0.5f - center;
+                float weight = lanczos(pos * invScale);
+                weights[j] = weight; sum += weight;
+            }
+            float normalization = 1.0f / sum;
+            for (int j = 0; j < taps; j++) weights[j] = weights[j] * normalization;
+            for (int ch = 0; ch < 3; ++ch) {
+                float result = 0;
+                for (int j = 0; j < taps; ++j) {
+                    int pos = start + j;
+                    if (pos < 0 || pos >= sourceRes) pos = repeat ? modulo(pos, sourceRes) : clampi(pos, 0, sourceRes - 1);
+                    result += source[sourceStride * 3 * (size_t) pos + ch] * weights[j];
+                }
+                target[targetStride * 3 * (size_t) i + ch] = std::min(kInf, std::max(0.0f, result));
+            }
+        }
+    }
+    // mipmap.h:245-271 + 296-302: every level from the fp32 image of the level above it
+    void buildPyramid(std::vector<float> img) {
+        levels.clear(); levels.push_back(Level()); levels[0].w = w; levels[0].h = h;
+        int sx = w, sy = h;
+        while (sx > 1 || sy > 1) {
+            const int tx = std::max(1, (sx + 1) / 2), ty = std::max(1, (sy + 1) / 2);
+            std::vector<float> tmp, out((size_t) 3 * tx * ty);
+            const std::vector<float> *src = &img;
+            if (sx != tx) {            // horizontal pass, ERepeat
+                tmp.resize((size_t) 3 * tx * sy);
+                for (int y = 0; y < sy; ++y) resampleLine(img.data() + (size_t) 3 * y * sx, 1, sx, tmp.data() + (size_t) 3 * y * tx, 1, tx, true);
+                src = &tmp;
+            }
+            if (sy != ty) {            // vertical pass, EClamp
+                for (int x = 0; x < tx; ++x) resampleLine(src->data() + (size_t) 3 * x, (size_t) tx, sy, out.data() + (size_t) 3 * x, (size_t) tx, ty, false);
+            } else out = *src;
+            Level L; L.w = tx; L.h = ty; L.t.resize(out.size());
+            for (size_t i = 0; i < out.size(); ++i) L.t[i] = float_to_half(out[i]);
+            levels.push_back(std::move(L));
+            img.swap(out); sx = tx; sy = ty;
+        }
+        for (int i = 0; i < 64; ++i) { float r2 = (float) i / (float) (64 - 1); weightLut[i] = cr::exp(-2.0f * r2) - cr::exp(-2.0f); }
+    }
+    V3 evalTexel(int level, int x, int y) const {
+        if (level == 0) return evalTexel(x, y);
+        const Level &L = levels[level];
+        if (x < 0 || x >= L.w) x = modulo(x, L.w);
+        if (y < 0 || y >= L.h) y = clampi(y, 0, L.h - 1);
+        const uint16_t *p = &L.t[3 * ((size_t) y * L.w + x)];
+        return V3(half_to_float(p[0]), half_to_float(p[1]), half_to_float(p[2]));
+    }
+    V3 evalBox(int level, float uvx, float uvy) const { return evalTexel(level, floorToInt(uvx * levels[level].w), floorToInt(uvy * levels[level].h)); }
+    V3 evalBilinear(int level, float uvx, float uvy) const {
+        if (!std::isfinite(uvx) || !std::isfinite(uvy)) return V3(0.0f);
+        if (level >= (int) levels.size()) return evalBox((int) levels.size() - 1, uvx, uvy);
+        const int lw = levels[level].w, lh = levels[level].h;
+        float u = uvx * lw - 0.5f, v = uvy * lh - 0.5f;
+        int xPos = floorToInt(u), yPos = floorToInt(v);
+        float dx1 = u - xPos, dx2 = 1.0f - dx1, dy1 = v - yPos, dy2 = 1.0f - dy1;
+        return evalTexel(level, xPos, yPos) * dx2 * dy2 + evalTexel(level, xPos, yPos + 1) * dx2 * dy1
+             + evalTexel(level, xPos + 1, yPos) * dx1 * dy2 + evalTexel(level, xPos + 1, yPos + 1) * dx1 * dy1;
+    }
+    // mipmap.h:760-836
+    V3 evalEWA(int level, float uvx, float uvy, float A, float B, float C) const {
+        if (!std::isfinite(A + B + C + uvx + uvy)) return V3(0.0f);
+        if (level >= (int) levels.size()) return evalBox((int) levels.size() - 1, uvx, uvy);
+        const int lw = levels[level].w, lh = levels[level].h;
+        float u = uvx * lw - 0.5f, v = uvy * lh - 0.5f;
+        const float ratioX = (float) lw / (float) w, ratioY = (float) lh / (float) h;
+        A /= ratioX * ratioX; B /= ratioX * ratioY; C /= ratioY * ratioY;
+        float invDet = 1.0f / (-B * B + 4.0f * A * C), deltaU = 2.0f * std::sqrt(C * invDet), deltaV = 2.0f * std::sqrt(A * invDet);
+        int u0 = ceilToInt(u - deltaU), u1 = floorToInt(u + deltaU), v0 = ceilToInt(v - deltaV), v1 = floorToInt(v + deltaV);
+        float As = A * 64, Bs = B * 64, Cs = C * 64;
+        V3 result(0.0f); float denominator = 0.0f;
+        float ddq = 2 * As, uu0 = (float) u0 - u;
+        for (int vt = v0; vt <= v1; ++vt) {
+            const float vv = (float) vt - v;
+            float q = As * uu0 * uu0 + (Bs * uu0 + Cs * vv) * vv;
+            float dq = As * (2 * uu0 + 1) + Bs * vv;
+            for (int ut = u0; ut <= u1; ++ut) {
+                if (q < 64.0f) {
+                    uint32_t qi = (uint32_t) q;
+                    if (qi < 64) { const float weight = weightLut[(int) q]; result = result + evalTexel(level, ut, vt) * weight; denominator += weight; }
+                }
+                q += dq; dq += ddq;
+            }
+        }
+        if (denominator == 0) return evalBilinear(level, uvx, uvy);
+        return result / denominator;
+    }
 
     V3 texel(int x, int y) const { const uint16_t *p = &texels[3 * ((size_t) y * w + x)]; return V3(half_to_float(p[0]), half_to_float(p[1]), half_to_float(p[2])); }
     // mipmap.h:503-560 with bcu=ERepeat, bcv=EClamp (envmap.cpp:167-170)
@@ -57,6 +171,7 @@ struct EnvMap {
         if (!invert(toWorld, toLocal)) throw std::runtime_error("oracle: singular envmap transform");
         texels.resize((size_t) 3 * w * h);
         for (size_t i = 0; i < texels.size(); ++i) texels[i] = float_to_half(std::max(rgb[i], 0.0f)); // mipmap.h:232-240 clamps negatives
+        { std::vector<float> base(rgb, rgb + (size_t) 3 * w * h); for (float &v : base) v = std::max(v, 0.0f); buildPyramid(std::move(base)); }
         cdfCols.assign((size_t) (w + 1) * h, 0.0f); cdfRows.assign(h + 1, 0.0f); rowWeights.assign(h, 0.0f);
         size_t colPos = 0, rowPos = 0;
         float rowSum = 0.0f;
@@ -107,23 +222,43 @@ struct EnvMap {
         }
         return value * scale;
     }
-    // mipmap.h:629-700 (EWA filter type, maxAnisotropy 10).  Every branch that ends in
-    // evalBilinear(0, uv) is restated; footprints >= 1 texel need the Lanczos MIP pyramid, which
-    // the oracle does not build -- those lookups are counted and answered at level 0.
+    // MIPMap::eval, mipmap.h:629-725 (EWA filter type, maxAnisotropy 10)
+    static float log2f32(float x) { const float invLn2 = 1.0f / cr::log(2.0f); return cr::log(x) * invLn2; }       // math.cpp:103-106
+    static float hypot2(float a, float b) {                                                                         // math.cpp:74-86
+        float r;
+        if (std::abs(a) > std::abs(b)) { r = b / a; r = std::abs(a) * std::sqrt(1.0f + r * r); }
+        else if (b != 0.0f) { r = a / b; r = std::abs(b) * std::sqrt(1.0f + r * r); }
+        else r = 0.0f;
+        return r;
+    }
     V3 evalFiltered(float uvx, float uvy, float d0x, float d0y, float d1x, float d1y) const {
         float du0 = d0x * w, dv0 = d0y * h, du1 = d1x * w, dv1 = d1y * h;
         float A = dv0 * dv0 + dv1 * dv1, B = -2.0f * (du0 * dv0 + du1 * dv1), C = du0 * du0 + du1 * du1, F = A * C - B * B * 0.25f;
-        float root = cr::hypot(A - C, B), Aprime = 0.5f * (A + C - root), Cprime = 0.5f * (A + C + root);
+        float root = hypot2(A - C, B), Aprime = 0.5f * (A + C - root), Cprime = 0.5f * (A + C + root);
         float majorRadius = Aprime != 0 ? std::sqrt(F / Aprime) : 0, minorRadius = Cprime != 0 ? std::sqrt(F / Cprime) : 0;
         if (!(minorRadius > 0) || !(majorRadius > 0) || F < 0) {
-            float level = cr::log2(std::max(majorRadius, kEpsilon));
-            if (floorToInt(level) < 0) return evalBilinear(uvx, uvy);
-            unsupportedFiltered++;
-            return evalBilinear(uvx, uvy);
+            float level = log2f32(std::max(majorRadius, kEpsilon));
+            int ilevel = floorToInt(level);
+            if (ilevel < 0) return evalBilinear(0, uvx, uvy);
+            float a = level - ilevel;
+            return evalBilinear(ilevel, uvx, uvy) * (1.0f - a) + evalBilinear(ilevel + 1, uvx, uvy) * a;
         }
-        if (majorRadius < 1) return evalBilinear(uvx, uvy); // level = max(0, log2(minor)) = 0 since minor <= major < 1
-        unsupportedFiltered++;
-        return evalBilinear(uvx, uvy);
+        const float maxAnisotropy = 10.0f;
+        if (minorRadius * maxAnisotropy < majorRadius) {
+            minorRadius = majorRadius / maxAnisotropy;
+            float theta = 0.5f * (float) std::atan((double) (B / (A - C))), sinTheta, cosTheta;
+            cr::sincos(theta, &sinTheta, &cosTheta);
+            float a2 = majorRadius * majorRadius, b2 = minorRadius * minorRadius, sinTheta2 = sinTheta * sinTheta, cosTheta2 = cosTheta * cosTheta,
+                  sin2Theta = 2 * sinTheta * cosTheta;
+            A = a2 * cosTheta2 + b2 * sinTheta2; B = (a2 - b2) * sin2Theta; C = a2 * sinTheta2 + b2 * cosTheta2; F = a2 * b2;
+        }
+        float scaleF = 1.0f / F;
+        A *= scaleF; B *= scaleF; C *= scaleF;
+        float level = std::max(0.0f, log2f32(minorRadius));
+        int ilevel = (int) level;
+        float a = level - ilevel;
+        if (majorRadius < 1 || !(A > 0 && C > 0)) return evalBilinear(ilevel, uvx, uvy);
+        return evalEWA(ilevel, uvx, uvy, A, B, C) * (1.0f - a) + evalEWA(ilevel + 1, uvx, uvy, A, B, C) * a;
     }
 
     // envmap.cpp:657-662

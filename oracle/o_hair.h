@@ -349,9 +349,6 @@ struct Intersection {
     V3 wi;
 };
 
-#ifdef ORC_COUNT
-static unsigned long long g_cnt[4];
-#endif
 struct BVHNode { AABB box; uint32_t left, right; uint32_t first, count; }; // leaf if count>0
 
 struct Geometry {
@@ -635,9 +632,6 @@ struct Geometry {
             const Entry e = stack[--sp];
             if (!shadow && e.tnear > maxt) continue;
             if (e.node & 0x80000000u) {
-#ifdef ORC_COUNT
-                g_cnt[1]++;
-#endif
                 const FastRef &r = frefs[e.node & 0x7fffffffu];
                 const uint32_t rshape = r.shapeFlags >> 3;
                 if (r.shapeFlags & 1u) {
@@ -674,9 +668,6 @@ struct Geometry {
                 uint64_t &slot = mailbox[(r.iv * 2654435761u) >> 29];
                 if (slot == key) continue;
                 slot = key;
-#ifdef ORC_COUNT
-                g_cnt[2]++;
-#endif
                 const float hi = std::min(pmax[rshape], maxt);
                 if (!(hi > pmin[rshape])) continue;
                 float t; V3 p;
@@ -686,9 +677,6 @@ struct Geometry {
                 }
                 continue;
             }
-#ifdef ORC_COUNT
-            g_cnt[0]++;
-#endif
             const Wide &nd = wide[e.node];
             float tn[8], tf[8];
             for (int k = 0; k < 8; ++k) { tn[k] = mint; tf[k] = maxt; }

@@ -71,7 +71,23 @@ static inline D3 normalize(D3 a) { double r = 1.0 / std::sqrt(dot(a, a)); return
 // libm builds; several formulas on this path amplify that bit by O(1/v) = O(400).  The oracle therefore pins every
 // elementary function to its correctly rounded fp32 value (fp64 evaluation rounded once) -- any faithful libm agrees with
 // that to 1 ulp -- and the CUDA path does the same, so oracle and device can be compared almost bit for bit.
+// The timing build (liboracle_fast.so, -DORC_FAST) calls the platform's fp32 libm instead, as the reference's binaries do.
 namespace cr {
+#ifdef ORC_FAST
+static inline float sin(float x) { return ::sinf(x); }
+static inline float cos(float x) { return ::cosf(x); }
+static inline float tan(float x) { return ::tanf(x); }
+static inline float asin(float x) { return ::asinf(x); }
+static inline float acos(float x) { return ::acosf(x); }
+static inline float atan2(float y, float x) { return ::atan2f(y, x); }
+static inline float exp(float x) { return (float) std::exp((double) x); }        // math::fastexp / fastlog on Linux x86-64 (math.h:175-199)
+static inline float log(float x) { return (float) std::log((double) x); }
+static inline float log2(float x) { return ::log2f(x); }
+static inline float pow(float x, float y) { return ::powf(x, y); }
+static inline float sinh(float x) { return ::sinhf(x); }
+static inline float hypot(float x, float y) { return ::hypotf(x, y); }
+static inline void sincos(float x, float *s, float *c) { ::sincosf(x, s, c); }
+#else
 static inline float sin(float x) { return (float) std::sin((double) x); }
 static inline float cos(float x) { return (float) std::cos((double) x); }
 static inline float tan(float x) { return (float) std::tan((double) x); }
@@ -84,6 +100,8 @@ static inline float log2(float x) { return (float) std::log2((double) x); }
 static inline float pow(float x, float y) { return (float) std::pow((double) x, (double) y); }
 static inline float sinh(float x) { return (float) std::sinh((double) x); }
 static inline float hypot(float x, float y) { return (float) std::sqrt((double) x * x + (double) y * y); }
+static inline void sincos(float x, float *s, float *c) { *s = (float) std::sin((double) x); *c = (float) std::cos((double) x); }
+#endif
 }
 
 static inline float clampf(float v, float lo, float hi) { return std::min(hi, std::max(lo, v)); }
@@ -91,6 +109,7 @@ static inline int clampi(int v, int lo, int hi) { return std::min(hi, std::max(l
 static inline float safe_sqrt(float v) { return std::sqrt(std::max(0.0f, v)); }  // math.h:260
 static inline float safe_acos(float v) { return cr::acos(std::min(1.0f, std::max(-1.0f, v))); } // math.h:250
 static inline int floorToInt(float v) { return (int) std::floor(v); } // math.h:100
+static inline int ceilToInt(float v) { return (int) std::ceil(v); }   // math.h:105
 static inline int modulo(int a, int b) { int r = a % b; return (r < 0) ? r + b : r; } // math.h:67
 
 // src/libcore/util.cpp:592-601

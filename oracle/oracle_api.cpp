@@ -18,6 +18,8 @@
 #include "o_bsdf.h"
 #include "o_env.h"
 #include "o_render.h"
+#include <thread>
+#include <mutex>
 #include <dlfcn.h>
 #include <cstring>
 
@@ -27,13 +29,28 @@ static thread_local std::string g_err;
 #define ORC_TRY try {
 #define ORC_CATCH } catch (const std::exception &e) { g_err = e.what(); return -1; } catch (...) { g_err = "unknown error"; return -1; }
 
+// Batch entry points split their index range over the host's cores (each tuple / ray is independent; results are position-wise).
+template <class F> static void parallel_for(uint64_t n, F &&body) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char *e = getenv("ORC_THREADS")) nt = (unsigned) std::max(1, atoi(e));
+    if (nt < 2 || n < 4096) { body((uint64_t) 0, n); return; }
+    nt = (unsigned) std::min<uint64_t>(nt, n / 2048);
+    std::vector<std::thread> th;
+    std::exception_ptr error; std::mutex m;
+    const uint64_t chunk = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        const uint64_t b = t * chunk, e = std::min(n, b + chunk);
+        if (b >= e) break;
+        th.emplace_back([&, b, e]() { try { body(b, e); } catch (...) { std::lock_guard<std::mutex> g(m); error = std::current_exception(); } });
+    }
+    for (auto &t : th) t.join();
+    if (error) std::rethrow_exception(error);
+}
+
 extern "C" {
 
 // what accelerates the ray queries of this build (reported with the CPU baseline)
 const char *orc_accel_description() { return orc::Geometry::accelDescription(); }
-#ifdef ORC_COUNT
-void orc_counts(unsigned long long *out) { for (int i = 0; i < 4; ++i) { out[i] = orc::g_cnt[i]; orc::g_cnt[i] = 0; } }
-#endif
 const char *orc_last_error() { return g_err.c_str(); }
 
 void *orc_scene_create() { return new Scene(); }
@@ -237,12 +254,14 @@ int orc_bsdf_eval_batch(void *sp, int bsdf, uint64_t n, const float *wi, const f
     ORC_TRY
     Scene *s = (Scene *) sp;
     const BSDFAny &b = s->bsdfs.at(bsdf);
-    for (uint64_t i = 0; i < n; ++i) {
-        V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), c(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
-        V3 e = b.eval(a, c);
-        outEval[3 * i] = e.x; outEval[3 * i + 1] = e.y; outEval[3 * i + 2] = e.z;
-        outPdf[i] = b.pdf(a, c);
-    }
+    parallel_for(n, [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), c(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+            V3 e = b.eval(a, c);
+            outEval[3 * i] = e.x; outEval[3 * i + 1] = e.y; outEval[3 * i + 2] = e.z;
+            outPdf[i] = b.pdf(a, c);
+        }
+    });
     return 0;
     ORC_CATCH
 }
@@ -267,13 +286,15 @@ int orc_bsdf_sample_batch(void *sp, int bsdf, uint64_t n, const float *wi, const
     Scene *s = (Scene *) sp;
     const BSDFAny &b = s->bsdfs.at(bsdf);
     const float zero[4] = {0, 0, 0, 0};
-    for (uint64_t i = 0; i < n; ++i) {
-        V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
-        BSDFSample r = b.sample(a, sample[2 * i], sample[2 * i + 1], extra ? extra + 4 * i : zero);
-        outWo[3 * i] = r.wo.x; outWo[3 * i + 1] = r.wo.y; outWo[3 * i + 2] = r.wo.z;
-        outWeight[3 * i] = r.weight.x; outWeight[3 * i + 1] = r.weight.y; outWeight[3 * i + 2] = r.weight.z;
-        outPdf[i] = r.pdf; outType[i] = r.sampledType | (r.sampledComponent << 8);
-    }
+    parallel_for(n, [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+            BSDFSample r = b.sample(a, sample[2 * i], sample[2 * i + 1], extra ? extra + 4 * i : zero);
+            outWo[3 * i] = r.wo.x; outWo[3 * i + 1] = r.wo.y; outWo[3 * i + 2] = r.wo.z;
+            outWeight[3 * i] = r.weight.x; outWeight[3 * i + 1] = r.weight.y; outWeight[3 * i + 2] = r.weight.z;
+            outPdf[i] = r.pdf; outType[i] = r.sampledType | (r.sampledComponent << 8);
+        }
+    });
     return 0;
     ORC_CATCH
 }
@@ -307,13 +328,15 @@ int orc_intersect_batch(void *sp, uint64_t n, const float *o, const float *d, co
                         int32_t *outShape, uint32_t *outPrim, float *outT) {
     ORC_TRY
     Scene *s = (Scene *) sp;
-    for (uint64_t i = 0; i < n; ++i) {
-        Ray r(V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), mint[i], maxt[i]);
-        Hit h; bool hit;
-        if (mode < 2) hit = s->geo.intersectBVH(r, mode == 1, h);
-        else hit = s->geo.intersectBrute(r, mode == 3, h);
-        outShape[i] = hit ? h.shape : -1; outPrim[i] = hit ? h.iv : 0xffffffffu; outT[i] = hit ? h.t : kInf;
-    }
+    parallel_for(n, [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            Ray r(V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), mint[i], maxt[i]);
+            Hit h; bool hit;
+            if (mode < 2) hit = s->geo.intersectBVH(r, mode == 1, h);
+            else hit = s->geo.intersectBrute(r, mode == 3, h);
+            outShape[i] = hit ? h.shape : -1; outPrim[i] = hit ? h.iv : 0xffffffffu; outT[i] = hit ? h.t : kInf;
+        }
+    });
     return 0;
     ORC_CATCH
 }
@@ -453,6 +476,26 @@ int orc_env_eval_batch(void *sp, uint64_t n, const float *d, float *outRGB, floa
         outPdf[i] = s->env.pdfDirect(dir);
     }
     return 0;
+}
+// evalEnvironment of rays with differentials (EWA lookups in the MIP pyramid)
+int orc_env_eval_filtered_batch(void *sp, uint64_t n, const float *d, const float *rx, const float *ry, float *outRGB) {
+    Scene *s = (Scene *) sp;
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 v = s->env.evalEnvironment(V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), true, V3(rx[3 * i], rx[3 * i + 1], rx[3 * i + 2]), V3(ry[3 * i], ry[3 * i + 1], ry[3 * i + 2]));
+        outRGB[3 * i] = v.x; outRGB[3 * i + 1] = v.y; outRGB[3 * i + 2] = v.z;
+    }
+    return 0;
+}
+// one level of the MIP pyramid (half-quantised texels as fp32); returns the number of levels
+int orc_env_mip_level(void *sp, int level, int *outW, int *outH, float *outRGB) {
+    Scene *s = (Scene *) sp;
+    const int n = (int) s->env.levels.size();
+    if (level < 0 || level >= n) return -1;
+    const int w = s->env.levels[level].w, h = s->env.levels[level].h;
+    if (outW) *outW = w;
+    if (outH) *outH = h;
+    if (outRGB) for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) { V3 t = s->env.evalTexel(level, x, y); float *o = outRGB + 3 * ((size_t) y * w + x); o[0] = t.x; o[1] = t.y; o[2] = t.z; }
+    return n;
 }
 int orc_env_sample_batch(void *sp, uint64_t n, const float *ref, const float *sample, float *outD, float *outValue, float *outPdfDist) {
     Scene *s = (Scene *) sp;

@@ -5,11 +5,15 @@
 //   src/emitters/envmap.cpp  :260-329 configure() (row / column CDFs, row weights, normalisation), :358-374 fillDirectSamplingRecord,
 //                            :380-410 evalEnvironment, :516-543 sampleDirect, :545-556 pdfDirect, :567-602 internalSampleDirection,
 //                            :603-635 internalPdfDirection, :657-662 sampleReuse
-//   include/mitsuba/render/mipmap.h :503-566 evalTexel (repeat / clamp boundary handling), :577-596 evalBilinear (+ evalBox)
+//   include/mitsuba/render/mipmap.h :503-566 evalTexel (repeat / clamp boundary handling), :577-596 evalBilinear (+ evalBox),
+//                            :629-725 eval (EWA filter type: ellipse from the uv Jacobian, anisotropy clamp, level choice), :760-836 evalEWA
+//   include/mitsuba/core/rfilter.h :107-460 Resampler<Scalar> (whole struct); src/rfilters/lanczos.cpp :42-55 LanczosSincFilter::eval;
+//   src/libcore/math.cpp :74-86 hypot2, :103-106 log2 -- the MIP pyramid is built by the driver loop below exactly like
+//   TMIPMap's constructor (mipmap.h:245-271) + Bitmap::resample (bitmap.cpp:2230-2328) drive these pieces
 //   include/mitsuba/core/bsphere.h :88-95 BSphere::rayIntersect;  src/libcore/util.cpp :448-482 solveQuadratic;
 //   src/libcore/warp.cpp :143-162 intervalToTent / squareToTent
 // Texels are stored as IEEE binary16 (`_Float16`, round to nearest even), the compiler's own conversion -- independent of the oracle's
-// half routines; the MIP pyramid above level 0 and the EWA lookup (mipmap.h:629-700) are not part of this path.
+// half routines.
 // Output: part of oracle/_ref/libref_geom.so.
 #include "mitsuba_shim.h"
 
@@ -22,19 +26,79 @@ struct SpectrumHalf { typedef void IsSpectrumType; half s[3]; };
 namespace math {
     using namespace mitsuba::math;
     template <typename Scalar> inline int floorToInt(Scalar value) { return (int) std::floor(value); }      // math.h:100
+    template <typename Scalar> inline int ceilToInt(Scalar value) { return (int) std::ceil(value); }        // math.h:105
     inline int32_t modulo(int32_t a, int32_t b) { int32_t r = a % b; return (r < 0) ? r + b : r; }          // math.h:67-70
+    inline float fastlog(float value) { return (float) ::log((double) value); }                             // math.h:193-195 (Linux / x86-64)
+    inline float fastexp(float value) { return (float) ::exp((double) value); }                             // math.h:185-187
+#include "ref_env_mathfn.inc"
 }
-struct ReconstructionFilter { enum EBoundaryCondition { EClamp = 0, ERepeat, EMirror, EZero, EOne }; };
+#define SAssert(x) ((void) 0)
+#define EXPECT_NOT_TAKEN(x) (x)
+#define FINLINE inline
+#define MTS_EXPORT_CORE
+#define MTS_MIPMAP_LUT_SIZE 64
+struct ReconstructionFilter {
+    enum EBoundaryCondition { EClamp = 0, ERepeat, EMirror, EZero, EOne };
+    Float m_radius = 2;                                     // LanczosSincFilter(props): lobes = 2 (envmap.cpp:160-163)
+    Float getRadius() const { return m_radius; }
+#include "ref_env_lanczos.inc"
+};
+#include "ref_env_resampler.inc"
+enum EMIPFilterType { ENearest = 0, EBilinear = 1, ETrilinear = 2, EEWA = 3 };
 struct Array2D { Vector2i size; std::vector<SpectrumHalf> data;
     const Vector2i &getSize() const { return size; }
     const SpectrumHalf &operator()(int x, int y) const { return data[(size_t) y * size.x + x]; } };
+namespace stats { struct Counter { Counter &operator++() { return *this; } Counter &operator+=(int) { return *this; } void incrementBase() {} };
+                  static Counter filteredLookups, clampedAnisotropy, avgEWASamples; }
 struct MIPMap {
     typedef Spectrum Value; typedef Array2D Array2DType;
-    Array2D m_pyramid[1]; int m_levels = 1;
+    Array2D m_pyramid[20]; Vector2 m_sizeRatio[20]; int m_levels = 1;
     ReconstructionFilter::EBoundaryCondition m_bcu = ReconstructionFilter::ERepeat, m_bcv = ReconstructionFilter::EClamp;    // envmap.cpp:178-179
+    EMIPFilterType m_filterType = EEWA; Float m_maxAnisotropy = 10.0f; Float m_weightLut[MTS_MIPMAP_LUT_SIZE];                 // envmap.cpp:150-152
     const Array2D &getArray() const { return m_pyramid[0]; }
 #include "ref_env_mipmap.inc"
-    Value eval(const Point2 &uv, const Vector2 &, const Vector2 &) const { return evalBilinear(0, uv); }      // EWA: outside this path
+    // TMIPMap constructor, steps 1-3 (mipmap.h:180-192, 232-271, 296-302) with bitmap->resample(rfilter, bcu, bcv, size, 0.0f, inf) spelled
+    // out as Bitmap::resample does it (bitmap.cpp:2258-2326): X pass into a temporary, then Y pass, both through resampleAndClamp
+    void build(const float *rgb, int w, int h) {
+        std::vector<float> img(rgb, rgb + (size_t) 3 * w * h);
+        for (float &v : img) v = std::max(v, 0.0f);
+        auto store = [&](int level, const std::vector<float> &src, int lw, int lh) {
+            m_pyramid[level].size = Vector2i(lw, lh); m_pyramid[level].data.resize((size_t) lw * lh);
+            for (size_t i = 0; i < (size_t) lw * lh; ++i) for (int k = 0; k < 3; ++k) m_pyramid[level].data[i].s[k] = (half) src[3 * i + k];
+        };
+        store(0, img, w, h);
+        m_sizeRatio[0] = Vector2(1, 1);
+        ReconstructionFilter rfilter;
+        const Float minValue = 0.0f, maxValue = std::numeric_limits<Float>::infinity();
+        Vector2i size(w, h);
+        m_levels = 1;
+        while (size.x > 1 || size.y > 1) {
+            const Vector2i srcSize = size;
+            size.x = std::max(1, (size.x + 1) / 2);
+            size.y = std::max(1, (size.y + 1) / 2);
+            std::vector<float> target((size_t) 3 * size.x * size.y), temp;
+            const float *source = img.data();
+            if (srcSize.x != size.x) {
+                Resampler<float> r(&rfilter, m_bcu, srcSize.x, size.x);
+                float *out = target.data();
+                if (srcSize.y != size.y) { temp.resize((size_t) 3 * size.x * srcSize.y); out = temp.data(); }
+                for (int y = 0; y < srcSize.y; ++y) r.resampleAndClamp(source + (size_t) y * srcSize.x * 3, 1, out + (size_t) y * size.x * 3, 1, 3, minValue, maxValue);
+                source = out;
+            }
+            if (srcSize.y != size.y) {
+                Resampler<float> r(&rfilter, m_bcv, srcSize.y, size.y);
+                for (int x = 0; x < size.x; ++x) r.resampleAndClamp(source + (size_t) x * 3, (size_t) size.x, target.data() + (size_t) x * 3, (size_t) size.x, 3, minValue, maxValue);
+            } else if (srcSize.x == size.x) target = img;
+            store(m_levels, target, size.x, size.y);
+            m_sizeRatio[m_levels] = Vector2((Float) size.x / (Float) m_pyramid[0].getSize().x, (Float) size.y / (Float) m_pyramid[0].getSize().y);
+            img.swap(target);
+            ++m_levels;
+        }
+        for (int i = 0; i < MTS_MIPMAP_LUT_SIZE; ++i) {
+            Float r2 = (Float) i / (Float) (MTS_MIPMAP_LUT_SIZE - 1);
+            m_weightLut[i] = math::fastexp(-2.0f * r2) - math::fastexp(-2.0f);
+        }
+    }
 };
 
 // include/mitsuba/core/transform.h:175-183 (vectors only are transformed here) with both matrices stored like Transform does
@@ -56,7 +120,6 @@ struct BSphere { Point center; Float radius = 0;
 #include "ref_env_bsphere.inc"
 };
 struct DirectSamplingRecord { Point ref, p; Normal n; Vector d; Float dist = 0, pdf = 0, time = 0; EMeasure measure = ESolidAngle; const void *object = nullptr; };
-namespace stats { struct Counter { Counter &operator++() { return *this; } void incrementBase() {} }; static Counter filteredLookups; }
 struct Timer { int getMilliseconds() const { return 0; } };
 namespace warp {
 #include "ref_env_tent.inc"
@@ -79,9 +142,7 @@ extern "C" {
 void *ref_env_create(const float *rgb, int w, int h, const float *toWorld16, const float *toLocal16, float scale, const float *bsCenter, float bsRadius) {
     EnvironmentMap *e = new EnvironmentMap();
     e->m_mipmap = new MIPMap();
-    e->m_mipmap->m_pyramid[0].size = Vector2i(w, h);
-    e->m_mipmap->m_pyramid[0].data.resize((size_t) w * h);
-    for (size_t i = 0; i < (size_t) w * h; ++i) for (int k = 0; k < 3; ++k) e->m_mipmap->m_pyramid[0].data[i].s[k] = (half) std::max(rgb[3 * i + k], 0.0f);   // mipmap.h:232-240 clamps negatives
+    e->m_mipmap->build(rgb, w, h);          // level 0: (half) max(rgb, 0) (mipmap.h:232-240 clamps negatives), then the Lanczos pyramid
     e->m_worldTransform = new AnimatedTransform();
     for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { e->m_worldTransform->t.m[i][j] = toWorld16[4 * i + j]; e->m_worldTransform->t.inv[i][j] = toLocal16[4 * i + j]; }
     e->m_scale = scale;
@@ -103,6 +164,27 @@ void ref_env_eval(void *h, int n, const float *d, float *outRGB, float *outPdf) 
         DirectSamplingRecord dRec; dRec.d = r.d; dRec.measure = ESolidAngle;
         outPdf[i] = e->pdfDirect(dRec);
     }
+}
+// evalEnvironment with ray differentials (the EWA branch of MIPMap::eval)
+void ref_env_eval_filtered(void *h, int n, const float *d, const float *rx, const float *ry, float *outRGB) {
+    const EnvironmentMap *e = (const EnvironmentMap *) h;
+    for (int i = 0; i < n; ++i) {
+        RayDifferential r(Vector(0, 0, 0), Vector(d[3 * i], d[3 * i + 1], d[3 * i + 2]), 0);
+        r.hasDifferentials = true;
+        r.rxDirection = Vector(rx[3 * i], rx[3 * i + 1], rx[3 * i + 2]); r.ryDirection = Vector(ry[3 * i], ry[3 * i + 1], ry[3 * i + 2]);
+        const mitsuba::Spectrum v = e->evalEnvironment(r);
+        outRGB[3 * i] = v[0]; outRGB[3 * i + 1] = v[1]; outRGB[3 * i + 2] = v[2];
+    }
+}
+int ref_env_mip_level(void *h, int level, int *outW, int *outH, float *outRGB) {
+    const EnvironmentMap *e = (const EnvironmentMap *) h;
+    const MIPMap *m = e->m_mipmap;
+    if (level < 0 || level >= m->m_levels) return -1;
+    const Array2D &a = m->m_pyramid[level];
+    if (outW) *outW = a.size.x;
+    if (outH) *outH = a.size.y;
+    if (outRGB) for (size_t i = 0; i < a.data.size(); ++i) for (int k = 0; k < 3; ++k) outRGB[3 * i + k] = (float) a.data[i].s[k];
+    return m->m_levels;
 }
 void ref_env_sample(void *h, int n, const float *ref, const float *sample, float *outD, float *outValue, float *outPdfDist) {
     const EnvironmentMap *e = (const EnvironmentMap *) h;

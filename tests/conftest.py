@@ -20,6 +20,11 @@ def oracle():
 
 @pytest.fixture(scope='session')
 def cp():
+    """The product's Python mirror.  New contexts of the test session default to the STRICT math mode (every elementary function of the
+    shading stages correctly rounded), in which the device replays the oracle bit for bit -- the path-replay and golden-vector tests
+    depend on it.  The product's own default, the fast mode (include/cudapath.h: cudapath_set_math_mode), is selected explicitly by the
+    tests that cover it: test_fast_math_*, the converged 4096-spp images, the multi-GPU film test, and __graft_entry__.smoke()."""
+    os.environ.setdefault('CUDAPATH_MATH', 'strict')
     import cudapath
     cudapath.lib()
     return cudapath

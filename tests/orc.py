@@ -246,6 +246,23 @@ class Scene:
         self.L.orc_env_eval_batch(self.h, ctypes.c_uint64(n), p(d), p(rgb), p(pdf))
         return rgb, pdf
 
+    def env_eval_filtered(self, d, rx, ry):
+        d = f32(d).reshape(-1, 3); rx = f32(rx).reshape(-1, 3); ry = f32(ry).reshape(-1, 3); n = len(d)
+        rgb = np.zeros((n, 3), np.float32)
+        self.L.orc_env_eval_filtered_batch(self.h, ctypes.c_uint64(n), p(d), p(rx), p(ry), p(rgb))
+        return rgb
+
+    def env_mip_levels(self):
+        out = []
+        w = ctypes.c_int(); h = ctypes.c_int()
+        n = self.L.orc_env_mip_level(self.h, 0, ctypes.byref(w), ctypes.byref(h), None)
+        for l in range(n):
+            self.L.orc_env_mip_level(self.h, l, ctypes.byref(w), ctypes.byref(h), None)
+            a = np.zeros((h.value, w.value, 3), np.float32)
+            self.L.orc_env_mip_level(self.h, l, ctypes.byref(w), ctypes.byref(h), p(a))
+            out.append(a)
+        return out
+
     def env_sample(self, ref, sample):
         ref = f32(ref).reshape(-1, 3); sample = f32(sample).reshape(-1, 2); n = len(ref)
         d = np.zeros((n, 3), np.float32); v = np.zeros((n, 3), np.float32); pd = np.zeros((n, 2), np.float32)

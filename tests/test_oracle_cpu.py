@@ -1369,6 +1369,62 @@ def test_oracle_envmap_pinned_against_reference_text(cp, oracle, which):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_GEOM), reason='oracle/_ref/libref_geom.so not built (needs /root/reference)')
+@pytest.mark.parametrize('which', ['sunsky', 'odd-size'])
+def test_envmap_mip_pyramid_and_ewa_pinned_against_reference_text(cp, oracle, which):
+    """The filtered environment lookup of camera rays that leave the scene: the reference's Resampler<float> (rfilter.h:107-460),
+    LanczosSincFilter::eval (lanczos.cpp:42-55), MIPMap::eval and evalEWA (mipmap.h:629-725, 760-836), hypot2 / log2 (math.cpp) cut out and
+    executed as written, driven like TMIPMap's constructor drives them (oracle/ref_shim/ref_env.cpp) -- against the oracle AND the product's
+    host-side pyramid builder (csrc/cp_host_mip.cpp).  Pyramid: same level sizes; texels identical except where libm's sinf (reference) and the
+    correctly rounded sine (oracle, product) differ in the last bit of a filter weight, which can move a value across a half rounding
+    boundary (one half ulp).  Lookups: footprints from a hundredth of a texel to a quarter of the map, isotropic and 40:1 anisotropic."""
+    L = ctypes.CDLL(REF_GEOM); L.ref_env_create.restype = ctypes.c_void_p
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rng = np.random.default_rng(5)
+    if which == 'sunsky':
+        img = cp.bake_sunsky(**cp.scenes.sunsky_params('hair-curl'))
+    else:                                                                   # odd sizes exercise max(1, (size + 1) / 2) and the 1-wide tail of the pyramid
+        yy, xx = np.mgrid[0:37, 0:101]
+        img = np.stack([2 + np.sin(xx / 5.0) * np.cos(yy / 4.0), 1.5 + np.cos(xx / 7.0), 1 + 0.5 * np.sin(yy / 3.0)], axis=2)
+        img = (img + 300.0 * np.exp(-((xx - 70) ** 2 + (yy - 9) ** 2) / 3.0)[..., None] * [1.0, 0.9, 0.6]).astype(np.float32); img[30:] = 0; img[3, 5] = -1.0
+    img = np.ascontiguousarray(img, np.float32); h, w = img.shape[:2]
+    tw = np.eye(4, dtype=np.float32)
+    s = oracle.scene_from_description('curly-hair', scale=0.002, overrides=dict(width=16, height=16, spp=1, maxDepth=2), envmap=img)
+    aabb, bs = s.scene_bounds()
+    e = ctypes.c_void_p(L.ref_env_create(P(img), w, h, P(tw), P(tw), ctypes.c_float(1.0), P(np.ascontiguousarray(bs[:3], np.float32)), ctypes.c_float(bs[3])))
+    olev = s.env_mip_levels()
+    plev = cp.env_pyramid(img)
+    lw = ctypes.c_int(); lh = ctypes.c_int()
+    nlev = L.ref_env_mip_level(e, 0, ctypes.byref(lw), ctypes.byref(lh), None)
+    assert nlev == len(olev) == len(plev) and olev[-1].shape[:2] == (1, 1)
+    for l in range(nlev):
+        L.ref_env_mip_level(e, l, ctypes.byref(lw), ctypes.byref(lh), None)
+        ref = np.zeros((lh.value, lw.value, 3), np.float32)
+        L.ref_env_mip_level(e, l, ctypes.byref(lw), ctypes.byref(lh), P(ref))
+        assert ref.shape == olev[l].shape == plev[l].shape and (ref >= 0).all()
+        prod = plev[l].astype(np.float16).astype(np.float32)               # the device quantises the product's fp32 levels to half (round to nearest even)
+        assert np.array_equal(prod, olev[l]), 'level %d: product and oracle pyramids differ' % l
+        half_ulp = np.maximum(np.abs(ref), 6.1e-5) * 2.0 ** -10
+        assert (np.abs(ref - olev[l]) <= half_ulp).all() and (ref == olev[l]).mean() > 0.97, 'level %d' % l
+    n = 60000
+    d = sphere_dirs(rng, n)
+    foot = np.exp(rng.uniform(np.log(1e-5), np.log(0.4), size=(n, 1))).astype(np.float32)                # angular footprint (radians), log-uniform
+    aniso = np.where(rng.random((n, 1)) < 0.5, 1.0, np.exp(rng.uniform(0, np.log(40.0), size=(n, 1)))).astype(np.float32)
+    t1 = np.cross(d, sphere_dirs(rng, n)); t1 /= np.linalg.norm(t1, axis=1, keepdims=True); t2 = np.cross(d, t1)
+    rx = (d + t1 * foot).astype(np.float32); ry = (d + t2 * foot / aniso).astype(np.float32)
+    d[:4] = [[0, 1, 0], [0, -1, 0], [0, 0, 1], [1, 0, 0]]; rx[4] = d[4]; ry[5] = d[5]                       # poles, the seam, degenerate footprints
+    ref = np.zeros((n, 3), np.float32)
+    L.ref_env_eval_filtered(e, n, P(d), P(rx), P(ry), P(ref))
+    ours = s.env_eval_filtered(d, rx, ry)
+    assert np.isfinite(ref).all() and np.array_equal(np.isfinite(ours), np.isfinite(ref))
+    scale = float(np.abs(ref).max())
+    err = np.abs(ours - ref) / np.maximum(np.abs(ref), 1e-3 * scale)
+    print('%s: %d levels; filtered lookups: %.4f bit-identical, rel err q99 %.2e max %.2e' % (which, nlev, (ours == ref).all(axis=1).mean(), np.quantile(err, 0.99), err.max()))
+    # the last bit of atan2f / acosf / sincosf in a texture coordinate, and the half-ulp texel differences above, scaled by the texel gradient
+    assert np.quantile(err, 0.99) <= 2e-4 and err.max() <= 5e-3
+    assert (ours == ref).all(axis=1).mean() > 0.5
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GEOM), reason='oracle/_ref/libref_geom.so not built (needs /root/reference)')
 @pytest.mark.parametrize('rfilter,param', [('tent', 0.0), ('box', 0.0), ('gaussian', 0.0), ('gaussian', 0.8)])
 def test_film_splat_pinned_against_reference(cp, oracle, rfilter, param):
     """ImageBlock::put (imageblock.h:124-186) cut out of the reference and executed as written, over the reference's own filter files compiled
