@@ -193,7 +193,7 @@ def workload_config(args, sc):
     return {'workload': '%s: %s BSDF, path integrator maxDepth=%d rrDepth=5 strictNormals, %dx%d at %d spp %s, sunsky envmap 512x256, tent filter'
                         % (args.scene, sc['shapes'][0]['bsdf']['type'], sc['maxDepth'], sc['width'], sc['height'], sc['spp'], per),
             'geometry': 'procedural fibers (reference .mitshair blobs missing), generator scale %.3g' % args.scale,
-            'parallelism': '%s sharding (%s scaling), one NCCL film reduce' % ('sample-range' if args.scaling == 'weak' or args.shard == 'samples' else '64x64 pixel-block', args.scaling),
+            'parallelism': '%s sharding (%s scaling), one NCCL film reduce' % ('sample-range' if args.scaling == 'weak' or args.shard == 'samples' else '32x32 pixel-block', args.scaling),
             'l2_policy': 'inputs larger than L2 (BVH + vertices + path queues >> 126 MB)'}
 
 
@@ -366,7 +366,7 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0, help='strand-count scale of the procedural generators')
     ap.add_argument('--spp', type=int, default=0, help='override samples per pixel (default: the config value)')
     ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'], help='N > 1: split the fixed job (strong) or render spp per GPU (weak)')
-    ap.add_argument('--shard', default='pixels', choices=['pixels', 'samples'], help='strong scaling: split the image by 64x64 pixel blocks or by sample ranges')
+    ap.add_argument('--shard', default='pixels', choices=['pixels', 'samples'], help='strong scaling: split the image by 32x32 pixel blocks or by sample ranges')
     ap.add_argument('--shard-test', default='', help='development: i/G renders only pixel shard i of G on this GPU')
     ap.add_argument('--config', type=int, default=2, help='5: the per-stage micro-benchmark of BASELINE.json configs[4]')
     ap.add_argument('--log2n', type=int, default=26, help='--config 5: log2 of the batch size')
@@ -402,7 +402,7 @@ def main():
     elif args.shard == 'samples':
         total_spp = spp; s_begin, s_end = sample_range(spp, rank, world)               # the fixed image, sample indices split over the ranks
     else:
-        total_spp = spp; s_begin, s_end = 0, spp; shard = (rank, world)                # the fixed image, 64x64 pixel blocks dealt out to the ranks
+        total_spp = spp; s_begin, s_end = 0, spp; shard = (rank, world)                # the fixed image, 32x32 pixel blocks dealt out to the ranks
     if args.shard_test:                                                                # development: one GPU renders shard i of G of the image
         i, g = (int(v) for v in args.shard_test.split('/')); shard = (i, g)
     ctx = make_context(cudapath, sc, shapes, env, local)

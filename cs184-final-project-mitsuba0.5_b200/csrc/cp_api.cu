@@ -942,8 +942,8 @@ static int render_multi(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
     }
     // Which axis of the pixel-sample space is split: pixel blocks when the image has enough of them to balance the devices (every
     // device then keeps all sample indices of its pixels, i.e. the ray density of the single-device render), sample ranges otherwise.
-    const uint32_t blocks = (uint32_t) ((ctx->cam.w + 63) / 64) * (uint32_t) ((ctx->cam.h + 63) / 64);
-    const bool byPixels = blocks >= 8u * (uint32_t) n && !getenv("CUDAPATH_SHARD_SAMPLES");
+    const uint32_t blocks = (uint32_t) ((ctx->cam.w + 31) / 32) * (uint32_t) ((ctx->cam.h + 31) / 32);
+    const bool byPixels = blocks >= 16u * (uint32_t) n && !getenv("CUDAPATH_SHARD_SAMPLES");
     // one host thread per device: zero the private film, render this device's share
     std::vector<int> rc(n, 0); std::vector<std::string> msg(n);
     auto work = [&](int i) {

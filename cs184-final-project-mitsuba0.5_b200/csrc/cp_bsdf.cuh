@@ -14,10 +14,12 @@
 // units that contain BSDF code are compiled with -fmad=false (the reference's x86 build has no FMA either).
 //
 // Two builds of this header exist in the library (csrc/Makefile): the strict one (every call correctly rounded: bit-identical to
-// the oracle) and the default, -DCP_FAST_MATH one, in which only the amplified chain keeps its exact bits -- thetaI = asin(wi.y)
+// the oracle) and the default, -DCP_FAST_MATH one, in which only the sensitive quantities keep their exact bits -- thetaI = asin(wi.y)
 // and the sines / cosines of the three shifted lobe angles that enter M() (ma_lobe_angles below: one fp64 sincos and a few fp64
-// multiply-adds instead of six fp64 libm calls) -- while every nc_* call (table coordinates, the exp / log inside M(), whose
-// argument is O(1), sampled directions) uses the 1-2 ulp fp32 functions.  Measured difference between the modes: ~1e-6 relative.
+// multiply-adds instead of six fp64 libm calls), and the coordinates of the azimuthal tables (thetaO, cos thetaD, phi: the tables
+// hold caustic peaks, so one ulp of a coordinate can be 1e-3 of the interpolated value) -- while every nc_* call (the exp / log
+// inside M(), whose argument is O(1), the rough-transmittance warp, everything that only shapes a sampled direction) uses the
+// 1-2 ulp fp32 functions.  Measured difference between the modes: ~1e-6 relative.
 #pragma once
 #include "cp_common.cuh"
 
@@ -102,10 +104,20 @@ CP_D BsdfSampleOut kk_sample(const BsdfDev &b, const V3 &wi, float sx, float sy)
 CP_D float ma_trigInverse(float x) { return fminf(sqrtf(fmaxf(__fsub_rn(1.0f, __fmul_rn(x, x)), 0.0f)), 1.0f); }
 
 CP_D float ma_I0(float x) { // :279-290
+#if CP_MATH_IS_FAST
+    // the same ten-term series with the reciprocal denominators 1 / (4^i (i!)^2) as constants (Horner form): the value only enters
+    // log(I0) -- an absolute error of an ulp there is not amplified -- and the ten fp32 divisions were a tenth of the whole BSDF
+    const float t = x * x;
+    float r = 7.242258480192779e-20f;        // i = 10
+    r = r * t + 2.896903392077112e-17f; r = r * t + 9.385966990329842e-15f; r = r * t + 2.4028075495244395e-12f; r = r * t + 4.709502797067901e-10f;
+    r = r * t + 6.781684027777778e-08f; r = r * t + 6.781684027777777e-06f; r = r * t + 4.3402777777777775e-04f; r = r * t + 1.5625e-02f; r = r * t + 0.25f;
+    return r * t + 1.0f;
+#else
     float result = 1.0f, xSq = x * x, xi = xSq, denom = 4.0f;
 #pragma unroll
     for (int i = 1; i <= 10; ++i) { result += xi / denom; xi *= xSq; denom *= 4.0f * float((i + 1) * (i + 1)); }
     return result;
+#endif
 }
 CP_D float ma_logI0(float x) { // :292-299
     if (x > 12.0f) return x + 0.5f * (nc_log(1.0f / (kPi * 2.0f * x)) + 1.0f / (8.0f * x));
@@ -156,7 +168,11 @@ CP_D float ma_sample_phi(const float *__restrict__ cdf, float cosThetaD, float x
 }
 // RoughTransmittance::eval, alpha and eta fixed (rtrans.h:183-194,233) -> Catmull-Rom over rtSize samples
 CP_D float ma_T(const BsdfDev &b, float cosTheta) {
+#if CP_MATH_IS_FAST
+    float warped = sqrtf(sqrtf(fabsf(cosTheta)));      // |cos|^(1/4): feeds a spline, not amplified
+#else
     float warped = nc_pow(fabsf(cosTheta), 0.25f);
+#endif
     if (!(cosTheta >= 0)) return 0.0f;
     float x = warped;
     if (!(x >= 0.0f && x <= 1.0f)) return 0.0f;       // spline.cpp:25-26 (min(1,max(0,0)) = 0)
@@ -205,11 +221,13 @@ CP_D LobeAngles ma_lobe_angles(const BsdfDev &b, float thetaI) {
 CP_D V3 ma_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float sinThetaI = wi.y, sinThetaO = wo.y;            // the `t` axis, not the tangent (quirk 2)
     float cosThetaO = ma_trigInverse(sinThetaO);
-    float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));   // feeds the lobe angles: exact in both modes
-    float thetaO = nc_asin(clampf(sinThetaO, -1.0f, 1.0f));
+    // exact in both math modes: thetaI feeds the lobe angles that M() amplifies; thetaO / thetaD / phi are the coordinates of the
+    // azimuthal tables, whose caustic peaks turn one ulp of a coordinate into up to 1e-3 of the interpolated value
+    float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
+    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
     float thetaD = (thetaO - thetaI) * 0.5f;
-    float cosThetaD = nc_cos(thetaD);
-    float phi = nc_atan2(wo.x, wo.z);                     // depends on wo only (quirk 2)
+    float cosThetaD = cr_cos(thetaD);
+    float phi = cr_atan2(wo.x, wo.z);                     // depends on wo only (quirk 2)
     if (phi < 0.0f) phi += kPi * 2.0f;
     const LobeAngles la = ma_lobe_angles(b, thetaI);
     float MR = ma_M(b.vR, la.sinR, sinThetaO, la.cosR, cosThetaO);
@@ -279,10 +297,10 @@ CP_D V3 mf_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float sinThetaI = wi.y, sinThetaO = wo.y;
     float cosThetaO = ma_trigInverse(sinThetaO);
     float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
-    float thetaO = nc_asin(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
     float thetaD = (thetaO - thetaI) * 0.5f;
-    float cosThetaD = nc_cos(thetaD);
-    float phi = nc_atan2(wo.x, wo.z);
+    float cosThetaD = cr_cos(thetaD);
+    float phi = cr_atan2(wo.x, wo.z);
     if (phi < 0.0f) phi += kPi * 2.0f;
     const LobeAngles la = ma_lobe_angles(b, thetaI);
     float MTRT = ma_M(b.vTRT, la.sinTRT, sinThetaO, la.cosTRT, cosThetaO);
@@ -293,10 +311,10 @@ CP_D float mf_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float sinThetaI = wi.y, sinThetaO = wo.y;
     float cosThetaI = ma_trigInverse(sinThetaI), cosThetaO = ma_trigInverse(sinThetaO);
     float thetaI = cr_asin(clampf(sinThetaI, -1.0f, 1.0f));
-    float thetaO = nc_asin(clampf(sinThetaO, -1.0f, 1.0f));
+    float thetaO = cr_asin(clampf(sinThetaO, -1.0f, 1.0f));
     float thetaD = (thetaO - thetaI) * 0.5f;
-    float cosThetaD = nc_cos(thetaD);
-    float phi = nc_atan2(wo.x, wo.z);
+    float cosThetaD = cr_cos(thetaD);
+    float phi = cr_atan2(wo.x, wo.z);
     if (phi < 0.0f) phi += 2.0f * kPi;
     const LobeAngles la = ma_lobe_angles(b, thetaI);
     float weightR = ma_weight(b.sums, cosThetaI), weightTT = ma_weight(b.sums + 64, cosThetaI), weightTRT = ma_weight(b.sums + 128, cosThetaI);

@@ -192,20 +192,19 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
     uint64_t realPix = (uint64_t) wp.filmW * wp.filmH;           // pixels this context renders
     if (shardCount <= 1) wp.pixPadded = (uint64_t) wp.tilesX * ((wp.filmH + 7) / 8) * 64;
     else {
-        const uint32_t blocksX = (wp.filmW + 63) / 64, blocksY = (wp.filmH + 63) / 64;
+        const uint32_t blocksX = (wp.filmW + 31) / 32, blocksY = (wp.filmH + 31) / 32;
         wp.shardIndex = shardIndex; wp.shardCount = shardCount;
-        wp.shardSkew = shardCount % 3u == 0u ? 1u : 3u;         // coprime with the shard count for 2, 4, 8 (and 1 otherwise): diagonal bands
-        if (shardCount < 4) wp.shardSkew = 1;
-        wp.blocksPerRow = (blocksX + shardCount - 1) / shardCount;
-        wp.pixPadded = (uint64_t) wp.blocksPerRow * blocksY * 4096ull;
+        wp.cellW = shardCount; wp.cellH = 1;                     // cell shape: as square as the shard count allows (8 -> 4 x 2, 4 -> 2 x 2, 6 -> 3 x 2)
+        for (uint32_t hgt = 2; hgt * hgt <= shardCount; ++hgt) if (shardCount % hgt == 0) { wp.cellH = hgt; wp.cellW = shardCount / hgt; }
+        wp.cellsPerRow = (blocksX + wp.cellW - 1) / wp.cellW;
+        const uint32_t cellRows = (blocksY + wp.cellH - 1) / wp.cellH;
+        wp.pixPadded = (uint64_t) wp.cellsPerRow * cellRows * 1024ull;
         realPix = 0;
-        for (uint32_t by = 0; by < blocksY; ++by) {
-            const uint32_t first = (shardIndex + shardCount - (wp.shardSkew * by) % shardCount) % shardCount;
-            for (uint32_t k = 0; k < wp.blocksPerRow; ++k) {
-                const uint32_t bx = first + k * shardCount;
-                if (bx >= blocksX) continue;
-                realPix += (uint64_t) std::min(64u, wp.filmW - bx * 64u) * std::min(64u, wp.filmH - by * 64u);
-            }
+        for (uint32_t cy = 0; cy < cellRows; ++cy) for (uint32_t cx = 0; cx < wp.cellsPerRow; ++cx) {
+            const uint32_t slot = (shardIndex + cx + 3u * cy) % shardCount;
+            const uint32_t bx = cx * wp.cellW + slot % wp.cellW, by = cy * wp.cellH + slot / wp.cellW;
+            if (bx >= blocksX || by >= blocksY) continue;
+            realPix += (uint64_t) std::min(32u, wp.filmW - bx * 32u) * std::min(32u, wp.filmH - by * 32u);
         }
         if (wp.pixPadded == 0 || realPix == 0) return true;     // this shard owns no pixel
     }

@@ -24,10 +24,10 @@ struct WaveParams {
     uint64_t waveBase = 0, pixPadded = 0;
     uint32_t filmW = 0, filmH = 0, tilesX = 0, sampleBegin = 0, seedLo = 0, seedHi = 0;
     float diffScale = 1.0f;
-    // pixel shard (cudapath_set_pixel_shard): this context renders the 64x64-pixel blocks owned by shard `shardIndex` of `shardCount`.
-    // Block (bx, by) of the grid -- its width padded to a multiple of shardCount -- belongs to shard (bx + shardSkew * by) mod shardCount,
-    // so every row of blocks gives each shard blocksPerRow blocks and the owners form diagonal bands across the image.
-    uint32_t shardIndex = 0, shardCount = 1, shardSkew = 1, blocksPerRow = 0;
+    // pixel shard (cudapath_set_pixel_shard): this context renders the 32x32-pixel blocks owned by shard `shardIndex` of `shardCount`.
+    // The block grid is cut into cells of cellW x cellH = shardCount blocks; every shard owns exactly one block of every cell (which one
+    // rotates from cell to cell), so each shard's pixels are spread evenly over the image whatever the image shows.
+    uint32_t shardIndex = 0, shardCount = 1, cellW = 1, cellH = 1, cellsPerRow = 0;
 };
 struct RenderStats {
     uint64_t paths = 0, rays = 0, shadowRays = 0, launches = 0, bounces = 0, hostSyncs = 0;
@@ -101,13 +101,13 @@ __device__ __forceinline__ bool path_to_pixel(const WaveParams &wp, uint64_t g, 
     if (wp.shardCount == 1u) {
         x = (tile % wp.tilesX) * 8u + (within & 7u);
         y = (tile / wp.tilesX) * 8u + (within >> 3);
-    } else {      // owned 64x64 block -> 8x8 tile inside it -> pixel
-        const uint32_t block = tile >> 6, t = tile & 63u;
-        const uint32_t by = block / wp.blocksPerRow, k = block - by * wp.blocksPerRow;
-        const uint32_t first = (wp.shardIndex + wp.shardCount - (wp.shardSkew * by) % wp.shardCount) % wp.shardCount;
-        const uint32_t bx = first + k * wp.shardCount;
-        x = bx * 64u + (t & 7u) * 8u + (within & 7u);
-        y = by * 64u + (t >> 3) * 8u + (within >> 3);
+    } else {      // owned 32x32 block (one per cell) -> 8x8 tile inside it -> pixel
+        const uint32_t cell = tile >> 4, t = tile & 15u;
+        const uint32_t cy = cell / wp.cellsPerRow, cx = cell - cy * wp.cellsPerRow;
+        const uint32_t slot = (wp.shardIndex + cx + 3u * cy) % wp.shardCount;          // which block of the cell is ours
+        const uint32_t bx = cx * wp.cellW + slot % wp.cellW, by = cy * wp.cellH + slot / wp.cellW;
+        x = bx * 32u + (t & 3u) * 8u + (within & 7u);
+        y = by * 32u + (t >> 2) * 8u + (within >> 3);
     }
     return x < wp.filmW && y < wp.filmH;
 }

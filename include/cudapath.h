@@ -163,9 +163,10 @@ int cudapath_render(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sam
 /* Same, accumulating into a caller-provided DEVICE buffer on a caller-provided CUDA stream (cudaStream_t as void*, may be 0);
  * the buffer must be zeroed by the caller before the first range.  Used with torch/NCCL for the multi-GPU film reduce. */
 int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t sample_begin, uint32_t sample_end, float *film_dev, void *stream);
-/* Pixel-space sharding (the "image tiles" of BlockedRenderProcess, src/librender/renderproc.cpp:117-182, at 64x64 granularity): after
- * this call cudapath_render / cudapath_render_dev only trace the paths of the pixel blocks owned by shard `shard_index` of `shard_count`
- * (blocks are dealt out in diagonal bands, so every shard sees every part of the image); all other pixels stay zero except for the
+/* Pixel-space sharding (the image tiles of BlockedRenderProcess, src/librender/renderproc.cpp:117-182; its default tile is the same
+ * 32x32 pixels, src/mitsuba/mitsuba.cpp:144): after this call cudapath_render / cudapath_render_dev only trace the paths of the pixel
+ * blocks owned by shard `shard_index` of `shard_count` (every group of shard_count neighbouring blocks gives one block to each shard,
+ * so each shard's pixels are spread evenly over the image); all other pixels stay zero except for the
  * reconstruction filter's one-pixel border, so the films of the `shard_count` shards ADD UP to the full image exactly like the films of
  * disjoint sample ranges do.  Keeping all sample indices of a pixel on one device keeps the ray density per region of the scene --
  * and with it the cache hit rates of the traversal -- at the level of the single-device render, which sample-range sharding does
