@@ -657,6 +657,20 @@ int orc_splat_batch(void *sp, uint64_t n, const float *pos, const float *rgb, co
 }
 
 // sunsky bake through the compiled reference pieces (oracle/_ref/libref_pieces.so)
+// computeSunRadiance (sunmodel.h:316-371) of the oracle alone: elevation angle from the zenith, linear RGB out
+int orc_sun_radiance(const char *refLib, float theta, float turbidity, float *outRGB) {
+    ORC_TRY
+    void *h = dlopen(refLib, RTLD_NOW | RTLD_LOCAL);
+    if (!h) throw std::runtime_error(std::string("oracle/_ref not built: ") + dlerror());
+    RefPieces ref;
+    auto cie = (int (*)(const float **, const float **, const float **, const float **)) dlsym(h, "ref_cie_tables");
+    if (!cie) throw std::runtime_error("oracle/_ref library lacks expected symbols");
+    ref.cie_n = cie(&ref.cie_wl, &ref.cie_x, &ref.cie_y, &ref.cie_z);
+    const V3 r = computeSunRadiance(theta, turbidity, ref);
+    outRGB[0] = r.x; outRGB[1] = r.y; outRGB[2] = r.z;
+    return 0;
+    ORC_CATCH
+}
 int orc_bake_sunsky(const char *refLib, float turbidity, float albedo, const float *sunDir, float skyScale, float sunScale,
                     float sunRadiusScale, int resolution, float *outRGB) {
     ORC_TRY
