@@ -74,30 +74,33 @@ def main():
             f.write('| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n')
             for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 f.write('| `%s` | %d | %.3f | %.1f %% |\n' % (name, n, ms, 100 * ms / total))
-            render = {k: v for k, v in agg.items() if any(s in k for s in ('k_intersect', 'k_shadow', 'k_shade', 'k_raygen', 'k_splat', 'k_sort_keys', 'DeviceRadixSort', 'k_apply'))}
+            render = {k: v for k, v in agg.items() if any(s in k for s in ('k_trace', 'k_ray_keys', 'k_intersect', 'k_shadow', 'k_shade', 'k_raygen', 'k_splat', 'k_sort_keys', 'DeviceRadixSort', 'k_apply'))}
             rt = sum(v[1] for v in render.values())
             f.write('\nRender-loop kernels only (%.2f ms): ' % rt + ', '.join('%s %.1f %%' % (k.split('::')[-1].split('<')[0], 100 * v[1] / rt) for k, v in sorted(render.items(), key=lambda kv: -kv[1][1])) + '\n')
             if bench:
                 f.write('\nbench.py (same build, CUDA events, 64 spp): stage share of step = %s\n' % json.dumps(bench['roofline'].get('stage_share_of_step')))
 
     # ---- full capture of k_intersect
-    rep = os.path.join(OUT, 'prof_%s_intersect.ncu-rep' % tag)
+    kname = 'k_trace'
+    rep = os.path.join(OUT, 'prof_%s_trace.ncu-rep' % tag)
+    if not os.path.exists(rep):
+        kname = 'k_intersect'; rep = os.path.join(OUT, 'prof_%s_intersect.ncu-rep' % tag)
     if os.path.exists(rep):
         raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
         rows = list(csv.reader(l for l in raw.splitlines() if l.startswith('"')))
         hdr, units, vals = rows[0], rows[1], rows[2]
         d = dict(zip(hdr, vals)); u = dict(zip(hdr, units))
         dram = to_bytes(d['dram__bytes_read.sum'], u['dram__bytes_read.sum']) + to_bytes(d['dram__bytes_write.sum'], u['dram__bytes_write.sum'])
-        with open(os.path.join(PROF, '%s_k_intersect_ncu_%s.md' % (rnd, tag)), 'w') as f:
-            f.write('# ncu --set full: one `k_intersect` launch (%s)\n\n' % tag)
-            f.write('Command: `ncu --set full --clock-control none --import-source on -k regex:k_intersect -s 2 -c 1 python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e`\n')
+        with open(os.path.join(PROF, '%s_%s_ncu_%s.md' % (rnd, kname, tag)), 'w') as f:
+            f.write('# ncu --set full: one `%s` launch (%s)\n\n' % (kname, tag))
+            f.write('Command: `ncu --set full --clock-control none --import-source on -k regex:%s -s 2 -c 1 python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e`\n' % kname)
             f.write('Kernel: `%s`\n\n| metric | value | unit |\n|---|---:|---|\n' % d.get('Kernel Name'))
             for k in KEYS:
                 if k in d:
                     f.write('| %s | %s | %s |\n' % (k, d[k], u[k]))
             f.write('\nDRAM traffic of this launch: %.1f MB (read + write).\n' % (dram / 1e6))
         with open(os.path.join(PROF, 'k_intersect_traffic.json'), 'w') as f:
-            json.dump({'source': '%s_k_intersect_ncu_%s.md' % (rnd, tag), 'launch': 'third k_intersect launch of bench.py --spp 8 (8.4 M secondary rays, hair-curl)',
+            json.dump({'source': '%s_%s_ncu_%s.md' % (rnd, kname, tag), 'launch': 'third %s launch of bench.py --spp 8 (secondary + shadow rays of one bounce, hair-curl)' % kname,
                        'dram_bytes': dram, 'duration_ms': float(d['gpu__time_duration.sum'].replace(',', '')) * ({'ms': 1, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}[u['gpu__time_duration.sum']])}, f, indent=1)
     # ---- full captures of the other stages (tools/gpu_evidence_stages.sh): k_shade, k_shadow, the BSDF batch kernels of config 5a
     EXTRA = ['sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fmalite.avg.pct_of_peak_sustained_active',
@@ -105,7 +108,7 @@ def main():
              'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'smsp__thread_inst_executed.sum',
              'sm__inst_executed_pipe_fp64.sum', 'sm__sass_thread_inst_executed_op_dfma_pred_on.sum', 'sm__sass_thread_inst_executed_op_ffma_pred_on.sum',
              'smsp__sass_thread_inst_executed_op_fp32_pred_on.sum', 'smsp__sass_thread_inst_executed_op_fp64_pred_on.sum']
-    for stage, cmd in (('k_shade', 'python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e  (-k regex:k_shade -s 2 -c 1)'),
+    for stage, cmd in (('shade', 'python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e  (-k regex:k_shade -s 2 -c 1)'), ('k_shade', 'python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e  (-k regex:k_shade -s 2 -c 1)'),
                        ('k_shadow', 'python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e  (-k regex:k_shadow -s 2 -c 1)'),
                        ('k_bsdf', 'python tools/microbench.py --log2n 24 --reps 1 --bsdf-only  (-k regex:k_bsdf_ -s 3 -c 2: Marschner eval+pdf, then sample)')):
         rep = os.path.join(OUT, 'prof_%s_%s.ncu-rep' % (tag, stage))
@@ -122,7 +125,7 @@ def main():
                 for k in KEYS + EXTRA:
                     if k in d:
                         f.write('| %s | %s | %s |\n' % (k, d[k], u[k]))
-    for extra in ('microbench_%s.jsonl' % tag, 'e2e_phases_%s.log' % tag):
+    for extra in ('microbench_%s.jsonl' % tag, 'e2e_phases_%s.log' % tag, 'bench_config5_%s.json' % tag, 'pytest_gpu_%s.log' % tag):
         if os.path.exists(os.path.join(OUT, extra)):
             shutil.copy(os.path.join(OUT, extra), os.path.join(PROF, '%s_%s' % (rnd, extra)))
     print('profiles/ updated for', tag)
