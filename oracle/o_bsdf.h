@@ -900,24 +900,44 @@ struct RoughPlastic {
 // SmoothDiffuse (`diffuse` plugin, constant reflectance) -- src/bsdfs/diffuse.cpp:92-156, optionally wrapped in
 // `twosided` (src/bsdfs/twosided.cpp:101-181) with the same nested BRDF on both sides.  Used for triangle meshes.
 // ---------------------------------------------------------------------------------------------
-struct SmoothDiffuse {
-    V3 reflectance; bool twoSided = false;
-    void configure(V3 r, bool two) {
-        const float mx = maxc(r);                       // ensureEnergyConservation(tex, "reflectance", 1.0f), bsdf.cpp:88-113
-        if (mx > 1.0f) r = r * (0.99f * (1.0f / mx));
-        reflectance = r; twoSided = two;
+// A 2-D texture as the BSDFs of this path see it: a constant Spectrum (ConstantSpectrumTexture, include/mitsuba/hw/basicshader.h:33-70) or
+// the procedural `checkerboard` (src/textures/checkerboard.cpp:47-72) behind Texture2D's uv transform (src/librender/texture.cpp:81-121).
+// A ScaleTexture wrapped around it by ensureEnergyConservation (bsdf.cpp:88-113) is folded into the colours (same product per lookup).
+struct Texture2D {
+    int kind = 0;                      // 0 constant, 1 checkerboard
+    V3 color0 = V3(0.5f), color1 = V3(0.5f);     // constant: color0
+    float uoffset = 0, voffset = 0, uscale = 1, vscale = 1;
+    void setConstant(V3 v) { kind = 0; color0 = color1 = v; }
+    void setCheckerboard(V3 c0, V3 c1, float uo, float vo, float us, float vs) { kind = 1; color0 = c0; color1 = c1; uoffset = uo; voffset = vo; uscale = us; vscale = vs; }
+    bool isConstant() const { return kind == 0; }
+    V3 getMaximum() const { return kind == 0 ? color0 : V3(std::max(color0.x, color1.x), std::max(color0.y, color1.y), std::max(color0.z, color1.z)); }
+    V3 getAverage() const { return kind == 0 ? color0 : (color0 + color1) * 0.5f; }
+    void scale(float f) { color0 = color0 * f; color1 = color1 * f; }
+    // bsdf.cpp:88-113
+    void ensureEnergyConservation(float mx = 1.0f) { const float actualMax = maxc(getMaximum()); if (actualMax > mx) scale(0.99f * (mx / actualMax)); }
+    V3 eval(float u, float v) const {
+        if (kind == 0) return color0;
+        const float uu = u * uscale + uoffset, vv = v * vscale + voffset;        // texture.cpp:112-113
+        const int x = 2 * modulo((int) (uu * 2), 2) - 1, y = 2 * modulo((int) (vv * 2), 2) - 1;    // checkerboard.cpp:65-72
+        return x * y == 1 ? color0 : color1;
     }
-    V3 eval(V3 wi, V3 wo) const {
+};
+
+struct SmoothDiffuse {
+    Texture2D reflectance; bool twoSided = false;
+    void configure(V3 r, bool two) { reflectance.setConstant(r); reflectance.ensureEnergyConservation(); twoSided = two; }
+    void configure(const Texture2D &t, bool two) { reflectance = t; reflectance.ensureEnergyConservation(); twoSided = two; }
+    V3 eval(V3 wi, V3 wo, float u = 0, float v = 0) const {
         if (twoSided && wi.z <= 0) { wi.z *= -1; wo.z *= -1; }     // twosided.cpp:101-115 (wi.z > 0 ? front : flipped)
         if (wi.z <= 0 || wo.z <= 0) return V3(0.0f);
-        return reflectance * (kInvPi * wo.z);
+        return reflectance.eval(u, v) * (kInvPi * wo.z);
     }
     float pdf(V3 wi, V3 wo) const {
         if (twoSided && wi.z <= 0) { wi.z *= -1; wo.z *= -1; }
         if (wi.z <= 0 || wo.z <= 0) return 0.0f;
         return kInvPi * wo.z;                                       // warp::squareToCosineHemispherePdf
     }
-    BSDFSample sample(V3 wi, float sx, float sy) const {
+    BSDFSample sample(V3 wi, float sx, float sy, float u = 0, float v = 0) const {
         BSDFSample r; r.weight = V3(0.0f); r.pdf = 0;
         bool flipped = false;
         if (twoSided && wi.z < 0) { wi.z *= -1; flipped = true; }   // twosided.cpp:162-181
@@ -925,8 +945,72 @@ struct SmoothDiffuse {
         r.wo = squareToCosineHemisphere(sx, sy);
         r.eta = 1.0f; r.sampledComponent = 0; r.sampledType = EDiffuseReflection;
         r.pdf = kInvPi * r.wo.z;
-        r.weight = reflectance;
+        r.weight = reflectance.eval(u, v);
         if (flipped && !isZero(r.weight) && r.pdf != 0) { r.wo.z *= -1; r.sampledComponent += 1; }
+        return r;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// SmoothPlastic (`plastic` plugin, models/teapot/scene.xml:31-38) -- src/bsdfs/plastic.cpp:140-167 (ctor), :186-217 (configure),
+// :246-281 (eval), :283-313 (pdf), :381-445 (sample with pdf).  A delta reflection (component 0) over a diffuse base (component 1),
+// front side only; typeMask = EAll, component = -1 as the path tracer asks.  specularReflectance is a constant here.
+// ---------------------------------------------------------------------------------------------
+struct SmoothPlastic {
+    float eta, invEta2, fdrInt, fdrExt, specularSamplingWeight; bool nonlinear = false;
+    V3 specR; Texture2D diffuse;
+    void configure(float intIOR, float extIOR, const Texture2D &d, V3 s, bool nonlin) {
+        eta = intIOR / extIOR; nonlinear = nonlin;
+        Texture2D st; st.setConstant(s); st.ensureEnergyConservation(); specR = st.color0;
+        diffuse = d; diffuse.ensureEnergyConservation();
+        fdrInt = fresnelDiffuseReflectance(1 / eta); fdrExt = fresnelDiffuseReflectance(eta);
+        const float dAvg = luminance(diffuse.getAverage()), sAvg = luminance(specR);
+        specularSamplingWeight = sAvg / (dAvg + sAvg);
+        invEta2 = 1 / (eta * eta);
+    }
+    static V3 reflect(const V3 &wi) { return V3(-wi.x, -wi.y, wi.z); }
+    V3 diffTerm(float u, float v) const {
+        V3 diff = diffuse.eval(u, v);
+        if (nonlinear) diff = V3(diff.x / (1.0f - diff.x * fdrInt), diff.y / (1.0f - diff.y * fdrInt), diff.z / (1.0f - diff.z * fdrInt));
+        else diff = diff / (1 - fdrInt);
+        return diff;
+    }
+    float probSpecular(float Fi) const { return (Fi * specularSamplingWeight) / (Fi * specularSamplingWeight + (1 - Fi) * (1 - specularSamplingWeight)); }
+    V3 eval(const V3 &wi, const V3 &wo, bool discrete, float u = 0, float v = 0) const {
+        if (wo.z <= 0 || wi.z <= 0) return V3(0.0f);
+        const float Fi = fresnelDielectricExt(wi.z, eta);
+        if (discrete) {
+            if (std::abs(dot(reflect(wi), wo) - 1) < kDeltaEpsilon) return specR * Fi;
+        } else {
+            const float Fo = fresnelDielectricExt(wo.z, eta);
+            return diffTerm(u, v) * ((kInvPi * wo.z) * invEta2 * (1 - Fi) * (1 - Fo));
+        }
+        return V3(0.0f);
+    }
+    float pdf(const V3 &wi, const V3 &wo, bool discrete) const {
+        if (wo.z <= 0 || wi.z <= 0) return 0.0f;
+        const float ps = probSpecular(fresnelDielectricExt(wi.z, eta));
+        if (discrete) {
+            if (std::abs(dot(reflect(wi), wo) - 1) < kDeltaEpsilon) return ps;
+        } else return (kInvPi * wo.z) * (1 - ps);
+        return 0.0f;
+    }
+    BSDFSample sample(const V3 &wi, float sx, float sy, float u = 0, float v = 0) const {
+        BSDFSample r; r.weight = V3(0.0f); r.pdf = 0;
+        if (wi.z <= 0) return r;
+        const float Fi = fresnelDielectricExt(wi.z, eta);
+        r.eta = 1.0f;
+        const float ps = probSpecular(Fi);
+        if (sx < ps) {
+            r.sampledComponent = 0; r.sampledType = EDeltaReflection; r.wo = reflect(wi); r.pdf = ps;
+            r.weight = specR * Fi / ps;
+        } else {
+            r.sampledComponent = 1; r.sampledType = EDiffuseReflection;
+            r.wo = squareToCosineHemisphere((sx - ps) / (1 - ps), sy);
+            const float Fo = fresnelDielectricExt(r.wo.z, eta);
+            r.pdf = (1 - ps) * (kInvPi * r.wo.z);
+            r.weight = diffTerm(u, v) * (invEta2 * (1 - Fi) * (1 - Fo) / (1 - ps));
+        }
         return r;
     }
 };

@@ -108,13 +108,60 @@ struct TriAccel {
 };
 
 // A triangle mesh as ShapeKDTree sees it (TriMesh::getVertexPositions/Normals/Triangles after configure()).
+// The `rectangle` shape (src/shapes/rectangle.cpp:79-183): the unit square [-1,1]^2 x {0} under toWorld, one primitive of the
+// top-level tree, intersected analytically in object space (no triangles).
+struct Rectangle {
+    M44 objectToWorld = M44::identity(), worldToObject = M44::identity();
+    V3 dpdu, dpdv; Frame frame;
+    // ctor :81-86 + configure :100-112.  `toWorldInv` is the inverse Transform() carries (Gauss-Jordan for a <matrix>)
+    void configure(const M44 &toWorld, const M44 &toWorldInv, bool flipNormals) {
+        objectToWorld = toWorld; worldToObject = toWorldInv;
+        if (flipNormals) {                                                   // m_objectToWorld * Transform::scale(Vector(1, 1, -1)), transform.cpp:28-31,66-80
+            M44 sc = M44::identity(); sc.m[2][2] = -1.0f;
+            M44 scInv = M44::identity(); scInv.m[2][2] = 1.0f / -1.0f;
+            objectToWorld = mul(toWorld, sc); worldToObject = mul(scInv, toWorldInv);
+        }
+        dpdu = xfmVector(objectToWorld, V3(2, 0, 0)); dpdv = xfmVector(objectToWorld, V3(0, 2, 0));
+        // Transform::operator()(Normal): the transpose of the inverse (transform.h:203-211)
+        const M44 &iv = worldToObject; const V3 nl(0, 0, 1);
+        const V3 nw(iv.m[0][0] * nl.x + iv.m[1][0] * nl.y + iv.m[2][0] * nl.z, iv.m[0][1] * nl.x + iv.m[1][1] * nl.y + iv.m[2][1] * nl.z,
+                    iv.m[0][2] * nl.x + iv.m[1][2] * nl.y + iv.m[2][2] * nl.z);
+        frame.s = normalize(dpdu); frame.t = normalize(dpdv); frame.n = normalize(nw);
+        if (std::abs(dot(normalize(dpdu), normalize(dpdv))) > kEpsilon) throw std::runtime_error("Error: 'toWorld' transformation contains shear!");
+    }
+    AABB getAABB() const {                                                   // :114-121
+        AABB a; a.expand(xfmPoint(objectToWorld, V3(-1, -1, 0))); a.expand(xfmPoint(objectToWorld, V3(1, -1, 0)));
+        a.expand(xfmPoint(objectToWorld, V3(1, 1, 0))); a.expand(xfmPoint(objectToWorld, V3(-1, 1, 0))); return a;
+    }
+    // :127-151 after Transform::transformAffine(Ray) (transform.h:128-146,292-307)
+    bool rayIntersect(const V3 &ro, const V3 &rd, float mint, float maxt, float &lx, float &ly, float &t) const {
+        const M44 &w = worldToObject;
+        const V3 o(w.m[0][0] * ro.x + w.m[0][1] * ro.y + w.m[0][2] * ro.z + w.m[0][3], w.m[1][0] * ro.x + w.m[1][1] * ro.y + w.m[1][2] * ro.z + w.m[1][3],
+                   w.m[2][0] * ro.x + w.m[2][1] * ro.y + w.m[2][2] * ro.z + w.m[2][3]);
+        const V3 d = xfmVector(w, rd);
+        const float hit = -o.z / d.z;
+        if (!(hit >= mint && hit <= maxt)) return false;
+        const V3 local = o + d * hit;                                        // Ray::operator()(t) = o + t * d
+        if (std::abs(local.x) <= 1 && std::abs(local.y) <= 1) { t = hit; lx = local.x; ly = local.y; return true; }
+        return false;
+    }
+};
+
 struct TriMesh {
     std::vector<V3> pos, nrm;       // nrm empty = face normals (skdtree.h:389-391)
+    std::vector<float> uv;          // 2 per vertex; empty = no texture coordinates (its.uv = barycentrics, skdtree.h:399-406)
     std::vector<uint32_t> idx;      // 3 per triangle
     std::vector<TriAccel> accel;    // skdtree.cpp:78-110
-    size_t triCount() const { return idx.size() / 3; }
+    bool isRect = false; Rectangle rect;   // a `rectangle` shape rides in the mesh slot of the shape list as ONE analytic primitive
+    size_t triCount() const { return isRect ? 1 : idx.size() / 3; }
     AABB triAABB(uint32_t j) const { // triangle.h:40-45
+        if (isRect) return rect.getAABB();
         AABB r; r.expand(pos[idx[3 * j]]); r.expand(pos[idx[3 * j + 1]]); r.expand(pos[idx[3 * j + 2]]); return r;
+    }
+    // the primitive test of the top-level tree (skdtree.h:293-312): TriAccel for triangles, Shape::rayIntersect otherwise
+    bool intersectPrim(uint32_t j, const V3 &ro, const V3 &rd, float mint, float maxt, float &u, float &v, float &t) const {
+        if (isRect) return rect.rayIntersect(ro, rd, mint, maxt, u, v, t);
+        return accel[j].rayIntersect(ro, rd, mint, maxt, u, v, t);
     }
 };
 
@@ -201,8 +248,9 @@ struct HairShape {
     // skdtree.cpp:78-110: TriAccel per triangle; bounds = union of the triangle boxes (what the kd-tree build sees)
     void finalizeMesh(uint32_t shapeIndex) {
         isMesh = true;
-        mesh.accel.resize(mesh.triCount());
         aabb = AABB();
+        if (mesh.isRect) { aabb = mesh.rect.getAABB(); return; }
+        mesh.accel.resize(mesh.triCount());
         for (uint32_t j = 0; j < mesh.triCount(); ++j) {
             mesh.accel[j].load(mesh.pos[mesh.idx[3 * j]], mesh.pos[mesh.idx[3 * j + 1]], mesh.pos[mesh.idx[3 * j + 2]]);
             mesh.accel[j].shapeIndex = shapeIndex; mesh.accel[j].primIndex = j;
@@ -347,6 +395,7 @@ struct Intersection {
     V3 p;
     Frame geoFrame, shFrame;
     V3 wi;
+    float u = 0, v = 0;   // its.uv
 };
 
 struct BVHNode { AABB box; uint32_t left, right; uint32_t first, count; }; // leaf if count>0
@@ -399,7 +448,7 @@ struct Geometry {
             if (s.isMesh) { // triangles live in the top-level tree: they see [mint, maxt] directly (skdtree.h:293-304)
                 for (uint32_t j = 0; j < s.mesh.triCount(); ++j) {
                     float t, u, v;
-                    if (s.mesh.accel[j].rayIntersect(ray.o, ray.d, mint, maxt, u, v, t)) {
+                    if (s.mesh.intersectPrim(j, ray.o, ray.d, mint, maxt, u, v, t)) {
                         if (shadow) { hit.t = t; hit.shape = (int) si; hit.iv = j; return true; }
                         maxt = t; hit.t = t; hit.shape = (int) si; hit.iv = j; hit.u = u; hit.v = v; found = true;
                     }
@@ -636,7 +685,7 @@ struct Geometry {
                 const uint32_t rshape = r.shapeFlags >> 3;
                 if (r.shapeFlags & 1u) {
                     float t, u, v;
-                    if (shapes[rshape].mesh.accel[r.iv].rayIntersect(ray.o, ray.d, mint, maxt, u, v, t)) {
+                    if (shapes[rshape].mesh.intersectPrim(r.iv, ray.o, ray.d, mint, maxt, u, v, t)) {
                         if (shadow) { hit.t = t; hit.shape = (int) rshape; hit.iv = r.iv; return true; }
                         maxt = t; hit.t = t; hit.shape = (int) rshape; hit.iv = r.iv; hit.u = u; hit.v = v; found = true;
                     }
@@ -804,7 +853,7 @@ struct Geometry {
                     const PrimRef &pr = prims[i];
                     if (shapes[pr.shape].isMesh) {
                         float t, u, v;
-                        if (shapes[pr.shape].mesh.accel[pr.iv].rayIntersect(ray.o, ray.d, mint, maxt, u, v, t)) {
+                        if (shapes[pr.shape].mesh.intersectPrim(pr.iv, ray.o, ray.d, mint, maxt, u, v, t)) {
                             if (shadow) { hit.t = t; hit.shape = (int) pr.shape; hit.iv = pr.iv; return true; }
                             maxt = t; hit.t = t; hit.shape = (int) pr.shape; hit.iv = pr.iv; hit.u = u; hit.v = v; found = true;
                         }
@@ -839,6 +888,16 @@ struct Geometry {
     void fillIntersection(const Ray &ray, const Hit &hit, Intersection &its) const {
         const HairShape &s = shapes[hit.shape];
         its.valid = true; its.t = hit.t; its.shape = hit.shape; its.iv = hit.iv;
+        if (s.isMesh && s.mesh.isRect) { // rectangle.cpp:158-171, then skdtree.h:426-427
+            const Rectangle &r = s.mesh.rect;
+            its.geoFrame = r.frame;
+            its.shFrame.n = r.frame.n;
+            its.u = 0.5f * (hit.u + 1); its.v = 0.5f * (hit.v + 1);
+            its.p = ray.o + ray.d * hit.t;
+            computeShadingFrame(its.shFrame.n, r.dpdu, its.shFrame);
+            its.wi = its.shFrame.toLocal(-ray.d);
+            return;
+        }
         if (s.isMesh) { // skdtree.h:346-427 with BarycentricPos = true (skdtree.cpp:136)
             const TriMesh &m = s.mesh;
             const V3 b(1 - hit.u - hit.v, hit.u, hit.v);
@@ -855,6 +914,10 @@ struct Geometry {
                 if (dot(faceNormal, its.shFrame.n) < 0) faceNormal = -faceNormal;
             } else its.shFrame.n = faceNormal;
             its.geoFrame = Frame(faceNormal);
+            if (!m.uv.empty()) {                                              // skdtree.h:399-406
+                its.u = m.uv[2 * idx0] * b.x + m.uv[2 * idx1] * b.y + m.uv[2 * idx2] * b.z;
+                its.v = m.uv[2 * idx0 + 1] * b.x + m.uv[2 * idx1 + 1] * b.y + m.uv[2 * idx2 + 1] * b.z;
+            } else { its.u = b.y; its.v = b.z; }
             computeShadingFrame(its.shFrame.n, dpdu, its.shFrame);
             its.wi = its.shFrame.toLocal(-ray.d);
             return;

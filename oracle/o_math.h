@@ -188,6 +188,74 @@ static inline float fresnelDielectricExt(float cosThetaI_, float eta) {
 }
 
 // src/libcore/warp.cpp:81-102
+// ---------------------------------------------------------------------------------------------
+// GaussLobattoIntegrator -- src/libcore/quad.cpp:287-420 (adaptive Gauss-Lobatto with Kronrod extension, fp32), restated with
+// the reference's defaults useConvergenceEstimate = true (include/mitsuba/core/quad.h:155-159).  The six recursive calls of one
+// step are summed left to right.
+// ---------------------------------------------------------------------------------------------
+struct GaussLobatto {
+    float absError, relError; size_t maxEvals; bool useConvergenceEstimate = true;
+    GaussLobatto(size_t maxEvals_, float absError_, float relError_) : absError(absError_), relError(relError_), maxEvals(maxEvals_) {}
+    static float alpha() { return (float) std::sqrt(2.0 / 3.0); }
+    static float beta() { return (float) (1.0 / std::sqrt(5.0)); }
+    template <class F> float integrate(const F &f, float a, float b) const {
+        float factor = 1; size_t evals = 0;
+        if (a == b) return 0;
+        if (b < a) { std::swap(a, b); factor = -1; }
+        const float absTolerance = calculateAbsTolerance(f, a, b, evals);
+        evals += 2;
+        const float fa = f(a), fb = f(b);
+        return factor * step(f, a, b, fa, fb, absTolerance, evals);
+    }
+    template <class F> float calculateAbsTolerance(const F &f, float a, float b, size_t &evals) const {
+        const float x1 = (float) 0.94288241569547971906, x2 = (float) 0.64185334234578130578, x3 = (float) 0.23638319966214988028;
+        const float m = (a + b) / 2, h = (b - a) / 2;
+        const float y1 = f(a), y3 = f(m - alpha() * h), y5 = f(m - beta() * h), y7 = f(m), y9 = f(m + beta() * h), y11 = f(m + alpha() * h), y13 = f(b);
+        const float f1a = f(m - x1 * h), f1b = f(m + x1 * h), f2a = f(m - x2 * h), f2b = f(m + x2 * h), f3a = f(m - x3 * h), f3b = f(m + x3 * h);
+        float acc = h * ((float) 0.0158271919734801831 * (y1 + y13) + (float) 0.0942738402188500455 * (f1a + f1b)
+                       + (float) 0.1550719873365853963 * (y3 + y11) + (float) 0.1888215739601824544 * (f2a + f2b)
+                       + (float) 0.1997734052268585268 * (y5 + y9) + (float) 0.2249264653333395270 * (f3a + f3b)
+                       + (float) 0.2426110719014077338 * y7);
+        evals += 13;
+        float r = 1.0f;
+        if (useConvergenceEstimate) {
+            const float integral2 = (h / 6) * (y1 + y13 + 5 * (y5 + y9));
+            const float integral1 = (h / 1470) * (77 * (y1 + y13) + 432 * (y3 + y11) + 625 * (y5 + y9) + 672 * y7);
+            if (std::abs(integral2 - acc) != 0.0f) r = std::abs(integral1 - acc) / std::abs(integral2 - acc);
+            if (r == 0.0f || r > 1.0f) r = 1.0f;
+        }
+        float result = std::numeric_limits<float>::infinity();
+        const float eps = std::numeric_limits<float>::epsilon();
+        if (relError != 0 && acc != 0) result = acc * std::max(relError, eps) / (r * eps);
+        if (absError != 0) result = std::min(result, absError / (r * eps));
+        return result;
+    }
+    template <class F> float step(const F &f, float a, float b, float fa, float fb, float acc, size_t &evals) const {
+        const float h = (b - a) / 2, m = (a + b) / 2;
+        const float mll = m - alpha() * h, ml = m - beta() * h, mr = m + beta() * h, mrr = m + alpha() * h;
+        const float fmll = f(mll), fml = f(ml), fm = f(m), fmr = f(mr), fmrr = f(mrr);
+        const float integral2 = (h / 6) * (fa + fb + 5 * (fml + fmr));
+        const float integral1 = (h / 1470) * (77 * (fa + fb) + 432 * (fmll + fmrr) + 625 * (fml + fmr) + 672 * fm);
+        evals += 5;
+        if (evals >= maxEvals) return integral1;
+        const float dist = acc + (integral1 - integral2);
+        if (dist == acc || mll <= a || b <= mrr) return integral1;
+        const float s0 = step(f, a, mll, fa, fmll, acc, evals);
+        const float s1 = step(f, mll, ml, fmll, fml, acc, evals);
+        const float s2 = step(f, ml, m, fml, fm, acc, evals);
+        const float s3 = step(f, m, mr, fm, fmr, acc, evals);
+        const float s4 = step(f, mr, mrr, fmr, fmrr, acc, evals);
+        const float s5 = step(f, mrr, b, fmrr, fb, acc, evals);
+        return s0 + s1 + s2 + s3 + s4 + s5;
+    }
+};
+
+// src/libcore/util.cpp:807-862 with fast = false: the diffuse Fresnel reflectance by adaptive quadrature of F(sqrt(xi), eta) over [0, 1]
+static inline float fresnelDiffuseReflectance(float eta) {
+    GaussLobatto quad(1024, 0, 1e-5f);
+    return quad.integrate([eta](float xi) { return fresnelDielectricExt(std::sqrt(xi), eta); }, 0.0f, 1.0f);
+}
+
 static inline void squareToUniformDiskConcentric(float sx, float sy, float &ox, float &oy) {
     float r1 = 2.0f * sx - 1.0f;
     float r2 = 2.0f * sy - 1.0f;

@@ -121,25 +121,48 @@ struct BSDFAny {
     std::shared_ptr<RoughPlastic> rp;      // kind 4: `roughplastic` (default BSDF of the models/*/scene.xml files)
     ThinDielectric td;                     // kind 5: `thindielectric` (models/straight-hair/scene_thindielectric.xml)
     MarschnerDielectric md;                // kind 6: `marschnerdielectric` (models/straight-hair/scene_dielectric*.xml)
-    // measure: ESolidAngle unless `discrete` (only the two dielectric kinds have discrete components)
-    V3 eval(const V3 &wi, const V3 &wo, bool discrete = false) const {
+    SmoothPlastic pl;                      // kind 7: `plastic` (models/teapot/scene.xml:31-38)
+    // `twosided` (src/bsdfs/twosided.cpp:101-181) around a roughplastic / plastic with the same nested BRDF on both sides; the diffuse
+    // kind keeps its own flag (SmoothDiffuse::twoSided)
+    bool twoSided = false;
+    int componentCount() const { return kind == 2 ? 1 : 2; }
+    // measure: ESolidAngle unless `discrete` (only the dielectric kinds and `plastic` have discrete components); (u, v) = its.uv
+    V3 evalOne(const V3 &wi, const V3 &wo, bool discrete, float u, float v) const {
         if (kind == 5) return td.eval(wi, wo, discrete);
         if (kind == 6) return md.eval(wi, wo, discrete);
+        if (kind == 7) return pl.eval(wi, wo, discrete, u, v);
         if (discrete) return V3(0.0f);
-        return kind == 0 ? kk.eval(wi, wo) : kind == 1 ? ma->eval(wi, wo) : kind == 2 ? df.eval(wi, wo) : kind == 3 ? mf->eval(wi, wo) : rp->eval(wi, wo);
+        return kind == 0 ? kk.eval(wi, wo) : kind == 1 ? ma->eval(wi, wo) : kind == 2 ? df.eval(wi, wo, u, v) : kind == 3 ? mf->eval(wi, wo) : rp->eval(wi, wo);
     }
-    float pdf(const V3 &wi, const V3 &wo, bool discrete = false) const {
+    float pdfOne(const V3 &wi, const V3 &wo, bool discrete) const {
         if (kind == 5) return td.pdf(wi, wo, discrete);
         if (kind == 6) return md.pdf(wi, wo, discrete);
+        if (kind == 7) return pl.pdf(wi, wo, discrete);
         if (discrete) return 0.0f;
         return kind == 0 ? kk.pdf(wi, wo) : kind == 1 ? ma->pdf(wi, wo) : kind == 2 ? df.pdf(wi, wo) : kind == 3 ? mf->pdf(wi, wo) : rp->pdf(wi, wo);
     }
-    // `extra` = four more uniform numbers: only the fixed Marschner draws them (two sampler->next2D() calls inside its sample())
-    BSDFSample sample(const V3 &wi, float sx, float sy, const float *extra) const {
+    BSDFSample sampleOne(const V3 &wi, float sx, float sy, const float *extra, float u, float v) const {
         if (kind == 5) return td.sample(wi, sx, sy);
         if (kind == 6) return md.sample(wi, sx, sy);
-        return kind == 0 ? kk.sample(wi, sx, sy) : kind == 1 ? ma->sample(wi, sx, sy) : kind == 2 ? df.sample(wi, sx, sy)
+        if (kind == 7) return pl.sample(wi, sx, sy, u, v);
+        return kind == 0 ? kk.sample(wi, sx, sy) : kind == 1 ? ma->sample(wi, sx, sy) : kind == 2 ? df.sample(wi, sx, sy, u, v)
              : kind == 3 ? mf->sample(wi, extra[0], extra[1], extra[2], extra[3]) : rp->sample(wi, sx, sy);
+    }
+    V3 eval(V3 wi, V3 wo, bool discrete = false, float u = 0, float v = 0) const {
+        if (twoSided && !(wi.z > 0)) { wi.z *= -1; wo.z *= -1; }           // twosided.cpp:101-115
+        return evalOne(wi, wo, discrete, u, v);
+    }
+    float pdf(V3 wi, V3 wo, bool discrete = false) const {
+        if (twoSided && !(wi.z > 0)) { wi.z *= -1; wo.z *= -1; }           // twosided.cpp:117-130
+        return pdfOne(wi, wo, discrete);
+    }
+    // `extra` = four more uniform numbers: only the fixed Marschner draws them (two sampler->next2D() calls inside its sample())
+    BSDFSample sample(V3 wi, float sx, float sy, const float *extra, float u = 0, float v = 0) const {
+        bool flipped = false;
+        if (twoSided && wi.z < 0) { wi.z *= -1; flipped = true; }           // twosided.cpp:162-181
+        BSDFSample r = sampleOne(wi, sx, sy, extra, u, v);
+        if (flipped && !isZero(r.weight) && r.pdf != 0) { r.wo.z *= -1; r.sampledComponent += componentCount(); }
+        return r;
     }
     // BSDF::getType() & ESmooth: the thin dielectric has only discrete components (path.cpp:174-175 then skips emitter sampling)
     bool hasSmooth() const { return kind != 5; }
@@ -209,7 +232,7 @@ struct Scene {
                 }
                 if (!isZero(value)) {
                     V3 wo = its.shFrame.toLocal(ds.d);
-                    const V3 bsdfVal = bsdf.eval(its.wi, wo);
+                    const V3 bsdfVal = bsdf.eval(its.wi, wo, false, its.u, its.v);
                     if (!isZero(bsdfVal) && (!strictNormals || dot(its.geoFrame.n, ds.d) * wo.z > 0)) {
                         float bsdfPdf = bsdf.pdf(its.wi, wo);
                         float weight = miWeight(ds.pdf, bsdfPdf);
@@ -223,7 +246,7 @@ struct Scene {
                 Philox4 ue = philox4x32_10(pix, samp, (uint32_t) depth, 2, k0, k1);
                 for (int k = 0; k < 4; ++k) extra[k] = u32_to_unit(ue.v[k]);
             }
-            BSDFSample bs = bsdf.sample(its.wi, u32_to_unit(u.v[2]), u32_to_unit(u.v[3]), extra);
+            BSDFSample bs = bsdf.sample(its.wi, u32_to_unit(u.v[2]), u32_to_unit(u.v[3]), extra, its.u, its.v);
             if (isZero(bs.weight)) break;
             scattered |= bs.sampledType != ENull;
             const V3 wo = its.shFrame.toWorld(bs.wo);

@@ -138,11 +138,118 @@ int orc_add_bsdf_diffuse(void *sp, const float *reflectance, int twoSided) {
     ORC_CATCH
 }
 
-// Triangle mesh as TriMesh exposes it after configure(): positions, optional vertex normals (null = face normals), indices
-int orc_add_mesh(void *sp, const float *xyz, const float *normals, uint32_t nVerts, const uint32_t *indices, uint32_t nTris, int bsdf) {
+// `plastic` plugin (src/bsdfs/plastic.cpp) with constant reflectances; a checkerboard can replace the diffuse one afterwards
+int orc_add_bsdf_plastic(void *sp, float intIOR, float extIOR, const float *diffuse, const float *specular, int nonlinear) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    BSDFAny b; b.kind = 7;
+    Texture2D d; d.setConstant(V3(diffuse[0], diffuse[1], diffuse[2]));
+    b.pl.configure(intIOR, extIOR, d, V3(specular[0], specular[1], specular[2]), nonlinear != 0);
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+    ORC_CATCH
+}
+// <texture type="checkerboard"> as the (diffuse) reflectance of a `diffuse` or `plastic` BSDF: the BSDF is configured again with it
+int orc_bsdf_set_checkerboard(void *sp, int bsdf, const float *color0, const float *color1, float uoffset, float voffset, float uscale, float vscale) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    BSDFAny &b = s->bsdfs.at(bsdf);
+    Texture2D t; t.setCheckerboard(V3(color0[0], color0[1], color0[2]), V3(color1[0], color1[1], color1[2]), uoffset, voffset, uscale, vscale);
+    if (b.kind == 2) b.df.configure(t, b.df.twoSided);
+    else if (b.kind == 7) { const SmoothPlastic old = b.pl; b.pl.diffuse = t; b.pl.diffuse.ensureEnergyConservation();
+                            b.pl.specularSamplingWeight = luminance(old.specR) / (luminance(b.pl.diffuse.getAverage()) + luminance(old.specR)); }
+    else throw std::runtime_error("textured reflectance: only `diffuse` and `plastic` carry a texture on this path");
+    return 0;
+    ORC_CATCH
+}
+// <bsdf type="twosided"> around a roughplastic / plastic / diffuse BSDF (the same nested BRDF on both sides)
+int orc_bsdf_set_twosided(void *sp, int bsdf) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    BSDFAny &b = s->bsdfs.at(bsdf);
+    if (b.kind == 2) b.df.twoSided = true;
+    else if (b.kind == 4 || b.kind == 7) b.twoSided = true;
+    else throw std::runtime_error("twosided: only materials without a transmission component can be nested");
+    return 0;
+    ORC_CATCH
+}
+int orc_plastic_constants(void *sp, int bsdf, float *out4) {
+    ORC_TRY
+    const BSDFAny &b = ((Scene *) sp)->bsdfs.at(bsdf);
+    if (b.kind != 7) throw std::runtime_error("not a plastic BSDF");
+    out4[0] = b.pl.fdrInt; out4[1] = b.pl.fdrExt; out4[2] = b.pl.specularSamplingWeight; out4[3] = b.pl.invEta2;
+    return 0;
+    ORC_CATCH
+}
+float orc_fresnel_diffuse_reflectance(float eta) { return fresnelDiffuseReflectance(eta); }
+// eval / pdf / sample with texture coordinates (its.uv); measure: 0 solid angle, 1 discrete
+int orc_bsdf_eval_batch_uv(void *sp, int bsdf, uint64_t n, const float *wi, const float *wo, const float *uv, int discrete, float *outEval, float *outPdf) {
+    ORC_TRY
+    const BSDFAny &b = ((Scene *) sp)->bsdfs.at(bsdf);
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), c(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+        V3 e = b.eval(a, c, discrete != 0, uv[2 * i], uv[2 * i + 1]);
+        outEval[3 * i] = e.x; outEval[3 * i + 1] = e.y; outEval[3 * i + 2] = e.z;
+        outPdf[i] = b.pdf(a, c, discrete != 0);
+    }
+    return 0;
+    ORC_CATCH
+}
+int orc_bsdf_sample_batch_uv(void *sp, int bsdf, uint64_t n, const float *wi, const float *sample, const float *uv, float *outWo, float *outWeight,
+                             float *outPdf, int32_t *outType) {
+    ORC_TRY
+    const BSDFAny &b = ((Scene *) sp)->bsdfs.at(bsdf);
+    const float zero[4] = {0, 0, 0, 0};
+    for (uint64_t i = 0; i < n; ++i) {
+        V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+        BSDFSample r = b.sample(a, sample[2 * i], sample[2 * i + 1], zero, uv[2 * i], uv[2 * i + 1]);
+        outWo[3 * i] = r.wo.x; outWo[3 * i + 1] = r.wo.y; outWo[3 * i + 2] = r.wo.z;
+        outWeight[3 * i] = r.weight.x; outWeight[3 * i + 1] = r.weight.y; outWeight[3 * i + 2] = r.weight.z;
+        outPdf[i] = r.pdf; outType[i] = r.sampledType | (r.sampledComponent << 8);
+    }
+    return 0;
+    ORC_CATCH
+}
+// `rectangle` shape (src/shapes/rectangle.cpp): toWorld as one row-major 4x4 matrix, inverted like Transform(const Matrix4x4 &) does
+int orc_add_rectangle(void *sp, const float *toWorld16, int flipNormals, int bsdf) {
     ORC_TRY
     Scene *s = (Scene *) sp;
     HairShape h;
+    const M44 tw = M44::fromRowMajor(toWorld16); M44 inv;
+    if (!invert(tw, inv)) throw std::runtime_error("rectangle: singular toWorld transform");
+    h.mesh.isRect = true; h.mesh.rect.configure(tw, inv, flipNormals != 0);
+    h.bsdf = bsdf;
+    h.finalizeMesh((uint32_t) s->geo.shapes.size());
+    s->geo.shapes.push_back(std::move(h));
+    return (int) s->geo.shapes.size() - 1;
+    ORC_CATCH
+}
+// texture coordinates and geometric normal of the closest hit (its.uv, its.geoFrame.n): 5 floats per ray
+int orc_intersect_uv_batch(void *sp, uint64_t n, const float *o, const float *d, const float *mint, const float *maxt, float *out5) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray r(V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), mint[i], maxt[i]);
+        Intersection its;
+        const bool hit = s->geo.rayIntersect(r, its);
+        float *q = out5 + 5 * i;
+        q[0] = hit ? its.u : 0; q[1] = hit ? its.v : 0; q[2] = hit ? its.geoFrame.n.x : 0; q[3] = hit ? its.geoFrame.n.y : 0; q[4] = hit ? its.geoFrame.n.z : 0;
+    }
+    return 0;
+    ORC_CATCH
+}
+
+// Triangle mesh as TriMesh exposes it after configure(): positions, optional vertex normals (null = face normals), indices
+int orc_add_mesh_uv(void *sp, const float *xyz, const float *normals, const float *uvs, uint32_t nVerts, const uint32_t *indices, uint32_t nTris, int bsdf);
+int orc_add_mesh(void *sp, const float *xyz, const float *normals, uint32_t nVerts, const uint32_t *indices, uint32_t nTris, int bsdf) {
+    return orc_add_mesh_uv(sp, xyz, normals, nullptr, nVerts, indices, nTris, bsdf);
+}
+// ... with optional per-vertex texture coordinates (TriMesh::getVertexTexcoords)
+int orc_add_mesh_uv(void *sp, const float *xyz, const float *normals, const float *uvs, uint32_t nVerts, const uint32_t *indices, uint32_t nTris, int bsdf) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    HairShape h;
+    if (uvs) h.mesh.uv.assign(uvs, uvs + 2 * (size_t) nVerts);
     h.mesh.pos.resize(nVerts);
     for (uint32_t i = 0; i < nVerts; ++i) h.mesh.pos[i] = V3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
     if (normals) { h.mesh.nrm.resize(nVerts); for (uint32_t i = 0; i < nVerts; ++i) h.mesh.nrm[i] = V3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]); }
@@ -353,7 +460,7 @@ int orc_intersect_candidates(void *sp, const float *o, const float *d, float min
         if (h.isMesh) {
             for (uint32_t j = 0; j < h.mesh.triCount(); ++j) {
                 float t, u, v;
-                if (h.mesh.accel[j].rayIntersect(r.o, r.d, smin, smax, u, v, t) && cnt < maxOut) { outShape[cnt] = (int) si; outPrim[cnt] = j; outT[cnt] = t; cnt++; }
+                if (h.mesh.intersectPrim(j, r.o, r.d, smin, smax, u, v, t) && cnt < maxOut) { outShape[cnt] = (int) si; outPrim[cnt] = j; outT[cnt] = t; cnt++; }
             }
             continue;
         }

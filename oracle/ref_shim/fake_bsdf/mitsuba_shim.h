@@ -156,12 +156,10 @@ namespace math {
     inline Float safe_sqrt(Float v) { return std::sqrt(std::max((Float) 0, v)); }
     inline void sincos(Float t, Float *s, Float *c) { ::sincosf(t, s, c); }
     template <typename T> inline T clamp(T v, T lo, T hi) { return std::min(hi, std::max(lo, v)); }
-    inline Float fastexp(Float v) { return std::exp(v); }        // math.h: plain expf unless MTS_FAST_MATH... (only inside MicrofacetDistribution, not on the tested path)
-    inline Float fastlog(Float v) { return std::log(v); }
+    inline float fastexp(float value) { return (float) ::exp((double) value); }      // math.h:185-195: the Linux / x86-64 branch
+    inline float fastlog(float value) { return (float) ::log((double) value); }
     inline Float signum(Float v) { return v < 0 ? (Float) -1 : (v > 0 ? (Float) 1 : (Float) 0); }
-    inline Float hypot2(Float a, Float b) { return std::sqrt(a * a + b * b); }
-    inline Float erf(Float v) { return std::erf(v); }
-    inline Float erfinv(Float v) { return v; }                   // placeholder: visible-normal sampling is not on the tested path
+    float hypot2(float a, float b); Float erf(Float x); Float erfinv(Float x);   // bodies cut out of src/libcore/math.cpp:25-86 at build time (ref_bsdf.cpp)
     inline Float safe_acos(Float v) { return std::acos(std::min((Float) 1, std::max((Float) -1, v))); }
     inline Float safe_asin(Float v) { return std::asin(std::min((Float) 1, std::max((Float) -1, v))); }
 }
@@ -402,6 +400,7 @@ Float evalCubicInterp3DN(const Point3 &p, const Float **nodes, const Float *valu
 // bodies cut out of the reference at build time (oracle/Makefile): src/libcore/util.cpp:651-681, src/libcore/warp.cpp:43-52,81-102
 Float fresnelDielectricExt(Float cosThetaI_, Float &cosThetaT_, Float eta);
 inline Float fresnelDielectricExt(Float cosThetaI, Float eta) { Float cosThetaT; return fresnelDielectricExt(cosThetaI, cosThetaT, eta); }   // util.h:479-480
+Float fresnelDiffuseReflectance(Float eta, bool fast = false);                                                                              // util.h:593-594; body cut out of util.cpp:814-862 (ref_bsdf.cpp)
 namespace warp {
     Point2 squareToUniformDiskConcentric(const Point2 &sample);
     Vector squareToCosineHemisphere(const Point2 &sample);

@@ -5,9 +5,35 @@
 // (with its own microfacet.h, rtrans.h, ior.h, gausssexylingerie.hpp, InterpolatedDistribution1D.hpp) and src/libcore/spline.cpp.
 // Output: oracle/_ref/libref_bsdf.so.  The oracle restatements (oracle/o_bsdf.h) are pinned against it in tests/test_oracle_cpu.py.
 #include "mitsuba_shim.h"
+#include <functional>
+
+namespace boost { using std::function; using namespace std::placeholders; template <class... A> auto bind(A &&...a) { return std::bind(std::forward<A>(a)...); } }
+using namespace std::placeholders;
 
 namespace mitsuba {
 #include "ref_fresnel.inc"          // src/libcore/util.cpp:592-601 (coordinateSystem) and :651-681 (fresnelDielectricExt), cut out at build time
+class GaussLobattoIntegrator {      // include/mitsuba/core/quad.h:132-210 (declarations only); bodies: src/libcore/quad.cpp:287-420, cut out at build time
+public:
+    typedef boost::function<Float (Float)> Integrand;
+    GaussLobattoIntegrator(size_t maxEvals, Float absError = 0, Float relError = 0, bool useConvergenceEstimate = true, bool warn = true);
+    Float integrate(const Integrand &f, Float a, Float b, size_t *evals = NULL) const;
+protected:
+    Float adaptiveGaussLobattoStep(const Integrand &f, Float a, Float b, Float fa, Float fb, Float is, size_t &evals) const;
+    Float calculateAbsTolerance(const Integrand &f, Float a, Float b, size_t &evals) const;
+    Float m_absError, m_relError;
+    size_t m_maxEvals;
+    bool m_useConvergenceEstimate;
+    bool m_warn;
+    static const Float m_alpha, m_beta, m_x1, m_x2, m_x3;
+};
+#include "ref_bsdf_quad.inc"
+namespace {
+#include "ref_fdr_integrand.inc"    // src/libcore/util.cpp:809-811 (the integrand; its anonymous namespace is supplied here)
+}
+#include "ref_fdr.inc"              // src/libcore/util.cpp:814-862 (fresnelDiffuseReflectance)
+namespace math {
+#include "ref_math.inc"             // src/libcore/math.cpp:25-86 (erfinv, erf, hypot2: what Beckmann visible-normal sampling runs on), cut out at build time
+}
 namespace warp {
 #include "ref_warp.inc"             // src/libcore/warp.cpp:43-52 and :81-102, cut out at build time
 }
@@ -24,6 +50,8 @@ void *ref_create_Marschner(const Properties *);
 void *ref_create_RoughPlastic(const Properties *);
 void *ref_create_SmoothDiffuse(const Properties *);
 void *ref_create_TwoSidedBRDF(const Properties *);
+void *ref_create_SmoothPlastic(const Properties *);
+float ref_fresnel_diffuse_reflectance(float eta) { return fresnelDiffuseReflectance(eta, false); }
 
 // params: nFloat (name, value) pairs and nSpec (name, r, g, b) entries
 void *ref_bsdf_create(const char *plugin, int nFloat, const char **floatNames, const float *floatValues, int nSpec, const char **specNames, const float *specValues) {
@@ -43,9 +71,11 @@ void *ref_bsdf_create(const char *plugin, int nFloat, const char **floatNames, c
         else if (p == "marschner_fixed") b = (BSDF *) ref_create_Marschner(&props);           // src/bsdfs/marschner.cpp, the class the fork's build leaves out
         else if (p == "roughplastic") b = (BSDF *) ref_create_RoughPlastic(&props);
         else if (p == "diffuse") b = (BSDF *) ref_create_SmoothDiffuse(&props);
-        else if (p == "twosided") {                                                           // <bsdf type="twosided"><bsdf type="diffuse"/></bsdf>
+        else if (p == "plastic") b = (BSDF *) ref_create_SmoothPlastic(&props);
+        else if (p == "twosided" || p == "twosided:plastic" || p == "twosided:roughplastic") {  // <bsdf type="twosided"><bsdf type="diffuse | plastic | roughplastic"/></bsdf>
             b = (BSDF *) ref_create_TwoSidedBRDF(&props);
-            BSDF *nested = (BSDF *) ref_create_SmoothDiffuse(&props); nested->configure();
+            BSDF *nested = (BSDF *) (p == "twosided" ? ref_create_SmoothDiffuse(&props) : p == "twosided:plastic" ? ref_create_SmoothPlastic(&props) : ref_create_RoughPlastic(&props));
+            nested->configure();
             b->addChild("", nested);
         }
         else return nullptr;

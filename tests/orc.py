@@ -31,6 +31,7 @@ def lib():
         L.orc_hair_file_vertex_count.restype = ctypes.c_uint32
         L.orc_hair_file_segment_count.restype = ctypes.c_uint32
         L.orc_hair_file_radius.restype = ctypes.c_float
+        L.orc_fresnel_diffuse_reflectance.restype = ctypes.c_float
         _lib = L
     return _lib
 
@@ -138,19 +139,59 @@ class Scene:
         if type in ('diffuse', 'twosided'):
             r = f32(np.broadcast_to(props.get('reflectance', 0.5), 3))
             return check(self.L.orc_add_bsdf_diffuse(self.h, p(r), 1 if (type == 'twosided' or props.get('twoSided', False)) else 0))
+        if type == 'plastic':
+            d = f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3)); s = f32(np.broadcast_to(props.get('specularReflectance', 1.0), 3))
+            return check(self.L.orc_add_bsdf_plastic(self.h, ctypes.c_float(props.get('intIOR', 1.49)), ctypes.c_float(props.get('extIOR', 1.000277)), p(d), p(s),
+                                                     1 if props.get('nonlinear', False) else 0))
         d = f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3)); s = f32(np.broadcast_to(props.get('specularReflectance', 0.5), 3))
         return check(self.L.orc_add_bsdf_marschner(self.h, ctypes.c_float(props.get('intIOR', 1.5046)), ctypes.c_float(props.get('extIOR', 1.000277)), p(d), p(s),
                                                    ctypes.c_float(props.get('alpha', 0.1)), DISTR[props.get('distribution', 'beckmann')],
                                                    1 if props.get('nonlinear', False) else 0, DATA_DIR.encode()))
 
+    def set_checkerboard(self, bsdf, color0=0.4, color1=0.2, uoffset=0.0, voffset=0.0, uscale=1.0, vscale=1.0):
+        c0 = f32(np.broadcast_to(color0, 3)); c1 = f32(np.broadcast_to(color1, 3))
+        check(self.L.orc_bsdf_set_checkerboard(self.h, int(bsdf), p(c0), p(c1), ctypes.c_float(uoffset), ctypes.c_float(voffset), ctypes.c_float(uscale), ctypes.c_float(vscale)))
+
+    def set_twosided(self, bsdf):
+        check(self.L.orc_bsdf_set_twosided(self.h, int(bsdf)))
+
+    def plastic_constants(self, bsdf):
+        out = np.zeros(4, np.float32); check(self.L.orc_plastic_constants(self.h, int(bsdf), p(out)))
+        return dict(fdrInt=out[0], fdrExt=out[1], specW=out[2], invEta2=out[3])
+
+    def add_rectangle(self, toWorld=None, flipNormals=False, bsdf=0):
+        tw = f32(IDENT if toWorld is None else toWorld).reshape(16)
+        return check(self.L.orc_add_rectangle(self.h, p(tw), 1 if flipNormals else 0, int(bsdf)))
+
+    def bsdf_eval_uv(self, bsdf, wi, wo, uv, discrete=False):
+        wi = f32(wi).reshape(-1, 3); wo = f32(wo).reshape(-1, 3); uv = f32(uv).reshape(-1, 2); n = len(wi)
+        ev = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32)
+        check(self.L.orc_bsdf_eval_batch_uv(self.h, int(bsdf), ctypes.c_uint64(n), p(wi), p(wo), p(uv), 1 if discrete else 0, p(ev), p(pdf)))
+        return ev, pdf
+
+    def bsdf_sample_uv(self, bsdf, wi, sample, uv):
+        wi = f32(wi).reshape(-1, 3); sample = f32(sample).reshape(-1, 2); uv = f32(uv).reshape(-1, 2); n = len(wi)
+        wo = np.zeros((n, 3), np.float32); wt = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32); ty = np.zeros(n, np.int32)
+        check(self.L.orc_bsdf_sample_batch_uv(self.h, int(bsdf), ctypes.c_uint64(n), p(wi), p(sample), p(uv), p(wo), p(wt), p(pdf), p(ty)))
+        return wo, wt, pdf, ty
+
+    def intersect_uv(self, o, d, mint, maxt):
+        o = f32(o).reshape(-1, 3); d = f32(d).reshape(-1, 3); n = len(o)
+        mint = f32(np.broadcast_to(mint, n)); maxt = f32(np.broadcast_to(maxt, n))
+        out = np.zeros((n, 5), np.float32)
+        check(self.L.orc_intersect_uv_batch(self.h, ctypes.c_uint64(n), p(o), p(d), p(mint), p(maxt), p(out)))
+        return out[:, :2].copy(), out[:, 2:].copy()
+
     def add_hair(self, xyz, starts, radius, bsdf):
         xyz = f32(xyz).reshape(-1, 3); st = np.ascontiguousarray(starts, dtype=np.uint8)
         return check(self.L.orc_add_hair(self.h, p(xyz), p(st), ctypes.c_uint32(len(st)), ctypes.c_float(radius), int(bsdf)))
 
-    def add_mesh(self, xyz, indices, bsdf, normals=None):
+    def add_mesh(self, xyz, indices, bsdf, normals=None, uvs=None):
         xyz = f32(xyz).reshape(-1, 3); idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
         nrm = None if normals is None else f32(normals).reshape(-1, 3)
-        return check(self.L.orc_add_mesh(self.h, p(xyz), None if nrm is None else p(nrm), ctypes.c_uint32(len(xyz)), p(idx), ctypes.c_uint32(len(idx)), int(bsdf)))
+        uv = None if uvs is None else f32(uvs).reshape(-1, 2)
+        return check(self.L.orc_add_mesh_uv(self.h, p(xyz), None if nrm is None else p(nrm), None if uv is None else p(uv), ctypes.c_uint32(len(xyz)), p(idx),
+                                            ctypes.c_uint32(len(idx)), int(bsdf)))
 
     def set_envmap(self, rgb, toWorld=None, scale=1.0):
         rgb = f32(rgb); h, w = rgb.shape[:2]

@@ -1116,8 +1116,8 @@ def test_oracle_marschner_pinned_against_compiled_reference_plugin(oracle, props
     ('marschner_fixed', dict(intIOR=1.55, extIOR=1.000277))])
 def test_oracle_mesh_and_next_row_bsdfs_pinned_against_compiled_reference_plugins(oracle, plugin, props):
     """src/bsdfs/{diffuse,twosided,roughplastic,marschner}.cpp compiled unmodified (marschner.cpp is the class the fork's build leaves out:
-    the `fixed` mode, with its two extra sampler draws) against the oracle restatements.  The scaffolding's erfinv is a placeholder, so
-    Beckmann visible-normal SAMPLING is not compared; every eval / pdf is."""
+    the `fixed` mode, with its two extra sampler draws) against the oracle restatements; math::erf / erfinv / hypot2 behind the Beckmann
+    visible-normal sampling are the reference's own (src/libcore/math.cpp:25-86, cut out at build time)."""
     os.environ['REF_DATA_DIR'] = oracle.DATA_DIR
     distr = {'beckmann': 0.0, 'ggx': 1.0, 'phong': 2.0}
     floats = {k: (distr[v] if k == 'distribution' else float(v)) for k, v in props.items() if not isinstance(v, tuple)}
@@ -1138,8 +1138,6 @@ def test_oracle_mesh_and_next_row_bsdfs_pinned_against_compiled_reference_plugin
     perr = np.abs(rp - op) / np.maximum(np.abs(op), 1e-6)
     assert err.max() <= tol and perr.max() <= tol, '%s: eval %.3g pdf %.3g' % (plugin, err.max(), perr.max())
     assert np.median(err) < 2e-7 and np.median(perr) < 2e-7
-    if plugin == 'roughplastic' and props.get('distribution') == 'beckmann':
-        return
     rwo, rwt, rpdf, rty = ref.sample(wi, smp, extra)
     owo, owt, opdf, oty = s.bsdf_sample(b, wi, smp, extra)
     alive = (rwt != 0).any(axis=1)
@@ -1681,3 +1679,128 @@ def test_sun_radiance_pinned_against_reference_text(cp, oracle):
             worst_p = max(worst_p, float(np.abs(prod - ref).max() / ref.max())); worst_o = max(worst_o, float(np.abs(orc_rgb - ref).max() / ref.max()))
     print('sun radiance vs the compiled reference: product %.2e, oracle %.2e of the largest channel' % (worst_p, worst_o))
     assert worst_p <= 1e-4 and worst_o <= 1e-4            # the tolerance the reference itself asks of its integrator (GaussLobattoIntegrator(10000, Epsilon, Epsilon), spectrum.cpp:547)
+
+
+@needs_ref_bsdf
+def test_fresnel_diffuse_reflectance_pinned_against_reference_text(oracle):
+    """fresnelDiffuseReflectance(eta, fast = false) (src/libcore/util.cpp:807-862) over the adaptive Gauss-Lobatto rule (src/libcore/quad.cpp:287-420),
+    both cut out of the reference and compiled as written, against the oracle's restatement (o_math.h): the same bits from eta = 0.4 to 3."""
+    R = ctypes.CDLL(REF_BSDF); R.ref_fresnel_diffuse_reflectance.restype = ctypes.c_float
+    L = oracle.lib()
+    for eta in np.concatenate([np.linspace(0.4, 0.98, 30), np.linspace(1.02, 3.0, 60), [1.49 / 1.000277, 1.000277 / 1.49, 1.5, 1 / 1.5]]).astype(np.float32):
+        a = R.ref_fresnel_diffuse_reflectance(ctypes.c_float(eta)); b = L.orc_fresnel_diffuse_reflectance(ctypes.c_float(eta))
+        assert np.float32(a) == np.float32(b) and 0 < a < 1, (eta, a, b)
+
+
+@needs_ref_bsdf
+@pytest.mark.parametrize('plugin,props', [
+    ('plastic', dict(intIOR=1.5, extIOR=1.0, nonlinear=True, diffuseReflectance=(0.9, 0.9, 0.9))),        # models/teapot/scene.xml:31-38
+    ('plastic', dict(diffuseReflectance=(0.2, 0.5, 0.7), specularReflectance=(0.9, 0.8, 1.3))),
+    ('twosided:plastic', dict(intIOR=1.5, extIOR=1.0, nonlinear=True, diffuseReflectance=(0.9, 0.9, 0.9))),
+    ('twosided:roughplastic', dict(intIOR=1.55, extIOR=1.0, alpha=0.2, distribution='ggx', diffuseReflectance=(0.4, 0.3, 0.2)))])
+def test_oracle_plastic_and_twosided_pinned_against_compiled_reference_plugins(oracle, plugin, props):
+    """src/bsdfs/plastic.cpp compiled unmodified (with fresnelDiffuseReflectance and the Gauss-Lobatto rule cut out of libcore), alone and inside
+    src/bsdfs/twosided.cpp, against the oracle: both measures (the delta reflection lives in the discrete one), all of eval / pdf / sample.
+    plastic: bit-identical.  twosided over roughplastic: the tolerances of the one-sided test."""
+    os.environ['REF_DATA_DIR'] = oracle.DATA_DIR
+    distr = {'beckmann': 0.0, 'ggx': 1.0, 'phong': 2.0}
+    floats = {k: (distr[v] if k == 'distribution' else float(v)) for k, v in props.items() if not isinstance(v, tuple)}
+    spectra = {k: v for k, v in props.items() if isinstance(v, tuple)}
+    ref = RefBSDF(plugin, floats, spectra)
+    s = oracle.Scene()
+    base = plugin.split(':')[-1]
+    q = dict(props); q.setdefault('intIOR', 1.49); q.setdefault('extIOR', 1.000277)
+    b = s.add_bsdf(base, **q)
+    if plugin.startswith('twosided'):
+        s.set_twosided(b)
+    rng = np.random.default_rng(53)
+    n = 100000
+    wi = sphere_dirs(rng, n); wo = sphere_dirs(rng, n); smp = rng.random((n, 2)).astype(np.float32)
+    wo[: n // 4] = wi[: n // 4] * np.array([-1, -1, 1], np.float32)             # exact mirror pairs: the delta component
+    exact = base == 'plastic'
+    for discrete in (False, True):
+        rev, rp = ref.eval(wi, wo, discrete); oev, op = s.bsdf_eval(b, wi, wo, discrete)
+        if exact:
+            assert np.array_equal(rev, oev) and np.array_equal(rp, op)
+            assert (rev != 0).any() and (rp != 0).any()
+        else:
+            assert np.array_equal((rev != 0).any(axis=1), (oev != 0).any(axis=1)) and np.array_equal(rp != 0, op != 0)
+            assert (np.abs(rev - oev) / np.maximum(np.abs(oev).max(axis=1, keepdims=True), 1e-6)).max() <= 1e-4
+    if plugin.startswith('twosided'):
+        rev, _ = ref.eval(wi, wo, False)
+        assert (rev[wi[:, 2] < 0] != 0).any()                                    # the back side scatters as well
+    rwo, rwt, rpdf, rty = ref.sample(wi, smp)
+    owo, owt, opdf, oty = s.bsdf_sample(b, wi, smp)
+    if exact:
+        alive = (rwt != 0).any(axis=1)
+        assert np.array_equal(alive, (owt != 0).any(axis=1)) and np.array_equal(rty[alive], oty[alive])
+        delta = alive & ((rty & 0xff) == 0x20)                                   # EDeltaReflection (bsdf.h:84): bit-identical
+        assert delta.sum() > 1000 and (alive & ~delta).sum() > 1000              # both components are drawn
+        assert np.array_equal(rwt[delta], owt[delta]) and np.array_equal(rpdf[delta], opdf[delta]) and np.array_equal(rwo[delta], owo[delta])
+        # the diffuse lobe draws its direction with sincosf in the reference (warp.cpp:43-52) and correctly rounded in the oracle: one ulp in wo, hence in Fo
+        assert np.abs(rwo[alive] - owo[alive]).max() < 1e-5 and np.abs(rwt[alive] - owt[alive]).max() < 2e-5 and np.abs(rpdf[alive] - opdf[alive]).max() < 1e-6 and np.median(np.abs(rwt[alive] - owt[alive])) == 0
+    else:
+        alive = (rwt != 0).any(axis=1)
+        same = (alive == (owt != 0).any(axis=1)) & (~alive | (rty == oty))
+        assert same.mean() > 0.999
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GEOM), reason='oracle/_ref/libref_geom.so not built (needs /root/reference)')
+def test_rectangle_and_checkerboard_pinned_against_reference_text(cp, oracle):
+    """Rectangle::configure / getAABB / rayIntersect / fillIntersectionRecord (src/shapes/rectangle.cpp:100-171) over the reference's Transform
+    (transform.h / transform.cpp / matrix.inl text) and Checkerboard::eval behind Texture2D::eval (src/textures/checkerboard.cpp:65-72,
+    src/librender/texture.cpp:112-121), cut out and executed as written (oracle/ref_shim/ref_rect.cpp), against the oracle: hit / miss, t, hit
+    point, both normals, uv and the bounds bit-identical on the floor of models/teapot/scene.xml:56-62 and on a rotated, flipped rectangle; texture
+    colours identical on 10^5 lookups including negative and huge coordinates."""
+    R = ctypes.CDLL(REF_GEOM); R.ref_rect_create.restype = ctypes.c_void_p
+    rng = np.random.default_rng(59)
+    floor = np.array([-39.9766, 39.9766, -1.74743e-006, 0, 4.94249e-006, 2.47125e-006, -56.5355, 0, -39.9766, -39.9766, -5.2423e-006, 0, 0, 0, 0, 1], np.float32).reshape(4, 4)
+    c, s_ = np.cos(0.7), np.sin(0.7)
+    rot = (np.array([[c, 0, s_, 1.5], [0, 1, 0, -2.0], [-s_, 0, c, 0.25], [0, 0, 0, 1]]) @ np.diag([3.0, 0.5, 1.0, 1.0])).astype(np.float32)
+    for tw, flip in ((floor, False), (rot, False), (rot, True), (np.eye(4, dtype=np.float32), True)):
+        err = ctypes.create_string_buffer(256)
+        h = ctypes.c_void_p(R.ref_rect_create(tw.ctypes.data_as(ctypes.c_void_p), 1 if flip else 0, err, 256)); assert h.value, err.value
+        s = oracle.Scene(); b = s.add_bsdf('diffuse', reflectance=0.5)
+        s.add_rectangle(tw, flip, b)
+        s.set_camera(np.eye(4, dtype=np.float32), width=8, height=8); s.build()
+        rb = np.zeros(6, np.float32); R.ref_rect_bounds(h, rb.ctypes.data_as(ctypes.c_void_p))
+        n = 40000
+        centre = (tw @ np.array([0, 0, 0, 1], np.float32))[:3]; ext = float(np.abs(tw[:3, :3]).sum(axis=1).max())
+        target = centre + (rng.random((n, 3)).astype(np.float32) - 0.5) * 2.4 * ext * np.array([1, 1, 1], np.float32)
+        target = (tw @ np.concatenate([(rng.random((n, 2)) * 2.6 - 1.3), np.zeros((n, 1)), np.ones((n, 1))], axis=1).T).T[:, :3].astype(np.float32)
+        o = (centre + sphere_dirs(rng, n) * ext * (0.5 + 2 * rng.random((n, 1)))).astype(np.float32)
+        d = target - o; d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        mint = np.full(n, 1e-4, np.float32); maxt = np.where(rng.random(n) < 0.2, ext, np.inf).astype(np.float32)
+        hit = np.zeros(n, np.int32); t = np.zeros(n, np.float32); rec = np.zeros((n, 14), np.float32)
+        R.ref_rect_intersect(h, n, o.ctypes.data_as(ctypes.c_void_p), d.ctypes.data_as(ctypes.c_void_p), mint.ctypes.data_as(ctypes.c_void_p), maxt.ctypes.data_as(ctypes.c_void_p),
+                             hit.ctypes.data_as(ctypes.c_void_p), t.ctypes.data_as(ctypes.c_void_p), rec.ctypes.data_as(ctypes.c_void_p))
+        assert (hit >= 0).all() and 0.2 < hit.mean() < 0.9
+        sh, pr, ot, orec = s.intersect_full(o, d, mint, maxt)
+        # the scene query clips the ray against the (enlarged) scene box first (skdtree.cpp:112-142): compare where that box cannot matter
+        ouv, ogn = s.intersect_uv(o, d, mint, maxt)
+        assert np.array_equal(sh >= 0, hit == 1)
+        k = hit == 1
+        assert np.array_equal(ot[k], t[k]) and np.array_equal(orec[k, 0:3], rec[k, 0:3])          # t, p
+        assert np.array_equal(ogn[k], rec[k, 3:6]) and np.array_equal(orec[k, 3:6], rec[k, 6:9])    # geoFrame.n, shFrame.n
+        assert np.array_equal(ouv[k], rec[k, 12:14])
+        bmin, bmax = s.scene_bounds()[0][:3], s.scene_bounds()[0][3:]
+        assert (bmin <= rb[:3]).all() and (bmax >= rb[3:]).all() and np.allclose(bmin, rb[:3], rtol=2e-3, atol=2e-3 * ext)   # the tree box is the shape box enlarged (gkdtree.h:1213-1220)
+    sheared = np.eye(4, dtype=np.float32); sheared[0, 1] = 0.3
+    err = ctypes.create_string_buffer(256)
+    assert not R.ref_rect_create(sheared.ctypes.data_as(ctypes.c_void_p), 0, err, 256) and b'shear' in err.value
+    s = oracle.Scene(); b = s.add_bsdf('diffuse', reflectance=0.5)
+    with pytest.raises(RuntimeError, match='shear'):
+        s.add_rectangle(sheared, False, b)
+    # checkerboard
+    n = 100000
+    uv = np.concatenate([rng.random((n // 2, 2)) * 4 - 2, (rng.random((n // 2, 2)) - 0.5) * 1e6]).astype(np.float32)
+    uv[:8] = [[0, 0], [0.5, 0.5], [0.25, 0.75], [-0.25, 0.25], [1, 1], [-1e-8, 0.3], [0.49999997, 0.1], [2.5, -3.5]]
+    c0 = np.array([0.725, 0.71, 0.68], np.float32); c1 = np.array([0.325, 0.31, 0.25], np.float32)
+    for (uo, vo, us, vs) in ((0, 0, 10, 10), (0.25, -0.5, 3, 0.5), (0, 0, 1, 1)):
+        ref = np.zeros((n, 3), np.float32)
+        R.ref_checkerboard_eval(c0.ctypes.data_as(ctypes.c_void_p), c1.ctypes.data_as(ctypes.c_void_p), ctypes.c_float(uo), ctypes.c_float(vo), ctypes.c_float(us), ctypes.c_float(vs),
+                                n, uv.ctypes.data_as(ctypes.c_void_p), ref.ctypes.data_as(ctypes.c_void_p))
+        s = oracle.Scene(); b = s.add_bsdf('diffuse', reflectance=0.5); s.set_checkerboard(b, c0, c1, uo, vo, us, vs)
+        wi = np.tile(np.array([[0, 0, 1]], np.float32), (n, 1))
+        _, wt, _, _ = s.bsdf_sample_uv(b, wi, np.full((n, 2), 0.5, np.float32), uv)           # SmoothDiffuse::sample returns the reflectance (diffuse.cpp:140-156)
+        assert np.array_equal(wt, ref) and 0.3 < (ref[:, 0] == c0[0]).mean() < 0.7
