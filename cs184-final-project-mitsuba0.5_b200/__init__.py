@@ -84,9 +84,9 @@ def load_hair_file(filename, radius=0.025, angleThreshold=1.0, reduction=0.0, to
     return xyz, starts, float(r)
 
 
-def load_obj_file(filename, toWorld=None, faceNormals=False, flipNormals=False):
+def load_obj_file(filename, toWorld=None, faceNormals=False, flipNormals=False, texcoords=False):
     """WavefrontOBJ(props) + TriMesh::computeNormals (src/shapes/obj.cpp:186-349, src/librender/trimesh.cpp:608-672) ->
-    (xyz (n,3) f32, indices (m,3) u32, normals (n,3) f32 or None)."""
+    (xyz (n,3) f32, indices (m,3) u32, normals (n,3) f32 or None); with texcoords=True also the `vt` coordinates (n,2) or None."""
     L = lib()
     h = ctypes.c_void_p()
     tw = _f32(_IDENTITY if toWorld is None else toWorld).reshape(16)
@@ -95,8 +95,18 @@ def load_obj_file(filename, toWorld=None, faceNormals=False, flipNormals=False):
     xyz = np.zeros((nv, 3), np.float32); idx = np.zeros((nt, 3), np.uint32)
     nrm = np.zeros((nv, 3), np.float32) if L.cudapath_mesh_file_has_normals(h) else None
     L.cudapath_mesh_file_copy(h, _p(xyz), None if nrm is None else _p(nrm), _p(idx))
+    uv = None
+    if texcoords and L.cudapath_mesh_file_has_texcoords(h):
+        uv = np.zeros((nv, 2), np.float32); L.cudapath_mesh_file_copy_texcoords(h, _p(uv))
     L.cudapath_mesh_file_free(h)
-    return xyz, idx, nrm
+    return (xyz, idx, nrm, uv) if texcoords else (xyz, idx, nrm)
+
+
+def fresnel_diffuse_reflectance(eta):
+    """fresnelDiffuseReflectance(eta, fast=false), src/libcore/util.cpp:814-862 (host only)."""
+    out = ctypes.c_float()
+    _check(lib().cudapath_fresnel_diffuse_reflectance(ctypes.c_float(eta), ctypes.byref(out)))
+    return np.float32(out.value)
 
 
 def validate_scene_xml(filename, defines=None):
@@ -218,6 +228,18 @@ class Context:
             # the fork's unbuilt src/bsdfs/marschner.cpp ("fixed" mode: TRT-only eval, real pdf); defaults amber / air
             ior = lambda v: float(_IOR[v.lower()]) if isinstance(v, str) else float(v)
             return _check(self._L.cudapath_add_bsdf_marschner_fixed(self._h, ctypes.c_float(ior(props.get('intIOR', 'amber'))), ctypes.c_float(ior(props.get('extIOR', 'air')))))
+        if type == 'marschner_full':
+            # the same class with all three lobes in eval() and scene-driven constants (cudapath_add_bsdf_marschner_full)
+            ior = lambda v: float(_IOR[v.lower()]) if isinstance(v, str) else float(v)
+            sa = _f32(np.broadcast_to(props.get('sigmaA', 0.22), 3))
+            return _check(self._L.cudapath_add_bsdf_marschner_full(self._h, ctypes.c_float(ior(props.get('intIOR', 'amber'))), ctypes.c_float(ior(props.get('extIOR', 'air'))), _p(sa),
+                                                                   ctypes.c_float(props.get('betaR', 0.1)), ctypes.c_float(props.get('scaleAngleRad', -0.1)), int(props.get('lobes', 7))))
+        if type == 'plastic':
+            # src/bsdfs/plastic.cpp:140-167; defaults polypropylene / air, specular 1, diffuse 0.5
+            ior = lambda v: float(_IOR[v.lower()]) if isinstance(v, str) else float(v)
+            d = _f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3)); s = _f32(np.broadcast_to(props.get('specularReflectance', 1.0), 3))
+            return _check(self._L.cudapath_add_bsdf_plastic(self._h, ctypes.c_float(ior(props.get('intIOR', 'polypropylene'))), ctypes.c_float(ior(props.get('extIOR', 'air'))),
+                                                            _p(d), _p(s), 1 if props.get('nonlinear', False) else 0))
         if type in ('diffuse', 'twosided'):
             # `diffuse` with a constant reflectance (src/bsdfs/diffuse.cpp:70-103); type 'twosided' = <bsdf type="twosided"><bsdf type="diffuse"/></bsdf>
             r = _f32(np.broadcast_to(props.get('reflectance', 0.5), 3))
@@ -234,15 +256,33 @@ class Context:
             r = _f32(np.broadcast_to(props.get('specularReflectance', 0.1), 3)); t = _f32(np.broadcast_to(props.get('specularTransmittance', 0.1), 3))
             return _check(self._L.cudapath_add_bsdf_marschnerdielectric(self._h, ctypes.c_float(ior(props.get('intIOR', 'benzene'))), ctypes.c_float(ior(props.get('extIOR', 'air'))),
                                                                         _p(d), _p(r), _p(t), ctypes.c_float(props.get('exponent', 30.0))))
-        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, marschnerdielectric, thindielectric, roughplastic, diffuse, twosided)' % type)
+        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, marschnerdielectric, thindielectric, roughplastic, plastic, diffuse, twosided)' % type)
 
-    def add_mesh(self, xyz, indices, bsdf_id, normals=None):
-        """Triangle mesh (TriMesh positions / optional vertex normals / index triples); joins the fibers in the device BVH."""
+    def set_checkerboard(self, bsdf_id, color0=0.4, color1=0.2, uoffset=0.0, voffset=0.0, uscale=1.0, vscale=1.0):
+        """`<texture type="checkerboard">` as the reflectance of a `diffuse` / the diffuseReflectance of a `plastic` BSDF (src/textures/checkerboard.cpp)."""
+        c0 = _f32(np.broadcast_to(color0, 3)); c1 = _f32(np.broadcast_to(color1, 3))
+        _check(self._L.cudapath_bsdf_set_checkerboard(self._h, int(bsdf_id), _p(c0), _p(c1), ctypes.c_float(uoffset), ctypes.c_float(voffset), ctypes.c_float(uscale), ctypes.c_float(vscale)))
+
+    def set_twosided(self, bsdf_id):
+        """`<bsdf type="twosided">` around a diffuse / roughplastic / plastic BSDF (src/bsdfs/twosided.cpp)."""
+        _check(self._L.cudapath_bsdf_set_twosided(self._h, int(bsdf_id)))
+
+    def add_rectangle(self, bsdf_id, toWorld=None, flipNormals=False):
+        """`<shape type="rectangle">` (src/shapes/rectangle.cpp): [-1,1]^2 x {0} under toWorld."""
+        tw = _f32(_IDENTITY if toWorld is None else toWorld).reshape(16)
+        return _check(self._L.cudapath_add_rectangle(self._h, _p(tw), 1 if flipNormals else 0, int(bsdf_id)))
+
+    def add_mesh(self, xyz, indices, bsdf_id, normals=None, uvs=None):
+        """Triangle mesh (TriMesh positions / optional vertex normals / optional texture coordinates / index triples); joins the fibers in the device BVH."""
         xyz = _f32(xyz).reshape(-1, 3); idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
         nrm = None if normals is None else _f32(normals).reshape(-1, 3)
+        uv = None if uvs is None else _f32(uvs).reshape(-1, 2)
         if nrm is not None and len(nrm) != len(xyz):
             raise CudapathError('normals must have one entry per vertex')
-        return _check(self._L.cudapath_add_mesh(self._h, _p(xyz), None if nrm is None else _p(nrm), ctypes.c_uint32(len(xyz)), _p(idx), ctypes.c_uint32(len(idx)), int(bsdf_id)))
+        if uv is not None and len(uv) != len(xyz):
+            raise CudapathError('uvs must have one entry per vertex')
+        return _check(self._L.cudapath_add_mesh_uv(self._h, _p(xyz), None if nrm is None else _p(nrm), None if uv is None else _p(uv), ctypes.c_uint32(len(xyz)), _p(idx),
+                                                   ctypes.c_uint32(len(idx)), int(bsdf_id)))
 
     def add_hair(self, xyz, starts_fiber, radius, bsdf_id):
         xyz = _f32(xyz).reshape(-1, 3); st = np.ascontiguousarray(starts_fiber, dtype=np.uint8)
@@ -385,6 +425,27 @@ class Context:
         ev = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32)
         _check((self._L.cudapath_bsdf_eval_batch_discrete if discrete else self._L.cudapath_bsdf_eval_batch)(self._h, int(bsdf_id), ctypes.c_uint64(n), _p(wi), _p(wo), _p(ev), _p(pdf)))
         return ev, pdf
+
+    def bsdf_eval_uv(self, bsdf_id, wi, wo, uv, discrete=False):
+        """BSDF::eval + pdf with texture coordinates per tuple (its.uv): the textured kinds."""
+        wi = _f32(wi).reshape(-1, 3); wo = _f32(wo).reshape(-1, 3); uv = _f32(uv).reshape(-1, 2); n = len(wi)
+        ev = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32)
+        _check(self._L.cudapath_bsdf_eval_batch_uv(self._h, int(bsdf_id), ctypes.c_uint64(n), _p(wi), _p(wo), _p(uv), 1 if discrete else 0, _p(ev), _p(pdf)))
+        return ev, pdf
+
+    def bsdf_sample_uv(self, bsdf_id, wi, sample, uv):
+        wi = _f32(wi).reshape(-1, 3); sample = _f32(sample).reshape(-1, 2); uv = _f32(uv).reshape(-1, 2); n = len(wi)
+        wo = np.zeros((n, 3), np.float32); wt = np.zeros((n, 3), np.float32); pdf = np.zeros(n, np.float32); ty = np.zeros(n, np.int32)
+        _check(self._L.cudapath_bsdf_sample_batch_uv(self._h, int(bsdf_id), ctypes.c_uint64(n), _p(wi), _p(sample), _p(uv), _p(wo), _p(wt), _p(pdf), _p(ty)))
+        return wo, wt, pdf, ty
+
+    def intersect_uv(self, o, d, mint, maxt):
+        """Closest hit with the record, its.uv and the geometric normal: (shape, prim, t, record (n,15), uv (n,2), geoN (n,3))."""
+        o = _f32(o).reshape(-1, 3); d = _f32(d).reshape(-1, 3); n = len(o)
+        mint = _f32(np.broadcast_to(mint, n)); maxt = _f32(np.broadcast_to(maxt, n))
+        sh = np.zeros(n, np.int32); pr = np.zeros(n, np.uint32); t = np.zeros(n, np.float32); rec = np.zeros((n, 15), np.float32); uv = np.zeros((n, 5), np.float32)
+        _check(self._L.cudapath_intersect_batch_uv(self._h, ctypes.c_uint64(n), _p(o), _p(d), _p(mint), _p(maxt), _p(sh), _p(pr), _p(t), _p(rec), _p(uv)))
+        return sh, pr, t, rec, uv[:, :2].copy(), uv[:, 2:].copy()
 
     def bsdf_eval_world(self, bsdf_id, frames, wi_world, wo_world):
         """BSDF::eval + pdf from world-space directions and per-tuple shading frames (n, 3, 3) = rows s, t, n (Frame::toLocal on the device)."""

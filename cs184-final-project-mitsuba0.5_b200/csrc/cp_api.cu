@@ -61,10 +61,11 @@ struct cudapath_ctx {
     std::vector<BsdfHost> bsdfs;
     // per shape: raw caller arrays staged on the device (xyz fp32 triples + starts bytes); packed into `d_vtx` by build()
     // (meshes: xyz / optional normals fp32 triples + shape-local uint32 index triples)
-    struct Staged { float *xyz = nullptr; uint8_t *starts = nullptr; uint32_t n = 0; float *nrm = nullptr; uint32_t *idx = nullptr; uint32_t nTris = 0; };
+    struct Staged { float *xyz = nullptr; uint8_t *starts = nullptr; uint32_t n = 0; float *nrm = nullptr; uint32_t *idx = nullptr; uint32_t nTris = 0; float *uv = nullptr; };
     std::vector<Staged> staged;
     uint32_t vtxTotal = 0, meshVtxTotal = 0, triTotal = 0;
-    float4 *d_meshPos = nullptr, *d_meshNrm = nullptr, *d_triAccel = nullptr; uint32_t *d_meshIdx = nullptr;
+    float4 *d_meshPos = nullptr, *d_meshNrm = nullptr, *d_triAccel = nullptr; uint32_t *d_meshIdx = nullptr; float2 *d_meshUV = nullptr;
+    std::vector<float4> rects; float4 *d_rects = nullptr;      // CP_RECT_STRIDE float4 per `rectangle` shape (cp_tri.cuh)
     std::vector<ShapeDev> shapes;
     EnvHost env; EnvTables envTables;
     CamHost cam;
@@ -94,15 +95,15 @@ struct cudapath_ctx {
     void freeBuilt() {
         cudaDeviceSynchronize();
         dfree(d_vtx); dfree(d_shapes); dfree(d_bsdfs); dfree(bvh.nodes); dfree(bvh.prims); dfree(bvh.leafSeg);
-        dfree(d_meshPos); dfree(d_meshNrm); dfree(d_triAccel); dfree(d_meshIdx);
-        d_meshPos = d_meshNrm = d_triAccel = nullptr; d_meshIdx = nullptr;
+        dfree(d_meshPos); dfree(d_meshNrm); dfree(d_triAccel); dfree(d_meshIdx); dfree(d_meshUV); dfree(d_rects);
+        d_meshPos = d_meshNrm = d_triAccel = nullptr; d_meshIdx = nullptr; d_meshUV = nullptr; d_rects = nullptr;
         dfree(envTables.texels); dfree(envTables.cdfCols); dfree(envTables.cdfRows); dfree(envTables.rowWeights); dfree(envTables.mipTexels); dfree(envTables.mipInfo);
         d_vtx = nullptr; d_shapes = nullptr; d_bsdfs = nullptr; bvh = BVHDev(); envTables = EnvTables(); built = false;
     }
     ~cudapath_ctx() {
         DevGuard guard_(device);
         freeBuilt();                  // synchronises the device
-        for (auto &st : staged) { dfree(st.xyz); dfree(st.starts); dfree(st.nrm); dfree(st.idx); }
+        for (auto &st : staged) { dfree(st.xyz); dfree(st.starts); dfree(st.nrm); dfree(st.idx); dfree(st.uv); }
         for (auto &b : bsdfs) { dfree(b.tables.tab); dfree(b.tables.cdf); dfree(b.tables.sums); dfree(b.tables.pdf); dfree(b.rt); }
         wf.release();
         if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
@@ -254,25 +255,31 @@ int cudapath_add_bsdf_roughplastic(cudapath_ctx *ctx, float int_ior, float ext_i
 }
 
 int cudapath_add_bsdf_marschner_fixed(cudapath_ctx *ctx, float int_ior, float ext_ior) {
-    if (!ctx) return fail("null context");
+    const float sigmaA[3] = {0.22f, 0.22f, 0.22f};                               // marschner.cpp:122, :130-137 (hard-coded); eval keeps TRT only (:333-334)
+    return cudapath_add_bsdf_marschner_full(ctx, int_ior, ext_ior, sigmaA, 0.1f, -0.1f, 4);
+}
+int cudapath_add_bsdf_marschner_full(cudapath_ctx *ctx, float int_ior, float ext_ior, const float sigmaA[3], float betaR, float scale_angle_rad, int lobe_mask) {
+    if (!ctx || !sigmaA) return fail("null argument");
     if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
+    if (!(betaR > 0)) return fail("marschner: the longitudinal roughness betaR must be positive");
+    if (lobe_mask < 1 || lobe_mask > 7) return fail("marschner: lobe_mask selects at least one of R (1), TT (2), TRT (4)");
     CP_GUARD(ctx);
     BsdfHost b; std::memset((void *) &b.dev, 0, sizeof(b.dev));
     b.dev.kind = 3;
     b.dev.eta = int_ior / ext_ior;
-    const float betaR = 0.1f, betaTT = betaR * 0.5f, betaTRT = betaR * 2.0f;     // marschner.cpp:130-137 (hard-coded)
+    const float betaTT = betaR * 0.5f, betaTRT = betaR * 2.0f;                   // marschner.cpp:133-134
     b.dev.vR = betaR * betaR; b.dev.vTT = betaTT * betaTT; b.dev.vTRT = betaTRT * betaTRT;
-    b.dev.scaleAngle = -0.1f;
+    b.dev.scaleAngle = scale_angle_rad;
+    b.dev.lobeMask = lobe_mask;
     set_lobe_constants(b.dev);
     b.dev.diffuse = V3(0.0f); b.dev.specular = V3(1.0f);
     float pts[140], wts[140];
     gauss_legendre_140(pts, wts);
-    const float sigmaA[3] = {0.22f, 0.22f, 0.22f};                               // marschner.cpp:122
     std::string err;
     if (!build_marschner_tables(b.dev.eta, betaR, sigmaA, pts, wts, ctx->stream, b.tables, err)) return fail(err);
     b.dev.tab = b.tables.tab; b.dev.cdf = b.tables.cdf; b.dev.sums = b.tables.sums; b.dev.pdfs = b.tables.pdf;
     ctx->bsdfs.push_back(b); ctx->built = false;
-    return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_marschner_fixed(p, int_ior, ext_ior); });
+    return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_marschner_full(p, int_ior, ext_ior, sigmaA, betaR, scale_angle_rad, lobe_mask); });
 }
 
 static V3 ensure_energy_conservation(const float v[3]) {      // BSDF::ensureEnergyConservation for a constant texture, bsdf.cpp:88-113
@@ -320,7 +327,98 @@ int cudapath_add_bsdf_diffuse(cudapath_ctx *ctx, const float reflectance[3], int
     return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_diffuse(p, reflectance, two_sided); });
 }
 
+// `plastic` (src/bsdfs/plastic.cpp:140-217): constant reflectances; a checkerboard can replace the diffuse one (cudapath_bsdf_set_checkerboard)
+int cudapath_add_bsdf_plastic(cudapath_ctx *ctx, float int_ior, float ext_ior, const float d[3], const float s[3], int nonlinear) {
+    if (!ctx || !d || !s) return fail("null argument");
+    if (int_ior < 0 || ext_ior < 0) return fail("The interior and exterior indices of refraction must be positive!");
+    BsdfHost b; std::memset((void *) &b.dev, 0, sizeof(b.dev));
+    b.dev.kind = 7;
+    b.dev.eta = int_ior / ext_ior;                               // :152
+    b.dev.specular = ensure_energy_conservation(s);              // :188-191
+    b.dev.diffuse = ensure_energy_conservation(d);
+    b.dev.color1 = b.dev.diffuse;
+    b.dev.nonlinear = nonlinear ? 1 : 0;
+    b.dev.Fdr = fresnel_diffuse_reflectance(1 / b.dev.eta);      // m_fdrInt, :194 (m_fdrExt only feeds getDiffuseReflectance)
+    const float dAvg = luminance(b.dev.diffuse), sAvg = luminance(b.dev.specular);
+    b.dev.specW = sAvg / (dAvg + sAvg);                          // :199-202
+    b.dev.invEta2 = 1 / (b.dev.eta * b.dev.eta);
+    b.dev.uvScale[0] = b.dev.uvScale[1] = 1.0f;
+    ctx->bsdfs.push_back(b); ctx->built = false;
+    return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_plastic(p, int_ior, ext_ior, d, s, nonlinear); });
+}
+
+// <texture type="checkerboard"> as the (diffuse) reflectance of a `diffuse` or `plastic` BSDF (src/textures/checkerboard.cpp:49-52,
+// src/librender/texture.cpp:81-95); the BSDF's configure() runs again on it: energy conservation over both colours (bsdf.cpp:88-113),
+// sampling weights from the average colour (plastic.cpp:199-202)
+int cudapath_bsdf_set_checkerboard(cudapath_ctx *ctx, int bsdf_id, const float color0[3], const float color1[3], float uoffset, float voffset, float uscale, float vscale) {
+    if (!ctx || !color0 || !color1) return fail("null argument");
+    if (bsdf_id < 0 || bsdf_id >= (int) ctx->bsdfs.size()) return fail("unknown bsdf id");
+    BsdfDev &b = ctx->bsdfs[bsdf_id].dev;
+    if (b.kind != 2 && b.kind != 7) return fail("textured reflectance: only `diffuse` and `plastic` carry a texture on this path");
+    V3 c0(color0[0], color0[1], color0[2]), c1(color1[0], color1[1], color1[2]);
+    const float actualMax = std::max(maxc(c0), maxc(c1));
+    if (actualMax > 1.0f) { const float sc = 0.99f * (1.0f / actualMax); c0 = c0 * sc; c1 = c1 * sc; }
+    b.texKind = 1; b.diffuse = c0; b.color1 = c1;
+    b.uvOffset[0] = uoffset; b.uvOffset[1] = voffset; b.uvScale[0] = uscale; b.uvScale[1] = vscale;
+    if (b.kind == 7) { const float dAvg = luminance((c0 + c1) * 0.5f), sAvg = luminance(b.specular); b.specW = sAvg / (dAvg + sAvg); }
+    ctx->built = false;
+    return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_bsdf_set_checkerboard(p, bsdf_id, color0, color1, uoffset, voffset, uscale, vscale); });
+}
+
+// <bsdf type="twosided"> around a diffuse / roughplastic / plastic BSDF, the same nested BRDF on both sides (src/bsdfs/twosided.cpp:84-110)
+int cudapath_bsdf_set_twosided(cudapath_ctx *ctx, int bsdf_id) {
+    if (!ctx) return fail("null argument");
+    if (bsdf_id < 0 || bsdf_id >= (int) ctx->bsdfs.size()) return fail("unknown bsdf id");
+    BsdfDev &b = ctx->bsdfs[bsdf_id].dev;
+    if (b.kind != 2 && b.kind != 4 && b.kind != 7) return fail("Only materials without a transmission component can be nested!");
+    b.twoSided = 1; ctx->built = false;
+    return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_bsdf_set_twosided(p, bsdf_id); });
+}
+
+int cudapath_fresnel_diffuse_reflectance(float eta, float *out) { if (!out) return fail("null argument"); *out = fresnel_diffuse_reflectance(eta); return 0; }
+
+// `rectangle` (src/shapes/rectangle.cpp:81-125): the square [-1,1]^2 x {0} under toWorld, one analytic primitive.  Host arithmetic in plain
+// fp32 without FMA, like the reference: Transform(Matrix4x4) inverts by Gauss-Jordan, flipNormals multiplies by scale(1, 1, -1).
+int cudapath_add_rectangle(cudapath_ctx *ctx, const float to_world[16], int flip_normals, int bsdf_id) {
+    if (!ctx || !to_world) return fail("null argument");
+    if (bsdf_id < 0 || bsdf_id >= (int) ctx->bsdfs.size()) return fail("rectangle references an unknown bsdf id");
+    if (ctx->shapes.size() >= (1u << 23)) return fail("too many shapes");
+    float o2w[16], w2o[16];
+    std::memcpy(o2w, to_world, 64);
+    if (!mat_inv(o2w, w2o)) return fail("rectangle: singular toWorld transform");
+    if (flip_normals) {
+        float sc[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 1}, scInv[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1.0f / -1.0f, 0, 0, 0, 0, 1}, a[16], b[16];
+        mat_mul(o2w, sc, a); mat_mul(scInv, w2o, b);                // Transform::operator* : (A.m B.m, B.inv A.inv), transform.cpp:28-31
+        std::memcpy(o2w, a, 64); std::memcpy(w2o, b, 64);
+    }
+    auto xv = [&](const float *m, V3 v) { return V3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z, m[8] * v.x + m[9] * v.y + m[10] * v.z); };
+    const V3 dpdu = xv(o2w, V3(2, 0, 0)), dpdv = xv(o2w, V3(0, 2, 0));
+    const V3 nl(0, 0, 1);                                          // Transform::operator()(Normal): transpose of the inverse
+    const V3 nw(w2o[0] * nl.x + w2o[4] * nl.y + w2o[8] * nl.z, w2o[1] * nl.x + w2o[5] * nl.y + w2o[9] * nl.z, w2o[2] * nl.x + w2o[6] * nl.y + w2o[10] * nl.z);
+    const V3 n = normalize(nw);
+    if (std::abs(dot(normalize(dpdu), normalize(dpdv))) > kEpsilon) return fail("Error: 'toWorld' transformation contains shear!");
+    float bmin[3] = {INFINITY, INFINITY, INFINITY}, bmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const V3 corners[4] = {V3(-1, -1, 0), V3(1, -1, 0), V3(1, 1, 0), V3(-1, 1, 0)};
+    for (const V3 &c : corners) { const V3 q = h_xfm_point(o2w, c); bmin[0] = std::min(bmin[0], q.x); bmin[1] = std::min(bmin[1], q.y); bmin[2] = std::min(bmin[2], q.z);
+                                  bmax[0] = std::max(bmax[0], q.x); bmax[1] = std::max(bmax[1], q.y); bmax[2] = std::max(bmax[2], q.z); }
+    const uint32_t shapeIndex = (uint32_t) ctx->shapes.size();
+    float4 rec[CP_RECT_STRIDE];
+    for (int r = 0; r < 3; ++r) rec[r] = make_float4(w2o[4 * r], w2o[4 * r + 1], w2o[4 * r + 2], w2o[4 * r + 3]);
+    uint32_t si = shapeIndex; float sif; std::memcpy(&sif, &si, 4);
+    rec[3] = make_float4(dpdu.x, dpdu.y, dpdu.z, sif); rec[4] = make_float4(n.x, n.y, n.z, 0.0f); rec[5] = make_float4(dpdv.x, dpdv.y, dpdv.z, 0.0f);
+    rec[6] = make_float4(bmin[0], bmin[1], bmin[2], 0.0f); rec[7] = make_float4(bmax[0], bmax[1], bmax[2], 0.0f);
+    ShapeDev sd; std::memset(&sd, 0, sizeof(sd));
+    sd.kind = 2; sd.bsdf = bsdf_id; sd.triOffset = (uint32_t) (ctx->rects.size() / CP_RECT_STRIDE); sd.triCount = 1;
+    ctx->rects.insert(ctx->rects.end(), rec, rec + CP_RECT_STRIDE);
+    ctx->staged.push_back(cudapath_ctx::Staged());
+    ctx->shapes.push_back(sd); ctx->built = false;
+    return fan_out(ctx, (int) ctx->shapes.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_rectangle(p, to_world, flip_normals, bsdf_id); });
+}
+
 int cudapath_add_mesh(cudapath_ctx *ctx, const float *xyz, const float *normals, uint32_t n_vertices, const uint32_t *indices, uint32_t n_triangles, int bsdf_id) {
+    return cudapath_add_mesh_uv(ctx, xyz, normals, nullptr, n_vertices, indices, n_triangles, bsdf_id);
+}
+int cudapath_add_mesh_uv(cudapath_ctx *ctx, const float *xyz, const float *normals, const float *uvs, uint32_t n_vertices, const uint32_t *indices, uint32_t n_triangles, int bsdf_id) {
     if (!ctx || !xyz || !indices) return fail("null argument");
     if (bsdf_id < 0 || bsdf_id >= (int) ctx->bsdfs.size()) return fail("mesh references an unknown bsdf id");
     if (n_vertices == 0 || n_triangles == 0) return fail("mesh needs at least one vertex and one triangle");
@@ -330,8 +428,12 @@ int cudapath_add_mesh(cudapath_ctx *ctx, const float *xyz, const float *normals,
     CP_GUARD(ctx);
     ShapeDev sd; std::memset(&sd, 0, sizeof(sd));
     sd.kind = 1; sd.bsdf = bsdf_id; sd.vertexOffset = ctx->meshVtxTotal; sd.vertexCount = n_vertices; sd.triOffset = ctx->triTotal; sd.triCount = n_triangles;
-    sd.hasNormals = normals ? 1 : 0;
+    sd.hasNormals = normals ? 1 : 0; sd.hasUV = uvs ? 1 : 0;
     cudapath_ctx::Staged st; st.n = n_vertices; st.nTris = n_triangles;
+    if (uvs) {
+        CKA(dev_alloc(&st.uv, sizeof(float) * 2 * (size_t) n_vertices));
+        CKA(cudaMemcpyAsync(st.uv, uvs, sizeof(float) * 2 * (size_t) n_vertices, cudaMemcpyHostToDevice, ctx->stream));
+    }
     CKA(dev_alloc(&st.xyz, sizeof(float) * 3 * (size_t) n_vertices));
     CKA(cudaMemcpyAsync(st.xyz, xyz, sizeof(float) * 3 * (size_t) n_vertices, cudaMemcpyHostToDevice, ctx->stream));
     if (normals) {
@@ -344,7 +446,7 @@ int cudapath_add_mesh(cudapath_ctx *ctx, const float *xyz, const float *normals,
     ctx->staged.push_back(st);
     ctx->meshVtxTotal += n_vertices; ctx->triTotal += n_triangles;
     ctx->shapes.push_back(sd); ctx->built = false;
-    return fan_out(ctx, (int) ctx->shapes.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_mesh(p, xyz, normals, n_vertices, indices, n_triangles, bsdf_id); });
+    return fan_out(ctx, (int) ctx->shapes.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_mesh_uv(p, xyz, normals, uvs, n_vertices, indices, n_triangles, bsdf_id); });
 }
 
 int cudapath_mesh_file_load(const char *filename, const float to_world[16], int face_normals, int flip_normals, cudapath_mesh_file **out) {
@@ -358,6 +460,8 @@ int cudapath_mesh_file_load(const char *filename, const float to_world[16], int 
 uint32_t cudapath_mesh_file_vertex_count(const cudapath_mesh_file *m) { return m ? (uint32_t) (m->data.xyz.size() / 3) : 0; }
 uint32_t cudapath_mesh_file_triangle_count(const cudapath_mesh_file *m) { return m ? (uint32_t) (m->data.indices.size() / 3) : 0; }
 int cudapath_mesh_file_has_normals(const cudapath_mesh_file *m) { return m && !m->data.normals.empty() ? 1 : 0; }
+int cudapath_mesh_file_has_texcoords(const cudapath_mesh_file *m) { return m && !m->data.uvs.empty() ? 1 : 0; }
+void cudapath_mesh_file_copy_texcoords(const cudapath_mesh_file *m, float *uvs) { if (m && uvs && !m->data.uvs.empty()) std::memcpy(uvs, m->data.uvs.data(), m->data.uvs.size() * 4); }
 void cudapath_mesh_file_copy(const cudapath_mesh_file *m, float *xyz, float *normals, uint32_t *indices) {
     if (!m) return;
     if (xyz) std::memcpy(xyz, m->data.xyz.data(), m->data.xyz.size() * 4);
@@ -369,8 +473,8 @@ void cudapath_mesh_file_free(cudapath_mesh_file *m) { delete m; }
 int cudapath_add_mesh_file(cudapath_ctx *ctx, const char *filename, const float to_world[16], int face_normals, int flip_normals, int bsdf_id) {
     cudapath_mesh_file *m = nullptr;
     if (cudapath_mesh_file_load(filename, to_world, face_normals, flip_normals, &m) != 0) return -1;
-    int r = cudapath_add_mesh(ctx, m->data.xyz.data(), m->data.normals.empty() ? nullptr : m->data.normals.data(), (uint32_t) (m->data.xyz.size() / 3),
-                              m->data.indices.data(), (uint32_t) (m->data.indices.size() / 3), bsdf_id);
+    int r = cudapath_add_mesh_uv(ctx, m->data.xyz.data(), m->data.normals.empty() ? nullptr : m->data.normals.data(), m->data.uvs.empty() ? nullptr : m->data.uvs.data(),
+                                 (uint32_t) (m->data.xyz.size() / 3), m->data.indices.data(), (uint32_t) (m->data.indices.size() / 3), bsdf_id);
     cudapath_mesh_file_free(m);
     return r;
 }
@@ -540,7 +644,15 @@ static int build_one(cudapath_ctx *ctx) {
     CKA(dev_alloc(&ctx->d_vtx, sizeof(float4) * ((size_t) ctx->vtxTotal + 4)));
     CKA(cudaMemsetAsync(ctx->d_vtx, 0, sizeof(float4) * ((size_t) ctx->vtxTotal + 4), ctx->stream));
     MeshDev mesh; std::memset(&mesh, 0, sizeof(mesh));
+    if (!ctx->rects.empty()) {
+        CKA(dev_alloc(&ctx->d_rects, sizeof(float4) * ctx->rects.size()));
+        CKA(cudaMemcpyAsync(ctx->d_rects, ctx->rects.data(), sizeof(float4) * ctx->rects.size(), cudaMemcpyHostToDevice, ctx->stream));
+        mesh.rects = ctx->d_rects; mesh.rectCount = (uint32_t) (ctx->rects.size() / CP_RECT_STRIDE);
+    }
     if (ctx->triTotal) {
+        CKA(dev_alloc(&ctx->d_meshUV, sizeof(float2) * (size_t) ctx->meshVtxTotal));
+        CKA(cudaMemsetAsync(ctx->d_meshUV, 0, sizeof(float2) * (size_t) ctx->meshVtxTotal, ctx->stream));
+        mesh.uv = ctx->d_meshUV;
         CKA(dev_alloc(&ctx->d_meshPos, sizeof(float4) * (size_t) ctx->meshVtxTotal)); CKA(dev_alloc(&ctx->d_meshNrm, sizeof(float4) * (size_t) ctx->meshVtxTotal));
         CKA(dev_alloc(&ctx->d_meshIdx, sizeof(uint32_t) * 3 * (size_t) ctx->triTotal)); CKA(dev_alloc(&ctx->d_triAccel, sizeof(float4) * 3 * (size_t) ctx->triTotal));
         mesh.triAccel = ctx->d_triAccel; mesh.pos = ctx->d_meshPos; mesh.nrm = ctx->d_meshNrm; mesh.idx = ctx->d_meshIdx;
@@ -550,8 +662,10 @@ static int build_one(cudapath_ctx *ctx) {
     for (size_t i = 0; i < ctx->staged.size(); ++i) {
         const cudapath_ctx::Staged &st = ctx->staged[i];
         const ShapeDev &sd = ctx->shapes[i];
+        if (sd.kind == 2) continue;                 // rectangle: its record is already in d_rects
         if (sd.kind == 1) {
             pack_mesh(st.xyz, st.nrm, st.n, ctx->d_meshPos + sd.vertexOffset, ctx->d_meshNrm + sd.vertexOffset, ctx->stream);
+            if (st.uv) CKA(cudaMemcpyAsync(ctx->d_meshUV + sd.vertexOffset, st.uv, sizeof(float2) * (size_t) st.n, cudaMemcpyDeviceToDevice, ctx->stream));
             build_tri_accel(st.idx, st.nTris, sd.vertexOffset, (uint32_t) i, ctx->d_meshPos, ctx->d_meshIdx + 3 * (size_t) sd.triOffset,
                             ctx->d_triAccel + 3 * (size_t) sd.triOffset, ctx->stream);
         } else {
@@ -588,7 +702,7 @@ static int build_one(cudapath_ctx *ctx) {
     std::memset(&S, 0, sizeof(S));
     S.vtx = ctx->d_vtx; S.vtxCount = ctx->vtxTotal; S.shapes = ctx->d_shapes; S.shapeCount = (int) ctx->shapes.size();
     S.bsdfs = ctx->d_bsdfs; S.bsdfCount = (int) devs.size(); S.bvh = ctx->bvh; S.integ = ctx->integ;
-    S.mesh = mesh; S.clipPerShape = (hairShapes > 1 || ctx->triTotal > 0) ? 1 : 0;
+    S.mesh = mesh; S.clipPerShape = (hairShapes > 1 || ctx->triTotal > 0 || !ctx->rects.empty()) ? 1 : 0;
     for (int k = 0; k < 3; ++k) { S.sceneMin[k] = INFINITY; S.sceneMax[k] = -INFINITY; }
     for (auto &sh : ctx->shapes) for (int k = 0; k < 3; ++k) { S.sceneMin[k] = std::min(S.sceneMin[k], sh.bmin[k]); S.sceneMax[k] = std::max(S.sceneMax[k], sh.bmax[k]); }
     enlarge(S.sceneMin, S.sceneMax);
@@ -1076,7 +1190,7 @@ int cudapath_bsdf_eval_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const f
     CP_GUARD(ctx);
     DevBuf a, b, e, p; std::string err;
     CKA(a.upload(wi, n * 12, ctx->stream)); CKA(b.upload(wo, n * 12, ctx->stream)); CKA(e.alloc(n * 12)); CKA(p.alloc(n * 4));
-    if (!(ctx->fastMath ? bsdf_eval_batch_fast : bsdf_eval_batch)(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err, false)) return fail(err);
+    if (!(ctx->fastMath ? bsdf_eval_batch_fast : bsdf_eval_batch)(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err, false, nullptr)) return fail(err);
     CKA(e.download(out_eval, ctx->stream)); CKA(p.download(out_pdf, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1086,8 +1200,32 @@ int cudapath_bsdf_eval_batch_discrete(cudapath_ctx *ctx, int bsdf_id, uint64_t n
     CP_GUARD(ctx);
     DevBuf a, b, e, p; std::string err;
     CKA(a.upload(wi, n * 12, ctx->stream)); CKA(b.upload(wo, n * 12, ctx->stream)); CKA(e.alloc(n * 12)); CKA(p.alloc(n * 4));
-    if (!(ctx->fastMath ? bsdf_eval_batch_fast : bsdf_eval_batch)(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err, true)) return fail(err);
+    if (!(ctx->fastMath ? bsdf_eval_batch_fast : bsdf_eval_batch)(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err, true, nullptr)) return fail(err);
     CKA(e.download(out_eval, ctx->stream)); CKA(p.download(out_pdf, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+// ... with texture coordinates per tuple (its.uv): the textured kinds (`diffuse` / `plastic` with a checkerboard); discrete != 0: EDiscrete measure
+int cudapath_bsdf_eval_batch_uv(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, const float *uv, int discrete, float *out_eval, float *out_pdf) {
+    if (require_built(ctx)) return -1;
+    if (!wi || !wo || !uv || !out_eval || !out_pdf) return fail("null argument");
+    CP_GUARD(ctx);
+    DevBuf a, b, t, e, p; std::string err;
+    CKA(a.upload(wi, n * 12, ctx->stream)); CKA(b.upload(wo, n * 12, ctx->stream)); CKA(t.upload(uv, n * 8, ctx->stream)); CKA(e.alloc(n * 12)); CKA(p.alloc(n * 4));
+    if (!(ctx->fastMath ? bsdf_eval_batch_fast : bsdf_eval_batch)(ctx->scene, bsdf_id, n, a.as<float>(), b.as<float>(), e.as<float>(), p.as<float>(), ctx->stream, err, discrete != 0, t.as<float>())) return fail(err);
+    CKA(e.download(out_eval, ctx->stream)); CKA(p.download(out_pdf, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int cudapath_bsdf_sample_batch_uv(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, const float *uv, float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type) {
+    if (require_built(ctx)) return -1;
+    if (!wi || !sample || !uv || !out_wo || !out_weight || !out_pdf || !out_type) return fail("null argument");
+    CP_GUARD(ctx);
+    DevBuf a, s, x, wo, wt, p, t; std::string err;
+    CKA(a.upload(wi, n * 12, ctx->stream)); CKA(s.upload(sample, n * 8, ctx->stream)); CKA(x.upload(uv, n * 8, ctx->stream));
+    CKA(wo.alloc(n * 12)); CKA(wt.alloc(n * 12)); CKA(p.alloc(n * 4)); CKA(t.alloc(n * 4));
+    if (!(ctx->fastMath ? bsdf_sample_batch_fast : bsdf_sample_batch)(ctx->scene, bsdf_id, n, a.as<float>(), s.as<float>(), nullptr, wo.as<float>(), wt.as<float>(), p.as<float>(), t.as<int32_t>(), ctx->stream, err, x.as<float>())) return fail(err);
+    CKA(wo.download(out_wo, ctx->stream)); CKA(wt.download(out_weight, ctx->stream)); CKA(p.download(out_pdf, ctx->stream)); CKA(t.download(out_type, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -1112,7 +1250,7 @@ int cudapath_bsdf_sample_batch_ex(cudapath_ctx *ctx, int bsdf_id, uint64_t n, co
     CKA(a.upload(wi, n * 12, ctx->stream)); CKA(s.upload(sample, n * 8, ctx->stream));
     if (extra) CKA(x.upload(extra, n * 16, ctx->stream));
     CKA(wo.alloc(n * 12)); CKA(wt.alloc(n * 12)); CKA(p.alloc(n * 4)); CKA(t.alloc(n * 4));
-    if (!(ctx->fastMath ? bsdf_sample_batch_fast : bsdf_sample_batch)(ctx->scene, bsdf_id, n, a.as<float>(), s.as<float>(), extra ? x.as<float>() : nullptr, wo.as<float>(), wt.as<float>(), p.as<float>(), t.as<int32_t>(), ctx->stream, err)) return fail(err);
+    if (!(ctx->fastMath ? bsdf_sample_batch_fast : bsdf_sample_batch)(ctx->scene, bsdf_id, n, a.as<float>(), s.as<float>(), extra ? x.as<float>() : nullptr, wo.as<float>(), wt.as<float>(), p.as<float>(), t.as<int32_t>(), ctx->stream, err, nullptr)) return fail(err);
     CKA(wo.download(out_wo, ctx->stream)); CKA(wt.download(out_weight, ctx->stream)); CKA(p.download(out_pdf, ctx->stream)); CKA(t.download(out_type, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1129,6 +1267,22 @@ int cudapath_intersect_batch(cudapath_ctx *ctx, uint64_t n, const float *origin,
                          out_record ? rec.as<float>() : nullptr, nullptr, ctx->stream, err)) return fail(err);
     CKA(sh.download(out_shape, ctx->stream)); CKA(pr.download(out_prim, ctx->stream)); CKA(t.download(out_t, ctx->stream));
     if (out_record) CKA(rec.download(out_record, ctx->stream));
+    CKA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+// closest hit with the full record, its.uv and the geometric normal (out_uv_geo_n: 5 floats per ray)
+int cudapath_intersect_batch_uv(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,
+                                int32_t *out_shape, uint32_t *out_prim, float *out_t, float *out_record, float *out_uv_geo_n) {
+    if (require_built(ctx)) return -1;
+    if (!origin || !direction || !mint || !maxt || !out_shape || !out_prim || !out_t || !out_record || !out_uv_geo_n) return fail("null argument");
+    CP_GUARD(ctx);
+    DevBuf o, d, mn, mx, sh, pr, t, rec, uv; std::string err;
+    CKA(o.upload(origin, n * 12, ctx->stream)); CKA(d.upload(direction, n * 12, ctx->stream)); CKA(mn.upload(mint, n * 4, ctx->stream)); CKA(mx.upload(maxt, n * 4, ctx->stream));
+    CKA(sh.alloc(n * 4)); CKA(pr.alloc(n * 4)); CKA(t.alloc(n * 4)); CKA(rec.alloc(n * 60)); CKA(uv.alloc(n * 20));
+    if (!intersect_batch(ctx->scene, n, o.as<float>(), d.as<float>(), mn.as<float>(), mx.as<float>(), 0, false, sh.as<int32_t>(), pr.as<uint32_t>(), t.as<float>(),
+                         rec.as<float>(), nullptr, ctx->stream, err, uv.as<float>())) return fail(err);
+    CKA(sh.download(out_shape, ctx->stream)); CKA(pr.download(out_prim, ctx->stream)); CKA(t.download(out_t, ctx->stream));
+    CKA(rec.download(out_record, ctx->stream)); CKA(uv.download(out_uv_geo_n, ctx->stream));
     CKA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -1242,14 +1396,14 @@ int cudapath_bsdf_eval_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, con
     if (require_built(ctx)) return -1;
     CP_GUARD(ctx);
     std::string err;
-    if (!(ctx->fastMath ? bsdf_eval_batch_fast : bsdf_eval_batch)(ctx->scene, bsdf_id, n, wi, wo, out_eval, out_pdf, stream ? (cudaStream_t) stream : ctx->stream, err, false)) return fail(err);
+    if (!(ctx->fastMath ? bsdf_eval_batch_fast : bsdf_eval_batch)(ctx->scene, bsdf_id, n, wi, wo, out_eval, out_pdf, stream ? (cudaStream_t) stream : ctx->stream, err, false, nullptr)) return fail(err);
     return 0;
 }
 int cudapath_bsdf_sample_batch_dev(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type, void *stream) {
     if (require_built(ctx)) return -1;
     CP_GUARD(ctx);
     std::string err;
-    if (!(ctx->fastMath ? bsdf_sample_batch_fast : bsdf_sample_batch)(ctx->scene, bsdf_id, n, wi, sample, nullptr, out_wo, out_weight, out_pdf, out_type, stream ? (cudaStream_t) stream : ctx->stream, err)) return fail(err);
+    if (!(ctx->fastMath ? bsdf_sample_batch_fast : bsdf_sample_batch)(ctx->scene, bsdf_id, n, wi, sample, nullptr, out_wo, out_weight, out_pdf, out_type, stream ? (cudaStream_t) stream : ctx->stream, err, nullptr)) return fail(err);
     return 0;
 }
 int cudapath_intersect_batch_dev(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,

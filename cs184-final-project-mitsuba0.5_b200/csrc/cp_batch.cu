@@ -17,7 +17,7 @@ namespace cp {
 // ray source / sink over flat fp32 arrays
 struct BatchIO {
     const float *o, *d, *mint, *maxt; int32_t *shape; uint32_t *prim; float *tOut; float *rec;
-    const float4 *vtx; const ShapeDev *shapes; const float4 *triAccel;
+    const float4 *vtx; const ShapeDev *shapes; const float4 *triAccel; const float4 *rects;
     CP_D bool load(uint32_t i, V3 &ro, V3 &rd, float &mn, float &mx, bool &, uint32_t &) const {
         ro = V3(o[3 * (size_t) i], o[3 * (size_t) i + 1], o[3 * (size_t) i + 2]); rd = V3(d[3 * (size_t) i], d[3 * (size_t) i + 1], d[3 * (size_t) i + 2]);
         mn = mint[i]; mx = maxt[i];
@@ -25,8 +25,10 @@ struct BatchIO {
     }
     CP_D void store(uint32_t i, bool, bool hit, const RayHit &h) const {
         if (hit) {
-            if (h.gv & CP_TRI_FLAG) {   // triangle: shape / primitive index come from the TriAccel record (skdtree.h:296-299)
-                const float4 C = __ldg(triAccel + 3 * (size_t) (h.gv & ~CP_TRI_FLAG) + 2);
+            if (h.gv & CP_RECT_FLAG) {  // rectangle: one primitive per shape
+                shape[i] = (int32_t) __float_as_uint(__ldg(rects + CP_RECT_STRIDE * (size_t) (h.gv & CP_PRIM_MASK) + 3).w); prim[i] = 0u;
+            } else if (h.gv & CP_TRI_FLAG) {   // triangle: shape / primitive index come from the TriAccel record (skdtree.h:296-299)
+                const float4 C = __ldg(triAccel + 3 * (size_t) (h.gv & CP_PRIM_MASK) + 2);
                 shape[i] = (int32_t) __float_as_uint(C.z); prim[i] = __float_as_uint(C.w);
             } else {
                 const uint32_t sh = vtx_shape(__ldg(vtx + h.gv));
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(CP_TRACE_THREADS, CP_MIN_BLOCKS) k_intersect_b
 static inline unsigned grid_for(uint64_t n, int block) { return (unsigned) ((n + block - 1) / block); }
 
 bool intersect_batch(const SceneDev &S, uint64_t n, const float *d_o, const float *d_d, const float *d_mint, const float *d_maxt, int anyHit, bool stats,
-                     int32_t *d_shape, uint32_t *d_prim, float *d_t, float *d_rec, unsigned long long *d_stats, cudaStream_t s, std::string &err) {
+                     int32_t *d_shape, uint32_t *d_prim, float *d_t, float *d_rec, unsigned long long *d_stats, cudaStream_t s, std::string &err, float *d_uv) {
     if (n == 0) return true;
     if (n > 0xfffffff0ull) { err = "ray batch too large (split it into chunks below 2^32 rays)"; return false; }
     int dev = 0, numSMs = 0;
@@ -65,17 +67,17 @@ bool intersect_batch(const SceneDev &S, uint64_t n, const float *d_o, const floa
     struct CtlGuard { int *p; cudaStream_t s; ~CtlGuard() { cudaStreamSynchronize(s); dev_free(p); } } ctlGuard{d_ctl, s};
     CKB(cudaMemsetAsync(d_ctl, 0, 2 * sizeof(int), s));
     const unsigned need = (unsigned) ((n + 127) / 128), g = need < (unsigned) numSMs * 8u ? need : (unsigned) numSMs * 8u;
-    BatchIO io{d_o, d_d, d_mint, d_maxt, d_shape, d_prim, d_t, anyHit ? nullptr : d_rec, S.vtx, S.shapes, S.mesh.triAccel};
+    BatchIO io{d_o, d_d, d_mint, d_maxt, d_shape, d_prim, d_t, anyHit ? nullptr : d_rec, S.vtx, S.shapes, S.mesh.triAccel, S.mesh.rects};
     uint32_t *ctr = (uint32_t *) (d_ctl + 1);
 #define CP_LAUNCH_BATCH(AN, ST, ME) k_intersect_batch<AN, ST, ME><<<g, CP_TRACE_THREADS, 0, s>>>(S, io, (uint32_t) n, ctr, d_stats, d_ctl)
-    const int variant = (anyHit ? 4 : 0) | (stats ? 2 : 0) | (S.mesh.triCount > 0 ? 1 : 0);
+    const int variant = (anyHit ? 4 : 0) | (stats ? 2 : 0) | (S.mesh.triCount + S.mesh.rectCount > 0 ? 1 : 0);
     switch (variant) {
         case 0: CP_LAUNCH_BATCH(false, false, false); break; case 1: CP_LAUNCH_BATCH(false, false, true); break;
         case 2: CP_LAUNCH_BATCH(false, true, false); break;  case 3: CP_LAUNCH_BATCH(false, true, true); break;
         case 4: CP_LAUNCH_BATCH(true, false, false); break;  case 5: CP_LAUNCH_BATCH(true, false, true); break;
         case 6: CP_LAUNCH_BATCH(true, true, false); break;   default: CP_LAUNCH_BATCH(true, true, true); break;
     }
-    if (d_rec && !anyHit) fill_records_batch(S, n, d_d, d_shape, d_rec, s);
+    if (d_rec && !anyHit) fill_records_batch(S, n, d_o, d_d, d_t, d_shape, d_rec, d_uv, s);
     int herr = 0;
     CKB(cudaMemcpyAsync(&herr, d_ctl, sizeof(int), cudaMemcpyDeviceToHost, s));
     CKB(cudaStreamSynchronize(s));

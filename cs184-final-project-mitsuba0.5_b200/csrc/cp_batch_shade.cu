@@ -30,12 +30,12 @@
 namespace cp {
 
 __global__ void __launch_bounds__(256) k_bsdf_eval(const BsdfDev *__restrict__ bsdfs, int bsdf, uint64_t n, const float *__restrict__ wi,
-                                                   const float *__restrict__ wo, float *eval, float *pdf, bool discrete) {
+                                                   const float *__restrict__ wo, float *eval, float *pdf, bool discrete, const float *__restrict__ uv) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const BsdfDev &b = bsdfs[bsdf];
     const V3 a(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), c(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
-    const V3 e = bsdf_eval(b, a, c, discrete);
+    const V3 e = bsdf_eval(b, a, c, discrete, uv ? uv[2 * i] : 0.0f, uv ? uv[2 * i + 1] : 0.0f);
     eval[3 * i] = e.x; eval[3 * i + 1] = e.y; eval[3 * i + 2] = e.z;
     pdf[i] = bsdf_pdf(b, a, c, discrete);
 }
@@ -54,13 +54,13 @@ __global__ void __launch_bounds__(256) k_bsdf_eval_world(const BsdfDev *__restri
     pdf[i] = bsdf_pdf(b, a, c, false);
 }
 __global__ void __launch_bounds__(256) k_bsdf_sample(const BsdfDev *__restrict__ bsdfs, int bsdf, uint64_t n, const float *__restrict__ wi,
-                                                     const float *__restrict__ sample, const float *__restrict__ extra, float *wo, float *weight, float *pdf, int32_t *type) {
+                                                     const float *__restrict__ sample, const float *__restrict__ extra, float *wo, float *weight, float *pdf, int32_t *type, const float *__restrict__ uv) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const BsdfDev &b = bsdfs[bsdf];
     float4 ex = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (extra) ex = make_float4(extra[4 * i], extra[4 * i + 1], extra[4 * i + 2], extra[4 * i + 3]);
-    const BsdfSampleOut r = bsdf_sample(b, V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), sample[2 * i], sample[2 * i + 1], ex);
+    const BsdfSampleOut r = bsdf_sample(b, V3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), sample[2 * i], sample[2 * i + 1], ex, uv ? uv[2 * i] : 0.0f, uv ? uv[2 * i + 1] : 0.0f);
     wo[3 * i] = r.wo.x; wo[3 * i + 1] = r.wo.y; wo[3 * i + 2] = r.wo.z;
     weight[3 * i] = r.weight.x; weight[3 * i + 1] = r.weight.y; weight[3 * i + 2] = r.weight.z;
     pdf[i] = r.pdf; type[i] = r.type | (r.component << 8);
@@ -101,30 +101,35 @@ __global__ void k_camera_rays(SceneDev S, uint64_t n, const float *__restrict__ 
 }
 
 // HairShape::fillIntersectionRecord + computeShadingFrame for the hits of k_intersect_batch (in place: rec[0..3] = p, gv)
-__global__ void k_fill_records(SceneDev S, uint64_t n, const float *__restrict__ d, const int32_t *__restrict__ shape, float *rec) {
+// uvOut (optional): its.uv and its.geoFrame.n, 5 floats per ray
+__global__ void k_fill_records(SceneDev S, uint64_t n, const float *__restrict__ o, const float *__restrict__ d, const float *__restrict__ t,
+                               const int32_t *__restrict__ shape, float *rec, float *uvOut) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || shape[i] < 0) return;
+    if (i >= n) return;
+    if (shape[i] < 0) { if (uvOut) for (int k = 0; k < 5; ++k) uvOut[5 * i + k] = 0.0f; return; }
     float *p = rec + 15 * i;
     const uint32_t gv = __float_as_uint(p[3]);
     HitRecord r;
-    if (gv & CP_TRI_FLAG) fill_intersection_mesh(S.mesh, S.shapes, gv & ~CP_TRI_FLAG, p[0], p[1], V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), r);
+    if (gv & CP_RECT_FLAG) fill_intersection_rect(S.mesh, gv & CP_PRIM_MASK, p[0], p[1], t[i], V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), r);
+    else if (gv & CP_TRI_FLAG) fill_intersection_mesh(S.mesh, S.shapes, gv & CP_PRIM_MASK, p[0], p[1], V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), r);
     else fill_intersection(__ldg(S.vtx + gv), __ldg(S.vtx + gv + 1), S.shapes[shape[i]].radius, V3(p[0], p[1], p[2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), r);
     p[0] = r.p.x; p[1] = r.p.y; p[2] = r.p.z; p[3] = r.sh.n.x; p[4] = r.sh.n.y; p[5] = r.sh.n.z;
     p[6] = r.sh.s.x; p[7] = r.sh.s.y; p[8] = r.sh.s.z; p[9] = r.sh.t.x; p[10] = r.sh.t.y; p[11] = r.sh.t.z;
     p[12] = r.wi.x; p[13] = r.wi.y; p[14] = r.wi.z;
+    if (uvOut) { uvOut[5 * i] = r.u; uvOut[5 * i + 1] = r.v; uvOut[5 * i + 2] = r.geoN.x; uvOut[5 * i + 3] = r.geoN.y; uvOut[5 * i + 4] = r.geoN.z; }
 }
-void fill_records_batch(const SceneDev &S, uint64_t n, const float *d_d, const int32_t *d_shape, float *d_rec, cudaStream_t s) {
-    if (n) k_fill_records<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(S, n, d_d, d_shape, d_rec);
+void fill_records_batch(const SceneDev &S, uint64_t n, const float *d_o, const float *d_d, const float *d_t, const int32_t *d_shape, float *d_rec, float *d_uv, cudaStream_t s) {
+    if (n) k_fill_records<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(S, n, d_o, d_d, d_t, d_shape, d_rec, d_uv);
 }
 #endif // !CP_FAST_MATH
 
 #define CKB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 static inline unsigned grid_for(uint64_t n, int block) { return (unsigned) ((n + block - 1) / block); }
 
-bool bsdf_eval_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err, bool discrete) {
+bool bsdf_eval_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_wo, float *d_eval, float *d_pdf, cudaStream_t s, std::string &err, bool discrete, const float *d_uv) {
     if (bsdf < 0 || bsdf >= S.bsdfCount) { err = "bsdf id out of range"; return false; }
     if (n == 0) return true;
-    k_bsdf_eval<<<grid_for(n, 256), 256, 0, s>>>(S.bsdfs, bsdf, n, d_wi, d_wo, d_eval, d_pdf, discrete);
+    k_bsdf_eval<<<grid_for(n, 256), 256, 0, s>>>(S.bsdfs, bsdf, n, d_wi, d_wo, d_eval, d_pdf, discrete, d_uv);
     CKB(cudaGetLastError());
     return true;
 }
@@ -135,10 +140,10 @@ bool bsdf_eval_world_batch(const SceneDev &S, int bsdf, uint64_t n, const float 
     CKB(cudaGetLastError());
     return true;
 }
-bool bsdf_sample_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_sample, const float *d_extra, float *d_wo, float *d_weight, float *d_pdf, int32_t *d_type, cudaStream_t s, std::string &err) {
+bool bsdf_sample_batch(const SceneDev &S, int bsdf, uint64_t n, const float *d_wi, const float *d_sample, const float *d_extra, float *d_wo, float *d_weight, float *d_pdf, int32_t *d_type, cudaStream_t s, std::string &err, const float *d_uv) {
     if (bsdf < 0 || bsdf >= S.bsdfCount) { err = "bsdf id out of range"; return false; }
     if (n == 0) return true;
-    k_bsdf_sample<<<grid_for(n, 256), 256, 0, s>>>(S.bsdfs, bsdf, n, d_wi, d_sample, d_extra, d_wo, d_weight, d_pdf, d_type);
+    k_bsdf_sample<<<grid_for(n, 256), 256, 0, s>>>(S.bsdfs, bsdf, n, d_wi, d_sample, d_extra, d_wo, d_weight, d_pdf, d_type, d_uv);
     CKB(cudaGetLastError());
     return true;
 }

@@ -31,7 +31,13 @@ struct BsdfDev {
                          // 4 = roughplastic (src/bsdfs/roughplastic.cpp; the default BSDF of the models/*/scene.xml files)
                          // 5 = thindielectric (src/bsdfs/thindielectric.cpp; specular reflectance in `specular`, transmittance in `diffuse`)
                          // 6 = marschnerdielectric (src/bsdfs/marschnerdielectric.cpp; transmittance in `specT`)
-    int twoSided;        // kind 2 only: wrapped in `twosided` with the same nested BRDF on both sides
+                         // 7 = plastic (src/bsdfs/plastic.cpp; fdrInt in `Fdr`)
+    int twoSided;        // kinds 2, 4, 7: wrapped in `twosided` (src/bsdfs/twosided.cpp) with the same nested BRDF on both sides
+    // diffuse reflectance texture of kinds 2 and 7: 0 = the constant in `diffuse`, 1 = checkerboard (src/textures/checkerboard.cpp) of
+    // `diffuse` (color0) and `color1` behind Texture2D's uv transform (src/librender/texture.cpp:81-121)
+    int texKind;
+    V3 color1;
+    float uvOffset[2], uvScale[2];
     // kajiyakay (kajiyakay.cpp:60-107) / marschner diffuse colour
     V3 diffuse, specular;
     V3 specT;            // marschnerdielectric: m_specularTransmittance
@@ -40,6 +46,7 @@ struct BsdfDev {
     // marschner (marschner_diffuse.cpp:113-160,193-247)
     float eta, invEta2, alpha, Fdr, vR, vTT, vTRT, scaleAngle;
     int nonlinear, rtSize;
+    int lobeMask;        // kind 3: lobes eval() keeps (bit 0 R, 1 TT, 2 TRT): 4 = src/bsdfs/marschner.cpp as committed (:333-334), 7 = all three
     int distr, sampleVisible;   // roughplastic: microfacet distribution 0 beckmann / 1 ggx / 2 phong (exponent in `exponent`), visible-normal sampling
     const float4 *tab;   // 3 lobes x 64x64 x (r,g,b,-)
     const float *cdf;    // 3 x 64 rows x 65
@@ -303,9 +310,11 @@ CP_D V3 mf_eval(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float phi = cr_atan2(wo.x, wo.z);
     if (phi < 0.0f) phi += kPi * 2.0f;
     const LobeAngles la = ma_lobe_angles(b, thetaI);
-    float MTRT = ma_M(b.vTRT, la.sinTRT, sinThetaO, la.cosTRT, cosThetaO);
-    const V3 zero(0.0f);      // MR = MTT = 0 in the reference (:333-334): their lobes contribute 0 * table value
-    return zero * ma_azimuthal(b.tab, phi, cosThetaD) + zero * ma_azimuthal(b.tab + 4096, phi, cosThetaD) + MTRT * ma_azimuthal(b.tab + 8192, phi, cosThetaD);
+    // MR = MTT = 0 in the reference (:333-334): their lobes contribute 0 * table value; the scene-driven variant keeps all three
+    const float MR = (b.lobeMask & 1) ? ma_M(b.vR, la.sinR, sinThetaO, la.cosR, cosThetaO) : 0.0f;
+    const float MTT = (b.lobeMask & 2) ? ma_M(b.vTT, la.sinTT, sinThetaO, la.cosTT, cosThetaO) : 0.0f;
+    const float MTRT = (b.lobeMask & 4) ? ma_M(b.vTRT, la.sinTRT, sinThetaO, la.cosTRT, cosThetaO) : 0.0f;
+    return MR * ma_azimuthal(b.tab, phi, cosThetaD) + MTT * ma_azimuthal(b.tab + 4096, phi, cosThetaD) + MTRT * ma_azimuthal(b.tab + 8192, phi, cosThetaD);
 }
 CP_D float mf_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo) {
     float sinThetaI = wi.y, sinThetaO = wo.y;
@@ -541,19 +550,31 @@ CP_D BsdfSampleOut rp_sample(const BsdfDev &b, const V3 &wi, float sx, float sy)
     return r;
 }
 
+// ------------------------------------------------------------------------------------------ textures
+// Texture2D::eval (texture.cpp:112-121, no filtering: Checkerboard ignores the differentials) + Checkerboard::eval (checkerboard.cpp:65-72)
+CP_D V3 bsdf_reflectance(const BsdfDev &b, float u, float v) {
+    if (b.texKind == 0) return b.diffuse;
+    const float uu = u * b.uvScale[0] + b.uvOffset[0], vv = v * b.uvScale[1] + b.uvOffset[1];
+    int mx = ((int) (uu * 2)) % 2, my = ((int) (vv * 2)) % 2;           // math::modulo(int, 2): always-positive remainder
+    if (mx < 0) mx += 2;
+    if (my < 0) my += 2;
+    const int x = 2 * mx - 1, y = 2 * my - 1;
+    return x * y == 1 ? b.diffuse : b.color1;
+}
+
 // ------------------------------------------------------------------------------------------ SmoothDiffuse (+ TwoSided)
-// src/bsdfs/diffuse.cpp:109-156 with a constant reflectance; src/bsdfs/twosided.cpp:101-181 when b.twoSided
-CP_D V3 df_eval(const BsdfDev &b, V3 wi, V3 wo) {
+// src/bsdfs/diffuse.cpp:109-156; src/bsdfs/twosided.cpp:101-181 when b.twoSided
+CP_D V3 df_eval(const BsdfDev &b, V3 wi, V3 wo, float u, float v) {
     if (b.twoSided && wi.z <= 0) { wi.z *= -1; wo.z *= -1; }
     if (wi.z <= 0 || wo.z <= 0) return V3(0.0f);
-    return b.diffuse * (kInvPi * wo.z);
+    return bsdf_reflectance(b, u, v) * (kInvPi * wo.z);
 }
 CP_D float df_pdf(const BsdfDev &b, V3 wi, V3 wo) {
     if (b.twoSided && wi.z <= 0) { wi.z *= -1; wo.z *= -1; }
     if (wi.z <= 0 || wo.z <= 0) return 0.0f;
     return kInvPi * wo.z;
 }
-CP_D BsdfSampleOut df_sample(const BsdfDev &b, V3 wi, float sx, float sy) {
+CP_D BsdfSampleOut df_sample(const BsdfDev &b, V3 wi, float sx, float sy, float u, float v) {
     BsdfSampleOut r; r.wo = V3(0.0f); r.weight = V3(0.0f); r.pdf = 0.0f; r.type = 0; r.component = -1;
     bool flipped = false;
     if (b.twoSided && wi.z < 0) { wi.z *= -1; flipped = true; }
@@ -561,8 +582,52 @@ CP_D BsdfSampleOut df_sample(const BsdfDev &b, V3 wi, float sx, float sy) {
     r.wo = squareToCosineHemisphere(sx, sy);
     r.component = 0; r.type = EDiffuseReflection;
     r.pdf = kInvPi * r.wo.z;
-    r.weight = b.diffuse;
+    r.weight = bsdf_reflectance(b, u, v);
     if (flipped && !isZero(r.weight) && r.pdf != 0) { r.wo.z *= -1; r.component += 1; }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------ SmoothPlastic
+// src/bsdfs/plastic.cpp:246-281 (eval), :283-313 (pdf), :381-445 (sample with pdf): a delta reflection (component 0, discrete measure)
+// over a diffuse base (component 1), front side only; typeMask = EAll, component = -1.  fdrInt rides in b.Fdr.
+CP_D V3 pl_diff(const BsdfDev &b, float u, float v) {
+    V3 diff = bsdf_reflectance(b, u, v);
+    if (b.nonlinear) diff = V3(diff.x / (1.0f - diff.x * b.Fdr), diff.y / (1.0f - diff.y * b.Fdr), diff.z / (1.0f - diff.z * b.Fdr));
+    else diff = diff / (1 - b.Fdr);
+    return diff;
+}
+CP_D float pl_probSpecular(const BsdfDev &b, float Fi) { return (Fi * b.specW) / (Fi * b.specW + (1 - Fi) * (1 - b.specW)); }
+CP_D V3 pl_eval(const BsdfDev &b, const V3 &wi, const V3 &wo, bool discrete, float u, float v) {
+    if (wo.z <= 0 || wi.z <= 0) return V3(0.0f);
+    const float Fi = fresnelDielectricExt(wi.z, b.eta);
+    if (discrete) {
+        if (fabsf(dot(kk_reflect(wi), wo) - 1) < kDeltaEpsilon) return b.specular * Fi;
+        return V3(0.0f);
+    }
+    const float Fo = fresnelDielectricExt(wo.z, b.eta);
+    return pl_diff(b, u, v) * ((kInvPi * wo.z) * b.invEta2 * (1 - Fi) * (1 - Fo));
+}
+CP_D float pl_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo, bool discrete) {
+    if (wo.z <= 0 || wi.z <= 0) return 0.0f;
+    const float ps = pl_probSpecular(b, fresnelDielectricExt(wi.z, b.eta));
+    if (discrete) return fabsf(dot(kk_reflect(wi), wo) - 1) < kDeltaEpsilon ? ps : 0.0f;
+    return (kInvPi * wo.z) * (1 - ps);
+}
+CP_D BsdfSampleOut pl_sample(const BsdfDev &b, const V3 &wi, float sx, float sy, float u, float v) {
+    BsdfSampleOut r; r.wo = V3(0.0f); r.weight = V3(0.0f); r.pdf = 0.0f; r.type = 0; r.component = -1;
+    if (wi.z <= 0) return r;
+    const float Fi = fresnelDielectricExt(wi.z, b.eta);
+    const float ps = pl_probSpecular(b, Fi);
+    if (sx < ps) {
+        r.component = 0; r.type = EDeltaReflection; r.wo = kk_reflect(wi); r.pdf = ps;
+        r.weight = b.specular * Fi / ps;
+    } else {
+        r.component = 1; r.type = EDiffuseReflection;
+        r.wo = squareToCosineHemisphere((sx - ps) / (1 - ps), sy);
+        const float Fo = fresnelDielectricExt(r.wo.z, b.eta);
+        r.pdf = (1 - ps) * (kInvPi * r.wo.z);
+        r.weight = pl_diff(b, u, v) * (b.invEta2 * (1 - Fi) * (1 - Fo) / (1 - ps));
+    }
     return r;
 }
 
@@ -616,14 +681,21 @@ CP_D BsdfSampleOut md_sample(const BsdfDev &b, const V3 &wi, float sx, float sy)
 }
 
 // ------------------------------------------------------------------------------------------ dispatch
-CP_D V3 bsdf_eval(const BsdfDev &b, const V3 &wi, const V3 &wo, bool discrete = false) {
+// (u, v) = its.uv, only read by the textured kinds.  `twosided` around roughplastic / plastic is applied here (twosided.cpp:101-181);
+// the diffuse kind handles its own flag.
+CP_D bool bsdf_wrapped(const BsdfDev &b) { return b.twoSided && (b.kind == 4 || b.kind == 7); }
+CP_D V3 bsdf_eval(const BsdfDev &b, V3 wi, V3 wo, bool discrete = false, float u = 0.0f, float v = 0.0f) {
+    if (bsdf_wrapped(b) && !(wi.z > 0)) { wi.z *= -1; wo.z *= -1; }
     if (b.kind == 5) return td_eval(b, wi, wo, discrete);
+    if (b.kind == 7) return pl_eval(b, wi, wo, discrete, u, v);
     if (b.kind == 6 || discrete) return V3(0.0f);
-    return b.kind == 0 ? kk_eval(b, wi, wo) : b.kind == 1 ? ma_eval(b, wi, wo) : b.kind == 2 ? df_eval(b, wi, wo) : b.kind == 3 ? mf_eval(b, wi, wo) : rp_eval(b, wi, wo);
+    return b.kind == 0 ? kk_eval(b, wi, wo) : b.kind == 1 ? ma_eval(b, wi, wo) : b.kind == 2 ? df_eval(b, wi, wo, u, v) : b.kind == 3 ? mf_eval(b, wi, wo) : rp_eval(b, wi, wo);
 }
-CP_D float bsdf_pdf(const BsdfDev &b, const V3 &wi, const V3 &wo, bool discrete = false) {
+CP_D float bsdf_pdf(const BsdfDev &b, V3 wi, V3 wo, bool discrete = false) {
+    if (bsdf_wrapped(b) && !(wi.z > 0)) { wi.z *= -1; wo.z *= -1; }
     if (b.kind == 5) return td_pdf(b, wi, wo, discrete);
     if (b.kind == 6) return md_pdf(wi, wo, discrete);
+    if (b.kind == 7) return pl_pdf(b, wi, wo, discrete);
     if (discrete) return 0.0f;
     return b.kind == 0 ? kk_pdf(b, wi, wo) : b.kind == 1 ? 1.0f : b.kind == 2 ? df_pdf(b, wi, wo) : b.kind == 3 ? mf_pdf(b, wi, wo) : rp_pdf(b, wi, wo);
 }
@@ -633,11 +705,15 @@ CP_D bool bsdf_draws_extra(const BsdfDev &b) { return b.kind == 3; }
 CP_D bool bsdf_has_smooth(const BsdfDev &b) { return b.kind != 5; }
 // eval() in the solid-angle measure is identically zero: emitter samples are drawn and counted, but can never contribute
 CP_D bool bsdf_eval_is_zero(const BsdfDev &b) { return b.kind == 6; }
-CP_D BsdfSampleOut bsdf_sample(const BsdfDev &b, const V3 &wi, float sx, float sy, const float4 &extra) {
+CP_D BsdfSampleOut bsdf_sample(const BsdfDev &b, V3 wi, float sx, float sy, const float4 &extra, float u = 0.0f, float v = 0.0f) {
     if (b.kind == 5) return thin_sample(wi, b.eta, b.specular, b.diffuse, sx);
     if (b.kind == 6) return md_sample(b, wi, sx, sy);
-    return b.kind == 0 ? kk_sample(b, wi, sx, sy) : b.kind == 1 ? ma_sample(b, wi, sx, sy) : b.kind == 2 ? df_sample(b, wi, sx, sy)
-         : b.kind == 3 ? mf_sample(b, wi, extra.x, extra.y, extra.z, extra.w) : rp_sample(b, wi, sx, sy);
+    bool flipped = false;
+    if (bsdf_wrapped(b) && wi.z < 0) { wi.z *= -1; flipped = true; }
+    BsdfSampleOut r = b.kind == 0 ? kk_sample(b, wi, sx, sy) : b.kind == 1 ? ma_sample(b, wi, sx, sy) : b.kind == 2 ? df_sample(b, wi, sx, sy, u, v)
+         : b.kind == 3 ? mf_sample(b, wi, extra.x, extra.y, extra.z, extra.w) : b.kind == 7 ? pl_sample(b, wi, sx, sy, u, v) : rp_sample(b, wi, sx, sy);
+    if (flipped && !isZero(r.weight) && r.pdf != 0) { r.wo.z *= -1; r.component += 2; }
+    return r;
 }
 
 } // namespace cp

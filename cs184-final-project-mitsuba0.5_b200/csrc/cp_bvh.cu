@@ -161,6 +161,26 @@ __global__ void k_tri_bounds(MeshDev mesh, uint32_t refBase, ShapeDev *shapes, f
     refPrim[refBase + j] = CP_TRI_FLAG | j;
 }
 
+// per rectangle: the shape box (the four transformed corners, computed on the host like Rectangle::getAABB) and one padded BVH reference
+__global__ void k_rect_bounds(MeshDev mesh, uint32_t refBase, ShapeDev *shapes, float *leafBox, uint32_t *refPrim, float *centroidBox) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= mesh.rectCount) return;
+    const float4 lo = mesh.rects[CP_RECT_STRIDE * (size_t) j + 6], hi = mesh.rects[CP_RECT_STRIDE * (size_t) j + 7];
+    float bmin[3] = {lo.x, lo.y, lo.z}, bmax[3] = {hi.x, hi.y, hi.z};
+    ShapeDev &sd = shapes[__float_as_uint(mesh.rects[CP_RECT_STRIDE * (size_t) j + 3].w)];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { atomicMinFloat(&sd.bmin[k], bmin[k]); atomicMaxFloat(&sd.bmax[k], bmax[k]); }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float pad = 1e-5f * (bmax[k] - bmin[k]) + 2e-6f * fmaxf(fabsf(bmin[k]), fabsf(bmax[k])) + 1e-30f;
+        bmin[k] -= pad; bmax[k] += pad;
+        leafBox[6 * (size_t) (refBase + j) + k] = bmin[k]; leafBox[6 * (size_t) (refBase + j) + 3 + k] = bmax[k];
+        const float c = 0.5f * (bmin[k] + bmax[k]);
+        atomicMinFloat(&centroidBox[k], c); atomicMaxFloat(&centroidBox[3 + k], c);
+    }
+    refPrim[refBase + j] = CP_TRI_FLAG | CP_RECT_FLAG | j;
+}
+
 __device__ __forceinline__ uint64_t expandBits21(uint64_t v) {
     v &= 0x1fffffull;
     v = (v | v << 32) & 0x1f00000000ffffull;
@@ -412,7 +432,7 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
         nSeg = (uint32_t) h;
     }
     info.segments = nSeg; info.triangles = mesh.triCount;
-    if (nSeg == 0 && mesh.triCount == 0) { err = "scene contains no hair segments and no triangles"; return false; }
+    if (nSeg == 0 && mesh.triCount == 0 && mesh.rectCount == 0) { err = "scene contains no hair segments, triangles or rectangles"; return false; }
     if (nSeg >= (1u << 28)) { err = "too many segments for the leaf encoding"; return false; }
 
     // references: every segment contributes split_count() boxes
@@ -430,13 +450,14 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
         CK(cudaStreamSynchronize(stream));
     }
     const uint32_t nHairRef = nRef;
-    nRef += mesh.triCount;     // one reference per triangle, after the hair references
+    nRef += mesh.triCount + mesh.rectCount;     // one reference per triangle / rectangle, after the hair references
     info.references = nRef;
-    if ((uint64_t) nHairRef + mesh.triCount >= (1u << 28)) { err = "too many BVH references for the leaf encoding"; return false; }
+    if ((uint64_t) nHairRef + mesh.triCount + mesh.rectCount >= (1u << 28)) { err = "too many BVH references for the leaf encoding"; return false; }
     CK(S.alloc(&d_leafBox, sizeof(float) * 6 * (size_t) nRef));
     CK(S.alloc(&d_refPrim, sizeof(uint32_t) * (size_t) nRef));
     if (nSeg) k_segment_bounds<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_vtx, d_segs, nSeg, d_offsets, maxSplit, d_shapes, d_leafBox, d_refPrim, d_cbox);
     if (mesh.triCount) k_tri_bounds<<<(mesh.triCount + B - 1) / B, B, 0, stream>>>(mesh, nHairRef, d_shapes, d_leafBox, d_refPrim, d_cbox);
+    if (mesh.rectCount) k_rect_bounds<<<(mesh.rectCount + B - 1) / B, B, 0, stream>>>(mesh, nHairRef + mesh.triCount, d_shapes, d_leafBox, d_refPrim, d_cbox);
     nSeg = nRef;   // from here on the builder works on references
     CK(S.alloc(&d_keys, sizeof(uint64_t) * (size_t) nSeg)); CK(S.alloc(&d_keysSorted, sizeof(uint64_t) * (size_t) nSeg));
     CK(S.alloc(&d_ids, sizeof(uint32_t) * (size_t) nSeg)); CK(S.alloc(&d_idsSorted, sizeof(uint32_t) * (size_t) nSeg));

@@ -25,6 +25,7 @@ struct ShapeDev {
     int kind;                 // 0 = hair, 1 = triangle mesh (cp_tri.cuh)
     uint32_t triOffset, triCount;
     int hasNormals;
+    int hasUV;                // mesh: per-vertex texture coordinates present (MeshDev::uv)
 };
 
 CP_D uint32_t vtx_bits(const float4 &v) { return __float_as_uint(v.w); }
@@ -112,7 +113,7 @@ CP_D bool segment_intersect(const float4 &v0, const float4 &v1, const float4 &v2
     return true;
 }
 
-struct HitRecord { V3 p; Frame sh; V3 geoN; V3 wi; };
+struct HitRecord { V3 p; Frame sh; V3 geoN; V3 wi; float u, v; };      // u, v = its.uv (meshes and rectangles; the hair BSDFs carry no textures)
 
 // hair.cpp:825-862 then computeShadingFrame (util.cpp:603-608) and wi = toLocal(-ray.d)
 CP_D void fill_intersection(const float4 &v1, const float4 &v2, float radius, const V3 &pHit, const V3 &rd, HitRecord &rec) {
@@ -128,6 +129,7 @@ CP_D void fill_intersection(const float4 &v1, const float4 &v2, float radius, co
     rec.sh.s = normalize(axis - n * dot(n, axis));
     rec.sh.t = cross(n, rec.sh.s);
     rec.wi = rec.sh.toLocal(-rd);
+    rec.u = 0.0f; rec.v = 0.0f;
 }
 
 // ----- segment bounds (build only): tight box of the two miter-cut end ellipses, radius*(1-Epsilon)

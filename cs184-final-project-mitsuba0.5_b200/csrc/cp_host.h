@@ -49,10 +49,12 @@ struct HairFileData { std::vector<float> xyz; std::vector<uint8_t> startsFiber; 
 bool load_hair_file(const std::string &path, float radius, float angleThresholdDeg, float reduction, const float toWorld[16],
                     HairFileData &out, std::string &err);
 
-struct MeshFileData { std::vector<float> xyz, normals /* empty = face normals */; std::vector<uint32_t> indices; };
+struct MeshFileData { std::vector<float> xyz, normals /* empty = face normals */, uvs /* 2 per vertex; empty = the file has no texture coordinates */; std::vector<uint32_t> indices; };
 // Radiance RGBE (.hdr) image -> top-down RGB fp32 (Bitmap::readRGBE, src/libcore/bitmap.cpp:3590-3678)
 bool load_rgbe_file(const std::string &path, std::vector<float> &rgb, int &w, int &h, std::string &err);
 bool mat4_invert_f32(const float *a, float *out);     // Matrix<4,4,float>::invert of the reference (matrix.inl:138-193), row-major
+// fresnelDiffuseReflectance(eta, fast = false): adaptive Gauss-Lobatto quadrature of F(sqrt(xi), eta) over [0, 1] (util.cpp:807-862, quad.cpp:287-420)
+float fresnel_diffuse_reflectance(float eta);
 bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNormals, bool flipNormals, bool flipTexCoords, MeshFileData &out, std::string &err);
 
 // cp_host_mip.cpp -- Lanczos MIP pyramid of the environment map + EWA weight table (mipmap.h:180-302)

@@ -7,6 +7,7 @@
 //   GaussLegendre<140> nodes and weights                       src/bsdfs/gausssexylingerie.hpp:14-68
 #include "cp_host.h"
 #include <cmath>
+#include <limits>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -347,7 +348,7 @@ bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNo
     struct Key { float v[8]; bool operator<(const Key &o) const { for (int i = 0; i < 8; ++i) { if (v[i] < o.v[i]) return true; if (v[i] > o.v[i]) return false; } return false; } };
     std::map<Key, uint32_t> vertexMap;
     bool hasNormals = false;
-    std::vector<Vec> P, N;
+    std::vector<Vec> P, N; std::vector<std::array<float, 2>> UV; bool hasTexcoords = false;
     for (auto &f : faces) {
         for (int j = 0; j < 3; ++j) {
             int vid = f[j].p, nid = f[j].n, uid = f[j].uv;
@@ -367,12 +368,13 @@ bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNo
             if (uid != 0) {
                 if (uid > (int) texcoords.size() || uid < 0) { err = "Out of bounds: tried to access uv " + std::to_string(uid) + " (max: " + std::to_string(texcoords.size()) + ")"; return false; }
                 uv[0] = texcoords[uid - 1][0]; uv[1] = texcoords[uid - 1][1];
+                hasTexcoords = true;                                              // obj.cpp:633-636
             }
             const Key key{{p.x, p.y, p.z, n.x, n.y, n.z, uv[0], uv[1]}};
             auto it = vertexMap.find(key);
             uint32_t id;
             if (it != vertexMap.end()) id = it->second;
-            else { id = (uint32_t) P.size(); vertexMap[key] = id; P.push_back(p); N.push_back(n); }
+            else { id = (uint32_t) P.size(); vertexMap[key] = id; P.push_back(p); N.push_back(n); UV.push_back({uv[0], uv[1]}); }
             out.indices.push_back(id);
         }
     }
@@ -411,7 +413,60 @@ bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNo
     out.xyz.reserve(3 * P.size());
     for (const Vec &p : P) { out.xyz.push_back(p.x); out.xyz.push_back(p.y); out.xyz.push_back(p.z); }
     if (hasNormals) { out.normals.reserve(3 * N.size()); for (const Vec &n : N) { out.normals.push_back(n.x); out.normals.push_back(n.y); out.normals.push_back(n.z); } }
+    if (hasTexcoords) { out.uvs.reserve(2 * UV.size()); for (const auto &t : UV) { out.uvs.push_back(t[0]); out.uvs.push_back(t[1]); } }   // obj.cpp:672-675
     return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// fresnelDiffuseReflectance(eta, false), src/libcore/util.cpp:807-862: GaussLobattoIntegrator(1024, 0, 1e-5f) (src/libcore/quad.cpp:287-420,
+// useConvergenceEstimate = true) over xi -> fresnelDielectricExt(sqrt(xi), eta) on [0, 1].  fp32 throughout, like the reference; the six
+// sub-intervals of a refinement step are summed left to right.  `plastic` stores the result for eta and 1/eta (plastic.cpp:194-195).
+namespace {
+struct LobattoRule {
+    float eta, absTol = 0; size_t evals = 0; static constexpr size_t maxEvals = 1024;
+    const float alpha = (float) std::sqrt(2.0 / 3.0), beta = (float) (1.0 / std::sqrt(5.0));
+    float f(float xi) const { return fresnelDielectricExt(std::sqrt(xi), eta); }
+    float tolerance(float a, float b) {                                           // calculateAbsTolerance, relError = 1e-5, absError = 0
+        const float x1 = (float) 0.94288241569547971906, x2 = (float) 0.64185334234578130578, x3 = (float) 0.23638319966214988028;
+        const float m = (a + b) / 2, h = (b - a) / 2;
+        const float y1 = f(a), y3 = f(m - alpha * h), y5 = f(m - beta * h), y7 = f(m), y9 = f(m + beta * h), y11 = f(m + alpha * h), y13 = f(b);
+        const float p1 = f(m - x1 * h) + f(m + x1 * h), p2 = f(m - x2 * h) + f(m + x2 * h), p3 = f(m - x3 * h) + f(m + x3 * h);
+        const float acc = h * ((float) 0.0158271919734801831 * (y1 + y13) + (float) 0.0942738402188500455 * p1 + (float) 0.1550719873365853963 * (y3 + y11)
+                             + (float) 0.1888215739601824544 * p2 + (float) 0.1997734052268585268 * (y5 + y9) + (float) 0.2249264653333395270 * p3
+                             + (float) 0.2426110719014077338 * y7);
+        evals += 13;
+        const float integral2 = (h / 6) * (y1 + y13 + 5 * (y5 + y9));
+        const float integral1 = (h / 1470) * (77 * (y1 + y13) + 432 * (y3 + y11) + 625 * (y5 + y9) + 672 * y7);
+        float r = 1.0f;
+        if (std::abs(integral2 - acc) != 0.0f) r = std::abs(integral1 - acc) / std::abs(integral2 - acc);
+        if (r == 0.0f || r > 1.0f) r = 1.0f;
+        const float eps = std::numeric_limits<float>::epsilon();
+        float result = std::numeric_limits<float>::infinity();
+        if (acc != 0) result = acc * std::max(1e-5f, eps) / (r * eps);
+        return result;
+    }
+    float refine(float a, float b, float fa, float fb) {                           // adaptiveGaussLobattoStep
+        const float h = (b - a) / 2, m = (a + b) / 2;
+        const float mll = m - alpha * h, ml = m - beta * h, mr = m + beta * h, mrr = m + alpha * h;
+        const float fmll = f(mll), fml = f(ml), fm = f(m), fmr = f(mr), fmrr = f(mrr);
+        const float integral2 = (h / 6) * (fa + fb + 5 * (fml + fmr));
+        const float integral1 = (h / 1470) * (77 * (fa + fb) + 432 * (fmll + fmrr) + 625 * (fml + fmr) + 672 * fm);
+        evals += 5;
+        if (evals >= maxEvals) return integral1;
+        const float dist = absTol + (integral1 - integral2);
+        if (dist == absTol || mll <= a || b <= mrr) return integral1;
+        float sum = refine(a, mll, fa, fmll);
+        sum = sum + refine(mll, ml, fmll, fml); sum = sum + refine(ml, m, fml, fm); sum = sum + refine(m, mr, fm, fmr);
+        sum = sum + refine(mr, mrr, fmr, fmrr); sum = sum + refine(mrr, b, fmrr, fb);
+        return sum;
+    }
+};
+}
+float fresnel_diffuse_reflectance(float eta) {
+    LobattoRule q; q.eta = eta;
+    q.absTol = q.tolerance(0.0f, 1.0f);
+    q.evals += 2;
+    return q.refine(0.0f, 1.0f, q.f(0.0f), q.f(1.0f));
 }
 
 } // namespace cp

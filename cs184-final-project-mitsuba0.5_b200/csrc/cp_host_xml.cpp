@@ -7,8 +7,9 @@
 //   Transform::lookAt / rotate / translate / scale                            src/libcore/transform.cpp
 //   PerspectiveCamera fov handling                                            src/librender/sensor.cpp:225-300
 // Plugins understood: integrator `path`; sensor `perspective` (film `ldrfilm`/`hdrfilm`, rfilter `tent`/`box`/`gaussian`,
-// any sampler: only sampleCount is used); bsdf `kajiyakay`, `marschner`, `marschner_fixed`, `marschnerdielectric`, `thindielectric`, `roughplastic`, `diffuse`, `twosided`; shape `hair`,
-// `obj`; emitter `sunsky`, `envmap` (Radiance .hdr file).
+// any sampler: only sampleCount is used); bsdf `kajiyakay`, `marschner`, `marschner_fixed`, `marschnerdielectric`, `thindielectric`, `roughplastic`, `plastic`, `diffuse`,
+// `twosided` (around diffuse / plastic / roughplastic); texture `checkerboard` (as the reflectance of diffuse / plastic); shape `hair`, `obj`, `rectangle`;
+// emitter `sunsky`, `envmap` (Radiance .hdr file).  models/teapot/scene.xml loads unchanged.
 // Anything else raises an error naming the plugin (the reference would dlopen plugins/<type>.so, src/libcore/plugin.cpp:222-245).
 #include "../../include/cudapath.h"
 #include <algorithm>
@@ -187,6 +188,16 @@ struct Loader {
     static void toFloat(const Mat4 &m, float out[16]) { for (int i = 0; i < 16; ++i) out[i] = (float) m.m[i]; }
     void check(int rc) const { if (rc < 0) throw std::runtime_error(cudapath_last_error()); }
 
+    // <texture type="checkerboard"> (src/textures/checkerboard.cpp:49-52; Texture2D parameters src/librender/texture.cpp:81-95)
+    void setTexture(int bsdf, const Node &t) {
+        if (t.get("type") != "checkerboard") throw std::runtime_error("texture plugin \"" + t.get("type") + "\" is not supported (checkerboard)");
+        if (getString(t, "coordinates", "uv") != "uv") throw std::runtime_error("Only UV coordinates are supported at the moment!");
+        float c0[3], c1[3]; getColor(t, "color0", 0.4f, c0); getColor(t, "color1", 0.2f, c1);
+        const double uvscale = getFloat(t, "uvscale", 1.0);
+        if (dry) { note("texture checkerboard"); return; }
+        check(cudapath_bsdf_set_checkerboard(ctx, bsdf, c0, c1, (float) getFloat(t, "uoffset", 0.0), (float) getFloat(t, "voffset", 0.0),
+                                             (float) getFloat(t, "uscale", uvscale), (float) getFloat(t, "vscale", uvscale)));
+    }
     int loadBsdf(const Node &n) {
         const std::string type = n.get("type");
         int id;
@@ -229,7 +240,7 @@ struct Loader {
             if (child(n, "texture", "alpha") || child(n, "texture", "diffuseReflectance") || child(n, "texture", "specularReflectance")) throw std::runtime_error("roughplastic: textured parameters are not supported");
             id = (dry ? note("bsdf roughplastic") : cudapath_add_bsdf_roughplastic(ctx, (float) ior("intIOR", 1.49), (float) ior("extIOR", 1.000277), d, s, (float) getFloat(n, "alpha", 0.1), di,
                                                 getBool(n, "sampleVisible", true) ? 1 : 0, getBool(n, "nonlinear", false) ? 1 : 0));
-        } else if (type == "marschner_fixed") {      // the class of src/bsdfs/marschner.cpp, which the fork's build leaves out
+        } else if (type == "marschner_fixed" || type == "marschner_full") {      // the class of src/bsdfs/marschner.cpp, which the fork's build leaves out
             auto ior = [&](const char *name, double def) {
                 if (child(n, "float", name)) return getFloat(n, name, def);
                 auto c = child(n, "string", name);
@@ -238,23 +249,49 @@ struct Loader {
                 if (v == "amber") return 1.55; if (v == "air") return 1.000277; if (v == "bk7") return 1.5046; if (v == "vacuum") return 1.0; if (v == "water") return 1.3330;
                 throw std::runtime_error("Unable to find an IOR value for \"" + v + "\"");
             };
+            if (type == "marschner_full") {          // all three lobes, constants from the scene: sigmaA, betaR (or roughness), scaleAngle (degrees) / scaleAngleRad
+                float sa[3]; getColor(n, "sigmaA", 0.22f, sa);
+                const double beta = getFloat(n, "betaR", getFloat(n, "roughness", 0.1));
+                const double ang = child(n, "float", "scaleAngle") ? getFloat(n, "scaleAngle", 0.0) * M_PI / 180.0 : getFloat(n, "scaleAngleRad", -0.1);
+                id = (dry ? note("bsdf marschner_full") : cudapath_add_bsdf_marschner_full(ctx, (float) ior("intIOR", 1.55), (float) ior("extIOR", 1.000277), sa, (float) beta, (float) ang,
+                                                                                           (int) getInt(n, "lobes", 7)));
+            } else
             id = (dry ? note("bsdf marschner_fixed") : cudapath_add_bsdf_marschner_fixed(ctx, (float) ior("intIOR", 1.55), (float) ior("extIOR", 1.000277)));
-        } else if (type == "diffuse" || type == "twosided") {
-            // `diffuse` with a constant reflectance (diffuse.cpp:70-76: "reflectance" or "diffuseReflectance"); `twosided` around one nested `diffuse`
-            const Node *d = &n;
-            if (type == "twosided") {
-                d = nullptr;
-                for (auto &c : n.children) if (c->tag == "bsdf") {
-                    if (d) throw std::runtime_error("twosided: two different nested BRDFs are not supported");
-                    if (c->get("type") != "diffuse") throw std::runtime_error("twosided: only a nested `diffuse` is supported on this path");
-                    d = c.get();
-                }
-                if (!d) throw std::runtime_error("twosided: A nested one-sided material is required.");
+        } else if (type == "twosided") {
+            // TwoSidedBRDF::addChild / configure (src/bsdfs/twosided.cpp:84-110, 163-177): one nested BRDF serves both sides
+            const Node *nested = nullptr;
+            for (auto &c : n.children) if (c->tag == "bsdf") {
+                if (nested) throw std::runtime_error("twosided: two different nested BRDFs are not supported");
+                nested = c.get();
             }
-            if (child(*d, "texture", "reflectance") || child(*d, "texture", "diffuseReflectance")) throw std::runtime_error("diffuse: textured reflectance is not supported");
-            float r[3]; getColor(*d, "reflectance", 0.5f, r);
-            if (child(*d, "rgb", "diffuseReflectance") || child(*d, "spectrum", "diffuseReflectance")) getColor(*d, "diffuseReflectance", 0.5f, r);
-            id = (dry ? note("bsdf diffuse/twosided") : cudapath_add_bsdf_diffuse(ctx, r, type == "twosided" ? 1 : 0));
+            if (!nested) throw std::runtime_error("twosided: A nested one-sided material is required!");
+            const std::string nt = nested->get("type");
+            if (nt != "diffuse" && nt != "plastic" && nt != "roughplastic") throw std::runtime_error("twosided: only a nested `diffuse`, `plastic` or `roughplastic` is supported on this path");
+            id = loadBsdf(*nested);
+            if (!dry) check(cudapath_bsdf_set_twosided(ctx, id)); else note("twosided adapter around the nested bsdf");
+        } else if (type == "diffuse") {
+            // `diffuse` (diffuse.cpp:70-76: "reflectance" or "diffuseReflectance"), constant or a checkerboard
+            float r[3]; getColor(n, "reflectance", 0.5f, r);
+            if (child(n, "rgb", "diffuseReflectance") || child(n, "spectrum", "diffuseReflectance")) getColor(n, "diffuseReflectance", 0.5f, r);
+            id = (dry ? note("bsdf diffuse") : cudapath_add_bsdf_diffuse(ctx, r, 0));
+            check(id);
+            const Node *tex = child(n, "texture", "reflectance"); if (!tex) tex = child(n, "texture", "diffuseReflectance");
+            if (tex) setTexture(id, *tex);
+        } else if (type == "plastic") {
+            auto ior = [&](const char *name, double def) {
+                if (child(n, "float", name)) return getFloat(n, name, def);
+                auto c = child(n, "string", name);
+                if (!c) return def;
+                std::string v = lower(c->get("value"));
+                if (v == "polypropylene") return 1.49; if (v == "amber") return 1.55; if (v == "air") return 1.000277; if (v == "bk7") return 1.5046;
+                if (v == "vacuum") return 1.0; if (v == "water") return 1.3330;
+                throw std::runtime_error("Unable to find an IOR value for \"" + v + "\"");
+            };
+            if (child(n, "texture", "specularReflectance")) throw std::runtime_error("plastic: a textured specularReflectance is not supported");
+            float d[3], sp[3]; getColor(n, "diffuseReflectance", 0.5f, d); getColor(n, "specularReflectance", 1.0f, sp);
+            id = (dry ? note("bsdf plastic") : cudapath_add_bsdf_plastic(ctx, (float) ior("intIOR", 1.49), (float) ior("extIOR", 1.000277), d, sp, getBool(n, "nonlinear", false) ? 1 : 0));
+            check(id);
+            if (const Node *tex = child(n, "texture", "diffuseReflectance")) setTexture(id, *tex);
         } else if (type == "thindielectric" || type == "marschnerdielectric") {
             // src/bsdfs/thindielectric.cpp:73-91 / src/bsdfs/marschnerdielectric.cpp:128-167 (defaults bk7 resp. benzene over air)
             auto ior = [&](const char *name, double def) {
@@ -277,14 +314,14 @@ struct Loader {
                 id = (dry ? note("bsdf marschnerdielectric") : cudapath_add_bsdf_marschnerdielectric(ctx, (float) ior("intIOR", 1.501), (float) ior("extIOR", 1.000277), d, r, t,
                                                                                                       (float) getFloat(n, "exponent", 30.0)));
             }
-        } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, marschnerdielectric, thindielectric, roughplastic, diffuse, twosided)");
+        } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, marschner_full, marschnerdielectric, thindielectric, roughplastic, plastic, diffuse, twosided)");
         check(id);
         if (n.has("id")) bsdfIds[n.get("id")] = id;
         return id;
     }
     void loadShape(const Node &n) {
-        const bool isObj = n.get("type") == "obj";
-        if (n.get("type") != "hair" && !isObj) throw std::runtime_error("shape plugin \"" + n.get("type") + "\" is outside the hair hot path (supported: hair, obj)");
+        const bool isObj = n.get("type") == "obj", isRect = n.get("type") == "rectangle";
+        if (n.get("type") != "hair" && !isObj && !isRect) throw std::runtime_error("shape plugin \"" + n.get("type") + "\" is outside the hair hot path (supported: hair, obj, rectangle)");
         int bsdf = -1;
         for (auto &c : n.children) {
             if (c->tag == "bsdf") bsdf = loadBsdf(*c);
@@ -293,6 +330,11 @@ struct Loader {
         if (bsdf < 0) {          // Shape::configure falls back to a default `diffuse` (src/librender/shape.cpp)
             const float half[3] = {0.5f, 0.5f, 0.5f};
             check(bsdf = (dry ? note("bsdf diffuse (default)") : cudapath_add_bsdf_diffuse(ctx, half, 0)));
+        }
+        if (isRect) {                                  // src/shapes/rectangle.cpp:81-86
+            float tw[16]; toFloat(getTransform(n, "toWorld"), tw);
+            check(dry ? note("shape rectangle") : cudapath_add_rectangle(ctx, tw, getBool(n, "flipNormals", false) ? 1 : 0, bsdf));
+            return;
         }
         std::string file = getString(n, "filename", "");
         if (file.empty()) throw std::runtime_error(n.get("type") + " shape: missing 'filename'");

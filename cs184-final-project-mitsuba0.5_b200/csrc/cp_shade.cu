@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
             const float4 hp = hitPT[i];
             HitRecord rec;
             uint32_t shapeIdx;
-            if (gv & CP_TRI_FLAG) shapeIdx = fill_intersection_mesh(S.mesh, S.shapes, gv & ~CP_TRI_FLAG, hp.x, hp.y, rayD, rec);
+            if (gv & CP_RECT_FLAG) shapeIdx = fill_intersection_rect(S.mesh, gv & CP_PRIM_MASK, hp.x, hp.y, hp.w, rayO, rayD, rec);
+            else if (gv & CP_TRI_FLAG) shapeIdx = fill_intersection_mesh(S.mesh, S.shapes, gv & CP_PRIM_MASK, hp.x, hp.y, rayD, rec);
             else {
                 const float4 v1 = __ldg(S.vtx + gv), v2 = __ldg(S.vtx + gv + 1);
                 shapeIdx = vtx_shape(v1);
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
                     V3 contrib(0.0f);
                     if (!isZero(es.value) && !bsdf_eval_is_zero(bsdf)) {
                         const V3 wo = rec.sh.toLocal(es.d);
-                        const V3 bsdfVal = bsdf_eval(bsdf, rec.wi, wo);
+                        const V3 bsdfVal = bsdf_eval(bsdf, rec.wi, wo, false, rec.u, rec.v);
                         if (!isZero(bsdfVal) && (!S.integ.strictNormals || dot(rec.geoN, es.d) * wo.z > 0)) {
                             const float bsdfPdf = bsdf_pdf(bsdf, rec.wi, wo);
                             contrib = thr * es.value * bsdfVal * mi_weight(es.pdf, bsdfPdf);
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
                 const Philox4 ue = philox4x32_10(pix, samp, (uint32_t) depth, 2u, wp.seedLo, wp.seedHi);
                 extra = make_float4(u32_to_unit(ue.v[0]), u32_to_unit(ue.v[1]), u32_to_unit(ue.v[2]), u32_to_unit(ue.v[3]));
             }
-            const BsdfSampleOut bs = bsdf_sample(bsdf, rec.wi, u32_to_unit(u.v[2]), u32_to_unit(u.v[3]), extra);
+            const BsdfSampleOut bs = bsdf_sample(bsdf, rec.wi, u32_to_unit(u.v[2]), u32_to_unit(u.v[3]), extra, rec.u, rec.v);
             if (isZero(bs.weight)) break;
             const V3 wo = rec.sh.toWorld(bs.wo);
             if (S.integ.strictNormals && dot(rec.geoN, wo) * bs.wo.z <= 0) break;

@@ -237,12 +237,13 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *rayC
                 candMask &= candMask - 1;
                 const uint32_t gv = __float_as_uint(__ldg(leafSeg + 2 * (size_t) (leafFirst + ci) + 1).w);
                 if (MESH && (gv & CP_TRI_FLAG)) {
-                    const float4 *ta = S.mesh.triAccel + 3 * (size_t) (gv & ~CP_TRI_FLAG);
+                    const bool isRect = (gv & CP_RECT_FLAG) != 0u;
+                    const float4 *ta = isRect ? S.mesh.rects + CP_RECT_STRIDE * (size_t) (gv & CP_PRIM_MASK) : S.mesh.triAccel + 3 * (size_t) (gv & CP_PRIM_MASK);
                     const float4 A = __ldg(ta), B = __ldg(ta + 1), C = __ldg(ta + 2);
                     if (STATS) tc[any ? 1 : 0].fullTests++;
                     float t, u, v;
-                    if (tri_intersect(A, B, C, o, d, mint, maxt, u, v, t)) {
-                        hitT = t; hitGv = gv; found = true;       // barycentrics ride in the point slot
+                    if (isRect ? rect_intersect(A, B, C, o, d, mint, maxt, u, v, t) : tri_intersect(A, B, C, o, d, mint, maxt, u, v, t)) {
+                        hitT = t; hitGv = gv; found = true;       // barycentrics (rectangle: local x, y) ride in the point slot
                         s_hitP[tid] = u; s_hitP[CP_TRACE_THREADS + tid] = v; s_hitP[2 * CP_TRACE_THREADS + tid] = 0.0f;
                         if (any) { done = true; break; }
                         maxt = t;

@@ -21,13 +21,19 @@
 namespace cp {
 
 #define CP_TRI_FLAG 0x80000000u
+#define CP_RECT_FLAG 0x40000000u      // with CP_TRI_FLAG: a `rectangle` shape (one analytic primitive of the top-level tree), index into MeshDev::rects
+#define CP_PRIM_MASK 0x0fffffffu
+
+#define CP_RECT_STRIDE 8              // float4 per rectangle: rows 0..2 of worldToObject | (dpdu, shape index) | (normal, -) | - | box min | box max
 
 struct MeshDev {
     const float4 *triAccel;     // 3 x float4 per triangle
     const float4 *pos;          // xyz, -
     const float4 *nrm;          // xyz, - (zero where the owning shape has no vertex normals)
-    const uint32_t *idx;        // 3 per triangle, indices into pos / nrm
-    uint32_t triCount, vertCount;
+    const float2 *uv;           // texture coordinates per vertex (zero where the owning shape has none)
+    const uint32_t *idx;        // 3 per triangle, indices into pos / nrm / uv
+    const float4 *rects;        // CP_RECT_STRIDE x float4 per rectangle (src/shapes/rectangle.cpp)
+    uint32_t triCount, vertCount, rectCount;
 };
 
 // triaccel.h:99-158
@@ -50,6 +56,37 @@ CP_D bool tri_intersect(const float4 &A, const float4 &B, const float4 &C, const
     return u >= 0 && v >= 0 && __fadd_rn(u, v) <= 1.0f;
 }
 
+// Rectangle::rayIntersect (src/shapes/rectangle.cpp:127-151) after Transform::transformAffine(Ray) (transform.h:139-146,292-307): the ray goes to
+// object space through the three rows of worldToObject, meets z = 0 and must land in [-1, 1]^2.  One IEEE operation per source operation.
+CP_D bool rect_intersect(const float4 &R0, const float4 &R1, const float4 &R2, const V3 &ro, const V3 &rd, float mint, float maxt,
+                         float &lx, float &ly, float &t) {
+#define CP_ROW_P(R) __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R.x, ro.x), __fmul_rn(R.y, ro.y)), __fmul_rn(R.z, ro.z)), R.w)
+#define CP_ROW_V(R) __fadd_rn(__fadd_rn(__fmul_rn(R.x, rd.x), __fmul_rn(R.y, rd.y)), __fmul_rn(R.z, rd.z))
+    const float oz = CP_ROW_P(R2), dz = CP_ROW_V(R2);
+    const float hit = __fdiv_rn(-oz, dz);
+    if (!(hit >= mint && hit <= maxt)) return false;
+    const float ox = CP_ROW_P(R0), oy = CP_ROW_P(R1), dx = CP_ROW_V(R0), dy = CP_ROW_V(R1);
+#undef CP_ROW_P
+#undef CP_ROW_V
+    const float x = __fadd_rn(ox, __fmul_rn(hit, dx)), y = __fadd_rn(oy, __fmul_rn(hit, dy));      // Ray::operator()(t) = o + t * d
+    if (fabsf(x) <= 1 && fabsf(y) <= 1) { t = hit; lx = x; ly = y; return true; }
+    return false;
+}
+
+// Rectangle::fillIntersectionRecord (rectangle.cpp:158-171), then computeShadingFrame + wi (skdtree.h:426-427).
+// Only called from translation units built with -fmad=false.
+CP_D uint32_t fill_intersection_rect(const MeshDev &M, uint32_t rect, float lx, float ly, float t, const V3 &ro, const V3 &rd, HitRecord &rec) {
+    const float4 du = __ldg(M.rects + CP_RECT_STRIDE * (size_t) rect + 3), nn = __ldg(M.rects + CP_RECT_STRIDE * (size_t) rect + 4);
+    const V3 dpdu(du.x, du.y, du.z), n(nn.x, nn.y, nn.z);
+    rec.geoN = n; rec.sh.n = n;
+    rec.u = 0.5f * (lx + 1); rec.v = 0.5f * (ly + 1);
+    rec.p = ro + rd * t;
+    rec.sh.s = normalize(dpdu - n * dot(n, dpdu));
+    rec.sh.t = cross(n, rec.sh.s);
+    rec.wi = rec.sh.toLocal(-rd);
+    return __float_as_uint(du.w);
+}
+
 // skdtree.h:346-427 with BarycentricPos = true (skdtree.cpp:136), then computeShadingFrame + wi = toLocal(-ray.d).
 // Only called from translation units built with -fmad=false.
 CP_D uint32_t fill_intersection_mesh(const MeshDev &M, const ShapeDev *__restrict__ shapes, uint32_t tri, float u, float v, const V3 &rd, HitRecord &rec) {
@@ -69,6 +106,10 @@ CP_D uint32_t fill_intersection_mesh(const MeshDev &M, const ShapeDev *__restric
         if (dot(faceNormal, rec.sh.n) < 0) faceNormal = -faceNormal;   // geometric and shading normals face the same way
     } else rec.sh.n = faceNormal;
     rec.geoN = faceNormal;
+    if (shapes[shape].hasUV) {                                           // skdtree.h:399-406
+        const float2 t0 = __ldg(M.uv + idx0), t1 = __ldg(M.uv + idx1), t2 = __ldg(M.uv + idx2);
+        rec.u = t0.x * b.x + t1.x * b.y + t2.x * b.z; rec.v = t0.y * b.x + t1.y * b.y + t2.y * b.z;
+    } else { rec.u = b.y; rec.v = b.z; }
     rec.sh.s = normalize(side1 - rec.sh.n * dot(rec.sh.n, side1));      // computeShadingFrame(n, dpdu = side1), util.cpp:603-608
     rec.sh.t = cross(rec.sh.n, rec.sh.s);
     rec.wi = rec.sh.toLocal(-rd);

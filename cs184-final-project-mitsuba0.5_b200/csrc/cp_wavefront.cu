@@ -213,7 +213,7 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
         if (tiles < waveSize) waveSize = (uint32_t) std::max<uint64_t>(tiles, 1024);
     }
     if (waveSize > 0x3fffffffu) waveSize = 0x3fffffffu;
-    const bool hasMesh = S.mesh.triCount > 0;
+    const bool hasMesh = S.mesh.triCount + S.mesh.rectCount > 0;
     const bool trace = getenv("CUDAPATH_TRACE") != nullptr;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tr0 = now();

@@ -67,6 +67,13 @@ int cudapath_add_bsdf_roughplastic(cudapath_ctx *ctx, float int_ior, float ext_i
  * sample() that draws two additional 2-D numbers from the sampler (:421-535).  Reference defaults: int_ior 1.55 (amber), ext_ior
  * 1.000277 (air).  Returns the bsdf id. */
 int cudapath_add_bsdf_marschner_fixed(cudapath_ctx *ctx, float int_ior, float ext_ior);
+/* The same class as a physically meaningful, scene-driven mode: what the constructor hard-codes comes from the caller --
+ * sigma_a (absorption, :122), beta_r (longitudinal roughness of the R lobe; TT = beta_r / 2, TRT = 2 beta_r, :131-134) and the scale
+ * angle in radians (:135) -- and lobe_mask says which lobes eval() keeps (bit 0 R, bit 1 TT, bit 2 TRT; 7 = all three, i.e. the file without
+ * the two lines :333-334 that zero R and TT; 4 = cudapath_add_bsdf_marschner_fixed).  pdf (:347-407) and sample (:421-535) always cover the
+ * three lobes, so with lobe_mask = 7 the sampling density matches the function it samples.  Returns the bsdf id. */
+int cudapath_add_bsdf_marschner_full(cudapath_ctx *ctx, float int_ior, float ext_ior, const float sigma_a[3], float beta_r, float scale_angle_rad,
+                                     int lobe_mask);
 /* `diffuse` plugin with a constant reflectance: SmoothDiffuse ctor+configure(), src/bsdfs/diffuse.cpp:70-103; two_sided != 0
  * wraps it in the `twosided` adapter (src/bsdfs/twosided.cpp:50-181) with the same BRDF on both sides.  For triangle meshes
  * that accompany the fibers (a scalp or head under the hair).  Returns the bsdf id. */
@@ -81,6 +88,20 @@ int cudapath_add_bsdf_thindielectric(cudapath_ctx *ctx, float int_ior, float ext
  * Returns the bsdf id. */
 int cudapath_add_bsdf_marschnerdielectric(cudapath_ctx *ctx, float int_ior, float ext_ior, const float diffuse_reflectance[3],
                                           const float specular_reflectance[3], const float specular_transmittance[3], float exponent);
+/* `plastic` plugin (models/teapot/scene.xml:31-38): SmoothPlastic ctor+configure(), src/bsdfs/plastic.cpp:140-217 -- a delta reflection over a
+ * diffuse base, fdrInt / fdrExt from fresnelDiffuseReflectance (src/libcore/util.cpp:807-862).  Reference defaults: int_ior 1.49
+ * (polypropylene), ext_ior 1.000277 (air), specular 1, diffuse 0.5.  Returns the bsdf id. */
+int cudapath_add_bsdf_plastic(cudapath_ctx *ctx, float int_ior, float ext_ior, const float diffuse_reflectance[3], const float specular_reflectance[3], int nonlinear);
+/* <texture type="checkerboard"> (src/textures/checkerboard.cpp:49-72 behind Texture2D, src/librender/texture.cpp:81-121) as the `reflectance` of a
+ * `diffuse` or the `diffuseReflectance` of a `plastic` BSDF (models/teapot/scene.xml:43-52); the BSDF's configure() runs again on it.
+ * Reference defaults: color0 0.4, color1 0.2, offsets 0, scales 1. */
+int cudapath_bsdf_set_checkerboard(cudapath_ctx *ctx, int bsdf_id, const float color0[3], const float color1[3], float uoffset, float voffset,
+                                   float uscale, float vscale);
+/* <bsdf type="twosided"> around an existing `diffuse`, `roughplastic` or `plastic` BSDF with the same nested BRDF on both sides:
+ * TwoSidedBRDF::configure / eval / pdf / sample, src/bsdfs/twosided.cpp:84-181. */
+int cudapath_bsdf_set_twosided(cudapath_ctx *ctx, int bsdf_id);
+/* fresnelDiffuseReflectance(eta, fast = false), src/libcore/util.cpp:814-862 (host only: adaptive Gauss-Lobatto, src/libcore/quad.cpp:287-420). */
+int cudapath_fresnel_diffuse_reflectance(float eta, float *out);
 
 /* ---- shapes ------------------------------------------------------------------------------------------------ */
 /* Triangle mesh as ShapeKDTree sees it: TriMesh::getVertexPositions() / getVertexNormals() (NULL = face normals) /
@@ -88,6 +109,14 @@ int cudapath_add_bsdf_marschnerdielectric(cudapath_ctx *ctx, float int_ior, floa
  * BVH and are tested with Wald's projection test (TriAccel, include/mitsuba/render/triaccel.h:61-158).  Returns the shape id. */
 int cudapath_add_mesh(cudapath_ctx *ctx, const float *xyz, const float *normals, uint32_t n_vertices, const uint32_t *indices,
                       uint32_t n_triangles, int bsdf_id);
+/* ... with TriMesh::getVertexTexcoords() (2 floats per vertex, NULL = none: its.uv is then the barycentric pair, include/mitsuba/render/skdtree.h:399-406). */
+int cudapath_add_mesh_uv(cudapath_ctx *ctx, const float *xyz, const float *normals, const float *uvs, uint32_t n_vertices, const uint32_t *indices,
+                         uint32_t n_triangles, int bsdf_id);
+/* `rectangle` shape (models/teapot/scene.xml:56-62): Rectangle ctor+configure() / getAABB / rayIntersect / fillIntersectionRecord,
+ * src/shapes/rectangle.cpp:81-171 -- the square [-1,1]^2 x {0} under to_world (row-major 4x4; inverted like Transform(const Matrix4x4 &),
+ * include/mitsuba/core/transform.h:50-55), one analytic primitive of the top-level tree with uv = (x+1, y+1)/2.  A sheared to_world fails
+ * with the reference's message.  Returns the shape id. */
+int cudapath_add_rectangle(cudapath_ctx *ctx, const float to_world[16], int flip_normals, int bsdf_id);
 /* `obj` shape: WavefrontOBJ(props) with all faces collapsed into one mesh (src/shapes/obj.cpp:186-349, createMesh :608-700) followed
  * by TriMesh::computeNormals (src/librender/trimesh.cpp:608-672).  Materials of the file are ignored.  Returns the shape id. */
 int cudapath_add_mesh_file(cudapath_ctx *ctx, const char *filename, const float to_world[16], int face_normals, int flip_normals, int bsdf_id);
@@ -95,6 +124,8 @@ int cudapath_add_mesh_file(cudapath_ctx *ctx, const char *filename, const float 
 typedef struct cudapath_mesh_file cudapath_mesh_file;
 int cudapath_mesh_file_load(const char *filename, const float to_world[16], int face_normals, int flip_normals, cudapath_mesh_file **out);
 uint32_t cudapath_mesh_file_vertex_count(const cudapath_mesh_file *m);
+int cudapath_mesh_file_has_texcoords(const cudapath_mesh_file *m);                 /* `vt` records referenced by a face (src/shapes/obj.cpp:633-636) */
+void cudapath_mesh_file_copy_texcoords(const cudapath_mesh_file *m, float *uvs);  /* 2 floats per vertex */
 uint32_t cudapath_mesh_file_triangle_count(const cudapath_mesh_file *m);
 int cudapath_mesh_file_has_normals(const cudapath_mesh_file *m);
 void cudapath_mesh_file_copy(const cudapath_mesh_file *m, float *xyz, float *normals, uint32_t *indices);
@@ -248,12 +279,22 @@ int cudapath_bsdf_sample_batch(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const
  * tuple = xiN.x, xiN.y, xiM.x, xiM.y of the fixed Marschner; may be NULL). */
 int cudapath_bsdf_sample_batch_ex(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, const float *extra,
                                   float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type);
+/* Same with texture coordinates per tuple (its.uv, 2 floats): what Texture2D::eval hands the textured BSDFs (src/librender/texture.cpp:112-121);
+ * discrete != 0 selects the EDiscrete measure (the delta reflection of `plastic`, src/bsdfs/plastic.cpp:246-313). */
+int cudapath_bsdf_eval_batch_uv(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *wo, const float *uv, int discrete,
+                                float *out_eval, float *out_pdf);
+int cudapath_bsdf_sample_batch_uv(cudapath_ctx *ctx, int bsdf_id, uint64_t n, const float *wi, const float *sample, const float *uv,
+                                  float *out_wo, float *out_weight, float *out_pdf, int32_t *out_type);
 /* Scene::rayIntersect (any_hit = 0) / shadow-ray query (any_hit = 1).  out_prim = shape-local first-vertex index iv
  * (the reference's primitive id, src/shapes/hair.cpp:151-155) or, for a mesh, the triangle index within the mesh
  * (TriAccel::primIndex); out_record (optional) = p, n, s, t, wi (15 floats per ray) as filled by
  * HairShape::fillIntersectionRecord (src/shapes/hair.cpp:825-862) / the mesh branch of include/mitsuba/render/skdtree.h:346-427. */
 int cudapath_intersect_batch(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,
                              int any_hit, int32_t *out_shape, uint32_t *out_prim, float *out_t, float *out_record);
+/* Closest hit with the record plus its.uv and its.geoFrame.n (out_uv_geo_n: 5 floats per ray; zero on a miss): the mesh branch of
+ * include/mitsuba/render/skdtree.h:346-427 (uv :399-406) and Rectangle::fillIntersectionRecord (src/shapes/rectangle.cpp:158-171). */
+int cudapath_intersect_batch_uv(cudapath_ctx *ctx, uint64_t n, const float *origin, const float *direction, const float *mint, const float *maxt,
+                                int32_t *out_shape, uint32_t *out_prim, float *out_t, float *out_record, float *out_uv_geo_n);
 int cudapath_env_eval_batch(cudapath_ctx *ctx, uint64_t n, const float *direction, float *out_rgb, float *out_pdf);
 /* Emitter::evalEnvironment for rays WITH differentials (camera rays that leave the scene): MIPMap::eval with the EWA filter over the
  * 2-lobed-Lanczos MIP pyramid, maxAnisotropy 10 (src/emitters/envmap.cpp:150-181,391-407; include/mitsuba/render/mipmap.h:629-836).

@@ -585,9 +585,15 @@ struct Marschner {
 // ---------------------------------------------------------------------------------------------
 struct MarschnerFixed {
     Marschner base;      // tables, variances, scale angle
-    void configure(float intIOR, float extIOR) {
+    int lobeMask = 4;    // lobes eval() keeps: bit 0 R, bit 1 TT, bit 2 TRT.  4 = the file as committed (MR = MTT = 0, :333-334); 7 = all three
+    void configure(float intIOR, float extIOR) { configure(intIOR, extIOR, V3(0.22f), 0.1f, -0.1f, 4); }
+    // the scene-driven variant: what the constructor hard-codes (:122, :131-137) comes from the scene
+    void configure(float intIOR, float extIOR, V3 sigmaA, float betaR, float scaleAngleRad, int mask) {
         base.eta = intIOR / extIOR;
-        base.sigmaA = V3(0.22f);
+        base.sigmaA = sigmaA;
+        base.betaR = betaR; base.betaTT = betaR * 0.5f; base.betaTRT = betaR * 2.0f;
+        base.scaleAngleRad = scaleAngleRad;
+        lobeMask = mask;
         base.precomputeAzimuthalDistributions();
         base.vR = base.betaR * base.betaR; base.vTT = base.betaTT * base.betaTT; base.vTRT = base.betaTRT * base.betaTRT;
     }
@@ -600,11 +606,12 @@ struct MarschnerFixed {
         float cosThetaD = cr::cos(thetaD);
         float phi = cr::atan2(wo.x, wo.z);
         if (phi < 0.0f) phi += kPi * 2.0f;
-        float thetaITRT = thetaI + 4.0f * base.scaleAngleRad;
-        float MTRT = Marschner::M(base.vTRT, cr::sin(thetaITRT), sinThetaO, cr::cos(thetaITRT), cosThetaO);
+        float thetaIR = thetaI - 2.0f * base.scaleAngleRad, thetaITT = thetaI + base.scaleAngleRad, thetaITRT = thetaI + 4.0f * base.scaleAngleRad;
         // MR and MTT are computed and then zeroed in the reference; 0 * eval() contributes exactly +0 for finite tables
-        V3 zero(0.0f);
-        return zero * base.nR.eval(phi, cosThetaD) + zero * base.nTT.eval(phi, cosThetaD) + MTRT * base.nTRT.eval(phi, cosThetaD);
+        float MR = (lobeMask & 1) ? Marschner::M(base.vR, cr::sin(thetaIR), sinThetaO, cr::cos(thetaIR), cosThetaO) : 0.0f;
+        float MTT = (lobeMask & 2) ? Marschner::M(base.vTT, cr::sin(thetaITT), sinThetaO, cr::cos(thetaITT), cosThetaO) : 0.0f;
+        float MTRT = (lobeMask & 4) ? Marschner::M(base.vTRT, cr::sin(thetaITRT), sinThetaO, cr::cos(thetaITRT), cosThetaO) : 0.0f;
+        return MR * base.nR.eval(phi, cosThetaD) + MTT * base.nTT.eval(phi, cosThetaD) + MTRT * base.nTRT.eval(phi, cosThetaD);
     }
     float pdf(const V3 &wi, const V3 &wo) const { // :347-407
         float sinThetaI = wi.y, sinThetaO = wo.y;

@@ -91,6 +91,18 @@ int orc_add_bsdf_marschner_fixed(void *sp, float intIOR, float extIOR) {
     ORC_CATCH
 }
 
+// the same class with all three lobes in eval() and its constants taken from the scene (lobeMask: bit 0 R, 1 TT, 2 TRT)
+int orc_add_bsdf_marschner_full(void *sp, float intIOR, float extIOR, const float *sigmaA, float betaR, float scaleAngleRad, int lobeMask) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    BSDFAny b; b.kind = 3;
+    b.mf = std::make_shared<MarschnerFixed>();
+    b.mf->configure(intIOR, extIOR, V3(sigmaA[0], sigmaA[1], sigmaA[2]), betaR, scaleAngleRad, lobeMask);
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+    ORC_CATCH
+}
+
 // `roughplastic` plugin (src/bsdfs/roughplastic.cpp); distribution: 0 beckmann, 1 ggx, 2 phong
 int orc_add_bsdf_roughplastic(void *sp, float intIOR, float extIOR, const float *diffuse, const float *specular, float alpha, int distribution,
                               int sampleVisible, int nonlinear, const char *dataDir) {

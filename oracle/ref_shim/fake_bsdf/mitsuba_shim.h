@@ -45,7 +45,11 @@
 #define MTS_DECLARE_CLASS()
 #define MTS_IMPLEMENT_CLASS(name, abstract, super)
 #define MTS_IMPLEMENT_CLASS_S(name, abstract, super)
+#ifdef MTS_PLUGIN_EXPORT_NAME     /* a second build of one plugin source (oracle/Makefile: marschner_full) exports under its own name */
+#define MTS_EXPORT_PLUGIN(name, descr) extern "C" void *MTS_PLUGIN_EXPORT_NAME(const mitsuba::Properties *props) { return new MTS_PLUGIN_SCOPE::name(*props); }
+#else
 #define MTS_EXPORT_PLUGIN(name, descr) extern "C" void *ref_create_##name(const mitsuba::Properties *props) { return new MTS_PLUGIN_SCOPE::name(*props); }
+#endif
 #define MTS_CLASS(x) (#x)
 #define EXPECT_NOT_TAKEN(x) (x)
 #define EXPECT_TAKEN(x) (x)

@@ -128,6 +128,10 @@ class Scene:
                                                           1 if props.get('sampleVisible', True) else 0, 1 if props.get('nonlinear', False) else 0, DATA_DIR.encode()))
         if type == 'marschner_fixed':
             return check(self.L.orc_add_bsdf_marschner_fixed(self.h, ctypes.c_float(props.get('intIOR', 1.55)), ctypes.c_float(props.get('extIOR', 1.000277))))
+        if type == 'marschner_full':
+            sa = f32(np.broadcast_to(props.get('sigmaA', 0.22), 3))
+            return check(self.L.orc_add_bsdf_marschner_full(self.h, ctypes.c_float(props.get('intIOR', 1.55)), ctypes.c_float(props.get('extIOR', 1.000277)), p(sa),
+                                                            ctypes.c_float(props.get('betaR', 0.1)), ctypes.c_float(props.get('scaleAngleRad', -0.1)), int(props.get('lobes', 7))))
         if type == 'thindielectric':
             r = f32(np.broadcast_to(props.get('specularReflectance', 1.0), 3)); t = f32(np.broadcast_to(props.get('specularTransmittance', 1.0), 3))
             return check(self.L.orc_add_bsdf_thindielectric(self.h, ctypes.c_float(props.get('intIOR', 1.5046)), ctypes.c_float(props.get('extIOR', 1.000277)), p(r), p(t)))

@@ -145,11 +145,15 @@ def test_bsdf_large_batch(bsdf_pair):
         assert rel_err(gpdf[valid], opdf[valid], 1e-9).max() <= 1e-4
 
 
-def test_marschner_fixed_mode_bit_exact(cp, oracle):
-    """the unbuilt src/bsdfs/marschner.cpp -- tables, eval, pdf and the 4-number sample against the oracle."""
+@pytest.mark.parametrize('mode', ['fixed', 'full', 'full-scene-driven'])
+def test_marschner_fixed_mode_bit_exact(cp, oracle, mode):
+    """the unbuilt src/bsdfs/marschner.cpp -- tables, eval, pdf and the 4-number sample against the oracle; as committed (TRT lobe only,
+    hard-coded constants) and as the scene-driven mode of SURVEY 8f rank 3 (all three lobes; sigmaA, betaR and the scale angle from the scene)."""
     ctx = cp.Context(0); osc = oracle.Scene()
     for s in (ctx, osc):
-        s.add_bsdf('marschner_fixed', intIOR=1.55, extIOR=1.000277)
+        if mode == 'fixed': s.add_bsdf('marschner_fixed', intIOR=1.55, extIOR=1.000277)
+        elif mode == 'full': s.add_bsdf('marschner_full', intIOR=1.55, extIOR=1.000277)
+        else: s.add_bsdf('marschner_full', intIOR=1.5, extIOR=1.0, sigmaA=(0.6, 0.9, 1.6), betaR=0.17, scaleAngleRad=-0.05)
         s.add_hair(np.array([[0, 0, 0], [0, 1, 0], [0.1, 2, 0]], np.float32), np.array([1, 0, 0], np.uint8), 0.05, 0)
         s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=16, height=16)
         s.build()
@@ -162,6 +166,11 @@ def test_marschner_fixed_mode_bit_exact(cp, oracle):
     ge, gp = ctx.bsdf_eval(0, wi, wo); oe, op = osc.bsdf_eval(0, wi, wo)
     # the tables differ by an ulp or two between the device and host builds (fp32 sums in another order): 1e-4 relative, not bit-exact
     assert rel_err(ge, oe, 1e-6 * np.abs(oe).max()).max() <= 1e-4 and rel_err(gp, op, 1e-6).max() <= 1e-4
+    if mode != 'fixed':      # the R and TT lobes are there: the forward-scattering (TT) side carries energy, and colour once sigmaA has one
+        fixed = oracle.Scene(); fixed.add_bsdf('marschner_fixed', intIOR=1.55, extIOR=1.000277)
+        fe, _ = fixed.bsdf_eval(0, wi, wo)
+        assert mode == 'full-scene-driven' or (oe.sum() > 1.5 * fe.sum() and (oe >= fe * (1 - 1e-6)).all())
+        assert mode == 'full' or oe[:, 0].sum() > 1.2 * oe[:, 2].sum()
     smp = rng.random((n, 2)).astype(np.float32); ex = rng.random((n, 4)).astype(np.float32)
     gw, gwt, gpdf, gty = ctx.bsdf_sample(0, wi, smp, ex); ow, owt, opdf, oty = osc.bsdf_sample(0, wi, smp, ex)
     same = np.abs(gw - ow).max(axis=1) <= 1e-4          # an ulp in a CDF can move a sample into the neighbouring azimuthal cell
@@ -1208,4 +1217,174 @@ def test_env_filtered_lookup_and_pyramid(cp, oracle):
     # the filtered lookup matters at this resolution: answering at level 0 instead would change the sky pixels
     lvl0 = osc.env_eval(d[:1000])[0]; flt = osc.env_eval_filtered(d[:1000], d[:1000] + 0.05 * t1[:1000], d[:1000] + 0.05 * t2[:1000])
     assert np.abs(lvl0 - flt).max() > 1e-3 * np.abs(lvl0).max()
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ the plugins of models/teapot/scene.xml
+def _teapot_materials(s):
+    """Material / Floor of models/teapot/scene.xml:31-54 plus a one-sided textured plastic and a two-sided roughplastic."""
+    mat = s.add_bsdf('plastic', intIOR=1.5, extIOR=1.0, nonlinear=True, diffuseReflectance=(0.9, 0.9, 0.9)); s.set_twosided(mat)
+    floor = s.add_bsdf('diffuse', reflectance=0.5); s.set_checkerboard(floor, (0.725, 0.71, 0.68), (0.325, 0.31, 0.25), 0, 0, 10, 10); s.set_twosided(floor)
+    pl = s.add_bsdf('plastic', diffuseReflectance=(0.2, 0.5, 0.7), specularReflectance=(0.9, 0.8, 1.3)); s.set_checkerboard(pl, (1.4, 0.3, 0.2), (0.1, 0.2, 0.9), 0.25, -0.5, 3, 0.5)
+    rp = s.add_bsdf('roughplastic', intIOR=1.55, extIOR=1.0, alpha=0.2, distribution='ggx', diffuseReflectance=(0.4, 0.3, 0.2)); s.set_twosided(rp)
+    return mat, floor, pl, rp
+
+
+@pytest.mark.gpu
+def test_plastic_checkerboard_twosided_bit_exact(cp, oracle):
+    """SmoothPlastic (src/bsdfs/plastic.cpp), Checkerboard behind Texture2D (src/textures/checkerboard.cpp, src/librender/texture.cpp) and the
+    generic TwoSidedBRDF (src/bsdfs/twosided.cpp) on the device against the oracle (itself pinned against the compiled plugins): eval / pdf in
+    both measures and sample, with texture coordinates per tuple, bit for bit in the strict math mode."""
+    ctx = cp.Context(0); osc = oracle.Scene()
+    ids = []
+    for s in (ctx, osc):
+        ids = _teapot_materials(s)
+        s.add_mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), [[0, 1, 2]], ids[0])
+        s.set_camera(np.eye(4, dtype=np.float32), 35.0, width=16, height=16)
+        s.build()
+    assert cp.fresnel_diffuse_reflectance(1 / 1.5) == osc.plastic_constants(ids[0])['fdrInt']
+    rng = np.random.default_rng(61)
+    n = 200000
+    wi, wo = sphere_dirs(rng, n), sphere_dirs(rng, n); smp = rng.random((n, 2)).astype(np.float32)
+    wo[: n // 4] = wi[: n // 4] * np.array([-1, -1, 1], np.float32)               # mirror pairs: the delta reflection of plastic
+    uv = (rng.random((n, 2)) * 6 - 3).astype(np.float32)
+    for b in ids:
+        for discrete in (False, True):
+            ge, gp = ctx.bsdf_eval_uv(b, wi, wo, uv, discrete); oe, op = osc.bsdf_eval_uv(b, wi, wo, uv, discrete)
+            assert np.array_equal(ge, oe) and np.array_equal(gp, op), (b, discrete)
+        g = ctx.bsdf_sample_uv(b, wi, smp, uv); o = osc.bsdf_sample_uv(b, wi, smp, uv)
+        for a, c in zip(g, o):
+            assert np.array_equal(a, c), b
+        assert (g[1] != 0).any()
+    ge, _ = ctx.bsdf_eval_uv(ids[0], wi, wo, uv, True)
+    assert (ge[: n // 4] != 0).any(axis=1).mean() > 0.4 and (ge[n // 4:] != 0).any(axis=1).mean() < 2e-3   # discrete measure: the mirror pairs (and random pairs within DeltaEpsilon of one)
+    ge, _ = ctx.bsdf_eval_uv(ids[1], wi, wo, uv)
+    assert len(np.unique(ge[ge[:, 0] > 0][:, 0] / np.abs(wo[ge[:, 0] > 0][:, 2]))) >= 2   # both checker colours show up
+    ctx.close()
+
+
+def _teapot_like_scene(s, cp):
+    """A rectangle floor (the matrix of models/teapot/scene.xml:57-59), a textured UV sphere and a plastic ellipsoid."""
+    mat, floor, pl, rp = _teapot_materials(s)
+    tw = np.array([-39.9766, 39.9766, -1.74743e-006, 0, 4.94249e-006, 2.47125e-006, -56.5355, 0, -39.9766, -39.9766, -5.2423e-006, 0, 0, 0, 0, 1], np.float32).reshape(4, 4)
+    s.add_rectangle(tw, False, floor) if hasattr(s, 'L') else s.add_rectangle(floor, tw, False)
+    xyz, idx, nrm = cp.scenes.gen_ellipsoid((0, 6, 0), (5, 6, 5), 24)
+    s.add_mesh(xyz, idx, mat, normals=nrm)
+    xyz2, idx2, nrm2 = cp.scenes.gen_ellipsoid((11, 3, -4), (3, 3, 3), 16)
+    uvs = np.stack([np.arctan2(xyz2[:, 2] + 4, xyz2[:, 0] - 11) / (2 * np.pi) + 0.5, (xyz2[:, 1]) / 6.0], axis=1).astype(np.float32)
+    s.add_mesh(xyz2, idx2, pl, normals=nrm2, uvs=uvs)
+    rot = np.array([[0, 0, 2.0, -12.0], [0, 3.0, 0, 4.0], [-1.0, 0, 0, 6.0], [0, 0, 0, 1]], np.float32)
+    s.add_rectangle(rot, True, rp) if hasattr(s, 'L') else s.add_rectangle(rp, rot, True)
+    return tw
+
+
+@pytest.mark.gpu
+def test_rectangle_and_mesh_uv_parity(cp, oracle):
+    """Rectangle::rayIntersect / fillIntersectionRecord (src/shapes/rectangle.cpp:127-171) and the texture coordinates of mesh hits
+    (skdtree.h:399-406) on the device against the oracle (pinned against the reference text): shape, primitive, t, record, uv and geometric
+    normal of closest hits, any-hit agreement, on chords through the scene and on secondary rays leaving the surfaces."""
+    ctx = cp.Context(0); osc = oracle.Scene()
+    for s in (ctx, osc):
+        _teapot_like_scene(s, cp)
+        cam = np.array([-0.00550949, -0.342144, -0.939631, 23.895, 1.07844e-005, 0.939646, -0.342149, 11.2207, 0.999985, -0.00189103, -0.00519335, 0.0400773, 0, 0, 0, 1], np.float32).reshape(4, 4)
+        s.set_camera(cam, 35.0, width=64, height=36)
+        s.build()
+    ga, gb = ctx.scene_bounds(); oa, ob = osc.scene_bounds()
+    assert np.allclose(ga, oa, rtol=1e-6, atol=1e-6)
+    rng = np.random.default_rng(62)
+    o, d = chord_rays(rng, 200000, np.array([0, 5, 0], np.float32), 30.0)
+    for (oo, dd, mint) in ((o, d, 0.0),):
+        gs, gp, gt, grec, guv, ggn = ctx.intersect_uv(oo, dd, mint, np.inf)
+        os_, op, ot, orec = osc.intersect_full(oo, dd, mint, np.inf); ouv, ogn = osc.intersect_uv(oo, dd, mint, np.inf)
+        same = (gs == os_) & (gp == op)
+        assert same.mean() > 0.999 and np.array_equal(gs >= 0, os_ >= 0)        # shared-edge ties of the two spheres only
+        for shape in (0, 1, 2, 3):
+            assert ((os_ == shape) & same).sum() > 300, shape
+        k = same & (os_ >= 0)
+        assert np.array_equal(gt[k], ot[k]) and np.array_equal(guv[k], ouv[k]) and np.array_equal(ggn[k], ogn[k]) and np.array_equal(grec[k], orec[k])
+    m = os_ >= 0
+    hitp = orec[m, :3]; d2 = sphere_dirs(rng, int(m.sum()))
+    gs2, gp2, gt2, grec2, guv2, ggn2 = ctx.intersect_uv(hitp, d2, 1e-4, np.inf)
+    os2, op2, ot2, orec2 = osc.intersect_full(hitp, d2, 1e-4, np.inf); ouv2, _ = osc.intersect_uv(hitp, d2, 1e-4, np.inf)
+    k = (gs2 == os2) & (gp2 == op2) & (os2 >= 0)
+    assert ((gs2 == os2) & (gp2 == op2)).mean() > 0.999 and np.array_equal(gt2[k], ot2[k]) and np.array_equal(guv2[k], ouv2[k]) and k.sum() > 10000
+    ga2 = ctx.intersect(hitp, d2, 1e-4, 20.0, any_hit=True)[0]; oa2 = osc.intersect(hitp, d2, 1e-4, 20.0, mode=1)[0]
+    assert np.array_equal(ga2 >= 0, oa2 >= 0)
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_teapot_scene_plugins_render(cp, oracle, tmp_path):
+    """A scene file with every plugin of models/teapot/scene.xml -- `rectangle` with a checkerboard `diffuse` in `twosided`, `obj` meshes (one with
+    `vt` records) under a two-sided `plastic`, an `envmap` emitter from a Radiance file, the `sobol` sampler tag, `ldrfilm` -- loaded from XML
+    and rendered on the device: every pixel's first sample replays the oracle's radiance, and the film matches the oracle's."""
+    from test_oracle_cpu import _write_rgbe
+    rng = np.random.default_rng(63)
+    os.makedirs(tmp_path / 'models'); os.makedirs(tmp_path / 'textures')
+    w, h = 64, 32
+    q = np.zeros((h, w, 4), np.uint8); q[..., :3] = rng.integers(40, 256, size=(h, w, 3)); q[..., 3] = 128; q[3:6, 10:14] = (250, 240, 200, 134)
+    _write_rgbe(tmp_path / 'textures' / 'envmap.hdr', q, rle=True)
+    def write_obj(path, xyz, idx, uvs=None):
+        with open(path, 'w') as f:
+            for p in xyz: f.write('v %r %r %r\n' % tuple(float(c) for c in p))
+            if uvs is not None:
+                for t in uvs: f.write('vt %r %r\n' % tuple(float(c) for c in t))
+            for t in idx:
+                f.write('f ' + ' '.join(('%d/%d' % (i + 1, i + 1)) if uvs is not None else str(i + 1) for i in t) + '\n')
+    xyz, idx, _ = cp.scenes.gen_ellipsoid((0, 6, 0), (5, 6, 5), 20)
+    write_obj(tmp_path / 'models' / 'Mesh001.obj', xyz, idx)
+    xyz2, idx2, _ = cp.scenes.gen_ellipsoid((11, 3, -4), (3, 3, 3), 12)
+    uvs = np.stack([xyz2[:, 0] * 0.1, xyz2[:, 1] * 0.2], axis=1).astype(np.float32)
+    write_obj(tmp_path / 'models' / 'Mesh000.obj', xyz2, idx2, uvs)
+    W, H, spp = 96, 54, 8
+    xml = '''<?xml version="1.0" encoding="utf-8"?>
+<scene version="0.6.0">
+	<integrator type="path"><integer name="maxDepth" value="9"/><boolean name="strictNormals" value="true"/></integrator>
+	<sensor type="perspective">
+		<float name="fov" value="35"/>
+		<transform name="toWorld"><matrix value="-0.00550949 -0.342144 -0.939631 23.895 1.07844e-005 0.939646 -0.342149 11.2207 0.999985 -0.00189103 -0.00519335 0.0400773 0 0 0 1"/></transform>
+		<sampler type="sobol"><integer name="sampleCount" value="%d"/></sampler>
+		<film type="ldrfilm"><integer name="width" value="%d"/><integer name="height" value="%d"/><string name="fileFormat" value="png"/><string name="pixelFormat" value="rgb"/>
+			<float name="gamma" value="2.2"/><boolean name="banner" value="false"/><rfilter type="tent"/></film>
+	</sensor>
+	<bsdf type="twosided" id="Material"><bsdf type="plastic"><float name="intIOR" value="1.5"/><float name="extIOR" value="1"/><boolean name="nonlinear" value="true"/>
+		<rgb name="diffuseReflectance" value="0.9, 0.9, 0.9"/></bsdf></bsdf>
+	<bsdf type="twosided" id="Floor"><bsdf type="diffuse"><texture name="reflectance" type="checkerboard"><rgb name="color1" value="0.325, 0.31, 0.25"/><rgb name="color0" value="0.725, 0.71, 0.68"/>
+		<float name="uoffset" value="0"/><float name="voffset" value="0"/><float name="uscale" value="10"/><float name="vscale" value="10"/></texture></bsdf></bsdf>
+	<bsdf type="twosided" id="Checkered"><bsdf type="diffuse"><texture name="reflectance" type="checkerboard"><float name="uvscale" value="4"/></texture></bsdf></bsdf>
+	<shape type="rectangle"><transform name="toWorld"><matrix value="-39.9766 39.9766 -1.74743e-006 0 4.94249e-006 2.47125e-006 -56.5355 0 -39.9766 -39.9766 -5.2423e-006 0 0 0 0 1"/></transform><ref id="Floor"/></shape>
+	<shape type="obj"><string name="filename" value="models/Mesh001.obj"/><transform name="toWorld"><matrix value="1 0 0 0 0 1 0 0 0 0 1 0 0 0 0 1"/></transform><ref id="Material"/></shape>
+	<shape type="obj"><string name="filename" value="models/Mesh000.obj"/><transform name="toWorld"><matrix value="1 0 0 0 0 1 0 0 0 0 1 0 0 0 0 1"/></transform><ref id="Checkered"/></shape>
+	<emitter type="envmap"><transform name="toWorld"><matrix value="-0.922278 0 0.386527 0 0 1 0 0 -0.386527 0 -0.922278 1.17369 0 0 0 1"/></transform><string name="filename" value="textures/envmap.hdr"/></emitter>
+</scene>''' % (spp, W, H)
+    path = str(tmp_path / 'scene.xml'); open(path, 'w').write(xml)
+    rep = cp.validate_scene_xml(path)
+    assert 'shape rectangle' in rep and 'bsdf plastic' in rep and 'texture checkerboard' in rep and not any('missing' in r for r in rep)
+    ctx = cp.Context(0)
+    assert ctx.load_xml(path) == spp
+    ctx.build()
+    film = ctx.render(spp, seed=11)
+    st = ctx.stats()
+    assert st['unsupported_filtered_lookups'] == 0 and st['dropped_samples'] == 0
+    # the same scene through the flattened-array interface of the oracle
+    osc = oracle.Scene()
+    mat = osc.add_bsdf('plastic', intIOR=1.5, extIOR=1.0, nonlinear=True, diffuseReflectance=(0.9, 0.9, 0.9)); osc.set_twosided(mat)
+    floor = osc.add_bsdf('diffuse', reflectance=0.5); osc.set_checkerboard(floor, (0.725, 0.71, 0.68), (0.325, 0.31, 0.25), 0, 0, 10, 10); osc.set_twosided(floor)
+    chk = osc.add_bsdf('diffuse', reflectance=0.5); osc.set_checkerboard(chk, 0.4, 0.2, 0, 0, 4, 4); osc.set_twosided(chk)
+    tw = np.array([-39.9766, 39.9766, -1.74743e-006, 0, 4.94249e-006, 2.47125e-006, -56.5355, 0, -39.9766, -39.9766, -5.2423e-006, 0, 0, 0, 0, 1], np.float32).reshape(4, 4)
+    osc.add_rectangle(tw, False, floor)
+    m1 = cp.load_obj_file(str(tmp_path / 'models' / 'Mesh001.obj'), texcoords=True); assert m1[3] is None
+    osc.add_mesh(m1[0], m1[1], mat, normals=m1[2])
+    m0 = cp.load_obj_file(str(tmp_path / 'models' / 'Mesh000.obj'), texcoords=True); assert m0[3] is not None and len(m0[3]) == len(m0[0])
+    osc.add_mesh(m0[0], m0[1], chk, normals=m0[2], uvs=m0[3])
+    osc.set_envmap(cp.load_rgbe(tmp_path / 'textures' / 'envmap.hdr'), toWorld=np.array([[-0.922278, 0, 0.386527, 0], [0, 1, 0, 0], [-0.386527, 0, -0.922278, 1.17369], [0, 0, 0, 1]], np.float32))
+    cam = np.array([-0.00550949, -0.342144, -0.939631, 23.895, 1.07844e-005, 0.939646, -0.342149, 11.2207, 0.999985, -0.00189103, -0.00519335, 0.0400773, 0, 0, 0, 1], np.float32).reshape(4, 4)
+    osc.set_camera(cam, 35.0, width=W, height=H); osc.set_film('tent'); osc.set_integrator(maxDepth=9, rrDepth=5, strictNormals=True)
+    osc.build()
+    ofilm = osc.render(spp, seed=11)
+    a, b = cp.develop(film), cp.develop(ofilm)
+    assert b.sum() > 0 and rel_mse(a, b) < 1e-4
+    close = np.abs(a - b).max(axis=2) <= 1e-3 * (np.abs(b).max(axis=2) + 1e-3)
+    assert close.mean() > 0.995, close.mean()
+    assert abs(st['rays'] - osc.last_stats['rays']) <= 2e-3 * osc.last_stats['rays'] and abs(st['shadow_rays'] - osc.last_stats['shadow_rays']) <= 2e-3 * osc.last_stats['shadow_rays']
     ctx.close()

@@ -1113,7 +1113,10 @@ def test_oracle_marschner_pinned_against_compiled_reference_plugin(oracle, props
     ('roughplastic', dict(intIOR=1.55, extIOR=1.0, alpha=0.2, distribution='ggx', diffuseReflectance=HAIR_RGB)),            # default BSDF of models/*/scene.xml
     ('roughplastic', dict(alpha=0.1, distribution='beckmann', nonlinear=True, diffuseReflectance=(0.6, 0.5, 0.4))),
     ('roughplastic', dict(intIOR=1.55, extIOR=1.0, alpha=0.3, distribution='phong', diffuseReflectance=(0.2, 0.3, 0.4))),
-    ('marschner_fixed', dict(intIOR=1.55, extIOR=1.000277))])
+    ('marschner_fixed', dict(intIOR=1.55, extIOR=1.000277)),
+    # the scene-driven full-lobe mode: marschner.cpp with the five edits listed in oracle/Makefile (R and TT kept in eval, sigmaA / betaR / scale angle from the scene)
+    ('marschner_full', dict(intIOR=1.55, extIOR=1.000277)),
+    ('marschner_full', dict(intIOR=1.5, extIOR=1.0, sigmaAr=0.6, sigmaAg=0.9, sigmaAb=1.6, betaR=0.17, scaleAngleRad=-0.05))])
 def test_oracle_mesh_and_next_row_bsdfs_pinned_against_compiled_reference_plugins(oracle, plugin, props):
     """src/bsdfs/{diffuse,twosided,roughplastic,marschner}.cpp compiled unmodified (marschner.cpp is the class the fork's build leaves out:
     the `fixed` mode, with its two extra sampler draws) against the oracle restatements; math::erf / erfinv / hypot2 behind the Beckmann
@@ -1127,13 +1130,15 @@ def test_oracle_mesh_and_next_row_bsdfs_pinned_against_compiled_reference_plugin
     q = dict(props)
     if plugin == 'roughplastic':
         q.setdefault('intIOR', 1.49); q.setdefault('extIOR', 1.000277)
+    if plugin == 'marschner_full':
+        q['sigmaA'] = (q.pop('sigmaAr', 0.22), q.pop('sigmaAg', 0.22), q.pop('sigmaAb', 0.22))
     b = s.add_bsdf(plugin, **q)
     rng = np.random.default_rng(47)
     n = 100000
     wi = sphere_dirs(rng, n); wo = sphere_dirs(rng, n); smp = rng.random((n, 2)).astype(np.float32); extra = rng.random((n, 4)).astype(np.float32)
     rev, rp = ref.eval(wi, wo); oev, op = s.bsdf_eval(b, wi, wo)
     assert np.array_equal((rev != 0).any(axis=1), (oev != 0).any(axis=1)) and np.array_equal(rp != 0, op != 0)
-    tol = {'marschner_fixed': 3e-4, 'roughplastic': 1e-4}.get(plugin, 0.0)       # M() of the Marschner model turns one ulp of a libm call into 3e-5 (cp_bsdf.cuh)
+    tol = {'marschner_fixed': 3e-4, 'marschner_full': 3e-4, 'roughplastic': 1e-4}.get(plugin, 0.0)       # M() of the Marschner model turns one ulp of a libm call into 3e-5 (cp_bsdf.cuh)
     err = np.abs(rev - oev) / np.maximum(np.abs(oev).max(axis=1, keepdims=True), 1e-6)
     perr = np.abs(rp - op) / np.maximum(np.abs(op), 1e-6)
     assert err.max() <= tol and perr.max() <= tol, '%s: eval %.3g pdf %.3g' % (plugin, err.max(), perr.max())
@@ -1804,3 +1809,36 @@ def test_rectangle_and_checkerboard_pinned_against_reference_text(cp, oracle):
         wi = np.tile(np.array([[0, 0, 1]], np.float32), (n, 1))
         _, wt, _, _ = s.bsdf_sample_uv(b, wi, np.full((n, 2), 0.5, np.float32), uv)           # SmoothDiffuse::sample returns the reflectance (diffuse.cpp:140-156)
         assert np.array_equal(wt, ref) and 0.3 < (ref[:, 0] == c0[0]).mean() < 0.7
+
+
+def test_teapot_scene_plugins_host_side(cp, oracle, tmp_path):
+    """Host side of SURVEY 8f rank 2 without a GPU: the product's fresnelDiffuseReflectance equals the oracle's (and through it the reference text)
+    bit for bit; the OBJ loader carries `vt` coordinates through the vertex merge (src/shapes/obj.cpp:633-636,672-675); a scene file with the
+    plugin set of models/teapot/scene.xml validates, and the reference's own file does when the tree is present."""
+    L = oracle.lib()
+    for eta in np.concatenate([np.linspace(0.4, 0.98, 15), np.linspace(1.02, 3.0, 30)]).astype(np.float32):
+        assert cp.fresnel_diffuse_reflectance(float(eta)) == np.float32(L.orc_fresnel_diffuse_reflectance(ctypes.c_float(eta)))
+    obj = tmp_path / 'q.obj'
+    obj.write_text('v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvt 0.5 0.5\nf 1/1 2/2 3/3\nf 1/1 3/3 4/4\nf 1/5 2/2 3/3\n')
+    xyz, idx, nrm, uv = cp.load_obj_file(str(obj), texcoords=True)
+    assert len(xyz) == 5 and uv.shape == (5, 2)                                   # the corner with another uv is a vertex of its own
+    assert np.array_equal(uv[idx[0]], [[0, 1], [1, 1], [1, 0]]) and np.array_equal(uv[idx[2][0]], [0.5, 0.5])    # flipTexCoords default: v -> 1 - v (obj.cpp:215)
+    obj2 = tmp_path / 'p.obj'; obj2.write_text('v 0 0 0\nv 1 0 0\nv 1 1 0\nf 1 2 3\n')
+    assert cp.load_obj_file(str(obj2), texcoords=True)[3] is None
+    xml = tmp_path / 's.xml'
+    xml.write_text('''<scene version="0.6.0"><sensor type="perspective"><sampler type="sobol"><integer name="sampleCount" value="4"/></sampler>
+      <film type="ldrfilm"><integer name="width" value="8"/><integer name="height" value="8"/></film></sensor>
+      <bsdf type="twosided" id="m"><bsdf type="plastic"><string name="intIOR" value="polypropylene"/><boolean name="nonlinear" value="true"/></bsdf></bsdf>
+      <bsdf type="twosided" id="f"><bsdf type="diffuse"><texture name="reflectance" type="checkerboard"><float name="uscale" value="10"/></texture></bsdf></bsdf>
+      <shape type="rectangle"><transform name="toWorld"><scale x="3" y="2"/></transform><ref id="f"/></shape>
+      <shape type="rectangle"><boolean name="flipNormals" value="true"/><ref id="m"/></shape></scene>''')
+    rep = cp.validate_scene_xml(str(xml))
+    assert rep.count('shape rectangle') == 2 and 'bsdf plastic' in rep and 'texture checkerboard' in rep and sum('twosided' in r for r in rep) == 2
+    bad = tmp_path / 'b.xml'
+    bad.write_text(xml.read_text().replace('type="checkerboard"', 'type="bitmap"'))
+    with pytest.raises(cp.CudapathError, match='bitmap'):
+        cp.validate_scene_xml(str(bad))
+    ref = '/root/reference/models/teapot/scene.xml'
+    if os.path.exists(ref):
+        rep = cp.validate_scene_xml(ref)
+        assert 'shape rectangle' in rep and 'bsdf plastic' in rep and 'texture checkerboard' in rep and 'sampleCount 64' in rep
