@@ -375,6 +375,7 @@ int cudapath_bsdf_set_twosided(cudapath_ctx *ctx, int bsdf_id) {
     return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_bsdf_set_twosided(p, bsdf_id); });
 }
 
+int cudapath_random_floats(uint64_t seed, uint64_t n, float *out) { if (!out) return fail("null argument"); mitsuba_random_floats(seed, (size_t) n, out); return 0; }
 int cudapath_fresnel_diffuse_reflectance(float eta, float *out) { if (!out) return fail("null argument"); *out = fresnel_diffuse_reflectance(eta); return 0; }
 
 // `rectangle` (src/shapes/rectangle.cpp:81-125): the square [-1,1]^2 x {0} under toWorld, one analytic primitive.  Host arithmetic in plain

@@ -55,6 +55,8 @@ bool load_rgbe_file(const std::string &path, std::vector<float> &rgb, int &w, in
 bool mat4_invert_f32(const float *a, float *out);     // Matrix<4,4,float>::invert of the reference (matrix.inl:138-193), row-major
 // fresnelDiffuseReflectance(eta, fast = false): adaptive Gauss-Lobatto quadrature of F(sqrt(xi), eta) over [0, 1] (util.cpp:807-862, quad.cpp:287-420)
 float fresnel_diffuse_reflectance(float eta);
+// Random(seed).nextFloat() of the reference, n times (SFMT-19937: src/libcore/random.cpp); the hair loader's `reduction` draws from Random()
+void mitsuba_random_floats(uint64_t seed, size_t n, float *out);
 bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNormals, bool flipNormals, bool flipTexCoords, MeshFileData &out, std::string &err);
 
 // cp_host_mip.cpp -- Lanczos MIP pyramid of the environment map + EWA weight table (mipmap.h:180-302)

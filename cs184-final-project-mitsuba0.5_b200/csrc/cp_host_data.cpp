@@ -194,10 +194,55 @@ struct FiberBuilder {
 };
 }
 
+// Mitsuba's `Random` as the hair loader uses it (`reduction`, hair.cpp:629,672-673,769-770): SFMT-19937 seeded with the default 5489
+// (include/mitsuba/core/random.h:113; src/libcore/random.cpp:72-96 parameters, :129-220 recursion, :325-347 period certification, :350-390
+// regeneration, :396-405 init_gen_rand, :551-553 nextULong, :630-639 nextFloat).  The state is kept as 32-bit words; the reference's 64- and
+// 128-bit views are the little-endian overlays of the same words.
+namespace {
+struct MitsubaRandom {
+    static constexpr int N = 19937 / 128 + 1, N32 = N * 4, N64 = N * 2, POS1 = 122;
+    uint32_t w[N32]; int idx;
+    explicit MitsubaRandom(uint64_t seed = 5489ULL) {
+        uint64_t prev = seed;
+        w[0] = (uint32_t) prev; w[1] = (uint32_t) (prev >> 32);
+        for (int i = 1; i < N64; ++i) { prev = 6364136223846793005ULL * (prev ^ (prev >> 62)) + (uint64_t) i; w[2 * i] = (uint32_t) prev; w[2 * i + 1] = (uint32_t) (prev >> 32); }
+        idx = N32;
+        static const uint32_t parity[4] = {0x00000001U, 0x00000000U, 0x00000000U, 0x13c9e684U};
+        uint32_t inner = 0;
+        for (int i = 0; i < 4; ++i) inner ^= w[i] & parity[i];
+        for (int i = 16; i > 0; i >>= 1) inner ^= inner >> i;
+        if ((inner & 1u) == 0u) {
+            for (int i = 0; i < 4; ++i) { uint32_t work = 1; bool done = false;
+                for (int j = 0; j < 32; ++j) { if (work & parity[i]) { w[i] ^= work; done = true; break; } work <<= 1; }
+                if (done) break; }
+        }
+    }
+    void recursion(uint32_t *r, const uint32_t *a, const uint32_t *b, const uint32_t *c, const uint32_t *d) const {
+        static const uint32_t msk[4] = {0xdfffffefU, 0xddfecb7fU, 0xbffaffffU, 0xbffffff6U};
+        // x = a << 8 and y = c >> 8 as 128-bit integers (SL2 = SR2 = 1 byte)
+        const uint64_t al = a[0] | ((uint64_t) a[1] << 32), ah = a[2] | ((uint64_t) a[3] << 32), cl = c[0] | ((uint64_t) c[1] << 32), ch = c[2] | ((uint64_t) c[3] << 32);
+        const uint64_t xh = (ah << 8) | (al >> 56), xl = al << 8, yh = ch >> 8, yl = (cl >> 8) | (ch << 56);
+        const uint32_t x[4] = {(uint32_t) xl, (uint32_t) (xl >> 32), (uint32_t) xh, (uint32_t) (xh >> 32)}, y[4] = {(uint32_t) yl, (uint32_t) (yl >> 32), (uint32_t) yh, (uint32_t) (yh >> 32)};
+        for (int k = 0; k < 4; ++k) r[k] = a[k] ^ x[k] ^ ((b[k] >> 11) & msk[k]) ^ y[k] ^ (d[k] << 18);
+    }
+    void regenerate() {
+        const uint32_t *r1 = w + 4 * (N - 2), *r2 = w + 4 * (N - 1);
+        int i = 0;
+        for (; i < N - POS1; ++i) { recursion(w + 4 * i, w + 4 * i, w + 4 * (i + POS1), r1, r2); r1 = r2; r2 = w + 4 * i; }
+        for (; i < N; ++i) { recursion(w + 4 * i, w + 4 * i, w + 4 * (i + POS1 - N), r1, r2); r1 = r2; r2 = w + 4 * i; }
+    }
+    uint64_t nextULong() { if (idx >= N32) { regenerate(); idx = 0; } const uint64_t r = w[idx] | ((uint64_t) w[idx + 1] << 32); idx += 2; return r; }
+    float nextFloat() { uint32_t u = (uint32_t) ((nextULong() & 0xFFFFFFFFull) >> 9) | 0x3f800000u; float f; std::memcpy(&f, &u, 4); return f - 1.0f; }
+};
+}
+void mitsuba_random_floats(uint64_t seed, size_t n, float *out) { MitsubaRandom r(seed); for (size_t i = 0; i < n; ++i) out[i] = r.nextFloat(); }
+
 bool load_hair_file(const std::string &path, float radius, float angleThresholdDeg, float reduction, const float toWorld[16],
                     HairFileData &out, std::string &err) {
     if (reduction < 0 || reduction >= 1) { err = "The 'reduction' parameter must have a value in [0, 1)!"; return false; }
-    if (reduction > 0) { err = "reduction > 0 draws from the reference's Mersenne-Twister stream and is not supported"; return false; }
+    if (reduction > 0) radius *= 1.0f / (1 - reduction);      // hair.cpp:623-628: the surviving fibers are thickened
+    MitsubaRandom random;                                     // :629; one draw per fiber marker decides whether the fiber is skipped
+    bool ignore = false;
     out.xyz.clear(); out.startsFiber.clear();
     // radius scales with the length of toWorld * (0,0,1) (hair.cpp:632-633)
     { float x = toWorld[2], y = toWorld[6], z = toWorld[10]; out.radius = radius * std::sqrt(x * x + y * y + z * z); }
@@ -216,9 +261,11 @@ bool load_hair_file(const std::string &path, float radius, float angleThresholdD
         for (uint32_t n = 0; n < count; ++n) {
             float a; Vec p;
             if (!rd(a)) { err = "unexpected end of hair file"; return false; }
-            if (std::isinf(a)) { newFiber = true; if (!rd(p.x) || !rd(p.y) || !rd(p.z)) { err = "unexpected end of hair file"; return false; } }
-            else { p.x = a; if (!rd(p.y) || !rd(p.z)) { err = "unexpected end of hair file"; return false; } }
-            fb.add(xfmP(toWorld, p), newFiber);
+            if (std::isinf(a)) {
+                newFiber = true; if (!rd(p.x) || !rd(p.y) || !rd(p.z)) { err = "unexpected end of hair file"; return false; }
+                if (reduction > 0) ignore = random.nextFloat() < reduction;          // :672-673
+            } else { p.x = a; if (!rd(p.y) || !rd(p.z)) { err = "unexpected end of hair file"; return false; } }
+            if (!ignore) fb.add(xfmP(toWorld, p), newFiber);
             newFiber = false;
         }
     } else {
@@ -231,8 +278,8 @@ bool load_hair_file(const std::string &path, float radius, float angleThresholdD
             std::istringstream iss(line);
             Vec p;
             iss >> p.x >> p.y >> p.z;
-            if (iss.fail()) { newFiber = true; continue; }
-            fb.add(xfmP(toWorld, p), newFiber);
+            if (iss.fail()) { newFiber = true; if (reduction > 0) ignore = random.nextFloat() < reduction; continue; }      // :767-770
+            if (!ignore) fb.add(xfmP(toWorld, p), newFiber);
             newFiber = false;
         }
     }

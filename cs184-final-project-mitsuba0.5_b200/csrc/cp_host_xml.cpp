@@ -344,7 +344,6 @@ struct Loader {
             std::ifstream probe(file, std::ios::binary);
             note(std::string("shape ") + n.get("type") + " \"" + file + "\"" + (probe ? "" : " (file missing)"));
             if (isObj && child(n, "float", "maxSmoothAngle")) throw std::runtime_error("obj: 'maxSmoothAngle' is not supported");
-            if (!isObj && getFloat(n, "reduction", 0.0) > 0) throw std::runtime_error("reduction > 0 draws from the reference's Mersenne-Twister stream and is not supported");
             return;
         }
         if (isObj) {

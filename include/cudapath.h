@@ -102,6 +102,9 @@ int cudapath_bsdf_set_checkerboard(cudapath_ctx *ctx, int bsdf_id, const float c
 int cudapath_bsdf_set_twosided(cudapath_ctx *ctx, int bsdf_id);
 /* fresnelDiffuseReflectance(eta, fast = false), src/libcore/util.cpp:814-862 (host only: adaptive Gauss-Lobatto, src/libcore/quad.cpp:287-420). */
 int cudapath_fresnel_diffuse_reflectance(float eta, float *out);
+/* Random(seed).nextFloat(), n times: Mitsuba's SFMT-19937 generator (src/libcore/random.cpp:396-405,551-553,630-639; default seed 5489,
+ * include/mitsuba/core/random.h:113) -- the stream the hair loader's `reduction` parameter draws from (src/shapes/hair.cpp:629,672-673).  Host only. */
+int cudapath_random_floats(uint64_t seed, uint64_t n, float *out);
 
 /* ---- shapes ------------------------------------------------------------------------------------------------ */
 /* Triangle mesh as ShapeKDTree sees it: TriMesh::getVertexPositions() / getVertexNormals() (NULL = face normals) /

@@ -299,11 +299,15 @@ struct HairShape {
     }
 };
 
-// hair.cpp:609-785.  `reduction` needs the reference's SFMT `Random`; only 0 is supported.
+// hair.cpp:609-785.  `reduction` > 0 skips whole fibers with one draw of Random() per fiber marker (:629,672-673,769-770) and thickens the rest.
 static inline void loadHairFile(const std::string &path, float radius, float angleThresholdDeg,
-                                const M44 &toWorld, HairShape &out) {
+                                const M44 &toWorld, HairShape &out, float reduction = 0.0f) {
     float angleThreshold = angleThresholdDeg * (kPi / 180.0f);
     float dpThresh = std::cos(angleThreshold);
+    if (reduction < 0 || reduction >= 1) throw std::runtime_error("The 'reduction' parameter must have a value in [0, 1)!");
+    else if (reduction > 0) { float correction = 1.0f / (1 - reduction); radius *= correction; }
+    MitsubaRandom random;
+    bool ignore = false;
     radius *= length(xfmVector(toWorld, V3(0, 0, 1)));
     std::ifstream bs(path, std::ios::binary);
     if (!bs) throw std::runtime_error("oracle: cannot open hair file " + path);
@@ -354,11 +358,12 @@ static inline void loadHairFile(const std::string &path, float radius, float ang
             if (std::isinf(value)) {
                 q.x = readSingle(); q.y = readSingle(); q.z = readSingle();
                 newFiber = true;
+                if (reduction > 0) ignore = random.nextFloat() < reduction;
             } else {
                 q.x = value; q.y = readSingle(); q.z = readSingle();
             }
             verticesRead++;
-            consume(q);
+            if (ignore) newFiber = false; else consume(q);
         }
     } else {
         std::ifstream is(path);
@@ -369,8 +374,8 @@ static inline void loadHairFile(const std::string &path, float radius, float ang
             std::istringstream iss(line);
             V3 q;
             iss >> q.x >> q.y >> q.z;
-            if (!iss.fail()) consume(q);
-            else newFiber = true;
+            if (!iss.fail()) { if (ignore) newFiber = false; else consume(q); }
+            else { newFiber = true; if (reduction > 0) ignore = random.nextFloat() < reduction; }
         }
     }
     vsf.push_back(1);

@@ -361,6 +361,55 @@ static inline float half_to_float(uint16_t h) {
 }
 
 // 4x4 row-major matrix helpers (include/mitsuba/core/transform.h: point transform divides by w)
+// ---------------------------------------------------------------------------------------------
+// Mitsuba's Random (SFMT-19937), src/libcore/random.cpp: parameters :72-96, 128-bit shifts :129-173, do_recursion :204-219, period_certification
+// :325-347, gen_rand_all :373-389, init_gen_rand :396-405, nextULong :551-553, single-precision nextFloat :630-639.  Default seed 5489
+// (include/mitsuba/core/random.h:113).  The hair loader's `reduction` draws from it (hair.cpp:629,672-673,769-770).
+// ---------------------------------------------------------------------------------------------
+struct MitsubaRandom {
+    enum { MEXP = 19937, N = MEXP / 128 + 1, N32 = N * 4, N64 = N * 2, POS1 = 122, SL1 = 18, SL2 = 1, SR1 = 11, SR2 = 1 };
+    union W128 { uint64_t u64[2]; uint32_t u[4]; };
+    union { W128 sfmt[N]; uint32_t psfmt32[N32]; uint64_t psfmt64[N64]; };
+    int idx = -1;
+    explicit MitsubaRandom(uint64_t seed = 5489ULL) {
+        psfmt64[0] = seed;
+        for (int i = 1; i < N64; ++i) psfmt64[i] = 6364136223846793005ULL * (psfmt64[i - 1] ^ (psfmt64[i - 1] >> 62)) + (uint64_t) i;
+        idx = N32;
+        const uint32_t parity[4] = {0x00000001U, 0x00000000U, 0x00000000U, 0x13c9e684U};
+        int inner = 0;
+        for (int i = 0; i < 4; ++i) inner ^= psfmt32[i] & parity[i];
+        for (int i = 16; i > 0; i >>= 1) inner ^= inner >> i;
+        inner &= 1;
+        if (inner == 1) return;
+        for (int i = 0; i < 4; ++i) {
+            uint32_t work = 1;
+            for (int j = 0; j < 32; ++j) { if ((work & parity[i]) != 0) { psfmt32[i] ^= work; return; } work = work << 1; }
+        }
+    }
+    static void rshift128(W128 &out, const W128 &in, int shift) {
+        const uint64_t th = in.u64[1], tl = in.u64[0];
+        out.u64[1] = th >> (shift * 8); out.u64[0] = (tl >> (shift * 8)) | (th << (64 - shift * 8));
+    }
+    static void lshift128(W128 &out, const W128 &in, int shift) {
+        const uint64_t th = in.u64[1], tl = in.u64[0];
+        out.u64[0] = tl << (shift * 8); out.u64[1] = (th << (shift * 8)) | (tl >> (64 - shift * 8));
+    }
+    static void doRecursion(W128 &r, const W128 &a, const W128 &b, const W128 &c, const W128 &d) {
+        const uint32_t msk[4] = {0xdfffffefU, 0xddfecb7fU, 0xbffaffffU, 0xbffffff6U};
+        W128 x, y;
+        lshift128(x, a, SL2); rshift128(y, c, SR2);
+        for (int k = 0; k < 4; ++k) r.u[k] = a.u[k] ^ x.u[k] ^ ((b.u[k] >> SR1) & msk[k]) ^ y.u[k] ^ (d.u[k] << SL1);
+    }
+    void genRandAll() {
+        W128 *r1 = &sfmt[N - 2], *r2 = &sfmt[N - 1];
+        int i = 0;
+        for (; i < N - POS1; ++i) { doRecursion(sfmt[i], sfmt[i], sfmt[i + POS1], *r1, *r2); r1 = r2; r2 = &sfmt[i]; }
+        for (; i < N; ++i) { doRecursion(sfmt[i], sfmt[i], sfmt[i + POS1 - N], *r1, *r2); r1 = r2; r2 = &sfmt[i]; }
+    }
+    uint64_t nextULong() { if (idx >= N32) { genRandAll(); idx = 0; } uint64_t r = psfmt64[idx / 2]; idx += 2; return r; }
+    float nextFloat() { union { uint32_t u; float f; } x; x.u = (uint32_t) ((nextULong() & 0xFFFFFFFF) >> 9) | 0x3f800000UL; return x.f - 1.0f; }
+};
+
 struct M44 {
     float m[4][4];
     static M44 identity() { M44 r; std::memset(r.m, 0, sizeof(r.m)); for (int i = 0; i < 4; ++i) r.m[i][i] = 1; return r; }

@@ -300,13 +300,16 @@ int orc_load_rgbe(const char *path, float *out, int *w, int *h) {
 }
 
 // Two-phase hair file load: returns a handle, then sizes / copies.
-void *orc_hair_file_load(const char *path, float radius, float angleThresholdDeg, const float *toWorld16) {
+void *orc_hair_file_load_reduced(const char *path, float radius, float angleThresholdDeg, const float *toWorld16, float reduction) {
     try {
         HairShape *h = new HairShape();
-        loadHairFile(path, radius, angleThresholdDeg, M44::fromRowMajor(toWorld16), *h);
+        loadHairFile(path, radius, angleThresholdDeg, M44::fromRowMajor(toWorld16), *h, reduction);
         return h;
     } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
 }
+void *orc_hair_file_load(const char *path, float radius, float angleThresholdDeg, const float *toWorld16) { return orc_hair_file_load_reduced(path, radius, angleThresholdDeg, toWorld16, 0.0f); }
+// Random(seed).nextFloat(), n times
+void orc_random_floats(uint64_t seed, uint64_t n, float *out) { MitsubaRandom r(seed); for (uint64_t i = 0; i < n; ++i) out[i] = r.nextFloat(); }
 uint32_t orc_hair_file_vertex_count(void *h) { return (uint32_t) ((HairShape *) h)->verts.size(); }
 uint32_t orc_hair_file_segment_count(void *h) { return (uint32_t) ((HairShape *) h)->segIndex.size(); }
 float orc_hair_file_radius(void *h) { return ((HairShape *) h)->radius; }

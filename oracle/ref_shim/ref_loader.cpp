@@ -76,7 +76,30 @@ namespace fs {
 }
 struct FileResolver { fs::path resolve(const std::string &s) const { return fs::path(s); } };
 struct Thread { static Thread *getThread() { static Thread t; return &t; } FileResolver *getFileResolver() { static FileResolver r; return &r; } };
-struct Random { Float nextFloat() { throw std::runtime_error("reduction > 0 draws from Mitsuba's SFMT stream: outside this path"); } };
+// Random: the SFMT-19937 state, its recursion and seeding cut out of src/libcore/random.cpp at build time (ref_random_*.inc: parameters :72-96,
+// helpers :117-220 with the non-SSE branch, struct Random::State :225-392, init_gen_rand :396-405); the four members the loader reaches are declared here
+#define MTS_SFMT_SSE 0
+#define FINLINE inline
+#define SAssert(x) ((void) 0)
+struct RStream { void readULongArray(uint64_t *, size_t) {} int readInt() { return 0; } void writeULongArray(const uint64_t *, size_t) const {} void writeInt(int) const {} };
+#define Stream RStream
+#include "ref_random_params.inc"
+#include "ref_random_helpers.inc"
+struct Random {
+    struct State;
+    State *mt;
+    Random();
+    uint64_t nextULong();
+    Float nextFloat();
+};
+#include "ref_random_state.inc"
+const uint32_t Random::State::parity[4] = {PARITY1, PARITY2, PARITY3, PARITY4};
+#include "ref_random_init.inc"
+#undef Stream
+#undef N
+Random::Random() : mt(new State()) { mt->init_gen_rand(5489ULL); }              // Random() -> seed() with the default of include/mitsuba/core/random.h:113
+uint64_t Random::nextULong() { return mt->gen_rand64(); }                        // random.cpp:551-553
+Float Random::nextFloat() { union { uint32_t u; float f; } x; x.u = ((nextULong() & 0xFFFFFFFF) >> 9) | 0x3f800000UL; return x.f - 1.0f; }   // :630-639
 struct Timer { int getMilliseconds() const { return 0; } };
 struct Stream { enum EByteOrder { EBigEndian, ELittleEndian }; };
 struct FileStream : public Stream {
@@ -109,9 +132,12 @@ struct HairShape : public Shape {
 using namespace reflsdr;
 extern "C" {
 // returns a handle or null (message in *err, 256 bytes); sizes / arrays through the accessors (sentinel excluded like the product's loader)
-void *ref_hair_load(const char *path, float radius, float angleThresholdDeg, const float *toWorld16, char *err) {
+void ref_random_floats(int n, float *out) { Random r; for (int i = 0; i < n; ++i) out[i] = r.nextFloat(); }
+void *ref_hair_load_reduced(const char *path, float radius, float angleThresholdDeg, const float *toWorld16, float reduction, char *err);
+void *ref_hair_load(const char *path, float radius, float angleThresholdDeg, const float *toWorld16, char *err) { return ref_hair_load_reduced(path, radius, angleThresholdDeg, toWorld16, 0.0f, err); }
+void *ref_hair_load_reduced(const char *path, float radius, float angleThresholdDeg, const float *toWorld16, float reduction, char *err) {
     try {
-        Properties props; props.s["filename"] = path; props.f["radius"] = radius; props.f["angleThreshold"] = angleThresholdDeg;
+        Properties props; props.s["filename"] = path; props.f["radius"] = radius; props.f["angleThreshold"] = angleThresholdDeg; props.f["reduction"] = reduction;
         for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) props.t.m[i][j] = toWorld16[4 * i + j];
         HairShape *h = new HairShape(props);
         return h->m_kdtree.p;

@@ -28,6 +28,7 @@ def lib():
         L.orc_last_error.restype = ctypes.c_char_p
         L.orc_accel_description.restype = ctypes.c_char_p
         L.orc_hair_file_load.restype = ctypes.c_void_p
+        L.orc_hair_file_load_reduced.restype = ctypes.c_void_p
         L.orc_hair_file_vertex_count.restype = ctypes.c_uint32
         L.orc_hair_file_segment_count.restype = ctypes.c_uint32
         L.orc_hair_file_radius.restype = ctypes.c_float
@@ -68,10 +69,10 @@ DISTR = {'beckmann': 0, 'ggx': 1, 'phong': 2}
 FILTERS = {'tent': 0, 'box': 1, 'gaussian': 2}
 
 
-def load_hair_file(path, radius=0.025, angleThreshold=1.0, toWorld=None):
+def load_hair_file(path, radius=0.025, angleThreshold=1.0, toWorld=None, reduction=0.0):
     L = lib()
     tw = f32(IDENT if toWorld is None else toWorld).reshape(16)
-    h = L.orc_hair_file_load(path.encode(), ctypes.c_float(radius), ctypes.c_float(angleThreshold), p(tw))
+    h = L.orc_hair_file_load_reduced(path.encode(), ctypes.c_float(radius), ctypes.c_float(angleThreshold), p(tw), ctypes.c_float(reduction))
     if not h:
         raise RuntimeError(L.orc_last_error().decode())
     h = ctypes.c_void_p(h)

@@ -811,9 +811,15 @@ def test_hair_loader_binary_and_ascii(cp, oracle, tmp_path):
 def test_hair_loaders_pinned_against_reference_constructor(cp, oracle, tmp_path):
     """HairShape::HairShape(const Properties &) (src/shapes/hair.cpp:609-785), cut out of the reference and executed as written
     (oracle/ref_shim/ref_loader.cpp), against the oracle's loader AND the product's host loader: binary and ASCII files, exact duplicates,
-    nearly collinear runs at several angle thresholds, comment / blank-line fiber breaks, a toWorld with rotation, scale and translation --
-    vertices, fiber flags and the scaled radius are bit-identical."""
-    L = ctypes.CDLL(REF_GEOM); L.ref_hair_load.restype = ctypes.c_void_p; L.ref_hair_load_radius.restype = ctypes.c_float
+    nearly collinear runs at several angle thresholds, comment / blank-line fiber breaks, a toWorld with rotation, scale and translation, and the
+    `reduction` parameter, whose draws come from Mitsuba's Random -- the SFMT-19937 state, recursion and seeding cut out of src/libcore/random.cpp
+    into the same shim -- vertices, fiber flags and the scaled radius are bit-identical, and so are the three random streams."""
+    L = ctypes.CDLL(REF_GEOM); L.ref_hair_load.restype = ctypes.c_void_p; L.ref_hair_load_reduced.restype = ctypes.c_void_p; L.ref_hair_load_radius.restype = ctypes.c_float
+    nr = 5000
+    ra = np.zeros(nr, np.float32); L.ref_random_floats(nr, ra.ctypes.data_as(ctypes.c_void_p))
+    rb = np.zeros(nr, np.float32); oracle.lib().orc_random_floats(ctypes.c_uint64(5489), ctypes.c_uint64(nr), rb.ctypes.data_as(ctypes.c_void_p))
+    rc = np.zeros(nr, np.float32); cp.lib().cudapath_random_floats(ctypes.c_uint64(5489), ctypes.c_uint64(nr), rc.ctypes.data_as(ctypes.c_void_p))
+    assert np.array_equal(ra, rb) and np.array_equal(ra, rc) and 0 <= ra.min() and ra.max() < 1 and abs(ra.mean() - 0.5) < 0.02
     rng = np.random.default_rng(61)
     xyz, st = cp.scenes.gen_curly(strands=300, segments=24)
     xyz = xyz.copy(); st = st.copy()
@@ -830,12 +836,14 @@ def test_hair_loaders_pinned_against_reference_constructor(cp, oracle, tmp_path)
     cp.scenes.write_mitshair(b, xyz, st); write_ascii(a, xyz, st)
     th = np.deg2rad(30.0); c, s_ = np.cos(th), np.sin(th)
     tw = np.array([[1.5 * c, -1.5 * s_, 0, 0.25], [1.5 * s_, 1.5 * c, 0, -1.0], [0, 0, 1.5, 3.0], [0, 0, 0, 1]], np.float32)
+    counts = {}
     for path in (b, a):
-        for kw in (dict(), dict(angleThreshold=0.2), dict(toWorld=tw, angleThreshold=5.0), dict(toWorld=tw, radius=0.003)):
-            radius = kw.get('radius', 0.01); ang = kw.get('angleThreshold', 1.0); m = kw.get('toWorld', np.eye(4, dtype=np.float32))
+        for kw in (dict(), dict(angleThreshold=0.2), dict(toWorld=tw, angleThreshold=5.0), dict(toWorld=tw, radius=0.003), dict(reduction=0.3), dict(toWorld=tw, reduction=0.9),
+                   dict(reduction=0.999)):
+            radius = kw.get('radius', 0.01); ang = kw.get('angleThreshold', 1.0); m = kw.get('toWorld', np.eye(4, dtype=np.float32)); red = kw.get('reduction', 0.0)
             err = ctypes.create_string_buffer(256)
             m32 = np.ascontiguousarray(m, np.float32)
-            h = L.ref_hair_load(path.encode(), ctypes.c_float(radius), ctypes.c_float(ang), m32.ctypes.data_as(ctypes.c_void_p), err)
+            h = L.ref_hair_load_reduced(path.encode(), ctypes.c_float(radius), ctypes.c_float(ang), m32.ctypes.data_as(ctypes.c_void_p), ctypes.c_float(red), err)
             assert h, err.value
             h = ctypes.c_void_p(h)
             n = L.ref_hair_load_count(h) - 1                      # the reference appends the sentinel flag, not a vertex: count = vertices
@@ -843,11 +851,18 @@ def test_hair_loaders_pinned_against_reference_constructor(cp, oracle, tmp_path)
             rx = np.zeros((n, 3), np.float32); rs = np.zeros(n, np.uint8)
             L.ref_hair_load_copy(h, rx.ctypes.data_as(ctypes.c_void_p), rs.ctypes.data_as(ctypes.c_void_p))
             rr = float(L.ref_hair_load_radius(h))
-            args = dict(radius=radius, angleThreshold=ang); args.update({k: v for k, v in kw.items() if k == 'toWorld'})
+            args = dict(radius=radius, angleThreshold=ang, reduction=red); args.update({k: v for k, v in kw.items() if k == 'toWorld'})
             for loader in (cp.load_hair_file, oracle.load_hair_file):
                 px, ps, pr = loader(path, **args)[:3]
                 assert np.array_equal(px, rx) and np.array_equal(ps, rs) and np.float32(pr) == np.float32(rr)
             assert 0 < n < len(st)
+            if red:
+                counts[(path, red)] = int(rs.sum())
+    for path in (b, a):      # the first fiber of a file is never drawn for (no marker precedes it); about 1 - reduction of the rest survive
+        assert 0.55 * int(st.sum()) < counts[(path, 0.3)] < 0.85 * int(st.sum()) and counts[(path, 0.9)] < 0.2 * int(st.sum()) and 1 <= counts[(path, 0.999)] <= 3
+    for bad in (-0.1, 1.0):
+        with pytest.raises(cp.CudapathError, match='reduction'):
+            cp.load_hair_file(b, reduction=bad)
     # a file shorter than the 11-byte magic: the reference's FileStream throws, so do both loaders
     tiny = str(tmp_path / 'tiny.txt'); open(tiny, 'w').write('0 0 0\n')
     err = ctypes.create_string_buffer(256)
