@@ -375,6 +375,13 @@ int cudapath_bsdf_set_twosided(cudapath_ctx *ctx, int bsdf_id) {
     return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_bsdf_set_twosided(p, bsdf_id); });
 }
 
+int cudapath_write_exr(const char *filename, const float *rgb, int w, int h, int half_float) {
+    if (!filename || !rgb) return fail("null argument");
+    std::string err;
+    if (!write_exr_file(filename, rgb, w, h, half_float != 0, err)) return fail(err);
+    return 0;
+}
+int cudapath_float_to_half(const float *in, uint64_t n, uint16_t *out) { if (!in || !out) return fail("null argument"); float_to_half_array(in, (size_t) n, out); return 0; }
 int cudapath_random_floats(uint64_t seed, uint64_t n, float *out) { if (!out) return fail("null argument"); mitsuba_random_floats(seed, (size_t) n, out); return 0; }
 int cudapath_fresnel_diffuse_reflectance(float eta, float *out) { if (!out) return fail("null argument"); *out = fresnel_diffuse_reflectance(eta); return 0; }
 

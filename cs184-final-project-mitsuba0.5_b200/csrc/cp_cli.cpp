@@ -1,8 +1,12 @@
 // cp_cli.cpp -- `cudapath_render`: renders a scene file of the reference's XML format through libcudapath.so.
 //
 // Mirrors the part of the reference's command line that concerns this path (src/mitsuba/mitsuba.cpp:154-260):
-//   cudapath_render [-o out.{png,pfm,ppm}] [-D name=value]... [-p N] [--gpus N] [-q] [--gpu i] [--spp n] [--seed s] scene.xml
-//     -o   output file (mitsuba.cpp:190); default: the scene's name with the extension the film asks for (.png for ldrfilm, .pfm for hdrfilm)
+//   cudapath_render [-o out.{png,exr,pfm,ppm}] [-D name=value]... [-p N] [--gpus N] [-r sec] [-q] [--gpu i] [--spp n] [--seed s] scene.xml
+//     -o   output file (mitsuba.cpp:190); default: the scene's name with the extension the film asks for (.png for ldrfilm, .exr for hdrfilm)
+//     -r   `mitsuba -r sec` (mitsuba.cpp:228-229): write the (partial) output image every `sec` seconds while rendering.  The job is then rendered
+//          as a sequence of sample-index ranges whose films add up (the random numbers are keyed by the sample index, so the final image is the
+//          one a single call produces, up to the order of fp32 additions); a partial image is the film developed so far -- fewer samples per
+//          pixel, correctly normalised
 //     -D   parameter substitution of $name in the file (mitsuba.cpp:168)
 //     -p   `mitsuba -p N` asks for N local workers (mitsuba.cpp:218-222,280-282); the workers of this path are GPUs: the job is split
 //          over min(N, visible GPUs) devices (cudapath_create_multi: sample-range sharding, one ncclReduce of the film)
@@ -11,7 +15,7 @@
 // Ctrl-C cancels the render (cudapath_cancel) and exits with 130 without writing an image; a progress line goes to a terminal's stderr.
 // and prints the "Render time" line of RenderJob::run (src/librender/renderjob.cpp:108) plus Mpaths/s and Mrays/s.
 // Uses nothing but the C ABI of include/cudapath.h (this file is also the smallest example of a host program on that boundary).
-// Image writers: PNG (8 bit, zlib "stored/deflate" through libz), PPM, PFM (linear float, bottom-up as the format wants it).
+// Image writers: PNG (8 bit, zlib "stored/deflate" through libz), PPM, PFM (linear float, bottom-up as the format wants it), OpenEXR (cudapath_write_exr: half RGB).
 #include "../../include/cudapath.h"
 #include <chrono>
 #include <csignal>
@@ -72,7 +76,7 @@ static int die(const char *what) { fprintf(stderr, "cudapath_render: %s: %s\n", 
 
 int main(int argc, char **argv) {
     std::string out, defines, scene, dataDir;
-    int gpu = 0, workers = 0, gpus = 0; long spp = 0; unsigned long long seed = 0; bool quiet = false;
+    int gpu = 0, workers = 0, gpus = 0; long spp = 0; unsigned long long seed = 0; bool quiet = false; double flushSec = -1; long chunk = 0;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto need = [&](const char *opt) -> const char * { if (i + 1 >= argc) { fprintf(stderr, "cudapath_render: %s needs an argument\n", opt); exit(2); } return argv[++i]; };
@@ -82,12 +86,14 @@ int main(int argc, char **argv) {
         else if (a == "-p") workers = atoi(need("-p"));
         else if (a == "--gpus") gpus = atoi(need("--gpus"));
         else if (a == "-b") need(a.c_str());
+        else if (a == "-r") flushSec = atof(need("-r"));
+        else if (a == "--chunk") chunk = atol(need("--chunk"));
         else if (a == "-q") quiet = true;
         else if (a == "--gpu") gpu = atoi(need("--gpu"));
         else if (a == "--spp") spp = atol(need("--spp"));
         else if (a == "--seed") seed = strtoull(need("--seed"), nullptr, 10);
         else if (a == "--data-dir") dataDir = need("--data-dir");
-        else if (a == "-h" || a == "--help") { printf("usage: cudapath_render [-o out.{png,pfm,ppm}] [-D name=value]... [-p N] [--gpus N] [-q] [--gpu i] [--spp n] [--seed s] [--data-dir dir] scene.xml\n"); return 0; }
+        else if (a == "-h" || a == "--help") { printf("usage: cudapath_render [-o out.{png,exr,pfm,ppm}] [-D name=value]... [-p N] [--gpus N] [-r sec] [--chunk spp] [-q] [--gpu i] [--spp n] [--seed s] [--data-dir dir] scene.xml\n"); return 0; }
         else if (!a.empty() && a[0] == '-') { fprintf(stderr, "cudapath_render: unknown option %s\n", a.c_str()); return 2; }
         else scene = a;
     }
@@ -116,7 +122,40 @@ int main(int argc, char **argv) {
     std::vector<float> film((size_t) w * h * 5);
     g_ctx = ctx; signal(SIGINT, on_signal); signal(SIGTERM, on_signal);
     if (!quiet && isatty(2)) cudapath_set_progress_callback(ctx, on_progress, nullptr);     // the progress bar of the reference's console (ProgressReporter)
-    const int rc = cudapath_render(ctx, n, seed, 0, n, film.data());
+    if (out.empty()) { out = scene; const size_t dot = out.rfind('.'); if (dot != std::string::npos) out.resize(dot); out += hdr ? ".exr" : ".png"; }
+    auto writeImage = [&](const std::vector<float> &f) -> int {
+        bool ok;
+        if (ends_with(out, ".pfm") || ends_with(out, ".exr")) {
+            std::vector<float> rgb((size_t) w * h * 3);
+            cudapath_develop(f.data(), w, h, rgb.data());
+            ok = ends_with(out, ".pfm") ? write_pfm(out.c_str(), rgb.data(), w, h) : cudapath_write_exr(out.c_str(), rgb.data(), w, h, 1) == 0;
+        } else {
+            std::vector<uint8_t> rgb8((size_t) w * h * 3);
+            if (cudapath_develop_ldr(f.data(), w, h, gamma, exposure, rgb8.data()) != 0) return die("develop");
+            ok = ends_with(out, ".ppm") ? write_ppm(out.c_str(), rgb8.data(), w, h) : write_png(out.c_str(), rgb8.data(), w, h);
+        }
+        if (!ok) { fprintf(stderr, "cudapath_render: cannot write %s\n", out.c_str()); return 1; }
+        return 0;
+    };
+    int rc = 0, flushes = 0;
+    if (flushSec < 0 && chunk <= 0) rc = cudapath_render(ctx, n, seed, 0, n, film.data());
+    else {
+        // progressive: ranges of sample indices, the film of each added to the running sum; flush when `-r` seconds have passed
+        const uint32_t step = chunk > 0 ? (uint32_t) chunk : (n >= 16 ? n / 16 : 1);
+        std::vector<float> part(film.size());
+        double lastFlush = now();
+        for (uint32_t s0 = 0; s0 < n && rc == 0; s0 += step) {
+            const uint32_t s1 = s0 + step < n ? s0 + step : n;
+            rc = cudapath_render(ctx, n, seed, s0, s1, part.data());
+            if (rc != 0) break;
+            for (size_t i = 0; i < film.size(); ++i) film[i] += part[i];
+            if (flushSec >= 0 && s1 < n && now() - lastFlush >= flushSec) {
+                if (writeImage(film) != 0) return 1;
+                ++flushes; lastFlush = now();
+                if (!quiet) printf("Flushed a partial image (%u of %u samples per pixel) to \"%s\"\n", s1, n, out.c_str());
+            }
+        }
+    }
     g_ctx = nullptr; signal(SIGINT, SIG_DFL); signal(SIGTERM, SIG_DFL);
     if (rc != 0) {
         if (std::string(cudapath_last_error()) == "render cancelled") { fprintf(stderr, "\ncudapath_render: render cancelled, no image written\n"); cudapath_destroy(ctx); return 130; }
@@ -124,19 +163,7 @@ int main(int argc, char **argv) {
     }
     const double t3 = now();
     cudapath_stats st; cudapath_get_stats(ctx, &st);
-
-    if (out.empty()) { out = scene; const size_t dot = out.rfind('.'); if (dot != std::string::npos) out.resize(dot); out += hdr ? ".pfm" : ".png"; }
-    bool ok;
-    if (ends_with(out, ".pfm")) {
-        std::vector<float> rgb((size_t) w * h * 3);
-        cudapath_develop(film.data(), w, h, rgb.data());
-        ok = write_pfm(out.c_str(), rgb.data(), w, h);
-    } else {
-        std::vector<uint8_t> rgb8((size_t) w * h * 3);
-        if (cudapath_develop_ldr(film.data(), w, h, gamma, exposure, rgb8.data()) != 0) return die("develop");
-        ok = ends_with(out, ".ppm") ? write_ppm(out.c_str(), rgb8.data(), w, h) : write_png(out.c_str(), rgb8.data(), w, h);
-    }
-    if (!ok) { fprintf(stderr, "cudapath_render: cannot write %s\n", out.c_str()); return 1; }
+    if (writeImage(film) != 0) return 1;
     if (!quiet) {
         const double paths = (double) w * h * n, rays = (double) st.rays + (double) st.shadow_rays;
         printf("Loaded \"%s\" in %.3f s; %llu segments, %llu triangles -> %llu BVH references, %llu nodes (built in %.3f s)\n", scene.c_str(), t1 - t0,

@@ -57,6 +57,9 @@ bool mat4_invert_f32(const float *a, float *out);     // Matrix<4,4,float>::inve
 float fresnel_diffuse_reflectance(float eta);
 // Random(seed).nextFloat() of the reference, n times (SFMT-19937: src/libcore/random.cpp); the hair loader's `reduction` draws from Random()
 void mitsuba_random_floats(uint64_t seed, size_t n, float *out);
+// hdrfilm's OpenEXR output (scan lines, uncompressed, half or float RGB)
+bool write_exr_file(const std::string &path, const float *rgb, int w, int h, bool half, std::string &err);
+void float_to_half_array(const float *in, size_t n, uint16_t *out);
 bool load_obj_file(const std::string &path, const float toWorld[16], bool faceNormals, bool flipNormals, bool flipTexCoords, MeshFileData &out, std::string &err);
 
 // cp_host_mip.cpp -- Lanczos MIP pyramid of the environment map + EWA weight table (mipmap.h:180-302)

@@ -606,3 +606,73 @@ bool load_rgbe_file(const std::string &path, std::vector<float> &rgb, int &w, in
     } catch (const std::exception &e) { err = e.what(); return false; }
 }
 } // namespace cp
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// OpenEXR writer for `hdrfilm` (src/films/hdrfilm.cpp:213-246 defaults: fileFormat openexr, pixelFormat rgb, componentFormat float16;
+// HDRFilm::develop -> Bitmap::write(EOpenEXR), src/libcore/bitmap.cpp writeOpenEXR): a single-part scan-line file, channels B, G, R
+// (the order the format prescribes), increasing-y line order, one scan line per chunk, no compression -- every OpenEXR reader accepts it.
+// float -> half rounds to nearest even with overflow to infinity, like OpenEXR's half(float).
+namespace cp {
+namespace {
+inline uint16_t exr_half(float f) {
+    uint32_t x; std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u; x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return (uint16_t) (sign | 0x7c00u | ((x > 0x7f800000u) ? (0x200u | ((x >> 13) & 0x3ffu)) : 0u));   // inf / NaN
+    if (x >= 0x477ff000u) return (uint16_t) (sign | 0x7c00u);                                                               // rounds to or beyond 65520: infinity
+    if (x < 0x33000001u) return (uint16_t) sign;                                                                             // below half of the smallest subnormal
+    if (x < 0x38800000u) {                                                                                                  // subnormal half
+        const int shift = 126 - (int) (x >> 23);                          // 14 .. 24: value = m 2^(E-150), one half subnormal = 2^-24
+        const uint32_t m = (x & 0x7fffffu) | 0x800000u;
+        const uint32_t q = m >> shift, rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+        return (uint16_t) (sign | (q + ((rem > halfway || (rem == halfway && (q & 1u))) ? 1u : 0u)));
+    }
+    uint32_t h = ((x - 0x38000000u) >> 13);
+    const uint32_t rem = x & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++;
+    return (uint16_t) (sign | h);
+}
+struct ExrOut {
+    std::vector<unsigned char> b;
+    void raw(const void *p, size_t n) { const unsigned char *q = (const unsigned char *) p; b.insert(b.end(), q, q + n); }
+    void str(const char *s) { raw(s, std::strlen(s) + 1); }
+    void i32(int32_t v) { raw(&v, 4); }
+    void f32(float v) { raw(&v, 4); }
+    void attr(const char *name, const char *type, int32_t size) { str(name); str(type); i32(size); }
+};
+}
+bool write_exr_file(const std::string &path, const float *rgb, int w, int h, bool half, std::string &err) {
+    if (!rgb || w <= 0 || h <= 0) { err = "write_exr: empty image"; return false; }
+    ExrOut o;
+    const unsigned char magic[8] = {0x76, 0x2f, 0x31, 0x01, 2, 0, 0, 0};
+    o.raw(magic, 8);
+    const int32_t ptype = half ? 1 : 2;
+    o.attr("channels", "chlist", 3 * (2 + 16) + 1);
+    for (const char *c : {"B", "G", "R"}) { o.str(c); o.i32(ptype); const unsigned char lin[4] = {0, 0, 0, 0}; o.raw(lin, 4); o.i32(1); o.i32(1); }
+    o.b.push_back(0);
+    o.attr("compression", "compression", 1); o.b.push_back(0);
+    o.attr("dataWindow", "box2i", 16); o.i32(0); o.i32(0); o.i32(w - 1); o.i32(h - 1);
+    o.attr("displayWindow", "box2i", 16); o.i32(0); o.i32(0); o.i32(w - 1); o.i32(h - 1);
+    o.attr("lineOrder", "lineOrder", 1); o.b.push_back(0);
+    o.attr("pixelAspectRatio", "float", 4); o.f32(1.0f);
+    o.attr("screenWindowCenter", "v2f", 8); o.f32(0.0f); o.f32(0.0f);
+    o.attr("screenWindowWidth", "float", 4); o.f32(1.0f);
+    o.b.push_back(0);
+    const size_t bpp = half ? 2 : 4, lineBytes = 3 * bpp * (size_t) w, tableAt = o.b.size();
+    o.b.resize(tableAt + 8 * (size_t) h);
+    for (int y = 0; y < h; ++y) {
+        const uint64_t off = o.b.size();
+        std::memcpy(&o.b[tableAt + 8 * (size_t) y], &off, 8);
+        o.i32(y); o.i32((int32_t) lineBytes);
+        for (int c = 2; c >= 0; --c) {                                   // B, G, R
+            if (half) for (int x = 0; x < w; ++x) { const uint16_t v = exr_half(rgb[((size_t) y * w + x) * 3 + c]); o.raw(&v, 2); }
+            else for (int x = 0; x < w; ++x) o.f32(rgb[((size_t) y * w + x) * 3 + c]);
+        }
+    }
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) { err = "cannot write \"" + path + "\""; return false; }
+    const bool ok = fwrite(o.b.data(), 1, o.b.size(), f) == o.b.size();
+    if (fclose(f) != 0 || !ok) { err = "cannot write \"" + path + "\""; return false; }
+    return true;
+}
+void float_to_half_array(const float *in, size_t n, uint16_t *out) { for (size_t i = 0; i < n; ++i) out[i] = exr_half(in[i]); }
+} // namespace cp

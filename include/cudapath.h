@@ -217,6 +217,11 @@ int cudapath_cancel(cudapath_ctx *ctx);
 int cudapath_set_progress_callback(cudapath_ctx *ctx, void (*callback)(void *user, uint64_t paths_done, uint64_t paths_total), void *user);
 /* Film::develop normalisation, src/libcore/fmtconv.cpp:955-1056: rgb = sum / weight (0 where weight == 0). */
 int cudapath_develop(const float *film, int width, int height, float *out_rgb);
+/* HDRFilm::develop with its default fileFormat "openexr" (src/films/hdrfilm.cpp:213-246, 580-640): writes developed linear RGB (cudapath_develop) as a
+ * single-part scan-line OpenEXR file, channels B / G / R, uncompressed; half_float != 0: componentFormat float16 (the plugin's default, round to
+ * nearest even), else float32.  Host only. */
+int cudapath_write_exr(const char *filename, const float *rgb, int w, int h, int half_float);
+int cudapath_float_to_half(const float *in, uint64_t n, uint16_t *out);
 /* LDRFilm::develop with the `gamma` tonemapper, src/films/ldrfilm.cpp:300-321 -> Bitmap::convert(ERGB, EUInt8, gamma, 2^exposure)
  * (src/libcore/fmtconv.cpp:984-995,1104-1111,1137-1160): width*height*3 bytes.  gamma = -1 selects the sRGB curve (the ldrfilm
  * default); the hair scene files use 2.2.  Banner, Reinhard tonemapping and the PNG/JPEG encoders are not part of this path. */

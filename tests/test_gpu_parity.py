@@ -921,6 +921,20 @@ def test_native_cli_renders_a_scene_file(cp, tmp_path):
     assert np.allclose(data, cp.develop(film), rtol=1e-5, atol=1e-6)          # another run: the atomic splat order differs in the last bits
     bad = subprocess.run([cp.CLI_PATH, '-o', png, path], capture_output=True, text=True, env=env)       # $depth left undefined
     assert bad.returncode == 1 and 'depth' in bad.stderr
+    # `mitsuba -r sec` (mitsuba.cpp:228-229): partial images while rendering; hdrfilm's OpenEXR output (hdrfilm.cpp:213-246)
+    from test_oracle_cpu import _read_exr
+    exr = str(tmp_path / 'out.exr')
+    r3 = subprocess.run([cp.CLI_PATH, '-r', '0', '--chunk', '1', '-Ddepth=5', '--seed', '3', '-o', exr, path], capture_output=True, text=True, env=env)
+    assert r3.returncode == 0, r3.stderr
+    assert r3.stdout.count('Flushed a partial image') == 3 and '(1 of 4 samples per pixel)' in r3.stdout
+    ch = _read_exr(exr)
+    got = np.stack([ch['R'], ch['G'], ch['B']], axis=2)
+    with np.errstate(over='ignore'):
+        want = cp.develop(film).astype(np.float16).astype(np.float32)
+    assert got.shape == (48, 64, 3) and np.abs(got - want).max() <= 2e-3 * max(1.0, float(want.max()))   # four chunk films summed on the host: fp32 order + one half ulp
+    hdrxml = str(tmp_path / 'hdr.xml'); open(hdrxml, 'w').write(xml.replace('type="ldrfilm"', 'type="hdrfilm"').replace('<float name="gamma" value="2.2"/>', ''))
+    r4 = subprocess.run([cp.CLI_PATH, '-q', '-Ddepth=5', hdrxml], capture_output=True, text=True, env=env)
+    assert r4.returncode == 0 and os.path.exists(str(tmp_path / 'hdr.exr')), r4.stderr       # the film plugin picks the extension
 
 
 def test_envmap_emitter_from_hdr_file(cp, oracle, tmp_path):

@@ -1857,3 +1857,63 @@ def test_teapot_scene_plugins_host_side(cp, oracle, tmp_path):
     if os.path.exists(ref):
         rep = cp.validate_scene_xml(ref)
         assert 'shape rectangle' in rep and 'bsdf plastic' in rep and 'texture checkerboard' in rep and 'sampleCount 64' in rep
+
+
+def _read_exr(path):
+    """Minimal reader of single-part, uncompressed scan-line OpenEXR files (half or float channels): returns {channel: (h, w) float32}."""
+    import struct
+    b = open(path, 'rb').read()
+    assert b[:4] == bytes([0x76, 0x2f, 0x31, 0x01]) and struct.unpack('<I', b[4:8])[0] == 2
+    pos = 8; attrs = {}
+    while b[pos] != 0:
+        e = b.index(b'\0', pos); name = b[pos:e].decode(); pos = e + 1
+        e = b.index(b'\0', pos); typ = b[pos:e].decode(); pos = e + 1
+        size = struct.unpack('<i', b[pos:pos + 4])[0]; pos += 4
+        attrs[name] = (typ, b[pos:pos + size]); pos += size
+    pos += 1
+    assert attrs['compression'] == ('compression', b'\0') and attrs['lineOrder'] == ('lineOrder', b'\0')
+    x0, y0, x1, y1 = struct.unpack('<4i', attrs['dataWindow'][1]); w, h = x1 - x0 + 1, y1 - y0 + 1
+    chans = []; c = attrs['channels'][1]; q = 0
+    while c[q] != 0:
+        e = c.index(b'\0', q); nm = c[q:e].decode(); q = e + 1
+        pt = struct.unpack('<i', c[q:q + 4])[0]; q += 16; chans.append((nm, pt))
+    assert [n for n, _ in chans] == sorted(n for n, _ in chans)
+    offs = struct.unpack('<%dQ' % h, b[pos:pos + 8 * h])
+    out = {n: np.zeros((h, w), np.float32) for n, _ in chans}
+    for y in range(h):
+        p = offs[y]; yy, nbytes = struct.unpack('<ii', b[p:p + 8]); p += 8
+        assert yy == y0 + y
+        for n, pt in chans:
+            dt, sz = (np.float16, 2) if pt == 1 else (np.float32, 4)
+            out[n][y] = np.frombuffer(b, dt, w, p).astype(np.float32); p += sz * w
+    return out
+
+
+def test_exr_writer(cp, tmp_path):
+    """hdrfilm's default output (src/films/hdrfilm.cpp:213-246: openexr, rgb, float16): cudapath_write_exr against an independent parse of the
+    file format and, where OpenCV was built with OpenEXR, against its reader; the half conversion against numpy's IEEE round-to-nearest-even."""
+    rng = np.random.default_rng(71)
+    x = np.concatenate([rng.normal(size=20000) * 10.0 ** rng.integers(-9, 6, 20000), [0, -0.0, 65504, 65519.99, 65520, 1e9, -1e9, np.inf, -np.inf, 6e-8, 2.98e-8, 2.99e-8, 5.96e-8, 6.1e-5,
+                                                                                       6.097e-5, 1.0009765625, 1.00048828125, 1.00146484375]]).astype(np.float32)
+    hq = np.zeros(len(x), np.uint16)
+    assert cp.lib().cudapath_float_to_half(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(len(x)), hq.ctypes.data_as(ctypes.c_void_p)) == 0
+    with np.errstate(over='ignore'):
+        assert np.array_equal(hq, x.astype(np.float16).view(np.uint16))
+    w, h = 37, 23
+    img = (rng.random((h, w, 3)) * np.array([1.0, 50.0, 0.01])).astype(np.float32); img[3, 4] = (0, 1e6, 65504)
+    for half in (1, 0):
+        path = str(tmp_path / ('a%d.exr' % half))
+        assert cp.lib().cudapath_write_exr(path.encode(), img.ctypes.data_as(ctypes.c_void_p), w, h, half) == 0
+        ch = _read_exr(path)
+        with np.errstate(over='ignore'):
+            want = img.astype(np.float16).astype(np.float32) if half else img
+        assert np.array_equal(ch['R'], want[..., 0]) and np.array_equal(ch['G'], want[..., 1]) and np.array_equal(ch['B'], want[..., 2])
+        os.environ['OPENCV_IO_ENABLE_OPENEXR'] = '1'
+        try:
+            import cv2
+            im = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        except Exception:
+            im = None
+        if im is not None:
+            assert im.shape == (h, w, 3) and np.array_equal(im[..., ::-1].astype(np.float32), want)
+    assert cp.lib().cudapath_write_exr(str(tmp_path / 'no' / 'such' / 'dir.exr').encode(), img.ctypes.data_as(ctypes.c_void_p), w, h, 1) != 0
