@@ -174,10 +174,25 @@ struct Loader {
                 m.m[4] = x * y * (1 - c2) + z * s; m.m[5] = y * y + (1 - y * y) * c2; m.m[6] = y * z * (1 - c2) - x * s;
                 m.m[8] = x * z * (1 - c2) - y * s; m.m[9] = y * z * (1 - c2) + x * s; m.m[10] = z * z + (1 - z * z) * c2;
             } else if (op->tag == "lookat" || op->tag == "lookAt") {
-                auto o = numbers(op->get("origin")), tg = numbers(op->get("target")); std::vector<double> up = op->has("up") ? numbers(op->get("up")) : std::vector<double>{0, 1, 0};
-                if (o.size() != 3 || tg.size() != 3 || up.size() != 3) throw std::runtime_error("<lookat> needs origin, target (and up) triples");
-                double d[3] = {tg[0] - o[0], tg[1] - o[1], tg[2] - o[2]}; double dl = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]); for (double &q : d) q /= dl;
-                double l[3] = {up[1] * d[2] - up[2] * d[1], up[2] * d[0] - up[0] * d[2], up[0] * d[1] - up[1] * d[0]}; double ll = std::sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]); for (double &q : l) q /= ll;
+                // scenehandler.cpp:362-398 + Transform::lookAt (transform.cpp:191-214): a missing or zero `up` picks an arbitrary axis with
+                // coordinateSystem(normalize(t - o)) (util.cpp:592-601); coinciding points and a parallel `up` are errors
+                auto o = numbers(op->get("origin")), tg = numbers(op->get("target")); std::vector<double> up = op->has("up") ? numbers(op->get("up")) : std::vector<double>{0, 0, 0};
+                if (o.size() != 3) throw std::runtime_error("<lookat>: invalid 'origin' argument");
+                if (tg.size() != 3) throw std::runtime_error("<lookat>: invalid 'target' argument");
+                if (up.size() != 3 && !up.empty()) throw std::runtime_error("<lookat>: invalid 'up' argument");
+                if (up.empty()) up = {0, 0, 0};
+                double d[3] = {tg[0] - o[0], tg[1] - o[1], tg[2] - o[2]}; const double dl = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                if (dl == 0) throw std::runtime_error("lookAt(): 'origin' and 'target' coincide!");
+                for (double &q : d) q /= dl;
+                if (up[0] * up[0] + up[1] * up[1] + up[2] * up[2] == 0) {
+                    double c[3];
+                    if (std::abs(d[0]) > std::abs(d[1])) { const double il = 1.0 / std::sqrt(d[0] * d[0] + d[2] * d[2]); c[0] = d[2] * il; c[1] = 0; c[2] = -d[0] * il; }
+                    else { const double il = 1.0 / std::sqrt(d[1] * d[1] + d[2] * d[2]); c[0] = 0; c[1] = d[2] * il; c[2] = -d[1] * il; }
+                    up = {c[1] * d[2] - c[2] * d[1], c[2] * d[0] - c[0] * d[2], c[0] * d[1] - c[1] * d[0]};      // b = cross(c, a)
+                }
+                double l[3] = {up[1] * d[2] - up[2] * d[1], up[2] * d[0] - up[0] * d[2], up[0] * d[1] - up[1] * d[0]}; const double ll = std::sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+                if (ll == 0) throw std::runtime_error("lookAt(): the forward and upward direction must be linearly independent!");
+                for (double &q : l) q /= ll;
                 double u[3] = {d[1] * l[2] - d[2] * l[1], d[2] * l[0] - d[0] * l[2], d[0] * l[1] - d[1] * l[0]};
                 for (int r = 0; r < 3; ++r) { m.m[r * 4] = l[r]; m.m[r * 4 + 1] = u[r]; m.m[r * 4 + 2] = d[r]; m.m[r * 4 + 3] = o[r]; }
             } else throw std::runtime_error("unsupported transform element <" + op->tag + ">");

@@ -979,6 +979,24 @@ def test_scene_xml_text(cp):
     assert cp.scenes.SCENES['straight-hair']['shapes'][0]['bsdf']['type'] == 'kajiyakay'
 
 
+def test_lookat_without_up_and_degenerate_cases(cp, tmp_path):
+    """<lookat> as scenehandler.cpp:362-398 + Transform::lookAt (transform.cpp:191-214) treat it: no `up` (or a zero one) picks an axis with
+    coordinateSystem(); coinciding origin / target and an `up` parallel to the view direction raise the reference's messages (dry run: no GPU)."""
+    def scene(lookat):
+        p = tmp_path / 'l.xml'
+        p.write_text('<scene version="0.6.0"><sensor type="perspective"><transform name="toWorld">%s</transform><film type="ldrfilm"/></sensor>'
+                     '<bsdf type="diffuse" id="d"/><shape type="rectangle"><ref id="d"/></shape></scene>' % lookat)
+        return str(p)
+    assert 'sensor perspective' in cp.validate_scene_xml(scene('<lookat origin="0,0,5" target="0,0,0"/>'))
+    assert 'sensor perspective' in cp.validate_scene_xml(scene('<lookat origin="1,2,3" target="0,0,0" up="0,0,0"/>'))
+    with pytest.raises(cp.CudapathError, match='coincide'):
+        cp.validate_scene_xml(scene('<lookat origin="1,2,3" target="1,2,3"/>'))
+    with pytest.raises(cp.CudapathError, match='linearly independent'):
+        cp.validate_scene_xml(scene('<lookat origin="0,0,0" target="0,2,0" up="0,1,0"/>'))
+    with pytest.raises(cp.CudapathError, match="invalid 'up'"):
+        cp.validate_scene_xml(scene('<lookat origin="0,0,0" target="0,2,0" up="0,1"/>'))
+
+
 # ------------------------------------------------------------------------------------------------ pinning against the reference's own plugin sources
 REF_BSDF = os.path.join(os.path.dirname(GOLDEN), '..', 'oracle', '_ref', 'libref_bsdf.so')
 needs_ref_bsdf = pytest.mark.skipif(not os.path.exists(REF_BSDF), reason='oracle/_ref/libref_bsdf.so not built (needs /root/reference)')
