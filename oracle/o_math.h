@@ -5,6 +5,7 @@
 // (paths relative to /root/reference).
 #pragma once
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstring>
 #include <algorithm>
@@ -408,6 +409,92 @@ struct MitsubaRandom {
     }
     uint64_t nextULong() { if (idx >= N32) { genRandAll(); idx = 0; } uint64_t r = psfmt64[idx / 2]; idx += 2; return r; }
     float nextFloat() { union { uint32_t u; float f; } x; x.u = (uint32_t) ((nextULong() & 0xFFFFFFFF) >> 9) | 0x3f800000UL; return x.f - 1.0f; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// The `sobol` sampler (src/samplers/sobol.cpp) over Gruenschloss' Sobol code (src/samplers/sobolseq.h:59-135): sampleSingle, look_up
+// (the (0,2)-sequence enumerated per pixel), sampleTEA for the scramble (include/mitsuba/core/qmc.h:146-156).  The direction numbers
+// (src/samplers/sobolseq.cpp, data) are read from refdata/sobol.bin (tools/mirror_refdata.py).
+// ---------------------------------------------------------------------------------------------
+struct SobolTables {
+    enum { NumDimensions = 1024, Size = 52 };
+    std::vector<uint32_t> m32; std::vector<uint64_t> vdc, inv; uint32_t rowsVdc = 0, rowsInv = 0;
+    void load(const std::string &path) {
+        FILE *f = fopen(path.c_str(), "rb");
+        if (!f) throw std::runtime_error("cannot open " + path + " (run tools/mirror_refdata.py)");
+        uint32_t h[5];
+        bool ok = fread(h, 4, 5, f) == 5 && h[0] == 0x4c424f53u && h[1] == NumDimensions && h[2] == Size;
+        if (ok) { rowsVdc = h[3]; rowsInv = h[4]; m32.resize((size_t) NumDimensions * Size); vdc.resize((size_t) rowsVdc * Size); inv.resize((size_t) rowsInv * Size);
+                  ok = fread(m32.data(), 4, m32.size(), f) == m32.size() && fread(vdc.data(), 8, vdc.size(), f) == vdc.size() && fread(inv.data(), 8, inv.size(), f) == inv.size(); }
+        fclose(f);
+        if (!ok) throw std::runtime_error("malformed " + path);
+    }
+    float sample(uint64_t index, uint32_t dimension, uint32_t scramble) const {          // sobolseq.h:59-74
+        uint32_t result = scramble;
+        for (uint32_t i = dimension * Size; index; index >>= 1, ++i) if (index & 1) result ^= m32[i];
+        return std::min(result * (1.0f / (1ULL << 32)), 0.999999940395355225f);
+    }
+    uint64_t lookUp(uint32_t m, uint32_t frame, uint32_t px, uint32_t py, uint64_t scramble) const {   // sobolseq.h:104-133 (SINGLE_PRECISION)
+        if (m < 1 || m > rowsVdc || m > rowsInv) throw std::runtime_error("sobol: film resolution outside the enumeration tables");
+        const uint32_t m2 = m << 1;
+        uint64_t index = uint64_t(frame) << m2, delta = 0;
+        for (uint32_t c = 0; frame; frame >>= 1, ++c) if (frame & 1) delta ^= vdc[(size_t) (m - 1) * Size + c];
+        scramble = (scramble & 0xFFFFFFFF) >> (32 - m);
+        uint64_t b = (((uint64_t) (px ^ scramble) << m) | (py ^ scramble)) ^ delta;
+        for (uint32_t c = 0; b; b >>= 1, ++c) if (b & 1) index ^= inv[(size_t) (m - 1) * Size + c];
+        return index;
+    }
+};
+static inline uint64_t sampleTEA(uint32_t v0, uint32_t v1, int rounds = 4) {
+    uint32_t sum = 0;
+    for (int i = 0; i < rounds; ++i) {
+        sum += 0x9e3779b9;
+        v0 += ((v1 << 4) + 0xA341316C) ^ (v1 + sum) ^ ((v1 >> 5) + 0xC8013EA4);
+        v1 += ((v0 << 4) + 0xAD90777D) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7E95761E);
+    }
+    return ((uint64_t) v1 << 32) + v0;
+}
+// SobolSampler as a block-based render drives it (sobol.cpp:90-105 ctor, :146-156 setFilmResolution(res, bucketed = true), :170-200 generate,
+// :202-217 advance / setSampleIndex, :219-245 next1D / next2D; no sample arrays are requested by the path tracer, so arrayStartDim = arrayEndDim = 5)
+struct SobolSampler {
+    const SobolTables *T = nullptr;
+    uint64_t scramble = 0, sobolSampleIndex = 0; size_t sampleIndex = 0;
+    float resolution = 1; uint32_t logResolution = 0, dimension = 0; int px = 0, py = 0;
+    void configure(const SobolTables *t, uint64_t scrambleProp, int filmW, int filmH) {
+        T = t; scramble = scrambleProp;
+        if (scramble) scramble = sampleTEA((uint32_t) scramble, (uint32_t) (scramble >> 32));
+        uint32_t r = (uint32_t) std::max(filmW, filmH);                                  // math::roundToPowerOfTwo, math.cpp:128-134
+        r--; r |= r >> 1; r |= r >> 2; r |= r >> 4; r |= r >> 8; r |= r >> 16; r++;
+        resolution = (float) r;
+        logResolution = 0; while ((1u << (logResolution + 1)) <= r) ++logResolution;     // math::log2i
+    }
+    void generate(int x, int y) { px = x; py = y; setSampleIndex(0); }
+    void advance() { setSampleIndex(sampleIndex + 1); }
+    void setSampleIndex(size_t i) {
+        dimension = 0; sampleIndex = i;
+        if (logResolution > 1 && px >= 0) sobolSampleIndex = T->lookUp(logResolution, (uint32_t) sampleIndex, (uint32_t) px, (uint32_t) py, scramble);
+        else sobolSampleIndex = (uint64_t) sampleIndex;
+    }
+    void check(uint32_t d) const { if (d >= SobolTables::NumDimensions) throw std::runtime_error("Lookup dimension exceeds the direction number table size! You may have to reduce the 'maxDepth' parameter of your integrator."); }
+    // The dimensions reserved for sample arrays start and end at 5 when none are requested (:176-178); the range tests still fire: a 2-D request
+    // that would begin at dimension 4 moves to 5 (4 + 1 >= arrayStartDim && 4 < arrayEndDim), so dimension 4 is never used by a path tracer
+    // (pixel 0-1, emitter 2-3, BSDF 5-6, ...).
+    enum { ArrayStartDim = 5, ArrayEndDim = 5 };
+    float next1D() {
+        if (dimension >= ArrayStartDim && dimension < ArrayEndDim) dimension = ArrayEndDim;
+        check(dimension); return T->sample(sobolSampleIndex, dimension++, (uint32_t) scramble);
+    }
+    void next2D(float &a, float &b) {
+        if (dimension + 1 >= ArrayStartDim && dimension < ArrayEndDim) dimension = ArrayEndDim;
+        check(dimension + 1);
+        if (dimension == 0 && sobolSampleIndex != (uint64_t) sampleIndex) {
+            a = T->sample(sobolSampleIndex, dimension++, (uint32_t) scramble) * resolution - px;
+            b = T->sample(sobolSampleIndex, dimension++, (uint32_t) scramble) * resolution - py;
+        } else {
+            a = T->sample(sobolSampleIndex, dimension++, (uint32_t) scramble);
+            b = T->sample(sobolSampleIndex, dimension++, (uint32_t) scramble);
+        }
+    }
 };
 
 struct M44 {

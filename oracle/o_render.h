@@ -181,6 +181,11 @@ struct Scene {
     int maxDepth = -1, rrDepth = 5; bool strictNormals = false, hideEmitters = false;
     uint64_t seed = 0;
     RenderStats stats;
+    // sampler: 0 = the counter-based Philox stream (default), 1 = the reference's `sobol` sampler (src/samplers/sobol.cpp), consumed in the
+    // order renderBlock and MIPathTracer::Li call next2D / next1D
+    int samplerKind = 0; uint64_t sobolScramble = 0;
+    std::shared_ptr<SobolTables> sobolTables;
+    SobolSampler makeSobol() const { SobolSampler sb; sb.configure(sobolTables.get(), sobolScramble, cam.filmW, cam.filmH); return sb; }
 
     void finalize() {
         geo.finalize();
@@ -197,7 +202,7 @@ struct Scene {
     static float miWeight(float pdfA, float pdfB) { pdfA *= pdfA; pdfB *= pdfB; return pdfA / (pdfA + pdfB); } // path.cpp:296-300
 
     // path.cpp:119-294.  `alpha` mirrors RadianceQueryRecord::alpha (records.inl:117-144)
-    V3 Li(Ray ray, const V3 &rxDir, const V3 &ryDir, uint32_t pix, uint32_t samp, float &alpha, int *depthOut = nullptr) {
+    V3 Li(Ray ray, const V3 &rxDir, const V3 &ryDir, uint32_t pix, uint32_t samp, float &alpha, int *depthOut = nullptr, SobolSampler *sob = nullptr) {
         const uint32_t k0 = (uint32_t) seed, k1 = (uint32_t) (seed >> 32);
         V3 Li(0.0f);
         bool scattered = false;
@@ -223,7 +228,9 @@ struct Scene {
             Philox4 u = philox4x32_10(pix, samp, (uint32_t) depth, 0, k0, k1);
             /* direct illumination sampling, only for BSDFs with a smooth component (path.cpp:174-175) */
             if (hasEnv && bsdf.hasSmooth()) {
-                EnvMap::DirectSample ds = env.sampleDirect(its.p, u32_to_unit(u.v[0]), u32_to_unit(u.v[1]));
+                float e0 = u32_to_unit(u.v[0]), e1 = u32_to_unit(u.v[1]);
+                if (sob) sob->next2D(e0, e1);                                          // rRec.nextSample2D(), path.cpp:179
+                EnvMap::DirectSample ds = env.sampleDirect(its.p, e0, e1);
                 V3 value(0.0f);
                 if (ds.pdf != 0) {
                     Ray shadow(its.p, ds.d, kEpsilon, ds.dist * (1 - kShadowEpsilon));
@@ -242,11 +249,14 @@ struct Scene {
             }
             /* BSDF sampling */
             float extra[4] = {0, 0, 0, 0};
+            float b0 = u32_to_unit(u.v[2]), b1 = u32_to_unit(u.v[3]);
+            if (sob) sob->next2D(b0, b1);                                              // the `sample` argument of bsdf->sample(), path.cpp:210
             if (bsdf.drawsExtra()) {                       // counter stream 2 of this vertex (stream 0: emitter + BSDF sample, 1: roulette)
                 Philox4 ue = philox4x32_10(pix, samp, (uint32_t) depth, 2, k0, k1);
                 for (int k = 0; k < 4; ++k) extra[k] = u32_to_unit(ue.v[k]);
+                if (sob) { sob->next2D(extra[0], extra[1]); sob->next2D(extra[2], extra[3]); }   // bRec.sampler->next2D() twice inside sample(), marschner.cpp:473-474
             }
-            BSDFSample bs = bsdf.sample(its.wi, u32_to_unit(u.v[2]), u32_to_unit(u.v[3]), extra, its.u, its.v);
+            BSDFSample bs = bsdf.sample(its.wi, b0, b1, extra, its.u, its.v);
             if (isZero(bs.weight)) break;
             scattered |= bs.sampledType != ENull;
             const V3 wo = its.shFrame.toWorld(bs.wo);
@@ -278,7 +288,8 @@ struct Scene {
             if (depth++ >= rrDepth) {
                 float q = std::min(maxc(throughput) * eta * eta, 0.95f);
                 Philox4 ur = philox4x32_10(pix, samp, (uint32_t) (depth - 1), 1, k0, k1);
-                if (u32_to_unit(ur.v[0]) >= q) break;
+                const float rr = sob ? sob->next1D() : u32_to_unit(ur.v[0]);          // rRec.nextSample1D(), path.cpp:284
+                if (rr >= q) break;
                 throughput = throughput / q;
             }
         }
@@ -293,13 +304,19 @@ struct Scene {
         uint32_t pix = y * (uint32_t) cam.filmW + x;
         Philox4 u = philox4x32_10(pix, samp, 0, 0, k0, k1);
         float px = (float) x + u32_to_unit(u.v[0]), py = (float) y + u32_to_unit(u.v[1]);
+        SobolSampler sob;
+        if (samplerKind == 1) {                                                    // sampler->generate(offset) ... advance() up to this sample (integrator.cpp:167-185)
+            sob = makeSobol(); sob.px = (int) x; sob.py = (int) y; sob.setSampleIndex(samp);
+            float a, b; sob.next2D(a, b);                                          // samplePos = Point2(offset) + Vector2(rRec.nextSample2D())
+            px = (float) (int) x + a; py = (float) (int) y + b;
+        }
         Ray ray; V3 rx, ry;
         cam.sampleRayDifferential(px, py, ray, rx, ry);
         // RayDifferential::scaleDifferential (ray.h:160-168) with 1/sqrt(spp)
         float ds = 1.0f / std::sqrt((float) spp);
         rx = ray.d + (rx - ray.d) * ds; ry = ray.d + (ry - ray.d) * ds;
         float alpha;
-        V3 L = Li(ray, rx, ry, pix, samp, alpha);
+        V3 L = Li(ray, rx, ry, pix, samp, alpha, nullptr, samplerKind == 1 ? &sob : nullptr);
         if (!filmHasAlpha) alpha = 1.0f; // integrator.cpp:157-160 + RadianceQueryRecord::newQuery alpha=1
         if (LiOut) *LiOut = L;
         if (posOut) { posOut[0] = px; posOut[1] = py; }

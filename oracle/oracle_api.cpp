@@ -642,6 +642,32 @@ int orc_env_tables(void *sp, float *outCdfRows, float *outCdfCols, float *outRow
 int orc_filter_table(void *sp, float *out32) { Scene *s = (Scene *) sp; std::memcpy(out32, s->filter.values, 32 * 4); return 0; }
 
 // Render sample range [sBegin,sEnd) of spp into outFilm (5 x w x h, accumulated sums; not normalised)
+// sampler: 0 Philox counters (default), 1 the reference's `sobol` sampler with `scramble`; the tables come from <dataDir>/sobol.bin
+int orc_set_sampler(void *sp, int kind, uint64_t scramble, const char *dataDir) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    if (kind != 0 && kind != 1) throw std::runtime_error("sampler: 0 = philox, 1 = sobol");
+    if (kind == 1 && !s->sobolTables) { s->sobolTables = std::make_shared<SobolTables>(); s->sobolTables->load(std::string(dataDir) + "/sobol.bin"); }
+    s->samplerKind = kind; s->sobolScramble = scramble;
+    return 0;
+    ORC_CATCH
+}
+// raw sampler sequence for one pixel: `pattern` holds 1 / 2 per request (next1D / next2D), per sample index; out gets the numbers in order
+int orc_sobol_sequence(void *sp, int px, int py, uint32_t firstSample, uint32_t nSamples, int nReq, const int32_t *pattern, float *out) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    if (!s->sobolTables) throw std::runtime_error("orc_set_sampler(1) first");
+    SobolSampler sb = s->makeSobol();
+    sb.generate(px, py);
+    for (uint32_t k = 0; k < firstSample; ++k) sb.advance();
+    for (uint32_t j = 0; j < nSamples; ++j) {
+        for (int r = 0; r < nReq; ++r) { if (pattern[r] == 1) *out++ = sb.next1D(); else { float a, b; sb.next2D(a, b); *out++ = a; *out++ = b; } }
+        sb.advance();
+    }
+    return 0;
+    ORC_CATCH
+}
+
 int orc_render(void *sp, uint32_t spp, uint64_t seed, uint32_t sBegin, uint32_t sEnd, int nThreads, float *outFilm, uint64_t *outStats) {
     ORC_TRY
     Scene *s = (Scene *) sp;
@@ -677,7 +703,7 @@ int orc_render_samples(void *sp, uint64_t n, const uint32_t *xy, const uint32_t 
 // outcome isolates the integrator logic.  Same camera rays and Philox counters as renderSample(); compared with orc_render_samples().
 #include "ref_shim/ref_path_callbacks.h"
 namespace {
-struct LiBridge { Scene *s; uint32_t pix, samp, k0, k1; };
+struct LiBridge { Scene *s; uint32_t pix, samp, k0, k1; SobolSampler *sob = nullptr; };
 int br_rayIntersect(void *u, const float o[3], const float d[3], float mint, float maxt, RefPathIts *out) {
     LiBridge *b = (LiBridge *) u;
     Ray r(V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), mint, maxt);
@@ -725,17 +751,19 @@ void br_bsdfSample(void *u, int id, int depth, const float wi[3], float sx, floa
     LiBridge *b = (LiBridge *) u;
     const BSDFAny &m = b->s->bsdfs[id];
     float extra[4] = {0, 0, 0, 0};
-    if (m.drawsExtra()) { Philox4 ue = philox4x32_10(b->pix, b->samp, (uint32_t) depth, 2, b->k0, b->k1); for (int k = 0; k < 4; ++k) extra[k] = u32_to_unit(ue.v[k]); }
+    if (m.drawsExtra()) { Philox4 ue = philox4x32_10(b->pix, b->samp, (uint32_t) depth, 2, b->k0, b->k1); for (int k = 0; k < 4; ++k) extra[k] = u32_to_unit(ue.v[k]);
+                          if (b->sob) { b->sob->next2D(extra[0], extra[1]); b->sob->next2D(extra[2], extra[3]); } }
     const BSDFSample bs = m.sample(V3(wi[0], wi[1], wi[2]), sx, sy, extra);
     wo[0] = bs.wo.x; wo[1] = bs.wo.y; wo[2] = bs.wo.z; weight[0] = bs.weight.x; weight[1] = bs.weight.y; weight[2] = bs.weight.z;
     *pdf = bs.pdf; *type = (unsigned) bs.sampledType; *eta = bs.eta;
 }
 void br_next2D(void *u, int depth, int which, float out[2]) {
     LiBridge *b = (LiBridge *) u;
+    if (b->sob) { b->sob->next2D(out[0], out[1]); return; }        // the stateful sampler: whatever order path.cpp asks in
     const Philox4 v = philox4x32_10(b->pix, b->samp, (uint32_t) depth, 0, b->k0, b->k1);
     out[0] = u32_to_unit(v.v[which ? 2 : 0]); out[1] = u32_to_unit(v.v[which ? 3 : 1]);
 }
-float br_next1D(void *u, int depth) { LiBridge *b = (LiBridge *) u; return u32_to_unit(philox4x32_10(b->pix, b->samp, (uint32_t) depth, 1, b->k0, b->k1).v[0]); }
+float br_next1D(void *u, int depth) { LiBridge *b = (LiBridge *) u; if (b->sob) return b->sob->next1D(); return u32_to_unit(philox4x32_10(b->pix, b->samp, (uint32_t) depth, 1, b->k0, b->k1).v[0]); }
 }
 
 int orc_render_samples_ref_li(void *sp, const char *refPathLib, uint64_t n, const uint32_t *xy, const uint32_t *samp, uint32_t spp, uint64_t seed,
@@ -755,7 +783,14 @@ int orc_render_samples_ref_li(void *sp, const char *refPathLib, uint64_t n, cons
                             br_bsdfType, br_bsdfEval, br_bsdfPdf, br_bsdfSample, br_next2D, br_next1D};
         // the camera ray exactly as Scene::renderSample() makes it (integrator.cpp:140-188)
         const Philox4 u = philox4x32_10(b.pix, b.samp, 0, 0, k0, k1);
-        const float px = (float) xy[2 * i] + u32_to_unit(u.v[0]), py = (float) xy[2 * i + 1] + u32_to_unit(u.v[1]);
+        float px = (float) xy[2 * i] + u32_to_unit(u.v[0]), py = (float) xy[2 * i + 1] + u32_to_unit(u.v[1]);
+        SobolSampler sob;
+        if (s->samplerKind == 1) {       // the reference's sampler object, asked by path.cpp itself from here on
+            sob = s->makeSobol(); sob.px = (int) xy[2 * i]; sob.py = (int) xy[2 * i + 1]; sob.setSampleIndex(samp[i]);
+            float a0, a1; sob.next2D(a0, a1);
+            px = (float) (int) xy[2 * i] + a0; py = (float) (int) xy[2 * i + 1] + a1;
+            b.sob = &sob;
+        }
         Ray ray; V3 rx, ry;
         s->cam.sampleRayDifferential(px, py, ray, rx, ry);
         const float ds = 1.0f / std::sqrt((float) spp);

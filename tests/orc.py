@@ -153,6 +153,14 @@ class Scene:
                                                    ctypes.c_float(props.get('alpha', 0.1)), DISTR[props.get('distribution', 'beckmann')],
                                                    1 if props.get('nonlinear', False) else 0, DATA_DIR.encode()))
 
+    def set_sampler(self, kind='philox', scramble=0):
+        check(self.L.orc_set_sampler(self.h, {'philox': 0, 'sobol': 1}[kind], ctypes.c_uint64(scramble), DATA_DIR.encode()))
+
+    def sobol_sequence(self, px, py, first_sample, n_samples, pattern):
+        pat = np.ascontiguousarray(pattern, np.int32); out = np.zeros(n_samples * int(pat.sum()), np.float32)
+        check(self.L.orc_sobol_sequence(self.h, int(px), int(py), ctypes.c_uint32(first_sample), ctypes.c_uint32(n_samples), len(pat), p(pat), p(out)))
+        return out.reshape(n_samples, -1)
+
     def set_checkerboard(self, bsdf, color0=0.4, color1=0.2, uoffset=0.0, voffset=0.0, uscale=1.0, vscale=1.0):
         c0 = f32(np.broadcast_to(color0, 3)); c1 = f32(np.broadcast_to(color1, 3))
         check(self.L.orc_bsdf_set_checkerboard(self.h, int(bsdf), p(c0), p(c1), ctypes.c_float(uoffset), ctypes.c_float(voffset), ctypes.c_float(uscale), ctypes.c_float(vscale)))

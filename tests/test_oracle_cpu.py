@@ -1326,19 +1326,26 @@ def test_oracle_scene_query_pinned_against_reference_text(cp, oracle):
 @pytest.mark.parametrize('name,variant', [('straight-hair', {}), ('curly-hair', {}), ('hair-on-head', {}), ('straight-hair-default', {}),
                                           ('straight-hair-thindielectric', dict(maxDepth=24)), ('straight-hair-dielectric', dict(maxDepth=24, hideEmitters=True)),
                                           ('curly-hair', dict(fixed=True)), ('straight-hair', dict(maxDepth=-1, strictNormals=False, hideEmitters=True, rrDepth=2)),
-                                          ('furball', dict(maxDepth=2))])
+                                          ('furball', dict(maxDepth=2)),
+                                          # the `sobol` sampler: path.cpp asks the sampler object itself, in its own order
+                                          ('straight-hair', dict(sobol=True)), ('curly-hair', dict(sobol=True, fixed=True, scramble=7)),
+                                          ('straight-hair-thindielectric', dict(sobol=True, maxDepth=24)), ('hair-on-head', dict(sobol=True, rrDepth=2, maxDepth=20))])
 def test_oracle_li_pinned_against_compiled_reference_integrator(cp, oracle, name, variant):
     """MIPathTracer::Li: src/integrators/path/path.cpp compiled UNMODIFIED from /root/reference (oracle/_ref/libref_path.so) and run on the
     oracle's own scene components through a callback table -- same camera rays, same Philox counters -- against the oracle's Li():
     radiance of every path is bit-identical.  Covers emitter sampling + MIS, the ESmooth test, ENull / delta vertices and the `scattered`
     flag with hideEmitters, strictNormals, maxDepth (finite, 2, infinite), Russian roulette from rrDepth, the extra sampler draws of the
-    fixed Marschner, fibers and meshes."""
+    fixed Marschner, fibers and meshes.  With sobol=True the random numbers come from the oracle's restatement of the `sobol` sampler: the
+    compiled path.cpp draws from it as a stateful object (next2D / next1D in whatever order it asks), the oracle's Li() in the order it believes
+    the reference asks -- equal radiance pins the consumption order: emitter sample, BSDF sample, the BSDF's own draws, roulette."""
     ov = dict(width=40, height=32, spp=4, maxDepth=variant.get('maxDepth', 8))
     if variant.get('fixed'):
         sh = dict(cp.scenes.SCENES[name]['shapes'][0], bsdf=dict(type='marschner_fixed', id='hair', intIOR=1.55, extIOR=1.0)); ov['shapes'] = [sh]
     env = cp.bake_sunsky(**cp.scenes.sunsky_params(name))
     sc = oracle.scene_from_description(name, scale=0.004, overrides=ov, envmap=env)
     sc.set_integrator(maxDepth=ov['maxDepth'], rrDepth=variant.get('rrDepth', 5), strictNormals=variant.get('strictNormals', True), hideEmitters=variant.get('hideEmitters', False))
+    if variant.get('sobol'):
+        sc.set_sampler('sobol', scramble=variant.get('scramble', 0))
     ys, xs, ss = np.meshgrid(np.arange(32), np.arange(40), np.arange(4), indexing='ij')
     xy = np.stack([xs.ravel(), ys.ravel()], axis=1).astype(np.uint32); samp = ss.ravel().astype(np.uint32)
     ours, _ = sc.render_samples(xy, samp, 4, seed=21)
@@ -1346,6 +1353,40 @@ def test_oracle_li_pinned_against_compiled_reference_integrator(cp, oracle, name
     assert np.isfinite(ref).all() and ref.sum() > 0 and depth.max() >= 2
     assert np.array_equal(ours, ref), '%d of %d paths differ' % ((ours != ref).any(axis=1).sum(), len(ref))
     assert (alpha == 1).all()                                                     # films without an alpha channel: EOpacity is masked out
+    if variant.get('sobol'):
+        sc.set_sampler('philox')
+        other, _ = sc.render_samples(xy, samp, 4, seed=21)
+        assert not np.array_equal(other, ours)
+
+
+REF_SOBOL = os.path.join(os.path.dirname(GOLDEN), '..', 'oracle', '_ref', 'libref_sobol.so')
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SOBOL), reason='oracle/_ref/libref_sobol.so not built (needs /root/reference)')
+def test_sobol_sampler_pinned_against_compiled_reference_plugin(cp, oracle):
+    """src/samplers/sobol.cpp + sobolseq.cpp compiled UNMODIFIED (oracle/_ref/libref_sobol.so), driven like renderBlock drives a sampler
+    (setFilmResolution(size, true), generate(pixel), next2D / next1D, advance), against the oracle's restatement reading the mirrored direction
+    numbers: every number bit-identical -- pixel offsets inside [0, 1), power-of-two and odd film sizes, scrambled and not, 300 dimensions deep."""
+    R = ctypes.CDLL(REF_SOBOL); R.ref_sobol_create.restype = ctypes.c_void_p
+    rng = np.random.default_rng(73)
+    for (w, h, spp, scramble) in ((1024, 1024, 64, 0), (1280, 720, 64, 0), (96, 54, 8, 0), (512, 512, 16, 12345), (3, 2, 4, 0), (2048, 2048, 256, 2 ** 40 + 17)):
+        hdl = ctypes.c_void_p(R.ref_sobol_create(spp, ctypes.c_ulonglong(scramble), w, h)); assert hdl.value
+        sc = oracle.Scene(); b = sc.add_bsdf('diffuse', reflectance=0.5); sc.add_rectangle(None, False, b)
+        sc.set_camera(np.eye(4, dtype=np.float32), width=w, height=h); sc.set_sampler('sobol', scramble=scramble)
+        pattern = np.array([2] + [2, 2, 1] * 60, np.int32)                      # pixel sample, then (emitter, bsdf, roulette) per vertex
+        n = int(pattern.sum())
+        for _ in range(12):
+            px, py = int(rng.integers(0, w)), int(rng.integers(0, h)); first = int(rng.integers(0, spp)); cnt = min(3, spp - first)
+            ref = np.zeros(cnt * n, np.float32)
+            assert R.ref_sobol_sequence(hdl, px, py, first, cnt, len(pattern), pattern.ctypes.data_as(ctypes.c_void_p), ref.ctypes.data_as(ctypes.c_void_p)) == 0
+            ours = sc.sobol_sequence(px, py, first, cnt, pattern)
+            assert np.array_equal(ours.ravel(), ref)
+            assert (ours[:, :2] >= 0).all() and (ours[:, :2] < 1).all() and (ours >= 0).all() and (ours < 1).all()
+    # beyond 1024 dimensions the plugin raises (sobol.cpp:222-224): so does the restatement
+    sc = oracle.Scene(); b = sc.add_bsdf('diffuse', reflectance=0.5); sc.add_rectangle(None, False, b)
+    sc.set_camera(np.eye(4, dtype=np.float32), width=64, height=64); sc.set_sampler('sobol')
+    with pytest.raises(RuntimeError, match='direction number table'):
+        sc.sobol_sequence(3, 4, 0, 1, np.full(600, 2, np.int32))
 
 
 @pytest.mark.skipif(not os.path.exists(REF_GEOM), reason='oracle/_ref/libref_geom.so not built (needs /root/reference)')

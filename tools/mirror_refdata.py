@@ -11,6 +11,9 @@ Layout written:
   refdata/microfacet/{beckmann,ggx,phong}.dat      byte copies
   refdata/sunsky/hosek_rgb.f64                     3 channels x (1080 config + 120 radiance) float64, little endian
   refdata/cie1931.f32                              4 x 471 float32: wavelengths, X, Y, Z
+  refdata/sobol.bin                                the direction-number tables compiled into the `sobol` sampler plugin (src/samplers/sobolseq.cpp: Joe & Kuo's numbers
+                                                   as 1024 x 52 32-bit matrices, and the van-der-Corput / Sobol enumeration matrices with their inverses for m = 1..26):
+                                                   uint32 magic 'SOBL', dims, size, rowsVdc, rowsInv; matrices32[dims*size] uint32; vdc[rowsVdc*size] uint64; vdc_inv[rowsInv*size] uint64
 """
 import os, re, shutil, struct, sys
 
@@ -40,6 +43,28 @@ def main(ref, out):
             v = parse_c_array(spec, name)
             assert len(v) == 471, (name, len(v))
             f.write(struct.pack('<471f', *v))
+    sob = open(os.path.join(ref, 'src', 'samplers', 'sobolseq.cpp')).read()
+    def block(name):
+        i = sob.index('Matrices::' + name); i = sob.index('{', sob.index('=', i))
+        j = sob.index('\n};', i)
+        return sob[i + 1:j + 2]
+    m32 = [int(t.rstrip('U'), 16) for t in re.findall(r'0x[0-9a-fA-F]+U?\b', block('matrices32['))]
+    assert len(m32) == 1024 * 52, len(m32)
+    def rows(name):
+        out_rows = []
+        for body in re.findall(r'\{\s*// m = \d+(.*?)\}', block(name), re.S):
+            v = [int(t[:-3], 16) for t in re.findall(r'0x[0-9a-fA-F]+ULL', body)]
+            assert 0 < len(v) <= 52
+            out_rows.append(v + [0] * (52 - len(v)))
+        return out_rows
+    vdc, inv = rows('vdc_sobol_matrices[]'), rows('vdc_sobol_matrices_inv[]')
+    assert len(vdc) >= 16 and len(inv) >= 16, (len(vdc), len(inv))
+    with open(os.path.join(out, 'sobol.bin'), 'wb') as f:
+        f.write(struct.pack('<5I', 0x4c424f53, 1024, 52, len(vdc), len(inv)))
+        f.write(struct.pack('<%dI' % len(m32), *m32))
+        for table in (vdc, inv):
+            for r in table:
+                f.write(struct.pack('<52Q', *r))
     print('refdata written to', out)
 
 if __name__ == '__main__':
