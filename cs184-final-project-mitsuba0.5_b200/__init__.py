@@ -329,6 +329,11 @@ class Context:
     def set_integrator(self, maxDepth=-1, rrDepth=5, strictNormals=False, hideEmitters=False):
         _check(self._L.cudapath_set_integrator(self._h, int(maxDepth), int(rrDepth), 1 if strictNormals else 0, 1 if hideEmitters else 0))
 
+    def set_sampler(self, kind='philox', scramble=0):
+        """'philox' (default: counter-based stream), 'sobol' (the reference's src/samplers/sobol.cpp reproduced number for number) or 'file'
+        (the <sampler> of the scene file loaded next: sobol is honoured, anything else refused)."""
+        _check(self._L.cudapath_set_sampler(self._h, {'philox': 0, 'sobol': 1, 'file': 2}[kind], ctypes.c_uint64(scramble)))
+
     def set_options(self, wave_size=0, collect_stats=False, profile_stages=False):
         _check(self._L.cudapath_set_options(self._h, ctypes.c_uint32(wave_size), 1 if collect_stats else 0, 1 if profile_stages else 0))
 

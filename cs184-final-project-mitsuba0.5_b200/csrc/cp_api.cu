@@ -65,7 +65,9 @@ struct cudapath_ctx {
     std::vector<Staged> staged;
     uint32_t vtxTotal = 0, meshVtxTotal = 0, triTotal = 0;
     float4 *d_meshPos = nullptr, *d_meshNrm = nullptr, *d_triAccel = nullptr; uint32_t *d_meshIdx = nullptr; float2 *d_meshUV = nullptr;
-    std::vector<float4> rects; float4 *d_rects = nullptr;      // CP_RECT_STRIDE float4 per `rectangle` shape (cp_tri.cuh)
+    std::vector<float4> rects; float4 *d_rects = nullptr;
+    int samplerKind = 0; uint64_t samplerScramble = 0; uint32_t sobolRows[2] = {0, 0};     // cudapath_set_sampler
+    uint32_t *d_sobolM32 = nullptr; uint64_t *d_sobolVdc = nullptr, *d_sobolInv = nullptr;      // CP_RECT_STRIDE float4 per `rectangle` shape (cp_tri.cuh)
     std::vector<ShapeDev> shapes;
     EnvHost env; EnvTables envTables;
     CamHost cam;
@@ -104,6 +106,7 @@ struct cudapath_ctx {
         DevGuard guard_(device);
         freeBuilt();                  // synchronises the device
         for (auto &st : staged) { dfree(st.xyz); dfree(st.starts); dfree(st.nrm); dfree(st.idx); dfree(st.uv); }
+        dfree(d_sobolM32); dfree(d_sobolVdc); dfree(d_sobolInv);
         for (auto &b : bsdfs) { dfree(b.tables.tab); dfree(b.tables.cdf); dfree(b.tables.sums); dfree(b.tables.pdf); dfree(b.rt); }
         wf.release();
         if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
@@ -629,6 +632,38 @@ int cudapath_set_integrator(cudapath_ctx *ctx, int max_depth, int rr_depth, int 
     if (ctx->built) ctx->scene.integ = ctx->integ;
     return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_integrator(p, max_depth, rr_depth, strict_normals, hide_emitters); });
 }
+int cudapath_set_sampler(cudapath_ctx *ctx, int kind, uint64_t scramble) {
+    if (!ctx) return fail("null context");
+    if (kind == 2) {                       // "what the scene file asks for": resolved by cudapath_load_scene_xml when it meets the <sampler> element
+        ctx->samplerKind = 2; ctx->built = false;
+        return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_sampler(p, kind, scramble); });
+    }
+    if (kind != 0 && kind != 1) return fail("sampler: 0 = counter-based Philox stream, 1 = the reference's sobol sampler, 2 = the sampler of the scene file loaded next");
+    if (kind == 1 && !ctx->d_sobolM32) {
+        if (ctx->dataDir.empty()) return fail("the sobol sampler needs sobol.bin: call cudapath_set_data_dir() first");
+        CP_GUARD(ctx);
+        const std::string path = ctx->dataDir + "/sobol.bin";
+        FILE *f = fopen(path.c_str(), "rb");
+        if (!f) return fail("cannot open \"" + path + "\" (tools/mirror_refdata.py writes it)");
+        uint32_t h[5] = {0, 0, 0, 0, 0};
+        bool ok = fread(h, 4, 5, f) == 5 && h[0] == 0x4c424f53u && h[1] == CP_SOBOL_DIMS && h[2] == CP_SOBOL_SIZE && h[3] >= 1 && h[3] <= 64 && h[4] >= 1 && h[4] <= 64;
+        std::vector<uint32_t> m32; std::vector<uint64_t> vdc, inv;
+        if (ok) { m32.resize((size_t) CP_SOBOL_DIMS * CP_SOBOL_SIZE); vdc.resize((size_t) h[3] * CP_SOBOL_SIZE); inv.resize((size_t) h[4] * CP_SOBOL_SIZE);
+                  ok = fread(m32.data(), 4, m32.size(), f) == m32.size() && fread(vdc.data(), 8, vdc.size(), f) == vdc.size() && fread(inv.data(), 8, inv.size(), f) == inv.size(); }
+        fclose(f);
+        if (!ok) return fail("malformed \"" + path + "\"");
+        CKA(dev_alloc(&ctx->d_sobolM32, m32.size() * 4)); CKA(dev_alloc(&ctx->d_sobolVdc, vdc.size() * 8)); CKA(dev_alloc(&ctx->d_sobolInv, inv.size() * 8));
+        CKA(cudaMemcpyAsync(ctx->d_sobolM32, m32.data(), m32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CKA(cudaMemcpyAsync(ctx->d_sobolVdc, vdc.data(), vdc.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CKA(cudaMemcpyAsync(ctx->d_sobolInv, inv.data(), inv.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CKA(cudaStreamSynchronize(ctx->stream));
+        ctx->sobolRows[0] = h[3]; ctx->sobolRows[1] = h[4];
+    }
+    ctx->samplerKind = kind; ctx->samplerScramble = scramble; ctx->built = false;
+    return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_sampler(p, kind, scramble); });
+}
+int cudapath_get_sampler(cudapath_ctx *ctx) { return ctx ? ctx->samplerKind : -1; }
+
 int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stats, int profile_stages) {
     if (!ctx) return fail("null context");
     if (wave_size) ctx->waveSize = std::max(wave_size, 1024u);
@@ -710,6 +745,22 @@ static int build_one(cudapath_ctx *ctx) {
     std::memset(&S, 0, sizeof(S));
     S.vtx = ctx->d_vtx; S.vtxCount = ctx->vtxTotal; S.shapes = ctx->d_shapes; S.shapeCount = (int) ctx->shapes.size();
     S.bsdfs = ctx->d_bsdfs; S.bsdfCount = (int) devs.size(); S.bvh = ctx->bvh; S.integ = ctx->integ;
+    S.sobol.kind = 0;
+    if (ctx->samplerKind == 2) return fail("cudapath_set_sampler(2) waits for a scene file: no <sampler> element has been loaded");
+    if (ctx->samplerKind == 1) {        // SobolSampler::setFilmResolution(crop size, bucketed = true), sobol.cpp:146-156
+        uint32_t r = (uint32_t) std::max(ctx->cam.w, ctx->cam.h);
+        r--; r |= r >> 1; r |= r >> 2; r |= r >> 4; r |= r >> 8; r |= r >> 16; r++;
+        uint32_t lg = 0; while ((1u << (lg + 1)) <= r) ++lg;
+        if (lg > 1 && (lg > ctx->sobolRows[0] || lg > ctx->sobolRows[1])) return fail("sobol: film resolution outside the enumeration tables");
+        uint64_t scr = ctx->samplerScramble;
+        if (scr) {                       // sampleTEA(lo, hi), qmc.h:146-156 (sobol.cpp:96-103)
+            uint32_t v0 = (uint32_t) scr, v1 = (uint32_t) (scr >> 32), sum = 0;
+            for (int i = 0; i < 4; ++i) { sum += 0x9e3779b9; v0 += ((v1 << 4) + 0xA341316C) ^ (v1 + sum) ^ ((v1 >> 5) + 0xC8013EA4); v1 += ((v0 << 4) + 0xAD90777D) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7E95761E); }
+            scr = ((uint64_t) v1 << 32) + v0;
+        }
+        S.sobol.kind = 1; S.sobol.m32 = ctx->d_sobolM32; S.sobol.vdc = ctx->d_sobolVdc; S.sobol.inv = ctx->d_sobolInv;
+        S.sobol.logRes = lg; S.sobol.res = (float) r; S.sobol.scramble = (uint32_t) scr; S.sobol.err = nullptr;
+    }
     S.mesh = mesh; S.clipPerShape = (hairShapes > 1 || ctx->triTotal > 0 || !ctx->rects.empty()) ? 1 : 0;
     for (int k = 0; k < 3; ++k) { S.sceneMin[k] = INFINITY; S.sceneMax[k] = -INFINITY; }
     for (auto &sh : ctx->shapes) for (int k = 0; k < 3; ++k) { S.sceneMin[k] = std::min(S.sceneMin[k], sh.bmin[k]); S.sceneMax[k] = std::max(S.sceneMax[k], sh.bmax[k]); }

@@ -7,6 +7,7 @@
 //          as a sequence of sample-index ranges whose films add up (the random numbers are keyed by the sample index, so the final image is the
 //          one a single call produces, up to the order of fp32 additions); a partial image is the film developed so far -- fewer samples per
 //          pixel, correctly normalised
+//     --faithful-sampler   draw the random numbers of the file's <sampler type="sobol"> (src/samplers/sobol.cpp) instead of the Philox counters
 //     -D   parameter substitution of $name in the file (mitsuba.cpp:168)
 //     -p   `mitsuba -p N` asks for N local workers (mitsuba.cpp:218-222,280-282); the workers of this path are GPUs: the job is split
 //          over min(N, visible GPUs) devices (cudapath_create_multi: sample-range sharding, one ncclReduce of the film)
@@ -76,7 +77,7 @@ static int die(const char *what) { fprintf(stderr, "cudapath_render: %s: %s\n", 
 
 int main(int argc, char **argv) {
     std::string out, defines, scene, dataDir;
-    int gpu = 0, workers = 0, gpus = 0; long spp = 0; unsigned long long seed = 0; bool quiet = false; double flushSec = -1; long chunk = 0;
+    int gpu = 0, workers = 0, gpus = 0; long spp = 0; unsigned long long seed = 0; bool quiet = false, faithful = false; double flushSec = -1; long chunk = 0;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto need = [&](const char *opt) -> const char * { if (i + 1 >= argc) { fprintf(stderr, "cudapath_render: %s needs an argument\n", opt); exit(2); } return argv[++i]; };
@@ -88,12 +89,13 @@ int main(int argc, char **argv) {
         else if (a == "-b") need(a.c_str());
         else if (a == "-r") flushSec = atof(need("-r"));
         else if (a == "--chunk") chunk = atol(need("--chunk"));
+        else if (a == "--faithful-sampler") faithful = true;
         else if (a == "-q") quiet = true;
         else if (a == "--gpu") gpu = atoi(need("--gpu"));
         else if (a == "--spp") spp = atol(need("--spp"));
         else if (a == "--seed") seed = strtoull(need("--seed"), nullptr, 10);
         else if (a == "--data-dir") dataDir = need("--data-dir");
-        else if (a == "-h" || a == "--help") { printf("usage: cudapath_render [-o out.{png,exr,pfm,ppm}] [-D name=value]... [-p N] [--gpus N] [-r sec] [--chunk spp] [-q] [--gpu i] [--spp n] [--seed s] [--data-dir dir] scene.xml\n"); return 0; }
+        else if (a == "-h" || a == "--help") { printf("usage: cudapath_render [-o out.{png,exr,pfm,ppm}] [-D name=value]... [-p N] [--gpus N] [-r sec] [--chunk spp] [--faithful-sampler] [-q] [--gpu i] [--spp n] [--seed s] [--data-dir dir] scene.xml\n"); return 0; }
         else if (!a.empty() && a[0] == '-') { fprintf(stderr, "cudapath_render: unknown option %s\n", a.c_str()); return 2; }
         else scene = a;
     }
@@ -109,6 +111,7 @@ int main(int argc, char **argv) {
     for (int k = 0; k < nDev; ++k) devices.push_back(gpu + k);
     if (cudapath_create_multi(devices.data(), nDev, &ctx) != 0) return die("cannot create a context");
     if (cudapath_set_data_dir(ctx, dataDir.c_str()) != 0) return die("data directory");
+    if (faithful && cudapath_set_sampler(ctx, 2, 0) != 0) return die("sampler");     // the <sampler type="sobol"> of the file, number for number
     const double t0 = now();
     uint32_t fileSpp = 0;
     if (cudapath_load_scene_xml(ctx, scene.c_str(), defines.empty() ? nullptr : defines.c_str(), &fileSpp) != 0) return die("cannot load the scene");

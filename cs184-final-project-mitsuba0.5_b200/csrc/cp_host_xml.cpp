@@ -373,7 +373,15 @@ struct Loader {
         if (n.get("type") != "perspective") throw std::runtime_error("sensor plugin \"" + n.get("type") + "\" is outside the hair hot path (supported: perspective)");
         int w = 768, h = 576, filter = 2; float fparam = 0; bool alpha = false;   // film.cpp defaults; hdrfilm/ldrfilm default rfilter is gaussian
         for (auto &c : n.children) {
-            if (c->tag == "sampler") spp = (uint32_t) getInt(*c, "sampleCount", 4);
+            if (c->tag == "sampler") {
+                spp = (uint32_t) getInt(*c, "sampleCount", 4);
+                // sampler-faithful mode (cudapath_set_sampler(ctx, 2, 0) before loading): `sobol` is reproduced, anything else cannot be
+                if (!dry && cudapath_get_sampler(ctx) == 2) {
+                    if (c->get("type") != "sobol") throw std::runtime_error("sampler plugin \"" + c->get("type") + "\" cannot be reproduced number for number on this path (only `sobol`: "
+                                                                             "`independent` hands every worker one sequential stream whose position depends on all paths traced before)");
+                    check(cudapath_set_sampler(ctx, 1, (uint64_t) getInt(*c, "scramble", 0)));
+                }
+            }
             if (c->tag == "film") {
                 w = (int) getInt(*c, "width", 768); h = (int) getInt(*c, "height", 576);
                 std::string pf = lower(getString(*c, "pixelFormat", c->get("type") == "hdrfilm" ? "rgb" : "rgb"));

@@ -71,6 +71,48 @@ struct FilmDev {
 
 struct IntegratorDev { int maxDepth, rrDepth, strictNormals, hideEmitters; };
 
+// Sampler-faithful mode: the reference's `sobol` sampler (src/samplers/sobol.cpp over src/samplers/sobolseq.h) instead of the counter-based
+// Philox stream.  kind 0 = Philox (default), 1 = sobol.  The direction numbers (src/samplers/sobolseq.cpp: 1024 dimensions x 52 32-bit columns,
+// and the enumeration matrices with their inverses per log2 resolution) live in HBM (234 KB, L2-resident).
+#define CP_SOBOL_DIMS 1024u
+#define CP_SOBOL_SIZE 52u
+struct SobolDev {
+    int kind;
+    const uint32_t *m32; const uint64_t *vdc, *inv;
+    uint32_t logRes, scramble;      // log2 of the film resolution rounded up to a power of two (sobol.cpp:146-156); low word of the TEA-hashed scramble
+    float res;
+    int *err;                       // set to 2 when a path asks for a dimension beyond the table (the plugin raises an error there, sobol.cpp:222-224)
+};
+// sobolseq.h:59-74 (sampleSingle)
+CP_D float sobol_sample(const SobolDev &Q, uint64_t index, uint32_t dimension) {
+    uint32_t result = Q.scramble;
+    for (uint32_t i = dimension * CP_SOBOL_SIZE; index; index >>= 1, ++i) if (index & 1ull) result ^= __ldg(Q.m32 + i);
+    return fminf(__uint2float_rn(result) * (1.0f / 4294967296.0f), 0.999999940395355225f);
+}
+// sobolseq.h:104-133 (look_up, SINGLE_PRECISION): index of sample `frame` of pixel (px, py) in the global sequence
+CP_D uint64_t sobol_look_up(const SobolDev &Q, uint32_t frame, uint32_t px, uint32_t py) {
+    const uint32_t m = Q.logRes, m2 = m << 1;
+    uint64_t index = (uint64_t) frame << m2, delta = 0;
+    for (uint32_t c = 0; frame; frame >>= 1, ++c) if (frame & 1u) delta ^= __ldg(Q.vdc + (size_t) (m - 1) * CP_SOBOL_SIZE + c);
+    const uint64_t scr = (uint64_t) (Q.scramble >> (32u - m));
+    uint64_t b = ((((uint64_t) px ^ scr) << m) | ((uint64_t) py ^ scr)) ^ delta;
+    for (uint32_t c = 0; b; b >>= 1, ++c) if (b & 1ull) index ^= __ldg(Q.inv + (size_t) (m - 1) * CP_SOBOL_SIZE + c);
+    return index;
+}
+// SobolSampler::setSampleIndex (sobol.cpp:206-217): the enumerated index when the film spans more than one pixel per axis
+CP_D uint64_t sobol_index(const SobolDev &Q, uint32_t samp, uint32_t px, uint32_t py) { return Q.logRes > 1u ? sobol_look_up(Q, samp, px, py) : (uint64_t) samp; }
+// next1D / next2D (sobol.cpp:219-245) on an explicit dimension counter; no sample arrays are requested on this path, so the reserved range is
+// [5, 5) -- whose tests still move a 2-D request that would begin at dimension 4 to dimension 5
+CP_D float sobol_next1D(const SobolDev &Q, uint64_t index, uint32_t &dim, bool &overflow) {
+    if (dim >= CP_SOBOL_DIMS) { overflow = true; return 0.0f; }
+    return sobol_sample(Q, index, dim++);
+}
+CP_D void sobol_next2D(const SobolDev &Q, uint64_t index, uint32_t &dim, float &a, float &b, bool &overflow) {
+    if (dim + 1u >= 5u && dim < 5u) dim = 5u;
+    if (dim + 1u >= CP_SOBOL_DIMS) { overflow = true; a = b = 0.0f; return; }
+    a = sobol_sample(Q, index, dim++); b = sobol_sample(Q, index, dim++);
+}
+
 struct SceneDev {
     const float4 *vtx;          // see cp_hair.cuh
     uint32_t vtxCount;
@@ -87,6 +129,7 @@ struct SceneDev {
     CameraDev cam;
     FilmDev film;
     IntegratorDev integ;
+    SobolDev sobol;
 };
 
 } // namespace cp

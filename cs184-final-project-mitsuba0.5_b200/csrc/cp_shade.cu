@@ -21,6 +21,22 @@
 #endif
 
 namespace cp {
+
+// samplePos of renderBlock (integrator.cpp:171): pixel + the sampler's first 2-D number.  Philox: counter stream 0 of vertex 0; sobol: dimensions
+// 0 and 1, scaled to the pixel the enumerated index belongs to (sobol.cpp:233-239)
+__device__ __forceinline__ void pixel_sample(const SceneDev &S, const WaveParams &wp, uint32_t x, uint32_t y, uint32_t samp, float &px, float &py) {
+    if (S.sobol.kind == 1) {
+        const uint64_t idx = sobol_index(S.sobol, samp, x, y);
+        float a = sobol_sample(S.sobol, idx, 0u), b = sobol_sample(S.sobol, idx, 1u);
+        if (idx != (uint64_t) samp) { a = a * S.sobol.res - (float) (int) x; b = b * S.sobol.res - (float) (int) y; }
+        px = (float) (int) x + a; py = (float) (int) y + b;
+        return;
+    }
+    const Philox4 u = philox4x32_10(y * wp.filmW + x, samp, 0u, 0u, wp.seedLo, wp.seedHi);
+    px = (float) x + u32_to_unit(u.v[0]); py = (float) y + u32_to_unit(u.v[1]);
+}
+#define CP_DIM_SHIFT 20       // flags word, bits 20..31: the next Sobol dimension of the path (sampler-faithful mode)
+
 #ifndef CP_FAST_MATH
 
 __global__ void __launch_bounds__(256) k_raygen(SceneDev S, WaveParams wp, PathQueue q, float4 *liAcc, uint32_t n, uint32_t *initSlot) {
@@ -35,13 +51,13 @@ __global__ void __launch_bounds__(256) k_raygen(SceneDev S, WaveParams wp, PathQ
         q.thr[i] = make_float4(0, 0, 0, 0); q.id[i] = make_uint2(i, F_INVALID | F_FIRST | 1u);
         return;
     }
-    const Philox4 u = philox4x32_10(y * wp.filmW + x, samp, 0u, 0u, wp.seedLo, wp.seedHi);
-    const float px = (float) x + u32_to_unit(u.v[0]), py = (float) y + u32_to_unit(u.v[1]);
+    float px, py;
+    pixel_sample(S, wp, x, y, samp, px, py);
     const CameraRay r = camera_ray(S.cam, px, py, wp.diffScale);
     q.ro[i] = make_float4(r.o.x, r.o.y, r.o.z, r.mint);
     q.rd[i] = make_float4(r.d.x, r.d.y, r.d.z, r.maxt);
     q.thr[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-    q.id[i] = make_uint2(i, F_FIRST | 1u);                 // depth starts at 1 (integrator.h:218-224)
+    q.id[i] = make_uint2(i, F_FIRST | 1u | (2u << CP_DIM_SHIFT));                 // depth starts at 1 (integrator.h:218-224); two sampler dimensions are spent
 }
 
 #endif // !CP_FAST_MATH
@@ -74,6 +90,9 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
             uint32_t x, y, samp;
             path_to_pixel(wp, wp.waveBase + pathId, x, y, samp);
             const uint32_t pix = y * wp.filmW + x;
+            const bool sobol = S.sobol.kind == 1;
+            uint32_t dim = flags >> CP_DIM_SHIFT; bool dimOverflow = false;
+            const uint64_t sobolIdx = sobol ? sobol_index(S.sobol, samp, x, y) : 0ull;
 
             if (gv == 0xffffffffu) {
                 // ---- the ray escaped
@@ -81,8 +100,9 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
                 if (first) {
                     acc.w = S.film.hasAlpha ? 0.0f : 1.0f;                      // records.inl:117-135
                     if (S.env.present && !S.integ.hideEmitters) {               // path.cpp:136-143
-                        const Philox4 u = philox4x32_10(pix, samp, 0u, 0u, wp.seedLo, wp.seedHi);
-                        const CameraRay cr = camera_ray(S.cam, (float) x + u32_to_unit(u.v[0]), (float) y + u32_to_unit(u.v[1]), wp.diffScale);
+                        float spx, spy;
+                        pixel_sample(S, wp, x, y, samp, spx, spy);
+                        const CameraRay cr = camera_ray(S.cam, spx, spy, wp.diffScale);
                         V3 L = thr * env_eval_filtered(S.env, rayD, cr.rx, cr.ry, unsupportedLookups);
                         acc.x += L.x; acc.y += L.y; acc.z += L.z;
                     }
@@ -101,8 +121,10 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
                 // ---- tail of the previous iteration: Russian roulette (path.cpp:276-286); eta == 1 for both hair BSDFs
                 if (depth >= S.integ.rrDepth) {
                     const float qv = fminf(maxc(thr), 0.95f);
-                    const Philox4 ur = philox4x32_10(pix, samp, (uint32_t) depth, 1u, wp.seedLo, wp.seedHi);
-                    if (u32_to_unit(ur.v[0]) >= qv) break;
+                    float rr;
+                    if (sobol) { rr = sobol_next1D(S.sobol, sobolIdx, dim, dimOverflow); if (dimOverflow) { *S.sobol.err = 2; break; } }
+                    else rr = u32_to_unit(philox4x32_10(pix, samp, (uint32_t) depth, 1u, wp.seedLo, wp.seedHi).v[0]);
+                    if (rr >= qv) break;
                     thr = thr / qv;
                 }
                 depth++;
@@ -123,10 +145,20 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
             if ((depth >= S.integ.maxDepth && S.integ.maxDepth > 0) ||
                 (S.integ.strictNormals && dot(rayD, rec.geoN) * rec.wi.z >= 0)) break;   // path.cpp:156-165
             const BsdfDev &bsdf = S.bsdfs[shape.bsdf];
-            const Philox4 u = philox4x32_10(pix, samp, (uint32_t) depth, 0u, wp.seedLo, wp.seedHi);
+            // the random numbers of this vertex: Philox counter stream 0 = (emitter.x, emitter.y, bsdf.x, bsdf.y); sobol: drawn in the order path.cpp asks
+            float e0, e1, b0, b1;
+            if (!sobol) {
+                const Philox4 u = philox4x32_10(pix, samp, (uint32_t) depth, 0u, wp.seedLo, wp.seedHi);
+                e0 = u32_to_unit(u.v[0]); e1 = u32_to_unit(u.v[1]); b0 = u32_to_unit(u.v[2]); b1 = u32_to_unit(u.v[3]);
+            } else {
+                e0 = e1 = 0.0f;
+                if (bsdf_has_smooth(bsdf)) sobol_next2D(S.sobol, sobolIdx, dim, e0, e1, dimOverflow);     // path.cpp:179: drawn whether or not the scene has an emitter
+                sobol_next2D(S.sobol, sobolIdx, dim, b0, b1, dimOverflow);                                                // path.cpp:210
+                if (dimOverflow) { *S.sobol.err = 2; break; }
+            }
             // ---- emitter sampling (path.cpp:174-200)
             if (S.env.present && bsdf_has_smooth(bsdf)) {       // path.cpp:174-175: only BSDFs with a smooth component
-                const EnvSample es = env_sample_direct(S.env, rec.p, u32_to_unit(u.v[0]), u32_to_unit(u.v[1]));
+                const EnvSample es = env_sample_direct(S.env, rec.p, e0, e1);
                 if (es.pdf != 0) {
                     // The shadow ray is always traced when pdf != 0 (scene.cpp:838-845); its contribution may be zero.
                     V3 contrib(0.0f);
@@ -150,10 +182,15 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
             // ---- BSDF sampling (path.cpp:207-226)
             float4 extra = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if (bsdf_draws_extra(bsdf)) {          // counter stream 2 of this vertex (0: emitter + BSDF sample, 1: roulette)
-                const Philox4 ue = philox4x32_10(pix, samp, (uint32_t) depth, 2u, wp.seedLo, wp.seedHi);
-                extra = make_float4(u32_to_unit(ue.v[0]), u32_to_unit(ue.v[1]), u32_to_unit(ue.v[2]), u32_to_unit(ue.v[3]));
+                if (sobol) {                       // bRec.sampler->next2D() twice inside sample() (marschner.cpp:473-474)
+                    sobol_next2D(S.sobol, sobolIdx, dim, extra.x, extra.y, dimOverflow); sobol_next2D(S.sobol, sobolIdx, dim, extra.z, extra.w, dimOverflow);
+                    if (dimOverflow) { *S.sobol.err = 2; break; }
+                } else {
+                    const Philox4 ue = philox4x32_10(pix, samp, (uint32_t) depth, 2u, wp.seedLo, wp.seedHi);
+                    extra = make_float4(u32_to_unit(ue.v[0]), u32_to_unit(ue.v[1]), u32_to_unit(ue.v[2]), u32_to_unit(ue.v[3]));
+                }
             }
-            const BsdfSampleOut bs = bsdf_sample(bsdf, rec.wi, u32_to_unit(u.v[2]), u32_to_unit(u.v[3]), extra, rec.u, rec.v);
+            const BsdfSampleOut bs = bsdf_sample(bsdf, rec.wi, b0, b1, extra, rec.u, rec.v);
             if (isZero(bs.weight)) break;
             const V3 wo = rec.sh.toWorld(bs.wo);
             if (S.integ.strictNormals && dot(rec.geoN, wo) * bs.wo.z <= 0) break;
@@ -161,7 +198,7 @@ __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, 
             nro = make_float4(rec.p.x, rec.p.y, rec.p.z, kEpsilon);
             nrd = make_float4(wo.x, wo.y, wo.z, CP_INF);
             nthr = make_float4(thr.x, thr.y, thr.z, bs.pdf);
-            nid = make_uint2(pathId, (uint32_t) depth | ((bs.type & EDelta) ? F_DELTA : 0u) | ((bs.type != ENull || (flags & F_SCATTERED)) ? F_SCATTERED : 0u));
+            nid = make_uint2(pathId, (uint32_t) depth | ((bs.type & EDelta) ? F_DELTA : 0u) | ((bs.type != ENull || (flags & F_SCATTERED)) ? F_SCATTERED : 0u) | (dim << CP_DIM_SHIFT));
             survive = true;
         } while (false);
     }
@@ -200,10 +237,10 @@ __global__ void __launch_bounds__(256) k_splat(SceneDev S, WaveParams wp, const 
     if (i >= n) return;
     uint32_t x, y, samp;
     if (!path_to_pixel(wp, wp.waveBase + i, x, y, samp)) return;
-    const Philox4 u = philox4x32_10(y * wp.filmW + x, samp, 0u, 0u, wp.seedLo, wp.seedHi);
+    float px, py;
+    pixel_sample(S, wp, x, y, samp, px, py);            // the sample position is recomputed, not stored
     const float4 acc = liAcc[i];
-    film_put(S.film, film, (int) wp.filmW, (int) wp.filmH, (float) x + u32_to_unit(u.v[0]), (float) y + u32_to_unit(u.v[1]),
-             V3(acc.x, acc.y, acc.z), acc.w, dropped);
+    film_put(S.film, film, (int) wp.filmW, (int) wp.filmH, px, py, V3(acc.x, acc.y, acc.z), acc.w, dropped);
 }
 
 // Parity hook for F1: splat explicit samples

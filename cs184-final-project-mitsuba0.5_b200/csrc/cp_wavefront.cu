@@ -183,9 +183,10 @@ void Wavefront::release() {
 // has seen the counters of bounce b-2 (which bound those of b-1: a path queue only shrinks, and a path emits at most one shadow
 // ray), so the device always has the next bounce queued while the host learns how the last but one ended; the wave is over when a
 // bounce leaves no path alive -- its shadow rays are traced by the launch that is already queued.
-bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t sampleBegin, uint32_t sampleEnd, float *d_film,
+bool Wavefront::render(const SceneDev &scene, uint32_t spp, uint64_t seed, uint32_t sampleBegin, uint32_t sampleEnd, float *d_film,
                        uint32_t waveSize, bool collectStats, bool profileStages, cudaStream_t stream, RenderStats &rs, std::string &err) {
     if (sampleEnd <= sampleBegin) return true;
+    SceneDev S = scene;                  // the copy handed to the kernels (S.sobol.err points at this wavefront's error word once it exists)
     WaveParams wp;
     wp.filmW = (uint32_t) S.cam.filmW; wp.filmH = (uint32_t) S.cam.filmH;
     wp.tilesX = (wp.filmW + 7) / 8;
@@ -218,6 +219,7 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tr0 = now();
     if (!reserve(waveSize, stream, err)) return false;
+    S.sobol.err = errFlag;
     if (trace) { cudaStreamSynchronize(stream); fprintf(stderr, "[cudapath] queue reserve (%u paths): %.3f s\n", waveSize, now() - tr0); }
     // optional per-launch stage timing: one event pair per launch, resolved after the last wave
     struct Span { cudaEvent_t a, b; int stage; };
@@ -305,6 +307,7 @@ bool Wavefront::render(const SceneDev &S, uint32_t spp, uint64_t seed, uint32_t 
     CKW(cudaMemcpyAsync(&herr, errFlag, sizeof(int), cudaMemcpyDeviceToHost, stream));
     CKW(cudaStreamSynchronize(stream));
     CKW(cudaGetLastError());
+    if (herr == 2) { dropSpans(); err = "Lookup dimension exceeds the direction number table size! You may have to reduce the 'maxDepth' parameter of your integrator."; return false; }   // sobol.cpp:222-224
     if (herr) { dropSpans(); err = "BVH traversal stack overflow"; return false; }
     for (auto &sp : spans) {
         float ms = 0; cudaEventElapsedTime(&ms, sp.a, sp.b);

@@ -226,6 +226,17 @@ int cudapath_float_to_half(const float *in, uint64_t n, uint16_t *out);
  * (src/libcore/fmtconv.cpp:984-995,1104-1111,1137-1160): width*height*3 bytes.  gamma = -1 selects the sRGB curve (the ldrfilm
  * default); the hair scene files use 2.2.  Banner, Reinhard tonemapping and the PNG/JPEG encoders are not part of this path. */
 int cudapath_develop_ldr(const float *film, int width, int height, float gamma, float exposure, uint8_t *out_rgb8);
+/* Sampler.  kind 0 (default): the counter-based Philox4x32-10 stream keyed by (pixel, sample index, path vertex, seed) that replaces the sampler
+ * plugins (include/mitsuba/render/sampler.h:105-117) -- any <sampler> of a scene file selects it.  kind 1, the sampler-faithful mode: the
+ * reference's `sobol` plugin reproduced number for number -- SobolSampler (src/samplers/sobol.cpp:90-245: scramble through sampleTEA,
+ * setFilmResolution(size, bucketed), generate / advance / setSampleIndex, next1D / next2D with the skipped dimension 4) over Gruenschloss'
+ * enumeration of the (0,2)-sequence per pixel (src/samplers/sobolseq.h:59-133), with the direction numbers of src/samplers/sobolseq.cpp read from
+ * <data dir>/sobol.bin; the path tracer draws in the order renderBlock and MIPathTracer::Li do (integrator.cpp:171, path.cpp:176,210,284,
+ * marschner.cpp:473-474).  A path that needs more than 1024 dimensions fails the render with the plugin's message.  `independent`
+ * (src/samplers/independent.cpp) cannot be reproduced on a wavefront: every worker of the reference consumes ONE sequential SFMT stream whose
+ * position at a pixel depends on the lengths of all paths the worker traced before (and on which blocks the scheduler handed it). */
+int cudapath_set_sampler(cudapath_ctx *ctx, int kind, uint64_t scramble);
+int cudapath_get_sampler(cudapath_ctx *ctx);
 /* Tunables: wave size in paths (0 = default), collect traversal statistics (slower, counting kernels),
  * profile_stages (CUDA events around every stage launch). */
 int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stats, int profile_stages);

@@ -227,9 +227,9 @@ struct Scene {
                 break;
             Philox4 u = philox4x32_10(pix, samp, (uint32_t) depth, 0, k0, k1);
             /* direct illumination sampling, only for BSDFs with a smooth component (path.cpp:174-175) */
+            float e0 = u32_to_unit(u.v[0]), e1 = u32_to_unit(u.v[1]);
+            if (sob && bsdf.hasSmooth()) sob->next2D(e0, e1);                          // rRec.nextSample2D(), path.cpp:179: an argument of sampleEmitterDirect, drawn with or without emitters
             if (hasEnv && bsdf.hasSmooth()) {
-                float e0 = u32_to_unit(u.v[0]), e1 = u32_to_unit(u.v[1]);
-                if (sob) sob->next2D(e0, e1);                                          // rRec.nextSample2D(), path.cpp:179
                 EnvMap::DirectSample ds = env.sampleDirect(its.p, e0, e1);
                 V3 value(0.0f);
                 if (ds.pdf != 0) {

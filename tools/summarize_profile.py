@@ -99,9 +99,17 @@ def main():
                 if k in d:
                     f.write('| %s | %s | %s |\n' % (k, d[k], u[k]))
             f.write('\nDRAM traffic of this launch: %.1f MB (read + write).\n' % (dram / 1e6))
-        with open(os.path.join(PROF, 'k_intersect_traffic.json'), 'w') as f:
-            json.dump({'source': '%s_%s_ncu_%s.md' % (rnd, kname, tag), 'launch': 'third %s launch of bench.py --spp 8 (secondary + shadow rays of one bounce, hair-curl)' % kname,
-                       'dram_bytes': dram, 'duration_ms': float(d['gpu__time_duration.sum'].replace(',', '')) * ({'ms': 1, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}[u['gpu__time_duration.sum']])}, f, indent=1)
+        def num(k):
+            try: return float(d[k].replace(',', ''))
+            except Exception: return None
+        with open(os.path.join(PROF, 'k_trace_ncu.json' if kname == 'k_trace' else 'k_intersect_traffic.json'), 'w') as f:
+            json.dump({'source': '%s_%s_ncu_%s.md' % (rnd, kname, tag), 'launch': 'third %s launch of bench.py --spp 8 (secondary + shadow rays of one bounce, hair-curl; a launch of the 64-spp step is 8x this one)' % kname,
+                       'dram_bytes': dram,
+                       'lanes_per_instruction': num('smsp__thread_inst_executed_per_inst_executed.ratio'), 'issue_active_pct': num('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                       'dram_throughput_pct': num('dram__throughput.avg.pct_of_peak_sustained_elapsed'), 'l2_throughput_pct': num('lts__throughput.avg.pct_of_peak_sustained_elapsed'),
+                       'l2_hit_pct': num('lts__t_sector_hit_rate.pct'), 'l1_hit_pct': num('l1tex__t_sector_hit_rate.pct'), 'warps_active_pct': num('sm__warps_active.avg.pct_of_peak_sustained_active'),
+                       'registers': num('launch__registers_per_thread'), 'long_scoreboard_stall_per_issue': num('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio'),
+                       'duration_ms': float(d['gpu__time_duration.sum'].replace(',', '')) * ({'ms': 1, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}[u['gpu__time_duration.sum']])}, f, indent=1)
     # ---- full captures of the other stages (tools/gpu_evidence_stages.sh): k_shade, k_shadow, the BSDF batch kernels of config 5a
     EXTRA = ['sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fmalite.avg.pct_of_peak_sustained_active',
              'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
