@@ -281,6 +281,8 @@ struct Loader {
             }
             if (!nested) throw std::runtime_error("twosided: A nested one-sided material is required!");
             const std::string nt = nested->get("type");
+            // models/teapot/dielectric.xml nests a `dielectric`: TwoSidedBRDF::configure refuses that in the reference as well (twosided.cpp:106-108)
+            if (nt == "dielectric" || nt == "thindielectric" || nt == "roughdielectric" || nt == "marschnerdielectric") throw std::runtime_error("Only materials without a transmission component can be nested!");
             if (nt != "diffuse" && nt != "plastic" && nt != "roughplastic") throw std::runtime_error("twosided: only a nested `diffuse`, `plastic` or `roughplastic` is supported on this path");
             id = loadBsdf(*nested);
             if (!dry) check(cudapath_bsdf_set_twosided(ctx, id)); else note("twosided adapter around the nested bsdf");

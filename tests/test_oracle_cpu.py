@@ -1976,3 +1976,24 @@ def test_exr_writer(cp, tmp_path):
         if im is not None:
             assert im.shape == (h, w, 3) and np.array_equal(im[..., ::-1].astype(np.float32), want)
     assert cp.lib().cudapath_write_exr(str(tmp_path / 'no' / 'such' / 'dir.exr').encode(), img.ctypes.data_as(ctypes.c_void_p), w, h, 1) != 0
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='needs /root/reference')
+def test_every_reference_scene_file_validates(cp):
+    """Every scene file the reference ships under models/ goes through the loader's dry run: all of them parse and name only plugins of this
+    path -- except the three the reference itself cannot load: scene_dielectric2.xml is not well-formed (an unclosed <float>), teapot/dielectric.xml
+    nests a transmissive `dielectric` in `twosided` (TwoSidedBRDF::configure raises, twosided.cpp:106-108: same message here) and
+    teapot/mirror_scene.xml asks for a `mirror` plugin that src/bsdfs does not have (under an irrcache / photonmapper integrator)."""
+    import glob
+    expected_failures = {'straight-hair/scene_dielectric2.xml': 'parse error', 'teapot/dielectric.xml': 'transmission component', 'teapot/mirror_scene.xml': ''}
+    files = sorted(glob.glob('/root/reference/models/*/*.xml'))
+    assert len(files) >= 17
+    for f in files:
+        key = f.split('models/')[1]
+        if key in expected_failures:
+            with pytest.raises(cp.CudapathError, match=expected_failures[key]):
+                cp.validate_scene_xml(f)
+            continue
+        rep = cp.validate_scene_xml(f)
+        assert any(r.startswith('bsdf') for r in rep) and any(r.startswith('shape') for r in rep) and rep[-1].startswith('sampleCount'), key
+    assert not os.path.exists('/root/reference/src/bsdfs/mirror.cpp')
