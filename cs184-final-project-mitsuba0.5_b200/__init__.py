@@ -234,6 +234,9 @@ class Context:
             sa = _f32(np.broadcast_to(props.get('sigmaA', 0.22), 3))
             return _check(self._L.cudapath_add_bsdf_marschner_full(self._h, ctypes.c_float(ior(props.get('intIOR', 'amber'))), ctypes.c_float(ior(props.get('extIOR', 'air'))), _p(sa),
                                                                    ctypes.c_float(props.get('betaR', 0.1)), ctypes.c_float(props.get('scaleAngleRad', -0.1)), int(props.get('lobes', 7))))
+        if type == 'mirror':
+            # the fork's src/bsdfs/mirror.cpp: default specularReflectance 1
+            return _check(self._L.cudapath_add_bsdf_mirror(self._h, _p(_f32(np.broadcast_to(props.get('specularReflectance', 1.0), 3)))))
         if type == 'plastic':
             # src/bsdfs/plastic.cpp:140-167; defaults polypropylene / air, specular 1, diffuse 0.5
             ior = lambda v: float(_IOR[v.lower()]) if isinstance(v, str) else float(v)
@@ -256,7 +259,7 @@ class Context:
             r = _f32(np.broadcast_to(props.get('specularReflectance', 0.1), 3)); t = _f32(np.broadcast_to(props.get('specularTransmittance', 0.1), 3))
             return _check(self._L.cudapath_add_bsdf_marschnerdielectric(self._h, ctypes.c_float(ior(props.get('intIOR', 'benzene'))), ctypes.c_float(ior(props.get('extIOR', 'air'))),
                                                                         _p(d), _p(r), _p(t), ctypes.c_float(props.get('exponent', 30.0))))
-        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, marschnerdielectric, thindielectric, roughplastic, plastic, diffuse, twosided)' % type)
+        raise CudapathError('bsdf plugin "%s" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, marschnerdielectric, thindielectric, roughplastic, plastic, mirror, diffuse, twosided)' % type)
 
     def set_checkerboard(self, bsdf_id, color0=0.4, color1=0.2, uoffset=0.0, voffset=0.0, uscale=1.0, vscale=1.0):
         """`<texture type="checkerboard">` as the reflectance of a `diffuse` / the diffuseReflectance of a `plastic` BSDF (src/textures/checkerboard.cpp)."""

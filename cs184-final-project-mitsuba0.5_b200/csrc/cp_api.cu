@@ -350,6 +350,16 @@ int cudapath_add_bsdf_plastic(cudapath_ctx *ctx, float int_ior, float ext_ior, c
     return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_plastic(p, int_ior, ext_ior, d, s, nonlinear); });
 }
 
+// `mirror`, the fork's own plugin (src/bsdfs/mirror.cpp:187-221)
+int cudapath_add_bsdf_mirror(cudapath_ctx *ctx, const float s[3]) {
+    if (!ctx || !s) return fail("null argument");
+    BsdfHost b; std::memset((void *) &b.dev, 0, sizeof(b.dev));
+    b.dev.kind = 8;
+    b.dev.specular = ensure_energy_conservation(s);
+    ctx->bsdfs.push_back(b); ctx->built = false;
+    return fan_out(ctx, (int) ctx->bsdfs.size() - 1, [&](cudapath_ctx *p) { return cudapath_add_bsdf_mirror(p, s); });
+}
+
 // <texture type="checkerboard"> as the (diffuse) reflectance of a `diffuse` or `plastic` BSDF (src/textures/checkerboard.cpp:49-52,
 // src/librender/texture.cpp:81-95); the BSDF's configure() runs again on it: energy conservation over both colours (bsdf.cpp:88-113),
 // sampling weights from the average colour (plastic.cpp:199-202)
@@ -373,7 +383,7 @@ int cudapath_bsdf_set_twosided(cudapath_ctx *ctx, int bsdf_id) {
     if (!ctx) return fail("null argument");
     if (bsdf_id < 0 || bsdf_id >= (int) ctx->bsdfs.size()) return fail("unknown bsdf id");
     BsdfDev &b = ctx->bsdfs[bsdf_id].dev;
-    if (b.kind != 2 && b.kind != 4 && b.kind != 7) return fail("Only materials without a transmission component can be nested!");
+    if (b.kind != 2 && b.kind != 4 && b.kind != 7 && b.kind != 8) return fail("Only materials without a transmission component can be nested!");
     b.twoSided = 1; ctx->built = false;
     return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_bsdf_set_twosided(p, bsdf_id); });
 }

@@ -32,7 +32,8 @@ struct BsdfDev {
                          // 5 = thindielectric (src/bsdfs/thindielectric.cpp; specular reflectance in `specular`, transmittance in `diffuse`)
                          // 6 = marschnerdielectric (src/bsdfs/marschnerdielectric.cpp; transmittance in `specT`)
                          // 7 = plastic (src/bsdfs/plastic.cpp; fdrInt in `Fdr`)
-    int twoSided;        // kinds 2, 4, 7: wrapped in `twosided` (src/bsdfs/twosided.cpp) with the same nested BRDF on both sides
+                         // 8 = mirror (the fork's src/bsdfs/mirror.cpp: a delta reflection whose eval() is identically zero)
+    int twoSided;        // kinds 2, 4, 7, 8: wrapped in `twosided` (src/bsdfs/twosided.cpp) with the same nested BRDF on both sides
     // diffuse reflectance texture of kinds 2 and 7: 0 = the constant in `diffuse`, 1 = checkerboard (src/textures/checkerboard.cpp) of
     // `diffuse` (color0) and `color1` behind Texture2D's uv transform (src/librender/texture.cpp:81-121)
     int texKind;
@@ -683,12 +684,12 @@ CP_D BsdfSampleOut md_sample(const BsdfDev &b, const V3 &wi, float sx, float sy)
 // ------------------------------------------------------------------------------------------ dispatch
 // (u, v) = its.uv, only read by the textured kinds.  `twosided` around roughplastic / plastic is applied here (twosided.cpp:101-181);
 // the diffuse kind handles its own flag.
-CP_D bool bsdf_wrapped(const BsdfDev &b) { return b.twoSided && (b.kind == 4 || b.kind == 7); }
+CP_D bool bsdf_wrapped(const BsdfDev &b) { return b.twoSided && (b.kind == 4 || b.kind == 7 || b.kind == 8); }
 CP_D V3 bsdf_eval(const BsdfDev &b, V3 wi, V3 wo, bool discrete = false, float u = 0.0f, float v = 0.0f) {
     if (bsdf_wrapped(b) && !(wi.z > 0)) { wi.z *= -1; wo.z *= -1; }
     if (b.kind == 5) return td_eval(b, wi, wo, discrete);
     if (b.kind == 7) return pl_eval(b, wi, wo, discrete, u, v);
-    if (b.kind == 6 || discrete) return V3(0.0f);
+    if (b.kind == 6 || b.kind == 8 || discrete) return V3(0.0f);         // mirror.cpp:233-247: zero in both measures, as committed
     return b.kind == 0 ? kk_eval(b, wi, wo) : b.kind == 1 ? ma_eval(b, wi, wo) : b.kind == 2 ? df_eval(b, wi, wo, u, v) : b.kind == 3 ? mf_eval(b, wi, wo) : rp_eval(b, wi, wo);
 }
 CP_D float bsdf_pdf(const BsdfDev &b, V3 wi, V3 wo, bool discrete = false) {
@@ -696,13 +697,14 @@ CP_D float bsdf_pdf(const BsdfDev &b, V3 wi, V3 wo, bool discrete = false) {
     if (b.kind == 5) return td_pdf(b, wi, wo, discrete);
     if (b.kind == 6) return md_pdf(wi, wo, discrete);
     if (b.kind == 7) return pl_pdf(b, wi, wo, discrete);
+    if (b.kind == 8) return discrete ? 1.0f : 0.0f;                       // mirror.cpp:249-254
     if (discrete) return 0.0f;
     return b.kind == 0 ? kk_pdf(b, wi, wo) : b.kind == 1 ? 1.0f : b.kind == 2 ? df_pdf(b, wi, wo) : b.kind == 3 ? mf_pdf(b, wi, wo) : rp_pdf(b, wi, wo);
 }
 // true for BSDFs whose sample() pulls more numbers from the sampler than the two it is handed (fixed Marschner: 4)
 CP_D bool bsdf_draws_extra(const BsdfDev &b) { return b.kind == 3; }
 // BSDF::getType() & ESmooth (bsdf.h:278): everything except the thin dielectric, whose two components are discrete
-CP_D bool bsdf_has_smooth(const BsdfDev &b) { return b.kind != 5; }
+CP_D bool bsdf_has_smooth(const BsdfDev &b) { return b.kind != 5 && b.kind != 8; }
 // eval() in the solid-angle measure is identically zero: emitter samples are drawn and counted, but can never contribute
 CP_D bool bsdf_eval_is_zero(const BsdfDev &b) { return b.kind == 6; }
 CP_D BsdfSampleOut bsdf_sample(const BsdfDev &b, V3 wi, float sx, float sy, const float4 &extra, float u = 0.0f, float v = 0.0f) {
@@ -710,6 +712,12 @@ CP_D BsdfSampleOut bsdf_sample(const BsdfDev &b, V3 wi, float sx, float sy, cons
     if (b.kind == 6) return md_sample(b, wi, sx, sy);
     bool flipped = false;
     if (bsdf_wrapped(b) && wi.z < 0) { wi.z *= -1; flipped = true; }
+    if (b.kind == 8) {                                                   // mirror.cpp:256-276
+        BsdfSampleOut m; m.wo = V3(0.0f); m.weight = V3(0.0f); m.pdf = 0.0f; m.type = 0; m.component = -1;
+        if (wi.z > 0) { m.component = 0; m.type = EDeltaReflection; m.wo = kk_reflect(wi); m.pdf = 1.0f; m.weight = b.specular; }
+        if (flipped && !isZero(m.weight) && m.pdf != 0) { m.wo.z *= -1; m.component += 1; }
+        return m;
+    }
     BsdfSampleOut r = b.kind == 0 ? kk_sample(b, wi, sx, sy) : b.kind == 1 ? ma_sample(b, wi, sx, sy) : b.kind == 2 ? df_sample(b, wi, sx, sy, u, v)
          : b.kind == 3 ? mf_sample(b, wi, extra.x, extra.y, extra.z, extra.w) : b.kind == 7 ? pl_sample(b, wi, sx, sy, u, v) : rp_sample(b, wi, sx, sy);
     if (flipped && !isZero(r.weight) && r.pdf != 0) { r.wo.z *= -1; r.component += 2; }

@@ -283,7 +283,7 @@ struct Loader {
             const std::string nt = nested->get("type");
             // models/teapot/dielectric.xml nests a `dielectric`: TwoSidedBRDF::configure refuses that in the reference as well (twosided.cpp:106-108)
             if (nt == "dielectric" || nt == "thindielectric" || nt == "roughdielectric" || nt == "marschnerdielectric") throw std::runtime_error("Only materials without a transmission component can be nested!");
-            if (nt != "diffuse" && nt != "plastic" && nt != "roughplastic") throw std::runtime_error("twosided: only a nested `diffuse`, `plastic` or `roughplastic` is supported on this path");
+            if (nt != "diffuse" && nt != "plastic" && nt != "roughplastic" && nt != "mirror") throw std::runtime_error("twosided: only a nested `diffuse`, `plastic`, `roughplastic` or `mirror` is supported on this path");
             id = loadBsdf(*nested);
             if (!dry) check(cudapath_bsdf_set_twosided(ctx, id)); else note("twosided adapter around the nested bsdf");
         } else if (type == "diffuse") {
@@ -294,6 +294,10 @@ struct Loader {
             check(id);
             const Node *tex = child(n, "texture", "reflectance"); if (!tex) tex = child(n, "texture", "diffuseReflectance");
             if (tex) setTexture(id, *tex);
+        } else if (type == "mirror") {                 // the fork's src/bsdfs/mirror.cpp
+            if (child(n, "texture", "specularReflectance")) throw std::runtime_error("mirror: a textured specularReflectance is not supported");
+            float sp[3]; getColor(n, "specularReflectance", 1.0f, sp);
+            id = (dry ? note("bsdf mirror") : cudapath_add_bsdf_mirror(ctx, sp));
         } else if (type == "plastic") {
             auto ior = [&](const char *name, double def) {
                 if (child(n, "float", name)) return getFloat(n, name, def);
@@ -331,7 +335,7 @@ struct Loader {
                 id = (dry ? note("bsdf marschnerdielectric") : cudapath_add_bsdf_marschnerdielectric(ctx, (float) ior("intIOR", 1.501), (float) ior("extIOR", 1.000277), d, r, t,
                                                                                                       (float) getFloat(n, "exponent", 30.0)));
             }
-        } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, marschner_full, marschnerdielectric, thindielectric, roughplastic, plastic, diffuse, twosided)");
+        } else throw std::runtime_error("bsdf plugin \"" + type + "\" is outside the hair hot path (supported: kajiyakay, marschner, marschner_fixed, marschner_full, marschnerdielectric, thindielectric, roughplastic, plastic, mirror, diffuse, twosided)");
         check(id);
         if (n.has("id")) bsdfIds[n.get("id")] = id;
         return id;

@@ -92,12 +92,15 @@ int cudapath_add_bsdf_marschnerdielectric(cudapath_ctx *ctx, float int_ior, floa
  * diffuse base, fdrInt / fdrExt from fresnelDiffuseReflectance (src/libcore/util.cpp:807-862).  Reference defaults: int_ior 1.49
  * (polypropylene), ext_ior 1.000277 (air), specular 1, diffuse 0.5.  Returns the bsdf id. */
 int cudapath_add_bsdf_plastic(cudapath_ctx *ctx, float int_ior, float ext_ior, const float diffuse_reflectance[3], const float specular_reflectance[3], int nonlinear);
+/* `mirror`, a plugin the fork adds (src/bsdfs/mirror.cpp:187-276; models/teapot/mirror_scene.xml:32-36): one delta reflection on the front side, reproduced as
+ * committed -- eval() is zero in both measures, pdf() is 1 in the discrete one.  Reference default: specularReflectance 1.  Returns the bsdf id. */
+int cudapath_add_bsdf_mirror(cudapath_ctx *ctx, const float specular_reflectance[3]);
 /* <texture type="checkerboard"> (src/textures/checkerboard.cpp:49-72 behind Texture2D, src/librender/texture.cpp:81-121) as the `reflectance` of a
  * `diffuse` or the `diffuseReflectance` of a `plastic` BSDF (models/teapot/scene.xml:43-52); the BSDF's configure() runs again on it.
  * Reference defaults: color0 0.4, color1 0.2, offsets 0, scales 1. */
 int cudapath_bsdf_set_checkerboard(cudapath_ctx *ctx, int bsdf_id, const float color0[3], const float color1[3], float uoffset, float voffset,
                                    float uscale, float vscale);
-/* <bsdf type="twosided"> around an existing `diffuse`, `roughplastic` or `plastic` BSDF with the same nested BRDF on both sides:
+/* <bsdf type="twosided"> around an existing `diffuse`, `roughplastic`, `plastic` or `mirror` BSDF with the same nested BRDF on both sides:
  * TwoSidedBRDF::configure / eval / pdf / sample, src/bsdfs/twosided.cpp:84-181. */
 int cudapath_bsdf_set_twosided(cudapath_ctx *ctx, int bsdf_id);
 /* fresnelDiffuseReflectance(eta, fast = false), src/libcore/util.cpp:814-862 (host only: adaptive Gauss-Lobatto, src/libcore/quad.cpp:287-420). */

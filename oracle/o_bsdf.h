@@ -1023,6 +1023,24 @@ struct SmoothPlastic {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Mirror (`mirror`, the fork's own plugin: models/teapot/mirror_scene.xml:32-36) -- src/bsdfs/mirror.cpp:187-199 (ctor), :210-221 (configure),
+// :233-247 (eval), :249-254 (pdf), :256-276 (sample).  One EDeltaReflection component.  As committed: eval() is identically zero (it asks for
+// ESolidAngle AND for a flag that needs EDiscrete), pdf() is 1 in the discrete measure whatever the directions, sample() mirrors wi on the front side.
+// ---------------------------------------------------------------------------------------------
+struct Mirror {
+    V3 specR;
+    void configure(V3 r) { Texture2D t; t.setConstant(r); t.ensureEnergyConservation(); specR = t.color0; }
+    V3 eval(const V3 &, const V3 &, bool) const { return V3(0.0f); }
+    float pdf(const V3 &, const V3 &, bool discrete) const { return discrete ? 1.0f : 0.0f; }
+    BSDFSample sample(const V3 &wi, float, float) const {
+        BSDFSample r; r.weight = V3(0.0f); r.pdf = 0;
+        if (wi.z <= 0) return r;
+        r.sampledComponent = 0; r.sampledType = EDeltaReflection; r.wo = V3(-wi.x, -wi.y, wi.z); r.eta = 1.0f; r.pdf = 1.0f; r.weight = specR;
+        return r;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // ThinDielectric (`thindielectric`, models/straight-hair/scene_thindielectric.xml) -- src/bsdfs/thindielectric.cpp:73-300.
 // Two discrete components (EDeltaReflection, ENull), both sides; nothing smooth, so the path tracer skips emitter sampling
 // at such a vertex (path.cpp:174-175).  eval/pdf are non-zero only in the discrete measure.

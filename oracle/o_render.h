@@ -122,15 +122,17 @@ struct BSDFAny {
     ThinDielectric td;                     // kind 5: `thindielectric` (models/straight-hair/scene_thindielectric.xml)
     MarschnerDielectric md;                // kind 6: `marschnerdielectric` (models/straight-hair/scene_dielectric*.xml)
     SmoothPlastic pl;                      // kind 7: `plastic` (models/teapot/scene.xml:31-38)
+    Mirror mi;                             // kind 8: `mirror` (the fork's plugin, models/teapot/mirror_scene.xml:32-36)
     // `twosided` (src/bsdfs/twosided.cpp:101-181) around a roughplastic / plastic with the same nested BRDF on both sides; the diffuse
     // kind keeps its own flag (SmoothDiffuse::twoSided)
     bool twoSided = false;
-    int componentCount() const { return kind == 2 ? 1 : 2; }
+    int componentCount() const { return (kind == 2 || kind == 8) ? 1 : 2; }
     // measure: ESolidAngle unless `discrete` (only the dielectric kinds and `plastic` have discrete components); (u, v) = its.uv
     V3 evalOne(const V3 &wi, const V3 &wo, bool discrete, float u, float v) const {
         if (kind == 5) return td.eval(wi, wo, discrete);
         if (kind == 6) return md.eval(wi, wo, discrete);
         if (kind == 7) return pl.eval(wi, wo, discrete, u, v);
+        if (kind == 8) return mi.eval(wi, wo, discrete);
         if (discrete) return V3(0.0f);
         return kind == 0 ? kk.eval(wi, wo) : kind == 1 ? ma->eval(wi, wo) : kind == 2 ? df.eval(wi, wo, u, v) : kind == 3 ? mf->eval(wi, wo) : rp->eval(wi, wo);
     }
@@ -138,6 +140,7 @@ struct BSDFAny {
         if (kind == 5) return td.pdf(wi, wo, discrete);
         if (kind == 6) return md.pdf(wi, wo, discrete);
         if (kind == 7) return pl.pdf(wi, wo, discrete);
+        if (kind == 8) return mi.pdf(wi, wo, discrete);
         if (discrete) return 0.0f;
         return kind == 0 ? kk.pdf(wi, wo) : kind == 1 ? ma->pdf(wi, wo) : kind == 2 ? df.pdf(wi, wo) : kind == 3 ? mf->pdf(wi, wo) : rp->pdf(wi, wo);
     }
@@ -145,6 +148,7 @@ struct BSDFAny {
         if (kind == 5) return td.sample(wi, sx, sy);
         if (kind == 6) return md.sample(wi, sx, sy);
         if (kind == 7) return pl.sample(wi, sx, sy, u, v);
+        if (kind == 8) return mi.sample(wi, sx, sy);
         return kind == 0 ? kk.sample(wi, sx, sy) : kind == 1 ? ma->sample(wi, sx, sy) : kind == 2 ? df.sample(wi, sx, sy, u, v)
              : kind == 3 ? mf->sample(wi, extra[0], extra[1], extra[2], extra[3]) : rp->sample(wi, sx, sy);
     }
@@ -165,7 +169,7 @@ struct BSDFAny {
         return r;
     }
     // BSDF::getType() & ESmooth: the thin dielectric has only discrete components (path.cpp:174-175 then skips emitter sampling)
-    bool hasSmooth() const { return kind != 5; }
+    bool hasSmooth() const { return kind != 5 && kind != 8; }
     bool drawsExtra() const { return kind == 3; }
 };
 

@@ -161,6 +161,16 @@ int orc_add_bsdf_plastic(void *sp, float intIOR, float extIOR, const float *diff
     return (int) s->bsdfs.size() - 1;
     ORC_CATCH
 }
+// `mirror` plugin of the fork (src/bsdfs/mirror.cpp)
+int orc_add_bsdf_mirror(void *sp, const float *specular) {
+    ORC_TRY
+    Scene *s = (Scene *) sp;
+    BSDFAny b; b.kind = 8;
+    b.mi.configure(V3(specular[0], specular[1], specular[2]));
+    s->bsdfs.push_back(b);
+    return (int) s->bsdfs.size() - 1;
+    ORC_CATCH
+}
 // <texture type="checkerboard"> as the (diffuse) reflectance of a `diffuse` or `plastic` BSDF: the BSDF is configured again with it
 int orc_bsdf_set_checkerboard(void *sp, int bsdf, const float *color0, const float *color1, float uoffset, float voffset, float uscale, float vscale) {
     ORC_TRY
@@ -180,7 +190,7 @@ int orc_bsdf_set_twosided(void *sp, int bsdf) {
     Scene *s = (Scene *) sp;
     BSDFAny &b = s->bsdfs.at(bsdf);
     if (b.kind == 2) b.df.twoSided = true;
-    else if (b.kind == 4 || b.kind == 7) b.twoSided = true;
+    else if (b.kind == 4 || b.kind == 7 || b.kind == 8) b.twoSided = true;
     else throw std::runtime_error("twosided: only materials without a transmission component can be nested");
     return 0;
     ORC_CATCH

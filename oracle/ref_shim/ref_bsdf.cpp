@@ -51,6 +51,7 @@ void *ref_create_RoughPlastic(const Properties *);
 void *ref_create_SmoothDiffuse(const Properties *);
 void *ref_create_TwoSidedBRDF(const Properties *);
 void *ref_create_SmoothPlastic(const Properties *);
+void *ref_create_Mirror(const Properties *);
 void *ref_create_MarschnerFull(const Properties *);           // oracle/_ref/marschner_full.cpp: marschner.cpp with the five edits listed in oracle/Makefile
 float ref_fresnel_diffuse_reflectance(float eta) { return fresnelDiffuseReflectance(eta, false); }
 
@@ -73,10 +74,11 @@ void *ref_bsdf_create(const char *plugin, int nFloat, const char **floatNames, c
         else if (p == "roughplastic") b = (BSDF *) ref_create_RoughPlastic(&props);
         else if (p == "diffuse") b = (BSDF *) ref_create_SmoothDiffuse(&props);
         else if (p == "plastic") b = (BSDF *) ref_create_SmoothPlastic(&props);
+        else if (p == "mirror") b = (BSDF *) ref_create_Mirror(&props);
         else if (p == "marschner_full") b = (BSDF *) ref_create_MarschnerFull(&props);
-        else if (p == "twosided" || p == "twosided:plastic" || p == "twosided:roughplastic") {  // <bsdf type="twosided"><bsdf type="diffuse | plastic | roughplastic"/></bsdf>
+        else if (p == "twosided" || p == "twosided:plastic" || p == "twosided:roughplastic" || p == "twosided:mirror") {  // <bsdf type="twosided"><bsdf type="diffuse | plastic | roughplastic"/></bsdf>
             b = (BSDF *) ref_create_TwoSidedBRDF(&props);
-            BSDF *nested = (BSDF *) (p == "twosided" ? ref_create_SmoothDiffuse(&props) : p == "twosided:plastic" ? ref_create_SmoothPlastic(&props) : ref_create_RoughPlastic(&props));
+            BSDF *nested = (BSDF *) (p == "twosided" ? ref_create_SmoothDiffuse(&props) : p == "twosided:plastic" ? ref_create_SmoothPlastic(&props) : p == "twosided:mirror" ? ref_create_Mirror(&props) : ref_create_RoughPlastic(&props));
             nested->configure();
             b->addChild("", nested);
         }

@@ -144,6 +144,8 @@ class Scene:
         if type in ('diffuse', 'twosided'):
             r = f32(np.broadcast_to(props.get('reflectance', 0.5), 3))
             return check(self.L.orc_add_bsdf_diffuse(self.h, p(r), 1 if (type == 'twosided' or props.get('twoSided', False)) else 0))
+        if type == 'mirror':
+            return check(self.L.orc_add_bsdf_mirror(self.h, p(f32(np.broadcast_to(props.get('specularReflectance', 1.0), 3)))))
         if type == 'plastic':
             d = f32(np.broadcast_to(props.get('diffuseReflectance', 0.5), 3)); s = f32(np.broadcast_to(props.get('specularReflectance', 1.0), 3))
             return check(self.L.orc_add_bsdf_plastic(self.h, ctypes.c_float(props.get('intIOR', 1.49)), ctypes.c_float(props.get('extIOR', 1.000277)), p(d), p(s),

@@ -1241,7 +1241,8 @@ def _teapot_materials(s):
     floor = s.add_bsdf('diffuse', reflectance=0.5); s.set_checkerboard(floor, (0.725, 0.71, 0.68), (0.325, 0.31, 0.25), 0, 0, 10, 10); s.set_twosided(floor)
     pl = s.add_bsdf('plastic', diffuseReflectance=(0.2, 0.5, 0.7), specularReflectance=(0.9, 0.8, 1.3)); s.set_checkerboard(pl, (1.4, 0.3, 0.2), (0.1, 0.2, 0.9), 0.25, -0.5, 3, 0.5)
     rp = s.add_bsdf('roughplastic', intIOR=1.55, extIOR=1.0, alpha=0.2, distribution='ggx', diffuseReflectance=(0.4, 0.3, 0.2)); s.set_twosided(rp)
-    return mat, floor, pl, rp
+    mi = s.add_bsdf('mirror', specularReflectance=(0.9, 0.8, 0.7)); s.set_twosided(mi)          # models/teapot/mirror_scene.xml:32-36 (the fork's own plugin)
+    return mat, floor, pl, rp, mi
 
 
 @pytest.mark.gpu
@@ -1279,11 +1280,13 @@ def test_plastic_checkerboard_twosided_bit_exact(cp, oracle):
 
 def _teapot_like_scene(s, cp):
     """A rectangle floor (the matrix of models/teapot/scene.xml:57-59), a textured UV sphere and a plastic ellipsoid."""
-    mat, floor, pl, rp = _teapot_materials(s)
+    mat, floor, pl, rp, mi = _teapot_materials(s)
     tw = np.array([-39.9766, 39.9766, -1.74743e-006, 0, 4.94249e-006, 2.47125e-006, -56.5355, 0, -39.9766, -39.9766, -5.2423e-006, 0, 0, 0, 0, 1], np.float32).reshape(4, 4)
     s.add_rectangle(tw, False, floor) if hasattr(s, 'L') else s.add_rectangle(floor, tw, False)
     xyz, idx, nrm = cp.scenes.gen_ellipsoid((0, 6, 0), (5, 6, 5), 24)
     s.add_mesh(xyz, idx, mat, normals=nrm)
+    xyz3, idx3, nrm3 = cp.scenes.gen_ellipsoid((-9, 2.5, -9), (2.5, 2.5, 2.5), 12)
+    s.add_mesh(xyz3, idx3, mi, normals=nrm3)
     xyz2, idx2, nrm2 = cp.scenes.gen_ellipsoid((11, 3, -4), (3, 3, 3), 16)
     uvs = np.stack([np.arctan2(xyz2[:, 2] + 4, xyz2[:, 0] - 11) / (2 * np.pi) + 0.5, (xyz2[:, 1]) / 6.0], axis=1).astype(np.float32)
     s.add_mesh(xyz2, idx2, pl, normals=nrm2, uvs=uvs)
@@ -1312,7 +1315,7 @@ def test_rectangle_and_mesh_uv_parity(cp, oracle):
         os_, op, ot, orec = osc.intersect_full(oo, dd, mint, np.inf); ouv, ogn = osc.intersect_uv(oo, dd, mint, np.inf)
         same = (gs == os_) & (gp == op)
         assert same.mean() > 0.999 and np.array_equal(gs >= 0, os_ >= 0)        # shared-edge ties of the two spheres only
-        for shape in (0, 1, 2, 3):
+        for shape in (0, 1, 2, 3, 4):
             assert ((os_ == shape) & same).sum() > 100, shape
         k = same & (os_ >= 0)
         assert np.array_equal(gt[k], ot[k]) and np.array_equal(guv[k], ouv[k]) and np.array_equal(ggn[k], ogn[k]) and np.array_equal(grec[k], orec[k])
@@ -1470,3 +1473,22 @@ def test_sobol_sampler_dimension_limit_and_file_policy(cp, tmp_path):
         c.load_xml(path)
     c.close()
     c = cp.Context(0); assert c.load_xml(path) == 4; c.close()                     # the default policy: any sampler type selects the Philox stream
+
+
+def test_teapot_like_scene_with_mirror_renders_like_the_oracle(cp, oracle):
+    """The flattened-array path for the whole teapot family at once: rectangle floor (checkerboard, two-sided), a two-sided plastic ellipsoid, a textured
+    plastic sphere with uv, a two-sided `mirror` sphere (delta reflection: no emitter sampling, MIS weight 1 on the escape) and a flipped roughplastic
+    rectangle, under the sunsky: film against the oracle's."""
+    ctx = cp.Context(0); osc = oracle.Scene()
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params('straight-hair'))
+    cam = np.array([-0.00550949, -0.342144, -0.939631, 23.895, 1.07844e-005, 0.939646, -0.342149, 11.2207, 0.999985, -0.00189103, -0.00519335, 0.0400773, 0, 0, 0, 1], np.float32).reshape(4, 4)
+    for s in (ctx, osc):
+        _teapot_like_scene(s, cp)
+        s.set_envmap(env); s.set_camera(cam, 35.0, width=96, height=54); s.set_film('tent'); s.set_integrator(maxDepth=8, rrDepth=5, strictNormals=True)
+        s.build()
+    g = ctx.render(8, seed=9); st = ctx.stats(); o = osc.render(8, seed=9)
+    a, b = cp.develop(g), cp.develop(o)
+    close = np.abs(a - b).max(axis=2) <= 1e-3 * (np.abs(b).max(axis=2) + 1e-3)
+    assert b.sum() > 0 and close.mean() > 0.995 and rel_mse(a, b) < 1e-4, (close.mean(), rel_mse(a, b))
+    assert abs(st['rays'] - osc.last_stats['rays']) <= 2e-3 * osc.last_stats['rays'] and abs(st['shadow_rays'] - osc.last_stats['shadow_rays']) <= 2e-3 * osc.last_stats['shadow_rays']
+    ctx.close()
