@@ -65,7 +65,11 @@ __global__ void __launch_bounds__(256) k_raygen(SceneDev S, WaveParams wp, PathQ
 __device__ __forceinline__ float mi_weight(float pdfA, float pdfB) { pdfA *= pdfA; pdfB *= pdfB; return pdfA / (pdfA + pdfB); } // path.cpp:296-300
 
 #ifndef CP_SHADE_MIN_BLOCKS
-#define CP_SHADE_MIN_BLOCKS 4
+#ifdef CP_FAST_MATH
+#define CP_SHADE_MIN_BLOCKS 5      // 96 registers, 64 B of spills: 280 / 280 vs 274 / 257 Mpaths/s at 4 CTAs (120 registers) and 277 / 273 at 6, two interleaved rounds (round 2, g12)
+#else
+#define CP_SHADE_MIN_BLOCKS 4      // the strict mode (fp64-evaluated elementary functions) needs its 122 registers
+#endif
 #endif
 __global__ void __launch_bounds__(128, CP_SHADE_MIN_BLOCKS) k_shade(SceneDev S, WaveParams wp, PathQueue in, const uint32_t *__restrict__ nPtr, const float4 *__restrict__ hitPT,
                                                const uint32_t *__restrict__ hitPrim, PathQueue out, ShadowQueue sq, float4 *liAcc,
