@@ -132,9 +132,8 @@ def make_context(cudapath, sc, shapes, env, device):
 
 
 def sample_range(total_spp, rank, world):
-    base, rem = divmod(int(total_spp), world)
-    begin = rank * base + min(rank, rem)
-    return begin, begin + base + (1 if rank < rem else 0)
+    import cudapath
+    return cudapath.dist.sample_range(total_spp, rank, world)        # the host-side split the gloo test covers (tests/test_dist_gloo.py)
 
 
 def run_reference(args, rank, world):
@@ -423,7 +422,7 @@ def main():
         if s_end > s_begin:
             ctx.render_into(film.data_ptr(), total_spp, seed=seed, sample_begin=s_begin, sample_end=s_end, stream=stream.cuda_stream)
         if world > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+            cudapath.dist.reduce_film(film, dst=0)
 
     sampler = ClockSampler(local); sampler.start()
     for w in range(args.warmup):
@@ -495,7 +494,7 @@ def main():
                 film.zero_()
                 if s_end > s_begin:
                     c2.render_into(film.data_ptr(), total_spp, seed=2000 + k, sample_begin=s_begin, sample_end=s_end, stream=stream.cuda_stream)
-                dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+                cudapath.dist.reduce_film(film, dst=0)
                 if rank == 0:
                     host_film.copy_(film, non_blocking=True)
             torch.cuda.synchronize()

@@ -1492,3 +1492,22 @@ def test_teapot_like_scene_with_mirror_renders_like_the_oracle(cp, oracle):
     assert b.sum() > 0 and close.mean() > 0.995 and rel_mse(a, b) < 1e-4, (close.mean(), rel_mse(a, b))
     assert abs(st['rays'] - osc.last_stats['rays']) <= 2e-3 * osc.last_stats['rays'] and abs(st['shadow_rays'] - osc.last_stats['shadow_rays']) <= 2e-3 * osc.last_stats['shadow_rays']
     ctx.close()
+
+
+def test_sobol_sampler_at_full_size(cp, oracle):
+    """The sampler-faithful mode on BASELINE.json configs[0] at its full size (straight-hair, all fibers, 512x512 at 16 spp: enumerated indices up to
+    2^22, the last sample index of every pixel): device film against the oracle's, sample for sample."""
+    name = 'straight-hair'
+    sc = cp.scenes.SCENES[name]; W, H, spp = sc['width'], sc['height'], sc['spp']
+    ctx = cp.scene_from_description(name, scale=1.0); ctx.set_sampler('sobol'); ctx.build()
+    g = ctx.render(spp, seed=3, sample_begin=spp - 1, sample_end=spp); st = ctx.stats()
+    ctx.close()
+    env = cp.bake_sunsky(**cp.scenes.sunsky_params(name))
+    osc = oracle.scene_from_description(name, scale=1.0, envmap=env); osc.set_sampler('sobol')
+    o = osc.render(spp, seed=3, sample_begin=spp - 1, sample_end=spp)
+    assert st['paths'] == W * H == osc.last_stats['paths']
+    assert np.abs(g[..., 4] - o[..., 4]).max() <= 1e-4 * o[..., 4].max()
+    a, b = cp.develop(g), cp.develop(o)
+    close = np.abs(a - b).max(axis=2) <= 1e-3 * (np.abs(b).max(axis=2) + 1e-3)
+    assert close.mean() > 0.998 and rel_mse(a, b) < 1e-3, (close.mean(), rel_mse(a, b))
+    assert abs(st['rays'] - osc.last_stats['rays']) <= 2e-4 * osc.last_stats['rays']
