@@ -879,3 +879,24 @@ void orc_half_roundtrip(const float *in, int n, uint16_t *outHalf, float *outFlo
 }
 
 } // extern "C"
+
+#ifdef ORC_FAST_STATS
+extern "C" void orc_fast_stats(uint64_t *out5) {
+    out5[0] = orc::Geometry::stRays.exchange(0); out5[1] = orc::Geometry::stNodes.exchange(0); out5[2] = orc::Geometry::stPre.exchange(0);
+    out5[3] = orc::Geometry::stExact.exchange(0); out5[4] = orc::Geometry::stLeafPop.exchange(0);
+}
+// tree metrics: out[0] wide nodes, out[1] refs, out[2] sum area(inner child boxes)/area(root), out[3] sum area(ref boxes)/area(root), out[4] max depth, out[5] mean ref depth, out[6] mean fill
+extern "C" void orc_fast_tree_metrics(void *sp, double *out) {
+    using namespace orc;
+    Scene *s = (Scene *) sp; const auto &W = s->geo.wide;
+    auto area = [&](const Geometry::Wide &w, int k) { double ex = w.hi[0][k] - w.lo[0][k], ey = w.hi[1][k] - w.lo[1][k], ez = w.hi[2][k] - w.lo[2][k]; return ex * ey + ey * ez + ez * ex; };
+    double rootA = 0; { double lo[3] = {1e30, 1e30, 1e30}, hi[3] = {-1e30, -1e30, -1e30}; for (int k = 0; k < 8; ++k) if (W[0].child[k] != 0xffffffffu) for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], (double) W[0].lo[c][k]); hi[c] = std::max(hi[c], (double) W[0].hi[c][k]); }
+      double ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2]; rootA = ex * ey + ey * ez + ez * ex; }
+    double sumInner = 0, sumRef = 0, depthSum = 0, fill = 0; uint64_t refs = 0; int maxDepth = 0;
+    std::vector<std::pair<uint32_t, int>> st; st.push_back({0u, 1});
+    while (!st.empty()) { auto [i, dpt] = st.back(); st.pop_back(); maxDepth = std::max(maxDepth, dpt);
+        for (int k = 0; k < 8; ++k) { uint32_t c = W[i].child[k]; if (c == 0xffffffffu) continue; fill += 1;
+            if (c & 0x80000000u) { sumRef += area(W[i], k) / rootA; refs++; depthSum += dpt; } else { sumInner += area(W[i], k) / rootA; st.push_back({c, dpt + 1}); } } }
+    out[0] = (double) W.size(); out[1] = (double) refs; out[2] = sumInner; out[3] = sumRef; out[4] = maxDepth; out[5] = depthSum / refs; out[6] = fill / W.size();
+}
+#endif
