@@ -255,6 +255,8 @@ def stage_rooflines(prof, cnt, hbm_peak, l2_peak, sm_mhz, peak_src, scene):
     splat = {'kernel': 'k_splat (9 filter taps x 5 fp32 atomics per path)', 'bound': 'l2 atomics', 'achieved': (16.0 + 180.0) * cnt['paths'] / t_sp / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
              'frac': (16.0 + 180.0) * cnt['paths'] / t_sp / 1e9 / hbm_peak, 'ms': prof['splat_ms'], 'note': 'held against the HBM peak for lack of an atomic-throughput peak'}
     trace['stage_share_of_step'] = {k: prof[k + '_ms'] / max(prof['render_ms'], 1e-9) for k in ('trace', 'shade', 'sort', 'raygen', 'splat')}
+    # sum of the per-launch stage times against the render time of the same (profiled) pass: the rest is launch gaps / host round trips
+    trace['profiled_pass'] = {'render_ms': prof['render_ms'], 'stage_sum_ms': sum(prof[k + '_ms'] for k in ('trace', 'shade', 'sort', 'raygen', 'splat'))}
     head = {k: trace[k] for k in ('kernel', 'bound', 'achieved', 'peak', 'unit', 'frac', 'mrays_per_s', 'avg_launch_ms', 'launches_per_step')}
     trace['stages'] = [head, shade, sort, raygen, splat]
     trace['peak_sources'] = {'hbm': peak_src, 'l2': trace['peak_source'], 'fp32': '148 SMs x 128 lanes x 2 x %.0f MHz' % sm_mhz}

@@ -341,7 +341,8 @@ class Context:
         _check(self._L.cudapath_set_options(self._h, ctypes.c_uint32(wave_size), 1 if collect_stats else 0, 1 if profile_stages else 0))
 
     def set_pixel_shard(self, index=0, count=1):
-        """Render only the 64x64-pixel blocks owned by shard `index` of `count` (the films of all shards add up to the image)."""
+        """Render only the pixel blocks owned by shard `index` of `count` (the films of all shards add up to the image; block side 8 / 16 / 32
+        pixels, CUDAPATH_SHARD_BLOCK)."""
         _check(self._L.cudapath_set_pixel_shard(self._h, ctypes.c_uint32(index), ctypes.c_uint32(count)))
 
     def set_math_mode(self, mode):
@@ -353,7 +354,7 @@ class Context:
     def math_mode(self):
         return 'strict' if self._L.cudapath_get_math_mode(self._h) == 1 else 'fast'
 
-    def set_build_options(self, max_split=8):
+    def set_build_options(self, max_split=16):
         _check(self._L.cudapath_set_build_options(self._h, int(max_split)))
 
     def load_xml(self, filename, defines=None):

@@ -81,7 +81,7 @@ struct cudapath_ctx {
     bool built = false;
     Wavefront wf;
     uint32_t waveSize = 0; int collectStats = 0, profileStages = 0;     // 0 = sized from the free device memory at render time
-    int maxSplit = 8;
+    int maxSplit = getenv("CUDAPATH_MAX_SPLIT") ? std::max(1, std::min(64, atoi(getenv("CUDAPATH_MAX_SPLIT")))) : 16;    // cudapath_set_build_options; hair-curl: 286 / 299 / 311 / 322 / 328 Mpaths/s at 8 / 12 / 16 / 24 / 32 (build 19 ms per 32 M references)
     uint32_t shardIndex = 0, shardCount = 1;     // cudapath_set_pixel_shard
     float leafSplitCost = getenv("CUDAPATH_LEAF_SPLIT_COST") ? (float) atof(getenv("CUDAPATH_LEAF_SPLIT_COST")) : 1.0f;    // see k_collapse (cp_bvh.cu); < 0: leaves of up to CP_LEAF_MAX references, never opened
     int sortRays = getenv("CUDAPATH_NO_SORT") ? 0 : 1;
@@ -898,6 +898,7 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
     RenderStats rs; std::string err;
     ctx->wf.sortRays = ctx->sortRays != 0; ctx->wf.fastMath = ctx->fastMath != 0;
     ctx->wf.shardIndex = ctx->shardIndex; ctx->wf.shardCount = ctx->shardCount;
+    if (const char *e = getenv("CUDAPATH_SHARD_BLOCK")) { const int px = atoi(e); uint32_t sh = 0; while (sh < 6u && (16 << sh) <= px) ++sh; ctx->wf.shardBlockShift = sh; }     // pixels per block side: 8, 16, 32 (default) ... 512
     if (const char *e = getenv("CUDAPATH_RUNAHEAD_MAX")) ctx->wf.runAheadMax = (uint32_t) strtoul(e, nullptr, 0);
     ctx->wf.cancelRequested.store(0); ctx->wf.inRender.store(1);
     struct RenderScope { Wavefront &w; cudaEvent_t a, b; ~RenderScope() { w.inRender.store(0); w.cancelRequested.store(0); cudaEventDestroy(a); cudaEventDestroy(b); } } scope_{ctx->wf, e0, e1};

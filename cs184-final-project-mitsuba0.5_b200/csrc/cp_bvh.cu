@@ -6,7 +6,7 @@
 // bit-compatible with the reference: the segment list (hair.cpp:117-124), the per-shape bounds
 // (union of getAABB(index), hair.cpp:368-397, gkdtree.h:997-1002) and the scene bounds.
 //
-// Pipeline (all on the device): segment compaction -> bounds + centroid box -> 63-bit Morton keys ->
+// Pipeline (all on the device): segment compaction -> bounds + centroid box -> 48-bit Morton keys on a cubic grid ->
 // radix sort (cub::DeviceRadixSort, build-time only) -> Karras 2012 binary radix tree -> bottom-up refit
 // -> collapse into 128-byte 4-wide nodes with leaves of up to CP_LEAF_MAX consecutive sorted segments.
 #include "cp_scene.cuh"
@@ -181,6 +181,11 @@ __global__ void k_rect_bounds(MeshDev mesh, uint32_t refBase, ShapeDev *shapes, 
     refPrim[refBase + j] = CP_TRI_FLAG | CP_RECT_FLAG | j;
 }
 
+// Grid bits per axis of the Morton key.  16 bits (cells of 1.5e-5 of the scene's largest extent) order hair references as well as 21 do and the
+// radix sort of the 48-bit keys takes six 8-bit passes instead of eight.
+#ifndef CP_MORTON_BITS
+#define CP_MORTON_BITS 16
+#endif
 __device__ __forceinline__ uint64_t expandBits21(uint64_t v) {
     v &= 0x1fffffull;
     v = (v | v << 32) & 0x1f00000000ffffull;
@@ -190,16 +195,19 @@ __device__ __forceinline__ uint64_t expandBits21(uint64_t v) {
     v = (v | v << 2) & 0x1249249249249249ull;
     return v;
 }
-__global__ void k_morton(const float *__restrict__ leafBox, uint32_t nSeg, const float *__restrict__ centroidBox, uint64_t *keys, uint32_t *ids) {
+// cubic: all three axes are quantised with the LARGEST extent of the centroid box, so that the grid cells are cubes whatever the
+// aspect of the scene (a flat scene otherwise gets cells that are thin along its short axis, i.e. splits along it come too early)
+__global__ void k_morton(const float *__restrict__ leafBox, uint32_t nSeg, const float *__restrict__ centroidBox, uint64_t *keys, uint32_t *ids, int cubic) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nSeg) return;
     uint64_t code = 0;
+    const float extMax = fmaxf(fmaxf(centroidBox[3] - centroidBox[0], centroidBox[4] - centroidBox[1]), centroidBox[5] - centroidBox[2]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float c = 0.5f * (leafBox[6 * (size_t) i + k] + leafBox[6 * (size_t) i + 3 + k]);
-        float ext = centroidBox[3 + k] - centroidBox[k];
+        float ext = cubic ? extMax : centroidBox[3 + k] - centroidBox[k];
         float f = ext > 0 ? (c - centroidBox[k]) / ext : 0.0f;
-        uint64_t q = (uint64_t) fminf(fmaxf(f * 2097152.0f, 0.0f), 2097151.0f);
+        uint64_t q = (uint64_t) fminf(fmaxf(f * (float) (1u << CP_MORTON_BITS), 0.0f), (float) ((1u << CP_MORTON_BITS) - 1u));
         code |= expandBits21(q) << (2 - k);
     }
     keys[i] = code; ids[i] = i;
@@ -461,12 +469,12 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
     nSeg = nRef;   // from here on the builder works on references
     CK(S.alloc(&d_keys, sizeof(uint64_t) * (size_t) nSeg)); CK(S.alloc(&d_keysSorted, sizeof(uint64_t) * (size_t) nSeg));
     CK(S.alloc(&d_ids, sizeof(uint32_t) * (size_t) nSeg)); CK(S.alloc(&d_idsSorted, sizeof(uint32_t) * (size_t) nSeg));
-    k_morton<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_leafBox, nSeg, d_cbox, d_keys, d_ids);
+    k_morton<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_leafBox, nSeg, d_cbox, d_keys, d_ids, getenv("CUDAPATH_MORTON_CUBE") ? atoi(getenv("CUDAPATH_MORTON_CUBE")) : 1);
     {
         void *d_temp2 = nullptr;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, need, d_keys, d_keysSorted, d_ids, d_idsSorted, (int) nSeg, 0, 63, stream));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, need, d_keys, d_keysSorted, d_ids, d_idsSorted, (int) nSeg, 0, 3 * CP_MORTON_BITS, stream));
         CK(S.alloc(&d_temp2, need));
-        CK(cub::DeviceRadixSort::SortPairs(d_temp2, need, d_keys, d_keysSorted, d_ids, d_idsSorted, (int) nSeg, 0, 63, stream));
+        CK(cub::DeviceRadixSort::SortPairs(d_temp2, need, d_keys, d_keysSorted, d_ids, d_idsSorted, (int) nSeg, 0, 3 * CP_MORTON_BITS, stream));
     }
     CK(S.alloc(&d_sortedBox, sizeof(float) * 6 * (size_t) nSeg));
     CK(S.alloc(&d_prims, sizeof(uint32_t) * (size_t) nSeg));
@@ -488,14 +496,14 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
         k_radix_tree<<<(nInner + B - 1) / B, B, 0, stream>>>(d_keysSorted, (int) nSeg, d_children, d_parentInner, d_parentLeaf, d_ranges);
         k_refit<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_children, d_parentInner, d_parentLeaf, d_sortedBox, (int) nSeg, d_innerBox, d_flags);
         // Collapse level by level.  A wide node is created only for a binary inner node (the one it absorbs), and distinct wide
-        // nodes absorb distinct binary nodes, so nInner bounds the wide-node count.  In practice a third of that is never reached
-        // (hair scenes: 0.17 nodes per reference), so the scratch array starts there (1.4 GB instead of 4 GB for 32 M references)
+        // nodes absorb distinct binary nodes, so nInner bounds the wide-node count.  In practice half of that is never reached
+        // (hair scenes: 0.24 to 0.38 nodes per reference, growing with the pre-split cap), so the scratch array starts there
         // and the collapse is repeated with the full bound in the unlikely case that it overflows.
         CK(S.alloc(&d_q0, sizeof(CollapseItem) * (size_t) nInner)); CK(S.alloc(&d_q1, sizeof(CollapseItem) * (size_t) nInner));
         CK(S.alloc(&d_counters, sizeof(int) * 4));
         int levels = 0;
         for (int attempt = 0; attempt < 2; ++attempt) {
-            int capacity = attempt == 0 ? (int) std::min<long long>(nInner, (long long) nSeg / 3 + 1024) : nInner;
+            int capacity = attempt == 0 ? (int) std::min<long long>(nInner, (long long) nSeg / 2 + 1024) : nInner;
             if (attempt == 0 && getenv("CUDAPATH_TEST_COLLAPSE_CAP")) capacity = std::max(1, std::min(nInner, atoi(getenv("CUDAPATH_TEST_COLLAPSE_CAP"))));   // tests: force the retry
             CK(S.alloc(&d_wide, sizeof(BVH4Node) * (size_t) capacity));
             CollapseItem root{0, 0};

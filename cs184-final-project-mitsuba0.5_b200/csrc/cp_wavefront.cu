@@ -193,19 +193,21 @@ bool Wavefront::render(const SceneDev &scene, uint32_t spp, uint64_t seed, uint3
     uint64_t realPix = (uint64_t) wp.filmW * wp.filmH;           // pixels this context renders
     if (shardCount <= 1) wp.pixPadded = (uint64_t) wp.tilesX * ((wp.filmH + 7) / 8) * 64;
     else {
-        const uint32_t blocksX = (wp.filmW + 31) / 32, blocksY = (wp.filmH + 31) / 32;
+        wp.blockShift = shardBlockShift;
+        const uint32_t bpx = 8u << wp.blockShift;               // pixels per block side
+        const uint32_t blocksX = (wp.filmW + bpx - 1) / bpx, blocksY = (wp.filmH + bpx - 1) / bpx;
         wp.shardIndex = shardIndex; wp.shardCount = shardCount;
         wp.cellW = shardCount; wp.cellH = 1;                     // cell shape: as square as the shard count allows (8 -> 4 x 2, 4 -> 2 x 2, 6 -> 3 x 2)
         for (uint32_t hgt = 2; hgt * hgt <= shardCount; ++hgt) if (shardCount % hgt == 0) { wp.cellH = hgt; wp.cellW = shardCount / hgt; }
         wp.cellsPerRow = (blocksX + wp.cellW - 1) / wp.cellW;
         const uint32_t cellRows = (blocksY + wp.cellH - 1) / wp.cellH;
-        wp.pixPadded = (uint64_t) wp.cellsPerRow * cellRows * 1024ull;
+        wp.pixPadded = (uint64_t) wp.cellsPerRow * cellRows * (uint64_t) bpx * bpx;
         realPix = 0;
         for (uint32_t cy = 0; cy < cellRows; ++cy) for (uint32_t cx = 0; cx < wp.cellsPerRow; ++cx) {
             const uint32_t slot = (shardIndex + cx + 3u * cy) % shardCount;
             const uint32_t bx = cx * wp.cellW + slot % wp.cellW, by = cy * wp.cellH + slot / wp.cellW;
             if (bx >= blocksX || by >= blocksY) continue;
-            realPix += (uint64_t) std::min(32u, wp.filmW - bx * 32u) * std::min(32u, wp.filmH - by * 32u);
+            realPix += (uint64_t) std::min(bpx, wp.filmW - bx * bpx) * std::min(bpx, wp.filmH - by * bpx);
         }
         if (wp.pixPadded == 0 || realPix == 0) return true;     // this shard owns no pixel
     }

@@ -24,10 +24,11 @@ struct WaveParams {
     uint64_t waveBase = 0, pixPadded = 0;
     uint32_t filmW = 0, filmH = 0, tilesX = 0, sampleBegin = 0, seedLo = 0, seedHi = 0;
     float diffScale = 1.0f;
-    // pixel shard (cudapath_set_pixel_shard): this context renders the 32x32-pixel blocks owned by shard `shardIndex` of `shardCount`.
-    // The block grid is cut into cells of cellW x cellH = shardCount blocks; every shard owns exactly one block of every cell (which one
-    // rotates from cell to cell), so each shard's pixels are spread evenly over the image whatever the image shows.
-    uint32_t shardIndex = 0, shardCount = 1, cellW = 1, cellH = 1, cellsPerRow = 0;
+    // pixel shard (cudapath_set_pixel_shard): this context renders the pixel blocks owned by shard `shardIndex` of `shardCount`; a block is
+    // (8 << blockShift)^2 pixels = 4^blockShift tiles of 8x8.  The block grid is cut into cells of cellW x cellH = shardCount blocks; every
+    // shard owns exactly one block of every cell (which one rotates from cell to cell), so each shard's pixels are spread evenly over the
+    // image whatever the image shows.
+    uint32_t shardIndex = 0, shardCount = 1, cellW = 1, cellH = 1, cellsPerRow = 0, blockShift = 2;
 };
 struct RenderStats {
     uint64_t paths = 0, rays = 0, shadowRays = 0, launches = 0, bounces = 0, hostSyncs = 0;
@@ -56,7 +57,7 @@ struct Wavefront {
     uint32_t *sortKeys[2] = {nullptr, nullptr}, *sortVals[2] = {nullptr, nullptr};
     void *sortTemp = nullptr; size_t sortTempBytes = 0;
     bool sortRays = true;
-    uint32_t shardIndex = 0, shardCount = 1;    // pixel shard of this context (WaveParams)
+    uint32_t shardIndex = 0, shardCount = 1, shardBlockShift = 2;    // pixel shard of this context (WaveParams); block side = 8 << shift pixels
     bool fastMath = true;               // shade with the -DCP_FAST_MATH build of cp_shade.cu (cudapath_set_math_mode)
     uint32_t runAheadMax = 1u << 22;    // bounces with more rays than this are sized from exact counters (one host wait), smaller ones run ahead
     // Integrator::cancel() (include/mitsuba/render/integrator.h:76-84) may be called from another thread while render() blocks: the flag
@@ -101,13 +102,13 @@ __device__ __forceinline__ bool path_to_pixel(const WaveParams &wp, uint64_t g, 
     if (wp.shardCount == 1u) {
         x = (tile % wp.tilesX) * 8u + (within & 7u);
         y = (tile / wp.tilesX) * 8u + (within >> 3);
-    } else {      // owned 32x32 block (one per cell) -> 8x8 tile inside it -> pixel
-        const uint32_t cell = tile >> 4, t = tile & 15u;
+    } else {      // owned block (one per cell) -> 8x8 tile inside it -> pixel
+        const uint32_t bs = wp.blockShift, cell = tile >> (2u * bs), t = tile & ((1u << (2u * bs)) - 1u);
         const uint32_t cy = cell / wp.cellsPerRow, cx = cell - cy * wp.cellsPerRow;
         const uint32_t slot = (wp.shardIndex + cx + 3u * cy) % wp.shardCount;          // which block of the cell is ours
         const uint32_t bx = cx * wp.cellW + slot % wp.cellW, by = cy * wp.cellH + slot / wp.cellW;
-        x = bx * 32u + (t & 3u) * 8u + (within & 7u);
-        y = by * 32u + (t >> 2) * 8u + (within >> 3);
+        x = ((bx << bs) + (t & ((1u << bs) - 1u))) * 8u + (within & 7u);
+        y = ((by << bs) + (t >> bs)) * 8u + (within >> 3);
     }
     return x < wp.filmW && y < wp.filmH;
 }

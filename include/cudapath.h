@@ -254,7 +254,7 @@ int cudapath_set_options(cudapath_ctx *ctx, uint32_t wave_size, int collect_stat
 int cudapath_set_math_mode(cudapath_ctx *ctx, int strict);
 int cudapath_get_math_mode(cudapath_ctx *ctx);
 
-/* BVH build tunable: a long thin segment is referenced by up to max_split boxes cut along its axis (default 8; 1 = off). */
+/* BVH build tunable: a long thin segment is referenced by up to max_split boxes cut along its axis (default 16; 1 = off). */
 int cudapath_set_build_options(cudapath_ctx *ctx, int max_split);
 
 typedef struct cudapath_stats {

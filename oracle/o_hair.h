@@ -18,6 +18,7 @@
 #include <sstream>
 #include <thread>
 #include <atomic>
+#include <mutex>
 
 namespace orc {
 
@@ -622,6 +623,22 @@ struct Geometry {
         // ray (hair-curl, 32 M references: 16.7 against 149 wide nodes per ray, 2.2 against 0.44 Mrays/s on 8 threads); the sweep stays
         // selectable with ORC_FAST_SPLITMODE=0 for the record.
         static const int splitMode = getenv("ORC_FAST_SPLITMODE") ? atoi(getenv("ORC_FAST_SPLITMODE")) : 2;
+#ifdef ORC_FAST_STATS
+        if (splitMode == 5 || splitMode == 6) {   // experiment: what a Morton-code LBVH does -- global grid, axes x, y, z in turn (5: every axis normalised by its own extent, 6: by the largest)
+            static AABB g; static std::once_flag once; static V3 gext;
+            std::call_once(once, [&]() { g = cbox; V3 e = cbox.mx - cbox.mn; float m = std::max(e.x, std::max(e.y, e.z)); gext = splitMode == 6 ? V3(m, m, m) : e; });
+            // find the first grid bit (from the top) at which the centroids of [lo, hi) differ
+            auto cell = [&](uint32_t id, int axis) { float f = (boxes[id].center()[axis] - g.mn[axis]) / gext[axis]; return (uint32_t) std::min(std::max(f * 2097152.0f, 0.0f), 2097151.0f); };
+            bool done = false;
+            for (int bit = 20; bit >= 0 && !done; --bit) for (int axis = 0; axis < 3 && !done; ++axis) {
+                const uint32_t first = cell(order[lo], axis) >> bit; bool differ = false;
+                for (uint32_t i = lo + 1; i < hi; ++i) if ((cell(order[i], axis) >> bit) != first) { differ = true; break; }
+                if (!differ) continue;
+                auto it = std::partition(order.begin() + lo, order.begin() + hi, [&](uint32_t id) { return ((cell(id, axis) >> bit) & 1u) == 0u; });
+                mid = (uint32_t) (it - order.begin()); done = true;
+            }
+        } else
+#endif
         if (splitMode == 2) {
             float bestC = kInf; int bestA = -1;
             for (int axis = 0; axis < 3; ++axis) {

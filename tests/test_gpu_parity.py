@@ -1043,6 +1043,27 @@ def test_multi_gpu_film_equals_single_gpu(cp):
     multi.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize('block', [8, 16, 32])
+def test_pixel_shards_add_up_to_the_image(cp, block, monkeypatch):
+    """cudapath_set_pixel_shard (the pixel-block split cudapath_create_multi gives every device, replacing the tile queue of
+    src/librender/renderproc.cpp:117-182): the films of the G shards of an image add up to the unsharded film up to fp32 summation order,
+    every shard renders its share of the paths, for block sides of 8 / 16 / 32 pixels and shard counts that do and do not divide the block grid."""
+    monkeypatch.setenv('CUDAPATH_SHARD_BLOCK', str(block))
+    ov = dict(width=200, height=136, spp=4, maxDepth=12)
+    ctx = cp.scene_from_description('hair-curl', device=0, scale=0.02, overrides=ov); ctx.build()
+    ref = ctx.render(4, seed=9); st = ctx.stats()
+    for g in (2, 3, 8):
+        acc = np.zeros_like(ref, dtype=np.float64); paths = 0; rays = 0
+        for i in range(g):
+            ctx.set_pixel_shard(i, g)
+            acc += ctx.render(4, seed=9); s = ctx.stats(); paths += s['paths']; rays += s['rays']
+        ctx.set_pixel_shard(0, 1)
+        assert paths == st['paths'] and rays == st['rays'], (g, paths, st['paths'])
+        assert np.abs(acc - ref).max() <= 1e-5 * np.abs(ref).max(), 'shards of %d do not add up: %g' % (g, np.abs(acc - ref).max() / np.abs(ref).max())
+    ctx.close()
+
+
 def test_fast_math_bsdf_within_tolerance(bsdf_pair, cp, oracle):
     """The product's default math mode (cudapath_set_math_mode(ctx, 0): fp32 CUDA functions wherever the last bits are not amplified,
     exact bits kept for the asin / shifted-angle sin / cos chain that M() multiplies by 1/v) against the oracle on 2^22 random tuples
