@@ -88,7 +88,13 @@ class ClockSampler(threading.Thread):
         if not sm:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
         load = sorted(sm)[len(sm) // 2:]   # upper half = samples under load
-        return {'sm_mhz': float(np.median(load)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons)}
+        pw = []
+        for s in (inside if len(inside) >= 2 else [s for (_, s) in self.samples]):
+            try:
+                pw.append(float(s[3]))
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(load)), 'sm_max_mhz': float(max(mx)), 'sm_min_mhz': float(min(sm)), 'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
 def scene_arrays(name, scale):
@@ -441,12 +447,12 @@ def main():
     torch.cuda.synchronize()
     t_begin = time.time()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    launches = 0; rays = 0; shadow = 0; waits = 0
+    launches = 0; rays = 0; shadow = 0; waits = 0; step_render_ms = []
     e0.record(stream)
     for k in range(args.steps):
         step(1000 + k)
         if s_end > s_begin:
-            st = ctx.stats(); launches += st['kernel_launches'] + 1; rays += st['rays']; shadow += st['shadow_rays_traced']; waits += st['host_waits']      # rays actually traced (zero-contribution shadow rays are only counted)
+            st = ctx.stats(); step_render_ms.append(round(st['render_ms'], 2)); launches += st['kernel_launches'] + 1; rays += st['rays']; shadow += st['shadow_rays_traced']; waits += st['host_waits']      # rays actually traced (zero-contribution shadow rays are only counted)
     e1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -523,7 +529,7 @@ def main():
         line = {'metric': 'Mpaths/s', 'value': value, 'unit': 'Mpaths/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
                 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32 (fp64 cylinder test)', 'data': 'synthetic',
                 'config': workload_config(args, sc), 'mrays_per_s': mrays, 'rays_per_path': (rays + shadow) / args.steps / paths_per_step,
-                'gpu_launches': int(launches), 'host_waits_per_step': waits / max(1, args.steps), 'clocks': clocks, 'e2e': e2e, 'roofline': roof, 'cpu_baseline': cpu,
+                'gpu_launches': int(launches), 'host_waits_per_step': waits / max(1, args.steps), 'step_render_ms': step_render_ms, 'clocks': clocks, 'e2e': e2e, 'roofline': roof, 'cpu_baseline': cpu,
                 'build': {'segments': build['segments'], 'bvh_references': build['bvh_references'], 'bvh_nodes': build['bvh_nodes'], 'build_ms': build['build_ms'], 'build_ms_note': 'first build of the process (cold device allocator); the steady-state build is the second entry of e2e.phases_s'}}
         print(json.dumps(line), flush=True)
     if world > 1:
