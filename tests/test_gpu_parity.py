@@ -719,7 +719,7 @@ def test_third_golden_set(cp):
 
 
 def test_collapse_scratch_overflow_retries(cp, monkeypatch):
-    """The wide-node scratch array of the BVH collapse starts at a third of its worst case; an overflow repeats the collapse with the
+    """The wide-node scratch array of the BVH collapse starts at half of its worst case; an overflow repeats the collapse with the
     full bound and yields the same tree (CUDAPATH_TEST_COLLAPSE_CAP forces the first attempt to overflow)."""
     ov = dict(width=32, height=32, spp=2, maxDepth=4)
     films = []
