@@ -125,8 +125,10 @@ def pin(arr):
     return t.numpy(), t
 
 
-def make_context(cudapath, sc, shapes, env, device):
+def make_context(cudapath, sc, shapes, env, device, paths_per_device=None):
     ctx = cudapath.Context(device)
+    if paths_per_device:
+        ctx.set_job_size_hint(paths_per_device)     # build effort from the size of the job (cudapath.h)
     for xyz, st, radius, b in shapes:
         b = dict(b); t = b.pop('type'); b.pop('id', None)
         ctx.add_hair(xyz, st, radius, ctx.add_bsdf(t, **b))
@@ -412,7 +414,9 @@ def main():
         total_spp = spp; s_begin, s_end = 0, spp; shard = (rank, world)                # the fixed image, 32x32 pixel blocks dealt out to the ranks
     if args.shard_test:                                                                # development: one GPU renders shard i of G of the image
         i, g = (int(v) for v in args.shard_test.split('/')); shard = (i, g)
-    ctx = make_context(cudapath, sc, shapes, env, local)
+    # camera paths this rank traces per step: picks the build effort of the scene (cudapath_set_job_size_hint)
+    job_paths = W * H * (s_end - s_begin) // (shard[1] if shard[1] > 1 else 1)
+    ctx = make_context(cudapath, sc, shapes, env, local, job_paths)
     ctx.set_pixel_shard(*shard)
     if args.max_split:
         ctx.set_build_options(args.max_split)
@@ -489,7 +493,7 @@ def main():
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            c2 = make_context(cudapath, sc, pshapes, penv, local)
+            c2 = make_context(cudapath, sc, pshapes, penv, local, job_paths)
             c2.set_pixel_shard(*shard)
             if args.wave:
                 c2.set_options(wave_size=args.wave)

@@ -357,6 +357,10 @@ class Context:
     def set_build_options(self, max_split=16):
         _check(self._L.cudapath_set_build_options(self._h, int(max_split)))
 
+    def set_job_size_hint(self, paths_per_device):
+        """width x height x spp / devices of the job this scene is built for: picks the build effort (see cudapath.h); call before build()."""
+        _check(self._L.cudapath_set_job_size_hint(self._h, ctypes.c_uint64(int(paths_per_device))))
+
     def load_xml(self, filename, defines=None):
         """SceneHandler for the hair scenes; `defines` = dict for $name substitution (mitsuba -D).  Returns sampleCount."""
         spp = ctypes.c_uint32(0)

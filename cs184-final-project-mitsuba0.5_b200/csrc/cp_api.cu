@@ -82,6 +82,7 @@ struct cudapath_ctx {
     Wavefront wf;
     uint32_t waveSize = 0; int collectStats = 0, profileStages = 0;     // 0 = sized from the free device memory at render time
     int maxSplit = getenv("CUDAPATH_MAX_SPLIT") ? std::max(1, std::min(64, atoi(getenv("CUDAPATH_MAX_SPLIT")))) : 16;    // cudapath_set_build_options; hair-curl: 286 / 299 / 311 / 322 / 328 Mpaths/s at 8 / 12 / 16 / 24 / 32 (build 19 ms per 32 M references)
+    bool maxSplitExplicit = false;
     uint32_t shardIndex = 0, shardCount = 1;     // cudapath_set_pixel_shard
     float leafSplitCost = getenv("CUDAPATH_LEAF_SPLIT_COST") ? (float) atof(getenv("CUDAPATH_LEAF_SPLIT_COST")) : 1.0f;    // see k_collapse (cp_bvh.cu); < 0: leaves of up to CP_LEAF_MAX references, never opened
     int sortRays = getenv("CUDAPATH_NO_SORT") ? 0 : 1;
@@ -1024,8 +1025,16 @@ int cudapath_get_math_mode(cudapath_ctx *ctx) { return ctx ? (ctx->fastMath ? 0 
 int cudapath_set_build_options(cudapath_ctx *ctx, int max_split) {
     if (!ctx) return fail("null context");
     if (max_split < 1 || max_split > 64) return fail("max_split must be in [1, 64]");
-    ctx->maxSplit = max_split; ctx->built = false;
+    ctx->maxSplit = max_split; ctx->maxSplitExplicit = true; ctx->built = false;
     return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_build_options(p, max_split); });
+}
+int cudapath_set_job_size_hint(cudapath_ctx *ctx, uint64_t paths_per_device) {
+    if (!ctx) return fail("null context");
+    if (!ctx->maxSplitExplicit && !getenv("CUDAPATH_MAX_SPLIT")) {
+        const int want = paths_per_device >= (1ull << 25) ? 16 : 8;
+        if (want != ctx->maxSplit) { ctx->maxSplit = want; ctx->built = false; }
+    }
+    return fan_out(ctx, 0, [&](cudapath_ctx *p) { return cudapath_set_job_size_hint(p, paths_per_device); });
 }
 int cudapath_get_stats(cudapath_ctx *ctx, cudapath_stats *out) { if (!ctx || !out) return fail("null argument"); *out = ctx->stats; return 0; }
 int cudapath_film_size(cudapath_ctx *ctx, int *w, int *h) {

@@ -275,24 +275,44 @@ __global__ void k_leaf_records(const float4 *__restrict__ vtx, const uint32_t *_
     leafSeg[2 * (size_t) i + 1] = make_float4(v2.x, v2.y, v2.z, __uint_as_float(gv));
 }
 
+__device__ __forceinline__ float boxArea(const float *b) {
+    float ex = b[3] - b[0], ey = b[4] - b[1], ez = b[5] - b[2];
+    return ex * ey + ey * ez + ez * ex;
+}
+
+// Bottom-up boxes of the binary tree.  The thread that completes a node holds its box and both child boxes, so it also decides what the collapse
+// needs to know about the node -- whether a wide node may OPEN it -- and leaves the answer in bit 31 of ranges[node].y:
+// a binary subtree with more than CP_LEAF_MAX references is always opened; a smaller one may become ONE leaf (one box, every reference pre-tested on
+// entry) or stay a subtree (a box per child).  Surface-area heuristic, one level deep: it is opened when
+//     splitCost * A(node) + A(left) n_left + A(right) n_right  <  A(node) n,
+// i.e. when the children's boxes are so much smaller than their union that testing them first saves pre-tests (short fibers in open space); bundles of
+// long, diagonal, pre-split fibers, whose pieces' boxes overlap anyway, stay leaves.  splitCost < 0: never.
+#define CP_OPEN_FLAG 0x80000000u
 __global__ void k_refit(const int2 *__restrict__ children, const int *__restrict__ parentInner, const int *__restrict__ parentLeaf,
-                        const float *__restrict__ sortedBox, int n, float *innerBox, int *flags) {
+                        const float *__restrict__ sortedBox, int n, float *innerBox, int *flags, int2 *ranges, float splitCost) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int node = parentLeaf[i];
     while (node >= 0) {
+        const int2 ch = children[node], r = ranges[node];  // read-only inputs of this node: in flight while the arrival counter is updated
         if (atomicAdd(&flags[node], 1) == 0) return;      // first arrival waits for the sibling
         __threadfence();
-        int2 ch = children[node];
-        float b[6];
+        float a[6], c[6], b[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            float a = ch.x >= 0 ? __ldcg(&innerBox[6 * (size_t) ch.x + k]) : sortedBox[6 * (size_t) (~ch.x) + k];
-            float c = ch.y >= 0 ? __ldcg(&innerBox[6 * (size_t) ch.y + k]) : sortedBox[6 * (size_t) (~ch.y) + k];
-            b[k] = k < 3 ? fminf(a, c) : fmaxf(a, c);
+            a[k] = ch.x >= 0 ? __ldcg(&innerBox[6 * (size_t) ch.x + k]) : sortedBox[6 * (size_t) (~ch.x) + k];
+            c[k] = ch.y >= 0 ? __ldcg(&innerBox[6 * (size_t) ch.y + k]) : sortedBox[6 * (size_t) (~ch.y) + k];
+            b[k] = k < 3 ? fminf(a[k], c[k]) : fmaxf(a[k], c[k]);
         }
 #pragma unroll
         for (int k = 0; k < 6; ++k) __stcg(&innerBox[6 * (size_t) node + k], b[k]);
+        {
+            const int gamma = ch.x >= 0 ? ch.x : ~ch.x;             // the left child ends at the split position (k_radix_tree)
+            const int cnt = r.y - r.x + 1, nL = gamma - r.x + 1, nR = r.y - gamma;
+            bool open = cnt > CP_LEAF_MAX;
+            if (!open && splitCost >= 0.0f) { const float aN = boxArea(b); open = splitCost * aN + boxArea(a) * nL + boxArea(c) * nR < aN * cnt; }
+            if (open) ranges[node].y = (int) ((uint32_t) r.y | CP_OPEN_FLAG);
+        }
         __threadfence();
         node = parentInner[node];
     }
@@ -300,48 +320,48 @@ __global__ void k_refit(const int2 *__restrict__ children, const int *__restrict
 
 struct CollapseItem { int bin; int wide; };
 
-__device__ __forceinline__ float boxArea(const float *b) {
-    float ex = b[3] - b[0], ey = b[4] - b[1], ez = b[5] - b[2];
-    return ex * ey + ey * ez + ez * ex;
-}
-
-// One thread per wide node to emit.  A binary subtree with <= CP_LEAF_MAX segments becomes a leaf reference.
+// One thread per wide node to emit.  A binary subtree that k_refit did not mark as open becomes a leaf reference; the candidates of a wide node are
+// opened largest box first.  The child wide nodes of a warp's items are allocated with ONE atomic per counter (the two counters advance in lockstep).
 __global__ void k_collapse(const CollapseItem *__restrict__ in, int nIn, CollapseItem *out, int *outCount, int *wideCount,
                            const int2 *__restrict__ children, const int2 *__restrict__ ranges,
-                           const float *__restrict__ innerBox, const float *__restrict__ sortedBox, BVH4Node *nodes, int maxWide, int *err, float splitCost) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nIn) return;
-    const CollapseItem it = in[idx];
-    int cand[4]; int nc = 0;
-    int2 ch = children[it.bin];
-    cand[nc++] = ch.x; cand[nc++] = ch.y;
-    // A binary subtree with at most CP_LEAF_MAX references may become ONE leaf (one box, every reference pre-tested on entry) or stay
-    // a subtree (a box per child).  Surface-area heuristic, one level deep: it is opened when
-    //     splitCost * A(node) + A(left) n_left + A(right) n_right  <  A(node) n,
-    // i.e. when the children's boxes are so much smaller than their union that testing them first saves pre-tests (short fibers in
-    // open space); bundles of long, diagonal, pre-split fibers, whose pieces' boxes overlap anyway, stay leaves.  splitCost < 0: never.
-    auto expandable = [&](int c) {
-        if (c < 0) return false;
-        const int n = ranges[c].y - ranges[c].x + 1;
-        if (n > CP_LEAF_MAX) return true;
-        if (splitCost < 0.0f) return false;
-        const int2 k = children[c];
-        const float aN = boxArea(innerBox + 6 * (size_t) c);
-        const float aL = k.x >= 0 ? boxArea(innerBox + 6 * (size_t) k.x) : boxArea(sortedBox + 6 * (size_t) (~k.x));
-        const float aR = k.y >= 0 ? boxArea(innerBox + 6 * (size_t) k.y) : boxArea(sortedBox + 6 * (size_t) (~k.y));
-        const int nL = k.x >= 0 ? ranges[k.x].y - ranges[k.x].x + 1 : 1, nR = k.y >= 0 ? ranges[k.y].y - ranges[k.y].x + 1 : 1;
-        return splitCost * aN + aL * nL + aR * nR < aN * n;
-    };
-    while (nc < 4) {
-        int best = -1; float bestArea = -1.0f;
-        for (int k = 0; k < nc; ++k) if (expandable(cand[k])) {
-            float a = boxArea(innerBox + 6 * (size_t) cand[k]);
-            if (a > bestArea) { bestArea = a; best = k; }
+                           const float *__restrict__ innerBox, const float *__restrict__ sortedBox, BVH4Node *nodes, int maxWide, int *err) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = idx < nIn;                              // every lane stays for the warp scan below
+    CollapseItem it{0, 0};
+    int cand[4]; int2 rng[4]; float area[4]; int nc = 0;      // area < 0: not to be opened (a reference, or a subtree that stays one leaf)
+    auto add = [&](int c) {
+        cand[nc] = c; rng[nc] = make_int2(0, 0); area[nc] = -1.0f;
+        if (c >= 0) {
+            rng[nc] = ranges[c];
+            if ((uint32_t) rng[nc].y & CP_OPEN_FLAG) area[nc] = boxArea(innerBox + 6 * (size_t) c);
         }
-        if (best < 0) break;
-        int2 c2 = children[cand[best]];
-        cand[best] = c2.x; cand[nc++] = c2.y;
+        ++nc;
+    };
+    int mine = 0;
+    if (live) {
+        it = in[idx];
+        { const int2 ch = children[it.bin]; add(ch.x); add(ch.y); }
+        while (nc < 4) {
+            int best = -1; float bestArea = -1.0f;
+            for (int k = 0; k < nc; ++k) if (area[k] > bestArea) { bestArea = area[k]; best = k; }
+            if (best < 0) break;
+            const int2 c2 = children[cand[best]];
+            const int keep = nc; nc = best; add(c2.x); nc = keep; add(c2.y);
+        }
+        for (int k = 0; k < nc; ++k) if (area[k] >= 0.0f) ++mine;
     }
+    __syncwarp();
+    int wBase = 0, oBase = 0;
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        int incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= (unsigned) off) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 31u && total > 0) { wBase = atomicAdd(wideCount, total); oBase = atomicAdd(outCount, total); }
+        wBase = __shfl_sync(0xffffffffu, wBase, 31) + incl - mine; oBase = __shfl_sync(0xffffffffu, oBase, 31) + incl - mine;
+    }
+    if (!live) return;
     float lo[3][4], hi[3][4]; int ref[4];
     for (int k = 0; k < 4; ++k) {
         if (k >= nc) {
@@ -353,14 +373,13 @@ __global__ void k_collapse(const CollapseItem *__restrict__ in, int nIn, Collaps
         const float *b = c >= 0 ? innerBox + 6 * (size_t) c : sortedBox + 6 * (size_t) (~c);
         for (int a = 0; a < 3; ++a) { lo[a][k] = b[a]; hi[a][k] = b[3 + a]; }
         if (c < 0) ref[k] = ~(int) ((((uint32_t) ~c) << 3) | 0u);
-        else if (!expandable(c)) {
-            int2 r = ranges[c];
+        else if (area[k] < 0.0f) {
+            const int2 r = rng[k];
             ref[k] = ~(int) ((((uint32_t) r.x) << 3) | (uint32_t) (r.y - r.x));
         } else {
-            int w = atomicAdd(wideCount, 1);
+            const int w = wBase++, o = oBase++;
             if (w >= maxWide) { *err = 1; ref[k] = (int) 0x80000000; continue; }
             ref[k] = w;
-            int o = atomicAdd(outCount, 1);
             out[o].bin = c; out[o].wide = w;
         }
     }
@@ -494,18 +513,19 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
         CK(S.alloc(&d_flags, sizeof(int) * (size_t) nInner)); CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * (size_t) nInner, stream));
         CK(S.alloc(&d_innerBox, sizeof(float) * 6 * (size_t) nInner));
         k_radix_tree<<<(nInner + B - 1) / B, B, 0, stream>>>(d_keysSorted, (int) nSeg, d_children, d_parentInner, d_parentLeaf, d_ranges);
-        k_refit<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_children, d_parentInner, d_parentLeaf, d_sortedBox, (int) nSeg, d_innerBox, d_flags);
+        k_refit<<<(nSeg + B - 1) / B, B, 0, stream>>>(d_children, d_parentInner, d_parentLeaf, d_sortedBox, (int) nSeg, d_innerBox, d_flags, d_ranges, leafSplitCost);
         // Collapse level by level.  A wide node is created only for a binary inner node (the one it absorbs), and distinct wide
         // nodes absorb distinct binary nodes, so nInner bounds the wide-node count.  In practice half of that is never reached
         // (hair scenes: 0.24 to 0.38 nodes per reference, growing with the pre-split cap), so the scratch array starts there
         // and the collapse is repeated with the full bound in the unlikely case that it overflows.
         CK(S.alloc(&d_q0, sizeof(CollapseItem) * (size_t) nInner)); CK(S.alloc(&d_q1, sizeof(CollapseItem) * (size_t) nInner));
         CK(S.alloc(&d_counters, sizeof(int) * 4));
-        int levels = 0;
+        int levels = 0, wideCapacity = 0;
         for (int attempt = 0; attempt < 2; ++attempt) {
             int capacity = attempt == 0 ? (int) std::min<long long>(nInner, (long long) nSeg / 2 + 1024) : nInner;
             if (attempt == 0 && getenv("CUDAPATH_TEST_COLLAPSE_CAP")) capacity = std::max(1, std::min(nInner, atoi(getenv("CUDAPATH_TEST_COLLAPSE_CAP"))));   // tests: force the retry
-            CK(S.alloc(&d_wide, sizeof(BVH4Node) * (size_t) capacity));
+            if (d_wide) { S.release(d_wide); cudaStreamSynchronize(stream); dev_free(d_wide); d_wide = nullptr; }     // the first attempt's array
+            CK(S.alloc(&d_wide, sizeof(BVH4Node) * (size_t) capacity)); wideCapacity = capacity;
             CollapseItem root{0, 0};
             int init[4] = {0, 1, 0, 0}; // [0]=next-level count, [1]=wide count, [2]=error
             CK(cudaMemcpyAsync(d_q0, &root, sizeof(root), cudaMemcpyHostToDevice, stream));
@@ -514,7 +534,7 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
             levels = 0;
             while (nIn > 0) {
                 k_collapse<<<(nIn + 127) / 128, 128, 0, stream>>>(d_q0, nIn, d_q1, d_counters, d_counters + 1, d_children, d_ranges,
-                                                                 d_innerBox, d_sortedBox, d_wide, capacity, d_counters + 2, leafSplitCost);
+                                                                 d_innerBox, d_sortedBox, d_wide, capacity, d_counters + 2);
                 int h[3];
                 CK(cudaMemcpyAsync(h, d_counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
                 CK(cudaStreamSynchronize(stream));
@@ -528,8 +548,11 @@ bool build_bvh(const float4 *d_vtx, uint32_t vtxCount, ShapeDev *d_shapes, int s
             if (capacity == nInner) { err = "BVH collapse overflow"; return false; }
         }
         info.levels = levels;
-        CK(S.alloc(&d_final, sizeof(BVH4Node) * (size_t) wideCount));
-        CK(cudaMemcpyAsync(d_final, d_wide, sizeof(BVH4Node) * (size_t) wideCount, cudaMemcpyDeviceToDevice, stream));
+        if ((size_t) wideCount * 2 >= (size_t) wideCapacity) { d_final = d_wide; }      // the scratch array is mostly full: it becomes the node array as it is
+        else {
+            CK(S.alloc(&d_final, sizeof(BVH4Node) * (size_t) wideCount));
+            CK(cudaMemcpyAsync(d_final, d_wide, sizeof(BVH4Node) * (size_t) wideCount, cudaMemcpyDeviceToDevice, stream));
+        }
     }
     CK(cudaStreamSynchronize(stream));
     CK(cudaGetLastError());

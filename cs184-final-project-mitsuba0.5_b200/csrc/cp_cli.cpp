@@ -116,6 +116,11 @@ int main(int argc, char **argv) {
     uint32_t fileSpp = 0;
     if (cudapath_load_scene_xml(ctx, scene.c_str(), defines.empty() ? nullptr : defines.c_str(), &fileSpp) != 0) return die("cannot load the scene");
     const double t1 = now();
+    {   // build effort from the size of the job (cudapath_set_job_size_hint)
+        int fw = 0, fh = 0; cudapath_film_size(ctx, &fw, &fh);
+        const uint64_t jobSpp = spp > 0 ? (uint64_t) spp : fileSpp;
+        cudapath_set_job_size_hint(ctx, (uint64_t) fw * fh * jobSpp / (uint64_t) nDev);
+    }
     if (cudapath_build(ctx) != 0) return die("cannot build the scene");
     const double t2 = now();
     const uint32_t n = spp > 0 ? (uint32_t) spp : fileSpp;

@@ -734,6 +734,24 @@ def test_collapse_scratch_overflow_retries(cp, monkeypatch):
     assert np.allclose(films[0][0], films[1][0], rtol=1e-5, atol=1e-6)
 
 
+def test_job_size_hint_picks_the_build_effort(cp, monkeypatch):
+    """cudapath_set_job_size_hint: the pre-split cap follows the number of camera paths a device is going to trace (16 from 2^25 paths, 8
+    below), an explicit cudapath_set_build_options wins, and the image is the same either way (the BVH only decides which tests run;
+    the reference builds one kd-tree whatever the job, src/shapes/hair.cpp:108-159)."""
+    monkeypatch.delenv('CUDAPATH_MAX_SPLIT', raising=False)
+    ov = dict(width=48, height=48, spp=2, maxDepth=6)
+    refs, films = {}, {}
+    for tag, hint, explicit in (('small', 1 << 20, None), ('large', 1 << 26, None), ('explicit', 1 << 26, 4)):
+        ctx = cp.scene_from_description('hair-curl', scale=0.01, overrides=ov)
+        if explicit:
+            ctx.set_build_options(explicit)
+        ctx.set_job_size_hint(hint)
+        ctx.build(); refs[tag] = ctx.stats()['bvh_references']
+        films[tag] = ctx.render(2, seed=3); ctx.close()
+    assert refs['explicit'] < refs['small'] < refs['large'], refs
+    assert np.allclose(films['small'], films['large'], rtol=1e-5, atol=1e-6) and np.allclose(films['small'], films['explicit'], rtol=1e-5, atol=1e-6)
+
+
 def test_repeated_jobs_reuse_device_memory(cp):
     """create / build / render / destroy in a loop: after the first job every device block comes from the caching allocator
     (cp_mem.cpp); cudapath_trim_memory hands the parked blocks back."""
