@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <thread>
+#include <future>
 #include <dlfcn.h>
 #include <nccl.h>          // types and prototypes only: libnccl.so.2 is bound at run time (cp_multi section), never at link time
 
@@ -692,6 +693,11 @@ static int build_one(cudapath_ctx *ctx) {
     const double tb0 = now();
     ctx->freeBuilt();
     std::string err;
+    // The Lanczos MIP pyramid of the environment map is host work (3 ms for 512x256): it runs on a worker thread while this one drives the device build.
+    std::vector<EnvMipLevel> pyrLevels; EnvMipInfo pyrInfo; std::memset(&pyrInfo, 0, sizeof(pyrInfo));
+    std::future<void> pyramidJob;
+    struct JoinGuard { std::future<void> &f; ~JoinGuard() { if (f.valid()) f.wait(); } } pyramidGuard{pyramidJob};      // error returns must not leave the worker running
+    if (ctx->env.present) pyramidJob = std::async(std::launch::async, [&]() { build_env_pyramid(ctx->env.rgb.data(), ctx->env.w, ctx->env.h, pyrLevels, pyrInfo.lut); });
     cudaEvent_t e0, e1; CKA(cudaEventCreate(&e0)); CKA(cudaEventCreate(&e1));
     CKA(cudaEventRecord(e0, ctx->stream));
     // geometry
@@ -836,8 +842,8 @@ static int build_one(cudapath_ctx *ctx) {
         dev_free(d_rgb);
         if (!ok) return fail(err);
         {   // Lanczos MIP pyramid + EWA weights for camera rays that leave the scene (MIPMap::eval, envmap.cpp:391-407)
-            std::vector<EnvMipLevel> levels; EnvMipInfo info; std::memset(&info, 0, sizeof(info));
-            build_env_pyramid(ctx->env.rgb.data(), ctx->env.w, ctx->env.h, levels, info.lut);
+            pyramidJob.get();            // host work that ran beside the BVH build (see the top of this function)
+            std::vector<EnvMipLevel> &levels = pyrLevels; EnvMipInfo &info = pyrInfo;
             if ((int) levels.size() > CP_ENV_MAX_LEVELS) return fail("environment map has too many MIP levels");
             info.levels = (int) levels.size();
             size_t total = 0;

@@ -15,6 +15,8 @@
 #include <sstream>
 #include <algorithm>
 #include <map>
+#include <mutex>
+#include <tuple>
 #include <array>
 
 namespace cp {
@@ -105,11 +107,29 @@ float spline3(float px, float py, float pz, const float *v, size_t nx, size_t ny
 }
 }
 
+// The slice only depends on (file, eta, alpha): results are remembered per process, so the BSDFs of a scene that share their parameters (the four
+// hair colours of models/hair-curl) read and reduce the 2 MB table once.
+static bool rough_transmittance_slice_uncached(const std::string &path, float eta, float alpha, std::vector<float> &outT, float &outFdr, std::string &err);
 bool rough_transmittance_slice(const std::string &dataDir, int distribution, float eta, float alpha,
                                std::vector<float> &outT, float &outFdr, std::string &err) {
     static const char *names[3] = {"beckmann", "ggx", "phong"};
     if (distribution < 0 || distribution > 2) { err = "RoughTransmittance: unsupported distribution type!"; return false; }
     const std::string path = dataDir + "/microfacet/" + names[distribution] + ".dat";
+    struct Entry { std::vector<float> T; float Fdr; };
+    static std::mutex m; static std::map<std::tuple<std::string, uint32_t, uint32_t>, Entry> memo;
+    uint32_t eb, ab; std::memcpy(&eb, &eta, 4); std::memcpy(&ab, &alpha, 4);
+    const auto key = std::make_tuple(path, eb, ab);
+    {
+        std::lock_guard<std::mutex> g(m);
+        auto it = memo.find(key);
+        if (it != memo.end()) { outT = it->second.T; outFdr = it->second.Fdr; return true; }
+    }
+    if (!rough_transmittance_slice_uncached(path, eta, alpha, outT, outFdr, err)) return false;
+    std::lock_guard<std::mutex> g(m);
+    if (memo.size() < 256) memo[key] = Entry{outT, outFdr};
+    return true;
+}
+static bool rough_transmittance_slice_uncached(const std::string &path, float eta, float alpha, std::vector<float> &outT, float &outFdr, std::string &err) {
     FILE *f = std::fopen(path.c_str(), "rb");
     if (!f) { err = "cannot open \"" + path + "\" (set the data directory to a Mitsuba data/ tree)"; return false; }
     char hdr[17]; uint64_t dims[3]; float rng[4];

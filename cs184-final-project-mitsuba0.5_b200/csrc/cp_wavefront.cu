@@ -258,7 +258,7 @@ bool Wavefront::render(const SceneDev &scene, uint32_t spp, uint64_t seed, uint3
             if (bounce >= 1) {
                 // Large bounces (milliseconds of device time) are sized exactly: waiting for the counters of the bounce before costs
                 // less than sorting the slack.  Small ones run ahead on the bounds of the bounce before that.
-                const int want = ubClosest > runAheadMax ? bounce - 1 : bounce - 2;
+                const int want = (bounce == 1 || ubClosest > runAheadMax) ? bounce - 1 : bounce - 2;     // bounce 1: the bound is every camera path, 3-4x the paths that hit something
                 bool stop = false;
                 while (lastRead < want) {
                     const uint32_t *h = readSlot(++lastRead);

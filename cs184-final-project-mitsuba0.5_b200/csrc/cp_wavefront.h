@@ -60,8 +60,8 @@ struct Wavefront {
     uint32_t shardIndex = 0, shardCount = 1, shardBlockShift = 2;    // pixel shard of this context (WaveParams); block side = 8 << shift pixels
     bool fastMath = true;               // shade with the -DCP_FAST_MATH build of cp_shade.cu (cudapath_set_math_mode)
     // Bounces with more rays than this are sized from exact counters (one host wait each), smaller ones run ahead on the bounds of the bounce before.
-    // Only the first bounce after the camera rays of a full wave is above the default: there the bound (every camera path) is 3-4x the queue
-    // (paths that hit something) and sorting the slack costs 1.5 % of the step, against one host round trip per wave.  With the round-1 / early
+    // The first bounce after the camera rays is always sized exactly: there the bound (every camera path) is 3-4x the queue (paths that hit
+    // something) and sorting the slack costs 1.5 % of the step, against one host round trip per wave.  With the round-1 / early
     // round-2 default of 2^22 (six waits per wave) a host that answers late stalls the device once per bounce: 233-243 ms per step against
     // 214 ms of device time on two of five GPU boxes of the shared pool.
     uint32_t runAheadMax = 1u << 25;
