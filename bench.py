@@ -51,13 +51,17 @@ class ClockSampler(threading.Thread):
     Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
+    period_ms = int(os.environ.get('BENCH_CLOCK_PERIOD_MS', '200'))     # the profiling recipe's 200 ms; 0 = no sampling (development)
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index; self.samples = []; self.stop_flag = False; self.proc = None
 
     def run(self):
+        if self.period_ms <= 0:
+            return
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '200'],
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
