@@ -14,9 +14,9 @@ cut -c1-400 $out/bench_ref_$tag.json
 timeout 600 python bench.py --config 5 --steps 3 > $out/bench_config5_$tag.json 2> $out/bench_config5_$tag.err; echo "config5 rc=$?"
 # launch list (cold-cache, serialised): same command at 8 spp so it stays short
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/launches_$tag.csv \
-    python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e > $out/ncu_launches_$tag.log 2>&1; echo "ncu launches rc=$?"
+    python bench.py --spp 8 --max-split 16 --steps 1 --warmup 1 --no-cpu --no-e2e > $out/ncu_launches_$tag.log 2>&1; echo "ncu launches rc=$?"
 # full capture of one mid-render k_trace launch (second bounce of the first wave)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_trace -s 2 -c 1 -o $out/prof_${tag}_trace \
-    python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e > $out/ncu_full_$tag.log 2>&1; echo "ncu full rc=$?"
+    python bench.py --spp 8 --max-split 16 --steps 1 --warmup 1 --no-cpu --no-e2e > $out/ncu_full_$tag.log 2>&1; echo "ncu full rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_shade -s 2 -c 1 -o $out/prof_${tag}_shade \
-    python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e > $out/ncu_full_shade_$tag.log 2>&1; echo "ncu full shade rc=$?"
+    python bench.py --spp 8 --max-split 16 --steps 1 --warmup 1 --no-cpu --no-e2e > $out/ncu_full_shade_$tag.log 2>&1; echo "ncu full shade rc=$?"

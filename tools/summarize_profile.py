@@ -69,7 +69,7 @@ def main():
         total = sum(v[1] for v in agg.values())
         with open(os.path.join(PROF, '%s_kernel_shares_%s.md' % (rnd, tag)), 'w') as f:
             f.write('# Launch list summary (%s)\n\n' % tag)
-            f.write('Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e`\n')
+            f.write('Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv python bench.py --spp 8 --max-split 16 --steps 1 --warmup 1 --no-cpu --no-e2e`\n')
             f.write('(cold-cache, serialised per-launch times; scene build + warm-up + profiled + counted + timed render; only the SHARE is comparable with bench.py)\n\n')
             f.write('| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n')
             for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -93,7 +93,7 @@ def main():
         dram = to_bytes(d['dram__bytes_read.sum'], u['dram__bytes_read.sum']) + to_bytes(d['dram__bytes_write.sum'], u['dram__bytes_write.sum'])
         with open(os.path.join(PROF, '%s_%s_ncu_%s.md' % (rnd, kname, tag)), 'w') as f:
             f.write('# ncu --set full: one `%s` launch (%s)\n\n' % (kname, tag))
-            f.write('Command: `ncu --set full --clock-control none --import-source on -k regex:%s -s 2 -c 1 python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e`\n' % kname)
+            f.write('Command: `ncu --set full --clock-control none --import-source on -k regex:%s -s 2 -c 1 python bench.py --spp 8 --max-split 16 --steps 1 --warmup 1 --no-cpu --no-e2e`\n' % kname)
             f.write('Kernel: `%s`\n\n| metric | value | unit |\n|---|---:|---|\n' % d.get('Kernel Name'))
             for k in KEYS:
                 if k in d:
@@ -103,7 +103,7 @@ def main():
             try: return float(d[k].replace(',', ''))
             except Exception: return None
         with open(os.path.join(PROF, 'k_trace_ncu.json' if kname == 'k_trace' else 'k_intersect_traffic.json'), 'w') as f:
-            json.dump({'source': '%s_%s_ncu_%s.md' % (rnd, kname, tag), 'launch': 'third %s launch of bench.py --spp 8 (secondary + shadow rays of one bounce, hair-curl; a launch of the 64-spp step is 8x this one)' % kname,
+            json.dump({'source': '%s_%s_ncu_%s.md' % (rnd, kname, tag), 'launch': 'third %s launch of bench.py --spp 8 --max-split 16 (secondary + shadow rays of one bounce, hair-curl; a launch of the 64-spp step is 8x this one)' % kname,
                        'dram_bytes': dram,
                        'lanes_per_instruction': num('smsp__thread_inst_executed_per_inst_executed.ratio'), 'issue_active_pct': num('smsp__issue_active.avg.pct_of_peak_sustained_active'),
                        'dram_throughput_pct': num('dram__throughput.avg.pct_of_peak_sustained_elapsed'), 'l2_throughput_pct': num('lts__throughput.avg.pct_of_peak_sustained_elapsed'),
@@ -116,8 +116,8 @@ def main():
              'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'smsp__thread_inst_executed.sum',
              'sm__inst_executed_pipe_fp64.sum', 'sm__sass_thread_inst_executed_op_dfma_pred_on.sum', 'sm__sass_thread_inst_executed_op_ffma_pred_on.sum',
              'smsp__sass_thread_inst_executed_op_fp32_pred_on.sum', 'smsp__sass_thread_inst_executed_op_fp64_pred_on.sum']
-    for stage, cmd in (('shade', 'python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e  (-k regex:k_shade -s 2 -c 1)'), ('k_shade', 'python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e  (-k regex:k_shade -s 2 -c 1)'),
-                       ('k_shadow', 'python bench.py --spp 8 --steps 1 --warmup 1 --no-cpu --no-e2e  (-k regex:k_shadow -s 2 -c 1)'),
+    for stage, cmd in (('shade', 'python bench.py --spp 8 --max-split 16 --steps 1 --warmup 1 --no-cpu --no-e2e  (-k regex:k_shade -s 2 -c 1)'), ('k_shade', 'python bench.py --spp 8 --max-split 16 --steps 1 --warmup 1 --no-cpu --no-e2e  (-k regex:k_shade -s 2 -c 1)'),
+                       ('k_shadow', 'python bench.py --spp 8 --max-split 16 --steps 1 --warmup 1 --no-cpu --no-e2e  (-k regex:k_shadow -s 2 -c 1)'),
                        ('k_bsdf', 'python tools/microbench.py --log2n 24 --reps 1 --bsdf-only  (-k regex:k_bsdf_ -s 3 -c 2: Marschner eval+pdf, then sample)')):
         rep = os.path.join(OUT, 'prof_%s_%s.ncu-rep' % (tag, stage))
         if not os.path.exists(rep):
