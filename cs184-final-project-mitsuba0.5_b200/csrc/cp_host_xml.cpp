@@ -516,6 +516,11 @@ static int load_or_validate(cudapath_ctx *ctx, bool dry, const char *filename, c
         }
         L.load(*root);
         if (out_spp) *out_spp = L.spp;
+        if (!dry) {   // the job the file describes (film size x sampleCount over the devices of the context) picks the build effort
+            int w = 0, h = 0;
+            if (cudapath_film_size(ctx, &w, &h) == 0 && w > 0 && h > 0)
+                cudapath_set_job_size_hint(ctx, (uint64_t) w * (uint64_t) h * (uint64_t) L.spp / (uint64_t) std::max(1, cudapath_device_count(ctx)));
+        }
         if (outReport) for (auto &r : L.report) *outReport += r + "\n";
         return 0;
     } catch (const std::exception &e) {

@@ -260,7 +260,7 @@ int cudapath_set_build_options(cudapath_ctx *ctx, int max_split);
  * rendered with.  The finer pre-split (16) costs 13 ms more build per 32 M references and saves 8 % of the render: it is chosen at
  * 2^25 paths per device and above, the cap of 8 below (a job split over many devices).  Like the reference's kd-tree build
  * (src/shapes/hair.cpp:108-159, one tree whatever the job) this never changes a result.  Call before cudapath_build(); an explicit
- * cudapath_set_build_options() or CUDAPATH_MAX_SPLIT wins. */
+ * cudapath_set_build_options() or CUDAPATH_MAX_SPLIT wins.  cudapath_load_scene_xml() calls it with the film size and sampleCount of the file. */
 int cudapath_set_job_size_hint(cudapath_ctx *ctx, uint64_t paths_per_device);
 
 typedef struct cudapath_stats {
