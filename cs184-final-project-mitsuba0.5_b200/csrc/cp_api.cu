@@ -909,19 +909,22 @@ int cudapath_render_dev(cudapath_ctx *ctx, uint32_t spp, uint64_t seed, uint32_t
     if (const char *e = getenv("CUDAPATH_RUNAHEAD_MAX")) ctx->wf.runAheadMax = (uint32_t) strtoul(e, nullptr, 0);
     ctx->wf.cancelRequested.store(0); ctx->wf.inRender.store(1);
     struct RenderScope { Wavefront &w; cudaEvent_t a, b; ~RenderScope() { w.inRender.store(0); w.cancelRequested.store(0); cudaEventDestroy(a); cudaEventDestroy(b); } } scope_{ctx->wf, e0, e1};
+    // Deep bounces leave only a few live paths per wave, so few, large waves keep the GPU full for longer (hair-curl at 64 spp: one 2^26 wave is
+    // 17 % faster than four 2^24 waves).  A path costs ~228 B of queue space; a wave is up to 2^26 paths (15 GB of a 180 GB B200; Wavefront::render
+    // never reserves more slots than the job has paths).  The size is NOT derived from cudaMemGetInfo: on the shared GPU hosts that query takes
+    // 0.6 ms most of the time and 25-80 ms now and then (it was inside every render until the end of round 2: the cause of the steps that took 10-45 ms
+    // longer, profiles/r2_step_time_spread_g25.log).  Instead the reservation is tried and halved while the device says it is out of memory.
     uint32_t waveSize = ctx->waveSize;
-    if (!waveSize) {
-        // Deep bounces leave only a few live paths per wave, so few, large waves keep the GPU full for longer (hair-curl at 64 spp:
-        // one 2^26 wave is 17 % faster than four 2^24 waves).  A path costs ~228 B of queue space; use up to 2^26 paths (15 GB) but
-        // never more than 40 % of the memory that is free right now (queues already held by this context count as free).
-        size_t freeB = 0, totalB = 0;
-        CKA(cudaMemGetInfo(&freeB, &totalB));
-        const double avail = 0.4 * ((double) freeB + (double) dev_cached_bytes() + 228.0 * (double) ctx->wf.capacity);   // blocks parked in the caching allocator are available too
-        waveSize = 1u << 26;
-        while (waveSize > (1u << 20) && 228.0 * waveSize > avail) waveSize >>= 1;
+    const bool autoSize = waveSize == 0;
+    if (autoSize) waveSize = 1u << 26;
+    for (;;) {
+        const bool ok = ctx->wf.render(ctx->scene, spp, seed, sample_begin, sample_end, film_dev, waveSize, ctx->collectStats != 0, ctx->profileStages != 0, st, rs, err);
+        if (ok) break;
+        if (!autoSize || waveSize <= (1u << 20) || err.find("out of memory") == std::string::npos || ctx->wf.capacity != 0) return fail(err);
+        cudaGetLastError();                  // the failed allocation is not sticky; nothing was launched (reserve() comes first and leaves capacity at 0)
+        ctx->wf.release();
+        waveSize >>= 1; rs = RenderStats(); err.clear();
     }
-    const bool ok = ctx->wf.render(ctx->scene, spp, seed, sample_begin, sample_end, film_dev, waveSize, ctx->collectStats != 0, ctx->profileStages != 0, st, rs, err);
-    if (!ok) return fail(err);
     CKA(cudaEventRecord(e1, st));
     CKA(cudaEventSynchronize(e1));
     float ms = 0; CKA(cudaEventElapsedTime(&ms, e0, e1));

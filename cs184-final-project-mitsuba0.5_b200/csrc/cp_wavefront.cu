@@ -224,9 +224,9 @@ bool Wavefront::render(const SceneDev &scene, uint32_t spp, uint64_t seed, uint3
     S.sobol.err = errFlag;
     if (trace) { cudaStreamSynchronize(stream); fprintf(stderr, "[cudapath] queue reserve (%u paths): %.3f s\n", waveSize, now() - tr0); }
     // optional per-launch stage timing: one event pair per launch, resolved after the last wave
-    struct Span { cudaEvent_t a, b; int stage; };
+    struct Span { cudaEvent_t a, b; int stage; double tHost; };
     std::vector<Span> spans;
-    auto begin = [&](int stage) { if (!profileStages) return; Span sp; cudaEventCreate(&sp.a); cudaEventCreate(&sp.b); sp.stage = stage; cudaEventRecord(sp.a, stream); spans.push_back(sp); };
+    auto begin = [&](int stage) { if (!profileStages) return; Span sp; cudaEventCreate(&sp.a); cudaEventCreate(&sp.b); sp.stage = stage; sp.tHost = now(); cudaEventRecord(sp.a, stream); spans.push_back(sp); };
     auto end = [&]() { if (profileStages) cudaEventRecord(spans.back().b, stream); };
     auto dropSpans = [&]() { for (auto &sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); } spans.clear(); };
     // the trace kernel variant of this scene and its machine-filling grid
@@ -314,6 +314,22 @@ bool Wavefront::render(const SceneDev &scene, uint32_t spp, uint64_t seed, uint3
     for (auto &sp : spans) {
         float ms = 0; cudaEventElapsedTime(&ms, sp.a, sp.b);
         rs.stageMs[sp.stage] += ms; rs.stageLaunches[sp.stage]++;
+    }
+    if (trace && spans.size() > 1) {      // where the device waited: idle time between consecutive launches, and how late the host issued the later one
+        static const char *names[] = {"trace", "shade", "sort", "raygen", "splat", "clear"};
+        double idle = 0; int shown = 0;
+        for (size_t k = 1; k < spans.size(); ++k) {
+            float gap = 0, sinceStart = 0; cudaEventElapsedTime(&gap, spans[k - 1].b, spans[k].a); cudaEventElapsedTime(&sinceStart, spans[0].a, spans[k - 1].b);
+            if (gap < 0.05f) continue;
+            idle += gap;
+            if (gap >= 0.5f && shown++ < 24)
+                fprintf(stderr, "[cudapath] idle %.2f ms before launch %zu (%s after %s); the device was free at %.2f ms, the host issued the launch at %.2f ms\n", gap, k,
+                        names[spans[k].stage], names[spans[k - 1].stage], sinceStart, (spans[k].tHost - spans[0].tHost) * 1e3);
+        }
+        float first2last = 0; cudaEventElapsedTime(&first2last, spans.front().a, spans.back().b);
+        fprintf(stderr, "[cudapath] profiled render: %zu launches, device idle between launches %.2f ms, first launch to last %.2f ms; host: entry to first launch %.2f ms, "
+                        "first launch to last issued %.2f ms, last issued to synchronised %.2f ms\n", spans.size(), idle, first2last,
+                (spans.front().tHost - tr0) * 1e3, (spans.back().tHost - spans.front().tHost) * 1e3, (now() - spans.back().tHost) * 1e3);
     }
     dropSpans();
     rs.nodesVisited += hs[0]; rs.primsTested += hs[1]; rs.shadowNodesVisited += hs[2]; rs.shadowPrimsTested += hs[3]; rs.unsupportedLookups += hs[4]; rs.droppedSamples += hs[5];
