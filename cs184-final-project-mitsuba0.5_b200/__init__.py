@@ -381,9 +381,14 @@ class Context:
         self.width, self.height = w.value, h.value
         return (self.height, self.width, 5)
 
-    def render(self, spp, seed=0, sample_begin=0, sample_end=None):
-        """Accumulated film (h,w,5) for sample indices [sample_begin, sample_end) of spp; host buffer in/out (the e2e path)."""
-        out = np.zeros(self.film_shape(), np.float32)
+    def render(self, spp, seed=0, sample_begin=0, sample_end=None, out=None):
+        """Accumulated film (h,w,5) for sample indices [sample_begin, sample_end) of spp; host buffer in/out (the e2e path).  `out`: a
+        caller-owned C-contiguous float32 array of the film's shape to receive it (e.g. the numpy view of a page-locked torch tensor:
+        the read-back then runs at PCIe speed instead of through pageable memory); it is overwritten, not accumulated into."""
+        if out is None:
+            out = np.zeros(self.film_shape(), np.float32)
+        elif out.dtype != np.float32 or tuple(out.shape) != tuple(self.film_shape()) or not out.flags['C_CONTIGUOUS']:
+            raise CudapathError('render(out=...): a C-contiguous float32 array of shape %s is required' % (tuple(self.film_shape()),))
         _check(self._L.cudapath_render(self._h, ctypes.c_uint32(spp), ctypes.c_uint64(seed), ctypes.c_uint32(sample_begin),
                                        ctypes.c_uint32(spp if sample_end is None else sample_end), _p(out)))
         return out

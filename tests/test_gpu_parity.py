@@ -734,6 +734,22 @@ def test_collapse_scratch_overflow_retries(cp, monkeypatch):
     assert np.allclose(films[0][0], films[1][0], rtol=1e-5, atol=1e-6)
 
 
+def test_render_into_a_caller_owned_host_buffer(cp):
+    """Context.render(out=...) hands cudapath_render a caller-owned host film (page-locked memory in bench.py's e2e leg): same film as the
+    buffer the mirror allocates itself, overwritten rather than accumulated into; a wrong shape or dtype is refused."""
+    ov = dict(width=40, height=24, spp=2, maxDepth=5)
+    ctx = cp.scene_from_description('straight-hair', scale=0.01, overrides=ov); ctx.build()
+    ref = ctx.render(2, seed=4)
+    buf = np.full(ref.shape, 7.0, np.float32)
+    got = ctx.render(2, seed=4, out=buf)
+    assert got is buf and np.allclose(buf, ref, rtol=1e-5, atol=1e-6)
+    with pytest.raises(cp.CudapathError):
+        ctx.render(2, seed=4, out=np.zeros(ref.shape, np.float64))
+    with pytest.raises(cp.CudapathError):
+        ctx.render(2, seed=4, out=np.zeros((3, 3, 5), np.float32))
+    ctx.close()
+
+
 def test_job_size_hint_picks_the_build_effort(cp, monkeypatch):
     """cudapath_set_job_size_hint: the pre-split cap follows the number of camera paths a device is going to trace (16 from 2^25 paths, 8
     below), an explicit cudapath_set_build_options wins, and the image is the same either way (the BVH only decides which tests run;
