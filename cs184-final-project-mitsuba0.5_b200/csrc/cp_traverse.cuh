@@ -22,8 +22,11 @@
 //
 // On-chip state: the top CP_SMEM_STACK entries of every lane's traversal stack live in shared memory (one 8-byte slot per
 // lane and level, conflict-free), only deeper entries go to local memory; the hit point and the ray slot of a lane, which
-// are written once per hit / ray and read once per ray, live there as well (they would otherwise be spilled: the FP64
-// cylinder test pins the kernel at its register cap).
+// are written once per hit / ray and read once per ray, live there as well, and so does everything else a lane touches once per
+// leaf / hit / ray rather than once per node -- the ray direction (the slab test only needs the origin and the reciprocal direction),
+// the hit distance and primitive, the cached per-shape interval: 18 KB per CTA.  The kernel's rate is nearly proportional to its
+// resident warps (a third of the persistent CTAs: 0.53 of the rate), and what caps them is registers: with the cold state out of the
+// way the descent loop fits 72 registers (7 CTAs per SM) with the spills the 80-register version had.
 #pragma once
 #include "cp_scene.cuh"
 
@@ -38,7 +41,8 @@ struct RayHit { float t; uint32_t gv; V3 p; };
 #endif
 
 #ifndef CP_MIN_BLOCKS
-#define CP_MIN_BLOCKS 6        // resident CTAs per SM the traversal kernels are compiled for (80 registers; measured best of 4/5/6/8)
+#define CP_MIN_BLOCKS 7        // resident CTAs per SM the traversal kernels are compiled for (72 registers).  With the cold per-lane state in shared memory:
+                               // 326 / 335 / 320 Mpaths/s at 6 / 7 / 8 CTAs against 312 at 6 with that state in registers (hair-curl, round 2, g31)
 #endif
 
 #ifndef CP_DESCENT_MIN_LANES
@@ -78,18 +82,26 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *rayC
 #endif
     __shared__ float s_hitP[3 * CP_TRACE_THREADS];
     __shared__ uint32_t s_slot[CP_TRACE_THREADS];
+    // state a lane touches once per leaf / hit / ray, not per node: the ray direction (the slab test only needs the origin and the reciprocal
+    // direction), the hit record and the cached per-shape interval -- in shared memory so that the descent loop fits a lower register cap
+    __shared__ float s_d[3 * CP_TRACE_THREADS];
+    __shared__ float s_hitT[CP_TRACE_THREADS];
+    __shared__ uint32_t s_hitGv[CP_TRACE_THREADS];
+    __shared__ float s_shapeIv[2 * CP_TRACE_THREADS];
+    __shared__ uint32_t s_cachedShape[CP_TRACE_THREADS];      // bit 31: the ray misses the cached shape's box
     uint2 stack[CP_STACK_SIZE - CP_SMEM_STACK];          // (node reference, entry distance bits): one 8-byte store per push
     // per-lane ray state
     bool idle = true, exhausted = false, any = (MODE == TRACE_ANY);
-    V3 o(0.0f), d(0.0f), dRcp(0.0f);
+    V3 o(0.0f), dRcp(0.0f);
+#define CP_RAY_D() V3(s_d[tid], s_d[CP_TRACE_THREADS + tid], s_d[2 * CP_TRACE_THREADS + tid])
+#define CP_HIT_T s_hitT[tid]
+#define CP_HIT_GV s_hitGv[tid]
     float mint = 0, maxt = 0, radius = 0;
     int sp = 0, cur = CP_EMPTY_CHILD;
-    float hitT = CP_INF; uint32_t hitGv = 0xffffffffu;
     bool found = false;
-    uint32_t cachedShape = 0xffffffffu; float sNear = 0, sFar = 0; bool sOk = true;
     uint32_t candMask = 0, leafFirst = 0;               // FP64 candidates of the leaf this lane holds (bit i: reference leafFirst + i)
 
-#define CP_STORE_RAY() { RayHit h_; h_.t = hitT; h_.gv = hitGv; h_.p = V3(s_hitP[tid], s_hitP[CP_TRACE_THREADS + tid], s_hitP[2 * CP_TRACE_THREADS + tid]); \
+#define CP_STORE_RAY() { RayHit h_; h_.t = CP_HIT_T; h_.gv = CP_HIT_GV; h_.p = V3(s_hitP[tid], s_hitP[CP_TRACE_THREADS + tid], s_hitP[2 * CP_TRACE_THREADS + tid]); \
                          io.store(s_slot[tid], any, found, h_); }
 
     while (true) {
@@ -107,7 +119,8 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *rayC
                     if (idx >= n) exhausted = true;
                     else {
                         float rmin, rmax; uint32_t slot = idx; bool rayAny = (MODE == TRACE_ANY);
-                        found = false; hitT = CP_INF; hitGv = 0xffffffffu;
+                        found = false; CP_HIT_T = CP_INF; CP_HIT_GV = 0xffffffffu;
+                        V3 d(0.0f);
                         s_hitP[tid] = 0.0f; s_hitP[CP_TRACE_THREADS + tid] = 0.0f; s_hitP[2 * CP_TRACE_THREADS + tid] = 0.0f;
                         bool alive = io.load(idx, o, d, rmin, rmax, rayAny, slot) && S.bvh.nodeCount > 0;
                         if (MODE == TRACE_MIXED) any = rayAny;
@@ -126,7 +139,8 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *rayC
                             if (rmax < maxt) maxt = rmax;
                             alive = alive && (maxt > mint);
                         }
-                        if (alive) { idle = false; sp = 0; cur = 0; cachedShape = 0xffffffffu; radius = S.shapes[0].radius; sOk = true; candMask = 0; }
+                        s_d[tid] = d.x; s_d[CP_TRACE_THREADS + tid] = d.y; s_d[2 * CP_TRACE_THREADS + tid] = d.z;
+                        if (alive) { idle = false; sp = 0; cur = 0; s_cachedShape[tid] = 0x7fffffffu; radius = S.shapes[0].radius; candMask = 0; }
                         else CP_STORE_RAY()
                     }
                 }
@@ -188,6 +202,7 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *rayC
             const uint32_t ref = ~(uint32_t) cur;
             const uint32_t count = (ref & 7u) + 1u;
             leafFirst = ref >> 3;
+            const V3 d = CP_RAY_D();
             for (uint32_t i = 0; i < count; ++i) {
                 const float4 v1 = __ldg(leafSeg + 2 * (size_t) (leafFirst + i)), v2 = __ldg(leafSeg + 2 * (size_t) (leafFirst + i) + 1);
                 if (STATS) tc[any ? 1 : 0].prims++;
@@ -232,6 +247,7 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *rayC
         }
         if (candMask) {
             bool done = false;
+            const V3 d = CP_RAY_D();
             while (candMask) {
                 const int ci = __ffs(candMask) - 1;
                 candMask &= candMask - 1;
@@ -243,7 +259,7 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *rayC
                     if (STATS) tc[any ? 1 : 0].fullTests++;
                     float t, u, v;
                     if (isRect ? rect_intersect(A, B, C, o, d, mint, maxt, u, v, t) : tri_intersect(A, B, C, o, d, mint, maxt, u, v, t)) {
-                        hitT = t; hitGv = gv; found = true;       // barycentrics (rectangle: local x, y) ride in the point slot
+                        CP_HIT_T = t; CP_HIT_GV = gv; found = true;       // barycentrics (rectangle: local x, y) ride in the point slot
                         s_hitP[tid] = u; s_hitP[CP_TRACE_THREADS + tid] = v; s_hitP[2 * CP_TRACE_THREADS + tid] = 0.0f;
                         if (any) { done = true; break; }
                         maxt = t;
@@ -255,12 +271,13 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *rayC
                 float tmin = mint, tmax = maxt;
                 if (multiShape) {   // per-shape clipped interval, cached for the last shape seen (hair.cpp:205-209)
                     const uint32_t sh = vtx_shape(v1);
-                    if (sh != cachedShape) {
-                        cachedShape = sh;
+                    float sNear, sFar; bool sOk;
+                    if (sh != (s_cachedShape[tid] & 0x7fffffffu)) {
                         const ShapeDev &sd = S.shapes[sh];
                         radius = sd.radius;
                         sOk = aabb_ray(sd.bmin, sd.bmax, o, d, dRcp, sNear, sFar);
-                    }
+                        s_cachedShape[tid] = sh | (sOk ? 0u : 0x80000000u); s_shapeIv[tid] = sNear; s_shapeIv[CP_TRACE_THREADS + tid] = sFar;
+                    } else { sOk = !(s_cachedShape[tid] & 0x80000000u); sNear = s_shapeIv[tid]; sFar = s_shapeIv[CP_TRACE_THREADS + tid]; }
                     if (!sOk) continue;
                     if (sNear > tmin) tmin = sNear;
                     if (sFar < tmax) tmax = sFar;
@@ -269,7 +286,7 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *rayC
                 if (STATS) tc[any ? 1 : 0].fullTests++;
                 float t; V3 p;
                 if (segment_intersect(v0, v1, v2, v3, radius, o, d, tmin, tmax, t, p)) {
-                    hitT = t; hitGv = gv; found = true;
+                    CP_HIT_T = t; CP_HIT_GV = gv; found = true;
                     s_hitP[tid] = p.x; s_hitP[CP_TRACE_THREADS + tid] = p.y; s_hitP[2 * CP_TRACE_THREADS + tid] = p.z;
                     if (any) { done = true; break; }
                     maxt = t;
@@ -283,6 +300,9 @@ CP_D void trace_persistent(const SceneDev &S, IO &io, uint32_t n, uint32_t *rayC
 #undef CP_PUSH
 #undef CP_STACK_AT
 #undef CP_STORE_RAY
+#undef CP_RAY_D
+#undef CP_HIT_T
+#undef CP_HIT_GV
     }
 }
 
